@@ -1,0 +1,229 @@
+/*
+ * silo_b200.h — C ABI of libsilo_b200.so: the B200 (sm_100a) drop-in for the bitmap filter +
+ * Mutations hot path of RhyDB/SILO (GenSpectrum/LAPIS-SILO v0.13.3).
+ *
+ * The reference has no FFI seam on this path; the boundary replaces the BODIES of three call sites
+ * (paths relative to /root/reference/src/rhydb), leaving every signature above them untouched:
+ *
+ *   S1 upload  storage/table.cpp:87-94 (Table::finalize) and :227-235 (Table::loadData):
+ *              walk SequenceColumn::{vertical_sequence_index.vertical_bitmaps,
+ *              horizontal_coverage_index, null_bitmap, local_reference_sequence_string}
+ *              (storage/column/sequence_column.h:104-114) + Table::row_layout
+ *              -> silo_gpu_table_create / silo_gpu_column_upload
+ *   S2 filter  query_engine/operators/compute_filter.cpp:14-21 (and database.cpp:275-278):
+ *              after rewrite()+compile(), the Operator tree (filter/operators/operator.h:11-39) is
+ *              lowered to a flat filter program -> silo_gpu_filter_eval
+ *   S3 action  query_engine/operators/mutations_node.cpp:268-288 (calculateMutationsPerPosition)
+ *              -> silo_gpu_mutation_counts; addMutationsToOutput (:290-366) stays on the host.
+ *              query_engine/operators/count_filter_node.cpp:35-71 -> silo_gpu_filter_cardinality
+ *
+ * Plain C: opaque handles, plain pointers and sizes, caller-owned outputs. Every function returns
+ * 0 on success or a negative silo_status; silo_gpu_last_error() returns the thread-local message.
+ * There is NO CPU fallback: without a CUDA device every entry point fails with SILO_E_NO_DEVICE.
+ *
+ * Row ids are the reference's sparse global ids (storage/column/row_id.h:16-37):
+ *   id = (chunk_id << 16) | row_in_chunk, chunk k owns [k<<16, (k<<16)+chunk_size(k)).
+ * A table handle may hold a SHARD of the chunks (multi-GPU: one process per GPU, contiguous chunk
+ * ranges); `first_chunk` is the global chunk id of the shard's first chunk.
+ */
+#ifndef SILO_B200_H
+#define SILO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+   SILO_OK = 0,
+   SILO_E_INVALID_ARGUMENT = -1,
+   SILO_E_NO_DEVICE = -2,
+   SILO_E_CUDA = -3,
+   SILO_E_OUT_OF_MEMORY = -4,
+   SILO_E_BAD_PROGRAM = -5,
+   SILO_E_OUT_OF_LAYOUT = -6, /* a leaf bitmap holds ids outside the row layout (row_layout.h:49-52
+                                 states the precondition the reference relies on) */
+   SILO_E_UNSUPPORTED = -7
+} silo_status;
+
+typedef struct silo_gpu_ctx silo_gpu_ctx;       /* one per process+device: streams, scratch pools */
+typedef struct silo_gpu_table silo_gpu_table;   /* row layout of one table (shard) + its columns */
+typedef struct silo_gpu_filter silo_gpu_filter; /* device-resident dense filter result */
+
+const char* silo_gpu_last_error(void);
+/* "libsilo_b200 <version> sm_100a" */
+const char* silo_gpu_version(void);
+
+int silo_gpu_init(int device_ordinal, silo_gpu_ctx** out);
+void silo_gpu_shutdown(silo_gpu_ctx* ctx);
+
+/* ---- S1: upload ------------------------------------------------------------------------------ */
+
+/* One stored diff container: key of VerticalSequenceIndex::SequenceDiffKey
+ * (storage/column/vertical_sequence_index.h:22-39) + the RoaringContainer bookkeeping
+ * (roaring_util/roaring_container.h:24-26). payload = exactly what
+ * roaring::internal::container_write emits (roaring_container.h:104-116):
+ *   typecode 1 bitset: 1024 x u64 LE | 2 array: cardinality x u16 ascending
+ *   | 3 run: u16 n_runs, then n_runs x {u16 start, u16 length_minus_1} */
+typedef struct {
+   uint32_t position;
+   uint16_t v_index; /* GLOBAL chunk id */
+   uint8_t symbol;
+   uint8_t typecode;
+   uint32_t cardinality;
+   uint32_t payload_bytes;
+   uint64_t payload_offset; /* into silo_column_desc.payload */
+} silo_container_desc;
+
+typedef struct {
+   uint32_t struct_size; /* sizeof(silo_column_desc), for ABI evolution */
+   uint32_t n_symbols;   /* 16 nucleotide (nucleotide_symbols.h:42), 28 amino acid (aa_symbols.h:57) */
+   uint32_t genome_length;
+   uint32_t missing_symbol;        /* Nucleotide::N = 15, AminoAcid::X = 27 */
+   const uint8_t* local_reference; /* [genome_length] symbol ids, sequence_column.h:104 */
+   /* vertical index, in std::map order (position, v_index, symbol); only chunks of this shard */
+   uint64_t n_containers;
+   const silo_container_desc* containers;
+   const uint8_t* payload;
+   uint64_t payload_bytes;
+   /* horizontal coverage index (horizontal_coverage_index.h:25-35) */
+   const uint32_t* start_end; /* {start,end} per row, rows of the shard's chunks back to back */
+   uint64_t n_rows_with_missing;     /* horizontal_bitmaps.size() */
+   const uint32_t* missing_row_ids;  /* ascending global row ids */
+   const uint64_t* missing_offsets;  /* [n_rows_with_missing + 1], in runs */
+   const uint32_t* missing_runs;     /* {first, end_exclusive} runs of the row's N positions */
+   uint64_t n_null_rows; /* null_bitmap, sequence_column.h:111 */
+   const uint32_t* null_row_ids;
+} silo_column_desc;
+
+int silo_gpu_table_create(
+   silo_gpu_ctx* ctx,
+   uint32_t first_chunk,
+   const uint32_t* chunk_sizes, /* RowLayout::chunk_sizes of the shard, row_layout.h:28 */
+   uint32_t n_chunks,
+   silo_gpu_table** out
+);
+void silo_gpu_table_free(silo_gpu_table* table);
+/* Copies everything; the caller keeps ownership of the inputs. Returns the column index (>= 0). */
+int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* column);
+/* bytes of HBM held by the table's pools */
+uint64_t silo_gpu_table_device_bytes(const silo_gpu_table* table);
+
+/* ---- S2: filter program ---------------------------------------------------------------------- */
+
+/* Stack machine evaluated independently per chunk over dense 64 Ki-row tiles (1024 x u64).
+ * Leaves push a tile, operators pop/push. Mapping from the reference's operators:
+ *   Empty/Full (empty.cpp:25, full.cpp:26)            PUSH_EMPTY / PUSH_FULL
+ *   IndexScan over vertical-index views (symbol_in_set.cpp:216-228)   PUSH_SYMBOLS
+ *   IndexScan over a foreign roaring (lineage_filter.cpp:96-99, null_bitmap) PUSH_BITMAP / PUSH_NULLS
+ *   Selection(IsInCoveredRegion) (is_in_covered_region.cpp:53-62)     PUSH_COVERED (flag: negated)
+ *   RangeSelection (range_selection.cpp:54-87)        PUSH_RANGES
+ *   Intersection (intersection.cpp:59-105)            chain of AND / ANDNOT
+ *   Union (union.cpp:34-42)                           chain of OR
+ *   Complement (complement.cpp:51-56)                 NOT  (flip inside [0, chunk_size) only)
+ *   Threshold (threshold.cpp:64-138)                  THR_BEGIN .. THR_ADD* .. THR_END */
+typedef enum {
+   SILO_OP_PUSH_EMPTY = 1,
+   SILO_OP_PUSH_FULL = 2,
+   SILO_OP_PUSH_SYMBOLS = 3, /* column, a = position, b = symbol bit mask */
+   SILO_OP_PUSH_COVERED = 4, /* column, a = position, flags&1: NOT covered (within the layout) */
+   SILO_OP_PUSH_NULLS = 5,   /* column */
+   SILO_OP_PUSH_BITMAP = 6,  /* a = index into silo_filter_program.bitmaps */
+   SILO_OP_PUSH_RANGES = 7,  /* a = number of ranges, b = byte offset into blob of {u32 start,u32 end} */
+   SILO_OP_AND = 16,         /* pop y, pop x, push x & y */
+   SILO_OP_ANDNOT = 17,      /* pop y, pop x, push x & ~y */
+   SILO_OP_OR = 18,          /* pop y, pop x, push x | y */
+   SILO_OP_NOT = 19,         /* top ^= layout mask */
+   SILO_OP_THR_BEGIN = 32,   /* a = number_of_matchers, flags&1: match_exactly */
+   SILO_OP_THR_ADD = 33,     /* pop child tile; flags&1: negated child (counts rows NOT in it) */
+   SILO_OP_THR_ADD_SYMBOLS = 34, /* column, a = position, b = mask; flags&1: subtract instead */
+   SILO_OP_THR_ADD_COVERED = 35, /* column, a = n positions, b = blob offset of sorted u32 positions:
+                                    +1 per listed position the row covers */
+   SILO_OP_THR_PROFILE = 36, /* column, b = blob offset of u32[2*genome_length]: per position
+                                {add_mask, sub_mask}; every stored container (pos,sym) adds +1 to its
+                                rows if sym in add_mask, -1 if in sub_mask. One streaming pass. */
+   SILO_OP_THR_END = 37      /* push (count >= k) or (count == k), restricted to the layout */
+} silo_filter_opcode;
+
+typedef struct {
+   uint8_t opcode;
+   uint8_t flags;
+   uint16_t column;
+   uint32_t a;
+   uint64_t b;
+} silo_filter_instr;
+
+/* A ready-made roaring bitmap entering the program (lineage / dictionary index, host-evaluated
+ * Selection result ...), in the portable Roaring format that Roaring::write emits
+ * (roaring_util/roaring_serialize.h:15-30), global row ids. */
+typedef struct {
+   const uint8_t* data;
+   uint64_t size;
+} silo_roaring_bytes;
+
+typedef struct {
+   uint32_t struct_size;
+   uint32_t n_instrs;
+   const silo_filter_instr* instrs;
+   const uint8_t* blob;
+   uint64_t blob_bytes;
+   uint32_t n_bitmaps;
+   const silo_roaring_bytes* bitmaps;
+} silo_filter_program;
+
+/* Evaluates the program over every chunk of the table. cardinality may be NULL. */
+int silo_gpu_filter_eval(
+   silo_gpu_table* table,
+   const silo_filter_program* program,
+   silo_gpu_filter** out,
+   uint64_t* cardinality
+);
+/* Wraps caller-provided dense words: bit r of words[c*1024 + r/64] = row ((first_chunk+c)<<16)|r. */
+int silo_gpu_filter_from_words(silo_gpu_table* table, const uint64_t* words, silo_gpu_filter** out);
+int silo_gpu_filter_cardinality(const silo_gpu_filter* filter, uint64_t* cardinality);
+/* words[1024 * n_chunks] */
+int silo_gpu_filter_download(const silo_gpu_filter* filter, uint64_t* words);
+void silo_gpu_filter_free(silo_gpu_filter* filter);
+
+/* ---- S3: Mutations action -------------------------------------------------------------------- */
+
+/* counts[symbol * genome_length + position] = SymbolMap<Sym, vector<u32>> of
+ * calculateMutationsPerPosition (mutations_node.cpp:268-288), for the rows of this shard.
+ * filter == NULL means "all rows" (the cardinality == numRows path, :280-281). uint32 arithmetic is
+ * modular exactly like the reference's count_per_local_reference_position. Shards are plain
+ * addends: the multi-GPU result is the element-wise sum over ranks. */
+int silo_gpu_mutation_counts(
+   silo_gpu_table* table,
+   int column,
+   const silo_gpu_filter* filter,
+   uint32_t* counts
+);
+
+/* Same, but leaves the counts in device memory (d_counts: n_symbols*genome_length u32) and only
+ * enqueues on `cuda_stream` (a cudaStream_t; NULL = the table's own stream) without synchronising,
+ * so that a collective (ncclAllReduce on the same stream) can follow with no host round trip. */
+int silo_gpu_mutation_counts_async(
+   silo_gpu_table* table,
+   int column,
+   const silo_gpu_filter* filter,
+   void* d_counts,
+   void* cuda_stream
+);
+
+/* ---- measurement hooks (bench.py / profiles; not needed by the reference) --------------------- */
+
+typedef struct {
+   uint64_t containers;          /* containers touched by the last mutation_counts call */
+   uint64_t algorithmic_bytes;   /* descriptor + payload + filter tiles + coverage rows + counts */
+   uint64_t kernel_launches;     /* launched by this library since ctx init */
+   float last_counts_kernel_ms;  /* CUDA-event duration of the dominant (container AND) kernel */
+   float last_total_ms;          /* CUDA-event duration of the whole last mutation_counts enqueue */
+} silo_gpu_stats;
+int silo_gpu_get_stats(const silo_gpu_table* table, silo_gpu_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SILO_B200_H */
