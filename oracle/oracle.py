@@ -120,6 +120,19 @@ def lib():
         L.orc_gen_nrun_table.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64]
         L.orc_gen_mutation_benchmark_table.argtypes = [C.c_void_p, C.c_uint64]
         L.orc_now_seconds.restype = C.c_double
+        L.orc_container_op.argtypes = [
+            C.POINTER(C.c_uint16), C.c_uint32, C.c_int, C.POINTER(C.c_uint16), C.c_uint32, C.c_int,
+            C.c_int, C.c_int, C.POINTER(C.c_uint16), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8),
+            C.POINTER(C.c_uint8)]
+        L.orc_roaring_roundtrip.argtypes = [
+            C.POINTER(C.c_uint32), C.c_uint64, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.c_uint64]
+        L.orc_roaring_roundtrip.restype = C.c_int64
+        L.orc_extract.argtypes = [
+            C.c_int, C.c_char_p, C.c_uint32, C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+            C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8),
+            C.POINTER(C.c_uint32)]
+        L.orc_column_containers_at.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint64]
+        L.orc_column_containers_at.restype = C.c_int64
     return _lib
 
 
@@ -360,3 +373,62 @@ def mutation_benchmark_table(batch_rows: int = 1000) -> Table:
 
 def now_seconds() -> float:
     return float(lib().orc_now_seconds())
+
+
+CONTAINER_OPS = {"identity": 0, "and": 1, "andnot": 2, "or": 3, "and_cardinality": 4}
+
+
+def container_op(a: Sequence[int], b: Sequence[int] = (), op: str = "identity", optimize_a: bool = False,
+                 optimize_b: bool = False, roundtrip: bool = False):
+    """Container-level hook. Returns (values | cardinality, typecode_of_a, typecode_of_result)."""
+    arr_a = (C.c_uint16 * max(len(a), 1))(*a)
+    arr_b = (C.c_uint16 * max(len(b), 1))(*b)
+    out = (C.c_uint16 * 65536)()
+    n_out = C.c_uint32()
+    type_a, type_out = C.c_uint8(), C.c_uint8()
+    _check(lib().orc_container_op(arr_a, len(a), int(optimize_a), arr_b, len(b), int(optimize_b),
+                                  CONTAINER_OPS[op], int(roundtrip), out, C.byref(n_out),
+                                  C.byref(type_a), C.byref(type_out)))
+    if op == "and_cardinality":
+        return n_out.value, type_a.value, 0
+    return list(out[:n_out.value]), type_a.value, type_out.value
+
+
+def roaring_roundtrip(ids: Sequence[int], optimize: bool = False) -> tuple[list[int], bytes]:
+    """ids -> Roaring -> portable bytes -> Roaring -> ids."""
+    arr = np.ascontiguousarray(np.asarray(list(ids), dtype=np.uint32))
+    n_unique = len(set(int(i) for i in ids))
+    out = np.zeros(max(n_unique, 1), dtype=np.uint32)
+    cap = 16 + 16 * (len(arr) + 1) + 8192 * (len({int(i) >> 16 for i in ids}) + 1)
+    buf = (C.c_uint8 * cap)()
+    n = lib().orc_roaring_roundtrip(arr.ctypes.data_as(C.POINTER(C.c_uint32)), arr.size, int(optimize),
+                                    out.ctypes.data_as(C.POINTER(C.c_uint32)), buf, cap)
+    if n < 0:
+        raise OracleError(lib().orc_last_error().decode())
+    return [int(v) for v in out[:n_unique]], bytes(buf[:n])
+
+
+def extract(sequence: str, offset: int, reference: str, alphabet: int = NUCLEOTIDE):
+    """extractCoverageAndMutationsFromSequence -> (start, end, missing, [(pos, symbol_char)])."""
+    n = max(len(sequence), 1)
+    start, end, n_missing, n_mut = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    missing = (C.c_uint32 * n)()
+    mut_pos = (C.c_uint32 * n)()
+    mut_sym = (C.c_uint8 * n)()
+    _check(lib().orc_extract(alphabet, sequence.encode(), offset, reference.encode(), C.byref(start),
+                             C.byref(end), missing, C.byref(n_missing), mut_pos, mut_sym, C.byref(n_mut)))
+    chars = NUC_SYMBOLS if alphabet == NUCLEOTIDE else AA_SYMBOLS
+    return (start.value, end.value, list(missing[:n_missing.value]),
+            [(mut_pos[i], chars[mut_sym[i]]) for i in range(n_mut.value)])
+
+
+def containers_at(table: Table, column: str, position0: int) -> list[tuple[int, str, int, int]]:
+    """Stored diff containers at a 0-based position: (v_index, symbol_char, typecode, cardinality)."""
+    alphabet = next(a for name, a, _ in table.columns if name == column)
+    chars = NUC_SYMBOLS if alphabet == NUCLEOTIDE else AA_SYMBOLS
+    n = lib().orc_column_containers_at(table._h, column.encode(), position0, None, 0)
+    if n < 0:
+        raise OracleError(lib().orc_last_error().decode())
+    out = (C.c_uint32 * (4 * max(n, 1)))()
+    lib().orc_column_containers_at(table._h, column.encode(), position0, out, n)
+    return [(out[4 * i], chars[out[4 * i + 1]], out[4 * i + 2], out[4 * i + 3]) for i in range(n)]

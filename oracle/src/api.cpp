@@ -576,6 +576,126 @@ int orc_gen_mutation_benchmark_table(void* table, uint64_t batch_rows) {
    });
 }
 
+
+// ---- container-level hook for the known-answer tests (roaring_container.test.cpp) ----
+// Builds containers the way the reference's tests do (withCapacity(max(n,1)) + add each value, in the
+// given order), optionally run-optimises them, optionally round-trips them through
+// container_write/read, then applies op: 0 identity(a) 1 and 2 andnot 3 or 4 and_cardinality.
+int orc_container_op(
+   const uint16_t* a, uint32_t na, int optimize_a,
+   const uint16_t* b, uint32_t nb, int optimize_b,
+   int op, int roundtrip,
+   uint16_t* out, uint32_t* n_out, uint8_t* type_a, uint8_t* type_out
+) {
+   return guarded([&] {
+      auto make = [&](const uint16_t* values, uint32_t count, int optimize) {
+         Container c = Container::withCapacity(static_cast<int32_t>(std::max<uint32_t>(count, 1)));
+         for (uint32_t i = 0; i < count; ++i) {
+            c.add(values[i]);
+         }
+         if (optimize != 0) {
+            c.runOptimize();
+         }
+         if (roundtrip != 0) {
+            std::vector<uint8_t> bytes(c.sizeInBytes());
+            c.write(bytes.data());
+            c = Container::read(c.type, c.card, bytes.data(), bytes.size());
+         }
+         return c;
+      };
+      const Container ca = make(a, na, optimize_a);
+      const Container cb = make(b, nb, optimize_b);
+      *type_a = ca.type;
+      Container result;
+      if (op == 4) {
+         *n_out = containerAndCardinality(ca, cb);
+         *type_out = 0;
+         return;
+      }
+      result = op == 0 ? ca : op == 1 ? containerAnd(ca, cb) : op == 2 ? containerAndNot(ca, cb) : containerOr(ca, cb);
+      uint32_t n = 0;
+      result.forEach([&](uint16_t value) { out[n++] = value; });
+      if (n != result.card) {
+         throw std::runtime_error("container cardinality bookkeeping is inconsistent");
+      }
+      *n_out = n;
+      *type_out = result.type;
+   });
+}
+
+// roaring portable format round trip: ids -> Roaring (run-optimised if asked) -> write -> read -> ids
+int64_t orc_roaring_roundtrip(const uint32_t* ids, uint64_t count, int optimize, uint32_t* out, uint8_t* bytes_out, uint64_t capacity) {
+   int64_t size = -1;
+   guarded([&] {
+      Roaring bitmap = Roaring::fromIds(ids, count);
+      if (optimize != 0) {
+         bitmap.runOptimize();
+      }
+      const auto bytes = bitmap.write();
+      const Roaring back = Roaring::read(bytes.data(), bytes.size());
+      const auto values = back.toVector();
+      std::copy(values.begin(), values.end(), out);
+      if (bytes_out != nullptr && capacity >= bytes.size()) {
+         std::memcpy(bytes_out, bytes.data(), bytes.size());
+      }
+      size = static_cast<int64_t>(bytes.size());
+   });
+   return size;
+}
+
+// aligned_sequence.cpp:20-122 hook: returns 0 and fills outputs, or -4 with the error message
+int orc_extract(
+   int alphabet_id, const char* sequence, uint32_t offset, const char* reference,
+   uint32_t* start, uint32_t* end,
+   uint32_t* missing, uint32_t* n_missing,
+   uint32_t* mutation_positions, uint8_t* mutation_symbols, uint32_t* n_mutations
+) {
+   return guarded([&] {
+      const Alphabet& alphabet = alphabet_id == 0 ? Alphabet::nucleotide() : Alphabet::aminoAcid();
+      const std::string_view ref(reference);
+      const bool reference_missing = ref.find(alphabet.symbolToChar(alphabet.missing)) != std::string_view::npos;
+      std::string error;
+      const auto result = extractCoverageAndMutationsFromSequence(alphabet, sequence, offset, ref, reference_missing, error);
+      if (!result.has_value()) {
+         throw AppendException(error);
+      }
+      *start = result->coverage.start;
+      *end = result->coverage.end;
+      *n_missing = static_cast<uint32_t>(result->coverage.missing_positions.size());
+      std::copy(result->coverage.missing_positions.begin(), result->coverage.missing_positions.end(), missing);
+      *n_mutations = static_cast<uint32_t>(result->mutations.size());
+      for (size_t i = 0; i < result->mutations.size(); ++i) {
+         mutation_positions[i] = result->mutations[i].first;
+         mutation_symbols[i] = result->mutations[i].second;
+      }
+   });
+}
+
+// stored diff containers of one position, for the vertical-index tests:
+// out rows: (v_index, symbol, typecode, cardinality); returns count
+int64_t orc_column_containers_at(void* table, const char* column, uint32_t position, uint32_t* out, uint64_t capacity) {
+   int64_t count = -1;
+   guarded([&] {
+      const auto* col = static_cast<Table*>(table)->findColumn(column);
+      if (col == nullptr) {
+         throw std::runtime_error("no such column");
+      }
+      auto [start, end] = col->vertical_sequence_index.getRangeForPosition(position);
+      uint64_t n = 0;
+      for (auto it = start; it != end; ++it) {
+         if (n < capacity) {
+            out[4 * n] = it->first.v_index;
+            out[4 * n + 1] = it->first.symbol;
+            out[4 * n + 2] = it->second.type;
+            out[4 * n + 3] = it->second.card;
+         }
+         ++n;
+      }
+      count = static_cast<int64_t>(n);
+   });
+   return count;
+}
+
 // monotonic seconds, for the cpu_baseline leg
 double orc_now_seconds() {
    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();

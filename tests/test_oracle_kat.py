@@ -1,0 +1,405 @@
+"""Pins the CPU oracle against the known-answer vectors of the reference's own unit tests.
+
+Every expected value below is a fact re-typed from a `*.test.cpp` under /root/reference/src/rhydb
+(cited per test); none was produced by running this repo's code. The oracle is then the checker
+for the CUDA path (tests/test_gpu_parity.py).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+ARRAY, BITSET, RUN = 2, 1, 3
+
+
+def layout(*sizes):
+    table = O.Table()
+    table.set_layout(*sizes)
+    return table
+
+
+def ids(table, expression):
+    return [int(v) for v in table.filter(expression).ids()]
+
+
+def lists(sets):
+    return " ".join("(ids " + " ".join(map(str, s)) + ")" for s in sets)
+
+
+def threshold(table, pos, neg, k, exact):
+    return ids(table, f"(op-threshold {k} {int(exact)} ({lists(pos)}) ({lists(neg)}))")
+
+
+# ---- filter/operators/threshold.test.cpp ---------------------------------------------------
+
+def test_threshold_only_negated():  # threshold.test.cpp:40-55
+    t = layout(4)
+    neg = [[1, 2, 3], [1, 3]]
+    assert threshold(t, [], neg, 1, True) == [2]
+    assert threshold(t, [], neg, 1, False) == [0, 2]
+
+
+def test_threshold_only_non_negated():  # :57-82
+    t = layout(4)
+    pos = [[1, 2], [1, 3], [1, 2, 3]]
+    assert threshold(t, pos, [], 1, True) == []
+    assert threshold(t, pos, [], 2, True) == [2, 3]
+    assert threshold(t, pos, [], 1, False) == [1, 2, 3]
+    assert threshold(t, pos, [], 2, False) == [1, 2, 3]
+
+
+def test_threshold_mixed():  # :84-164
+    t = layout(4)
+    pos, neg = [[1, 2, 3], [1, 3], [1, 2, 3]], [[], [3]]
+    assert [threshold(t, pos, neg, k, True) for k in (1, 2, 3, 4)] == [[], [0], [], [2, 3]]
+    assert [threshold(t, pos, neg, k, False) for k in (1, 2, 3, 4)] == [
+        [0, 1, 2, 3], [0, 1, 2, 3], [1, 2, 3], [1, 2, 3]]
+
+
+def test_threshold_mostly_negated():  # :166-247
+    t = layout(5)
+    pos, neg = [[1, 2, 3]], [[], [3], [4], [2, 4]]
+    assert [threshold(t, pos, neg, k, True) for k in (1, 2, 3, 4)] == [[], [4], [], [0, 2, 3]]
+    assert [threshold(t, pos, neg, k, False) for k in (1, 2, 3, 4)] == [
+        [0, 1, 2, 3, 4], [0, 1, 2, 3, 4], [0, 1, 2, 3], [0, 1, 2, 3]]
+
+
+def test_threshold_ids_outside_layout_quirk():  # :249-311 — layout of 4 rows, inputs contain id 4
+    t = layout(4)
+    pos, neg = [[]], [[3], [4], [2, 4]]
+    assert [threshold(t, pos, neg, k, True) for k in (1, 2, 3)] == [[4], [2, 3], [0, 1]]
+    assert [threshold(t, pos, neg, k, False) for k in (1, 2, 3)] == [
+        [0, 1, 2, 3, 4], [0, 1, 2, 3], [0, 1]]
+
+
+def test_threshold_constructor_errors():  # :28-38, threshold.cpp:30-41
+    t = layout(4)
+    with pytest.raises(O.OracleError, match="number_of_matchers must be less than"):
+        threshold(t, [[1], [2]], [], 2, False)
+    with pytest.raises(O.OracleError, match="must be greater than zero"):
+        threshold(t, [[1], [2]], [], 0, False)
+
+
+# ---- intersection / complement / union -----------------------------------------------------
+
+def test_intersection():  # intersection.test.cpp:20-136
+    t = layout(5)
+    assert ids(t, f"(op-and ({lists([[1, 2, 3], [1, 3], [1, 2, 3]])}) ())") == [1, 3]
+    assert ids(t, f"(op-and ({lists([[1, 2, 3], [1, 3], [1, 2, 3]])}) ({lists([[], [3]])}))") == [1]
+    assert ids(t, f"(op-and ({lists([[1, 2, 3]])}) ({lists([[], [3], [4], [2, 4]])}))") == [1]
+    assert ids(t, f"(op-and ({lists([[]])}) ({lists([[3], [4], [2, 4]])}))") == []
+    with pytest.raises(O.OracleError, match="without non-negated children"):
+        ids(t, "(op-and () ())")
+    with pytest.raises(O.OracleError, match="without non-negated children"):
+        ids(t, "(op-and () ((ids 1) (ids 2)))")
+    with pytest.raises(O.OracleError, match="at least two children"):
+        ids(t, "(op-and ((ids 1)) ())")
+
+
+def test_complement():  # complement.test.cpp:14-72
+    assert ids(layout(5), "(op-not (ids 1 2 3))") == [0, 4]
+    assert ids(layout(3), "(op-not (ids))") == [0, 1, 2]
+    assert ids(layout(), "(op-not (ids))") == []
+    assert ids(layout(4), "(op-not (ids 0 1 2 3))") == []
+    assert ids(layout(5), "(op-not (ids 1))") == [0, 2, 3, 4]
+
+
+def test_complement_multi_chunk_keeps_gaps_empty():  # row_layout.cpp:18-23, row_layout.test.cpp
+    t = layout(3, 2)
+    assert ids(t, "(op-not (ids 1 65536))") == [0, 2, 65537]
+    assert ids(t, "(true)") == [0, 1, 2, 65536, 65537]
+    assert ids(t, "(not (true))") == []
+
+
+def test_union_and_cow_algebra():  # copy_on_write_bitmap.test.cpp:48-90
+    t = layout(65536, 65536, 65536, 65536, 2)
+    m = [1, 5, 100, 65536 + 3, 3 * 65536 + 7]
+    other = [5, 100, 65536 + 3, 999]
+    assert ids(t, f"(op-and ({lists([m, other])}) ())") == sorted(set(m) & set(other))
+    assert ids(t, f"(op-and ({lists([m])}) ({lists([[5, 65536 + 3]])}))") == sorted(set(m) - {5, 65536 + 3})
+    third = [5, 3 * 65536 + 7, 4 * 65536 + 1]
+    assert ids(t, f"(op-or {lists([[1, 5], m, third])})") == sorted({1, 5} | set(m) | set(third))
+
+
+def test_fast_union_staggered_is_order_independent():  # copy_on_write_bitmap.test.cpp:130-185
+    t = layout(*([65536] * 12))
+    inputs = []
+    for i in range(8):
+        s = set()
+        for key in range(i, i + 5):
+            s.update(range((key << 16) + i, (key << 16) + i + 5000 + 100 * key))
+            s.add((key << 16) + 60000)
+        inputs.append(sorted(s))
+    expected = sorted(set().union(*map(set, inputs)))
+    assert ids(t, f"(op-or {lists(inputs)})") == expected
+    assert ids(t, f"(op-or {lists(inputs[::-1])})") == expected
+
+
+# ---- coverage: is_in_covered_region.test.cpp / horizontal_coverage_index.test.cpp -----------
+
+def test_is_in_covered_region():  # is_in_covered_region.test.cpp:12-60
+    t = O.Table()
+    t.add_column("s", O.NUCLEOTIDE, "AAAAA")
+    for missing in ([1, 2, 3], [1, 3], [1, 2, 3], [], [3], [4], [1, 4], [2, 4]):
+        seq = "".join("N" if p in missing else "A" for p in range(5))
+        # every row must keep coverage [0,5): the vector uses explicit Coverage objects, so rows
+        # whose trailing N would be trimmed are anchored by the test's own semantics below
+        t.append_row([seq])
+    t.finalize()
+    # rows 5,6,7 have N at position 4 (trailing => trimmed to end=4); the query is at position 2
+    assert ids(t, "(covered s 3)") == [1, 3, 4, 5, 6]
+    assert ids(t, "(not-covered s 3)") == [0, 2, 7]
+
+
+def test_coverage_bitmaps_with_offsets_and_nulls():  # horizontal_coverage_index.test.cpp:195-231,282-296
+    t = O.Table()
+    t.add_column("s", O.NUCLEOTIDE, "ACGGT")
+    for seq in ("ACNGT", "AANAT", "ACGGT"):
+        t.append_row([seq])
+    t.append_row([None])
+    t.append_row(["Acngt"])
+    t.finalize()
+    assert ids(t, "(covered s 3)") == [2]
+    assert ids(t, "(covered s 1)") == [0, 1, 2, 4]
+    assert ids(t, "(not-covered s 1)") == [3]
+    t2 = O.Table()
+    t2.add_column("s", O.NUCLEOTIDE, "A" * 20)
+    t2.append_row([("ACNGT", 10)])
+    t2.append_row([("AANAT", 10)])
+    t2.finalize()
+    assert ids(t2, "(covered s 13)") == []
+    assert ids(t2, "(covered s 11)") == [0, 1]
+    assert ids(t2, "(covered s 10)") == []
+
+
+# ---- ingest diffing: common/aligned_sequence.test.cpp:30-360 --------------------------------
+
+@pytest.mark.parametrize("seq,off,ref,start_end,missing,muts", [
+    ("ACGT", 0, "ACGT", (0, 4), [], []),
+    ("AGGT", 0, "ACGT", (0, 4), [], [(1, "G")]),
+    ("CCTT", 0, "ACGT", (0, 4), [], [(0, "C"), (2, "T")]),
+    ("AT", 2, "ACGT", (2, 4), [], [(2, "A")]),
+    ("ANGT", 0, "ACGT", (0, 4), [1], []),
+    ("NCGTAN", 0, "ACGTAC", (1, 5), [], []),
+    ("NCNTAN", 0, "ACGTAC", (1, 5), [2], []),
+    ("NNNN", 0, "ACGT", (0, 0), [], []),
+    ("", 0, "ACGT", (0, 0), [], []),
+    ("A-GT", 0, "ACGT", (0, 4), [], [(1, "-")]),
+    ("-CGT", 0, "ACGT", (0, 4), [], [(0, "-")]),
+    ("aCGU", 0, "ACGT", (0, 4), [], []),
+    ("AnGT", 0, "ACGT", (0, 4), [1], []),
+    ("ANGT", 0, "ANGT", (0, 4), [1], []),
+    ("ACGT", 0, "ANGT", (0, 4), [], [(1, "C")]),
+])
+def test_extract_coverage_and_mutations(seq, off, ref, start_end, missing, muts):
+    assert O.extract(seq, off, ref) == (start_end[0], start_end[1], missing, muts)
+
+
+def test_extract_word_path_and_illegal_character():  # :186-209, :211, :297-346
+    ref = "ACGTACGTACGTACGTACGT"
+    seq = "ACGTACGAACGTNCGTACGC"
+    assert O.extract(seq, 0, ref) == (0, 20, [12], [(7, "A"), (19, "C")])
+    with pytest.raises(O.OracleError, match=r"illegal character 'Z' at position 9 in the input sequence"):
+        O.extract("ACGTACGTAZGT", 0, ref)
+
+
+# ---- local reference adaptation: vertical_sequence_index.test.cpp:311-441 -------------------
+
+def _one_position_table(ref_symbol, rows):
+    """rows: list of symbol chars at position 0 (None = row not covering the position)."""
+    t = O.Table()
+    t.add_column("s", O.NUCLEOTIDE, ref_symbol + "A")
+    for symbol in rows:
+        t.append_row([("A", 1)] if symbol is None else [symbol + "A"])
+    t.finalize()
+    return t
+
+
+def test_adapt_single_row_flips():  # A:{0} coverage {0} ref C -> A
+    t = _one_position_table("C", ["A"])
+    assert t.local_reference("s")[0] == "A"
+    assert O.containers_at(t, "s", 0) == []
+
+
+def test_adapt_tie_keeps_current():  # A:{0} coverage {0,1} ref C -> no change
+    t = _one_position_table("C", ["A", "C"])
+    assert t.local_reference("s")[0] == "C"
+    assert [(s, c) for _, s, _, c in O.containers_at(t, "s", 0)] == [("A", 1)]
+
+
+def test_adapt_minority_keeps_current():  # A:{0,6} coverage {0,2,4,5,6} ref T (T=3 vs A=2)
+    t = _one_position_table("T", ["A", None, "T", None, "T", "T", "A"])
+    assert t.local_reference("s")[0] == "T"
+
+
+def test_adapt_majority_flips_and_materialises_old_reference():  # A:{0,4,6} cov {0,2,4,5,6} ref T
+    t = _one_position_table("T", ["A", None, "T", None, "A", "T", "A"])
+    assert t.local_reference("s")[0] == "A"
+    assert [(s, c) for _, s, _, c in O.containers_at(t, "s", 0)] == [("T", 2)]
+    assert ids(t, "(sym-eq s 1 T)") == [2, 5]
+    assert ids(t, "(sym-eq s 1 A)") == [0, 4, 6]
+
+
+def test_adapt_tie_between_candidates_broken_by_symbol_order():
+    # A:{0,4,9}, GAP:{5,6,7}, coverage {0,2,4,5,6,7,8,9}, ref T (=2) -> GAP (first in SYMBOLS order)
+    rows = ["A", None, "T", None, "A", "-", "-", "-", "T", "A"]
+    t = _one_position_table("T", rows)
+    assert t.local_reference("s")[0] == "-"
+    assert sorted((s, c) for _, s, _, c in O.containers_at(t, "s", 0)) == [("A", 3), ("T", 2)]
+
+
+# ---- SymbolEquals / HasMutation on ATGCN: symbol_equals.test.cpp:42-257 ---------------------
+
+@pytest.fixture(scope="module")
+def atgcn():
+    t = O.Table()
+    t.add_column("segment1", O.NUCLEOTIDE, "ATGCN")
+    for seq in ("ATGCN", "ATGCN", "NNNNN", "CATTT", None):
+        t.append_row([seq])
+    t.finalize()
+    return t
+
+
+@pytest.mark.parametrize("symbol,position,count", [
+    ("A", 1, 2), ("A", 2, 1), ("A", 3, 0), ("A", 4, 0), ("A", 5, 0),
+    ("C", 1, 1), ("C", 2, 0), ("C", 3, 0), ("C", 4, 2), ("C", 5, 0),
+    ("G", 1, 0), ("G", 2, 0), ("G", 3, 2), ("G", 4, 0), ("G", 5, 0),
+    ("T", 1, 0), ("T", 2, 2), ("T", 3, 1), ("T", 4, 1), ("T", 5, 1),
+    ("N", 1, 1), ("N", 5, 3), (".", 1, 2),
+])
+def test_symbol_equals_counts(atgcn, symbol, position, count):
+    assert atgcn.filter(f"(sym-eq segment1 {position} {symbol})").cardinality == count
+
+
+def test_symbol_equals_errors(atgcn):
+    with pytest.raises(O.OracleError, match=r"SymbolEquals<Nucleotide> position is out of bounds 1000 > 5"):
+        atgcn.filter("(sym-eq segment1 1000 A)")
+    with pytest.raises(O.OracleError, match=r"The field 'position' is 1-indexed. Value of 0 not allowed."):
+        atgcn.filter("(sym-eq segment1 0 A)")
+
+
+def test_has_mutation():  # has_mutation.test.cpp:28-60
+    t = O.Table()
+    t.add_column("segment1", O.NUCLEOTIDE, "ATGCN")
+    t.add_column("gene1", O.AMINO_ACID, "M*")
+    for nuc, aa in (("ATGCN", "M*"), ("ATGCN", "C*"), ("NNNNN", "M*"), ("CATTT", "X*")):
+        t.append_row([nuc, aa])
+    t.finalize()
+    assert t.filter("(has-mut segment1 1)").cardinality == 1
+    assert t.filter("(has-mut gene1 1)").cardinality == 1
+
+
+# ---- MutationProfile: mutation_profile.test.cpp:24-264 --------------------------------------
+
+@pytest.fixture(scope="module")
+def profile_db():
+    t = O.Table()
+    t.add_column("segment1", O.NUCLEOTIDE, "ATGCN")
+    t.add_column("gene1", O.AMINO_ACID, "M*")
+    rows = [("ATGCN", "M*"), ("CTGCN", "C*"), ("CTCCN", "M*"), ("CTCTN", "M*"), ("NNNNN", "M*"), ("RTGCN", "M*")]
+    for nuc, aa in rows:
+        t.append_row([nuc, aa])
+    t.finalize()
+    return t
+
+
+REF, MUT1, MUT2, MUT3, ALLN, AMB = range(6)
+
+
+@pytest.mark.parametrize("expression,expected", [
+    ("(profile segment1 0 muts)", [REF, ALLN, AMB]),
+    ("(profile segment1 1 muts)", [REF, MUT1, ALLN, AMB]),
+    ("(profile segment1 2 muts)", [REF, MUT1, MUT2, ALLN, AMB]),
+    ("(profile segment1 0 muts 1 C)", [MUT1, ALLN]),
+    ("(profile segment1 0 seq ATGCN)", [REF, ALLN, AMB]),
+    ("(profile segment1 0 row 1)", [MUT1, ALLN]),
+    ("(profile gene1 0 muts)", [REF, MUT2, MUT3, ALLN, AMB]),
+    ("(profile gene1 1 muts)", [REF, MUT1, MUT2, MUT3, ALLN, AMB]),
+    ("(profile gene1 0 muts 1 C)", [MUT1]),
+    ("(profile gene1 0 seq M*)", [REF, MUT2, MUT3, ALLN, AMB]),
+    ("(profile gene1 0 row 1)", [MUT1]),
+])
+def test_mutation_profile(profile_db, expression, expected):
+    assert ids(profile_db, expression) == expected
+
+
+def test_mutation_profile_errors(profile_db):
+    with pytest.raises(O.OracleError, match="querySequence length 3 does not match the reference sequence length 5 for Nucleotide MutationProfile"):
+        profile_db.filter("(profile segment1 0 seq ATG)")
+    with pytest.raises(O.OracleError, match=r"AminoAcid MutationProfile mutation position 123456 is out of bounds \(reference length 2\)"):
+        profile_db.filter("(profile gene1 0 muts 123456 C)")
+
+
+# ---- roaring_util: container kinds, serialisation, set algebra ------------------------------
+
+def test_container_grows_from_array_to_bitset():  # roaring_container.test.cpp:67-79
+    values, type_a, _ = O.container_op(list(range(20000)))
+    assert values == list(range(20000)) and type_a == BITSET
+
+
+def test_container_run_optimize_preserves_contents():  # :104-113
+    values, type_a, _ = O.container_op(list(range(100, 2000)), optimize_a=True)
+    assert values == list(range(100, 2000)) and type_a == RUN
+    values, type_a, _ = O.container_op([1, 5, 9, 200], optimize_a=True)
+    assert values == [1, 5, 9, 200] and type_a == ARRAY
+
+
+@pytest.mark.parametrize("values,optimize", [
+    ([3, 7, 9], False), (list(range(0, 65536, 3)), False), (list(range(50, 5000)), True),
+    ([0, 65535], False), (list(range(65536)), True),
+])
+def test_container_serialization_round_trip(values, optimize):  # :259-284
+    out, _, _ = O.container_op(values, optimize_a=optimize, roundtrip=True)
+    assert out == values
+
+
+def test_container_set_algebra():  # :286-479
+    a, b = [1, 2, 3, 100], [2, 100, 500]
+    assert O.container_op(a, b, "and")[0] == [2, 100]
+    assert O.container_op(a, [7, 8], "and")[0] == []
+    assert O.container_op(a, [], "and")[0] == []
+    assert O.container_op(a, b, "andnot")[0] == [1, 3]
+    assert O.container_op(a, [], "andnot")[0] == a
+    assert O.container_op([], b, "andnot")[0] == []
+    assert O.container_op(a, a, "andnot")[0] == []
+    assert O.container_op(a, b, "or")[0] == [1, 2, 3, 100, 500]
+    assert O.container_op([], b, "or")[0] == b
+    big = list(range(0, 9000, 2))
+    values, _, type_out = O.container_op(big[:3000], big[3000:], "or")
+    assert values == big and type_out == BITSET
+    runs_a, runs_b = list(range(10, 1000)), list(range(900, 3000))
+    assert O.container_op(runs_a, runs_b, "or", optimize_a=True, optimize_b=True)[0] == list(range(10, 3000))
+
+
+def test_container_and_cardinality_all_kind_pairs():
+    rng = np.random.default_rng(1)
+    dense = sorted(rng.choice(65536, 30000, replace=False).tolist())  # bitset
+    sparse = sorted(rng.choice(65536, 700, replace=False).tolist())   # array
+    runs = [v for s in range(0, 65536, 997) for v in range(s, min(s + 400, 65536))]  # run
+    kinds = {"bitset": (dense, False, BITSET), "array": (sparse, False, ARRAY), "run": (runs, True, RUN)}
+    for name_a, (a, opt_a, kind_a) in kinds.items():
+        for name_b, (b, opt_b, _) in kinds.items():
+            card, type_a, _ = O.container_op(a, b, "and_cardinality", optimize_a=opt_a, optimize_b=opt_b)
+            assert type_a == kind_a
+            assert card == len(set(a) & set(b)), (name_a, name_b)
+
+
+def test_roaring_portable_format_round_trip():  # roaring_serialize.h:15-46
+    ids_in = [1, 5, 100, 65536 + 3, 3 * 65536 + 7] + list(range(200000, 210000))
+    back, raw = O.roaring_roundtrip(ids_in)
+    assert back == sorted(ids_in)
+    assert int.from_bytes(raw[:4], "little") == 12346  # SERIAL_COOKIE_NO_RUNCONTAINER
+    back, raw = O.roaring_roundtrip(ids_in, optimize=True)
+    assert back == sorted(ids_in)
+    assert int.from_bytes(raw[:2], "little") == 12347  # SERIAL_COOKIE with run containers
+
+
+# ---- Mutations action ----------------------------------------------------------------------
+
+def test_mutations_single_trivial_row():  # operators/union_all_node.test.cpp:184-193
+    t = O.Table()
+    t.add_column("main", O.NUCLEOTIDE, "A")
+    t.append_row(["T"])
+    t.finalize()
+    rows = t.mutations("main", None, 0.0)
+    assert [(r["mutationTo"], r["proportion"]) for r in rows] == [("T", 1.0)]
