@@ -1,0 +1,266 @@
+// Internal declarations of libsilo_b200.so (sm_100a only). Public surface: include/silo_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/silo_b200.h"
+
+namespace silo {
+
+// ---------------------------------------------------------------------------------------------
+// HBM layout of one sequence column (see DESIGN.md "Data layout in HBM")
+// ---------------------------------------------------------------------------------------------
+
+constexpr uint32_t TILE_WORDS = 1024;        // one chunk's dense filter tile: 1024 x u64 = 8 KiB
+constexpr uint32_t TILE_BYTES = TILE_WORDS * 8;
+constexpr uint32_t SEG_PAYLOAD_BYTES = 16384;  // max payload bytes of one segment (>= 8192 + slack)
+constexpr uint32_t SEG_MAX_DESCS = 256;        // max containers of one segment
+
+constexpr uint32_t TYPE_BITSET = 1;  // CRoaring typecodes, roaring_container.h:131-145
+constexpr uint32_t TYPE_ARRAY = 2;
+constexpr uint32_t TYPE_RUN = 3;
+
+// 16-byte device descriptor of one stored diff container (chunk-major order).
+struct __align__(16) DevContainer {
+   uint32_t position;
+   uint32_t offset4;  // payload offset from the slab start, in 4-byte units
+   uint32_t packed;   // [15:0] cardinality-1 | [23:16] symbol | [29:24] local-reference symbol | [31:30] type
+   uint32_t n_runs;   // run containers: number of {start,len-1} pairs; otherwise 0
+
+   __host__ __device__ uint32_t cardinality() const { return (packed & 0xFFFFu) + 1u; }
+   __host__ __device__ uint32_t symbol() const { return (packed >> 16) & 0xFFu; }
+   __host__ __device__ uint32_t refSymbol() const { return (packed >> 24) & 0x3Fu; }
+   __host__ __device__ uint32_t type() const { return packed >> 30; }
+};
+static_assert(sizeof(DevContainer) == 16);
+
+// A segment = consecutive containers of ONE chunk whose descriptors and payloads are contiguous,
+// moved into shared memory by two 1-D bulk (TMA) copies.
+struct __align__(16) DevSegment {
+   uint64_t payload_offset;  // bytes from the slab start, 16-byte aligned
+   uint32_t payload_bytes;   // multiple of 16
+   uint32_t desc_begin;
+   uint32_t desc_count;
+   uint32_t chunk;  // local chunk index
+   uint32_t pad[2];
+};
+static_assert(sizeof(DevSegment) == 32);
+
+struct DevColumn {
+   uint32_t n_symbols;
+   uint32_t genome_length;
+   uint32_t missing_symbol;
+   uint32_t n_chunks;
+   uint64_t n_containers;
+   uint32_t n_segments;
+   const uint8_t* local_reference;      // [genome_length]
+   const DevContainer* containers;      // sorted (chunk, position, symbol)
+   const uint8_t* payload;              // slab
+   const uint32_t* chunk_desc_begin;    // [n_chunks + 1]
+   const DevSegment* segments;          // [n_segments]
+   const uint32_t* chunk_seg_begin;     // [n_chunks + 1]
+   const uint2* start_end;              // rows of the shard back to back
+   const uint32_t* chunk_row_begin;     // [n_chunks + 1] into start_end
+   const uint32_t* chunk_missing_begin; // [n_chunks + 1] into missing_row / missing_offsets
+   const uint16_t* missing_row;         // row_in_chunk of each row with N positions
+   const uint64_t* missing_offsets;     // [n_rows_with_missing + 1] into missing_runs
+   const uint2* missing_runs;           // {first, end_exclusive}
+   const uint64_t* null_words;          // [n_chunks * 1024] or nullptr when the column has no nulls
+};
+
+// ---------------------------------------------------------------------------------------------
+// host-side objects behind the opaque handles
+// ---------------------------------------------------------------------------------------------
+
+struct Stats {
+   uint64_t containers = 0;
+   uint64_t algorithmic_bytes = 0;
+   uint64_t kernel_launches = 0;
+   float last_counts_kernel_ms = 0;
+   float last_total_ms = 0;
+};
+
+struct HostColumn {
+   DevColumn dev{};
+   std::vector<void*> allocations;
+   // per-chunk byte totals for the algorithmic-bytes accounting
+   std::vector<uint64_t> chunk_desc_payload_bytes;  // 16 B/descriptor + payload bytes
+   std::vector<uint64_t> chunk_missing_rows;
+   std::vector<uint64_t> chunk_containers;
+   uint64_t device_bytes = 0;
+};
+
+}  // namespace silo
+
+struct silo_gpu_ctx {
+   int device = 0;
+   int sm_count = 0;
+   cudaStream_t stream = nullptr;
+};
+
+struct silo_gpu_table {
+   silo_gpu_ctx* ctx = nullptr;
+   uint32_t first_chunk = 0;
+   uint32_t n_chunks = 0;
+   std::vector<uint32_t> chunk_sizes;
+   uint64_t n_rows = 0;
+   uint32_t* d_chunk_sizes = nullptr;
+   std::vector<silo::HostColumn*> columns;
+   // per-query scratch (calls on one table are serialised by `mutex`; tables are independent)
+   std::mutex mutex;
+   uint32_t* d_work_prefix = nullptr;  // [n_chunks + 1]
+   uint32_t* d_coverage_diff = nullptr;  // [max genome_length + 1]
+   uint32_t coverage_diff_capacity = 0;
+   uint32_t* d_counts = nullptr;  // staging for the synchronous API
+   uint64_t counts_capacity = 0;
+   uint32_t* h_counts_pinned = nullptr;
+   uint32_t* d_chunk_popcount_full = nullptr;  // popcounts of the "all rows" filter (= chunk sizes)
+   uint64_t* d_full_words = nullptr;           // layout mask tiles [n_chunks * 1024]
+   cudaEvent_t ev_begin = nullptr, ev_k1_begin = nullptr, ev_k1_end = nullptr, ev_end = nullptr;
+   silo::Stats stats;
+   uint64_t device_bytes = 0;
+};
+
+struct silo_gpu_filter {
+   silo_gpu_table* table = nullptr;
+   uint64_t* d_words = nullptr;           // [n_chunks * 1024]
+   uint32_t* d_chunk_popcount = nullptr;  // [n_chunks]
+   unsigned long long* d_cardinality = nullptr;
+   uint32_t* d_error_flag = nullptr;
+};
+
+namespace silo {
+
+void setLastError(const std::string& message);
+
+struct ApiError : std::runtime_error {
+   int status;
+   ApiError(int status, const std::string& message) : std::runtime_error(message), status(status) {}
+};
+
+#define SILO_CUDA_CHECK(expr)                                                                      \
+   do {                                                                                            \
+      cudaError_t silo_cuda_status = (expr);                                                       \
+      if (silo_cuda_status != cudaSuccess) {                                                       \
+         throw ::silo::ApiError(                                                                   \
+            silo_cuda_status == cudaErrorMemoryAllocation ? SILO_E_OUT_OF_MEMORY : SILO_E_CUDA,    \
+            std::string(#expr) + ": " + cudaGetErrorString(silo_cuda_status)                       \
+         );                                                                                        \
+      }                                                                                            \
+   } while (0)
+
+template <typename Fn>
+int guarded(Fn&& fn) {
+   try {
+      fn();
+      return SILO_OK;
+   } catch (const ApiError& error) {
+      setLastError(error.what());
+      return error.status;
+   } catch (const std::exception& error) {
+      setLastError(error.what());
+      return SILO_E_INVALID_ARGUMENT;
+   }
+}
+
+inline void require(bool condition, const char* message) {
+   if (!condition) {
+      throw ApiError(SILO_E_INVALID_ARGUMENT, message);
+   }
+}
+
+template <typename T>
+T* deviceAlloc(size_t count, uint64_t* accounting = nullptr) {
+   void* ptr = nullptr;
+   const size_t bytes = (count == 0 ? 1 : count) * sizeof(T);
+   SILO_CUDA_CHECK(cudaMalloc(&ptr, bytes));
+   if (accounting != nullptr) {
+      *accounting += bytes;
+   }
+   return static_cast<T*>(ptr);
+}
+
+template <typename T>
+T* deviceUpload(const std::vector<T>& host, cudaStream_t stream, uint64_t* accounting = nullptr) {
+   T* ptr = deviceAlloc<T>(host.size(), accounting);
+   if (!host.empty()) {
+      SILO_CUDA_CHECK(cudaMemcpyAsync(ptr, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+   }
+   return ptr;
+}
+
+// ---- device helpers shared by the kernels ---------------------------------------------------
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smemAddr(const void* ptr) {
+   return static_cast<uint32_t>(__cvta_generic_to_shared(ptr));
+}
+
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count) {
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes)
+                : "memory");
+}
+
+__device__ __forceinline__ void mbarArrive(uint64_t* bar) {
+   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
+   asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smemAddr(bar)),
+      "r"(parity)
+      : "memory"
+   );
+}
+
+// 1-D bulk (TMA) copy global -> shared, completion signalled on `bar` (SASS: UBLKCP).
+// dst, src 16-byte aligned; bytes a multiple of 16.
+__device__ __forceinline__ void bulkLoad(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+   asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+         smemAddr(dst)
+      ),
+      "l"(src),
+      "r"(bytes),
+      "r"(smemAddr(bar))
+      : "memory"
+   );
+}
+
+__device__ __forceinline__ void fenceBarrierInit() {
+   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// mask of the rows [0, chunk_size) inside 64-bit word `word_index` of a tile
+__device__ __forceinline__ uint64_t layoutWord(uint32_t chunk_size, uint32_t word_index) {
+   const uint32_t first = word_index * 64;
+   if (chunk_size >= first + 64) {
+      return ~0ULL;
+   }
+   if (chunk_size <= first) {
+      return 0ULL;
+   }
+   return (~0ULL) >> (64 - (chunk_size - first));
+}
+
+#endif  // __CUDACC__
+
+}  // namespace silo

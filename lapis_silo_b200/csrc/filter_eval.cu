@@ -1,0 +1,916 @@
+// S2: filter-program evaluation on device.
+//
+// Replaces Operator::evaluate() of the compiled filter tree
+// (/root/reference/src/rhydb/query_engine/filter/operators/*.cpp, reached from
+// operators/compute_filter.cpp:14-21). The reference folds roaring containers operator by operator
+// on one thread; here ONE CTA per 2^16-row chunk interprets the whole flat program over dense
+// 8 KiB tiles held in shared memory, so intermediate results never touch HBM:
+//   IndexScan views (symbol_in_set.cpp:216-228)         -> orContainerIntoTile (array/bitset/run decode)
+//   IsInCoveredRegion::makeBitmap (is_in_covered_region.cpp:53-62,
+//        horizontal_coverage_index.h:57-98)              -> coveredTile (start/end scan + N runs)
+//   RangeSelection::evaluate (range_selection.cpp:54-87) -> rangesTile
+//   Intersection / Union / Complement (intersection.cpp:59-105, union.cpp:34-42,
+//        complement.cpp:51-56 + row_layout.cpp:18-23)    -> word-wise AND / ANDNOT / OR / XOR-with-layout
+//   Threshold::evaluate (threshold.cpp:64-138)           -> per-row u16 counters in shared memory
+//        (the DP over k roaring bitmaps computes exactly "at least / exactly k children match")
+#include <algorithm>
+#include <cstring>
+#include <memory>
+
+#include "common.cuh"
+
+namespace silo {
+
+namespace {
+
+constexpr int EVAL_THREADS = 1024;
+constexpr int EVAL_WARPS = EVAL_THREADS / 32;
+constexpr int STACK_DEPTH = 6;
+
+struct DevBitmap {
+   const DevContainer* containers;  // `position` holds the GLOBAL chunk key, ascending
+   uint32_t n_containers;
+   uint32_t pad;
+};
+
+struct EvalParams {
+   const silo_filter_instr* instrs;
+   uint32_t n_instrs;
+   uint32_t n_chunks;
+   const DevColumn* columns;
+   const uint8_t* blob;
+   const DevBitmap* bitmaps;
+   const uint8_t* bitmap_payload;
+   const uint32_t* chunk_sizes;
+   uint32_t first_chunk;
+   uint32_t pad;
+   uint64_t* out_words;
+   uint32_t* out_popcount;
+   unsigned long long* out_cardinality;
+   uint32_t* error_flag;
+};
+
+struct EvalShared {
+   uint64_t stack[STACK_DEPTH][TILE_WORDS];
+   uint32_t counters32[32768];  // 65536 x u16 per-row match counters (Threshold)
+   uint32_t range[2];
+   uint32_t reduce[EVAL_WARPS];
+};
+
+__device__ __forceinline__ void orBits32(uint32_t* tile32, uint32_t first, uint32_t last /*inclusive*/) {
+   const uint32_t fw = first >> 5;
+   const uint32_t lw = last >> 5;
+   const uint32_t head = 0xFFFFFFFFu << (first & 31);
+   const uint32_t tail = 0xFFFFFFFFu >> (31 - (last & 31));
+   if (fw == lw) {
+      atomicOr(&tile32[fw], head & tail);
+      return;
+   }
+   atomicOr(&tile32[fw], head);
+   for (uint32_t w = fw + 1; w < lw; ++w) {
+      atomicOr(&tile32[w], 0xFFFFFFFFu);
+   }
+   atomicOr(&tile32[lw], tail);
+}
+
+// tile |= container (whole CTA). payload is the slab the descriptor's offset4 refers to.
+__device__ void orContainerIntoTile(uint64_t* tile, const uint8_t* slab, const DevContainer& desc) {
+   const uint8_t* payload = slab + (static_cast<size_t>(desc.offset4) << 2);
+   const uint32_t type = desc.type();
+   if (type == TYPE_BITSET) {
+      tile[threadIdx.x] |= reinterpret_cast<const uint64_t*>(payload)[threadIdx.x];
+   } else if (type == TYPE_ARRAY) {
+      const uint16_t* values = reinterpret_cast<const uint16_t*>(payload);
+      uint32_t* tile32 = reinterpret_cast<uint32_t*>(tile);
+      const uint32_t cardinality = desc.cardinality();
+      for (uint32_t i = threadIdx.x; i < cardinality; i += EVAL_THREADS) {
+         const uint32_t value = values[i];
+         atomicOr(&tile32[value >> 5], 1u << (value & 31));
+      }
+   } else {
+      const uint32_t* runs = reinterpret_cast<const uint32_t*>(payload);
+      uint32_t* tile32 = reinterpret_cast<uint32_t*>(tile);
+      for (uint32_t i = threadIdx.x; i < desc.n_runs; i += EVAL_THREADS) {
+         const uint32_t run = runs[i];
+         const uint32_t first = run & 0xFFFFu;
+         orBits32(tile32, first, first + (run >> 16));
+      }
+   }
+}
+
+// counters[row] += delta for every row of the container (one warp). delta is +1 or -1 applied to a
+// u16 lane of a packed u32; the host-chosen bias keeps every lane inside [0, 65535].
+__device__ void addContainerToCounters(
+   uint32_t* counters32,
+   const uint8_t* slab,
+   const DevContainer& desc,
+   bool subtract,
+   uint32_t lane
+) {
+   const uint8_t* payload = slab + (static_cast<size_t>(desc.offset4) << 2);
+   const uint32_t type = desc.type();
+   auto bump = [&](uint32_t row) {
+      const uint32_t unit = 1u << ((row & 1u) << 4);
+      atomicAdd(&counters32[row >> 1], subtract ? 0u - unit : unit);
+   };
+   if (type == TYPE_ARRAY) {
+      const uint16_t* values = reinterpret_cast<const uint16_t*>(payload);
+      const uint32_t cardinality = desc.cardinality();
+      for (uint32_t i = lane; i < cardinality; i += 32) {
+         bump(values[i]);
+      }
+   } else if (type == TYPE_RUN) {
+      const uint32_t* runs = reinterpret_cast<const uint32_t*>(payload);
+      for (uint32_t r = 0; r < desc.n_runs; ++r) {
+         const uint32_t run = runs[r];
+         const uint32_t first = run & 0xFFFFu;
+         const uint32_t last = first + (run >> 16);
+         for (uint32_t row = first + lane; row <= last; row += 32) {
+            bump(row);
+         }
+      }
+   } else {
+      const uint64_t* words = reinterpret_cast<const uint64_t*>(payload);
+      for (uint32_t w = lane; w < TILE_WORDS; w += 32) {
+         uint64_t word = words[w];
+         while (word != 0) {
+            bump(w * 64 + static_cast<uint32_t>(__ffsll(static_cast<long long>(word)) - 1));
+            word &= word - 1;
+         }
+      }
+   }
+}
+
+// [lo, hi) = descriptors of `chunk` at `position` (thread 0 searches, result broadcast via smem)
+__device__ void findPositionRange(EvalShared& sh, const DevColumn& column, uint32_t chunk, uint32_t position) {
+   if (threadIdx.x == 0) {
+      uint32_t lo = column.chunk_desc_begin[chunk];
+      uint32_t hi = column.chunk_desc_begin[chunk + 1];
+      const uint32_t end = hi;
+      while (lo < hi) {
+         const uint32_t mid = (lo + hi) >> 1;
+         if (column.containers[mid].position < position) {
+            lo = mid + 1;
+         } else {
+            hi = mid;
+         }
+      }
+      uint32_t stop = lo;
+      while (stop < end && column.containers[stop].position == position) {
+         ++stop;
+      }
+      sh.range[0] = lo;
+      sh.range[1] = stop;
+   }
+   __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t lowerBound(const uint32_t* sorted, uint32_t count, uint32_t value) {
+   uint32_t lo = 0;
+   uint32_t hi = count;
+   while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (sorted[mid] < value) {
+         lo = mid + 1;
+      } else {
+         hi = mid;
+      }
+   }
+   return lo;
+}
+
+__device__ __forceinline__ bool rowMissingAt(const DevColumn& column, uint32_t missing_index, uint32_t position) {
+   uint64_t lo = column.missing_offsets[missing_index];
+   uint64_t hi = column.missing_offsets[missing_index + 1];
+   while (lo < hi) {  // first run with end_exclusive > position
+      const uint64_t mid = (lo + hi) >> 1;
+      if (column.missing_runs[mid].y <= position) {
+         lo = mid + 1;
+      } else {
+         hi = mid;
+      }
+   }
+   return lo < column.missing_offsets[missing_index + 1] && column.missing_runs[lo].x <= position;
+}
+
+__global__ void __launch_bounds__(EVAL_THREADS, 1) evalProgramKernel(EvalParams p) {
+   extern __shared__ __align__(128) uint8_t smem_raw[];
+   EvalShared& sh = *reinterpret_cast<EvalShared*>(smem_raw);
+   const uint32_t chunk = blockIdx.x;
+   const uint32_t tid = threadIdx.x;
+   const uint32_t lane = tid & 31;
+   const uint32_t warp = tid >> 5;
+   const uint32_t chunk_size = p.chunk_sizes[chunk];
+   const uint64_t layout_word = layoutWord(chunk_size, tid);
+   const uint32_t chunk_base = (p.first_chunk + chunk) << 16;
+
+   int sp = 0;  // number of tiles on the stack
+   uint32_t thr_target = 0;
+   bool thr_exact = false;
+
+   for (uint32_t pc = 0; pc < p.n_instrs; ++pc) {
+      const silo_filter_instr ins = p.instrs[pc];
+      switch (ins.opcode) {
+         case SILO_OP_PUSH_EMPTY:
+            sh.stack[sp++][tid] = 0;
+            break;
+         case SILO_OP_PUSH_FULL:
+            sh.stack[sp++][tid] = layout_word;
+            break;
+         case SILO_OP_PUSH_SYMBOLS: {
+            const DevColumn& column = p.columns[ins.column];
+            uint64_t* tile = sh.stack[sp++];
+            tile[tid] = 0;
+            findPositionRange(sh, column, chunk, ins.a);  // includes a __syncthreads
+            const uint32_t lo = sh.range[0];
+            const uint32_t hi = sh.range[1];
+            for (uint32_t i = lo; i < hi; ++i) {
+               const DevContainer desc = column.containers[i];
+               if (((ins.b >> desc.symbol()) & 1ULL) != 0) {
+                  orContainerIntoTile(tile, column.payload, desc);
+               }
+               __syncthreads();  // the next container may mix plain and atomic updates of the same word
+            }
+            break;
+         }
+         case SILO_OP_PUSH_COVERED: {
+            const DevColumn& column = p.columns[ins.column];
+            uint32_t* tile32 = reinterpret_cast<uint32_t*>(sh.stack[sp++]);
+            const uint2* rows = column.start_end + column.chunk_row_begin[chunk];
+            const uint32_t position = ins.a;
+            for (uint32_t base = 0; base < 65536; base += EVAL_THREADS) {
+               const uint32_t row = base + tid;
+               bool covered = false;
+               if (row < chunk_size) {
+                  const uint2 range = rows[row];
+                  covered = range.x <= position && position < range.y;
+               }
+               const uint32_t bits = __ballot_sync(0xFFFFFFFFu, covered);
+               if (lane == 0) {
+                  tile32[row >> 5] = bits;
+               }
+            }
+            __syncthreads();
+            const uint32_t missing_begin = column.chunk_missing_begin[chunk];
+            const uint32_t missing_end = column.chunk_missing_begin[chunk + 1];
+            for (uint32_t i = missing_begin + tid; i < missing_end; i += EVAL_THREADS) {
+               if (rowMissingAt(column, i, position)) {
+                  const uint32_t row = column.missing_row[i];
+                  atomicAnd(&tile32[row >> 5], ~(1u << (row & 31)));
+               }
+            }
+            __syncthreads();
+            if ((ins.flags & 1) != 0) {
+               sh.stack[sp - 1][tid] ^= layout_word;
+            }
+            break;
+         }
+         case SILO_OP_PUSH_NULLS: {
+            const DevColumn& column = p.columns[ins.column];
+            sh.stack[sp++][tid] =
+               column.null_words != nullptr ? column.null_words[static_cast<size_t>(chunk) * TILE_WORDS + tid] : 0ULL;
+            break;
+         }
+         case SILO_OP_PUSH_BITMAP: {
+            const DevBitmap bitmap = p.bitmaps[ins.a];
+            uint64_t* tile = sh.stack[sp++];
+            tile[tid] = 0;
+            if (tid == 0) {
+               uint32_t lo = 0;
+               uint32_t hi = bitmap.n_containers;
+               const uint32_t key = p.first_chunk + chunk;
+               while (lo < hi) {
+                  const uint32_t mid = (lo + hi) >> 1;
+                  if (bitmap.containers[mid].position < key) {
+                     lo = mid + 1;
+                  } else {
+                     hi = mid;
+                  }
+               }
+               sh.range[0] = lo;
+               sh.range[1] = (lo < bitmap.n_containers && bitmap.containers[lo].position == key) ? 1u : 0u;
+            }
+            __syncthreads();
+            if (sh.range[1] != 0) {
+               const DevContainer desc = bitmap.containers[sh.range[0]];
+               orContainerIntoTile(tile, p.bitmap_payload, desc);
+               __syncthreads();
+               if ((tile[tid] & ~layout_word) != 0) {
+                  atomicOr(p.error_flag, 1u);  // ids outside the row layout
+               }
+            }
+            break;
+         }
+         case SILO_OP_PUSH_RANGES: {
+            const uint32_t* ranges = reinterpret_cast<const uint32_t*>(p.blob + ins.b);
+            const uint32_t word_first = chunk_base + tid * 64;
+            uint64_t word = 0;
+            for (uint32_t i = 0; i < ins.a; ++i) {
+               const uint32_t start = max(ranges[2 * i], word_first);
+               const uint64_t end = min(static_cast<uint64_t>(ranges[2 * i + 1]), static_cast<uint64_t>(word_first) + 64);
+               if (start < end) {
+                  const uint32_t first_bit = start - word_first;
+                  const uint32_t last_bit = static_cast<uint32_t>(end - 1 - word_first);
+                  word |= (~0ULL << first_bit) & (~0ULL >> (63 - last_bit));
+               }
+            }
+            sh.stack[sp++][tid] = word & layout_word;
+            break;
+         }
+         case SILO_OP_AND:
+            sh.stack[sp - 2][tid] &= sh.stack[sp - 1][tid];
+            --sp;
+            break;
+         case SILO_OP_ANDNOT:
+            sh.stack[sp - 2][tid] &= ~sh.stack[sp - 1][tid];
+            --sp;
+            break;
+         case SILO_OP_OR:
+            sh.stack[sp - 2][tid] |= sh.stack[sp - 1][tid];
+            --sp;
+            break;
+         case SILO_OP_NOT:
+            sh.stack[sp - 1][tid] ^= layout_word;
+            break;
+         case SILO_OP_THR_BEGIN: {
+            const uint32_t bias = static_cast<uint32_t>(ins.b & 0xFFFFu);
+            thr_target = ins.a + bias;
+            thr_exact = (ins.flags & 1) != 0;
+            for (uint32_t i = tid; i < 32768; i += EVAL_THREADS) {
+               sh.counters32[i] = bias | (bias << 16);
+            }
+            break;
+         }
+         case SILO_OP_THR_ADD: {
+            uint64_t word = sh.stack[--sp][tid];
+            if ((ins.flags & 1) != 0) {
+               word = ~word & layout_word;
+            }
+            uint16_t* counters16 = reinterpret_cast<uint16_t*>(sh.counters32);
+            while (word != 0) {
+               const uint32_t bit = static_cast<uint32_t>(__ffsll(static_cast<long long>(word)) - 1);
+               counters16[tid * 64 + bit] += 1;  // rows 64*tid.. are owned by this thread in this op
+               word &= word - 1;
+            }
+            break;
+         }
+         case SILO_OP_THR_ADD_SYMBOLS: {
+            const DevColumn& column = p.columns[ins.column];
+            findPositionRange(sh, column, chunk, ins.a);
+            const uint32_t lo = sh.range[0];
+            const uint32_t hi = sh.range[1];
+            for (uint32_t i = lo + warp; i < hi; i += EVAL_WARPS) {
+               const DevContainer desc = column.containers[i];
+               if (((ins.b >> desc.symbol()) & 1ULL) != 0) {
+                  addContainerToCounters(sh.counters32, column.payload, desc, (ins.flags & 1) != 0, lane);
+               }
+            }
+            break;
+         }
+         case SILO_OP_THR_ADD_COVERED: {
+            const DevColumn& column = p.columns[ins.column];
+            const uint32_t* positions = reinterpret_cast<const uint32_t*>(p.blob + ins.b);
+            const uint32_t n_positions = ins.a;
+            const uint2* rows = column.start_end + column.chunk_row_begin[chunk];
+            uint16_t* counters16 = reinterpret_cast<uint16_t*>(sh.counters32);
+            for (uint32_t row = tid; row < chunk_size; row += EVAL_THREADS) {
+               const uint2 range = rows[row];
+               const uint32_t inside =
+                  lowerBound(positions, n_positions, range.y) - lowerBound(positions, n_positions, range.x);
+               counters16[row] += static_cast<uint16_t>(inside);
+            }
+            __syncthreads();
+            const uint32_t missing_begin = column.chunk_missing_begin[chunk];
+            const uint32_t missing_end = column.chunk_missing_begin[chunk + 1];
+            for (uint32_t i = missing_begin + tid; i < missing_end; i += EVAL_THREADS) {
+               uint32_t hidden = 0;
+               for (uint64_t run = column.missing_offsets[i]; run < column.missing_offsets[i + 1]; ++run) {
+                  const uint2 r = column.missing_runs[run];
+                  hidden += lowerBound(positions, n_positions, r.y) - lowerBound(positions, n_positions, r.x);
+               }
+               counters16[column.missing_row[i]] -= static_cast<uint16_t>(hidden);
+            }
+            break;
+         }
+         case SILO_OP_THR_PROFILE: {
+            const DevColumn& column = p.columns[ins.column];
+            const uint2* table = reinterpret_cast<const uint2*>(p.blob + ins.b);  // {add_mask, sub_mask}
+            const uint32_t lo = column.chunk_desc_begin[chunk];
+            const uint32_t hi = column.chunk_desc_begin[chunk + 1];
+            for (uint32_t i = lo + warp; i < hi; i += EVAL_WARPS) {
+               const DevContainer desc = column.containers[i];
+               const uint2 masks = table[desc.position];
+               const uint32_t bit = 1u << desc.symbol();
+               if ((masks.x & bit) != 0) {
+                  addContainerToCounters(sh.counters32, column.payload, desc, false, lane);
+               } else if ((masks.y & bit) != 0) {
+                  addContainerToCounters(sh.counters32, column.payload, desc, true, lane);
+               }
+            }
+            break;
+         }
+         case SILO_OP_THR_END: {
+            const uint16_t* counters16 = reinterpret_cast<const uint16_t*>(sh.counters32);
+            uint64_t word = 0;
+            for (uint32_t bit = 0; bit < 64; ++bit) {
+               // rotate the start so that the 32 lanes of a warp hit 32 different banks
+               const uint32_t b = (bit + lane * 2) & 63;
+               const uint32_t count = counters16[tid * 64 + b];
+               const bool hit = thr_exact ? count == thr_target : count >= thr_target;
+               word |= static_cast<uint64_t>(hit) << b;
+            }
+            sh.stack[sp++][tid] = word & layout_word;
+            break;
+         }
+         default:
+            break;
+      }
+      __syncthreads();
+   }
+
+   const uint64_t result = sp > 0 ? sh.stack[sp - 1][tid] : 0ULL;
+   p.out_words[static_cast<size_t>(chunk) * TILE_WORDS + tid] = result;
+   uint32_t total = __reduce_add_sync(0xFFFFFFFFu, static_cast<uint32_t>(__popcll(result)));
+   if (lane == 0) {
+      sh.reduce[warp] = total;
+   }
+   __syncthreads();
+   if (warp == 0) {
+      total = __reduce_add_sync(0xFFFFFFFFu, sh.reduce[lane]);
+      if (lane == 0) {
+         p.out_popcount[chunk] = total;
+         atomicAdd(p.out_cardinality, static_cast<unsigned long long>(total));
+      }
+   }
+}
+
+__global__ void popcountTilesKernel(
+   const uint64_t* __restrict__ words,
+   uint32_t* __restrict__ out_popcount,
+   unsigned long long* __restrict__ out_cardinality
+) {
+   __shared__ uint32_t reduce[32];
+   const uint32_t chunk = blockIdx.x;
+   const uint32_t lane = threadIdx.x & 31;
+   const uint32_t warp = threadIdx.x >> 5;
+   uint32_t total = __reduce_add_sync(
+      0xFFFFFFFFu, static_cast<uint32_t>(__popcll(words[static_cast<size_t>(chunk) * TILE_WORDS + threadIdx.x]))
+   );
+   if (lane == 0) {
+      reduce[warp] = total;
+   }
+   __syncthreads();
+   if (warp == 0) {
+      total = __reduce_add_sync(0xFFFFFFFFu, reduce[lane]);
+      if (lane == 0) {
+         out_popcount[chunk] = total;
+         atomicAdd(out_cardinality, static_cast<unsigned long long>(total));
+      }
+   }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+
+struct ParsedBitmaps {
+   std::vector<DevContainer> containers;
+   std::vector<DevBitmap> bitmaps;  // `containers` holds an index until patched with the device base
+   std::vector<uint32_t> first_container;
+   std::vector<uint8_t> payload;
+};
+
+uint32_t readU16(const uint8_t* data) {
+   uint16_t value;
+   std::memcpy(&value, data, 2);
+   return value;
+}
+uint32_t readU32(const uint8_t* data) {
+   uint32_t value;
+   std::memcpy(&value, data, 4);
+   return value;
+}
+
+// Portable Roaring format (RoaringFormatSpec; what roaring::Roaring::write emits,
+// roaring_util/roaring_serialize.h:15-30) -> aligned payload slab + descriptors.
+void parseRoaring(const silo_roaring_bytes& bytes, ParsedBitmaps& out) {
+   constexpr uint32_t SERIAL_COOKIE_NO_RUNCONTAINER = 12346;
+   constexpr uint32_t SERIAL_COOKIE = 12347;
+   constexpr uint32_t NO_OFFSET_THRESHOLD = 4;
+   auto bad = [](const char* what) { throw ApiError(SILO_E_BAD_PROGRAM, std::string("roaring bitmap: ") + what); };
+   const uint8_t* data = bytes.data;
+   const uint64_t size = bytes.size;
+   if (data == nullptr || size < 4) {
+      bad("too short");
+   }
+   uint64_t pos = 0;
+   const uint32_t cookie = readU32(data);
+   pos += 4;
+   uint32_t n = 0;
+   const uint8_t* run_flags = nullptr;
+   if ((cookie & 0xFFFF) == SERIAL_COOKIE) {
+      n = (cookie >> 16) + 1;
+      if (pos + (n + 7) / 8 > size) {
+         bad("truncated run flags");
+      }
+      run_flags = data + pos;
+      pos += (n + 7) / 8;
+   } else if (cookie == SERIAL_COOKIE_NO_RUNCONTAINER) {
+      if (pos + 4 > size) {
+         bad("truncated header");
+      }
+      n = readU32(data + pos);
+      pos += 4;
+   } else {
+      bad("bad cookie");
+   }
+   if (n > 65536 || pos + 4ULL * n > size) {
+      bad("truncated key table");
+   }
+   const uint8_t* keys = data + pos;
+   pos += 4ULL * n;
+   if (run_flags == nullptr || n >= NO_OFFSET_THRESHOLD) {
+      pos += 4ULL * n;
+   }
+   DevBitmap bitmap{};
+   bitmap.n_containers = n;
+   out.first_container.push_back(static_cast<uint32_t>(out.containers.size()));
+   for (uint32_t i = 0; i < n; ++i) {
+      const uint32_t key = readU16(keys + 4 * i);
+      const uint32_t cardinality = readU16(keys + 4 * i + 2) + 1;
+      if (i > 0 && readU16(keys + 4 * (i - 1)) >= key) {
+         bad("keys not ascending");
+      }
+      const bool is_run = run_flags != nullptr && ((run_flags[i / 8] >> (i % 8)) & 1) != 0;
+      DevContainer desc{};
+      desc.position = key;
+      uint64_t payload_bytes = 0;
+      uint32_t type = 0;
+      const uint8_t* src = nullptr;
+      if (is_run) {
+         if (pos + 2 > size) {
+            bad("truncated run container");
+         }
+         desc.n_runs = readU16(data + pos);
+         payload_bytes = 4ULL * desc.n_runs;
+         src = data + pos + 2;
+         pos += 2 + payload_bytes;
+         type = TYPE_RUN;
+      } else if (cardinality <= 4096) {
+         payload_bytes = 2ULL * cardinality;
+         src = data + pos;
+         pos += payload_bytes;
+         type = TYPE_ARRAY;
+      } else {
+         payload_bytes = 8192;
+         src = data + pos;
+         pos += payload_bytes;
+         type = TYPE_BITSET;
+      }
+      if (pos > size) {
+         bad("truncated container payload");
+      }
+      out.payload.resize((out.payload.size() + 15) / 16 * 16, 0);
+      desc.offset4 = static_cast<uint32_t>(out.payload.size() / 4);
+      desc.packed = (cardinality - 1) | (type << 30);
+      out.payload.insert(out.payload.end(), src, src + payload_bytes);
+      out.containers.push_back(desc);
+   }
+   out.bitmaps.push_back(bitmap);
+}
+
+void validateProgram(const silo_gpu_table* table, const silo_filter_program* program) {
+   auto bad = [](const std::string& what) { throw ApiError(SILO_E_BAD_PROGRAM, "filter program: " + what); };
+   if (program->struct_size != sizeof(silo_filter_program)) {
+      bad("struct_size mismatch");
+   }
+   if (program->n_instrs == 0 || program->instrs == nullptr) {
+      bad("empty program");
+   }
+   int depth = 0;
+   bool in_threshold = false;
+   int threshold_base = 0;
+   uint64_t adds = 0;
+   uint64_t bias = 0;
+   uint64_t target = 0;
+   auto needColumn = [&](const silo_filter_instr& ins) -> const DevColumn& {
+      if (ins.column >= table->columns.size()) {
+         bad("column index out of range");
+      }
+      return table->columns[ins.column]->dev;
+   };
+   auto needBlob = [&](uint64_t offset, uint64_t bytes) {
+      if (offset % 4 != 0 || offset + bytes > program->blob_bytes || (bytes > 0 && program->blob == nullptr)) {
+         bad("blob reference out of range or misaligned");
+      }
+   };
+   for (uint32_t pc = 0; pc < program->n_instrs; ++pc) {
+      const silo_filter_instr& ins = program->instrs[pc];
+      switch (ins.opcode) {
+         case SILO_OP_PUSH_EMPTY:
+         case SILO_OP_PUSH_FULL:
+            ++depth;
+            break;
+         case SILO_OP_PUSH_SYMBOLS:
+         case SILO_OP_PUSH_COVERED: {
+            const DevColumn& column = needColumn(ins);
+            if (ins.a >= column.genome_length) {
+               bad("position out of range");
+            }
+            ++depth;
+            break;
+         }
+         case SILO_OP_PUSH_NULLS:
+            needColumn(ins);
+            ++depth;
+            break;
+         case SILO_OP_PUSH_BITMAP:
+            if (ins.a >= program->n_bitmaps) {
+               bad("bitmap index out of range");
+            }
+            ++depth;
+            break;
+         case SILO_OP_PUSH_RANGES:
+            needBlob(ins.b, 8ULL * ins.a);
+            for (uint32_t i = 0; i < ins.a; ++i) {
+               const uint32_t* range = reinterpret_cast<const uint32_t*>(program->blob + ins.b) + 2 * i;
+               if (range[0] > range[1]) {
+                  bad("range start > end");
+               }
+            }
+            ++depth;
+            break;
+         case SILO_OP_AND:
+         case SILO_OP_ANDNOT:
+         case SILO_OP_OR:
+            if (depth - (in_threshold ? threshold_base : 0) < 2) {
+               bad("binary operator needs two operands");
+            }
+            --depth;
+            break;
+         case SILO_OP_NOT:
+            if (depth - (in_threshold ? threshold_base : 0) < 1) {
+               bad("NOT needs an operand");
+            }
+            break;
+         case SILO_OP_THR_BEGIN:
+            if (in_threshold) {
+               bad("nested thresholds are not supported by the shared-memory counter tile");
+            }
+            in_threshold = true;
+            threshold_base = depth;
+            adds = 0;
+            bias = ins.b & 0xFFFF;
+            target = ins.a;
+            break;
+         case SILO_OP_THR_ADD:
+            if (!in_threshold || depth - threshold_base < 1) {
+               bad("THR_ADD needs a child tile inside a threshold");
+            }
+            --depth;
+            ++adds;
+            break;
+         case SILO_OP_THR_ADD_SYMBOLS: {
+            const DevColumn& column = needColumn(ins);
+            if (!in_threshold || ins.a >= column.genome_length) {
+               bad("THR_ADD_SYMBOLS outside a threshold or position out of range");
+            }
+            ++adds;
+            break;
+         }
+         case SILO_OP_THR_ADD_COVERED: {
+            const DevColumn& column = needColumn(ins);
+            if (!in_threshold) {
+               bad("THR_ADD_COVERED outside a threshold");
+            }
+            needBlob(ins.b, 4ULL * ins.a);
+            const uint32_t* positions = reinterpret_cast<const uint32_t*>(program->blob + ins.b);
+            for (uint32_t i = 0; i < ins.a; ++i) {
+               if (positions[i] >= column.genome_length || (i > 0 && positions[i - 1] >= positions[i])) {
+                  bad("THR_ADD_COVERED positions must be strictly ascending and in range");
+               }
+            }
+            adds += ins.a;
+            break;
+         }
+         case SILO_OP_THR_PROFILE: {
+            const DevColumn& column = needColumn(ins);
+            if (!in_threshold) {
+               bad("THR_PROFILE outside a threshold");
+            }
+            if (ins.b % 8 != 0) {
+               bad("THR_PROFILE table must be 8-byte aligned");
+            }
+            needBlob(ins.b, 8ULL * column.genome_length);
+            adds += column.genome_length;
+            break;
+         }
+         case SILO_OP_THR_END:
+            if (!in_threshold || depth != threshold_base) {
+               bad("THR_END with children left on the stack");
+            }
+            if (bias + adds > 65535 || target + bias > 65535) {
+               throw ApiError(SILO_E_UNSUPPORTED, "threshold needs more than 65535 counts per row");
+            }
+            in_threshold = false;
+            ++depth;
+            break;
+         default:
+            bad("unknown opcode");
+      }
+      if (depth > STACK_DEPTH) {
+         throw ApiError(SILO_E_UNSUPPORTED, "filter program needs a deeper tile stack than the kernel provides");
+      }
+   }
+   if (in_threshold || depth != 1) {
+      bad("program must leave exactly one tile on the stack");
+   }
+}
+
+silo_gpu_filter* allocFilter(silo_gpu_table* table) {
+   auto filter = std::make_unique<silo_gpu_filter>();
+   filter->table = table;
+   filter->d_words = deviceAlloc<uint64_t>(static_cast<size_t>(table->n_chunks) * TILE_WORDS);
+   filter->d_chunk_popcount = deviceAlloc<uint32_t>(table->n_chunks);
+   filter->d_cardinality = deviceAlloc<unsigned long long>(1);
+   filter->d_error_flag = deviceAlloc<uint32_t>(1);
+   return filter.release();
+}
+
+}  // namespace
+
+}  // namespace silo
+
+using namespace silo;
+
+extern "C" {
+
+void silo_gpu_filter_free(silo_gpu_filter* filter) {
+   if (filter == nullptr) {
+      return;
+   }
+   cudaSetDevice(filter->table->ctx->device);
+   cudaFree(filter->d_words);
+   cudaFree(filter->d_chunk_popcount);
+   cudaFree(filter->d_cardinality);
+   cudaFree(filter->d_error_flag);
+   delete filter;
+}
+
+int silo_gpu_filter_eval(
+   silo_gpu_table* table,
+   const silo_filter_program* program,
+   silo_gpu_filter** out,
+   uint64_t* cardinality
+) {
+   return guarded([&] {
+      require(table != nullptr && program != nullptr && out != nullptr, "silo_gpu_filter_eval: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      cudaStream_t stream = table->ctx->stream;
+      validateProgram(table, program);
+
+      ParsedBitmaps parsed;
+      for (uint32_t i = 0; i < program->n_bitmaps; ++i) {
+         parseRoaring(program->bitmaps[i], parsed);
+      }
+      parsed.payload.resize((parsed.payload.size() + 15) / 16 * 16 + 16, 0);
+
+      // one staging buffer, one H2D copy: [instrs | columns | bitmap descs | bitmap table | blob | payload]
+      std::vector<uint8_t> staging;
+      auto place = [&](const void* src, size_t bytes) {
+         staging.resize((staging.size() + 15) / 16 * 16, 0);
+         const size_t offset = staging.size();
+         staging.resize(offset + bytes);
+         if (bytes > 0) {
+            std::memcpy(staging.data() + offset, src, bytes);
+         }
+         return offset;
+      };
+      const size_t off_instrs = place(program->instrs, sizeof(silo_filter_instr) * program->n_instrs);
+      std::vector<DevColumn> columns;
+      for (const HostColumn* column : table->columns) {
+         columns.push_back(column->dev);
+      }
+      const size_t off_columns = place(columns.data(), sizeof(DevColumn) * columns.size());
+      const size_t off_bitmap_descs = place(parsed.containers.data(), sizeof(DevContainer) * parsed.containers.size());
+      const size_t off_bitmaps = place(parsed.bitmaps.data(), sizeof(DevBitmap) * parsed.bitmaps.size());
+      const size_t off_blob = place(program->blob, program->blob_bytes);
+      const size_t off_payload = place(parsed.payload.data(), parsed.payload.size());
+
+      uint8_t* d_staging = deviceAlloc<uint8_t>(staging.size() + 16);
+      std::unique_ptr<silo_gpu_filter, void (*)(silo_gpu_filter*)> filter(allocFilter(table), silo_gpu_filter_free);
+      try {
+         // patch the per-bitmap container pointers now that the device base is known
+         for (size_t i = 0; i < parsed.bitmaps.size(); ++i) {
+            auto* bitmap = reinterpret_cast<DevBitmap*>(staging.data() + off_bitmaps) + i;
+            bitmap->containers =
+               reinterpret_cast<const DevContainer*>(d_staging + off_bitmap_descs) + parsed.first_container[i];
+         }
+         SILO_CUDA_CHECK(cudaMemcpyAsync(d_staging, staging.data(), staging.size(), cudaMemcpyHostToDevice, stream));
+         SILO_CUDA_CHECK(cudaMemsetAsync(filter->d_cardinality, 0, sizeof(unsigned long long), stream));
+         SILO_CUDA_CHECK(cudaMemsetAsync(filter->d_error_flag, 0, sizeof(uint32_t), stream));
+         if (table->n_chunks > 0) {
+            EvalParams params{};
+            params.instrs = reinterpret_cast<const silo_filter_instr*>(d_staging + off_instrs);
+            params.n_instrs = program->n_instrs;
+            params.n_chunks = table->n_chunks;
+            params.columns = reinterpret_cast<const DevColumn*>(d_staging + off_columns);
+            params.blob = d_staging + off_blob;
+            params.bitmaps = reinterpret_cast<const DevBitmap*>(d_staging + off_bitmaps);
+            params.bitmap_payload = d_staging + off_payload;
+            params.chunk_sizes = table->d_chunk_sizes;
+            params.first_chunk = table->first_chunk;
+            params.out_words = filter->d_words;
+            params.out_popcount = filter->d_chunk_popcount;
+            params.out_cardinality = filter->d_cardinality;
+            params.error_flag = filter->d_error_flag;
+            static bool attribute_set = false;
+            if (!attribute_set) {
+               SILO_CUDA_CHECK(cudaFuncSetAttribute(
+                  evalProgramKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(EvalShared))
+               ));
+               attribute_set = true;
+            }
+            evalProgramKernel<<<table->n_chunks, EVAL_THREADS, sizeof(EvalShared), stream>>>(params);
+            SILO_CUDA_CHECK(cudaGetLastError());
+            table->stats.kernel_launches++;
+         }
+         unsigned long long host_cardinality = 0;
+         uint32_t host_error = 0;
+         SILO_CUDA_CHECK(cudaMemcpyAsync(&host_cardinality, filter->d_cardinality, sizeof(host_cardinality), cudaMemcpyDeviceToHost, stream));
+         SILO_CUDA_CHECK(cudaMemcpyAsync(&host_error, filter->d_error_flag, sizeof(host_error), cudaMemcpyDeviceToHost, stream));
+         SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+         cudaFree(d_staging);
+         d_staging = nullptr;
+         if (host_error != 0) {
+            throw ApiError(SILO_E_OUT_OF_LAYOUT, "a leaf bitmap holds row ids outside the row layout");
+         }
+         if (cardinality != nullptr) {
+            *cardinality = host_cardinality;
+         }
+      } catch (...) {
+         cudaFree(d_staging);
+         throw;
+      }
+      *out = filter.release();
+   });
+}
+
+int silo_gpu_filter_from_words(silo_gpu_table* table, const uint64_t* words, silo_gpu_filter** out) {
+   return guarded([&] {
+      require(table != nullptr && out != nullptr, "silo_gpu_filter_from_words: NULL argument");
+      require(table->n_chunks == 0 || words != nullptr, "silo_gpu_filter_from_words: words is NULL");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      cudaStream_t stream = table->ctx->stream;
+      for (uint32_t chunk = 0; chunk < table->n_chunks; ++chunk) {
+         const uint32_t size = table->chunk_sizes[chunk];
+         for (uint32_t w = 0; w < TILE_WORDS; ++w) {
+            const uint64_t layout = size >= (w + 1) * 64 ? ~0ULL : (size <= w * 64 ? 0ULL : (~0ULL >> (64 - (size - w * 64))));
+            if ((words[static_cast<size_t>(chunk) * TILE_WORDS + w] & ~layout) != 0) {
+               throw ApiError(SILO_E_OUT_OF_LAYOUT, "filter words hold rows outside the row layout");
+            }
+         }
+      }
+      std::unique_ptr<silo_gpu_filter, void (*)(silo_gpu_filter*)> filter(allocFilter(table), silo_gpu_filter_free);
+      SILO_CUDA_CHECK(cudaMemsetAsync(filter->d_cardinality, 0, sizeof(unsigned long long), stream));
+      if (table->n_chunks > 0) {
+         SILO_CUDA_CHECK(cudaMemcpyAsync(
+            filter->d_words, words, static_cast<size_t>(table->n_chunks) * TILE_BYTES, cudaMemcpyHostToDevice, stream
+         ));
+         popcountTilesKernel<<<table->n_chunks, EVAL_THREADS, 0, stream>>>(
+            filter->d_words, filter->d_chunk_popcount, filter->d_cardinality
+         );
+         SILO_CUDA_CHECK(cudaGetLastError());
+         table->stats.kernel_launches++;
+      }
+      SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+      *out = filter.release();
+   });
+}
+
+int silo_gpu_filter_cardinality(const silo_gpu_filter* filter, uint64_t* cardinality) {
+   return guarded([&] {
+      require(filter != nullptr && cardinality != nullptr, "silo_gpu_filter_cardinality: NULL argument");
+      SILO_CUDA_CHECK(cudaSetDevice(filter->table->ctx->device));
+      unsigned long long value = 0;
+      SILO_CUDA_CHECK(cudaMemcpyAsync(&value, filter->d_cardinality, sizeof(value), cudaMemcpyDeviceToHost, filter->table->ctx->stream));
+      SILO_CUDA_CHECK(cudaStreamSynchronize(filter->table->ctx->stream));
+      *cardinality = value;
+   });
+}
+
+int silo_gpu_filter_download(const silo_gpu_filter* filter, uint64_t* words) {
+   return guarded([&] {
+      require(filter != nullptr && (words != nullptr || filter->table->n_chunks == 0), "silo_gpu_filter_download: NULL argument");
+      SILO_CUDA_CHECK(cudaSetDevice(filter->table->ctx->device));
+      if (filter->table->n_chunks > 0) {
+         SILO_CUDA_CHECK(cudaMemcpyAsync(
+            words, filter->d_words, static_cast<size_t>(filter->table->n_chunks) * TILE_BYTES, cudaMemcpyDeviceToHost,
+            filter->table->ctx->stream
+         ));
+      }
+      SILO_CUDA_CHECK(cudaStreamSynchronize(filter->table->ctx->stream));
+   });
+}
+
+}  // extern "C"

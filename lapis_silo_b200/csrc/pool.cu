@@ -1,0 +1,439 @@
+// S1: context, table layout and the device-resident container pool of a sequence column.
+//
+// Replaces the host-memory layout of rhydb::storage::column::SequenceColumn
+// (/root/reference/src/rhydb/storage/column/sequence_column.h:104-114): the std::map of
+// individually malloc'ed roaring containers (vertical_sequence_index.h:44) becomes ONE payload slab
+// plus a 16-byte descriptor array in chunk-major order, cut into <=16 KiB segments that a CTA pulls
+// into shared memory with 1-D bulk (TMA) copies. See DESIGN.md "Data layout in HBM".
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <numeric>
+
+#include "common.cuh"
+
+namespace silo {
+
+namespace {
+thread_local std::string g_last_error;
+}
+
+void setLastError(const std::string& message) {
+   g_last_error = message;
+}
+
+namespace {
+
+__global__ void fillLayoutTiles(uint64_t* words, const uint32_t* chunk_sizes, uint32_t n_chunks) {
+   const uint32_t chunk = blockIdx.x;
+   if (chunk >= n_chunks) {
+      return;
+   }
+   for (uint32_t w = threadIdx.x; w < TILE_WORDS; w += blockDim.x) {
+      words[static_cast<size_t>(chunk) * TILE_WORDS + w] = layoutWord(chunk_sizes[chunk], w);
+   }
+}
+
+uint32_t alignUp(uint32_t value, uint32_t alignment) {
+   return (value + alignment - 1) / alignment * alignment;
+}
+
+}  // namespace
+
+}  // namespace silo
+
+using namespace silo;
+
+extern "C" {
+
+const char* silo_gpu_last_error(void) {
+   return g_last_error.c_str();
+}
+
+const char* silo_gpu_version(void) {
+   return "libsilo_b200 0.1.0 sm_100a";
+}
+
+int silo_gpu_init(int device_ordinal, silo_gpu_ctx** out) {
+   return guarded([&] {
+      require(out != nullptr, "silo_gpu_init: out is NULL");
+      int device_count = 0;
+      const cudaError_t status = cudaGetDeviceCount(&device_count);
+      if (status != cudaSuccess || device_count == 0) {
+         throw ApiError(
+            SILO_E_NO_DEVICE,
+            std::string("no CUDA device available (there is no CPU fallback): ") +
+               cudaGetErrorString(status)
+         );
+      }
+      require(device_ordinal >= 0 && device_ordinal < device_count, "silo_gpu_init: bad device ordinal");
+      SILO_CUDA_CHECK(cudaSetDevice(device_ordinal));
+      cudaDeviceProp prop{};
+      SILO_CUDA_CHECK(cudaGetDeviceProperties(&prop, device_ordinal));
+      if (prop.major < 10) {
+         throw ApiError(
+            SILO_E_NO_DEVICE,
+            std::string("device '") + prop.name + "' is not sm_100-class; this library ships sm_100a code only"
+         );
+      }
+      auto ctx = std::make_unique<silo_gpu_ctx>();
+      ctx->device = device_ordinal;
+      ctx->sm_count = prop.multiProcessorCount;
+      SILO_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+      *out = ctx.release();
+   });
+}
+
+void silo_gpu_shutdown(silo_gpu_ctx* ctx) {
+   if (ctx == nullptr) {
+      return;
+   }
+   cudaSetDevice(ctx->device);
+   if (ctx->stream != nullptr) {
+      cudaStreamDestroy(ctx->stream);
+   }
+   delete ctx;
+}
+
+int silo_gpu_table_create(
+   silo_gpu_ctx* ctx,
+   uint32_t first_chunk,
+   const uint32_t* chunk_sizes,
+   uint32_t n_chunks,
+   silo_gpu_table** out
+) {
+   return guarded([&] {
+      require(ctx != nullptr && out != nullptr, "silo_gpu_table_create: NULL argument");
+      require(n_chunks == 0 || chunk_sizes != nullptr, "silo_gpu_table_create: chunk_sizes is NULL");
+      // row_layout.h:40-45: chunks are never empty, hold <= 2^16 rows, and there are < 65535 of them
+      require(static_cast<uint64_t>(first_chunk) + n_chunks < 65535, "too many chunks for 16-bit chunk ids");
+      SILO_CUDA_CHECK(cudaSetDevice(ctx->device));
+      auto table = std::make_unique<silo_gpu_table>();
+      table->ctx = ctx;
+      table->first_chunk = first_chunk;
+      table->n_chunks = n_chunks;
+      table->chunk_sizes.assign(chunk_sizes, chunk_sizes + n_chunks);
+      for (uint32_t size : table->chunk_sizes) {
+         require(size >= 1 && size <= 65536, "chunk sizes must be in [1, 65536]");
+         table->n_rows += size;
+      }
+      table->d_chunk_sizes = deviceUpload(table->chunk_sizes, ctx->stream, &table->device_bytes);
+      table->d_chunk_popcount_full = deviceUpload(table->chunk_sizes, ctx->stream, &table->device_bytes);
+      table->d_work_prefix = deviceAlloc<uint32_t>(static_cast<size_t>(n_chunks) + 2, &table->device_bytes);
+      table->d_full_words =
+         deviceAlloc<uint64_t>(static_cast<size_t>(n_chunks) * TILE_WORDS, &table->device_bytes);
+      if (n_chunks > 0) {
+         fillLayoutTiles<<<n_chunks, 256, 0, ctx->stream>>>(table->d_full_words, table->d_chunk_sizes, n_chunks);
+         SILO_CUDA_CHECK(cudaGetLastError());
+         table->stats.kernel_launches++;
+      }
+      SILO_CUDA_CHECK(cudaEventCreate(&table->ev_begin));
+      SILO_CUDA_CHECK(cudaEventCreate(&table->ev_k1_begin));
+      SILO_CUDA_CHECK(cudaEventCreate(&table->ev_k1_end));
+      SILO_CUDA_CHECK(cudaEventCreate(&table->ev_end));
+      SILO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      *out = table.release();
+   });
+}
+
+void silo_gpu_table_free(silo_gpu_table* table) {
+   if (table == nullptr) {
+      return;
+   }
+   cudaSetDevice(table->ctx->device);
+   cudaStreamSynchronize(table->ctx->stream);
+   for (HostColumn* column : table->columns) {
+      for (void* allocation : column->allocations) {
+         cudaFree(allocation);
+      }
+      delete column;
+   }
+   cudaFree(table->d_chunk_sizes);
+   cudaFree(table->d_chunk_popcount_full);
+   cudaFree(table->d_work_prefix);
+   cudaFree(table->d_full_words);
+   cudaFree(table->d_coverage_diff);
+   cudaFree(table->d_counts);
+   if (table->h_counts_pinned != nullptr) {
+      cudaFreeHost(table->h_counts_pinned);
+   }
+   for (cudaEvent_t event : {table->ev_begin, table->ev_k1_begin, table->ev_k1_end, table->ev_end}) {
+      if (event != nullptr) {
+         cudaEventDestroy(event);
+      }
+   }
+   delete table;
+}
+
+uint64_t silo_gpu_table_device_bytes(const silo_gpu_table* table) {
+   if (table == nullptr) {
+      return 0;
+   }
+   uint64_t total = table->device_bytes;
+   for (const HostColumn* column : table->columns) {
+      total += column->device_bytes;
+   }
+   return total;
+}
+
+int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
+   int column_index = -1;
+   const int status = guarded([&] {
+      require(table != nullptr && in != nullptr, "silo_gpu_column_upload: NULL argument");
+      require(in->struct_size == sizeof(silo_column_desc), "silo_column_desc.struct_size mismatch");
+      require(in->n_symbols >= 2 && in->n_symbols <= 32, "n_symbols must be in [2, 32]");
+      require(in->genome_length > 0, "genome_length must be positive");
+      require(in->missing_symbol < in->n_symbols, "missing_symbol out of range");
+      require(in->local_reference != nullptr, "local_reference is NULL");
+      require(table->n_rows == 0 || in->start_end != nullptr, "start_end is NULL");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      cudaStream_t stream = table->ctx->stream;
+      const uint32_t n_chunks = table->n_chunks;
+      const uint32_t first_chunk = table->first_chunk;
+
+      for (uint32_t position = 0; position < in->genome_length; ++position) {
+         require(in->local_reference[position] < in->n_symbols, "local_reference holds an invalid symbol id");
+      }
+
+      // ---- containers: validate, re-order chunk-major, cut into segments, re-lay the payload ----
+      std::vector<uint64_t> order(in->n_containers);
+      std::iota(order.begin(), order.end(), 0);
+      for (uint64_t i = 0; i < in->n_containers; ++i) {
+         const silo_container_desc& c = in->containers[i];
+         require(c.v_index >= first_chunk && c.v_index < first_chunk + n_chunks, "container v_index outside the shard");
+         require(c.position < in->genome_length, "container position >= genome_length");
+         require(c.symbol < in->n_symbols, "container symbol out of range");
+         require(c.cardinality >= 1 && c.cardinality <= 65536, "container cardinality must be in [1, 65536]");
+         require(c.payload_offset + c.payload_bytes <= in->payload_bytes, "container payload out of bounds");
+         if (c.typecode == TYPE_BITSET) {
+            require(c.payload_bytes == 8192, "bitset payload must be 8192 bytes");
+         } else if (c.typecode == TYPE_ARRAY) {
+            require(c.payload_bytes == 2 * c.cardinality && c.cardinality <= 65536, "array payload must be 2*cardinality bytes");
+         } else if (c.typecode == TYPE_RUN) {
+            require(c.payload_bytes >= 2, "run payload too short");
+            uint16_t n_runs = 0;
+            std::memcpy(&n_runs, in->payload + c.payload_offset, 2);
+            require(c.payload_bytes == 2 + 4u * n_runs, "run payload must be 2+4*n_runs bytes");
+         } else {
+            throw ApiError(SILO_E_INVALID_ARGUMENT, "unknown roaring container typecode");
+         }
+      }
+      std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) {
+         const auto& ca = in->containers[a];
+         const auto& cb = in->containers[b];
+         if (ca.v_index != cb.v_index) {
+            return ca.v_index < cb.v_index;
+         }
+         if (ca.position != cb.position) {
+            return ca.position < cb.position;
+         }
+         return ca.symbol < cb.symbol;
+      });
+      for (uint64_t i = 1; i < order.size(); ++i) {
+         const auto& prev = in->containers[order[i - 1]];
+         const auto& cur = in->containers[order[i]];
+         require(
+            !(prev.v_index == cur.v_index && prev.position == cur.position && prev.symbol == cur.symbol),
+            "duplicate (position, v_index, symbol) container key"
+         );
+      }
+
+      auto column = std::make_unique<HostColumn>();
+      std::vector<DevContainer> descs(in->n_containers);
+      std::vector<DevSegment> segments;
+      std::vector<uint32_t> chunk_desc_begin(n_chunks + 1, 0);
+      std::vector<uint32_t> chunk_seg_begin(n_chunks + 1, 0);
+      std::vector<uint8_t> slab;
+      slab.reserve(in->payload_bytes + in->n_containers * 2 + 4096);
+      column->chunk_desc_payload_bytes.assign(n_chunks, 0);
+      column->chunk_containers.assign(n_chunks, 0);
+
+      uint64_t cursor = 0;
+      for (uint32_t chunk = 0; chunk < n_chunks; ++chunk) {
+         chunk_desc_begin[chunk] = static_cast<uint32_t>(cursor);
+         chunk_seg_begin[chunk] = static_cast<uint32_t>(segments.size());
+         DevSegment segment{};
+         bool open = false;
+         auto closeSegment = [&]() {
+            if (!open) {
+               return;
+            }
+            slab.resize(alignUp(static_cast<uint32_t>(slab.size() - segment.payload_offset), 16) + segment.payload_offset, 0);
+            segment.payload_bytes = static_cast<uint32_t>(slab.size() - segment.payload_offset);
+            segments.push_back(segment);
+            open = false;
+         };
+         while (cursor < order.size() && in->containers[order[cursor]].v_index == first_chunk + chunk) {
+            const silo_container_desc& c = in->containers[order[cursor]];
+            const uint8_t* src = in->payload + c.payload_offset;
+            uint32_t bytes = c.payload_bytes;
+            uint32_t alignment = 4;
+            uint32_t n_runs = 0;
+            if (c.typecode == TYPE_BITSET) {
+               alignment = 16;
+            } else if (c.typecode == TYPE_RUN) {
+               uint16_t header = 0;
+               std::memcpy(&header, src, 2);
+               n_runs = header;
+               src += 2;  // the device layout drops the u16 header: pairs become aligned u32 words
+               bytes -= 2;
+            }
+            if (open) {
+               const uint32_t used = static_cast<uint32_t>(slab.size() - segment.payload_offset);
+               if (segment.desc_count == SEG_MAX_DESCS || alignUp(used, alignment) + bytes > SEG_PAYLOAD_BYTES) {
+                  closeSegment();
+               }
+            }
+            if (!open) {
+               slab.resize((slab.size() + 15) / 16 * 16, 0);
+               segment = DevSegment{};
+               segment.payload_offset = slab.size();
+               segment.desc_begin = static_cast<uint32_t>(cursor);
+               segment.chunk = chunk;
+               open = true;
+            }
+            slab.resize((slab.size() + alignment - 1) / alignment * alignment, 0);
+            const uint64_t offset = slab.size();
+            require(offset / 4 <= UINT32_MAX, "column payload exceeds the 16 GiB per-shard addressing limit");
+            slab.insert(slab.end(), src, src + bytes);
+            DevContainer& d = descs[cursor];
+            d.position = c.position;
+            d.offset4 = static_cast<uint32_t>(offset / 4);
+            d.packed = (c.cardinality - 1) | (static_cast<uint32_t>(c.symbol) << 16) |
+                       (static_cast<uint32_t>(in->local_reference[c.position]) << 24) |
+                       (static_cast<uint32_t>(c.typecode) << 30);
+            d.n_runs = n_runs;
+            segment.desc_count++;
+            column->chunk_desc_payload_bytes[chunk] += sizeof(DevContainer) + c.payload_bytes;
+            column->chunk_containers[chunk]++;
+            ++cursor;
+         }
+         closeSegment();
+      }
+      chunk_desc_begin[n_chunks] = static_cast<uint32_t>(cursor);
+      chunk_seg_begin[n_chunks] = static_cast<uint32_t>(segments.size());
+      slab.resize((slab.size() + 15) / 16 * 16 + 16, 0);
+
+      // ---- coverage ----
+      std::vector<uint32_t> chunk_row_begin(n_chunks + 1, 0);
+      for (uint32_t chunk = 0; chunk < n_chunks; ++chunk) {
+         chunk_row_begin[chunk + 1] = chunk_row_begin[chunk] + table->chunk_sizes[chunk];
+      }
+      std::vector<uint2> start_end(table->n_rows);
+      for (uint64_t row = 0; row < table->n_rows; ++row) {
+         start_end[row] = make_uint2(in->start_end[2 * row], in->start_end[2 * row + 1]);
+         require(start_end[row].x <= start_end[row].y && start_end[row].y <= in->genome_length, "coverage range out of bounds");
+      }
+      std::vector<uint32_t> chunk_missing_begin(n_chunks + 1, 0);
+      std::vector<uint16_t> missing_row(in->n_rows_with_missing);
+      std::vector<uint64_t> missing_offsets(in->n_rows_with_missing + 1, 0);
+      column->chunk_missing_rows.assign(n_chunks, 0);
+      uint64_t total_runs = 0;
+      {
+         uint32_t chunk = 0;
+         for (uint64_t i = 0; i < in->n_rows_with_missing; ++i) {
+            const uint32_t row_id = in->missing_row_ids[i];
+            require(i == 0 || in->missing_row_ids[i - 1] < row_id, "missing_row_ids must be strictly ascending");
+            const uint32_t global_chunk = row_id >> 16;
+            require(global_chunk >= first_chunk && global_chunk < first_chunk + n_chunks, "missing row outside the shard");
+            const uint32_t local_chunk = global_chunk - first_chunk;
+            require((row_id & 0xFFFF) < table->chunk_sizes[local_chunk], "missing row outside the row layout");
+            while (chunk < local_chunk) {
+               chunk_missing_begin[++chunk] = static_cast<uint32_t>(i);
+            }
+            missing_row[i] = static_cast<uint16_t>(row_id & 0xFFFF);
+            require(in->missing_offsets[i] <= in->missing_offsets[i + 1], "missing_offsets must be ascending");
+            missing_offsets[i] = in->missing_offsets[i];
+            column->chunk_missing_rows[local_chunk]++;
+         }
+         while (chunk < n_chunks) {
+            chunk_missing_begin[++chunk] = static_cast<uint32_t>(in->n_rows_with_missing);
+         }
+         if (in->n_rows_with_missing > 0) {
+            require(in->missing_offsets[0] == 0, "missing_offsets[0] must be 0");
+            total_runs = in->missing_offsets[in->n_rows_with_missing];
+            missing_offsets[in->n_rows_with_missing] = total_runs;
+         }
+      }
+      std::vector<uint2> missing_runs(total_runs);
+      for (uint64_t run = 0; run < total_runs; ++run) {
+         missing_runs[run] = make_uint2(in->missing_runs[2 * run], in->missing_runs[2 * run + 1]);
+         require(missing_runs[run].x < missing_runs[run].y && missing_runs[run].y <= in->genome_length, "missing run out of bounds");
+      }
+      // nulls as dense tiles (only when present)
+      std::vector<uint64_t> null_words;
+      if (in->n_null_rows > 0) {
+         null_words.assign(static_cast<size_t>(n_chunks) * TILE_WORDS, 0);
+         for (uint64_t i = 0; i < in->n_null_rows; ++i) {
+            const uint32_t row_id = in->null_row_ids[i];
+            const uint32_t global_chunk = row_id >> 16;
+            require(global_chunk >= first_chunk && global_chunk < first_chunk + n_chunks, "null row outside the shard");
+            const uint32_t local_chunk = global_chunk - first_chunk;
+            require((row_id & 0xFFFF) < table->chunk_sizes[local_chunk], "null row outside the row layout");
+            null_words[static_cast<size_t>(local_chunk) * TILE_WORDS + ((row_id & 0xFFFF) >> 6)] |= 1ULL << (row_id & 63);
+         }
+      }
+
+      // ---- upload ----
+      uint64_t* acc = &column->device_bytes;
+      auto track = [&](auto* ptr) {
+         column->allocations.push_back(const_cast<void*>(static_cast<const void*>(ptr)));
+         return ptr;
+      };
+      DevColumn& dev = column->dev;
+      dev.n_symbols = in->n_symbols;
+      dev.genome_length = in->genome_length;
+      dev.missing_symbol = in->missing_symbol;
+      dev.n_chunks = n_chunks;
+      dev.n_containers = in->n_containers;
+      dev.n_segments = static_cast<uint32_t>(segments.size());
+      std::vector<uint8_t> local_reference(in->local_reference, in->local_reference + in->genome_length);
+      dev.local_reference = track(deviceUpload(local_reference, stream, acc));
+      dev.containers = track(deviceUpload(descs, stream, acc));
+      dev.payload = track(deviceUpload(slab, stream, acc));
+      dev.chunk_desc_begin = track(deviceUpload(chunk_desc_begin, stream, acc));
+      dev.segments = track(deviceUpload(segments, stream, acc));
+      dev.chunk_seg_begin = track(deviceUpload(chunk_seg_begin, stream, acc));
+      dev.start_end = track(deviceUpload(start_end, stream, acc));
+      dev.chunk_row_begin = track(deviceUpload(chunk_row_begin, stream, acc));
+      dev.chunk_missing_begin = track(deviceUpload(chunk_missing_begin, stream, acc));
+      dev.missing_row = track(deviceUpload(missing_row, stream, acc));
+      dev.missing_offsets = track(deviceUpload(missing_offsets, stream, acc));
+      dev.missing_runs = track(deviceUpload(missing_runs, stream, acc));
+      dev.null_words = null_words.empty() ? nullptr : track(deviceUpload(null_words, stream, acc));
+      SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+
+      if (in->genome_length + 1 > table->coverage_diff_capacity) {
+         cudaFree(table->d_coverage_diff);
+         table->d_coverage_diff = deviceAlloc<uint32_t>(in->genome_length + 1, &table->device_bytes);
+         table->coverage_diff_capacity = in->genome_length + 1;
+      }
+      const uint64_t counts_elems = static_cast<uint64_t>(in->n_symbols) * in->genome_length;
+      if (counts_elems > table->counts_capacity) {
+         cudaFree(table->d_counts);
+         if (table->h_counts_pinned != nullptr) {
+            cudaFreeHost(table->h_counts_pinned);
+         }
+         table->d_counts = deviceAlloc<uint32_t>(counts_elems, &table->device_bytes);
+         SILO_CUDA_CHECK(cudaMallocHost(&table->h_counts_pinned, counts_elems * sizeof(uint32_t)));
+         table->counts_capacity = counts_elems;
+      }
+      table->columns.push_back(column.release());
+      column_index = static_cast<int>(table->columns.size()) - 1;
+   });
+   return status == SILO_OK ? column_index : status;
+}
+
+int silo_gpu_get_stats(const silo_gpu_table* table, silo_gpu_stats* out) {
+   return guarded([&] {
+      require(table != nullptr && out != nullptr, "silo_gpu_get_stats: NULL argument");
+      out->containers = table->stats.containers;
+      out->algorithmic_bytes = table->stats.algorithmic_bytes;
+      out->kernel_launches = table->stats.kernel_launches;
+      out->last_counts_kernel_ms = table->stats.last_counts_kernel_ms;
+      out->last_total_ms = table->stats.last_total_ms;
+   });
+}
+
+}  // extern "C"
