@@ -1,0 +1,89 @@
+/*
+ * silo_b200_host.h — C entry points of the HOST layer (libsilo_b200_host.so), for the Python
+ * harness (tests/, bench.py) only.
+ *
+ * The host layer is the C++ code that, in an integrated build, lives inside the reference's query
+ * engine: it mirrors the reference's ScalarExpression -> Operator compilation
+ * (/root/reference/src/rhydb/query_engine/scalar_expressions/, filter/operators/) and the
+ * MutationsNode / CountFilterNode sinks (query_engine/operators/), and talks to the device only
+ * through include/silo_b200.h. A maintainer of the reference would not use THIS header: it exists
+ * because the reference's front-end (SaneQL, Planner, Arrow sinks) cannot be built here, so tests
+ * and bench.py need some way to drive the host layer. See INTEGRATION.md.
+ */
+#ifndef SILO_B200_HOST_H
+#define SILO_B200_HOST_H
+
+#include <stdint.h>
+
+#include "silo_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct silo_host_table silo_host_table;
+typedef struct silo_host_filter silo_host_filter;
+typedef struct silo_host_rows silo_host_rows;
+
+/* thread-local message of the last failed silo_host_* call; prefixed with the exception class
+ * ("IllegalQueryException: ", "QueryCompilationException: ", "DeviceError[<status>]: ") */
+const char* silo_host_last_error(void);
+
+silo_host_table* silo_host_table_create(silo_gpu_ctx* ctx, uint32_t first_chunk, const uint32_t* chunk_sizes, uint32_t n_chunks);
+void silo_host_table_free(silo_host_table* table);
+/* alphabet: 0 nucleotide, 1 amino acid. Uploads through silo_gpu_column_upload. */
+int silo_host_table_add_column(silo_host_table* table, const char* name, int alphabet, const char* reference, const silo_column_desc* column);
+/* ready-made roaring bitmap (portable format) standing in for a lineage / dictionary index */
+int silo_host_table_register_bitmap(silo_host_table* table, const char* name, const uint8_t* bytes, uint64_t size);
+silo_gpu_table* silo_host_table_device(silo_host_table* table);
+uint64_t silo_host_table_num_rows(const silo_host_table* table);
+
+/* computeFilter: parse (harness s-expression notation) -> rewrite(NONE) -> compile -> evaluate */
+silo_host_filter* silo_host_filter_eval(silo_host_table* table, const char* expression);
+void silo_host_filter_free(silo_host_filter* filter);
+uint64_t silo_host_filter_cardinality(const silo_host_filter* filter);
+const silo_gpu_filter* silo_host_filter_device(const silo_host_filter* filter);
+int silo_host_filter_words(const silo_host_filter* filter, uint64_t* words /* 1024 x n_chunks */);
+/* the lowered program as text, one instruction per line (debugging / tests of the lowering) */
+int silo_host_filter_explain(silo_host_table* table, const char* expression, char* out, uint64_t capacity);
+
+/* calculateMutationsPerPosition incl. the full / mixed / empty dispatch (mutations_node.cpp:279-286);
+ * filter == NULL means the filter `true`. counts[n_symbols * genome_length]. */
+int silo_host_mutation_counts(silo_host_table* table, const char* column, const silo_host_filter* filter, uint32_t* counts);
+/* MutationsNode: filter expression (NULL = true) + columns + minProportion -> output rows */
+silo_host_rows* silo_host_mutations(silo_host_table* table, const char* expression, const char* const* columns, uint32_t n_columns, double min_proportion);
+/* thresholding only, on counts the caller summed over shards (multi-GPU) */
+silo_host_rows* silo_host_mutation_rows_from_counts(silo_host_table* table, const char* column, const uint32_t* counts, double min_proportion);
+void silo_host_rows_free(silo_host_rows* rows);
+uint64_t silo_host_rows_size(const silo_host_rows* rows);
+int silo_host_rows_get(const silo_host_rows* rows, uint64_t index, char* from, char* to, int32_t* position, const char** sequence_name, double* proportion, int32_t* count, int32_t* coverage);
+
+/* ---- synthetic benchmark inputs (performance/sequence_generator.h restated on the product side) */
+
+typedef struct silo_host_synthetic silo_host_synthetic;
+/* Evolution tree over a seeded random reference of `genome_length` nt (tree seed 42, mutation rate
+ * 0.001, death rate 0.1, 3 children: SequenceTreeGenerator defaults) */
+silo_host_synthetic* silo_host_synthetic_create(uint32_t genome_length, uint64_t reference_seed, uint32_t generations);
+void silo_host_synthetic_free(silo_host_synthetic* synthetic);
+uint32_t silo_host_synthetic_num_sequences(const silo_host_synthetic* synthetic);
+const char* silo_host_synthetic_reference(const silo_host_synthetic* synthetic);
+const char* silo_host_synthetic_sequence(const silo_host_synthetic* synthetic, uint32_t index);
+uint32_t silo_host_synthetic_parent(const silo_host_synthetic* synthetic, uint32_t index);
+uint32_t silo_host_synthetic_generation(const silo_host_synthetic* synthetic, uint32_t index);
+/* Builds the shard [first_chunk, first_chunk + n_chunks) of the table "row i = sequence[i % E]"
+ * with total_rows rows directly in the upload format; *out stays valid until the synthetic object
+ * is freed or the next build. */
+int silo_host_synthetic_build_column(silo_host_synthetic* synthetic, uint64_t total_rows, uint32_t first_chunk, uint32_t n_chunks, uint32_t threads, const silo_column_desc** out);
+/* releases the host copy of the last built column (after it was uploaded) */
+void silo_host_synthetic_release_column(silo_host_synthetic* synthetic);
+/* lineage stand-in: portable roaring bytes of the shard's rows descending from `ancestor` */
+int64_t silo_host_synthetic_lineage_bitmap(const silo_host_synthetic* synthetic, uint32_t ancestor, uint64_t total_rows, uint32_t first_chunk, uint32_t n_chunks, uint8_t* out, uint64_t capacity);
+/* date stand-in: the "(ranges ...)" expression text of DateBetween on the sorted synthetic date column */
+int silo_host_synthetic_date_ranges(uint64_t total_rows, uint32_t span_days, uint32_t from_day, uint32_t to_day_inclusive, uint32_t first_chunk, uint32_t n_chunks, char* out, uint64_t capacity);
+/* partition scheduler: boundaries[n_ranks + 1] of contiguous chunk ranges balanced by weight */
+int silo_host_partition_chunks(const uint64_t* chunk_weights, uint32_t n_chunks, uint32_t n_ranks, uint32_t* boundaries);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SILO_B200_HOST_H */

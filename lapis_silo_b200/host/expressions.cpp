@@ -1,0 +1,936 @@
+#include "expressions.h"
+
+#include <algorithm>
+#include <cctype>
+#include <map>
+#include <utility>
+
+#include "roaring_writer.h"
+
+namespace silo_host {
+
+namespace {
+
+void checkQuery(bool condition, const std::string& message) {
+   if (!condition) {
+      throw IllegalQueryException(message);
+   }
+}
+
+const SequenceColumnInfo& requireColumn(const Table& table, const std::string& name) {
+   const SequenceColumnInfo* column = table.findColumn(name);
+   // validateSequenceName, query_engine/query_parse_sequence_name.h:10-20
+   checkQuery(column != nullptr, "Database does not contain the Sequence with name: '" + name + "'");
+   return *column;
+}
+
+uint32_t maskOf(const std::vector<Symbol>& symbols) {
+   uint32_t mask = 0;
+   for (Symbol symbol : symbols) {
+      mask |= 1u << symbol;
+   }
+   return mask;
+}
+
+std::vector<Symbol> symbolsOf(uint32_t mask) {
+   std::vector<Symbol> symbols;
+   for (uint32_t symbol = 0; symbol < 32; ++symbol) {
+      if (((mask >> symbol) & 1u) != 0) {
+         symbols.push_back(static_cast<Symbol>(symbol));
+      }
+   }
+   return symbols;
+}
+
+uint32_t allSymbolsMask(const Alphabet& alphabet) {
+   return alphabet.count() == 32 ? 0xFFFFFFFFu : (1u << alphabet.count()) - 1u;
+}
+
+Symbol toSymbol(const Alphabet& alphabet, char character) {
+   const auto symbol = alphabet.charToSymbol(character);
+   checkQuery(
+      symbol.has_value(), "Invalid " + alphabet.symbol_name + " symbol '" + std::string(1, character) + "'"
+   );
+   return symbol.value();
+}
+
+}  // namespace
+
+AmbiguityMode invertMode(AmbiguityMode mode) {
+   switch (mode) {
+      case AmbiguityMode::UPPER_BOUND:
+         return AmbiguityMode::LOWER_BOUND;
+      case AmbiguityMode::LOWER_BOUND:
+         return AmbiguityMode::UPPER_BOUND;
+      case AmbiguityMode::NONE:
+         return AmbiguityMode::NONE;
+   }
+   return mode;
+}
+
+// ---- literals --------------------------------------------------------------------------------
+
+ExpressionPtr BoolLiteral::rewrite(const Table&, AmbiguityMode) const {
+   return std::make_shared<BoolLiteral>(value);
+}
+
+std::unique_ptr<Operator> BoolLiteral::compile(const Table&) const {
+   if (value) {
+      return std::make_unique<Full>();
+   }
+   return std::make_unique<Empty>();
+}
+
+// ---- SymbolInSet -----------------------------------------------------------------------------
+
+std::string SymbolInSet::toString() const {
+   return "(" + column + ":symbol at position " + std::to_string(position_idx + 1) + " in a set of " +
+          std::to_string(symbols.size()) + ")";
+}
+
+ExpressionPtr SymbolInSet::rewrite(const Table&, AmbiguityMode) const {
+   throw QueryCompilationException(
+      "Cannot rewrite SymbolInSet - this expression should only be created during query rewrites "
+      "and not directly used"
+   );
+}
+
+std::unique_ptr<Operator> SymbolInSet::compile(const Table& table) const {
+   return compileSymbolInSet(requireColumn(table, column), position_idx, symbols);
+}
+
+std::unique_ptr<Operator> compileSymbolInSet(
+   const SequenceColumnInfo& sequence_column,
+   uint32_t position_idx,
+   const std::vector<Symbol>& symbols
+) {
+   const Alphabet& alphabet = *sequence_column.alphabet;
+   checkQuery(
+      position_idx < sequence_column.reference_sequence.size(),
+      "SymbolInSet<" + alphabet.symbol_name + "> position is out of bounds " +
+         std::to_string(position_idx + 1) + " > " + std::to_string(sequence_column.reference_sequence.size())
+   );
+   const int column = sequence_column.device_column;
+   const uint32_t requested = maskOf(symbols);
+   const uint32_t reference_bit = 1u << sequence_column.local_reference.at(position_idx);
+   const uint32_t missing_bit = 1u << alphabet.missing;
+   const bool includes_reference = (requested & reference_bit) != 0;
+   const bool includes_missing = (requested & missing_bit) != 0;
+
+   // rows whose sequence is null are stored with an empty covered region; the compilations that
+   // start from "not covered" must drop them again (symbol_in_set.cpp:80-98)
+   auto excludeNullSequences = [&](std::unique_ptr<Operator> op) -> std::unique_ptr<Operator> {
+      if (!sequence_column.has_null_rows) {
+         return op;
+      }
+      OperatorVector keep;
+      keep.push_back(std::move(op));
+      OperatorVector drop;
+      drop.push_back(IndexScan::overNulls(column));
+      return std::make_unique<Intersection>(std::move(keep), std::move(drop));
+   };
+
+   if (includes_reference && includes_missing) {
+      // everything except the rows that hold one of the symbols that were NOT asked for
+      const uint32_t others = allSymbolsMask(alphabet) & ~requested;
+      return excludeNullSequences(std::make_unique<Complement>(IndexScan::overSymbols(column, position_idx, others)));
+   }
+   if (includes_missing) {
+      OperatorVector alternatives;
+      alternatives.push_back(std::make_unique<Selection>(CoveragePredicate{column, position_idx, false}));
+      alternatives.push_back(IndexScan::overSymbols(column, position_idx, requested));
+      return excludeNullSequences(std::make_unique<Union>(std::move(alternatives)));
+   }
+   if (includes_reference) {
+      // covered rows minus the ones that hold a non-missing symbol outside the request
+      const uint32_t others = allSymbolsMask(alphabet) & ~requested & ~missing_bit;
+      OperatorVector keep;
+      keep.push_back(std::make_unique<Selection>(CoveragePredicate{column, position_idx, true}));
+      OperatorVector drop;
+      drop.push_back(IndexScan::overSymbols(column, position_idx, others));
+      return std::make_unique<Intersection>(std::move(keep), std::move(drop));
+   }
+   return IndexScan::overSymbols(column, position_idx, requested);
+}
+
+// ---- SymbolEquals / HasMutation --------------------------------------------------------------
+
+std::string SymbolEquals::toString() const {
+   return column + ":" + std::to_string(position_idx + 1) + std::string(1, symbol.value_or('.'));
+}
+
+ExpressionPtr SymbolEquals::rewrite(const Table& table, AmbiguityMode mode) const {
+   const auto& sequence_column = requireColumn(table, column);
+   const Alphabet& alphabet = *sequence_column.alphabet;
+   checkQuery(
+      position_idx < sequence_column.reference_sequence.size(),
+      "SymbolEquals<" + alphabet.symbol_name + "> position is out of bounds " +
+         std::to_string(position_idx + 1) + " > " + std::to_string(sequence_column.reference_sequence.size())
+   );
+   const Symbol wanted = symbol.has_value() ? toSymbol(alphabet, symbol.value())
+                                            : sequence_column.reference_sequence.at(position_idx);
+   if (mode == AmbiguityMode::UPPER_BOUND) {
+      return std::make_shared<SymbolInSet>(column, position_idx, alphabet.ambiguity_symbols.at(wanted));
+   }
+   return std::make_shared<SymbolInSet>(column, position_idx, std::vector<Symbol>{wanted});
+}
+
+std::unique_ptr<Operator> SymbolEquals::compile(const Table&) const {
+   throw QueryCompilationException("SymbolEquals should have been rewritten before compilation");
+}
+
+std::string HasMutation::toString() const {
+   return column + ":" + std::to_string(position_idx);
+}
+
+ExpressionPtr HasMutation::rewrite(const Table& table, AmbiguityMode mode) const {
+   const auto& sequence_column = requireColumn(table, column);
+   const Alphabet& alphabet = *sequence_column.alphabet;
+   checkQuery(
+      position_idx < sequence_column.reference_sequence.size(),
+      "Has" + alphabet.symbol_name + "Mutation position is out of bounds " + std::to_string(position_idx + 1) +
+         " > " + std::to_string(sequence_column.reference_sequence.size())
+   );
+   const Symbol reference_symbol = sequence_column.reference_sequence.at(position_idx);
+   uint32_t mask = allSymbolsMask(alphabet);
+   if (mode == AmbiguityMode::UPPER_BOUND) {
+      mask &= ~(1u << reference_symbol);
+   } else {
+      mask &= ~maskOf(alphabet.ambiguity_symbols.at(reference_symbol));
+   }
+   return std::make_shared<SymbolInSet>(column, position_idx, symbolsOf(mask));
+}
+
+std::unique_ptr<Operator> HasMutation::compile(const Table&) const {
+   throw QueryCompilationException("HasMutation expression must be eliminated in query rewrite phase");
+}
+
+// ---- Negation / Maybe / Exact ----------------------------------------------------------------
+
+ExpressionPtr Negation::rewrite(const Table& table, AmbiguityMode mode) const {
+   return std::make_shared<Negation>(child->rewrite(table, invertMode(mode)));
+}
+std::unique_ptr<Operator> Negation::compile(const Table& table) const {
+   return Operator::negate(child->compile(table));
+}
+ExpressionPtr Maybe::rewrite(const Table& table, AmbiguityMode) const {
+   return child->rewrite(table, AmbiguityMode::UPPER_BOUND);
+}
+std::unique_ptr<Operator> Maybe::compile(const Table&) const {
+   throw QueryCompilationException("Maybe expression must be elimitated in query rewrite phase");
+}
+ExpressionPtr Exact::rewrite(const Table& table, AmbiguityMode) const {
+   return child->rewrite(table, AmbiguityMode::LOWER_BOUND);
+}
+std::unique_ptr<Operator> Exact::compile(const Table&) const {
+   throw QueryCompilationException("Exact expression must be elimitated in query rewrite phase");
+}
+
+// ---- And -------------------------------------------------------------------------------------
+
+std::string And::toString() const {
+   std::string res = "And(";
+   for (const auto& child : children) {
+      res += child->toString() + " & ";
+   }
+   return res + ")";
+}
+
+ExpressionPtr And::rewrite(const Table& table, AmbiguityMode mode) const {
+   ExpressionVector rewritten;
+   rewritten.reserve(children.size());
+   for (const auto& child : children) {
+      rewritten.push_back(child->rewrite(table, mode));
+   }
+   return std::make_shared<And>(std::move(rewritten));
+}
+
+std::unique_ptr<Operator> And::compile(const Table& table) const {
+   // and.cpp:91-143: flatten nested intersections, un-negate complements, dissolve selections into a
+   // predicate list wrapped around the index-arithmetic child
+   OperatorVector pending;
+   for (const auto& child : children) {
+      pending.push_back(child->compile(table));
+   }
+   OperatorVector non_negated;
+   OperatorVector negated;
+   std::vector<CoveragePredicate> predicates;
+   while (!pending.empty()) {
+      auto child = std::move(pending.back());
+      pending.pop_back();
+      switch (child->type()) {
+         case FULL:
+            break;
+         case EMPTY:
+            return std::make_unique<Empty>();  // and.cpp:150-166 with the shortcut of :103-108
+         case INTERSECTION: {
+            auto* nested = static_cast<Intersection*>(child.get());
+            for (auto& grandchild : nested->children) {
+               non_negated.push_back(std::move(grandchild));
+            }
+            for (auto& grandchild : nested->negated_children) {
+               negated.push_back(std::move(grandchild));
+            }
+            break;
+         }
+         case COMPLEMENT:
+            negated.push_back(Operator::negate(std::move(child)));
+            break;
+         case SELECTION: {
+            auto* selection = static_cast<Selection*>(child.get());
+            predicates.insert(predicates.end(), selection->predicates.begin(), selection->predicates.end());
+            if (selection->child_operator.has_value()) {
+               pending.push_back(std::move(selection->child_operator.value()));
+            }
+            break;
+         }
+         default:
+            non_negated.push_back(std::move(child));
+      }
+   }
+   if (non_negated.empty() && negated.empty()) {
+      if (predicates.empty()) {
+         return std::make_unique<Full>();
+      }
+      return std::make_unique<Selection>(std::nullopt, std::move(predicates));
+   }
+   std::unique_ptr<Operator> index_arithmetic;
+   if (non_negated.size() == 1 && negated.empty()) {
+      index_arithmetic = std::move(non_negated[0]);
+   } else if (negated.size() == 1 && non_negated.empty()) {
+      index_arithmetic = std::make_unique<Complement>(std::move(negated[0]));
+   } else if (non_negated.empty()) {
+      index_arithmetic = std::make_unique<Complement>(std::make_unique<Union>(std::move(negated)));
+   } else {
+      index_arithmetic = std::make_unique<Intersection>(std::move(non_negated), std::move(negated));
+   }
+   if (predicates.empty()) {
+      return index_arithmetic;
+   }
+   return std::make_unique<Selection>(
+      std::optional<std::unique_ptr<Operator>>{std::move(index_arithmetic)}, std::move(predicates)
+   );
+}
+
+// ---- Or --------------------------------------------------------------------------------------
+
+std::string Or::toString() const {
+   std::string res = "Or(";
+   for (const auto& child : children) {
+      res += child->toString() + " | ";
+   }
+   return res + ")";
+}
+
+ExpressionPtr Or::rewrite(const Table& table, AmbiguityMode mode) const {
+   // or.cpp:47-68: flatten nested disjunctions before rewriting
+   std::vector<const ScalarExpression*> flat;
+   std::vector<const ScalarExpression*> stack;
+   for (const auto& child : children) {
+      stack.push_back(child.get());
+   }
+   while (!stack.empty()) {
+      const ScalarExpression* current = stack.back();
+      stack.pop_back();
+      if (const auto* nested = dynamic_cast<const Or*>(current)) {
+         for (const auto& child : nested->children) {
+            stack.push_back(child.get());
+         }
+      } else {
+         flat.push_back(current);
+      }
+   }
+   ExpressionVector rewritten;
+   for (const ScalarExpression* child : flat) {
+      rewritten.push_back(child->rewrite(table, mode));
+   }
+   // or.cpp:70-95: drop constant false, short-circuit on constant true, flatten again
+   ExpressionVector simplified;
+   while (!rewritten.empty()) {
+      ExpressionPtr child = std::move(rewritten.back());
+      rewritten.pop_back();
+      if (const auto* literal = dynamic_cast<const BoolLiteral*>(child.get())) {
+         if (literal->value) {
+            simplified.clear();
+            simplified.push_back(std::make_shared<BoolLiteral>(true));
+            rewritten.clear();
+            break;
+         }
+         continue;
+      }
+      if (const auto* nested = dynamic_cast<const Or*>(child.get())) {
+         rewritten.insert(rewritten.end(), nested->children.begin(), nested->children.end());
+      } else {
+         simplified.push_back(std::move(child));
+      }
+   }
+   // or.cpp:97-124: SymbolInSet children on the same (column, position) merge into one set
+   ExpressionVector merged_children;
+   std::map<std::pair<std::string, uint32_t>, std::vector<Symbol>> merged;
+   std::vector<std::pair<std::string, uint32_t>> merge_order_nucleotide;
+   std::vector<std::pair<std::string, uint32_t>> merge_order_amino_acid;
+   for (auto& child : simplified) {
+      if (const auto* in_set = dynamic_cast<const SymbolInSet*>(child.get())) {
+         const auto key = std::make_pair(in_set->column, in_set->position_idx);
+         auto& symbols = merged[key];
+         symbols.insert(symbols.end(), in_set->symbols.begin(), in_set->symbols.end());
+      } else {
+         merged_children.push_back(std::move(child));
+      }
+   }
+   // the reference runs the nucleotide pass before the amino-acid pass; each appends its merged
+   // sets in map order
+   for (int pass = 0; pass < 2; ++pass) {
+      for (auto& [key, symbols] : merged) {
+         const SequenceColumnInfo* column = table.findColumn(key.first);
+         const bool is_nucleotide = column != nullptr && column->alphabet == &Alphabet::nucleotide();
+         if ((pass == 0) == is_nucleotide) {
+            merged_children.push_back(std::make_shared<SymbolInSet>(key.first, key.second, symbols));
+         }
+      }
+   }
+   if (merged_children.size() == 1) {
+      return merged_children[0];
+   }
+   return std::make_shared<Or>(std::move(merged_children));
+}
+
+std::unique_ptr<Operator> Or::compile(const Table& table) const {
+   OperatorVector kept;
+   for (const auto& child_expression : children) {
+      auto child = child_expression->compile(table);
+      if (child->type() == EMPTY) {
+         continue;
+      }
+      if (child->type() == FULL) {
+         return std::make_unique<Full>();
+      }
+      if (child->type() == UNION) {
+         for (auto& grandchild : static_cast<Union*>(child.get())->children) {
+            kept.push_back(std::move(grandchild));
+         }
+      } else {
+         kept.push_back(std::move(child));
+      }
+   }
+   if (kept.empty()) {
+      return std::make_unique<Empty>();
+   }
+   if (kept.size() == 1) {
+      return std::move(kept[0]);
+   }
+   const bool any_complement =
+      std::any_of(kept.begin(), kept.end(), [](const auto& child) { return child->type() == COMPLEMENT; });
+   if (any_complement) {
+      return Complement::fromDeMorgan(std::move(kept));
+   }
+   return std::make_unique<Union>(std::move(kept));
+}
+
+// ---- NOf -------------------------------------------------------------------------------------
+
+std::string NOf::toString() const {
+   return std::string(match_exactly ? "[exactly-" : "[") + std::to_string(number_of_matchers) + "-of:" +
+          std::to_string(children.size()) + " children]";
+}
+
+ExpressionPtr NOf::rewrite(const Table& table, AmbiguityMode mode) const {
+   auto rewriteChildren = [&]() {
+      ExpressionVector rewritten;
+      rewritten.reserve(children.size());
+      for (const auto& child : children) {
+         rewritten.push_back(child->rewrite(table, mode));
+      }
+      return rewritten;
+   };
+   // an exact count cannot carry an ambiguity mode: exactly-k = at-least-k and not at-least-(k+1)
+   // (nof.cpp:219-248)
+   if (mode != AmbiguityMode::NONE && match_exactly && std::cmp_less(number_of_matchers, children.size())) {
+      ExpressionVector both;
+      both.push_back(std::make_shared<NOf>(rewriteChildren(), number_of_matchers, false));
+      both.push_back(std::make_shared<Negation>(std::make_shared<NOf>(rewriteChildren(), number_of_matchers + 1, false)));
+      return std::make_shared<And>(std::move(both));
+   }
+   return std::make_shared<NOf>(rewriteChildren(), number_of_matchers, match_exactly);
+}
+
+std::unique_ptr<Operator> NOf::compile(const Table& table) const {
+   // nof.cpp:184-215: Empty children can never match, Full children always do, complements are
+   // kept as negated children
+   OperatorVector non_negated;
+   OperatorVector negated;
+   int k = number_of_matchers;
+   for (const auto& child_expression : children) {
+      auto child = child_expression->compile(table);
+      if (child->type() == EMPTY) {
+         continue;
+      }
+      if (child->type() == FULL) {
+         --k;
+      } else if (child->type() == COMPLEMENT) {
+         negated.push_back(Operator::negate(std::move(child)));
+      } else {
+         non_negated.push_back(std::move(child));
+      }
+   }
+   const int n = static_cast<int>(non_negated.size() + negated.size());
+   // nof.cpp:33-84 trivial cases
+   if (k > n) {
+      return std::make_unique<Empty>();
+   }
+   if (k < 0) {
+      if (match_exactly) {
+         return std::make_unique<Empty>();
+      }
+      return std::make_unique<Full>();
+   }
+   if (k == 0) {
+      if (!match_exactly || n == 0) {
+         return std::make_unique<Full>();
+      }
+      if (n == 1) {
+         if (non_negated.empty()) {
+            return std::move(negated[0]);
+         }
+         return std::make_unique<Complement>(std::move(non_negated[0]));
+      }
+      if (negated.empty()) {
+         return std::make_unique<Complement>(std::make_unique<Union>(std::move(non_negated)));
+      }
+      return std::make_unique<Intersection>(std::move(negated), std::move(non_negated));
+   }
+   if (k == 1 && n == 1) {
+      if (negated.empty()) {
+         return std::move(non_negated[0]);
+      }
+      return std::make_unique<Complement>(std::move(negated[0]));
+   }
+   if (k == n) {  // nof.cpp:86-98: all must match
+      if (non_negated.empty()) {
+         return std::make_unique<Complement>(std::make_unique<Union>(std::move(negated)));
+      }
+      return std::make_unique<Intersection>(std::move(non_negated), std::move(negated));
+   }
+   if (k == 1 && !match_exactly) {  // nof.cpp:100-114: any may match
+      if (negated.empty()) {
+         return std::make_unique<Union>(std::move(non_negated));
+      }
+      return std::make_unique<Complement>(std::make_unique<Intersection>(std::move(negated), std::move(non_negated)));
+   }
+   return std::make_unique<Threshold>(std::move(non_negated), std::move(negated), static_cast<uint32_t>(k), match_exactly);
+}
+
+// ---- MutationProfile -------------------------------------------------------------------------
+
+std::string MutationProfile::toString() const {
+   return "MutationProfile(" + column + ":distance=" + std::to_string(distance) + ")";
+}
+
+ExpressionPtr MutationProfile::rewrite(const Table& table, AmbiguityMode) const {
+   const auto& sequence_column = requireColumn(table, column);
+   const Alphabet& alphabet = *sequence_column.alphabet;
+   const size_t reference_length = sequence_column.reference_sequence.size();
+   std::vector<Symbol> profile;
+   if (const auto* query = std::get_if<QuerySequence>(&input)) {
+      checkQuery(
+         query->sequence.size() == reference_length,
+         "querySequence length " + std::to_string(query->sequence.size()) +
+            " does not match the reference sequence length " + std::to_string(reference_length) + " for " +
+            alphabet.symbol_name + " MutationProfile"
+      );
+      profile.reserve(reference_length);
+      for (char character : query->sequence) {
+         const auto symbol = alphabet.charToSymbol(character);
+         checkQuery(
+            symbol.has_value(),
+            "Invalid " + alphabet.symbol_name + " symbol '" + std::string(1, character) +
+               "' in querySequence for MutationProfile"
+         );
+         profile.push_back(symbol.value());
+      }
+   } else {
+      profile = sequence_column.reference_sequence;
+      for (const auto& [position, character] : std::get<Mutations>(input).mutations) {
+         checkQuery(
+            position < reference_length,
+            alphabet.symbol_name + " MutationProfile mutation position " + std::to_string(position + 1) +
+               " is out of bounds (reference length " + std::to_string(reference_length) + ")"
+         );
+         profile[position] = toSymbol(alphabet, character);
+      }
+   }
+   // one "definitely different" child per position: the symbols that are NOT compatible with the
+   // profile symbol (mutation_profile.cpp:222-247); the filter is "fewer than distance+1 differ"
+   ExpressionVector differences;
+   for (size_t position = 0; position < profile.size(); ++position) {
+      if (profile[position] == alphabet.missing) {
+         continue;
+      }
+      const uint32_t incompatible =
+         allSymbolsMask(alphabet) & ~maskOf(alphabet.ambiguity_symbols.at(profile[position]));
+      if (incompatible == 0) {
+         continue;
+      }
+      differences.push_back(
+         std::make_shared<SymbolInSet>(column, static_cast<uint32_t>(position), symbolsOf(incompatible))
+      );
+   }
+   return std::make_shared<Negation>(
+      std::make_shared<NOf>(std::move(differences), static_cast<int>(distance) + 1, false)
+   );
+}
+
+std::unique_ptr<Operator> MutationProfile::compile(const Table&) const {
+   throw QueryCompilationException("MutationProfile expression must be eliminated in the query rewrite phase");
+}
+
+// ---- boundary leaves -------------------------------------------------------------------------
+
+std::unique_ptr<Operator> BitmapFilter::compile(const Table& table) const {
+   auto iter = table.named_bitmaps.find(name);
+   if (iter == table.named_bitmaps.end()) {
+      return std::make_unique<Empty>();  // unknown value, lineage_filter.cpp:93-95
+   }
+   return IndexScan::overBitmap(&iter->second);
+}
+
+std::unique_ptr<Operator> RowRanges::compile(const Table& table) const {
+   auto copy = ranges;
+   const uint32_t begin = table.row_layout.first_chunk << 16;
+   const uint32_t end = (table.row_layout.first_chunk + static_cast<uint32_t>(table.row_layout.numChunks())) << 16;
+   return std::make_unique<RangeSelection>(std::move(copy), begin, end);
+}
+
+DeviceBitmap computeFilter(const ScalarExpression& filter, const Table& table) {
+   const ExpressionPtr rewritten = filter.rewrite(table, AmbiguityMode::NONE);
+   const std::unique_ptr<Operator> compiled = rewritten->compile(table);
+   return compiled->evaluate(table);
+}
+
+// ---- harness notation ------------------------------------------------------------------------
+
+namespace {
+
+// physical forms, used by the operator-level known-answer tests only
+struct IdsLeaf : ScalarExpression {
+   std::vector<uint8_t> bytes;
+   explicit IdsLeaf(std::vector<uint32_t> ids) {
+      std::sort(ids.begin(), ids.end());
+      ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+      bytes = writePortableRoaring(ids);
+   }
+   std::string toString() const override { return "ids"; }
+   ExpressionPtr rewrite(const Table&, AmbiguityMode) const override { return shared_from_this(); }
+   std::unique_ptr<Operator> compile(const Table&) const override { return IndexScan::overBitmap(&bytes); }
+};
+
+struct CoveredLeaf : ScalarExpression {
+   std::string column;
+   uint32_t position_idx;
+   bool covered;
+   CoveredLeaf(std::string column, uint32_t position_idx, bool covered)
+       : column(std::move(column)),
+         position_idx(position_idx),
+         covered(covered) {}
+   std::string toString() const override { return "covered"; }
+   ExpressionPtr rewrite(const Table&, AmbiguityMode) const override { return shared_from_this(); }
+   std::unique_ptr<Operator> compile(const Table& table) const override {
+      const auto& sequence_column = requireColumn(table, column);
+      checkQuery(position_idx < sequence_column.reference_sequence.size(), "position is out of bounds");
+      return std::make_unique<Selection>(CoveragePredicate{sequence_column.device_column, position_idx, covered});
+   }
+};
+
+struct RawSymbolInSet : ScalarExpression {
+   std::string column;
+   uint32_t position_idx;
+   std::string chars;
+   std::string toString() const override { return "sym-in"; }
+   ExpressionPtr rewrite(const Table& table, AmbiguityMode) const override {
+      const auto& sequence_column = requireColumn(table, column);
+      std::vector<Symbol> symbols;
+      for (char character : chars) {
+         symbols.push_back(toSymbol(*sequence_column.alphabet, character));
+      }
+      return std::make_shared<SymbolInSet>(column, position_idx, std::move(symbols));
+   }
+   std::unique_ptr<Operator> compile(const Table& table) const override {
+      return rewrite(table, AmbiguityMode::NONE)->compile(table);
+   }
+};
+
+struct PhysicalOperator : ScalarExpression {
+   enum Kind { AND, OR, NOT, THRESHOLD } kind = AND;
+   ExpressionVector first;
+   ExpressionVector second;
+   uint32_t number_of_matchers = 0;
+   bool match_exactly = false;
+   std::string toString() const override { return "physical"; }
+   ExpressionPtr rewrite(const Table& table, AmbiguityMode mode) const override {
+      auto copy = std::make_shared<PhysicalOperator>(*this);
+      for (auto& child : copy->first) {
+         child = child->rewrite(table, mode);
+      }
+      for (auto& child : copy->second) {
+         child = child->rewrite(table, mode);
+      }
+      return copy;
+   }
+   std::unique_ptr<Operator> compile(const Table& table) const override {
+      OperatorVector first_operators;
+      OperatorVector second_operators;
+      for (const auto& child : first) {
+         first_operators.push_back(child->compile(table));
+      }
+      for (const auto& child : second) {
+         second_operators.push_back(child->compile(table));
+      }
+      switch (kind) {
+         case AND:
+            return std::make_unique<Intersection>(std::move(first_operators), std::move(second_operators));
+         case OR:
+            return std::make_unique<Union>(std::move(first_operators));
+         case NOT:
+            return std::make_unique<Complement>(std::move(first_operators.at(0)));
+         case THRESHOLD:
+            return std::make_unique<Threshold>(
+               std::move(first_operators), std::move(second_operators), number_of_matchers, match_exactly
+            );
+      }
+      throw std::logic_error("unreachable");
+   }
+};
+
+struct Node {
+   bool is_atom = false;
+   std::string atom;
+   std::vector<Node> items;
+};
+
+class Reader {
+   const std::string& text;
+   size_t cursor = 0;
+
+   void skipSpace() {
+      while (cursor < text.size() && std::isspace(static_cast<unsigned char>(text[cursor])) != 0) {
+         ++cursor;
+      }
+   }
+
+  public:
+   explicit Reader(const std::string& text) : text(text) {}
+
+   Node next() {
+      skipSpace();
+      checkQuery(cursor < text.size(), "filter expression ended unexpectedly");
+      Node node;
+      const char head = text[cursor];
+      checkQuery(head != ')', "filter expression: unexpected ')'");
+      if (head == '(') {
+         ++cursor;
+         for (;;) {
+            skipSpace();
+            checkQuery(cursor < text.size(), "filter expression: missing ')'");
+            if (text[cursor] == ')') {
+               ++cursor;
+               return node;
+            }
+            node.items.push_back(next());
+         }
+      }
+      node.is_atom = true;
+      if (head == '"') {
+         const size_t close = text.find('"', cursor + 1);
+         checkQuery(close != std::string::npos, "filter expression: unterminated string");
+         node.atom = text.substr(cursor + 1, close - cursor - 1);
+         cursor = close + 1;
+         return node;
+      }
+      const size_t begin = cursor;
+      while (cursor < text.size() && std::isspace(static_cast<unsigned char>(text[cursor])) == 0 &&
+             text[cursor] != '(' && text[cursor] != ')') {
+         ++cursor;
+      }
+      node.atom = text.substr(begin, cursor - begin);
+      return node;
+   }
+
+   bool exhausted() {
+      skipSpace();
+      return cursor >= text.size();
+   }
+};
+
+const std::string& atom(const Node& node) {
+   checkQuery(node.is_atom, "filter expression: expected an atom");
+   return node.atom;
+}
+
+uint64_t number(const Node& node) {
+   const std::string& text = atom(node);
+   checkQuery(
+      !text.empty() && std::all_of(text.begin(), text.end(), [](char c) { return c >= '0' && c <= '9'; }),
+      "filter expression: expected a non-negative integer, got '" + text + "'"
+   );
+   return std::stoull(text);
+}
+
+uint32_t position(const Node& node) {
+   const uint64_t one_based = number(node);
+   checkQuery(one_based != 0, "The field 'position' is 1-indexed. Value of 0 not allowed.");
+   return static_cast<uint32_t>(one_based - 1);
+}
+
+ExpressionPtr build(const Node& node);
+
+ExpressionVector buildList(const Node& list, size_t from = 0) {
+   checkQuery(!list.is_atom, "filter expression: expected a list");
+   ExpressionVector result;
+   for (size_t i = from; i < list.items.size(); ++i) {
+      result.push_back(build(list.items[i]));
+   }
+   return result;
+}
+
+ExpressionPtr build(const Node& node) {
+   checkQuery(!node.is_atom && !node.items.empty(), "filter expression: expected a non-empty list");
+   const auto& items = node.items;
+   const std::string& head = atom(items[0]);
+   auto arity = [&](size_t count) {
+      checkQuery(items.size() == count + 1, "filter expression: wrong number of arguments for " + head);
+   };
+   if (head == "true" || head == "false") {
+      arity(0);
+      return std::make_shared<BoolLiteral>(head == "true");
+   }
+   if (head == "sym-eq") {
+      arity(3);
+      const std::string& symbol = atom(items[3]);
+      checkQuery(symbol.size() == 1, "symbol must be a single character");
+      return std::make_shared<SymbolEquals>(
+         atom(items[1]), position(items[2]), symbol == "." ? std::nullopt : std::optional<char>(symbol[0])
+      );
+   }
+   if (head == "sym-in") {
+      arity(3);
+      auto expression = std::make_shared<RawSymbolInSet>();
+      expression->column = atom(items[1]);
+      expression->position_idx = position(items[2]);
+      expression->chars = atom(items[3]);
+      return expression;
+   }
+   if (head == "has-mut") {
+      arity(2);
+      return std::make_shared<HasMutation>(atom(items[1]), position(items[2]));
+   }
+   if (head == "and") {
+      return std::make_shared<And>(buildList(node, 1));
+   }
+   if (head == "or") {
+      return std::make_shared<Or>(buildList(node, 1));
+   }
+   if (head == "not") {
+      arity(1);
+      return std::make_shared<Negation>(build(items[1]));
+   }
+   if (head == "maybe") {
+      arity(1);
+      return std::make_shared<Maybe>(build(items[1]));
+   }
+   if (head == "exact") {
+      arity(1);
+      return std::make_shared<Exact>(build(items[1]));
+   }
+   if (head == "n-of") {
+      checkQuery(items.size() >= 3, "filter expression: n-of needs K and EXACT");
+      return std::make_shared<NOf>(buildList(node, 3), static_cast<int>(number(items[1])), number(items[2]) != 0);
+   }
+   if (head == "profile") {
+      checkQuery(items.size() >= 4, "filter expression: profile needs COL DIST KIND ..");
+      const std::string& column = atom(items[1]);
+      const auto distance = static_cast<uint32_t>(number(items[2]));
+      const std::string& kind = atom(items[3]);
+      if (kind == "seq") {
+         arity(4);
+         return std::make_shared<MutationProfile>(column, distance, MutationProfile::QuerySequence{atom(items[4])});
+      }
+      if (kind == "muts") {
+         checkQuery((items.size() - 4) % 2 == 0, "filter expression: profile muts needs POS SYM pairs");
+         MutationProfile::Mutations mutations;
+         for (size_t i = 4; i + 1 < items.size(); i += 2) {
+            const std::string& symbol = atom(items[i + 1]);
+            checkQuery(symbol.size() == 1, "symbol must be a single character");
+            mutations.mutations.emplace_back(position(items[i]), symbol[0]);
+         }
+         return std::make_shared<MutationProfile>(column, distance, std::move(mutations));
+      }
+      // `row` (sequenceId, mutation_profile.cpp:109-158) needs the primary-key column and a row
+      // reconstruction, both owned by the unchanged host engine: it hands over `seq` instead
+      throw IllegalQueryException("filter expression: unsupported profile kind " + kind);
+   }
+   if (head == "bitmap") {
+      arity(1);
+      return std::make_shared<BitmapFilter>(atom(items[1]));
+   }
+   if (head == "ranges") {
+      checkQuery((items.size() - 1) % 2 == 0, "filter expression: ranges needs START END pairs");
+      std::vector<RangeSelection::Range> ranges;
+      for (size_t i = 1; i + 1 < items.size(); i += 2) {
+         ranges.push_back({static_cast<uint32_t>(number(items[i])), static_cast<uint32_t>(number(items[i + 1]))});
+      }
+      return std::make_shared<RowRanges>(std::move(ranges));
+   }
+   if (head == "ids") {
+      std::vector<uint32_t> ids;
+      for (size_t i = 1; i < items.size(); ++i) {
+         ids.push_back(static_cast<uint32_t>(number(items[i])));
+      }
+      return std::make_shared<IdsLeaf>(std::move(ids));
+   }
+   if (head == "covered" || head == "not-covered") {
+      arity(2);
+      return std::make_shared<CoveredLeaf>(atom(items[1]), position(items[2]), head == "covered");
+   }
+   if (head == "op-and" || head == "op-threshold") {
+      auto expression = std::make_shared<PhysicalOperator>();
+      size_t lists_from = 1;
+      if (head == "op-threshold") {
+         checkQuery(items.size() == 5, "filter expression: op-threshold K EXACT (pos..) (neg..)");
+         expression->kind = PhysicalOperator::THRESHOLD;
+         expression->number_of_matchers = static_cast<uint32_t>(number(items[1]));
+         expression->match_exactly = number(items[2]) != 0;
+         lists_from = 3;
+      } else {
+         arity(2);
+         expression->kind = PhysicalOperator::AND;
+      }
+      expression->first = buildList(items[lists_from]);
+      expression->second = buildList(items[lists_from + 1]);
+      return expression;
+   }
+   if (head == "op-or") {
+      auto expression = std::make_shared<PhysicalOperator>();
+      expression->kind = PhysicalOperator::OR;
+      expression->first = buildList(node, 1);
+      return expression;
+   }
+   if (head == "op-not") {
+      arity(1);
+      auto expression = std::make_shared<PhysicalOperator>();
+      expression->kind = PhysicalOperator::NOT;
+      expression->first.push_back(build(items[1]));
+      return expression;
+   }
+   throw IllegalQueryException("filter expression: unknown form '" + head + "'");
+}
+
+}  // namespace
+
+ExpressionPtr parseFilterExpression(const std::string& text) {
+   Reader reader(text);
+   const Node node = reader.next();
+   checkQuery(reader.exhausted(), "filter expression: trailing input");
+   return build(node);
+}
+
+}  // namespace silo_host

@@ -1,0 +1,334 @@
+// C entry points of the host layer for the Python harness (include/silo_b200_host.h).
+#include <cstring>
+#include <memory>
+#include <sstream>
+#include <string>
+
+#include "../../include/silo_b200_host.h"
+#include "expressions.h"
+#include "mutations_node.h"
+#include "operators.h"
+#include "roaring_writer.h"
+#include "synthetic.h"
+#include "table.h"
+
+using namespace silo_host;
+
+struct silo_host_table {
+   std::unique_ptr<Table> table;
+};
+
+struct silo_host_filter {
+   DeviceBitmap bitmap;
+   size_t n_chunks = 0;
+};
+
+struct silo_host_rows {
+   std::vector<MutationRow> rows;
+};
+
+struct silo_host_synthetic {
+   std::string reference;
+   EvolvedTree tree;
+   std::unique_ptr<PackedColumn> column;
+};
+
+namespace {
+thread_local std::string g_last_error;
+
+template <typename Fn>
+int guarded(Fn&& fn) {
+   try {
+      fn();
+      return 0;
+   } catch (const IllegalQueryException& error) {
+      g_last_error = std::string("IllegalQueryException: ") + error.what();
+      return -2;
+   } catch (const QueryCompilationException& error) {
+      g_last_error = std::string("QueryCompilationException: ") + error.what();
+      return -3;
+   } catch (const DeviceError& error) {
+      g_last_error = "DeviceError[" + std::to_string(error.status) + "]: " + error.what();
+      return -5;
+   } catch (const std::exception& error) {
+      g_last_error = error.what();
+      return -1;
+   }
+}
+
+const SequenceColumnInfo& columnOf(const Table& table, const char* name) {
+   const SequenceColumnInfo* column = table.findColumn(name);
+   if (column == nullptr) {
+      throw IllegalQueryException(std::string("Database does not contain the Sequence with name: '") + name + "'");
+   }
+   return *column;
+}
+
+ExpressionPtr parseOrTrue(const char* expression) {
+   if (expression == nullptr) {
+      return std::make_shared<BoolLiteral>(true);
+   }
+   return parseFilterExpression(expression);
+}
+
+int copyText(const std::string& text, char* out, uint64_t capacity) {
+   if (out == nullptr || capacity < text.size() + 1) {
+      g_last_error = "output buffer too small: need " + std::to_string(text.size() + 1) + " bytes";
+      return -1;
+   }
+   std::memcpy(out, text.c_str(), text.size() + 1);
+   return 0;
+}
+}  // namespace
+
+extern "C" {
+
+const char* silo_host_last_error(void) {
+   return g_last_error.c_str();
+}
+
+silo_host_table* silo_host_table_create(silo_gpu_ctx* ctx, uint32_t first_chunk, const uint32_t* chunk_sizes, uint32_t n_chunks) {
+   silo_host_table* result = nullptr;
+   guarded([&] {
+      RowLayout layout;
+      layout.first_chunk = first_chunk;
+      layout.chunk_sizes.assign(chunk_sizes, chunk_sizes + n_chunks);
+      auto owned = std::make_unique<silo_host_table>();
+      owned->table = std::make_unique<Table>(ctx, std::move(layout));
+      result = owned.release();
+   });
+   return result;
+}
+
+void silo_host_table_free(silo_host_table* table) {
+   delete table;
+}
+
+int silo_host_table_add_column(silo_host_table* table, const char* name, int alphabet, const char* reference, const silo_column_desc* column) {
+   return guarded([&] {
+      table->table->addSequenceColumn(
+         name, alphabet == 0 ? Alphabet::nucleotide() : Alphabet::aminoAcid(), reference, *column
+      );
+   });
+}
+
+int silo_host_table_register_bitmap(silo_host_table* table, const char* name, const uint8_t* bytes, uint64_t size) {
+   return guarded([&] { table->table->named_bitmaps[name] = std::vector<uint8_t>(bytes, bytes + size); });
+}
+
+silo_gpu_table* silo_host_table_device(silo_host_table* table) {
+   return table->table->device;
+}
+
+uint64_t silo_host_table_num_rows(const silo_host_table* table) {
+   return table->table->row_layout.numRows();
+}
+
+silo_host_filter* silo_host_filter_eval(silo_host_table* table, const char* expression) {
+   silo_host_filter* result = nullptr;
+   guarded([&] {
+      const ExpressionPtr parsed = parseFilterExpression(expression);
+      auto owned = std::make_unique<silo_host_filter>();
+      owned->bitmap = computeFilter(*parsed, *table->table);
+      owned->n_chunks = table->table->row_layout.numChunks();
+      result = owned.release();
+   });
+   return result;
+}
+
+void silo_host_filter_free(silo_host_filter* filter) {
+   delete filter;
+}
+
+uint64_t silo_host_filter_cardinality(const silo_host_filter* filter) {
+   return filter->bitmap.cardinality();
+}
+
+const silo_gpu_filter* silo_host_filter_device(const silo_host_filter* filter) {
+   return filter->bitmap.get();
+}
+
+int silo_host_filter_words(const silo_host_filter* filter, uint64_t* words) {
+   return guarded([&] {
+      const std::vector<uint64_t> downloaded = filter->bitmap.toWords(filter->n_chunks);
+      std::memcpy(words, downloaded.data(), downloaded.size() * sizeof(uint64_t));
+   });
+}
+
+int silo_host_filter_explain(silo_host_table* table, const char* expression, char* out, uint64_t capacity) {
+   std::string text;
+   const int status = guarded([&] {
+      const ExpressionPtr parsed = parseFilterExpression(expression);
+      const ExpressionPtr rewritten = parsed->rewrite(*table->table, AmbiguityMode::NONE);
+      const std::unique_ptr<Operator> compiled = rewritten->compile(*table->table);
+      ProgramBuilder builder;
+      builder.table = table->table.get();
+      compiled->lower(builder);
+      std::ostringstream stream;
+      stream << "operator: " << compiled->toString() << "\n";
+      for (const silo_filter_instr& instr : builder.instrs) {
+         stream << "op=" << static_cast<int>(instr.opcode) << " flags=" << static_cast<int>(instr.flags)
+                << " column=" << instr.column << " a=" << instr.a << " b=" << instr.b << "\n";
+      }
+      text = stream.str();
+   });
+   if (status != 0) {
+      return status;
+   }
+   return copyText(text, out, capacity);
+}
+
+int silo_host_mutation_counts(silo_host_table* table, const char* column, const silo_host_filter* filter, uint32_t* counts) {
+   return guarded([&] {
+      const Table& t = *table->table;
+      const SequenceColumnInfo& info = columnOf(t, column);
+      SymbolCounts result;
+      if (filter == nullptr) {
+         const DeviceBitmap everything = computeFilter(BoolLiteral(true), t);
+         result = calculateMutationsPerPosition(t, info, everything, t.row_layout.numRows());
+      } else {
+         result = calculateMutationsPerPosition(t, info, filter->bitmap, t.row_layout.numRows());
+      }
+      std::memcpy(counts, result.values.data(), result.values.size() * sizeof(uint32_t));
+   });
+}
+
+silo_host_rows* silo_host_mutations(silo_host_table* table, const char* expression, const char* const* columns, uint32_t n_columns, double min_proportion) {
+   silo_host_rows* result = nullptr;
+   guarded([&] {
+      std::vector<std::string> names(columns, columns + n_columns);
+      const MutationsNode node(*table->table, parseOrTrue(expression), std::move(names), min_proportion);
+      auto owned = std::make_unique<silo_host_rows>();
+      owned->rows = node.execute();
+      result = owned.release();
+   });
+   return result;
+}
+
+silo_host_rows* silo_host_mutation_rows_from_counts(silo_host_table* table, const char* column, const uint32_t* counts, double min_proportion) {
+   silo_host_rows* result = nullptr;
+   guarded([&] {
+      const SequenceColumnInfo& info = columnOf(*table->table, column);
+      SymbolCounts symbol_counts;
+      symbol_counts.n_symbols = info.alphabet->count();
+      symbol_counts.genome_length = static_cast<uint32_t>(info.reference_sequence.size());
+      symbol_counts.values.assign(counts, counts + static_cast<size_t>(symbol_counts.n_symbols) * symbol_counts.genome_length);
+      auto owned = std::make_unique<silo_host_rows>();
+      appendMutationRows(info, symbol_counts, min_proportion, owned->rows);
+      result = owned.release();
+   });
+   return result;
+}
+
+void silo_host_rows_free(silo_host_rows* rows) {
+   delete rows;
+}
+
+uint64_t silo_host_rows_size(const silo_host_rows* rows) {
+   return rows->rows.size();
+}
+
+int silo_host_rows_get(const silo_host_rows* rows, uint64_t index, char* from, char* to, int32_t* position, const char** sequence_name, double* proportion, int32_t* count, int32_t* coverage) {
+   return guarded([&] {
+      const MutationRow& row = rows->rows.at(index);
+      *from = row.mutation_from;
+      *to = row.mutation_to;
+      *position = row.position;
+      *sequence_name = row.sequence_name.c_str();
+      *proportion = row.proportion;
+      *count = row.count;
+      *coverage = row.coverage;
+   });
+}
+
+// ---- synthetic ---------------------------------------------------------------------------------
+
+silo_host_synthetic* silo_host_synthetic_create(uint32_t genome_length, uint64_t reference_seed, uint32_t generations) {
+   silo_host_synthetic* result = nullptr;
+   guarded([&] {
+      auto owned = std::make_unique<silo_host_synthetic>();
+      owned->reference = randomNucleotideReference(genome_length, reference_seed);
+      owned->tree = generateEvolvedSequences(owned->reference, 42, 0.001, 0.1, generations, 3);
+      result = owned.release();
+   });
+   return result;
+}
+
+void silo_host_synthetic_free(silo_host_synthetic* synthetic) {
+   delete synthetic;
+}
+
+uint32_t silo_host_synthetic_num_sequences(const silo_host_synthetic* synthetic) {
+   return static_cast<uint32_t>(synthetic->tree.sequences.size());
+}
+const char* silo_host_synthetic_reference(const silo_host_synthetic* synthetic) {
+   return synthetic->reference.c_str();
+}
+const char* silo_host_synthetic_sequence(const silo_host_synthetic* synthetic, uint32_t index) {
+   return index < synthetic->tree.sequences.size() ? synthetic->tree.sequences[index].c_str() : nullptr;
+}
+uint32_t silo_host_synthetic_parent(const silo_host_synthetic* synthetic, uint32_t index) {
+   return synthetic->tree.parent.at(index);
+}
+uint32_t silo_host_synthetic_generation(const silo_host_synthetic* synthetic, uint32_t index) {
+   return synthetic->tree.generation.at(index);
+}
+
+int silo_host_synthetic_build_column(silo_host_synthetic* synthetic, uint64_t total_rows, uint32_t first_chunk, uint32_t n_chunks, uint32_t threads, const silo_column_desc** out) {
+   return guarded([&] {
+      synthetic->column = std::make_unique<PackedColumn>();
+      buildCycledColumn(
+         Alphabet::nucleotide(), synthetic->reference, synthetic->tree.sequences, total_rows, first_chunk, n_chunks,
+         threads, *synthetic->column
+      );
+      *out = &synthetic->column->desc;
+   });
+}
+
+void silo_host_synthetic_release_column(silo_host_synthetic* synthetic) {
+   synthetic->column.reset();
+}
+
+int64_t silo_host_synthetic_lineage_bitmap(const silo_host_synthetic* synthetic, uint32_t ancestor, uint64_t total_rows, uint32_t first_chunk, uint32_t n_chunks, uint8_t* out, uint64_t capacity) {
+   int64_t size = -1;
+   guarded([&] {
+      const std::vector<uint8_t> bytes =
+         writePortableRoaring(lineageRowIds(synthetic->tree, ancestor, total_rows, first_chunk, n_chunks));
+      size = static_cast<int64_t>(bytes.size());
+      if (out != nullptr && capacity >= bytes.size()) {
+         std::memcpy(out, bytes.data(), bytes.size());
+      }
+   });
+   return size;
+}
+
+int silo_host_synthetic_date_ranges(uint64_t total_rows, uint32_t span_days, uint32_t from_day, uint32_t to_day_inclusive, uint32_t first_chunk, uint32_t n_chunks, char* out, uint64_t capacity) {
+   std::string text;
+   const int status = guarded([&] {
+      const std::vector<uint32_t> flat = sortedDateRanges(total_rows, span_days, from_day, to_day_inclusive, first_chunk, n_chunks);
+      std::ostringstream stream;
+      stream << "(ranges";
+      for (uint32_t value : flat) {
+         stream << ' ' << value;
+      }
+      stream << ')';
+      text = stream.str();
+   });
+   if (status != 0) {
+      return status;
+   }
+   return copyText(text, out, capacity);
+}
+
+int silo_host_partition_chunks(const uint64_t* chunk_weights, uint32_t n_chunks, uint32_t n_ranks, uint32_t* boundaries) {
+   return guarded([&] {
+      if (n_ranks == 0) {
+         throw std::invalid_argument("n_ranks must be positive");
+      }
+      const std::vector<uint32_t> result =
+         partitionChunks(std::vector<uint64_t>(chunk_weights, chunk_weights + n_chunks), n_ranks);
+      std::copy(result.begin(), result.end(), boundaries);
+   });
+}
+
+}  // extern "C"

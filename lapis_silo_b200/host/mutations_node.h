@@ -1,0 +1,74 @@
+// The Mutations / AminoAcidMutations action and the count sink of the host layer.
+//
+// Same split as /root/reference/src/rhydb/query_engine/operators/mutations_node.cpp:
+//   calculateMutationsPerPosition :268-288  -> one call into the device (silo_gpu_mutation_counts)
+//   addMutationsToOutput :290-366           -> unchanged host arithmetic (uint32 totals, the
+//        threshold  ceil(double(total) * minProportion) - 1  and the double proportion), so the
+//        emitted rows are bit-identical
+// and operators/count_filter_node.cpp:35-71 (count = filter cardinality).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "expressions.h"
+#include "operators.h"
+#include "table.h"
+
+namespace silo_host {
+
+// SymbolMap<SymbolType, std::vector<uint32_t>>: counts[symbol * genome_length + position]
+struct SymbolCounts {
+   uint32_t n_symbols = 0;
+   uint32_t genome_length = 0;
+   std::vector<uint32_t> values;
+   [[nodiscard]] uint32_t at(Symbol symbol, uint32_t position) const {
+      return values[static_cast<size_t>(symbol) * genome_length + position];
+   }
+};
+
+SymbolCounts calculateMutationsPerPosition(
+   const Table& table,
+   const SequenceColumnInfo& sequence_column,
+   const DeviceBitmap& bitmap_filter,
+   uint64_t sequence_count_in_column
+);
+
+struct MutationRow {
+   char mutation_from;
+   char mutation_to;
+   int32_t position;  // 1-based
+   std::string sequence_name;
+   double proportion;
+   int32_t count;
+   int32_t coverage;
+};
+
+// the per-position part of addMutationsToOutput (:307-363), also used on all-reduced counts
+void appendMutationRows(
+   const SequenceColumnInfo& sequence_column,
+   const SymbolCounts& counts,
+   double min_proportion,
+   std::vector<MutationRow>& out
+);
+
+class MutationsNode {
+  public:
+   const Table& table;
+   ExpressionPtr filter;
+   std::vector<std::string> sequence_columns;
+   double min_proportion;
+
+   MutationsNode(const Table& table, ExpressionPtr filter, std::vector<std::string> sequence_columns, double min_proportion)
+       : table(table),
+         filter(std::move(filter)),
+         sequence_columns(std::move(sequence_columns)),
+         min_proportion(min_proportion) {}
+
+   // addToExecPlan + producer (:372-428): the filter is evaluated once, then every column
+   [[nodiscard]] std::vector<MutationRow> execute() const;
+};
+
+// CountFilterNode: `filter(...).groupBy({count:=count()})`
+uint64_t countFilter(const Table& table, const ScalarExpression& filter);
+
+}  // namespace silo_host

@@ -1,0 +1,489 @@
+#include "operators.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+
+namespace silo_host {
+
+// ---- DeviceBitmap ------------------------------------------------------------------------------
+
+DeviceBitmap::DeviceBitmap(silo_gpu_filter* filter, uint64_t cardinality)
+    : handle(filter, [](silo_gpu_filter* owned) { silo_gpu_filter_free(owned); }),
+      cached_cardinality(cardinality) {}
+
+std::vector<uint64_t> DeviceBitmap::toWords(size_t n_chunks) const {
+   std::vector<uint64_t> words(n_chunks * 1024);
+   throwOnDeviceError(silo_gpu_filter_download(handle.get(), words.data()));
+   return words;
+}
+
+// ---- ProgramBuilder ----------------------------------------------------------------------------
+
+void ProgramBuilder::emit(uint8_t opcode, uint8_t flags, uint16_t column, uint32_t a, uint64_t b) {
+   silo_filter_instr instr{};
+   instr.opcode = opcode;
+   instr.flags = flags;
+   instr.column = column;
+   instr.a = a;
+   instr.b = b;
+   instrs.push_back(instr);
+}
+
+uint64_t ProgramBuilder::addBlob(const void* data, size_t bytes, size_t alignment) {
+   blob.resize((blob.size() + alignment - 1) / alignment * alignment, 0);
+   const uint64_t offset = blob.size();
+   const auto* src = static_cast<const uint8_t*>(data);
+   blob.insert(blob.end(), src, src + bytes);
+   return offset;
+}
+
+uint32_t ProgramBuilder::addBitmap(const std::vector<uint8_t>& portable_roaring_bytes) {
+   for (size_t i = 0; i < bitmaps.size(); ++i) {
+      if (bitmaps[i].data == portable_roaring_bytes.data()) {
+         return static_cast<uint32_t>(i);
+      }
+   }
+   bitmaps.push_back(silo_roaring_bytes{portable_roaring_bytes.data(), portable_roaring_bytes.size()});
+   return static_cast<uint32_t>(bitmaps.size() - 1);
+}
+
+// ---- Operator ----------------------------------------------------------------------------------
+
+DeviceBitmap Operator::evaluate(const Table& table) const {
+   ProgramBuilder builder;
+   builder.table = &table;
+   lower(builder);
+   silo_filter_program program{};
+   program.struct_size = sizeof(silo_filter_program);
+   program.n_instrs = static_cast<uint32_t>(builder.instrs.size());
+   program.instrs = builder.instrs.data();
+   program.blob = builder.blob.data();
+   program.blob_bytes = builder.blob.size();
+   program.n_bitmaps = static_cast<uint32_t>(builder.bitmaps.size());
+   program.bitmaps = builder.bitmaps.data();
+   silo_gpu_filter* filter = nullptr;
+   uint64_t cardinality = 0;
+   throwOnDeviceError(silo_gpu_filter_eval(table.device, &program, &filter, &cardinality));
+   return DeviceBitmap{filter, cardinality};
+}
+
+namespace {
+template <typename T>
+std::unique_ptr<T> downcast(std::unique_ptr<Operator>&& op) {
+   return std::unique_ptr<T>(static_cast<T*>(op.release()));
+}
+}  // namespace
+
+std::unique_ptr<Operator> Operator::negate(std::unique_ptr<Operator>&& some_operator) {
+   switch (some_operator->type()) {
+      case EMPTY:
+         return std::make_unique<Full>();  // empty.cpp:29-31
+      case FULL:
+         return std::make_unique<Empty>();  // full.cpp:31-33
+      case COMPLEMENT:  // complement.cpp:58-60
+         return std::move(downcast<Complement>(std::move(some_operator))->child);
+      case RANGE_SELECTION: {  // range_selection.cpp:89-111
+         auto range_selection = downcast<RangeSelection>(std::move(some_operator));
+         std::vector<RangeSelection::Range> new_ranges;
+         uint32_t last_end = range_selection->begin_of_layout;
+         if (range_selection->begin_of_layout != range_selection->end_of_layout) {
+            for (const auto& current : range_selection->ranges) {
+               if (last_end != current.start) {
+                  new_ranges.push_back({last_end, current.start});
+               }
+               last_end = current.end;
+            }
+            if (last_end != range_selection->end_of_layout) {
+               new_ranges.push_back({last_end, range_selection->end_of_layout});
+            }
+         }
+         return std::make_unique<RangeSelection>(
+            std::move(new_ranges), range_selection->begin_of_layout, range_selection->end_of_layout
+         );
+      }
+      case SELECTION: {  // selection.cpp:143-151
+         auto* selection = static_cast<Selection*>(some_operator.get());
+         if (!selection->child_operator.has_value() && selection->predicates.size() == 1) {
+            CoveragePredicate negated = selection->predicates[0];
+            negated.is_covered = !negated.is_covered;
+            return std::make_unique<Selection>(negated);
+         }
+         return std::make_unique<Complement>(std::move(some_operator));
+      }
+      case INDEX_SCAN:
+      case INTERSECTION:
+      case THRESHOLD:
+      case UNION:
+      case BITMAP_PRODUCER:
+         return std::make_unique<Complement>(std::move(some_operator));
+   }
+   throw std::logic_error("unreachable operator type");
+}
+
+void Empty::lower(ProgramBuilder& program) const {
+   program.emit(SILO_OP_PUSH_EMPTY);
+}
+
+void Full::lower(ProgramBuilder& program) const {
+   program.emit(SILO_OP_PUSH_FULL);
+}
+
+// ---- IndexScan ---------------------------------------------------------------------------------
+
+std::unique_ptr<IndexScan> IndexScan::overSymbols(int device_column, uint32_t position_idx, uint32_t symbol_mask) {
+   auto scan = std::make_unique<IndexScan>();
+   scan->source = Source::SYMBOLS;
+   scan->device_column = device_column;
+   scan->position_idx = position_idx;
+   scan->symbol_mask = symbol_mask;
+   return scan;
+}
+
+std::unique_ptr<IndexScan> IndexScan::overBitmap(const std::vector<uint8_t>* portable_roaring_bytes) {
+   auto scan = std::make_unique<IndexScan>();
+   scan->source = Source::BITMAP;
+   scan->bitmap_bytes = portable_roaring_bytes;
+   return scan;
+}
+
+std::unique_ptr<IndexScan> IndexScan::overNulls(int device_column) {
+   auto scan = std::make_unique<IndexScan>();
+   scan->source = Source::NULLS;
+   scan->device_column = device_column;
+   return scan;
+}
+
+std::string IndexScan::toString() const {
+   switch (source) {
+      case Source::SYMBOLS:
+         return "IndexScan(column " + std::to_string(device_column) + ", position " +
+                std::to_string(position_idx + 1) + ", symbols 0x" + std::to_string(symbol_mask) + ")";
+      case Source::BITMAP:
+         return "IndexScan(bitmap, " + std::to_string(bitmap_bytes->size()) + " bytes)";
+      case Source::NULLS:
+         return "IndexScan(nulls of column " + std::to_string(device_column) + ")";
+   }
+   return "IndexScan";
+}
+
+void IndexScan::lower(ProgramBuilder& program) const {
+   switch (source) {
+      case Source::SYMBOLS:
+         if (symbol_mask == 0) {
+            program.emit(SILO_OP_PUSH_EMPTY);
+         } else {
+            program.emit(SILO_OP_PUSH_SYMBOLS, 0, static_cast<uint16_t>(device_column), position_idx, symbol_mask);
+         }
+         break;
+      case Source::BITMAP:
+         program.emit(SILO_OP_PUSH_BITMAP, 0, 0, program.addBitmap(*bitmap_bytes), 0);
+         break;
+      case Source::NULLS:
+         program.emit(SILO_OP_PUSH_NULLS, 0, static_cast<uint16_t>(device_column));
+         break;
+   }
+}
+
+// ---- Intersection / Union / Complement ------------------------------------------------------------
+
+Intersection::Intersection(OperatorVector&& children_, OperatorVector&& negated_children_)
+    : children(std::move(children_)),
+      negated_children(std::move(negated_children_)) {
+   if (children.empty()) {
+      throw QueryCompilationException(
+         "Compilation bug: Intersection without non-negated children is not allowed. "
+         "Should be compiled as a union."
+      );
+   }
+   if (children.size() + negated_children.size() < 2) {
+      throw QueryCompilationException("Compilation bug: Intersection needs at least two children.");
+   }
+}
+
+std::string Intersection::toString() const {
+   std::string res = "Intersection(non_negated: (";
+   for (const auto& child : children) {
+      res += child->toString() + ", ";
+   }
+   res += ") negated: (";
+   for (const auto& child : negated_children) {
+      res += child->toString() + ", ";
+   }
+   return res + "))";
+}
+
+void Intersection::lower(ProgramBuilder& program) const {
+   // The reference orders operands by cardinality to keep roaring intermediates small
+   // (intersection.cpp:73-87); on dense tiles the order is irrelevant.
+   children[0]->lower(program);
+   for (size_t i = 1; i < children.size(); ++i) {
+      children[i]->lower(program);
+      program.emit(SILO_OP_AND);
+   }
+   for (const auto& child : negated_children) {
+      child->lower(program);
+      program.emit(SILO_OP_ANDNOT);
+   }
+}
+
+std::string Union::toString() const {
+   std::string res = "(";
+   for (const auto& child : children) {
+      res += child->toString() + " | ";
+   }
+   return res + ")";
+}
+
+void Union::lower(ProgramBuilder& program) const {
+   if (children.empty()) {
+      program.emit(SILO_OP_PUSH_EMPTY);
+      return;
+   }
+   children[0]->lower(program);
+   for (size_t i = 1; i < children.size(); ++i) {
+      children[i]->lower(program);
+      program.emit(SILO_OP_OR);
+   }
+}
+
+std::unique_ptr<Complement> Complement::fromDeMorgan(OperatorVector disjunction) {
+   OperatorVector non_negated_child_operators;
+   OperatorVector negated_child_operators;
+   for (auto& disjunction_child : disjunction) {
+      if (disjunction_child->type() == COMPLEMENT) {
+         negated_child_operators.emplace_back(Operator::negate(std::move(disjunction_child)));
+      } else {
+         non_negated_child_operators.push_back(std::move(disjunction_child));
+      }
+   }
+   // a disjunction with negated members becomes  !(negated... & !non_negated...)
+   auto intersection = std::make_unique<Intersection>(
+      std::move(negated_child_operators), std::move(non_negated_child_operators)
+   );
+   return std::make_unique<Complement>(std::move(intersection));
+}
+
+void Complement::lower(ProgramBuilder& program) const {
+   child->lower(program);
+   program.emit(SILO_OP_NOT);
+}
+
+// ---- RangeSelection / Selection ------------------------------------------------------------------
+
+void RangeSelection::lower(ProgramBuilder& program) const {
+   std::vector<uint32_t> flat;
+   flat.reserve(ranges.size() * 2);
+   for (const auto& range : ranges) {
+      flat.push_back(range.start);
+      flat.push_back(range.end);
+   }
+   const uint64_t offset = program.addBlob(flat.data(), flat.size() * sizeof(uint32_t), 4);
+   program.emit(SILO_OP_PUSH_RANGES, 0, 0, static_cast<uint32_t>(ranges.size()), offset);
+}
+
+std::string Selection::toString() const {
+   std::string res = "Select[";
+   for (const auto& predicate : predicates) {
+      res += std::string(predicate.is_covered ? "" : "!") + "IsInCoveredRegion(" +
+             std::to_string(predicate.position_idx) + "),";
+   }
+   res += "](";
+   if (child_operator.has_value()) {
+      res += child_operator.value()->toString();
+   }
+   return res + ")";
+}
+
+void Selection::lower(ProgramBuilder& program) const {
+   // selection.cpp:94-141 picks between row-wise matching and makeBitmap by cardinality; both give
+   // child AND predicate_1 AND ... which is what is emitted here.
+   bool have_tile = false;
+   if (child_operator.has_value()) {
+      child_operator.value()->lower(program);
+      have_tile = true;
+   }
+   for (const auto& predicate : predicates) {
+      program.emit(
+         SILO_OP_PUSH_COVERED,
+         predicate.is_covered ? 0 : 1,
+         static_cast<uint16_t>(predicate.device_column),
+         predicate.position_idx
+      );
+      if (have_tile) {
+         program.emit(SILO_OP_AND);
+      }
+      have_tile = true;
+   }
+}
+
+// ---- Threshold -----------------------------------------------------------------------------------
+
+Threshold::Threshold(
+   OperatorVector&& non_negated_children_,
+   OperatorVector&& negated_children_,
+   uint32_t number_of_matchers,
+   bool match_exactly
+)
+    : non_negated_children(std::move(non_negated_children_)),
+      negated_children(std::move(negated_children_)),
+      number_of_matchers(number_of_matchers),
+      match_exactly(match_exactly) {
+   if (number_of_matchers >= non_negated_children.size() + negated_children.size()) {
+      throw QueryCompilationException(
+         "Compilation Error: number_of_matchers must be less than the number of children of a "
+         "threshold expression"
+      );
+   }
+   if (number_of_matchers == 0) {
+      throw QueryCompilationException("Compilation Error: number_of_matchers must be greater than zero");
+   }
+}
+
+std::string Threshold::toString() const {
+   return std::string("Threshold(") + (match_exactly ? "=" : ">=") + std::to_string(number_of_matchers) +
+          "-of " + std::to_string(non_negated_children.size()) + " non_negated, " +
+          std::to_string(negated_children.size()) + " negated)";
+}
+
+namespace {
+
+// Recognises  Selection[IsCovered(col,p)] minus IndexScan(symbols at (col,p))  — what
+// compileWithReference builds (symbol_in_set.cpp:179-206). Every stored symbol is inside the covered
+// region, so the child contributes  covered(p) - [row holds one of the scanned symbols].
+bool matchCoveredMinusSymbols(const Operator& op, CoveragePredicate& predicate, uint32_t& mask) {
+   if (op.type() != INTERSECTION) {
+      return false;
+   }
+   const auto& intersection = static_cast<const Intersection&>(op);
+   if (intersection.children.size() != 1 || intersection.negated_children.size() != 1) {
+      return false;
+   }
+   const Operator& left = *intersection.children[0];
+   const Operator& right = *intersection.negated_children[0];
+   if (left.type() != SELECTION || right.type() != INDEX_SCAN) {
+      return false;
+   }
+   const auto& selection = static_cast<const Selection&>(left);
+   const auto& scan = static_cast<const IndexScan&>(right);
+   if (selection.child_operator.has_value() || selection.predicates.size() != 1 ||
+       !selection.predicates[0].is_covered || scan.source != IndexScan::Source::SYMBOLS ||
+       scan.device_column != selection.predicates[0].device_column ||
+       scan.position_idx != selection.predicates[0].position_idx) {
+      return false;
+   }
+   predicate = selection.predicates[0];
+   mask = scan.symbol_mask;
+   return true;
+}
+
+constexpr size_t PROFILE_MIN_LEAVES = 24;  // below this, per-position binary searches are cheaper
+
+struct FusedLeaves {
+   std::vector<std::pair<uint32_t, uint32_t>> adds;  // (position, mask)
+   std::vector<std::pair<uint32_t, uint32_t>> subs;
+   std::vector<uint32_t> covered_positions;
+};
+
+}  // namespace
+
+void Threshold::lower(ProgramBuilder& program) const {
+   // Threshold::evaluate (threshold.cpp:64-138) is a DP over k roaring bitmaps whose result is
+   // "at least / exactly k of the children contain the row". The device keeps one u16 counter per
+   // row instead; leaves over the vertical index are scattered into the counters without ever
+   // materialising a tile.
+   std::map<int, FusedLeaves> fused;  // by device column
+   std::vector<const Operator*> generic;
+   for (const auto& child : non_negated_children) {
+      CoveragePredicate predicate{};
+      uint32_t mask = 0;
+      if (child->type() == INDEX_SCAN &&
+          static_cast<const IndexScan&>(*child).source == IndexScan::Source::SYMBOLS) {
+         const auto& scan = static_cast<const IndexScan&>(*child);
+         if (scan.symbol_mask != 0) {
+            fused[scan.device_column].adds.emplace_back(scan.position_idx, scan.symbol_mask);
+         }
+      } else if (matchCoveredMinusSymbols(*child, predicate, mask)) {
+         FusedLeaves& leaves = fused[predicate.device_column];
+         leaves.covered_positions.push_back(predicate.position_idx);
+         if (mask != 0) {
+            leaves.subs.emplace_back(predicate.position_idx, mask);
+         }
+      } else {
+         generic.push_back(child.get());
+      }
+   }
+   uint64_t bias = 0;
+   for (const auto& [column, leaves] : fused) {
+      bias += leaves.subs.size();
+   }
+   program.emit(SILO_OP_THR_BEGIN, match_exactly ? 1 : 0, 0, number_of_matchers, bias);
+   for (const Operator* child : generic) {
+      child->lower(program);
+      program.emit(SILO_OP_THR_ADD, 0);
+   }
+   for (const auto& child : negated_children) {
+      child->lower(program);
+      program.emit(SILO_OP_THR_ADD, 1);
+   }
+   for (auto& [column, leaves] : fused) {
+      const auto device_column = static_cast<uint16_t>(column);
+      std::vector<std::pair<uint32_t, uint32_t>> single_adds;
+      std::vector<std::pair<uint32_t, uint32_t>> single_subs;
+      if (leaves.adds.size() + leaves.subs.size() >= PROFILE_MIN_LEAVES) {
+         // one streaming pass over the chunk's containers; the table holds at most one add mask and
+         // one disjoint sub mask per position, anything else falls back to single leaves
+         const size_t genome_length = program.table->columns.at(static_cast<size_t>(column)).reference_sequence.size();
+         std::vector<uint32_t> table(2 * genome_length, 0);
+         for (const auto& [position, mask] : leaves.adds) {
+            if (table[2 * position] == 0 && (table[2 * position + 1] & mask) == 0) {
+               table[2 * position] = mask;
+            } else {
+               single_adds.emplace_back(position, mask);
+            }
+         }
+         for (const auto& [position, mask] : leaves.subs) {
+            if (table[2 * position + 1] == 0 && (table[2 * position] & mask) == 0) {
+               table[2 * position + 1] = mask;
+            } else {
+               single_subs.emplace_back(position, mask);
+            }
+         }
+         const uint64_t offset = program.addBlob(table.data(), table.size() * sizeof(uint32_t), 8);
+         program.emit(SILO_OP_THR_PROFILE, 0, device_column, 0, offset);
+      } else {
+         single_adds = leaves.adds;
+         single_subs = leaves.subs;
+      }
+      for (const auto& [position, mask] : single_adds) {
+         program.emit(SILO_OP_THR_ADD_SYMBOLS, 0, device_column, position, mask);
+      }
+      for (const auto& [position, mask] : single_subs) {
+         program.emit(SILO_OP_THR_ADD_SYMBOLS, 1, device_column, position, mask);
+      }
+      // covered positions: strictly ascending lists; a position used by several children goes into
+      // further lists
+      std::vector<uint32_t> remaining = leaves.covered_positions;
+      std::sort(remaining.begin(), remaining.end());
+      while (!remaining.empty()) {
+         std::vector<uint32_t> unique_positions;
+         std::vector<uint32_t> duplicates;
+         for (uint32_t position : remaining) {
+            if (!unique_positions.empty() && unique_positions.back() == position) {
+               duplicates.push_back(position);
+            } else {
+               unique_positions.push_back(position);
+            }
+         }
+         const uint64_t offset =
+            program.addBlob(unique_positions.data(), unique_positions.size() * sizeof(uint32_t), 4);
+         program.emit(
+            SILO_OP_THR_ADD_COVERED, 0, device_column, static_cast<uint32_t>(unique_positions.size()), offset
+         );
+         remaining = std::move(duplicates);
+      }
+   }
+   program.emit(SILO_OP_THR_END);
+}
+
+}  // namespace silo_host

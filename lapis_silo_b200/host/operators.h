@@ -1,0 +1,190 @@
+// Physical filter operators of the host layer: same names, constructor checks and negate() rules as
+// /root/reference/src/rhydb/query_engine/filter/operators/ (operator.h:11-39, operator.cpp:19-67),
+// but evaluate() lowers the tree to a flat filter program (include/silo_b200.h) and runs it on the
+// device instead of folding roaring containers on the CPU. The result type is a device-resident
+// dense bitset (DeviceBitmap) where the reference returns a CopyOnWriteBitmap
+// (query_engine/copy_on_write_bitmap.h:28-147).
+#pragma once
+#include <memory>
+#include <optional>
+#include <string>
+#include <vector>
+
+#include "table.h"
+
+namespace silo_host {
+
+enum OperatorType : uint8_t {
+   EMPTY,
+   FULL,
+   INDEX_SCAN,
+   INTERSECTION,
+   COMPLEMENT,
+   RANGE_SELECTION,
+   SELECTION,
+   THRESHOLD,
+   UNION,
+   BITMAP_PRODUCER
+};
+
+// Owns a silo_gpu_filter. Consumers that stay on the device (Mutations, count) use the handle;
+// the others download it (silo_gpu_filter_download) and wrap it as a roaring bitmap.
+class DeviceBitmap {
+   std::shared_ptr<silo_gpu_filter> handle;
+   uint64_t cached_cardinality = 0;
+
+  public:
+   DeviceBitmap() = default;
+   DeviceBitmap(silo_gpu_filter* filter, uint64_t cardinality);
+   [[nodiscard]] uint64_t cardinality() const { return cached_cardinality; }
+   [[nodiscard]] bool isEmpty() const { return cached_cardinality == 0; }
+   [[nodiscard]] const silo_gpu_filter* get() const { return handle.get(); }
+   // dense words, 1024 per chunk (bit r of chunk c = row ((first_chunk + c) << 16) | r)
+   [[nodiscard]] std::vector<uint64_t> toWords(size_t n_chunks) const;
+};
+
+class ProgramBuilder {
+  public:
+   const Table* table = nullptr;  // for per-column facts the lowering needs (genome length)
+   std::vector<silo_filter_instr> instrs;
+   std::vector<uint8_t> blob;
+   std::vector<silo_roaring_bytes> bitmaps;
+
+   void emit(uint8_t opcode, uint8_t flags = 0, uint16_t column = 0, uint32_t a = 0, uint64_t b = 0);
+   uint64_t addBlob(const void* data, size_t bytes, size_t alignment);
+   uint32_t addBitmap(const std::vector<uint8_t>& portable_roaring_bytes);
+};
+
+class Operator {
+  public:
+   virtual ~Operator() = default;
+   [[nodiscard]] virtual OperatorType type() const = 0;
+   [[nodiscard]] virtual std::string toString() const = 0;
+   // appends instructions that leave exactly one more tile on the program's stack
+   virtual void lower(ProgramBuilder& program) const = 0;
+   [[nodiscard]] DeviceBitmap evaluate(const Table& table) const;
+   static std::unique_ptr<Operator> negate(std::unique_ptr<Operator>&& some_operator);
+};
+using OperatorVector = std::vector<std::unique_ptr<Operator>>;
+
+class Empty : public Operator {
+  public:
+   OperatorType type() const override { return EMPTY; }
+   std::string toString() const override { return "Empty"; }
+   void lower(ProgramBuilder& program) const override;
+};
+
+class Full : public Operator {
+  public:
+   OperatorType type() const override { return FULL; }
+   std::string toString() const override { return "Full"; }
+   void lower(ProgramBuilder& program) const override;
+};
+
+// IndexScan keeps its provenance instead of container views: the union of stored containers
+// (symbol_in_set.cpp:216-228), a foreign roaring bitmap (lineage_filter.cpp:96-99) or the column's
+// null_bitmap (symbol_in_set.cpp:86-92).
+class IndexScan : public Operator {
+  public:
+   enum class Source : uint8_t { SYMBOLS, BITMAP, NULLS };
+   Source source;
+   int device_column = 0;
+   uint32_t position_idx = 0;
+   uint32_t symbol_mask = 0;
+   const std::vector<uint8_t>* bitmap_bytes = nullptr;
+
+   static std::unique_ptr<IndexScan> overSymbols(int device_column, uint32_t position_idx, uint32_t symbol_mask);
+   static std::unique_ptr<IndexScan> overBitmap(const std::vector<uint8_t>* portable_roaring_bytes);
+   static std::unique_ptr<IndexScan> overNulls(int device_column);
+   OperatorType type() const override { return INDEX_SCAN; }
+   std::string toString() const override;
+   void lower(ProgramBuilder& program) const override;
+};
+
+class Intersection : public Operator {
+  public:
+   OperatorVector children;
+   OperatorVector negated_children;
+   Intersection(OperatorVector&& children, OperatorVector&& negated_children);  // intersection.cpp:19-41
+   OperatorType type() const override { return INTERSECTION; }
+   std::string toString() const override;
+   void lower(ProgramBuilder& program) const override;
+};
+
+class Union : public Operator {
+  public:
+   OperatorVector children;
+   explicit Union(OperatorVector&& children) : children(std::move(children)) {}
+   OperatorType type() const override { return UNION; }
+   std::string toString() const override;
+   void lower(ProgramBuilder& program) const override;
+};
+
+class Complement : public Operator {
+  public:
+   std::unique_ptr<Operator> child;
+   explicit Complement(std::unique_ptr<Operator> child) : child(std::move(child)) {}
+   static std::unique_ptr<Complement> fromDeMorgan(OperatorVector disjunction);  // complement.cpp:23-41
+   OperatorType type() const override { return COMPLEMENT; }
+   std::string toString() const override { return "!" + child->toString(); }
+   void lower(ProgramBuilder& program) const override;
+};
+
+class Threshold : public Operator {
+  public:
+   OperatorVector non_negated_children;
+   OperatorVector negated_children;
+   uint32_t number_of_matchers;
+   bool match_exactly;
+   Threshold(
+      OperatorVector&& non_negated_children,
+      OperatorVector&& negated_children,
+      uint32_t number_of_matchers,
+      bool match_exactly
+   );  // threshold.cpp:19-41
+   OperatorType type() const override { return THRESHOLD; }
+   std::string toString() const override;
+   void lower(ProgramBuilder& program) const override;
+};
+
+class RangeSelection : public Operator {
+  public:
+   struct Range {
+      uint32_t start;  // global sparse row ids, [start, end)
+      uint32_t end;
+   };
+   std::vector<Range> ranges;
+   uint32_t begin_of_layout;  // first_chunk << 16 (*row_layout.begin(), range_selection.cpp:97)
+   uint32_t end_of_layout;    // (first_chunk + numChunks) << 16, range_selection.cpp:103-106
+   RangeSelection(std::vector<Range>&& ranges, uint32_t begin_of_layout, uint32_t end_of_layout)
+       : ranges(std::move(ranges)),
+         begin_of_layout(begin_of_layout),
+         end_of_layout(end_of_layout) {}
+   OperatorType type() const override { return RANGE_SELECTION; }
+   std::string toString() const override { return "RangeSelection"; }
+   void lower(ProgramBuilder& program) const override;
+};
+
+// Selection restricted to the one predicate kind that lives on this path
+// (filter/operators/is_in_covered_region.h); predicates over value columns stay on the host side of
+// the boundary and re-enter as IndexScan::overBitmap.
+struct CoveragePredicate {
+   int device_column;
+   uint32_t position_idx;
+   bool is_covered;  // IS_COVERED / IS_NOT_COVERED
+};
+
+class Selection : public Operator {
+  public:
+   std::optional<std::unique_ptr<Operator>> child_operator;
+   std::vector<CoveragePredicate> predicates;
+   Selection(std::optional<std::unique_ptr<Operator>> child_operator, std::vector<CoveragePredicate> predicates)
+       : child_operator(std::move(child_operator)),
+         predicates(std::move(predicates)) {}
+   explicit Selection(CoveragePredicate predicate) { predicates.push_back(predicate); }
+   OperatorType type() const override { return SELECTION; }
+   std::string toString() const override;
+   void lower(ProgramBuilder& program) const override;
+};
+
+}  // namespace silo_host

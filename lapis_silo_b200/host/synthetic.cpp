@@ -1,0 +1,445 @@
+#include "synthetic.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <random>
+#include <thread>
+
+namespace silo_host {
+
+EvolvedTree generateEvolvedSequences(
+   const std::string& reference,
+   uint64_t seed,
+   double mutation_rate,
+   double death_rate,
+   size_t generations,
+   size_t children_per_node
+) {
+   // RNG call order per child: survives -> binomial(#mutations) -> per mutation: position, then
+   // base draws until the base changes. mutateBase picks among the first four nucleotide symbols
+   // ('-', 'A', 'C', 'G'), as the reference does.
+   static constexpr char FIRST_FOUR_SYMBOLS[4] = {'-', 'A', 'C', 'G'};
+   std::mt19937 rng(seed);
+   EvolvedTree tree;
+   tree.sequences.push_back(reference);
+   tree.parent.push_back(0);
+   tree.generation.push_back(0);
+   std::vector<uint32_t> frontier = {0};
+   std::bernoulli_distribution survives(1.0 - death_rate);
+   for (size_t generation = 0; generation < generations; ++generation) {
+      std::vector<uint32_t> next_frontier;
+      for (uint32_t parent : frontier) {
+         for (size_t child = 0; child < children_per_node; ++child) {
+            if (!survives(rng)) {
+               continue;
+            }
+            std::string mutated = tree.sequences[parent];
+            std::binomial_distribution<size_t> mutation_count(mutated.size(), mutation_rate);
+            const size_t n_mutations = mutation_count(rng);
+            std::uniform_int_distribution<size_t> position_distribution(0, mutated.size() - 1);
+            for (size_t i = 0; i < n_mutations; ++i) {
+               const size_t position = position_distribution(rng);
+               std::uniform_int_distribution<size_t> base_distribution(0, 3);
+               char replacement;
+               do {
+                  replacement = FIRST_FOUR_SYMBOLS[base_distribution(rng)];
+               } while (replacement == mutated[position]);
+               mutated[position] = replacement;
+            }
+            tree.sequences.push_back(std::move(mutated));
+            tree.parent.push_back(parent);
+            tree.generation.push_back(static_cast<uint32_t>(generation + 1));
+            next_frontier.push_back(static_cast<uint32_t>(tree.sequences.size() - 1));
+         }
+      }
+      if (next_frontier.empty()) {
+         next_frontier.push_back(static_cast<uint32_t>(tree.sequences.size() - 1));
+      }
+      frontier = std::move(next_frontier);
+   }
+   return tree;
+}
+
+std::string randomNucleotideReference(size_t length, uint64_t seed) {
+   static constexpr char BASES[4] = {'A', 'C', 'G', 'T'};
+   std::mt19937 rng(seed);
+   std::uniform_int_distribution<size_t> base_distribution(0, 3);
+   std::string reference(length, 'A');
+   for (char& base : reference) {
+      base = BASES[base_distribution(rng)];
+   }
+   return reference;
+}
+
+std::vector<uint32_t> denseChunkSizes(uint64_t total_rows) {
+   std::vector<uint32_t> sizes(total_rows / 65536, 65536);
+   if (total_rows % 65536 != 0) {
+      sizes.push_back(static_cast<uint32_t>(total_rows % 65536));
+   }
+   return sizes;
+}
+
+namespace {
+
+struct DiffGroup {
+   uint32_t position;
+   Symbol symbol;
+   std::vector<uint32_t> members;  // ascending indices into `sequences`
+};
+
+// What convert_run_optimize leaves behind ([external] CRoaring): the run form if it serialises
+// strictly smaller, otherwise an array up to 4096 values, otherwise a bitset. Appends the
+// container_write bytes to `payload`.
+void encodeContainer(
+   const uint64_t* words,
+   uint32_t position,
+   uint16_t v_index,
+   Symbol symbol,
+   std::vector<silo_container_desc>& descs,
+   std::vector<uint8_t>& payload
+) {
+   uint32_t cardinality = 0;
+   uint32_t n_runs = 0;
+   uint64_t carry = 0;
+   for (size_t w = 0; w < 1024; ++w) {
+      const uint64_t word = words[w];
+      cardinality += static_cast<uint32_t>(__builtin_popcountll(word));
+      n_runs += static_cast<uint32_t>(__builtin_popcountll(word & ~((word << 1) | carry)));
+      carry = word >> 63;
+   }
+   if (cardinality == 0) {
+      return;
+   }
+   const size_t size_as_run = 2 + 4 * static_cast<size_t>(n_runs);
+   const bool array_fits = cardinality <= 4096;
+   const size_t size_non_run = array_fits ? 2 * static_cast<size_t>(cardinality) + 2 : 8192;
+   silo_container_desc desc{};
+   desc.position = position;
+   desc.v_index = v_index;
+   desc.symbol = symbol;
+   desc.cardinality = cardinality;
+   desc.payload_offset = payload.size();
+   if (size_as_run < size_non_run) {
+      desc.typecode = 3;
+      desc.payload_bytes = static_cast<uint32_t>(size_as_run);
+      payload.resize(payload.size() + size_as_run);
+      uint8_t* dst = payload.data() + desc.payload_offset;
+      const auto header = static_cast<uint16_t>(n_runs);
+      std::memcpy(dst, &header, 2);
+      dst += 2;
+      int32_t run_start = -1;
+      int32_t previous = -2;
+      auto flush = [&]() {
+         const uint16_t pair[2] = {static_cast<uint16_t>(run_start), static_cast<uint16_t>(previous - run_start)};
+         std::memcpy(dst, pair, 4);
+         dst += 4;
+      };
+      for (size_t w = 0; w < 1024; ++w) {
+         uint64_t word = words[w];
+         while (word != 0) {
+            const auto value = static_cast<int32_t>(w * 64 + static_cast<size_t>(__builtin_ctzll(word)));
+            // consume the whole stretch of consecutive ones inside this word at once
+            if (value != previous + 1) {
+               if (run_start >= 0) {
+                  flush();
+               }
+               run_start = value;
+            }
+            previous = value;
+            word &= word - 1;
+         }
+      }
+      flush();
+   } else if (array_fits) {
+      desc.typecode = 2;
+      desc.payload_bytes = 2 * cardinality;
+      payload.resize(payload.size() + desc.payload_bytes);
+      auto* dst = reinterpret_cast<uint16_t*>(payload.data() + desc.payload_offset);
+      for (size_t w = 0; w < 1024; ++w) {
+         uint64_t word = words[w];
+         while (word != 0) {
+            const auto value = static_cast<uint16_t>(w * 64 + static_cast<size_t>(__builtin_ctzll(word)));
+            std::memcpy(dst++, &value, 2);
+            word &= word - 1;
+         }
+      }
+   } else {
+      desc.typecode = 1;
+      desc.payload_bytes = 8192;
+      payload.resize(payload.size() + 8192);
+      std::memcpy(payload.data() + desc.payload_offset, words, 8192);
+   }
+   descs.push_back(desc);
+}
+
+}  // namespace
+
+void buildCycledColumn(
+   const Alphabet& alphabet,
+   const std::string& reference,
+   const std::vector<std::string>& sequences,
+   uint64_t total_rows,
+   uint32_t first_chunk,
+   uint32_t n_chunks,
+   unsigned threads,
+   PackedColumn& out
+) {
+   const size_t genome_length = reference.size();
+   const size_t n_sequences = sequences.size();
+   if (n_sequences == 0 || genome_length == 0) {
+      throw std::invalid_argument("buildCycledColumn: empty input");
+   }
+   const std::vector<uint32_t> all_chunk_sizes = denseChunkSizes(total_rows);
+   if (static_cast<uint64_t>(first_chunk) + n_chunks > all_chunk_sizes.size()) {
+      throw std::invalid_argument("buildCycledColumn: shard exceeds the table");
+   }
+   std::vector<Symbol> reference_symbols(genome_length);
+   for (size_t p = 0; p < genome_length; ++p) {
+      const auto symbol = alphabet.charToSymbol(reference[p]);
+      if (!symbol.has_value() || symbol.value() == alphabet.missing) {
+         throw std::invalid_argument("buildCycledColumn: the reference must not hold missing / illegal symbols");
+      }
+      reference_symbols[p] = symbol.value();
+   }
+   // rows per sequence index over the WHOLE table
+   std::vector<uint64_t> rows_of(n_sequences);
+   for (size_t e = 0; e < n_sequences; ++e) {
+      rows_of[e] = total_rows / n_sequences + (e < total_rows % n_sequences ? 1 : 0);
+   }
+   // diffs against the initial local reference (= the global one), grouped by (position, symbol)
+   std::map<std::pair<uint32_t, Symbol>, std::vector<uint32_t>> diffs;
+   for (size_t e = 0; e < n_sequences; ++e) {
+      const std::string& sequence = sequences[e];
+      if (sequence.size() != genome_length) {
+         throw std::invalid_argument("buildCycledColumn: sequences must be full length");
+      }
+      for (size_t p = 0; p < genome_length; ++p) {
+         if (sequence[p] == reference[p]) {
+            continue;
+         }
+         const auto symbol = alphabet.charToSymbol(sequence[p]);
+         if (!symbol.has_value() || symbol.value() == alphabet.missing) {
+            throw std::invalid_argument("buildCycledColumn: sequences must not hold missing / illegal symbols");
+         }
+         if (symbol.value() != reference_symbols[p]) {
+            diffs[{static_cast<uint32_t>(p), symbol.value()}].push_back(static_cast<uint32_t>(e));
+         }
+      }
+   }
+   // local reference adaptation, one finalize() over the whole table
+   // (vertical_sequence_index.cpp:57-164): the first symbol (in SYMBOLS order) whose count strictly
+   // exceeds the running best replaces the reference symbol; its containers vanish and the old
+   // reference symbol gets containers for every covered row that held it
+   out.local_reference.assign(reference_symbols.begin(), reference_symbols.end());
+   std::vector<DiffGroup> groups;
+   auto iter = diffs.begin();
+   while (iter != diffs.end()) {
+      const uint32_t position = iter->first.first;
+      auto position_end = iter;
+      std::vector<uint64_t> symbol_rows(alphabet.count(), 0);
+      uint64_t differing_rows = 0;
+      while (position_end != diffs.end() && position_end->first.first == position) {
+         for (uint32_t e : position_end->second) {
+            symbol_rows[position_end->first.second] += rows_of[e];
+            differing_rows += rows_of[e];
+         }
+         ++position_end;
+      }
+      const Symbol current = reference_symbols[position];
+      symbol_rows[current] = total_rows - differing_rows;
+      Symbol best = current;
+      uint64_t best_rows = symbol_rows[current];
+      for (uint32_t symbol = 0; symbol < alphabet.count(); ++symbol) {
+         if (symbol != current && symbol_rows[symbol] > best_rows) {
+            best = static_cast<Symbol>(symbol);
+            best_rows = symbol_rows[symbol];
+         }
+      }
+      out.local_reference[position] = best;
+      std::vector<bool> differs(n_sequences, false);
+      for (auto group = iter; group != position_end; ++group) {
+         for (uint32_t e : group->second) {
+            differs[e] = true;
+         }
+         if (group->first.second != best) {
+            groups.push_back(DiffGroup{position, group->first.second, group->second});
+         }
+      }
+      if (best != current) {
+         DiffGroup old_reference{position, current, {}};
+         for (uint32_t e = 0; e < n_sequences; ++e) {
+            if (!differs[e]) {
+               old_reference.members.push_back(e);
+            }
+         }
+         if (!old_reference.members.empty()) {
+            groups.push_back(std::move(old_reference));
+         }
+      }
+      iter = position_end;
+   }
+   std::sort(groups.begin(), groups.end(), [](const DiffGroup& a, const DiffGroup& b) {
+      return a.position != b.position ? a.position < b.position : a.symbol < b.symbol;
+   });
+
+   // containers, chunk by chunk
+   std::vector<std::vector<silo_container_desc>> chunk_descs(n_chunks);
+   std::vector<std::vector<uint8_t>> chunk_payload(n_chunks);
+   auto buildChunk = [&](uint32_t local_chunk) {
+      const uint32_t global_chunk = first_chunk + local_chunk;
+      const uint32_t chunk_size = all_chunk_sizes[global_chunk];
+      const uint64_t base_row = static_cast<uint64_t>(global_chunk) * 65536;
+      const auto phase = static_cast<uint32_t>(base_row % n_sequences);
+      auto& descs = chunk_descs[local_chunk];
+      auto& payload = chunk_payload[local_chunk];
+      std::vector<uint64_t> words(1024);
+      for (const DiffGroup& group : groups) {
+         std::fill(words.begin(), words.end(), 0);
+         for (uint32_t e : group.members) {
+            // first row r of the chunk with (base_row + r) % n_sequences == e
+            const uint32_t first = (e + static_cast<uint32_t>(n_sequences) - phase) % static_cast<uint32_t>(n_sequences);
+            for (uint32_t row = first; row < chunk_size; row += static_cast<uint32_t>(n_sequences)) {
+               words[row >> 6] |= uint64_t{1} << (row & 63);
+            }
+         }
+         encodeContainer(words.data(), group.position, static_cast<uint16_t>(global_chunk), group.symbol, descs, payload);
+      }
+   };
+   threads = std::max(1u, std::min(threads, n_chunks == 0 ? 1u : n_chunks));
+   std::vector<std::thread> workers;
+   for (unsigned t = 0; t < threads; ++t) {
+      workers.emplace_back([&, t]() {
+         for (uint32_t chunk = t; chunk < n_chunks; chunk += threads) {
+            buildChunk(chunk);
+         }
+      });
+   }
+   for (auto& worker : workers) {
+      worker.join();
+   }
+   uint64_t total_payload = 0;
+   uint64_t total_descs = 0;
+   for (uint32_t chunk = 0; chunk < n_chunks; ++chunk) {
+      total_payload += chunk_payload[chunk].size();
+      total_descs += chunk_descs[chunk].size();
+   }
+   out.containers.clear();
+   out.containers.reserve(total_descs);
+   out.payload.clear();
+   out.payload.reserve(total_payload);
+   uint64_t shard_rows = 0;
+   for (uint32_t chunk = 0; chunk < n_chunks; ++chunk) {
+      const uint64_t payload_base = out.payload.size();
+      for (silo_container_desc desc : chunk_descs[chunk]) {
+         desc.payload_offset += payload_base;
+         out.containers.push_back(desc);
+      }
+      out.payload.insert(out.payload.end(), chunk_payload[chunk].begin(), chunk_payload[chunk].end());
+      std::vector<silo_container_desc>().swap(chunk_descs[chunk]);
+      std::vector<uint8_t>().swap(chunk_payload[chunk]);
+      shard_rows += all_chunk_sizes[first_chunk + chunk];
+   }
+   out.start_end.resize(2 * shard_rows);
+   for (uint64_t row = 0; row < shard_rows; ++row) {
+      out.start_end[2 * row] = 0;
+      out.start_end[2 * row + 1] = static_cast<uint32_t>(genome_length);
+   }
+   silo_column_desc& desc = out.desc;
+   desc = silo_column_desc{};
+   desc.struct_size = sizeof(silo_column_desc);
+   desc.n_symbols = alphabet.count();
+   desc.genome_length = static_cast<uint32_t>(genome_length);
+   desc.missing_symbol = alphabet.missing;
+   desc.local_reference = out.local_reference.data();
+   desc.n_containers = out.containers.size();
+   desc.containers = out.containers.data();
+   desc.payload = out.payload.data();
+   desc.payload_bytes = out.payload.size();
+   desc.start_end = out.start_end.data();
+}
+
+std::vector<uint32_t> lineageRowIds(
+   const EvolvedTree& tree,
+   uint32_t ancestor,
+   uint64_t total_rows,
+   uint32_t first_chunk,
+   uint32_t n_chunks
+) {
+   const size_t n_sequences = tree.sequences.size();
+   std::vector<bool> in_lineage(n_sequences, false);
+   in_lineage.at(ancestor) = true;
+   for (size_t e = ancestor + 1; e < n_sequences; ++e) {  // parents precede their children
+      in_lineage[e] = in_lineage[tree.parent[e]];
+   }
+   const std::vector<uint32_t> sizes = denseChunkSizes(total_rows);
+   std::vector<uint32_t> ids;
+   for (uint32_t chunk = first_chunk; chunk < first_chunk + n_chunks; ++chunk) {
+      const uint64_t base_row = static_cast<uint64_t>(chunk) * 65536;
+      for (uint32_t row = 0; row < sizes.at(chunk); ++row) {
+         if (in_lineage[(base_row + row) % n_sequences]) {
+            ids.push_back((chunk << 16) | row);
+         }
+      }
+   }
+   return ids;
+}
+
+std::vector<uint32_t> sortedDateRanges(
+   uint64_t total_rows,
+   uint32_t span_days,
+   uint32_t from_day,
+   uint32_t to_day_inclusive,
+   uint32_t first_chunk,
+   uint32_t n_chunks
+) {
+   // day(i) = floor(i * span_days / total_rows). lower_bound(from) and upper_bound(to) over rows:
+   auto firstRowWithDayAtLeast = [&](uint64_t day) -> uint64_t {
+      // smallest i with i * span >= day * total  <=>  i >= ceil(day * total / span)
+      const unsigned __int128 numerator = static_cast<unsigned __int128>(day) * total_rows;
+      const auto row = static_cast<uint64_t>((numerator + span_days - 1) / span_days);
+      return std::min<uint64_t>(row, total_rows);
+   };
+   const uint64_t lower_row = firstRowWithDayAtLeast(from_day);
+   const uint64_t upper_row = firstRowWithDayAtLeast(static_cast<uint64_t>(to_day_inclusive) + 1);
+   const std::vector<uint32_t> sizes = denseChunkSizes(total_rows);
+   std::vector<uint32_t> flat;
+   for (uint32_t chunk = first_chunk; chunk < first_chunk + n_chunks; ++chunk) {
+      const uint64_t base_row = static_cast<uint64_t>(chunk) * 65536;
+      const uint32_t size = sizes.at(chunk);
+      auto clampToChunk = [&](uint64_t row) -> uint32_t {
+         if (row <= base_row) {
+            return 0;
+         }
+         return static_cast<uint32_t>(std::min<uint64_t>(row - base_row, size));
+      };
+      const uint32_t lower = clampToChunk(lower_row);
+      const uint32_t upper = clampToChunk(upper_row);
+      // an index equal to the chunk size is expressed as row 0 of the next chunk (date_between.cpp:113-127)
+      flat.push_back(lower == size ? (chunk + 1) << 16 : (chunk << 16) | lower);
+      flat.push_back(upper == size ? (chunk + 1) << 16 : (chunk << 16) | upper);
+   }
+   return flat;
+}
+
+std::vector<uint32_t> partitionChunks(const std::vector<uint64_t>& chunk_weights, uint32_t n_ranks) {
+   const auto n_chunks = static_cast<uint32_t>(chunk_weights.size());
+   std::vector<uint32_t> boundaries(n_ranks + 1, n_chunks);
+   boundaries[0] = 0;
+   uint64_t total = 0;
+   for (uint64_t weight : chunk_weights) {
+      total += weight;
+   }
+   uint64_t running = 0;
+   uint32_t rank = 1;
+   for (uint32_t chunk = 0; chunk < n_chunks && rank < n_ranks; ++chunk) {
+      running += chunk_weights[chunk];
+      // close rank `rank-1` once it holds its share of the total weight
+      while (rank < n_ranks && static_cast<unsigned __int128>(running) * n_ranks >= static_cast<unsigned __int128>(total) * rank) {
+         boundaries[rank++] = chunk + 1;
+      }
+   }
+   return boundaries;
+}
+
+}  // namespace silo_host

@@ -1,0 +1,92 @@
+// Synthetic inputs of the reference's own benchmarks, produced on the product side so that bench.py
+// never touches the oracle: the evolution model of
+// /root/reference/performance/sequence_generator.h:113-185 (SequenceTreeGenerator; same std::mt19937
+// call sequence, including the quirk that mutateBase never draws 'T') and the "row i =
+// evolved[i % |evolved|]" table of writeFullSequenceNdjson (:367-384).
+//
+// 10 M x 29,903 nt as strings would be 300 GB, so the column is built DIRECTLY in the S1 upload
+// format: per chunk and per (position, symbol) the rows come from the periodic row -> sequence map.
+// The result is what the reference's ingest + finalize() would store (diffs against the adapted
+// local reference, run-optimised containers); tests compare it with the oracle's string ingest.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/silo_b200.h"
+#include "table.h"
+
+namespace silo_host {
+
+struct EvolvedTree {
+   std::vector<std::string> sequences;
+   std::vector<uint32_t> parent;      // parent[0] == 0
+   std::vector<uint32_t> generation;  // generation[0] == 0
+};
+
+EvolvedTree generateEvolvedSequences(
+   const std::string& reference,
+   uint64_t seed = 42,
+   double mutation_rate = 0.001,
+   double death_rate = 0.1,
+   size_t generations = 5,
+   size_t children_per_node = 3
+);
+
+// uniformly random A/C/G/T reference (the real SARS-CoV-2 genome is reference data we do not ship)
+std::string randomNucleotideReference(size_t length, uint64_t seed);
+
+// A column in the upload format that owns its buffers; `desc` points into them.
+struct PackedColumn {
+   silo_column_desc desc{};
+   std::vector<uint8_t> local_reference;
+   std::vector<silo_container_desc> containers;
+   std::vector<uint8_t> payload;
+   std::vector<uint32_t> start_end;
+   PackedColumn() = default;
+   PackedColumn(const PackedColumn&) = delete;
+   PackedColumn& operator=(const PackedColumn&) = delete;
+};
+
+// Rows [first_chunk << 16, ...) of the table with `total_rows` rows where row i holds
+// sequences[i % sequences.size()] (full length, offset 0). The local reference is adapted over ALL
+// total_rows rows (sequence_column.cpp:158-212), so every shard sees the same one.
+void buildCycledColumn(
+   const Alphabet& alphabet,
+   const std::string& reference,
+   const std::vector<std::string>& sequences,
+   uint64_t total_rows,
+   uint32_t first_chunk,
+   uint32_t n_chunks,
+   unsigned threads,
+   PackedColumn& out
+);
+
+// chunk sizes of a dense table with total_rows rows: all 65536 except possibly the last
+std::vector<uint32_t> denseChunkSizes(uint64_t total_rows);
+
+// metadata stand-ins for the config-2 filter (SURVEY.md §8d input 2)
+// rows whose sequence descends from `ancestor` (inclusive), restricted to the shard, as ascending ids
+std::vector<uint32_t> lineageRowIds(
+   const EvolvedTree& tree,
+   uint32_t ancestor,
+   uint64_t total_rows,
+   uint32_t first_chunk,
+   uint32_t n_chunks
+);
+// DateBetween on the sorted synthetic date column date(i) = day0 + (i * span_days) / total_rows:
+// one RangeSelection::Range per chunk of the shard (date_between.cpp:94-134), flattened {start,end}
+std::vector<uint32_t> sortedDateRanges(
+   uint64_t total_rows,
+   uint32_t span_days,
+   uint32_t from_day,
+   uint32_t to_day_inclusive,
+   uint32_t first_chunk,
+   uint32_t n_chunks
+);
+
+// Multi-GPU partition scheduler: contiguous chunk ranges, balanced by weight (payload bytes or rows).
+// Returns n_ranks + 1 boundaries.
+std::vector<uint32_t> partitionChunks(const std::vector<uint64_t>& chunk_weights, uint32_t n_ranks);
+
+}  // namespace silo_host

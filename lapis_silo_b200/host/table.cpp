@@ -1,0 +1,151 @@
+#include "table.h"
+
+#include <algorithm>
+
+namespace silo_host {
+
+namespace {
+
+Alphabet makeAlphabet(
+   const std::string& symbol_name,
+   const std::string& chars,
+   char missing_char,
+   const std::string& valid_chars,
+   const std::vector<std::pair<char, std::string>>& ambiguity_codes,
+   const std::string& extra_aliases  // pairs "xy": character x is read as symbol y
+) {
+   Alphabet alphabet;
+   alphabet.symbol_name = symbol_name;
+   alphabet.chars = chars;
+   alphabet.from_char.fill(-1);
+   for (size_t id = 0; id < chars.size(); ++id) {
+      const char upper = chars[id];
+      alphabet.from_char[static_cast<unsigned char>(upper)] = static_cast<int8_t>(id);
+      if (upper >= 'A' && upper <= 'Z') {
+         alphabet.from_char[static_cast<unsigned char>(upper + ('a' - 'A'))] = static_cast<int8_t>(id);
+      }
+   }
+   for (size_t i = 0; i + 1 < extra_aliases.size(); i += 2) {
+      alphabet.from_char[static_cast<unsigned char>(extra_aliases[i])] =
+         alphabet.from_char[static_cast<unsigned char>(extra_aliases[i + 1])];
+   }
+   alphabet.missing = alphabet.charToSymbol(missing_char).value();
+   for (char c : valid_chars) {
+      alphabet.valid_mutation_symbols.push_back(alphabet.charToSymbol(c).value());
+   }
+   // CODES_FOR: a concrete symbol codes for itself, an ambiguity code for its listed members, the
+   // missing symbol for everything (nucleotide_symbols.cpp:10-45, aa_symbols.cpp:13-46)
+   alphabet.codes_for.assign(chars.size(), 0);
+   for (size_t id = 0; id < chars.size(); ++id) {
+      alphabet.codes_for[id] = 1u << id;
+   }
+   for (const auto& [code, members] : ambiguity_codes) {
+      uint32_t bits = 0;
+      for (char member : members) {
+         bits |= 1u << alphabet.charToSymbol(member).value();
+      }
+      alphabet.codes_for[alphabet.charToSymbol(code).value()] = bits;
+   }
+   alphabet.codes_for[alphabet.missing] = (chars.size() == 32 ? 0xFFFFFFFFu : (1u << chars.size()) - 1u);
+   // AMBIGUITY_SYMBOLS[s] = every y whose CODES_FOR is a superset of CODES_FOR[s]
+   alphabet.ambiguity_symbols.resize(chars.size());
+   for (size_t s = 0; s < chars.size(); ++s) {
+      for (size_t y = 0; y < chars.size(); ++y) {
+         if ((alphabet.codes_for[s] & ~alphabet.codes_for[y]) == 0) {
+            alphabet.ambiguity_symbols[s].push_back(static_cast<Symbol>(y));
+         }
+      }
+   }
+   return alphabet;
+}
+
+}  // namespace
+
+const Alphabet& Alphabet::nucleotide() {
+   static const Alphabet instance = makeAlphabet(
+      "Nucleotide",
+      "-ACGTRYSWKMBDHVN",
+      'N',
+      "-ACGT",
+      {{'R', "AG"}, {'Y', "CT"}, {'S', "GC"}, {'W', "AT"}, {'K', "GT"}, {'M', "AC"},
+       {'B', "CGT"}, {'D', "AGT"}, {'H', "ACT"}, {'V', "ACG"}},
+      "UTut"
+   );
+   return instance;
+}
+
+const Alphabet& Alphabet::aminoAcid() {
+   static const Alphabet instance = makeAlphabet(
+      "AminoAcid",
+      "-ACDEFGHIKLMNOPQRSTUVWYBJZ*X",
+      'X',
+      "-ACDEFGHIKLMNOPQRSTUVWY*",
+      {{'B', "DN"}, {'J', "LI"}, {'Z', "QE"}},
+      ""
+   );
+   return instance;
+}
+
+void throwOnDeviceError(int status) {
+   if (status < 0) {
+      throw DeviceError(status, silo_gpu_last_error());
+   }
+}
+
+Table::Table(silo_gpu_ctx* ctx, RowLayout layout)
+    : row_layout(std::move(layout)),
+      ctx(ctx) {
+   throwOnDeviceError(silo_gpu_table_create(
+      ctx,
+      row_layout.first_chunk,
+      row_layout.chunk_sizes.data(),
+      static_cast<uint32_t>(row_layout.chunk_sizes.size()),
+      &device
+   ));
+}
+
+Table::~Table() {
+   silo_gpu_table_free(device);
+}
+
+int Table::addSequenceColumn(
+   const std::string& name,
+   const Alphabet& alphabet,
+   const std::string& global_reference,
+   const silo_column_desc& column
+) {
+   if (findColumn(name) != nullptr) {
+      throw std::invalid_argument("duplicate column name " + name);
+   }
+   if (column.n_symbols != alphabet.count() || column.genome_length != global_reference.size()) {
+      throw std::invalid_argument("column descriptor does not match the alphabet / reference length");
+   }
+   SequenceColumnInfo info;
+   info.name = name;
+   info.alphabet = &alphabet;
+   for (char character : global_reference) {
+      const auto symbol = alphabet.charToSymbol(character);
+      if (!symbol.has_value()) {
+         throw std::invalid_argument("illegal character in the reference sequence");
+      }
+      info.reference_sequence.push_back(symbol.value());
+   }
+   info.local_reference.assign(column.local_reference, column.local_reference + column.genome_length);
+   info.has_null_rows = column.n_null_rows > 0;
+   const int device_column = silo_gpu_column_upload(device, &column);
+   throwOnDeviceError(device_column);
+   info.device_column = device_column;
+   columns.push_back(std::move(info));
+   return device_column;
+}
+
+const SequenceColumnInfo* Table::findColumn(const std::string& name) const {
+   for (const auto& column : columns) {
+      if (column.name == name) {
+         return &column;
+      }
+   }
+   return nullptr;
+}
+
+}  // namespace silo_host

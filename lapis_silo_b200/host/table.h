@@ -1,0 +1,112 @@
+// Host-side view of a table whose sequence columns live in the device pool.
+//
+// Mirrors what the reference's query compiler reads from rhydb::storage::Table
+// (/root/reference/src/rhydb/storage/table.h) on this path -- and nothing else:
+//   row_layout (storage/column/row_layout.h:27-55), per sequence column the global reference
+//   (sequence_column.h:47-56 metadata->reference_sequence), the adapted local reference
+//   (:104, getLocalReferencePosition :135-138) and whether null_bitmap is empty (:111).
+// Containers, coverage and N runs are NOT kept on the host: they are resident in HBM.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/silo_b200.h"
+
+namespace silo_host {
+
+// user-facing validation error: query_engine/illegal_query_exception.h:8 (CHECK_SILO_QUERY)
+struct IllegalQueryException : std::runtime_error {
+   using std::runtime_error::runtime_error;
+};
+// query_engine/query_compilation_exception.h
+struct QueryCompilationException : std::runtime_error {
+   using std::runtime_error::runtime_error;
+};
+// failures reported by libsilo_b200.so
+struct DeviceError : std::runtime_error {
+   int status;
+   DeviceError(int status, const std::string& message) : std::runtime_error(message), status(status) {}
+};
+
+using Symbol = uint8_t;
+
+// common/nucleotide_symbols.h:23-200 and common/aa_symbols.h:23-300, as data
+class Alphabet {
+  public:
+   std::string symbol_name;
+   std::string chars;  // symbolToChar, indexed by symbol id
+   Symbol missing = 0;
+   std::vector<Symbol> valid_mutation_symbols;
+   std::vector<uint32_t> codes_for;          // bit set of concrete/ambiguous symbols each id codes for
+   std::vector<std::vector<Symbol>> ambiguity_symbols;
+   std::array<int8_t, 256> from_char{};
+
+   [[nodiscard]] uint32_t count() const { return static_cast<uint32_t>(chars.size()); }
+   [[nodiscard]] std::optional<Symbol> charToSymbol(char character) const {
+      const int8_t id = from_char[static_cast<unsigned char>(character)];
+      return id < 0 ? std::nullopt : std::optional<Symbol>(static_cast<Symbol>(id));
+   }
+   [[nodiscard]] char symbolToChar(Symbol symbol) const { return chars[symbol]; }
+
+   static const Alphabet& nucleotide();
+   static const Alphabet& aminoAcid();
+};
+
+struct RowLayout {
+   uint32_t first_chunk = 0;  // global id of chunk 0 of this shard
+   std::vector<uint32_t> chunk_sizes;
+   [[nodiscard]] uint64_t numRows() const {
+      uint64_t total = 0;
+      for (uint32_t size : chunk_sizes) {
+         total += size;
+      }
+      return total;
+   }
+   [[nodiscard]] size_t numChunks() const { return chunk_sizes.size(); }
+};
+
+struct SequenceColumnInfo {
+   std::string name;
+   const Alphabet* alphabet = nullptr;
+   std::vector<Symbol> reference_sequence;  // global reference
+   std::vector<Symbol> local_reference;     // adapted, sequence_column.cpp:158-212
+   bool has_null_rows = false;
+   int device_column = -1;  // index returned by silo_gpu_column_upload
+};
+
+class Table {
+  public:
+   RowLayout row_layout;
+   std::vector<SequenceColumnInfo> columns;
+   // stand-ins for indexes owned by out-of-scope columns (LineageIndex, dictionary index): ready-made
+   // roaring bitmaps in the portable format, as the reference would hand them over
+   // (lineage_filter.cpp:96-99, roaring_serialize.h:15-30)
+   std::map<std::string, std::vector<uint8_t>> named_bitmaps;
+
+   silo_gpu_ctx* ctx = nullptr;
+   silo_gpu_table* device = nullptr;
+
+   Table(silo_gpu_ctx* ctx, RowLayout layout);
+   ~Table();
+   Table(const Table&) = delete;
+   Table& operator=(const Table&) = delete;
+
+   // S1: uploads the column (silo_gpu_column_upload) and records the host-side metadata
+   int addSequenceColumn(
+      const std::string& name,
+      const Alphabet& alphabet,
+      const std::string& global_reference,
+      const silo_column_desc& column
+   );
+   [[nodiscard]] const SequenceColumnInfo* findColumn(const std::string& name) const;
+};
+
+void throwOnDeviceError(int status);
+
+}  // namespace silo_host

@@ -1,0 +1,329 @@
+"""ctypes view of include/silo_b200_host.h (libsilo_b200_host.so): the C++ host layer that mirrors
+the reference's expression -> operator compilation and the Mutations / count sinks.
+
+Harness only (tests, bench.py). No compute happens in Python and nothing here falls back to a CPU
+path: every filter and every count goes host layer -> C ABI -> sm_100a kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(_HERE, "libsilo_b200_host.so")
+
+HOST_EXPORTED_SYMBOLS = [
+    "silo_host_last_error", "silo_host_table_create", "silo_host_table_free", "silo_host_table_add_column",
+    "silo_host_table_register_bitmap", "silo_host_table_device", "silo_host_table_num_rows",
+    "silo_host_filter_eval", "silo_host_filter_free", "silo_host_filter_cardinality",
+    "silo_host_filter_device", "silo_host_filter_words", "silo_host_filter_explain",
+    "silo_host_mutation_counts", "silo_host_mutations", "silo_host_mutation_rows_from_counts",
+    "silo_host_rows_free", "silo_host_rows_size", "silo_host_rows_get",
+    "silo_host_synthetic_create", "silo_host_synthetic_free", "silo_host_synthetic_num_sequences",
+    "silo_host_synthetic_reference", "silo_host_synthetic_sequence", "silo_host_synthetic_parent",
+    "silo_host_synthetic_generation", "silo_host_synthetic_build_column",
+    "silo_host_synthetic_release_column", "silo_host_synthetic_lineage_bitmap",
+    "silo_host_synthetic_date_ranges", "silo_host_partition_chunks",
+]
+
+NUCLEOTIDE = 0
+AMINO_ACID = 1
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        abi.lib()  # libsilo_b200.so first (the host library links against it)
+        if not os.path.exists(HOST_LIB_PATH):
+            raise RuntimeError(f"{HOST_LIB_PATH} is missing: run __graft_entry__.build()")
+        L = C.CDLL(HOST_LIB_PATH)
+        vp = C.c_void_p
+        L.silo_host_last_error.restype = C.c_char_p
+        L.silo_host_table_create.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]
+        L.silo_host_table_create.restype = vp
+        L.silo_host_table_free.argtypes = [vp]
+        L.silo_host_table_free.restype = None
+        L.silo_host_table_add_column.argtypes = [vp, C.c_char_p, C.c_int, C.c_char_p, vp]
+        L.silo_host_table_register_bitmap.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint64]
+        L.silo_host_table_device.argtypes = [vp]
+        L.silo_host_table_device.restype = vp
+        L.silo_host_table_num_rows.argtypes = [vp]
+        L.silo_host_table_num_rows.restype = C.c_uint64
+        L.silo_host_filter_eval.argtypes = [vp, C.c_char_p]
+        L.silo_host_filter_eval.restype = vp
+        L.silo_host_filter_free.argtypes = [vp]
+        L.silo_host_filter_free.restype = None
+        L.silo_host_filter_cardinality.argtypes = [vp]
+        L.silo_host_filter_cardinality.restype = C.c_uint64
+        L.silo_host_filter_device.argtypes = [vp]
+        L.silo_host_filter_device.restype = vp
+        L.silo_host_filter_words.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.silo_host_filter_explain.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint64]
+        L.silo_host_mutation_counts.argtypes = [vp, C.c_char_p, vp, C.POINTER(C.c_uint32)]
+        L.silo_host_mutations.argtypes = [vp, C.c_char_p, C.POINTER(C.c_char_p), C.c_uint32, C.c_double]
+        L.silo_host_mutations.restype = vp
+        L.silo_host_mutation_rows_from_counts.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint32), C.c_double]
+        L.silo_host_mutation_rows_from_counts.restype = vp
+        L.silo_host_rows_free.argtypes = [vp]
+        L.silo_host_rows_free.restype = None
+        L.silo_host_rows_size.argtypes = [vp]
+        L.silo_host_rows_size.restype = C.c_uint64
+        L.silo_host_rows_get.argtypes = [
+            vp, C.c_uint64, C.POINTER(C.c_char), C.POINTER(C.c_char), C.POINTER(C.c_int32),
+            C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.silo_host_synthetic_create.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32]
+        L.silo_host_synthetic_create.restype = vp
+        L.silo_host_synthetic_free.argtypes = [vp]
+        L.silo_host_synthetic_free.restype = None
+        L.silo_host_synthetic_num_sequences.argtypes = [vp]
+        L.silo_host_synthetic_num_sequences.restype = C.c_uint32
+        L.silo_host_synthetic_reference.argtypes = [vp]
+        L.silo_host_synthetic_reference.restype = C.c_char_p
+        L.silo_host_synthetic_sequence.argtypes = [vp, C.c_uint32]
+        L.silo_host_synthetic_sequence.restype = C.c_char_p
+        L.silo_host_synthetic_parent.argtypes = [vp, C.c_uint32]
+        L.silo_host_synthetic_parent.restype = C.c_uint32
+        L.silo_host_synthetic_generation.argtypes = [vp, C.c_uint32]
+        L.silo_host_synthetic_generation.restype = C.c_uint32
+        L.silo_host_synthetic_build_column.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+        L.silo_host_synthetic_release_column.argtypes = [vp]
+        L.silo_host_synthetic_release_column.restype = None
+        L.silo_host_synthetic_lineage_bitmap.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64]
+        L.silo_host_synthetic_lineage_bitmap.restype = C.c_int64
+        L.silo_host_synthetic_date_ranges.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64]
+        L.silo_host_partition_chunks.argtypes = [C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+        _lib = L
+    return _lib
+
+
+class HostError(RuntimeError):
+    pass
+
+
+def _check(status: int) -> None:
+    if status != 0:
+        raise HostError(lib().silo_host_last_error().decode())
+
+
+def _rows(handle) -> list[dict]:
+    if not handle:
+        raise HostError(lib().silo_host_last_error().decode())
+    out = []
+    try:
+        for i in range(lib().silo_host_rows_size(handle)):
+            frm, to = C.c_char(), C.c_char()
+            pos, cnt, cov = C.c_int32(), C.c_int32(), C.c_int32()
+            prop = C.c_double()
+            name = C.c_char_p()
+            _check(lib().silo_host_rows_get(handle, i, C.byref(frm), C.byref(to), C.byref(pos), C.byref(name),
+                                            C.byref(prop), C.byref(cnt), C.byref(cov)))
+            out.append({
+                "mutationFrom": frm.value.decode(), "mutationTo": to.value.decode(), "position": pos.value,
+                "sequenceName": name.value.decode(), "proportion": prop.value, "count": cnt.value,
+                "coverage": cov.value,
+            })
+    finally:
+        lib().silo_host_rows_free(handle)
+    return out
+
+
+class HostFilter:
+    def __init__(self, table: "HostTable", handle):
+        self.table = table
+        self._h = handle
+
+    @property
+    def cardinality(self) -> int:
+        return int(lib().silo_host_filter_cardinality(self._h))
+
+    @property
+    def device_handle(self) -> int:
+        return lib().silo_host_filter_device(self._h)
+
+    def words(self) -> np.ndarray:
+        out = np.zeros(self.table.n_chunks * 1024, dtype=np.uint64)
+        _check(lib().silo_host_filter_words(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def ids(self) -> np.ndarray:
+        bits = np.unpackbits(self.words().view(np.uint8), bitorder="little")
+        local = np.flatnonzero(bits).astype(np.uint64)
+        return (local + (np.uint64(self.table.first_chunk) << np.uint64(16))).astype(np.uint32)
+
+    def close(self):
+        if self._h:
+            lib().silo_host_filter_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HostTable:
+    """rhydb::storage::Table as the query compiler sees it, with its sequence columns in HBM."""
+
+    def __init__(self, ctx: abi.Context, chunk_sizes: Sequence[int], first_chunk: int = 0):
+        self.ctx = ctx
+        self.chunk_sizes = [int(s) for s in chunk_sizes]
+        self.n_chunks = len(self.chunk_sizes)
+        self.first_chunk = first_chunk
+        self.columns: dict[str, tuple[int, int]] = {}
+        arr = (C.c_uint32 * max(self.n_chunks, 1))(*self.chunk_sizes)
+        self._h = lib().silo_host_table_create(ctx._h, first_chunk, arr, self.n_chunks)
+        if not self._h:
+            raise HostError(lib().silo_host_last_error().decode())
+
+    def add_column(self, name: str, alphabet: int, reference: str, desc_ptr) -> None:
+        _check(lib().silo_host_table_add_column(
+            self._h, name.encode(), alphabet, reference.encode(), C.cast(desc_ptr, C.c_void_p)))
+        self.columns[name] = (16 if alphabet == NUCLEOTIDE else 28, len(reference))
+
+    def register_bitmap(self, name: str, portable_roaring_bytes: bytes) -> None:
+        _check(lib().silo_host_table_register_bitmap(
+            self._h, name.encode(), portable_roaring_bytes, len(portable_roaring_bytes)))
+
+    @property
+    def num_rows(self) -> int:
+        return int(lib().silo_host_table_num_rows(self._h))
+
+    @property
+    def device_table(self) -> int:
+        return lib().silo_host_table_device(self._h)
+
+    def filter(self, expression: str) -> HostFilter:
+        handle = lib().silo_host_filter_eval(self._h, expression.encode())
+        if not handle:
+            raise HostError(lib().silo_host_last_error().decode())
+        return HostFilter(self, handle)
+
+    def explain(self, expression: str) -> str:
+        buf = C.create_string_buffer(1 << 22)
+        _check(lib().silo_host_filter_explain(self._h, expression.encode(), buf, len(buf)))
+        return buf.value.decode()
+
+    def mutation_counts(self, column: str, flt: Optional[HostFilter] = None) -> np.ndarray:
+        n_symbols, genome_length = self.columns[column]
+        out = np.zeros(n_symbols * genome_length, dtype=np.uint32)
+        _check(lib().silo_host_mutation_counts(
+            self._h, column.encode(), flt._h if flt is not None else None, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out.reshape(n_symbols, genome_length)
+
+    def mutations(self, columns: Sequence[str], expression: Optional[str], min_proportion: float) -> list[dict]:
+        names = (C.c_char_p * len(columns))(*[c.encode() for c in columns])
+        handle = lib().silo_host_mutations(
+            self._h, expression.encode() if expression is not None else None, names, len(columns), min_proportion)
+        return _rows(handle)
+
+    def mutation_rows_from_counts(self, column: str, counts: np.ndarray, min_proportion: float) -> list[dict]:
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        handle = lib().silo_host_mutation_rows_from_counts(
+            self._h, column.encode(), counts.ctypes.data_as(C.POINTER(C.c_uint32)), min_proportion)
+        return _rows(handle)
+
+    def stats(self) -> abi.Stats:
+        out = abi.Stats()
+        abi.check(abi.lib().silo_gpu_get_stats(self.device_table, C.byref(out)))
+        return out
+
+    def mutation_counts_async(self, column_index: int, flt: Optional[HostFilter], d_counts_ptr: int, stream_ptr: int) -> None:
+        abi.check(abi.lib().silo_gpu_mutation_counts_async(
+            self.device_table, column_index, flt.device_handle if flt is not None else None,
+            C.c_void_p(d_counts_ptr), C.c_void_p(stream_ptr)))
+
+    def close(self):
+        if self._h:
+            lib().silo_host_table_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Synthetic:
+    """performance/sequence_generator.h restated on the product side (host/synthetic.h)."""
+
+    def __init__(self, genome_length: int = 29903, reference_seed: int = 1, generations: int = 5):
+        self._h = lib().silo_host_synthetic_create(genome_length, reference_seed, generations)
+        if not self._h:
+            raise HostError(lib().silo_host_last_error().decode())
+        self.genome_length = genome_length
+
+    @property
+    def reference(self) -> str:
+        return lib().silo_host_synthetic_reference(self._h).decode()
+
+    @property
+    def num_sequences(self) -> int:
+        return int(lib().silo_host_synthetic_num_sequences(self._h))
+
+    def sequence(self, index: int) -> str:
+        return lib().silo_host_synthetic_sequence(self._h, index).decode()
+
+    def parent(self, index: int) -> int:
+        return int(lib().silo_host_synthetic_parent(self._h, index))
+
+    def generation(self, index: int) -> int:
+        return int(lib().silo_host_synthetic_generation(self._h, index))
+
+    def build_column(self, total_rows: int, first_chunk: int, n_chunks: int, threads: int = 8):
+        """Returns POINTER(ColumnDesc), valid until release_column()/the next build."""
+        out = C.c_void_p()
+        _check(lib().silo_host_synthetic_build_column(self._h, total_rows, first_chunk, n_chunks, threads, C.byref(out)))
+        return C.cast(out, C.POINTER(abi.ColumnDesc))
+
+    def release_column(self) -> None:
+        lib().silo_host_synthetic_release_column(self._h)
+
+    def lineage_bitmap(self, ancestor: int, total_rows: int, first_chunk: int, n_chunks: int) -> bytes:
+        n = lib().silo_host_synthetic_lineage_bitmap(self._h, ancestor, total_rows, first_chunk, n_chunks, None, 0)
+        if n < 0:
+            raise HostError(lib().silo_host_last_error().decode())
+        buf = C.create_string_buffer(int(n))
+        lib().silo_host_synthetic_lineage_bitmap(self._h, ancestor, total_rows, first_chunk, n_chunks, buf, n)
+        return buf.raw
+
+    def close(self):
+        if self._h:
+            lib().silo_host_synthetic_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def date_ranges_expression(total_rows: int, span_days: int, from_day: int, to_day_inclusive: int,
+                           first_chunk: int, n_chunks: int) -> str:
+    buf = C.create_string_buffer(64 + 24 * max(n_chunks, 1))
+    _check(lib().silo_host_synthetic_date_ranges(
+        total_rows, span_days, from_day, to_day_inclusive, first_chunk, n_chunks, buf, len(buf)))
+    return buf.value.decode()
+
+
+def dense_chunk_sizes(total_rows: int) -> list[int]:
+    sizes = [65536] * (total_rows // 65536)
+    if total_rows % 65536:
+        sizes.append(total_rows % 65536)
+    return sizes
+
+
+def partition_chunks(chunk_weights: Sequence[int], n_ranks: int) -> list[int]:
+    weights = (C.c_uint64 * max(len(chunk_weights), 1))(*chunk_weights)
+    out = (C.c_uint32 * (n_ranks + 1))()
+    _check(lib().silo_host_partition_chunks(weights, len(chunk_weights), n_ranks, out))
+    return list(out)

@@ -1,0 +1,362 @@
+"""GPU parity proper: filter expressions and the Mutations action through the product's host layer
+(libsilo_b200_host.so -> C ABI -> sm_100a kernels) against the CPU oracle on the same inputs, and
+against the literal expectations of the reference's own unit tests. Bit-exact: row-id sets, u32
+counts, and the thresholded output rows including the double proportions."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from lapis_silo_b200 import abi
+    context = abi.Context(0)
+    yield context
+    context.close()
+
+
+def mirror(ctx, oracle_table, bitmaps=()):
+    """The same table on the device: every column uploaded from the oracle's S1 export."""
+    from lapis_silo_b200 import host_api
+    table = host_api.HostTable(ctx, oracle_table.chunk_sizes)
+    for name, alphabet, reference in oracle_table.columns:
+        export = oracle_table.export_column(name)
+        table.add_column(name, alphabet, reference, export.desc)
+        export.close()
+    for name in bitmaps:
+        table.register_bitmap(name, oracle_table.bitmap_bytes(name))
+    return table
+
+
+def layout_pair(ctx, *sizes):
+    from lapis_silo_b200 import host_api
+    from oracle import oracle as O
+    oracle_table = O.Table()
+    oracle_table.set_layout(*sizes)
+    return oracle_table, host_api.HostTable(ctx, list(sizes))
+
+
+def ids(table, expression):
+    return [int(v) for v in table.filter(expression).ids()]
+
+
+def lists(sets):
+    return " ".join("(ids " + " ".join(map(str, s)) + ")" for s in sets)
+
+
+def both(pair, expression):
+    oracle_table, device_table = pair
+    want = ids(oracle_table, expression)
+    flt = device_table.filter(expression)
+    got = [int(v) for v in flt.ids()]
+    assert got == want, expression
+    assert flt.cardinality == len(want), expression
+    return got
+
+
+# ---- the reference's operator-level vectors (in-layout inputs) -------------------------------
+
+def test_threshold_vectors(ctx):  # filter/operators/threshold.test.cpp:40-247
+    def threshold(pair, pos, neg, k, exact):
+        return both(pair, f"(op-threshold {k} {int(exact)} ({lists(pos)}) ({lists(neg)}))")
+
+    pair = layout_pair(ctx, 4)
+    assert threshold(pair, [], [[1, 2, 3], [1, 3]], 1, True) == [2]
+    assert threshold(pair, [], [[1, 2, 3], [1, 3]], 1, False) == [0, 2]
+    pos = [[1, 2], [1, 3], [1, 2, 3]]
+    assert threshold(pair, pos, [], 1, True) == []
+    assert threshold(pair, pos, [], 2, True) == [2, 3]
+    assert threshold(pair, pos, [], 1, False) == [1, 2, 3]
+    assert threshold(pair, pos, [], 2, False) == [1, 2, 3]
+    pos, neg = [[1, 2, 3], [1, 3], [1, 2, 3]], [[], [3]]
+    assert [threshold(pair, pos, neg, k, True) for k in (1, 2, 3, 4)] == [[], [0], [], [2, 3]]
+    assert [threshold(pair, pos, neg, k, False) for k in (1, 2, 3, 4)] == [
+        [0, 1, 2, 3], [0, 1, 2, 3], [1, 2, 3], [1, 2, 3]]
+    pair = layout_pair(ctx, 5)
+    pos, neg = [[1, 2, 3]], [[], [3], [4], [2, 4]]
+    assert [threshold(pair, pos, neg, k, True) for k in (1, 2, 3, 4)] == [[], [4], [], [0, 2, 3]]
+    assert [threshold(pair, pos, neg, k, False) for k in (1, 2, 3, 4)] == [
+        [0, 1, 2, 3, 4], [0, 1, 2, 3, 4], [0, 1, 2, 3], [0, 1, 2, 3]]
+
+
+def test_threshold_rejects_ids_outside_the_layout(ctx):
+    """threshold.test.cpp:249-311 feeds id 4 into a 4-row layout; row_layout.h:49-52 documents that
+    inputs are expected to be a subset of the universe. The device refuses such input loudly."""
+    from lapis_silo_b200 import host_api
+    _, device_table = layout_pair(ctx, 4)
+    with pytest.raises(host_api.HostError, match=r"DeviceError\[-6\]"):
+        device_table.filter("(op-threshold 1 1 ((ids)) ((ids 3) (ids 4) (ids 2 4)))")
+
+
+def test_constructor_errors_match(ctx):  # threshold.cpp:30-41, intersection.cpp:26-40
+    from lapis_silo_b200 import host_api
+    from oracle import oracle as O
+    oracle_table, device_table = layout_pair(ctx, 5)
+    for expression in ("(op-threshold 2 0 ((ids 1) (ids 2)) ())", "(op-threshold 0 0 ((ids 1) (ids 2)) ())",
+                       "(op-and () ())", "(op-and () ((ids 1) (ids 2)))", "(op-and ((ids 1)) ())"):
+        with pytest.raises(O.OracleError) as want:
+            oracle_table.filter(expression)
+        with pytest.raises(host_api.HostError) as got:
+            device_table.filter(expression)
+        assert str(got.value) == str(want.value)
+
+
+def test_intersection_complement_union_vectors(ctx):
+    pair = layout_pair(ctx, 5)  # intersection.test.cpp:20-136
+    assert both(pair, f"(op-and ({lists([[1, 2, 3], [1, 3], [1, 2, 3]])}) ())") == [1, 3]
+    assert both(pair, f"(op-and ({lists([[1, 2, 3], [1, 3], [1, 2, 3]])}) ({lists([[], [3]])}))") == [1]
+    assert both(pair, f"(op-and ({lists([[1, 2, 3]])}) ({lists([[], [3], [4], [2, 4]])}))") == [1]
+    assert both(pair, f"(op-and ({lists([[]])}) ({lists([[3], [4], [2, 4]])}))") == []
+    assert both(pair, "(op-not (ids 1 2 3))") == [0, 4]  # complement.test.cpp:14-72
+    assert both(pair, "(op-not (ids 1))") == [0, 2, 3, 4]
+    assert both(layout_pair(ctx, 3), "(op-not (ids))") == [0, 1, 2]
+    assert both(layout_pair(ctx, 4), "(op-not (ids 0 1 2 3))") == []
+    assert both(layout_pair(ctx), "(op-not (ids))") == []
+    pair = layout_pair(ctx, 3, 2)  # row_layout.cpp:18-23: the gap between chunks stays empty
+    assert both(pair, "(op-not (ids 1 65536))") == [0, 2, 65537]
+    assert both(pair, "(true)") == [0, 1, 2, 65536, 65537]
+    assert both(pair, "(not (true))") == []
+    pair = layout_pair(ctx, 65536, 65536, 65536, 65536, 2)  # copy_on_write_bitmap.test.cpp:48-90
+    m = [1, 5, 100, 65536 + 3, 3 * 65536 + 7]
+    both(pair, f"(op-and ({lists([m, [5, 100, 65536 + 3, 999]])}) ())")
+    both(pair, f"(op-and ({lists([m])}) ({lists([[5, 65536 + 3]])}))")
+    both(pair, f"(op-or {lists([[1, 5], m, [5, 3 * 65536 + 7, 4 * 65536 + 1]])})")
+
+
+def test_fast_union_staggered(ctx):  # copy_on_write_bitmap.test.cpp:130-185
+    pair = layout_pair(ctx, *([65536] * 12))
+    inputs = []
+    for i in range(8):
+        s = set()
+        for key in range(i, i + 5):
+            s.update(range((key << 16) + i, (key << 16) + i + 5000 + 100 * key))
+            s.add((key << 16) + 60000)
+        inputs.append(sorted(s))
+    expected = sorted(set().union(*map(set, inputs)))
+    assert both(pair, f"(op-or {lists(inputs)})") == expected
+
+
+# ---- expression-level vectors ----------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def atgcn(ctx):
+    from oracle import oracle as O
+    t = O.Table()
+    t.add_column("segment1", O.NUCLEOTIDE, "ATGCN")
+    for seq in ("ATGCN", "ATGCN", "NNNNN", "CATTT", None):
+        t.append_row([seq])
+    t.finalize()
+    return t, mirror(ctx, t)
+
+
+@pytest.mark.parametrize("symbol,position,count", [
+    ("A", 1, 2), ("A", 2, 1), ("A", 3, 0), ("A", 4, 0), ("A", 5, 0),
+    ("C", 1, 1), ("C", 2, 0), ("C", 3, 0), ("C", 4, 2), ("C", 5, 0),
+    ("G", 1, 0), ("G", 2, 0), ("G", 3, 2), ("G", 4, 0), ("G", 5, 0),
+    ("T", 1, 0), ("T", 2, 2), ("T", 3, 1), ("T", 4, 1), ("T", 5, 1),
+    ("N", 1, 1), ("N", 5, 3), (".", 1, 2),
+])
+def test_symbol_equals_counts(atgcn, symbol, position, count):  # symbol_equals.test.cpp:42-257
+    assert len(both(atgcn, f"(sym-eq segment1 {position} {symbol})")) == count
+
+
+def test_symbol_equals_errors_match(atgcn):
+    from lapis_silo_b200 import host_api
+    from oracle import oracle as O
+    oracle_table, device_table = atgcn
+    for expression in ("(sym-eq segment1 1000 A)", "(sym-eq segment1 0 A)", "(sym-eq nope 1 A)",
+                       "(has-mut segment1 6)", "(sym-eq segment1 1 Z)"):
+        with pytest.raises(O.OracleError) as want:
+            oracle_table.filter(expression)
+        with pytest.raises(host_api.HostError) as got:
+            device_table.filter(expression)
+        assert str(got.value) == str(want.value)
+
+
+def test_has_mutation(ctx):  # has_mutation.test.cpp:28-60
+    from oracle import oracle as O
+    t = O.Table()
+    t.add_column("segment1", O.NUCLEOTIDE, "ATGCN")
+    t.add_column("gene1", O.AMINO_ACID, "M*")
+    for nuc, aa in (("ATGCN", "M*"), ("ATGCN", "C*"), ("NNNNN", "M*"), ("CATTT", "X*")):
+        t.append_row([nuc, aa])
+    t.finalize()
+    pair = (t, mirror(ctx, t))
+    assert len(both(pair, "(has-mut segment1 1)")) == 1
+    assert len(both(pair, "(has-mut gene1 1)")) == 1
+    both(pair, "(maybe (has-mut gene1 1))")
+    both(pair, "(not (maybe (has-mut segment1 1)))")
+
+
+def test_mutation_profile_vectors(ctx):  # mutation_profile.test.cpp:24-264
+    from oracle import oracle as O
+    t = O.Table()
+    t.add_column("segment1", O.NUCLEOTIDE, "ATGCN")
+    t.add_column("gene1", O.AMINO_ACID, "M*")
+    for nuc, aa in (("ATGCN", "M*"), ("CTGCN", "C*"), ("CTCCN", "M*"), ("CTCTN", "M*"), ("NNNNN", "M*"), ("RTGCN", "M*")):
+        t.append_row([nuc, aa])
+    t.finalize()
+    pair = (t, mirror(ctx, t))
+    ref, mut1, mut2, mut3, alln, amb = range(6)
+    assert both(pair, "(profile segment1 0 muts)") == [ref, alln, amb]
+    assert both(pair, "(profile segment1 1 muts)") == [ref, mut1, alln, amb]
+    assert both(pair, "(profile segment1 2 muts)") == [ref, mut1, mut2, alln, amb]
+    assert both(pair, "(profile segment1 0 muts 1 C)") == [mut1, alln]
+    assert both(pair, "(profile segment1 0 seq ATGCN)") == [ref, alln, amb]
+    assert both(pair, "(profile segment1 0 seq CTGCN)") == [mut1, alln]  # = sequenceId:='seq_1mut'
+    assert both(pair, "(profile gene1 0 muts)") == [ref, mut2, mut3, alln, amb]
+    assert both(pair, "(profile gene1 1 muts)") == [ref, mut1, mut2, mut3, alln, amb]
+    assert both(pair, "(profile gene1 0 muts 1 C)") == [mut1]
+    assert both(pair, "(profile gene1 0 seq M*)") == [ref, mut2, mut3, alln, amb]
+    assert both(pair, "(profile gene1 0 seq C*)") == [mut1]
+
+
+# ---- randomised parity: every expression kind, ragged chunks, nulls, offsets, N runs -----------
+
+def build_random(seed, n_rows, length, flushes, alphabet_id=0):
+    from test_gpu_kernels import random_table
+    return random_table(seed, n_rows, length, flushes=flushes, alphabet=alphabet_id)
+
+
+@pytest.mark.parametrize("seed,alphabet_id", [(101, 0), (102, 1)])
+def test_random_expressions(ctx, seed, alphabet_id):
+    t = build_random(seed, 1200, 45, (299, 300, 700), alphabet_id)
+    rng = np.random.default_rng(seed)
+    picked = sorted(set(int(v) for v in rng.integers(0, 300, 120)) | {(1 << 16)} | {(3 << 16) + int(v) for v in rng.integers(0, 499, 200)})
+    t.register_bitmap("lineage", picked)
+    pair = (t, mirror(ctx, t, ["lineage"]))
+    chars = "-ACGTRYSWKMBDHVN" if alphabet_id == 0 else "-ACDEFGHIKLMNOPQRSTUVWYBJZ*X"
+    leaves = []
+    for _ in range(40):
+        position = int(rng.integers(1, 46))
+        symbol = chars[int(rng.integers(0, len(chars)))]
+        leaves.append(f"(sym-eq c {position} {symbol})")
+        leaves.append(f"(has-mut c {position})")
+    leaves += ["(bitmap lineage)", "(ranges 5 250 65536 65537 196608 196900)", "(true)", "(false)", "(sym-eq c 3 .)"]
+    for leaf in leaves:
+        both(pair, leaf)
+        both(pair, f"(maybe {leaf})")
+        both(pair, f"(not {leaf})")
+        both(pair, f"(not (maybe {leaf}))")
+
+    def pick(n):
+        return [leaves[int(i)] for i in rng.integers(0, len(leaves), n)]
+
+    for _ in range(60):
+        a, b, c, d = pick(4)
+        both(pair, f"(and {a} {b})")
+        both(pair, f"(or {a} {b} {c})")
+        both(pair, f"(and {a} (not {b}) (or {c} (not {d})))")
+        both(pair, f"(or (and {a} {b}) (not (and {c} {d})))")
+        both(pair, f"(exact (or {a} (maybe {b})))")
+        both(pair, f"(and (not {a}) (not {b}))")
+        both(pair, f"(not (or {a} (and {b} (bitmap lineage))))")
+    for _ in range(40):
+        n = int(rng.integers(2, 9))
+        children = " ".join(pick(n))
+        k = int(rng.integers(0, n + 2))
+        for exact in (0, 1):
+            both(pair, f"(n-of {k} {exact} {children})")
+            both(pair, f"(maybe (n-of {k} {exact} {children}))")
+            both(pair, f"(and (bitmap lineage) (not (n-of {k} {exact} {children})))")
+    # many children on one column: exercises the one-pass profile lowering
+    for k in (1, 2, 5, 12, 30):
+        children = " ".join(f"(sym-in c {p} {''.join(rng.choice(list(chars[:-1]), 3, replace=False))})" for p in range(1, 46))
+        both(pair, f"(n-of {k} 0 {children})")
+        both(pair, f"(n-of {k} 1 {children})")
+    reference = t.columns[0][2]
+    for distance in (0, 1, 3, 10, 44):
+        both(pair, f"(profile c {distance} muts)")
+        query = list(reference)
+        for p in rng.integers(0, 45, 6):
+            query[int(p)] = chars[int(rng.integers(0, len(chars)))]
+        both(pair, f"(profile c {distance} seq {''.join(query)})")
+        both(pair, f"(and (bitmap lineage) (profile c {distance} seq {''.join(query)}))")
+
+
+@pytest.mark.parametrize("seed,alphabet_id", [(201, 0), (202, 1)])
+def test_mutations_action_rows(ctx, seed, alphabet_id):
+    t = build_random(seed, 900, 60, (99, 130, 131), alphabet_id)
+    rng = np.random.default_rng(seed)
+    t.register_bitmap("lineage", sorted({int(v) for v in rng.integers(0, 100, 60)} | {(3 << 16) + int(v) for v in rng.integers(0, 700, 400)}))
+    oracle_table, device_table = t, mirror(ctx, t, ["lineage"])
+    filters = [None, "(true)", "(false)", "(bitmap lineage)", "(not (bitmap lineage))", "(has-mut c 7)",
+               "(and (bitmap lineage) (not (sym-eq c 12 N)))", "(ranges 3 90 196608 197000)", "(profile c 4 muts)"]
+    for expression in filters:
+        for min_proportion in (0.0, 0.05, 0.3, 1.0):
+            want = oracle_table.mutations("c", expression, min_proportion)
+            got = device_table.mutations(["c"], expression, min_proportion)
+            assert got == want, (expression, min_proportion)
+        flt_o = oracle_table.filter(expression) if expression else None
+        flt_d = device_table.filter(expression) if expression else None
+        np.testing.assert_array_equal(device_table.mutation_counts("c", flt_d), oracle_table.mutation_counts("c", flt_o))
+
+
+def test_mutations_two_columns_and_union_all_vector(ctx):
+    from oracle import oracle as O
+    t = O.Table()  # operators/union_all_node.test.cpp:184-193
+    t.add_column("main", O.NUCLEOTIDE, "A")
+    t.append_row(["T"])
+    t.finalize()
+    device_table = mirror(ctx, t)
+    rows = device_table.mutations(["main"], None, 0.0)
+    assert [(r["mutationTo"], r["proportion"]) for r in rows] == [("T", 1.0)]
+    t2 = O.Table()
+    t2.add_column("segment1", O.NUCLEOTIDE, "ATGCN")
+    t2.add_column("gene1", O.AMINO_ACID, "M*")
+    for nuc, aa in (("ATGCN", "M*"), ("CTGCN", "C*"), ("CTCCN", None), (None, "M*"), ("NNNNN", "XX"), ("RTGCN", "M-")):
+        t2.append_row([nuc, aa])
+    t2.finalize()
+    d2 = mirror(ctx, t2)
+    for expression in (None, "(sym-eq gene1 1 M)", "(not (sym-eq segment1 1 N))"):
+        want = t2.mutations("segment1", expression, 0.0) + t2.mutations("gene1", expression, 0.0)
+        assert d2.mutations(["segment1", "gene1"], expression, 0.0) == want
+
+
+def test_synthetic_shards_sum_to_the_whole(ctx):
+    """Multi-GPU invariant on one device: per-shard counts are plain addends."""
+    from lapis_silo_b200 import host_api
+    from oracle import oracle as O
+    total_rows = 4 * 65536 + 12345
+    synthetic = host_api.Synthetic(genome_length=1500, reference_seed=9, generations=5)
+    sizes = host_api.dense_chunk_sizes(total_rows)
+    date_filter = lambda first, n: host_api.date_ranges_expression(total_rows, 1095, 200, 800, first, n)
+    ancestor = next(i for i in range(synthetic.num_sequences) if synthetic.generation(i) == 2)
+
+    def shard(first, n):
+        table = host_api.HostTable(ctx, sizes[first:first + n], first_chunk=first)
+        table.add_column("main", host_api.NUCLEOTIDE, synthetic.reference, synthetic.build_column(total_rows, first, n, 4))
+        table.register_bitmap("lineage", synthetic.lineage_bitmap(ancestor, total_rows, first, n))
+        expression = f"(and {date_filter(first, n)} (bitmap lineage))"
+        flt = table.filter(expression)
+        return table, flt, table.mutation_counts("main", flt), table.mutation_counts("main")
+
+    whole_table, whole_filter, whole_counts, whole_full = shard(0, len(sizes))
+    bounds = host_api.partition_chunks([1] * len(sizes), 3)
+    parts = [shard(a, b - a) for a, b in zip(bounds, bounds[1:])]
+    assert sum(p[1].cardinality for p in parts) == whole_filter.cardinality > 0
+    np.testing.assert_array_equal(sum(p[2].astype(np.uint64) for p in parts).astype(np.uint32), whole_counts)
+    np.testing.assert_array_equal(sum(p[3].astype(np.uint64) for p in parts).astype(np.uint32), whole_full)
+    # and the whole agrees with the oracle fed the SAME packed column through its import path
+    oracle_table = O.Table()
+    oracle_table.set_layout(*sizes)
+    oracle_table.import_column("main", O.NUCLEOTIDE, synthetic.reference, synthetic.build_column(total_rows, 0, len(sizes), 4))
+    # the lineage row set, recomputed independently of the product generator
+    n_sequences = synthetic.num_sequences
+    in_lineage = np.zeros(n_sequences, dtype=bool)
+    in_lineage[ancestor] = True
+    for e in range(ancestor + 1, n_sequences):
+        in_lineage[e] = in_lineage[synthetic.parent(e)]
+    lineage_rows = np.flatnonzero(in_lineage[np.arange(total_rows) % n_sequences])
+    oracle_table.register_bitmap("lineage", lineage_rows.tolist())  # dense table: sparse id == row number
+    np.testing.assert_array_equal(whole_table.filter("(bitmap lineage)").ids(), lineage_rows.astype(np.uint32))
+    expression = f"(and {date_filter(0, len(sizes))} (bitmap lineage))"
+    oracle_filter = oracle_table.filter(expression)
+    assert oracle_filter.cardinality == whole_filter.cardinality
+    np.testing.assert_array_equal(whole_counts, oracle_table.mutation_counts("main", oracle_filter))
+    np.testing.assert_array_equal(whole_full, oracle_table.mutation_counts("main"))
+    rows = whole_table.mutation_rows_from_counts("main", whole_counts, 0.05)
+    assert rows == oracle_table.mutation_rows("main", whole_counts, 0.05)
+    # size-independent property: per position the symbol counts add up to the covered filtered rows
+    assert (whole_counts.sum(axis=0) == whole_filter.cardinality).all()
