@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py — Mutations query throughput (seq·positions/s) on B200, with roofline and CPU baseline.
+
+Workload (BASELINE.json configs[1], SURVEY.md §8d input 2): synthetic SARS-CoV-2-length table,
+row i = evolved[i % |evolved|] (performance/sequence_generator.h tree model), 10 M rows x 29,903 nt
+PER GPU (weak scaling; 8 GPUs = the 80 M-row config), query
+
+    default.filter(date.between('2021-01-01','2021-06-30') && pango_lineage.lineage(<gen-2 node>,
+                   includeSublineages:=true)).mutations(minProportion:=0.05, sequenceNames:={main})
+
+A step = one such query: filter program (RangeSelection AND lineage IndexScan) -> dense filter ->
+Mutations counts over every stored container of the touched chunks -> [NCCL allreduce of the
+16 x 29,903 u32 counts] -> (e2e only) D2H + the reference's host-side thresholding.
+
+  value  device-resident inputs (program prepared once), only kernels + collective in the timed region
+  e2e    through the host layer / C ABI with HOST buffers: program H2D, cardinality + counts D2H,
+         thresholding on the host, every step
+
+`--impl reference` times the CPU restatement of the reference's path (oracle/, the reference itself
+cannot be built in this image) on the box's host cores, one query per thread as the reference
+deploys it (one Poco worker per request, no intra-query parallelism).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GENOME_LENGTH = 29903
+N_SYMBOLS = 16
+REFERENCE_SEED = 20200101
+GENERATIONS = 5           # writeFullSequenceNdjson: SequenceTreeGenerator defaults
+SPAN_DAYS = 1095          # dates 2020-01-01 .. 2022-12-30 spread evenly over the rows (sorted column)
+FROM_DAY, TO_DAY = 366, 546  # 2021-01-01 .. 2021-06-30
+MIN_PROPORTION = 0.05
+METRIC = "mutations_query_seq_positions_per_s"
+UNIT = "seq*positions/s"
+
+
+def log(*args):
+    print(*args, file=sys.stderr, flush=True)
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as handle:
+            return float(json.load(handle)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.process = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.process = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._drain, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.process = None
+
+    def _drain(self):
+        for line in self.process.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.process is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.process.terminate()
+        try:
+            self.process.wait(timeout=2)
+        except Exception:
+            self.process.kill()
+        sm, sm_max, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                sm_max.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, value in zip(names, parts[5:9]):
+                if value.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(sm_max) if sm_max else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# the CPU side: oracle restatement of the reference path (cpu_baseline leg and --impl reference)
+# ---------------------------------------------------------------------------------------------
+
+def build_oracle_sample(sample_chunks: int):
+    """Same generator and the same filter fractions on a bounded table of sample_chunks x 65536 rows,
+    built by the oracle's own string ingest (no product code on this path)."""
+    import numpy as np
+    from oracle import oracle as O
+    rng_reference = O.lib()  # load
+    del rng_reference
+    # the product generator's reference is a seeded std::mt19937 string; the oracle side only needs
+    # *a* random 29,903-nt reference of the same composition
+    rng = np.random.default_rng(REFERENCE_SEED)
+    reference = "".join("ACGT"[int(i)] for i in rng.integers(0, 4, GENOME_LENGTH))
+    rows = sample_chunks * 65536
+    started = time.perf_counter()
+    table = O.full_sequence_table(reference, rows, GENERATIONS)
+    evolved, parents = O.gen_evolved(reference, seed=42, generations=GENERATIONS)
+    n_sequences = len(evolved)
+    generation = [0] * n_sequences
+    for e in range(1, n_sequences):
+        generation[e] = generation[parents[e]] + 1
+    ancestor = next(e for e in range(n_sequences) if generation[e] == 2)
+    in_lineage = np.zeros(n_sequences, dtype=bool)
+    in_lineage[ancestor] = True
+    for e in range(ancestor + 1, n_sequences):
+        in_lineage[e] = in_lineage[parents[e]]
+    lineage_rows = np.flatnonzero(in_lineage[np.arange(rows) % n_sequences])
+    table.register_bitmap("lineage", lineage_rows.tolist())
+    days = (np.arange(rows, dtype=np.uint64) * SPAN_DAYS) // rows
+    lower = int(np.searchsorted(days, FROM_DAY, side="left"))
+    upper = int(np.searchsorted(days, TO_DAY, side="right"))
+    ranges = []
+    for chunk in range(sample_chunks):  # one range per chunk, date_between.cpp:94-134
+        lo = min(max(lower - chunk * 65536, 0), 65536)
+        hi = min(max(upper - chunk * 65536, 0), 65536)
+        ranges += [((chunk + 1) << 16) if lo == 65536 else (chunk << 16) | lo,
+                   ((chunk + 1) << 16) if hi == 65536 else (chunk << 16) | hi]
+    expression = "(and (ranges " + " ".join(map(str, ranges)) + ") (bitmap lineage))"
+    log(f"[oracle] sample table: {rows} rows, {table.num_containers('main')} containers, "
+        f"built in {time.perf_counter() - started:.1f}s")
+    return table, expression
+
+
+def oracle_query(table, expression) -> int:
+    """One Mutations query on the CPU: computeFilter -> calculateMutationsPerPosition -> thresholding."""
+    flt = table.filter(expression)
+    counts = table.mutation_counts("main", flt)
+    table.mutation_rows("main", counts, MIN_PROPORTION)
+    return flt.cardinality
+
+
+def time_oracle(table, expression, threads: int, min_seconds: float, max_queries: int):
+    """threads concurrent independent queries (the reference's one-worker-per-request model)."""
+    oracle_query(table, expression)  # warm-up
+    results = [0] * threads
+    counts = [0] * threads
+    stop_at = time.perf_counter() + min_seconds
+
+    def worker(index):
+        while True:
+            results[index] = oracle_query(table, expression)
+            counts[index] += 1
+            if time.perf_counter() >= stop_at or counts[index] >= max_queries:
+                break
+
+    started = time.perf_counter()
+    workers = [threading.Thread(target=worker, args=(i,)) for i in range(threads)]
+    for w in workers:
+        w.start()
+    for w in workers:
+        w.join()
+    elapsed = time.perf_counter() - started
+    queries = sum(counts)
+    cardinality = results[0]
+    return cardinality * GENOME_LENGTH * queries / elapsed, elapsed, queries, cardinality
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    table, expression = build_oracle_sample(args.cpu_sample_chunks)
+    per_step = []
+    cardinality = 0
+    for step in range(args.warmup + args.steps):
+        value, elapsed, queries, cardinality = time_oracle(table, expression, cores, args.reference_step_seconds, 10 ** 9)
+        if step >= args.warmup:
+            per_step.append((value, elapsed))
+    value = sum(v for v, _ in per_step) / len(per_step)
+    ms_per_step = 1000.0 * sum(e for _, e in per_step) / len(per_step)
+    sample = (f"{args.cpu_sample_chunks} chunks ({args.cpu_sample_chunks * 65536} rows x {GENOME_LENGTH} nt) of the same "
+              f"generator and filter; {cores} concurrent single-threaded queries for {args.reference_step_seconds}s per step")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args, cardinality, None),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cardinality, extra):
+    config = {
+        "workload": "performance/mutation_benchmark-style synthetic full-length table, Mutations with date-range + lineage filter "
+                    "(BASELINE.json configs[1])",
+        "rows_per_gpu": args.rows_per_gpu, "genome_length": GENOME_LENGTH, "min_proportion": MIN_PROPORTION,
+        "filter": "date.between(2021-01-01, 2021-06-30) && lineage(generation-2 node, includeSublineages)",
+        "filter_cardinality": cardinality,
+        "l2": "the container payload touched per step exceeds the 126 MB L2, no explicit flush",
+    }
+    if extra:
+        config.update(extra)
+    return config
+
+
+# ---------------------------------------------------------------------------------------------
+# the GPU arm
+# ---------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lapis_silo_b200 import abi, host_api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+    n_gpus = world
+
+    total_rows = args.rows_per_gpu * n_gpus
+    sizes = host_api.dense_chunk_sizes(total_rows)
+    bounds = host_api.partition_chunks([1] * len(sizes), n_gpus)  # partition scheduler: contiguous chunk ranges
+    first, n_chunks = bounds[rank], bounds[rank + 1] - bounds[rank]
+
+    started = time.perf_counter()
+    synthetic = host_api.Synthetic(GENOME_LENGTH, REFERENCE_SEED, GENERATIONS)
+    ancestor = next(e for e in range(synthetic.num_sequences) if synthetic.generation(e) == 2)
+    threads = max(1, (os.cpu_count() or 8) // max(1, min(n_gpus, 8)))
+    column = synthetic.build_column(total_rows, first, n_chunks, threads)
+    payload_bytes = int(column.contents.payload_bytes)
+    n_containers = int(column.contents.n_containers)
+    built = time.perf_counter()
+    ctx = abi.Context(local_rank)
+    table = host_api.HostTable(ctx, sizes[first:first + n_chunks], first_chunk=first)
+    table.add_column("main", host_api.NUCLEOTIDE, synthetic.reference, column)
+    synthetic.release_column()
+    table.register_bitmap("lineage", synthetic.lineage_bitmap(ancestor, total_rows, first, n_chunks))
+    expression = (f"(and {host_api.date_ranges_expression(total_rows, SPAN_DAYS, FROM_DAY, TO_DAY, first, n_chunks)} "
+                  f"(bitmap lineage))")
+    torch.cuda.synchronize()
+    uploaded = time.perf_counter()
+    if rank == 0:
+        log(f"[bench] rank 0 shard: chunks [{first}, {first + n_chunks}), {n_containers} containers, "
+            f"{payload_bytes / 1e9:.2f} GB payload; generated in {built - started:.1f}s, uploaded in {uploaded - built:.1f}s; "
+            f"{synthetic.num_sequences} evolved sequences")
+
+    stream = torch.cuda.current_stream()
+    counts = torch.zeros(N_SYMBOLS * GENOME_LENGTH, dtype=torch.int32, device="cuda")
+    pinned = torch.zeros(N_SYMBOLS * GENOME_LENGTH, dtype=torch.int32).pin_memory()
+    prepared = table.prepare(expression)
+
+    def device_step():
+        prepared.run_async(stream.cuda_stream)
+        table.mutation_counts_async(0, prepared, counts.data_ptr(), stream.cuda_stream)
+        if n_gpus > 1:
+            dist.all_reduce(counts)  # u32 counts viewed as i32: modular sum, same bits
+
+    def barrier():
+        if n_gpus > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(value: float) -> float:
+        if n_gpus == 1:
+            return value
+        t = torch.tensor([value], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(value: int) -> int:
+        if n_gpus == 1:
+            return value
+        t = torch.tensor([value], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        return int(t.item())
+
+    # ---- value: device-resident inputs ----
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    table.stats()  # resets the per-kernel timing window
+    launches_before = table.stats().kernel_launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    begin.record(stream)
+    for _ in range(args.steps):
+        device_step()
+    end.record(stream)
+    barrier()
+    device_ms = max_over_ranks(begin.elapsed_time(end))
+    clocks = sampler.stop() if rank == 0 else None
+    stats = table.stats()
+    gpu_launches = int(stats.kernel_launches - launches_before)
+    cardinality = sum_over_ranks(prepared.cardinality())
+    device_counts = counts.cpu().numpy().view(np.uint32).reshape(N_SYMBOLS, GENOME_LENGTH).copy()
+    value = cardinality * GENOME_LENGTH * args.steps / (device_ms / 1000.0)
+
+    # ---- e2e: host buffers in, host rows out, every step ----
+    def e2e_step():
+        if n_gpus == 1:
+            return table.mutations(["main"], expression, MIN_PROPORTION)  # MutationsNode through the C ABI
+        flt = table.filter(expression)  # parse/compile/lower, program H2D, cardinality D2H
+        table.mutation_counts_async(0, flt, counts.data_ptr(), stream.cuda_stream)
+        dist.all_reduce(counts)
+        pinned.copy_(counts, non_blocking=True)
+        stream.synchronize()
+        return table.mutation_rows_from_counts("main", pinned.numpy().view(np.uint32), MIN_PROPORTION)
+
+    rows = None
+    for _ in range(args.warmup):
+        rows = e2e_step()
+    barrier()
+    wall = time.perf_counter()
+    for _ in range(args.steps):
+        rows = e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - wall) * 1000.0)
+    e2e_value = cardinality * GENOME_LENGTH * args.steps / (e2e_ms / 1000.0)
+    counts_bytes = N_SYMBOLS * GENOME_LENGTH * 4
+
+    # size-independent parity properties at full size (tests/ hold the bit-exact oracle comparisons)
+    if n_gpus == 1:
+        column_sums = device_counts.sum(axis=0, dtype=np.uint64)
+        assert (column_sums == cardinality).all(), "per-position symbol counts must add up to |filter|"
+        direct = table.mutation_rows_from_counts("main", device_counts, MIN_PROPORTION)
+        assert direct == rows, "device-resident and host-buffer paths must emit identical rows"
+
+    if rank != 0:
+        return
+    peak, peak_source = measured_peak_gbs()
+    kernel_ms = float(stats.last_counts_kernel_ms)
+    achieved = stats.counts_kernel_bytes / (kernel_ms / 1000.0) / 1e9 if kernel_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": device_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args, cardinality, {
+            "total_rows": total_rows, "chunks_per_gpu": n_chunks, "containers_per_gpu": n_containers,
+            "payload_gb_per_gpu": round(payload_bytes / 1e9, 3), "parallelism": f"chunk-range shards x{n_gpus}, "
+            "NCCL allreduce of the u32 counts" if n_gpus > 1 else "single GPU", "output_rows": len(rows),
+        }),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": prepared.staged_bytes, "d2h_bytes_per_step": counts_bytes + 12},
+        "gpu_launches": gpu_launches,
+        "roofline": {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": args.traffic_bytes, "kernel": "containerAndCountKernel",
+            "algorithmic_bytes_per_launch": int(stats.counts_kernel_bytes), "kernel_ms": kernel_ms,
+            "timed_launches": int(stats.timed_calls), "peak_source": peak_source,
+            "whole_query_algorithmic_bytes": int(stats.algorithmic_bytes), "whole_query_ms": float(stats.last_total_ms),
+        },
+    }
+    if n_gpus == 1 and not args.skip_cpu_baseline:
+        oracle_table, oracle_expression = build_oracle_sample(args.cpu_sample_chunks)
+        cpu_value, cpu_elapsed, cpu_queries, cpu_cardinality = time_oracle(
+            oracle_table, oracle_expression, 1, args.cpu_seconds, 10 ** 9)
+        line["cpu_baseline"] = {
+            "value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{args.cpu_sample_chunks} chunks ({args.cpu_sample_chunks * 65536} rows x {GENOME_LENGTH} nt) of the same "
+                      f"generator and filter fractions; {cpu_queries} single-threaded queries in {cpu_elapsed:.1f}s "
+                      f"(|filter| = {cpu_cardinality}); host has {os.cpu_count()} cores",
+        }
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if n_gpus > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--gpus", type=int, default=1)
+    parser.add_argument("--steps", type=int, default=20)
+    parser.add_argument("--warmup", type=int, default=3)
+    parser.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    parser.add_argument("--rows-per-gpu", type=int, default=10_000_000)
+    parser.add_argument("--cpu-sample-chunks", type=int, default=6)
+    parser.add_argument("--cpu-seconds", type=float, default=12.0)
+    parser.add_argument("--reference-step-seconds", type=float, default=4.0)
+    parser.add_argument("--skip-cpu-baseline", action="store_true")
+    parser.add_argument("--traffic-bytes", type=int, default=None,
+                        help="dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture")
+    args = parser.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

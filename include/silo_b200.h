@@ -180,6 +180,16 @@ int silo_gpu_filter_eval(
    silo_gpu_filter** out,
    uint64_t* cardinality
 );
+/* The same evaluation with DEVICE-RESIDENT inputs, for callers that run one filter many times or must
+ * not touch the host in the hot loop: _prepare validates the program and uploads instructions, blob
+ * and bitmaps once; _run only enqueues the kernel on `cuda_stream` (cudaStream_t, NULL = the
+ * table's stream) into the filter handle created by _prepare, without synchronising. */
+typedef struct silo_gpu_program silo_gpu_program;
+int silo_gpu_program_prepare(silo_gpu_table* table, const silo_filter_program* program, silo_gpu_program** out, silo_gpu_filter** filter_out);
+int silo_gpu_program_run_async(silo_gpu_program* prepared, void* cuda_stream);
+uint64_t silo_gpu_program_device_bytes(const silo_gpu_program* prepared); /* bytes uploaded by _prepare */
+void silo_gpu_program_free(silo_gpu_program* prepared); /* does not free the filter handle */
+
 /* Wraps caller-provided dense words: bit r of words[c*1024 + r/64] = row ((first_chunk+c)<<16)|r. */
 int silo_gpu_filter_from_words(silo_gpu_table* table, const uint64_t* words, silo_gpu_filter** out);
 int silo_gpu_filter_cardinality(const silo_gpu_filter* filter, uint64_t* cardinality);
@@ -215,13 +225,19 @@ int silo_gpu_mutation_counts_async(
 /* ---- measurement hooks (bench.py / profiles; not needed by the reference) --------------------- */
 
 typedef struct {
-   uint64_t containers;          /* containers touched by the last mutation_counts call */
-   uint64_t algorithmic_bytes;   /* descriptor + payload + filter tiles + coverage rows + counts */
-   uint64_t kernel_launches;     /* launched by this library since ctx init */
-   float last_counts_kernel_ms;  /* CUDA-event duration of the dominant (container AND) kernel */
-   float last_total_ms;          /* CUDA-event duration of the whole last mutation_counts enqueue */
+   uint64_t containers;          /* containers of the chunks touched by the last mutation_counts call */
+   uint64_t algorithmic_bytes;   /* whole call: descriptors + payloads + filter tiles + 8 B/row of the
+                                    touched chunks + the counts written */
+   uint64_t counts_kernel_bytes; /* dominant kernel only: descriptors + payloads + filter tiles */
+   uint64_t kernel_launches;     /* kernels launched through this table since it was created */
+   float last_counts_kernel_ms;  /* CUDA-event duration of the dominant (container AND) kernel ... */
+   float last_total_ms;          /* ... and of the whole mutation_counts enqueue: averages over */
+   uint64_t timed_calls;         /* ... this many calls since the previous silo_gpu_get_stats */
 } silo_gpu_stats;
-int silo_gpu_get_stats(const silo_gpu_table* table, silo_gpu_stats* out);
+/* Synchronises the stream of the last mutation_counts call, reads the per-call CUDA events recorded on
+ * the launching stream (a ring of 256 calls) and resets the averaging window. Byte counts describe
+ * the last call. */
+int silo_gpu_get_stats(silo_gpu_table* table, silo_gpu_stats* out);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,15 @@ int silo_host_filter_words(const silo_host_filter* filter, uint64_t* words /* 10
 /* the lowered program as text, one instruction per line (debugging / tests of the lowering) */
 int silo_host_filter_explain(silo_host_table* table, const char* expression, char* out, uint64_t capacity);
 
+/* the same filter with device-resident inputs: compile + lower + upload once (silo_gpu_program_prepare),
+ * then each run only enqueues the kernel on `cuda_stream` (silo_gpu_program_run_async) */
+typedef struct silo_host_prepared silo_host_prepared;
+silo_host_prepared* silo_host_filter_prepare(silo_host_table* table, const char* expression);
+int silo_host_prepared_run_async(silo_host_prepared* prepared, void* cuda_stream);
+const silo_gpu_filter* silo_host_prepared_filter(const silo_host_prepared* prepared);
+uint64_t silo_host_prepared_staged_bytes(const silo_host_prepared* prepared);
+void silo_host_prepared_free(silo_host_prepared* prepared);
+
 /* calculateMutationsPerPosition incl. the full / mixed / empty dispatch (mutations_node.cpp:279-286);
  * filter == NULL means the filter `true`. counts[n_symbols * genome_length]. */
 int silo_host_mutation_counts(silo_host_table* table, const char* column, const silo_host_filter* filter, uint32_t* counts);

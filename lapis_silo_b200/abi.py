@@ -93,16 +93,20 @@ class Stats(C.Structure):
     _fields_ = [
         ("containers", C.c_uint64),
         ("algorithmic_bytes", C.c_uint64),
+        ("counts_kernel_bytes", C.c_uint64),
         ("kernel_launches", C.c_uint64),
         ("last_counts_kernel_ms", C.c_float),
         ("last_total_ms", C.c_float),
+        ("timed_calls", C.c_uint64),
     ]
 
 
 EXPORTED_SYMBOLS = [
     "silo_gpu_last_error", "silo_gpu_version", "silo_gpu_init", "silo_gpu_shutdown",
     "silo_gpu_table_create", "silo_gpu_table_free", "silo_gpu_column_upload",
-    "silo_gpu_table_device_bytes", "silo_gpu_filter_eval", "silo_gpu_filter_from_words",
+    "silo_gpu_table_device_bytes", "silo_gpu_filter_eval", "silo_gpu_program_prepare",
+    "silo_gpu_program_run_async", "silo_gpu_program_device_bytes", "silo_gpu_program_free",
+    "silo_gpu_filter_from_words",
     "silo_gpu_filter_cardinality", "silo_gpu_filter_download", "silo_gpu_filter_free",
     "silo_gpu_mutation_counts", "silo_gpu_mutation_counts_async", "silo_gpu_get_stats",
 ]
@@ -140,6 +144,12 @@ def lib() -> C.CDLL:
         L.silo_gpu_table_device_bytes.argtypes = [vp]
         L.silo_gpu_table_device_bytes.restype = C.c_uint64
         L.silo_gpu_filter_eval.argtypes = [vp, C.POINTER(FilterProgram), C.POINTER(vp), C.POINTER(C.c_uint64)]
+        L.silo_gpu_program_prepare.argtypes = [vp, C.POINTER(FilterProgram), C.POINTER(vp), C.POINTER(vp)]
+        L.silo_gpu_program_run_async.argtypes = [vp, vp]
+        L.silo_gpu_program_device_bytes.argtypes = [vp]
+        L.silo_gpu_program_device_bytes.restype = C.c_uint64
+        L.silo_gpu_program_free.argtypes = [vp]
+        L.silo_gpu_program_free.restype = None
         L.silo_gpu_filter_from_words.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(vp)]
         L.silo_gpu_filter_cardinality.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.silo_gpu_filter_download.argtypes = [vp, C.POINTER(C.c_uint64)]

@@ -81,9 +81,11 @@ struct DevColumn {
 struct Stats {
    uint64_t containers = 0;
    uint64_t algorithmic_bytes = 0;
+   uint64_t counts_kernel_bytes = 0;
    uint64_t kernel_launches = 0;
    float last_counts_kernel_ms = 0;
    float last_total_ms = 0;
+   uint64_t timed_calls = 0;
 };
 
 struct HostColumn {
@@ -122,7 +124,16 @@ struct silo_gpu_table {
    uint32_t* h_counts_pinned = nullptr;
    uint32_t* d_chunk_popcount_full = nullptr;  // popcounts of the "all rows" filter (= chunk sizes)
    uint64_t* d_full_words = nullptr;           // layout mask tiles [n_chunks * 1024]
-   cudaEvent_t ev_begin = nullptr, ev_k1_begin = nullptr, ev_k1_end = nullptr, ev_end = nullptr;
+   // ring of CUDA-event pairs recorded on the launching stream around every mutation_counts
+   // enqueue (whole call) and around its dominant kernel; silo_gpu_get_stats averages and resets
+   static constexpr int EVENT_RING = 256;
+   cudaEvent_t ev_begin[EVENT_RING] = {}, ev_k1_begin[EVENT_RING] = {}, ev_k1_end[EVENT_RING] = {}, ev_end[EVENT_RING] = {};
+   uint64_t timed_calls = 0;  // since the last silo_gpu_get_stats
+   // what the last mutation_counts enqueue ran on / with (read back by silo_gpu_get_stats)
+   cudaStream_t last_stream = nullptr;
+   int last_column = -1;
+   const uint32_t* last_popcounts = nullptr;
+   bool last_was_full = false;
    silo::Stats stats;
    uint64_t device_bytes = 0;
 };

@@ -755,6 +755,110 @@ void silo_gpu_filter_free(silo_gpu_filter* filter) {
    delete filter;
 }
 
+// staged program: everything the kernel reads, uploaded once
+static void stageProgram(
+   silo_gpu_table* table,
+   const silo_filter_program* program,
+   cudaStream_t stream,
+   uint8_t** d_staging_out,
+   uint64_t* staged_bytes_out,
+   EvalParams* params_out
+) {
+   validateProgram(table, program);
+   ParsedBitmaps parsed;
+   for (uint32_t i = 0; i < program->n_bitmaps; ++i) {
+      parseRoaring(program->bitmaps[i], parsed);
+   }
+   parsed.payload.resize((parsed.payload.size() + 15) / 16 * 16 + 16, 0);
+
+   // one staging buffer, one H2D copy: [instrs | columns | bitmap descs | bitmap table | blob | payload]
+   std::vector<uint8_t> staging;
+   auto place = [&](const void* src, size_t bytes) {
+      staging.resize((staging.size() + 15) / 16 * 16, 0);
+      const size_t offset = staging.size();
+      staging.resize(offset + bytes);
+      if (bytes > 0) {
+         std::memcpy(staging.data() + offset, src, bytes);
+      }
+      return offset;
+   };
+   const size_t off_instrs = place(program->instrs, sizeof(silo_filter_instr) * program->n_instrs);
+   std::vector<DevColumn> columns;
+   for (const HostColumn* column : table->columns) {
+      columns.push_back(column->dev);
+   }
+   const size_t off_columns = place(columns.data(), sizeof(DevColumn) * columns.size());
+   const size_t off_bitmap_descs = place(parsed.containers.data(), sizeof(DevContainer) * parsed.containers.size());
+   const size_t off_bitmaps = place(parsed.bitmaps.data(), sizeof(DevBitmap) * parsed.bitmaps.size());
+   const size_t off_blob = place(program->blob, program->blob_bytes);
+   const size_t off_payload = place(parsed.payload.data(), parsed.payload.size());
+
+   uint8_t* d_staging = deviceAlloc<uint8_t>(staging.size() + 16);
+   // patch the per-bitmap container pointers now that the device base is known
+   for (size_t i = 0; i < parsed.bitmaps.size(); ++i) {
+      auto* bitmap = reinterpret_cast<DevBitmap*>(staging.data() + off_bitmaps) + i;
+      bitmap->containers =
+         reinterpret_cast<const DevContainer*>(d_staging + off_bitmap_descs) + parsed.first_container[i];
+   }
+   const cudaError_t status = cudaMemcpyAsync(d_staging, staging.data(), staging.size(), cudaMemcpyHostToDevice, stream);
+   if (status == cudaSuccess) {
+      // the source is pageable: the copy has been staged by the driver when the call returns, but
+      // be explicit before `staging` goes out of scope
+      cudaStreamSynchronize(stream);
+   }
+   if (status != cudaSuccess) {
+      cudaFree(d_staging);
+      throw ApiError(SILO_E_CUDA, std::string("program upload failed: ") + cudaGetErrorString(status));
+   }
+   EvalParams params{};
+   params.instrs = reinterpret_cast<const silo_filter_instr*>(d_staging + off_instrs);
+   params.n_instrs = program->n_instrs;
+   params.n_chunks = table->n_chunks;
+   params.columns = reinterpret_cast<const DevColumn*>(d_staging + off_columns);
+   params.blob = d_staging + off_blob;
+   params.bitmaps = reinterpret_cast<const DevBitmap*>(d_staging + off_bitmaps);
+   params.bitmap_payload = d_staging + off_payload;
+   params.chunk_sizes = table->d_chunk_sizes;
+   params.first_chunk = table->first_chunk;
+   *d_staging_out = d_staging;
+   *staged_bytes_out = staging.size();
+   *params_out = params;
+}
+
+static void launchProgram(silo_gpu_table* table, EvalParams params, silo_gpu_filter* filter, cudaStream_t stream) {
+   params.out_words = filter->d_words;
+   params.out_popcount = filter->d_chunk_popcount;
+   params.out_cardinality = filter->d_cardinality;
+   params.error_flag = filter->d_error_flag;
+   SILO_CUDA_CHECK(cudaMemsetAsync(filter->d_cardinality, 0, sizeof(unsigned long long), stream));
+   SILO_CUDA_CHECK(cudaMemsetAsync(filter->d_error_flag, 0, sizeof(uint32_t), stream));
+   if (table->n_chunks == 0) {
+      return;
+   }
+   static bool attribute_set = false;
+   if (!attribute_set) {
+      SILO_CUDA_CHECK(cudaFuncSetAttribute(
+         evalProgramKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(EvalShared))
+      ));
+      attribute_set = true;
+   }
+   evalProgramKernel<<<table->n_chunks, EVAL_THREADS, sizeof(EvalShared), stream>>>(params);
+   SILO_CUDA_CHECK(cudaGetLastError());
+   table->stats.kernel_launches++;
+}
+
+}  // extern "C"
+
+struct silo_gpu_program {
+   silo_gpu_table* table = nullptr;
+   uint8_t* d_staging = nullptr;
+   uint64_t staged_bytes = 0;
+   silo::EvalParams* params = nullptr;  // heap copy (EvalParams lives in an unnamed namespace)
+   silo_gpu_filter* filter = nullptr;
+};
+
+extern "C" {
+
 int silo_gpu_filter_eval(
    silo_gpu_table* table,
    const silo_filter_program* program,
@@ -766,74 +870,14 @@ int silo_gpu_filter_eval(
       std::lock_guard<std::mutex> lock(table->mutex);
       SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
       cudaStream_t stream = table->ctx->stream;
-      validateProgram(table, program);
-
-      ParsedBitmaps parsed;
-      for (uint32_t i = 0; i < program->n_bitmaps; ++i) {
-         parseRoaring(program->bitmaps[i], parsed);
-      }
-      parsed.payload.resize((parsed.payload.size() + 15) / 16 * 16 + 16, 0);
-
-      // one staging buffer, one H2D copy: [instrs | columns | bitmap descs | bitmap table | blob | payload]
-      std::vector<uint8_t> staging;
-      auto place = [&](const void* src, size_t bytes) {
-         staging.resize((staging.size() + 15) / 16 * 16, 0);
-         const size_t offset = staging.size();
-         staging.resize(offset + bytes);
-         if (bytes > 0) {
-            std::memcpy(staging.data() + offset, src, bytes);
-         }
-         return offset;
-      };
-      const size_t off_instrs = place(program->instrs, sizeof(silo_filter_instr) * program->n_instrs);
-      std::vector<DevColumn> columns;
-      for (const HostColumn* column : table->columns) {
-         columns.push_back(column->dev);
-      }
-      const size_t off_columns = place(columns.data(), sizeof(DevColumn) * columns.size());
-      const size_t off_bitmap_descs = place(parsed.containers.data(), sizeof(DevContainer) * parsed.containers.size());
-      const size_t off_bitmaps = place(parsed.bitmaps.data(), sizeof(DevBitmap) * parsed.bitmaps.size());
-      const size_t off_blob = place(program->blob, program->blob_bytes);
-      const size_t off_payload = place(parsed.payload.data(), parsed.payload.size());
-
-      uint8_t* d_staging = deviceAlloc<uint8_t>(staging.size() + 16);
-      std::unique_ptr<silo_gpu_filter, void (*)(silo_gpu_filter*)> filter(allocFilter(table), silo_gpu_filter_free);
+      uint8_t* d_staging = nullptr;
+      uint64_t staged_bytes = 0;
+      EvalParams params{};
+      stageProgram(table, program, stream, &d_staging, &staged_bytes, &params);
+      std::unique_ptr<silo_gpu_filter, void (*)(silo_gpu_filter*)> filter(nullptr, silo_gpu_filter_free);
       try {
-         // patch the per-bitmap container pointers now that the device base is known
-         for (size_t i = 0; i < parsed.bitmaps.size(); ++i) {
-            auto* bitmap = reinterpret_cast<DevBitmap*>(staging.data() + off_bitmaps) + i;
-            bitmap->containers =
-               reinterpret_cast<const DevContainer*>(d_staging + off_bitmap_descs) + parsed.first_container[i];
-         }
-         SILO_CUDA_CHECK(cudaMemcpyAsync(d_staging, staging.data(), staging.size(), cudaMemcpyHostToDevice, stream));
-         SILO_CUDA_CHECK(cudaMemsetAsync(filter->d_cardinality, 0, sizeof(unsigned long long), stream));
-         SILO_CUDA_CHECK(cudaMemsetAsync(filter->d_error_flag, 0, sizeof(uint32_t), stream));
-         if (table->n_chunks > 0) {
-            EvalParams params{};
-            params.instrs = reinterpret_cast<const silo_filter_instr*>(d_staging + off_instrs);
-            params.n_instrs = program->n_instrs;
-            params.n_chunks = table->n_chunks;
-            params.columns = reinterpret_cast<const DevColumn*>(d_staging + off_columns);
-            params.blob = d_staging + off_blob;
-            params.bitmaps = reinterpret_cast<const DevBitmap*>(d_staging + off_bitmaps);
-            params.bitmap_payload = d_staging + off_payload;
-            params.chunk_sizes = table->d_chunk_sizes;
-            params.first_chunk = table->first_chunk;
-            params.out_words = filter->d_words;
-            params.out_popcount = filter->d_chunk_popcount;
-            params.out_cardinality = filter->d_cardinality;
-            params.error_flag = filter->d_error_flag;
-            static bool attribute_set = false;
-            if (!attribute_set) {
-               SILO_CUDA_CHECK(cudaFuncSetAttribute(
-                  evalProgramKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(EvalShared))
-               ));
-               attribute_set = true;
-            }
-            evalProgramKernel<<<table->n_chunks, EVAL_THREADS, sizeof(EvalShared), stream>>>(params);
-            SILO_CUDA_CHECK(cudaGetLastError());
-            table->stats.kernel_launches++;
-         }
+         filter.reset(allocFilter(table));
+         launchProgram(table, params, filter.get(), stream);
          unsigned long long host_cardinality = 0;
          uint32_t host_error = 0;
          SILO_CUDA_CHECK(cudaMemcpyAsync(&host_cardinality, filter->d_cardinality, sizeof(host_cardinality), cudaMemcpyDeviceToHost, stream));
@@ -853,6 +897,53 @@ int silo_gpu_filter_eval(
       }
       *out = filter.release();
    });
+}
+
+int silo_gpu_program_prepare(silo_gpu_table* table, const silo_filter_program* program, silo_gpu_program** out, silo_gpu_filter** filter_out) {
+   return guarded([&] {
+      require(table != nullptr && program != nullptr && out != nullptr && filter_out != nullptr, "silo_gpu_program_prepare: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      auto prepared = std::make_unique<silo_gpu_program>();
+      prepared->table = table;
+      EvalParams params{};
+      stageProgram(table, program, table->ctx->stream, &prepared->d_staging, &prepared->staged_bytes, &params);
+      try {
+         prepared->params = new EvalParams(params);
+         prepared->filter = allocFilter(table);
+      } catch (...) {
+         cudaFree(prepared->d_staging);
+         delete prepared->params;
+         throw;
+      }
+      *filter_out = prepared->filter;
+      *out = prepared.release();
+   });
+}
+
+int silo_gpu_program_run_async(silo_gpu_program* prepared, void* cuda_stream) {
+   return guarded([&] {
+      require(prepared != nullptr, "silo_gpu_program_run_async: NULL argument");
+      silo_gpu_table* table = prepared->table;
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      cudaStream_t stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : table->ctx->stream;
+      launchProgram(table, *prepared->params, prepared->filter, stream);
+   });
+}
+
+uint64_t silo_gpu_program_device_bytes(const silo_gpu_program* prepared) {
+   return prepared == nullptr ? 0 : prepared->staged_bytes;
+}
+
+void silo_gpu_program_free(silo_gpu_program* prepared) {
+   if (prepared == nullptr) {
+      return;
+   }
+   cudaSetDevice(prepared->table->ctx->device);
+   cudaFree(prepared->d_staging);
+   delete prepared->params;
+   delete prepared;
 }
 
 int silo_gpu_filter_from_words(silo_gpu_table* table, const uint64_t* words, silo_gpu_filter** out) {

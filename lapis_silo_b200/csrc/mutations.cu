@@ -492,32 +492,42 @@ void enqueueMutationCounts(
    const uint32_t n_chunks = table->n_chunks;
    const size_t counts_bytes = static_cast<size_t>(column.n_symbols) * column.genome_length * sizeof(uint32_t);
 
-   SILO_CUDA_CHECK(cudaEventRecord(table->ev_begin, stream));
+   table->last_stream = stream;
+   table->last_column = column_index;
+   table->last_popcounts = filter != nullptr ? filter->d_chunk_popcount : table->d_chunk_popcount_full;
+   table->last_was_full = filter == nullptr;
+   const uint64_t slot = table->timed_calls % silo_gpu_table::EVENT_RING;
+   table->timed_calls++;
+   cudaEvent_t ev_begin = table->ev_begin[slot];
+   cudaEvent_t ev_k1_begin = table->ev_k1_begin[slot];
+   cudaEvent_t ev_k1_end = table->ev_k1_end[slot];
+   cudaEvent_t ev_end = table->ev_end[slot];
+   SILO_CUDA_CHECK(cudaEventRecord(ev_begin, stream));
    SILO_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, counts_bytes, stream));
    SILO_CUDA_CHECK(cudaMemsetAsync(table->d_coverage_diff, 0, (column.genome_length + 1) * sizeof(uint32_t), stream));
    if (n_chunks == 0) {
-      SILO_CUDA_CHECK(cudaEventRecord(table->ev_k1_begin, stream));
-      SILO_CUDA_CHECK(cudaEventRecord(table->ev_k1_end, stream));
-      SILO_CUDA_CHECK(cudaEventRecord(table->ev_end, stream));
+      SILO_CUDA_CHECK(cudaEventRecord(ev_k1_begin, stream));
+      SILO_CUDA_CHECK(cudaEventRecord(ev_k1_end, stream));
+      SILO_CUDA_CHECK(cudaEventRecord(ev_end, stream));
       return;
    }
    const uint64_t* words = filter != nullptr ? filter->d_words : table->d_full_words;
    const uint32_t* popcounts = filter != nullptr ? filter->d_chunk_popcount : table->d_chunk_popcount_full;
 
    if (filter == nullptr) {
-      SILO_CUDA_CHECK(cudaEventRecord(table->ev_k1_begin, stream));
+      SILO_CUDA_CHECK(cudaEventRecord(ev_k1_begin, stream));
       if (column.n_containers > 0) {
          const int blocks = static_cast<int>(std::min<uint64_t>((column.n_containers + 255) / 256, static_cast<uint64_t>(table->ctx->sm_count) * 8));
          containerCardinalityKernel<<<blocks, 256, 0, stream>>>(column, d_counts);
          SILO_CUDA_CHECK(cudaGetLastError());
          table->stats.kernel_launches++;
       }
-      SILO_CUDA_CHECK(cudaEventRecord(table->ev_k1_end, stream));
+      SILO_CUDA_CHECK(cudaEventRecord(ev_k1_end, stream));
    } else {
       buildWorkListKernel<<<1, 1024, 0, stream>>>(popcounts, column.chunk_seg_begin, n_chunks, table->d_work_prefix);
       SILO_CUDA_CHECK(cudaGetLastError());
       table->stats.kernel_launches++;
-      SILO_CUDA_CHECK(cudaEventRecord(table->ev_k1_begin, stream));
+      SILO_CUDA_CHECK(cudaEventRecord(ev_k1_begin, stream));
       if (column.n_segments > 0) {
          static bool attribute_set = false;
          if (!attribute_set) {
@@ -531,7 +541,7 @@ void enqueueMutationCounts(
          SILO_CUDA_CHECK(cudaGetLastError());
          table->stats.kernel_launches++;
       }
-      SILO_CUDA_CHECK(cudaEventRecord(table->ev_k1_end, stream));
+      SILO_CUDA_CHECK(cudaEventRecord(ev_k1_end, stream));
    }
    coverageDiffKernel<<<n_chunks * K6_SLICES, K6_THREADS, 0, stream>>>(
       column, words, popcounts, table->d_chunk_sizes, table->d_coverage_diff
@@ -540,7 +550,7 @@ void enqueueMutationCounts(
    finalizeCountsKernel<<<1, FIN_THREADS, 0, stream>>>(column, table->d_coverage_diff, d_counts);
    SILO_CUDA_CHECK(cudaGetLastError());
    table->stats.kernel_launches += 2;
-   SILO_CUDA_CHECK(cudaEventRecord(table->ev_end, stream));
+   SILO_CUDA_CHECK(cudaEventRecord(ev_end, stream));
 }
 
 }  // namespace
@@ -582,37 +592,8 @@ int silo_gpu_mutation_counts(
       const HostColumn& host = *table->columns[static_cast<size_t>(column)];
       const size_t counts_bytes = static_cast<size_t>(host.dev.n_symbols) * host.dev.genome_length * sizeof(uint32_t);
       SILO_CUDA_CHECK(cudaMemcpyAsync(table->h_counts_pinned, table->d_counts, counts_bytes, cudaMemcpyDeviceToHost, stream));
-      // per-chunk popcounts come back too: they drive the algorithmic-bytes accounting
-      std::vector<uint32_t> popcounts(table->n_chunks);
-      if (table->n_chunks > 0) {
-         SILO_CUDA_CHECK(cudaMemcpyAsync(
-            popcounts.data(),
-            filter != nullptr ? filter->d_chunk_popcount : table->d_chunk_popcount_full,
-            popcounts.size() * sizeof(uint32_t),
-            cudaMemcpyDeviceToHost,
-            stream
-         ));
-      }
       SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
       std::memcpy(counts, table->h_counts_pinned, counts_bytes);
-
-      Stats& stats = table->stats;
-      stats.containers = 0;
-      stats.algorithmic_bytes = counts_bytes;
-      for (uint32_t chunk = 0; chunk < table->n_chunks; ++chunk) {
-         if (popcounts[chunk] == 0) {
-            continue;
-         }
-         stats.containers += host.chunk_containers[chunk];
-         // descriptors (+ payloads unless the filter is full) + the filter tile +
-         // 8 B per row of the chunk + the missing-row index of the chunk
-         stats.algorithmic_bytes += filter != nullptr
-                                       ? host.chunk_desc_payload_bytes[chunk] + TILE_BYTES
-                                       : host.chunk_containers[chunk] * sizeof(DevContainer);
-         stats.algorithmic_bytes += 8ULL * table->chunk_sizes[chunk] + 2ULL * host.chunk_missing_rows[chunk];
-      }
-      SILO_CUDA_CHECK(cudaEventElapsedTime(&stats.last_counts_kernel_ms, table->ev_k1_begin, table->ev_k1_end));
-      SILO_CUDA_CHECK(cudaEventElapsedTime(&stats.last_total_ms, table->ev_begin, table->ev_end));
    });
 }
 

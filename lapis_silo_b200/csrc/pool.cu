@@ -127,10 +127,12 @@ int silo_gpu_table_create(
          SILO_CUDA_CHECK(cudaGetLastError());
          table->stats.kernel_launches++;
       }
-      SILO_CUDA_CHECK(cudaEventCreate(&table->ev_begin));
-      SILO_CUDA_CHECK(cudaEventCreate(&table->ev_k1_begin));
-      SILO_CUDA_CHECK(cudaEventCreate(&table->ev_k1_end));
-      SILO_CUDA_CHECK(cudaEventCreate(&table->ev_end));
+      for (int i = 0; i < silo_gpu_table::EVENT_RING; ++i) {
+         SILO_CUDA_CHECK(cudaEventCreate(&table->ev_begin[i]));
+         SILO_CUDA_CHECK(cudaEventCreate(&table->ev_k1_begin[i]));
+         SILO_CUDA_CHECK(cudaEventCreate(&table->ev_k1_end[i]));
+         SILO_CUDA_CHECK(cudaEventCreate(&table->ev_end[i]));
+      }
       SILO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
       *out = table.release();
    });
@@ -157,9 +159,11 @@ void silo_gpu_table_free(silo_gpu_table* table) {
    if (table->h_counts_pinned != nullptr) {
       cudaFreeHost(table->h_counts_pinned);
    }
-   for (cudaEvent_t event : {table->ev_begin, table->ev_k1_begin, table->ev_k1_end, table->ev_end}) {
-      if (event != nullptr) {
-         cudaEventDestroy(event);
+   for (int i = 0; i < silo_gpu_table::EVENT_RING; ++i) {
+      for (cudaEvent_t event : {table->ev_begin[i], table->ev_k1_begin[i], table->ev_k1_end[i], table->ev_end[i]}) {
+         if (event != nullptr) {
+            cudaEventDestroy(event);
+         }
       }
    }
    delete table;
@@ -425,14 +429,64 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
    return status == SILO_OK ? column_index : status;
 }
 
-int silo_gpu_get_stats(const silo_gpu_table* table, silo_gpu_stats* out) {
+int silo_gpu_get_stats(silo_gpu_table* table, silo_gpu_stats* out) {
    return guarded([&] {
       require(table != nullptr && out != nullptr, "silo_gpu_get_stats: NULL argument");
-      out->containers = table->stats.containers;
-      out->algorithmic_bytes = table->stats.algorithmic_bytes;
-      out->kernel_launches = table->stats.kernel_launches;
-      out->last_counts_kernel_ms = table->stats.last_counts_kernel_ms;
-      out->last_total_ms = table->stats.last_total_ms;
+      std::lock_guard<std::mutex> lock(table->mutex);
+      Stats& stats = table->stats;
+      if (table->last_column >= 0) {
+         SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+         const HostColumn& host = *table->columns[static_cast<size_t>(table->last_column)];
+         std::vector<uint32_t> popcounts(table->n_chunks);
+         if (table->n_chunks > 0) {
+            SILO_CUDA_CHECK(cudaMemcpyAsync(
+               popcounts.data(), table->last_popcounts, popcounts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+               table->last_stream
+            ));
+         }
+         SILO_CUDA_CHECK(cudaStreamSynchronize(table->last_stream));
+         stats.containers = 0;
+         stats.counts_kernel_bytes = 0;
+         stats.algorithmic_bytes = static_cast<uint64_t>(host.dev.n_symbols) * host.dev.genome_length * sizeof(uint32_t);
+         for (uint32_t chunk = 0; chunk < table->n_chunks; ++chunk) {
+            if (popcounts[chunk] == 0) {
+               continue;
+            }
+            stats.containers += host.chunk_containers[chunk];
+            // descriptors (+ payloads and the filter tile unless the filter is full)
+            stats.counts_kernel_bytes += table->last_was_full
+                                            ? host.chunk_containers[chunk] * sizeof(DevContainer)
+                                            : host.chunk_desc_payload_bytes[chunk] + TILE_BYTES;
+            // + 8 B per row of the chunk (start, end) + the missing-row index of the chunk
+            stats.algorithmic_bytes += 8ULL * table->chunk_sizes[chunk] + 2ULL * host.chunk_missing_rows[chunk];
+         }
+         stats.algorithmic_bytes += stats.counts_kernel_bytes;
+         // average over the calls recorded since the previous get_stats (at most the ring size)
+         const uint64_t n_timed = std::min<uint64_t>(table->timed_calls, silo_gpu_table::EVENT_RING);
+         double kernel_ms = 0;
+         double total_ms = 0;
+         for (uint64_t back = 0; back < n_timed; ++back) {
+            const uint64_t slot = (table->timed_calls - 1 - back) % silo_gpu_table::EVENT_RING;
+            float ms = 0;
+            SILO_CUDA_CHECK(cudaEventElapsedTime(&ms, table->ev_k1_begin[slot], table->ev_k1_end[slot]));
+            kernel_ms += ms;
+            SILO_CUDA_CHECK(cudaEventElapsedTime(&ms, table->ev_begin[slot], table->ev_end[slot]));
+            total_ms += ms;
+         }
+         if (n_timed > 0) {
+            stats.last_counts_kernel_ms = static_cast<float>(kernel_ms / static_cast<double>(n_timed));
+            stats.last_total_ms = static_cast<float>(total_ms / static_cast<double>(n_timed));
+         }
+         stats.timed_calls = n_timed;
+         table->timed_calls = 0;
+      }
+      out->containers = stats.containers;
+      out->algorithmic_bytes = stats.algorithmic_bytes;
+      out->counts_kernel_bytes = stats.counts_kernel_bytes;
+      out->kernel_launches = stats.kernel_launches;
+      out->last_counts_kernel_ms = stats.last_counts_kernel_ms;
+      out->last_total_ms = stats.last_total_ms;
+      out->timed_calls = stats.timed_calls;
    });
 }
 

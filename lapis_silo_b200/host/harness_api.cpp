@@ -23,6 +23,15 @@ struct silo_host_filter {
    size_t n_chunks = 0;
 };
 
+struct silo_host_prepared {
+   // keeps everything the uploaded program points into alive
+   ExpressionPtr expression;
+   ExpressionPtr rewritten;
+   std::unique_ptr<Operator> compiled;
+   silo_gpu_program* program = nullptr;
+   silo_gpu_filter* filter = nullptr;
+};
+
 struct silo_host_rows {
    std::vector<MutationRow> rows;
 };
@@ -153,6 +162,51 @@ int silo_host_filter_words(const silo_host_filter* filter, uint64_t* words) {
       const std::vector<uint64_t> downloaded = filter->bitmap.toWords(filter->n_chunks);
       std::memcpy(words, downloaded.data(), downloaded.size() * sizeof(uint64_t));
    });
+}
+
+silo_host_prepared* silo_host_filter_prepare(silo_host_table* table, const char* expression) {
+   silo_host_prepared* result = nullptr;
+   guarded([&] {
+      auto owned = std::make_unique<silo_host_prepared>();
+      owned->expression = parseFilterExpression(expression);
+      owned->rewritten = owned->expression->rewrite(*table->table, AmbiguityMode::NONE);
+      owned->compiled = owned->rewritten->compile(*table->table);
+      ProgramBuilder builder;
+      builder.table = table->table.get();
+      owned->compiled->lower(builder);
+      silo_filter_program program{};
+      program.struct_size = sizeof(silo_filter_program);
+      program.n_instrs = static_cast<uint32_t>(builder.instrs.size());
+      program.instrs = builder.instrs.data();
+      program.blob = builder.blob.data();
+      program.blob_bytes = builder.blob.size();
+      program.n_bitmaps = static_cast<uint32_t>(builder.bitmaps.size());
+      program.bitmaps = builder.bitmaps.data();
+      throwOnDeviceError(silo_gpu_program_prepare(table->table->device, &program, &owned->program, &owned->filter));
+      result = owned.release();
+   });
+   return result;
+}
+
+int silo_host_prepared_run_async(silo_host_prepared* prepared, void* cuda_stream) {
+   return guarded([&] { throwOnDeviceError(silo_gpu_program_run_async(prepared->program, cuda_stream)); });
+}
+
+const silo_gpu_filter* silo_host_prepared_filter(const silo_host_prepared* prepared) {
+   return prepared->filter;
+}
+
+uint64_t silo_host_prepared_staged_bytes(const silo_host_prepared* prepared) {
+   return silo_gpu_program_device_bytes(prepared->program);
+}
+
+void silo_host_prepared_free(silo_host_prepared* prepared) {
+   if (prepared == nullptr) {
+      return;
+   }
+   silo_gpu_program_free(prepared->program);
+   silo_gpu_filter_free(prepared->filter);
+   delete prepared;
 }
 
 int silo_host_filter_explain(silo_host_table* table, const char* expression, char* out, uint64_t capacity) {

@@ -22,6 +22,8 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_table_register_bitmap", "silo_host_table_device", "silo_host_table_num_rows",
     "silo_host_filter_eval", "silo_host_filter_free", "silo_host_filter_cardinality",
     "silo_host_filter_device", "silo_host_filter_words", "silo_host_filter_explain",
+    "silo_host_filter_prepare", "silo_host_prepared_run_async", "silo_host_prepared_filter",
+    "silo_host_prepared_staged_bytes", "silo_host_prepared_free",
     "silo_host_mutation_counts", "silo_host_mutations", "silo_host_mutation_rows_from_counts",
     "silo_host_rows_free", "silo_host_rows_size", "silo_host_rows_get",
     "silo_host_synthetic_create", "silo_host_synthetic_free", "silo_host_synthetic_num_sequences",
@@ -66,6 +68,15 @@ def lib() -> C.CDLL:
         L.silo_host_filter_device.restype = vp
         L.silo_host_filter_words.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.silo_host_filter_explain.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint64]
+        L.silo_host_filter_prepare.argtypes = [vp, C.c_char_p]
+        L.silo_host_filter_prepare.restype = vp
+        L.silo_host_prepared_run_async.argtypes = [vp, vp]
+        L.silo_host_prepared_filter.argtypes = [vp]
+        L.silo_host_prepared_filter.restype = vp
+        L.silo_host_prepared_staged_bytes.argtypes = [vp]
+        L.silo_host_prepared_staged_bytes.restype = C.c_uint64
+        L.silo_host_prepared_free.argtypes = [vp]
+        L.silo_host_prepared_free.restype = None
         L.silo_host_mutation_counts.argtypes = [vp, C.c_char_p, vp, C.POINTER(C.c_uint32)]
         L.silo_host_mutations.argtypes = [vp, C.c_char_p, C.POINTER(C.c_char_p), C.c_uint32, C.c_double]
         L.silo_host_mutations.restype = vp
@@ -169,6 +180,41 @@ class HostFilter:
             pass
 
 
+class PreparedFilter:
+    """A filter whose program is resident on the device; run_async() only enqueues its kernel."""
+
+    def __init__(self, table: "HostTable", handle):
+        self.table = table
+        self._h = handle
+
+    def run_async(self, stream_ptr: int) -> None:
+        _check(lib().silo_host_prepared_run_async(self._h, C.c_void_p(stream_ptr)))
+
+    @property
+    def device_handle(self) -> int:
+        return lib().silo_host_prepared_filter(self._h)
+
+    @property
+    def staged_bytes(self) -> int:
+        return int(lib().silo_host_prepared_staged_bytes(self._h))
+
+    def cardinality(self) -> int:
+        value = C.c_uint64()
+        abi.check(abi.lib().silo_gpu_filter_cardinality(self.device_handle, C.byref(value)))
+        return int(value.value)
+
+    def close(self):
+        if self._h:
+            lib().silo_host_prepared_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class HostTable:
     """rhydb::storage::Table as the query compiler sees it, with its sequence columns in HBM."""
 
@@ -206,6 +252,12 @@ class HostTable:
             raise HostError(lib().silo_host_last_error().decode())
         return HostFilter(self, handle)
 
+    def prepare(self, expression: str) -> PreparedFilter:
+        handle = lib().silo_host_filter_prepare(self._h, expression.encode())
+        if not handle:
+            raise HostError(lib().silo_host_last_error().decode())
+        return PreparedFilter(self, handle)
+
     def explain(self, expression: str) -> str:
         buf = C.create_string_buffer(1 << 22)
         _check(lib().silo_host_filter_explain(self._h, expression.encode(), buf, len(buf)))
@@ -235,7 +287,8 @@ class HostTable:
         abi.check(abi.lib().silo_gpu_get_stats(self.device_table, C.byref(out)))
         return out
 
-    def mutation_counts_async(self, column_index: int, flt: Optional[HostFilter], d_counts_ptr: int, stream_ptr: int) -> None:
+    def mutation_counts_async(self, column_index: int, flt, d_counts_ptr: int, stream_ptr: int) -> None:
+        """flt: HostFilter | PreparedFilter | None (all rows). Enqueues only; no host synchronisation."""
         abi.check(abi.lib().silo_gpu_mutation_counts_async(
             self.device_table, column_index, flt.device_handle if flt is not None else None,
             C.c_void_p(d_counts_ptr), C.c_void_p(stream_ptr)))
