@@ -280,7 +280,9 @@ def run_ours(args):
             f"{payload_bytes / 1e9:.2f} GB payload; generated in {built - started:.1f}s, uploaded in {uploaded - built:.1f}s; "
             f"{synthetic.num_sequences} evolved sequences")
 
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: the library's kernels, NCCL and the timing events all use it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     counts = torch.zeros(N_SYMBOLS * GENOME_LENGTH, dtype=torch.int32, device="cuda")
     pinned = torch.zeros(N_SYMBOLS * GENOME_LENGTH, dtype=torch.int32).pin_memory()
     prepared = table.prepare(expression)

@@ -65,6 +65,11 @@ silo_host_rows* silo_host_mutations(silo_host_table* table, const char* expressi
 silo_host_rows* silo_host_mutation_rows_from_counts(silo_host_table* table, const char* column, const uint32_t* counts, double min_proportion);
 void silo_host_rows_free(silo_host_rows* rows);
 uint64_t silo_host_rows_size(const silo_host_rows* rows);
+/* all rows at once (struct-of-arrays, each array silo_host_rows_size long); name_ids index
+ * silo_host_rows_name */
+int silo_host_rows_export(const silo_host_rows* rows, char* from, char* to, int32_t* position, uint32_t* name_ids, double* proportion, int32_t* count, int32_t* coverage);
+uint32_t silo_host_rows_num_names(const silo_host_rows* rows);
+const char* silo_host_rows_name(const silo_host_rows* rows, uint32_t name_id);
 int silo_host_rows_get(const silo_host_rows* rows, uint64_t index, char* from, char* to, int32_t* position, const char** sequence_name, double* proportion, int32_t* count, int32_t* coverage);
 
 /* ---- synthetic benchmark inputs (performance/sequence_generator.h restated on the product side) */

@@ -20,23 +20,32 @@ namespace silo {
 constexpr uint32_t TILE_WORDS = 1024;        // one chunk's dense filter tile: 1024 x u64 = 8 KiB
 constexpr uint32_t TILE_BYTES = TILE_WORDS * 8;
 constexpr uint32_t SEG_PAYLOAD_BYTES = 16384;  // max payload bytes of one segment (>= 8192 + slack)
-constexpr uint32_t SEG_MAX_DESCS = 256;        // max containers of one segment
+constexpr uint32_t SEG_MAX_DESCS = 128;        // max pieces of one segment
 
 constexpr uint32_t TYPE_BITSET = 1;  // CRoaring typecodes, roaring_container.h:131-145
 constexpr uint32_t TYPE_ARRAY = 2;
 constexpr uint32_t TYPE_RUN = 3;
+
+// device-side piece kinds (DevContainer::packed[31:30]); 1..3 keep the CRoaring typecode meaning
+constexpr uint32_t KIND_INLINE = 0;  // array of 1..2 values stored in DevContainer::n_runs, no payload
+constexpr uint32_t KIND_BITSET = TYPE_BITSET;  // n_runs = first_word | (n_words << 16)
+constexpr uint32_t KIND_ARRAY = TYPE_ARRAY;    // cardinality sorted u16 values
+constexpr uint32_t KIND_RUN = TYPE_RUN;        // n_runs pairs {start, length-1}
+constexpr uint32_t PIECE_BYTES = 1024;         // payload of one piece of a stored container
 
 // 16-byte device descriptor of one stored diff container (chunk-major order).
 struct __align__(16) DevContainer {
    uint32_t position;
    uint32_t offset4;  // payload offset from the slab start, in 4-byte units
    uint32_t packed;   // [15:0] cardinality-1 | [23:16] symbol | [29:24] local-reference symbol | [31:30] type
-   uint32_t n_runs;   // run containers: number of {start,len-1} pairs; otherwise 0
+   uint32_t n_runs;   // KIND_RUN: number of pairs | KIND_BITSET: first_word | n_words << 16 | KIND_INLINE: the values
 
    __host__ __device__ uint32_t cardinality() const { return (packed & 0xFFFFu) + 1u; }
    __host__ __device__ uint32_t symbol() const { return (packed >> 16) & 0xFFu; }
    __host__ __device__ uint32_t refSymbol() const { return (packed >> 24) & 0x3Fu; }
    __host__ __device__ uint32_t type() const { return packed >> 30; }
+   __host__ __device__ uint32_t firstWord() const { return n_runs & 0xFFFFu; }
+   __host__ __device__ uint32_t wordCount() const { return n_runs >> 16; }
 };
 static_assert(sizeof(DevContainer) == 16);
 
@@ -117,11 +126,16 @@ struct silo_gpu_table {
    // per-query scratch (calls on one table are serialised by `mutex`; tables are independent)
    std::mutex mutex;
    uint32_t* d_work_prefix = nullptr;  // [n_chunks + 1]
+   uint32_t* d_work_items = nullptr;   // [max n_segments over the columns]
+   uint32_t work_items_capacity = 0;
    uint32_t* d_coverage_diff = nullptr;  // [max genome_length + 1]
    uint32_t coverage_diff_capacity = 0;
    uint32_t* d_counts = nullptr;  // staging for the synchronous API
    uint64_t counts_capacity = 0;
    uint32_t* h_counts_pinned = nullptr;
+   uint8_t* h_staging_pinned = nullptr;  // program upload staging (grow-only)
+   size_t staging_capacity = 0;
+   cudaEvent_t ev_free_fence = nullptr;  // orders stream-ordered frees after foreign-stream users
    uint32_t* d_chunk_popcount_full = nullptr;  // popcounts of the "all rows" filter (= chunk sizes)
    uint64_t* d_full_words = nullptr;           // layout mask tiles [n_chunks * 1024]
    // ring of CUDA-event pairs recorded on the launching stream around every mutation_counts
@@ -140,6 +154,7 @@ struct silo_gpu_table {
 
 struct silo_gpu_filter {
    silo_gpu_table* table = nullptr;
+   // one stream-ordered allocation: [words | per-chunk popcounts | cardinality | error flag]
    uint64_t* d_words = nullptr;           // [n_chunks * 1024]
    uint32_t* d_chunk_popcount = nullptr;  // [n_chunks]
    unsigned long long* d_cardinality = nullptr;
@@ -197,6 +212,15 @@ T* deviceAlloc(size_t count, uint64_t* accounting = nullptr) {
    return static_cast<T*>(ptr);
 }
 
+// per-query scratch comes from the device's stream-ordered pool (cudaMallocAsync with an unlimited
+// release threshold, set in silo_gpu_init): after warm-up an allocation costs microseconds
+template <typename T>
+T* poolAlloc(size_t count, cudaStream_t stream) {
+   void* ptr = nullptr;
+   SILO_CUDA_CHECK(cudaMallocAsync(&ptr, (count == 0 ? 1 : count) * sizeof(T), stream));
+   return static_cast<T*>(ptr);
+}
+
 template <typename T>
 T* deviceUpload(const std::vector<T>& host, cudaStream_t stream, uint64_t* accounting = nullptr) {
    T* ptr = deviceAlloc<T>(host.size(), accounting);
@@ -228,16 +252,18 @@ __device__ __forceinline__ void mbarArrive(uint64_t* bar) {
 }
 
 __device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
+   // try_wait suspends the warp in hardware (up to the time hint) instead of burning issue slots
    asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
       "}\n" ::"r"(smemAddr(bar)),
-      "r"(parity)
+      "r"(parity),
+      "r"(0x989680u)
       : "memory"
    );
 }

@@ -43,6 +43,8 @@ struct EvalParams {
    const uint8_t* bitmap_payload;
    const uint32_t* chunk_sizes;
    uint32_t first_chunk;
+   uint32_t stack_depth;    // tiles the program needs at most
+   uint32_t has_threshold;  // whether the counter tile is needed
    uint32_t pad;
    uint64_t* out_words;
    uint32_t* out_popcount;
@@ -50,12 +52,27 @@ struct EvalParams {
    uint32_t* error_flag;
 };
 
-struct EvalShared {
-   uint64_t stack[STACK_DEPTH][TILE_WORDS];
-   uint32_t counters32[32768];  // 65536 x u16 per-row match counters (Threshold)
+// Dynamic shared memory of the interpreter: [small | stack_depth tiles | 128 KiB of counters if the
+// program holds a Threshold]. A boolean-only program needs 8 KiB per stack level, so several CTAs
+// share an SM; only Threshold programs take the whole SM.
+struct EvalSmall {
    uint32_t range[2];
    uint32_t reduce[EVAL_WARPS];
+   uint32_t pad[2];
 };
+constexpr size_t COUNTER_BYTES = 65536 * sizeof(uint16_t);
+
+struct EvalShared {
+   EvalSmall* small;
+   uint64_t (*stack)[TILE_WORDS];
+   uint32_t* counters32;  // 65536 x u16 per-row match counters (Threshold)
+   uint32_t* range;
+   uint32_t* reduce;
+};
+
+__host__ __device__ inline size_t evalSharedBytes(uint32_t stack_depth, bool has_threshold) {
+   return sizeof(EvalSmall) + static_cast<size_t>(stack_depth) * TILE_BYTES + (has_threshold ? COUNTER_BYTES : 0);
+}
 
 __device__ __forceinline__ void orBits32(uint32_t* tile32, uint32_t first, uint32_t last /*inclusive*/) {
    const uint32_t fw = first >> 5;
@@ -73,32 +90,40 @@ __device__ __forceinline__ void orBits32(uint32_t* tile32, uint32_t first, uint3
    atomicOr(&tile32[lw], tail);
 }
 
-// tile |= container (whole CTA). payload is the slab the descriptor's offset4 refers to.
+// tile |= piece (whole CTA). `slab` is the payload slab the descriptor's offset4 refers to. Pieces of
+// a column are <= 512 B; containers of a host bitmap come whole (arrays up to 4096 values, 1024-word
+// bitsets, any number of runs) and take the same code through the strided loops.
 __device__ void orContainerIntoTile(uint64_t* tile, const uint8_t* slab, const DevContainer& desc) {
    const uint8_t* payload = slab + (static_cast<size_t>(desc.offset4) << 2);
-   const uint32_t type = desc.type();
-   if (type == TYPE_BITSET) {
-      tile[threadIdx.x] |= reinterpret_cast<const uint64_t*>(payload)[threadIdx.x];
-   } else if (type == TYPE_ARRAY) {
+   const uint32_t kind = desc.type();
+   uint32_t* tile32 = reinterpret_cast<uint32_t*>(tile);
+   if (kind == KIND_BITSET) {
+      const uint64_t* words = reinterpret_cast<const uint64_t*>(payload);
+      const uint32_t first = desc.firstWord();
+      for (uint32_t w = threadIdx.x; w < desc.wordCount(); w += EVAL_THREADS) {
+         tile[first + w] |= words[w];  // callers separate pieces by __syncthreads, so no other writer
+      }
+   } else if (kind == KIND_ARRAY) {
       const uint16_t* values = reinterpret_cast<const uint16_t*>(payload);
-      uint32_t* tile32 = reinterpret_cast<uint32_t*>(tile);
       const uint32_t cardinality = desc.cardinality();
       for (uint32_t i = threadIdx.x; i < cardinality; i += EVAL_THREADS) {
          const uint32_t value = values[i];
          atomicOr(&tile32[value >> 5], 1u << (value & 31));
       }
-   } else {
+   } else if (kind == KIND_RUN) {
       const uint32_t* runs = reinterpret_cast<const uint32_t*>(payload);
-      uint32_t* tile32 = reinterpret_cast<uint32_t*>(tile);
       for (uint32_t i = threadIdx.x; i < desc.n_runs; i += EVAL_THREADS) {
          const uint32_t run = runs[i];
          const uint32_t first = run & 0xFFFFu;
          orBits32(tile32, first, first + (run >> 16));
       }
+   } else if (threadIdx.x < desc.cardinality()) {  // KIND_INLINE
+      const uint32_t value = (desc.n_runs >> (16 * threadIdx.x)) & 0xFFFFu;
+      atomicOr(&tile32[value >> 5], 1u << (value & 31));
    }
 }
 
-// counters[row] += delta for every row of the container (one warp). delta is +1 or -1 applied to a
+// counters[row] += delta for every row of the piece (one warp). delta is +1 or -1 applied to a
 // u16 lane of a packed u32; the host-chosen bias keeps every lane inside [0, 65535].
 __device__ void addContainerToCounters(
    uint32_t* counters32,
@@ -108,18 +133,18 @@ __device__ void addContainerToCounters(
    uint32_t lane
 ) {
    const uint8_t* payload = slab + (static_cast<size_t>(desc.offset4) << 2);
-   const uint32_t type = desc.type();
+   const uint32_t kind = desc.type();
    auto bump = [&](uint32_t row) {
       const uint32_t unit = 1u << ((row & 1u) << 4);
       atomicAdd(&counters32[row >> 1], subtract ? 0u - unit : unit);
    };
-   if (type == TYPE_ARRAY) {
+   if (kind == KIND_ARRAY) {
       const uint16_t* values = reinterpret_cast<const uint16_t*>(payload);
       const uint32_t cardinality = desc.cardinality();
       for (uint32_t i = lane; i < cardinality; i += 32) {
          bump(values[i]);
       }
-   } else if (type == TYPE_RUN) {
+   } else if (kind == KIND_RUN) {
       const uint32_t* runs = reinterpret_cast<const uint32_t*>(payload);
       for (uint32_t r = 0; r < desc.n_runs; ++r) {
          const uint32_t run = runs[r];
@@ -129,20 +154,23 @@ __device__ void addContainerToCounters(
             bump(row);
          }
       }
-   } else {
+   } else if (kind == KIND_BITSET) {
       const uint64_t* words = reinterpret_cast<const uint64_t*>(payload);
-      for (uint32_t w = lane; w < TILE_WORDS; w += 32) {
+      const uint32_t first = desc.firstWord();
+      for (uint32_t w = lane; w < desc.wordCount(); w += 32) {
          uint64_t word = words[w];
          while (word != 0) {
-            bump(w * 64 + static_cast<uint32_t>(__ffsll(static_cast<long long>(word)) - 1));
+            bump((first + w) * 64 + static_cast<uint32_t>(__ffsll(static_cast<long long>(word)) - 1));
             word &= word - 1;
          }
       }
+   } else if (lane < desc.cardinality()) {  // KIND_INLINE
+      bump((desc.n_runs >> (16 * lane)) & 0xFFFFu);
    }
 }
 
 // [lo, hi) = descriptors of `chunk` at `position` (thread 0 searches, result broadcast via smem)
-__device__ void findPositionRange(EvalShared& sh, const DevColumn& column, uint32_t chunk, uint32_t position) {
+__device__ void findPositionRange(const EvalShared& sh, const DevColumn& column, uint32_t chunk, uint32_t position) {
    if (threadIdx.x == 0) {
       uint32_t lo = column.chunk_desc_begin[chunk];
       uint32_t hi = column.chunk_desc_begin[chunk + 1];
@@ -193,9 +221,14 @@ __device__ __forceinline__ bool rowMissingAt(const DevColumn& column, uint32_t m
    return lo < column.missing_offsets[missing_index + 1] && column.missing_runs[lo].x <= position;
 }
 
-__global__ void __launch_bounds__(EVAL_THREADS, 1) evalProgramKernel(EvalParams p) {
+__global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams p) {
    extern __shared__ __align__(128) uint8_t smem_raw[];
-   EvalShared& sh = *reinterpret_cast<EvalShared*>(smem_raw);
+   EvalShared sh;
+   sh.small = reinterpret_cast<EvalSmall*>(smem_raw);
+   sh.stack = reinterpret_cast<uint64_t(*)[TILE_WORDS]>(smem_raw + sizeof(EvalSmall));
+   sh.counters32 = reinterpret_cast<uint32_t*>(smem_raw + sizeof(EvalSmall) + static_cast<size_t>(p.stack_depth) * TILE_BYTES);
+   sh.range = sh.small->range;
+   sh.reduce = sh.small->reduce;
    const uint32_t chunk = blockIdx.x;
    const uint32_t tid = threadIdx.x;
    const uint32_t lane = tid & 31;
@@ -564,6 +597,7 @@ void parseRoaring(const silo_roaring_bytes& bytes, ParsedBitmaps& out) {
          src = data + pos;
          pos += payload_bytes;
          type = TYPE_BITSET;
+         desc.n_runs = TILE_WORDS << 16;  // first word 0, all 1024 words
       }
       if (pos > size) {
          bad("truncated container payload");
@@ -577,7 +611,7 @@ void parseRoaring(const silo_roaring_bytes& bytes, ParsedBitmaps& out) {
    out.bitmaps.push_back(bitmap);
 }
 
-void validateProgram(const silo_gpu_table* table, const silo_filter_program* program) {
+void validateProgram(const silo_gpu_table* table, const silo_filter_program* program, uint32_t* max_depth_out, bool* has_threshold_out) {
    auto bad = [](const std::string& what) { throw ApiError(SILO_E_BAD_PROGRAM, "filter program: " + what); };
    if (program->struct_size != sizeof(silo_filter_program)) {
       bad("struct_size mismatch");
@@ -586,6 +620,8 @@ void validateProgram(const silo_gpu_table* table, const silo_filter_program* pro
       bad("empty program");
    }
    int depth = 0;
+   int max_depth = 1;
+   bool any_threshold = false;
    bool in_threshold = false;
    int threshold_base = 0;
    uint64_t adds = 0;
@@ -656,6 +692,7 @@ void validateProgram(const silo_gpu_table* table, const silo_filter_program* pro
                bad("nested thresholds are not supported by the shared-memory counter tile");
             }
             in_threshold = true;
+            any_threshold = true;
             threshold_base = depth;
             adds = 0;
             bias = ins.b & 0xFFFF;
@@ -716,10 +753,13 @@ void validateProgram(const silo_gpu_table* table, const silo_filter_program* pro
          default:
             bad("unknown opcode");
       }
+      max_depth = std::max(max_depth, depth);
       if (depth > STACK_DEPTH) {
          throw ApiError(SILO_E_UNSUPPORTED, "filter program needs a deeper tile stack than the kernel provides");
       }
    }
+   *max_depth_out = static_cast<uint32_t>(max_depth);
+   *has_threshold_out = any_threshold;
    if (in_threshold || depth != 1) {
       bad("program must leave exactly one tile on the stack");
    }
@@ -728,11 +768,36 @@ void validateProgram(const silo_gpu_table* table, const silo_filter_program* pro
 silo_gpu_filter* allocFilter(silo_gpu_table* table) {
    auto filter = std::make_unique<silo_gpu_filter>();
    filter->table = table;
-   filter->d_words = deviceAlloc<uint64_t>(static_cast<size_t>(table->n_chunks) * TILE_WORDS);
-   filter->d_chunk_popcount = deviceAlloc<uint32_t>(table->n_chunks);
-   filter->d_cardinality = deviceAlloc<unsigned long long>(1);
-   filter->d_error_flag = deviceAlloc<uint32_t>(1);
+   const size_t words_bytes = static_cast<size_t>(table->n_chunks) * TILE_BYTES;
+   const size_t popcount_bytes = (static_cast<size_t>(table->n_chunks) * sizeof(uint32_t) + 15) / 16 * 16;
+   uint8_t* base = poolAlloc<uint8_t>(words_bytes + popcount_bytes + 32, table->ctx->stream);
+   filter->d_words = reinterpret_cast<uint64_t*>(base);
+   filter->d_chunk_popcount = reinterpret_cast<uint32_t*>(base + words_bytes);
+   filter->d_cardinality = reinterpret_cast<unsigned long long*>(base + words_bytes + popcount_bytes);
+   filter->d_error_flag = reinterpret_cast<uint32_t*>(base + words_bytes + popcount_bytes + 16);
    return filter.release();
+}
+
+// stream-ordered free on the table's stream, ordered after whatever foreign stream used the memory last
+void poolFreeAfterUsers(silo_gpu_table* table, void* ptr) {
+   if (ptr == nullptr) {
+      return;
+   }
+   cudaStream_t stream = table->ctx->stream;
+   if (table->last_stream != nullptr && table->last_stream != stream) {
+      cudaEventRecord(table->ev_free_fence, table->last_stream);
+      cudaStreamWaitEvent(stream, table->ev_free_fence, 0);
+   }
+   cudaFreeAsync(ptr, stream);
+}
+
+// caller holds table->mutex
+void freeFilterLocked(silo_gpu_filter* filter) {
+   if (filter == nullptr) {
+      return;
+   }
+   poolFreeAfterUsers(filter->table, filter->d_words);
+   delete filter;
 }
 
 }  // namespace
@@ -748,11 +813,8 @@ void silo_gpu_filter_free(silo_gpu_filter* filter) {
       return;
    }
    cudaSetDevice(filter->table->ctx->device);
-   cudaFree(filter->d_words);
-   cudaFree(filter->d_chunk_popcount);
-   cudaFree(filter->d_cardinality);
-   cudaFree(filter->d_error_flag);
-   delete filter;
+   std::lock_guard<std::mutex> lock(filter->table->mutex);
+   freeFilterLocked(filter);
 }
 
 // staged program: everything the kernel reads, uploaded once
@@ -764,7 +826,9 @@ static void stageProgram(
    uint64_t* staged_bytes_out,
    EvalParams* params_out
 ) {
-   validateProgram(table, program);
+   uint32_t stack_depth = 1;
+   bool has_threshold = false;
+   validateProgram(table, program, &stack_depth, &has_threshold);
    ParsedBitmaps parsed;
    for (uint32_t i = 0; i < program->n_bitmaps; ++i) {
       parseRoaring(program->bitmaps[i], parsed);
@@ -793,21 +857,34 @@ static void stageProgram(
    const size_t off_blob = place(program->blob, program->blob_bytes);
    const size_t off_payload = place(parsed.payload.data(), parsed.payload.size());
 
-   uint8_t* d_staging = deviceAlloc<uint8_t>(staging.size() + 16);
+   uint8_t* d_staging = poolAlloc<uint8_t>(staging.size() + 16, stream);
    // patch the per-bitmap container pointers now that the device base is known
    for (size_t i = 0; i < parsed.bitmaps.size(); ++i) {
       auto* bitmap = reinterpret_cast<DevBitmap*>(staging.data() + off_bitmaps) + i;
       bitmap->containers =
          reinterpret_cast<const DevContainer*>(d_staging + off_bitmap_descs) + parsed.first_container[i];
    }
-   const cudaError_t status = cudaMemcpyAsync(d_staging, staging.data(), staging.size(), cudaMemcpyHostToDevice, stream);
-   if (status == cudaSuccess) {
-      // the source is pageable: the copy has been staged by the driver when the call returns, but
-      // be explicit before `staging` goes out of scope
-      cudaStreamSynchronize(stream);
+   // one H2D copy out of pinned memory; the pinned buffer is reused by the next call on this table,
+   // which is safe because every caller synchronises the stream before it returns
+   if (staging.size() > table->staging_capacity) {
+      if (table->h_staging_pinned != nullptr) {
+         cudaFreeHost(table->h_staging_pinned);
+         table->h_staging_pinned = nullptr;
+         table->staging_capacity = 0;
+      }
+      const size_t capacity = std::max<size_t>(staging.size() * 2, 1 << 20);
+      const cudaError_t pinned_status = cudaMallocHost(reinterpret_cast<void**>(&table->h_staging_pinned), capacity);
+      if (pinned_status != cudaSuccess) {
+         cudaFreeAsync(d_staging, stream);
+         throw ApiError(SILO_E_OUT_OF_MEMORY, std::string("pinned staging: ") + cudaGetErrorString(pinned_status));
+      }
+      table->staging_capacity = capacity;
    }
+   std::memcpy(table->h_staging_pinned, staging.data(), staging.size());
+   const cudaError_t status =
+      cudaMemcpyAsync(d_staging, table->h_staging_pinned, staging.size(), cudaMemcpyHostToDevice, stream);
    if (status != cudaSuccess) {
-      cudaFree(d_staging);
+      cudaFreeAsync(d_staging, stream);
       throw ApiError(SILO_E_CUDA, std::string("program upload failed: ") + cudaGetErrorString(status));
    }
    EvalParams params{};
@@ -820,6 +897,8 @@ static void stageProgram(
    params.bitmap_payload = d_staging + off_payload;
    params.chunk_sizes = table->d_chunk_sizes;
    params.first_chunk = table->first_chunk;
+   params.stack_depth = stack_depth;
+   params.has_threshold = has_threshold ? 1u : 0u;
    *d_staging_out = d_staging;
    *staged_bytes_out = staging.size();
    *params_out = params;
@@ -838,11 +917,13 @@ static void launchProgram(silo_gpu_table* table, EvalParams params, silo_gpu_fil
    static bool attribute_set = false;
    if (!attribute_set) {
       SILO_CUDA_CHECK(cudaFuncSetAttribute(
-         evalProgramKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(EvalShared))
+         evalProgramKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+         static_cast<int>(evalSharedBytes(STACK_DEPTH, true))
       ));
       attribute_set = true;
    }
-   evalProgramKernel<<<table->n_chunks, EVAL_THREADS, sizeof(EvalShared), stream>>>(params);
+   const size_t shared_bytes = evalSharedBytes(params.stack_depth, params.has_threshold != 0);
+   evalProgramKernel<<<table->n_chunks, EVAL_THREADS, shared_bytes, stream>>>(params);
    SILO_CUDA_CHECK(cudaGetLastError());
    table->stats.kernel_launches++;
 }
@@ -874,7 +955,7 @@ int silo_gpu_filter_eval(
       uint64_t staged_bytes = 0;
       EvalParams params{};
       stageProgram(table, program, stream, &d_staging, &staged_bytes, &params);
-      std::unique_ptr<silo_gpu_filter, void (*)(silo_gpu_filter*)> filter(nullptr, silo_gpu_filter_free);
+      std::unique_ptr<silo_gpu_filter, void (*)(silo_gpu_filter*)> filter(nullptr, freeFilterLocked);
       try {
          filter.reset(allocFilter(table));
          launchProgram(table, params, filter.get(), stream);
@@ -882,9 +963,9 @@ int silo_gpu_filter_eval(
          uint32_t host_error = 0;
          SILO_CUDA_CHECK(cudaMemcpyAsync(&host_cardinality, filter->d_cardinality, sizeof(host_cardinality), cudaMemcpyDeviceToHost, stream));
          SILO_CUDA_CHECK(cudaMemcpyAsync(&host_error, filter->d_error_flag, sizeof(host_error), cudaMemcpyDeviceToHost, stream));
-         SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
-         cudaFree(d_staging);
+         SILO_CUDA_CHECK(cudaFreeAsync(d_staging, stream));
          d_staging = nullptr;
+         SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
          if (host_error != 0) {
             throw ApiError(SILO_E_OUT_OF_LAYOUT, "a leaf bitmap holds row ids outside the row layout");
          }
@@ -892,7 +973,10 @@ int silo_gpu_filter_eval(
             *cardinality = host_cardinality;
          }
       } catch (...) {
-         cudaFree(d_staging);
+         if (d_staging != nullptr) {
+            cudaFreeAsync(d_staging, stream);
+         }
+         cudaStreamSynchronize(stream);
          throw;
       }
       *out = filter.release();
@@ -911,8 +995,10 @@ int silo_gpu_program_prepare(silo_gpu_table* table, const silo_filter_program* p
       try {
          prepared->params = new EvalParams(params);
          prepared->filter = allocFilter(table);
+         SILO_CUDA_CHECK(cudaStreamSynchronize(table->ctx->stream));  // the upload left pinned memory
       } catch (...) {
-         cudaFree(prepared->d_staging);
+         cudaFreeAsync(prepared->d_staging, table->ctx->stream);
+         cudaStreamSynchronize(table->ctx->stream);
          delete prepared->params;
          throw;
       }
@@ -941,7 +1027,10 @@ void silo_gpu_program_free(silo_gpu_program* prepared) {
       return;
    }
    cudaSetDevice(prepared->table->ctx->device);
-   cudaFree(prepared->d_staging);
+   {
+      std::lock_guard<std::mutex> lock(prepared->table->mutex);
+      poolFreeAfterUsers(prepared->table, prepared->d_staging);
+   }
    delete prepared->params;
    delete prepared;
 }
@@ -962,7 +1051,7 @@ int silo_gpu_filter_from_words(silo_gpu_table* table, const uint64_t* words, sil
             }
          }
       }
-      std::unique_ptr<silo_gpu_filter, void (*)(silo_gpu_filter*)> filter(allocFilter(table), silo_gpu_filter_free);
+      std::unique_ptr<silo_gpu_filter, void (*)(silo_gpu_filter*)> filter(allocFilter(table), freeFilterLocked);
       SILO_CUDA_CHECK(cudaMemsetAsync(filter->d_cardinality, 0, sizeof(unsigned long long), stream));
       if (table->n_chunks > 0) {
          SILO_CUDA_CHECK(cudaMemcpyAsync(

@@ -69,26 +69,53 @@ __global__ void buildWorkListKernel(
    }
    if (threadIdx.x == 0) {
       work_prefix[n_chunks] = carry;
+      work_prefix[n_chunks + 1] = 0;  // the grid-wide claim counter of containerAndCountKernel
+   }
+}
+
+// work_items[work_prefix[c] + i] = global index of the i-th segment of active chunk c
+__global__ void fillWorkItemsKernel(
+   const uint32_t* __restrict__ chunk_popcount,
+   const uint32_t* __restrict__ chunk_seg_begin,
+   const uint32_t* __restrict__ work_prefix,
+   uint32_t* __restrict__ work_items
+) {
+   const uint32_t chunk = blockIdx.x;
+   if (chunk_popcount[chunk] == 0) {
+      return;
+   }
+   const uint32_t first = chunk_seg_begin[chunk];
+   const uint32_t count = chunk_seg_begin[chunk + 1] - first;
+   const uint32_t out = work_prefix[chunk];
+   for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
+      work_items[out + i] = first + i;
    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // K1: fused container AND filter-tile + popcount
+//
+// Persistent CTAs (2 per SM). Warp 0 is the producer: it claims batches of work items (segments)
+// from a grid-wide counter and streams each segment's descriptors and payload into a ring of
+// shared-memory stages with two 1-D bulk (TMA) copies that complete on an mbarrier. The 16 consumer
+// warps take one piece (<= 1 KiB of payload) each, AND it with the chunk's filter tile held in
+// shared memory, and issue one RED per piece with a non-zero count.
 // ---------------------------------------------------------------------------------------------
 
-constexpr int K1_STAGES = 4;
+constexpr int K1_STAGES = 5;
 constexpr int K1_CONSUMER_WARPS = 16;
-constexpr int K1_THREADS = (K1_CONSUMER_WARPS + 1) * 32;  // warp 0 = bulk-copy producer
+constexpr int K1_CONSUMER_THREADS = K1_CONSUMER_WARPS * 32;
+constexpr int K1_THREADS = K1_CONSUMER_THREADS + 32;  // warp 0 = bulk-copy producer
+constexpr uint32_t K1_BATCH = 8;                       // work items claimed per atomicAdd
+constexpr uint32_t K1_STOP = 0xFFFFFFFFu;              // meta_desc_count marker: no more work
+constexpr uint32_t TILE32_WORDS = 2 * TILE_WORDS;
 
 struct __align__(16) K1Stage {
    uint8_t payload[SEG_PAYLOAD_BYTES];
    DevContainer descs[SEG_MAX_DESCS];
 };
 
-struct __align__(16) K1Shared {
-   uint64_t tile[TILE_WORDS];       // dense filter tile of the current chunk
-   uint16_t rank[TILE_WORDS];       // exclusive popcount prefix per 64-bit word (run containers)
-   uint32_t warp_sums[K1_CONSUMER_WARPS];
+struct __align__(16) K1Dynamic {
    K1Stage stages[K1_STAGES];
    uint64_t full_bar[K1_STAGES];
    uint64_t empty_bar[K1_STAGES];
@@ -96,66 +123,89 @@ struct __align__(16) K1Shared {
    uint32_t meta_desc_count[K1_STAGES];
    uint32_t meta_base4[K1_STAGES];  // slab offset (4-byte units) of the stage's payload[0]
    uint32_t meta_new_tile[K1_STAGES];
-   uint32_t next_container[K1_STAGES];  // dynamic container scheduling inside a stage
+   uint32_t warp_sums[K1_CONSUMER_WARPS];
 };
 
 __device__ __forceinline__ uint32_t warpSum(uint32_t value) {
    return __reduce_add_sync(0xFFFFFFFFu, value);
 }
 
-// |container AND tile| for one container whose payload sits in shared memory; whole warp cooperates.
-__device__ __forceinline__ uint32_t andCardinality(
+__device__ __forceinline__ uint32_t lowMask(uint32_t bits) {  // (1 << bits) - 1 for bits in [0, 31]
+   uint32_t mask;
+   asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(mask) : "r"(bits));
+   return mask;
+}
+
+// number of filter rows below `row` (row in [0, 65536]): exclusive rank from the per-32-bit-word
+// prefix table plus the bits below `row` inside its word. tile32[2048] is a zero pad word.
+__device__ __forceinline__ uint32_t rankBelow(const uint32_t* tile32, const uint32_t* rank32, uint32_t row) {
+   const uint32_t word = row >> 5;
+   return rank32[word] + __popc(tile32[word] & lowMask(row & 31u));
+}
+
+template <bool CHECKED>
+__device__ __forceinline__ uint32_t arrayVector(const uint32_t* tile32, uint4 eight, uint32_t valid) {
+   const uint32_t words[4] = {eight.x, eight.y, eight.z, eight.w};
+   uint32_t total = 0;
+#pragma unroll
+   for (uint32_t k = 0; k < 4; ++k) {
+      const uint32_t lo = words[k] & 0xFFFFu;
+      const uint32_t hi = words[k] >> 16;
+      const uint32_t lo_bit = (tile32[lo >> 5] >> (lo & 31u)) & 1u;
+      const uint32_t hi_bit = (tile32[hi >> 5] >> (hi & 31u)) & 1u;
+      if (CHECKED) {
+         total += (2 * k < valid ? lo_bit : 0u) + (2 * k + 1 < valid ? hi_bit : 0u);
+      } else {
+         total += lo_bit + hi_bit;
+      }
+   }
+   return total;
+}
+
+// |piece AND tile| for one piece (16-byte aligned payload in shared memory): every lane takes whole
+// 128-bit vectors of the payload (8 array values / 4 runs / 2 bitset words).
+__device__ __forceinline__ uint32_t pieceAndCardinality(
    const DevContainer& desc,
-   const uint8_t* payload,  // shared
-   const uint64_t* tile,    // shared
-   const uint16_t* rank,    // shared
+   const uint8_t* payload,    // shared
+   const uint32_t* tile32,    // shared, 2049 words
+   const uint32_t* rank32,    // shared, 2049 words
    uint32_t lane
 ) {
-   const uint32_t type = desc.type();
+   const uint32_t kind = desc.type();
+   const uint4* vectors = reinterpret_cast<const uint4*>(payload);
    uint32_t local = 0;
-   if (type == TYPE_ARRAY) {
+   if (kind == KIND_ARRAY) {
       const uint32_t cardinality = desc.cardinality();
-      const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
-      const uint32_t* pairs = reinterpret_cast<const uint32_t*>(payload);
-      const uint32_t n_pairs = cardinality >> 1;
-      for (uint32_t i = lane; i < n_pairs; i += 32) {
-         const uint32_t two = pairs[i];
-         const uint32_t lo = two & 0xFFFFu;
-         const uint32_t hi = two >> 16;
-         local += (tile32[lo >> 5] >> (lo & 31)) & 1u;
-         local += (tile32[hi >> 5] >> (hi & 31)) & 1u;
+      const uint32_t full_vectors = cardinality >> 3;
+      for (uint32_t v = lane; v < full_vectors; v += 32) {
+         local += arrayVector<false>(tile32, vectors[v], 8);
       }
-      if ((cardinality & 1u) != 0 && lane == 0) {
-         const uint32_t last = reinterpret_cast<const uint16_t*>(payload)[cardinality - 1];
-         local += (tile32[last >> 5] >> (last & 31)) & 1u;
+      const uint32_t rest = cardinality & 7u;
+      if (rest != 0 && lane == (full_vectors & 31u)) {
+         local += arrayVector<true>(tile32, vectors[full_vectors], rest);
       }
-   } else if (type == TYPE_RUN) {
+   } else if (kind == KIND_RUN) {
+      const uint32_t n_runs = desc.n_runs;
       const uint32_t* runs = reinterpret_cast<const uint32_t*>(payload);
-      for (uint32_t i = lane; i < desc.n_runs; i += 32) {
-         const uint32_t run = runs[i];
+      // one run per lane and iteration: branch-free rank difference
+      for (uint32_t r = lane; r < n_runs; r += 32) {
+         const uint32_t run = runs[r];
          const uint32_t first = run & 0xFFFFu;
-         const uint32_t last = first + (run >> 16);  // inclusive
-         const uint32_t fw = first >> 6;
-         const uint32_t lw = last >> 6;
-         const uint64_t head = ~0ULL << (first & 63);
-         const uint64_t tail = ~0ULL >> (63 - (last & 63));
-         if (fw == lw) {
-            local += __popcll(tile[fw] & head & tail);
-         } else {
-            // rows of the words strictly between come from the rank table
-            local += __popcll(tile[fw] & head) + __popcll(tile[lw] & tail) +
-                     (static_cast<uint32_t>(rank[lw]) - static_cast<uint32_t>(rank[fw]) -
-                      static_cast<uint32_t>(__popcll(tile[fw])));
-         }
+         const uint32_t end = first + (run >> 16) + 1;  // exclusive, <= 65536
+         local += rankBelow(tile32, rank32, end) - rankBelow(tile32, rank32, first);
       }
-   } else {
-      const uint4* words = reinterpret_cast<const uint4*>(payload);
-      const uint4* tile4 = reinterpret_cast<const uint4*>(tile);
-#pragma unroll 4
-      for (uint32_t i = lane; i < TILE_WORDS / 2; i += 32) {
-         const uint4 a = words[i];
-         const uint4 b = tile4[i];
+   } else if (kind == KIND_BITSET) {
+      const uint4* tile4 = reinterpret_cast<const uint4*>(tile32 + 2 * desc.firstWord());
+      const uint32_t n_vectors = desc.wordCount() >> 1;
+      for (uint32_t v = lane; v < n_vectors; v += 32) {
+         const uint4 a = vectors[v];
+         const uint4 b = tile4[v];
          local += __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
+      }
+   } else {  // KIND_INLINE: one or two values inside the descriptor
+      if (lane < desc.cardinality()) {
+         const uint32_t value = (desc.n_runs >> (16 * lane)) & 0xFFFFu;
+         local = (tile32[value >> 5] >> (value & 31u)) & 1u;
       }
    }
    return warpSum(local);
@@ -164,21 +214,21 @@ __device__ __forceinline__ uint32_t andCardinality(
 __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
    DevColumn column,
    const uint64_t* __restrict__ filter_words,   // [n_chunks * 1024]
-   const uint32_t* __restrict__ work_prefix,    // [n_chunks + 1]
+   const uint32_t* __restrict__ work_prefix,    // [n_chunks + 2]; [n_chunks] = number of work items
+   uint32_t* __restrict__ work_counter,         // grid-wide claim counter (zeroed by buildWorkListKernel)
+   const uint32_t* __restrict__ work_items,     // segment index per work item
    uint32_t* __restrict__ counts                // [n_symbols * genome_length]
 ) {
+   // the filter tile and its rank table sit in STATIC shared memory: fixed addresses let the
+   // compiler fold them into the LDS immediates of the bit tests
+   __shared__ __align__(16) uint32_t tile32[TILE32_WORDS + 4];  // [2048] = zero pad word
+   __shared__ __align__(16) uint32_t rank32[TILE32_WORDS + 4];  // exclusive prefix; [2048] = total
    extern __shared__ __align__(128) uint8_t smem_raw[];
-   K1Shared& sh = *reinterpret_cast<K1Shared*>(smem_raw);
+   K1Dynamic& sh = *reinterpret_cast<K1Dynamic*>(smem_raw);
 
    const uint32_t warp = threadIdx.x >> 5;
    const uint32_t lane = threadIdx.x & 31;
    const uint32_t total = work_prefix[column.n_chunks];
-   // contiguous, balanced slice of the work list for this CTA
-   const uint32_t begin = static_cast<uint32_t>(static_cast<uint64_t>(total) * blockIdx.x / gridDim.x);
-   const uint32_t end = static_cast<uint32_t>(static_cast<uint64_t>(total) * (blockIdx.x + 1) / gridDim.x);
-   if (begin >= end) {
-      return;
-   }
 
    if (threadIdx.x == 0) {
       for (int s = 0; s < K1_STAGES; ++s) {
@@ -187,78 +237,111 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
       }
       fenceBarrierInit();
    }
+   if (threadIdx.x < 4) {
+      tile32[TILE32_WORDS + threadIdx.x] = 0;
+   }
    __syncthreads();
 
    if (warp == 0) {
-      // ---------------- producer: one elected lane streams segments with bulk copies --------------
+      // ---------------- producer warp -----------------------------------------------------------
+      // Lanes 0..K1_BATCH-1 fetch the segment descriptors of the NEXT claimed batch while lane 0
+      // issues the current one, so no global-memory latency sits between two bulk copies.
+      auto claim = [&]() -> uint32_t {
+         uint32_t first = 0;
+         if (lane == 0) {
+            first = atomicAdd(work_counter, K1_BATCH);
+         }
+         return __shfl_sync(0xFFFFFFFFu, first, 0);
+      };
+      auto fetch = [&](uint32_t first) -> DevSegment {
+         DevSegment segment{};
+         if (lane < K1_BATCH && first + lane < total) {
+            segment = column.segments[work_items[first + lane]];
+         }
+         return segment;
+      };
+      uint32_t current_tile_chunk = 0xFFFFFFFFu;
+      uint32_t it = 0;  // stages issued so far by this CTA
+      uint32_t batch_first = claim();
+      DevSegment upcoming = fetch(batch_first);
+      while (batch_first < total) {
+         const DevSegment mine = upcoming;
+         const uint32_t batch = min(K1_BATCH, total - batch_first);
+         batch_first = claim();
+         upcoming = fetch(batch_first);
+         for (uint32_t j = 0; j < batch; ++j) {
+            const uint32_t offset_lo = __shfl_sync(0xFFFFFFFFu, static_cast<uint32_t>(mine.payload_offset), j);
+            const uint32_t offset_hi = __shfl_sync(0xFFFFFFFFu, static_cast<uint32_t>(mine.payload_offset >> 32), j);
+            const uint32_t payload_bytes = __shfl_sync(0xFFFFFFFFu, mine.payload_bytes, j);
+            const uint32_t desc_begin = __shfl_sync(0xFFFFFFFFu, mine.desc_begin, j);
+            const uint32_t desc_count = __shfl_sync(0xFFFFFFFFu, mine.desc_count, j);
+            const uint32_t chunk = __shfl_sync(0xFFFFFFFFu, mine.chunk, j);
+            if (lane == 0) {
+               const uint64_t payload_offset = (static_cast<uint64_t>(offset_hi) << 32) | offset_lo;
+               const uint32_t stage = it % K1_STAGES;
+               const uint32_t round = it / K1_STAGES;
+               const bool new_tile = chunk != current_tile_chunk;
+               if (new_tile) {
+                  // the single filter tile is shared by all stages: drain the pipeline before replacing it
+                  for (uint32_t back = 1; back < K1_STAGES && back <= it; ++back) {
+                     const uint32_t prev = it - back;
+                     mbarWait(&sh.empty_bar[prev % K1_STAGES], (prev / K1_STAGES) & 1u);
+                  }
+                  current_tile_chunk = chunk;
+               }
+               if (round > 0) {
+                  mbarWait(&sh.empty_bar[stage], (round - 1) & 1u);
+               }
+               sh.meta_desc_count[stage] = desc_count;
+               sh.meta_base4[stage] = static_cast<uint32_t>(payload_offset >> 2);
+               sh.meta_new_tile[stage] = new_tile ? 1u : 0u;
+               const uint32_t desc_bytes = desc_count * static_cast<uint32_t>(sizeof(DevContainer));
+               mbarExpectTx(&sh.full_bar[stage], desc_bytes + payload_bytes + (new_tile ? TILE_BYTES : 0u));
+               if (new_tile) {
+                  bulkLoad(tile32, filter_words + static_cast<size_t>(chunk) * TILE_WORDS, TILE_BYTES, &sh.full_bar[stage]);
+               }
+               bulkLoad(sh.stages[stage].descs, column.containers + desc_begin, desc_bytes, &sh.full_bar[stage]);
+               if (payload_bytes != 0) {
+                  bulkLoad(sh.stages[stage].payload, column.payload + payload_offset, payload_bytes, &sh.full_bar[stage]);
+               }
+            }
+            ++it;
+            __syncwarp();
+         }
+      }
       if (lane == 0) {
-         uint32_t chunk = 0;
-         // locate the chunk of the first work item
-         {
-            uint32_t lo = 0;
-            uint32_t hi = column.n_chunks;  // work_prefix[lo] <= begin < work_prefix[hi]
-            while (hi - lo > 1) {
-               const uint32_t mid = (lo + hi) >> 1;
-               if (work_prefix[mid] <= begin) {
-                  lo = mid;
-               } else {
-                  hi = mid;
-               }
-            }
-            chunk = lo;
+         // tell the consumers that nothing follows
+         const uint32_t stage = it % K1_STAGES;
+         const uint32_t round = it / K1_STAGES;
+         if (round > 0) {
+            mbarWait(&sh.empty_bar[stage], (round - 1) & 1u);
          }
-         uint32_t current_tile_chunk = 0xFFFFFFFFu;
-         for (uint32_t item = begin; item < end; ++item) {
-            while (work_prefix[chunk + 1] <= item) {
-               ++chunk;
-            }
-            const uint32_t it = item - begin;
-            const uint32_t stage = it % K1_STAGES;
-            const uint32_t round = it / K1_STAGES;
-            const bool new_tile = chunk != current_tile_chunk;
-            if (new_tile) {
-               // the single filter tile is shared by all stages: drain the pipeline before replacing it
-               for (uint32_t back = 1; back < K1_STAGES && back <= it; ++back) {
-                  const uint32_t prev = it - back;
-                  mbarWait(&sh.empty_bar[prev % K1_STAGES], (prev / K1_STAGES) & 1u);
-               }
-               current_tile_chunk = chunk;
-            }
-            if (round > 0) {
-               mbarWait(&sh.empty_bar[stage], (round - 1) & 1u);
-            }
-            const DevSegment segment = column.segments[column.chunk_seg_begin[chunk] + (item - work_prefix[chunk])];
-            sh.meta_desc_count[stage] = segment.desc_count;
-            sh.meta_base4[stage] = static_cast<uint32_t>(segment.payload_offset >> 2);
-            sh.meta_new_tile[stage] = new_tile ? 1u : 0u;
-            sh.next_container[stage] = 0;
-            const uint32_t desc_bytes = segment.desc_count * static_cast<uint32_t>(sizeof(DevContainer));
-            mbarExpectTx(
-               &sh.full_bar[stage], desc_bytes + segment.payload_bytes + (new_tile ? TILE_BYTES : 0u)
-            );
-            if (new_tile) {
-               bulkLoad(sh.tile, filter_words + static_cast<size_t>(chunk) * TILE_WORDS, TILE_BYTES, &sh.full_bar[stage]);
-            }
-            bulkLoad(sh.stages[stage].descs, column.containers + segment.desc_begin, desc_bytes, &sh.full_bar[stage]);
-            bulkLoad(sh.stages[stage].payload, column.payload + segment.payload_offset, segment.payload_bytes, &sh.full_bar[stage]);
-         }
+         sh.meta_desc_count[stage] = K1_STOP;
+         mbarArrive(&sh.full_bar[stage]);
       }
       return;
    }
 
-   // ---------------- consumers: 16 warps, one container per warp at a time ----------------------
+   // ---------------- consumers: 16 warps, one piece per warp at a time ---------------------------
    const uint32_t cwarp = warp - 1;
    const uint32_t cthread = threadIdx.x - 32;  // 0..511
    const uint32_t genome_length = column.genome_length;
-   for (uint32_t item = begin; item < end; ++item) {
-      const uint32_t it = item - begin;
+   for (uint32_t it = 0;; ++it) {
       const uint32_t stage = it % K1_STAGES;
       mbarWait(&sh.full_bar[stage], (it / K1_STAGES) & 1u);
+      const uint32_t desc_count = sh.meta_desc_count[stage];
+      if (desc_count == K1_STOP) {
+         break;
+      }
       if (sh.meta_new_tile[stage] != 0) {
-         // rebuild the per-word exclusive rank table of the freshly loaded tile (512 threads x 2 words)
-         const uint32_t p0 = __popcll(sh.tile[2 * cthread]);
-         const uint32_t p1 = __popcll(sh.tile[2 * cthread + 1]);
-         uint32_t inclusive = p0 + p1;
+         // rebuild the exclusive rank table of the freshly loaded tile: 512 threads x 4 words
+         const uint4 four = reinterpret_cast<const uint4*>(tile32)[cthread];
+         const uint32_t p0 = __popc(four.x);
+         const uint32_t p1 = __popc(four.y);
+         const uint32_t p2 = __popc(four.z);
+         const uint32_t p3 = __popc(four.w);
+         const uint32_t mine = p0 + p1 + p2 + p3;
+         uint32_t inclusive = mine;
          for (int offset = 1; offset < 32; offset <<= 1) {
             const uint32_t other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
             if (lane >= static_cast<uint32_t>(offset)) {
@@ -268,31 +351,23 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
          if (lane == 31) {
             sh.warp_sums[cwarp] = inclusive;
          }
-         asm volatile("bar.sync 1, %0;" ::"n"(K1_CONSUMER_WARPS * 32) : "memory");
-         uint32_t warp_offset = 0;
+         asm volatile("bar.sync 1, %0;" ::"n"(K1_CONSUMER_THREADS) : "memory");
+         uint32_t exclusive = inclusive - mine;
          for (uint32_t w = 0; w < cwarp; ++w) {
-            warp_offset += sh.warp_sums[w];
+            exclusive += sh.warp_sums[w];
          }
-         const uint32_t exclusive = warp_offset + inclusive - (p0 + p1);
-         sh.rank[2 * cthread] = static_cast<uint16_t>(exclusive);
-         sh.rank[2 * cthread + 1] = static_cast<uint16_t>(exclusive + p0);
-         asm volatile("bar.sync 1, %0;" ::"n"(K1_CONSUMER_WARPS * 32) : "memory");
+         reinterpret_cast<uint4*>(rank32)[cthread] = make_uint4(exclusive, exclusive + p0, exclusive + p0 + p1, exclusive + p0 + p1 + p2);
+         if (cthread == K1_CONSUMER_THREADS - 1) {
+            rank32[TILE32_WORDS] = exclusive + mine;
+         }
+         asm volatile("bar.sync 1, %0;" ::"n"(K1_CONSUMER_THREADS) : "memory");
       }
-      const uint32_t desc_count = sh.meta_desc_count[stage];
       const uint32_t base4 = sh.meta_base4[stage];
       const K1Stage& st = sh.stages[stage];
-      while (true) {
-         uint32_t index = 0;
-         if (lane == 0) {
-            index = atomicAdd(&sh.next_container[stage], 1u);
-         }
-         index = __shfl_sync(0xFFFFFFFFu, index, 0);
-         if (index >= desc_count) {
-            break;
-         }
+      for (uint32_t index = cwarp; index < desc_count; index += K1_CONSUMER_WARPS) {
          const DevContainer desc = st.descs[index];
          const uint8_t* payload = st.payload + (static_cast<size_t>(desc.offset4 - base4) << 2);
-         const uint32_t count = andCardinality(desc, payload, sh.tile, sh.rank, lane);
+         const uint32_t count = pieceAndCardinality(desc, payload, tile32, rank32, lane);
          if (lane == 0 && count != 0) {
             atomicAdd(&counts[desc.symbol() * genome_length + desc.position], count);
          }
@@ -321,7 +396,7 @@ __global__ void containerCardinalityKernel(DevColumn column, uint32_t* __restric
 // ---------------------------------------------------------------------------------------------
 
 constexpr int K6_THREADS = 256;
-constexpr int K6_SLICES = 4;  // CTAs per chunk
+constexpr int K6_SLICES = 16;  // CTAs per chunk
 
 struct PendingAdd {
    uint32_t key;
@@ -429,49 +504,70 @@ __global__ void __launch_bounds__(K6_THREADS) coverageDiffKernel(
 // finalize: covered(p) = prefix sum of diff; counts[local_ref[p]][p] = covered(p) - sum(others)
 // ---------------------------------------------------------------------------------------------
 
-constexpr int FIN_THREADS = 1024;
+// covered(p) = prefix sum of the coverage difference array; counts[local_ref[p]][p] = covered(p) -
+// sum of the other symbols' counts. One thread per position; every CTA first sums the (L2-resident)
+// difference array in front of its block instead of waiting for a separate scan kernel.
+constexpr int FIN_THREADS = 256;
 
 __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    DevColumn column,
    const uint32_t* __restrict__ diff,
    uint32_t* __restrict__ counts
 ) {
-   __shared__ uint32_t warp_totals[32];
+   __shared__ uint32_t warp_totals[FIN_THREADS / 32];
+   __shared__ uint32_t block_offset;
    const uint32_t genome_length = column.genome_length;
-   const uint32_t per_thread = (genome_length + FIN_THREADS - 1) / FIN_THREADS;
-   const uint32_t first = threadIdx.x * per_thread;
-   const uint32_t last = min(first + per_thread, genome_length);
-   uint32_t local = 0;
-   for (uint32_t p = first; p < last; ++p) {
-      local += diff[p];
-   }
-   uint32_t inclusive = local;
+   const uint32_t block_first = blockIdx.x * FIN_THREADS;
    const uint32_t lane = threadIdx.x & 31;
+   const uint32_t warp = threadIdx.x >> 5;
+   // sum of diff[0, block_first)
+   uint32_t partial = 0;
+   for (uint32_t i = threadIdx.x; i < block_first; i += FIN_THREADS) {
+      partial += diff[i];
+   }
+   partial = __reduce_add_sync(0xFFFFFFFFu, partial);
+   if (lane == 0) {
+      warp_totals[warp] = partial;
+   }
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      uint32_t total = 0;
+      for (uint32_t w = 0; w < FIN_THREADS / 32; ++w) {
+         total += warp_totals[w];
+      }
+      block_offset = total;
+   }
+   __syncthreads();
+   // inclusive scan of this block's 256 elements
+   const uint32_t p = block_first + threadIdx.x;
+   const uint32_t mine = p < genome_length ? diff[p] : 0u;
+   uint32_t inclusive = mine;
    for (int offset = 1; offset < 32; offset <<= 1) {
       const uint32_t other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
       if (lane >= static_cast<uint32_t>(offset)) {
          inclusive += other;
       }
    }
+   __syncthreads();
    if (lane == 31) {
-      warp_totals[threadIdx.x >> 5] = inclusive;
+      warp_totals[warp] = inclusive;
    }
    __syncthreads();
-   uint32_t running = inclusive - local;
-   for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) {
-      running += warp_totals[w];
+   uint32_t covered = block_offset + inclusive;
+   for (uint32_t w = 0; w < warp; ++w) {
+      covered += warp_totals[w];
    }
-   for (uint32_t p = first; p < last; ++p) {
-      running += diff[p];  // rows of the filter that cover position p
-      const uint32_t reference_symbol = column.local_reference[p];
-      uint32_t others = 0;
-      for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
-         if (symbol != reference_symbol) {
-            others += counts[symbol * genome_length + p];
-         }
+   if (p >= genome_length) {
+      return;
+   }
+   const uint32_t reference_symbol = column.local_reference[p];
+   uint32_t others = 0;
+   for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
+      if (symbol != reference_symbol) {
+         others += counts[symbol * genome_length + p];
       }
-      counts[reference_symbol * genome_length + p] = running - others;
    }
+   counts[reference_symbol * genome_length + p] = covered - others;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -526,18 +622,24 @@ void enqueueMutationCounts(
    } else {
       buildWorkListKernel<<<1, 1024, 0, stream>>>(popcounts, column.chunk_seg_begin, n_chunks, table->d_work_prefix);
       SILO_CUDA_CHECK(cudaGetLastError());
-      table->stats.kernel_launches++;
+      fillWorkItemsKernel<<<n_chunks, 128, 0, stream>>>(
+         popcounts, column.chunk_seg_begin, table->d_work_prefix, table->d_work_items
+      );
+      SILO_CUDA_CHECK(cudaGetLastError());
+      table->stats.kernel_launches += 2;
       SILO_CUDA_CHECK(cudaEventRecord(ev_k1_begin, stream));
       if (column.n_segments > 0) {
          static bool attribute_set = false;
          if (!attribute_set) {
             SILO_CUDA_CHECK(cudaFuncSetAttribute(
-               containerAndCountKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Shared))
+               containerAndCountKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))
             ));
             attribute_set = true;
          }
          const int blocks = static_cast<int>(std::min<uint32_t>(column.n_segments, static_cast<uint32_t>(table->ctx->sm_count) * 2));
-         containerAndCountKernel<<<blocks, K1_THREADS, sizeof(K1Shared), stream>>>(column, words, table->d_work_prefix, d_counts);
+         containerAndCountKernel<<<blocks, K1_THREADS, sizeof(K1Dynamic), stream>>>(
+            column, words, table->d_work_prefix, table->d_work_prefix + n_chunks + 1, table->d_work_items, d_counts
+         );
          SILO_CUDA_CHECK(cudaGetLastError());
          table->stats.kernel_launches++;
       }
@@ -547,7 +649,9 @@ void enqueueMutationCounts(
       column, words, popcounts, table->d_chunk_sizes, table->d_coverage_diff
    );
    SILO_CUDA_CHECK(cudaGetLastError());
-   finalizeCountsKernel<<<1, FIN_THREADS, 0, stream>>>(column, table->d_coverage_diff, d_counts);
+   finalizeCountsKernel<<<(column.genome_length + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, stream>>>(
+      column, table->d_coverage_diff, d_counts
+   );
    SILO_CUDA_CHECK(cudaGetLastError());
    table->stats.kernel_launches += 2;
    SILO_CUDA_CHECK(cudaEventRecord(ev_end, stream));

@@ -76,6 +76,10 @@ int silo_gpu_init(int device_ordinal, silo_gpu_ctx** out) {
             std::string("device '") + prop.name + "' is not sm_100-class; this library ships sm_100a code only"
          );
       }
+      cudaMemPool_t pool = nullptr;
+      SILO_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device_ordinal));
+      uint64_t keep_everything = UINT64_MAX;
+      SILO_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_everything));
       auto ctx = std::make_unique<silo_gpu_ctx>();
       ctx->device = device_ordinal;
       ctx->sm_count = prop.multiProcessorCount;
@@ -133,6 +137,7 @@ int silo_gpu_table_create(
          SILO_CUDA_CHECK(cudaEventCreate(&table->ev_k1_end[i]));
          SILO_CUDA_CHECK(cudaEventCreate(&table->ev_end[i]));
       }
+      SILO_CUDA_CHECK(cudaEventCreateWithFlags(&table->ev_free_fence, cudaEventDisableTiming));
       SILO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
       *out = table.release();
    });
@@ -153,11 +158,18 @@ void silo_gpu_table_free(silo_gpu_table* table) {
    cudaFree(table->d_chunk_sizes);
    cudaFree(table->d_chunk_popcount_full);
    cudaFree(table->d_work_prefix);
+   cudaFree(table->d_work_items);
    cudaFree(table->d_full_words);
    cudaFree(table->d_coverage_diff);
    cudaFree(table->d_counts);
    if (table->h_counts_pinned != nullptr) {
       cudaFreeHost(table->h_counts_pinned);
+   }
+   if (table->h_staging_pinned != nullptr) {
+      cudaFreeHost(table->h_staging_pinned);
+   }
+   if (table->ev_free_fence != nullptr) {
+      cudaEventDestroy(table->ev_free_fence);
    }
    for (int i = 0; i < silo_gpu_table::EVENT_RING; ++i) {
       for (cudaEvent_t event : {table->ev_begin[i], table->ev_k1_begin[i], table->ev_k1_end[i], table->ev_end[i]}) {
@@ -244,18 +256,23 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
       }
 
       auto column = std::make_unique<HostColumn>();
-      std::vector<DevContainer> descs(in->n_containers);
+      // Every stored container is cut into PIECES of at most PIECE_BYTES of payload, each with its own
+      // 16-byte descriptor: counts are additive, so a piece is an independent unit of work and a warp
+      // never sits on a multi-kilobyte container while its CTA waits. Arrays of one or two values
+      // carry their values inside the descriptor and own no payload at all.
+      std::vector<DevContainer> descs;
+      descs.reserve(in->n_containers + in->payload_bytes / PIECE_BYTES + 16);
       std::vector<DevSegment> segments;
       std::vector<uint32_t> chunk_desc_begin(n_chunks + 1, 0);
       std::vector<uint32_t> chunk_seg_begin(n_chunks + 1, 0);
       std::vector<uint8_t> slab;
-      slab.reserve(in->payload_bytes + in->n_containers * 2 + 4096);
+      slab.reserve(in->payload_bytes + in->payload_bytes / 16 + 4096);
       column->chunk_desc_payload_bytes.assign(n_chunks, 0);
       column->chunk_containers.assign(n_chunks, 0);
 
       uint64_t cursor = 0;
       for (uint32_t chunk = 0; chunk < n_chunks; ++chunk) {
-         chunk_desc_begin[chunk] = static_cast<uint32_t>(cursor);
+         chunk_desc_begin[chunk] = static_cast<uint32_t>(descs.size());
          chunk_seg_begin[chunk] = static_cast<uint32_t>(segments.size());
          DevSegment segment{};
          bool open = false;
@@ -263,29 +280,18 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
             if (!open) {
                return;
             }
-            slab.resize(alignUp(static_cast<uint32_t>(slab.size() - segment.payload_offset), 16) + segment.payload_offset, 0);
+            slab.resize((slab.size() + 15) / 16 * 16, 0);
             segment.payload_bytes = static_cast<uint32_t>(slab.size() - segment.payload_offset);
             segments.push_back(segment);
             open = false;
          };
-         while (cursor < order.size() && in->containers[order[cursor]].v_index == first_chunk + chunk) {
-            const silo_container_desc& c = in->containers[order[cursor]];
-            const uint8_t* src = in->payload + c.payload_offset;
-            uint32_t bytes = c.payload_bytes;
-            uint32_t alignment = 4;
-            uint32_t n_runs = 0;
-            if (c.typecode == TYPE_BITSET) {
-               alignment = 16;
-            } else if (c.typecode == TYPE_RUN) {
-               uint16_t header = 0;
-               std::memcpy(&header, src, 2);
-               n_runs = header;
-               src += 2;  // the device layout drops the u16 header: pairs become aligned u32 words
-               bytes -= 2;
-            }
+         // appends one piece: descriptor + (16-byte aligned) payload, opening a new segment if needed
+         auto emitPiece = [&](const silo_container_desc& c, uint32_t kind, uint32_t cardinality, uint32_t aux,
+                              const uint8_t* src, uint32_t bytes) {
+            const uint32_t padded = (bytes + 15) / 16 * 16;
             if (open) {
-               const uint32_t used = static_cast<uint32_t>(slab.size() - segment.payload_offset);
-               if (segment.desc_count == SEG_MAX_DESCS || alignUp(used, alignment) + bytes > SEG_PAYLOAD_BYTES) {
+               const auto used = static_cast<uint32_t>(slab.size() - segment.payload_offset);
+               if (segment.desc_count == SEG_MAX_DESCS || used + padded > SEG_PAYLOAD_BYTES) {
                   closeSegment();
                }
             }
@@ -293,29 +299,83 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
                slab.resize((slab.size() + 15) / 16 * 16, 0);
                segment = DevSegment{};
                segment.payload_offset = slab.size();
-               segment.desc_begin = static_cast<uint32_t>(cursor);
+               segment.desc_begin = static_cast<uint32_t>(descs.size());
                segment.chunk = chunk;
                open = true;
             }
-            slab.resize((slab.size() + alignment - 1) / alignment * alignment, 0);
             const uint64_t offset = slab.size();
             require(offset / 4 <= UINT32_MAX, "column payload exceeds the 16 GiB per-shard addressing limit");
-            slab.insert(slab.end(), src, src + bytes);
-            DevContainer& d = descs[cursor];
+            if (bytes > 0) {
+               slab.insert(slab.end(), src, src + bytes);
+               slab.resize(offset + padded, 0);
+            }
+            DevContainer d{};
             d.position = c.position;
             d.offset4 = static_cast<uint32_t>(offset / 4);
-            d.packed = (c.cardinality - 1) | (static_cast<uint32_t>(c.symbol) << 16) |
-                       (static_cast<uint32_t>(in->local_reference[c.position]) << 24) |
-                       (static_cast<uint32_t>(c.typecode) << 30);
-            d.n_runs = n_runs;
+            d.packed = (cardinality - 1) | (static_cast<uint32_t>(c.symbol) << 16) |
+                       (static_cast<uint32_t>(in->local_reference[c.position]) << 24) | (kind << 30);
+            d.n_runs = aux;
+            descs.push_back(d);
             segment.desc_count++;
+         };
+         while (cursor < order.size() && in->containers[order[cursor]].v_index == first_chunk + chunk) {
+            const silo_container_desc& c = in->containers[order[cursor]];
+            const uint8_t* src = in->payload + c.payload_offset;
+            if (c.typecode == TYPE_ARRAY) {
+               if (c.cardinality <= 2) {
+                  uint16_t values[2] = {0, 0};
+                  std::memcpy(values, src, 2 * c.cardinality);
+                  emitPiece(c, KIND_INLINE, c.cardinality, values[0] | (static_cast<uint32_t>(values[1]) << 16), nullptr, 0);
+               } else {
+                  constexpr uint32_t VALUES_PER_PIECE = PIECE_BYTES / 2;
+                  for (uint32_t first = 0; first < c.cardinality; first += VALUES_PER_PIECE) {
+                     const uint32_t count = std::min(VALUES_PER_PIECE, c.cardinality - first);
+                     emitPiece(c, KIND_ARRAY, count, 0, src + 2ULL * first, 2 * count);
+                  }
+               }
+            } else if (c.typecode == TYPE_RUN) {
+               uint16_t n_runs = 0;
+               std::memcpy(&n_runs, src, 2);
+               const uint8_t* runs = src + 2;  // the device layout drops the u16 header: pairs are aligned u32 words
+               constexpr uint32_t RUNS_PER_PIECE = PIECE_BYTES / 4;
+               uint64_t covered = 0;
+               for (uint32_t first = 0; first < n_runs; first += RUNS_PER_PIECE) {
+                  const uint32_t count = std::min<uint32_t>(RUNS_PER_PIECE, n_runs - first);
+                  uint32_t cardinality = 0;
+                  for (uint32_t r = first; r < first + count; ++r) {
+                     uint16_t length_minus_one = 0;
+                     std::memcpy(&length_minus_one, runs + 4ULL * r + 2, 2);
+                     cardinality += static_cast<uint32_t>(length_minus_one) + 1;
+                  }
+                  covered += cardinality;
+                  emitPiece(c, KIND_RUN, cardinality, count, runs + 4ULL * first, 4 * count);
+               }
+               require(covered == c.cardinality, "run container cardinality does not match its runs");
+            } else {
+               constexpr uint32_t WORDS_PER_PIECE = PIECE_BYTES / 8;
+               uint64_t covered = 0;
+               for (uint32_t word = 0; word < TILE_WORDS; word += WORDS_PER_PIECE) {
+                  uint32_t cardinality = 0;
+                  for (uint32_t w = word; w < word + WORDS_PER_PIECE; ++w) {
+                     uint64_t value = 0;
+                     std::memcpy(&value, src + 8ULL * w, 8);
+                     cardinality += static_cast<uint32_t>(__builtin_popcountll(value));
+                  }
+                  covered += cardinality;
+                  if (cardinality != 0) {
+                     emitPiece(c, KIND_BITSET, cardinality, word | (WORDS_PER_PIECE << 16), src + 8ULL * word, PIECE_BYTES);
+                  }
+               }
+               require(covered == c.cardinality, "bitset container cardinality does not match its bits");
+            }
             column->chunk_desc_payload_bytes[chunk] += sizeof(DevContainer) + c.payload_bytes;
             column->chunk_containers[chunk]++;
             ++cursor;
          }
          closeSegment();
       }
-      chunk_desc_begin[n_chunks] = static_cast<uint32_t>(cursor);
+      require(descs.size() <= UINT32_MAX, "too many container pieces for 32-bit descriptor indices");
+      chunk_desc_begin[n_chunks] = static_cast<uint32_t>(descs.size());
       chunk_seg_begin[n_chunks] = static_cast<uint32_t>(segments.size());
       slab.resize((slab.size() + 15) / 16 * 16 + 16, 0);
 
@@ -390,7 +450,7 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
       dev.genome_length = in->genome_length;
       dev.missing_symbol = in->missing_symbol;
       dev.n_chunks = n_chunks;
-      dev.n_containers = in->n_containers;
+      dev.n_containers = descs.size();  // pieces
       dev.n_segments = static_cast<uint32_t>(segments.size());
       std::vector<uint8_t> local_reference(in->local_reference, in->local_reference + in->genome_length);
       dev.local_reference = track(deviceUpload(local_reference, stream, acc));
@@ -408,6 +468,11 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
       dev.null_words = null_words.empty() ? nullptr : track(deviceUpload(null_words, stream, acc));
       SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
 
+      if (dev.n_segments > table->work_items_capacity) {
+         cudaFree(table->d_work_items);
+         table->d_work_items = deviceAlloc<uint32_t>(dev.n_segments, &table->device_bytes);
+         table->work_items_capacity = dev.n_segments;
+      }
       if (in->genome_length + 1 > table->coverage_diff_capacity) {
          cudaFree(table->d_coverage_diff);
          table->d_coverage_diff = deviceAlloc<uint32_t>(in->genome_length + 1, &table->device_bytes);

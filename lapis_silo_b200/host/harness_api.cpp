@@ -34,6 +34,20 @@ struct silo_host_prepared {
 
 struct silo_host_rows {
    std::vector<MutationRow> rows;
+   std::vector<std::string> names;  // distinct sequence names in order of first appearance
+   std::vector<uint32_t> name_ids;
+   void indexNames() {
+      for (const MutationRow& row : rows) {
+         uint32_t id = 0;
+         while (id < names.size() && names[id] != row.sequence_name) {
+            ++id;
+         }
+         if (id == names.size()) {
+            names.push_back(row.sequence_name);
+         }
+         name_ids.push_back(id);
+      }
+   }
 };
 
 struct silo_host_synthetic {
@@ -254,6 +268,7 @@ silo_host_rows* silo_host_mutations(silo_host_table* table, const char* expressi
       const MutationsNode node(*table->table, parseOrTrue(expression), std::move(names), min_proportion);
       auto owned = std::make_unique<silo_host_rows>();
       owned->rows = node.execute();
+      owned->indexNames();
       result = owned.release();
    });
    return result;
@@ -269,6 +284,7 @@ silo_host_rows* silo_host_mutation_rows_from_counts(silo_host_table* table, cons
       symbol_counts.values.assign(counts, counts + static_cast<size_t>(symbol_counts.n_symbols) * symbol_counts.genome_length);
       auto owned = std::make_unique<silo_host_rows>();
       appendMutationRows(info, symbol_counts, min_proportion, owned->rows);
+      owned->indexNames();
       result = owned.release();
    });
    return result;
@@ -280,6 +296,29 @@ void silo_host_rows_free(silo_host_rows* rows) {
 
 uint64_t silo_host_rows_size(const silo_host_rows* rows) {
    return rows->rows.size();
+}
+
+int silo_host_rows_export(const silo_host_rows* rows, char* from, char* to, int32_t* position, uint32_t* name_ids, double* proportion, int32_t* count, int32_t* coverage) {
+   return guarded([&] {
+      for (size_t i = 0; i < rows->rows.size(); ++i) {
+         const MutationRow& row = rows->rows[i];
+         from[i] = row.mutation_from;
+         to[i] = row.mutation_to;
+         position[i] = row.position;
+         name_ids[i] = rows->name_ids[i];
+         proportion[i] = row.proportion;
+         count[i] = row.count;
+         coverage[i] = row.coverage;
+      }
+   });
+}
+
+uint32_t silo_host_rows_num_names(const silo_host_rows* rows) {
+   return static_cast<uint32_t>(rows->names.size());
+}
+
+const char* silo_host_rows_name(const silo_host_rows* rows, uint32_t name_id) {
+   return name_id < rows->names.size() ? rows->names[name_id].c_str() : nullptr;
 }
 
 int silo_host_rows_get(const silo_host_rows* rows, uint64_t index, char* from, char* to, int32_t* position, const char** sequence_name, double* proportion, int32_t* count, int32_t* coverage) {

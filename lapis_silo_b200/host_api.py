@@ -25,7 +25,8 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_filter_prepare", "silo_host_prepared_run_async", "silo_host_prepared_filter",
     "silo_host_prepared_staged_bytes", "silo_host_prepared_free",
     "silo_host_mutation_counts", "silo_host_mutations", "silo_host_mutation_rows_from_counts",
-    "silo_host_rows_free", "silo_host_rows_size", "silo_host_rows_get",
+    "silo_host_rows_free", "silo_host_rows_size", "silo_host_rows_get", "silo_host_rows_export",
+    "silo_host_rows_num_names", "silo_host_rows_name",
     "silo_host_synthetic_create", "silo_host_synthetic_free", "silo_host_synthetic_num_sequences",
     "silo_host_synthetic_reference", "silo_host_synthetic_sequence", "silo_host_synthetic_parent",
     "silo_host_synthetic_generation", "silo_host_synthetic_build_column",
@@ -89,6 +90,13 @@ def lib() -> C.CDLL:
         L.silo_host_rows_get.argtypes = [
             vp, C.c_uint64, C.POINTER(C.c_char), C.POINTER(C.c_char), C.POINTER(C.c_int32),
             C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.silo_host_rows_export.argtypes = [
+            vp, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_double),
+            C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.silo_host_rows_num_names.argtypes = [vp]
+        L.silo_host_rows_num_names.restype = C.c_uint32
+        L.silo_host_rows_name.argtypes = [vp, C.c_uint32]
+        L.silo_host_rows_name.restype = C.c_char_p
         L.silo_host_synthetic_create.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32]
         L.silo_host_synthetic_create.restype = vp
         L.silo_host_synthetic_free.argtypes = [vp]
@@ -124,25 +132,32 @@ def _check(status: int) -> None:
 
 
 def _rows(handle) -> list[dict]:
+    """One bulk export call per result set (struct of arrays), then plain Python dicts."""
     if not handle:
         raise HostError(lib().silo_host_last_error().decode())
-    out = []
     try:
-        for i in range(lib().silo_host_rows_size(handle)):
-            frm, to = C.c_char(), C.c_char()
-            pos, cnt, cov = C.c_int32(), C.c_int32(), C.c_int32()
-            prop = C.c_double()
-            name = C.c_char_p()
-            _check(lib().silo_host_rows_get(handle, i, C.byref(frm), C.byref(to), C.byref(pos), C.byref(name),
-                                            C.byref(prop), C.byref(cnt), C.byref(cov)))
-            out.append({
-                "mutationFrom": frm.value.decode(), "mutationTo": to.value.decode(), "position": pos.value,
-                "sequenceName": name.value.decode(), "proportion": prop.value, "count": cnt.value,
-                "coverage": cov.value,
-            })
+        n = int(lib().silo_host_rows_size(handle))
+        if n == 0:
+            return []
+        frm, to = C.create_string_buffer(n), C.create_string_buffer(n)
+        position = np.empty(n, dtype=np.int32)
+        name_ids = np.empty(n, dtype=np.uint32)
+        proportion = np.empty(n, dtype=np.float64)
+        count = np.empty(n, dtype=np.int32)
+        coverage = np.empty(n, dtype=np.int32)
+        _check(lib().silo_host_rows_export(
+            handle, frm, to, position.ctypes.data_as(C.POINTER(C.c_int32)),
+            name_ids.ctypes.data_as(C.POINTER(C.c_uint32)), proportion.ctypes.data_as(C.POINTER(C.c_double)),
+            count.ctypes.data_as(C.POINTER(C.c_int32)), coverage.ctypes.data_as(C.POINTER(C.c_int32))))
+        names = [lib().silo_host_rows_name(handle, i).decode() for i in range(lib().silo_host_rows_num_names(handle))]
+        frm_text, to_text = frm.raw.decode("latin-1"), to.raw.decode("latin-1")
+        return [{
+            "mutationFrom": frm_text[i], "mutationTo": to_text[i], "position": int(position[i]),
+            "sequenceName": names[name_ids[i]], "proportion": float(proportion[i]), "count": int(count[i]),
+            "coverage": int(coverage[i]),
+        } for i in range(n)]
     finally:
         lib().silo_host_rows_free(handle)
-    return out
 
 
 class HostFilter:
