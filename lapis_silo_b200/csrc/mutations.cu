@@ -12,6 +12,7 @@
 //        -> finalizeCountsKernel: prefix sum of D = rows covering p; the local-reference symbol's
 //           count is  covered(p) - sum of the other symbols' counts  (uint32 modular, as the reference)
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -143,18 +144,36 @@ __device__ __forceinline__ uint32_t rankBelow(const uint32_t* tile32, const uint
    return rank32[word] + __popc(tile32[word] & lowMask(row & 31u));
 }
 
+// Integer shifts by constants are issued as IMAD.HI (x * 2^k >> 32) on the FMA pipe instead of SHF
+// on the ALU pipe: the bit tests below are bound by the 16-lane ALU pipe (LOP3 / SHF / IADD3), the
+// FMA pipe is idle otherwise. The multipliers come from opaque registers so that the compiler does
+// not turn the multiplications back into shifts.
+struct PipeBalance {
+   uint32_t two_pow_11;  // x * 2^11 >> 32 == x >> 21
+   uint32_t two_pow_16;  // x * 2^16 >> 32 == x >> 16
+};
+
+__device__ __forceinline__ uint32_t mulHigh(uint32_t value, uint32_t multiplier) {
+   uint32_t result;
+   asm("mul.hi.u32 %0, %1, %2;" : "=r"(result) : "r"(value), "r"(multiplier));
+   return result;
+}
+
 template <bool CHECKED>
-__device__ __forceinline__ uint32_t arrayVector(const uint32_t* tile32, uint4 eight, uint32_t valid) {
+__device__ __forceinline__ uint32_t arrayVector(const uint32_t* tile32, const PipeBalance& k, uint4 eight, uint32_t valid) {
    const uint32_t words[4] = {eight.x, eight.y, eight.z, eight.w};
    uint32_t total = 0;
 #pragma unroll
-   for (uint32_t k = 0; k < 4; ++k) {
-      const uint32_t lo = words[k] & 0xFFFFu;
-      const uint32_t hi = words[k] >> 16;
-      const uint32_t lo_bit = (tile32[lo >> 5] >> (lo & 31u)) & 1u;
-      const uint32_t hi_bit = (tile32[hi >> 5] >> (hi & 31u)) & 1u;
+   for (uint32_t i = 0; i < 4; ++i) {
+      // two u16 rows per 32-bit word; funnel shifts use the low five bits of the shift register
+      const uint32_t word = words[i];
+      const uint32_t hi = mulHigh(word, k.two_pow_16);                         // word >> 16
+      const uint32_t hi_index = mulHigh(word, k.two_pow_11);                   // (word >> 16) >> 5
+      const uint32_t lo_index = mulHigh(word * 65536u, k.two_pow_11);          // (word & 0xFFFF) >> 5
+      const uint32_t lo_bit = __funnelshift_r(tile32[lo_index], 0u, word) & 1u;
+      const uint32_t hi_bit = __funnelshift_r(tile32[hi_index], 0u, hi) & 1u;
       if (CHECKED) {
-         total += (2 * k < valid ? lo_bit : 0u) + (2 * k + 1 < valid ? hi_bit : 0u);
+         total += (2 * i < valid ? lo_bit : 0u) + (2 * i + 1 < valid ? hi_bit : 0u);
       } else {
          total += lo_bit + hi_bit;
       }
@@ -169,30 +188,41 @@ __device__ __forceinline__ uint32_t pieceAndCardinality(
    const uint8_t* payload,    // shared
    const uint32_t* tile32,    // shared, 2049 words
    const uint32_t* rank32,    // shared, 2049 words
+   const PipeBalance& k,
    uint32_t lane
 ) {
    const uint32_t kind = desc.type();
    const uint4* vectors = reinterpret_cast<const uint4*>(payload);
    uint32_t local = 0;
    if (kind == KIND_ARRAY) {
+      // One value per lane and iteration: the 32 simultaneous tile lookups then belong to 32
+      // CONSECUTIVE sorted values, whose words ascend (mostly distinct banks, neighbours broadcast).
+      // Eight values per lane (128-bit loads) would make the lookups stride-8 in sorted order and
+      // cost ~3.4 shared-memory wavefronts each.
       const uint32_t cardinality = desc.cardinality();
-      const uint32_t full_vectors = cardinality >> 3;
-      for (uint32_t v = lane; v < full_vectors; v += 32) {
-         local += arrayVector<false>(tile32, vectors[v], 8);
-      }
-      const uint32_t rest = cardinality & 7u;
-      if (rest != 0 && lane == (full_vectors & 31u)) {
-         local += arrayVector<true>(tile32, vectors[full_vectors], rest);
+      const uint16_t* values = reinterpret_cast<const uint16_t*>(payload);
+#pragma unroll 4
+      for (uint32_t i = lane; i < cardinality; i += 32) {
+         const uint32_t value = values[i];
+         local += __funnelshift_r(tile32[value >> 5], 0u, value) & 1u;
       }
    } else if (kind == KIND_RUN) {
       const uint32_t n_runs = desc.n_runs;
       const uint32_t* runs = reinterpret_cast<const uint32_t*>(payload);
-      // one run per lane and iteration: branch-free rank difference
+      // one run per lane and iteration. Runs of up to 31 rows (the common case) are answered from a
+      // 64-bit window of the tile aligned at the run's first row; longer runs from the rank table.
       for (uint32_t r = lane; r < n_runs; r += 32) {
          const uint32_t run = runs[r];
-         const uint32_t first = run & 0xFFFFu;
-         const uint32_t end = first + (run >> 16) + 1;  // exclusive, <= 65536
-         local += rankBelow(tile32, rank32, end) - rankBelow(tile32, rank32, first);
+         const uint32_t length_minus_one = mulHigh(run, k.two_pow_16);  // run >> 16
+         if (length_minus_one < 31) {
+            const uint32_t word = mulHigh(run * 65536u, k.two_pow_11);  // (run & 0xFFFF) >> 5
+            const uint32_t window = __funnelshift_r(tile32[word], tile32[word + 1], run);  // shift = first & 31
+            local += __popc(window & lowMask(length_minus_one + 1));
+         } else {
+            const uint32_t first = run & 0xFFFFu;
+            const uint32_t end = first + length_minus_one + 1;  // exclusive, <= 65536
+            local += rankBelow(tile32, rank32, end) - rankBelow(tile32, rank32, first);
+         }
       }
    } else if (kind == KIND_BITSET) {
       const uint4* tile4 = reinterpret_cast<const uint4*>(tile32 + 2 * desc.firstWord());
@@ -211,6 +241,9 @@ __device__ __forceinline__ uint32_t pieceAndCardinality(
    return warpSum(local);
 }
 
+// STREAM_ONLY (profiling aid, SILO_K1_STREAM_ONLY=1): consumers skip the intersection, which measures
+// what the bulk-copy pipeline alone can stream.
+template <int STREAM_ONLY>
 __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
    DevColumn column,
    const uint64_t* __restrict__ filter_words,   // [n_chunks * 1024]
@@ -326,6 +359,11 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
    const uint32_t cwarp = warp - 1;
    const uint32_t cthread = threadIdx.x - 32;  // 0..511
    const uint32_t genome_length = column.genome_length;
+   // opaque to the compiler (gridDim.y is 1): keeps the IMAD.HI forms, see PipeBalance
+   PipeBalance k;
+   k.two_pow_11 = gridDim.y << 11;
+   k.two_pow_16 = gridDim.y << 16;
+   uint32_t rotation = 0;
    for (uint32_t it = 0;; ++it) {
       const uint32_t stage = it % K1_STAGES;
       mbarWait(&sh.full_bar[stage], (it / K1_STAGES) & 1u);
@@ -364,12 +402,31 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
       }
       const uint32_t base4 = sh.meta_base4[stage];
       const K1Stage& st = sh.stages[stage];
-      for (uint32_t index = cwarp; index < desc_count; index += K1_CONSUMER_WARPS) {
+      // pieces go round-robin to the warps ACROSS stages (the rotation continues where the previous
+      // stage stopped), so a stage with 16n + m pieces does not always burden the same m warps
+      const uint32_t first_index = (cwarp - rotation) & (K1_CONSUMER_WARPS - 1);
+      rotation = (rotation + desc_count) & (K1_CONSUMER_WARPS - 1);
+      for (uint32_t index = first_index; index < desc_count && STREAM_ONLY != 1; index += K1_CONSUMER_WARPS) {
          const DevContainer desc = st.descs[index];
          const uint8_t* payload = st.payload + (static_cast<size_t>(desc.offset4 - base4) << 2);
-         const uint32_t count = pieceAndCardinality(desc, payload, tile32, rank32, lane);
-         if (lane == 0 && count != 0) {
+         uint32_t count;
+         if (STREAM_ONLY == 3) {  // profiling: touch the payload only
+            const uint4* vectors = reinterpret_cast<const uint4*>(payload);
+            uint32_t local = 0;
+            const uint32_t n = desc.type() == KIND_ARRAY ? (desc.cardinality() + 7) >> 3 : (desc.type() == KIND_RUN ? (desc.n_runs + 3) >> 2 : 0);
+            for (uint32_t v = lane; v < n; v += 32) {
+               const uint4 x = vectors[v];
+               local += x.x ^ x.y ^ x.z ^ x.w;
+            }
+            count = warpSum(local) == 0x12345678u ? 1u : 0u;
+         } else {
+            count = pieceAndCardinality(desc, payload, tile32, rank32, k, lane);
+         }
+         if (lane == 0 && count != 0 && STREAM_ONLY != 2) {
             atomicAdd(&counts[desc.symbol() * genome_length + desc.position], count);
+         }
+         if (STREAM_ONLY == 2 && count == 0xFFFFFFFFu) {
+            counts[0] = 1;
          }
       }
       __syncwarp();
@@ -630,16 +687,28 @@ void enqueueMutationCounts(
       SILO_CUDA_CHECK(cudaEventRecord(ev_k1_begin, stream));
       if (column.n_segments > 0) {
          static bool attribute_set = false;
+         static int stream_only = 0;
          if (!attribute_set) {
-            SILO_CUDA_CHECK(cudaFuncSetAttribute(
-               containerAndCountKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))
-            ));
+            SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
+            SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
+            SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
+            SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
+            const char* flag = std::getenv("SILO_K1_STREAM_ONLY");
+            stream_only = flag != nullptr ? flag[0] - '0' : 0;
             attribute_set = true;
          }
          const int blocks = static_cast<int>(std::min<uint32_t>(column.n_segments, static_cast<uint32_t>(table->ctx->sm_count) * 2));
-         containerAndCountKernel<<<blocks, K1_THREADS, sizeof(K1Dynamic), stream>>>(
-            column, words, table->d_work_prefix, table->d_work_prefix + n_chunks + 1, table->d_work_items, d_counts
-         );
+#define SILO_LAUNCH_K1(MODE)                                                                             \
+   containerAndCountKernel<MODE><<<blocks, K1_THREADS, sizeof(K1Dynamic), stream>>>(                     \
+      column, words, table->d_work_prefix, table->d_work_prefix + n_chunks + 1, table->d_work_items, d_counts \
+   )
+         switch (stream_only) {
+            case 1: SILO_LAUNCH_K1(1); break;
+            case 2: SILO_LAUNCH_K1(2); break;
+            case 3: SILO_LAUNCH_K1(3); break;
+            default: SILO_LAUNCH_K1(0); break;
+         }
+#undef SILO_LAUNCH_K1
          SILO_CUDA_CHECK(cudaGetLastError());
          table->stats.kernel_launches++;
       }
