@@ -103,7 +103,7 @@ __global__ void fillWorkItemsKernel(
 // shared memory, and issue one RED per piece with a non-zero count.
 // ---------------------------------------------------------------------------------------------
 
-constexpr int K1_STAGES = 5;
+constexpr int K1_STAGES = 4;
 constexpr int K1_CONSUMER_WARPS = 16;
 constexpr int K1_CONSUMER_THREADS = K1_CONSUMER_WARPS * 32;
 constexpr int K1_THREADS = K1_CONSUMER_THREADS + 32;  // warp 0 = bulk-copy producer
@@ -124,6 +124,7 @@ struct __align__(16) K1Dynamic {
    uint32_t meta_desc_count[K1_STAGES];
    uint32_t meta_base4[K1_STAGES];  // slab offset (4-byte units) of the stage's payload[0]
    uint32_t meta_new_tile[K1_STAGES];
+   uint32_t meta_tile_slot[K1_STAGES];  // which of the two filter-tile buffers the stage reads
    uint32_t warp_sums[K1_CONSUMER_WARPS];
 };
 
@@ -254,8 +255,10 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
 ) {
    // the filter tile and its rank table sit in STATIC shared memory: fixed addresses let the
    // compiler fold them into the LDS immediates of the bit tests
-   __shared__ __align__(16) uint32_t tile32[TILE32_WORDS + 4];  // [2048] = zero pad word
-   __shared__ __align__(16) uint32_t rank32[TILE32_WORDS + 4];  // exclusive prefix; [2048] = total
+   // Two tile buffers: the producer loads the next chunk's tile while stages of the current chunk
+   // are still being consumed, so a chunk switch does not drain the pipeline.
+   __shared__ __align__(16) uint32_t tile_buffers[2][TILE32_WORDS + 4];  // [2048] = zero pad word
+   __shared__ __align__(16) uint32_t rank_buffers[2][TILE32_WORDS + 4];  // exclusive prefix; [2048] = total
    extern __shared__ __align__(128) uint8_t smem_raw[];
    K1Dynamic& sh = *reinterpret_cast<K1Dynamic*>(smem_raw);
 
@@ -270,8 +273,8 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
       }
       fenceBarrierInit();
    }
-   if (threadIdx.x < 4) {
-      tile32[TILE32_WORDS + threadIdx.x] = 0;
+   if (threadIdx.x < 8) {
+      tile_buffers[threadIdx.x >> 2][TILE32_WORDS + (threadIdx.x & 3)] = 0;
    }
    __syncthreads();
 
@@ -294,7 +297,9 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
          return segment;
       };
       uint32_t current_tile_chunk = 0xFFFFFFFFu;
-      uint32_t it = 0;  // stages issued so far by this CTA
+      uint32_t tile_slot = 1;         // buffer holding the current chunk's tile
+      uint32_t tile_first_stage = 0;  // first stage that reads the current tile
+      uint32_t it = 0;                // stages issued so far by this CTA
       uint32_t batch_first = claim();
       DevSegment upcoming = fetch(batch_first);
       while (batch_first < total) {
@@ -314,24 +319,28 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
                const uint32_t stage = it % K1_STAGES;
                const uint32_t round = it / K1_STAGES;
                const bool new_tile = chunk != current_tile_chunk;
+               if (round > 0) {
+                  mbarWait(&sh.empty_bar[stage], (round - 1) & 1u);  // => every stage <= it - K1_STAGES is consumed
+               }
                if (new_tile) {
-                  // the single filter tile is shared by all stages: drain the pipeline before replacing it
-                  for (uint32_t back = 1; back < K1_STAGES && back <= it; ++back) {
-                     const uint32_t prev = it - back;
+                  // The new tile goes into the OTHER buffer, last read by the stages before
+                  // tile_first_stage. Those are normally long consumed; wait for any that are not.
+                  const uint32_t consumed_below = it >= K1_STAGES ? it - K1_STAGES + 1 : 0;
+                  for (uint32_t prev = consumed_below; prev < tile_first_stage; ++prev) {
                      mbarWait(&sh.empty_bar[prev % K1_STAGES], (prev / K1_STAGES) & 1u);
                   }
+                  tile_slot ^= 1u;
+                  tile_first_stage = it;
                   current_tile_chunk = chunk;
-               }
-               if (round > 0) {
-                  mbarWait(&sh.empty_bar[stage], (round - 1) & 1u);
                }
                sh.meta_desc_count[stage] = desc_count;
                sh.meta_base4[stage] = static_cast<uint32_t>(payload_offset >> 2);
                sh.meta_new_tile[stage] = new_tile ? 1u : 0u;
+               sh.meta_tile_slot[stage] = tile_slot;
                const uint32_t desc_bytes = desc_count * static_cast<uint32_t>(sizeof(DevContainer));
                mbarExpectTx(&sh.full_bar[stage], desc_bytes + payload_bytes + (new_tile ? TILE_BYTES : 0u));
                if (new_tile) {
-                  bulkLoad(tile32, filter_words + static_cast<size_t>(chunk) * TILE_WORDS, TILE_BYTES, &sh.full_bar[stage]);
+                  bulkLoad(tile_buffers[tile_slot], filter_words + static_cast<size_t>(chunk) * TILE_WORDS, TILE_BYTES, &sh.full_bar[stage]);
                }
                bulkLoad(sh.stages[stage].descs, column.containers + desc_begin, desc_bytes, &sh.full_bar[stage]);
                if (payload_bytes != 0) {
@@ -371,6 +380,8 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
       if (desc_count == K1_STOP) {
          break;
       }
+      const uint32_t* tile32 = tile_buffers[sh.meta_tile_slot[stage]];
+      uint32_t* rank32 = rank_buffers[sh.meta_tile_slot[stage]];
       if (sh.meta_new_tile[stage] != 0) {
          // rebuild the exclusive rank table of the freshly loaded tile: 512 threads x 4 words
          const uint4 four = reinterpret_cast<const uint4*>(tile32)[cthread];
