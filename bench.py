@@ -156,37 +156,13 @@ def build_oracle_sample(sample_chunks: int):
     return table, expression
 
 
-def oracle_query(table, expression) -> int:
-    """One Mutations query on the CPU: computeFilter -> calculateMutationsPerPosition -> thresholding."""
-    flt = table.filter(expression)
-    counts = table.mutation_counts("main", flt)
-    table.mutation_rows("main", counts, MIN_PROPORTION)
-    return flt.cardinality
-
-
 def time_oracle(table, expression, threads: int, min_seconds: float, max_queries: int):
-    """threads concurrent independent queries (the reference's one-worker-per-request model)."""
-    oracle_query(table, expression)  # warm-up
-    results = [0] * threads
-    counts = [0] * threads
-    stop_at = time.perf_counter() + min_seconds
-
-    def worker(index):
-        while True:
-            results[index] = oracle_query(table, expression)
-            counts[index] += 1
-            if time.perf_counter() >= stop_at or counts[index] >= max_queries:
-                break
-
-    started = time.perf_counter()
-    workers = [threading.Thread(target=worker, args=(i,)) for i in range(threads)]
-    for w in workers:
-        w.start()
-    for w in workers:
-        w.join()
-    elapsed = time.perf_counter() - started
-    queries = sum(counts)
-    cardinality = results[0]
+    """threads concurrent independent native queries (the reference's one-worker-per-request model,
+    no intra-query parallelism): computeFilter -> calculateMutationsPerPosition -> thresholding, with
+    parsing/compiling inside the timer. Python only starts the run and reads the totals."""
+    table.mutations_query("main", expression, MIN_PROPORTION)  # warm-up
+    queries, elapsed, cardinality = table.mutations_query_bench(
+        "main", expression, MIN_PROPORTION, threads, min_seconds, max_queries)
     return cardinality * GENOME_LENGTH * queries / elapsed, elapsed, queries, cardinality
 
 

@@ -59,6 +59,12 @@ const char* silo_gpu_version(void);
 int silo_gpu_init(int device_ordinal, silo_gpu_ctx** out);
 void silo_gpu_shutdown(silo_gpu_ctx* ctx);
 
+/* Page-locked host memory for caller-allocated outputs. silo_gpu_mutation_counts and
+ * silo_gpu_filter_download accept any host pointer; into a buffer obtained here the DMA engine
+ * writes directly (no staging copy). A long-lived caller keeps a few of these and reuses them. */
+void* silo_gpu_host_alloc(silo_gpu_ctx* ctx, uint64_t bytes);
+void silo_gpu_host_free(silo_gpu_ctx* ctx, void* ptr);
+
 /* ---- S1: upload ------------------------------------------------------------------------------ */
 
 /* One stored diff container: key of VerticalSequenceIndex::SequenceDiffKey
@@ -117,7 +123,7 @@ uint64_t silo_gpu_table_device_bytes(const silo_gpu_table* table);
  * Leaves push a tile, operators pop/push. Mapping from the reference's operators:
  *   Empty/Full (empty.cpp:25, full.cpp:26)            PUSH_EMPTY / PUSH_FULL
  *   IndexScan over vertical-index views (symbol_in_set.cpp:216-228)   PUSH_SYMBOLS
- *   IndexScan over a foreign roaring (lineage_filter.cpp:96-99, null_bitmap) PUSH_BITMAP / PUSH_NULLS
+ *   IndexScan over a foreign roaring (lineage_filter.cpp:96-99, null_bitmap) PUSH_BITMAP / PUSH_INDEX_BITMAP / PUSH_NULLS
  *   Selection(IsInCoveredRegion) (is_in_covered_region.cpp:53-62)     PUSH_COVERED (flag: negated)
  *   RangeSelection (range_selection.cpp:54-87)        PUSH_RANGES
  *   Intersection (intersection.cpp:59-105)            chain of AND / ANDNOT
@@ -132,6 +138,7 @@ typedef enum {
    SILO_OP_PUSH_NULLS = 5,   /* column */
    SILO_OP_PUSH_BITMAP = 6,  /* a = index into silo_filter_program.bitmaps */
    SILO_OP_PUSH_RANGES = 7,  /* a = number of ranges, b = byte offset into blob of {u32 start,u32 end} */
+   SILO_OP_PUSH_INDEX_BITMAP = 8, /* a = id returned by silo_gpu_bitmap_register */
    SILO_OP_AND = 16,         /* pop y, pop x, push x & y */
    SILO_OP_ANDNOT = 17,      /* pop y, pop x, push x & ~y */
    SILO_OP_OR = 18,          /* pop y, pop x, push x | y */
@@ -172,6 +179,14 @@ typedef struct {
    uint32_t n_bitmaps;
    const silo_roaring_bytes* bitmaps;
 } silo_filter_program;
+
+/* Makes a STATIC index bitmap device resident (the lineage index of lineage_index.h:18-22, a
+ * dictionary index, the per-value bitmaps of an indexed string column ...; portable Roaring bytes,
+ * global row ids), so that programs refer to it with PUSH_INDEX_BITMAP instead of uploading the bytes
+ * with every query. Such indexes are immutable until the next Table::finalize(), which rebuilds the
+ * table handle anyway (S1). Do not unregister an id while prepared programs that use it exist. */
+int silo_gpu_bitmap_register(silo_gpu_table* table, const uint8_t* data, uint64_t size, uint32_t* id_out);
+int silo_gpu_bitmap_unregister(silo_gpu_table* table, uint32_t id);
 
 /* Evaluates the program over every chunk of the table. cardinality may be NULL. */
 int silo_gpu_filter_eval(

@@ -34,7 +34,9 @@ void silo_host_table_free(silo_host_table* table);
 /* alphabet: 0 nucleotide, 1 amino acid. Uploads through silo_gpu_column_upload. */
 int silo_host_table_add_column(silo_host_table* table, const char* name, int alphabet, const char* reference, const silo_column_desc* column);
 /* ready-made roaring bitmap (portable format) standing in for a lineage / dictionary index */
-int silo_host_table_register_bitmap(silo_host_table* table, const char* name, const uint8_t* bytes, uint64_t size);
+/* resident != 0: made device resident once (silo_gpu_bitmap_register), programs refer to it by id;
+ * resident == 0: the bytes travel with every program that uses it (PUSH_BITMAP). */
+int silo_host_table_register_bitmap(silo_host_table* table, const char* name, const uint8_t* bytes, uint64_t size, int resident);
 silo_gpu_table* silo_host_table_device(silo_host_table* table);
 uint64_t silo_host_table_num_rows(const silo_host_table* table);
 

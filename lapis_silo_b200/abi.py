@@ -27,6 +27,7 @@ SILO_E_UNSUPPORTED = -7
 OP_PUSH_EMPTY, OP_PUSH_FULL, OP_PUSH_SYMBOLS, OP_PUSH_COVERED = 1, 2, 3, 4
 OP_PUSH_NULLS, OP_PUSH_BITMAP, OP_PUSH_RANGES = 5, 6, 7
 OP_AND, OP_ANDNOT, OP_OR, OP_NOT = 16, 17, 18, 19
+OP_PUSH_INDEX_BITMAP = 8
 OP_THR_BEGIN, OP_THR_ADD, OP_THR_ADD_SYMBOLS, OP_THR_ADD_COVERED, OP_THR_PROFILE, OP_THR_END = 32, 33, 34, 35, 36, 37
 
 
@@ -106,7 +107,8 @@ EXPORTED_SYMBOLS = [
     "silo_gpu_table_create", "silo_gpu_table_free", "silo_gpu_column_upload",
     "silo_gpu_table_device_bytes", "silo_gpu_filter_eval", "silo_gpu_program_prepare",
     "silo_gpu_program_run_async", "silo_gpu_program_device_bytes", "silo_gpu_program_free",
-    "silo_gpu_filter_from_words",
+    "silo_gpu_host_alloc", "silo_gpu_host_free",
+    "silo_gpu_filter_from_words", "silo_gpu_bitmap_register", "silo_gpu_bitmap_unregister",
     "silo_gpu_filter_cardinality", "silo_gpu_filter_download", "silo_gpu_filter_free",
     "silo_gpu_mutation_counts", "silo_gpu_mutation_counts_async", "silo_gpu_get_stats",
 ]
@@ -151,6 +153,12 @@ def lib() -> C.CDLL:
         L.silo_gpu_program_free.argtypes = [vp]
         L.silo_gpu_program_free.restype = None
         L.silo_gpu_filter_from_words.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(vp)]
+        L.silo_gpu_host_alloc.argtypes = [vp, C.c_uint64]
+        L.silo_gpu_host_alloc.restype = vp
+        L.silo_gpu_host_free.argtypes = [vp, vp]
+        L.silo_gpu_host_free.restype = None
+        L.silo_gpu_bitmap_register.argtypes = [vp, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32)]
+        L.silo_gpu_bitmap_unregister.argtypes = [vp, C.c_uint32]
         L.silo_gpu_filter_cardinality.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.silo_gpu_filter_download.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.silo_gpu_filter_free.argtypes = [vp]
@@ -261,6 +269,14 @@ class Table:
         cardinality = C.c_uint64()
         check(lib().silo_gpu_filter_eval(self._h, C.byref(program), C.byref(handle), C.byref(cardinality)))
         return Filter(self, handle, int(cardinality.value))
+
+    def register_bitmap(self, portable_roaring_bytes: bytes) -> int:
+        out = C.c_uint32()
+        check(lib().silo_gpu_bitmap_register(self._h, portable_roaring_bytes, len(portable_roaring_bytes), C.byref(out)))
+        return out.value
+
+    def unregister_bitmap(self, bitmap_id: int) -> None:
+        check(lib().silo_gpu_bitmap_unregister(self._h, bitmap_id))
 
     def filter_from_words(self, words: np.ndarray) -> Filter:
         words = np.ascontiguousarray(words, dtype=np.uint64)

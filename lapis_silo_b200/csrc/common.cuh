@@ -150,6 +150,15 @@ struct silo_gpu_table {
    bool last_was_full = false;
    silo::Stats stats;
    uint64_t device_bytes = 0;
+   // index bitmaps made device resident by silo_gpu_bitmap_register (one block each:
+   // [descriptors | payload]); id = index, a freed slot keeps d_block == nullptr
+   struct RegisteredBitmap {
+      uint8_t* d_block = nullptr;
+      uint32_t n_containers = 0;
+      uint64_t payload_offset = 0;  // of the payload inside the block
+      uint64_t bytes = 0;
+   };
+   std::vector<RegisteredBitmap> registered;
 };
 
 struct silo_gpu_filter {

@@ -29,6 +29,7 @@ constexpr int STACK_DEPTH = 6;
 
 struct DevBitmap {
    const DevContainer* containers;  // `position` holds the GLOBAL chunk key, ascending
+   const uint8_t* payload;          // base the descriptors' offsets refer to
    uint32_t n_containers;
    uint32_t pad;
 };
@@ -40,7 +41,6 @@ struct EvalParams {
    const DevColumn* columns;
    const uint8_t* blob;
    const DevBitmap* bitmaps;
-   const uint8_t* bitmap_payload;
    const uint32_t* chunk_sizes;
    uint32_t first_chunk;
    uint32_t stack_depth;    // tiles the program needs at most
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
             __syncthreads();
             if (sh.range[1] != 0) {
                const DevContainer desc = bitmap.containers[sh.range[0]];
-               orContainerIntoTile(tile, p.bitmap_payload, desc);
+               orContainerIntoTile(tile, bitmap.payload, desc);
                __syncthreads();
                if ((tile[tid] & ~layout_word) != 0) {
                   atomicOr(p.error_flag, 1u);  // ids outside the row layout
@@ -504,11 +504,13 @@ __global__ void popcountTilesKernel(
 
 // ---- host side ---------------------------------------------------------------------------------
 
-struct ParsedBitmaps {
-   std::vector<DevContainer> containers;
-   std::vector<DevBitmap> bitmaps;  // `containers` holds an index until patched with the device base
-   std::vector<uint32_t> first_container;
-   std::vector<uint8_t> payload;
+// Portable Roaring format (RoaringFormatSpec; what roaring::Roaring::write emits,
+// roaring_util/roaring_serialize.h:15-30) -> descriptors + a 16-byte aligned payload slab.
+// Two passes over the same code: with descs_out == nullptr only the sizes are measured, so that the
+// second pass can write straight into pinned staging memory (no intermediate copies).
+struct RoaringSizes {
+   uint32_t n_containers = 0;
+   uint64_t payload_bytes = 0;  // multiple of 16
 };
 
 uint32_t readU16(const uint8_t* data) {
@@ -522,15 +524,11 @@ uint32_t readU32(const uint8_t* data) {
    return value;
 }
 
-// Portable Roaring format (RoaringFormatSpec; what roaring::Roaring::write emits,
-// roaring_util/roaring_serialize.h:15-30) -> aligned payload slab + descriptors.
-void parseRoaring(const silo_roaring_bytes& bytes, ParsedBitmaps& out) {
+RoaringSizes parseRoaring(const uint8_t* data, uint64_t size, DevContainer* descs_out, uint8_t* payload_out) {
    constexpr uint32_t SERIAL_COOKIE_NO_RUNCONTAINER = 12346;
    constexpr uint32_t SERIAL_COOKIE = 12347;
    constexpr uint32_t NO_OFFSET_THRESHOLD = 4;
    auto bad = [](const char* what) { throw ApiError(SILO_E_BAD_PROGRAM, std::string("roaring bitmap: ") + what); };
-   const uint8_t* data = bytes.data;
-   const uint64_t size = bytes.size;
    if (data == nullptr || size < 4) {
       bad("too short");
    }
@@ -563,9 +561,8 @@ void parseRoaring(const silo_roaring_bytes& bytes, ParsedBitmaps& out) {
    if (run_flags == nullptr || n >= NO_OFFSET_THRESHOLD) {
       pos += 4ULL * n;
    }
-   DevBitmap bitmap{};
-   bitmap.n_containers = n;
-   out.first_container.push_back(static_cast<uint32_t>(out.containers.size()));
+   RoaringSizes sizes;
+   sizes.n_containers = n;
    for (uint32_t i = 0; i < n; ++i) {
       const uint32_t key = readU16(keys + 4 * i);
       const uint32_t cardinality = readU16(keys + 4 * i + 2) + 1;
@@ -602,13 +599,17 @@ void parseRoaring(const silo_roaring_bytes& bytes, ParsedBitmaps& out) {
       if (pos > size) {
          bad("truncated container payload");
       }
-      out.payload.resize((out.payload.size() + 15) / 16 * 16, 0);
-      desc.offset4 = static_cast<uint32_t>(out.payload.size() / 4);
-      desc.packed = (cardinality - 1) | (type << 30);
-      out.payload.insert(out.payload.end(), src, src + payload_bytes);
-      out.containers.push_back(desc);
+      if (descs_out != nullptr) {
+         desc.offset4 = static_cast<uint32_t>(sizes.payload_bytes / 4);
+         desc.packed = (cardinality - 1) | (type << 30);
+         std::memcpy(payload_out + sizes.payload_bytes, src, payload_bytes);
+         const uint64_t padded = (payload_bytes + 15) / 16 * 16;
+         std::memset(payload_out + sizes.payload_bytes + payload_bytes, 0, padded - payload_bytes);
+         descs_out[i] = desc;
+      }
+      sizes.payload_bytes += (payload_bytes + 15) / 16 * 16;
    }
-   out.bitmaps.push_back(bitmap);
+   return sizes;
 }
 
 void validateProgram(const silo_gpu_table* table, const silo_filter_program* program, uint32_t* max_depth_out, bool* has_threshold_out) {
@@ -661,6 +662,12 @@ void validateProgram(const silo_gpu_table* table, const silo_filter_program* pro
          case SILO_OP_PUSH_BITMAP:
             if (ins.a >= program->n_bitmaps) {
                bad("bitmap index out of range");
+            }
+            ++depth;
+            break;
+         case SILO_OP_PUSH_INDEX_BITMAP:
+            if (ins.a >= table->registered.size() || table->registered[ins.a].d_block == nullptr) {
+               bad("index bitmap id is not registered");
             }
             ++depth;
             break;
@@ -817,7 +824,8 @@ void silo_gpu_filter_free(silo_gpu_filter* filter) {
    freeFilterLocked(filter);
 }
 
-// staged program: everything the kernel reads, uploaded once
+// staged program: everything the kernel reads, written straight into pinned memory and uploaded with
+// one H2D copy: [instrs | columns | bitmap table | blob | per-bitmap descriptors | payloads | pad]
 static void stageProgram(
    silo_gpu_table* table,
    const silo_filter_program* program,
@@ -829,60 +837,101 @@ static void stageProgram(
    uint32_t stack_depth = 1;
    bool has_threshold = false;
    validateProgram(table, program, &stack_depth, &has_threshold);
-   ParsedBitmaps parsed;
-   for (uint32_t i = 0; i < program->n_bitmaps; ++i) {
-      parseRoaring(program->bitmaps[i], parsed);
-   }
-   parsed.payload.resize((parsed.payload.size() + 15) / 16 * 16 + 16, 0);
 
-   // one staging buffer, one H2D copy: [instrs | columns | bitmap descs | bitmap table | blob | payload]
-   std::vector<uint8_t> staging;
-   auto place = [&](const void* src, size_t bytes) {
-      staging.resize((staging.size() + 15) / 16 * 16, 0);
-      const size_t offset = staging.size();
-      staging.resize(offset + bytes);
-      if (bytes > 0) {
-         std::memcpy(staging.data() + offset, src, bytes);
+   std::vector<RoaringSizes> sizes(program->n_bitmaps);
+   uint64_t total_descs = 0;
+   uint64_t total_payload = 0;
+   for (uint32_t i = 0; i < program->n_bitmaps; ++i) {
+      sizes[i] = parseRoaring(program->bitmaps[i].data, program->bitmaps[i].size, nullptr, nullptr);
+      total_descs += sizes[i].n_containers;
+      total_payload += sizes[i].payload_bytes;
+   }
+   // registered (device-resident) index bitmaps referenced by the program get a slot of the
+   // program's own bitmap table behind the uploaded ones
+   std::vector<uint32_t> registered_used;
+   for (uint32_t pc = 0; pc < program->n_instrs; ++pc) {
+      if (program->instrs[pc].opcode == SILO_OP_PUSH_INDEX_BITMAP) {
+         registered_used.push_back(program->instrs[pc].a);
       }
+   }
+   std::sort(registered_used.begin(), registered_used.end());
+   registered_used.erase(std::unique(registered_used.begin(), registered_used.end()), registered_used.end());
+
+   size_t cursor = 0;
+   auto reserve = [&](size_t bytes) {
+      cursor = (cursor + 15) / 16 * 16;
+      const size_t offset = cursor;
+      cursor += bytes;
       return offset;
    };
-   const size_t off_instrs = place(program->instrs, sizeof(silo_filter_instr) * program->n_instrs);
-   std::vector<DevColumn> columns;
-   for (const HostColumn* column : table->columns) {
-      columns.push_back(column->dev);
-   }
-   const size_t off_columns = place(columns.data(), sizeof(DevColumn) * columns.size());
-   const size_t off_bitmap_descs = place(parsed.containers.data(), sizeof(DevContainer) * parsed.containers.size());
-   const size_t off_bitmaps = place(parsed.bitmaps.data(), sizeof(DevBitmap) * parsed.bitmaps.size());
-   const size_t off_blob = place(program->blob, program->blob_bytes);
-   const size_t off_payload = place(parsed.payload.data(), parsed.payload.size());
+   const size_t n_table = program->n_bitmaps + registered_used.size();
+   const size_t off_instrs = reserve(sizeof(silo_filter_instr) * program->n_instrs);
+   const size_t off_columns = reserve(sizeof(DevColumn) * table->columns.size());
+   const size_t off_bitmaps = reserve(sizeof(DevBitmap) * n_table);
+   const size_t off_blob = reserve(program->blob_bytes);
+   const size_t off_descs = reserve(sizeof(DevContainer) * total_descs);
+   const size_t off_payload = reserve(total_payload + 16);  // the kernel reads whole 16-byte vectors
+   const size_t staging_bytes = (cursor + 15) / 16 * 16;
 
-   uint8_t* d_staging = poolAlloc<uint8_t>(staging.size() + 16, stream);
-   // patch the per-bitmap container pointers now that the device base is known
-   for (size_t i = 0; i < parsed.bitmaps.size(); ++i) {
-      auto* bitmap = reinterpret_cast<DevBitmap*>(staging.data() + off_bitmaps) + i;
-      bitmap->containers =
-         reinterpret_cast<const DevContainer*>(d_staging + off_bitmap_descs) + parsed.first_container[i];
-   }
-   // one H2D copy out of pinned memory; the pinned buffer is reused by the next call on this table,
-   // which is safe because every caller synchronises the stream before it returns
-   if (staging.size() > table->staging_capacity) {
+   // the pinned buffer is reused by the next call on this table, which is safe because every caller
+   // synchronises the stream before it returns
+   if (staging_bytes > table->staging_capacity) {
       if (table->h_staging_pinned != nullptr) {
          cudaFreeHost(table->h_staging_pinned);
          table->h_staging_pinned = nullptr;
          table->staging_capacity = 0;
       }
-      const size_t capacity = std::max<size_t>(staging.size() * 2, 1 << 20);
+      const size_t capacity = std::max<size_t>(staging_bytes * 2, 1 << 20);
       const cudaError_t pinned_status = cudaMallocHost(reinterpret_cast<void**>(&table->h_staging_pinned), capacity);
       if (pinned_status != cudaSuccess) {
-         cudaFreeAsync(d_staging, stream);
          throw ApiError(SILO_E_OUT_OF_MEMORY, std::string("pinned staging: ") + cudaGetErrorString(pinned_status));
       }
       table->staging_capacity = capacity;
    }
-   std::memcpy(table->h_staging_pinned, staging.data(), staging.size());
-   const cudaError_t status =
-      cudaMemcpyAsync(d_staging, table->h_staging_pinned, staging.size(), cudaMemcpyHostToDevice, stream);
+   uint8_t* staging = table->h_staging_pinned;
+   uint8_t* d_staging = poolAlloc<uint8_t>(staging_bytes, stream);
+
+   auto* instrs = reinterpret_cast<silo_filter_instr*>(staging + off_instrs);
+   std::memcpy(instrs, program->instrs, sizeof(silo_filter_instr) * program->n_instrs);
+   for (uint32_t pc = 0; pc < program->n_instrs; ++pc) {
+      if (instrs[pc].opcode == SILO_OP_PUSH_INDEX_BITMAP) {
+         const auto slot = std::lower_bound(registered_used.begin(), registered_used.end(), instrs[pc].a);
+         instrs[pc].opcode = SILO_OP_PUSH_BITMAP;
+         instrs[pc].a = program->n_bitmaps + static_cast<uint32_t>(slot - registered_used.begin());
+      }
+   }
+   auto* columns = reinterpret_cast<DevColumn*>(staging + off_columns);
+   for (size_t i = 0; i < table->columns.size(); ++i) {
+      columns[i] = table->columns[i]->dev;
+   }
+   if (program->blob_bytes > 0) {
+      std::memcpy(staging + off_blob, program->blob, program->blob_bytes);
+   }
+   auto* bitmaps = reinterpret_cast<DevBitmap*>(staging + off_bitmaps);
+   size_t desc_cursor = 0;
+   size_t payload_cursor = 0;
+   for (uint32_t i = 0; i < program->n_bitmaps; ++i) {
+      parseRoaring(
+         program->bitmaps[i].data, program->bitmaps[i].size,
+         reinterpret_cast<DevContainer*>(staging + off_descs) + desc_cursor, staging + off_payload + payload_cursor
+      );
+      bitmaps[i].containers = reinterpret_cast<const DevContainer*>(d_staging + off_descs) + desc_cursor;
+      bitmaps[i].payload = d_staging + off_payload + payload_cursor;
+      bitmaps[i].n_containers = sizes[i].n_containers;
+      bitmaps[i].pad = 0;
+      desc_cursor += sizes[i].n_containers;
+      payload_cursor += sizes[i].payload_bytes;
+   }
+   std::memset(staging + off_payload + payload_cursor, 0, 16);
+   for (size_t k = 0; k < registered_used.size(); ++k) {
+      const silo_gpu_table::RegisteredBitmap& registered = table->registered[registered_used[k]];
+      DevBitmap& bitmap = bitmaps[program->n_bitmaps + k];
+      bitmap.containers = reinterpret_cast<const DevContainer*>(registered.d_block);
+      bitmap.payload = registered.d_block + registered.payload_offset;
+      bitmap.n_containers = registered.n_containers;
+      bitmap.pad = 0;
+   }
+   const cudaError_t status = cudaMemcpyAsync(d_staging, staging, staging_bytes, cudaMemcpyHostToDevice, stream);
    if (status != cudaSuccess) {
       cudaFreeAsync(d_staging, stream);
       throw ApiError(SILO_E_CUDA, std::string("program upload failed: ") + cudaGetErrorString(status));
@@ -893,14 +942,13 @@ static void stageProgram(
    params.n_chunks = table->n_chunks;
    params.columns = reinterpret_cast<const DevColumn*>(d_staging + off_columns);
    params.blob = d_staging + off_blob;
-   params.bitmaps = reinterpret_cast<const DevBitmap*>(d_staging + off_bitmaps);
-   params.bitmap_payload = d_staging + off_payload;
+   params.bitmaps = bitmaps == nullptr ? nullptr : reinterpret_cast<const DevBitmap*>(d_staging + off_bitmaps);
    params.chunk_sizes = table->d_chunk_sizes;
    params.first_chunk = table->first_chunk;
    params.stack_depth = stack_depth;
    params.has_threshold = has_threshold ? 1u : 0u;
    *d_staging_out = d_staging;
-   *staged_bytes_out = staging.size();
+   *staged_bytes_out = staging_bytes;
    *params_out = params;
 }
 
@@ -1033,6 +1081,56 @@ void silo_gpu_program_free(silo_gpu_program* prepared) {
    }
    delete prepared->params;
    delete prepared;
+}
+
+int silo_gpu_bitmap_register(silo_gpu_table* table, const uint8_t* data, uint64_t size, uint32_t* id_out) {
+   return guarded([&] {
+      require(table != nullptr && data != nullptr && id_out != nullptr, "silo_gpu_bitmap_register: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      const RoaringSizes sizes = parseRoaring(data, size, nullptr, nullptr);
+      silo_gpu_table::RegisteredBitmap registered;
+      registered.n_containers = sizes.n_containers;
+      registered.payload_offset = (sizeof(DevContainer) * static_cast<uint64_t>(sizes.n_containers) + 15) / 16 * 16;
+      registered.bytes = registered.payload_offset + sizes.payload_bytes + 16;
+      std::vector<uint8_t> block(registered.bytes, 0);
+      parseRoaring(data, size, reinterpret_cast<DevContainer*>(block.data()), block.data() + registered.payload_offset);
+      // ids outside this shard's chunk range are ignored by the interpreter (it looks containers up
+      // by chunk key); ids inside a chunk but beyond its size are rejected when a program runs
+      SILO_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&registered.d_block), registered.bytes));
+      const cudaError_t status = cudaMemcpy(registered.d_block, block.data(), registered.bytes, cudaMemcpyHostToDevice);
+      if (status != cudaSuccess) {
+         cudaFree(registered.d_block);
+         SILO_CUDA_CHECK(status);
+      }
+      table->device_bytes += registered.bytes;
+      size_t slot = 0;
+      while (slot < table->registered.size() && table->registered[slot].d_block != nullptr) {
+         ++slot;
+      }
+      if (slot == table->registered.size()) {
+         table->registered.emplace_back();
+      }
+      table->registered[slot] = registered;
+      *id_out = static_cast<uint32_t>(slot);
+   });
+}
+
+int silo_gpu_bitmap_unregister(silo_gpu_table* table, uint32_t id) {
+   return guarded([&] {
+      require(table != nullptr, "silo_gpu_bitmap_unregister: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      require(id < table->registered.size() && table->registered[id].d_block != nullptr, "silo_gpu_bitmap_unregister: unknown id");
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      // programs in flight may still read the block
+      SILO_CUDA_CHECK(cudaStreamSynchronize(table->ctx->stream));
+      if (table->last_stream != nullptr) {
+         SILO_CUDA_CHECK(cudaStreamSynchronize(table->last_stream));
+      }
+      cudaFree(table->registered[id].d_block);
+      table->device_bytes -= table->registered[id].bytes;
+      table->registered[id] = silo_gpu_table::RegisteredBitmap{};
+   });
 }
 
 int silo_gpu_filter_from_words(silo_gpu_table* table, const uint64_t* words, silo_gpu_filter** out) {

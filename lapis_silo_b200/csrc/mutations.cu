@@ -775,9 +775,17 @@ int silo_gpu_mutation_counts(
       enqueueMutationCounts(table, column, filter, table->d_counts, stream);
       const HostColumn& host = *table->columns[static_cast<size_t>(column)];
       const size_t counts_bytes = static_cast<size_t>(host.dev.n_symbols) * host.dev.genome_length * sizeof(uint32_t);
-      SILO_CUDA_CHECK(cudaMemcpyAsync(table->h_counts_pinned, table->d_counts, counts_bytes, cudaMemcpyDeviceToHost, stream));
+      // page-locked destination (silo_gpu_host_alloc): the copy engine writes it directly
+      cudaPointerAttributes attributes{};
+      const bool pinned_destination =
+         cudaPointerGetAttributes(&attributes, counts) == cudaSuccess && attributes.type == cudaMemoryTypeHost;
+      cudaGetLastError();
+      uint32_t* destination = pinned_destination ? counts : table->h_counts_pinned;
+      SILO_CUDA_CHECK(cudaMemcpyAsync(destination, table->d_counts, counts_bytes, cudaMemcpyDeviceToHost, stream));
       SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
-      std::memcpy(counts, table->h_counts_pinned, counts_bytes);
+      if (!pinned_destination) {
+         std::memcpy(counts, table->h_counts_pinned, counts_bytes);
+      }
    });
 }
 

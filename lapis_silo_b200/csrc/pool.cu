@@ -99,6 +99,23 @@ void silo_gpu_shutdown(silo_gpu_ctx* ctx) {
    delete ctx;
 }
 
+void* silo_gpu_host_alloc(silo_gpu_ctx* ctx, uint64_t bytes) {
+   void* ptr = nullptr;
+   const int status = guarded([&] {
+      require(ctx != nullptr, "silo_gpu_host_alloc: NULL context");
+      SILO_CUDA_CHECK(cudaSetDevice(ctx->device));
+      SILO_CUDA_CHECK(cudaMallocHost(&ptr, std::max<uint64_t>(bytes, 1)));
+   });
+   return status == SILO_OK ? ptr : nullptr;
+}
+
+void silo_gpu_host_free(silo_gpu_ctx* ctx, void* ptr) {
+   if (ctx != nullptr && ptr != nullptr) {
+      cudaSetDevice(ctx->device);
+      cudaFreeHost(ptr);
+   }
+}
+
 int silo_gpu_table_create(
    silo_gpu_ctx* ctx,
    uint32_t first_chunk,
@@ -154,6 +171,9 @@ void silo_gpu_table_free(silo_gpu_table* table) {
          cudaFree(allocation);
       }
       delete column;
+   }
+   for (const silo_gpu_table::RegisteredBitmap& registered : table->registered) {
+      cudaFree(registered.d_block);
    }
    cudaFree(table->d_chunk_sizes);
    cudaFree(table->d_chunk_popcount_full);

@@ -591,7 +591,10 @@ std::unique_ptr<Operator> BitmapFilter::compile(const Table& table) const {
    if (iter == table.named_bitmaps.end()) {
       return std::make_unique<Empty>();  // unknown value, lineage_filter.cpp:93-95
    }
-   return IndexScan::overBitmap(&iter->second);
+   if (iter->second.resident) {
+      return IndexScan::overIndexBitmap(iter->second.device_id);
+   }
+   return IndexScan::overBitmap(&iter->second.bytes);
 }
 
 std::unique_ptr<Operator> RowRanges::compile(const Table& table) const {

@@ -135,8 +135,8 @@ int silo_host_table_add_column(silo_host_table* table, const char* name, int alp
    });
 }
 
-int silo_host_table_register_bitmap(silo_host_table* table, const char* name, const uint8_t* bytes, uint64_t size) {
-   return guarded([&] { table->table->named_bitmaps[name] = std::vector<uint8_t>(bytes, bytes + size); });
+int silo_host_table_register_bitmap(silo_host_table* table, const char* name, const uint8_t* bytes, uint64_t size, int resident) {
+   return guarded([&] { table->table->registerBitmap(name, bytes, size, resident != 0); });
 }
 
 silo_gpu_table* silo_host_table_device(silo_host_table* table) {
@@ -257,7 +257,7 @@ int silo_host_mutation_counts(silo_host_table* table, const char* column, const 
       } else {
          result = calculateMutationsPerPosition(t, info, filter->bitmap, t.row_layout.numRows());
       }
-      std::memcpy(counts, result.values.data(), result.values.size() * sizeof(uint32_t));
+      std::memcpy(counts, result.values, result.size() * sizeof(uint32_t));
    });
 }
 
@@ -281,7 +281,7 @@ silo_host_rows* silo_host_mutation_rows_from_counts(silo_host_table* table, cons
       SymbolCounts symbol_counts;
       symbol_counts.n_symbols = info.alphabet->count();
       symbol_counts.genome_length = static_cast<uint32_t>(info.reference_sequence.size());
-      symbol_counts.values.assign(counts, counts + static_cast<size_t>(symbol_counts.n_symbols) * symbol_counts.genome_length);
+      symbol_counts.values = counts;  // a view: the caller's (all-reduced) buffer is only read
       auto owned = std::make_unique<silo_host_rows>();
       appendMutationRows(info, symbol_counts, min_proportion, owned->rows);
       owned->indexNames();

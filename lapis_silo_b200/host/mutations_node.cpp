@@ -1,6 +1,7 @@
 #include "mutations_node.h"
 
 #include <cmath>
+#include <cstring>
 
 namespace silo_host {
 
@@ -13,18 +14,21 @@ SymbolCounts calculateMutationsPerPosition(
    SymbolCounts counts;
    counts.n_symbols = sequence_column.alphabet->count();
    counts.genome_length = static_cast<uint32_t>(sequence_column.reference_sequence.size());
-   counts.values.assign(static_cast<size_t>(counts.n_symbols) * counts.genome_length, 0);
+   counts.owner = table.acquireCountsBuffer(counts.size());
+   counts.values = counts.owner.get();
    const uint64_t filter_cardinality = bitmap_filter.cardinality();
    if (filter_cardinality == sequence_count_in_column) {
       // addMutationCountsForFullBitmaps (:239-266): stored cardinalities only, no intersections
       throwOnDeviceError(
-         silo_gpu_mutation_counts(table.device, sequence_column.device_column, nullptr, counts.values.data())
+         silo_gpu_mutation_counts(table.device, sequence_column.device_column, nullptr, counts.owner.get())
       );
    } else if (filter_cardinality > 0) {
       // addMutationCountsForMixedBitmaps (:205-237)
       throwOnDeviceError(silo_gpu_mutation_counts(
-         table.device, sequence_column.device_column, bitmap_filter.get(), counts.values.data()
+         table.device, sequence_column.device_column, bitmap_filter.get(), counts.owner.get()
       ));
+   } else {
+      std::memset(counts.owner.get(), 0, counts.size() * sizeof(uint32_t));
    }
    return counts;
 }

@@ -17,10 +17,14 @@
 namespace silo_host {
 
 // SymbolMap<SymbolType, std::vector<uint32_t>>: counts[symbol * genome_length + position]
+// A view: `values` points into a page-locked buffer of the table's pool (kept alive by `owner`) that
+// the device wrote directly, or into caller memory (all-reduced counts of the multi-GPU scheduler).
 struct SymbolCounts {
    uint32_t n_symbols = 0;
    uint32_t genome_length = 0;
-   std::vector<uint32_t> values;
+   const uint32_t* values = nullptr;
+   std::shared_ptr<uint32_t> owner;
+   [[nodiscard]] size_t size() const { return static_cast<size_t>(n_symbols) * genome_length; }
    [[nodiscard]] uint32_t at(Symbol symbol, uint32_t position) const {
       return values[static_cast<size_t>(symbol) * genome_length + position];
    }

@@ -147,6 +147,13 @@ std::unique_ptr<IndexScan> IndexScan::overBitmap(const std::vector<uint8_t>* por
    return scan;
 }
 
+std::unique_ptr<IndexScan> IndexScan::overIndexBitmap(uint32_t device_id) {
+   auto scan = std::make_unique<IndexScan>();
+   scan->source = Source::INDEX_BITMAP;
+   scan->index_bitmap_id = device_id;
+   return scan;
+}
+
 std::unique_ptr<IndexScan> IndexScan::overNulls(int device_column) {
    auto scan = std::make_unique<IndexScan>();
    scan->source = Source::NULLS;
@@ -161,6 +168,8 @@ std::string IndexScan::toString() const {
                 std::to_string(position_idx + 1) + ", symbols 0x" + std::to_string(symbol_mask) + ")";
       case Source::BITMAP:
          return "IndexScan(bitmap, " + std::to_string(bitmap_bytes->size()) + " bytes)";
+      case Source::INDEX_BITMAP:
+         return "IndexScan(device-resident index bitmap " + std::to_string(index_bitmap_id) + ")";
       case Source::NULLS:
          return "IndexScan(nulls of column " + std::to_string(device_column) + ")";
    }
@@ -178,6 +187,9 @@ void IndexScan::lower(ProgramBuilder& program) const {
          break;
       case Source::BITMAP:
          program.emit(SILO_OP_PUSH_BITMAP, 0, 0, program.addBitmap(*bitmap_bytes), 0);
+         break;
+      case Source::INDEX_BITMAP:
+         program.emit(SILO_OP_PUSH_INDEX_BITMAP, 0, 0, index_bitmap_id, 0);
          break;
       case Source::NULLS:
          program.emit(SILO_OP_PUSH_NULLS, 0, static_cast<uint16_t>(device_column));

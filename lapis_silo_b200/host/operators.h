@@ -86,15 +86,17 @@ class Full : public Operator {
 // null_bitmap (symbol_in_set.cpp:86-92).
 class IndexScan : public Operator {
   public:
-   enum class Source : uint8_t { SYMBOLS, BITMAP, NULLS };
+   enum class Source : uint8_t { SYMBOLS, BITMAP, INDEX_BITMAP, NULLS };
    Source source;
    int device_column = 0;
    uint32_t position_idx = 0;
    uint32_t symbol_mask = 0;
    const std::vector<uint8_t>* bitmap_bytes = nullptr;
+   uint32_t index_bitmap_id = 0;  // silo_gpu_bitmap_register id (Source::INDEX_BITMAP)
 
    static std::unique_ptr<IndexScan> overSymbols(int device_column, uint32_t position_idx, uint32_t symbol_mask);
    static std::unique_ptr<IndexScan> overBitmap(const std::vector<uint8_t>* portable_roaring_bytes);
+   static std::unique_ptr<IndexScan> overIndexBitmap(uint32_t device_id);
    static std::unique_ptr<IndexScan> overNulls(int device_column);
    OperatorType type() const override { return INDEX_SCAN; }
    std::string toString() const override;

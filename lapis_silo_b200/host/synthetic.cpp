@@ -424,20 +424,28 @@ std::vector<uint32_t> sortedDateRanges(
 
 std::vector<uint32_t> partitionChunks(const std::vector<uint64_t>& chunk_weights, uint32_t n_ranks) {
    const auto n_chunks = static_cast<uint32_t>(chunk_weights.size());
+   std::vector<uint64_t> prefix(n_chunks + 1, 0);
+   for (uint32_t chunk = 0; chunk < n_chunks; ++chunk) {
+      prefix[chunk + 1] = prefix[chunk] + chunk_weights[chunk];
+   }
+   const uint64_t total = prefix[n_chunks];
    std::vector<uint32_t> boundaries(n_ranks + 1, n_chunks);
    boundaries[0] = 0;
-   uint64_t total = 0;
-   for (uint64_t weight : chunk_weights) {
-      total += weight;
-   }
-   uint64_t running = 0;
-   uint32_t rank = 1;
-   for (uint32_t chunk = 0; chunk < n_chunks && rank < n_ranks; ++chunk) {
-      running += chunk_weights[chunk];
-      // close rank `rank-1` once it holds its share of the total weight
-      while (rank < n_ranks && static_cast<unsigned __int128>(running) * n_ranks >= static_cast<unsigned __int128>(total) * rank) {
-         boundaries[rank++] = chunk + 1;
+   for (uint32_t rank = 1; rank < n_ranks; ++rank) {
+      // the cut whose prefix weight is nearest to rank/n_ranks of the total ...
+      const auto target = static_cast<uint64_t>(static_cast<unsigned __int128>(total) * rank / n_ranks);
+      auto cut = static_cast<uint32_t>(std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin());
+      if (cut > 0 && target - prefix[cut - 1] < prefix[cut] - target) {
+         --cut;
       }
+      // ... kept monotone, and -- when there are enough chunks -- leaving every rank at least one
+      uint32_t lowest = boundaries[rank - 1];
+      uint32_t highest = n_chunks;
+      if (n_chunks >= n_ranks) {
+         lowest += 1;
+         highest = n_chunks - (n_ranks - rank);
+      }
+      boundaries[rank] = std::min(std::max(cut, lowest), highest);
    }
    return boundaries;
 }

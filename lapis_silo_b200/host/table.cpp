@@ -102,10 +102,61 @@ Table::Table(silo_gpu_ctx* ctx, RowLayout layout)
       static_cast<uint32_t>(row_layout.chunk_sizes.size()),
       &device
    ));
+   pinned_pool = std::make_shared<PinnedPool>();
+   pinned_pool->ctx = ctx;
 }
 
 Table::~Table() {
    silo_gpu_table_free(device);
+}
+
+Table::PinnedPool::~PinnedPool() {
+   for (auto& [buffer, capacity] : free_buffers) {
+      silo_gpu_host_free(ctx, buffer);
+   }
+}
+
+std::shared_ptr<uint32_t> Table::acquireCountsBuffer(size_t n_values) const {
+   PinnedPool& pool = *pinned_pool;
+   uint32_t* buffer = nullptr;
+   size_t capacity = 0;
+   {
+      std::lock_guard<std::mutex> lock(pool.mutex);
+      for (size_t i = 0; i < pool.free_buffers.size(); ++i) {
+         if (pool.free_buffers[i].second >= n_values) {
+            std::tie(buffer, capacity) = pool.free_buffers[i];
+            pool.free_buffers.erase(pool.free_buffers.begin() + static_cast<std::ptrdiff_t>(i));
+            break;
+         }
+      }
+   }
+   if (buffer == nullptr) {
+      capacity = n_values;
+      buffer = static_cast<uint32_t*>(silo_gpu_host_alloc(ctx, capacity * sizeof(uint32_t)));
+      if (buffer == nullptr) {
+         throw DeviceError(SILO_E_OUT_OF_MEMORY, silo_gpu_last_error());
+      }
+   }
+   std::shared_ptr<PinnedPool> keep_alive = pinned_pool;
+   return std::shared_ptr<uint32_t>(buffer, [keep_alive, capacity](uint32_t* released) {
+      std::lock_guard<std::mutex> lock(keep_alive->mutex);
+      keep_alive->free_buffers.emplace_back(released, capacity);
+   });
+}
+
+void Table::registerBitmap(const std::string& name, const uint8_t* bytes, uint64_t size, bool resident) {
+   auto existing = named_bitmaps.find(name);
+   if (existing != named_bitmaps.end() && existing->second.resident) {
+      throwOnDeviceError(silo_gpu_bitmap_unregister(device, existing->second.device_id));
+      named_bitmaps.erase(existing);
+   }
+   NamedBitmap bitmap;
+   bitmap.bytes.assign(bytes, bytes + size);
+   bitmap.resident = resident;
+   if (resident) {
+      throwOnDeviceError(silo_gpu_bitmap_register(device, bitmap.bytes.data(), bitmap.bytes.size(), &bitmap.device_id));
+   }
+   named_bitmaps[name] = std::move(bitmap);
 }
 
 int Table::addSequenceColumn(

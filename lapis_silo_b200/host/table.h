@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -87,10 +88,33 @@ class Table {
    // stand-ins for indexes owned by out-of-scope columns (LineageIndex, dictionary index): ready-made
    // roaring bitmaps in the portable format, as the reference would hand them over
    // (lineage_filter.cpp:96-99, roaring_serialize.h:15-30)
-   std::map<std::string, std::vector<uint8_t>> named_bitmaps;
+   // A `resident` one was made device resident once with silo_gpu_bitmap_register (static indexes:
+   // the S1 hook registers them next to the columns); the others travel with every program.
+   struct NamedBitmap {
+      std::vector<uint8_t> bytes;
+      bool resident = false;
+      uint32_t device_id = 0;
+   };
+   std::map<std::string, NamedBitmap> named_bitmaps;
+   void registerBitmap(const std::string& name, const uint8_t* bytes, uint64_t size, bool resident);
+
+   // Page-locked result buffers (silo_gpu_host_alloc), recycled between queries: the device writes
+   // the u32[n_symbols][genome_length] counts straight into them. Thread safe.
+   [[nodiscard]] std::shared_ptr<uint32_t> acquireCountsBuffer(size_t n_values) const;
 
    silo_gpu_ctx* ctx = nullptr;
    silo_gpu_table* device = nullptr;
+
+  private:
+   struct PinnedPool {
+      std::mutex mutex;
+      std::vector<std::pair<uint32_t*, size_t>> free_buffers;  // {buffer, capacity in values}
+      silo_gpu_ctx* ctx = nullptr;
+      ~PinnedPool();
+   };
+   std::shared_ptr<PinnedPool> pinned_pool;  // outlives the table while results are in flight
+
+  public:
 
    Table(silo_gpu_ctx* ctx, RowLayout layout);
    ~Table();

@@ -54,7 +54,7 @@ def lib() -> C.CDLL:
         L.silo_host_table_free.argtypes = [vp]
         L.silo_host_table_free.restype = None
         L.silo_host_table_add_column.argtypes = [vp, C.c_char_p, C.c_int, C.c_char_p, vp]
-        L.silo_host_table_register_bitmap.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint64]
+        L.silo_host_table_register_bitmap.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint64, C.c_int]
         L.silo_host_table_device.argtypes = [vp]
         L.silo_host_table_device.restype = vp
         L.silo_host_table_num_rows.argtypes = [vp]
@@ -249,9 +249,11 @@ class HostTable:
             self._h, name.encode(), alphabet, reference.encode(), C.cast(desc_ptr, C.c_void_p)))
         self.columns[name] = (16 if alphabet == NUCLEOTIDE else 28, len(reference))
 
-    def register_bitmap(self, name: str, portable_roaring_bytes: bytes) -> None:
+    def register_bitmap(self, name: str, portable_roaring_bytes: bytes, resident: bool = True) -> None:
+        """resident: a static index bitmap, uploaded once (silo_gpu_bitmap_register); otherwise the
+        bytes travel with every program that uses the bitmap (PUSH_BITMAP)."""
         _check(lib().silo_host_table_register_bitmap(
-            self._h, name.encode(), portable_roaring_bytes, len(portable_roaring_bytes)))
+            self._h, name.encode(), portable_roaring_bytes, len(portable_roaring_bytes), 1 if resident else 0))
 
     @property
     def num_rows(self) -> int:

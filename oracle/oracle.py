@@ -120,6 +120,11 @@ def lib():
         L.orc_gen_nrun_table.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64]
         L.orc_gen_mutation_benchmark_table.argtypes = [C.c_void_p, C.c_uint64]
         L.orc_now_seconds.restype = C.c_double
+        L.orc_mutations_query.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double, C.POINTER(C.c_uint64)]
+        L.orc_mutations_query.restype = C.c_int64
+        L.orc_mutations_query_bench.argtypes = [
+            C.c_void_p, C.c_char_p, C.c_char_p, C.c_double, C.c_uint32, C.c_double, C.c_uint64,
+            C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         L.orc_container_op.argtypes = [
             C.POINTER(C.c_uint16), C.c_uint32, C.c_int, C.POINTER(C.c_uint16), C.c_uint32, C.c_int,
             C.c_int, C.c_int, C.POINTER(C.c_uint16), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8),
@@ -314,6 +319,24 @@ class Table:
         finally:
             lib().orc_mutation_rows_free(handle)
         return rows
+
+    def mutations_query(self, column: str, expression: str, min_proportion: float) -> tuple[int, int]:
+        """The whole query in one native call; returns (output rows, filter cardinality)."""
+        cardinality = C.c_uint64()
+        n_rows = lib().orc_mutations_query(self._h, expression.encode(), column.encode(), min_proportion, C.byref(cardinality))
+        if n_rows < 0:
+            raise OracleError(lib().orc_last_error().decode())
+        return int(n_rows), int(cardinality.value)
+
+    def mutations_query_bench(self, column: str, expression: str, min_proportion: float, threads: int,
+                              seconds: float, max_queries_per_thread: int = 1 << 62) -> tuple[int, float, int]:
+        """`threads` native workers running independent queries back to back; returns
+        (queries completed, elapsed seconds, filter cardinality)."""
+        queries, elapsed, cardinality = C.c_uint64(), C.c_double(), C.c_uint64()
+        _check(lib().orc_mutations_query_bench(
+            self._h, expression.encode(), column.encode(), min_proportion, threads, seconds, max_queries_per_thread,
+            C.byref(queries), C.byref(elapsed), C.byref(cardinality)))
+        return int(queries.value), float(elapsed.value), int(cardinality.value)
 
     def mutations(self, column: str, expression: Optional[str], min_proportion: float) -> list[dict]:
         flt = self.filter(expression) if expression is not None else None

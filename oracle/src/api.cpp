@@ -7,6 +7,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/silo_b200.h"
@@ -298,6 +299,90 @@ int orc_mutation_rows_get(
    *count = row.count;
    *coverage = row.coverage;
    return 0;
+}
+
+// ---- the whole Mutations query, natively (bench.py's CPU baseline legs) ----
+
+// computeFilter -> calculateMutationsPerPosition -> thresholding, on the calling thread, with
+// parsing/compiling inside (timer placement of performance/nof_sequence_filter.cpp:43-52).
+// Returns the number of output rows, -1 on error.
+int64_t orc_mutations_query(void* table, const char* expression, const char* column, double min_proportion, uint64_t* cardinality_out) {
+   int64_t n_rows = -1;
+   guarded([&] {
+      const auto* t = static_cast<Table*>(table);
+      const auto* col = t->findColumn(column);
+      if (col == nullptr) {
+         throw std::runtime_error("no such column");
+      }
+      const auto parsed = parseExpression(expression);
+      const CowBitmap bitmap = computeFilter(*parsed, *t);
+      const auto counts = calculateMutationsPerPosition(*col, bitmap, t->row_layout.numRows());
+      const auto rows = mutationRowsFromCounts(*col, counts, min_proportion);
+      if (cardinality_out != nullptr) {
+         *cardinality_out = bitmap.cardinality();
+      }
+      n_rows = static_cast<int64_t>(rows.size());
+   });
+   return n_rows;
+}
+
+// `threads` workers, each running independent queries back to back (the reference serves one
+// request per worker thread, api/api.cpp:39-51, and has no intra-query parallelism) until `seconds`
+// have passed or max_queries_per_thread ran.
+int orc_mutations_query_bench(
+   void* table,
+   const char* expression,
+   const char* column,
+   double min_proportion,
+   uint32_t threads,
+   double seconds,
+   uint64_t max_queries_per_thread,
+   uint64_t* queries_out,
+   double* elapsed_out,
+   uint64_t* cardinality_out
+) {
+   return guarded([&] {
+      if (threads == 0) {
+         throw std::runtime_error("threads must be > 0");
+      }
+      std::vector<uint64_t> done(threads, 0);
+      std::vector<int> failed(threads, 0);
+      const auto started = std::chrono::steady_clock::now();
+      auto worker = [&](uint32_t index) {
+         while (true) {
+            uint64_t cardinality = 0;
+            if (orc_mutations_query(table, expression, column, min_proportion, &cardinality) < 0) {
+               failed[index] = 1;
+               return;
+            }
+            if (index == 0 && cardinality_out != nullptr) {
+               *cardinality_out = cardinality;
+            }
+            ++done[index];
+            const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - started).count();
+            if (elapsed >= seconds || done[index] >= max_queries_per_thread) {
+               return;
+            }
+         }
+      };
+      std::vector<std::thread> pool;
+      for (uint32_t index = 1; index < threads; ++index) {
+         pool.emplace_back(worker, index);
+      }
+      worker(0);
+      for (std::thread& thread : pool) {
+         thread.join();
+      }
+      *elapsed_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - started).count();
+      uint64_t total = 0;
+      for (uint32_t index = 0; index < threads; ++index) {
+         if (failed[index] != 0) {
+            throw std::runtime_error("a query failed");
+         }
+         total += done[index];
+      }
+      *queries_out = total;
+   });
 }
 
 // ---- S1 interchange: export a column as the upload format / import one ----

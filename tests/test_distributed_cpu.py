@@ -1,0 +1,117 @@
+"""The N>1 path's host logic at world_size 2 on gloo (no GPU): chunk-range partitioning, per-shard
+filter expressions in global row coordinates, the u32-counts-as-i32 all-reduce, cardinality sum and
+thresholding of the reduced counts (bench.py runs the same steps with NCCL).
+
+The per-shard "device" is played by the oracle evaluating the shard's expression on the whole table:
+counts are additive over rows and a shard expression only selects rows of its own chunk range, so
+the shard's contribution is exactly what a rank's device table would produce (the GPU twin of this
+test is tests/test_gpu_parity.py::test_synthetic_shards_sum_to_the_whole)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+TOTAL_ROWS = 5 * 65536 + 4321
+GENOME_LENGTH = 700
+MIN_PROPORTION = 0.05
+
+
+def free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def build_inputs():
+    from lapis_silo_b200 import host_api
+    from oracle import oracle as O
+    synthetic = host_api.Synthetic(genome_length=GENOME_LENGTH, reference_seed=5, generations=5)
+    sizes = host_api.dense_chunk_sizes(TOTAL_ROWS)
+    table = O.Table()
+    table.set_layout(*sizes)
+    table.import_column("main", O.NUCLEOTIDE, synthetic.reference, synthetic.build_column(TOTAL_ROWS, 0, len(sizes), 2))
+    n_sequences = synthetic.num_sequences
+    ancestor = next(e for e in range(n_sequences) if synthetic.generation(e) == 2)
+    in_lineage = np.zeros(n_sequences, dtype=bool)
+    in_lineage[ancestor] = True
+    for e in range(ancestor + 1, n_sequences):
+        in_lineage[e] = in_lineage[synthetic.parent(e)]
+    table.register_bitmap("lineage", np.flatnonzero(in_lineage[np.arange(TOTAL_ROWS) % n_sequences]).tolist())
+    return host_api, synthetic, sizes, table
+
+
+def shard_expression(host_api, first, n_chunks):
+    return f"(and {host_api.date_ranges_expression(TOTAL_ROWS, 1095, 150, 900, first, n_chunks)} (bitmap lineage))"
+
+
+def worker(rank: int, world_size: int, port: int, result_path: str) -> None:
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        host_api, synthetic, sizes, table = build_inputs()
+        # uneven weights: the partition balances payload bytes, not chunk counts
+        weights = [3, 1, 1, 1, 3, 1]
+        bounds = host_api.partition_chunks(weights, world_size)
+        assert bounds[0] == 0 and bounds[-1] == len(sizes) and len(bounds) == world_size + 1
+        first, n_chunks = bounds[rank], bounds[rank + 1] - bounds[rank]
+        assert n_chunks > 0
+
+        flt = table.filter(shard_expression(host_api, first, n_chunks))
+        ids = flt.ids()
+        assert ((ids >> 16) >= first).all() and ((ids >> 16) < first + n_chunks).all(), "a shard selects only its own rows"
+        counts = table.mutation_counts("main", flt)  # u32[16][L] of this shard
+        # one extra element past 2^31 on every rank: the i32 view must still sum modulo 2^32
+        padded = np.concatenate([counts.reshape(-1), np.array([0xC0000000 + rank], dtype=np.uint32)])
+        reduced = torch.from_numpy(padded.view(np.int32).copy())
+        dist.all_reduce(reduced)
+        cardinality = torch.tensor([flt.cardinality], dtype=torch.int64)
+        dist.all_reduce(cardinality)
+
+        reduced_u32 = reduced.numpy().view(np.uint32)
+        assert int(reduced_u32[-1]) == (sum(0xC0000000 + r for r in range(world_size)) & 0xFFFFFFFF)
+        whole_filter = table.filter(shard_expression(host_api, 0, len(sizes)))
+        assert int(cardinality.item()) == whole_filter.cardinality > 0
+        whole_counts = table.mutation_counts("main", whole_filter)
+        np.testing.assert_array_equal(reduced_u32[:-1].reshape(whole_counts.shape), whole_counts)
+        if rank == 0:  # only rank 0 thresholds and returns rows
+            rows = table.mutation_rows("main", reduced_u32[:-1].reshape(whole_counts.shape), MIN_PROPORTION)
+            assert rows == table.mutations("main", shard_expression(host_api, 0, len(sizes)), MIN_PROPORTION)
+            assert len(rows) > 0
+            with open(result_path, "w") as out:
+                out.write(f"ok {len(rows)} {int(cardinality.item())}")
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_partition_and_count_allreduce(tmp_path):
+    torch = pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    result_path = str(tmp_path / "result.txt")
+    mp.spawn(worker, args=(2, free_port(), result_path), nprocs=2, join=True)
+    with open(result_path) as result:
+        assert result.read().startswith("ok ")
+
+
+def test_partition_covers_all_chunks_without_gaps():
+    sys.path.insert(0, ROOT)
+    from lapis_silo_b200 import host_api
+    rng = np.random.default_rng(0)
+    for n_chunks in (1, 2, 7, 153, 1221):
+        weights = [int(w) for w in rng.integers(1, 1000, n_chunks)]
+        for ranks in (1, 2, 4, 8):
+            bounds = host_api.partition_chunks(weights, ranks)
+            assert bounds[0] == 0 and bounds[-1] == n_chunks
+            assert all(a <= b for a, b in zip(bounds, bounds[1:]))
+            if n_chunks >= ranks:
+                assert all(a < b for a, b in zip(bounds, bounds[1:])), "no rank may be left without chunks"
+                loads = [sum(weights[a:b]) for a, b in zip(bounds, bounds[1:])]
+                assert max(loads) <= sum(weights) / ranks + max(weights)

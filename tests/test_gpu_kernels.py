@@ -205,6 +205,20 @@ def test_filter_program_leaves_and_boolean_ops(ctx):
     t.register_bitmap("lineage", chosen)
     raw = t.bitmap_bytes("lineage")
     check([(A.OP_PUSH_BITMAP, 0, 0, 0, 0)], "(bitmap lineage)", bitmaps=[raw])
+    # the same bitmap made device resident once: referenced by id, alone and next to an uploaded one
+    t.register_bitmap("other", [3, 9, 65536 + 7])
+    first_id = g.register_bitmap(t.bitmap_bytes("other"))
+    resident_id = g.register_bitmap(raw)
+    assert (first_id, resident_id) == (0, 1)
+    check([(A.OP_PUSH_INDEX_BITMAP, 0, 0, resident_id, 0)], "(bitmap lineage)")
+    check([(A.OP_PUSH_INDEX_BITMAP, 0, 0, resident_id, 0), (A.OP_PUSH_BITMAP, 0, 0, 0, 0), (A.OP_OR, 0, 0, 0, 0),
+           (A.OP_PUSH_INDEX_BITMAP, 0, 0, first_id, 0), (A.OP_ANDNOT, 0, 0, 0, 0)],
+          "(op-and ((op-or (bitmap lineage) (bitmap other))) ((bitmap other)))", bitmaps=[t.bitmap_bytes("other")])
+    g.unregister_bitmap(first_id)
+    with pytest.raises(A.SiloGpuError) as error:
+        g.filter_eval([(A.OP_PUSH_INDEX_BITMAP, 0, 0, first_id, 0)])
+    assert error.value.status == A.SILO_E_BAD_PROGRAM
+    assert g.register_bitmap(raw) == first_id  # freed slots are reused
     ranges = [(10, 150), (65536 + 5, 65536 + 250)]
     blob = b"".join(struct.pack("<II", s, e) for s, e in ranges)
     check([(A.OP_PUSH_RANGES, 0, 0, len(ranges), 0)], "(ranges 10 150 65541 65786)", blob=blob)
@@ -225,6 +239,10 @@ def test_filter_program_rejects_bitmap_outside_layout(ctx):
     g = A.Table(ctx, [4])
     with pytest.raises(A.SiloGpuError) as error:
         g.filter_eval([(A.OP_PUSH_BITMAP, 0, 0, 0, 0)], bitmaps=[t.bitmap_bytes("bad")])
+    assert error.value.status == A.SILO_E_OUT_OF_LAYOUT
+    bad_id = g.register_bitmap(t.bitmap_bytes("bad"))
+    with pytest.raises(A.SiloGpuError) as error:
+        g.filter_eval([(A.OP_PUSH_INDEX_BITMAP, 0, 0, bad_id, 0)])
     assert error.value.status == A.SILO_E_OUT_OF_LAYOUT
 
 

@@ -16,8 +16,9 @@ def ctx():
     context.close()
 
 
-def mirror(ctx, oracle_table, bitmaps=()):
-    """The same table on the device: every column uploaded from the oracle's S1 export."""
+def mirror(ctx, oracle_table, bitmaps=(), resident=True):
+    """The same table on the device: every column uploaded from the oracle's S1 export. Index bitmaps
+    are made device resident once (resident) or travel with every program."""
     from lapis_silo_b200 import host_api
     table = host_api.HostTable(ctx, oracle_table.chunk_sizes)
     for name, alphabet, reference in oracle_table.columns:
@@ -25,7 +26,7 @@ def mirror(ctx, oracle_table, bitmaps=()):
         table.add_column(name, alphabet, reference, export.desc)
         export.close()
     for name in bitmaps:
-        table.register_bitmap(name, oracle_table.bitmap_bytes(name))
+        table.register_bitmap(name, oracle_table.bitmap_bytes(name), resident)
     return table
 
 
@@ -225,7 +226,7 @@ def test_random_expressions(ctx, seed, alphabet_id):
     rng = np.random.default_rng(seed)
     picked = sorted(set(int(v) for v in rng.integers(0, 300, 120)) | {(1 << 16)} | {(3 << 16) + int(v) for v in rng.integers(0, 499, 200)})
     t.register_bitmap("lineage", picked)
-    pair = (t, mirror(ctx, t, ["lineage"]))
+    pair = (t, mirror(ctx, t, ["lineage"], resident=(alphabet_id == 0)))
     chars = "-ACGTRYSWKMBDHVN" if alphabet_id == 0 else "-ACDEFGHIKLMNOPQRSTUVWYBJZ*X"
     leaves = []
     for _ in range(40):
@@ -280,7 +281,7 @@ def test_mutations_action_rows(ctx, seed, alphabet_id):
     t = build_random(seed, 900, 60, (99, 130, 131), alphabet_id)
     rng = np.random.default_rng(seed)
     t.register_bitmap("lineage", sorted({int(v) for v in rng.integers(0, 100, 60)} | {(3 << 16) + int(v) for v in rng.integers(0, 700, 400)}))
-    oracle_table, device_table = t, mirror(ctx, t, ["lineage"])
+    oracle_table, device_table = t, mirror(ctx, t, ["lineage"], resident=(alphabet_id == 1))
     filters = [None, "(true)", "(false)", "(bitmap lineage)", "(not (bitmap lineage))", "(has-mut c 7)",
                "(and (bitmap lineage) (not (sym-eq c 12 N)))", "(ranges 3 90 196608 197000)", "(profile c 4 muts)"]
     for expression in filters:
