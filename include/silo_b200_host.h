@@ -65,6 +65,9 @@ int silo_host_mutation_counts(silo_host_table* table, const char* column, const 
 silo_host_rows* silo_host_mutations(silo_host_table* table, const char* expression, const char* const* columns, uint32_t n_columns, double min_proportion);
 /* thresholding only, on counts the caller summed over shards (multi-GPU) */
 silo_host_rows* silo_host_mutation_rows_from_counts(silo_host_table* table, const char* column, const uint32_t* counts, double min_proportion);
+/* microseconds of the calling thread's last silo_host_mutations call:
+ * {parse, rewrite+compile+lower, filter_eval, mutation_counts, thresholding} */
+void silo_host_last_query_profile(double out[5]);
 void silo_host_rows_free(silo_host_rows* rows);
 uint64_t silo_host_rows_size(const silo_host_rows* rows);
 /* all rows at once (struct-of-arrays, each array silo_host_rows_size long); name_ids index

@@ -110,7 +110,7 @@ EXPORTED_SYMBOLS = [
     "silo_gpu_host_alloc", "silo_gpu_host_free",
     "silo_gpu_filter_from_words", "silo_gpu_bitmap_register", "silo_gpu_bitmap_unregister",
     "silo_gpu_filter_cardinality", "silo_gpu_filter_download", "silo_gpu_filter_free",
-    "silo_gpu_mutation_counts", "silo_gpu_mutation_counts_async", "silo_gpu_get_stats",
+    "silo_gpu_mutation_counts", "silo_gpu_mutation_counts_symbols", "silo_gpu_mutation_counts_async", "silo_gpu_get_stats",
 ]
 
 
@@ -164,6 +164,7 @@ def lib() -> C.CDLL:
         L.silo_gpu_filter_free.argtypes = [vp]
         L.silo_gpu_filter_free.restype = None
         L.silo_gpu_mutation_counts.argtypes = [vp, C.c_int, vp, C.POINTER(C.c_uint32)]
+        L.silo_gpu_mutation_counts_symbols.argtypes = [vp, C.c_int, vp, C.c_uint64, C.POINTER(C.c_uint32)]
         L.silo_gpu_mutation_counts_async.argtypes = [vp, C.c_int, vp, vp, vp]
         L.silo_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
         _lib = L

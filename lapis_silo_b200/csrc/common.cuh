@@ -109,6 +109,20 @@ struct HostColumn {
 
 }  // namespace silo
 
+namespace silo {
+// The difference array is followed by the sums of its 256-element blocks (accumulated by the same
+// kernel), so that the finalize kernel gets the prefix in front of a block from <= 117 numbers
+// instead of re-summing up to 29,903.
+constexpr uint32_t DIFF_BLOCK = 256;
+__host__ __device__ inline uint32_t diffPadded(uint32_t genome_length) {
+   return (genome_length + 1 + DIFF_BLOCK - 1) / DIFF_BLOCK * DIFF_BLOCK;
+}
+__host__ __device__ inline uint32_t diffWords(uint32_t genome_length) {  // whole scratch array
+   return diffPadded(genome_length) + diffPadded(genome_length) / DIFF_BLOCK;
+}
+
+}  // namespace silo
+
 struct silo_gpu_ctx {
    int device = 0;
    int sm_count = 0;

@@ -55,10 +55,15 @@ struct EvalParams {
 // Dynamic shared memory of the interpreter: [small | stack_depth tiles | 128 KiB of counters if the
 // program holds a Threshold]. A boolean-only program needs 8 KiB per stack level, so several CTAs
 // share an SM; only Threshold programs take the whole SM.
+constexpr uint32_t RANGE_HITS = 62;
+constexpr uint32_t CACHED_INSTRS = 64;
 struct EvalSmall {
    uint32_t range[2];
    uint32_t reduce[EVAL_WARPS];
-   uint32_t pad[2];
+   uint32_t n_hits;
+   uint32_t pad;
+   uint2 hits[RANGE_HITS];                  // PUSH_RANGES: the ranges that overlap this chunk
+   silo_filter_instr instrs[CACHED_INSTRS];  // the head of the program, fetched once per CTA
 };
 constexpr size_t COUNTER_BYTES = 65536 * sizeof(uint16_t);
 
@@ -169,26 +174,37 @@ __device__ void addContainerToCounters(
    }
 }
 
-// [lo, hi) = descriptors of `chunk` at `position` (thread 0 searches, result broadcast via smem)
+// First index in [lo, hi) whose key is >= target, searched by ONE converged warp with 32 probes per
+// round (a 33-ary search: a chunk's ~4k descriptors take 3 rounds of global-memory latency instead
+// of 12). The result is warp-uniform.
+template <typename KeyAt>
+__device__ __forceinline__ uint32_t warpLowerBound(uint32_t lo, uint32_t hi, uint32_t target, uint32_t lane, KeyAt key_at) {
+   while (hi - lo > 32) {
+      const uint32_t span = hi - lo;
+      const uint32_t probe = lo + static_cast<uint32_t>(static_cast<uint64_t>(lane + 1) * span / 33);  // in (lo, hi)
+      const uint32_t n_less = __popc(__ballot_sync(0xFFFFFFFFu, key_at(probe) < target));  // monotone in the lane
+      const uint32_t below = __shfl_sync(0xFFFFFFFFu, probe, n_less == 0 ? 0 : n_less - 1);
+      const uint32_t above = __shfl_sync(0xFFFFFFFFu, probe, n_less == 32 ? 31 : n_less);
+      lo = n_less == 0 ? lo : below + 1;
+      hi = n_less == 32 ? hi : above;
+   }
+   const uint32_t index = lo + lane;
+   const bool less = index < hi && key_at(index) < target;
+   return lo + __popc(__ballot_sync(0xFFFFFFFFu, less));
+}
+
+// [lo, hi) = descriptors of `chunk` at `position` (warp 0 searches, result broadcast via smem)
 __device__ void findPositionRange(const EvalShared& sh, const DevColumn& column, uint32_t chunk, uint32_t position) {
-   if (threadIdx.x == 0) {
-      uint32_t lo = column.chunk_desc_begin[chunk];
-      uint32_t hi = column.chunk_desc_begin[chunk + 1];
-      const uint32_t end = hi;
-      while (lo < hi) {
-         const uint32_t mid = (lo + hi) >> 1;
-         if (column.containers[mid].position < position) {
-            lo = mid + 1;
-         } else {
-            hi = mid;
-         }
+   if (threadIdx.x < 32) {
+      const uint32_t begin = column.chunk_desc_begin[chunk];
+      const uint32_t end = column.chunk_desc_begin[chunk + 1];
+      auto key_at = [&](uint32_t index) { return column.containers[index].position; };
+      const uint32_t lo = warpLowerBound(begin, end, position, threadIdx.x, key_at);
+      const uint32_t stop = warpLowerBound(lo, end, position + 1, threadIdx.x, key_at);
+      if (threadIdx.x == 0) {
+         sh.range[0] = lo;
+         sh.range[1] = stop;
       }
-      uint32_t stop = lo;
-      while (stop < end && column.containers[stop].position == position) {
-         ++stop;
-      }
-      sh.range[0] = lo;
-      sh.range[1] = stop;
    }
    __syncthreads();
 }
@@ -241,8 +257,13 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
    uint32_t thr_target = 0;
    bool thr_exact = false;
 
+   if (tid < min(p.n_instrs, CACHED_INSTRS) * 4) {  // 16-byte instructions as 4 words each
+      reinterpret_cast<uint32_t*>(sh.small->instrs)[tid] = reinterpret_cast<const uint32_t*>(p.instrs)[tid];
+   }
+   __syncthreads();
+
    for (uint32_t pc = 0; pc < p.n_instrs; ++pc) {
-      const silo_filter_instr ins = p.instrs[pc];
+      const silo_filter_instr ins = pc < CACHED_INSTRS ? sh.small->instrs[pc] : p.instrs[pc];
       switch (ins.opcode) {
          case SILO_OP_PUSH_EMPTY:
             sh.stack[sp++][tid] = 0;
@@ -308,20 +329,15 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
             const DevBitmap bitmap = p.bitmaps[ins.a];
             uint64_t* tile = sh.stack[sp++];
             tile[tid] = 0;
-            if (tid == 0) {
-               uint32_t lo = 0;
-               uint32_t hi = bitmap.n_containers;
+            if (tid < 32) {
                const uint32_t key = p.first_chunk + chunk;
-               while (lo < hi) {
-                  const uint32_t mid = (lo + hi) >> 1;
-                  if (bitmap.containers[mid].position < key) {
-                     lo = mid + 1;
-                  } else {
-                     hi = mid;
-                  }
+               const uint32_t lo = warpLowerBound(0, bitmap.n_containers, key, tid, [&](uint32_t index) {
+                  return bitmap.containers[index].position;
+               });
+               if (tid == 0) {
+                  sh.range[0] = lo;
+                  sh.range[1] = (lo < bitmap.n_containers && bitmap.containers[lo].position == key) ? 1u : 0u;
                }
-               sh.range[0] = lo;
-               sh.range[1] = (lo < bitmap.n_containers && bitmap.containers[lo].position == key) ? 1u : 0u;
             }
             __syncthreads();
             if (sh.range[1] != 0) {
@@ -335,16 +351,48 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
             break;
          }
          case SILO_OP_PUSH_RANGES: {
-            const uint32_t* ranges = reinterpret_cast<const uint32_t*>(p.blob + ins.b);
+            // phase 1: every thread tests ranges tid, tid + 1024, ... against the chunk and appends the
+            // overlapping ones (usually zero to two: RangeSelection holds at most one per chunk) to a
+            // shared list; phase 2: every thread ORs the listed ranges into its own word.
+            const uint2* ranges = reinterpret_cast<const uint2*>(p.blob + ins.b);
+            if (tid == 0) {
+               sh.small->n_hits = 0;
+            }
+            __syncthreads();
+            const uint64_t chunk_end = static_cast<uint64_t>(chunk_base) + 65536;
+            uint32_t spilled = 0;
+            for (uint32_t i = tid; i < ins.a; i += EVAL_THREADS) {
+               const uint2 range = ranges[i];
+               if (range.x < chunk_end && range.y > chunk_base && range.x < range.y) {
+                  const uint32_t slot = atomicAdd(&sh.small->n_hits, 1u);
+                  if (slot < RANGE_HITS) {
+                     sh.small->hits[slot] = range;
+                  } else {
+                     spilled = 1;
+                  }
+               }
+            }
+            const bool any_spilled = __syncthreads_or(static_cast<int>(spilled)) != 0;
             const uint32_t word_first = chunk_base + tid * 64;
-            uint64_t word = 0;
-            for (uint32_t i = 0; i < ins.a; ++i) {
-               const uint32_t start = max(ranges[2 * i], word_first);
-               const uint64_t end = min(static_cast<uint64_t>(ranges[2 * i + 1]), static_cast<uint64_t>(word_first) + 64);
+            auto orRange = [&](uint64_t word, uint2 range) {
+               const uint32_t start = max(range.x, word_first);
+               const uint64_t end = min(static_cast<uint64_t>(range.y), static_cast<uint64_t>(word_first) + 64);
                if (start < end) {
                   const uint32_t first_bit = start - word_first;
                   const uint32_t last_bit = static_cast<uint32_t>(end - 1 - word_first);
                   word |= (~0ULL << first_bit) & (~0ULL >> (63 - last_bit));
+               }
+               return word;
+            };
+            uint64_t word = 0;
+            if (any_spilled) {  // more overlapping ranges than the list holds: the plain loop
+               for (uint32_t i = 0; i < ins.a; ++i) {
+                  word = orRange(word, ranges[i]);
+               }
+            } else {
+               const uint32_t n_hits = sh.small->n_hits;
+               for (uint32_t i = 0; i < n_hits; ++i) {
+                  word = orRange(word, sh.small->hits[i]);
                }
             }
             sh.stack[sp++][tid] = word & layout_word;

@@ -464,16 +464,27 @@ __global__ void containerCardinalityKernel(DevColumn column, uint32_t* __restric
 // ---------------------------------------------------------------------------------------------
 
 constexpr int K6_THREADS = 256;
-constexpr int K6_SLICES = 16;  // CTAs per chunk
+constexpr int K6_SLICES = 32;  // CTAs per chunk
+constexpr uint32_t K6_ROWS_PER_WARP = 65536 / K6_SLICES / (K6_THREADS / 32);  // 256 rows = 8 filter words
+constexpr uint32_t K6_UNROLL = 4;
+
+struct DiffArrays {
+   uint32_t* diff;          // [genome_length + 1]
+   uint32_t* block_totals;  // [diffPadded / 256]
+   __device__ __forceinline__ void add(uint32_t key, uint32_t amount) const {
+      atomicAdd(&diff[key], amount);
+      atomicAdd(&block_totals[key / DIFF_BLOCK], amount);
+   }
+};
 
 struct PendingAdd {
    uint32_t key;
    uint32_t count;
 };
 
-__device__ __forceinline__ void flushPending(PendingAdd& pending, uint32_t* diff, uint32_t lane, bool negate) {
+__device__ __forceinline__ void flushPending(PendingAdd& pending, const DiffArrays& out, uint32_t lane, bool negate) {
    if (pending.count != 0 && lane == 0) {
-      atomicAdd(&diff[pending.key], negate ? 0u - pending.count : pending.count);
+      out.add(pending.key, negate ? 0u - pending.count : pending.count);
    }
    pending.count = 0;
 }
@@ -482,22 +493,19 @@ __device__ __forceinline__ void flushPending(PendingAdd& pending, uint32_t* diff
 // is accumulated in registers across iterations (the common case: full-length genomes, sorted reads)
 __device__ __forceinline__ void aggregateAdd(
    PendingAdd& pending,
-   uint32_t* diff,
+   const DiffArrays& out,
    uint32_t key,
    bool active,
+   uint32_t active_mask,
    uint32_t lane,
    bool negate
 ) {
-   const uint32_t active_mask = __ballot_sync(0xFFFFFFFFu, active);
-   if (active_mask == 0) {
-      return;
-   }
    const uint32_t leader = __ffs(active_mask) - 1;
    const uint32_t leader_key = __shfl_sync(0xFFFFFFFFu, key, leader);
    const uint32_t same_mask = __ballot_sync(0xFFFFFFFFu, active && key == leader_key);
    if (same_mask == active_mask) {
       if (pending.count != 0 && pending.key != leader_key) {
-         flushPending(pending, diff, lane, negate);
+         flushPending(pending, out, lane, negate);
       }
       pending.key = leader_key;
       pending.count += __popc(active_mask);
@@ -507,7 +515,7 @@ __device__ __forceinline__ void aggregateAdd(
    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, active ? key : 0xFFFFFFFFu);
    if (active && lane == static_cast<uint32_t>(__ffs(peers) - 1)) {
       const uint32_t amount = __popc(peers);
-      atomicAdd(&diff[key], negate ? 0u - amount : amount);
+      out.add(key, negate ? 0u - amount : amount);
    }
 }
 
@@ -515,42 +523,48 @@ __global__ void __launch_bounds__(K6_THREADS) coverageDiffKernel(
    DevColumn column,
    const uint64_t* __restrict__ filter_words,
    const uint32_t* __restrict__ chunk_popcount,
-   const uint32_t* __restrict__ chunk_sizes,
-   uint32_t* __restrict__ diff  // [genome_length + 1]
+   uint32_t* __restrict__ diff_scratch  // [diffWords(genome_length)], zeroed
 ) {
    const uint32_t chunk = blockIdx.x / K6_SLICES;
    const uint32_t slice = blockIdx.x % K6_SLICES;
    if (chunk_popcount[chunk] == 0) {
       return;
    }
+   const DiffArrays out{diff_scratch, diff_scratch + diffPadded(column.genome_length)};
    const uint32_t lane = threadIdx.x & 31;
    const uint32_t warp = threadIdx.x >> 5;
-   const uint32_t chunk_size = chunk_sizes[chunk];
    const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(filter_words + static_cast<size_t>(chunk) * TILE_WORDS);
    const uint2* rows = column.start_end + column.chunk_row_begin[chunk];
 
-   constexpr uint32_t ROWS_PER_SLICE = 65536 / K6_SLICES;
-   constexpr uint32_t WARPS = K6_THREADS / 32;
-   constexpr uint32_t ROWS_PER_WARP = ROWS_PER_SLICE / WARPS;
-   const uint32_t warp_first = slice * ROWS_PER_SLICE + warp * ROWS_PER_WARP;
+   // Filter bits are confined to the row layout, so a set bit is always an existing row. The warp's
+   // eight filter words are fetched at once, and the (start, end) loads of K6_UNROLL words are in
+   // flight together: the kernel is bound by global-memory latency, not bandwidth.
+   const uint32_t warp_first = (slice * (K6_THREADS / 32) + warp) * K6_ROWS_PER_WARP;
+   const uint32_t my_word = lane < K6_ROWS_PER_WARP / 32 ? tile32[(warp_first >> 5) + lane] : 0u;
    PendingAdd pending_start{0, 0};
    PendingAdd pending_end{0, 0};
-   for (uint32_t base = warp_first; base < warp_first + ROWS_PER_WARP && base < chunk_size; base += 32) {
-      const uint32_t bits = tile32[base >> 5];
-      if (bits == 0) {
-         continue;
+   for (uint32_t group = 0; group < K6_ROWS_PER_WARP / 32; group += K6_UNROLL) {
+      uint32_t bits[K6_UNROLL];
+      uint2 range[K6_UNROLL];
+#pragma unroll
+      for (uint32_t j = 0; j < K6_UNROLL; ++j) {
+         bits[j] = __shfl_sync(0xFFFFFFFFu, my_word, group + j);
+         range[j] = make_uint2(0, 0);
+         if (((bits[j] >> lane) & 1u) != 0) {
+            range[j] = rows[warp_first + (group + j) * 32 + lane];
+         }
       }
-      const uint32_t row = base + lane;
-      const bool active = ((bits >> lane) & 1u) != 0 && row < chunk_size;
-      uint2 range = make_uint2(0, 0);
-      if (active) {
-         range = rows[row];
+#pragma unroll
+      for (uint32_t j = 0; j < K6_UNROLL; ++j) {
+         if (bits[j] != 0) {
+            const bool active = ((bits[j] >> lane) & 1u) != 0;
+            aggregateAdd(pending_start, out, range[j].x, active, bits[j], lane, false);
+            aggregateAdd(pending_end, out, range[j].y, active, bits[j], lane, true);
+         }
       }
-      aggregateAdd(pending_start, diff, range.x, active, lane, false);
-      aggregateAdd(pending_end, diff, range.y, active, lane, true);
    }
-   flushPending(pending_start, diff, lane, false);
-   flushPending(pending_end, diff, lane, true);
+   flushPending(pending_start, out, lane, false);
+   flushPending(pending_end, out, lane, true);
 
    // N positions inside the covered range, stored as runs per row
    const uint32_t missing_begin = column.chunk_missing_begin[chunk];
@@ -562,8 +576,8 @@ __global__ void __launch_bounds__(K6_THREADS) coverageDiffKernel(
       }
       for (uint64_t run = column.missing_offsets[i]; run < column.missing_offsets[i + 1]; ++run) {
          const uint2 r = column.missing_runs[run];
-         atomicAdd(&diff[r.x], 0u - 1u);
-         atomicAdd(&diff[r.y], 1u);
+         out.add(r.x, 0u - 1u);
+         out.add(r.y, 1u);
       }
    }
 }
@@ -572,43 +586,45 @@ __global__ void __launch_bounds__(K6_THREADS) coverageDiffKernel(
 // finalize: covered(p) = prefix sum of diff; counts[local_ref[p]][p] = covered(p) - sum(others)
 // ---------------------------------------------------------------------------------------------
 
-// covered(p) = prefix sum of the coverage difference array; counts[local_ref[p]][p] = covered(p) -
-// sum of the other symbols' counts. One thread per position; every CTA first sums the (L2-resident)
-// difference array in front of its block instead of waiting for a separate scan kernel.
-constexpr int FIN_THREADS = 256;
+// One thread per position. The prefix in front of a 256-position block comes from the block totals
+// that coverageDiffKernel accumulated next to the difference array.
+constexpr int FIN_THREADS = DIFF_BLOCK;
 
 __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    DevColumn column,
-   const uint32_t* __restrict__ diff,
+   const uint32_t* __restrict__ diff_scratch,
    uint32_t* __restrict__ counts
 ) {
    __shared__ uint32_t warp_totals[FIN_THREADS / 32];
    __shared__ uint32_t block_offset;
    const uint32_t genome_length = column.genome_length;
+   const uint32_t* diff = diff_scratch;
+   const uint32_t* block_totals = diff_scratch + diffPadded(genome_length);
    const uint32_t block_first = blockIdx.x * FIN_THREADS;
    const uint32_t lane = threadIdx.x & 31;
    const uint32_t warp = threadIdx.x >> 5;
-   // sum of diff[0, block_first)
-   uint32_t partial = 0;
-   for (uint32_t i = threadIdx.x; i < block_first; i += FIN_THREADS) {
-      partial += diff[i];
-   }
-   partial = __reduce_add_sync(0xFFFFFFFFu, partial);
-   if (lane == 0) {
-      warp_totals[warp] = partial;
-   }
-   __syncthreads();
-   if (threadIdx.x == 0) {
-      uint32_t total = 0;
-      for (uint32_t w = 0; w < FIN_THREADS / 32; ++w) {
-         total += warp_totals[w];
-      }
-      block_offset = total;
-   }
-   __syncthreads();
-   // inclusive scan of this block's 256 elements
    const uint32_t p = block_first + threadIdx.x;
+   // issue every global load up front: the kernel is one latency chain otherwise
    const uint32_t mine = p < genome_length ? diff[p] : 0u;
+   const uint32_t reference_symbol = p < genome_length ? column.local_reference[p] : 0u;
+   uint32_t others = 0;
+   if (p < genome_length) {
+      for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
+         const uint32_t value = counts[symbol * genome_length + p];
+         others += symbol != reference_symbol ? value : 0u;
+      }
+   }
+   if (warp == 0) {
+      uint32_t partial = 0;
+      for (uint32_t block = lane; block < blockIdx.x; block += 32) {
+         partial += block_totals[block];
+      }
+      partial = __reduce_add_sync(0xFFFFFFFFu, partial);
+      if (lane == 0) {
+         block_offset = partial;
+      }
+   }
+   // inclusive scan of this block's 256 elements
    uint32_t inclusive = mine;
    for (int offset = 1; offset < 32; offset <<= 1) {
       const uint32_t other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
@@ -616,7 +632,6 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
          inclusive += other;
       }
    }
-   __syncthreads();
    if (lane == 31) {
       warp_totals[warp] = inclusive;
    }
@@ -625,17 +640,9 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    for (uint32_t w = 0; w < warp; ++w) {
       covered += warp_totals[w];
    }
-   if (p >= genome_length) {
-      return;
+   if (p < genome_length) {
+      counts[reference_symbol * genome_length + p] = covered - others;
    }
-   const uint32_t reference_symbol = column.local_reference[p];
-   uint32_t others = 0;
-   for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
-      if (symbol != reference_symbol) {
-         others += counts[symbol * genome_length + p];
-      }
-   }
-   counts[reference_symbol * genome_length + p] = covered - others;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -668,7 +675,7 @@ void enqueueMutationCounts(
    cudaEvent_t ev_end = table->ev_end[slot];
    SILO_CUDA_CHECK(cudaEventRecord(ev_begin, stream));
    SILO_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, counts_bytes, stream));
-   SILO_CUDA_CHECK(cudaMemsetAsync(table->d_coverage_diff, 0, (column.genome_length + 1) * sizeof(uint32_t), stream));
+   SILO_CUDA_CHECK(cudaMemsetAsync(table->d_coverage_diff, 0, diffWords(column.genome_length) * sizeof(uint32_t), stream));
    if (n_chunks == 0) {
       SILO_CUDA_CHECK(cudaEventRecord(ev_k1_begin, stream));
       SILO_CUDA_CHECK(cudaEventRecord(ev_k1_end, stream));
@@ -726,7 +733,7 @@ void enqueueMutationCounts(
       SILO_CUDA_CHECK(cudaEventRecord(ev_k1_end, stream));
    }
    coverageDiffKernel<<<n_chunks * K6_SLICES, K6_THREADS, 0, stream>>>(
-      column, words, popcounts, table->d_chunk_sizes, table->d_coverage_diff
+      column, words, popcounts, table->d_coverage_diff
    );
    SILO_CUDA_CHECK(cudaGetLastError());
    finalizeCountsKernel<<<(column.genome_length + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, stream>>>(
@@ -761,32 +768,72 @@ int silo_gpu_mutation_counts_async(
    });
 }
 
+// the synchronous calls: enqueue, copy the rows of the wanted symbols to the host, synchronise
+static void mutationCountsToHost(
+   silo_gpu_table* table,
+   int column,
+   const silo_gpu_filter* filter,
+   uint64_t symbol_mask,
+   uint32_t* counts
+) {
+   require(table != nullptr && counts != nullptr, "mutation_counts: NULL argument");
+   std::lock_guard<std::mutex> lock(table->mutex);
+   SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+   cudaStream_t stream = table->ctx->stream;
+   enqueueMutationCounts(table, column, filter, table->d_counts, stream);
+   const HostColumn& host = *table->columns[static_cast<size_t>(column)];
+   const size_t row_values = host.dev.genome_length;
+   // page-locked destination (silo_gpu_host_alloc): the copy engine writes it directly
+   cudaPointerAttributes attributes{};
+   const bool pinned_destination =
+      cudaPointerGetAttributes(&attributes, counts) == cudaSuccess && attributes.type == cudaMemoryTypeHost;
+   cudaGetLastError();
+   uint32_t* destination = pinned_destination ? counts : table->h_counts_pinned;
+   // one copy per maximal range of consecutive wanted symbols
+   std::vector<std::pair<uint32_t, uint32_t>> ranges;
+   for (uint32_t symbol = 0; symbol < host.dev.n_symbols;) {
+      if (((symbol_mask >> symbol) & 1ULL) == 0) {
+         ++symbol;
+         continue;
+      }
+      uint32_t end = symbol;
+      while (end < host.dev.n_symbols && ((symbol_mask >> end) & 1ULL) != 0) {
+         ++end;
+      }
+      ranges.emplace_back(symbol, end);
+      symbol = end;
+   }
+   for (const auto& [first, end] : ranges) {
+      SILO_CUDA_CHECK(cudaMemcpyAsync(
+         destination + first * row_values, table->d_counts + first * row_values, (end - first) * row_values * sizeof(uint32_t),
+         cudaMemcpyDeviceToHost, stream
+      ));
+   }
+   SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+   if (!pinned_destination) {
+      for (const auto& [first, end] : ranges) {
+         std::memcpy(counts + first * row_values, table->h_counts_pinned + first * row_values, (end - first) * row_values * sizeof(uint32_t));
+      }
+   }
+}
+
 int silo_gpu_mutation_counts(
    silo_gpu_table* table,
    int column,
    const silo_gpu_filter* filter,
    uint32_t* counts
 ) {
-   return guarded([&] {
-      require(table != nullptr && counts != nullptr, "mutation_counts: NULL argument");
-      std::lock_guard<std::mutex> lock(table->mutex);
-      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
-      cudaStream_t stream = table->ctx->stream;
-      enqueueMutationCounts(table, column, filter, table->d_counts, stream);
-      const HostColumn& host = *table->columns[static_cast<size_t>(column)];
-      const size_t counts_bytes = static_cast<size_t>(host.dev.n_symbols) * host.dev.genome_length * sizeof(uint32_t);
-      // page-locked destination (silo_gpu_host_alloc): the copy engine writes it directly
-      cudaPointerAttributes attributes{};
-      const bool pinned_destination =
-         cudaPointerGetAttributes(&attributes, counts) == cudaSuccess && attributes.type == cudaMemoryTypeHost;
-      cudaGetLastError();
-      uint32_t* destination = pinned_destination ? counts : table->h_counts_pinned;
-      SILO_CUDA_CHECK(cudaMemcpyAsync(destination, table->d_counts, counts_bytes, cudaMemcpyDeviceToHost, stream));
-      SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
-      if (!pinned_destination) {
-         std::memcpy(counts, table->h_counts_pinned, counts_bytes);
-      }
-   });
+   return guarded([&] { mutationCountsToHost(table, column, filter, ~0ULL, counts); });
+}
+
+int silo_gpu_mutation_counts_symbols(
+   silo_gpu_table* table,
+   int column,
+   const silo_gpu_filter* filter,
+   uint64_t symbol_mask,
+   uint32_t* counts
+) {
+   return guarded([&] { mutationCountsToHost(table, column, filter, symbol_mask, counts); });
 }
 
 }  // extern "C"

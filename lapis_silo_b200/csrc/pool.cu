@@ -493,10 +493,10 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
          table->d_work_items = deviceAlloc<uint32_t>(dev.n_segments, &table->device_bytes);
          table->work_items_capacity = dev.n_segments;
       }
-      if (in->genome_length + 1 > table->coverage_diff_capacity) {
+      if (diffWords(in->genome_length) > table->coverage_diff_capacity) {
          cudaFree(table->d_coverage_diff);
-         table->d_coverage_diff = deviceAlloc<uint32_t>(in->genome_length + 1, &table->device_bytes);
-         table->coverage_diff_capacity = in->genome_length + 1;
+         table->d_coverage_diff = deviceAlloc<uint32_t>(diffWords(in->genome_length), &table->device_bytes);
+         table->coverage_diff_capacity = diffWords(in->genome_length);
       }
       const uint64_t counts_elems = static_cast<uint64_t>(in->n_symbols) * in->genome_length;
       if (counts_elems > table->counts_capacity) {

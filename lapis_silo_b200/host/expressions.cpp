@@ -605,8 +605,10 @@ std::unique_ptr<Operator> RowRanges::compile(const Table& table) const {
 }
 
 DeviceBitmap computeFilter(const ScalarExpression& filter, const Table& table) {
+   const double begin = nowMicroseconds();
    const ExpressionPtr rewritten = filter.rewrite(table, AmbiguityMode::NONE);
    const std::unique_ptr<Operator> compiled = rewritten->compile(table);
+   lastQueryProfile().compile_us = nowMicroseconds() - begin;
    return compiled->evaluate(table);
 }
 

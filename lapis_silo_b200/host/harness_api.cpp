@@ -265,7 +265,10 @@ silo_host_rows* silo_host_mutations(silo_host_table* table, const char* expressi
    silo_host_rows* result = nullptr;
    guarded([&] {
       std::vector<std::string> names(columns, columns + n_columns);
-      const MutationsNode node(*table->table, parseOrTrue(expression), std::move(names), min_proportion);
+      const double parse_begin = nowMicroseconds();
+      ExpressionPtr parsed = parseOrTrue(expression);
+      lastQueryProfile().parse_us = nowMicroseconds() - parse_begin;
+      const MutationsNode node(*table->table, std::move(parsed), std::move(names), min_proportion);
       auto owned = std::make_unique<silo_host_rows>();
       owned->rows = node.execute();
       owned->indexNames();
@@ -288,6 +291,15 @@ silo_host_rows* silo_host_mutation_rows_from_counts(silo_host_table* table, cons
       result = owned.release();
    });
    return result;
+}
+
+void silo_host_last_query_profile(double* out) {
+   const QueryProfile& profile = lastQueryProfile();
+   out[0] = profile.parse_us;
+   out[1] = profile.compile_us;
+   out[2] = profile.filter_us;
+   out[3] = profile.counts_us;
+   out[4] = profile.threshold_us;
 }
 
 void silo_host_rows_free(silo_host_rows* rows) {

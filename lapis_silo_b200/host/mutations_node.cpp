@@ -9,8 +9,16 @@ SymbolCounts calculateMutationsPerPosition(
    const Table& table,
    const SequenceColumnInfo& sequence_column,
    const DeviceBitmap& bitmap_filter,
-   uint64_t sequence_count_in_column
+   uint64_t sequence_count_in_column,
+   bool valid_mutation_symbols_only
 ) {
+   uint64_t symbol_mask = ~0ULL;
+   if (valid_mutation_symbols_only) {
+      symbol_mask = 0;
+      for (const Symbol symbol : sequence_column.alphabet->valid_mutation_symbols) {
+         symbol_mask |= 1ULL << symbol;
+      }
+   }
    SymbolCounts counts;
    counts.n_symbols = sequence_column.alphabet->count();
    counts.genome_length = static_cast<uint32_t>(sequence_column.reference_sequence.size());
@@ -19,13 +27,13 @@ SymbolCounts calculateMutationsPerPosition(
    const uint64_t filter_cardinality = bitmap_filter.cardinality();
    if (filter_cardinality == sequence_count_in_column) {
       // addMutationCountsForFullBitmaps (:239-266): stored cardinalities only, no intersections
-      throwOnDeviceError(
-         silo_gpu_mutation_counts(table.device, sequence_column.device_column, nullptr, counts.owner.get())
-      );
+      throwOnDeviceError(silo_gpu_mutation_counts_symbols(
+         table.device, sequence_column.device_column, nullptr, symbol_mask, counts.owner.get()
+      ));
    } else if (filter_cardinality > 0) {
       // addMutationCountsForMixedBitmaps (:205-237)
-      throwOnDeviceError(silo_gpu_mutation_counts(
-         table.device, sequence_column.device_column, bitmap_filter.get(), counts.owner.get()
+      throwOnDeviceError(silo_gpu_mutation_counts_symbols(
+         table.device, sequence_column.device_column, bitmap_filter.get(), symbol_mask, counts.owner.get()
       ));
    } else {
       std::memset(counts.owner.get(), 0, counts.size() * sizeof(uint32_t));
@@ -40,17 +48,35 @@ void appendMutationRows(
    std::vector<MutationRow>& out
 ) {
    const Alphabet& alphabet = *sequence_column.alphabet;
-   for (uint32_t pos = 0; pos < counts.genome_length; ++pos) {
-      uint32_t total = 0;
-      for (const Symbol symbol : alphabet.valid_mutation_symbols) {
-         total += counts.at(symbol, pos);
+   const uint32_t genome_length = counts.genome_length;
+   // Same arithmetic as the reference, position by position; only the memory order differs: the
+   // totals are summed symbol row by symbol row (sequential streams over the freshly DMA-written
+   // buffer, auto-vectorised) before the per-position pass.
+   thread_local std::vector<uint32_t> totals;
+   thread_local std::vector<uint32_t> any_other;  // OR of the counts of the valid non-reference symbols
+   totals.assign(genome_length, 0);
+   any_other.assign(genome_length, 0);
+   const Symbol* reference_sequence = sequence_column.reference_sequence.data();
+   for (const Symbol symbol : alphabet.valid_mutation_symbols) {
+      const uint32_t* row = counts.values + static_cast<size_t>(symbol) * genome_length;
+      uint32_t* out_totals = totals.data();
+      uint32_t* out_other = any_other.data();
+      for (uint32_t pos = 0; pos < genome_length; ++pos) {
+         const uint32_t value = row[pos];
+         out_totals[pos] += value;
+         out_other[pos] |= reference_sequence[pos] == symbol ? 0u : value;
       }
-      if (total == 0) {
+   }
+   for (uint32_t pos = 0; pos < genome_length; ++pos) {
+      const uint32_t total = totals[pos];
+      // no valid non-reference symbol was counted here (the common case): `count > threshold_count`
+      // cannot hold for a zero count, so no row is emitted
+      if (total == 0 || any_other[pos] == 0) {
          continue;
       }
       const uint32_t threshold_count =
          min_proportion == 0 ? 0 : static_cast<uint32_t>(std::ceil(static_cast<double>(total) * min_proportion) - 1);
-      const Symbol symbol_in_reference_genome = sequence_column.reference_sequence.at(pos);
+      const Symbol symbol_in_reference_genome = reference_sequence[pos];
       for (const Symbol symbol : alphabet.valid_mutation_symbols) {
          if (symbol == symbol_in_reference_genome) {
             continue;
@@ -72,6 +98,8 @@ void appendMutationRows(
 }
 
 std::vector<MutationRow> MutationsNode::execute() const {
+   lastQueryProfile().counts_us = 0;
+   lastQueryProfile().threshold_us = 0;
    const DeviceBitmap bitmap_filter = computeFilter(*filter, table);
    std::vector<MutationRow> rows;
    for (const std::string& name : sequence_columns) {
@@ -79,9 +107,13 @@ std::vector<MutationRow> MutationsNode::execute() const {
       if (column == nullptr) {
          throw IllegalQueryException("Database does not contain the Sequence with name: '" + name + "'");
       }
+      const double counts_begin = nowMicroseconds();
       const SymbolCounts counts =
-         calculateMutationsPerPosition(table, *column, bitmap_filter, table.row_layout.numRows());
+         calculateMutationsPerPosition(table, *column, bitmap_filter, table.row_layout.numRows(), true);
+      const double threshold_begin = nowMicroseconds();
       appendMutationRows(*column, counts, min_proportion, rows);
+      lastQueryProfile().counts_us += threshold_begin - counts_begin;
+      lastQueryProfile().threshold_us += nowMicroseconds() - threshold_begin;
    }
    return rows;
 }

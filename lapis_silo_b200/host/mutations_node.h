@@ -34,7 +34,10 @@ SymbolCounts calculateMutationsPerPosition(
    const Table& table,
    const SequenceColumnInfo& sequence_column,
    const DeviceBitmap& bitmap_filter,
-   uint64_t sequence_count_in_column
+   uint64_t sequence_count_in_column,
+   // fetch only the rows of Alphabet::valid_mutation_symbols (all that addMutationsToOutput reads);
+   // the other rows of the result are then unspecified
+   bool valid_mutation_symbols_only = false
 );
 
 struct MutationRow {

@@ -51,6 +51,7 @@ uint32_t ProgramBuilder::addBitmap(const std::vector<uint8_t>& portable_roaring_
 // ---- Operator ----------------------------------------------------------------------------------
 
 DeviceBitmap Operator::evaluate(const Table& table) const {
+   const double lower_begin = nowMicroseconds();
    ProgramBuilder builder;
    builder.table = &table;
    lower(builder);
@@ -64,7 +65,10 @@ DeviceBitmap Operator::evaluate(const Table& table) const {
    program.bitmaps = builder.bitmaps.data();
    silo_gpu_filter* filter = nullptr;
    uint64_t cardinality = 0;
+   const double eval_begin = nowMicroseconds();
    throwOnDeviceError(silo_gpu_filter_eval(table.device, &program, &filter, &cardinality));
+   lastQueryProfile().compile_us += eval_begin - lower_begin;
+   lastQueryProfile().filter_us = nowMicroseconds() - eval_begin;
    return DeviceBitmap{filter, cardinality};
 }
 

@@ -1,5 +1,7 @@
 #include "table.h"
 
+#include <chrono>
+
 #include <algorithm>
 
 namespace silo_host {
@@ -84,6 +86,15 @@ const Alphabet& Alphabet::aminoAcid() {
       ""
    );
    return instance;
+}
+
+QueryProfile& lastQueryProfile() {
+   thread_local QueryProfile profile;
+   return profile;
+}
+
+double nowMicroseconds() {
+   return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 void throwOnDeviceError(int status) {

@@ -133,4 +133,16 @@ class Table {
 
 void throwOnDeviceError(int status);
 
+// Wall-clock phases of the last query run by the calling thread (microseconds); what
+// profiles/e2e_breakdown.py prints. Costs a handful of steady_clock reads per query.
+struct QueryProfile {
+   double parse_us = 0;       // harness notation -> expression tree
+   double compile_us = 0;     // rewrite + compile + lower to a filter program
+   double filter_us = 0;      // silo_gpu_filter_eval: staging, H2D, kernel, cardinality D2H
+   double counts_us = 0;      // silo_gpu_mutation_counts: kernels + D2H of the counts
+   double threshold_us = 0;   // addMutationsToOutput arithmetic on the host
+};
+QueryProfile& lastQueryProfile();
+double nowMicroseconds();
+
 }  // namespace silo_host

@@ -19,7 +19,7 @@ HOST_LIB_PATH = os.path.join(_HERE, "libsilo_b200_host.so")
 
 HOST_EXPORTED_SYMBOLS = [
     "silo_host_last_error", "silo_host_table_create", "silo_host_table_free", "silo_host_table_add_column",
-    "silo_host_table_register_bitmap", "silo_host_table_device", "silo_host_table_num_rows",
+    "silo_host_last_query_profile", "silo_host_table_register_bitmap", "silo_host_table_device", "silo_host_table_num_rows",
     "silo_host_filter_eval", "silo_host_filter_free", "silo_host_filter_cardinality",
     "silo_host_filter_device", "silo_host_filter_words", "silo_host_filter_explain",
     "silo_host_filter_prepare", "silo_host_prepared_run_async", "silo_host_prepared_filter",
@@ -152,10 +152,10 @@ def _rows(handle) -> list[dict]:
         names = [lib().silo_host_rows_name(handle, i).decode() for i in range(lib().silo_host_rows_num_names(handle))]
         frm_text, to_text = frm.raw.decode("latin-1"), to.raw.decode("latin-1")
         return [{
-            "mutationFrom": frm_text[i], "mutationTo": to_text[i], "position": int(position[i]),
-            "sequenceName": names[name_ids[i]], "proportion": float(proportion[i]), "count": int(count[i]),
-            "coverage": int(coverage[i]),
-        } for i in range(n)]
+            "mutationFrom": f, "mutationTo": t, "position": p, "sequenceName": names[s], "proportion": q,
+            "count": c, "coverage": v,
+        } for f, t, p, s, q, c, v in zip(frm_text, to_text, position.tolist(), name_ids.tolist(),
+                                         proportion.tolist(), count.tolist(), coverage.tolist())]
     finally:
         lib().silo_host_rows_free(handle)
 
@@ -298,6 +298,13 @@ class HostTable:
         handle = lib().silo_host_mutation_rows_from_counts(
             self._h, column.encode(), counts.ctypes.data_as(C.POINTER(C.c_uint32)), min_proportion)
         return _rows(handle)
+
+    @staticmethod
+    def last_query_profile() -> dict:
+        """Microseconds per phase of this thread's last mutations() call."""
+        out = (C.c_double * 5)()
+        lib().silo_host_last_query_profile(out)
+        return dict(zip(("parse_us", "compile_us", "filter_us", "counts_us", "threshold_us"), out))
 
     def stats(self) -> abi.Stats:
         out = abi.Stats()

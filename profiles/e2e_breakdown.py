@@ -32,6 +32,12 @@ timed("mutation_counts(filter): kernels + D2H counts", lambda: table.mutation_co
 counts = table.mutation_counts("main", flt)
 timed("mutation_rows_from_counts: host thresholding", lambda: table.mutation_rows_from_counts("main", counts, 0.05))
 timed("mutations(): whole MutationsNode", lambda: table.mutations(["main"], expression, 0.05))
+acc = {}
+for _ in range(20):
+    table.mutations(["main"], expression, 0.05)
+    for key, value in table.last_query_profile().items():
+        acc[key] = acc.get(key, 0.0) + value / 20
+print("C++ phases of mutations() [us]:", {k: round(v, 1) for k, v in acc.items()}, "sum", round(sum(acc.values()), 1))
 timed("mutation_counts(None): full filter path", lambda: table.mutation_counts("main", None))
 s = table.stats()
 print("stats:", s.containers, s.algorithmic_bytes, s.counts_kernel_bytes, s.last_counts_kernel_ms, s.last_total_ms, s.timed_calls)
