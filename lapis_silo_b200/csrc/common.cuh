@@ -26,26 +26,71 @@ constexpr uint32_t TYPE_BITSET = 1;  // CRoaring typecodes, roaring_container.h:
 constexpr uint32_t TYPE_ARRAY = 2;
 constexpr uint32_t TYPE_RUN = 3;
 
-// device-side piece kinds (DevContainer::packed[31:30]); 1..3 keep the CRoaring typecode meaning
-constexpr uint32_t KIND_INLINE = 0;  // array of 1..2 values stored in DevContainer::n_runs, no payload
-constexpr uint32_t KIND_BITSET = TYPE_BITSET;  // n_runs = first_word | (n_words << 16)
-constexpr uint32_t KIND_ARRAY = TYPE_ARRAY;    // cardinality sorted u16 values
-constexpr uint32_t KIND_RUN = TYPE_RUN;        // n_runs pairs {start, length-1}
-constexpr uint32_t PIECE_BYTES = 1024;         // payload of one piece of a stored container
+// Device-side piece kinds (DevContainer::packed[28:26]). The payload of a stored container is
+// RE-ENCODED at upload into the form the container kernel decodes with the fewest instructions;
+// host bitmaps entering a filter program keep the CRoaring payloads (RAW kinds).
+constexpr uint32_t KIND_INLINE = 0;     // array of 1..2 values stored in DevContainer::aux, no payload
+constexpr uint32_t KIND_BITSET = 1;     // aux = first_word | (n_words << 16); n_words x u64
+constexpr uint32_t KIND_ARRAY_T = 2;    // lane-transposed u16 values, see below
+constexpr uint32_t KIND_RUNS_W = 3;     // runs cut at 32-row word boundaries, one u32 entry each; aux = entries
+constexpr uint32_t KIND_WORDRANGE = 4;  // whole 32-row words [wa, wb): u32 entries wa | wb << 16; aux = entries
+constexpr uint32_t KIND_RAW_ARRAY = 5;  // cardinality sorted u16 values (CRoaring array container)
+constexpr uint32_t KIND_RAW_RUN = 6;    // aux pairs {start, length-1} (CRoaring run container)
+constexpr uint32_t PIECE_BYTES = 1024;  // max payload of one piece of a stored container
 
-// 16-byte device descriptor of one stored diff container (chunk-major order).
+// Both array and run pieces are laid out in REGIONS of up to 512 bytes that a warp reads with ONE
+// 128-bit shared-memory load per lane (a piece is at most two regions, so a warp can pull a whole
+// piece into registers, hand the stage back to the producer, and only then do the lookups).
+//
+// KIND_ARRAY_T: n = cardinality <= 512 values; region r holds count = min(256, n - 256 r) of them in
+// P = ceil(count / 8) lanes: lane L's 16 bytes are the values with in-region index L + P*j, j = 0..7
+// (two per 32-bit word, low half first; indices >= count are padding). The 32 simultaneous tile
+// lookups of one j therefore belong to P CONSECUTIVE sorted values (mostly distinct banks).
+constexpr uint32_t ARRAY_REGION_VALUES = 256;
+__host__ __device__ inline uint32_t arrayRegionLanes(uint32_t count) {
+   return (count + 7) / 8;
+}
+__host__ __device__ inline uint32_t arrayPieceBytes(uint32_t n) {
+   return n <= ARRAY_REGION_VALUES ? arrayRegionLanes(n) * 16u : 512u + arrayRegionLanes(n - ARRAY_REGION_VALUES) * 16u;
+}
+
+// KIND_RUNS_W entry: [31:20] index of the tile's 32-bit word (2048 = the zero pad word: a padding
+// entry) | [19:10] zero | [9:5] (32 - length) & 31 | [4:0] first bit; 1 <= length <= 32 - first bit.
+// |run AND tile| = popc((tile32[word] >> first) << (32 - length)). n = aux <= 256 entries; region r
+// holds count = min(128, n - 128 r) of them in P = ceil(count / 4) lanes: lane L's 16 bytes are the
+// entries L + P*j, j = 0..3, padded with padding entries.
+constexpr uint32_t RUNS_REGION_ENTRIES = 128;
+constexpr uint32_t RUNS_PAD_ENTRY = 2048u << 20;
+__host__ __device__ inline uint32_t runsRegionLanes(uint32_t count) {
+   return (count + 3) / 4;
+}
+__host__ __device__ inline uint32_t runsPieceBytes(uint32_t n) {
+   return n <= RUNS_REGION_ENTRIES ? runsRegionLanes(n) * 16u : 512u + runsRegionLanes(n - RUNS_REGION_ENTRIES) * 16u;
+}
+__host__ __device__ inline uint32_t runEntry(uint32_t word, uint32_t first_bit, uint32_t length) {
+   return (word << 20) | (((32u - length) & 31u) << 5) | first_bit;
+}
+__host__ __device__ inline uint32_t runEntryMask(uint32_t entry) {  // the rows of the entry inside its word
+   const uint32_t length = 32u - ((entry >> 5) & 31u);
+   return (length == 32u ? 0xFFFFFFFFu : ((1u << length) - 1u)) << (entry & 31u);
+}
+
+// 16-byte device descriptor of one piece of a stored diff container (chunk-major order).
 struct __align__(16) DevContainer {
    uint32_t position;
    uint32_t offset4;  // payload offset from the slab start, in 4-byte units
-   uint32_t packed;   // [15:0] cardinality-1 | [23:16] symbol | [29:24] local-reference symbol | [31:30] type
-   uint32_t n_runs;   // KIND_RUN: number of pairs | KIND_BITSET: first_word | n_words << 16 | KIND_INLINE: the values
+   uint32_t packed;   // [15:0] rows-1 | [20:16] symbol | [25:21] local-reference symbol | [28:26] kind
+   uint32_t aux;      // see the kinds
 
    __host__ __device__ uint32_t cardinality() const { return (packed & 0xFFFFu) + 1u; }
-   __host__ __device__ uint32_t symbol() const { return (packed >> 16) & 0xFFu; }
-   __host__ __device__ uint32_t refSymbol() const { return (packed >> 24) & 0x3Fu; }
-   __host__ __device__ uint32_t type() const { return packed >> 30; }
-   __host__ __device__ uint32_t firstWord() const { return n_runs & 0xFFFFu; }
-   __host__ __device__ uint32_t wordCount() const { return n_runs >> 16; }
+   __host__ __device__ uint32_t symbol() const { return (packed >> 16) & 0x1Fu; }
+   __host__ __device__ uint32_t refSymbol() const { return (packed >> 21) & 0x1Fu; }
+   __host__ __device__ uint32_t type() const { return (packed >> 26) & 0x7u; }
+   __host__ __device__ uint32_t firstWord() const { return aux & 0xFFFFu; }
+   __host__ __device__ uint32_t wordCount() const { return aux >> 16; }
+   __host__ __device__ static uint32_t pack(uint32_t rows, uint32_t symbol, uint32_t ref_symbol, uint32_t kind) {
+      return (rows - 1u) | (symbol << 16) | (ref_symbol << 21) | (kind << 26);
+   }
 };
 static_assert(sizeof(DevContainer) == 16);
 
@@ -57,8 +102,10 @@ struct __align__(16) DevSegment {
    uint32_t desc_begin;
    uint32_t desc_count;
    uint32_t chunk;  // local chunk index
-   uint32_t pad[2];
+   uint32_t flags;  // SEG_NEEDS_RANK: holds a KIND_WORDRANGE piece (the consumers build the rank table)
+   uint32_t pad;
 };
+constexpr uint32_t SEG_NEEDS_RANK = 1;
 static_assert(sizeof(DevSegment) == 32);
 
 struct DevColumn {

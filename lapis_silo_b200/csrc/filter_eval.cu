@@ -95,9 +95,25 @@ __device__ __forceinline__ void orBits32(uint32_t* tile32, uint32_t first, uint3
    atomicOr(&tile32[lw], tail);
 }
 
+// Decoders of the column's device piece formats (common.cuh) for the interpreter. `slot` runs over
+// the stored slots of a piece in memory order; the order of the rows does not matter here.
+__device__ __forceinline__ uint32_t arrayPieceSlots(uint32_t n) {
+   return arrayPieceBytes(n) >> 1;
+}
+// whether stored u16 slot `slot` of a KIND_ARRAY_T piece of n values is a value (not padding)
+__device__ __forceinline__ bool arraySlotValid(uint32_t slot, uint32_t n) {
+   const uint32_t region = slot >> 8;  // 256 slots = 512 bytes per region
+   const uint32_t count = min(ARRAY_REGION_VALUES, n - region * ARRAY_REGION_VALUES);
+   const uint32_t in_region = slot & 255u;  // lane = in_region / 8, j = in_region % 8
+   return (in_region >> 3) + arrayRegionLanes(count) * (in_region & 7u) < count;
+}
+__device__ __forceinline__ uint32_t runsPieceSlots(uint32_t n) {  // u32 slots incl. padding entries
+   return runsPieceBytes(n) >> 2;
+}
+
 // tile |= piece (whole CTA). `slab` is the payload slab the descriptor's offset4 refers to. Pieces of
-// a column are <= 512 B; containers of a host bitmap come whole (arrays up to 4096 values, 1024-word
-// bitsets, any number of runs) and take the same code through the strided loops.
+// a column are <= 1 KiB; containers of a host bitmap come whole in the CRoaring layouts (arrays up to
+// 4096 values, 1024-word bitsets, any number of runs) and take the strided loops.
 __device__ void orContainerIntoTile(uint64_t* tile, const uint8_t* slab, const DevContainer& desc) {
    const uint8_t* payload = slab + (static_cast<size_t>(desc.offset4) << 2);
    const uint32_t kind = desc.type();
@@ -108,22 +124,47 @@ __device__ void orContainerIntoTile(uint64_t* tile, const uint8_t* slab, const D
       for (uint32_t w = threadIdx.x; w < desc.wordCount(); w += EVAL_THREADS) {
          tile[first + w] |= words[w];  // callers separate pieces by __syncthreads, so no other writer
       }
-   } else if (kind == KIND_ARRAY) {
+   } else if (kind == KIND_ARRAY_T) {
+      const uint16_t* values = reinterpret_cast<const uint16_t*>(payload);
+      const uint32_t n = desc.cardinality();
+      for (uint32_t slot = threadIdx.x; slot < arrayPieceSlots(n); slot += EVAL_THREADS) {
+         if (arraySlotValid(slot, n)) {
+            const uint32_t value = values[slot];
+            atomicOr(&tile32[value >> 5], 1u << (value & 31));
+         }
+      }
+   } else if (kind == KIND_RUNS_W) {
+      const uint32_t* entries = reinterpret_cast<const uint32_t*>(payload);
+      for (uint32_t i = threadIdx.x; i < runsPieceSlots(desc.aux); i += EVAL_THREADS) {
+         const uint32_t entry = entries[i];
+         if (entry < RUNS_PAD_ENTRY) {
+            atomicOr(&tile32[entry >> 20], runEntryMask(entry));
+         }
+      }
+   } else if (kind == KIND_WORDRANGE) {
+      const uint32_t* ranges = reinterpret_cast<const uint32_t*>(payload);
+      for (uint32_t r = 0; r < desc.aux; ++r) {
+         const uint32_t range = ranges[r];
+         for (uint32_t w = (range & 0xFFFFu) + threadIdx.x; w < (range >> 16); w += EVAL_THREADS) {
+            atomicOr(&tile32[w], 0xFFFFFFFFu);
+         }
+      }
+   } else if (kind == KIND_RAW_ARRAY) {
       const uint16_t* values = reinterpret_cast<const uint16_t*>(payload);
       const uint32_t cardinality = desc.cardinality();
       for (uint32_t i = threadIdx.x; i < cardinality; i += EVAL_THREADS) {
          const uint32_t value = values[i];
          atomicOr(&tile32[value >> 5], 1u << (value & 31));
       }
-   } else if (kind == KIND_RUN) {
+   } else if (kind == KIND_RAW_RUN) {
       const uint32_t* runs = reinterpret_cast<const uint32_t*>(payload);
-      for (uint32_t i = threadIdx.x; i < desc.n_runs; i += EVAL_THREADS) {
+      for (uint32_t i = threadIdx.x; i < desc.aux; i += EVAL_THREADS) {
          const uint32_t run = runs[i];
          const uint32_t first = run & 0xFFFFu;
          orBits32(tile32, first, first + (run >> 16));
       }
    } else if (threadIdx.x < desc.cardinality()) {  // KIND_INLINE
-      const uint32_t value = (desc.n_runs >> (16 * threadIdx.x)) & 0xFFFFu;
+      const uint32_t value = (desc.aux >> (16 * threadIdx.x)) & 0xFFFFu;
       atomicOr(&tile32[value >> 5], 1u << (value & 31));
    }
 }
@@ -143,19 +184,33 @@ __device__ void addContainerToCounters(
       const uint32_t unit = 1u << ((row & 1u) << 4);
       atomicAdd(&counters32[row >> 1], subtract ? 0u - unit : unit);
    };
-   if (kind == KIND_ARRAY) {
-      const uint16_t* values = reinterpret_cast<const uint16_t*>(payload);
-      const uint32_t cardinality = desc.cardinality();
-      for (uint32_t i = lane; i < cardinality; i += 32) {
-         bump(values[i]);
+   auto bumpWord = [&](uint32_t first_row, uint32_t bits) {
+      while (bits != 0) {
+         bump(first_row + static_cast<uint32_t>(__ffs(static_cast<int>(bits)) - 1));
+         bits &= bits - 1;
       }
-   } else if (kind == KIND_RUN) {
-      const uint32_t* runs = reinterpret_cast<const uint32_t*>(payload);
-      for (uint32_t r = 0; r < desc.n_runs; ++r) {
-         const uint32_t run = runs[r];
-         const uint32_t first = run & 0xFFFFu;
-         const uint32_t last = first + (run >> 16);
-         for (uint32_t row = first + lane; row <= last; row += 32) {
+   };
+   if (kind == KIND_ARRAY_T) {
+      const uint16_t* values = reinterpret_cast<const uint16_t*>(payload);
+      const uint32_t n = desc.cardinality();
+      for (uint32_t slot = lane; slot < arrayPieceSlots(n); slot += 32) {
+         if (arraySlotValid(slot, n)) {
+            bump(values[slot]);
+         }
+      }
+   } else if (kind == KIND_RUNS_W) {
+      const uint32_t* entries = reinterpret_cast<const uint32_t*>(payload);
+      for (uint32_t i = lane; i < runsPieceSlots(desc.aux); i += 32) {
+         const uint32_t entry = entries[i];
+         if (entry < RUNS_PAD_ENTRY) {
+            bumpWord((entry >> 20) * 32u, runEntryMask(entry));
+         }
+      }
+   } else if (kind == KIND_WORDRANGE) {
+      const uint32_t* ranges = reinterpret_cast<const uint32_t*>(payload);
+      for (uint32_t r = 0; r < desc.aux; ++r) {
+         const uint32_t range = ranges[r];
+         for (uint32_t row = (range & 0xFFFFu) * 32u + lane; row < (range >> 16) * 32u; row += 32) {
             bump(row);
          }
       }
@@ -169,8 +224,24 @@ __device__ void addContainerToCounters(
             word &= word - 1;
          }
       }
+   } else if (kind == KIND_RAW_ARRAY) {
+      const uint16_t* values = reinterpret_cast<const uint16_t*>(payload);
+      const uint32_t cardinality = desc.cardinality();
+      for (uint32_t i = lane; i < cardinality; i += 32) {
+         bump(values[i]);
+      }
+   } else if (kind == KIND_RAW_RUN) {
+      const uint32_t* runs = reinterpret_cast<const uint32_t*>(payload);
+      for (uint32_t r = 0; r < desc.aux; ++r) {
+         const uint32_t run = runs[r];
+         const uint32_t first = run & 0xFFFFu;
+         const uint32_t last = first + (run >> 16);
+         for (uint32_t row = first + lane; row <= last; row += 32) {
+            bump(row);
+         }
+      }
    } else if (lane < desc.cardinality()) {  // KIND_INLINE
-      bump((desc.n_runs >> (16 * lane)) & 0xFFFFu);
+      bump((desc.aux >> (16 * lane)) & 0xFFFFu);
    }
 }
 
@@ -627,29 +698,29 @@ RoaringSizes parseRoaring(const uint8_t* data, uint64_t size, DevContainer* desc
          if (pos + 2 > size) {
             bad("truncated run container");
          }
-         desc.n_runs = readU16(data + pos);
-         payload_bytes = 4ULL * desc.n_runs;
+         desc.aux = readU16(data + pos);
+         payload_bytes = 4ULL * desc.aux;
          src = data + pos + 2;
          pos += 2 + payload_bytes;
-         type = TYPE_RUN;
+         type = KIND_RAW_RUN;
       } else if (cardinality <= 4096) {
          payload_bytes = 2ULL * cardinality;
          src = data + pos;
          pos += payload_bytes;
-         type = TYPE_ARRAY;
+         type = KIND_RAW_ARRAY;
       } else {
          payload_bytes = 8192;
          src = data + pos;
          pos += payload_bytes;
-         type = TYPE_BITSET;
-         desc.n_runs = TILE_WORDS << 16;  // first word 0, all 1024 words
+         type = KIND_BITSET;
+         desc.aux = TILE_WORDS << 16;  // first word 0, all 1024 words
       }
       if (pos > size) {
          bad("truncated container payload");
       }
       if (descs_out != nullptr) {
          desc.offset4 = static_cast<uint32_t>(sizes.payload_bytes / 4);
-         desc.packed = (cardinality - 1) | (type << 30);
+         desc.packed = DevContainer::pack(cardinality, 0, 0, type);
          std::memcpy(payload_out + sizes.payload_bytes, src, payload_bytes);
          const uint64_t padded = (payload_bytes + 15) / 16 * 16;
          std::memset(payload_out + sizes.payload_bytes + payload_bytes, 0, padded - payload_bytes);

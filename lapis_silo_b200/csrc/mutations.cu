@@ -107,7 +107,7 @@ constexpr int K1_STAGES = 4;
 constexpr int K1_CONSUMER_WARPS = 16;
 constexpr int K1_CONSUMER_THREADS = K1_CONSUMER_WARPS * 32;
 constexpr int K1_THREADS = K1_CONSUMER_THREADS + 32;  // warp 0 = bulk-copy producer
-constexpr uint32_t K1_BATCH = 8;                       // work items claimed per atomicAdd
+constexpr uint32_t K1_BATCH_DEFAULT = 4;               // work items claimed per atomicAdd (<= 32)
 constexpr uint32_t K1_STOP = 0xFFFFFFFFu;              // meta_desc_count marker: no more work
 constexpr uint32_t TILE32_WORDS = 2 * TILE_WORDS;
 
@@ -116,15 +116,24 @@ struct __align__(16) K1Stage {
    DevContainer descs[SEG_MAX_DESCS];
 };
 
+// per-stage meta written by the producer before it arms full_bar; read with one 128-bit load
+struct __align__(16) K1Meta {
+   uint32_t desc_count;  // K1_STOP: no more work
+   uint32_t base4;       // slab offset (4-byte units) of the stage's payload[0]
+   uint32_t flags;       // K1_NEW_TILE | K1_TILE_SLOT | K1_NEEDS_RANK
+   uint32_t pad;
+};
+constexpr uint32_t K1_NEW_TILE = 1;    // the stage's bulk copies also (re)loaded the filter tile
+constexpr uint32_t K1_TILE_SLOT = 2;   // which of the two filter-tile buffers the stage reads
+constexpr uint32_t K1_NEEDS_RANK = 4;  // a KIND_WORDRANGE piece is inside: the rank table must exist
+
 struct __align__(16) K1Dynamic {
    K1Stage stages[K1_STAGES];
+   K1Meta meta[K1_STAGES];
    uint64_t full_bar[K1_STAGES];
-   uint64_t empty_bar[K1_STAGES];
-   // per-stage meta written by the producer before it arms full_bar
-   uint32_t meta_desc_count[K1_STAGES];
-   uint32_t meta_base4[K1_STAGES];  // slab offset (4-byte units) of the stage's payload[0]
-   uint32_t meta_new_tile[K1_STAGES];
-   uint32_t meta_tile_slot[K1_STAGES];  // which of the two filter-tile buffers the stage reads
+   uint64_t empty_bar[K1_STAGES];  // every consumer warp has pulled its pieces of the stage into registers
+   uint64_t done_bar[K1_STAGES];   // ... and has finished the tile lookups for them
+   uint32_t claim[K1_STAGES];      // next unclaimed piece of the stage (reset by the producer)
    uint32_t warp_sums[K1_CONSUMER_WARPS];
 };
 
@@ -132,129 +141,159 @@ __device__ __forceinline__ uint32_t warpSum(uint32_t value) {
    return __reduce_add_sync(0xFFFFFFFFu, value);
 }
 
-__device__ __forceinline__ uint32_t lowMask(uint32_t bits) {  // (1 << bits) - 1 for bits in [0, 31]
-   uint32_t mask;
-   asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(mask) : "r"(bits));
-   return mask;
-}
-
-// number of filter rows below `row` (row in [0, 65536]): exclusive rank from the per-32-bit-word
-// prefix table plus the bits below `row` inside its word. tile32[2048] is a zero pad word.
-__device__ __forceinline__ uint32_t rankBelow(const uint32_t* tile32, const uint32_t* rank32, uint32_t row) {
-   const uint32_t word = row >> 5;
-   return rank32[word] + __popc(tile32[word] & lowMask(row & 31u));
-}
-
-// Integer shifts by constants are issued as IMAD.HI (x * 2^k >> 32) on the FMA pipe instead of SHF
-// on the ALU pipe: the bit tests below are bound by the 16-lane ALU pipe (LOP3 / SHF / IADD3), the
-// FMA pipe is idle otherwise. The multipliers come from opaque registers so that the compiler does
-// not turn the multiplications back into shifts.
-struct PipeBalance {
-   uint32_t two_pow_11;  // x * 2^11 >> 32 == x >> 21
-   uint32_t two_pow_16;  // x * 2^16 >> 32 == x >> 16
+// The consumers are bound by instruction issue, so every bit test is spelled with the fewest
+// instructions the ISA offers: a byte offset into the tile is one IMAD.HI with accumulate
+// (x * 2^k >> 32, plus the tile's shared-memory address), shifts take their amount from the low
+// five bits of a register (funnel shifts in wrap mode), and the multipliers live in registers the
+// compiler cannot see through (otherwise it turns the multiplications back into shift + add).
+struct Multipliers {
+   uint32_t two_pow_13;  // (x & 0xFFE00000) * 2^13 >> 32 = (x >> 21) * 4
+   uint32_t two_pow_14;  //  x * 2^14 >> 32 = x >> 18
+   uint32_t two_pow_27;  //  x * 2^27 >> 32 = x >> 5
+   uint32_t two_pow_29;  // (x & 0xFFE0) * 2^29 >> 32 = ((x & 0xFFFF) >> 5) * 4
 };
 
-__device__ __forceinline__ uint32_t mulHigh(uint32_t value, uint32_t multiplier) {
-   uint32_t result;
-   asm("mul.hi.u32 %0, %1, %2;" : "=r"(result) : "r"(value), "r"(multiplier));
-   return result;
+__device__ __forceinline__ uint32_t madHi(uint32_t a, uint32_t b, uint32_t c) {
+   uint32_t d;
+   asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+   return d;
+}
+__device__ __forceinline__ uint32_t mulHi(uint32_t a, uint32_t b) {
+   uint32_t d;
+   asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+   return d;
+}
+// Reads of the filter tile / rank table by shared-memory BYTE address. Not volatile: the address
+// always derives from payload words loaded after the stage's full barrier was observed.
+__device__ __forceinline__ uint32_t ldShared32(uint32_t shared_address) {
+   uint32_t value;
+   asm("ld.shared.u32 %0, [%1];" : "=r"(value) : "r"(shared_address));
+   return value;
 }
 
-template <bool CHECKED>
-__device__ __forceinline__ uint32_t arrayVector(const uint32_t* tile32, const PipeBalance& k, uint4 eight, uint32_t valid) {
-   const uint32_t words[4] = {eight.x, eight.y, eight.z, eight.w};
-   uint32_t total = 0;
+// two u16 rows packed in one word -> number of them that are set in the tile
+__device__ __forceinline__ uint32_t pairBits(uint32_t tile_address, const Multipliers& k, uint32_t pair, uint32_t& lo_bit, uint32_t& hi_bit) {
+   const uint32_t lo_word = ldShared32(madHi(pair & 0x0000FFE0u, k.two_pow_29, tile_address));
+   const uint32_t hi_word = ldShared32(madHi(pair & 0xFFE00000u, k.two_pow_13, tile_address));
+   lo_bit = __funnelshift_r(lo_word, 0u, pair) & 1u;         // shift = pair & 31 = row & 31 of the low half
+   hi_bit = __funnelshift_r(hi_word, 0u, pair >> 16) & 1u;
+   return lo_bit + hi_bit;
+}
+
+// one KIND_RUNS_W entry -> rows of the run that are set in the tile
+__device__ __forceinline__ uint32_t runEntryCount(uint32_t tile_address, const Multipliers& k, uint32_t entry) {
+   const uint32_t word = ldShared32(madHi(entry, k.two_pow_14, tile_address));       // tile32[entry >> 20]
+   const uint32_t from_first = __funnelshift_r(word, 0u, entry);                      // word >> (entry & 31)
+   return __popc(__funnelshift_l(0u, from_first, mulHi(entry, k.two_pow_27)));        // << (32 - length)
+}
+
+// lookups of one array region held in registers (count values in P = ceil(count/8) lanes)
+__device__ __forceinline__ uint32_t arrayRegionCount(
+   uint32_t tile_address,
+   const Multipliers& k,
+   const uint4& eight,
+   uint32_t count,
+   uint32_t lane
+) {
+   uint32_t lo_bit, hi_bit;
+   if (count == ARRAY_REGION_VALUES) {  // the full region: no padding
+      return pairBits(tile_address, k, eight.x, lo_bit, hi_bit) + pairBits(tile_address, k, eight.y, lo_bit, hi_bit) +
+             pairBits(tile_address, k, eight.z, lo_bit, hi_bit) + pairBits(tile_address, k, eight.w, lo_bit, hi_bit);
+   }
+   const uint32_t lanes = arrayRegionLanes(count);
+   uint32_t local = 0;
+   if (lane < lanes) {
+      const uint32_t words[4] = {eight.x, eight.y, eight.z, eight.w};
+      uint32_t index = lane;  // in-region index of the low half of words[i]
 #pragma unroll
-   for (uint32_t i = 0; i < 4; ++i) {
-      // two u16 rows per 32-bit word; funnel shifts use the low five bits of the shift register
-      const uint32_t word = words[i];
-      const uint32_t hi = mulHigh(word, k.two_pow_16);                         // word >> 16
-      const uint32_t hi_index = mulHigh(word, k.two_pow_11);                   // (word >> 16) >> 5
-      const uint32_t lo_index = mulHigh(word * 65536u, k.two_pow_11);          // (word & 0xFFFF) >> 5
-      const uint32_t lo_bit = __funnelshift_r(tile32[lo_index], 0u, word) & 1u;
-      const uint32_t hi_bit = __funnelshift_r(tile32[hi_index], 0u, hi) & 1u;
-      if (CHECKED) {
-         total += (2 * i < valid ? lo_bit : 0u) + (2 * i + 1 < valid ? hi_bit : 0u);
-      } else {
-         total += lo_bit + hi_bit;
+      for (uint32_t i = 0; i < 4; ++i) {
+         pairBits(tile_address, k, words[i], lo_bit, hi_bit);
+         local += (index < count ? lo_bit : 0u) + (index + lanes < count ? hi_bit : 0u);
+         index += 2 * lanes;
       }
    }
-   return total;
+   return local;
 }
 
-// |piece AND tile| for one piece (16-byte aligned payload in shared memory): every lane takes whole
-// 128-bit vectors of the payload (8 array values / 4 runs / 2 bitset words).
-__device__ __forceinline__ uint32_t pieceAndCardinality(
+// one run region held in registers (padding entries count nothing; lanes beyond the region hold junk)
+__device__ __forceinline__ uint32_t runsRegionCount(
+   uint32_t tile_address,
+   const Multipliers& k,
+   const uint4& four,
+   uint32_t count,
+   uint32_t lane
+) {
+   if (lane >= runsRegionLanes(count)) {
+      return 0;
+   }
+   return runEntryCount(tile_address, k, four.x) + runEntryCount(tile_address, k, four.y) +
+          runEntryCount(tile_address, k, four.z) + runEntryCount(tile_address, k, four.w);
+}
+
+// |piece AND tile| for a piece whose (at most) two 512-byte regions sit in registers: lane L holds
+// bytes [16 L, 16 L + 16) of each region. Kinds with other layouts return false (the caller reads
+// them from the stage instead).
+__device__ __forceinline__ uint32_t pieceFromRegisters(
    const DevContainer& desc,
-   const uint8_t* payload,    // shared
-   const uint32_t* tile32,    // shared, 2049 words
-   const uint32_t* rank32,    // shared, 2049 words
-   const PipeBalance& k,
+   const uint4& first,
+   const uint4& second,
+   const uint32_t* tile32,  // shared, 2049 words ([2048] = 0)
+   const Multipliers& k,
    uint32_t lane
 ) {
    const uint32_t kind = desc.type();
-   const uint4* vectors = reinterpret_cast<const uint4*>(payload);
+   const uint32_t tile_address = static_cast<uint32_t>(__cvta_generic_to_shared(tile32));
    uint32_t local = 0;
-   if (kind == KIND_ARRAY) {
-      // One value per lane and iteration: the 32 simultaneous tile lookups then belong to 32
-      // CONSECUTIVE sorted values, whose words ascend (mostly distinct banks, neighbours broadcast).
-      // Eight values per lane (128-bit loads) would make the lookups stride-8 in sorted order and
-      // cost ~3.4 shared-memory wavefronts each.
-      const uint32_t cardinality = desc.cardinality();
-      const uint16_t* values = reinterpret_cast<const uint16_t*>(payload);
-#pragma unroll 4
-      for (uint32_t i = lane; i < cardinality; i += 32) {
-         const uint32_t value = values[i];
-         local += __funnelshift_r(tile32[value >> 5], 0u, value) & 1u;
+   if (kind == KIND_ARRAY_T) {
+      const uint32_t n = desc.cardinality();
+      local = arrayRegionCount(tile_address, k, first, min(n, ARRAY_REGION_VALUES), lane);
+      if (n > ARRAY_REGION_VALUES) {
+         local += arrayRegionCount(tile_address, k, second, n - ARRAY_REGION_VALUES, lane);
       }
-   } else if (kind == KIND_RUN) {
-      const uint32_t n_runs = desc.n_runs;
-      const uint32_t* runs = reinterpret_cast<const uint32_t*>(payload);
-      // one run per lane and iteration. Runs of up to 31 rows (the common case) are answered from a
-      // 64-bit window of the tile aligned at the run's first row; longer runs from the rank table.
-      for (uint32_t r = lane; r < n_runs; r += 32) {
-         const uint32_t run = runs[r];
-         const uint32_t length_minus_one = mulHigh(run, k.two_pow_16);  // run >> 16
-         if (length_minus_one < 31) {
-            const uint32_t word = mulHigh(run * 65536u, k.two_pow_11);  // (run & 0xFFFF) >> 5
-            const uint32_t window = __funnelshift_r(tile32[word], tile32[word + 1], run);  // shift = first & 31
-            local += __popc(window & lowMask(length_minus_one + 1));
-         } else {
-            const uint32_t first = run & 0xFFFFu;
-            const uint32_t end = first + length_minus_one + 1;  // exclusive, <= 65536
-            local += rankBelow(tile32, rank32, end) - rankBelow(tile32, rank32, first);
-         }
+   } else if (kind == KIND_RUNS_W) {
+      const uint32_t n = desc.aux;
+      local = runsRegionCount(tile_address, k, first, min(n, RUNS_REGION_ENTRIES), lane);
+      if (n > RUNS_REGION_ENTRIES) {
+         local += runsRegionCount(tile_address, k, second, n - RUNS_REGION_ENTRIES, lane);
       }
-   } else if (kind == KIND_BITSET) {
+   } else if (kind == KIND_BITSET) {  // 128 words: 64 vectors, two per lane
       const uint4* tile4 = reinterpret_cast<const uint4*>(tile32 + 2 * desc.firstWord());
-      const uint32_t n_vectors = desc.wordCount() >> 1;
-      for (uint32_t v = lane; v < n_vectors; v += 32) {
-         const uint4 a = vectors[v];
-         const uint4 b = tile4[v];
-         local += __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
-      }
-   } else {  // KIND_INLINE: one or two values inside the descriptor
+      const uint4 a = tile4[lane];
+      const uint4 b = tile4[32 + lane];
+      local = __popc(first.x & a.x) + __popc(first.y & a.y) + __popc(first.z & a.z) + __popc(first.w & a.w) +
+              __popc(second.x & b.x) + __popc(second.y & b.y) + __popc(second.z & b.z) + __popc(second.w & b.w);
+   } else if (kind == KIND_INLINE) {  // one or two values inside the descriptor
       if (lane < desc.cardinality()) {
-         const uint32_t value = (desc.n_runs >> (16 * lane)) & 0xFFFFu;
+         const uint32_t value = (desc.aux >> (16 * lane)) & 0xFFFFu;
          local = (tile32[value >> 5] >> (value & 31u)) & 1u;
       }
    }
    return warpSum(local);
 }
 
-// STREAM_ONLY (profiling aid, SILO_K1_STREAM_ONLY=1): consumers skip the intersection, which measures
-// what the bulk-copy pipeline alone can stream.
-template <int STREAM_ONLY>
+// KIND_WORDRANGE: whole 32-row words [wa, wb) from the exclusive rank table (payload in the stage)
+__device__ __forceinline__ uint32_t wordRangeCount(const DevContainer& desc, const uint8_t* payload, const uint32_t* rank32, uint32_t lane) {
+   const uint32_t* ranges = reinterpret_cast<const uint32_t*>(payload);
+   uint32_t local = 0;
+   for (uint32_t r = lane; r < desc.aux; r += 32) {
+      const uint32_t range = ranges[r];
+      local += rank32[range >> 16] - rank32[range & 0xFFFFu];
+   }
+   return warpSum(local);
+}
+
+// MODE (profiling aid, SILO_K1_STREAM_ONLY): 0 = the product; 1 = consumers skip the intersection
+// (what the bulk-copy pipeline alone can stream); 2 = no atomics; 3 = touch the payload only.
+template <int MODE>
 __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
    DevColumn column,
    const uint64_t* __restrict__ filter_words,   // [n_chunks * 1024]
    const uint32_t* __restrict__ work_prefix,    // [n_chunks + 2]; [n_chunks] = number of work items
    uint32_t* __restrict__ work_counter,         // grid-wide claim counter (zeroed by buildWorkListKernel)
    const uint32_t* __restrict__ work_items,     // segment index per work item
-   uint32_t* __restrict__ counts                // [n_symbols * genome_length]
+   uint32_t* __restrict__ counts,               // [n_symbols * genome_length]
+   uint32_t claim_batch                         // work items per claim
 ) {
-   // the filter tile and its rank table sit in STATIC shared memory: fixed addresses let the
-   // compiler fold them into the LDS immediates of the bit tests
    // Two tile buffers: the producer loads the next chunk's tile while stages of the current chunk
    // are still being consumed, so a chunk switch does not drain the pipeline.
    __shared__ __align__(16) uint32_t tile_buffers[2][TILE32_WORDS + 4];  // [2048] = zero pad word
@@ -270,6 +309,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
       for (int s = 0; s < K1_STAGES; ++s) {
          mbarInit(&sh.full_bar[s], 1);
          mbarInit(&sh.empty_bar[s], K1_CONSUMER_WARPS);
+         mbarInit(&sh.done_bar[s], K1_CONSUMER_WARPS);
       }
       fenceBarrierInit();
    }
@@ -280,18 +320,19 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
 
    if (warp == 0) {
       // ---------------- producer warp -----------------------------------------------------------
-      // Lanes 0..K1_BATCH-1 fetch the segment descriptors of the NEXT claimed batch while lane 0
-      // issues the current one, so no global-memory latency sits between two bulk copies.
-      auto claim = [&]() -> uint32_t {
+      // Three batches are in flight: the stages of batch n are being issued while lanes
+      // 0..claim_batch-1 fetch the segment descriptors of batch n+1 and lane 0's atomic claims batch
+      // n+2, so neither the claim's nor the fetch's global-memory latency sits between two bulk copies.
+      auto claimAsync = [&]() -> uint32_t {  // the result is only valid in lane 0, and only waited for when used
          uint32_t first = 0;
          if (lane == 0) {
-            first = atomicAdd(work_counter, K1_BATCH);
+            first = atomicAdd(work_counter, claim_batch);
          }
-         return __shfl_sync(0xFFFFFFFFu, first, 0);
+         return first;
       };
       auto fetch = [&](uint32_t first) -> DevSegment {
          DevSegment segment{};
-         if (lane < K1_BATCH && first + lane < total) {
+         if (lane < claim_batch && first + lane < total) {
             segment = column.segments[work_items[first + lane]];
          }
          return segment;
@@ -300,12 +341,14 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
       uint32_t tile_slot = 1;         // buffer holding the current chunk's tile
       uint32_t tile_first_stage = 0;  // first stage that reads the current tile
       uint32_t it = 0;                // stages issued so far by this CTA
-      uint32_t batch_first = claim();
+      uint32_t batch_first = __shfl_sync(0xFFFFFFFFu, claimAsync(), 0);
+      uint32_t claimed_ahead = claimAsync();
       DevSegment upcoming = fetch(batch_first);
       while (batch_first < total) {
          const DevSegment mine = upcoming;
-         const uint32_t batch = min(K1_BATCH, total - batch_first);
-         batch_first = claim();
+         const uint32_t batch = min(claim_batch, total - batch_first);
+         batch_first = __shfl_sync(0xFFFFFFFFu, claimed_ahead, 0);
+         claimed_ahead = claimAsync();
          upcoming = fetch(batch_first);
          for (uint32_t j = 0; j < batch; ++j) {
             const uint32_t offset_lo = __shfl_sync(0xFFFFFFFFu, static_cast<uint32_t>(mine.payload_offset), j);
@@ -314,6 +357,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
             const uint32_t desc_begin = __shfl_sync(0xFFFFFFFFu, mine.desc_begin, j);
             const uint32_t desc_count = __shfl_sync(0xFFFFFFFFu, mine.desc_count, j);
             const uint32_t chunk = __shfl_sync(0xFFFFFFFFu, mine.chunk, j);
+            const uint32_t segment_flags = __shfl_sync(0xFFFFFFFFu, mine.flags, j);
             if (lane == 0) {
                const uint64_t payload_offset = (static_cast<uint64_t>(offset_hi) << 32) | offset_lo;
                const uint32_t stage = it % K1_STAGES;
@@ -323,20 +367,27 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
                   mbarWait(&sh.empty_bar[stage], (round - 1) & 1u);  // => every stage <= it - K1_STAGES is consumed
                }
                if (new_tile) {
-                  // The new tile goes into the OTHER buffer, last read by the stages before
-                  // tile_first_stage. Those are normally long consumed; wait for any that are not.
-                  const uint32_t consumed_below = it >= K1_STAGES ? it - K1_STAGES + 1 : 0;
-                  for (uint32_t prev = consumed_below; prev < tile_first_stage; ++prev) {
-                     mbarWait(&sh.empty_bar[prev % K1_STAGES], (prev / K1_STAGES) & 1u);
+                  // The new tile goes into the OTHER buffer, last read by the lookups of the stages
+                  // before tile_first_stage. A warp hands a stage back BEFORE it does the lookups, so the
+                  // stage's empty barrier says nothing about the tile: wait for the done barriers. (Stages
+                  // below it - K1_STAGES are implied: a warp pulls stage q + K1_STAGES only after it has
+                  // finished stage q, and the empty wait above covered stage it - K1_STAGES.)
+                  const uint32_t computed_below = it >= K1_STAGES ? it - K1_STAGES : 0;
+                  for (uint32_t prev = computed_below; prev < tile_first_stage; ++prev) {
+                     mbarWait(&sh.done_bar[prev % K1_STAGES], (prev / K1_STAGES) & 1u);
                   }
                   tile_slot ^= 1u;
                   tile_first_stage = it;
                   current_tile_chunk = chunk;
                }
-               sh.meta_desc_count[stage] = desc_count;
-               sh.meta_base4[stage] = static_cast<uint32_t>(payload_offset >> 2);
-               sh.meta_new_tile[stage] = new_tile ? 1u : 0u;
-               sh.meta_tile_slot[stage] = tile_slot;
+               K1Meta meta;
+               meta.desc_count = desc_count;
+               meta.base4 = static_cast<uint32_t>(payload_offset >> 2);
+               meta.flags = (new_tile ? K1_NEW_TILE : 0u) | (tile_slot != 0 ? K1_TILE_SLOT : 0u) |
+                            ((segment_flags & SEG_NEEDS_RANK) != 0 ? K1_NEEDS_RANK : 0u);
+               meta.pad = 0;
+               sh.meta[stage] = meta;
+               sh.claim[stage] = 0;
                const uint32_t desc_bytes = desc_count * static_cast<uint32_t>(sizeof(DevContainer));
                mbarExpectTx(&sh.full_bar[stage], desc_bytes + payload_bytes + (new_tile ? TILE_BYTES : 0u));
                if (new_tile) {
@@ -358,92 +409,137 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
          if (round > 0) {
             mbarWait(&sh.empty_bar[stage], (round - 1) & 1u);
          }
-         sh.meta_desc_count[stage] = K1_STOP;
+         K1Meta meta{};
+         meta.desc_count = K1_STOP;
+         sh.meta[stage] = meta;
          mbarArrive(&sh.full_bar[stage]);
       }
       return;
    }
 
-   // ---------------- consumers: 16 warps, one piece per warp at a time ---------------------------
+   // ---------------- consumers: 16 warps ----------------------------------------------------------
+   // A warp CLAIMS the pieces of a stage one at a time from a shared counter: pieces differ in cost
+   // by two orders of magnitude, and with a fixed assignment the slowest warp of every stage would
+   // set the pace. It pulls the claimed piece (descriptor + at most two 512-byte regions) into
+   // REGISTERS, claims the next one, and -- if the stage has none left for it -- hands the stage back
+   // to the producer BEFORE doing the tile lookups: the ring's stages are in flight again while the
+   // arithmetic runs (with four 16 KiB stages per CTA the kernel is bound by the bytes in flight as
+   // soon as stages are held for the duration of the lookups). A warp leaves a stage only after a
+   // failed claim, i.e. when every piece is claimed, and every claimer loads its piece before it
+   // leaves, so "all 16 warps left" (the empty barrier) means the stage buffer is free.
    const uint32_t cwarp = warp - 1;
    const uint32_t cthread = threadIdx.x - 32;  // 0..511
    const uint32_t genome_length = column.genome_length;
-   // opaque to the compiler (gridDim.y is 1): keeps the IMAD.HI forms, see PipeBalance
-   PipeBalance k;
-   k.two_pow_11 = gridDim.y << 11;
-   k.two_pow_16 = gridDim.y << 16;
-   uint32_t rotation = 0;
-   for (uint32_t it = 0;; ++it) {
-      const uint32_t stage = it % K1_STAGES;
-      mbarWait(&sh.full_bar[stage], (it / K1_STAGES) & 1u);
-      const uint32_t desc_count = sh.meta_desc_count[stage];
+   // opaque to the compiler (gridDim.y is 1): keeps the IMAD.HI forms, see Multipliers
+   Multipliers k;
+   k.two_pow_13 = gridDim.y << 13;
+   k.two_pow_14 = gridDim.y << 14;
+   k.two_pow_27 = gridDim.y << 27;
+   k.two_pow_29 = gridDim.y << 29;
+   uint32_t rank_valid = 0;  // bit s: rank_buffers[s] belongs to the tile now in tile_buffers[s]
+   uint32_t stage = 0;
+   uint32_t phase = 0;
+   auto claimPiece = [&](uint32_t of_stage) -> uint32_t {
+      uint32_t claimed = 0;
+      if (lane == 0) {
+         claimed = atomicAdd(&sh.claim[of_stage], 1u);
+      }
+      return __shfl_sync(0xFFFFFFFFu, claimed, 0);
+   };
+   for (;;) {
+      mbarWait(&sh.full_bar[stage], phase);
+      const uint4 meta_words = *reinterpret_cast<const uint4*>(&sh.meta[stage]);
+      const uint32_t desc_count = meta_words.x;
       if (desc_count == K1_STOP) {
          break;
       }
-      const uint32_t* tile32 = tile_buffers[sh.meta_tile_slot[stage]];
-      uint32_t* rank32 = rank_buffers[sh.meta_tile_slot[stage]];
-      if (sh.meta_new_tile[stage] != 0) {
-         // rebuild the exclusive rank table of the freshly loaded tile: 512 threads x 4 words
-         const uint4 four = reinterpret_cast<const uint4*>(tile32)[cthread];
-         const uint32_t p0 = __popc(four.x);
-         const uint32_t p1 = __popc(four.y);
-         const uint32_t p2 = __popc(four.z);
-         const uint32_t p3 = __popc(four.w);
-         const uint32_t mine = p0 + p1 + p2 + p3;
-         uint32_t inclusive = mine;
-         for (int offset = 1; offset < 32; offset <<= 1) {
-            const uint32_t other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
-            if (lane >= static_cast<uint32_t>(offset)) {
-               inclusive += other;
+      uint32_t index = claimPiece(stage);
+      const uint32_t base4 = meta_words.y;
+      const uint32_t flags = meta_words.z;
+      const uint32_t slot = (flags / K1_TILE_SLOT) & 1u;
+      const uint32_t* tile32 = tile_buffers[slot];
+      uint32_t* rank32 = rank_buffers[slot];
+      if ((flags & (K1_NEW_TILE | K1_NEEDS_RANK)) != 0) {  // rare: a chunk switch or a long-run piece
+         if ((flags & K1_NEW_TILE) != 0) {
+            rank_valid &= ~(1u << slot);
+         }
+         if ((flags & K1_NEEDS_RANK) != 0 && ((rank_valid >> slot) & 1u) == 0) {
+            // (every consumer warp sees the same stages in the same order, so all of them get here)
+            // exclusive rank table of the tile: 512 threads x 4 words
+            rank_valid |= 1u << slot;
+            const uint4 four = reinterpret_cast<const uint4*>(tile32)[cthread];
+            const uint32_t p0 = __popc(four.x);
+            const uint32_t p1 = __popc(four.y);
+            const uint32_t p2 = __popc(four.z);
+            const uint32_t p3 = __popc(four.w);
+            const uint32_t mine = p0 + p1 + p2 + p3;
+            uint32_t inclusive = mine;
+            for (int offset = 1; offset < 32; offset <<= 1) {
+               const uint32_t other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
+               if (lane >= static_cast<uint32_t>(offset)) {
+                  inclusive += other;
+               }
             }
+            asm volatile("bar.sync 1, %0;" ::"n"(K1_CONSUMER_THREADS) : "memory");  // warp_sums of the previous build are read
+            if (lane == 31) {
+               sh.warp_sums[cwarp] = inclusive;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(K1_CONSUMER_THREADS) : "memory");
+            uint32_t exclusive = inclusive - mine;
+            for (uint32_t w = 0; w < cwarp; ++w) {
+               exclusive += sh.warp_sums[w];
+            }
+            reinterpret_cast<uint4*>(rank32)[cthread] = make_uint4(exclusive, exclusive + p0, exclusive + p0 + p1, exclusive + p0 + p1 + p2);
+            if (cthread == K1_CONSUMER_THREADS - 1) {
+               rank32[TILE32_WORDS] = exclusive + mine;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(K1_CONSUMER_THREADS) : "memory");
          }
-         if (lane == 31) {
-            sh.warp_sums[cwarp] = inclusive;
-         }
-         asm volatile("bar.sync 1, %0;" ::"n"(K1_CONSUMER_THREADS) : "memory");
-         uint32_t exclusive = inclusive - mine;
-         for (uint32_t w = 0; w < cwarp; ++w) {
-            exclusive += sh.warp_sums[w];
-         }
-         reinterpret_cast<uint4*>(rank32)[cthread] = make_uint4(exclusive, exclusive + p0, exclusive + p0 + p1, exclusive + p0 + p1 + p2);
-         if (cthread == K1_CONSUMER_THREADS - 1) {
-            rank32[TILE32_WORDS] = exclusive + mine;
-         }
-         asm volatile("bar.sync 1, %0;" ::"n"(K1_CONSUMER_THREADS) : "memory");
       }
-      const uint32_t base4 = sh.meta_base4[stage];
       const K1Stage& st = sh.stages[stage];
-      // pieces go round-robin to the warps ACROSS stages (the rotation continues where the previous
-      // stage stopped), so a stage with 16n + m pieces does not always burden the same m warps
-      const uint32_t first_index = (cwarp - rotation) & (K1_CONSUMER_WARPS - 1);
-      rotation = (rotation + desc_count) & (K1_CONSUMER_WARPS - 1);
-      for (uint32_t index = first_index; index < desc_count && STREAM_ONLY != 1; index += K1_CONSUMER_WARPS) {
+      bool released = false;
+      while (index < desc_count) {
          const DevContainer desc = st.descs[index];
          const uint8_t* payload = st.payload + (static_cast<size_t>(desc.offset4 - base4) << 2);
-         uint32_t count;
-         if (STREAM_ONLY == 3) {  // profiling: touch the payload only
-            const uint4* vectors = reinterpret_cast<const uint4*>(payload);
-            uint32_t local = 0;
-            const uint32_t n = desc.type() == KIND_ARRAY ? (desc.cardinality() + 7) >> 3 : (desc.type() == KIND_RUN ? (desc.n_runs + 3) >> 2 : 0);
-            for (uint32_t v = lane; v < n; v += 32) {
-               const uint4 x = vectors[v];
-               local += x.x ^ x.y ^ x.z ^ x.w;
-            }
-            count = warpSum(local) == 0x12345678u ? 1u : 0u;
+         // (reads past a short piece stay inside the stage buffer; those lanes are ignored)
+         const uint4 first = reinterpret_cast<const uint4*>(payload)[lane];
+         const uint4 second = reinterpret_cast<const uint4*>(payload)[32 + lane];
+         uint32_t count = 0;
+         if (desc.type() == KIND_WORDRANGE) {
+            count = wordRangeCount(desc, payload, rank32, lane);  // (reads the stage: claim afterwards)
+            index = claimPiece(stage);
          } else {
-            count = pieceAndCardinality(desc, payload, tile32, rank32, k, lane);
+            index = claimPiece(stage);
+            if (index >= desc_count) {  // nothing left here for this warp: the stage can go back
+               __syncwarp();
+               if (lane == 0) {
+                  mbarArrive(&sh.empty_bar[stage]);
+               }
+               released = true;
+            }
+            if (MODE == 3) {  // profiling: touch the payload only
+               const uint32_t local = first.x ^ first.y ^ first.z ^ first.w ^ second.x ^ second.y ^ second.z ^ second.w;
+               count = warpSum(local) == 0x12345678u ? 1u : 0u;
+            } else if (MODE != 1) {
+               count = pieceFromRegisters(desc, first, second, tile32, k, lane);
+            }
          }
-         if (lane == 0 && count != 0 && STREAM_ONLY != 2) {
+         if (lane == 0 && count != 0 && MODE != 2) {
             atomicAdd(&counts[desc.symbol() * genome_length + desc.position], count);
          }
-         if (STREAM_ONLY == 2 && count == 0xFFFFFFFFu) {
+         if (MODE == 2 && count == 0xFFFFFFFFu) {
             counts[0] = 1;
          }
       }
       __syncwarp();
       if (lane == 0) {
-         mbarArrive(&sh.empty_bar[stage]);
+         if (!released) {
+            mbarArrive(&sh.empty_bar[stage]);
+         }
+         mbarArrive(&sh.done_bar[stage]);
       }
+      stage = (stage + 1) % K1_STAGES;
+      phase ^= stage == 0 ? 1u : 0u;
    }
 }
 
@@ -706,6 +802,7 @@ void enqueueMutationCounts(
       if (column.n_segments > 0) {
          static bool attribute_set = false;
          static int stream_only = 0;
+         static uint32_t claim_batch = K1_BATCH_DEFAULT;
          if (!attribute_set) {
             SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
             SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
@@ -713,12 +810,16 @@ void enqueueMutationCounts(
             SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
             const char* flag = std::getenv("SILO_K1_STREAM_ONLY");
             stream_only = flag != nullptr ? flag[0] - '0' : 0;
+            const char* batch_flag = std::getenv("SILO_K1_BATCH");
+            if (batch_flag != nullptr) {
+               claim_batch = static_cast<uint32_t>(std::min(32, std::max(1, std::atoi(batch_flag))));
+            }
             attribute_set = true;
          }
          const int blocks = static_cast<int>(std::min<uint32_t>(column.n_segments, static_cast<uint32_t>(table->ctx->sm_count) * 2));
 #define SILO_LAUNCH_K1(MODE)                                                                             \
    containerAndCountKernel<MODE><<<blocks, K1_THREADS, sizeof(K1Dynamic), stream>>>(                     \
-      column, words, table->d_work_prefix, table->d_work_prefix + n_chunks + 1, table->d_work_items, d_counts \
+      column, words, table->d_work_prefix, table->d_work_prefix + n_chunks + 1, table->d_work_items, d_counts, claim_batch \
    )
          switch (stream_only) {
             case 1: SILO_LAUNCH_K1(1); break;

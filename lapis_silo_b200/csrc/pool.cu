@@ -44,6 +44,89 @@ uint32_t alignUp(uint32_t value, uint32_t alignment) {
 
 using namespace silo;
 
+// ---- re-encoding of stored containers into the device piece formats (common.cuh) --------------
+
+// n sorted u16 values -> KIND_ARRAY_T payload
+static void encodeArrayPiece(const uint8_t* sorted_values, uint32_t n, std::vector<uint8_t>& out) {
+   out.assign(arrayPieceBytes(n), 0);
+   auto valueAt = [&](uint32_t index) {
+      uint16_t value = 0;
+      std::memcpy(&value, sorted_values + 2ULL * std::min(index, n - 1), 2);  // padding repeats the last value
+      return value;
+   };
+   for (uint32_t first = 0; first < n; first += ARRAY_REGION_VALUES) {
+      const uint32_t count = std::min(ARRAY_REGION_VALUES, n - first);
+      const uint32_t lanes = arrayRegionLanes(count);
+      auto* slots = reinterpret_cast<uint16_t*>(out.data() + (first / ARRAY_REGION_VALUES) * 512u);
+      for (uint32_t lane = 0; lane < lanes; ++lane) {
+         for (uint32_t j = 0; j < 8; ++j) {
+            slots[lane * 8 + j] = valueAt(first + std::min(lane + lanes * j, count - 1));
+         }
+      }
+   }
+}
+
+// n KIND_RUNS_W entries (ascending) -> region order with padding entries
+static void encodeRunsPiece(const uint32_t* entries, uint32_t n, std::vector<uint8_t>& out) {
+   out.assign(runsPieceBytes(n), 0);
+   for (uint32_t first = 0; first < n; first += RUNS_REGION_ENTRIES) {
+      const uint32_t count = std::min(RUNS_REGION_ENTRIES, n - first);
+      const uint32_t lanes = runsRegionLanes(count);
+      auto* slots = reinterpret_cast<uint32_t*>(out.data() + (first / RUNS_REGION_ENTRIES) * 512u);
+      for (uint32_t lane = 0; lane < lanes; ++lane) {
+         for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t index = lane + lanes * j;
+            slots[lane * 4 + j] = index < count ? entries[first + index] : RUNS_PAD_ENTRY;
+         }
+      }
+   }
+}
+
+// CRoaring run pairs {start, length-1} -> runs confined to one 32-row word each (KIND_RUNS_W entries)
+// plus ranges of whole words for the long runs (KIND_WORDRANGE entries, answered from the rank table)
+static void splitRuns(
+   const uint8_t* pairs,
+   uint32_t n_runs,
+   std::vector<uint32_t>& word_entries,
+   std::vector<uint32_t>& word_ranges,
+   uint64_t* covered_rows
+) {
+   constexpr uint32_t MAX_INLINE_FULL_WORDS = 3;  // shorter stretches of whole words stay plain entries
+   word_entries.clear();
+   word_ranges.clear();
+   uint64_t covered = 0;
+   uint32_t previous_end = 0;
+   for (uint32_t r = 0; r < n_runs; ++r) {
+      uint16_t start = 0;
+      uint16_t length_minus_one = 0;
+      std::memcpy(&start, pairs + 4ULL * r, 2);
+      std::memcpy(&length_minus_one, pairs + 4ULL * r + 2, 2);
+      const uint32_t first = start;
+      const uint32_t last = first + length_minus_one;  // inclusive
+      require(last <= 65535 && (r == 0 || first >= previous_end), "run container runs must be ascending and inside the chunk");
+      previous_end = last + 1;
+      covered += length_minus_one + 1u;
+      const uint32_t first_word = first >> 5;
+      const uint32_t last_word = last >> 5;
+      if (first_word == last_word) {
+         word_entries.push_back(runEntry(first_word, first & 31u, last - first + 1));
+         continue;
+      }
+      word_entries.push_back(runEntry(first_word, first & 31u, 32u - (first & 31u)));
+      const uint32_t whole_first = first_word + 1;
+      const uint32_t whole_end = last_word;  // exclusive
+      if (whole_end - whole_first <= MAX_INLINE_FULL_WORDS) {
+         for (uint32_t word = whole_first; word < whole_end; ++word) {
+            word_entries.push_back(runEntry(word, 0, 32));
+         }
+      } else {
+         word_ranges.push_back(whole_first | (whole_end << 16));
+      }
+      word_entries.push_back(runEntry(last_word, 0, (last & 31u) + 1));
+   }
+   *covered_rows = covered;
+}
+
 extern "C" {
 
 const char* silo_gpu_last_error(void) {
@@ -290,6 +373,9 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
       column->chunk_desc_payload_bytes.assign(n_chunks, 0);
       column->chunk_containers.assign(n_chunks, 0);
 
+      std::vector<uint8_t> scratch;
+      std::vector<uint32_t> word_entries;
+      std::vector<uint32_t> word_ranges;
       uint64_t cursor = 0;
       for (uint32_t chunk = 0; chunk < n_chunks; ++chunk) {
          chunk_desc_begin[chunk] = static_cast<uint32_t>(descs.size());
@@ -332,9 +418,8 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
             DevContainer d{};
             d.position = c.position;
             d.offset4 = static_cast<uint32_t>(offset / 4);
-            d.packed = (cardinality - 1) | (static_cast<uint32_t>(c.symbol) << 16) |
-                       (static_cast<uint32_t>(in->local_reference[c.position]) << 24) | (kind << 30);
-            d.n_runs = aux;
+            d.packed = DevContainer::pack(cardinality, c.symbol, in->local_reference[c.position], kind);
+            d.aux = aux;
             descs.push_back(d);
             segment.desc_count++;
          };
@@ -350,27 +435,46 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
                   constexpr uint32_t VALUES_PER_PIECE = PIECE_BYTES / 2;
                   for (uint32_t first = 0; first < c.cardinality; first += VALUES_PER_PIECE) {
                      const uint32_t count = std::min(VALUES_PER_PIECE, c.cardinality - first);
-                     emitPiece(c, KIND_ARRAY, count, 0, src + 2ULL * first, 2 * count);
+                     encodeArrayPiece(reinterpret_cast<const uint8_t*>(src + 2ULL * first), count, scratch);
+                     emitPiece(c, KIND_ARRAY_T, count, 0, scratch.data(), static_cast<uint32_t>(scratch.size()));
                   }
                }
             } else if (c.typecode == TYPE_RUN) {
                uint16_t n_runs = 0;
                std::memcpy(&n_runs, src, 2);
-               const uint8_t* runs = src + 2;  // the device layout drops the u16 header: pairs are aligned u32 words
-               constexpr uint32_t RUNS_PER_PIECE = PIECE_BYTES / 4;
                uint64_t covered = 0;
-               for (uint32_t first = 0; first < n_runs; first += RUNS_PER_PIECE) {
-                  const uint32_t count = std::min<uint32_t>(RUNS_PER_PIECE, n_runs - first);
-                  uint32_t cardinality = 0;
-                  for (uint32_t r = first; r < first + count; ++r) {
-                     uint16_t length_minus_one = 0;
-                     std::memcpy(&length_minus_one, runs + 4ULL * r + 2, 2);
-                     cardinality += static_cast<uint32_t>(length_minus_one) + 1;
-                  }
-                  covered += cardinality;
-                  emitPiece(c, KIND_RUN, cardinality, count, runs + 4ULL * first, 4 * count);
-               }
+               splitRuns(src + 2, n_runs, word_entries, word_ranges, &covered);
                require(covered == c.cardinality, "run container cardinality does not match its runs");
+               constexpr uint32_t ENTRIES_PER_PIECE = PIECE_BYTES / 4;
+               for (size_t first = 0; first < word_entries.size(); first += ENTRIES_PER_PIECE) {
+                  const auto count = static_cast<uint32_t>(std::min<size_t>(ENTRIES_PER_PIECE, word_entries.size() - first));
+                  uint32_t rows = 0;
+                  for (uint32_t i = 0; i < count; ++i) {
+                     rows += static_cast<uint32_t>(__builtin_popcount(runEntryMask(word_entries[first + i])));
+                  }
+                  encodeRunsPiece(word_entries.data() + first, count, scratch);
+                  emitPiece(c, KIND_RUNS_W, rows, count, scratch.data(), static_cast<uint32_t>(scratch.size()));
+               }
+               for (size_t first = 0; first < word_ranges.size();) {
+                  // a piece's row count must fit the descriptor's 16 bits: close it before 65536 rows
+                  uint32_t rows = 0;
+                  size_t end = first;
+                  while (end < word_ranges.size() && end - first < ENTRIES_PER_PIECE) {
+                     const uint32_t range_rows = 32u * ((word_ranges[end] >> 16) - (word_ranges[end] & 0xFFFFu));
+                     if (rows + range_rows > 65536u) {
+                        break;
+                     }
+                     rows += range_rows;
+                     ++end;
+                  }
+                  scratch.assign(
+                     reinterpret_cast<const uint8_t*>(word_ranges.data() + first),
+                     reinterpret_cast<const uint8_t*>(word_ranges.data() + end)
+                  );
+                  emitPiece(c, KIND_WORDRANGE, rows, static_cast<uint32_t>(end - first), scratch.data(), static_cast<uint32_t>(scratch.size()));
+                  segment.flags |= SEG_NEEDS_RANK;
+                  first = end;
+               }
             } else {
                constexpr uint32_t WORDS_PER_PIECE = PIECE_BYTES / 8;
                uint64_t covered = 0;

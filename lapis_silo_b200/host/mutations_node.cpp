@@ -52,19 +52,18 @@ void appendMutationRows(
    // Same arithmetic as the reference, position by position; only the memory order differs: the
    // totals are summed symbol row by symbol row (sequential streams over the freshly DMA-written
    // buffer, auto-vectorised) before the per-position pass.
-   thread_local std::vector<uint32_t> totals;
-   thread_local std::vector<uint32_t> any_other;  // OR of the counts of the valid non-reference symbols
-   totals.assign(genome_length, 0);
-   any_other.assign(genome_length, 0);
-   const Symbol* reference_sequence = sequence_column.reference_sequence.data();
+   thread_local std::vector<uint32_t> scratch;  // (raw pointers below: no TLS lookup inside the loops)
+   scratch.assign(2ULL * genome_length, 0);
+   uint32_t* __restrict__ const totals = scratch.data();
+   uint32_t* __restrict__ const any_other = scratch.data() + genome_length;  // OR of the valid non-reference symbols' counts
+   const Symbol* __restrict__ const reference_sequence = sequence_column.reference_sequence.data();
    for (const Symbol symbol : alphabet.valid_mutation_symbols) {
-      const uint32_t* row = counts.values + static_cast<size_t>(symbol) * genome_length;
-      uint32_t* out_totals = totals.data();
-      uint32_t* out_other = any_other.data();
+      const uint32_t* __restrict__ const row = counts.values + static_cast<size_t>(symbol) * genome_length;
       for (uint32_t pos = 0; pos < genome_length; ++pos) {
          const uint32_t value = row[pos];
-         out_totals[pos] += value;
-         out_other[pos] |= reference_sequence[pos] == symbol ? 0u : value;
+         const uint32_t keep = static_cast<uint32_t>(reference_sequence[pos] == symbol) - 1u;  // 0 for the reference symbol
+         totals[pos] += value;
+         any_other[pos] |= value & keep;
       }
    }
    for (uint32_t pos = 0; pos < genome_length; ++pos) {
