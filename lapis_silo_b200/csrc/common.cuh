@@ -20,7 +20,8 @@ namespace silo {
 constexpr uint32_t TILE_WORDS = 1024;        // one chunk's dense filter tile: 1024 x u64 = 8 KiB
 constexpr uint32_t TILE_BYTES = TILE_WORDS * 8;
 constexpr uint32_t SEG_PAYLOAD_BYTES = 16384;  // max payload bytes of one segment (>= 8192 + slack)
-constexpr uint32_t SEG_MAX_DESCS = 128;        // max pieces of one segment
+constexpr uint32_t SEG_MAX_DESCS = 16;         // max pieces of one segment: one per consumer warp, so that a warp
+                                               // can always hand the stage back before it does the lookups
 
 constexpr uint32_t TYPE_BITSET = 1;  // CRoaring typecodes, roaring_container.h:131-145
 constexpr uint32_t TYPE_ARRAY = 2;
@@ -46,7 +47,10 @@ constexpr uint32_t PIECE_BYTES = 1024;  // max payload of one piece of a stored 
 // P = ceil(count / 8) lanes: lane L's 16 bytes are the values with in-region index L + P*j, j = 0..7
 // (two per 32-bit word, low half first; indices >= count are padding). The 32 simultaneous tile
 // lookups of one j therefore belong to P CONSECUTIVE sorted values (mostly distinct banks).
+// A stored value is row ^ 31 (the low five bits hold 31 - (row & 31), the left shift that moves the
+// row's bit of its tile word to bit 31).
 constexpr uint32_t ARRAY_REGION_VALUES = 256;
+constexpr uint32_t ARRAY_VALUE_FLIP = 31;
 __host__ __device__ inline uint32_t arrayRegionLanes(uint32_t count) {
    return (count + 7) / 8;
 }

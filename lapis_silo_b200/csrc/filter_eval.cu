@@ -129,7 +129,7 @@ __device__ void orContainerIntoTile(uint64_t* tile, const uint8_t* slab, const D
       const uint32_t n = desc.cardinality();
       for (uint32_t slot = threadIdx.x; slot < arrayPieceSlots(n); slot += EVAL_THREADS) {
          if (arraySlotValid(slot, n)) {
-            const uint32_t value = values[slot];
+            const uint32_t value = values[slot] ^ ARRAY_VALUE_FLIP;
             atomicOr(&tile32[value >> 5], 1u << (value & 31));
          }
       }
@@ -195,7 +195,7 @@ __device__ void addContainerToCounters(
       const uint32_t n = desc.cardinality();
       for (uint32_t slot = lane; slot < arrayPieceSlots(n); slot += 32) {
          if (arraySlotValid(slot, n)) {
-            bump(values[slot]);
+            bump(values[slot] ^ ARRAY_VALUE_FLIP);
          }
       }
    } else if (kind == KIND_RUNS_W) {

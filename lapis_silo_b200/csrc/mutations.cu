@@ -99,8 +99,13 @@ __global__ void fillWorkItemsKernel(
 // Persistent CTAs (2 per SM). Warp 0 is the producer: it claims batches of work items (segments)
 // from a grid-wide counter and streams each segment's descriptors and payload into a ring of
 // shared-memory stages with two 1-D bulk (TMA) copies that complete on an mbarrier. The 16 consumer
-// warps take one piece (<= 1 KiB of payload) each, AND it with the chunk's filter tile held in
-// shared memory, and issue one RED per piece with a non-zero count.
+// warps take one piece (<= 1 KiB of payload) each: a warp pulls its piece into REGISTERS, hands the
+// stage back to the producer, and only then ANDs the piece with the chunk's filter tile held in
+// shared memory, issuing one RED per piece with a non-zero count.
+//
+// Everything the consumers touch is addressed with 32-bit shared-memory addresses kept in registers
+// (inline PTX loads): the kernel is bound by instruction issue and by the 16-lane ALU pipe, and the
+// generic-pointer arithmetic of plain C++ costs as many instructions per piece as the lookups.
 // ---------------------------------------------------------------------------------------------
 
 constexpr int K1_STAGES = 4;
@@ -108,47 +113,113 @@ constexpr int K1_CONSUMER_WARPS = 16;
 constexpr int K1_CONSUMER_THREADS = K1_CONSUMER_WARPS * 32;
 constexpr int K1_THREADS = K1_CONSUMER_THREADS + 32;  // warp 0 = bulk-copy producer
 constexpr uint32_t K1_BATCH_DEFAULT = 4;               // work items claimed per atomicAdd (<= 32)
-constexpr uint32_t K1_STOP = 0xFFFFFFFFu;              // meta_desc_count marker: no more work
+constexpr uint32_t K1_STOP = 0xFFFFFFFFu;              // meta.x marker: no more work
 constexpr uint32_t TILE32_WORDS = 2 * TILE_WORDS;
+constexpr uint32_t TILE_BUFFER_BYTES = (TILE32_WORDS + 4) * 4;  // [2048] = the zero pad word
 
 struct __align__(16) K1Stage {
    uint8_t payload[SEG_PAYLOAD_BYTES];
    DevContainer descs[SEG_MAX_DESCS];
 };
 
-// per-stage meta written by the producer before it arms full_bar; read with one 128-bit load
-struct __align__(16) K1Meta {
+// per-stage control block: meta is written by the producer before it arms `full`
+struct __align__(16) K1Control {
    uint32_t desc_count;  // K1_STOP: no more work
    uint32_t base4;       // slab offset (4-byte units) of the stage's payload[0]
    uint32_t flags;       // K1_NEW_TILE | K1_TILE_SLOT | K1_NEEDS_RANK
-   uint32_t pad;
+   uint32_t pad0;
+   uint64_t full;   // the stage's bulk copies have landed
+   uint64_t empty;  // every consumer warp has pulled its pieces of the stage into registers
+   uint64_t done;   // ... and has finished the tile lookups for them
+   uint64_t pad1;
 };
+static_assert(sizeof(K1Control) == 48);
+constexpr uint32_t K1_CTRL_FULL = 16;
+constexpr uint32_t K1_CTRL_EMPTY = 24;
+constexpr uint32_t K1_CTRL_DONE = 32;
 constexpr uint32_t K1_NEW_TILE = 1;    // the stage's bulk copies also (re)loaded the filter tile
 constexpr uint32_t K1_TILE_SLOT = 2;   // which of the two filter-tile buffers the stage reads
 constexpr uint32_t K1_NEEDS_RANK = 4;  // a KIND_WORDRANGE piece is inside: the rank table must exist
 
 struct __align__(16) K1Dynamic {
    K1Stage stages[K1_STAGES];
-   K1Meta meta[K1_STAGES];
-   uint64_t full_bar[K1_STAGES];
-   uint64_t empty_bar[K1_STAGES];  // every consumer warp has pulled its pieces of the stage into registers
-   uint64_t done_bar[K1_STAGES];   // ... and has finished the tile lookups for them
-   uint32_t claim[K1_STAGES];      // next unclaimed piece of the stage (reset by the producer)
+   K1Control control[K1_STAGES];
    uint32_t warp_sums[K1_CONSUMER_WARPS];
 };
+constexpr uint32_t K1_CONTROL_OFFSET = sizeof(K1Stage) * K1_STAGES;
 
 __device__ __forceinline__ uint32_t warpSum(uint32_t value) {
    return __reduce_add_sync(0xFFFFFFFFu, value);
 }
 
-// The consumers are bound by instruction issue, so every bit test is spelled with the fewest
-// instructions the ISA offers: a byte offset into the tile is one IMAD.HI with accumulate
-// (x * 2^k >> 32, plus the tile's shared-memory address), shifts take their amount from the low
-// five bits of a register (funnel shifts in wrap mode), and the multipliers live in registers the
-// compiler cannot see through (otherwise it turns the multiplications back into shift + add).
+// ---- shared memory by 32-bit address ----------------------------------------------------------
+// Reads of stage data / tile / rank table. Not volatile: every address derives from words that were
+// loaded after the stage's full barrier was observed (a volatile asm with a memory clobber).
+#ifndef SILO_K1_PROBE
+#define SILO_K1_PROBE 0  // 1: tile lookups all hit one word (no bank conflicts); 2: no tile lookups at all
+#endif
+__device__ __forceinline__ uint32_t lds32(uint32_t address) {
+   uint32_t value;
+#if SILO_K1_PROBE == 1
+   asm("ld.shared.u32 %0, [%1];" : "=r"(value) : "r"(address & 0x3u));
+#elif SILO_K1_PROBE == 2
+   value = address;
+#else
+   asm("ld.shared.u32 %0, [%1];" : "=r"(value) : "r"(address));
+#endif
+   return value;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t address) {
+   uint4 value;
+   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                : "=r"(value.x), "=r"(value.y), "=r"(value.z), "=r"(value.w)
+                : "r"(address)
+                : "memory");
+   return value;
+}
+__device__ __forceinline__ void sts128(uint32_t address, const uint4& value) {
+   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(address), "r"(value.x), "r"(value.y), "r"(value.z), "r"(value.w)
+                : "memory");
+}
+__device__ __forceinline__ void mbarWaitAt(uint32_t address, uint32_t parity) {
+   asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(address),
+      "r"(parity),
+      "r"(0x989680u)
+      : "memory"
+   );
+}
+__device__ __forceinline__ void mbarArriveAt(uint32_t address) {
+   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(address) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTxAt(uint32_t address, uint32_t bytes) {
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(address), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkLoadAt(uint32_t destination, const void* source, uint32_t bytes, uint32_t barrier) {
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(destination),
+                "l"(source), "r"(bytes), "r"(barrier)
+                : "memory");
+}
+
+// The consumers are bound by instruction issue and the ALU pipe, so every bit test is spelled with
+// the fewest instructions the ISA offers: a byte offset into the tile is one IMAD.HI with
+// accumulate on the FMA pipe (x * 2^k >> 32, plus the tile's shared-memory address), shifts take
+// their amount from the low five bits of a register (funnel shifts in wrap mode), and the
+// multipliers live in registers the compiler cannot see through (otherwise it turns the
+// multiplications back into shift + add on the ALU pipe).
 struct Multipliers {
+   uint32_t one;         //  x * 1 + acc: an addition on the FMA pipe
+   uint32_t two;         //  x * 2 >> 32 = x >> 31
    uint32_t two_pow_13;  // (x & 0xFFE00000) * 2^13 >> 32 = (x >> 21) * 4
    uint32_t two_pow_14;  //  x * 2^14 >> 32 = x >> 18
+   uint32_t two_pow_16;  //  x * 2^16 >> 32 = x >> 16
    uint32_t two_pow_27;  //  x * 2^27 >> 32 = x >> 5
    uint32_t two_pow_29;  // (x & 0xFFE0) * 2^29 >> 32 = ((x & 0xFFFF) >> 5) * 4
 };
@@ -158,33 +229,37 @@ __device__ __forceinline__ uint32_t madHi(uint32_t a, uint32_t b, uint32_t c) {
    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
    return d;
 }
+__device__ __forceinline__ uint32_t madLo(uint32_t a, uint32_t b, uint32_t c) {
+   uint32_t d;
+   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+   return d;
+}
 __device__ __forceinline__ uint32_t mulHi(uint32_t a, uint32_t b) {
    uint32_t d;
    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
    return d;
 }
-// Reads of the filter tile / rank table by shared-memory BYTE address. Not volatile: the address
-// always derives from payload words loaded after the stage's full barrier was observed.
-__device__ __forceinline__ uint32_t ldShared32(uint32_t shared_address) {
-   uint32_t value;
-   asm("ld.shared.u32 %0, [%1];" : "=r"(value) : "r"(shared_address));
-   return value;
-}
 
-// two u16 rows packed in one word -> number of them that are set in the tile
-__device__ __forceinline__ uint32_t pairBits(uint32_t tile_address, const Multipliers& k, uint32_t pair, uint32_t& lo_bit, uint32_t& hi_bit) {
-   const uint32_t lo_word = ldShared32(madHi(pair & 0x0000FFE0u, k.two_pow_29, tile_address));
-   const uint32_t hi_word = ldShared32(madHi(pair & 0xFFE00000u, k.two_pow_13, tile_address));
-   lo_bit = __funnelshift_r(lo_word, 0u, pair) & 1u;         // shift = pair & 31 = row & 31 of the low half
-   hi_bit = __funnelshift_r(hi_word, 0u, pair >> 16) & 1u;
-   return lo_bit + hi_bit;
+// Two stored array values packed in one word -> the tile words of their rows, each shifted so that
+// the row's bit sits in bit 31. A stored value is row ^ 31: its low five bits are 31 - (row & 31), the
+// left shift that takes the row's bit to the top (funnel shifts use the low five bits of the amount).
+// The caller accumulates bit 31 with one IMAD.HI (x * 2 >> 32 + acc) on the FMA pipe, so a lookup
+// costs the 16-lane ALU pipe only the address mask and the shift.
+__device__ __forceinline__ void pairTopBits(uint32_t tile_address, const Multipliers& k, uint32_t pair, uint32_t& lo_top, uint32_t& hi_top) {
+   const uint32_t lo_word = lds32(madHi(pair & 0x0000FFE0u, k.two_pow_29, tile_address));
+   const uint32_t hi_word = lds32(madHi(pair & 0xFFE00000u, k.two_pow_13, tile_address));
+   lo_top = __funnelshift_l(0u, lo_word, pair);                        // lo_word << (pair & 31)
+   hi_top = __funnelshift_l(0u, hi_word, mulHi(pair, k.two_pow_16));   // hi_word << ((pair >> 16) & 31)
+}
+__device__ __forceinline__ uint32_t addTopBit(uint32_t value, const Multipliers& k, uint32_t accumulator) {
+   return madHi(value, k.two, accumulator);  // (value >> 31) + accumulator
 }
 
 // one KIND_RUNS_W entry -> rows of the run that are set in the tile
 __device__ __forceinline__ uint32_t runEntryCount(uint32_t tile_address, const Multipliers& k, uint32_t entry) {
-   const uint32_t word = ldShared32(madHi(entry, k.two_pow_14, tile_address));       // tile32[entry >> 20]
-   const uint32_t from_first = __funnelshift_r(word, 0u, entry);                      // word >> (entry & 31)
-   return __popc(__funnelshift_l(0u, from_first, mulHi(entry, k.two_pow_27)));        // << (32 - length)
+   const uint32_t word = lds32(madHi(entry, k.two_pow_14, tile_address));       // tile32[entry >> 20]
+   const uint32_t from_first = __funnelshift_r(word, 0u, entry);                 // word >> (entry & 31)
+   return __popc(__funnelshift_l(0u, from_first, mulHi(entry, k.two_pow_27)));   // << (32 - length)
 }
 
 // lookups of one array region held in registers (count values in P = ceil(count/8) lanes)
@@ -195,10 +270,16 @@ __device__ __forceinline__ uint32_t arrayRegionCount(
    uint32_t count,
    uint32_t lane
 ) {
-   uint32_t lo_bit, hi_bit;
+   uint32_t t0, t1, t2, t3, t4, t5, t6, t7;
    if (count == ARRAY_REGION_VALUES) {  // the full region: no padding
-      return pairBits(tile_address, k, eight.x, lo_bit, hi_bit) + pairBits(tile_address, k, eight.y, lo_bit, hi_bit) +
-             pairBits(tile_address, k, eight.z, lo_bit, hi_bit) + pairBits(tile_address, k, eight.w, lo_bit, hi_bit);
+      pairTopBits(tile_address, k, eight.x, t0, t1);
+      pairTopBits(tile_address, k, eight.y, t2, t3);
+      pairTopBits(tile_address, k, eight.z, t4, t5);
+      pairTopBits(tile_address, k, eight.w, t6, t7);
+      // two accumulation chains
+      const uint32_t even = addTopBit(t6, k, addTopBit(t4, k, addTopBit(t2, k, addTopBit(t0, k, 0u))));
+      const uint32_t odd = addTopBit(t7, k, addTopBit(t5, k, addTopBit(t3, k, addTopBit(t1, k, 0u))));
+      return even + odd;
    }
    const uint32_t lanes = arrayRegionLanes(count);
    uint32_t local = 0;
@@ -207,8 +288,13 @@ __device__ __forceinline__ uint32_t arrayRegionCount(
       uint32_t index = lane;  // in-region index of the low half of words[i]
 #pragma unroll
       for (uint32_t i = 0; i < 4; ++i) {
-         pairBits(tile_address, k, words[i], lo_bit, hi_bit);
-         local += (index < count ? lo_bit : 0u) + (index + lanes < count ? hi_bit : 0u);
+         pairTopBits(tile_address, k, words[i], t0, t1);
+         if (index < count) {
+            local = addTopBit(t0, k, local);
+         }
+         if (index + lanes < count) {
+            local = addTopBit(t1, k, local);
+         }
          index += 2 * lanes;
       }
    }
@@ -226,58 +312,58 @@ __device__ __forceinline__ uint32_t runsRegionCount(
    if (lane >= runsRegionLanes(count)) {
       return 0;
    }
-   return runEntryCount(tile_address, k, four.x) + runEntryCount(tile_address, k, four.y) +
-          runEntryCount(tile_address, k, four.z) + runEntryCount(tile_address, k, four.w);
+   // (sums on the FMA pipe: x * 1 + acc)
+   const uint32_t first_two = madLo(runEntryCount(tile_address, k, four.y), k.one, runEntryCount(tile_address, k, four.x));
+   const uint32_t last_two = madLo(runEntryCount(tile_address, k, four.w), k.one, runEntryCount(tile_address, k, four.z));
+   return madLo(first_two, k.one, last_two);
 }
 
 // |piece AND tile| for a piece whose (at most) two 512-byte regions sit in registers: lane L holds
-// bytes [16 L, 16 L + 16) of each region. Kinds with other layouts return false (the caller reads
-// them from the stage instead).
+// bytes [16 L, 16 L + 16) of each region. desc = the descriptor's four words.
 __device__ __forceinline__ uint32_t pieceFromRegisters(
-   const DevContainer& desc,
+   const uint4& desc,
+   uint32_t kind,
    const uint4& first,
    const uint4& second,
-   const uint32_t* tile32,  // shared, 2049 words ([2048] = 0)
+   uint32_t tile_address,  // shared: 2049 words ([2048] = 0)
    const Multipliers& k,
-   uint32_t lane
+   uint32_t lane,
+   uint32_t lane16
 ) {
-   const uint32_t kind = desc.type();
-   const uint32_t tile_address = static_cast<uint32_t>(__cvta_generic_to_shared(tile32));
    uint32_t local = 0;
    if (kind == KIND_ARRAY_T) {
-      const uint32_t n = desc.cardinality();
+      const uint32_t n = (desc.z & 0xFFFFu) + 1u;
       local = arrayRegionCount(tile_address, k, first, min(n, ARRAY_REGION_VALUES), lane);
       if (n > ARRAY_REGION_VALUES) {
          local += arrayRegionCount(tile_address, k, second, n - ARRAY_REGION_VALUES, lane);
       }
    } else if (kind == KIND_RUNS_W) {
-      const uint32_t n = desc.aux;
+      const uint32_t n = desc.w;
       local = runsRegionCount(tile_address, k, first, min(n, RUNS_REGION_ENTRIES), lane);
       if (n > RUNS_REGION_ENTRIES) {
          local += runsRegionCount(tile_address, k, second, n - RUNS_REGION_ENTRIES, lane);
       }
    } else if (kind == KIND_BITSET) {  // 128 words: 64 vectors, two per lane
-      const uint4* tile4 = reinterpret_cast<const uint4*>(tile32 + 2 * desc.firstWord());
-      const uint4 a = tile4[lane];
-      const uint4 b = tile4[32 + lane];
+      const uint32_t window = tile_address + (desc.w & 0xFFFFu) * 8u + lane16;
+      const uint4 a = lds128(window);
+      const uint4 b = lds128(window + 512);
       local = __popc(first.x & a.x) + __popc(first.y & a.y) + __popc(first.z & a.z) + __popc(first.w & a.w) +
               __popc(second.x & b.x) + __popc(second.y & b.y) + __popc(second.z & b.z) + __popc(second.w & b.w);
    } else if (kind == KIND_INLINE) {  // one or two values inside the descriptor
-      if (lane < desc.cardinality()) {
-         const uint32_t value = (desc.aux >> (16 * lane)) & 0xFFFFu;
-         local = (tile32[value >> 5] >> (value & 31u)) & 1u;
+      if (lane <= (desc.z & 0xFFFFu)) {
+         const uint32_t value = (desc.w >> (16 * lane)) & 0xFFFFu;
+         local = (lds32(tile_address + ((value >> 5) << 2)) >> (value & 31u)) & 1u;
       }
    }
    return warpSum(local);
 }
 
 // KIND_WORDRANGE: whole 32-row words [wa, wb) from the exclusive rank table (payload in the stage)
-__device__ __forceinline__ uint32_t wordRangeCount(const DevContainer& desc, const uint8_t* payload, const uint32_t* rank32, uint32_t lane) {
-   const uint32_t* ranges = reinterpret_cast<const uint32_t*>(payload);
+__device__ __forceinline__ uint32_t wordRangeCount(uint32_t entries, uint32_t payload_address, uint32_t rank_address, uint32_t lane) {
    uint32_t local = 0;
-   for (uint32_t r = lane; r < desc.aux; r += 32) {
-      const uint32_t range = ranges[r];
-      local += rank32[range >> 16] - rank32[range & 0xFFFFu];
+   for (uint32_t r = lane; r < entries; r += 32) {
+      const uint32_t range = lds32(payload_address + 4 * r);
+      local += lds32(rank_address + 4 * (range >> 16)) - lds32(rank_address + 4 * (range & 0xFFFFu));
    }
    return warpSum(local);
 }
@@ -304,12 +390,16 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
    const uint32_t warp = threadIdx.x >> 5;
    const uint32_t lane = threadIdx.x & 31;
    const uint32_t total = work_prefix[column.n_chunks];
+   const uint32_t ring_address = smemAddr(smem_raw);
+   const uint32_t control_address = ring_address + K1_CONTROL_OFFSET;
+   const uint32_t tile_address0 = smemAddr(tile_buffers[0]);
+   const uint32_t rank_address0 = smemAddr(rank_buffers[0]);
 
    if (threadIdx.x == 0) {
       for (int s = 0; s < K1_STAGES; ++s) {
-         mbarInit(&sh.full_bar[s], 1);
-         mbarInit(&sh.empty_bar[s], K1_CONSUMER_WARPS);
-         mbarInit(&sh.done_bar[s], K1_CONSUMER_WARPS);
+         mbarInit(&sh.control[s].full, 1);
+         mbarInit(&sh.control[s].empty, K1_CONSUMER_WARPS);
+         mbarInit(&sh.control[s].done, K1_CONSUMER_WARPS);
       }
       fenceBarrierInit();
    }
@@ -323,16 +413,24 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
       // Three batches are in flight: the stages of batch n are being issued while lanes
       // 0..claim_batch-1 fetch the segment descriptors of batch n+1 and lane 0's atomic claims batch
       // n+2, so neither the claim's nor the fetch's global-memory latency sits between two bulk copies.
-      auto claimAsync = [&]() -> uint32_t {  // the result is only valid in lane 0, and only waited for when used
+      // Lane j prepares stage j of the batch (addresses, byte counts, tile bookkeeping) in parallel
+      // with the others; only the barrier wait and the copies themselves are issued lane after lane.
+      // The first batch of every CTA is fixed (no atomic in front of the first copy); the dynamic
+      // claims start behind those. Near the end of the work list claims shrink to single items, so
+      // that the last CTAs to finish are at most one stage, not one batch, behind the others.
+      const uint32_t static_items = gridDim.x * claim_batch;
+      const uint32_t tail_begin = total > 2 * static_items ? total - 2 * static_items : 0;
+      uint32_t claim_size_next = claim_batch;  // size of the claim that claimAsync issues next
+      auto claimAsync = [&]() -> uint32_t {    // the result is only valid in lane 0, and only waited for when used
          uint32_t first = 0;
          if (lane == 0) {
-            first = atomicAdd(work_counter, claim_batch);
+            first = atomicAdd(work_counter, claim_size_next) + static_items;
          }
          return first;
       };
-      auto fetch = [&](uint32_t first) -> DevSegment {
+      auto fetch = [&](uint32_t first, uint32_t size) -> DevSegment {
          DevSegment segment{};
-         if (lane < claim_batch && first + lane < total) {
+         if (lane < size && first + lane < total) {
             segment = column.segments[work_items[first + lane]];
          }
          return segment;
@@ -341,125 +439,138 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
       uint32_t tile_slot = 1;         // buffer holding the current chunk's tile
       uint32_t tile_first_stage = 0;  // first stage that reads the current tile
       uint32_t it = 0;                // stages issued so far by this CTA
-      uint32_t batch_first = __shfl_sync(0xFFFFFFFFu, claimAsync(), 0);
+      uint32_t batch_first = blockIdx.x * claim_batch;
+      uint32_t batch_size = claim_batch;
       uint32_t claimed_ahead = claimAsync();
-      DevSegment upcoming = fetch(batch_first);
+      uint32_t claimed_ahead_size = claim_size_next;
+      DevSegment upcoming = fetch(batch_first, batch_size);
       while (batch_first < total) {
          const DevSegment mine = upcoming;
-         const uint32_t batch = min(claim_batch, total - batch_first);
+         const uint32_t batch = min(batch_size, total - batch_first);
          batch_first = __shfl_sync(0xFFFFFFFFu, claimed_ahead, 0);
+         batch_size = claimed_ahead_size;
+         claim_size_next = batch_first >= tail_begin ? 1u : claim_batch;
          claimed_ahead = claimAsync();
-         upcoming = fetch(batch_first);
+         claimed_ahead_size = claim_size_next;
+         upcoming = fetch(batch_first, batch_size);
+
+         // tile bookkeeping for all stages of the batch at once
+         uint32_t previous_chunk = __shfl_up_sync(0xFFFFFFFFu, mine.chunk, 1);
+         if (lane == 0) {
+            previous_chunk = current_tile_chunk;
+         }
+         const bool new_tile = lane < batch && mine.chunk != previous_chunk;
+         const uint32_t new_mask = __ballot_sync(0xFFFFFFFFu, new_tile);
+         const uint32_t new_below = new_mask & ((1u << lane) - 1u);  // tile switches at earlier stages of this batch
+         const uint32_t my_slot = tile_slot ^ (__popc(new_below | (new_tile ? 1u << lane : 0u)) & 1u);
+         // first stage of the tile that is current just before my stage
+         const uint32_t first_before = new_below != 0 ? it + (31u - __clz(new_below)) : tile_first_stage;
+         const uint32_t my_it = it + lane;
+         const uint32_t my_stage = my_it % K1_STAGES;
+         const uint32_t my_round = my_it / K1_STAGES;
+         const uint32_t my_control = control_address + my_stage * static_cast<uint32_t>(sizeof(K1Control));
+         const uint32_t my_ring = ring_address + my_stage * static_cast<uint32_t>(sizeof(K1Stage));
+         const uint32_t desc_bytes = mine.desc_count * static_cast<uint32_t>(sizeof(DevContainer));
+         const uint4 meta = make_uint4(
+            mine.desc_count, static_cast<uint32_t>(mine.payload_offset >> 2),
+            (new_tile ? K1_NEW_TILE : 0u) | (my_slot != 0 ? K1_TILE_SLOT : 0u) | ((mine.flags & SEG_NEEDS_RANK) != 0 ? K1_NEEDS_RANK : 0u), 0u
+         );
          for (uint32_t j = 0; j < batch; ++j) {
-            const uint32_t offset_lo = __shfl_sync(0xFFFFFFFFu, static_cast<uint32_t>(mine.payload_offset), j);
-            const uint32_t offset_hi = __shfl_sync(0xFFFFFFFFu, static_cast<uint32_t>(mine.payload_offset >> 32), j);
-            const uint32_t payload_bytes = __shfl_sync(0xFFFFFFFFu, mine.payload_bytes, j);
-            const uint32_t desc_begin = __shfl_sync(0xFFFFFFFFu, mine.desc_begin, j);
-            const uint32_t desc_count = __shfl_sync(0xFFFFFFFFu, mine.desc_count, j);
-            const uint32_t chunk = __shfl_sync(0xFFFFFFFFu, mine.chunk, j);
-            const uint32_t segment_flags = __shfl_sync(0xFFFFFFFFu, mine.flags, j);
-            if (lane == 0) {
-               const uint64_t payload_offset = (static_cast<uint64_t>(offset_hi) << 32) | offset_lo;
-               const uint32_t stage = it % K1_STAGES;
-               const uint32_t round = it / K1_STAGES;
-               const bool new_tile = chunk != current_tile_chunk;
-               if (round > 0) {
-                  mbarWait(&sh.empty_bar[stage], (round - 1) & 1u);  // => every stage <= it - K1_STAGES is consumed
+            if (lane == j) {
+               if (my_round > 0) {
+                  mbarWaitAt(my_control + K1_CTRL_EMPTY, (my_round - 1) & 1u);  // => every stage <= my_it - K1_STAGES is pulled
                }
                if (new_tile) {
                   // The new tile goes into the OTHER buffer, last read by the lookups of the stages
-                  // before tile_first_stage. A warp hands a stage back BEFORE it does the lookups, so the
-                  // stage's empty barrier says nothing about the tile: wait for the done barriers. (Stages
-                  // below it - K1_STAGES are implied: a warp pulls stage q + K1_STAGES only after it has
-                  // finished stage q, and the empty wait above covered stage it - K1_STAGES.)
-                  const uint32_t computed_below = it >= K1_STAGES ? it - K1_STAGES : 0;
-                  for (uint32_t prev = computed_below; prev < tile_first_stage; ++prev) {
-                     mbarWait(&sh.done_bar[prev % K1_STAGES], (prev / K1_STAGES) & 1u);
+                  // before first_before. A warp hands a stage back BEFORE it does the lookups, so the
+                  // stage's empty barrier says nothing about the tile: wait for the done barriers.
+                  // (Stages below my_it - K1_STAGES are implied: a warp pulls stage q + K1_STAGES only
+                  // after it has finished stage q, and the empty wait above covered my_it - K1_STAGES.)
+                  for (uint32_t prev = my_it >= K1_STAGES ? my_it - K1_STAGES : 0; prev < first_before; ++prev) {
+                     mbarWaitAt(
+                        control_address + (prev % K1_STAGES) * static_cast<uint32_t>(sizeof(K1Control)) + K1_CTRL_DONE, (prev / K1_STAGES) & 1u
+                     );
                   }
-                  tile_slot ^= 1u;
-                  tile_first_stage = it;
-                  current_tile_chunk = chunk;
                }
-               K1Meta meta;
-               meta.desc_count = desc_count;
-               meta.base4 = static_cast<uint32_t>(payload_offset >> 2);
-               meta.flags = (new_tile ? K1_NEW_TILE : 0u) | (tile_slot != 0 ? K1_TILE_SLOT : 0u) |
-                            ((segment_flags & SEG_NEEDS_RANK) != 0 ? K1_NEEDS_RANK : 0u);
-               meta.pad = 0;
-               sh.meta[stage] = meta;
-               sh.claim[stage] = 0;
-               const uint32_t desc_bytes = desc_count * static_cast<uint32_t>(sizeof(DevContainer));
-               mbarExpectTx(&sh.full_bar[stage], desc_bytes + payload_bytes + (new_tile ? TILE_BYTES : 0u));
+               sts128(my_control, meta);
+               mbarExpectTxAt(my_control + K1_CTRL_FULL, desc_bytes + mine.payload_bytes + (new_tile ? TILE_BYTES : 0u));
                if (new_tile) {
-                  bulkLoad(tile_buffers[tile_slot], filter_words + static_cast<size_t>(chunk) * TILE_WORDS, TILE_BYTES, &sh.full_bar[stage]);
+                  bulkLoadAt(
+                     tile_address0 + my_slot * TILE_BUFFER_BYTES, filter_words + static_cast<size_t>(mine.chunk) * TILE_WORDS, TILE_BYTES,
+                     my_control + K1_CTRL_FULL
+                  );
                }
-               bulkLoad(sh.stages[stage].descs, column.containers + desc_begin, desc_bytes, &sh.full_bar[stage]);
-               if (payload_bytes != 0) {
-                  bulkLoad(sh.stages[stage].payload, column.payload + payload_offset, payload_bytes, &sh.full_bar[stage]);
+               bulkLoadAt(my_ring + SEG_PAYLOAD_BYTES, column.containers + mine.desc_begin, desc_bytes, my_control + K1_CTRL_FULL);
+               if (mine.payload_bytes != 0) {
+                  bulkLoadAt(my_ring, column.payload + mine.payload_offset, mine.payload_bytes, my_control + K1_CTRL_FULL);
                }
             }
-            ++it;
             __syncwarp();
          }
+         if (new_mask != 0) {
+            tile_slot ^= __popc(new_mask) & 1u;
+            tile_first_stage = it + (31u - __clz(new_mask));
+         }
+         current_tile_chunk = __shfl_sync(0xFFFFFFFFu, mine.chunk, batch - 1);
+         it += batch;
       }
       if (lane == 0) {
          // tell the consumers that nothing follows
          const uint32_t stage = it % K1_STAGES;
          const uint32_t round = it / K1_STAGES;
+         const uint32_t stop_control = control_address + stage * static_cast<uint32_t>(sizeof(K1Control));
          if (round > 0) {
-            mbarWait(&sh.empty_bar[stage], (round - 1) & 1u);
+            mbarWaitAt(stop_control + K1_CTRL_EMPTY, (round - 1) & 1u);
          }
-         K1Meta meta{};
-         meta.desc_count = K1_STOP;
-         sh.meta[stage] = meta;
-         mbarArrive(&sh.full_bar[stage]);
+         sts128(stop_control, make_uint4(K1_STOP, 0u, 0u, 0u));
+         mbarArriveAt(stop_control + K1_CTRL_FULL);
       }
       return;
    }
 
    // ---------------- consumers: 16 warps ----------------------------------------------------------
-   // A warp CLAIMS the pieces of a stage one at a time from a shared counter: pieces differ in cost
-   // by two orders of magnitude, and with a fixed assignment the slowest warp of every stage would
-   // set the pace. It pulls the claimed piece (descriptor + at most two 512-byte regions) into
-   // REGISTERS, claims the next one, and -- if the stage has none left for it -- hands the stage back
-   // to the producer BEFORE doing the tile lookups: the ring's stages are in flight again while the
-   // arithmetic runs (with four 16 KiB stages per CTA the kernel is bound by the bytes in flight as
-   // soon as stages are held for the duration of the lookups). A warp leaves a stage only after a
-   // failed claim, i.e. when every piece is claimed, and every claimer loads its piece before it
-   // leaves, so "all 16 warps left" (the empty barrier) means the stage buffer is free.
+   // A stage holds at most one piece per consumer warp (SEG_MAX_DESCS == K1_CONSUMER_WARPS), handed out
+   // round-robin. A warp pulls its piece (descriptor + at most two 512-byte regions) into registers,
+   // hands the stage back to the producer at once, and only then does the tile lookups: the ring's
+   // stages are in flight again while the arithmetic runs. The loop body is written for the fewest
+   // instructions per stage visit -- the kernel is bound by instruction issue.
+   static_assert(SEG_MAX_DESCS == K1_CONSUMER_WARPS, "one piece per consumer warp and stage");
    const uint32_t cwarp = warp - 1;
    const uint32_t cthread = threadIdx.x - 32;  // 0..511
+   const uint32_t lane16 = lane * 16;
    const uint32_t genome_length = column.genome_length;
    // opaque to the compiler (gridDim.y is 1): keeps the IMAD.HI forms, see Multipliers
    Multipliers k;
+   k.one = gridDim.y;
+   k.two = gridDim.y << 1;
    k.two_pow_13 = gridDim.y << 13;
    k.two_pow_14 = gridDim.y << 14;
+   k.two_pow_16 = gridDim.y << 16;
    k.two_pow_27 = gridDim.y << 27;
    k.two_pow_29 = gridDim.y << 29;
-   uint32_t rank_valid = 0;  // bit s: rank_buffers[s] belongs to the tile now in tile_buffers[s]
-   uint32_t stage = 0;
-   uint32_t phase = 0;
-   auto claimPiece = [&](uint32_t of_stage) -> uint32_t {
-      uint32_t claimed = 0;
-      if (lane == 0) {
-         claimed = atomicAdd(&sh.claim[of_stage], 1u);
-      }
-      return __shfl_sync(0xFFFFFFFFu, claimed, 0);
-   };
-   for (;;) {
-      mbarWait(&sh.full_bar[stage], phase);
-      const uint4 meta_words = *reinterpret_cast<const uint4*>(&sh.meta[stage]);
-      const uint32_t desc_count = meta_words.x;
+   // base addresses as opaque register values (the compiler would otherwise re-derive the shared
+   // window from special registers at every use)
+   uint32_t ring_base = ring_address;
+   uint32_t control_base = control_address;
+   uint32_t tile_base = tile_address0;
+   asm volatile("" : "+r"(ring_base), "+r"(control_base), "+r"(tile_base));
+   uint32_t rotation = cwarp;  // piece index of this warp in the current stage, before the & 15
+   uint32_t rank_valid = 0;    // bit s: rank_buffers[s] belongs to the tile now in tile_buffers[s]
+   uint32_t visit = 0;         // stages visited so far
+   for (;; ++visit) {
+      const uint32_t stage = visit % K1_STAGES;
+      const uint32_t stage_address = ring_base + stage * static_cast<uint32_t>(sizeof(K1Stage));
+      const uint32_t my_control = control_base + stage * static_cast<uint32_t>(sizeof(K1Control));
+      mbarWaitAt(my_control + K1_CTRL_FULL, (visit / K1_STAGES) & 1u);
+      const uint4 meta = lds128(my_control);
+      const uint32_t desc_count = meta.x;
       if (desc_count == K1_STOP) {
          break;
       }
-      uint32_t index = claimPiece(stage);
-      const uint32_t base4 = meta_words.y;
-      const uint32_t flags = meta_words.z;
-      const uint32_t slot = (flags / K1_TILE_SLOT) & 1u;
-      const uint32_t* tile32 = tile_buffers[slot];
-      uint32_t* rank32 = rank_buffers[slot];
+      const uint32_t flags = meta.z;
+      const uint32_t slot_offset = (flags & K1_TILE_SLOT) != 0 ? TILE_BUFFER_BYTES : 0u;
       if ((flags & (K1_NEW_TILE | K1_NEEDS_RANK)) != 0) {  // rare: a chunk switch or a long-run piece
+         const uint32_t slot = (flags / K1_TILE_SLOT) & 1u;
          if ((flags & K1_NEW_TILE) != 0) {
             rank_valid &= ~(1u << slot);
          }
@@ -467,6 +578,8 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
             // (every consumer warp sees the same stages in the same order, so all of them get here)
             // exclusive rank table of the tile: 512 threads x 4 words
             rank_valid |= 1u << slot;
+            const uint32_t* tile32 = tile_buffers[slot];
+            uint32_t* rank32 = rank_buffers[slot];
             const uint4 four = reinterpret_cast<const uint4*>(tile32)[cthread];
             const uint32_t p0 = __popc(four.x);
             const uint32_t p1 = __popc(four.y);
@@ -496,50 +609,52 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
             asm volatile("bar.sync 1, %0;" ::"n"(K1_CONSUMER_THREADS) : "memory");
          }
       }
-      const K1Stage& st = sh.stages[stage];
-      bool released = false;
-      while (index < desc_count) {
-         const DevContainer desc = st.descs[index];
-         const uint8_t* payload = st.payload + (static_cast<size_t>(desc.offset4 - base4) << 2);
+      // the rotation continues where the previous stage stopped, so that a stage with fewer than 16
+      // pieces does not always leave the same warps idle
+      const uint32_t index = rotation & (K1_CONSUMER_WARPS - 1);
+      rotation -= desc_count;
+      if (index >= desc_count || MODE == 1) {  // nothing for this warp in this stage
+         __syncwarp();
+         if (lane == 0) {
+            mbarArriveAt(my_control + K1_CTRL_EMPTY);
+            mbarArriveAt(my_control + K1_CTRL_DONE);
+         }
+         continue;
+      }
+      const uint4 desc = lds128(stage_address + SEG_PAYLOAD_BYTES + index * 16);  // {position, offset4, packed, aux}
+      const uint32_t payload_address = stage_address + ((desc.y - meta.y) << 2);
+      const uint32_t kind = (desc.z >> 26) & 7u;
+      uint32_t count = 0;
+      if (kind == KIND_WORDRANGE) {  // rare; reads the stage while it works
+         count = wordRangeCount(desc.w, payload_address, rank_address0 + slot_offset, lane);
+         __syncwarp();
+         if (lane == 0) {
+            mbarArriveAt(my_control + K1_CTRL_EMPTY);
+         }
+      } else {
          // (reads past a short piece stay inside the stage buffer; those lanes are ignored)
-         const uint4 first = reinterpret_cast<const uint4*>(payload)[lane];
-         const uint4 second = reinterpret_cast<const uint4*>(payload)[32 + lane];
-         uint32_t count = 0;
-         if (desc.type() == KIND_WORDRANGE) {
-            count = wordRangeCount(desc, payload, rank32, lane);  // (reads the stage: claim afterwards)
-            index = claimPiece(stage);
+         const uint4 first = lds128(payload_address + lane16);
+         const uint4 second = lds128(payload_address + 512 + lane16);
+         __syncwarp();
+         if (lane == 0) {
+            mbarArriveAt(my_control + K1_CTRL_EMPTY);  // the stage can be refilled while the lookups run
+         }
+         if (MODE == 3) {  // profiling: touch the payload only
+            const uint32_t local = first.x ^ first.y ^ first.z ^ first.w ^ second.x ^ second.y ^ second.z ^ second.w;
+            count = warpSum(local) == 0x12345678u ? 1u : 0u;
          } else {
-            index = claimPiece(stage);
-            if (index >= desc_count) {  // nothing left here for this warp: the stage can go back
-               __syncwarp();
-               if (lane == 0) {
-                  mbarArrive(&sh.empty_bar[stage]);
-               }
-               released = true;
-            }
-            if (MODE == 3) {  // profiling: touch the payload only
-               const uint32_t local = first.x ^ first.y ^ first.z ^ first.w ^ second.x ^ second.y ^ second.z ^ second.w;
-               count = warpSum(local) == 0x12345678u ? 1u : 0u;
-            } else if (MODE != 1) {
-               count = pieceFromRegisters(desc, first, second, tile32, k, lane);
-            }
-         }
-         if (lane == 0 && count != 0 && MODE != 2) {
-            atomicAdd(&counts[desc.symbol() * genome_length + desc.position], count);
-         }
-         if (MODE == 2 && count == 0xFFFFFFFFu) {
-            counts[0] = 1;
+            count = pieceFromRegisters(desc, kind, first, second, tile_base + slot_offset, k, lane, lane16);
          }
       }
-      __syncwarp();
       if (lane == 0) {
-         if (!released) {
-            mbarArrive(&sh.empty_bar[stage]);
+         if (count != 0 && MODE != 2) {
+            atomicAdd(&counts[((desc.z >> 16) & 0x1Fu) * genome_length + desc.x], count);
          }
-         mbarArrive(&sh.done_bar[stage]);
+         mbarArriveAt(my_control + K1_CTRL_DONE);
       }
-      stage = (stage + 1) % K1_STAGES;
-      phase ^= stage == 0 ? 1u : 0u;
+      if (MODE == 2 && count == 0xFFFFFFFFu) {
+         counts[0] = 1;
+      }
    }
 }
 

@@ -52,7 +52,7 @@ static void encodeArrayPiece(const uint8_t* sorted_values, uint32_t n, std::vect
    auto valueAt = [&](uint32_t index) {
       uint16_t value = 0;
       std::memcpy(&value, sorted_values + 2ULL * std::min(index, n - 1), 2);  // padding repeats the last value
-      return value;
+      return static_cast<uint16_t>(value ^ ARRAY_VALUE_FLIP);
    };
    for (uint32_t first = 0; first < n; first += ARRAY_REGION_VALUES) {
       const uint32_t count = std::min(ARRAY_REGION_VALUES, n - first);
