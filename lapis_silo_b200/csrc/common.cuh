@@ -201,6 +201,10 @@ struct silo_gpu_table {
    uint8_t* h_staging_pinned = nullptr;  // program upload staging (grow-only)
    size_t staging_capacity = 0;
    cudaEvent_t ev_free_fence = nullptr;  // orders stream-ordered frees after foreign-stream users
+   // the coverage kernel runs beside the container kernel on an auxiliary stream (fork / join)
+   cudaStream_t aux_stream = nullptr;
+   cudaEvent_t ev_fork = nullptr;
+   cudaEvent_t ev_join = nullptr;
    uint32_t* d_chunk_popcount_full = nullptr;  // popcounts of the "all rows" filter (= chunk sizes)
    uint64_t* d_full_words = nullptr;           // layout mask tiles [n_chunks * 1024]
    // ring of CUDA-event pairs recorded on the launching stream around every mutation_counts

@@ -25,14 +25,20 @@ namespace {
 // work list: segments of the chunks that hold at least one filtered row
 // ---------------------------------------------------------------------------------------------
 
-__global__ void buildWorkListKernel(
+// One CTA: exclusive scan of the active chunks' segment counts, then the list itself
+// (work_items[work_prefix[c] + i] = global index of the i-th segment of active chunk c).
+__global__ void __launch_bounds__(1024) buildWorkListKernel(
    const uint32_t* __restrict__ chunk_popcount,
    const uint32_t* __restrict__ chunk_seg_begin,
    uint32_t n_chunks,
-   uint32_t* __restrict__ work_prefix  // [n_chunks + 1]; work_prefix[n_chunks] = total
+   uint32_t* __restrict__ work_prefix,  // [n_chunks + 2]; [n_chunks] = total, [n_chunks + 1] = K1's claim counter
+   uint32_t* __restrict__ work_items
 ) {
    __shared__ uint32_t warp_totals[32];
    __shared__ uint32_t carry;
+   __shared__ uint32_t chunk_count[1024];
+   __shared__ uint32_t chunk_out[1024];
+   __shared__ uint32_t chunk_first[1024];
    if (threadIdx.x == 0) {
       carry = 0;
    }
@@ -40,8 +46,10 @@ __global__ void buildWorkListKernel(
    for (uint32_t base = 0; base < n_chunks; base += blockDim.x) {
       const uint32_t chunk = base + threadIdx.x;
       uint32_t value = 0;
+      uint32_t first_segment = 0;
       if (chunk < n_chunks && chunk_popcount[chunk] != 0) {
-         value = chunk_seg_begin[chunk + 1] - chunk_seg_begin[chunk];
+         first_segment = chunk_seg_begin[chunk];
+         value = chunk_seg_begin[chunk + 1] - first_segment;
       }
       uint32_t inclusive = value;
       for (int offset = 1; offset < 32; offset <<= 1) {
@@ -59,8 +67,23 @@ __global__ void buildWorkListKernel(
          warp_offset += warp_totals[w];
       }
       const uint32_t block_carry = carry;
+      const uint32_t exclusive = block_carry + warp_offset + inclusive - value;
       if (chunk < n_chunks) {
-         work_prefix[chunk] = block_carry + warp_offset + inclusive - value;
+         work_prefix[chunk] = exclusive;
+      }
+      // the items: chunk c of this round is written by warp c % 32 (active chunks are usually
+      // neighbours, so this spreads them over all warps), 32 items at a time
+      chunk_count[threadIdx.x] = value;
+      chunk_out[threadIdx.x] = exclusive;
+      chunk_first[threadIdx.x] = first_segment;
+      __syncthreads();
+      for (uint32_t source = threadIdx.x >> 5; source < blockDim.x; source += 32) {
+         const uint32_t count = chunk_count[source];
+         const uint32_t out = chunk_out[source];
+         const uint32_t first = chunk_first[source];
+         for (uint32_t i = threadIdx.x & 31; i < count; i += 32) {
+            work_items[out + i] = first + i;
+         }
       }
       __syncthreads();
       if (threadIdx.x == blockDim.x - 1) {
@@ -71,25 +94,6 @@ __global__ void buildWorkListKernel(
    if (threadIdx.x == 0) {
       work_prefix[n_chunks] = carry;
       work_prefix[n_chunks + 1] = 0;  // the grid-wide claim counter of containerAndCountKernel
-   }
-}
-
-// work_items[work_prefix[c] + i] = global index of the i-th segment of active chunk c
-__global__ void fillWorkItemsKernel(
-   const uint32_t* __restrict__ chunk_popcount,
-   const uint32_t* __restrict__ chunk_seg_begin,
-   const uint32_t* __restrict__ work_prefix,
-   uint32_t* __restrict__ work_items
-) {
-   const uint32_t chunk = blockIdx.x;
-   if (chunk_popcount[chunk] == 0) {
-      return;
-   }
-   const uint32_t first = chunk_seg_begin[chunk];
-   const uint32_t count = chunk_seg_begin[chunk + 1] - first;
-   const uint32_t out = work_prefix[chunk];
-   for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
-      work_items[out + i] = first + i;
    }
 }
 
@@ -896,6 +900,16 @@ void enqueueMutationCounts(
    const uint64_t* words = filter != nullptr ? filter->d_words : table->d_full_words;
    const uint32_t* popcounts = filter != nullptr ? filter->d_chunk_popcount : table->d_chunk_popcount_full;
 
+   // fork: the coverage kernel only needs the filter and the zeroed difference array, so it runs on
+   // the auxiliary stream beside the container kernel (whose persistent CTAs leave room for it)
+   SILO_CUDA_CHECK(cudaEventRecord(table->ev_fork, stream));
+   SILO_CUDA_CHECK(cudaStreamWaitEvent(table->aux_stream, table->ev_fork, 0));
+   coverageDiffKernel<<<n_chunks * K6_SLICES, K6_THREADS, 0, table->aux_stream>>>(
+      column, words, popcounts, table->d_coverage_diff
+   );
+   SILO_CUDA_CHECK(cudaGetLastError());
+   SILO_CUDA_CHECK(cudaEventRecord(table->ev_join, table->aux_stream));
+
    if (filter == nullptr) {
       SILO_CUDA_CHECK(cudaEventRecord(ev_k1_begin, stream));
       if (column.n_containers > 0) {
@@ -906,13 +920,11 @@ void enqueueMutationCounts(
       }
       SILO_CUDA_CHECK(cudaEventRecord(ev_k1_end, stream));
    } else {
-      buildWorkListKernel<<<1, 1024, 0, stream>>>(popcounts, column.chunk_seg_begin, n_chunks, table->d_work_prefix);
-      SILO_CUDA_CHECK(cudaGetLastError());
-      fillWorkItemsKernel<<<n_chunks, 128, 0, stream>>>(
-         popcounts, column.chunk_seg_begin, table->d_work_prefix, table->d_work_items
+      buildWorkListKernel<<<1, 1024, 0, stream>>>(
+         popcounts, column.chunk_seg_begin, n_chunks, table->d_work_prefix, table->d_work_items
       );
       SILO_CUDA_CHECK(cudaGetLastError());
-      table->stats.kernel_launches += 2;
+      table->stats.kernel_launches += 1;
       SILO_CUDA_CHECK(cudaEventRecord(ev_k1_begin, stream));
       if (column.n_segments > 0) {
          static bool attribute_set = false;
@@ -948,10 +960,7 @@ void enqueueMutationCounts(
       }
       SILO_CUDA_CHECK(cudaEventRecord(ev_k1_end, stream));
    }
-   coverageDiffKernel<<<n_chunks * K6_SLICES, K6_THREADS, 0, stream>>>(
-      column, words, popcounts, table->d_coverage_diff
-   );
-   SILO_CUDA_CHECK(cudaGetLastError());
+   SILO_CUDA_CHECK(cudaStreamWaitEvent(stream, table->ev_join, 0));
    finalizeCountsKernel<<<(column.genome_length + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, stream>>>(
       column, table->d_coverage_diff, d_counts
    );

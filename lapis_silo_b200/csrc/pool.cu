@@ -238,6 +238,9 @@ int silo_gpu_table_create(
          SILO_CUDA_CHECK(cudaEventCreate(&table->ev_end[i]));
       }
       SILO_CUDA_CHECK(cudaEventCreateWithFlags(&table->ev_free_fence, cudaEventDisableTiming));
+      SILO_CUDA_CHECK(cudaEventCreateWithFlags(&table->ev_fork, cudaEventDisableTiming));
+      SILO_CUDA_CHECK(cudaEventCreateWithFlags(&table->ev_join, cudaEventDisableTiming));
+      SILO_CUDA_CHECK(cudaStreamCreateWithFlags(&table->aux_stream, cudaStreamNonBlocking));
       SILO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
       *out = table.release();
    });
@@ -270,6 +273,15 @@ void silo_gpu_table_free(silo_gpu_table* table) {
    }
    if (table->h_staging_pinned != nullptr) {
       cudaFreeHost(table->h_staging_pinned);
+   }
+   if (table->aux_stream != nullptr) {
+      cudaStreamSynchronize(table->aux_stream);
+      cudaStreamDestroy(table->aux_stream);
+   }
+   for (cudaEvent_t event : {table->ev_fork, table->ev_join}) {
+      if (event != nullptr) {
+         cudaEventDestroy(event);
+      }
    }
    if (table->ev_free_fence != nullptr) {
       cudaEventDestroy(table->ev_free_fence);
