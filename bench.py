@@ -245,34 +245,50 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL may print its version banner to stdout while it builds the communicator; stdout must hold
+        # the one JSON line only, so file descriptor 1 points at stderr until the first collective is done
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            warm = torch.ones(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
     n_gpus = world
 
     total_rows = args.rows_per_gpu * n_gpus
     sizes = host_api.dense_chunk_sizes(total_rows)
-    bounds = host_api.partition_chunks([1] * len(sizes), n_gpus)  # partition scheduler: contiguous chunk ranges
-    first, n_chunks = bounds[rank], bounds[rank + 1] - bounds[rank]
+    # Partition scheduler: chunk c belongs to rank c % n_gpus. The date column is sorted, so the date
+    # filter selects one contiguous row range; contiguous chunk ranges would hand it to one or two ranks.
+    # An interleaved shard is a table of its own with local chunk ids (counts are plain addends).
+    first, n_chunks, stride = host_api.interleaved_shard(len(sizes), n_gpus, rank)
 
     started = time.perf_counter()
     synthetic = host_api.Synthetic(GENOME_LENGTH, REFERENCE_SEED, GENERATIONS)
     ancestor = next(e for e in range(synthetic.num_sequences) if synthetic.generation(e) == 2)
     threads = max(1, (os.cpu_count() or 8) // max(1, min(n_gpus, 8)))
-    column = synthetic.build_column(total_rows, first, n_chunks, threads)
+    column = synthetic.build_column(total_rows, first, n_chunks, threads, stride)
     payload_bytes = int(column.contents.payload_bytes)
     n_containers = int(column.contents.n_containers)
     built = time.perf_counter()
     ctx = abi.Context(local_rank)
-    table = host_api.HostTable(ctx, sizes[first:first + n_chunks], first_chunk=first)
+    local_first = first if stride == 1 else 0
+    table = host_api.HostTable(ctx, host_api.shard_chunk_sizes(total_rows, first, n_chunks, stride), first_chunk=local_first)
     table.add_column("main", host_api.NUCLEOTIDE, synthetic.reference, column)
     synthetic.release_column()
-    table.register_bitmap("lineage", synthetic.lineage_bitmap(ancestor, total_rows, first, n_chunks))
-    expression = (f"(and {host_api.date_ranges_expression(total_rows, SPAN_DAYS, FROM_DAY, TO_DAY, first, n_chunks)} "
+    table.register_bitmap("lineage", synthetic.lineage_bitmap(ancestor, total_rows, first, n_chunks, stride))
+    expression = (f"(and {host_api.date_ranges_expression(total_rows, SPAN_DAYS, FROM_DAY, TO_DAY, first, n_chunks, stride)} "
                   f"(bitmap lineage))")
     torch.cuda.synchronize()
     uploaded = time.perf_counter()
     if rank == 0:
-        log(f"[bench] rank 0 shard: chunks [{first}, {first + n_chunks}), {n_containers} containers, "
+        log(f"[bench] rank 0 shard: chunks {first} + k*{stride}, k < {n_chunks}: {n_containers} containers, "
             f"{payload_bytes / 1e9:.2f} GB payload; generated in {built - started:.1f}s, uploaded in {uploaded - built:.1f}s; "
             f"{synthetic.num_sequences} evolved sequences")
 
@@ -385,7 +401,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(args, cardinality, {
             "total_rows": total_rows, "chunks_per_gpu": n_chunks, "containers_per_gpu": n_containers,
-            "payload_gb_per_gpu": round(payload_bytes / 1e9, 3), "parallelism": f"chunk-range shards x{n_gpus}, "
+            "payload_gb_per_gpu": round(payload_bytes / 1e9, 3), "parallelism": f"interleaved chunk shards (chunk c on rank c % {n_gpus}), "
             "NCCL allreduce of the u32 counts" if n_gpus > 1 else "single GPU", "output_rows": len(rows),
         }),
         "clocks": clocks,

@@ -92,13 +92,13 @@ uint32_t silo_host_synthetic_generation(const silo_host_synthetic* synthetic, ui
 /* Builds the shard [first_chunk, first_chunk + n_chunks) of the table "row i = sequence[i % E]"
  * with total_rows rows directly in the upload format; *out stays valid until the synthetic object
  * is freed or the next build. */
-int silo_host_synthetic_build_column(silo_host_synthetic* synthetic, uint64_t total_rows, uint32_t first_chunk, uint32_t n_chunks, uint32_t threads, const silo_column_desc** out);
+int silo_host_synthetic_build_column(silo_host_synthetic* synthetic, uint64_t total_rows, uint32_t first_chunk, uint32_t n_chunks, uint32_t threads, const silo_column_desc** out, uint32_t chunk_stride);
 /* releases the host copy of the last built column (after it was uploaded) */
 void silo_host_synthetic_release_column(silo_host_synthetic* synthetic);
 /* lineage stand-in: portable roaring bytes of the shard's rows descending from `ancestor` */
-int64_t silo_host_synthetic_lineage_bitmap(const silo_host_synthetic* synthetic, uint32_t ancestor, uint64_t total_rows, uint32_t first_chunk, uint32_t n_chunks, uint8_t* out, uint64_t capacity);
+int64_t silo_host_synthetic_lineage_bitmap(const silo_host_synthetic* synthetic, uint32_t ancestor, uint64_t total_rows, uint32_t first_chunk, uint32_t n_chunks, uint8_t* out, uint64_t capacity, uint32_t chunk_stride);
 /* date stand-in: the "(ranges ...)" expression text of DateBetween on the sorted synthetic date column */
-int silo_host_synthetic_date_ranges(uint64_t total_rows, uint32_t span_days, uint32_t from_day, uint32_t to_day_inclusive, uint32_t first_chunk, uint32_t n_chunks, char* out, uint64_t capacity);
+int silo_host_synthetic_date_ranges(uint64_t total_rows, uint32_t span_days, uint32_t from_day, uint32_t to_day_inclusive, uint32_t first_chunk, uint32_t n_chunks, char* out, uint64_t capacity, uint32_t chunk_stride);
 /* partition scheduler: boundaries[n_ranks + 1] of contiguous chunk ranges balanced by weight */
 int silo_host_partition_chunks(const uint64_t* chunk_weights, uint32_t n_chunks, uint32_t n_ranks, uint32_t* boundaries);
 

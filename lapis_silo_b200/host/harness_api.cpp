@@ -379,12 +379,12 @@ uint32_t silo_host_synthetic_generation(const silo_host_synthetic* synthetic, ui
    return synthetic->tree.generation.at(index);
 }
 
-int silo_host_synthetic_build_column(silo_host_synthetic* synthetic, uint64_t total_rows, uint32_t first_chunk, uint32_t n_chunks, uint32_t threads, const silo_column_desc** out) {
+int silo_host_synthetic_build_column(silo_host_synthetic* synthetic, uint64_t total_rows, uint32_t first_chunk, uint32_t n_chunks, uint32_t threads, const silo_column_desc** out, uint32_t chunk_stride) {
    return guarded([&] {
       synthetic->column = std::make_unique<PackedColumn>();
       buildCycledColumn(
          Alphabet::nucleotide(), synthetic->reference, synthetic->tree.sequences, total_rows, first_chunk, n_chunks,
-         threads, *synthetic->column
+         threads, *synthetic->column, chunk_stride
       );
       *out = &synthetic->column->desc;
    });
@@ -394,11 +394,11 @@ void silo_host_synthetic_release_column(silo_host_synthetic* synthetic) {
    synthetic->column.reset();
 }
 
-int64_t silo_host_synthetic_lineage_bitmap(const silo_host_synthetic* synthetic, uint32_t ancestor, uint64_t total_rows, uint32_t first_chunk, uint32_t n_chunks, uint8_t* out, uint64_t capacity) {
+int64_t silo_host_synthetic_lineage_bitmap(const silo_host_synthetic* synthetic, uint32_t ancestor, uint64_t total_rows, uint32_t first_chunk, uint32_t n_chunks, uint8_t* out, uint64_t capacity, uint32_t chunk_stride) {
    int64_t size = -1;
    guarded([&] {
       const std::vector<uint8_t> bytes =
-         writePortableRoaring(lineageRowIds(synthetic->tree, ancestor, total_rows, first_chunk, n_chunks));
+         writePortableRoaring(lineageRowIds(synthetic->tree, ancestor, total_rows, first_chunk, n_chunks, chunk_stride));
       size = static_cast<int64_t>(bytes.size());
       if (out != nullptr && capacity >= bytes.size()) {
          std::memcpy(out, bytes.data(), bytes.size());
@@ -407,10 +407,10 @@ int64_t silo_host_synthetic_lineage_bitmap(const silo_host_synthetic* synthetic,
    return size;
 }
 
-int silo_host_synthetic_date_ranges(uint64_t total_rows, uint32_t span_days, uint32_t from_day, uint32_t to_day_inclusive, uint32_t first_chunk, uint32_t n_chunks, char* out, uint64_t capacity) {
+int silo_host_synthetic_date_ranges(uint64_t total_rows, uint32_t span_days, uint32_t from_day, uint32_t to_day_inclusive, uint32_t first_chunk, uint32_t n_chunks, char* out, uint64_t capacity, uint32_t chunk_stride) {
    std::string text;
    const int status = guarded([&] {
-      const std::vector<uint32_t> flat = sortedDateRanges(total_rows, span_days, from_day, to_day_inclusive, first_chunk, n_chunks);
+      const std::vector<uint32_t> flat = sortedDateRanges(total_rows, span_days, from_day, to_day_inclusive, first_chunk, n_chunks, chunk_stride);
       std::ostringstream stream;
       stream << "(ranges";
       for (uint32_t value : flat) {

@@ -183,7 +183,8 @@ void buildCycledColumn(
    uint32_t first_chunk,
    uint32_t n_chunks,
    unsigned threads,
-   PackedColumn& out
+   PackedColumn& out,
+   uint32_t chunk_stride
 ) {
    const size_t genome_length = reference.size();
    const size_t n_sequences = sequences.size();
@@ -191,9 +192,13 @@ void buildCycledColumn(
       throw std::invalid_argument("buildCycledColumn: empty input");
    }
    const std::vector<uint32_t> all_chunk_sizes = denseChunkSizes(total_rows);
-   if (static_cast<uint64_t>(first_chunk) + n_chunks > all_chunk_sizes.size()) {
+   if (chunk_stride == 0 ||
+       (n_chunks > 0 && static_cast<uint64_t>(first_chunk) + static_cast<uint64_t>(n_chunks - 1) * chunk_stride >= all_chunk_sizes.size())) {
       throw std::invalid_argument("buildCycledColumn: shard exceeds the table");
    }
+   // the id a chunk carries in the output: global for a contiguous shard, local for an interleaved one
+   auto globalChunk = [&](uint32_t local_chunk) { return first_chunk + local_chunk * chunk_stride; };
+   auto emittedChunk = [&](uint32_t local_chunk) { return chunk_stride == 1 ? first_chunk + local_chunk : local_chunk; };
    std::vector<Symbol> reference_symbols(genome_length);
    for (size_t p = 0; p < genome_length; ++p) {
       const auto symbol = alphabet.charToSymbol(reference[p]);
@@ -287,7 +292,8 @@ void buildCycledColumn(
    std::vector<std::vector<silo_container_desc>> chunk_descs(n_chunks);
    std::vector<std::vector<uint8_t>> chunk_payload(n_chunks);
    auto buildChunk = [&](uint32_t local_chunk) {
-      const uint32_t global_chunk = first_chunk + local_chunk;
+      const uint32_t global_chunk = globalChunk(local_chunk);
+      const uint32_t emitted_chunk = emittedChunk(local_chunk);
       const uint32_t chunk_size = all_chunk_sizes[global_chunk];
       const uint64_t base_row = static_cast<uint64_t>(global_chunk) * 65536;
       const auto phase = static_cast<uint32_t>(base_row % n_sequences);
@@ -303,7 +309,7 @@ void buildCycledColumn(
                words[row >> 6] |= uint64_t{1} << (row & 63);
             }
          }
-         encodeContainer(words.data(), group.position, static_cast<uint16_t>(global_chunk), group.symbol, descs, payload);
+         encodeContainer(words.data(), group.position, static_cast<uint16_t>(emitted_chunk), group.symbol, descs, payload);
       }
    };
    threads = std::max(1u, std::min(threads, n_chunks == 0 ? 1u : n_chunks));
@@ -338,7 +344,7 @@ void buildCycledColumn(
       out.payload.insert(out.payload.end(), chunk_payload[chunk].begin(), chunk_payload[chunk].end());
       std::vector<silo_container_desc>().swap(chunk_descs[chunk]);
       std::vector<uint8_t>().swap(chunk_payload[chunk]);
-      shard_rows += all_chunk_sizes[first_chunk + chunk];
+      shard_rows += all_chunk_sizes[globalChunk(chunk)];
    }
    out.start_end.resize(2 * shard_rows);
    for (uint64_t row = 0; row < shard_rows; ++row) {
@@ -359,12 +365,22 @@ void buildCycledColumn(
    desc.start_end = out.start_end.data();
 }
 
+std::vector<uint32_t> shardChunkSizes(uint64_t total_rows, uint32_t first_chunk, uint32_t n_chunks, uint32_t chunk_stride) {
+   const std::vector<uint32_t> all = denseChunkSizes(total_rows);
+   std::vector<uint32_t> sizes;
+   for (uint32_t local_chunk = 0; local_chunk < n_chunks; ++local_chunk) {
+      sizes.push_back(all.at(first_chunk + static_cast<size_t>(local_chunk) * chunk_stride));
+   }
+   return sizes;
+}
+
 std::vector<uint32_t> lineageRowIds(
    const EvolvedTree& tree,
    uint32_t ancestor,
    uint64_t total_rows,
    uint32_t first_chunk,
-   uint32_t n_chunks
+   uint32_t n_chunks,
+   uint32_t chunk_stride
 ) {
    const size_t n_sequences = tree.sequences.size();
    std::vector<bool> in_lineage(n_sequences, false);
@@ -374,11 +390,13 @@ std::vector<uint32_t> lineageRowIds(
    }
    const std::vector<uint32_t> sizes = denseChunkSizes(total_rows);
    std::vector<uint32_t> ids;
-   for (uint32_t chunk = first_chunk; chunk < first_chunk + n_chunks; ++chunk) {
+   for (uint32_t local_chunk = 0; local_chunk < n_chunks; ++local_chunk) {
+      const uint32_t chunk = first_chunk + local_chunk * chunk_stride;
+      const uint32_t emitted_chunk = chunk_stride == 1 ? chunk : local_chunk;
       const uint64_t base_row = static_cast<uint64_t>(chunk) * 65536;
       for (uint32_t row = 0; row < sizes.at(chunk); ++row) {
          if (in_lineage[(base_row + row) % n_sequences]) {
-            ids.push_back((chunk << 16) | row);
+            ids.push_back((emitted_chunk << 16) | row);
          }
       }
    }
@@ -391,7 +409,8 @@ std::vector<uint32_t> sortedDateRanges(
    uint32_t from_day,
    uint32_t to_day_inclusive,
    uint32_t first_chunk,
-   uint32_t n_chunks
+   uint32_t n_chunks,
+   uint32_t chunk_stride
 ) {
    // day(i) = floor(i * span_days / total_rows). lower_bound(from) and upper_bound(to) over rows:
    auto firstRowWithDayAtLeast = [&](uint64_t day) -> uint64_t {
@@ -404,9 +423,11 @@ std::vector<uint32_t> sortedDateRanges(
    const uint64_t upper_row = firstRowWithDayAtLeast(static_cast<uint64_t>(to_day_inclusive) + 1);
    const std::vector<uint32_t> sizes = denseChunkSizes(total_rows);
    std::vector<uint32_t> flat;
-   for (uint32_t chunk = first_chunk; chunk < first_chunk + n_chunks; ++chunk) {
-      const uint64_t base_row = static_cast<uint64_t>(chunk) * 65536;
-      const uint32_t size = sizes.at(chunk);
+   for (uint32_t local_chunk = 0; local_chunk < n_chunks; ++local_chunk) {
+      const uint32_t global_chunk = first_chunk + local_chunk * chunk_stride;
+      const uint32_t chunk = chunk_stride == 1 ? global_chunk : local_chunk;  // the id the shard's table uses
+      const uint64_t base_row = static_cast<uint64_t>(global_chunk) * 65536;
+      const uint32_t size = sizes.at(global_chunk);
       auto clampToChunk = [&](uint64_t row) -> uint32_t {
          if (row <= base_row) {
             return 0;

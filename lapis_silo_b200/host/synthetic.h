@@ -48,9 +48,16 @@ struct PackedColumn {
    PackedColumn& operator=(const PackedColumn&) = delete;
 };
 
-// Rows [first_chunk << 16, ...) of the table with `total_rows` rows where row i holds
-// sequences[i % sequences.size()] (full length, offset 0). The local reference is adapted over ALL
-// total_rows rows (sequence_column.cpp:158-212), so every shard sees the same one.
+// A SHARD of the table with `total_rows` rows where row i holds sequences[i % sequences.size()]
+// (full length, offset 0): the chunks first_chunk + k * chunk_stride, k < n_chunks. The local
+// reference is adapted over ALL total_rows rows (sequence_column.cpp:158-212), so every shard sees
+// the same one.
+//   chunk_stride == 1: a contiguous range; containers, row ids and ranges keep their GLOBAL chunk ids
+//                      (the shard's table is created with first_chunk).
+//   chunk_stride  > 1: an interleaved shard (chunk c belongs to rank c % stride, which balances any
+//                      filter on a sorted column); it is a table of its own with LOCAL chunk ids
+//                      0..n_chunks-1 (created with first_chunk = 0). Counts and cardinalities are
+//                      addends, so nothing has to be translated back.
 void buildCycledColumn(
    const Alphabet& alphabet,
    const std::string& reference,
@@ -59,8 +66,11 @@ void buildCycledColumn(
    uint32_t first_chunk,
    uint32_t n_chunks,
    unsigned threads,
-   PackedColumn& out
+   PackedColumn& out,
+   uint32_t chunk_stride = 1
 );
+// chunk sizes of such a shard
+std::vector<uint32_t> shardChunkSizes(uint64_t total_rows, uint32_t first_chunk, uint32_t n_chunks, uint32_t chunk_stride);
 
 // chunk sizes of a dense table with total_rows rows: all 65536 except possibly the last
 std::vector<uint32_t> denseChunkSizes(uint64_t total_rows);
@@ -72,7 +82,8 @@ std::vector<uint32_t> lineageRowIds(
    uint32_t ancestor,
    uint64_t total_rows,
    uint32_t first_chunk,
-   uint32_t n_chunks
+   uint32_t n_chunks,
+   uint32_t chunk_stride = 1
 );
 // DateBetween on the sorted synthetic date column date(i) = day0 + (i * span_days) / total_rows:
 // one RangeSelection::Range per chunk of the shard (date_between.cpp:94-134), flattened {start,end}
@@ -82,7 +93,8 @@ std::vector<uint32_t> sortedDateRanges(
    uint32_t from_day,
    uint32_t to_day_inclusive,
    uint32_t first_chunk,
-   uint32_t n_chunks
+   uint32_t n_chunks,
+   uint32_t chunk_stride = 1
 );
 
 // Multi-GPU partition scheduler: contiguous chunk ranges, balanced by weight (payload bytes or rows).

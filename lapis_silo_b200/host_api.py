@@ -111,12 +111,12 @@ def lib() -> C.CDLL:
         L.silo_host_synthetic_parent.restype = C.c_uint32
         L.silo_host_synthetic_generation.argtypes = [vp, C.c_uint32]
         L.silo_host_synthetic_generation.restype = C.c_uint32
-        L.silo_host_synthetic_build_column.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+        L.silo_host_synthetic_build_column.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp), C.c_uint32]
         L.silo_host_synthetic_release_column.argtypes = [vp]
         L.silo_host_synthetic_release_column.restype = None
-        L.silo_host_synthetic_lineage_bitmap.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64]
+        L.silo_host_synthetic_lineage_bitmap.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64, C.c_uint32]
         L.silo_host_synthetic_lineage_bitmap.restype = C.c_int64
-        L.silo_host_synthetic_date_ranges.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64]
+        L.silo_host_synthetic_date_ranges.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64, C.c_uint32]
         L.silo_host_partition_chunks.argtypes = [C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
@@ -355,21 +355,22 @@ class Synthetic:
     def generation(self, index: int) -> int:
         return int(lib().silo_host_synthetic_generation(self._h, index))
 
-    def build_column(self, total_rows: int, first_chunk: int, n_chunks: int, threads: int = 8):
-        """Returns POINTER(ColumnDesc), valid until release_column()/the next build."""
+    def build_column(self, total_rows: int, first_chunk: int, n_chunks: int, threads: int = 8, stride: int = 1):
+        """Returns POINTER(ColumnDesc), valid until release_column()/the next build. The shard holds the
+        chunks first_chunk + k*stride; stride > 1 (an interleaved shard) uses shard-local chunk ids."""
         out = C.c_void_p()
-        _check(lib().silo_host_synthetic_build_column(self._h, total_rows, first_chunk, n_chunks, threads, C.byref(out)))
+        _check(lib().silo_host_synthetic_build_column(self._h, total_rows, first_chunk, n_chunks, threads, C.byref(out), stride))
         return C.cast(out, C.POINTER(abi.ColumnDesc))
 
     def release_column(self) -> None:
         lib().silo_host_synthetic_release_column(self._h)
 
-    def lineage_bitmap(self, ancestor: int, total_rows: int, first_chunk: int, n_chunks: int) -> bytes:
-        n = lib().silo_host_synthetic_lineage_bitmap(self._h, ancestor, total_rows, first_chunk, n_chunks, None, 0)
+    def lineage_bitmap(self, ancestor: int, total_rows: int, first_chunk: int, n_chunks: int, stride: int = 1) -> bytes:
+        n = lib().silo_host_synthetic_lineage_bitmap(self._h, ancestor, total_rows, first_chunk, n_chunks, None, 0, stride)
         if n < 0:
             raise HostError(lib().silo_host_last_error().decode())
         buf = C.create_string_buffer(int(n))
-        lib().silo_host_synthetic_lineage_bitmap(self._h, ancestor, total_rows, first_chunk, n_chunks, buf, n)
+        lib().silo_host_synthetic_lineage_bitmap(self._h, ancestor, total_rows, first_chunk, n_chunks, buf, n, stride)
         return buf.raw
 
     def close(self):
@@ -385,11 +386,24 @@ class Synthetic:
 
 
 def date_ranges_expression(total_rows: int, span_days: int, from_day: int, to_day_inclusive: int,
-                           first_chunk: int, n_chunks: int) -> str:
+                           first_chunk: int, n_chunks: int, stride: int = 1) -> str:
     buf = C.create_string_buffer(64 + 24 * max(n_chunks, 1))
     _check(lib().silo_host_synthetic_date_ranges(
-        total_rows, span_days, from_day, to_day_inclusive, first_chunk, n_chunks, buf, len(buf)))
+        total_rows, span_days, from_day, to_day_inclusive, first_chunk, n_chunks, buf, len(buf), stride))
     return buf.value.decode()
+
+
+def interleaved_shard(n_chunks_total: int, n_ranks: int, rank: int) -> tuple[int, int, int]:
+    """(first_chunk, n_chunks, stride) of rank's shard when chunk c belongs to rank c % n_ranks: any
+    filter on a sorted column (a date range selects a contiguous row range) then loads every rank
+    alike, which contiguous chunk ranges do not."""
+    count = (n_chunks_total - rank + n_ranks - 1) // n_ranks if rank < n_chunks_total else 0
+    return rank, count, n_ranks
+
+
+def shard_chunk_sizes(total_rows: int, first_chunk: int, n_chunks: int, stride: int = 1) -> list[int]:
+    sizes = dense_chunk_sizes(total_rows)
+    return [sizes[first_chunk + k * stride] for k in range(n_chunks)]
 
 
 def dense_chunk_sizes(total_rows: int) -> list[int]:

@@ -325,11 +325,13 @@ def test_synthetic_shards_sum_to_the_whole(ctx):
     date_filter = lambda first, n: host_api.date_ranges_expression(total_rows, 1095, 200, 800, first, n)
     ancestor = next(i for i in range(synthetic.num_sequences) if synthetic.generation(i) == 2)
 
-    def shard(first, n):
-        table = host_api.HostTable(ctx, sizes[first:first + n], first_chunk=first)
-        table.add_column("main", host_api.NUCLEOTIDE, synthetic.reference, synthetic.build_column(total_rows, first, n, 4))
-        table.register_bitmap("lineage", synthetic.lineage_bitmap(ancestor, total_rows, first, n))
-        expression = f"(and {date_filter(first, n)} (bitmap lineage))"
+    def shard(first, n, stride=1):
+        # a contiguous shard keeps global chunk ids; an interleaved one is a table of its own
+        table = host_api.HostTable(
+            ctx, host_api.shard_chunk_sizes(total_rows, first, n, stride), first_chunk=first if stride == 1 else 0)
+        table.add_column("main", host_api.NUCLEOTIDE, synthetic.reference, synthetic.build_column(total_rows, first, n, 4, stride))
+        table.register_bitmap("lineage", synthetic.lineage_bitmap(ancestor, total_rows, first, n, stride))
+        expression = f"(and {host_api.date_ranges_expression(total_rows, 1095, 200, 800, first, n, stride)} (bitmap lineage))"
         flt = table.filter(expression)
         return table, flt, table.mutation_counts("main", flt), table.mutation_counts("main")
 
@@ -339,6 +341,12 @@ def test_synthetic_shards_sum_to_the_whole(ctx):
     assert sum(p[1].cardinality for p in parts) == whole_filter.cardinality > 0
     np.testing.assert_array_equal(sum(p[2].astype(np.uint64) for p in parts).astype(np.uint32), whole_counts)
     np.testing.assert_array_equal(sum(p[3].astype(np.uint64) for p in parts).astype(np.uint32), whole_full)
+    # interleaved shards (chunk c on rank c % 3), what bench.py uses for N > 1: balanced under a date filter
+    interleaved = [shard(*host_api.interleaved_shard(len(sizes), 3, rank)) for rank in range(3)]
+    assert sum(p[1].cardinality for p in interleaved) == whole_filter.cardinality
+    assert max(p[1].cardinality for p in interleaved) < 0.6 * whole_filter.cardinality
+    np.testing.assert_array_equal(sum(p[2].astype(np.uint64) for p in interleaved).astype(np.uint32), whole_counts)
+    np.testing.assert_array_equal(sum(p[3].astype(np.uint64) for p in interleaved).astype(np.uint32), whole_full)
     # and the whole agrees with the oracle fed the SAME packed column through its import path
     oracle_table = O.Table()
     oracle_table.set_layout(*sizes)

@@ -152,3 +152,72 @@ def test_sorted_date_ranges_match_brute_force():
         table = O.Table()
         table.set_layout(*sizes)
         assert set(int(v) for v in table.filter(text).ids()) == want
+
+
+def test_interleaved_shards_cover_the_table_once():
+    """Chunk c belongs to rank c % n: the shards' (local) rows map back to every global row exactly once,
+    and their lineage / date-range stand-ins select the same global rows as the whole table's."""
+    from lapis_silo_b200 import host_api
+    total_rows = 7 * 65536 + 999
+    sizes = host_api.dense_chunk_sizes(total_rows)
+    synthetic = host_api.Synthetic(genome_length=300, reference_seed=3, generations=4)
+    ancestor = next(e for e in range(synthetic.num_sequences) if synthetic.generation(e) == 2)
+    whole = set(_roaring_ids(synthetic.lineage_bitmap(ancestor, total_rows, 0, len(sizes))))
+    n_ranks = 3
+    seen_chunks = []
+    merged = set()
+    for rank in range(n_ranks):
+        first, n_chunks, stride = host_api.interleaved_shard(len(sizes), n_ranks, rank)
+        assert host_api.shard_chunk_sizes(total_rows, first, n_chunks, stride) == [sizes[first + k * stride] for k in range(n_chunks)]
+        seen_chunks += [first + k * stride for k in range(n_chunks)]
+        for local_id in _roaring_ids(synthetic.lineage_bitmap(ancestor, total_rows, first, n_chunks, stride)):
+            local_chunk, row = local_id >> 16, local_id & 0xFFFF
+            merged.add(((first + local_chunk * stride) << 16) | row)
+        column = synthetic.build_column(total_rows, first, n_chunks, 2, stride).contents
+        v_indexes = {column.containers[i].v_index for i in range(column.n_containers)}
+        assert v_indexes <= set(range(n_chunks)), "an interleaved shard carries local chunk ids"
+    assert sorted(seen_chunks) == list(range(len(sizes)))
+    assert merged == whole
+
+
+def _roaring_ids(portable_bytes: bytes) -> list[int]:
+    """Minimal reader of the portable Roaring format (cookie 12346 / 12347) for the tests."""
+    import struct
+    data = memoryview(portable_bytes)
+    cookie = struct.unpack_from("<I", data, 0)[0]
+    pos = 4
+    run_flags = None
+    if cookie & 0xFFFF == 12347:
+        n = (cookie >> 16) + 1
+        run_flags = bytes(data[pos:pos + (n + 7) // 8])
+        pos += (n + 7) // 8
+    else:
+        assert cookie == 12346
+        n = struct.unpack_from("<I", data, pos)[0]
+        pos += 4
+    keys = [struct.unpack_from("<HH", data, pos + 4 * i) for i in range(n)]
+    pos += 4 * n
+    if run_flags is None or n >= 4:
+        pos += 4 * n
+    ids = []
+    for i, (key, card_minus_one) in enumerate(keys):
+        if run_flags is not None and (run_flags[i // 8] >> (i % 8)) & 1:
+            n_runs = struct.unpack_from("<H", data, pos)[0]
+            pos += 2
+            for r in range(n_runs):
+                start, length = struct.unpack_from("<HH", data, pos + 4 * r)
+                ids += [(key << 16) | v for v in range(start, start + length + 1)]
+            pos += 4 * n_runs
+        elif card_minus_one + 1 <= 4096:
+            values = struct.unpack_from(f"<{card_minus_one + 1}H", data, pos)
+            ids += [(key << 16) | v for v in values]
+            pos += 2 * (card_minus_one + 1)
+        else:
+            words = struct.unpack_from("<1024Q", data, pos)
+            for w, word in enumerate(words):
+                while word:
+                    bit = (word & -word).bit_length() - 1
+                    ids.append((key << 16) | (w * 64 + bit))
+                    word &= word - 1
+            pos += 8192
+    return ids
