@@ -106,10 +106,8 @@ struct __align__(16) DevSegment {
    uint32_t desc_begin;
    uint32_t desc_count;
    uint32_t chunk;  // local chunk index
-   uint32_t flags;  // SEG_NEEDS_RANK: holds a KIND_WORDRANGE piece (the consumers build the rank table)
-   uint32_t pad;
+   uint32_t pad[2];
 };
-constexpr uint32_t SEG_NEEDS_RANK = 1;
 static_assert(sizeof(DevSegment) == 32);
 
 struct DevColumn {

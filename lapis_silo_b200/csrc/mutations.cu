@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(1024) buildWorkListKernel(
 // generic-pointer arithmetic of plain C++ costs as many instructions per piece as the lookups.
 // ---------------------------------------------------------------------------------------------
 
-constexpr int K1_STAGES = 4;
+constexpr int K1_STAGES = 5;
 constexpr int K1_CONSUMER_WARPS = 16;
 constexpr int K1_CONSUMER_THREADS = K1_CONSUMER_WARPS * 32;
 constexpr int K1_THREADS = K1_CONSUMER_THREADS + 32;  // warp 0 = bulk-copy producer
@@ -130,7 +130,7 @@ struct __align__(16) K1Stage {
 struct __align__(16) K1Control {
    uint32_t desc_count;  // K1_STOP: no more work
    uint32_t base4;       // slab offset (4-byte units) of the stage's payload[0]
-   uint32_t flags;       // K1_NEW_TILE | K1_TILE_SLOT | K1_NEEDS_RANK
+   uint32_t flags;       // K1_NEW_TILE | K1_TILE_SLOT
    uint32_t pad0;
    uint64_t full;   // the stage's bulk copies have landed
    uint64_t empty;  // every consumer warp has pulled its pieces of the stage into registers
@@ -143,12 +143,10 @@ constexpr uint32_t K1_CTRL_EMPTY = 24;
 constexpr uint32_t K1_CTRL_DONE = 32;
 constexpr uint32_t K1_NEW_TILE = 1;    // the stage's bulk copies also (re)loaded the filter tile
 constexpr uint32_t K1_TILE_SLOT = 2;   // which of the two filter-tile buffers the stage reads
-constexpr uint32_t K1_NEEDS_RANK = 4;  // a KIND_WORDRANGE piece is inside: the rank table must exist
 
 struct __align__(16) K1Dynamic {
    K1Stage stages[K1_STAGES];
    K1Control control[K1_STAGES];
-   uint32_t warp_sums[K1_CONSUMER_WARPS];
 };
 constexpr uint32_t K1_CONTROL_OFFSET = sizeof(K1Stage) * K1_STAGES;
 
@@ -157,7 +155,7 @@ __device__ __forceinline__ uint32_t warpSum(uint32_t value) {
 }
 
 // ---- shared memory by 32-bit address ----------------------------------------------------------
-// Reads of stage data / tile / rank table. Not volatile: every address derives from words that were
+// Reads of stage data and of the filter tile. Not volatile: every address derives from words that were
 // loaded after the stage's full barrier was observed (a volatile asm with a memory clobber).
 #ifndef SILO_K1_PROBE
 #define SILO_K1_PROBE 0  // 1: tile lookups all hit one word (no bank conflicts); 2: no tile lookups at all
@@ -362,12 +360,16 @@ __device__ __forceinline__ uint32_t pieceFromRegisters(
    return warpSum(local);
 }
 
-// KIND_WORDRANGE: whole 32-row words [wa, wb) from the exclusive rank table (payload in the stage)
-__device__ __forceinline__ uint32_t wordRangeCount(uint32_t entries, uint32_t payload_address, uint32_t rank_address, uint32_t lane) {
+// KIND_WORDRANGE: the whole 32-row words [wa, wb) in the middle of long runs: the warp popcounts the
+// tile words of each range directly (a range of n words costs n/32 iterations per lane, less than
+// the lookups of an array piece of the same row count). The payload is read from the stage.
+__device__ __forceinline__ uint32_t wordRangeCount(uint32_t entries, uint32_t payload_address, uint32_t tile_address, uint32_t lane) {
    uint32_t local = 0;
-   for (uint32_t r = lane; r < entries; r += 32) {
+   for (uint32_t r = 0; r < entries; ++r) {
       const uint32_t range = lds32(payload_address + 4 * r);
-      local += lds32(rank_address + 4 * (range >> 16)) - lds32(rank_address + 4 * (range & 0xFFFFu));
+      for (uint32_t word = (range & 0xFFFFu) + lane; word < (range >> 16); word += 32) {
+         local += __popc(lds32(tile_address + 4 * word));
+      }
    }
    return warpSum(local);
 }
@@ -387,7 +389,6 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
    // Two tile buffers: the producer loads the next chunk's tile while stages of the current chunk
    // are still being consumed, so a chunk switch does not drain the pipeline.
    __shared__ __align__(16) uint32_t tile_buffers[2][TILE32_WORDS + 4];  // [2048] = zero pad word
-   __shared__ __align__(16) uint32_t rank_buffers[2][TILE32_WORDS + 4];  // exclusive prefix; [2048] = total
    extern __shared__ __align__(128) uint8_t smem_raw[];
    K1Dynamic& sh = *reinterpret_cast<K1Dynamic*>(smem_raw);
 
@@ -397,7 +398,6 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
    const uint32_t ring_address = smemAddr(smem_raw);
    const uint32_t control_address = ring_address + K1_CONTROL_OFFSET;
    const uint32_t tile_address0 = smemAddr(tile_buffers[0]);
-   const uint32_t rank_address0 = smemAddr(rank_buffers[0]);
 
    if (threadIdx.x == 0) {
       for (int s = 0; s < K1_STAGES; ++s) {
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
          const uint32_t desc_bytes = mine.desc_count * static_cast<uint32_t>(sizeof(DevContainer));
          const uint4 meta = make_uint4(
             mine.desc_count, static_cast<uint32_t>(mine.payload_offset >> 2),
-            (new_tile ? K1_NEW_TILE : 0u) | (my_slot != 0 ? K1_TILE_SLOT : 0u) | ((mine.flags & SEG_NEEDS_RANK) != 0 ? K1_NEEDS_RANK : 0u), 0u
+            (new_tile ? K1_NEW_TILE : 0u) | (my_slot != 0 ? K1_TILE_SLOT : 0u), 0u
          );
          for (uint32_t j = 0; j < batch; ++j) {
             if (lane == j) {
@@ -540,7 +540,6 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
    // instructions per stage visit -- the kernel is bound by instruction issue.
    static_assert(SEG_MAX_DESCS == K1_CONSUMER_WARPS, "one piece per consumer warp and stage");
    const uint32_t cwarp = warp - 1;
-   const uint32_t cthread = threadIdx.x - 32;  // 0..511
    const uint32_t lane16 = lane * 16;
    const uint32_t genome_length = column.genome_length;
    // opaque to the compiler (gridDim.y is 1): keeps the IMAD.HI forms, see Multipliers
@@ -559,60 +558,43 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
    uint32_t tile_base = tile_address0;
    asm volatile("" : "+r"(ring_base), "+r"(control_base), "+r"(tile_base));
    uint32_t rotation = cwarp;  // piece index of this warp in the current stage, before the & 15
-   uint32_t rank_valid = 0;    // bit s: rank_buffers[s] belongs to the tile now in tile_buffers[s]
    uint32_t visit = 0;         // stages visited so far
+   // MODE 4 (profiling): cycles this warp spent waiting for data, reported through the counts array
+   long long probe_begin = 0;
+   long long probe_waited = 0;
+   long long probe_first = 0;
+   if (MODE == 4) {
+      probe_begin = clock64();
+   }
    for (;; ++visit) {
       const uint32_t stage = visit % K1_STAGES;
       const uint32_t stage_address = ring_base + stage * static_cast<uint32_t>(sizeof(K1Stage));
       const uint32_t my_control = control_base + stage * static_cast<uint32_t>(sizeof(K1Control));
+      const long long wait_begin = MODE == 4 ? clock64() : 0;
       mbarWaitAt(my_control + K1_CTRL_FULL, (visit / K1_STAGES) & 1u);
+      if (MODE == 4) {
+         const long long now = clock64();
+         if (visit == 0) {
+            probe_first = now - probe_begin;
+         } else {
+            probe_waited += now - wait_begin;
+         }
+      }
       const uint4 meta = lds128(my_control);
       const uint32_t desc_count = meta.x;
       if (desc_count == K1_STOP) {
+         if (MODE == 4 && lane == 0) {
+            const uint32_t row = 15 * genome_length;  // a symbol row the finalize kernel never writes
+            atomicAdd(&counts[row + 0], static_cast<uint32_t>((clock64() - probe_begin) >> 6));  // total
+            atomicAdd(&counts[row + 1], static_cast<uint32_t>(probe_waited >> 6));               // waiting for data, after the first stage
+            atomicAdd(&counts[row + 2], static_cast<uint32_t>(probe_first >> 6));                // until the first stage landed
+            atomicAdd(&counts[row + 3], visit);
+            atomicAdd(&counts[row + 4], 1u);
+         }
          break;
       }
       const uint32_t flags = meta.z;
       const uint32_t slot_offset = (flags & K1_TILE_SLOT) != 0 ? TILE_BUFFER_BYTES : 0u;
-      if ((flags & (K1_NEW_TILE | K1_NEEDS_RANK)) != 0) {  // rare: a chunk switch or a long-run piece
-         const uint32_t slot = (flags / K1_TILE_SLOT) & 1u;
-         if ((flags & K1_NEW_TILE) != 0) {
-            rank_valid &= ~(1u << slot);
-         }
-         if ((flags & K1_NEEDS_RANK) != 0 && ((rank_valid >> slot) & 1u) == 0) {
-            // (every consumer warp sees the same stages in the same order, so all of them get here)
-            // exclusive rank table of the tile: 512 threads x 4 words
-            rank_valid |= 1u << slot;
-            const uint32_t* tile32 = tile_buffers[slot];
-            uint32_t* rank32 = rank_buffers[slot];
-            const uint4 four = reinterpret_cast<const uint4*>(tile32)[cthread];
-            const uint32_t p0 = __popc(four.x);
-            const uint32_t p1 = __popc(four.y);
-            const uint32_t p2 = __popc(four.z);
-            const uint32_t p3 = __popc(four.w);
-            const uint32_t mine = p0 + p1 + p2 + p3;
-            uint32_t inclusive = mine;
-            for (int offset = 1; offset < 32; offset <<= 1) {
-               const uint32_t other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
-               if (lane >= static_cast<uint32_t>(offset)) {
-                  inclusive += other;
-               }
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(K1_CONSUMER_THREADS) : "memory");  // warp_sums of the previous build are read
-            if (lane == 31) {
-               sh.warp_sums[cwarp] = inclusive;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(K1_CONSUMER_THREADS) : "memory");
-            uint32_t exclusive = inclusive - mine;
-            for (uint32_t w = 0; w < cwarp; ++w) {
-               exclusive += sh.warp_sums[w];
-            }
-            reinterpret_cast<uint4*>(rank32)[cthread] = make_uint4(exclusive, exclusive + p0, exclusive + p0 + p1, exclusive + p0 + p1 + p2);
-            if (cthread == K1_CONSUMER_THREADS - 1) {
-               rank32[TILE32_WORDS] = exclusive + mine;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(K1_CONSUMER_THREADS) : "memory");
-         }
-      }
       // the rotation continues where the previous stage stopped, so that a stage with fewer than 16
       // pieces does not always leave the same warps idle
       const uint32_t index = rotation & (K1_CONSUMER_WARPS - 1);
@@ -630,7 +612,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
       const uint32_t kind = (desc.z >> 26) & 7u;
       uint32_t count = 0;
       if (kind == KIND_WORDRANGE) {  // rare; reads the stage while it works
-         count = wordRangeCount(desc.w, payload_address, rank_address0 + slot_offset, lane);
+         count = wordRangeCount(desc.w, payload_address, tile_base + slot_offset, lane);
          __syncwarp();
          if (lane == 0) {
             mbarArriveAt(my_control + K1_CTRL_EMPTY);
@@ -935,6 +917,7 @@ void enqueueMutationCounts(
             SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
             SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
             SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
+            SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
             const char* flag = std::getenv("SILO_K1_STREAM_ONLY");
             stream_only = flag != nullptr ? flag[0] - '0' : 0;
             const char* batch_flag = std::getenv("SILO_K1_BATCH");
@@ -952,6 +935,7 @@ void enqueueMutationCounts(
             case 1: SILO_LAUNCH_K1(1); break;
             case 2: SILO_LAUNCH_K1(2); break;
             case 3: SILO_LAUNCH_K1(3); break;
+            case 4: SILO_LAUNCH_K1(4); break;
             default: SILO_LAUNCH_K1(0); break;
          }
 #undef SILO_LAUNCH_K1

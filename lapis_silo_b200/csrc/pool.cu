@@ -83,7 +83,7 @@ static void encodeRunsPiece(const uint32_t* entries, uint32_t n, std::vector<uin
 }
 
 // CRoaring run pairs {start, length-1} -> runs confined to one 32-row word each (KIND_RUNS_W entries)
-// plus ranges of whole words for the long runs (KIND_WORDRANGE entries, answered from the rank table)
+// plus ranges of whole words for the long runs (KIND_WORDRANGE entries, popcounted straight from the tile)
 static void splitRuns(
    const uint8_t* pairs,
    uint32_t n_runs,
@@ -484,7 +484,6 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
                      reinterpret_cast<const uint8_t*>(word_ranges.data() + end)
                   );
                   emitPiece(c, KIND_WORDRANGE, rows, static_cast<uint32_t>(end - first), scratch.data(), static_cast<uint32_t>(scratch.size()));
-                  segment.flags |= SEG_NEEDS_RANK;
                   first = end;
                }
             } else {
