@@ -384,14 +384,15 @@ def run_ours(args):
 
     # ---- e2e: host buffers in, host rows out, every step ----
     def e2e_step():
+        # (the result comes back as columns, like the record batch the reference hands to its Arrow sink)
         if n_gpus == 1:
-            return table.mutations(["main"], expression, MIN_PROPORTION)  # MutationsNode through the C ABI
+            return table.mutations_columns(["main"], expression, MIN_PROPORTION)  # MutationsNode through the C ABI
         flt = table.filter(expression)  # parse/compile/lower, program H2D, cardinality D2H
         table.mutation_counts_async(0, flt, counts.data_ptr(), stream.cuda_stream)
         dist.all_reduce(counts[:valid_values])  # rows of the 5 valid symbols: all that the thresholding reads
         pinned[:valid_values].copy_(counts[:valid_values], non_blocking=True)  # rows of the 5 valid symbols
         stream.synchronize()
-        return table.mutation_rows_from_counts("main", pinned.numpy().view(np.uint32), MIN_PROPORTION)
+        return table.mutation_columns_from_counts("main", pinned.numpy().view(np.uint32), MIN_PROPORTION)
 
     valid_values = VALID_MUTATION_SYMBOLS * GENOME_LENGTH  # symbol ids 0..4 (-, A, C, G, T) are contiguous
     rows = None
@@ -409,6 +410,7 @@ def run_ours(args):
     # size-independent parity properties at full size (tests/ hold the bit-exact oracle comparisons)
     column_sums = device_counts.sum(axis=0, dtype=np.uint64)
     assert (column_sums == cardinality).all(), "per-position symbol counts (all-reduced) must add up to the global |filter|"
+    rows = host_api.rows_from_columns(rows)
     if n_gpus == 1:
         direct = table.mutation_rows_from_counts("main", device_counts, MIN_PROPORTION)
         assert direct == rows, "device-resident and host-buffer paths must emit identical rows"

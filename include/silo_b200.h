@@ -238,6 +238,21 @@ int silo_gpu_mutation_counts_symbols(
    uint32_t* counts
 );
 
+/* Filter program + Mutations counts in ONE call with ONE host synchronisation (silo_gpu_filter_eval
+ * followed by silo_gpu_mutation_counts_symbols costs two): what MutationsNode does for a query with a
+ * single sequence column. The filter exists only inside the call; *cardinality (may be NULL) receives
+ * its cardinality. A program that is just PUSH_FULL takes the stored-cardinality path
+ * (mutations_node.cpp:280-281); any other program takes the intersecting path, which yields the same
+ * counts for every filter. */
+int silo_gpu_query_mutation_counts(
+   silo_gpu_table* table,
+   const silo_filter_program* program,
+   int column,
+   uint64_t symbol_mask,
+   uint32_t* counts,
+   uint64_t* cardinality
+);
+
 /* Same, but leaves the counts in device memory (d_counts: n_symbols*genome_length u32) and only
  * enqueues on `cuda_stream` (a cudaStream_t; NULL = the table's own stream) without synchronising,
  * so that a collective (ncclAllReduce on the same stream) can follow with no host round trip. */

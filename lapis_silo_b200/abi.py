@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import weakref
 
 import numpy as np
 
@@ -110,7 +111,7 @@ EXPORTED_SYMBOLS = [
     "silo_gpu_host_alloc", "silo_gpu_host_free",
     "silo_gpu_filter_from_words", "silo_gpu_bitmap_register", "silo_gpu_bitmap_unregister",
     "silo_gpu_filter_cardinality", "silo_gpu_filter_download", "silo_gpu_filter_free",
-    "silo_gpu_mutation_counts", "silo_gpu_mutation_counts_symbols", "silo_gpu_mutation_counts_async", "silo_gpu_get_stats",
+    "silo_gpu_mutation_counts", "silo_gpu_mutation_counts_symbols", "silo_gpu_query_mutation_counts", "silo_gpu_mutation_counts_async", "silo_gpu_get_stats",
 ]
 
 
@@ -200,6 +201,7 @@ class Filter:
         self.table = table
         self._h = handle
         self._cardinality = cardinality
+        table._children.add(self)  # a table frees its filters before its pools
 
     @property
     def cardinality(self) -> int:
@@ -239,6 +241,7 @@ class Table:
         self.n_chunks = len(self.chunk_sizes)
         self.first_chunk = first_chunk
         self.columns: list[tuple[int, int]] = []  # (n_symbols, genome_length)
+        self._children = weakref.WeakSet()
         self._h = C.c_void_p()
         arr = (C.c_uint32 * max(self.n_chunks, 1))(*self.chunk_sizes)
         check(lib().silo_gpu_table_create(ctx._h, first_chunk, arr, self.n_chunks, C.byref(self._h)))
@@ -304,6 +307,8 @@ class Table:
 
     def close(self):
         if self._h:
+            for child in list(self._children):
+                child.close()
             lib().silo_gpu_table_free(self._h)
             self._h = C.c_void_p()
 

@@ -241,6 +241,12 @@ namespace silo {
 
 void setLastError(const std::string& message);
 
+// filter_eval.cu, for the fused query call of mutations.cu. The caller holds table->mutex. Stages and
+// launches the program on `stream` WITHOUT synchronising; *d_staging_out must be freed
+// (cudaFreeAsync on the same stream) after the kernel, the filter with releaseFilterLocked.
+silo_gpu_filter* evalProgramAsync(silo_gpu_table* table, const silo_filter_program* program, cudaStream_t stream, uint8_t** d_staging_out);
+void releaseFilterLocked(silo_gpu_filter* filter);
+
 struct ApiError : std::runtime_error {
    int status;
    ApiError(int status, const std::string& message) : std::runtime_error(message), status(status) {}

@@ -1097,6 +1097,32 @@ static void launchProgram(silo_gpu_table* table, EvalParams params, silo_gpu_fil
 
 }  // extern "C"
 
+namespace silo {
+
+silo_gpu_filter* evalProgramAsync(silo_gpu_table* table, const silo_filter_program* program, cudaStream_t stream, uint8_t** d_staging_out) {
+   uint64_t staged_bytes = 0;
+   EvalParams params{};
+   stageProgram(table, program, stream, d_staging_out, &staged_bytes, &params);
+   silo_gpu_filter* filter = nullptr;
+   try {
+      filter = allocFilter(table);
+      launchProgram(table, params, filter, stream);
+   } catch (...) {
+      cudaFreeAsync(*d_staging_out, stream);
+      *d_staging_out = nullptr;
+      cudaStreamSynchronize(stream);
+      freeFilterLocked(filter);
+      throw;
+   }
+   return filter;
+}
+
+void releaseFilterLocked(silo_gpu_filter* filter) {
+   freeFilterLocked(filter);
+}
+
+}  // namespace silo
+
 struct silo_gpu_program {
    silo_gpu_table* table = nullptr;
    uint8_t* d_staging = nullptr;

@@ -977,53 +977,107 @@ int silo_gpu_mutation_counts_async(
    });
 }
 
-// the synchronous calls: enqueue, copy the rows of the wanted symbols to the host, synchronise
+// the synchronous calls: [evaluate a program,] enqueue, copy the rows of the wanted symbols to the
+// host, synchronise ONCE. With a program the filter lives only inside the call.
 static void mutationCountsToHost(
    silo_gpu_table* table,
    int column,
    const silo_gpu_filter* filter,
+   const silo_filter_program* program,
    uint64_t symbol_mask,
-   uint32_t* counts
+   uint32_t* counts,
+   uint64_t* cardinality_out
 ) {
    require(table != nullptr && counts != nullptr, "mutation_counts: NULL argument");
    std::lock_guard<std::mutex> lock(table->mutex);
    SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
    cudaStream_t stream = table->ctx->stream;
-   enqueueMutationCounts(table, column, filter, table->d_counts, stream);
-   const HostColumn& host = *table->columns[static_cast<size_t>(column)];
-   const size_t row_values = host.dev.genome_length;
-   // page-locked destination (silo_gpu_host_alloc): the copy engine writes it directly
-   cudaPointerAttributes attributes{};
-   const bool pinned_destination =
-      cudaPointerGetAttributes(&attributes, counts) == cudaSuccess && attributes.type == cudaMemoryTypeHost;
-   cudaGetLastError();
-   uint32_t* destination = pinned_destination ? counts : table->h_counts_pinned;
-   // one copy per maximal range of consecutive wanted symbols
-   std::vector<std::pair<uint32_t, uint32_t>> ranges;
-   for (uint32_t symbol = 0; symbol < host.dev.n_symbols;) {
-      if (((symbol_mask >> symbol) & 1ULL) == 0) {
-         ++symbol;
-         continue;
+   require(column >= 0 && static_cast<size_t>(column) < table->columns.size(), "mutation_counts: bad column index");
+   uint8_t* d_staging = nullptr;
+   silo_gpu_filter* own_filter = nullptr;
+   unsigned long long host_cardinality = 0;
+   uint32_t host_error = 0;
+   try {
+      if (program != nullptr) {
+         // a program that is just PUSH_FULL is the `cardinality == numRows` path (stored cardinalities)
+         const bool trivially_full = program->n_instrs == 1 && program->instrs != nullptr && program->instrs[0].opcode == SILO_OP_PUSH_FULL;
+         if (trivially_full) {
+            host_cardinality = table->n_rows;
+         } else {
+            own_filter = evalProgramAsync(table, program, stream, &d_staging);
+            filter = own_filter;
+            SILO_CUDA_CHECK(cudaMemcpyAsync(&host_cardinality, own_filter->d_cardinality, sizeof(host_cardinality), cudaMemcpyDeviceToHost, stream));
+            SILO_CUDA_CHECK(cudaMemcpyAsync(&host_error, own_filter->d_error_flag, sizeof(host_error), cudaMemcpyDeviceToHost, stream));
+         }
       }
-      uint32_t end = symbol;
-      while (end < host.dev.n_symbols && ((symbol_mask >> end) & 1ULL) != 0) {
-         ++end;
+      enqueueMutationCounts(table, column, filter, table->d_counts, stream);
+      const HostColumn& host = *table->columns[static_cast<size_t>(column)];
+      const size_t row_values = host.dev.genome_length;
+      // page-locked destination (silo_gpu_host_alloc): the copy engine writes it directly
+      cudaPointerAttributes attributes{};
+      const bool pinned_destination =
+         cudaPointerGetAttributes(&attributes, counts) == cudaSuccess && attributes.type == cudaMemoryTypeHost;
+      cudaGetLastError();
+      uint32_t* destination = pinned_destination ? counts : table->h_counts_pinned;
+      // one copy per maximal range of consecutive wanted symbols
+      std::vector<std::pair<uint32_t, uint32_t>> ranges;
+      for (uint32_t symbol = 0; symbol < host.dev.n_symbols;) {
+         if (((symbol_mask >> symbol) & 1ULL) == 0) {
+            ++symbol;
+            continue;
+         }
+         uint32_t end = symbol;
+         while (end < host.dev.n_symbols && ((symbol_mask >> end) & 1ULL) != 0) {
+            ++end;
+         }
+         ranges.emplace_back(symbol, end);
+         symbol = end;
       }
-      ranges.emplace_back(symbol, end);
-      symbol = end;
-   }
-   for (const auto& [first, end] : ranges) {
-      SILO_CUDA_CHECK(cudaMemcpyAsync(
-         destination + first * row_values, table->d_counts + first * row_values, (end - first) * row_values * sizeof(uint32_t),
-         cudaMemcpyDeviceToHost, stream
-      ));
-   }
-   SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
-   if (!pinned_destination) {
       for (const auto& [first, end] : ranges) {
-         std::memcpy(counts + first * row_values, table->h_counts_pinned + first * row_values, (end - first) * row_values * sizeof(uint32_t));
+         SILO_CUDA_CHECK(cudaMemcpyAsync(
+            destination + first * row_values, table->d_counts + first * row_values, (end - first) * row_values * sizeof(uint32_t),
+            cudaMemcpyDeviceToHost, stream
+         ));
       }
+      if (d_staging != nullptr) {
+         SILO_CUDA_CHECK(cudaFreeAsync(d_staging, stream));
+         d_staging = nullptr;
+      }
+      SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+      if (!pinned_destination) {
+         for (const auto& [first, end] : ranges) {
+            std::memcpy(counts + first * row_values, table->h_counts_pinned + first * row_values, (end - first) * row_values * sizeof(uint32_t));
+         }
+      }
+   } catch (...) {
+      if (d_staging != nullptr) {
+         cudaFreeAsync(d_staging, stream);
+      }
+      cudaStreamSynchronize(stream);
+      releaseFilterLocked(own_filter);
+      throw;
    }
+   releaseFilterLocked(own_filter);
+   if (host_error != 0) {
+      throw ApiError(SILO_E_OUT_OF_LAYOUT, "a leaf bitmap holds row ids outside the row layout");
+   }
+   if (cardinality_out != nullptr) {
+      *cardinality_out = host_cardinality;
+   }
+}
+
+int silo_gpu_query_mutation_counts(
+   silo_gpu_table* table,
+   const silo_filter_program* program,
+   int column,
+   uint64_t symbol_mask,
+   uint32_t* counts,
+   uint64_t* cardinality
+) {
+   return guarded([&] {
+      require(program != nullptr, "silo_gpu_query_mutation_counts: program is NULL");
+      mutationCountsToHost(table, column, nullptr, program, symbol_mask, counts, cardinality);
+   });
 }
 
 int silo_gpu_mutation_counts(
@@ -1032,7 +1086,7 @@ int silo_gpu_mutation_counts(
    const silo_gpu_filter* filter,
    uint32_t* counts
 ) {
-   return guarded([&] { mutationCountsToHost(table, column, filter, ~0ULL, counts); });
+   return guarded([&] { mutationCountsToHost(table, column, filter, nullptr, ~0ULL, counts, nullptr); });
 }
 
 int silo_gpu_mutation_counts_symbols(
@@ -1042,7 +1096,7 @@ int silo_gpu_mutation_counts_symbols(
    uint64_t symbol_mask,
    uint32_t* counts
 ) {
-   return guarded([&] { mutationCountsToHost(table, column, filter, symbol_mask, counts); });
+   return guarded([&] { mutationCountsToHost(table, column, filter, nullptr, symbol_mask, counts, nullptr); });
 }
 
 }  // extern "C"

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cctype>
 #include <map>
+#include <string_view>
 #include <utility>
 
 #include "roaring_writer.h"
@@ -708,7 +709,7 @@ struct PhysicalOperator : ScalarExpression {
 
 struct Node {
    bool is_atom = false;
-   std::string atom;
+   std::string_view atom;  // a view into the expression text (no allocation per token)
    std::vector<Node> items;
 };
 
@@ -733,6 +734,7 @@ class Reader {
       checkQuery(head != ')', "filter expression: unexpected ')'");
       if (head == '(') {
          ++cursor;
+         node.items.reserve(8);
          for (;;) {
             skipSpace();
             checkQuery(cursor < text.size(), "filter expression: missing ')'");
@@ -747,7 +749,7 @@ class Reader {
       if (head == '"') {
          const size_t close = text.find('"', cursor + 1);
          checkQuery(close != std::string::npos, "filter expression: unterminated string");
-         node.atom = text.substr(cursor + 1, close - cursor - 1);
+         node.atom = std::string_view(text).substr(cursor + 1, close - cursor - 1);
          cursor = close + 1;
          return node;
       }
@@ -756,7 +758,7 @@ class Reader {
              text[cursor] != '(' && text[cursor] != ')') {
          ++cursor;
       }
-      node.atom = text.substr(begin, cursor - begin);
+      node.atom = std::string_view(text).substr(begin, cursor - begin);
       return node;
    }
 
@@ -766,18 +768,22 @@ class Reader {
    }
 };
 
-const std::string& atom(const Node& node) {
+std::string atom(const Node& node) {
    checkQuery(node.is_atom, "filter expression: expected an atom");
-   return node.atom;
+   return std::string(node.atom);
 }
 
 uint64_t number(const Node& node) {
-   const std::string& text = atom(node);
-   checkQuery(
-      !text.empty() && std::all_of(text.begin(), text.end(), [](char c) { return c >= '0' && c <= '9'; }),
-      "filter expression: expected a non-negative integer, got '" + text + "'"
-   );
-   return std::stoull(text);
+   checkQuery(node.is_atom, "filter expression: expected an atom");
+   const std::string_view text = node.atom;
+   uint64_t value = 0;
+   bool valid = !text.empty() && text.size() <= 19;
+   for (const char c : text) {
+      valid = valid && c >= '0' && c <= '9';
+      value = value * 10 + static_cast<uint64_t>(c - '0');
+   }
+   checkQuery(valid, "filter expression: expected a non-negative integer, got '" + std::string(text) + "'");
+   return value;
 }
 
 uint32_t position(const Node& node) {

@@ -99,8 +99,43 @@ void appendMutationRows(
 std::vector<MutationRow> MutationsNode::execute() const {
    lastQueryProfile().counts_us = 0;
    lastQueryProfile().threshold_us = 0;
-   const DeviceBitmap bitmap_filter = computeFilter(*filter, table);
    std::vector<MutationRow> rows;
+   if (sequence_columns.size() == 1) {
+      // One sequence column (the common query): filter program and counts go to the device in ONE call
+      // with one synchronisation (silo_gpu_query_mutation_counts); the filter never leaves the device.
+      const SequenceColumnInfo* column = table.findColumn(sequence_columns.front());
+      if (column == nullptr) {
+         throw IllegalQueryException("Database does not contain the Sequence with name: '" + sequence_columns.front() + "'");
+      }
+      const double compile_begin = nowMicroseconds();
+      const ExpressionPtr rewritten = filter->rewrite(table, AmbiguityMode::NONE);  // computeFilter, compute_filter.cpp:14-21
+      const std::unique_ptr<Operator> compiled = rewritten->compile(table);
+      ProgramBuilder builder;
+      const silo_filter_program program = compiled->lowerProgram(table, builder);
+      const double counts_begin = nowMicroseconds();
+      SymbolCounts counts;
+      counts.n_symbols = column->alphabet->count();
+      counts.genome_length = static_cast<uint32_t>(column->reference_sequence.size());
+      counts.owner = table.acquireCountsBuffer(counts.size());
+      counts.values = counts.owner.get();
+      uint64_t symbol_mask = 0;
+      for (const Symbol symbol : column->alphabet->valid_mutation_symbols) {
+         symbol_mask |= 1ULL << symbol;
+      }
+      uint64_t cardinality = 0;
+      throwOnDeviceError(silo_gpu_query_mutation_counts(
+         table.device, &program, column->device_column, symbol_mask, counts.owner.get(), &cardinality
+      ));
+      const double threshold_begin = nowMicroseconds();
+      appendMutationRows(*column, counts, min_proportion, rows);
+      QueryProfile& profile = lastQueryProfile();
+      profile.compile_us = counts_begin - compile_begin;
+      profile.filter_us = 0;
+      profile.counts_us = threshold_begin - counts_begin;
+      profile.threshold_us = nowMicroseconds() - threshold_begin;
+      return rows;
+   }
+   const DeviceBitmap bitmap_filter = computeFilter(*filter, table);
    for (const std::string& name : sequence_columns) {
       const SequenceColumnInfo* column = table.findColumn(name);
       if (column == nullptr) {

@@ -50,9 +50,7 @@ uint32_t ProgramBuilder::addBitmap(const std::vector<uint8_t>& portable_roaring_
 
 // ---- Operator ----------------------------------------------------------------------------------
 
-DeviceBitmap Operator::evaluate(const Table& table) const {
-   const double lower_begin = nowMicroseconds();
-   ProgramBuilder builder;
+silo_filter_program Operator::lowerProgram(const Table& table, ProgramBuilder& builder) const {
    builder.table = &table;
    lower(builder);
    silo_filter_program program{};
@@ -63,6 +61,13 @@ DeviceBitmap Operator::evaluate(const Table& table) const {
    program.blob_bytes = builder.blob.size();
    program.n_bitmaps = static_cast<uint32_t>(builder.bitmaps.size());
    program.bitmaps = builder.bitmaps.data();
+   return program;
+}
+
+DeviceBitmap Operator::evaluate(const Table& table) const {
+   const double lower_begin = nowMicroseconds();
+   ProgramBuilder builder;
+   const silo_filter_program program = lowerProgram(table, builder);
    silo_gpu_filter* filter = nullptr;
    uint64_t cardinality = 0;
    const double eval_begin = nowMicroseconds();

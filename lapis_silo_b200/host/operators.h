@@ -63,6 +63,8 @@ class Operator {
    // appends instructions that leave exactly one more tile on the program's stack
    virtual void lower(ProgramBuilder& program) const = 0;
    [[nodiscard]] DeviceBitmap evaluate(const Table& table) const;
+   // the flat program of this tree; its pointers refer to `builder`, which must outlive it
+   [[nodiscard]] silo_filter_program lowerProgram(const Table& table, ProgramBuilder& builder) const;
    static std::unique_ptr<Operator> negate(std::unique_ptr<Operator>&& some_operator);
 };
 using OperatorVector = std::vector<std::unique_ptr<Operator>>;

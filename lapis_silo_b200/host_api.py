@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import Optional, Sequence
 
 import numpy as np
@@ -131,39 +132,52 @@ def _check(status: int) -> None:
         raise HostError(lib().silo_host_last_error().decode())
 
 
-def _rows(handle) -> list[dict]:
-    """One bulk export call per result set (struct of arrays), then plain Python dicts."""
+def _columns(handle) -> dict:
+    """The result set as columns (one bulk export call): what the reference hands to its Arrow sink as
+    a record batch (mutations_node.cpp:404-428). Keys: mutationFrom / mutationTo (bytes, one char per
+    row), position, sequenceNameId (+ sequenceNames), proportion, count, coverage (numpy arrays)."""
     if not handle:
         raise HostError(lib().silo_host_last_error().decode())
     try:
         n = int(lib().silo_host_rows_size(handle))
-        if n == 0:
-            return []
-        frm, to = C.create_string_buffer(n), C.create_string_buffer(n)
+        frm, to = C.create_string_buffer(max(n, 1)), C.create_string_buffer(max(n, 1))
         position = np.empty(n, dtype=np.int32)
         name_ids = np.empty(n, dtype=np.uint32)
         proportion = np.empty(n, dtype=np.float64)
         count = np.empty(n, dtype=np.int32)
         coverage = np.empty(n, dtype=np.int32)
-        _check(lib().silo_host_rows_export(
-            handle, frm, to, position.ctypes.data_as(C.POINTER(C.c_int32)),
-            name_ids.ctypes.data_as(C.POINTER(C.c_uint32)), proportion.ctypes.data_as(C.POINTER(C.c_double)),
-            count.ctypes.data_as(C.POINTER(C.c_int32)), coverage.ctypes.data_as(C.POINTER(C.c_int32))))
+        if n > 0:
+            _check(lib().silo_host_rows_export(
+                handle, frm, to, position.ctypes.data_as(C.POINTER(C.c_int32)),
+                name_ids.ctypes.data_as(C.POINTER(C.c_uint32)), proportion.ctypes.data_as(C.POINTER(C.c_double)),
+                count.ctypes.data_as(C.POINTER(C.c_int32)), coverage.ctypes.data_as(C.POINTER(C.c_int32))))
         names = [lib().silo_host_rows_name(handle, i).decode() for i in range(lib().silo_host_rows_num_names(handle))]
-        frm_text, to_text = frm.raw.decode("latin-1"), to.raw.decode("latin-1")
-        return [{
-            "mutationFrom": f, "mutationTo": t, "position": p, "sequenceName": names[s], "proportion": q,
-            "count": c, "coverage": v,
-        } for f, t, p, s, q, c, v in zip(frm_text, to_text, position.tolist(), name_ids.tolist(),
-                                         proportion.tolist(), count.tolist(), coverage.tolist())]
+        return {"mutationFrom": frm.raw[:n], "mutationTo": to.raw[:n], "position": position, "sequenceNameId": name_ids,
+                "sequenceNames": names, "proportion": proportion, "count": count, "coverage": coverage}
     finally:
         lib().silo_host_rows_free(handle)
+
+
+def rows_from_columns(columns: dict) -> list[dict]:
+    """The same result set as the list of row dicts the oracle binding returns."""
+    frm_text, to_text = columns["mutationFrom"].decode("latin-1"), columns["mutationTo"].decode("latin-1")
+    names = columns["sequenceNames"]
+    return [{
+        "mutationFrom": f, "mutationTo": t, "position": p, "sequenceName": names[s], "proportion": q,
+        "count": c, "coverage": v,
+    } for f, t, p, s, q, c, v in zip(frm_text, to_text, columns["position"].tolist(), columns["sequenceNameId"].tolist(),
+                                     columns["proportion"].tolist(), columns["count"].tolist(), columns["coverage"].tolist())]
+
+
+def _rows(handle) -> list[dict]:
+    return rows_from_columns(_columns(handle))
 
 
 class HostFilter:
     def __init__(self, table: "HostTable", handle):
         self.table = table
         self._h = handle
+        table._children.add(self)  # a table closes its filters before it frees the device pools
 
     @property
     def cardinality(self) -> int:
@@ -201,6 +215,7 @@ class PreparedFilter:
     def __init__(self, table: "HostTable", handle):
         self.table = table
         self._h = handle
+        table._children.add(self)
 
     def run_async(self, stream_ptr: int) -> None:
         _check(lib().silo_host_prepared_run_async(self._h, C.c_void_p(stream_ptr)))
@@ -239,6 +254,7 @@ class HostTable:
         self.n_chunks = len(self.chunk_sizes)
         self.first_chunk = first_chunk
         self.columns: dict[str, tuple[int, int]] = {}
+        self._children = weakref.WeakSet()  # live HostFilter / PreparedFilter objects of this table
         arr = (C.c_uint32 * max(self.n_chunks, 1))(*self.chunk_sizes)
         self._h = lib().silo_host_table_create(ctx._h, first_chunk, arr, self.n_chunks)
         if not self._h:
@@ -293,6 +309,19 @@ class HostTable:
             self._h, expression.encode() if expression is not None else None, names, len(columns), min_proportion)
         return _rows(handle)
 
+    def mutations_columns(self, columns: Sequence[str], expression: Optional[str], min_proportion: float) -> dict:
+        """mutations() with the result as columns (numpy arrays) instead of a list of row dicts."""
+        names = (C.c_char_p * len(columns))(*[c.encode() for c in columns])
+        handle = lib().silo_host_mutations(
+            self._h, expression.encode() if expression is not None else None, names, len(columns), min_proportion)
+        return _columns(handle)
+
+    def mutation_columns_from_counts(self, column: str, counts: np.ndarray, min_proportion: float) -> dict:
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        handle = lib().silo_host_mutation_rows_from_counts(
+            self._h, column.encode(), counts.ctypes.data_as(C.POINTER(C.c_uint32)), min_proportion)
+        return _columns(handle)
+
     def mutation_rows_from_counts(self, column: str, counts: np.ndarray, min_proportion: float) -> list[dict]:
         counts = np.ascontiguousarray(counts, dtype=np.uint32)
         handle = lib().silo_host_mutation_rows_from_counts(
@@ -319,6 +348,8 @@ class HostTable:
 
     def close(self):
         if self._h:
+            for child in list(self._children):
+                child.close()
             lib().silo_host_table_free(self._h)
             self._h = None
 
