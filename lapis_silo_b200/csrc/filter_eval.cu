@@ -184,26 +184,41 @@ __device__ void addContainerToCounters(
       const uint32_t unit = 1u << ((row & 1u) << 4);
       atomicAdd(&counters32[row >> 1], subtract ? 0u - unit : unit);
    };
-   auto bumpWord = [&](uint32_t first_row, uint32_t bits) {
-      while (bits != 0) {
-         bump(first_row + static_cast<uint32_t>(__ffs(static_cast<int>(bits)) - 1));
-         bits &= bits - 1;
-      }
-   };
    if (kind == KIND_ARRAY_T) {
-      const uint16_t* values = reinterpret_cast<const uint16_t*>(payload);
+      // one 128-bit load per lane and region, like the container kernel (common.cuh: lane L of a region
+      // with `count` values in P lanes holds the values L + P*j)
       const uint32_t n = desc.cardinality();
-      for (uint32_t slot = lane; slot < arrayPieceSlots(n); slot += 32) {
-         if (arraySlotValid(slot, n)) {
-            bump(values[slot] ^ ARRAY_VALUE_FLIP);
+      for (uint32_t first = 0; first < n; first += ARRAY_REGION_VALUES) {
+         const uint32_t count = min(ARRAY_REGION_VALUES, n - first);
+         const uint32_t lanes = arrayRegionLanes(count);
+         if (lane < lanes) {
+            const uint4 eight = reinterpret_cast<const uint4*>(payload + (first / ARRAY_REGION_VALUES) * 512u)[lane];
+            const uint32_t words[4] = {eight.x, eight.y, eight.z, eight.w};
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) {
+               if (lane + lanes * j < count) {
+                  bump(((words[j >> 1] >> (16 * (j & 1))) & 0xFFFFu) ^ ARRAY_VALUE_FLIP);
+               }
+            }
          }
       }
    } else if (kind == KIND_RUNS_W) {
-      const uint32_t* entries = reinterpret_cast<const uint32_t*>(payload);
-      for (uint32_t i = lane; i < runsPieceSlots(desc.aux); i += 32) {
-         const uint32_t entry = entries[i];
-         if (entry < RUNS_PAD_ENTRY) {
-            bumpWord((entry >> 20) * 32u, runEntryMask(entry));
+      const uint32_t n = desc.aux;
+      for (uint32_t first = 0; first < n; first += RUNS_REGION_ENTRIES) {
+         const uint32_t count = min(RUNS_REGION_ENTRIES, n - first);
+         if (lane < runsRegionLanes(count)) {
+            const uint4 four = reinterpret_cast<const uint4*>(payload + (first / RUNS_REGION_ENTRIES) * 512u)[lane];
+            const uint32_t entries[4] = {four.x, four.y, four.z, four.w};
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) {
+               if (entries[j] < RUNS_PAD_ENTRY) {  // a run inside one word: consecutive rows, no bit scan needed
+                  const uint32_t first_row = (entries[j] >> 20) * 32u + (entries[j] & 31u);
+                  const uint32_t length = 32u - ((entries[j] >> 5) & 31u);
+                  for (uint32_t row = first_row; row < first_row + length; ++row) {
+                     bump(row);
+                  }
+               }
+            }
          }
       }
    } else if (kind == KIND_WORDRANGE) {

@@ -17,6 +17,12 @@ void checkQuery(bool condition, const std::string& message) {
       throw IllegalQueryException(message);
    }
 }
+// (no std::string is built on the hot path of the reader: a literal message costs nothing unless thrown)
+void checkQuery(bool condition, const char* message) {
+   if (!condition) {
+      throw IllegalQueryException(message);
+   }
+}
 
 const SequenceColumnInfo& requireColumn(const Table& table, const std::string& name) {
    const SequenceColumnInfo* column = table.findColumn(name);
@@ -782,7 +788,9 @@ uint64_t number(const Node& node) {
       valid = valid && c >= '0' && c <= '9';
       value = value * 10 + static_cast<uint64_t>(c - '0');
    }
-   checkQuery(valid, "filter expression: expected a non-negative integer, got '" + std::string(text) + "'");
+   if (!valid) {
+      throw IllegalQueryException("filter expression: expected a non-negative integer, got '" + std::string(text) + "'");
+   }
    return value;
 }
 

@@ -82,6 +82,43 @@ template <typename T>
 std::unique_ptr<T> downcast(std::unique_ptr<Operator>&& op) {
    return std::unique_ptr<T>(static_cast<T*>(op.release()));
 }
+
+constexpr size_t WIDE_UNION_MIN_CHILDREN = 24;  // from here on a Union is lowered as "at least 1 of n"
+
+void lowerCounting(
+   ProgramBuilder& program,
+   const OperatorVector& non_negated_children,
+   const OperatorVector& negated_children,
+   uint32_t number_of_matchers,
+   bool match_exactly
+);
+
+// whether lowering the tree emits a counter program (THR_BEGIN .. THR_END); those do not nest
+bool containsThreshold(const Operator& node) {
+   auto any = [](const OperatorVector& nodes) {
+      return std::any_of(nodes.begin(), nodes.end(), [](const auto& child) { return containsThreshold(*child); });
+   };
+   switch (node.type()) {
+      case THRESHOLD:
+         return true;
+      case UNION: {
+         const auto& children = static_cast<const Union&>(node).children;
+         return children.size() >= WIDE_UNION_MIN_CHILDREN || any(children);
+      }
+      case INTERSECTION: {
+         const auto& intersection = static_cast<const Intersection&>(node);
+         return any(intersection.children) || any(intersection.negated_children);
+      }
+      case COMPLEMENT:
+         return containsThreshold(*static_cast<const Complement&>(node).child);
+      case SELECTION: {
+         const auto& child = static_cast<const Selection&>(node).child_operator;
+         return child.has_value() && containsThreshold(**child);
+      }
+      default:
+         return false;
+   }
+}
 }  // namespace
 
 std::unique_ptr<Operator> Operator::negate(std::unique_ptr<Operator>&& some_operator) {
@@ -261,6 +298,17 @@ void Union::lower(ProgramBuilder& program) const {
       program.emit(SILO_OP_PUSH_EMPTY);
       return;
    }
+   // A wide union (NOf with one matcher becomes an Or, nof.cpp; a MutationProfile of distance 0 has one
+   // child per genome position) is "at least 1 of n": one sweep of the chunk's containers into the row
+   // counters instead of n searches + ORs. Counter programs do not nest, so only when no child is one.
+   const bool any_threshold_child =
+      std::any_of(children.begin(), children.end(), [](const auto& child) { return containsThreshold(*child); });
+   if (children.size() >= WIDE_UNION_MIN_CHILDREN && children.size() <= 65535 && !any_threshold_child &&
+       !program.inside_counter_program) {
+      static const OperatorVector NO_CHILDREN;
+      lowerCounting(program, children, NO_CHILDREN, 1, false);
+      return;
+   }
    children[0]->lower(program);
    for (size_t i = 1; i < children.size(); ++i) {
       children[i]->lower(program);
@@ -406,9 +454,15 @@ struct FusedLeaves {
    std::vector<uint32_t> covered_positions;
 };
 
-}  // namespace
-
-void Threshold::lower(ProgramBuilder& program) const {
+// "at least / exactly k of the children contain the row" as a counter program. Shared by Threshold
+// and by wide Unions (k = 1).
+void lowerCounting(
+   ProgramBuilder& program,
+   const OperatorVector& non_negated_children,
+   const OperatorVector& negated_children,
+   uint32_t number_of_matchers,
+   bool match_exactly
+) {
    // Threshold::evaluate (threshold.cpp:64-138) is a DP over k roaring bitmaps whose result is
    // "at least / exactly k of the children contain the row". The device keeps one u16 counter per
    // row instead; leaves over the vertical index are scattered into the counters without ever
@@ -439,6 +493,8 @@ void Threshold::lower(ProgramBuilder& program) const {
       bias += leaves.subs.size();
    }
    program.emit(SILO_OP_THR_BEGIN, match_exactly ? 1 : 0, 0, number_of_matchers, bias);
+   const bool was_inside = program.inside_counter_program;
+   program.inside_counter_program = true;  // (a wide Union below must stay a chain of ORs)
    for (const Operator* child : generic) {
       child->lower(program);
       program.emit(SILO_OP_THR_ADD, 0);
@@ -447,6 +503,7 @@ void Threshold::lower(ProgramBuilder& program) const {
       child->lower(program);
       program.emit(SILO_OP_THR_ADD, 1);
    }
+   program.inside_counter_program = was_inside;
    for (auto& [column, leaves] : fused) {
       const auto device_column = static_cast<uint16_t>(column);
       std::vector<std::pair<uint32_t, uint32_t>> single_adds;
@@ -505,6 +562,12 @@ void Threshold::lower(ProgramBuilder& program) const {
       }
    }
    program.emit(SILO_OP_THR_END);
+}
+
+}  // namespace
+
+void Threshold::lower(ProgramBuilder& program) const {
+   lowerCounting(program, non_negated_children, negated_children, number_of_matchers, match_exactly);
 }
 
 }  // namespace silo_host

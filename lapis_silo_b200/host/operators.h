@@ -49,6 +49,7 @@ class ProgramBuilder {
    std::vector<silo_filter_instr> instrs;
    std::vector<uint8_t> blob;
    std::vector<silo_roaring_bytes> bitmaps;
+   bool inside_counter_program = false;  // between THR_BEGIN and THR_END: counter programs do not nest
 
    void emit(uint8_t opcode, uint8_t flags = 0, uint16_t column = 0, uint32_t a = 0, uint64_t b = 0);
    uint64_t addBlob(const void* data, size_t bytes, size_t alignment);

@@ -369,3 +369,54 @@ def test_synthetic_shards_sum_to_the_whole(ctx):
     assert rows == oracle_table.mutation_rows("main", whole_counts, 0.05)
     # size-independent property: per position the symbol counts add up to the covered filtered rows
     assert (whole_counts.sum(axis=0) == whole_filter.cardinality).all()
+
+
+def test_baseline_sizes_size_independent_properties(ctx):
+    """BASELINE.json configs 2 and 3 at full size (10 M rows x 29,903 nt; the oracle would need minutes per
+    query there), checked through properties that hold at any size: per position the symbol counts add up
+    to |filter|; shards of the filter sum to the whole; k-of-n is monotone in k; a profile filter of distance
+    d is contained in distance d + 1; And/Or/Not identities on the cardinalities."""
+    from lapis_silo_b200 import host_api
+    total_rows = 10_000_000
+    length = 29903
+    synthetic = host_api.Synthetic(genome_length=length, reference_seed=1, generations=5)
+    sizes = host_api.dense_chunk_sizes(total_rows)
+    table = host_api.HostTable(ctx, sizes)
+    table.add_column("main", host_api.NUCLEOTIDE, synthetic.reference, synthetic.build_column(total_rows, 0, len(sizes), 16))
+    synthetic.release_column()
+    ancestor = next(e for e in range(synthetic.num_sequences) if synthetic.generation(e) == 2)
+    table.register_bitmap("lineage", synthetic.lineage_bitmap(ancestor, total_rows, 0, len(sizes)))
+    date = host_api.date_ranges_expression(total_rows, 1095, 366, 546, 0, len(sizes))
+
+    # config 2: Mutations under date range AND lineage
+    flt = table.filter(f"(and {date} (bitmap lineage))")
+    counts = table.mutation_counts("main", flt)
+    assert flt.cardinality > 0
+    assert (counts.sum(axis=0, dtype=np.uint64) == flt.cardinality).all()
+    in_date = table.filter(date)
+    in_lineage = table.filter("(bitmap lineage)")
+    either = table.filter(f"(or {date} (bitmap lineage))")
+    assert in_date.cardinality + in_lineage.cardinality == flt.cardinality + either.cardinality  # inclusion-exclusion
+    assert table.filter(f"(not {date})").cardinality == total_rows - in_date.cardinality
+    outside = table.filter(f"(and (not {date}) (bitmap lineage))")
+    np.testing.assert_array_equal(
+        counts.astype(np.uint64) + table.mutation_counts("main", outside), table.mutation_counts("main", in_lineage))
+    whole = table.mutation_counts("main")
+    assert (whole.sum(axis=0, dtype=np.uint64) == total_rows).all()
+    rows = table.mutations(["main"], f"(and {date} (bitmap lineage))", 0.05)
+    assert rows == table.mutation_rows_from_counts("main", counts, 0.05) and len(rows) > 0
+    assert all(r["count"] * 20 >= r["coverage"] - 20 and r["coverage"] == flt.cardinality for r in rows)
+
+    # config 3: nucleotideMutationProfile(distance, querySequence = last evolved sequence) -> count()
+    query = synthetic.sequence(synthetic.num_sequences - 1)
+    cardinalities = [table.filter(f"(profile main {distance} seq {query})").cardinality for distance in (0, 5, 50, 200)]
+    assert cardinalities == sorted(cardinalities) and cardinalities[0] > 0
+    exact_rows = total_rows // synthetic.num_sequences  # rows that ARE the query sequence: at least every 133rd
+    assert cardinalities[0] >= exact_rows
+    # k-of-n over three single-position tests is monotone in k, and 1-of-n is their union
+    leaves = "(has-mut main 241) (has-mut main 3037) (has-mut main 14408)"
+    k_of_n = [table.filter(f"(n-of {k} 0 {leaves})").cardinality for k in (1, 2, 3)]
+    assert k_of_n == sorted(k_of_n, reverse=True)
+    assert k_of_n[0] == table.filter(f"(or {leaves})").cardinality
+    assert k_of_n[2] == table.filter(f"(and {leaves})").cardinality
+    table.close()
