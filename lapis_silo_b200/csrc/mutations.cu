@@ -439,6 +439,8 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
          }
          return segment;
       };
+      long long producer_waited = 0;  // MODE 4: cycles this lane waited for a free stage
+      const long long producer_begin = MODE == 4 ? clock64() : 0;
       uint32_t current_tile_chunk = 0xFFFFFFFFu;
       uint32_t tile_slot = 1;         // buffer holding the current chunk's tile
       uint32_t tile_first_stage = 0;  // first stage that reads the current tile
@@ -482,7 +484,11 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
          for (uint32_t j = 0; j < batch; ++j) {
             if (lane == j) {
                if (my_round > 0) {
+                  const long long wait_begin = MODE == 4 ? clock64() : 0;
                   mbarWaitAt(my_control + K1_CTRL_EMPTY, (my_round - 1) & 1u);  // => every stage <= my_it - K1_STAGES is pulled
+                  if (MODE == 4) {
+                     producer_waited += clock64() - wait_begin;
+                  }
                }
                if (new_tile) {
                   // The new tile goes into the OTHER buffer, last read by the lookups of the stages
@@ -517,6 +523,14 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
          }
          current_tile_chunk = __shfl_sync(0xFFFFFFFFu, mine.chunk, batch - 1);
          it += batch;
+      }
+      if (MODE == 4) {
+         const uint32_t row = 15 * column.genome_length;
+         atomicAdd(&counts[row + 5], static_cast<uint32_t>(producer_waited >> 6));  // all lanes: waiting for a free stage
+         if (lane == 0) {
+            atomicAdd(&counts[row + 6], static_cast<uint32_t>((clock64() - producer_begin) >> 6));
+            atomicAdd(&counts[row + 7], 1u);
+         }
       }
       if (lane == 0) {
          // tell the consumers that nothing follows

@@ -24,9 +24,11 @@ for label, expression in (("config2", f"(and {date} (bitmap lineage))"), ("all c
     for _ in range(3):
         prepared.run_async(stream.cuda_stream); table.mutation_counts_async(0, prepared, counts.data_ptr(), stream.cuda_stream)
     torch.cuda.synchronize()
-    probe = counts.cpu().numpy().view(np.uint32).reshape(16, bench.GENOME_LENGTH)[15, :5].astype(np.float64)
-    total, waited, first, visits, warps = probe
+    probe = counts.cpu().numpy().view(np.uint32).reshape(16, bench.GENOME_LENGTH)[15, :8].astype(np.float64)
+    total, waited, first, visits, warps, producer_waited, producer_total, producers = probe
     s = table.stats()
     print(f"{label:12s} K1 {s.last_counts_kernel_ms*1e3:7.1f} us | consumer warps {int(warps)}: mean lifetime {total/warps*64/1965:7.1f} us, "
           f"waiting for data {waited/warps*64/1965:6.1f} us ({100*waited/total:4.1f} %), first stage after {first/warps*64/1965:5.1f} us "
-          f"({100*first/total:4.1f} %), stage visits per warp {visits/warps:6.1f}")
+          f"({100*first/total:4.1f} %), stage visits per warp {visits/warps:6.1f} | producers {int(producers)}: lifetime "
+          f"{producer_total/producers*64/1965:6.1f} us, waiting for a free stage {producer_waited/producers*64/1965:6.1f} us "
+          f"({100*producer_waited/producer_total:4.1f} %)")
