@@ -201,6 +201,32 @@ __device__ __forceinline__ void mbarWaitAt(uint32_t address, uint32_t parity) {
 __device__ __forceinline__ void mbarArriveAt(uint32_t address) {
    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(address) : "memory");
 }
+// lane 0 arrives, without a branch (the divergence bookkeeping of `if (lane == 0)` costs the consumer
+// loop more issue slots than the arrive itself)
+__device__ __forceinline__ void mbarArriveLane0(uint32_t address, uint32_t lane) {
+   asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.eq.u32 p, %1, 0;\n"
+      "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+      "}\n" ::"r"(address),
+      "r"(lane)
+      : "memory"
+   );
+}
+// lane 0 adds `value` to *target if value != 0, without a branch
+__device__ __forceinline__ void redAddLane0(uint32_t* target, uint32_t value, uint32_t lane) {
+   asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.eq.u32 p, %2, 0;\n"
+      "setp.ne.and.u32 p, %1, 0, p;\n"
+      "@p red.global.add.u32 [%0], %1;\n"
+      "}\n" ::"l"(target),
+      "r"(value), "r"(lane)
+      : "memory"
+   );
+}
 __device__ __forceinline__ void mbarExpectTxAt(uint32_t address, uint32_t bytes) {
    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(address), "r"(bytes) : "memory");
 }
@@ -272,33 +298,26 @@ __device__ __forceinline__ uint32_t arrayRegionCount(
    uint32_t count,
    uint32_t lane
 ) {
+   // `count` values in P = ceil(count / 8) lanes; in a partial region the slots behind the last value
+   // repeat it (pool.cu encodeArrayPiece). Every slot is looked up -- no test per slot --, and the
+   // repeats are taken out again: slot 7 of lane P-1 always holds the region's last value, so that
+   // lane subtracts (8 P - count) times its bit. Lanes >= P hold other bytes of the stage; their
+   // lookups stay inside the tile (11-bit word index) and are dropped.
    uint32_t t0, t1, t2, t3, t4, t5, t6, t7;
-   if (count == ARRAY_REGION_VALUES) {  // the full region: no padding
-      pairTopBits(tile_address, k, eight.x, t0, t1);
-      pairTopBits(tile_address, k, eight.y, t2, t3);
-      pairTopBits(tile_address, k, eight.z, t4, t5);
-      pairTopBits(tile_address, k, eight.w, t6, t7);
-      // two accumulation chains
-      const uint32_t even = addTopBit(t6, k, addTopBit(t4, k, addTopBit(t2, k, addTopBit(t0, k, 0u))));
-      const uint32_t odd = addTopBit(t7, k, addTopBit(t5, k, addTopBit(t3, k, addTopBit(t1, k, 0u))));
-      return even + odd;
-   }
-   const uint32_t lanes = arrayRegionLanes(count);
-   uint32_t local = 0;
-   if (lane < lanes) {
-      const uint32_t words[4] = {eight.x, eight.y, eight.z, eight.w};
-      uint32_t index = lane;  // in-region index of the low half of words[i]
-#pragma unroll
-      for (uint32_t i = 0; i < 4; ++i) {
-         pairTopBits(tile_address, k, words[i], t0, t1);
-         if (index < count) {
-            local = addTopBit(t0, k, local);
-         }
-         if (index + lanes < count) {
-            local = addTopBit(t1, k, local);
-         }
-         index += 2 * lanes;
+   pairTopBits(tile_address, k, eight.x, t0, t1);
+   pairTopBits(tile_address, k, eight.y, t2, t3);
+   pairTopBits(tile_address, k, eight.z, t4, t5);
+   pairTopBits(tile_address, k, eight.w, t6, t7);
+   // two accumulation chains
+   const uint32_t even = addTopBit(t6, k, addTopBit(t4, k, addTopBit(t2, k, addTopBit(t0, k, 0u))));
+   const uint32_t odd = addTopBit(t7, k, addTopBit(t5, k, addTopBit(t3, k, addTopBit(t1, k, 0u))));
+   uint32_t local = even + odd;
+   if (count != ARRAY_REGION_VALUES) {
+      const uint32_t lanes = arrayRegionLanes(count);
+      if (lane + 1 == lanes) {
+         local -= (8u * lanes - count) * (t7 >> 31);
       }
+      local = lane < lanes ? local : 0u;
    }
    return local;
 }
@@ -572,7 +591,9 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
    uint32_t tile_base = tile_address0;
    asm volatile("" : "+r"(ring_base), "+r"(control_base), "+r"(tile_base));
    uint32_t rotation = cwarp;  // piece index of this warp in the current stage, before the & 15
-   uint32_t visit = 0;         // stages visited so far
+   uint32_t stage = 0;         // ring position and phase of the next visit
+   uint32_t parity = 0;
+   uint32_t visit = 0;         // MODE 4 only
    // MODE 4 (profiling): cycles this warp spent waiting for data, reported through the counts array
    long long probe_begin = 0;
    long long probe_waited = 0;
@@ -580,12 +601,11 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
    if (MODE == 4) {
       probe_begin = clock64();
    }
-   for (;; ++visit) {
-      const uint32_t stage = visit % K1_STAGES;
+   for (;;) {
       const uint32_t stage_address = ring_base + stage * static_cast<uint32_t>(sizeof(K1Stage));
       const uint32_t my_control = control_base + stage * static_cast<uint32_t>(sizeof(K1Control));
       const long long wait_begin = MODE == 4 ? clock64() : 0;
-      mbarWaitAt(my_control + K1_CTRL_FULL, (visit / K1_STAGES) & 1u);
+      mbarWaitAt(my_control + K1_CTRL_FULL, parity);
       if (MODE == 4) {
          const long long now = clock64();
          if (visit == 0) {
@@ -593,6 +613,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
          } else {
             probe_waited += now - wait_begin;
          }
+         ++visit;
       }
       const uint4 meta = lds128(my_control);
       const uint32_t desc_count = meta.x;
@@ -602,59 +623,56 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
             atomicAdd(&counts[row + 0], static_cast<uint32_t>((clock64() - probe_begin) >> 6));  // total
             atomicAdd(&counts[row + 1], static_cast<uint32_t>(probe_waited >> 6));               // waiting for data, after the first stage
             atomicAdd(&counts[row + 2], static_cast<uint32_t>(probe_first >> 6));                // until the first stage landed
-            atomicAdd(&counts[row + 3], visit);
+            atomicAdd(&counts[row + 3], visit - 1);
             atomicAdd(&counts[row + 4], 1u);
          }
          break;
       }
-      const uint32_t flags = meta.z;
-      const uint32_t slot_offset = (flags & K1_TILE_SLOT) != 0 ? TILE_BUFFER_BYTES : 0u;
+      // next ring position (no division: the stage count is not a power of two)
+      const bool wrap = stage == K1_STAGES - 1;
+      stage = wrap ? 0u : stage + 1u;
+      parity ^= wrap ? 1u : 0u;
+      const uint32_t slot_offset = (meta.z & K1_TILE_SLOT) != 0 ? TILE_BUFFER_BYTES : 0u;
       // the rotation continues where the previous stage stopped, so that a stage with fewer than 16
       // pieces does not always leave the same warps idle
       const uint32_t index = rotation & (K1_CONSUMER_WARPS - 1);
       rotation -= desc_count;
-      if (index >= desc_count || MODE == 1) {  // nothing for this warp in this stage
-         __syncwarp();
-         if (lane == 0) {
-            mbarArriveAt(my_control + K1_CTRL_EMPTY);
-            mbarArriveAt(my_control + K1_CTRL_DONE);
-         }
-         continue;
-      }
-      const uint4 desc = lds128(stage_address + SEG_PAYLOAD_BYTES + index * 16);  // {position, offset4, packed, aux}
-      const uint32_t payload_address = stage_address + ((desc.y - meta.y) << 2);
-      const uint32_t kind = (desc.z >> 26) & 7u;
+      // Lane 0's barrier arrives and the RED are predicated instructions (mbarArriveLane0,
+      // redAddLane0), not branches: a warp without a piece in this stage runs the same tail with a
+      // count of zero.
+      uint4 desc = make_uint4(0u, 0u, 0u, 0u);
       uint32_t count = 0;
-      if (kind == KIND_WORDRANGE) {  // rare; reads the stage while it works
-         count = wordRangeCount(desc.w, payload_address, tile_base + slot_offset, lane);
-         __syncwarp();
-         if (lane == 0) {
-            mbarArriveAt(my_control + K1_CTRL_EMPTY);
+      if (index < desc_count && MODE != 1) {
+         desc = lds128(stage_address + SEG_PAYLOAD_BYTES + index * 16);  // {position, offset4, packed, aux}
+         const uint32_t payload_address = stage_address + ((desc.y - meta.y) << 2);
+         const uint32_t kind = (desc.z >> 26) & 7u;
+         if (kind == KIND_WORDRANGE) {  // rare; reads the stage while it works
+            count = wordRangeCount(desc.w, payload_address, tile_base + slot_offset, lane);
+            __syncwarp();
+            mbarArriveLane0(my_control + K1_CTRL_EMPTY, lane);
+         } else {
+            // (reads past a short piece stay inside the stage buffer; those lanes are ignored)
+            const uint4 first = lds128(payload_address + lane16);
+            const uint4 second = lds128(payload_address + 512 + lane16);
+            __syncwarp();
+            mbarArriveLane0(my_control + K1_CTRL_EMPTY, lane);  // the stage can be refilled while the lookups run
+            if (MODE == 3) {  // profiling: touch the payload only
+               const uint32_t local = first.x ^ first.y ^ first.z ^ first.w ^ second.x ^ second.y ^ second.z ^ second.w;
+               count = warpSum(local) == 0x12345678u ? 1u : 0u;
+            } else {
+               count = pieceFromRegisters(desc, kind, first, second, tile_base + slot_offset, k, lane, lane16);
+            }
          }
       } else {
-         // (reads past a short piece stay inside the stage buffer; those lanes are ignored)
-         const uint4 first = lds128(payload_address + lane16);
-         const uint4 second = lds128(payload_address + 512 + lane16);
          __syncwarp();
-         if (lane == 0) {
-            mbarArriveAt(my_control + K1_CTRL_EMPTY);  // the stage can be refilled while the lookups run
-         }
-         if (MODE == 3) {  // profiling: touch the payload only
-            const uint32_t local = first.x ^ first.y ^ first.z ^ first.w ^ second.x ^ second.y ^ second.z ^ second.w;
-            count = warpSum(local) == 0x12345678u ? 1u : 0u;
-         } else {
-            count = pieceFromRegisters(desc, kind, first, second, tile_base + slot_offset, k, lane, lane16);
-         }
+         mbarArriveLane0(my_control + K1_CTRL_EMPTY, lane);
       }
-      if (lane == 0) {
-         if (count != 0 && MODE != 2) {
-            atomicAdd(&counts[((desc.z >> 16) & 0x1Fu) * genome_length + desc.x], count);
-         }
-         mbarArriveAt(my_control + K1_CTRL_DONE);
-      }
-      if (MODE == 2 && count == 0xFFFFFFFFu) {
+      if (MODE != 2) {
+         redAddLane0(&counts[((desc.z >> 16) & 0x1Fu) * genome_length + desc.x], count, lane);
+      } else if (count == 0xFFFFFFFFu) {
          counts[0] = 1;
       }
+      mbarArriveLane0(my_control + K1_CTRL_DONE, lane);
    }
 }
 
