@@ -253,6 +253,43 @@ int silo_gpu_query_mutation_counts(
    uint64_t* cardinality
 );
 
+/* ---- S3': the action's output pass on the device ------------------------------------------------
+ * addMutationsToOutput (mutations_node.cpp:292-366) reads the counts of VALID_MUTATION_SYMBOLS and
+ * emits one row per (position, symbol != reference genome symbol) whose count exceeds
+ *     threshold_count = min_proportion == 0 ? 0 : uint32(ceil(double(total) * min_proportion) - 1)
+ * with total = sum of the valid symbols' counts at the position. That test is IEEE double arithmetic
+ * and is evaluated by the finalize kernel with the same operations, so only the emitted
+ * (position, symbol, count, total) tuples cross PCIe -- a few KB instead of the count rows -- and the
+ * host neither scans nor thresholds. The host computes proportion = double(count) / double(total)
+ * exactly as the reference does. Needs the reference genome's symbols on the device
+ * (silo_gpu_column_set_reference, once per column). */
+typedef struct {
+   uint32_t position; /* 0-based */
+   uint32_t symbol;
+   uint32_t count;
+   uint32_t total; /* the "coverage" output field */
+} silo_mutation_hit;
+
+/* reference_symbols[genome_length]: metadata->reference_sequence (sequence_column.h:47-56) as symbol ids */
+int silo_gpu_column_set_reference(silo_gpu_table* table, int column, const uint8_t* reference_symbols);
+
+/* Filter + counts + output pass in ONE call with ONE host synchronisation. program != NULL: evaluated
+ * inside the call (filter is ignored); else filter (NULL = all rows). *hits points at n_hits tuples in
+ * page-locked memory owned by the table, ordered by (position, symbol id), valid until the next call on
+ * this table. cardinality may be NULL (and is only set when a program was given). The full counts stay
+ * in device memory (they are not copied to the host by this call). */
+int silo_gpu_query_mutation_hits(
+   silo_gpu_table* table,
+   const silo_filter_program* program,
+   const silo_gpu_filter* filter,
+   int column,
+   uint64_t valid_symbol_mask,
+   double min_proportion,
+   const silo_mutation_hit** hits,
+   uint64_t* n_hits,
+   uint64_t* cardinality
+);
+
 /* Same, but leaves the counts in device memory (d_counts: n_symbols*genome_length u32) and only
  * enqueues on `cuda_stream` (a cudaStream_t; NULL = the table's own stream) without synchronising,
  * so that a collective (ncclAllReduce on the same stream) can follow with no host round trip. */

@@ -99,16 +99,19 @@ struct __align__(16) DevContainer {
 static_assert(sizeof(DevContainer) == 16);
 
 // A segment = consecutive containers of ONE chunk whose descriptors and payloads are contiguous,
-// moved into shared memory by two 1-D bulk (TMA) copies.
+// moved into shared memory by two 1-D bulk (TMA) copies. 16 bytes: the producer warp of the container
+// kernel fetches one record per lane with a single 128-bit load and keeps two batches of them in flight.
 struct __align__(16) DevSegment {
-   uint64_t payload_offset;  // bytes from the slab start, 16-byte aligned
-   uint32_t payload_bytes;   // multiple of 16
+   uint32_t payload_offset16;  // from the slab start, in 16-byte units (the slab is <= 16 GiB, see DevContainer::offset4)
+   uint32_t payload_bytes;     // multiple of 16, <= SEG_PAYLOAD_BYTES
    uint32_t desc_begin;
-   uint32_t desc_count;
-   uint32_t chunk;  // local chunk index
-   uint32_t pad[2];
+   uint32_t chunk_and_count;   // [15:0] local chunk index | [31:16] number of descriptors (<= SEG_MAX_DESCS)
+
+   __host__ __device__ uint32_t chunk() const { return chunk_and_count & 0xFFFFu; }
+   __host__ __device__ uint32_t descCount() const { return chunk_and_count >> 16; }
+   __host__ __device__ uint64_t payloadOffset() const { return static_cast<uint64_t>(payload_offset16) << 4; }
 };
-static_assert(sizeof(DevSegment) == 32);
+static_assert(sizeof(DevSegment) == 16);
 
 struct DevColumn {
    uint32_t n_symbols;
@@ -130,6 +133,7 @@ struct DevColumn {
    const uint64_t* missing_offsets;     // [n_rows_with_missing + 1] into missing_runs
    const uint2* missing_runs;           // {first, end_exclusive}
    const uint64_t* null_words;          // [n_chunks * 1024] or nullptr when the column has no nulls
+   const uint8_t* global_reference;     // [genome_length] reference genome symbols, or nullptr (silo_gpu_column_set_reference)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -188,14 +192,22 @@ struct silo_gpu_table {
    std::vector<silo::HostColumn*> columns;
    // per-query scratch (calls on one table are serialised by `mutex`; tables are independent)
    std::mutex mutex;
-   uint32_t* d_work_prefix = nullptr;  // [n_chunks + 1]
-   uint32_t* d_work_items = nullptr;   // [max n_segments over the columns]
+   uint32_t* d_work_state = nullptr;   // [0] number of work items, [1] the container kernel's claim counter;
+                                       // both zero between queries (reset by the finalize kernel)
+   silo::DevSegment* d_work_items = nullptr;  // [max n_segments over the columns]: segments of the active chunks
    uint32_t work_items_capacity = 0;
-   uint32_t* d_coverage_diff = nullptr;  // [max genome_length + 1]
+   // two coverage difference arrays used alternately: a query finds its own all-zero (the prepare
+   // kernel of the query before cleared it), so the coverage kernel depends on nothing but the filter
+   uint32_t* d_coverage_diff[2] = {nullptr, nullptr};  // each [diffWords(max genome_length)]
    uint32_t coverage_diff_capacity = 0;
+   uint32_t coverage_diff_current = 0;
    uint32_t* d_counts = nullptr;  // staging for the synchronous API
    uint64_t counts_capacity = 0;
    uint32_t* h_counts_pinned = nullptr;
+   // output pass on the device (silo_gpu_query_mutation_hits): [0] = {number of hits, 0, 0, 0}, then the tuples
+   silo_mutation_hit* d_hits = nullptr;
+   silo_mutation_hit* h_hits_pinned = nullptr;
+   uint64_t hits_capacity = 0;  // tuples, without the header
    uint8_t* h_staging_pinned = nullptr;  // program upload staging (grow-only)
    size_t staging_capacity = 0;
    cudaEvent_t ev_free_fence = nullptr;  // orders stream-ordered frees after foreign-stream users

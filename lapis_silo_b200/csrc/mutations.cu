@@ -22,78 +22,73 @@ namespace silo {
 namespace {
 
 // ---------------------------------------------------------------------------------------------
-// work list: segments of the chunks that hold at least one filtered row
+// prepare: zero the outputs, list the segments of the chunks that hold at least one filtered row
 // ---------------------------------------------------------------------------------------------
 
-// One CTA: exclusive scan of the active chunks' segment counts, then the list itself
-// (work_items[work_prefix[c] + i] = global index of the i-th segment of active chunk c).
-__global__ void __launch_bounds__(1024) buildWorkListKernel(
-   const uint32_t* __restrict__ chunk_popcount,
-   const uint32_t* __restrict__ chunk_seg_begin,
-   uint32_t n_chunks,
-   uint32_t* __restrict__ work_prefix,  // [n_chunks + 2]; [n_chunks] = total, [n_chunks + 1] = K1's claim counter
-   uint32_t* __restrict__ work_items
+// work_state[0] = number of work items, work_state[1] = claim counter of containerAndCountKernel; both
+// are zero when a query starts (finalizeCountsKernel resets them).
+constexpr int PREP_THREADS = 256;
+
+__device__ __forceinline__ void zeroWords(uint32_t* words, uint32_t n_words, uint32_t thread, uint32_t n_threads) {
+   if ((reinterpret_cast<uintptr_t>(words) & 15u) == 0) {
+      uint4* vectors = reinterpret_cast<uint4*>(words);
+      for (uint32_t i = thread; i < n_words / 4; i += n_threads) {
+         vectors[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      for (uint32_t i = (n_words & ~3u) + thread; i < n_words; i += n_threads) {
+         words[i] = 0;
+      }
+   } else {
+      for (uint32_t i = thread; i < n_words; i += n_threads) {
+         words[i] = 0;
+      }
+   }
+}
+
+// One launch in front of the container kernel instead of two memsets and a scan: every CTA zeroes a
+// slice of the counts and of the coverage difference array that the NEXT query will use, and CTA c
+// -- when chunk c holds a filtered row -- reserves room in the work list with one atomic and copies
+// the chunk's segment records there. The order of the chunks in the list is whatever the atomics
+// decide; the counts are sums, so the result does not depend on it, and the segments of one chunk
+// stay contiguous (the container kernel reloads the filter tile only when the chunk changes).
+__global__ void __launch_bounds__(PREP_THREADS) prepareQueryKernel(
+   DevColumn column,
+   const uint32_t* __restrict__ chunk_popcount,  // nullptr: no work list (full filter)
+   uint32_t* __restrict__ work_state,
+   DevSegment* __restrict__ work_items,
+   uint32_t* __restrict__ counts,
+   uint32_t counts_words,
+   uint32_t* __restrict__ next_diff,
+   uint32_t diff_words,
+   silo_mutation_hit* __restrict__ hit_header  // nullptr unless the finalize kernel runs the output pass
 ) {
-   __shared__ uint32_t warp_totals[32];
-   __shared__ uint32_t carry;
-   __shared__ uint32_t chunk_count[1024];
-   __shared__ uint32_t chunk_out[1024];
-   __shared__ uint32_t chunk_first[1024];
-   if (threadIdx.x == 0) {
-      carry = 0;
+   __shared__ uint32_t list_base;
+   if (hit_header != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+      hit_header->position = 0;  // number of hits
    }
+   uint32_t first_segment = 0;
+   uint32_t n_segments = 0;
+   if (chunk_popcount != nullptr && blockIdx.x < column.n_chunks) {
+      // three independent loads in flight
+      const uint32_t popcount = chunk_popcount[blockIdx.x];
+      first_segment = column.chunk_seg_begin[blockIdx.x];
+      const uint32_t end_segment = column.chunk_seg_begin[blockIdx.x + 1];
+      n_segments = popcount != 0 ? end_segment - first_segment : 0u;
+      if (threadIdx.x == 0 && n_segments != 0) {
+         list_base = atomicAdd(&work_state[0], n_segments);
+      }
+   }
+   const uint32_t thread = blockIdx.x * PREP_THREADS + threadIdx.x;
+   const uint32_t n_threads = gridDim.x * PREP_THREADS;
+   zeroWords(counts, counts_words, thread, n_threads);
+   zeroWords(next_diff, diff_words, thread, n_threads);
    __syncthreads();
-   for (uint32_t base = 0; base < n_chunks; base += blockDim.x) {
-      const uint32_t chunk = base + threadIdx.x;
-      uint32_t value = 0;
-      uint32_t first_segment = 0;
-      if (chunk < n_chunks && chunk_popcount[chunk] != 0) {
-         first_segment = chunk_seg_begin[chunk];
-         value = chunk_seg_begin[chunk + 1] - first_segment;
+   if (n_segments != 0) {
+      const uint4* source = reinterpret_cast<const uint4*>(column.segments + first_segment);
+      uint4* target = reinterpret_cast<uint4*>(work_items + list_base);
+      for (uint32_t i = threadIdx.x; i < n_segments; i += PREP_THREADS) {
+         target[i] = source[i];
       }
-      uint32_t inclusive = value;
-      for (int offset = 1; offset < 32; offset <<= 1) {
-         const uint32_t other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
-         if ((threadIdx.x & 31) >= offset) {
-            inclusive += other;
-         }
-      }
-      if ((threadIdx.x & 31) == 31) {
-         warp_totals[threadIdx.x >> 5] = inclusive;
-      }
-      __syncthreads();
-      uint32_t warp_offset = 0;
-      for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) {
-         warp_offset += warp_totals[w];
-      }
-      const uint32_t block_carry = carry;
-      const uint32_t exclusive = block_carry + warp_offset + inclusive - value;
-      if (chunk < n_chunks) {
-         work_prefix[chunk] = exclusive;
-      }
-      // the items: chunk c of this round is written by warp c % 32 (active chunks are usually
-      // neighbours, so this spreads them over all warps), 32 items at a time
-      chunk_count[threadIdx.x] = value;
-      chunk_out[threadIdx.x] = exclusive;
-      chunk_first[threadIdx.x] = first_segment;
-      __syncthreads();
-      for (uint32_t source = threadIdx.x >> 5; source < blockDim.x; source += 32) {
-         const uint32_t count = chunk_count[source];
-         const uint32_t out = chunk_out[source];
-         const uint32_t first = chunk_first[source];
-         for (uint32_t i = threadIdx.x & 31; i < count; i += 32) {
-            work_items[out + i] = first + i;
-         }
-      }
-      __syncthreads();
-      if (threadIdx.x == blockDim.x - 1) {
-         carry = block_carry + warp_offset + inclusive;
-      }
-      __syncthreads();
-   }
-   if (threadIdx.x == 0) {
-      work_prefix[n_chunks] = carry;
-      work_prefix[n_chunks + 1] = 0;  // the grid-wide claim counter of containerAndCountKernel
    }
 }
 
@@ -399,9 +394,8 @@ template <int MODE>
 __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
    DevColumn column,
    const uint64_t* __restrict__ filter_words,   // [n_chunks * 1024]
-   const uint32_t* __restrict__ work_prefix,    // [n_chunks + 2]; [n_chunks] = number of work items
-   uint32_t* __restrict__ work_counter,         // grid-wide claim counter (zeroed by buildWorkListKernel)
-   const uint32_t* __restrict__ work_items,     // segment index per work item
+   uint32_t* __restrict__ work_state,           // [0] number of work items, [1] grid-wide claim counter (zero at launch)
+   const DevSegment* __restrict__ work_items,   // the segment record of every work item (prepareQueryKernel)
    uint32_t* __restrict__ counts,               // [n_symbols * genome_length]
    uint32_t claim_batch                         // work items per claim
 ) {
@@ -413,7 +407,6 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
 
    const uint32_t warp = threadIdx.x >> 5;
    const uint32_t lane = threadIdx.x & 31;
-   const uint32_t total = work_prefix[column.n_chunks];
    const uint32_t ring_address = smemAddr(smem_raw);
    const uint32_t control_address = ring_address + K1_CONTROL_OFFSET;
    const uint32_t tile_address0 = smemAddr(tile_buffers[0]);
@@ -433,58 +426,81 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
 
    if (warp == 0) {
       // ---------------- producer warp -----------------------------------------------------------
-      // Three batches are in flight: the stages of batch n are being issued while lanes
-      // 0..claim_batch-1 fetch the segment descriptors of batch n+1 and lane 0's atomic claims batch
-      // n+2, so neither the claim's nor the fetch's global-memory latency sits between two bulk copies.
-      // Lane j prepares stage j of the batch (addresses, byte counts, tile bookkeeping) in parallel
-      // with the others; only the barrier wait and the copies themselves are issued lane after lane.
-      // The first batch of every CTA is fixed (no atomic in front of the first copy); the dynamic
-      // claims start behind those. Near the end of the work list claims shrink to single items, so
-      // that the last CTAs to finish are at most one stage, not one batch, behind the others.
-      const uint32_t static_items = gridDim.x * claim_batch;
-      const uint32_t tail_begin = total > 2 * static_items ? total - 2 * static_items : 0;
-      uint32_t claim_size_next = claim_batch;  // size of the claim that claimAsync issues next
-      auto claimAsync = [&]() -> uint32_t {    // the result is only valid in lane 0, and only waited for when used
+      // The metadata of a batch (<= claim_batch work items) goes through three steps, each with loaded
+      // global-memory latency: CLAIM (lane 0's atomic on the grid-wide counter) -> FETCH (lane j loads
+      // the segment record of item j) -> ISSUE (lane j's bulk copies into ring stage it + j). Three
+      // claims and two fetches are in flight while a batch is issued, so a claim has three iterations
+      // and a fetch two to come back -- an iteration with free stages is much shorter than one memory
+      // round trip, and with a shallower pipeline the ring ran dry behind the producer (consumers waited
+      // for data 18 % of their time while the producer waited for a free stage only 9 % of its).
+      // Lane j prepares stage j of the batch (addresses, byte counts, tile bookkeeping) in parallel with
+      // the others; only the barrier wait and the copies themselves are issued lane after lane.
+      // The first two batches of every CTA are fixed (no atomic in front of the first copies); the
+      // dynamic claims start behind those. Near the end of the work list claims shrink to single
+      // items -- still three of them in flight --, so that the last CTAs to finish are a few stages,
+      // not a few batches, behind the others.
+      uint32_t* const work_counter = work_state + 1;
+      const uint32_t static_items = 2 * gridDim.x * claim_batch;
+      const uint32_t capacity = column.n_segments;
+      auto claimAsync = [&](uint32_t size) -> uint32_t {  // the result is only valid in lane 0, and only waited for when used
          uint32_t first = 0;
          if (lane == 0) {
-            first = atomicAdd(work_counter, claim_size_next) + static_items;
+            first = atomicAdd(work_counter, size) + static_items;
          }
          return first;
       };
+      // (not checked against the number of work items: records behind the end of the list are stale
+      // or uninitialised, and never used -- `batch` below cuts them off)
       auto fetch = [&](uint32_t first, uint32_t size) -> DevSegment {
          DevSegment segment{};
-         if (lane < size && first + lane < total) {
-            segment = column.segments[work_items[first + lane]];
+         if (lane < size && first + lane < capacity) {
+            segment = work_items[first + lane];
          }
          return segment;
       };
       long long producer_waited = 0;  // MODE 4: cycles this lane waited for a free stage
       const long long producer_begin = MODE == 4 ? clock64() : 0;
+      uint32_t batch_first = blockIdx.x * claim_batch;
+      uint32_t batch_size = claim_batch;
+      uint32_t next_first = (gridDim.x + blockIdx.x) * claim_batch;
+      uint32_t next_size = claim_batch;
+      DevSegment fetched = fetch(batch_first, batch_size);
+      DevSegment fetched_next = fetch(next_first, next_size);
+      uint32_t claim_a = claimAsync(claim_batch);
+      uint32_t claim_b = claimAsync(claim_batch);
+      uint32_t claim_c = claimAsync(claim_batch);
+      uint32_t size_a = claim_batch;
+      uint32_t size_b = claim_batch;
+      uint32_t size_c = claim_batch;
+      const uint32_t total = work_state[0];
+      const uint32_t tail_items = 2 * static_items;
+      const uint32_t tail_begin = total > tail_items ? total - tail_items : 0;
       uint32_t current_tile_chunk = 0xFFFFFFFFu;
       uint32_t tile_slot = 1;         // buffer holding the current chunk's tile
       uint32_t tile_first_stage = 0;  // first stage that reads the current tile
       uint32_t it = 0;                // stages issued so far by this CTA
-      uint32_t batch_first = blockIdx.x * claim_batch;
-      uint32_t batch_size = claim_batch;
-      uint32_t claimed_ahead = claimAsync();
-      uint32_t claimed_ahead_size = claim_size_next;
-      DevSegment upcoming = fetch(batch_first, batch_size);
       while (batch_first < total) {
-         const DevSegment mine = upcoming;
+         const DevSegment mine = fetched;
          const uint32_t batch = min(batch_size, total - batch_first);
-         batch_first = __shfl_sync(0xFFFFFFFFu, claimed_ahead, 0);
-         batch_size = claimed_ahead_size;
-         claim_size_next = batch_first >= tail_begin ? 1u : claim_batch;
-         claimed_ahead = claimAsync();
-         claimed_ahead_size = claim_size_next;
-         upcoming = fetch(batch_first, batch_size);
+         batch_first = next_first;
+         batch_size = next_size;
+         fetched = fetched_next;
+         next_first = __shfl_sync(0xFFFFFFFFu, claim_a, 0);
+         next_size = size_a;
+         fetched_next = fetch(next_first, next_size);
+         claim_a = claim_b;
+         size_a = size_b;
+         claim_b = claim_c;
+         size_b = size_c;
+         size_c = next_first >= tail_begin ? 1u : claim_batch;
+         claim_c = claimAsync(size_c);
 
          // tile bookkeeping for all stages of the batch at once
-         uint32_t previous_chunk = __shfl_up_sync(0xFFFFFFFFu, mine.chunk, 1);
+         uint32_t previous_chunk = __shfl_up_sync(0xFFFFFFFFu, mine.chunk(), 1);
          if (lane == 0) {
             previous_chunk = current_tile_chunk;
          }
-         const bool new_tile = lane < batch && mine.chunk != previous_chunk;
+         const bool new_tile = lane < batch && mine.chunk() != previous_chunk;
          const uint32_t new_mask = __ballot_sync(0xFFFFFFFFu, new_tile);
          const uint32_t new_below = new_mask & ((1u << lane) - 1u);  // tile switches at earlier stages of this batch
          const uint32_t my_slot = tile_slot ^ (__popc(new_below | (new_tile ? 1u << lane : 0u)) & 1u);
@@ -495,9 +511,9 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
          const uint32_t my_round = my_it / K1_STAGES;
          const uint32_t my_control = control_address + my_stage * static_cast<uint32_t>(sizeof(K1Control));
          const uint32_t my_ring = ring_address + my_stage * static_cast<uint32_t>(sizeof(K1Stage));
-         const uint32_t desc_bytes = mine.desc_count * static_cast<uint32_t>(sizeof(DevContainer));
+         const uint32_t desc_bytes = mine.descCount() * static_cast<uint32_t>(sizeof(DevContainer));
          const uint4 meta = make_uint4(
-            mine.desc_count, static_cast<uint32_t>(mine.payload_offset >> 2),
+            mine.descCount(), mine.payload_offset16 << 2,
             (new_tile ? K1_NEW_TILE : 0u) | (my_slot != 0 ? K1_TILE_SLOT : 0u), 0u
          );
          for (uint32_t j = 0; j < batch; ++j) {
@@ -525,13 +541,13 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
                mbarExpectTxAt(my_control + K1_CTRL_FULL, desc_bytes + mine.payload_bytes + (new_tile ? TILE_BYTES : 0u));
                if (new_tile) {
                   bulkLoadAt(
-                     tile_address0 + my_slot * TILE_BUFFER_BYTES, filter_words + static_cast<size_t>(mine.chunk) * TILE_WORDS, TILE_BYTES,
+                     tile_address0 + my_slot * TILE_BUFFER_BYTES, filter_words + static_cast<size_t>(mine.chunk()) * TILE_WORDS, TILE_BYTES,
                      my_control + K1_CTRL_FULL
                   );
                }
                bulkLoadAt(my_ring + SEG_PAYLOAD_BYTES, column.containers + mine.desc_begin, desc_bytes, my_control + K1_CTRL_FULL);
                if (mine.payload_bytes != 0) {
-                  bulkLoadAt(my_ring, column.payload + mine.payload_offset, mine.payload_bytes, my_control + K1_CTRL_FULL);
+                  bulkLoadAt(my_ring, column.payload + mine.payloadOffset(), mine.payload_bytes, my_control + K1_CTRL_FULL);
                }
             }
             __syncwarp();
@@ -540,7 +556,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
             tile_slot ^= __popc(new_mask) & 1u;
             tile_first_stage = it + (31u - __clz(new_mask));
          }
-         current_tile_chunk = __shfl_sync(0xFFFFFFFFu, mine.chunk, batch - 1);
+         current_tile_chunk = __shfl_sync(0xFFFFFFFFu, mine.chunk(), batch - 1);
          it += batch;
       }
       if (MODE == 4) {
@@ -819,11 +835,25 @@ __global__ void __launch_bounds__(K6_THREADS) coverageDiffKernel(
 // that coverageDiffKernel accumulated next to the difference array.
 constexpr int FIN_THREADS = DIFF_BLOCK;
 
+// The output pass of addMutationsToOutput (mutations_node.cpp:307-363) for one position, on request:
+// which (position, symbol) rows the action emits. hits[0].position counts them, tuples from hits[1].
+struct HitRequest {
+   silo_mutation_hit* hits = nullptr;
+   uint32_t capacity = 0;
+   uint64_t valid_mask = 0;  // SymbolType::VALID_MUTATION_SYMBOLS
+   double min_proportion = 0;
+};
+
 __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    DevColumn column,
    const uint32_t* __restrict__ diff_scratch,
-   uint32_t* __restrict__ counts
+   uint32_t* __restrict__ counts,
+   uint32_t* __restrict__ work_state,
+   HitRequest request
 ) {
+   if (blockIdx.x == 0 && threadIdx.x < 2) {
+      work_state[threadIdx.x] = 0;  // the work list and its claim counter are empty between queries
+   }
    __shared__ uint32_t warp_totals[FIN_THREADS / 32];
    __shared__ uint32_t block_offset;
    const uint32_t genome_length = column.genome_length;
@@ -836,11 +866,18 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    // issue every global load up front: the kernel is one latency chain otherwise
    const uint32_t mine = p < genome_length ? diff[p] : 0u;
    const uint32_t reference_symbol = p < genome_length ? column.local_reference[p] : 0u;
+   const bool output_pass = request.hits != nullptr && p < genome_length;
+   const uint32_t genome_symbol = output_pass ? column.global_reference[p] : 0u;
    uint32_t others = 0;
+   uint32_t valid_others = 0;  // the same sum over the valid mutation symbols only
+   uint32_t candidates = 0;    // OR of the counts that could be emitted (valid, not the reference genome's symbol)
    if (p < genome_length) {
       for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
-         const uint32_t value = counts[symbol * genome_length + p];
-         others += symbol != reference_symbol ? value : 0u;
+         const uint32_t value = symbol != reference_symbol ? counts[symbol * genome_length + p] : 0u;
+         others += value;
+         const uint32_t valid_value = ((request.valid_mask >> symbol) & 1ULL) != 0 ? value : 0u;
+         valid_others += valid_value;
+         candidates |= symbol != genome_symbol ? valid_value : 0u;
       }
    }
    if (warp == 0) {
@@ -869,8 +906,35 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    for (uint32_t w = 0; w < warp; ++w) {
       covered += warp_totals[w];
    }
+   const uint32_t reference_count = covered - others;
    if (p < genome_length) {
-      counts[reference_symbol * genome_length + p] = covered - others;
+      counts[reference_symbol * genome_length + p] = reference_count;
+   }
+   if (!output_pass) {
+      return;
+   }
+   const bool reference_is_valid = ((request.valid_mask >> reference_symbol) & 1ULL) != 0;
+   const uint32_t total = valid_others + (reference_is_valid ? reference_count : 0u);
+   if (reference_is_valid && reference_symbol != genome_symbol) {
+      candidates |= reference_count;
+   }
+   if (total == 0 || candidates == 0) {
+      return;  // `count > threshold_count` cannot hold for a zero count
+   }
+   // ceil(double(total) * min_proportion) - 1, the reference's operations in the reference's order
+   const uint32_t threshold_count =
+      request.min_proportion == 0 ? 0u : static_cast<uint32_t>(ceil(__dmul_rn(static_cast<double>(total), request.min_proportion)) - 1.0);
+   for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
+      if (((request.valid_mask >> symbol) & 1ULL) == 0 || symbol == genome_symbol) {
+         continue;
+      }
+      const uint32_t count = symbol == reference_symbol ? reference_count : counts[symbol * genome_length + p];
+      if (count > threshold_count) {
+         const uint32_t index = atomicAdd(&request.hits[0].position, 1u);
+         if (index < request.capacity) {
+            request.hits[1 + index] = silo_mutation_hit{p, symbol, count, total};
+         }
+      }
    }
 }
 
@@ -881,7 +945,8 @@ void enqueueMutationCounts(
    int column_index,
    const silo_gpu_filter* filter,
    uint32_t* d_counts,
-   cudaStream_t stream
+   cudaStream_t stream,
+   const HitRequest* request = nullptr
 ) {
    require(table != nullptr, "mutation_counts: table is NULL");
    require(column_index >= 0 && static_cast<size_t>(column_index) < table->columns.size(), "mutation_counts: bad column index");
@@ -903,9 +968,11 @@ void enqueueMutationCounts(
    cudaEvent_t ev_k1_end = table->ev_k1_end[slot];
    cudaEvent_t ev_end = table->ev_end[slot];
    SILO_CUDA_CHECK(cudaEventRecord(ev_begin, stream));
-   SILO_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, counts_bytes, stream));
-   SILO_CUDA_CHECK(cudaMemsetAsync(table->d_coverage_diff, 0, diffWords(column.genome_length) * sizeof(uint32_t), stream));
    if (n_chunks == 0) {
+      SILO_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, counts_bytes, stream));
+      if (request != nullptr) {
+         SILO_CUDA_CHECK(cudaMemsetAsync(request->hits, 0, sizeof(silo_mutation_hit), stream));
+      }
       SILO_CUDA_CHECK(cudaEventRecord(ev_k1_begin, stream));
       SILO_CUDA_CHECK(cudaEventRecord(ev_k1_end, stream));
       SILO_CUDA_CHECK(cudaEventRecord(ev_end, stream));
@@ -913,72 +980,75 @@ void enqueueMutationCounts(
    }
    const uint64_t* words = filter != nullptr ? filter->d_words : table->d_full_words;
    const uint32_t* popcounts = filter != nullptr ? filter->d_chunk_popcount : table->d_chunk_popcount_full;
+   // this query's coverage difference array is all-zero already (cleared by the prepare kernel of the
+   // query before, or at allocation); the other one is cleared now for the query after
+   uint32_t* const diff = table->d_coverage_diff[table->coverage_diff_current];
+   uint32_t* const diff_next = table->d_coverage_diff[table->coverage_diff_current ^ 1u];
+   table->coverage_diff_current ^= 1u;
 
-   // fork: the coverage kernel only needs the filter and the zeroed difference array, so it runs on
-   // the auxiliary stream beside the container kernel (whose persistent CTAs leave room for it)
+   // fork: the coverage kernel needs nothing but the filter, so it runs on the auxiliary stream beside
+   // the prepare kernel and the first microseconds of the container kernel
    SILO_CUDA_CHECK(cudaEventRecord(table->ev_fork, stream));
    SILO_CUDA_CHECK(cudaStreamWaitEvent(table->aux_stream, table->ev_fork, 0));
-   coverageDiffKernel<<<n_chunks * K6_SLICES, K6_THREADS, 0, table->aux_stream>>>(
-      column, words, popcounts, table->d_coverage_diff
-   );
+   coverageDiffKernel<<<n_chunks * K6_SLICES, K6_THREADS, 0, table->aux_stream>>>(column, words, popcounts, diff);
    SILO_CUDA_CHECK(cudaGetLastError());
    SILO_CUDA_CHECK(cudaEventRecord(table->ev_join, table->aux_stream));
 
+   const int prepare_blocks = static_cast<int>(std::max<uint32_t>(n_chunks, static_cast<uint32_t>(table->ctx->sm_count)));
+   prepareQueryKernel<<<prepare_blocks, PREP_THREADS, 0, stream>>>(
+      column, filter != nullptr ? popcounts : nullptr, table->d_work_state, table->d_work_items, d_counts,
+      static_cast<uint32_t>(counts_bytes / sizeof(uint32_t)), diff_next, diffWords(column.genome_length),
+      request != nullptr ? request->hits : nullptr
+   );
+   SILO_CUDA_CHECK(cudaGetLastError());
+   table->stats.kernel_launches += 1;
+
+   SILO_CUDA_CHECK(cudaEventRecord(ev_k1_begin, stream));
    if (filter == nullptr) {
-      SILO_CUDA_CHECK(cudaEventRecord(ev_k1_begin, stream));
       if (column.n_containers > 0) {
          const int blocks = static_cast<int>(std::min<uint64_t>((column.n_containers + 255) / 256, static_cast<uint64_t>(table->ctx->sm_count) * 8));
          containerCardinalityKernel<<<blocks, 256, 0, stream>>>(column, d_counts);
          SILO_CUDA_CHECK(cudaGetLastError());
          table->stats.kernel_launches++;
       }
-      SILO_CUDA_CHECK(cudaEventRecord(ev_k1_end, stream));
-   } else {
-      buildWorkListKernel<<<1, 1024, 0, stream>>>(
-         popcounts, column.chunk_seg_begin, n_chunks, table->d_work_prefix, table->d_work_items
-      );
-      SILO_CUDA_CHECK(cudaGetLastError());
-      table->stats.kernel_launches += 1;
-      SILO_CUDA_CHECK(cudaEventRecord(ev_k1_begin, stream));
-      if (column.n_segments > 0) {
-         static bool attribute_set = false;
-         static int stream_only = 0;
-         static uint32_t claim_batch = K1_BATCH_DEFAULT;
-         if (!attribute_set) {
-            SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
-            SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
-            SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
-            SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
-            SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
-            const char* flag = std::getenv("SILO_K1_STREAM_ONLY");
-            stream_only = flag != nullptr ? flag[0] - '0' : 0;
-            const char* batch_flag = std::getenv("SILO_K1_BATCH");
-            if (batch_flag != nullptr) {
-               claim_batch = static_cast<uint32_t>(std::min(32, std::max(1, std::atoi(batch_flag))));
-            }
-            attribute_set = true;
+   } else if (column.n_segments > 0) {
+      static bool attribute_set = false;
+      static int stream_only = 0;
+      static uint32_t claim_batch = K1_BATCH_DEFAULT;
+      if (!attribute_set) {
+         SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
+         SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
+         SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
+         SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
+         SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
+         const char* flag = std::getenv("SILO_K1_STREAM_ONLY");
+         stream_only = flag != nullptr ? flag[0] - '0' : 0;
+         const char* batch_flag = std::getenv("SILO_K1_BATCH");
+         if (batch_flag != nullptr) {
+            claim_batch = static_cast<uint32_t>(std::min(32, std::max(1, std::atoi(batch_flag))));
          }
-         const int blocks = static_cast<int>(std::min<uint32_t>(column.n_segments, static_cast<uint32_t>(table->ctx->sm_count) * 2));
-#define SILO_LAUNCH_K1(MODE)                                                                             \
-   containerAndCountKernel<MODE><<<blocks, K1_THREADS, sizeof(K1Dynamic), stream>>>(                     \
-      column, words, table->d_work_prefix, table->d_work_prefix + n_chunks + 1, table->d_work_items, d_counts, claim_batch \
-   )
-         switch (stream_only) {
-            case 1: SILO_LAUNCH_K1(1); break;
-            case 2: SILO_LAUNCH_K1(2); break;
-            case 3: SILO_LAUNCH_K1(3); break;
-            case 4: SILO_LAUNCH_K1(4); break;
-            default: SILO_LAUNCH_K1(0); break;
-         }
-#undef SILO_LAUNCH_K1
-         SILO_CUDA_CHECK(cudaGetLastError());
-         table->stats.kernel_launches++;
+         attribute_set = true;
       }
-      SILO_CUDA_CHECK(cudaEventRecord(ev_k1_end, stream));
+      const int blocks = static_cast<int>(std::min<uint32_t>(column.n_segments, static_cast<uint32_t>(table->ctx->sm_count) * 2));
+#define SILO_LAUNCH_K1(MODE)                                                                         \
+   containerAndCountKernel<MODE><<<blocks, K1_THREADS, sizeof(K1Dynamic), stream>>>(                 \
+      column, words, table->d_work_state, table->d_work_items, d_counts, claim_batch                 \
+   )
+      switch (stream_only) {
+         case 1: SILO_LAUNCH_K1(1); break;
+         case 2: SILO_LAUNCH_K1(2); break;
+         case 3: SILO_LAUNCH_K1(3); break;
+         case 4: SILO_LAUNCH_K1(4); break;
+         default: SILO_LAUNCH_K1(0); break;
+      }
+#undef SILO_LAUNCH_K1
+      SILO_CUDA_CHECK(cudaGetLastError());
+      table->stats.kernel_launches++;
    }
+   SILO_CUDA_CHECK(cudaEventRecord(ev_k1_end, stream));
    SILO_CUDA_CHECK(cudaStreamWaitEvent(stream, table->ev_join, 0));
    finalizeCountsKernel<<<(column.genome_length + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, stream>>>(
-      column, table->d_coverage_diff, d_counts
+      column, diff, d_counts, table->d_work_state, request != nullptr ? *request : HitRequest{}
    );
    SILO_CUDA_CHECK(cudaGetLastError());
    table->stats.kernel_launches += 2;
@@ -1096,6 +1166,130 @@ static void mutationCountsToHost(
    if (cardinality_out != nullptr) {
       *cardinality_out = host_cardinality;
    }
+}
+
+int silo_gpu_column_set_reference(silo_gpu_table* table, int column, const uint8_t* reference_symbols) {
+   return guarded([&] {
+      require(table != nullptr && reference_symbols != nullptr, "silo_gpu_column_set_reference: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      require(column >= 0 && static_cast<size_t>(column) < table->columns.size(), "silo_gpu_column_set_reference: bad column index");
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      HostColumn& host = *table->columns[static_cast<size_t>(column)];
+      for (uint32_t p = 0; p < host.dev.genome_length; ++p) {
+         require(reference_symbols[p] < host.dev.n_symbols, "silo_gpu_column_set_reference: symbol id out of range");
+      }
+      uint8_t* d_reference = const_cast<uint8_t*>(host.dev.global_reference);
+      if (d_reference == nullptr) {
+         d_reference = deviceAlloc<uint8_t>(host.dev.genome_length, &table->device_bytes);
+         host.allocations.push_back(d_reference);
+         host.dev.global_reference = d_reference;
+      }
+      SILO_CUDA_CHECK(cudaMemcpyAsync(d_reference, reference_symbols, host.dev.genome_length, cudaMemcpyHostToDevice, table->ctx->stream));
+      SILO_CUDA_CHECK(cudaStreamSynchronize(table->ctx->stream));
+   });
+}
+
+int silo_gpu_query_mutation_hits(
+   silo_gpu_table* table,
+   const silo_filter_program* program,
+   const silo_gpu_filter* filter,
+   int column,
+   uint64_t valid_symbol_mask,
+   double min_proportion,
+   const silo_mutation_hit** hits,
+   uint64_t* n_hits,
+   uint64_t* cardinality
+) {
+   return guarded([&] {
+      require(table != nullptr && hits != nullptr && n_hits != nullptr, "silo_gpu_query_mutation_hits: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      cudaStream_t stream = table->ctx->stream;
+      require(column >= 0 && static_cast<size_t>(column) < table->columns.size(), "silo_gpu_query_mutation_hits: bad column index");
+      const HostColumn& host = *table->columns[static_cast<size_t>(column)];
+      require(host.dev.global_reference != nullptr, "silo_gpu_query_mutation_hits: call silo_gpu_column_set_reference first");
+      if (host.dev.n_symbols < 64) {
+         valid_symbol_mask &= (1ULL << host.dev.n_symbols) - 1;
+      }
+      // worst case: every valid symbol but the reference genome's at every position
+      const uint64_t needed = static_cast<uint64_t>(__builtin_popcountll(valid_symbol_mask)) * host.dev.genome_length;
+      if (needed > table->hits_capacity || table->d_hits == nullptr) {
+         SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+         cudaFree(table->d_hits);
+         if (table->h_hits_pinned != nullptr) {
+            cudaFreeHost(table->h_hits_pinned);
+            table->h_hits_pinned = nullptr;
+         }
+         table->d_hits = nullptr;
+         table->d_hits = deviceAlloc<silo_mutation_hit>(needed + 1, &table->device_bytes);
+         SILO_CUDA_CHECK(cudaMallocHost(&table->h_hits_pinned, (needed + 1) * sizeof(silo_mutation_hit)));
+         table->hits_capacity = needed;
+      }
+      HitRequest request;
+      request.hits = table->d_hits;
+      request.capacity = static_cast<uint32_t>(table->hits_capacity);
+      request.valid_mask = valid_symbol_mask;
+      request.min_proportion = min_proportion;
+
+      uint8_t* d_staging = nullptr;
+      silo_gpu_filter* own_filter = nullptr;
+      unsigned long long host_cardinality = 0;
+      uint32_t host_error = 0;
+      // the header and this many tuples come back with the first copy; more only if the query emits more
+      constexpr uint64_t FIRST_COPY_HITS = 2047;
+      uint64_t count = 0;
+      try {
+         if (program != nullptr) {
+            const bool trivially_full = program->n_instrs == 1 && program->instrs != nullptr && program->instrs[0].opcode == SILO_OP_PUSH_FULL;
+            if (trivially_full) {
+               host_cardinality = table->n_rows;
+               filter = nullptr;
+            } else {
+               own_filter = evalProgramAsync(table, program, stream, &d_staging);
+               filter = own_filter;
+               SILO_CUDA_CHECK(cudaMemcpyAsync(&host_cardinality, own_filter->d_cardinality, sizeof(host_cardinality), cudaMemcpyDeviceToHost, stream));
+               SILO_CUDA_CHECK(cudaMemcpyAsync(&host_error, own_filter->d_error_flag, sizeof(host_error), cudaMemcpyDeviceToHost, stream));
+            }
+         }
+         enqueueMutationCounts(table, column, filter, table->d_counts, stream, &request);
+         const uint64_t first_copy = std::min<uint64_t>(FIRST_COPY_HITS, table->hits_capacity) + 1;
+         SILO_CUDA_CHECK(cudaMemcpyAsync(table->h_hits_pinned, table->d_hits, first_copy * sizeof(silo_mutation_hit), cudaMemcpyDeviceToHost, stream));
+         if (d_staging != nullptr) {
+            SILO_CUDA_CHECK(cudaFreeAsync(d_staging, stream));
+            d_staging = nullptr;
+         }
+         SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+         count = std::min<uint64_t>(table->h_hits_pinned[0].position, table->hits_capacity);
+         if (count + 1 > first_copy) {
+            SILO_CUDA_CHECK(cudaMemcpyAsync(
+               table->h_hits_pinned + first_copy, table->d_hits + first_copy, (count + 1 - first_copy) * sizeof(silo_mutation_hit),
+               cudaMemcpyDeviceToHost, stream
+            ));
+            SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+         }
+      } catch (...) {
+         if (d_staging != nullptr) {
+            cudaFreeAsync(d_staging, stream);
+         }
+         cudaStreamSynchronize(stream);
+         releaseFilterLocked(own_filter);
+         throw;
+      }
+      releaseFilterLocked(own_filter);
+      if (host_error != 0) {
+         throw ApiError(SILO_E_OUT_OF_LAYOUT, "a leaf bitmap holds row ids outside the row layout");
+      }
+      // the kernel appends in whatever order its threads get there: (position, symbol id) order
+      silo_mutation_hit* const first = table->h_hits_pinned + 1;
+      std::sort(first, first + count, [](const silo_mutation_hit& a, const silo_mutation_hit& b) {
+         return a.position != b.position ? a.position < b.position : a.symbol < b.symbol;
+      });
+      *hits = first;
+      *n_hits = count;
+      if (cardinality != nullptr && program != nullptr) {
+         *cardinality = host_cardinality;
+      }
+   });
 }
 
 int silo_gpu_query_mutation_counts(

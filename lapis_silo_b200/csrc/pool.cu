@@ -223,7 +223,8 @@ int silo_gpu_table_create(
       }
       table->d_chunk_sizes = deviceUpload(table->chunk_sizes, ctx->stream, &table->device_bytes);
       table->d_chunk_popcount_full = deviceUpload(table->chunk_sizes, ctx->stream, &table->device_bytes);
-      table->d_work_prefix = deviceAlloc<uint32_t>(static_cast<size_t>(n_chunks) + 2, &table->device_bytes);
+      table->d_work_state = deviceAlloc<uint32_t>(4, &table->device_bytes);
+      SILO_CUDA_CHECK(cudaMemsetAsync(table->d_work_state, 0, 4 * sizeof(uint32_t), ctx->stream));
       table->d_full_words =
          deviceAlloc<uint64_t>(static_cast<size_t>(n_chunks) * TILE_WORDS, &table->device_bytes);
       if (n_chunks > 0) {
@@ -263,11 +264,16 @@ void silo_gpu_table_free(silo_gpu_table* table) {
    }
    cudaFree(table->d_chunk_sizes);
    cudaFree(table->d_chunk_popcount_full);
-   cudaFree(table->d_work_prefix);
+   cudaFree(table->d_work_state);
    cudaFree(table->d_work_items);
    cudaFree(table->d_full_words);
-   cudaFree(table->d_coverage_diff);
+   cudaFree(table->d_coverage_diff[0]);
+   cudaFree(table->d_coverage_diff[1]);
    cudaFree(table->d_counts);
+   cudaFree(table->d_hits);
+   if (table->h_hits_pinned != nullptr) {
+      cudaFreeHost(table->h_hits_pinned);
+   }
    if (table->h_counts_pinned != nullptr) {
       cudaFreeHost(table->h_counts_pinned);
    }
@@ -399,7 +405,7 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
                return;
             }
             slab.resize((slab.size() + 15) / 16 * 16, 0);
-            segment.payload_bytes = static_cast<uint32_t>(slab.size() - segment.payload_offset);
+            segment.payload_bytes = static_cast<uint32_t>(slab.size() - segment.payloadOffset());
             segments.push_back(segment);
             open = false;
          };
@@ -408,17 +414,18 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
                               const uint8_t* src, uint32_t bytes) {
             const uint32_t padded = (bytes + 15) / 16 * 16;
             if (open) {
-               const auto used = static_cast<uint32_t>(slab.size() - segment.payload_offset);
-               if (segment.desc_count == SEG_MAX_DESCS || used + padded > SEG_PAYLOAD_BYTES) {
+               const auto used = static_cast<uint32_t>(slab.size() - segment.payloadOffset());
+               if (segment.descCount() == SEG_MAX_DESCS || used + padded > SEG_PAYLOAD_BYTES) {
                   closeSegment();
                }
             }
             if (!open) {
                slab.resize((slab.size() + 15) / 16 * 16, 0);
                segment = DevSegment{};
-               segment.payload_offset = slab.size();
+               require(slab.size() / 16 <= UINT32_MAX, "column payload exceeds the 16 GiB per-shard addressing limit");
+               segment.payload_offset16 = static_cast<uint32_t>(slab.size() / 16);
                segment.desc_begin = static_cast<uint32_t>(descs.size());
-               segment.chunk = chunk;
+               segment.chunk_and_count = chunk;  // no descriptors yet
                open = true;
             }
             const uint64_t offset = slab.size();
@@ -433,7 +440,7 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
             d.packed = DevContainer::pack(cardinality, c.symbol, in->local_reference[c.position], kind);
             d.aux = aux;
             descs.push_back(d);
-            segment.desc_count++;
+            segment.chunk_and_count += 1u << 16;
          };
          while (cursor < order.size() && in->containers[order[cursor]].v_index == first_chunk + chunk) {
             const silo_container_desc& c = in->containers[order[cursor]];
@@ -605,12 +612,17 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
 
       if (dev.n_segments > table->work_items_capacity) {
          cudaFree(table->d_work_items);
-         table->d_work_items = deviceAlloc<uint32_t>(dev.n_segments, &table->device_bytes);
+         table->d_work_items = deviceAlloc<DevSegment>(dev.n_segments, &table->device_bytes);
          table->work_items_capacity = dev.n_segments;
       }
       if (diffWords(in->genome_length) > table->coverage_diff_capacity) {
-         cudaFree(table->d_coverage_diff);
-         table->d_coverage_diff = deviceAlloc<uint32_t>(diffWords(in->genome_length), &table->device_bytes);
+         // (all-zero between queries, see silo_gpu_table; a fresh pair starts all-zero too)
+         SILO_CUDA_CHECK(cudaStreamSynchronize(table->ctx->stream));
+         for (uint32_t*& diff : table->d_coverage_diff) {
+            cudaFree(diff);
+            diff = deviceAlloc<uint32_t>(diffWords(in->genome_length), &table->device_bytes);
+            SILO_CUDA_CHECK(cudaMemset(diff, 0, diffWords(in->genome_length) * sizeof(uint32_t)));
+         }
          table->coverage_diff_capacity = diffWords(in->genome_length);
       }
       const uint64_t counts_elems = static_cast<uint64_t>(in->n_symbols) * in->genome_length;

@@ -1,5 +1,6 @@
 #include "mutations_node.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -96,13 +97,63 @@ void appendMutationRows(
    }
 }
 
+namespace {
+
+uint64_t validSymbolMask(const Alphabet& alphabet) {
+   uint64_t mask = 0;
+   for (const Symbol symbol : alphabet.valid_mutation_symbols) {
+      mask |= 1ULL << symbol;
+   }
+   return mask;
+}
+
+// rows from the tuples of the device's output pass (silo_gpu_query_mutation_hits): the same fields
+// addMutationsToOutput emits (:326-360), proportion computed here as double(count) / double(total)
+void appendRowsFromHits(
+   const SequenceColumnInfo& sequence_column,
+   const silo_mutation_hit* hits,
+   uint64_t n_hits,
+   std::vector<MutationRow>& out
+) {
+   const Alphabet& alphabet = *sequence_column.alphabet;
+   std::vector<silo_mutation_hit> reordered;
+   if (!std::is_sorted(alphabet.valid_mutation_symbols.begin(), alphabet.valid_mutation_symbols.end())) {
+      // the device orders by (position, symbol id); the reference walks VALID_MUTATION_SYMBOLS in its own order
+      std::vector<uint32_t> rank(alphabet.count(), 0);
+      for (size_t i = 0; i < alphabet.valid_mutation_symbols.size(); ++i) {
+         rank[alphabet.valid_mutation_symbols[i]] = static_cast<uint32_t>(i);
+      }
+      reordered.assign(hits, hits + n_hits);
+      std::stable_sort(reordered.begin(), reordered.end(), [&](const silo_mutation_hit& a, const silo_mutation_hit& b) {
+         return a.position != b.position ? a.position < b.position : rank[a.symbol] < rank[b.symbol];
+      });
+      hits = reordered.data();
+   }
+   out.reserve(out.size() + n_hits);
+   for (uint64_t i = 0; i < n_hits; ++i) {
+      const silo_mutation_hit& hit = hits[i];
+      MutationRow row;
+      row.mutation_from = alphabet.symbolToChar(sequence_column.reference_sequence[hit.position]);
+      row.mutation_to = alphabet.symbolToChar(static_cast<Symbol>(hit.symbol));
+      row.position = static_cast<int32_t>(hit.position + 1);
+      row.sequence_name = sequence_column.name;
+      row.proportion = static_cast<double>(hit.count) / static_cast<double>(hit.total);
+      row.count = static_cast<int32_t>(hit.count);
+      row.coverage = static_cast<int32_t>(hit.total);
+      out.push_back(std::move(row));
+   }
+}
+
+}  // namespace
+
 std::vector<MutationRow> MutationsNode::execute() const {
    lastQueryProfile().counts_us = 0;
    lastQueryProfile().threshold_us = 0;
    std::vector<MutationRow> rows;
    if (sequence_columns.size() == 1) {
-      // One sequence column (the common query): filter program and counts go to the device in ONE call
-      // with one synchronisation (silo_gpu_query_mutation_counts); the filter never leaves the device.
+      // One sequence column (the common query): filter program, counts and the output pass go to the
+      // device in ONE call with one synchronisation (silo_gpu_query_mutation_hits); neither the filter
+      // nor the counts leave the device, only the emitted (position, symbol, count, total) tuples.
       const SequenceColumnInfo* column = table.findColumn(sequence_columns.front());
       if (column == nullptr) {
          throw IllegalQueryException("Database does not contain the Sequence with name: '" + sequence_columns.front() + "'");
@@ -113,21 +164,15 @@ std::vector<MutationRow> MutationsNode::execute() const {
       ProgramBuilder builder;
       const silo_filter_program program = compiled->lowerProgram(table, builder);
       const double counts_begin = nowMicroseconds();
-      SymbolCounts counts;
-      counts.n_symbols = column->alphabet->count();
-      counts.genome_length = static_cast<uint32_t>(column->reference_sequence.size());
-      counts.owner = table.acquireCountsBuffer(counts.size());
-      counts.values = counts.owner.get();
-      uint64_t symbol_mask = 0;
-      for (const Symbol symbol : column->alphabet->valid_mutation_symbols) {
-         symbol_mask |= 1ULL << symbol;
-      }
+      const silo_mutation_hit* hits = nullptr;
+      uint64_t n_hits = 0;
       uint64_t cardinality = 0;
-      throwOnDeviceError(silo_gpu_query_mutation_counts(
-         table.device, &program, column->device_column, symbol_mask, counts.owner.get(), &cardinality
+      throwOnDeviceError(silo_gpu_query_mutation_hits(
+         table.device, &program, nullptr, column->device_column, validSymbolMask(*column->alphabet), min_proportion, &hits, &n_hits,
+         &cardinality
       ));
       const double threshold_begin = nowMicroseconds();
-      appendMutationRows(*column, counts, min_proportion, rows);
+      appendRowsFromHits(*column, hits, n_hits, rows);
       QueryProfile& profile = lastQueryProfile();
       profile.compile_us = counts_begin - compile_begin;
       profile.filter_us = 0;
@@ -136,16 +181,25 @@ std::vector<MutationRow> MutationsNode::execute() const {
       return rows;
    }
    const DeviceBitmap bitmap_filter = computeFilter(*filter, table);
+   const uint64_t filter_cardinality = bitmap_filter.cardinality();
    for (const std::string& name : sequence_columns) {
       const SequenceColumnInfo* column = table.findColumn(name);
       if (column == nullptr) {
          throw IllegalQueryException("Database does not contain the Sequence with name: '" + name + "'");
       }
+      if (filter_cardinality == 0) {
+         continue;  // all counts are zero: nothing is emitted
+      }
       const double counts_begin = nowMicroseconds();
-      const SymbolCounts counts =
-         calculateMutationsPerPosition(table, *column, bitmap_filter, table.row_layout.numRows(), true);
+      const silo_mutation_hit* hits = nullptr;
+      uint64_t n_hits = 0;
+      // cardinality == numRows: the stored-cardinality path (mutations_node.cpp:280-281)
+      throwOnDeviceError(silo_gpu_query_mutation_hits(
+         table.device, nullptr, filter_cardinality == table.row_layout.numRows() ? nullptr : bitmap_filter.get(), column->device_column,
+         validSymbolMask(*column->alphabet), min_proportion, &hits, &n_hits, nullptr
+      ));
       const double threshold_begin = nowMicroseconds();
-      appendMutationRows(*column, counts, min_proportion, rows);
+      appendRowsFromHits(*column, hits, n_hits, rows);
       lastQueryProfile().counts_us += threshold_begin - counts_begin;
       lastQueryProfile().threshold_us += nowMicroseconds() - threshold_begin;
    }

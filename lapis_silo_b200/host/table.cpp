@@ -197,6 +197,8 @@ int Table::addSequenceColumn(
    const int device_column = silo_gpu_column_upload(device, &column);
    throwOnDeviceError(device_column);
    info.device_column = device_column;
+   // the output pass of the Mutations action runs on the device and names the reference genome's symbols
+   throwOnDeviceError(silo_gpu_column_set_reference(device, device_column, info.reference_sequence.data()));
    columns.push_back(std::move(info));
    return device_column;
 }

@@ -285,7 +285,7 @@ def test_mutations_action_rows(ctx, seed, alphabet_id):
     filters = [None, "(true)", "(false)", "(bitmap lineage)", "(not (bitmap lineage))", "(has-mut c 7)",
                "(and (bitmap lineage) (not (sym-eq c 12 N)))", "(ranges 3 90 196608 197000)", "(profile c 4 muts)"]
     for expression in filters:
-        for min_proportion in (0.0, 0.05, 0.3, 1.0):
+        for min_proportion in (0.0, 1e-9, 0.05, 1.0 / 3.0, 0.3, 0.5, 0.999, 1.0):
             want = oracle_table.mutations("c", expression, min_proportion)
             got = device_table.mutations(["c"], expression, min_proportion)
             assert got == want, (expression, min_proportion)
