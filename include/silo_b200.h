@@ -301,6 +301,46 @@ int silo_gpu_mutation_counts_async(
    void* cuda_stream
 );
 
+/* ---- BitmapAggregationNode: co-occurrence / groupBy over sequence positions and indexed columns ---
+ * Replaces buildGroups + computeCombinations of operators/bitmap_aggregation_node.cpp:53-139,224-249
+ * (reached from BitmapAggregationNode::addToExecPlan :304-356). The groups of a dimension are disjoint,
+ * so the reference's recursive partition is a GROUP BY over per-row group codes:
+ *   sequence position: code = symbol id the row carries at the position (stored container -> that
+ *     symbol; covered and not N -> local reference symbol; otherwise the missing symbol), or n_symbols
+ *     of the column when the row's sequence is null (the null group, :80-90);
+ *   index bitmaps: code = index g of the value bitmap that holds the row, n_groups for the null bitmap;
+ *     a row in none of them is in no combination.
+ * key = the codes packed with dimension 0 in the most significant bits: 5 bits per sequence-position
+ * dimension, 8 bits per index-bitmap dimension, 63 bits in total at most; ascending key order is the
+ * reference's depth-first output order. */
+enum { SILO_DIM_SEQUENCE_POSITION = 0, SILO_DIM_INDEX_BITMAPS = 1 };
+typedef struct {
+   uint32_t kind;
+   int32_t column;             /* sequence position: column index */
+   uint32_t position;          /* sequence position: 0-based */
+   uint32_t n_groups;          /* index bitmaps: number of value bitmaps (<= 254), in output order */
+   const uint32_t* bitmap_ids; /* index bitmaps: ids from silo_gpu_bitmap_register */
+   uint32_t null_bitmap_id;    /* index bitmaps: id of the null bitmap, or UINT32_MAX */
+} silo_group_dimension;
+typedef struct {
+   uint64_t key;
+   uint64_t count;
+} silo_combination;
+/* program != NULL: the filter program is evaluated inside the call; else `filter` (NULL = all rows).
+ * *combinations points at n_combinations entries (count > 0 each) ordered by key, valid until the next
+ * call of this function on the calling thread. One host synchronisation unless more than 2047
+ * combinations come back or the hash table has to grow. */
+int silo_gpu_query_combinations(
+   silo_gpu_table* table,
+   const silo_filter_program* program,
+   const silo_gpu_filter* filter,
+   const silo_group_dimension* dimensions,
+   uint32_t n_dimensions,
+   const silo_combination** combinations,
+   uint64_t* n_combinations,
+   uint64_t* cardinality
+);
+
 /* ---- measurement hooks (bench.py / profiles; not needed by the reference) --------------------- */
 
 typedef struct {

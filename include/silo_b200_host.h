@@ -49,6 +49,13 @@ int silo_host_filter_words(const silo_host_filter* filter, uint64_t* words /* 10
 /* the lowered program as text, one instruction per line (debugging / tests of the lowering) */
 int silo_host_filter_explain(silo_host_table* table, const char* expression, char* out, uint64_t capacity);
 
+/* BitmapAggregationNode (operators/bitmap_aggregation_node.cpp:304-356) through the host layer.
+ * dimensions: ';'-separated, each "p:<column>:<0-based position>" (SequencePositionDimension) or
+ * "b:<value>=<bitmap name>,...|<null bitmap name or empty>" (IndexedColumnDimension; the inverted index
+ * of the dictionary column arrives as named bitmaps). out: one line per combination in the reference's
+ * depth-first order: the values (\\N = null) and the count, tab-separated. */
+int silo_host_bitmap_aggregation(silo_host_table* table, const char* expression, const char* dimensions, char* out, uint64_t capacity);
+
 /* the same filter with device-resident inputs: compile + lower + upload once (silo_gpu_program_prepare),
  * then each run only enqueues the kernel on `cuda_stream` (silo_gpu_program_run_async) */
 typedef struct silo_host_prepared silo_host_prepared;

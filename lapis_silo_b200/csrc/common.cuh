@@ -192,15 +192,14 @@ struct silo_gpu_table {
    std::vector<silo::HostColumn*> columns;
    // per-query scratch (calls on one table are serialised by `mutex`; tables are independent)
    std::mutex mutex;
-   uint32_t* d_work_state = nullptr;   // [0] number of work items, [1] the container kernel's claim counter;
-                                       // both zero between queries (reset by the finalize kernel)
+   uint32_t* d_work_state = nullptr;   // [0] number of work items, [1] the container kernel's claim counter,
+                                       // [2] finalize blocks done; all zero between queries (reset by the finalize kernel)
    silo::DevSegment* d_work_items = nullptr;  // [max n_segments over the columns]: segments of the active chunks
    uint32_t work_items_capacity = 0;
-   // two coverage difference arrays used alternately: a query finds its own all-zero (the prepare
-   // kernel of the query before cleared it), so the coverage kernel depends on nothing but the filter
-   uint32_t* d_coverage_diff[2] = {nullptr, nullptr};  // each [diffWords(max genome_length)]
+   // coverage difference array + block totals; all-zero between queries (the finalize kernel clears what
+   // it has read), so the coverage kernel depends on nothing but the filter
+   uint32_t* d_coverage_diff = nullptr;  // [diffWords(max genome_length)]
    uint32_t coverage_diff_capacity = 0;
-   uint32_t coverage_diff_current = 0;
    uint32_t* d_counts = nullptr;  // staging for the synchronous API
    uint64_t counts_capacity = 0;
    uint32_t* h_counts_pinned = nullptr;

@@ -46,7 +46,7 @@ __device__ __forceinline__ void zeroWords(uint32_t* words, uint32_t n_words, uin
 }
 
 // One launch in front of the container kernel instead of two memsets and a scan: every CTA zeroes a
-// slice of the counts and of the coverage difference array that the NEXT query will use, and CTA c
+// slice of the counts, and CTA c
 // -- when chunk c holds a filtered row -- reserves room in the work list with one atomic and copies
 // the chunk's segment records there. The order of the chunks in the list is whatever the atomics
 // decide; the counts are sums, so the result does not depend on it, and the segments of one chunk
@@ -58,8 +58,6 @@ __global__ void __launch_bounds__(PREP_THREADS) prepareQueryKernel(
    DevSegment* __restrict__ work_items,
    uint32_t* __restrict__ counts,
    uint32_t counts_words,
-   uint32_t* __restrict__ next_diff,
-   uint32_t diff_words,
    silo_mutation_hit* __restrict__ hit_header  // nullptr unless the finalize kernel runs the output pass
 ) {
    __shared__ uint32_t list_base;
@@ -81,7 +79,6 @@ __global__ void __launch_bounds__(PREP_THREADS) prepareQueryKernel(
    const uint32_t thread = blockIdx.x * PREP_THREADS + threadIdx.x;
    const uint32_t n_threads = gridDim.x * PREP_THREADS;
    zeroWords(counts, counts_words, thread, n_threads);
-   zeroWords(next_diff, diff_words, thread, n_threads);
    __syncthreads();
    if (n_segments != 0) {
       const uint4* source = reinterpret_cast<const uint4*>(column.segments + first_segment);
@@ -397,7 +394,8 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
    uint32_t* __restrict__ work_state,           // [0] number of work items, [1] grid-wide claim counter (zero at launch)
    const DevSegment* __restrict__ work_items,   // the segment record of every work item (prepareQueryKernel)
    uint32_t* __restrict__ counts,               // [n_symbols * genome_length]
-   uint32_t claim_batch                         // work items per claim
+   uint32_t claim_batch,                        // work items per claim
+   uint32_t tail_batches                        // the last tail_batches * gridDim.x * claim_batch items are claimed one by one
 ) {
    // Two tile buffers: the producer loads the next chunk's tile while stages of the current chunk
    // are still being consumed, so a chunk switch does not drain the pipeline.
@@ -473,7 +471,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
       uint32_t size_b = claim_batch;
       uint32_t size_c = claim_batch;
       const uint32_t total = work_state[0];
-      const uint32_t tail_items = 2 * static_items;
+      const uint32_t tail_items = tail_batches * gridDim.x * claim_batch;
       const uint32_t tail_begin = total > tail_items ? total - tail_items : 0;
       uint32_t current_tile_chunk = 0xFFFFFFFFu;
       uint32_t tile_slot = 1;         // buffer holding the current chunk's tile
@@ -844,27 +842,27 @@ struct HitRequest {
    double min_proportion = 0;
 };
 
+// Grid: diffPadded(genome_length) / 256 blocks (the difference array has genome_length + 1 entries).
+// The kernel leaves the difference array, its block totals and the work-list state all-zero for the
+// next query: every thread clears the element it read, the last block to finish clears the totals.
 __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    DevColumn column,
-   const uint32_t* __restrict__ diff_scratch,
+   uint32_t* __restrict__ diff_scratch,
    uint32_t* __restrict__ counts,
    uint32_t* __restrict__ work_state,
    HitRequest request
 ) {
-   if (blockIdx.x == 0 && threadIdx.x < 2) {
-      work_state[threadIdx.x] = 0;  // the work list and its claim counter are empty between queries
-   }
    __shared__ uint32_t warp_totals[FIN_THREADS / 32];
    __shared__ uint32_t block_offset;
    const uint32_t genome_length = column.genome_length;
-   const uint32_t* diff = diff_scratch;
-   const uint32_t* block_totals = diff_scratch + diffPadded(genome_length);
+   uint32_t* diff = diff_scratch;
+   uint32_t* block_totals = diff_scratch + diffPadded(genome_length);
    const uint32_t block_first = blockIdx.x * FIN_THREADS;
    const uint32_t lane = threadIdx.x & 31;
    const uint32_t warp = threadIdx.x >> 5;
    const uint32_t p = block_first + threadIdx.x;
    // issue every global load up front: the kernel is one latency chain otherwise
-   const uint32_t mine = p < genome_length ? diff[p] : 0u;
+   const uint32_t mine = diff[p];  // (the array is padded to whole blocks)
    const uint32_t reference_symbol = p < genome_length ? column.local_reference[p] : 0u;
    const bool output_pass = request.hits != nullptr && p < genome_length;
    const uint32_t genome_symbol = output_pass ? column.global_reference[p] : 0u;
@@ -890,6 +888,7 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
          block_offset = partial;
       }
    }
+   diff[p] = 0;
    // inclusive scan of this block's 256 elements
    uint32_t inclusive = mine;
    for (int offset = 1; offset < 32; offset <<= 1) {
@@ -910,29 +909,42 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    if (p < genome_length) {
       counts[reference_symbol * genome_length + p] = reference_count;
    }
-   if (!output_pass) {
-      return;
-   }
-   const bool reference_is_valid = ((request.valid_mask >> reference_symbol) & 1ULL) != 0;
-   const uint32_t total = valid_others + (reference_is_valid ? reference_count : 0u);
-   if (reference_is_valid && reference_symbol != genome_symbol) {
-      candidates |= reference_count;
-   }
-   if (total == 0 || candidates == 0) {
-      return;  // `count > threshold_count` cannot hold for a zero count
-   }
-   // ceil(double(total) * min_proportion) - 1, the reference's operations in the reference's order
-   const uint32_t threshold_count =
-      request.min_proportion == 0 ? 0u : static_cast<uint32_t>(ceil(__dmul_rn(static_cast<double>(total), request.min_proportion)) - 1.0);
-   for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
-      if (((request.valid_mask >> symbol) & 1ULL) == 0 || symbol == genome_symbol) {
-         continue;
+   // this block has consumed its block totals (block_offset went into `covered`): the last block to
+   // get here clears them and the work-list state
+   if (threadIdx.x == 0) {
+      __threadfence();
+      const uint32_t finished = atomicAdd(&work_state[2], 1u);
+      if (finished == gridDim.x - 1) {
+         for (uint32_t block = 0; block < gridDim.x; ++block) {
+            block_totals[block] = 0;
+         }
+         work_state[0] = 0;  // the work list and its claim counter are empty between queries
+         work_state[1] = 0;
+         work_state[2] = 0;
       }
-      const uint32_t count = symbol == reference_symbol ? reference_count : counts[symbol * genome_length + p];
-      if (count > threshold_count) {
-         const uint32_t index = atomicAdd(&request.hits[0].position, 1u);
-         if (index < request.capacity) {
-            request.hits[1 + index] = silo_mutation_hit{p, symbol, count, total};
+   }
+   if (output_pass) {
+      const bool reference_is_valid = ((request.valid_mask >> reference_symbol) & 1ULL) != 0;
+      const uint32_t total = valid_others + (reference_is_valid ? reference_count : 0u);
+      if (reference_is_valid && reference_symbol != genome_symbol) {
+         candidates |= reference_count;
+      }
+      // (`count > threshold_count` cannot hold for a zero count)
+      if (total != 0 && candidates != 0) {
+         // ceil(double(total) * min_proportion) - 1, the reference's operations in the reference's order
+         const uint32_t threshold_count =
+            request.min_proportion == 0 ? 0u : static_cast<uint32_t>(ceil(__dmul_rn(static_cast<double>(total), request.min_proportion)) - 1.0);
+         for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
+            if (((request.valid_mask >> symbol) & 1ULL) == 0 || symbol == genome_symbol) {
+               continue;
+            }
+            const uint32_t count = symbol == reference_symbol ? reference_count : counts[symbol * genome_length + p];
+            if (count > threshold_count) {
+               const uint32_t index = atomicAdd(&request.hits[0].position, 1u);
+               if (index < request.capacity) {
+                  request.hits[1 + index] = silo_mutation_hit{p, symbol, count, total};
+               }
+            }
          }
       }
    }
@@ -967,24 +979,24 @@ void enqueueMutationCounts(
    cudaEvent_t ev_k1_begin = table->ev_k1_begin[slot];
    cudaEvent_t ev_k1_end = table->ev_k1_end[slot];
    cudaEvent_t ev_end = table->ev_end[slot];
-   SILO_CUDA_CHECK(cudaEventRecord(ev_begin, stream));
+   // (Inside a stream capture -- a caller building a CUDA graph of prepared queries -- these records are
+   // capture bookkeeping only: recording them as event-record NODES costs ~5 us per node and replay, more
+   // than the launch gaps a graph saves. silo_gpu_get_stats then describes the last EAGER calls.)
+   const unsigned int timing_flags = cudaEventRecordDefault;
+   SILO_CUDA_CHECK(cudaEventRecordWithFlags(ev_begin, stream, timing_flags));
    if (n_chunks == 0) {
       SILO_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, counts_bytes, stream));
       if (request != nullptr) {
          SILO_CUDA_CHECK(cudaMemsetAsync(request->hits, 0, sizeof(silo_mutation_hit), stream));
       }
-      SILO_CUDA_CHECK(cudaEventRecord(ev_k1_begin, stream));
-      SILO_CUDA_CHECK(cudaEventRecord(ev_k1_end, stream));
-      SILO_CUDA_CHECK(cudaEventRecord(ev_end, stream));
+      SILO_CUDA_CHECK(cudaEventRecordWithFlags(ev_k1_begin, stream, timing_flags));
+      SILO_CUDA_CHECK(cudaEventRecordWithFlags(ev_k1_end, stream, timing_flags));
+      SILO_CUDA_CHECK(cudaEventRecordWithFlags(ev_end, stream, timing_flags));
       return;
    }
    const uint64_t* words = filter != nullptr ? filter->d_words : table->d_full_words;
    const uint32_t* popcounts = filter != nullptr ? filter->d_chunk_popcount : table->d_chunk_popcount_full;
-   // this query's coverage difference array is all-zero already (cleared by the prepare kernel of the
-   // query before, or at allocation); the other one is cleared now for the query after
-   uint32_t* const diff = table->d_coverage_diff[table->coverage_diff_current];
-   uint32_t* const diff_next = table->d_coverage_diff[table->coverage_diff_current ^ 1u];
-   table->coverage_diff_current ^= 1u;
+   uint32_t* const diff = table->d_coverage_diff;  // all-zero: the finalize kernel of the query before cleared it
 
    // fork: the coverage kernel needs nothing but the filter, so it runs on the auxiliary stream beside
    // the prepare kernel and the first microseconds of the container kernel
@@ -997,13 +1009,12 @@ void enqueueMutationCounts(
    const int prepare_blocks = static_cast<int>(std::max<uint32_t>(n_chunks, static_cast<uint32_t>(table->ctx->sm_count)));
    prepareQueryKernel<<<prepare_blocks, PREP_THREADS, 0, stream>>>(
       column, filter != nullptr ? popcounts : nullptr, table->d_work_state, table->d_work_items, d_counts,
-      static_cast<uint32_t>(counts_bytes / sizeof(uint32_t)), diff_next, diffWords(column.genome_length),
-      request != nullptr ? request->hits : nullptr
+      static_cast<uint32_t>(counts_bytes / sizeof(uint32_t)), request != nullptr ? request->hits : nullptr
    );
    SILO_CUDA_CHECK(cudaGetLastError());
    table->stats.kernel_launches += 1;
 
-   SILO_CUDA_CHECK(cudaEventRecord(ev_k1_begin, stream));
+   SILO_CUDA_CHECK(cudaEventRecordWithFlags(ev_k1_begin, stream, timing_flags));
    if (filter == nullptr) {
       if (column.n_containers > 0) {
          const int blocks = static_cast<int>(std::min<uint64_t>((column.n_containers + 255) / 256, static_cast<uint64_t>(table->ctx->sm_count) * 8));
@@ -1015,6 +1026,7 @@ void enqueueMutationCounts(
       static bool attribute_set = false;
       static int stream_only = 0;
       static uint32_t claim_batch = K1_BATCH_DEFAULT;
+      static uint32_t tail_batches = 4;
       if (!attribute_set) {
          SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
          SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
@@ -1027,12 +1039,16 @@ void enqueueMutationCounts(
          if (batch_flag != nullptr) {
             claim_batch = static_cast<uint32_t>(std::min(32, std::max(1, std::atoi(batch_flag))));
          }
+         const char* tail_flag = std::getenv("SILO_K1_TAIL");
+         if (tail_flag != nullptr) {
+            tail_batches = static_cast<uint32_t>(std::max(0, std::atoi(tail_flag)));
+         }
          attribute_set = true;
       }
       const int blocks = static_cast<int>(std::min<uint32_t>(column.n_segments, static_cast<uint32_t>(table->ctx->sm_count) * 2));
 #define SILO_LAUNCH_K1(MODE)                                                                         \
    containerAndCountKernel<MODE><<<blocks, K1_THREADS, sizeof(K1Dynamic), stream>>>(                 \
-      column, words, table->d_work_state, table->d_work_items, d_counts, claim_batch                 \
+      column, words, table->d_work_state, table->d_work_items, d_counts, claim_batch, tail_batches   \
    )
       switch (stream_only) {
          case 1: SILO_LAUNCH_K1(1); break;
@@ -1045,14 +1061,14 @@ void enqueueMutationCounts(
       SILO_CUDA_CHECK(cudaGetLastError());
       table->stats.kernel_launches++;
    }
-   SILO_CUDA_CHECK(cudaEventRecord(ev_k1_end, stream));
+   SILO_CUDA_CHECK(cudaEventRecordWithFlags(ev_k1_end, stream, timing_flags));
    SILO_CUDA_CHECK(cudaStreamWaitEvent(stream, table->ev_join, 0));
-   finalizeCountsKernel<<<(column.genome_length + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, stream>>>(
+   finalizeCountsKernel<<<diffPadded(column.genome_length) / FIN_THREADS, FIN_THREADS, 0, stream>>>(
       column, diff, d_counts, table->d_work_state, request != nullptr ? *request : HitRequest{}
    );
    SILO_CUDA_CHECK(cudaGetLastError());
    table->stats.kernel_launches += 2;
-   SILO_CUDA_CHECK(cudaEventRecord(ev_end, stream));
+   SILO_CUDA_CHECK(cudaEventRecordWithFlags(ev_end, stream, timing_flags));
 }
 
 }  // namespace

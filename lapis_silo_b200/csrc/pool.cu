@@ -267,8 +267,7 @@ void silo_gpu_table_free(silo_gpu_table* table) {
    cudaFree(table->d_work_state);
    cudaFree(table->d_work_items);
    cudaFree(table->d_full_words);
-   cudaFree(table->d_coverage_diff[0]);
-   cudaFree(table->d_coverage_diff[1]);
+   cudaFree(table->d_coverage_diff);
    cudaFree(table->d_counts);
    cudaFree(table->d_hits);
    if (table->h_hits_pinned != nullptr) {
@@ -616,13 +615,11 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
          table->work_items_capacity = dev.n_segments;
       }
       if (diffWords(in->genome_length) > table->coverage_diff_capacity) {
-         // (all-zero between queries, see silo_gpu_table; a fresh pair starts all-zero too)
+         // (all-zero between queries, see silo_gpu_table; a fresh one starts all-zero too)
          SILO_CUDA_CHECK(cudaStreamSynchronize(table->ctx->stream));
-         for (uint32_t*& diff : table->d_coverage_diff) {
-            cudaFree(diff);
-            diff = deviceAlloc<uint32_t>(diffWords(in->genome_length), &table->device_bytes);
-            SILO_CUDA_CHECK(cudaMemset(diff, 0, diffWords(in->genome_length) * sizeof(uint32_t)));
-         }
+         cudaFree(table->d_coverage_diff);
+         table->d_coverage_diff = deviceAlloc<uint32_t>(diffWords(in->genome_length), &table->device_bytes);
+         SILO_CUDA_CHECK(cudaMemset(table->d_coverage_diff, 0, diffWords(in->genome_length) * sizeof(uint32_t)));
          table->coverage_diff_capacity = diffWords(in->genome_length);
       }
       const uint64_t counts_elems = static_cast<uint64_t>(in->n_symbols) * in->genome_length;
@@ -677,19 +674,26 @@ int silo_gpu_get_stats(silo_gpu_table* table, silo_gpu_stats* out) {
          const uint64_t n_timed = std::min<uint64_t>(table->timed_calls, silo_gpu_table::EVENT_RING);
          double kernel_ms = 0;
          double total_ms = 0;
+         uint64_t n_valid = 0;
          for (uint64_t back = 0; back < n_timed; ++back) {
             const uint64_t slot = (table->timed_calls - 1 - back) % silo_gpu_table::EVENT_RING;
-            float ms = 0;
-            SILO_CUDA_CHECK(cudaEventElapsedTime(&ms, table->ev_k1_begin[slot], table->ev_k1_end[slot]));
-            kernel_ms += ms;
-            SILO_CUDA_CHECK(cudaEventElapsedTime(&ms, table->ev_begin[slot], table->ev_end[slot]));
-            total_ms += ms;
+            float k1_ms = 0;
+            float call_ms = 0;
+            // a call enqueued inside a stream capture (CUDA graph) leaves its events unrecorded: skipped
+            if (cudaEventElapsedTime(&k1_ms, table->ev_k1_begin[slot], table->ev_k1_end[slot]) != cudaSuccess ||
+                cudaEventElapsedTime(&call_ms, table->ev_begin[slot], table->ev_end[slot]) != cudaSuccess) {
+               cudaGetLastError();
+               continue;
+            }
+            kernel_ms += k1_ms;
+            total_ms += call_ms;
+            ++n_valid;
          }
-         if (n_timed > 0) {
-            stats.last_counts_kernel_ms = static_cast<float>(kernel_ms / static_cast<double>(n_timed));
-            stats.last_total_ms = static_cast<float>(total_ms / static_cast<double>(n_timed));
+         if (n_valid > 0) {
+            stats.last_counts_kernel_ms = static_cast<float>(kernel_ms / static_cast<double>(n_valid));
+            stats.last_total_ms = static_cast<float>(total_ms / static_cast<double>(n_valid));
          }
-         stats.timed_calls = n_timed;
+         stats.timed_calls = n_valid;
          table->timed_calls = 0;
       }
       out->containers = stats.containers;

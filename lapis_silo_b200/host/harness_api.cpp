@@ -6,6 +6,7 @@
 
 #include "../../include/silo_b200_host.h"
 #include "expressions.h"
+#include "bitmap_aggregation_node.h"
 #include "mutations_node.h"
 #include "operators.h"
 #include "roaring_writer.h"
@@ -291,6 +292,67 @@ silo_host_rows* silo_host_mutation_rows_from_counts(silo_host_table* table, cons
       result = owned.release();
    });
    return result;
+}
+
+// dimensions: ';'-separated, each "p:<column>:<0-based position>" (SequencePositionDimension) or
+// "b:<value>=<bitmap name>,...|<null bitmap name or empty>" (IndexedColumnDimension over named bitmaps).
+// out: one line per combination, the values (\N = null) and the count, tab-separated.
+int silo_host_bitmap_aggregation(silo_host_table* table, const char* expression, const char* dimensions, char* out, uint64_t capacity) {
+   std::string text;
+   const int status = guarded([&] {
+      std::vector<GroupingDimension> dims;
+      const std::string spec = dimensions;
+      size_t begin = 0;
+      while (!spec.empty() && begin <= spec.size()) {
+         size_t end = spec.find(';', begin);
+         if (end == std::string::npos) {
+            end = spec.size();
+         }
+         const std::string item = spec.substr(begin, end - begin);
+         if (item.rfind("p:", 0) == 0) {
+            const size_t colon = item.rfind(':');
+            SequencePositionDimension dimension;
+            dimension.column = item.substr(2, colon - 2);
+            dimension.position_idx = static_cast<uint32_t>(std::stoul(item.substr(colon + 1)));
+            dims.emplace_back(std::move(dimension));
+         } else if (item.rfind("b:", 0) == 0) {
+            IndexedColumnDimension dimension;
+            const size_t bar = item.rfind('|');
+            if (bar + 1 < item.size()) {
+               dimension.null_bitmap = item.substr(bar + 1);
+            }
+            const std::string groups = item.substr(2, bar - 2);
+            size_t group_begin = 0;
+            while (group_begin < groups.size()) {
+               size_t group_end = groups.find(',', group_begin);
+               if (group_end == std::string::npos) {
+                  group_end = groups.size();
+               }
+               const std::string group = groups.substr(group_begin, group_end - group_begin);
+               const size_t equals = group.find('=');
+               dimension.value_bitmaps.emplace_back(group.substr(0, equals), group.substr(equals + 1));
+               group_begin = group_end + 1;
+            }
+            dims.emplace_back(std::move(dimension));
+         } else {
+            throw std::invalid_argument("bad dimension spec: " + item);
+         }
+         begin = end + 1;
+      }
+      const BitmapAggregationNode node(*table->table, parseOrTrue(expression), std::move(dims));
+      for (const CombinationRow& row : node.execute()) {
+         for (const auto& value : row.values) {
+            text += value.has_value() ? value.value() : std::string("\\N");
+            text += '\t';
+         }
+         text += std::to_string(row.count);
+         text += '\n';
+      }
+   });
+   if (status != 0) {
+      return status;
+   }
+   return copyText(text, out, capacity);
 }
 
 void silo_host_last_query_profile(double* out) {

@@ -22,7 +22,7 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_last_error", "silo_host_table_create", "silo_host_table_free", "silo_host_table_add_column",
     "silo_host_last_query_profile", "silo_host_table_register_bitmap", "silo_host_table_device", "silo_host_table_num_rows",
     "silo_host_filter_eval", "silo_host_filter_free", "silo_host_filter_cardinality",
-    "silo_host_filter_device", "silo_host_filter_words", "silo_host_filter_explain",
+    "silo_host_filter_device", "silo_host_filter_words", "silo_host_filter_explain", "silo_host_bitmap_aggregation",
     "silo_host_filter_prepare", "silo_host_prepared_run_async", "silo_host_prepared_filter",
     "silo_host_prepared_staged_bytes", "silo_host_prepared_free",
     "silo_host_mutation_counts", "silo_host_mutations", "silo_host_mutation_rows_from_counts",
@@ -70,6 +70,7 @@ def lib() -> C.CDLL:
         L.silo_host_filter_device.restype = vp
         L.silo_host_filter_words.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.silo_host_filter_explain.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint64]
+        L.silo_host_bitmap_aggregation.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64]
         L.silo_host_filter_prepare.argtypes = [vp, C.c_char_p]
         L.silo_host_filter_prepare.restype = vp
         L.silo_host_prepared_run_async.argtypes = [vp, vp]
@@ -295,6 +296,25 @@ class HostTable:
         buf = C.create_string_buffer(1 << 22)
         _check(lib().silo_host_filter_explain(self._h, expression.encode(), buf, len(buf)))
         return buf.value.decode()
+
+    def bitmap_aggregation(self, dimensions: Sequence, expression: Optional[str] = None) -> list[tuple]:
+        """BitmapAggregationNode (co-occurrence / groupBy): dimensions are ("position", column, position0) or
+        ("bitmaps", [(value, bitmap name), ...], null bitmap name or None). Returns the combinations in the
+        reference's output order as (value-or-None per dimension ..., count) tuples."""
+        parts = []
+        for dim in dimensions:
+            if dim[0] == "position":
+                parts.append(f"p:{dim[1]}:{int(dim[2])}")
+            else:
+                parts.append("b:" + ",".join(f"{value}={name}" for value, name in dim[1]) + "|" + (dim[2] or ""))
+        buf = C.create_string_buffer(1 << 24)
+        _check(lib().silo_host_bitmap_aggregation(
+            self._h, expression.encode() if expression else None, ";".join(parts).encode(), buf, len(buf)))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            fields = line.split("\t")
+            rows.append(tuple(None if f == "\\N" else f for f in fields[:-1]) + (int(fields[-1]),))
+        return rows
 
     def mutation_counts(self, column: str, flt: Optional[HostFilter] = None) -> np.ndarray:
         n_symbols, genome_length = self.columns[column]

@@ -122,6 +122,8 @@ def lib():
         L.orc_now_seconds.restype = C.c_double
         L.orc_mutations_query.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double, C.POINTER(C.c_uint64)]
         L.orc_mutations_query.restype = C.c_int64
+        L.orc_bitmap_aggregation.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64]
+        L.orc_bitmap_aggregation.restype = C.c_int64
         L.orc_mutations_query_bench.argtypes = [
             C.c_void_p, C.c_char_p, C.c_char_p, C.c_double, C.c_uint32, C.c_double, C.c_uint64,
             C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
@@ -343,6 +345,33 @@ class Table:
         return self.mutation_rows(column, self.mutation_counts(column, flt), min_proportion)
 
     # ---- S1 interchange ----
+    def bitmap_aggregation(self, dimensions: Sequence, expression: Optional[str] = None) -> list[tuple]:
+        """BitmapAggregationNode (bitmap_aggregation_node.cpp): dimensions are ("position", column, position0)
+        or ("bitmaps", [(value, bitmap name), ...], null bitmap name or None). Returns the combinations in
+        the reference's output order as (value-or-None per dimension ..., count) tuples."""
+        parts = []
+        for dim in dimensions:
+            if dim[0] == "position":
+                parts.append(f"p:{dim[1]}:{int(dim[2])}")
+            else:
+                parts.append("b:" + ",".join(f"{value}={name}" for value, name in dim[1]) + "|" + (dim[2] or ""))
+        spec = ";".join(parts).encode()
+        text_expression = expression.encode() if expression else None
+        capacity = 1 << 16
+        while True:
+            buffer = C.create_string_buffer(capacity)
+            needed = lib().orc_bitmap_aggregation(self._h, text_expression, spec, buffer, capacity)
+            if needed < 0:
+                _check(int(needed))
+            if needed <= capacity:
+                break
+            capacity = int(needed)
+        rows = []
+        for line in buffer.raw[:needed].decode().splitlines():
+            fields = line.split("\t")
+            rows.append(tuple(None if f == "\\N" else f for f in fields[:-1]) + (int(fields[-1]),))
+        return rows
+
     def export_column(self, column: str, first_chunk: int = 0, n_chunks: Optional[int] = None) -> Export:
         if n_chunks is None:
             n_chunks = len(self.chunk_sizes) - first_chunk

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/silo_b200.h"
+#include "aggregation.h"
 #include "cow_bitmap.h"
 #include "expressions.h"
 #include "generator.h"
@@ -782,6 +783,70 @@ int64_t orc_column_containers_at(void* table, const char* column, uint32_t posit
 }
 
 // monotonic seconds, for the cpu_baseline leg
+// ---- BitmapAggregationNode ----
+// dimensions: ';'-separated, each "p:<column>:<0-based position>" (SequencePositionDimension) or
+// "b:<value>=<bitmap name>,...|<null bitmap name or empty>" (IndexedColumnDimension over named bitmaps).
+// Writes one line per combination: the values (\N = null) and the count, tab-separated. Returns the
+// number of bytes the whole result needs (the caller retries with a larger buffer), < 0 on error.
+int64_t orc_bitmap_aggregation(void* table, const char* expression, const char* dimensions, char* out, uint64_t capacity) {
+   int64_t needed = -1;
+   const int status = guarded([&] {
+      const auto* t = static_cast<Table*>(table);
+      const auto parsed = parseExpression(expression != nullptr ? expression : "(true)");
+      std::vector<GroupingDimension> dims;
+      const std::string spec = dimensions;
+      size_t begin = 0;
+      while (begin <= spec.size() && !spec.empty()) {
+         size_t end = spec.find(';', begin);
+         if (end == std::string::npos) {
+            end = spec.size();
+         }
+         const std::string item = spec.substr(begin, end - begin);
+         GroupingDimension dimension;
+         if (item.rfind("p:", 0) == 0) {
+            const size_t colon = item.rfind(':');
+            dimension.is_sequence_position = true;
+            dimension.column = item.substr(2, colon - 2);
+            dimension.position_idx = static_cast<uint32_t>(std::stoul(item.substr(colon + 1)));
+         } else if (item.rfind("b:", 0) == 0) {
+            dimension.is_sequence_position = false;
+            const size_t bar = item.rfind('|');
+            dimension.null_bitmap = item.substr(bar + 1);
+            const std::string groups = item.substr(2, bar - 2);
+            size_t group_begin = 0;
+            while (group_begin < groups.size()) {
+               size_t group_end = groups.find(',', group_begin);
+               if (group_end == std::string::npos) {
+                  group_end = groups.size();
+               }
+               const std::string group = groups.substr(group_begin, group_end - group_begin);
+               const size_t equals = group.find('=');
+               dimension.value_bitmaps.emplace_back(group.substr(0, equals), group.substr(equals + 1));
+               group_begin = group_end + 1;
+            }
+         } else {
+            throw std::runtime_error("bad dimension spec: " + item);
+         }
+         dims.push_back(std::move(dimension));
+         begin = end + 1;
+      }
+      std::string text;
+      for (const Combination& combination : bitmapAggregation(*t, *parsed, dims)) {
+         for (const auto& value : combination.values) {
+            text += value.has_value() ? value.value() : std::string("\\N");
+            text += '\t';
+         }
+         text += std::to_string(combination.count);
+         text += '\n';
+      }
+      needed = static_cast<int64_t>(text.size());
+      if (text.size() <= capacity) {
+         std::memcpy(out, text.data(), text.size());
+      }
+   });
+   return status == 0 ? needed : status;
+}
+
 double orc_now_seconds() {
    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
