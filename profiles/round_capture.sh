@@ -1,0 +1,15 @@
+# One GPU call that produces every artifact profiles/summarize_round.py reads (run under gpurun from the repo root):
+#   bash profiles/round_capture.sh r1
+tag=${1:-r1}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc $?" | tee -a gpurun_out/${tag}_pytest_gpu.log; tail -3 gpurun_out/${tag}_pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/${tag}_smoke.log
+python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -c 3000 gpurun_out/${tag}_bench.json
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.err; tail -c 1500 gpurun_out/${tag}_bench_reference.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
+  python bench.py --steps 3 --warmup 3 --skip-cpu-baseline --eager > gpurun_out/${tag}_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:containerAndCountKernel -s 4 -c 1 -f -o gpurun_out/${tag}_k1_full \
+  python bench.py --steps 3 --warmup 3 --skip-cpu-baseline --eager > gpurun_out/${tag}_k1_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'evalProgramKernel|coverageDiffKernel|prepare|finalizeCountsKernel' -s 12 -c 4 -f -o gpurun_out/${tag}_other_full \
+  python bench.py --steps 3 --warmup 3 --skip-cpu-baseline --eager > gpurun_out/${tag}_other_full.log 2>&1
+ls -la gpurun_out | tail -20
