@@ -207,6 +207,7 @@ struct silo_gpu_table {
    silo_mutation_hit* d_hits = nullptr;
    silo_mutation_hit* h_hits_pinned = nullptr;
    uint64_t hits_capacity = 0;  // tuples, without the header
+   unsigned long long* h_scalars_pinned = nullptr;  // [4]: a query's filter cardinality ([0]) and error flag ([2]) land here
    uint8_t* h_staging_pinned = nullptr;  // program upload staging (grow-only)
    size_t staging_capacity = 0;
    cudaEvent_t ev_free_fence = nullptr;  // orders stream-ordered frees after foreign-stream users

@@ -958,7 +958,8 @@ void enqueueMutationCounts(
    const silo_gpu_filter* filter,
    uint32_t* d_counts,
    cudaStream_t stream,
-   const HitRequest* request = nullptr
+   const HitRequest* request = nullptr,
+   bool timed = false  // record the per-call CUDA events that silo_gpu_get_stats reads (measurement only)
 ) {
    require(table != nullptr, "mutation_counts: table is NULL");
    require(column_index >= 0 && static_cast<size_t>(column_index) < table->columns.size(), "mutation_counts: bad column index");
@@ -973,25 +974,31 @@ void enqueueMutationCounts(
    table->last_column = column_index;
    table->last_popcounts = filter != nullptr ? filter->d_chunk_popcount : table->d_chunk_popcount_full;
    table->last_was_full = filter == nullptr;
+   // The synchronous query calls do not pay for the four event records; the _async entry (what bench.py and
+   // the probes time) does. (Inside a stream capture the records are capture bookkeeping only; silo_gpu_get_stats
+   // then describes the last EAGER calls.)
    const uint64_t slot = table->timed_calls % silo_gpu_table::EVENT_RING;
-   table->timed_calls++;
+   if (timed) {
+      table->timed_calls++;
+   }
    cudaEvent_t ev_begin = table->ev_begin[slot];
    cudaEvent_t ev_k1_begin = table->ev_k1_begin[slot];
    cudaEvent_t ev_k1_end = table->ev_k1_end[slot];
    cudaEvent_t ev_end = table->ev_end[slot];
-   // (Inside a stream capture -- a caller building a CUDA graph of prepared queries -- these records are
-   // capture bookkeeping only: recording them as event-record NODES costs ~5 us per node and replay, more
-   // than the launch gaps a graph saves. silo_gpu_get_stats then describes the last EAGER calls.)
-   const unsigned int timing_flags = cudaEventRecordDefault;
-   SILO_CUDA_CHECK(cudaEventRecordWithFlags(ev_begin, stream, timing_flags));
+   auto recordTiming = [&](cudaEvent_t event) {
+      if (timed) {
+         SILO_CUDA_CHECK(cudaEventRecord(event, stream));
+      }
+   };
+   recordTiming(ev_begin);
    if (n_chunks == 0) {
       SILO_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, counts_bytes, stream));
       if (request != nullptr) {
          SILO_CUDA_CHECK(cudaMemsetAsync(request->hits, 0, sizeof(silo_mutation_hit), stream));
       }
-      SILO_CUDA_CHECK(cudaEventRecordWithFlags(ev_k1_begin, stream, timing_flags));
-      SILO_CUDA_CHECK(cudaEventRecordWithFlags(ev_k1_end, stream, timing_flags));
-      SILO_CUDA_CHECK(cudaEventRecordWithFlags(ev_end, stream, timing_flags));
+      recordTiming(ev_k1_begin);
+      recordTiming(ev_k1_end);
+      recordTiming(ev_end);
       return;
    }
    const uint64_t* words = filter != nullptr ? filter->d_words : table->d_full_words;
@@ -1014,7 +1021,7 @@ void enqueueMutationCounts(
    SILO_CUDA_CHECK(cudaGetLastError());
    table->stats.kernel_launches += 1;
 
-   SILO_CUDA_CHECK(cudaEventRecordWithFlags(ev_k1_begin, stream, timing_flags));
+   recordTiming(ev_k1_begin);
    if (filter == nullptr) {
       if (column.n_containers > 0) {
          const int blocks = static_cast<int>(std::min<uint64_t>((column.n_containers + 255) / 256, static_cast<uint64_t>(table->ctx->sm_count) * 8));
@@ -1061,14 +1068,14 @@ void enqueueMutationCounts(
       SILO_CUDA_CHECK(cudaGetLastError());
       table->stats.kernel_launches++;
    }
-   SILO_CUDA_CHECK(cudaEventRecordWithFlags(ev_k1_end, stream, timing_flags));
+   recordTiming(ev_k1_end);
    SILO_CUDA_CHECK(cudaStreamWaitEvent(stream, table->ev_join, 0));
    finalizeCountsKernel<<<diffPadded(column.genome_length) / FIN_THREADS, FIN_THREADS, 0, stream>>>(
       column, diff, d_counts, table->d_work_state, request != nullptr ? *request : HitRequest{}
    );
    SILO_CUDA_CHECK(cudaGetLastError());
    table->stats.kernel_launches += 2;
-   SILO_CUDA_CHECK(cudaEventRecordWithFlags(ev_end, stream, timing_flags));
+   recordTiming(ev_end);
 }
 
 }  // namespace
@@ -1091,7 +1098,7 @@ int silo_gpu_mutation_counts_async(
       std::lock_guard<std::mutex> lock(table->mutex);
       SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
       cudaStream_t stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : table->ctx->stream;
-      enqueueMutationCounts(table, column, filter, static_cast<uint32_t*>(d_counts), stream);
+      enqueueMutationCounts(table, column, filter, static_cast<uint32_t*>(d_counts), stream, nullptr, true);
    });
 }
 
@@ -1115,6 +1122,7 @@ static void mutationCountsToHost(
    silo_gpu_filter* own_filter = nullptr;
    unsigned long long host_cardinality = 0;
    uint32_t host_error = 0;
+   bool scalars_pending = false;
    try {
       if (program != nullptr) {
          // a program that is just PUSH_FULL is the `cardinality == numRows` path (stored cardinalities)
@@ -1124,8 +1132,10 @@ static void mutationCountsToHost(
          } else {
             own_filter = evalProgramAsync(table, program, stream, &d_staging);
             filter = own_filter;
-            SILO_CUDA_CHECK(cudaMemcpyAsync(&host_cardinality, own_filter->d_cardinality, sizeof(host_cardinality), cudaMemcpyDeviceToHost, stream));
-            SILO_CUDA_CHECK(cudaMemcpyAsync(&host_error, own_filter->d_error_flag, sizeof(host_error), cudaMemcpyDeviceToHost, stream));
+            // cardinality and error flag sit 16 bytes apart (allocFilter): one copy into page-locked memory, read
+            // after the call's single synchronise (a copy into pageable memory would block the host right here)
+            SILO_CUDA_CHECK(cudaMemcpyAsync(table->h_scalars_pinned, own_filter->d_cardinality, 32, cudaMemcpyDeviceToHost, stream));
+            scalars_pending = true;
          }
       }
       enqueueMutationCounts(table, column, filter, table->d_counts, stream);
@@ -1162,6 +1172,10 @@ static void mutationCountsToHost(
          d_staging = nullptr;
       }
       SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+      if (scalars_pending) {
+         host_cardinality = table->h_scalars_pinned[0];
+         host_error = static_cast<uint32_t>(table->h_scalars_pinned[2]);
+      }
       if (!pinned_destination) {
          for (const auto& [first, end] : ranges) {
             std::memcpy(counts + first * row_values, table->h_counts_pinned + first * row_values, (end - first) * row_values * sizeof(uint32_t));
@@ -1251,6 +1265,7 @@ int silo_gpu_query_mutation_hits(
       silo_gpu_filter* own_filter = nullptr;
       unsigned long long host_cardinality = 0;
       uint32_t host_error = 0;
+      bool scalars_pending = false;
       // the header and this many tuples come back with the first copy; more only if the query emits more
       constexpr uint64_t FIRST_COPY_HITS = 2047;
       uint64_t count = 0;
@@ -1263,8 +1278,10 @@ int silo_gpu_query_mutation_hits(
             } else {
                own_filter = evalProgramAsync(table, program, stream, &d_staging);
                filter = own_filter;
-               SILO_CUDA_CHECK(cudaMemcpyAsync(&host_cardinality, own_filter->d_cardinality, sizeof(host_cardinality), cudaMemcpyDeviceToHost, stream));
-               SILO_CUDA_CHECK(cudaMemcpyAsync(&host_error, own_filter->d_error_flag, sizeof(host_error), cudaMemcpyDeviceToHost, stream));
+               // cardinality and error flag sit 16 bytes apart (allocFilter): one copy into page-locked memory, read
+               // after the call's single synchronise (a copy into pageable memory would block the host right here)
+               SILO_CUDA_CHECK(cudaMemcpyAsync(table->h_scalars_pinned, own_filter->d_cardinality, 32, cudaMemcpyDeviceToHost, stream));
+               scalars_pending = true;
             }
          }
          enqueueMutationCounts(table, column, filter, table->d_counts, stream, &request);
@@ -1275,6 +1292,10 @@ int silo_gpu_query_mutation_hits(
             d_staging = nullptr;
          }
          SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+         if (scalars_pending) {
+            host_cardinality = table->h_scalars_pinned[0];
+            host_error = static_cast<uint32_t>(table->h_scalars_pinned[2]);
+         }
          count = std::min<uint64_t>(table->h_hits_pinned[0].position, table->hits_capacity);
          if (count + 1 > first_copy) {
             SILO_CUDA_CHECK(cudaMemcpyAsync(

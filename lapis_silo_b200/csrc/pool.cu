@@ -238,6 +238,7 @@ int silo_gpu_table_create(
          SILO_CUDA_CHECK(cudaEventCreate(&table->ev_k1_end[i]));
          SILO_CUDA_CHECK(cudaEventCreate(&table->ev_end[i]));
       }
+      SILO_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&table->h_scalars_pinned), 4 * sizeof(unsigned long long)));
       SILO_CUDA_CHECK(cudaEventCreateWithFlags(&table->ev_free_fence, cudaEventDisableTiming));
       SILO_CUDA_CHECK(cudaEventCreateWithFlags(&table->ev_fork, cudaEventDisableTiming));
       SILO_CUDA_CHECK(cudaEventCreateWithFlags(&table->ev_join, cudaEventDisableTiming));
@@ -275,6 +276,9 @@ void silo_gpu_table_free(silo_gpu_table* table) {
    }
    if (table->h_counts_pinned != nullptr) {
       cudaFreeHost(table->h_counts_pinned);
+   }
+   if (table->h_scalars_pinned != nullptr) {
+      cudaFreeHost(table->h_scalars_pinned);
    }
    if (table->h_staging_pinned != nullptr) {
       cudaFreeHost(table->h_staging_pinned);
