@@ -70,6 +70,16 @@ void silo_host_prepared_free(silo_host_prepared* prepared);
 int silo_host_mutation_counts(silo_host_table* table, const char* column, const silo_host_filter* filter, uint32_t* counts);
 /* MutationsNode: filter expression (NULL = true) + columns + minProportion -> output rows */
 silo_host_rows* silo_host_mutations(silo_host_table* table, const char* expression, const char* const* columns, uint32_t n_columns, double min_proportion);
+/* The same query with the result as ONE record batch in a caller buffer (what the reference hands to
+ * its Arrow sink, mutations_node.cpp:404-428), so that a binding needs a single call per query. Layout
+ * for n rows, every section starting at a multiple of 8 bytes:
+ *   f64 proportion[n] | i32 position[n] | u32 sequence_name_id[n] | i32 count[n] | i32 coverage[n] |
+ *   char mutation_from[n] | char mutation_to[n] | the distinct sequence names, each NUL-terminated
+ * *n_rows / *n_names / *needed_bytes are always set; when needed_bytes > capacity nothing is written
+ * and the result is kept for silo_host_packed_fetch (same thread, before the next query). */
+int silo_host_mutations_packed(silo_host_table* table, const char* expression, const char* const* columns, uint32_t n_columns, double min_proportion,
+                               void* buffer, uint64_t capacity, uint64_t* n_rows, uint32_t* n_names, uint64_t* needed_bytes);
+int silo_host_packed_fetch(void* buffer, uint64_t capacity);
 /* thresholding only, on counts the caller summed over shards (multi-GPU) */
 silo_host_rows* silo_host_mutation_rows_from_counts(silo_host_table* table, const char* column, const uint32_t* counts, double min_proportion);
 /* microseconds of the calling thread's last silo_host_mutations call:

@@ -204,9 +204,20 @@ struct silo_gpu_table {
    uint64_t counts_capacity = 0;
    uint32_t* h_counts_pinned = nullptr;
    // output pass on the device (silo_gpu_query_mutation_hits): [0] = {number of hits, 0, 0, 0}, then the tuples
-   silo_mutation_hit* d_hits = nullptr;
    silo_mutation_hit* h_hits_pinned = nullptr;
    uint64_t hits_capacity = 0;  // tuples, without the header
+   // The fused query calls (silo_gpu_query_*) run on persistent buffers -- a device copy of the staged program
+   // and one filter -- so that the launch sequence of a query SHAPE can be replayed as a CUDA graph:
+   // what differs between two queries of one shape is only the content of the staging buffer.
+   uint8_t* d_staging_fixed = nullptr;  // device copy of h_staging_pinned (same capacity)
+   silo_gpu_filter* query_filter = nullptr;
+   struct CachedGraph {
+      std::string key;
+      cudaGraphExec_t exec = nullptr;
+   };
+   std::vector<CachedGraph> query_graphs;  // a few shapes, replaced round-robin
+   size_t next_graph_slot = 0;
+   std::string last_query_key;             // a shape is captured the second time in a row it is seen
    unsigned long long* h_scalars_pinned = nullptr;  // [4]: a query's filter cardinality ([0]) and error flag ([2]) land here
    uint8_t* h_staging_pinned = nullptr;  // program upload staging (grow-only)
    size_t staging_capacity = 0;
@@ -258,6 +269,19 @@ void setLastError(const std::string& message);
 // (cudaFreeAsync on the same stream) after the kernel, the filter with releaseFilterLocked.
 silo_gpu_filter* evalProgramAsync(silo_gpu_table* table, const silo_filter_program* program, cudaStream_t stream, uint8_t** d_staging_out);
 void releaseFilterLocked(silo_gpu_filter* filter);
+
+// The same for the fused query calls, split into a host part and an enqueue part so that the enqueue can be
+// captured into a CUDA graph: stageQueryLocked validates the program and writes everything the kernel reads
+// into table->h_staging_pinned (device addresses inside refer to table->d_staging_fixed);
+// enqueueStagedQuery issues the H2D copy and the interpreter kernel into table->query_filter.
+struct StagedQuery {
+   alignas(16) unsigned char params[128];  // the interpreter's kernel parameters (filter_eval.cu EvalParams)
+   uint64_t staged_bytes = 0;
+   uint32_t shared_bytes = 0;
+};
+void stageQueryLocked(silo_gpu_table* table, const silo_filter_program* program, StagedQuery* out);
+void enqueueStagedQuery(silo_gpu_table* table, const StagedQuery& staged, cudaStream_t stream);
+void dropQueryGraphsLocked(silo_gpu_table* table);
 
 struct ApiError : std::runtime_error {
    int status;

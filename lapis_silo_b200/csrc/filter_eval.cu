@@ -721,7 +721,8 @@ static void stageProgram(
    cudaStream_t stream,
    uint8_t** d_staging_out,
    uint64_t* staged_bytes_out,
-   EvalParams* params_out
+   EvalParams* params_out,
+   bool persistent = false  // device side = table->d_staging_fixed, the H2D copy is left to the caller
 ) {
    uint32_t stack_depth = 1;
    bool has_threshold = false;
@@ -765,10 +766,16 @@ static void stageProgram(
    // the pinned buffer is reused by the next call on this table, which is safe because every caller
    // synchronises the stream before it returns
    if (staging_bytes > table->staging_capacity) {
+      dropQueryGraphsLocked(table);  // their copy nodes read the old buffers
+      SILO_CUDA_CHECK(cudaStreamSynchronize(table->ctx->stream));
       if (table->h_staging_pinned != nullptr) {
          cudaFreeHost(table->h_staging_pinned);
          table->h_staging_pinned = nullptr;
          table->staging_capacity = 0;
+      }
+      if (table->d_staging_fixed != nullptr) {
+         cudaFree(table->d_staging_fixed);
+         table->d_staging_fixed = nullptr;
       }
       const size_t capacity = std::max<size_t>(staging_bytes * 2, 1 << 20);
       const cudaError_t pinned_status = cudaMallocHost(reinterpret_cast<void**>(&table->h_staging_pinned), capacity);
@@ -778,7 +785,10 @@ static void stageProgram(
       table->staging_capacity = capacity;
    }
    uint8_t* staging = table->h_staging_pinned;
-   uint8_t* d_staging = poolAlloc<uint8_t>(staging_bytes, stream);
+   if (persistent && table->d_staging_fixed == nullptr) {
+      table->d_staging_fixed = deviceAlloc<uint8_t>(table->staging_capacity, &table->device_bytes);
+   }
+   uint8_t* d_staging = persistent ? table->d_staging_fixed : poolAlloc<uint8_t>(staging_bytes, stream);
 
    auto* instrs = reinterpret_cast<silo_filter_instr*>(staging + off_instrs);
    std::memcpy(instrs, program->instrs, sizeof(silo_filter_instr) * program->n_instrs);
@@ -820,10 +830,12 @@ static void stageProgram(
       bitmap.n_containers = registered.n_containers;
       bitmap.pad = 0;
    }
-   const cudaError_t status = cudaMemcpyAsync(d_staging, staging, staging_bytes, cudaMemcpyHostToDevice, stream);
-   if (status != cudaSuccess) {
-      cudaFreeAsync(d_staging, stream);
-      throw ApiError(SILO_E_CUDA, std::string("program upload failed: ") + cudaGetErrorString(status));
+   if (!persistent) {
+      const cudaError_t status = cudaMemcpyAsync(d_staging, staging, staging_bytes, cudaMemcpyHostToDevice, stream);
+      if (status != cudaSuccess) {
+         cudaFreeAsync(d_staging, stream);
+         throw ApiError(SILO_E_CUDA, std::string("program upload failed: ") + cudaGetErrorString(status));
+      }
    }
    EvalParams params{};
    params.instrs = reinterpret_cast<const silo_filter_instr*>(d_staging + off_instrs);
@@ -841,13 +853,14 @@ static void stageProgram(
    *params_out = params;
 }
 
-static void launchProgram(silo_gpu_table* table, EvalParams params, silo_gpu_filter* filter, cudaStream_t stream) {
+static void launchProgram(silo_gpu_table* table, EvalParams params, silo_gpu_filter* filter, cudaStream_t stream, bool scalars_are_zero = false) {
    params.out_words = filter->d_words;
    params.out_popcount = filter->d_chunk_popcount;
    params.out_cardinality = filter->d_cardinality;
    params.error_flag = filter->d_error_flag;
-   SILO_CUDA_CHECK(cudaMemsetAsync(filter->d_cardinality, 0, sizeof(unsigned long long), stream));
-   SILO_CUDA_CHECK(cudaMemsetAsync(filter->d_error_flag, 0, sizeof(uint32_t), stream));
+   if (!scalars_are_zero) {
+      SILO_CUDA_CHECK(cudaMemsetAsync(filter->d_cardinality, 0, 32, stream));  // cardinality and, 16 bytes on, the error flag (allocFilter)
+   }
    if (table->n_chunks == 0) {
       return;
    }
@@ -889,6 +902,51 @@ silo_gpu_filter* evalProgramAsync(silo_gpu_table* table, const silo_filter_progr
 
 void releaseFilterLocked(silo_gpu_filter* filter) {
    freeFilterLocked(filter);
+}
+
+void dropQueryGraphsLocked(silo_gpu_table* table) {
+   for (silo_gpu_table::CachedGraph& cached : table->query_graphs) {
+      if (cached.exec != nullptr) {
+         cudaGraphExecDestroy(cached.exec);
+      }
+   }
+   table->query_graphs.clear();
+   table->last_query_key.clear();
+}
+
+void stageQueryLocked(silo_gpu_table* table, const silo_filter_program* program, StagedQuery* out) {
+   static_assert(sizeof(EvalParams) <= sizeof(out->params));
+   if (table->query_filter == nullptr) {  // persistent: plain device memory, not the stream-ordered pool
+      auto filter = std::make_unique<silo_gpu_filter>();
+      filter->table = table;
+      const size_t words_bytes = static_cast<size_t>(table->n_chunks) * TILE_BYTES;
+      const size_t popcount_bytes = (static_cast<size_t>(table->n_chunks) * sizeof(uint32_t) + 15) / 16 * 16;
+      uint8_t* base = deviceAlloc<uint8_t>(words_bytes + popcount_bytes + 32, &table->device_bytes);
+      filter->d_words = reinterpret_cast<uint64_t*>(base);
+      filter->d_chunk_popcount = reinterpret_cast<uint32_t*>(base + words_bytes);
+      filter->d_cardinality = reinterpret_cast<unsigned long long*>(base + words_bytes + popcount_bytes);
+      filter->d_error_flag = reinterpret_cast<uint32_t*>(base + words_bytes + popcount_bytes + 16);
+      // cardinality and error flag are zero between queries: the finalize kernel of a fused query resets them
+      SILO_CUDA_CHECK(cudaMemsetAsync(filter->d_cardinality, 0, 32, table->ctx->stream));
+      table->query_filter = filter.release();
+   }
+   uint8_t* d_staging = nullptr;
+   EvalParams params{};
+   stageProgram(table, program, table->ctx->stream, &d_staging, &out->staged_bytes, &params, true);
+   params.out_words = table->query_filter->d_words;
+   params.out_popcount = table->query_filter->d_chunk_popcount;
+   params.out_cardinality = table->query_filter->d_cardinality;
+   params.error_flag = table->query_filter->d_error_flag;
+   std::memset(out->params, 0, sizeof(out->params));
+   std::memcpy(out->params, &params, sizeof(params));
+   out->shared_bytes = static_cast<uint32_t>(evalSharedBytes(params.stack_depth, params.has_threshold != 0));
+}
+
+void enqueueStagedQuery(silo_gpu_table* table, const StagedQuery& staged, cudaStream_t stream) {
+   EvalParams params{};
+   std::memcpy(&params, staged.params, sizeof(params));
+   SILO_CUDA_CHECK(cudaMemcpyAsync(table->d_staging_fixed, table->h_staging_pinned, staged.staged_bytes, cudaMemcpyHostToDevice, stream));
+   launchProgram(table, params, table->query_filter, stream, true);
 }
 
 }  // namespace silo

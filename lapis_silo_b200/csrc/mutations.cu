@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <chrono>
+
 #include "common.cuh"
 
 namespace silo {
@@ -57,13 +59,9 @@ __global__ void __launch_bounds__(PREP_THREADS) prepareQueryKernel(
    uint32_t* __restrict__ work_state,
    DevSegment* __restrict__ work_items,
    uint32_t* __restrict__ counts,
-   uint32_t counts_words,
-   silo_mutation_hit* __restrict__ hit_header  // nullptr unless the finalize kernel runs the output pass
+   uint32_t counts_words
 ) {
    __shared__ uint32_t list_base;
-   if (hit_header != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
-      hit_header->position = 0;  // number of hits
-   }
    uint32_t first_segment = 0;
    uint32_t n_segments = 0;
    if (chunk_popcount != nullptr && blockIdx.x < column.n_chunks) {
@@ -834,10 +832,16 @@ __global__ void __launch_bounds__(K6_THREADS) coverageDiffKernel(
 constexpr int FIN_THREADS = DIFF_BLOCK;
 
 // The output pass of addMutationsToOutput (mutations_node.cpp:307-363) for one position, on request:
-// which (position, symbol) rows the action emits. hits[0].position counts them, tuples from hits[1].
+// which (position, symbol) rows the action emits. `hits` is PAGE-LOCKED HOST memory: the kernel stores the
+// tuples (from hits[1]) straight into it over PCIe -- a few hundred 16-byte posted writes --, and the last
+// block to finish writes the header hits[0] = {number of tuples, the filter's error flag, the filter's
+// cardinality (low, high word)}, so a fused query needs no device-to-host copy at all. The running tuple
+// count lives in work_state[3] (zero between queries).
 struct HitRequest {
    silo_mutation_hit* hits = nullptr;
    uint32_t capacity = 0;
+   unsigned long long* filter_scalars = nullptr;  // {cardinality, -, error flag (u32), -} of a filter evaluated inside
+                                                  // the call: reported in the header and zeroed for the next query
    uint64_t valid_mask = 0;  // SymbolType::VALID_MUTATION_SYMBOLS
    double min_proportion = 0;
 };
@@ -909,20 +913,6 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    if (p < genome_length) {
       counts[reference_symbol * genome_length + p] = reference_count;
    }
-   // this block has consumed its block totals (block_offset went into `covered`): the last block to
-   // get here clears them and the work-list state
-   if (threadIdx.x == 0) {
-      __threadfence();
-      const uint32_t finished = atomicAdd(&work_state[2], 1u);
-      if (finished == gridDim.x - 1) {
-         for (uint32_t block = 0; block < gridDim.x; ++block) {
-            block_totals[block] = 0;
-         }
-         work_state[0] = 0;  // the work list and its claim counter are empty between queries
-         work_state[1] = 0;
-         work_state[2] = 0;
-      }
-   }
    if (output_pass) {
       const bool reference_is_valid = ((request.valid_mask >> reference_symbol) & 1ULL) != 0;
       const uint32_t total = valid_others + (reference_is_valid ? reference_count : 0u);
@@ -940,12 +930,41 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
             }
             const uint32_t count = symbol == reference_symbol ? reference_count : counts[symbol * genome_length + p];
             if (count > threshold_count) {
-               const uint32_t index = atomicAdd(&request.hits[0].position, 1u);
+               const uint32_t index = atomicAdd(&work_state[3], 1u);
                if (index < request.capacity) {
                   request.hits[1 + index] = silo_mutation_hit{p, symbol, count, total};
                }
             }
          }
+      }
+   }
+   // This block has consumed its block totals (block_offset went into `covered`) and appended its tuples:
+   // the last block to get here clears the totals and the work-list state and writes the header.
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      __threadfence();
+      const uint32_t finished = atomicAdd(&work_state[2], 1u);
+      if (finished == gridDim.x - 1) {
+         __threadfence();
+         for (uint32_t block = 0; block < gridDim.x; ++block) {
+            block_totals[block] = 0;
+         }
+         if (request.hits != nullptr) {
+            silo_mutation_hit header{*reinterpret_cast<volatile uint32_t*>(&work_state[3]), 0u, 0u, 0u};
+            if (request.filter_scalars != nullptr) {
+               const unsigned long long cardinality = *reinterpret_cast<volatile unsigned long long*>(&request.filter_scalars[0]);
+               header.symbol = *reinterpret_cast<volatile uint32_t*>(&request.filter_scalars[2]);
+               header.count = static_cast<uint32_t>(cardinality);
+               header.total = static_cast<uint32_t>(cardinality >> 32);
+               request.filter_scalars[0] = 0;
+               request.filter_scalars[2] = 0;
+            }
+            request.hits[0] = header;
+         }
+         work_state[0] = 0;  // the work list and its claim counter are empty between queries
+         work_state[1] = 0;
+         work_state[2] = 0;
+         work_state[3] = 0;
       }
    }
 }
@@ -994,7 +1013,7 @@ void enqueueMutationCounts(
    if (n_chunks == 0) {
       SILO_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, counts_bytes, stream));
       if (request != nullptr) {
-         SILO_CUDA_CHECK(cudaMemsetAsync(request->hits, 0, sizeof(silo_mutation_hit), stream));
+         std::memset(request->hits, 0, sizeof(silo_mutation_hit));  // (host memory; nothing on the stream writes it)
       }
       recordTiming(ev_k1_begin);
       recordTiming(ev_k1_end);
@@ -1016,7 +1035,7 @@ void enqueueMutationCounts(
    const int prepare_blocks = static_cast<int>(std::max<uint32_t>(n_chunks, static_cast<uint32_t>(table->ctx->sm_count)));
    prepareQueryKernel<<<prepare_blocks, PREP_THREADS, 0, stream>>>(
       column, filter != nullptr ? popcounts : nullptr, table->d_work_state, table->d_work_items, d_counts,
-      static_cast<uint32_t>(counts_bytes / sizeof(uint32_t)), request != nullptr ? request->hits : nullptr
+      static_cast<uint32_t>(counts_bytes / sizeof(uint32_t))
    );
    SILO_CUDA_CHECK(cudaGetLastError());
    table->stats.kernel_launches += 1;
@@ -1219,6 +1238,38 @@ int silo_gpu_column_set_reference(silo_gpu_table* table, int column, const uint8
    });
 }
 
+// SILO_QUERY_TRACE=1: where a fused query call spends its host time (printed every 64 calls)
+struct QueryTrace {
+   static bool enabled() {
+      static const bool on = std::getenv("SILO_QUERY_TRACE") != nullptr;
+      return on;
+   }
+   std::chrono::steady_clock::time_point begin = std::chrono::steady_clock::now();
+   void mark(int phase) {
+      if (!enabled()) {
+         return;
+      }
+      static double sums[3] = {0, 0, 0};
+      static uint64_t calls = 0;
+      const auto now = std::chrono::steady_clock::now();
+      sums[phase] += std::chrono::duration<double, std::micro>(now - begin).count();
+      begin = now;
+      if (phase == 2 && ++calls % 64 == 0) {
+         std::fprintf(stderr, "[silo query trace] stage %.1f us, enqueue %.1f us, wait %.1f us (mean of 64)\n", sums[0] / 64, sums[1] / 64, sums[2] / 64);
+         sums[0] = sums[1] = sums[2] = 0;
+      }
+   }
+};
+
+// SILO_QUERY_GRAPHS=0 keeps the fused query calls on plain launches (debugging aid)
+static bool queryGraphsEnabled() {
+   static const bool enabled = [] {
+      const char* flag = std::getenv("SILO_QUERY_GRAPHS");
+      return flag == nullptr || flag[0] != '0';
+   }();
+   return enabled;
+}
+
 int silo_gpu_query_mutation_hits(
    silo_gpu_table* table,
    const silo_filter_program* program,
@@ -1243,76 +1294,120 @@ int silo_gpu_query_mutation_hits(
       }
       // worst case: every valid symbol but the reference genome's at every position
       const uint64_t needed = static_cast<uint64_t>(__builtin_popcountll(valid_symbol_mask)) * host.dev.genome_length;
-      if (needed > table->hits_capacity || table->d_hits == nullptr) {
+      if (needed > table->hits_capacity || table->h_hits_pinned == nullptr) {
          SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
-         cudaFree(table->d_hits);
+         dropQueryGraphsLocked(table);  // their kernel nodes write the old buffer
          if (table->h_hits_pinned != nullptr) {
             cudaFreeHost(table->h_hits_pinned);
             table->h_hits_pinned = nullptr;
          }
-         table->d_hits = nullptr;
-         table->d_hits = deviceAlloc<silo_mutation_hit>(needed + 1, &table->device_bytes);
          SILO_CUDA_CHECK(cudaMallocHost(&table->h_hits_pinned, (needed + 1) * sizeof(silo_mutation_hit)));
          table->hits_capacity = needed;
       }
       HitRequest request;
-      request.hits = table->d_hits;
+      request.hits = table->h_hits_pinned;  // page-locked host memory, written by the finalize kernel
       request.capacity = static_cast<uint32_t>(table->hits_capacity);
       request.valid_mask = valid_symbol_mask;
       request.min_proportion = min_proportion;
 
-      uint8_t* d_staging = nullptr;
-      silo_gpu_filter* own_filter = nullptr;
       unsigned long long host_cardinality = 0;
       uint32_t host_error = 0;
-      bool scalars_pending = false;
-      // the header and this many tuples come back with the first copy; more only if the query emits more
-      constexpr uint64_t FIRST_COPY_HITS = 2047;
       uint64_t count = 0;
-      try {
-         if (program != nullptr) {
-            const bool trivially_full = program->n_instrs == 1 && program->instrs != nullptr && program->instrs[0].opcode == SILO_OP_PUSH_FULL;
-            if (trivially_full) {
-               host_cardinality = table->n_rows;
-               filter = nullptr;
-            } else {
-               own_filter = evalProgramAsync(table, program, stream, &d_staging);
-               filter = own_filter;
-               // cardinality and error flag sit 16 bytes apart (allocFilter): one copy into page-locked memory, read
-               // after the call's single synchronise (a copy into pageable memory would block the host right here)
-               SILO_CUDA_CHECK(cudaMemcpyAsync(table->h_scalars_pinned, own_filter->d_cardinality, 32, cudaMemcpyDeviceToHost, stream));
-               scalars_pending = true;
-            }
+      const bool trivially_full =
+         program != nullptr && program->n_instrs == 1 && program->instrs != nullptr && program->instrs[0].opcode == SILO_OP_PUSH_FULL;
+      if (trivially_full) {
+         host_cardinality = table->n_rows;
+         filter = nullptr;
+      }
+      const bool own_program = program != nullptr && !trivially_full;
+      StagedQuery staged;
+      QueryTrace trace;
+      if (own_program) {
+         stageQueryLocked(table, program, &staged);  // host work only: the pinned staging buffer now holds this query
+         filter = table->query_filter;
+         request.filter_scalars = filter->d_cardinality;  // reported in the header, zeroed again by the finalize kernel
+      }
+      // everything the query puts on the stream; with a program it touches persistent buffers only, so the
+      // sequence is the same for every query of one shape and can be replayed as a graph
+      auto enqueueAll = [&]() {
+         if (own_program) {
+            enqueueStagedQuery(table, staged, stream);
          }
          enqueueMutationCounts(table, column, filter, table->d_counts, stream, &request);
-         const uint64_t first_copy = std::min<uint64_t>(FIRST_COPY_HITS, table->hits_capacity) + 1;
-         SILO_CUDA_CHECK(cudaMemcpyAsync(table->h_hits_pinned, table->d_hits, first_copy * sizeof(silo_mutation_hit), cudaMemcpyDeviceToHost, stream));
-         if (d_staging != nullptr) {
-            SILO_CUDA_CHECK(cudaFreeAsync(d_staging, stream));
-            d_staging = nullptr;
+      };
+      try {
+         cudaGraphExec_t replay = nullptr;
+         if (own_program && queryGraphsEnabled()) {
+            // the shape of the query: every kernel parameter and copy size that enqueueAll bakes into nodes
+            std::string key(reinterpret_cast<const char*>(staged.params), sizeof(staged.params));
+            const uint64_t scalars[] = {staged.staged_bytes, staged.shared_bytes, static_cast<uint64_t>(column), valid_symbol_mask,
+                                        reinterpret_cast<uint64_t>(table->h_hits_pinned), table->hits_capacity,
+                                        reinterpret_cast<uint64_t>(host.dev.containers), host.dev.n_segments,
+                                        reinterpret_cast<uint64_t>(host.dev.global_reference), reinterpret_cast<uint64_t>(table->d_counts),
+                                        reinterpret_cast<uint64_t>(table->d_work_items), reinterpret_cast<uint64_t>(table->d_coverage_diff)};
+            key.append(reinterpret_cast<const char*>(scalars), sizeof(scalars));
+            key.append(reinterpret_cast<const char*>(&min_proportion), sizeof(min_proportion));
+            for (const silo_gpu_table::CachedGraph& cached : table->query_graphs) {
+               if (cached.key == key) {
+                  replay = cached.exec;
+                  break;
+               }
+            }
+            if (replay == nullptr && key == table->last_query_key) {  // second time in a row: worth a graph
+               cudaGraph_t graph = nullptr;
+               SILO_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+               try {
+                  enqueueAll();
+               } catch (...) {
+                  cudaStreamEndCapture(stream, &graph);
+                  if (graph != nullptr) {
+                     cudaGraphDestroy(graph);
+                  }
+                  cudaGetLastError();
+                  throw;
+               }
+               SILO_CUDA_CHECK(cudaStreamEndCapture(stream, &graph));
+               cudaGraphExec_t exec = nullptr;
+               const cudaError_t instantiated = cudaGraphInstantiate(&exec, graph, 0);
+               cudaGraphDestroy(graph);
+               SILO_CUDA_CHECK(instantiated);
+               constexpr size_t MAX_QUERY_GRAPHS = 8;
+               if (table->query_graphs.size() < MAX_QUERY_GRAPHS) {
+                  table->query_graphs.push_back({key, exec});
+               } else {
+                  silo_gpu_table::CachedGraph& slot = table->query_graphs[table->next_graph_slot++ % MAX_QUERY_GRAPHS];
+                  cudaGraphExecDestroy(slot.exec);
+                  slot = {key, exec};
+               }
+               replay = exec;
+            }
+            table->last_query_key = std::move(key);
          }
+         trace.mark(0);  // staged (host work)
+         if (replay != nullptr) {
+            SILO_CUDA_CHECK(cudaGraphLaunch(replay, stream));
+            table->stats.kernel_launches += own_program ? 5 : 4;
+         } else {
+            enqueueAll();
+         }
+         trace.mark(1);  // on the stream
          SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
-         if (scalars_pending) {
-            host_cardinality = table->h_scalars_pinned[0];
-            host_error = static_cast<uint32_t>(table->h_scalars_pinned[2]);
-         }
-         count = std::min<uint64_t>(table->h_hits_pinned[0].position, table->hits_capacity);
-         if (count + 1 > first_copy) {
-            SILO_CUDA_CHECK(cudaMemcpyAsync(
-               table->h_hits_pinned + first_copy, table->d_hits + first_copy, (count + 1 - first_copy) * sizeof(silo_mutation_hit),
-               cudaMemcpyDeviceToHost, stream
-            ));
-            SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+         trace.mark(2);  // device done
+         const silo_mutation_hit header = table->h_hits_pinned[0];
+         count = std::min<uint64_t>(header.position, table->hits_capacity);
+         if (own_program) {
+            host_error = header.symbol;
+            host_cardinality = header.count | (static_cast<unsigned long long>(header.total) << 32);
          }
       } catch (...) {
-         if (d_staging != nullptr) {
-            cudaFreeAsync(d_staging, stream);
-         }
          cudaStreamSynchronize(stream);
-         releaseFilterLocked(own_filter);
+         if (own_program) {  // the finalize kernel may not have run: leave the persistent filter's scalars zero
+            cudaMemsetAsync(table->query_filter->d_cardinality, 0, 32, stream);
+            cudaMemsetAsync(table->d_work_state, 0, 4 * sizeof(uint32_t), stream);
+            cudaStreamSynchronize(stream);
+         }
          throw;
       }
-      releaseFilterLocked(own_filter);
       if (host_error != 0) {
          throw ApiError(SILO_E_OUT_OF_LAYOUT, "a leaf bitmap holds row ids outside the row layout");
       }

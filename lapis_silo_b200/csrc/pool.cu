@@ -270,7 +270,12 @@ void silo_gpu_table_free(silo_gpu_table* table) {
    cudaFree(table->d_full_words);
    cudaFree(table->d_coverage_diff);
    cudaFree(table->d_counts);
-   cudaFree(table->d_hits);
+   dropQueryGraphsLocked(table);
+   cudaFree(table->d_staging_fixed);
+   if (table->query_filter != nullptr) {
+      cudaFree(table->query_filter->d_words);
+      delete table->query_filter;
+   }
    if (table->h_hits_pinned != nullptr) {
       cudaFreeHost(table->h_hits_pinned);
    }
@@ -636,6 +641,7 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
          SILO_CUDA_CHECK(cudaMallocHost(&table->h_counts_pinned, counts_elems * sizeof(uint32_t)));
          table->counts_capacity = counts_elems;
       }
+      dropQueryGraphsLocked(table);  // the staged column table and the scratch buffers may have changed
       table->columns.push_back(column.release());
       column_index = static_cast<int>(table->columns.size()) - 1;
    });

@@ -278,6 +278,94 @@ silo_host_rows* silo_host_mutations(silo_host_table* table, const char* expressi
    return result;
 }
 
+namespace {
+
+uint64_t alignEight(uint64_t value) {
+   return (value + 7) / 8 * 8;
+}
+
+uint64_t packedBytes(const silo_host_rows& rows) {
+   const uint64_t n = rows.rows.size();
+   uint64_t bytes = alignEight(8 * n) + 4 * alignEight(4 * n) + 2 * alignEight(n);
+   for (const std::string& name : rows.names) {
+      bytes += name.size() + 1;
+   }
+   return bytes;
+}
+
+void packRows(const silo_host_rows& rows, uint8_t* out) {
+   const uint64_t n = rows.rows.size();
+   auto* proportion = reinterpret_cast<double*>(out);
+   auto* position = reinterpret_cast<int32_t*>(out + alignEight(8 * n));
+   auto* name_ids = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(position) + alignEight(4 * n));
+   auto* count = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(name_ids) + alignEight(4 * n));
+   auto* coverage = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(count) + alignEight(4 * n));
+   char* from = reinterpret_cast<char*>(coverage) + alignEight(4 * n);
+   char* to = from + alignEight(n);
+   for (uint64_t i = 0; i < n; ++i) {
+      const MutationRow& row = rows.rows[i];
+      proportion[i] = row.proportion;
+      position[i] = row.position;
+      name_ids[i] = rows.name_ids[i];
+      count[i] = row.count;
+      coverage[i] = row.coverage;
+      from[i] = row.mutation_from;
+      to[i] = row.mutation_to;
+   }
+   char* names = to + alignEight(n);
+   for (const std::string& name : rows.names) {
+      std::memcpy(names, name.c_str(), name.size() + 1);
+      names += name.size() + 1;
+   }
+}
+
+thread_local std::unique_ptr<silo_host_rows> g_pending_rows;  // a packed result that did not fit the caller's buffer
+
+}  // namespace
+
+int silo_host_mutations_packed(
+   silo_host_table* table,
+   const char* expression,
+   const char* const* columns,
+   uint32_t n_columns,
+   double min_proportion,
+   void* buffer,
+   uint64_t capacity,
+   uint64_t* n_rows,
+   uint32_t* n_names,
+   uint64_t* needed_bytes
+) {
+   return guarded([&] {
+      g_pending_rows.reset();
+      std::vector<std::string> names(columns, columns + n_columns);
+      const double parse_begin = nowMicroseconds();
+      ExpressionPtr parsed = parseOrTrue(expression);
+      lastQueryProfile().parse_us = nowMicroseconds() - parse_begin;
+      const MutationsNode node(*table->table, std::move(parsed), std::move(names), min_proportion);
+      auto owned = std::make_unique<silo_host_rows>();
+      owned->rows = node.execute();
+      owned->indexNames();
+      *n_rows = owned->rows.size();
+      *n_names = static_cast<uint32_t>(owned->names.size());
+      *needed_bytes = packedBytes(*owned);
+      if (*needed_bytes <= capacity) {
+         packRows(*owned, static_cast<uint8_t*>(buffer));
+      } else {
+         g_pending_rows = std::move(owned);
+      }
+   });
+}
+
+int silo_host_packed_fetch(void* buffer, uint64_t capacity) {
+   return guarded([&] {
+      if (g_pending_rows == nullptr || packedBytes(*g_pending_rows) > capacity) {
+         throw std::invalid_argument("silo_host_packed_fetch: no pending result of that size on this thread");
+      }
+      packRows(*g_pending_rows, static_cast<uint8_t*>(buffer));
+      g_pending_rows.reset();
+   });
+}
+
 silo_host_rows* silo_host_mutation_rows_from_counts(silo_host_table* table, const char* column, const uint32_t* counts, double min_proportion) {
    silo_host_rows* result = nullptr;
    guarded([&] {

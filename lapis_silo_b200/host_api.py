@@ -26,6 +26,7 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_filter_prepare", "silo_host_prepared_run_async", "silo_host_prepared_filter",
     "silo_host_prepared_staged_bytes", "silo_host_prepared_free",
     "silo_host_mutation_counts", "silo_host_mutations", "silo_host_mutation_rows_from_counts",
+    "silo_host_mutations_packed", "silo_host_packed_fetch",
     "silo_host_rows_free", "silo_host_rows_size", "silo_host_rows_get", "silo_host_rows_export",
     "silo_host_rows_num_names", "silo_host_rows_name",
     "silo_host_synthetic_create", "silo_host_synthetic_free", "silo_host_synthetic_num_sequences",
@@ -83,6 +84,10 @@ def lib() -> C.CDLL:
         L.silo_host_mutation_counts.argtypes = [vp, C.c_char_p, vp, C.POINTER(C.c_uint32)]
         L.silo_host_mutations.argtypes = [vp, C.c_char_p, C.POINTER(C.c_char_p), C.c_uint32, C.c_double]
         L.silo_host_mutations.restype = vp
+        L.silo_host_mutations_packed.argtypes = [
+            vp, C.c_char_p, C.POINTER(C.c_char_p), C.c_uint32, C.c_double, vp, C.c_uint64,
+            C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.silo_host_packed_fetch.argtypes = [vp, C.c_uint64]
         L.silo_host_mutation_rows_from_counts.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint32), C.c_double]
         L.silo_host_mutation_rows_from_counts.restype = vp
         L.silo_host_rows_free.argtypes = [vp]
@@ -157,6 +162,24 @@ def _columns(handle) -> dict:
                 "sequenceNames": names, "proportion": proportion, "count": count, "coverage": coverage}
     finally:
         lib().silo_host_rows_free(handle)
+
+
+def _unpack_record_batch(batch: np.ndarray, n: int, n_names: int) -> dict:
+    """Views over the record batch of silo_host_mutations_packed (include/silo_b200_host.h)."""
+    def pad(size):
+        return (size + 7) // 8 * 8
+    cursor = 0
+    out = {}
+    for key, dtype, width in (("proportion", np.float64, 8), ("position", np.int32, 4), ("sequenceNameId", np.uint32, 4),
+                              ("count", np.int32, 4), ("coverage", np.int32, 4)):
+        out[key] = batch[cursor:cursor + width * n].view(dtype)
+        cursor += pad(width * n)
+    out["mutationFrom"] = batch[cursor:cursor + n].tobytes()
+    cursor += pad(n)
+    out["mutationTo"] = batch[cursor:cursor + n].tobytes()
+    cursor += pad(n)
+    out["sequenceNames"] = batch[cursor:].tobytes().decode().split("\0")[:n_names]
+    return out
 
 
 def rows_from_columns(columns: dict) -> list[dict]:
@@ -256,6 +279,10 @@ class HostTable:
         self.first_chunk = first_chunk
         self.columns: dict[str, tuple[int, int]] = {}
         self._children = weakref.WeakSet()  # live HostFilter / PreparedFilter objects of this table
+        # mutations_columns: record-batch buffer (grown on demand) and the call's out-parameters
+        self._packed = np.empty(1 << 16, dtype=np.uint8)
+        self._packed_out = (C.c_uint64(), C.c_uint32(), C.c_uint64())
+        self._name_arrays: dict = {}
         arr = (C.c_uint32 * max(self.n_chunks, 1))(*self.chunk_sizes)
         self._h = lib().silo_host_table_create(ctx._h, first_chunk, arr, self.n_chunks)
         if not self._h:
@@ -330,11 +357,20 @@ class HostTable:
         return _rows(handle)
 
     def mutations_columns(self, columns: Sequence[str], expression: Optional[str], min_proportion: float) -> dict:
-        """mutations() with the result as columns (numpy arrays) instead of a list of row dicts."""
-        names = (C.c_char_p * len(columns))(*[c.encode() for c in columns])
-        handle = lib().silo_host_mutations(
-            self._h, expression.encode() if expression is not None else None, names, len(columns), min_proportion)
-        return _columns(handle)
+        """mutations() with the result as columns (numpy arrays over one record-batch buffer) instead of a
+        list of row dicts: ONE call into the host library per query (silo_host_mutations_packed)."""
+        names = self._name_arrays.get(tuple(columns))
+        if names is None:
+            names = self._name_arrays[tuple(columns)] = (C.c_char_p * len(columns))(*[c.encode() for c in columns])
+        n_rows, n_names, needed = self._packed_out
+        status = lib().silo_host_mutations_packed(
+            self._h, expression.encode() if expression is not None else None, names, len(columns), min_proportion,
+            self._packed.ctypes.data, self._packed.nbytes, n_rows, n_names, needed)
+        _check(status)
+        if needed.value > self._packed.nbytes:
+            self._packed = np.empty(int(needed.value) * 2, dtype=np.uint8)
+            _check(lib().silo_host_packed_fetch(self._packed.ctypes.data, self._packed.nbytes))
+        return _unpack_record_batch(self._packed[:needed.value].copy(), int(n_rows.value), int(n_names.value))
 
     def mutation_columns_from_counts(self, column: str, counts: np.ndarray, min_proportion: float) -> dict:
         counts = np.ascontiguousarray(counts, dtype=np.uint32)

@@ -294,6 +294,40 @@ def test_mutations_action_rows(ctx, seed, alphabet_id):
         np.testing.assert_array_equal(device_table.mutation_counts("c", flt_d), oracle_table.mutation_counts("c", flt_o))
 
 
+def test_mutations_query_graph_replay(ctx):
+    """The fused Mutations query replays a CUDA graph per query SHAPE from the second occurrence in a
+    row on (csrc/mutations.cu silo_gpu_query_mutation_hits). Queries of one shape with different
+    content, shapes that alternate, more shapes than the cache holds and a hits buffer that regrows
+    must all keep giving the oracle's rows."""
+    t = build_random(401, 900, 60, (99, 130, 131), 0)
+    rng = np.random.default_rng(401)
+    t.register_bitmap("lineage", sorted({int(v) for v in rng.integers(0, 100, 60)} | {(3 << 16) + int(v) for v in rng.integers(0, 700, 400)}))
+    oracle_table, device_table = t, mirror(ctx, t, ["lineage"], resident=True)
+
+    def check(expression, min_proportion=0.05):
+        assert device_table.mutations(["c"], expression, min_proportion) == oracle_table.mutations("c", expression, min_proportion), expression
+
+    # one shape, the content changes with every call (eager, capture, then replays)
+    for position in list(range(1, 40)) * 2:
+        check(f"(and (bitmap lineage) (not (sym-eq c {position} N)))")
+    # the same query many times
+    for _ in range(6):
+        check("(has-mut c 7)")
+    # shapes alternating, each repeated so that it gets a graph; 12 shapes > the 8 cached ones
+    shapes = [" ".join(f"(has-mut c {p})" for p in range(1, n + 2)) for n in range(12)]
+    for _ in range(3):
+        for n, children in enumerate(shapes):
+            for _ in range(3):
+                check(f"(or {children} (ranges {n} {80 + n}))")
+    # thresholds and proportions are part of the shape (kernel parameters)
+    for min_proportion in (0.0, 0.3, 0.0, 0.0, 0.3, 0.3, 1.0, 1.0):
+        check("(profile c 4 muts)", min_proportion)
+        check("(bitmap lineage)", min_proportion)
+    # no program / the full-filter path next to graph replays
+    for expression in (None, "(true)", "(false)", "(bitmap lineage)", "(bitmap lineage)", "(bitmap lineage)", None):
+        check(expression)
+
+
 def test_mutations_two_columns_and_union_all_vector(ctx):
     from oracle import oracle as O
     t = O.Table()  # operators/union_all_node.test.cpp:184-193
