@@ -471,10 +471,11 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": prepared.staged_bytes,
-                # N = 1: the output pass runs on the device, one copy of the hit header + the first 2047
-                # (position, symbol, count, total) tuples comes back (silo_gpu_query_mutation_hits), plus
-                # cardinality and error flag; N > 1: the all-reduced count rows of the valid symbols
-                "d2h_bytes_per_step": 2048 * 16 + 12 if n_gpus == 1 else valid_values * 4 + 12},
+                # N = 1: the output pass runs on the device; the finalize kernel stores the emitted (position,
+                # symbol, count, total) tuples and a 16-byte header (tuple count, filter cardinality, error
+                # flag) straight into page-locked host memory (silo_gpu_query_mutation_hits);
+                # N > 1: the all-reduced count rows of the valid symbols + cardinality and error flag
+                "d2h_bytes_per_step": (len(rows) + 1) * 16 if n_gpus == 1 else valid_values * 4 + 12},
         "gpu_launches": gpu_launches,
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

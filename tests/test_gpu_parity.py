@@ -278,6 +278,7 @@ def test_random_expressions(ctx, seed, alphabet_id):
 
 @pytest.mark.parametrize("seed,alphabet_id", [(201, 0), (202, 1)])
 def test_mutations_action_rows(ctx, seed, alphabet_id):
+    from lapis_silo_b200 import host_api
     t = build_random(seed, 900, 60, (99, 130, 131), alphabet_id)
     rng = np.random.default_rng(seed)
     t.register_bitmap("lineage", sorted({int(v) for v in rng.integers(0, 100, 60)} | {(3 << 16) + int(v) for v in rng.integers(0, 700, 400)}))
@@ -289,6 +290,10 @@ def test_mutations_action_rows(ctx, seed, alphabet_id):
             want = oracle_table.mutations("c", expression, min_proportion)
             got = device_table.mutations(["c"], expression, min_proportion)
             assert got == want, (expression, min_proportion)
+            # the same result as one record batch from one call (silo_host_mutations_packed)
+            assert host_api.rows_from_columns(device_table.mutations_columns(["c"], expression, min_proportion)) == want
+        device_table._packed = np.empty(8, dtype=np.uint8)  # too small: the result is fetched with a second call
+        assert host_api.rows_from_columns(device_table.mutations_columns(["c"], expression, 0.0)) == oracle_table.mutations("c", expression, 0.0)
         flt_o = oracle_table.filter(expression) if expression else None
         flt_d = device_table.filter(expression) if expression else None
         np.testing.assert_array_equal(device_table.mutation_counts("c", flt_d), oracle_table.mutation_counts("c", flt_o))
