@@ -293,6 +293,7 @@ def run_ours(args):
             f"{synthetic.num_sequences} evolved sequences")
 
     # a dedicated (non-default) stream: the library's kernels, NCCL and the timing events all use it
+    valid_values = VALID_MUTATION_SYMBOLS * GENOME_LENGTH  # symbol ids 0..4 (-, A, C, G, T) are contiguous
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     counts = torch.zeros(N_SYMBOLS * GENOME_LENGTH, dtype=torch.int32, device="cuda")
@@ -319,7 +320,9 @@ def run_ours(args):
             kernels_done[buffer].record(stream)
             comm_stream.wait_event(kernels_done[buffer])
             with torch.cuda.stream(comm_stream):
-                dist.all_reduce(count_buffers[buffer])  # u32 counts viewed as i32: modular sum, same bits
+                # the rows of the 5 valid mutation symbols (ids 0..4, contiguous): all that the action's output
+                # pass reads (addMutationsToOutput, mutations_node.cpp:307-363); u32 viewed as i32, same bits
+                dist.all_reduce(count_buffers[buffer][:valid_values])
                 reduced[buffer].record(comm_stream)
 
     def join_reductions():
@@ -416,6 +419,9 @@ def run_ours(args):
         clocks["sampled_over"] = "the timed region and 0.4 s of the same step right after it (nvidia-smi -lms 100)"
     cardinality = sum_over_ranks(prepared.cardinality())
     last_buffer = count_buffers[(issued[0] - 1) % len(count_buffers)]
+    if n_gpus > 1:  # outside the timed region: the other symbols' rows too, for the property check below
+        dist.all_reduce(last_buffer[valid_values:])
+        torch.cuda.synchronize()
     device_counts = last_buffer.cpu().numpy().view(np.uint32).reshape(N_SYMBOLS, GENOME_LENGTH).copy()
     value = cardinality * GENOME_LENGTH * args.steps / (device_ms / 1000.0)
 
@@ -424,14 +430,17 @@ def run_ours(args):
         # (the result comes back as columns, like the record batch the reference hands to its Arrow sink)
         if n_gpus == 1:
             return table.mutations_columns(["main"], expression, MIN_PROPORTION)  # MutationsNode through the C ABI
-        flt = table.filter(expression)  # parse/compile/lower, program H2D, cardinality D2H
-        table.mutation_counts_async(0, flt, counts.data_ptr(), stream.cuda_stream)
-        dist.all_reduce(counts[:valid_values])  # rows of the 5 valid symbols: all that the thresholding reads
-        pinned[:valid_values].copy_(counts[:valid_values], non_blocking=True)  # rows of the 5 valid symbols
+        # The sharded query (MutationsNode::enqueueShardCounts / collectRows): every rank parses + compiles the
+        # query against its shard and enqueues program H2D + filter + counts, the counts of the valid symbols
+        # are all-reduced on the same stream, rank 0 runs the output pass over the sums on the device and
+        # gets the emitted tuples back; one host synchronisation per rank and step.
+        table.mutations_enqueue("main", expression, counts.data_ptr(), stream.cuda_stream)
+        dist.all_reduce(counts[:valid_values])  # rows of the 5 valid symbols: all that the output pass reads
+        if rank == 0:
+            return table.mutations_collect("main", MIN_PROPORTION, counts.data_ptr(), stream.cuda_stream)[0]
         stream.synchronize()
-        return table.mutation_columns_from_counts("main", pinned.numpy().view(np.uint32), MIN_PROPORTION)
+        return None
 
-    valid_values = VALID_MUTATION_SYMBOLS * GENOME_LENGTH  # symbol ids 0..4 (-, A, C, G, T) are contiguous
     rows = None
     for _ in range(args.warmup):
         rows = e2e_step()
@@ -447,8 +456,9 @@ def run_ours(args):
     # size-independent parity properties at full size (tests/ hold the bit-exact oracle comparisons)
     column_sums = device_counts.sum(axis=0, dtype=np.uint64)
     assert (column_sums == cardinality).all(), "per-position symbol counts (all-reduced) must add up to the global |filter|"
-    rows = host_api.rows_from_columns(rows)
-    if n_gpus == 1:
+    if rank == 0:
+        rows = host_api.rows_from_columns(rows)
+        # (device_counts: the all-reduced counts of the device-resident loop; thresholded on the host here)
         direct = table.mutation_rows_from_counts("main", device_counts, MIN_PROPORTION)
         assert direct == rows, "device-resident and host-buffer paths must emit identical rows"
 
@@ -474,8 +484,8 @@ def run_ours(args):
                 # N = 1: the output pass runs on the device; the finalize kernel stores the emitted (position,
                 # symbol, count, total) tuples and a 16-byte header (tuple count, filter cardinality, error
                 # flag) straight into page-locked host memory (silo_gpu_query_mutation_hits);
-                # N > 1: the all-reduced count rows of the valid symbols + cardinality and error flag
-                "d2h_bytes_per_step": (len(rows) + 1) * 16 if n_gpus == 1 else valid_values * 4 + 12},
+                # at every N (N > 1: on rank 0, after the all-reduce of the counts on the device)
+                "d2h_bytes_per_step": (len(rows) + 1) * 16},
         "gpu_launches": gpu_launches,
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -301,6 +301,35 @@ int silo_gpu_mutation_counts_async(
    void* cuda_stream
 );
 
+/* The two halves of a Mutations query on a ROW-PARTITIONED table (one process per GPU, each
+ * holding a shard of the chunks): every rank evaluates the filter program on its shard and leaves its
+ * counts in device memory without synchronising (program H2D + filter + counts on `cuda_stream`); the
+ * scheduler sums the counts of the ranks on the same stream (ncclAllReduce: counts are plain addends,
+ * mutations_node.cpp:154-203); one rank then runs the output pass of addMutationsToOutput
+ * (mutations_node.cpp:292-366) over the summed counts and gets only the emitted tuples back, in
+ * page-locked memory owned by the table, ordered by (position, symbol id), valid until the next call.
+ * One query in flight per table: the staged program lives in per-table buffers until the stream has
+ * been synchronised (silo_gpu_mutation_hits_from_counts does). *shard_cardinality (may be NULL): rows of
+ * THIS shard that passed the filter of the preceding silo_gpu_query_mutation_counts_async. */
+int silo_gpu_query_mutation_counts_async(
+   silo_gpu_table* table,
+   const silo_filter_program* program,
+   int column,
+   void* d_counts,
+   void* cuda_stream
+);
+int silo_gpu_mutation_hits_from_counts(
+   silo_gpu_table* table,
+   int column,
+   const void* d_counts,
+   uint64_t valid_symbol_mask,
+   double min_proportion,
+   void* cuda_stream,
+   const silo_mutation_hit** hits,
+   uint64_t* n_hits,
+   uint64_t* shard_cardinality
+);
+
 /* ---- BitmapAggregationNode: co-occurrence / groupBy over sequence positions and indexed columns ---
  * Replaces buildGroups + computeCombinations of operators/bitmap_aggregation_node.cpp:53-139,224-249
  * (reached from BitmapAggregationNode::addToExecPlan :304-356). The groups of a dimension are disjoint,

@@ -80,6 +80,15 @@ silo_host_rows* silo_host_mutations(silo_host_table* table, const char* expressi
 int silo_host_mutations_packed(silo_host_table* table, const char* expression, const char* const* columns, uint32_t n_columns, double min_proportion,
                                void* buffer, uint64_t capacity, uint64_t* n_rows, uint32_t* n_names, uint64_t* needed_bytes);
 int silo_host_packed_fetch(void* buffer, uint64_t capacity);
+/* The Mutations query on a row-partitioned table in two halves (MutationsNode::enqueueShardCounts /
+ * collectRows): every rank parses + compiles the query against its shard and enqueues program upload, filter
+ * and counts on `cuda_stream` (d_counts: n_symbols * genome_length u32 in device memory), the scheduler
+ * all-reduces d_counts on that stream, then ONE rank collects the rows (record batch as above) from the
+ * summed counts. The caller synchronises nothing in between. */
+int silo_host_mutations_enqueue(silo_host_table* table, const char* expression, const char* column, void* d_counts, void* cuda_stream);
+int silo_host_mutations_collect_packed(silo_host_table* table, const char* column, double min_proportion, const void* d_summed_counts, void* cuda_stream,
+                                       void* buffer, uint64_t capacity, uint64_t* n_rows, uint32_t* n_names, uint64_t* needed_bytes,
+                                       uint64_t* shard_cardinality);
 /* thresholding only, on counts the caller summed over shards (multi-GPU) */
 silo_host_rows* silo_host_mutation_rows_from_counts(silo_host_table* table, const char* column, const uint32_t* counts, double min_proportion);
 /* microseconds of the calling thread's last silo_host_mutations call:

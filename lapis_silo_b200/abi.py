@@ -113,6 +113,7 @@ EXPORTED_SYMBOLS = [
     "silo_gpu_filter_cardinality", "silo_gpu_filter_download", "silo_gpu_filter_free",
     "silo_gpu_mutation_counts", "silo_gpu_mutation_counts_symbols", "silo_gpu_query_mutation_counts", "silo_gpu_mutation_counts_async", "silo_gpu_get_stats",
     "silo_gpu_column_set_reference", "silo_gpu_query_mutation_hits", "silo_gpu_query_combinations",
+    "silo_gpu_query_mutation_counts_async", "silo_gpu_mutation_hits_from_counts",
 ]
 
 

@@ -280,7 +280,7 @@ struct StagedQuery {
    uint32_t shared_bytes = 0;
 };
 void stageQueryLocked(silo_gpu_table* table, const silo_filter_program* program, StagedQuery* out);
-void enqueueStagedQuery(silo_gpu_table* table, const StagedQuery& staged, cudaStream_t stream);
+void enqueueStagedQuery(silo_gpu_table* table, const StagedQuery& staged, cudaStream_t stream, bool scalars_are_zero = true);
 void dropQueryGraphsLocked(silo_gpu_table* table);
 
 struct ApiError : std::runtime_error {

@@ -942,11 +942,11 @@ void stageQueryLocked(silo_gpu_table* table, const silo_filter_program* program,
    out->shared_bytes = static_cast<uint32_t>(evalSharedBytes(params.stack_depth, params.has_threshold != 0));
 }
 
-void enqueueStagedQuery(silo_gpu_table* table, const StagedQuery& staged, cudaStream_t stream) {
+void enqueueStagedQuery(silo_gpu_table* table, const StagedQuery& staged, cudaStream_t stream, bool scalars_are_zero) {
    EvalParams params{};
    std::memcpy(&params, staged.params, sizeof(params));
    SILO_CUDA_CHECK(cudaMemcpyAsync(table->d_staging_fixed, table->h_staging_pinned, staged.staged_bytes, cudaMemcpyHostToDevice, stream));
-   launchProgram(table, params, table->query_filter, stream, true);
+   launchProgram(table, params, table->query_filter, stream, scalars_are_zero);
 }
 
 }  // namespace silo

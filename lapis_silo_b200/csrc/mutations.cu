@@ -969,6 +969,68 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    }
 }
 
+// The output pass alone, over counts that are already final -- the multi-GPU scheduler all-reduces the
+// per-rank counts first (counts are plain addends over row partitions) and then asks one rank for the
+// rows: addMutationsToOutput (mutations_node.cpp:307-363) for one position per thread, header written by
+// the last block as in finalizeCountsKernel.
+__global__ void __launch_bounds__(FIN_THREADS) mutationHitsKernel(
+   DevColumn column,
+   const uint32_t* __restrict__ counts,
+   uint32_t* __restrict__ work_state,
+   HitRequest request
+) {
+   const uint32_t genome_length = column.genome_length;
+   const uint32_t p = blockIdx.x * FIN_THREADS + threadIdx.x;
+   if (p < genome_length) {
+      const uint32_t genome_symbol = column.global_reference[p];
+      uint32_t total = 0;
+      uint32_t candidates = 0;
+      for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
+         if (((request.valid_mask >> symbol) & 1ULL) != 0) {
+            const uint32_t value = counts[symbol * genome_length + p];
+            total += value;
+            candidates |= symbol != genome_symbol ? value : 0u;
+         }
+      }
+      if (total != 0 && candidates != 0) {
+         const uint32_t threshold_count =
+            request.min_proportion == 0 ? 0u : static_cast<uint32_t>(ceil(__dmul_rn(static_cast<double>(total), request.min_proportion)) - 1.0);
+         for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
+            if (((request.valid_mask >> symbol) & 1ULL) == 0 || symbol == genome_symbol) {
+               continue;
+            }
+            const uint32_t count = counts[symbol * genome_length + p];
+            if (count > threshold_count) {
+               const uint32_t index = atomicAdd(&work_state[3], 1u);
+               if (index < request.capacity) {
+                  request.hits[1 + index] = silo_mutation_hit{p, symbol, count, total};
+               }
+            }
+         }
+      }
+   }
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      __threadfence();
+      const uint32_t finished = atomicAdd(&work_state[2], 1u);
+      if (finished == gridDim.x - 1) {
+         __threadfence();
+         silo_mutation_hit header{*reinterpret_cast<volatile uint32_t*>(&work_state[3]), 0u, 0u, 0u};
+         if (request.filter_scalars != nullptr) {
+            const unsigned long long cardinality = *reinterpret_cast<volatile unsigned long long*>(&request.filter_scalars[0]);
+            header.symbol = *reinterpret_cast<volatile uint32_t*>(&request.filter_scalars[2]);
+            header.count = static_cast<uint32_t>(cardinality);
+            header.total = static_cast<uint32_t>(cardinality >> 32);
+            request.filter_scalars[0] = 0;
+            request.filter_scalars[2] = 0;
+         }
+         request.hits[0] = header;
+         work_state[2] = 0;
+         work_state[3] = 0;
+      }
+   }
+}
+
 // ---------------------------------------------------------------------------------------------
 
 void enqueueMutationCounts(
@@ -1270,6 +1332,102 @@ static bool queryGraphsEnabled() {
    return enabled;
 }
 
+// page-locked tuple buffer for the worst case: every valid symbol but the reference genome's at every position
+static void ensureHitsCapacity(silo_gpu_table* table, const HostColumn& host, uint64_t valid_symbol_mask, cudaStream_t stream) {
+   const uint64_t needed = static_cast<uint64_t>(__builtin_popcountll(valid_symbol_mask)) * host.dev.genome_length;
+   if (needed > table->hits_capacity || table->h_hits_pinned == nullptr) {
+      SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+      dropQueryGraphsLocked(table);  // their kernel nodes write the old buffer
+      if (table->h_hits_pinned != nullptr) {
+         cudaFreeHost(table->h_hits_pinned);
+         table->h_hits_pinned = nullptr;
+      }
+      SILO_CUDA_CHECK(cudaMallocHost(&table->h_hits_pinned, (needed + 1) * sizeof(silo_mutation_hit)));
+      table->hits_capacity = needed;
+   }
+}
+
+static void sortHits(silo_mutation_hit* first, uint64_t count) {
+   // the kernel appends in whatever order its threads get there: (position, symbol id) order
+   std::sort(first, first + count, [](const silo_mutation_hit& a, const silo_mutation_hit& b) {
+      return a.position != b.position ? a.position < b.position : a.symbol < b.symbol;
+   });
+}
+
+int silo_gpu_query_mutation_counts_async(
+   silo_gpu_table* table,
+   const silo_filter_program* program,
+   int column,
+   void* d_counts,
+   void* cuda_stream
+) {
+   return guarded([&] {
+      require(table != nullptr && program != nullptr && d_counts != nullptr, "silo_gpu_query_mutation_counts_async: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      cudaStream_t stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : table->ctx->stream;
+      const bool trivially_full = program->n_instrs == 1 && program->instrs != nullptr && program->instrs[0].opcode == SILO_OP_PUSH_FULL;
+      if (trivially_full) {
+         enqueueMutationCounts(table, column, nullptr, static_cast<uint32_t*>(d_counts), stream);
+         return;
+      }
+      StagedQuery staged;
+      stageQueryLocked(table, program, &staged);
+      enqueueStagedQuery(table, staged, stream, false);  // (nothing guarantees that a hits call reset the scalars)
+      enqueueMutationCounts(table, column, table->query_filter, static_cast<uint32_t*>(d_counts), stream);
+   });
+}
+
+int silo_gpu_mutation_hits_from_counts(
+   silo_gpu_table* table,
+   int column,
+   const void* d_counts,
+   uint64_t valid_symbol_mask,
+   double min_proportion,
+   void* cuda_stream,
+   const silo_mutation_hit** hits,
+   uint64_t* n_hits,
+   uint64_t* shard_cardinality
+) {
+   return guarded([&] {
+      require(table != nullptr && d_counts != nullptr && hits != nullptr && n_hits != nullptr, "silo_gpu_mutation_hits_from_counts: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      cudaStream_t stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : table->ctx->stream;
+      require(column >= 0 && static_cast<size_t>(column) < table->columns.size(), "silo_gpu_mutation_hits_from_counts: bad column index");
+      const HostColumn& host = *table->columns[static_cast<size_t>(column)];
+      require(host.dev.global_reference != nullptr, "silo_gpu_mutation_hits_from_counts: call silo_gpu_column_set_reference first");
+      if (host.dev.n_symbols < 64) {
+         valid_symbol_mask &= (1ULL << host.dev.n_symbols) - 1;
+      }
+      ensureHitsCapacity(table, host, valid_symbol_mask, stream);
+      HitRequest request;
+      request.hits = table->h_hits_pinned;
+      request.capacity = static_cast<uint32_t>(table->hits_capacity);
+      request.valid_mask = valid_symbol_mask;
+      request.min_proportion = min_proportion;
+      // the filter of a preceding silo_gpu_query_mutation_counts_async: its cardinality and error flag ride along
+      request.filter_scalars = table->query_filter != nullptr ? table->query_filter->d_cardinality : nullptr;
+      mutationHitsKernel<<<(host.dev.genome_length + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, stream>>>(
+         host.dev, static_cast<const uint32_t*>(d_counts), table->d_work_state, request
+      );
+      SILO_CUDA_CHECK(cudaGetLastError());
+      table->stats.kernel_launches++;
+      SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+      const silo_mutation_hit header = table->h_hits_pinned[0];
+      if (header.symbol != 0) {
+         throw ApiError(SILO_E_OUT_OF_LAYOUT, "a leaf bitmap holds row ids outside the row layout");
+      }
+      const uint64_t count = std::min<uint64_t>(header.position, table->hits_capacity);
+      sortHits(table->h_hits_pinned + 1, count);
+      *hits = table->h_hits_pinned + 1;
+      *n_hits = count;
+      if (shard_cardinality != nullptr) {
+         *shard_cardinality = header.count | (static_cast<unsigned long long>(header.total) << 32);
+      }
+   });
+}
+
 int silo_gpu_query_mutation_hits(
    silo_gpu_table* table,
    const silo_filter_program* program,
@@ -1292,18 +1450,7 @@ int silo_gpu_query_mutation_hits(
       if (host.dev.n_symbols < 64) {
          valid_symbol_mask &= (1ULL << host.dev.n_symbols) - 1;
       }
-      // worst case: every valid symbol but the reference genome's at every position
-      const uint64_t needed = static_cast<uint64_t>(__builtin_popcountll(valid_symbol_mask)) * host.dev.genome_length;
-      if (needed > table->hits_capacity || table->h_hits_pinned == nullptr) {
-         SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
-         dropQueryGraphsLocked(table);  // their kernel nodes write the old buffer
-         if (table->h_hits_pinned != nullptr) {
-            cudaFreeHost(table->h_hits_pinned);
-            table->h_hits_pinned = nullptr;
-         }
-         SILO_CUDA_CHECK(cudaMallocHost(&table->h_hits_pinned, (needed + 1) * sizeof(silo_mutation_hit)));
-         table->hits_capacity = needed;
-      }
+      ensureHitsCapacity(table, host, valid_symbol_mask, stream);
       HitRequest request;
       request.hits = table->h_hits_pinned;  // page-locked host memory, written by the finalize kernel
       request.capacity = static_cast<uint32_t>(table->hits_capacity);
@@ -1413,9 +1560,7 @@ int silo_gpu_query_mutation_hits(
       }
       // the kernel appends in whatever order its threads get there: (position, symbol id) order
       silo_mutation_hit* const first = table->h_hits_pinned + 1;
-      std::sort(first, first + count, [](const silo_mutation_hit& a, const silo_mutation_hit& b) {
-         return a.position != b.position ? a.position < b.position : a.symbol < b.symbol;
-      });
+      sortHits(first, count);
       *hits = first;
       *n_hits = count;
       if (cardinality != nullptr && program != nullptr) {

@@ -356,6 +356,46 @@ int silo_host_mutations_packed(
    });
 }
 
+int silo_host_mutations_enqueue(silo_host_table* table, const char* expression, const char* column, void* d_counts, void* cuda_stream) {
+   return guarded([&] {
+      const double parse_begin = nowMicroseconds();
+      ExpressionPtr parsed = parseOrTrue(expression);
+      lastQueryProfile().parse_us = nowMicroseconds() - parse_begin;
+      const MutationsNode node(*table->table, std::move(parsed), {std::string(column)}, 0.0);
+      node.enqueueShardCounts(d_counts, cuda_stream);
+   });
+}
+
+int silo_host_mutations_collect_packed(
+   silo_host_table* table,
+   const char* column,
+   double min_proportion,
+   const void* d_summed_counts,
+   void* cuda_stream,
+   void* buffer,
+   uint64_t capacity,
+   uint64_t* n_rows,
+   uint32_t* n_names,
+   uint64_t* needed_bytes,
+   uint64_t* shard_cardinality
+) {
+   return guarded([&] {
+      g_pending_rows.reset();
+      const MutationsNode node(*table->table, nullptr, {std::string(column)}, min_proportion);
+      auto owned = std::make_unique<silo_host_rows>();
+      owned->rows = node.collectRows(d_summed_counts, cuda_stream, shard_cardinality);
+      owned->indexNames();
+      *n_rows = owned->rows.size();
+      *n_names = static_cast<uint32_t>(owned->names.size());
+      *needed_bytes = packedBytes(*owned);
+      if (*needed_bytes <= capacity) {
+         packRows(*owned, static_cast<uint8_t*>(buffer));
+      } else {
+         g_pending_rows = std::move(owned);
+      }
+   });
+}
+
 int silo_host_packed_fetch(void* buffer, uint64_t capacity) {
    return guarded([&] {
       if (g_pending_rows == nullptr || packedBytes(*g_pending_rows) > capacity) {

@@ -206,6 +206,41 @@ std::vector<MutationRow> MutationsNode::execute() const {
    return rows;
 }
 
+namespace {
+const SequenceColumnInfo& singleColumn(const MutationsNode& node) {
+   if (node.sequence_columns.size() != 1) {
+      throw IllegalQueryException("the sharded Mutations query takes exactly one sequence column");
+   }
+   const SequenceColumnInfo* column = node.table.findColumn(node.sequence_columns.front());
+   if (column == nullptr) {
+      throw IllegalQueryException("Database does not contain the Sequence with name: '" + node.sequence_columns.front() + "'");
+   }
+   return *column;
+}
+}  // namespace
+
+void MutationsNode::enqueueShardCounts(void* d_counts, void* cuda_stream) const {
+   const SequenceColumnInfo& column = singleColumn(*this);
+   const ExpressionPtr rewritten = filter->rewrite(table, AmbiguityMode::NONE);  // computeFilter, compute_filter.cpp:14-21
+   const std::unique_ptr<Operator> compiled = rewritten->compile(table);
+   ProgramBuilder builder;
+   const silo_filter_program program = compiled->lowerProgram(table, builder);
+   throwOnDeviceError(silo_gpu_query_mutation_counts_async(table.device, &program, column.device_column, d_counts, cuda_stream));
+}
+
+std::vector<MutationRow> MutationsNode::collectRows(const void* d_summed_counts, void* cuda_stream, uint64_t* shard_cardinality) const {
+   const SequenceColumnInfo& column = singleColumn(*this);
+   const silo_mutation_hit* hits = nullptr;
+   uint64_t n_hits = 0;
+   throwOnDeviceError(silo_gpu_mutation_hits_from_counts(
+      table.device, column.device_column, d_summed_counts, validSymbolMask(*column.alphabet), min_proportion, cuda_stream, &hits, &n_hits,
+      shard_cardinality
+   ));
+   std::vector<MutationRow> rows;
+   appendRowsFromHits(column, hits, n_hits, rows);
+   return rows;
+}
+
 uint64_t countFilter(const Table& table, const ScalarExpression& filter) {
    return computeFilter(filter, table).cardinality();
 }

@@ -73,6 +73,14 @@ class MutationsNode {
 
    // addToExecPlan + producer (:372-428): the filter is evaluated once, then every column
    [[nodiscard]] std::vector<MutationRow> execute() const;
+
+   // The same query on a row-partitioned table (one process per GPU), in two halves with the
+   // scheduler's all-reduce of the counts in between. Every rank: compile the filter against its shard and
+   // leave the shard's counts of the (single) sequence column in device memory, nothing synchronised.
+   void enqueueShardCounts(void* d_counts, void* cuda_stream) const;
+   // One rank, after the counts of all ranks were summed on the same stream: the output pass over the summed
+   // counts; returns the rows and the number of this shard's rows that passed the filter.
+   [[nodiscard]] std::vector<MutationRow> collectRows(const void* d_summed_counts, void* cuda_stream, uint64_t* shard_cardinality) const;
 };
 
 // CountFilterNode: `filter(...).groupBy({count:=count()})`

@@ -26,7 +26,7 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_filter_prepare", "silo_host_prepared_run_async", "silo_host_prepared_filter",
     "silo_host_prepared_staged_bytes", "silo_host_prepared_free",
     "silo_host_mutation_counts", "silo_host_mutations", "silo_host_mutation_rows_from_counts",
-    "silo_host_mutations_packed", "silo_host_packed_fetch",
+    "silo_host_mutations_packed", "silo_host_packed_fetch", "silo_host_mutations_enqueue", "silo_host_mutations_collect_packed",
     "silo_host_rows_free", "silo_host_rows_size", "silo_host_rows_get", "silo_host_rows_export",
     "silo_host_rows_num_names", "silo_host_rows_name",
     "silo_host_synthetic_create", "silo_host_synthetic_free", "silo_host_synthetic_num_sequences",
@@ -88,6 +88,10 @@ def lib() -> C.CDLL:
             vp, C.c_char_p, C.POINTER(C.c_char_p), C.c_uint32, C.c_double, vp, C.c_uint64,
             C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.silo_host_packed_fetch.argtypes = [vp, C.c_uint64]
+        L.silo_host_mutations_enqueue.argtypes = [vp, C.c_char_p, C.c_char_p, vp, vp]
+        L.silo_host_mutations_collect_packed.argtypes = [
+            vp, C.c_char_p, C.c_double, vp, vp, vp, C.c_uint64,
+            C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.silo_host_mutation_rows_from_counts.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint32), C.c_double]
         L.silo_host_mutation_rows_from_counts.restype = vp
         L.silo_host_rows_free.argtypes = [vp]
@@ -371,6 +375,26 @@ class HostTable:
             self._packed = np.empty(int(needed.value) * 2, dtype=np.uint8)
             _check(lib().silo_host_packed_fetch(self._packed.ctypes.data, self._packed.nbytes))
         return _unpack_record_batch(self._packed[:needed.value].copy(), int(n_rows.value), int(n_names.value))
+
+    def mutations_enqueue(self, column: str, expression: Optional[str], d_counts_ptr: int, stream_ptr: int) -> None:
+        """First half of the Mutations query on a row-partitioned table: parse + compile against this shard,
+        then program upload, filter and counts enqueued on the stream (nothing synchronised). The scheduler
+        all-reduces the counts on the same stream next."""
+        _check(lib().silo_host_mutations_enqueue(
+            self._h, expression.encode() if expression is not None else None, column.encode(), d_counts_ptr, stream_ptr))
+
+    def mutations_collect(self, column: str, min_proportion: float, d_summed_counts_ptr: int, stream_ptr: int) -> tuple[dict, int]:
+        """Second half, on one rank: the output pass over the summed counts on the device, rows back as one
+        record batch. Returns (columns, number of this shard's rows that passed the filter)."""
+        n_rows, n_names, needed = self._packed_out
+        cardinality = C.c_uint64()
+        _check(lib().silo_host_mutations_collect_packed(
+            self._h, column.encode(), min_proportion, d_summed_counts_ptr, stream_ptr,
+            self._packed.ctypes.data, self._packed.nbytes, n_rows, n_names, needed, cardinality))
+        if needed.value > self._packed.nbytes:
+            self._packed = np.empty(int(needed.value) * 2, dtype=np.uint8)
+            _check(lib().silo_host_packed_fetch(self._packed.ctypes.data, self._packed.nbytes))
+        return _unpack_record_batch(self._packed[:needed.value].copy(), int(n_rows.value), int(n_names.value)), int(cardinality.value)
 
     def mutation_columns_from_counts(self, column: str, counts: np.ndarray, min_proportion: float) -> dict:
         counts = np.ascontiguousarray(counts, dtype=np.uint32)

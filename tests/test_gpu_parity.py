@@ -409,6 +409,28 @@ def test_synthetic_shards_sum_to_the_whole(ctx):
     # size-independent property: per position the symbol counts add up to the covered filtered rows
     assert (whole_counts.sum(axis=0) == whole_filter.cardinality).all()
 
+    # The sharded query as the scheduler runs it (bench.py at N > 1, the ranks played by three tables on one
+    # device): every shard enqueues program + filter + counts without synchronising, the counts are summed on
+    # the same stream (the all-reduce), one shard runs the output pass over the sums on the device.
+    import torch
+    stream = torch.cuda.Stream()
+    for repeat, min_proportion in enumerate((0.05, 0.0, 0.3, 0.05)):
+        with torch.cuda.stream(stream):
+            buffers = [torch.zeros(16 * 1500, dtype=torch.int32, device="cuda") for _ in interleaved]
+            for rank, (table, _, _, _) in enumerate(interleaved):
+                first, n, stride = host_api.interleaved_shard(len(sizes), 3, rank)
+                text = f"(and {host_api.date_ranges_expression(total_rows, 1095, 200, 800, first, n, stride)} (bitmap lineage))"
+                table.mutations_enqueue("main", text, buffers[rank].data_ptr(), stream.cuda_stream)
+            summed = buffers[0] + buffers[1] + buffers[2]
+            cardinalities = []
+            # (every shard collects, so that each one's filter scalars are read and reset)
+            for table, _, _, _ in interleaved:
+                columns, shard_cardinality = table.mutations_collect("main", min_proportion, summed.data_ptr(), stream.cuda_stream)
+                cardinalities.append(shard_cardinality)
+                assert host_api.rows_from_columns(columns) == oracle_table.mutations("main", expression, min_proportion)
+            assert sum(cardinalities) == whole_filter.cardinality
+            assert cardinalities == [p[1].cardinality for p in interleaved]
+
 
 def test_baseline_sizes_size_independent_properties(ctx):
     """BASELINE.json configs 2 and 3 at full size (10 M rows x 29,903 nt; the oracle would need minutes per
