@@ -353,8 +353,8 @@ def run_ours(args):
     # dependent kernels of a query and the library's per-kernel timing events are ~12 % of an eager step).
     # Event records inside a capture are not replayed, so the roofline numbers come from a second, EAGER
     # pass over the same K steps right after the timed region: CUDA events on the launching stream around
-    # every launch of the dominant kernel. N > 1 stays eager (NCCL on its own stream).
-    use_graph = n_gpus == 1 and not args.eager
+    # every launch of the dominant kernel. N > 1: the same, the all-reduces (on their own stream) captured too.
+    use_graph = not args.eager
     for _ in range(args.warmup):
         device_step()
     barrier()
@@ -366,9 +366,32 @@ def run_ours(args):
     graph = None
     if use_graph:
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=stream):
-            for _ in range(args.steps):
-                device_step()
+        if n_gpus == 1:
+            with torch.cuda.graph(graph, stream=stream):
+                for _ in range(args.steps):
+                    device_step()
+        else:
+            # N > 1: the same two-stream pipeline, with events that live inside the capture (a captured
+            # stream may only wait for work of the same capture) and the all-reduce stream joined at the end
+            with torch.cuda.graph(graph, stream=stream):
+                reduced_in_graph = []
+                for index in range(args.steps):
+                    buffer = index % len(count_buffers)
+                    if index >= len(count_buffers):
+                        stream.wait_event(reduced_in_graph[index - len(count_buffers)])
+                    prepared.run_async(stream.cuda_stream)
+                    table.mutation_counts_async(0, prepared, count_buffers[buffer].data_ptr(), stream.cuda_stream)
+                    done = torch.cuda.Event()
+                    done.record(stream)
+                    comm_stream.wait_event(done)
+                    with torch.cuda.stream(comm_stream):
+                        dist.all_reduce(count_buffers[buffer][:valid_values])
+                        event = torch.cuda.Event()
+                        event.record(comm_stream)
+                    reduced_in_graph.append(event)
+                for event in reduced_in_graph[-len(count_buffers):]:
+                    stream.wait_event(event)
+            issued[0] += args.steps
         graph.replay()  # instantiation / upload outside the timed region
         barrier()
 
@@ -462,7 +485,14 @@ def run_ours(args):
         direct = table.mutation_rows_from_counts("main", device_counts, MIN_PROPORTION)
         assert direct == rows, "device-resident and host-buffer paths must emit identical rows"
 
+    used_graph = graph is not None
+    if n_gpus > 1:
+        # release the captured graph (it holds NCCL kernels) before the communicator goes away, on every rank
+        graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
     if rank != 0:
+        dist.destroy_process_group()
         return
     peak, peak_source = measured_peak_gbs()
     kernel_ms = float(stats.last_counts_kernel_ms)
@@ -474,7 +504,8 @@ def run_ours(args):
         "config": workload_config(args, cardinality, {
             "total_rows": total_rows, "chunks_per_gpu": n_chunks, "containers_per_gpu": n_containers,
             "payload_gb_per_gpu": round(payload_bytes / 1e9, 3),
-            "launch": f"one CUDA graph holding the {args.steps} steps of the timed region" if graph is not None else "eager launches",
+            "launch": f"one CUDA graph holding the {args.steps} steps of the timed region" + (", all-reduces included" if n_gpus > 1 else "")
+            if used_graph else "eager launches",
             "parallelism": f"interleaved chunk shards (chunk c on rank c % {n_gpus}), "
             "NCCL allreduce of the u32 counts" if n_gpus > 1 else "single GPU", "output_rows": len(rows),
         }),
@@ -493,7 +524,7 @@ def run_ours(args):
             "algorithmic_bytes_per_launch": int(stats.counts_kernel_bytes), "kernel_ms": kernel_ms,
             "timed_launches": int(stats.timed_calls), "peak_source": peak_source,
             "timed_with": "CUDA events on the launching stream around every launch, " + (
-                "eager pass over the same steps right after the graph-timed region" if graph is not None else "inside the timed region"),
+                "eager pass over the same steps right after the graph-timed region" if used_graph else "inside the timed region"),
             "whole_query_algorithmic_bytes": int(stats.algorithmic_bytes), "whole_query_ms": float(stats.last_total_ms),
         },
     }
@@ -525,7 +556,7 @@ def main():
     parser.add_argument("--cpu-seconds", type=float, default=12.0)
     parser.add_argument("--reference-step-seconds", type=float, default=4.0)
     parser.add_argument("--skip-cpu-baseline", action="store_true")
-    parser.add_argument("--eager", action="store_true", help="N = 1: launch the timed steps one by one instead of as one CUDA graph")
+    parser.add_argument("--eager", action="store_true", help="launch the timed steps one by one instead of as one CUDA graph")
     parser.add_argument("--traffic-bytes", type=int, default=None,
                         help="dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture")
     args = parser.parse_args()
