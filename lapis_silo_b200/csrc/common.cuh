@@ -98,13 +98,14 @@ struct __align__(16) DevContainer {
 };
 static_assert(sizeof(DevContainer) == 16);
 
-// A segment = consecutive containers of ONE chunk whose descriptors and payloads are contiguous,
-// moved into shared memory by two 1-D bulk (TMA) copies. 16 bytes: the producer warp of the container
+// A segment = up to SEG_MAX_DESCS pieces of ONE chunk as one block of the slab, [descriptors | payloads] (the
+// descriptors are copies of the chunk-major ones the filter interpreter searches), moved into shared memory
+// by ONE 1-D bulk (TMA) copy. 16 bytes: the producer warp of the container
 // kernel fetches one record per lane with a single 128-bit load and keeps two batches of them in flight.
 struct __align__(16) DevSegment {
-   uint32_t payload_offset16;  // from the slab start, in 16-byte units (the slab is <= 16 GiB, see DevContainer::offset4)
-   uint32_t payload_bytes;     // multiple of 16, <= SEG_PAYLOAD_BYTES
-   uint32_t desc_begin;
+   uint32_t payload_offset16;  // block start from the slab start, in 16-byte units (the slab is <= 16 GiB, see DevContainer::offset4)
+   uint32_t payload_bytes;     // block bytes: 16 per descriptor + payloads; multiple of 16, <= SEG_PAYLOAD_BYTES + 16 * SEG_MAX_DESCS
+   uint32_t desc_begin;        // unused
    uint32_t chunk_and_count;   // [15:0] local chunk index | [31:16] number of descriptors (<= SEG_MAX_DESCS)
 
    __host__ __device__ uint32_t chunk() const { return chunk_and_count & 0xFFFFu; }

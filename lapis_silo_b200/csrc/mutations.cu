@@ -111,7 +111,7 @@ constexpr uint32_t K1_STOP = 0xFFFFFFFFu;              // meta.x marker: no more
 constexpr uint32_t TILE32_WORDS = 2 * TILE_WORDS;
 constexpr uint32_t TILE_BUFFER_BYTES = (TILE32_WORDS + 4) * 4;  // [2048] = the zero pad word
 
-struct __align__(16) K1Stage {
+struct __align__(16) K1Stage {  // one segment block: n descriptors, then their payloads (<= this size)
    uint8_t payload[SEG_PAYLOAD_BYTES];
    DevContainer descs[SEG_MAX_DESCS];
 };
@@ -507,7 +507,6 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
          const uint32_t my_round = my_it / K1_STAGES;
          const uint32_t my_control = control_address + my_stage * static_cast<uint32_t>(sizeof(K1Control));
          const uint32_t my_ring = ring_address + my_stage * static_cast<uint32_t>(sizeof(K1Stage));
-         const uint32_t desc_bytes = mine.descCount() * static_cast<uint32_t>(sizeof(DevContainer));
          const uint4 meta = make_uint4(
             mine.descCount(), mine.payload_offset16 << 2,
             (new_tile ? K1_NEW_TILE : 0u) | (my_slot != 0 ? K1_TILE_SLOT : 0u), 0u
@@ -534,17 +533,15 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
                   }
                }
                sts128(my_control, meta);
-               mbarExpectTxAt(my_control + K1_CTRL_FULL, desc_bytes + mine.payload_bytes + (new_tile ? TILE_BYTES : 0u));
+               mbarExpectTxAt(my_control + K1_CTRL_FULL, mine.payload_bytes + (new_tile ? TILE_BYTES : 0u));
                if (new_tile) {
                   bulkLoadAt(
                      tile_address0 + my_slot * TILE_BUFFER_BYTES, filter_words + static_cast<size_t>(mine.chunk()) * TILE_WORDS, TILE_BYTES,
                      my_control + K1_CTRL_FULL
                   );
                }
-               bulkLoadAt(my_ring + SEG_PAYLOAD_BYTES, column.containers + mine.desc_begin, desc_bytes, my_control + K1_CTRL_FULL);
-               if (mine.payload_bytes != 0) {
-                  bulkLoadAt(my_ring, column.payload + mine.payloadOffset(), mine.payload_bytes, my_control + K1_CTRL_FULL);
-               }
+               // the segment's block [descriptors | payloads] in one copy
+               bulkLoadAt(my_ring, column.payload + mine.payloadOffset(), mine.payload_bytes, my_control + K1_CTRL_FULL);
             }
             __syncwarp();
          }
@@ -655,7 +652,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
       uint4 desc = make_uint4(0u, 0u, 0u, 0u);
       uint32_t count = 0;
       if (index < desc_count && MODE != 1) {
-         desc = lds128(stage_address + SEG_PAYLOAD_BYTES + index * 16);  // {position, offset4, packed, aux}
+         desc = lds128(stage_address + index * 16);  // {position, offset4, packed, aux}: the block starts with its descriptors
          const uint32_t payload_address = stage_address + ((desc.y - meta.y) << 2);
          const uint32_t kind = (desc.z >> 26) & 7u;
          if (kind == KIND_WORDRANGE) {  // rare; reads the stage while it works

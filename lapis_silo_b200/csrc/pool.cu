@@ -399,6 +399,15 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
       column->chunk_desc_payload_bytes.assign(n_chunks, 0);
       column->chunk_containers.assign(n_chunks, 0);
 
+      struct PendingPiece {
+         DevContainer desc;
+         size_t byte_offset;
+         uint32_t bytes;
+         uint32_t cost_class;
+      };
+      std::vector<PendingPiece> chunk_pieces;
+      std::vector<uint8_t> chunk_bytes;
+      std::vector<uint32_t> piece_order;
       std::vector<uint8_t> scratch;
       std::vector<uint32_t> word_entries;
       std::vector<uint32_t> word_ranges;
@@ -406,49 +415,66 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
       for (uint32_t chunk = 0; chunk < n_chunks; ++chunk) {
          chunk_desc_begin[chunk] = static_cast<uint32_t>(descs.size());
          chunk_seg_begin[chunk] = static_cast<uint32_t>(segments.size());
-         DevSegment segment{};
-         bool open = false;
+         // A segment is ONE block of the slab: [its descriptors, 16 bytes each | the payloads they point at],
+         // so that the container kernel's producer moves it into a ring stage with a single bulk copy.
+         std::vector<uint32_t> segment_pieces;   // indices into chunk_pieces
+         std::vector<uint32_t> segment_offsets;  // payload offset of each piece behind the descriptors
+         uint32_t segment_payload = 0;
          auto closeSegment = [&]() {
-            if (!open) {
+            if (segment_pieces.empty()) {
                return;
             }
             slab.resize((slab.size() + 15) / 16 * 16, 0);
-            segment.payload_bytes = static_cast<uint32_t>(slab.size() - segment.payloadOffset());
-            segments.push_back(segment);
-            open = false;
-         };
-         // appends one piece: descriptor + (16-byte aligned) payload, opening a new segment if needed
-         auto emitPiece = [&](const silo_container_desc& c, uint32_t kind, uint32_t cardinality, uint32_t aux,
-                              const uint8_t* src, uint32_t bytes) {
-            const uint32_t padded = (bytes + 15) / 16 * 16;
-            if (open) {
-               const auto used = static_cast<uint32_t>(slab.size() - segment.payloadOffset());
-               if (segment.descCount() == SEG_MAX_DESCS || used + padded > SEG_PAYLOAD_BYTES) {
-                  closeSegment();
+            const uint64_t block_start = slab.size();
+            const uint64_t payload_start = block_start + sizeof(DevContainer) * segment_pieces.size();
+            require((payload_start + segment_payload) / 4 <= UINT32_MAX, "column payload exceeds the 16 GiB per-shard addressing limit");
+            slab.resize(payload_start + segment_payload, 0);
+            for (size_t i = 0; i < segment_pieces.size(); ++i) {
+               PendingPiece& piece = chunk_pieces[segment_pieces[i]];
+               piece.desc.offset4 = static_cast<uint32_t>((payload_start + segment_offsets[i]) / 4);
+               std::memcpy(slab.data() + block_start + sizeof(DevContainer) * i, &piece.desc, sizeof(DevContainer));
+               if (piece.bytes > 0) {
+                  std::memcpy(slab.data() + payload_start + segment_offsets[i], chunk_bytes.data() + piece.byte_offset, piece.bytes);
                }
             }
-            if (!open) {
-               slab.resize((slab.size() + 15) / 16 * 16, 0);
-               segment = DevSegment{};
-               require(slab.size() / 16 <= UINT32_MAX, "column payload exceeds the 16 GiB per-shard addressing limit");
-               segment.payload_offset16 = static_cast<uint32_t>(slab.size() / 16);
-               segment.desc_begin = static_cast<uint32_t>(descs.size());
-               segment.chunk_and_count = chunk;  // no descriptors yet
-               open = true;
-            }
-            const uint64_t offset = slab.size();
-            require(offset / 4 <= UINT32_MAX, "column payload exceeds the 16 GiB per-shard addressing limit");
+            DevSegment segment{};
+            segment.payload_offset16 = static_cast<uint32_t>(block_start / 16);
+            segment.payload_bytes = static_cast<uint32_t>(payload_start + segment_payload - block_start);
+            segment.desc_begin = 0;
+            segment.chunk_and_count = chunk | (static_cast<uint32_t>(segment_pieces.size()) << 16);
+            segments.push_back(segment);
+            segment_pieces.clear();
+            segment_offsets.clear();
+            segment_payload = 0;
+         };
+         // The pieces of the chunk are first collected in (position, symbol) order -- the order of `descs`, which
+         // the filter interpreter searches -- and then laid out for the container kernel (placePiece below).
+         chunk_pieces.clear();
+         chunk_bytes.clear();
+         auto emitPiece = [&](const silo_container_desc& c, uint32_t kind, uint32_t cardinality, uint32_t aux,
+                              const uint8_t* src, uint32_t bytes) {
+            PendingPiece piece{};
+            piece.desc.position = c.position;
+            piece.desc.packed = DevContainer::pack(cardinality, c.symbol, in->local_reference[c.position], kind);
+            piece.desc.aux = aux;
+            piece.byte_offset = chunk_bytes.size();
+            piece.bytes = bytes;
+            // what a consumer warp of the container kernel spends on the piece: regions of lookups
+            piece.cost_class = kind == KIND_INLINE ? 0u : kind == KIND_WORDRANGE ? 5u : kind == KIND_BITSET ? 4u : bytes <= 512 ? 1u : 2u;
             if (bytes > 0) {
-               slab.insert(slab.end(), src, src + bytes);
-               slab.resize(offset + padded, 0);
+               chunk_bytes.insert(chunk_bytes.end(), src, src + bytes);
             }
-            DevContainer d{};
-            d.position = c.position;
-            d.offset4 = static_cast<uint32_t>(offset / 4);
-            d.packed = DevContainer::pack(cardinality, c.symbol, in->local_reference[c.position], kind);
-            d.aux = aux;
-            descs.push_back(d);
-            segment.chunk_and_count += 1u << 16;
+            chunk_pieces.push_back(piece);
+         };
+         // appends one piece to the open segment (container-kernel order), closing it first when it is full
+         auto placePiece = [&](uint32_t index) {
+            const uint32_t padded = (chunk_pieces[index].bytes + 15) / 16 * 16;
+            if (segment_pieces.size() == SEG_MAX_DESCS || segment_payload + padded > SEG_PAYLOAD_BYTES) {
+               closeSegment();
+            }
+            segment_pieces.push_back(index);
+            segment_offsets.push_back(segment_payload);
+            segment_payload += padded;
          };
          while (cursor < order.size() && in->containers[order[cursor]].v_index == first_chunk + chunk) {
             const silo_container_desc& c = in->containers[order[cursor]];
@@ -522,7 +548,22 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
             column->chunk_containers[chunk]++;
             ++cursor;
          }
+         // Container-kernel order: pieces of equal cost next to each other, so that the (at most 16) pieces of
+         // a ring stage keep its 16 consumer warps busy for the same time -- a warp can run at most
+         // K1_STAGES - 1 stages ahead of the slowest one, and with 1- and 2-region pieces mixed in every stage
+         // the warps spent 16 % of their time waiting for each other. Counts are sums: the order is free.
+         piece_order.resize(chunk_pieces.size());
+         std::iota(piece_order.begin(), piece_order.end(), 0u);
+         std::stable_sort(piece_order.begin(), piece_order.end(), [&](uint32_t a, uint32_t b) {
+            return chunk_pieces[a].cost_class > chunk_pieces[b].cost_class;
+         });
+         for (const uint32_t index : piece_order) {
+            placePiece(index);
+         }
          closeSegment();
+         for (const PendingPiece& piece : chunk_pieces) {
+            descs.push_back(piece.desc);  // (position, symbol) order, same payload offsets
+         }
       }
       require(descs.size() <= UINT32_MAX, "too many container pieces for 32-bit descriptor indices");
       chunk_desc_begin[n_chunks] = static_cast<uint32_t>(descs.size());
