@@ -314,8 +314,7 @@ def run_ours(args):
         issued[0] += 1
         if n_gpus > 1:
             stream.wait_event(reduced[buffer])  # the all-reduce that used this buffer two queries ago
-        prepared.run_async(stream.cuda_stream)
-        table.mutation_counts_async(0, prepared, count_buffers[buffer].data_ptr(), stream.cuda_stream)
+        prepared.run_counts_async(0, count_buffers[buffer].data_ptr(), stream.cuda_stream)  # filter + counts kernels
         if n_gpus > 1:
             kernels_done[buffer].record(stream)
             comm_stream.wait_event(kernels_done[buffer])
@@ -379,8 +378,7 @@ def run_ours(args):
                     buffer = index % len(count_buffers)
                     if index >= len(count_buffers):
                         stream.wait_event(reduced_in_graph[index - len(count_buffers)])
-                    prepared.run_async(stream.cuda_stream)
-                    table.mutation_counts_async(0, prepared, count_buffers[buffer].data_ptr(), stream.cuda_stream)
+                    prepared.run_counts_async(0, count_buffers[buffer].data_ptr(), stream.cuda_stream)
                     done = torch.cuda.Event()
                     done.record(stream)
                     comm_stream.wait_event(done)

@@ -202,6 +202,10 @@ int silo_gpu_filter_eval(
 typedef struct silo_gpu_program silo_gpu_program;
 int silo_gpu_program_prepare(silo_gpu_table* table, const silo_filter_program* program, silo_gpu_program** out, silo_gpu_filter** filter_out);
 int silo_gpu_program_run_async(silo_gpu_program* prepared, void* cuda_stream);
+/* The prepared program and the Mutations counts of its filter for one column, enqueued on `cuda_stream`
+ * without synchronising: silo_gpu_program_run_async + silo_gpu_mutation_counts_async with one launch less
+ * (the interpreter also zeroes d_counts and builds the container kernel's work list). */
+int silo_gpu_program_run_counts_async(silo_gpu_program* prepared, int column, void* d_counts, void* cuda_stream);
 uint64_t silo_gpu_program_device_bytes(const silo_gpu_program* prepared); /* bytes uploaded by _prepare */
 void silo_gpu_program_free(silo_gpu_program* prepared); /* does not free the filter handle */
 

@@ -61,6 +61,8 @@ int silo_host_bitmap_aggregation(silo_host_table* table, const char* expression,
 typedef struct silo_host_prepared silo_host_prepared;
 silo_host_prepared* silo_host_filter_prepare(silo_host_table* table, const char* expression);
 int silo_host_prepared_run_async(silo_host_prepared* prepared, void* cuda_stream);
+/* filter + Mutations counts of one column (index in add order) into d_counts, enqueued only (silo_gpu_program_run_counts_async) */
+int silo_host_prepared_run_counts_async(silo_host_prepared* prepared, int column_index, void* d_counts, void* cuda_stream);
 const silo_gpu_filter* silo_host_prepared_filter(const silo_host_prepared* prepared);
 uint64_t silo_host_prepared_staged_bytes(const silo_host_prepared* prepared);
 void silo_host_prepared_free(silo_host_prepared* prepared);

@@ -107,7 +107,7 @@ EXPORTED_SYMBOLS = [
     "silo_gpu_last_error", "silo_gpu_version", "silo_gpu_init", "silo_gpu_shutdown",
     "silo_gpu_table_create", "silo_gpu_table_free", "silo_gpu_column_upload",
     "silo_gpu_table_device_bytes", "silo_gpu_filter_eval", "silo_gpu_program_prepare",
-    "silo_gpu_program_run_async", "silo_gpu_program_device_bytes", "silo_gpu_program_free",
+    "silo_gpu_program_run_async", "silo_gpu_program_run_counts_async", "silo_gpu_program_device_bytes", "silo_gpu_program_free",
     "silo_gpu_host_alloc", "silo_gpu_host_free",
     "silo_gpu_filter_from_words", "silo_gpu_bitmap_register", "silo_gpu_bitmap_unregister",
     "silo_gpu_filter_cardinality", "silo_gpu_filter_download", "silo_gpu_filter_free",
@@ -151,6 +151,7 @@ def lib() -> C.CDLL:
         L.silo_gpu_filter_eval.argtypes = [vp, C.POINTER(FilterProgram), C.POINTER(vp), C.POINTER(C.c_uint64)]
         L.silo_gpu_program_prepare.argtypes = [vp, C.POINTER(FilterProgram), C.POINTER(vp), C.POINTER(vp)]
         L.silo_gpu_program_run_async.argtypes = [vp, vp]
+        L.silo_gpu_program_run_counts_async.argtypes = [vp, C.c_int, vp, vp]
         L.silo_gpu_program_device_bytes.argtypes = [vp]
         L.silo_gpu_program_device_bytes.restype = C.c_uint64
         L.silo_gpu_program_free.argtypes = [vp]

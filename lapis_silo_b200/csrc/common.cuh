@@ -276,13 +276,18 @@ void releaseFilterLocked(silo_gpu_filter* filter);
 // into table->h_staging_pinned (device addresses inside refer to table->d_staging_fixed);
 // enqueueStagedQuery issues the H2D copy and the interpreter kernel into table->query_filter.
 struct StagedQuery {
-   alignas(16) unsigned char params[128];  // the interpreter's kernel parameters (filter_eval.cu EvalParams)
+   alignas(16) unsigned char params[160];  // the interpreter's kernel parameters (filter_eval.cu EvalParams)
    uint64_t staged_bytes = 0;
    uint32_t shared_bytes = 0;
 };
-void stageQueryLocked(silo_gpu_table* table, const silo_filter_program* program, StagedQuery* out);
+// prepare_column >= 0: the interpreter also zeroes prepare_counts and builds the container kernel's work list for that
+// column (the caller then passes prepared = true to enqueueMutationCounts)
+void stageQueryLocked(silo_gpu_table* table, const silo_filter_program* program, StagedQuery* out, int prepare_column = -1, uint32_t* prepare_counts = nullptr);
 void enqueueStagedQuery(silo_gpu_table* table, const StagedQuery& staged, cudaStream_t stream, bool scalars_are_zero = true);
 void dropQueryGraphsLocked(silo_gpu_table* table);
+// mutations.cu: coverage + container + finalize kernels for a filter whose interpreter launch already zeroed
+// d_counts and built the work list (caller holds table->mutex); records the per-call timing events
+void enqueuePreparedCountsLocked(silo_gpu_table* table, int column, const silo_gpu_filter* filter, uint32_t* d_counts, cudaStream_t stream);
 
 struct ApiError : std::runtime_error {
    int status;
@@ -352,6 +357,23 @@ T* deviceUpload(const std::vector<T>& host, cudaStream_t stream, uint64_t* accou
 // ---- device helpers shared by the kernels ---------------------------------------------------
 
 #ifdef __CUDACC__
+
+// zeroes words[0 .. n_words) with n_threads threads (128-bit stores when the array is 16-byte aligned)
+__device__ __forceinline__ void zeroCountWords(uint32_t* words, uint32_t n_words, uint32_t thread, uint32_t n_threads) {
+   if ((reinterpret_cast<uintptr_t>(words) & 15u) == 0) {
+      uint4* vectors = reinterpret_cast<uint4*>(words);
+      for (uint32_t i = thread; i < n_words / 4; i += n_threads) {
+         vectors[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      for (uint32_t i = (n_words & ~3u) + thread; i < n_words; i += n_threads) {
+         words[i] = 0;
+      }
+   } else {
+      for (uint32_t i = thread; i < n_words; i += n_threads) {
+         words[i] = 0;
+      }
+   }
+}
 
 __device__ __forceinline__ uint32_t smemAddr(const void* ptr) {
    return static_cast<uint32_t>(__cvta_generic_to_shared(ptr));

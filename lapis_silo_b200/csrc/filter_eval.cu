@@ -49,6 +49,16 @@ struct EvalParams {
    uint32_t* out_popcount;
    unsigned long long* out_cardinality;
    uint32_t* error_flag;
+   // Fused query only (nullptr otherwise): the interpreter also does what prepareQueryKernel does for the counts
+   // kernels of ONE column -- zero the counts, and CTA c appends the segment records of chunk c to the container
+   // kernel's work list when the chunk holds a filtered row -- so the query has one launch less.
+   const DevSegment* prepare_segments;
+   const uint32_t* prepare_chunk_seg_begin;
+   uint32_t* prepare_work_state;
+   DevSegment* prepare_work_items;
+   uint32_t* prepare_counts;
+   uint32_t prepare_counts_words;
+   uint32_t pad1;
 };
 
 // Dynamic shared memory of the interpreter: [small | stack_depth tiles | 128 KiB of counters if the
@@ -356,12 +366,30 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
    if (lane == 0) {
       sh.reduce[warp] = total;
    }
+   if (p.prepare_counts != nullptr) {
+      zeroCountWords(p.prepare_counts, p.prepare_counts_words, chunk * EVAL_THREADS + tid, gridDim.x * EVAL_THREADS);
+   }
    __syncthreads();
    if (warp == 0) {
       total = __reduce_add_sync(0xFFFFFFFFu, sh.reduce[lane]);
       if (lane == 0) {
          p.out_popcount[chunk] = total;
          atomicAdd(p.out_cardinality, static_cast<unsigned long long>(total));
+         if (p.prepare_work_items != nullptr) {
+            const uint32_t first_segment = p.prepare_chunk_seg_begin[chunk];
+            const uint32_t n_segments = total != 0 ? p.prepare_chunk_seg_begin[chunk + 1] - first_segment : 0u;
+            sh.range[0] = n_segments != 0 ? atomicAdd(&p.prepare_work_state[0], n_segments) : 0u;
+            sh.range[1] = n_segments;
+         }
+      }
+   }
+   if (p.prepare_work_items != nullptr) {  // (kernel parameter: uniform)
+      __syncthreads();
+      const uint32_t n_segments = sh.range[1];
+      const uint4* source = reinterpret_cast<const uint4*>(p.prepare_segments + p.prepare_chunk_seg_begin[chunk]);
+      uint4* target = reinterpret_cast<uint4*>(p.prepare_work_items + sh.range[0]);
+      for (uint32_t i = tid; i < n_segments; i += EVAL_THREADS) {
+         target[i] = source[i];
       }
    }
 }
@@ -914,7 +942,7 @@ void dropQueryGraphsLocked(silo_gpu_table* table) {
    table->last_query_key.clear();
 }
 
-void stageQueryLocked(silo_gpu_table* table, const silo_filter_program* program, StagedQuery* out) {
+void stageQueryLocked(silo_gpu_table* table, const silo_filter_program* program, StagedQuery* out, int prepare_column, uint32_t* prepare_counts) {
    static_assert(sizeof(EvalParams) <= sizeof(out->params));
    if (table->query_filter == nullptr) {  // persistent: plain device memory, not the stream-ordered pool
       auto filter = std::make_unique<silo_gpu_filter>();
@@ -937,6 +965,17 @@ void stageQueryLocked(silo_gpu_table* table, const silo_filter_program* program,
    params.out_popcount = table->query_filter->d_chunk_popcount;
    params.out_cardinality = table->query_filter->d_cardinality;
    params.error_flag = table->query_filter->d_error_flag;
+   if (prepare_column >= 0 && table->n_chunks > 0) {
+      const HostColumn& host = *table->columns[static_cast<size_t>(prepare_column)];
+      if (host.dev.n_segments > 0) {
+         params.prepare_segments = host.dev.segments;
+         params.prepare_chunk_seg_begin = host.dev.chunk_seg_begin;
+         params.prepare_work_state = table->d_work_state;
+         params.prepare_work_items = table->d_work_items;
+      }
+      params.prepare_counts = prepare_counts;
+      params.prepare_counts_words = host.dev.n_symbols * host.dev.genome_length;
+   }
    std::memset(out->params, 0, sizeof(out->params));
    std::memcpy(out->params, &params, sizeof(params));
    out->shared_bytes = static_cast<uint32_t>(evalSharedBytes(params.stack_depth, params.has_threshold != 0));
@@ -1036,6 +1075,31 @@ int silo_gpu_program_run_async(silo_gpu_program* prepared, void* cuda_stream) {
       SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
       cudaStream_t stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : table->ctx->stream;
       launchProgram(table, *prepared->params, prepared->filter, stream);
+   });
+}
+
+int silo_gpu_program_run_counts_async(silo_gpu_program* prepared, int column, void* d_counts, void* cuda_stream) {
+   return guarded([&] {
+      require(prepared != nullptr && d_counts != nullptr, "silo_gpu_program_run_counts_async: NULL argument");
+      silo_gpu_table* table = prepared->table;
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      require(column >= 0 && static_cast<size_t>(column) < table->columns.size(), "silo_gpu_program_run_counts_async: bad column index");
+      cudaStream_t stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : table->ctx->stream;
+      EvalParams params = *prepared->params;
+      const HostColumn& host = *table->columns[static_cast<size_t>(column)];
+      if (table->n_chunks > 0) {
+         if (host.dev.n_segments > 0) {
+            params.prepare_segments = host.dev.segments;
+            params.prepare_chunk_seg_begin = host.dev.chunk_seg_begin;
+            params.prepare_work_state = table->d_work_state;
+            params.prepare_work_items = table->d_work_items;
+         }
+         params.prepare_counts = static_cast<uint32_t*>(d_counts);
+         params.prepare_counts_words = host.dev.n_symbols * host.dev.genome_length;
+      }
+      launchProgram(table, params, prepared->filter, stream);
+      enqueuePreparedCountsLocked(table, column, prepared->filter, static_cast<uint32_t*>(d_counts), stream);
    });
 }
 

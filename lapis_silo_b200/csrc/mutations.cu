@@ -31,22 +31,6 @@ namespace {
 // are zero when a query starts (finalizeCountsKernel resets them).
 constexpr int PREP_THREADS = 256;
 
-__device__ __forceinline__ void zeroWords(uint32_t* words, uint32_t n_words, uint32_t thread, uint32_t n_threads) {
-   if ((reinterpret_cast<uintptr_t>(words) & 15u) == 0) {
-      uint4* vectors = reinterpret_cast<uint4*>(words);
-      for (uint32_t i = thread; i < n_words / 4; i += n_threads) {
-         vectors[i] = make_uint4(0u, 0u, 0u, 0u);
-      }
-      for (uint32_t i = (n_words & ~3u) + thread; i < n_words; i += n_threads) {
-         words[i] = 0;
-      }
-   } else {
-      for (uint32_t i = thread; i < n_words; i += n_threads) {
-         words[i] = 0;
-      }
-   }
-}
-
 // One launch in front of the container kernel instead of two memsets and a scan: every CTA zeroes a
 // slice of the counts, and CTA c
 // -- when chunk c holds a filtered row -- reserves room in the work list with one atomic and copies
@@ -76,7 +60,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prepareQueryKernel(
    }
    const uint32_t thread = blockIdx.x * PREP_THREADS + threadIdx.x;
    const uint32_t n_threads = gridDim.x * PREP_THREADS;
-   zeroWords(counts, counts_words, thread, n_threads);
+   zeroCountWords(counts, counts_words, thread, n_threads);
    __syncthreads();
    if (n_segments != 0) {
       const uint4* source = reinterpret_cast<const uint4*>(column.segments + first_segment);
@@ -1037,7 +1021,8 @@ void enqueueMutationCounts(
    uint32_t* d_counts,
    cudaStream_t stream,
    const HitRequest* request = nullptr,
-   bool timed = false  // record the per-call CUDA events that silo_gpu_get_stats reads (measurement only)
+   bool timed = false,    // record the per-call CUDA events that silo_gpu_get_stats reads (measurement only)
+   bool prepared = false  // the filter interpreter already zeroed d_counts and built the work list (fused query)
 ) {
    require(table != nullptr, "mutation_counts: table is NULL");
    require(column_index >= 0 && static_cast<size_t>(column_index) < table->columns.size(), "mutation_counts: bad column index");
@@ -1091,13 +1076,15 @@ void enqueueMutationCounts(
    SILO_CUDA_CHECK(cudaGetLastError());
    SILO_CUDA_CHECK(cudaEventRecord(table->ev_join, table->aux_stream));
 
-   const int prepare_blocks = static_cast<int>(std::max<uint32_t>(n_chunks, static_cast<uint32_t>(table->ctx->sm_count)));
-   prepareQueryKernel<<<prepare_blocks, PREP_THREADS, 0, stream>>>(
-      column, filter != nullptr ? popcounts : nullptr, table->d_work_state, table->d_work_items, d_counts,
-      static_cast<uint32_t>(counts_bytes / sizeof(uint32_t))
-   );
-   SILO_CUDA_CHECK(cudaGetLastError());
-   table->stats.kernel_launches += 1;
+   if (!prepared) {
+      const int prepare_blocks = static_cast<int>(std::max<uint32_t>(n_chunks, static_cast<uint32_t>(table->ctx->sm_count)));
+      prepareQueryKernel<<<prepare_blocks, PREP_THREADS, 0, stream>>>(
+         column, filter != nullptr ? popcounts : nullptr, table->d_work_state, table->d_work_items, d_counts,
+         static_cast<uint32_t>(counts_bytes / sizeof(uint32_t))
+      );
+      SILO_CUDA_CHECK(cudaGetLastError());
+      table->stats.kernel_launches += 1;
+   }
 
    recordTiming(ev_k1_begin);
    if (filter == nullptr) {
@@ -1157,6 +1144,10 @@ void enqueueMutationCounts(
 }
 
 }  // namespace
+
+void enqueuePreparedCountsLocked(silo_gpu_table* table, int column, const silo_gpu_filter* filter, uint32_t* d_counts, cudaStream_t stream) {
+   enqueueMutationCounts(table, column, filter, d_counts, stream, nullptr, true, true);
+}
 
 }  // namespace silo
 
@@ -1369,9 +1360,10 @@ int silo_gpu_query_mutation_counts_async(
          return;
       }
       StagedQuery staged;
-      stageQueryLocked(table, program, &staged);
+      require(column >= 0 && static_cast<size_t>(column) < table->columns.size(), "silo_gpu_query_mutation_counts_async: bad column index");
+      stageQueryLocked(table, program, &staged, column, static_cast<uint32_t*>(d_counts));
       enqueueStagedQuery(table, staged, stream, false);  // (nothing guarantees that a hits call reset the scalars)
-      enqueueMutationCounts(table, column, table->query_filter, static_cast<uint32_t*>(d_counts), stream);
+      enqueueMutationCounts(table, column, table->query_filter, static_cast<uint32_t*>(d_counts), stream, nullptr, false, true);
    });
 }
 
@@ -1467,7 +1459,8 @@ int silo_gpu_query_mutation_hits(
       StagedQuery staged;
       QueryTrace trace;
       if (own_program) {
-         stageQueryLocked(table, program, &staged);  // host work only: the pinned staging buffer now holds this query
+         // host work only: the pinned staging buffer now holds this query (the interpreter also prepares the counts kernels)
+         stageQueryLocked(table, program, &staged, column, table->d_counts);
          filter = table->query_filter;
          request.filter_scalars = filter->d_cardinality;  // reported in the header, zeroed again by the finalize kernel
       }
@@ -1477,7 +1470,7 @@ int silo_gpu_query_mutation_hits(
          if (own_program) {
             enqueueStagedQuery(table, staged, stream);
          }
-         enqueueMutationCounts(table, column, filter, table->d_counts, stream, &request);
+         enqueueMutationCounts(table, column, filter, table->d_counts, stream, &request, false, own_program);
       };
       try {
          cudaGraphExec_t replay = nullptr;

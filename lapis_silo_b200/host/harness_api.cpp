@@ -207,6 +207,10 @@ int silo_host_prepared_run_async(silo_host_prepared* prepared, void* cuda_stream
    return guarded([&] { throwOnDeviceError(silo_gpu_program_run_async(prepared->program, cuda_stream)); });
 }
 
+int silo_host_prepared_run_counts_async(silo_host_prepared* prepared, int column_index, void* d_counts, void* cuda_stream) {
+   return guarded([&] { throwOnDeviceError(silo_gpu_program_run_counts_async(prepared->program, column_index, d_counts, cuda_stream)); });
+}
+
 const silo_gpu_filter* silo_host_prepared_filter(const silo_host_prepared* prepared) {
    return prepared->filter;
 }

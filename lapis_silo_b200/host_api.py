@@ -23,7 +23,7 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_last_query_profile", "silo_host_table_register_bitmap", "silo_host_table_device", "silo_host_table_num_rows",
     "silo_host_filter_eval", "silo_host_filter_free", "silo_host_filter_cardinality",
     "silo_host_filter_device", "silo_host_filter_words", "silo_host_filter_explain", "silo_host_bitmap_aggregation",
-    "silo_host_filter_prepare", "silo_host_prepared_run_async", "silo_host_prepared_filter",
+    "silo_host_filter_prepare", "silo_host_prepared_run_async", "silo_host_prepared_run_counts_async", "silo_host_prepared_filter",
     "silo_host_prepared_staged_bytes", "silo_host_prepared_free",
     "silo_host_mutation_counts", "silo_host_mutations", "silo_host_mutation_rows_from_counts",
     "silo_host_mutations_packed", "silo_host_packed_fetch", "silo_host_mutations_enqueue", "silo_host_mutations_collect_packed",
@@ -75,6 +75,7 @@ def lib() -> C.CDLL:
         L.silo_host_filter_prepare.argtypes = [vp, C.c_char_p]
         L.silo_host_filter_prepare.restype = vp
         L.silo_host_prepared_run_async.argtypes = [vp, vp]
+        L.silo_host_prepared_run_counts_async.argtypes = [vp, C.c_int, vp, vp]
         L.silo_host_prepared_filter.argtypes = [vp]
         L.silo_host_prepared_filter.restype = vp
         L.silo_host_prepared_staged_bytes.argtypes = [vp]
@@ -247,6 +248,11 @@ class PreparedFilter:
 
     def run_async(self, stream_ptr: int) -> None:
         _check(lib().silo_host_prepared_run_async(self._h, C.c_void_p(stream_ptr)))
+
+    def run_counts_async(self, column_index: int, d_counts_ptr: int, stream_ptr: int) -> None:
+        """The filter and the Mutations counts of one column, enqueued only (one launch less than run_async +
+        HostTable.mutation_counts_async: the interpreter also prepares the counts kernels)."""
+        _check(lib().silo_host_prepared_run_counts_async(self._h, column_index, C.c_void_p(d_counts_ptr), C.c_void_p(stream_ptr)))
 
     @property
     def device_handle(self) -> int:

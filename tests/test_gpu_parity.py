@@ -414,6 +414,16 @@ def test_synthetic_shards_sum_to_the_whole(ctx):
     # the same stream (the all-reduce), one shard runs the output pass over the sums on the device.
     import torch
     stream = torch.cuda.Stream()
+    # a prepared program with the counts kernels behind it (what bench.py's device-resident loop launches)
+    prepared = whole_table.prepare(expression)
+    for _ in range(3):
+        with torch.cuda.stream(stream):
+            buffer = torch.full((16 * 1500,), -1, dtype=torch.int32, device="cuda")
+            prepared.run_counts_async(0, buffer.data_ptr(), stream.cuda_stream)
+            stream.synchronize()
+            np.testing.assert_array_equal(buffer.cpu().numpy().view(np.uint32).reshape(16, 1500), whole_counts)
+    assert prepared.cardinality() == whole_filter.cardinality
+    prepared.close()
     for repeat, min_proportion in enumerate((0.05, 0.0, 0.3, 0.05)):
         with torch.cuda.stream(stream):
             buffers = [torch.zeros(16 * 1500, dtype=torch.int32, device="cuda") for _ in interleaved]
