@@ -86,7 +86,10 @@ __global__ void __launch_bounds__(PREP_THREADS) prepareQueryKernel(
 // generic-pointer arithmetic of plain C++ costs as many instructions per piece as the lookups.
 // ---------------------------------------------------------------------------------------------
 
-constexpr int K1_STAGES = 5;
+#ifndef SILO_K1_STAGES
+#define SILO_K1_STAGES 5
+#endif
+constexpr int K1_STAGES = SILO_K1_STAGES;
 constexpr int K1_CONSUMER_WARPS = 16;
 constexpr int K1_CONSUMER_THREADS = K1_CONSUMER_WARPS * 32;
 constexpr int K1_THREADS = K1_CONSUMER_THREADS + 32;  // warp 0 = bulk-copy producer
@@ -121,6 +124,9 @@ constexpr uint32_t K1_TILE_SLOT = 2;   // which of the two filter-tile buffers t
 struct __align__(16) K1Dynamic {
    K1Stage stages[K1_STAGES];
    K1Control control[K1_STAGES];
+   // a warp pulls two whole 512-byte regions whatever the size of its piece: the reads behind a short piece at the
+   // end of the last stage must stay inside the CTA's shared-memory window
+   uint8_t overrun_pad[1024 - K1_STAGES * sizeof(K1Control) % 1024];
 };
 constexpr uint32_t K1_CONTROL_OFFSET = sizeof(K1Stage) * K1_STAGES;
 
@@ -157,7 +163,24 @@ __device__ __forceinline__ void sts128(uint32_t address, const uint4& value) {
    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(address), "r"(value.x), "r"(value.y), "r"(value.z), "r"(value.w)
                 : "memory");
 }
+#ifndef SILO_WAIT_HINT_NS
+#define SILO_WAIT_HINT_NS 0x989680u
+#endif
 __device__ __forceinline__ void mbarWaitAt(uint32_t address, uint32_t parity) {
+#if SILO_WAIT_HINT_NS == 0
+   asm volatile(  // spin on the phase test
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(address),
+      "r"(parity)
+      : "memory"
+   );
+#else
    asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -168,9 +191,10 @@ __device__ __forceinline__ void mbarWaitAt(uint32_t address, uint32_t parity) {
       "WAIT_DONE:\n"
       "}\n" ::"r"(address),
       "r"(parity),
-      "r"(0x989680u)
+      "r"(SILO_WAIT_HINT_NS)
       : "memory"
    );
+#endif
 }
 __device__ __forceinline__ void mbarArriveAt(uint32_t address) {
    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(address) : "memory");
