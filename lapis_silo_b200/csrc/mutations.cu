@@ -429,156 +429,138 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
    __syncthreads();
 
    if (warp == 0) {
-      // ---------------- producer warp -----------------------------------------------------------
-      // The metadata of a batch (<= claim_batch work items) goes through three steps, each with loaded
-      // global-memory latency: CLAIM (lane 0's atomic on the grid-wide counter) -> FETCH (lane j loads
-      // the segment record of item j) -> ISSUE (lane j's bulk copies into ring stage it + j). Three
-      // claims and two fetches are in flight while a batch is issued, so a claim has three iterations
-      // and a fetch two to come back -- an iteration with free stages is much shorter than one memory
-      // round trip, and with a shallower pipeline the ring ran dry behind the producer (consumers waited
-      // for data 18 % of their time while the producer waited for a free stage only 9 % of its).
-      // Lane j prepares stage j of the batch (addresses, byte counts, tile bookkeeping) in parallel with
-      // the others; only the barrier wait and the copies themselves are issued lane after lane.
-      // The first two batches of every CTA are fixed (no atomic in front of the first copies); the
-      // dynamic claims start behind those. Near the end of the work list claims shrink to single
-      // items -- still three of them in flight --, so that the last CTAs to finish are a few stages,
-      // not a few batches, behind the others.
+      // ---------------- producer: ONE thread ------------------------------------------------------
+      // Lane 0 alone claims batches of work items (segments) from the grid-wide counter, fetches their
+      // 16-byte records and issues one bulk copy per ring stage. A warp-wide producer (lane j preparing
+      // stage j, the copies issued lane after lane) spent 0.95 us per stage whatever the stage size, the
+      // batch size or the number of copies: its shuffles, ballots, warp syncs and barrier tests all queue
+      // behind the consumers' shared-memory loads, ~40 cycles per instruction, and the consumers waited for
+      // data 16 % of their time while the producer waited for a free stage only 12 % of its. A single
+      // thread needs no cross-lane instruction at all.
+      // Pipeline: the records of batch k + 2 are loaded right after the copies of batch k were issued and
+      // are used after those of batch k + 1; three claims are in flight (an atomic has three batches to
+      // come back). The first two batches of every CTA are fixed (no atomic in front of the first
+      // copies); near the end of the list claims shrink to single items, so that the last CTAs to finish
+      // are a few stages, not a few batches, behind the others.
+      if (lane != 0) {
+         return;
+      }
+      constexpr uint32_t HELD = 4;  // records of one batch held in registers
+      const uint32_t batch_items = min(claim_batch, HELD);
       uint32_t* const work_counter = work_state + 1;
-      const uint32_t static_items = 2 * gridDim.x * claim_batch;
+      const uint32_t static_items = 2 * gridDim.x * batch_items;
       const uint32_t capacity = column.n_segments;
-      auto claimAsync = [&](uint32_t size) -> uint32_t {  // the result is only valid in lane 0, and only waited for when used
-         uint32_t first = 0;
-         if (lane == 0) {
-            first = atomicAdd(work_counter, size) + static_items;
-         }
-         return first;
-      };
-      // (not checked against the number of work items: records behind the end of the list are stale
-      // or uninitialised, and never used -- `batch` below cuts them off)
-      auto fetch = [&](uint32_t first, uint32_t size) -> DevSegment {
-         DevSegment segment{};
-         if (lane < size && first + lane < capacity) {
-            segment = work_items[first + lane];
-         }
-         return segment;
-      };
-      long long producer_waited = 0;  // MODE 4: cycles this lane waited for a free stage
-      const long long producer_begin = MODE == 4 ? clock64() : 0;
-      uint32_t batch_first = blockIdx.x * claim_batch;
-      uint32_t batch_size = claim_batch;
-      uint32_t next_first = (gridDim.x + blockIdx.x) * claim_batch;
-      uint32_t next_size = claim_batch;
-      DevSegment fetched = fetch(batch_first, batch_size);
-      DevSegment fetched_next = fetch(next_first, next_size);
-      uint32_t claim_a = claimAsync(claim_batch);
-      uint32_t claim_b = claimAsync(claim_batch);
-      uint32_t claim_c = claimAsync(claim_batch);
-      uint32_t size_a = claim_batch;
-      uint32_t size_b = claim_batch;
-      uint32_t size_c = claim_batch;
       const uint32_t total = work_state[0];
-      const uint32_t tail_items = tail_batches * gridDim.x * claim_batch;
+      const uint32_t tail_items = tail_batches * gridDim.x * batch_items;
       const uint32_t tail_begin = total > tail_items ? total - tail_items : 0;
-      uint32_t current_tile_chunk = 0xFFFFFFFFu;
-      uint32_t tile_slot = 1;         // buffer holding the current chunk's tile
-      uint32_t tile_first_stage = 0;  // first stage that reads the current tile
-      uint32_t it = 0;                // stages issued so far by this CTA
-      while (batch_first < total) {
-         const DevSegment mine = fetched;
-         const uint32_t batch = min(batch_size, total - batch_first);
-         batch_first = next_first;
-         batch_size = next_size;
-         fetched = fetched_next;
-         next_first = __shfl_sync(0xFFFFFFFFu, claim_a, 0);
+      const uint4* const records = reinterpret_cast<const uint4*>(work_items);
+      // (records behind the end of the list are stale or uninitialised and never used: `n` below cuts them off)
+      auto load = [&](uint3 (&into)[HELD], uint32_t first, uint32_t size) {
+#pragma unroll
+         for (uint32_t j = 0; j < HELD; ++j) {
+            if (j < size && first + j < capacity) {
+               const uint4 record = records[first + j];
+               into[j] = make_uint3(record.x, record.y, record.w);  // (desc_begin is unused)
+            }
+         }
+      };
+      long long producer_waited = 0;  // MODE 4: cycles spent waiting for a free stage
+      const long long producer_begin = MODE == 4 ? clock64() : 0;
+      uint3 current[HELD];
+      uint3 next[HELD];
+      uint32_t current_first = blockIdx.x * batch_items;
+      uint32_t current_size = batch_items;
+      uint32_t next_first = (gridDim.x + blockIdx.x) * batch_items;
+      uint32_t next_size = batch_items;
+      load(current, current_first, current_size);
+      load(next, next_first, next_size);
+      uint32_t claim_a = atomicAdd(work_counter, batch_items) + static_items;
+      uint32_t claim_b = atomicAdd(work_counter, batch_items) + static_items;
+      uint32_t claim_c = atomicAdd(work_counter, batch_items) + static_items;
+      uint32_t size_a = batch_items;
+      uint32_t size_b = batch_items;
+      uint32_t size_c = batch_items;
+      uint32_t tile_chunk = 0xFFFFFFFFu;  // chunk whose tile the latest stage reads
+      uint32_t tile_slot = 1;             // ... and the buffer it sits in
+      uint32_t tile_first_stage = 0;      // first stage that reads it
+      uint32_t it = 0;                    // stages issued so far
+      uint32_t stage = 0;                 // it % K1_STAGES
+      uint32_t round = 0;                 // it / K1_STAGES
+      // one ring stage: {payload_offset16, block bytes, chunk | pieces << 16} of the DevSegment
+      auto issue = [&](const uint3& record) {
+         const uint32_t my_control = control_address + stage * static_cast<uint32_t>(sizeof(K1Control));
+         const uint32_t my_ring = ring_address + stage * static_cast<uint32_t>(sizeof(K1Stage));
+         if (round > 0) {
+            const long long wait_begin = MODE == 4 ? clock64() : 0;
+            mbarWaitAt(my_control + K1_CTRL_EMPTY, (round - 1) & 1u);  // => every stage <= it - K1_STAGES is pulled
+            if (MODE == 4) {
+               producer_waited += clock64() - wait_begin;
+            }
+         }
+         const uint32_t chunk = record.z & 0xFFFFu;
+         const bool new_tile = chunk != tile_chunk;
+         if (new_tile) {
+            // The new tile goes into the OTHER buffer, last read by the lookups of the stages before
+            // tile_first_stage. A warp hands a stage back BEFORE it does the lookups, so the stage's empty
+            // barrier says nothing about the tile: wait for the done barriers. (Stages below it - K1_STAGES
+            // are implied: a warp pulls stage q + K1_STAGES only after it has finished stage q, and the
+            // empty wait above covered it - K1_STAGES.)
+            for (uint32_t prev = it >= K1_STAGES ? it - K1_STAGES : 0; prev < tile_first_stage; ++prev) {
+               mbarWaitAt(control_address + (prev % K1_STAGES) * static_cast<uint32_t>(sizeof(K1Control)) + K1_CTRL_DONE, (prev / K1_STAGES) & 1u);
+            }
+            tile_slot ^= 1u;
+            tile_first_stage = it;
+            tile_chunk = chunk;
+         }
+         sts128(my_control, make_uint4(record.z >> 16, record.x << 2, (new_tile ? K1_NEW_TILE : 0u) | (tile_slot != 0 ? K1_TILE_SLOT : 0u), 0u));
+         mbarExpectTxAt(my_control + K1_CTRL_FULL, record.y + (new_tile ? TILE_BYTES : 0u));
+         if (new_tile) {
+            bulkLoadAt(tile_address0 + tile_slot * TILE_BUFFER_BYTES, filter_words + static_cast<size_t>(chunk) * TILE_WORDS, TILE_BYTES, my_control + K1_CTRL_FULL);
+         }
+         // the segment's block [descriptors | payloads] in one copy
+         bulkLoadAt(my_ring, column.payload + (static_cast<uint64_t>(record.x) << 4), record.y, my_control + K1_CTRL_FULL);
+         ++it;
+         const bool wrap = stage == K1_STAGES - 1;
+         stage = wrap ? 0u : stage + 1u;
+         round += wrap ? 1u : 0u;
+      };
+      while (current_first < total) {
+         const uint32_t n = min(current_size, total - current_first);
+#pragma unroll
+         for (uint32_t j = 0; j < HELD; ++j) {
+            if (j < n) {
+               issue(current[j]);
+            }
+         }
+#pragma unroll
+         for (uint32_t j = 0; j < HELD; ++j) {
+            current[j] = next[j];
+         }
+         current_first = next_first;
+         current_size = next_size;
+         next_first = claim_a;  // (waits for the atomic issued three batches ago)
          next_size = size_a;
-         fetched_next = fetch(next_first, next_size);
+         load(next, next_first, next_size);
          claim_a = claim_b;
          size_a = size_b;
          claim_b = claim_c;
          size_b = size_c;
-         size_c = next_first >= tail_begin ? 1u : claim_batch;
-         claim_c = claimAsync(size_c);
-
-         // tile bookkeeping for all stages of the batch at once
-         uint32_t previous_chunk = __shfl_up_sync(0xFFFFFFFFu, mine.chunk(), 1);
-         if (lane == 0) {
-            previous_chunk = current_tile_chunk;
-         }
-         const bool new_tile = lane < batch && mine.chunk() != previous_chunk;
-         const uint32_t new_mask = __ballot_sync(0xFFFFFFFFu, new_tile);
-         const uint32_t new_below = new_mask & ((1u << lane) - 1u);  // tile switches at earlier stages of this batch
-         const uint32_t my_slot = tile_slot ^ (__popc(new_below | (new_tile ? 1u << lane : 0u)) & 1u);
-         // first stage of the tile that is current just before my stage
-         const uint32_t first_before = new_below != 0 ? it + (31u - __clz(new_below)) : tile_first_stage;
-         const uint32_t my_it = it + lane;
-         const uint32_t my_stage = my_it % K1_STAGES;
-         const uint32_t my_round = my_it / K1_STAGES;
-         const uint32_t my_control = control_address + my_stage * static_cast<uint32_t>(sizeof(K1Control));
-         const uint32_t my_ring = ring_address + my_stage * static_cast<uint32_t>(sizeof(K1Stage));
-         const uint4 meta = make_uint4(
-            mine.descCount(), mine.payload_offset16 << 2,
-            (new_tile ? K1_NEW_TILE : 0u) | (my_slot != 0 ? K1_TILE_SLOT : 0u), 0u
-         );
-         for (uint32_t j = 0; j < batch; ++j) {
-            if (lane == j) {
-               if (my_round > 0) {
-                  const long long wait_begin = MODE == 4 ? clock64() : 0;
-                  mbarWaitAt(my_control + K1_CTRL_EMPTY, (my_round - 1) & 1u);  // => every stage <= my_it - K1_STAGES is pulled
-                  if (MODE == 4) {
-                     producer_waited += clock64() - wait_begin;
-                  }
-               }
-               if (new_tile) {
-                  // The new tile goes into the OTHER buffer, last read by the lookups of the stages
-                  // before first_before. A warp hands a stage back BEFORE it does the lookups, so the
-                  // stage's empty barrier says nothing about the tile: wait for the done barriers.
-                  // (Stages below my_it - K1_STAGES are implied: a warp pulls stage q + K1_STAGES only
-                  // after it has finished stage q, and the empty wait above covered my_it - K1_STAGES.)
-                  for (uint32_t prev = my_it >= K1_STAGES ? my_it - K1_STAGES : 0; prev < first_before; ++prev) {
-                     mbarWaitAt(
-                        control_address + (prev % K1_STAGES) * static_cast<uint32_t>(sizeof(K1Control)) + K1_CTRL_DONE, (prev / K1_STAGES) & 1u
-                     );
-                  }
-               }
-               sts128(my_control, meta);
-               mbarExpectTxAt(my_control + K1_CTRL_FULL, mine.payload_bytes + (new_tile ? TILE_BYTES : 0u));
-               if (new_tile) {
-                  bulkLoadAt(
-                     tile_address0 + my_slot * TILE_BUFFER_BYTES, filter_words + static_cast<size_t>(mine.chunk()) * TILE_WORDS, TILE_BYTES,
-                     my_control + K1_CTRL_FULL
-                  );
-               }
-               // the segment's block [descriptors | payloads] in one copy
-               bulkLoadAt(my_ring, column.payload + mine.payloadOffset(), mine.payload_bytes, my_control + K1_CTRL_FULL);
-            }
-            __syncwarp();
-         }
-         if (new_mask != 0) {
-            tile_slot ^= __popc(new_mask) & 1u;
-            tile_first_stage = it + (31u - __clz(new_mask));
-         }
-         current_tile_chunk = __shfl_sync(0xFFFFFFFFu, mine.chunk(), batch - 1);
-         it += batch;
+         size_c = next_first >= tail_begin ? 1u : batch_items;
+         claim_c = atomicAdd(work_counter, size_c) + static_items;
       }
       if (MODE == 4) {
          const uint32_t row = 15 * column.genome_length;
-         atomicAdd(&counts[row + 5], static_cast<uint32_t>(producer_waited >> 6));  // all lanes: waiting for a free stage
-         if (lane == 0) {
-            atomicAdd(&counts[row + 6], static_cast<uint32_t>((clock64() - producer_begin) >> 6));
-            atomicAdd(&counts[row + 7], 1u);
-         }
+         atomicAdd(&counts[row + 5], static_cast<uint32_t>(producer_waited >> 6));
+         atomicAdd(&counts[row + 6], static_cast<uint32_t>((clock64() - producer_begin) >> 6));
+         atomicAdd(&counts[row + 7], 1u);
       }
-      if (lane == 0) {
-         // tell the consumers that nothing follows
-         const uint32_t stage = it % K1_STAGES;
-         const uint32_t round = it / K1_STAGES;
-         const uint32_t stop_control = control_address + stage * static_cast<uint32_t>(sizeof(K1Control));
-         if (round > 0) {
-            mbarWaitAt(stop_control + K1_CTRL_EMPTY, (round - 1) & 1u);
-         }
-         sts128(stop_control, make_uint4(K1_STOP, 0u, 0u, 0u));
-         mbarArriveAt(stop_control + K1_CTRL_FULL);
+      // tell the consumers that nothing follows
+      const uint32_t stop_control = control_address + stage * static_cast<uint32_t>(sizeof(K1Control));
+      if (round > 0) {
+         mbarWaitAt(stop_control + K1_CTRL_EMPTY, (round - 1) & 1u);
       }
+      sts128(stop_control, make_uint4(K1_STOP, 0u, 0u, 0u));
+      mbarArriveAt(stop_control + K1_CTRL_FULL);
       return;
    }
 
