@@ -310,6 +310,9 @@ struct ApiError : std::runtime_error {
 
 template <typename Fn>
 int guarded(Fn&& fn) {
+   // a non-sticky error left behind by an earlier, unrelated runtime call on this thread (a free on a stream that
+   // was destroyed meanwhile, a pointer query on plain host memory ...) must not be blamed on this call's launches
+   cudaGetLastError();
    try {
       fn();
       return SILO_OK;
