@@ -723,8 +723,12 @@ class Reader {
    const std::string& text;
    size_t cursor = 0;
 
+   // (the "C" locale's white space, inline: std::isspace is a call per character, and a date filter over 153
+   // chunks is 2.4 KB of text)
+   static bool isSpace(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+
    void skipSpace() {
-      while (cursor < text.size() && std::isspace(static_cast<unsigned char>(text[cursor])) != 0) {
+      while (cursor < text.size() && isSpace(text[cursor])) {
          ++cursor;
       }
    }
@@ -740,7 +744,7 @@ class Reader {
       checkQuery(head != ')', "filter expression: unexpected ')'");
       if (head == '(') {
          ++cursor;
-         node.items.reserve(8);
+         node.items.reserve(16);
          for (;;) {
             skipSpace();
             checkQuery(cursor < text.size(), "filter expression: missing ')'");
@@ -760,8 +764,7 @@ class Reader {
          return node;
       }
       const size_t begin = cursor;
-      while (cursor < text.size() && std::isspace(static_cast<unsigned char>(text[cursor])) == 0 &&
-             text[cursor] != '(' && text[cursor] != ')') {
+      while (cursor < text.size() && !isSpace(text[cursor]) && text[cursor] != '(' && text[cursor] != ')') {
          ++cursor;
       }
       node.atom = std::string_view(text).substr(begin, cursor - begin);
