@@ -1529,7 +1529,7 @@ int silo_gpu_query_mutation_hits(
          trace.mark(0);  // staged (host work)
          if (replay != nullptr) {
             SILO_CUDA_CHECK(cudaGraphLaunch(replay, stream));
-            table->stats.kernel_launches += own_program ? 5 : 4;
+            table->stats.kernel_launches += 4;  // interpreter (+ prepare), coverage, container, finalize
          } else {
             enqueueAll();
          }
