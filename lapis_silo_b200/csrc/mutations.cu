@@ -550,6 +550,15 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
       }
       if (MODE == 4) {
          const uint32_t row = 15 * column.genome_length;
+         // per CTA (profiles/k1_wait_probe.py): wall clock (ns, low word) at which this producer ran out of work,
+         // the SM it ran on, the stages it issued
+         uint32_t now;
+         uint32_t smid;
+         asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(now));
+         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+         counts[row + 1024 + blockIdx.x] = now;
+         counts[row + 2048 + blockIdx.x] = smid;
+         counts[row + 3072 + blockIdx.x] = it;
          atomicAdd(&counts[row + 5], static_cast<uint32_t>(producer_waited >> 6));
          atomicAdd(&counts[row + 6], static_cast<uint32_t>((clock64() - producer_begin) >> 6));
          atomicAdd(&counts[row + 7], 1u);
@@ -624,6 +633,11 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
             atomicAdd(&counts[row + 2], static_cast<uint32_t>(probe_first >> 6));                // until the first stage landed
             atomicAdd(&counts[row + 3], visit - 1);
             atomicAdd(&counts[row + 4], 1u);
+            if (cwarp == 0) {  // per CTA: wall clock at which its consumers saw the end of the work
+               uint32_t now;
+               asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(now));
+               counts[row + 4096 + blockIdx.x] = now;
+            }
          }
          break;
       }

@@ -24,7 +24,18 @@ for label, expression in (("config2", f"(and {date} (bitmap lineage))"), ("all c
     for _ in range(3):
         prepared.run_async(stream.cuda_stream); table.mutation_counts_async(0, prepared, counts.data_ptr(), stream.cuda_stream)
     torch.cuda.synchronize()
-    probe = counts.cpu().numpy().view(np.uint32).reshape(16, bench.GENOME_LENGTH)[15, :8].astype(np.float64)
+    raw = counts.cpu().numpy().view(np.uint32).reshape(16, bench.GENOME_LENGTH)[15].astype(np.int64)
+    n_ctas = 296
+    exits, smids, stages, ends = (raw[at:at + n_ctas] for at in (1024, 2048, 3072, 4096))
+    base = min(exits.min(), ends.min())
+    exits, ends = (exits - base) / 1e3, (ends - base) / 1e3
+    slow = stages < stages.mean()
+    print(f"{label}: per-CTA wall clock of the last launch (us after the earliest exit): producers out of work, deciles "
+          f"{np.round(np.percentile(exits, [0, 10, 25, 50, 75, 90, 100]), 1)}; consumers done, deciles {np.round(np.percentile(ends, [0, 10, 25, 50, 75, 90, 100]), 1)}; "
+          f"stages per CTA min {stages.min()} mean {stages.mean():.1f} max {stages.max()}, correlation(end, stages) {np.corrcoef(ends, stages)[0, 1]:.2f}; "
+          f"CTAs with fewer stages than the mean end at median {np.median(ends[slow]):.1f}, the others at {np.median(ends[~slow]):.1f}; "
+          f"%smid: {len(set(smids.tolist()))} distinct, {smids.min()}..{smids.max()}, at most {np.bincount(smids).max()} CTAs each")
+    probe = raw[:8].astype(np.float64)
     total, waited, first, visits, warps, producer_waited, producer_total, producers = probe
     s = table.stats()
     print(f"{label:12s} K1 {s.last_counts_kernel_ms*1e3:7.1f} us | consumer warps {int(warps)}: mean lifetime {total/warps*64/1965:7.1f} us, "
