@@ -20,10 +20,10 @@ namespace silo {
 constexpr uint32_t TILE_WORDS = 1024;        // one chunk's dense filter tile: 1024 x u64 = 8 KiB
 constexpr uint32_t TILE_BYTES = TILE_WORDS * 8;
 #ifndef SILO_SEG_PAYLOAD_BYTES
-#define SILO_SEG_PAYLOAD_BYTES 16384
+#define SILO_SEG_PAYLOAD_BYTES 31744
 #endif
-constexpr uint32_t SEG_PAYLOAD_BYTES = SILO_SEG_PAYLOAD_BYTES;  // max payload bytes of one segment (>= 8192 + slack)
-constexpr uint32_t SEG_MAX_DESCS = 16;         // max pieces of one segment: one per consumer warp, so that a warp
+constexpr uint32_t SEG_PAYLOAD_BYTES = SILO_SEG_PAYLOAD_BYTES;  // max payload bytes of one segment: 31 pieces of <= 1 KiB
+constexpr uint32_t SEG_MAX_DESCS = 31;         // max pieces of one segment: one per consumer warp, so that a warp
                                                // can always hand the stage back before it does the lookups
 
 constexpr uint32_t TYPE_BITSET = 1;  // CRoaring typecodes, roaring_container.h:131-145

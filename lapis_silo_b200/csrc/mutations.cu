@@ -74,9 +74,13 @@ __global__ void __launch_bounds__(PREP_THREADS) prepareQueryKernel(
 // ---------------------------------------------------------------------------------------------
 // K1: fused container AND filter-tile + popcount
 //
-// Persistent CTAs (2 per SM). Warp 0 is the producer: it claims batches of work items (segments)
-// from a grid-wide counter and streams each segment's descriptors and payload into a ring of
-// shared-memory stages with two 1-D bulk (TMA) copies that complete on an mbarrier. The 16 consumer
+// Persistent CTAs, ONE per SM (1,024 threads, 56 registers: a 256-thread block of the coverage kernel still
+// fits beside it). Two CTAs of 17 warps per SM do not run at the same speed -- the warp schedulers favour one
+// of them, half of the CTAs visited ~66 stages in the time the other half visited ~45 -- and when the work
+// list ran out the slow ones still owned what they had claimed ahead: ~10 us of a 72 us kernel. One CTA per
+// SM has no such pair. Warp 0 is the producer (one thread): it claims batches of work items (segments)
+// from a grid-wide counter and streams each segment's block [descriptors | payloads] into a ring of
+// shared-memory stages with one 1-D bulk (TMA) copy that completes on an mbarrier. The 31 consumer
 // warps take one piece (<= 1 KiB of payload) each: a warp pulls its piece into REGISTERS, hands the
 // stage back to the producer, and only then ANDs the piece with the chunk's filter tile held in
 // shared memory, issuing one RED per piece with a non-zero count.
@@ -87,12 +91,12 @@ __global__ void __launch_bounds__(PREP_THREADS) prepareQueryKernel(
 // ---------------------------------------------------------------------------------------------
 
 #ifndef SILO_K1_STAGES
-#define SILO_K1_STAGES 5
+#define SILO_K1_STAGES 6
 #endif
 constexpr int K1_STAGES = SILO_K1_STAGES;
-constexpr int K1_CONSUMER_WARPS = 16;
+constexpr int K1_CONSUMER_WARPS = 31;
 constexpr int K1_CONSUMER_THREADS = K1_CONSUMER_WARPS * 32;
-constexpr int K1_THREADS = K1_CONSUMER_THREADS + 32;  // warp 0 = bulk-copy producer
+constexpr int K1_THREADS = K1_CONSUMER_THREADS + 32;  // warp 0 = bulk-copy producer; 1,024 threads: one CTA per SM
 constexpr uint32_t K1_BATCH_DEFAULT = 4;               // work items claimed per atomicAdd (<= 32)
 constexpr uint32_t K1_STOP = 0xFFFFFFFFu;              // meta.x marker: no more work
 constexpr uint32_t TILE32_WORDS = 2 * TILE_WORDS;
@@ -394,7 +398,7 @@ __device__ __forceinline__ uint32_t wordRangeCount(uint32_t entries, uint32_t pa
 // MODE (profiling aid, SILO_K1_STREAM_ONLY): 0 = the product; 1 = consumers skip the intersection
 // (what the bulk-copy pipeline alone can stream); 2 = no atomics; 3 = touch the payload only.
 template <int MODE>
-__global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
+__global__ void __maxnreg__(56) containerAndCountKernel(
    DevColumn column,
    const uint64_t* __restrict__ filter_words,   // [n_chunks * 1024]
    uint32_t* __restrict__ work_state,           // [0] number of work items, [1] grid-wide claim counter (zero at launch)
@@ -598,7 +602,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
    uint32_t control_base = control_address;
    uint32_t tile_base = tile_address0;
    asm volatile("" : "+r"(ring_base), "+r"(control_base), "+r"(tile_base));
-   uint32_t rotation = cwarp;  // piece index of this warp in the current stage, before the & 15
+   uint32_t rotation = cwarp;  // piece index of this warp in the current stage, in [0, K1_CONSUMER_WARPS)
    uint32_t stage = 0;         // ring position and phase of the next visit
    uint32_t parity = 0;
    uint32_t visit = 0;         // MODE 4 only
@@ -648,8 +652,8 @@ __global__ void __launch_bounds__(K1_THREADS, 2) containerAndCountKernel(
       const uint32_t slot_offset = (meta.z & K1_TILE_SLOT) != 0 ? TILE_BUFFER_BYTES : 0u;
       // the rotation continues where the previous stage stopped, so that a stage with fewer than 16
       // pieces does not always leave the same warps idle
-      const uint32_t index = rotation & (K1_CONSUMER_WARPS - 1);
-      rotation -= desc_count;
+      const uint32_t index = rotation;  // in [0, K1_CONSUMER_WARPS)
+      rotation = rotation >= desc_count ? rotation - desc_count : rotation + K1_CONSUMER_WARPS - desc_count;
       // Lane 0's barrier arrives and the RED are predicated instructions (mbarArriveLane0,
       // redAddLane0), not branches: a warp without a piece in this stage runs the same tail with a
       // count of zero.
@@ -1137,7 +1141,7 @@ void enqueueMutationCounts(
          }
          attribute_set = true;
       }
-      const int blocks = static_cast<int>(std::min<uint32_t>(column.n_segments, static_cast<uint32_t>(table->ctx->sm_count) * 2));
+      const int blocks = static_cast<int>(std::min<uint32_t>(column.n_segments, static_cast<uint32_t>(table->ctx->sm_count)));
 #define SILO_LAUNCH_K1(MODE)                                                                         \
    containerAndCountKernel<MODE><<<blocks, K1_THREADS, sizeof(K1Dynamic), stream>>>(                 \
       column, words, table->d_work_state, table->d_work_items, d_counts, claim_batch, tail_batches   \

@@ -25,7 +25,7 @@ for label, expression in (("config2", f"(and {date} (bitmap lineage))"), ("all c
         prepared.run_async(stream.cuda_stream); table.mutation_counts_async(0, prepared, counts.data_ptr(), stream.cuda_stream)
     torch.cuda.synchronize()
     raw = counts.cpu().numpy().view(np.uint32).reshape(16, bench.GENOME_LENGTH)[15].astype(np.int64)
-    n_ctas = 296
+    n_ctas = int(os.environ.get("K1_CTAS", "296"))
     exits, smids, stages, ends = (raw[at:at + n_ctas] for at in (1024, 2048, 3072, 4096))
     base = min(exits.min(), ends.min())
     exits, ends = (exits - base) / 1e3, (ends - base) / 1e3
