@@ -105,6 +105,28 @@ uint32_t silo_host_rows_num_names(const silo_host_rows* rows);
 const char* silo_host_rows_name(const silo_host_rows* rows, uint32_t name_id);
 int silo_host_rows_get(const silo_host_rows* rows, uint64_t index, char* from, char* to, int32_t* position, const char** sequence_name, double* proportion, int32_t* count, int32_t* coverage);
 
+/* ---- `.silo` -> device loader (host/silo_loader.h): the sequence columns of a table file written by
+ * Table::serializeData (storage/table.h:35-42), read straight into the S1 upload format */
+
+typedef struct silo_host_archive silo_host_archive;
+/* columns in the archive's order (nucleotide columns by name, then amino-acid columns by name);
+ * alphabets: 0 nucleotide, 1 amino acid; references: the global reference genomes. Host only, no device call. */
+silo_host_archive* silo_host_archive_read(const uint8_t* bytes, uint64_t size, const char* const* names, const int* alphabets,
+                                          const char* const* references, uint32_t n_columns);
+void silo_host_archive_free(silo_host_archive* archive);
+/* the column in the upload format; valid until the archive object is freed */
+const silo_column_desc* silo_host_archive_column(const silo_host_archive* archive, uint32_t index);
+/* info[6] = {n_chunks, sequence_count, tail_parsed (0: a non-empty insertion index hides the null bitmap),
+ * vertical_bitmaps_size, horizontal_bitmaps_size, num_chunks member} */
+int silo_host_archive_column_info(const silo_host_archive* archive, uint32_t index, uint64_t info[6]);
+int silo_host_archive_chunk_sizes(const silo_host_archive* archive, uint32_t index, uint32_t* chunk_sizes, uint32_t capacity);
+/* S1 for a saved database: creates the table (row layout from the coverage index) and uploads every column
+ * that was read completely */
+silo_host_table* silo_host_table_load_archive(silo_gpu_ctx* ctx, const uint8_t* bytes, uint64_t size, const char* const* names,
+                                              const int* alphabets, const char* const* references, uint32_t n_columns);
+/* ascending {first, end_exclusive} runs of a portable roaring bitmap; returns the number of runs or -1 */
+int64_t silo_host_roaring_runs(const uint8_t* bytes, uint64_t size, uint32_t* runs, uint64_t capacity_runs);
+
 /* ---- synthetic benchmark inputs (performance/sequence_generator.h restated on the product side) */
 
 typedef struct silo_host_synthetic silo_host_synthetic;

@@ -10,6 +10,7 @@
 #include "mutations_node.h"
 #include "operators.h"
 #include "roaring_writer.h"
+#include "silo_loader.h"
 #include "synthetic.h"
 #include "table.h"
 
@@ -49,6 +50,10 @@ struct silo_host_rows {
          name_ids.push_back(id);
       }
    }
+};
+
+struct silo_host_archive {
+   std::vector<std::unique_ptr<LoadedSequenceColumn>> columns;
 };
 
 struct silo_host_synthetic {
@@ -93,6 +98,16 @@ ExpressionPtr parseOrTrue(const char* expression) {
       return std::make_shared<BoolLiteral>(true);
    }
    return parseFilterExpression(expression);
+}
+
+std::vector<ArchiveColumnSpec> archiveSpecs(const char* const* names, const int* alphabets, const char* const* references, uint32_t n_columns) {
+   std::vector<ArchiveColumnSpec> specs(n_columns);
+   for (uint32_t i = 0; i < n_columns; ++i) {
+      specs[i].name = names[i];
+      specs[i].alphabet = alphabets[i] == 0 ? &Alphabet::nucleotide() : &Alphabet::aminoAcid();
+      specs[i].reference = references[i];
+   }
+   return specs;
 }
 
 int copyText(const std::string& text, char* out, uint64_t capacity) {
@@ -628,6 +643,72 @@ int silo_host_partition_chunks(const uint64_t* chunk_weights, uint32_t n_chunks,
          partitionChunks(std::vector<uint64_t>(chunk_weights, chunk_weights + n_chunks), n_ranks);
       std::copy(result.begin(), result.end(), boundaries);
    });
+}
+
+silo_host_archive* silo_host_archive_read(const uint8_t* bytes, uint64_t size, const char* const* names, const int* alphabets,
+                                          const char* const* references, uint32_t n_columns) {
+   silo_host_archive* result = nullptr;
+   guarded([&] {
+      auto owned = std::make_unique<silo_host_archive>();
+      owned->columns = readSequenceColumns(bytes, size, archiveSpecs(names, alphabets, references, n_columns));
+      result = owned.release();
+   });
+   return result;
+}
+
+void silo_host_archive_free(silo_host_archive* archive) {
+   delete archive;
+}
+
+const silo_column_desc* silo_host_archive_column(const silo_host_archive* archive, uint32_t index) {
+   return index < archive->columns.size() ? &archive->columns[index]->desc : nullptr;
+}
+
+int silo_host_archive_column_info(const silo_host_archive* archive, uint32_t index, uint64_t info[6]) {
+   return guarded([&] {
+      const LoadedSequenceColumn& column = *archive->columns.at(index);
+      info[0] = column.chunk_sizes.size();
+      info[1] = column.sequence_count;
+      info[2] = column.tail_parsed ? 1 : 0;
+      info[3] = column.vertical_bitmaps_size;
+      info[4] = column.horizontal_bitmaps_size;
+      info[5] = column.num_chunks;
+   });
+}
+
+int silo_host_archive_chunk_sizes(const silo_host_archive* archive, uint32_t index, uint32_t* chunk_sizes, uint32_t capacity) {
+   return guarded([&] {
+      const LoadedSequenceColumn& column = *archive->columns.at(index);
+      if (capacity < column.chunk_sizes.size()) {
+         throw std::invalid_argument("chunk_sizes buffer too small");
+      }
+      std::copy(column.chunk_sizes.begin(), column.chunk_sizes.end(), chunk_sizes);
+   });
+}
+
+silo_host_table* silo_host_table_load_archive(silo_gpu_ctx* ctx, const uint8_t* bytes, uint64_t size, const char* const* names,
+                                              const int* alphabets, const char* const* references, uint32_t n_columns) {
+   silo_host_table* result = nullptr;
+   guarded([&] {
+      auto owned = std::make_unique<silo_host_table>();
+      owned->table = loadTableFromArchive(ctx, bytes, size, archiveSpecs(names, alphabets, references, n_columns));
+      result = owned.release();
+   });
+   return result;
+}
+
+int64_t silo_host_roaring_runs(const uint8_t* bytes, uint64_t size, uint32_t* runs, uint64_t capacity_runs) {
+   int64_t n_runs = -1;
+   guarded([&] {
+      std::vector<uint32_t> decoded;
+      portableRoaringToRuns(bytes, size, decoded);
+      if (decoded.size() / 2 > capacity_runs) {
+         throw std::invalid_argument("runs buffer too small: need " + std::to_string(decoded.size() / 2));
+      }
+      std::copy(decoded.begin(), decoded.end(), runs);
+      n_runs = static_cast<int64_t>(decoded.size() / 2);
+   });
+   return n_runs;
 }
 
 }  // extern "C"

@@ -34,6 +34,8 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_synthetic_generation", "silo_host_synthetic_build_column",
     "silo_host_synthetic_release_column", "silo_host_synthetic_lineage_bitmap",
     "silo_host_synthetic_date_ranges", "silo_host_partition_chunks",
+    "silo_host_archive_read", "silo_host_archive_free", "silo_host_archive_column", "silo_host_archive_column_info",
+    "silo_host_archive_chunk_sizes", "silo_host_table_load_archive", "silo_host_roaring_runs",
 ]
 
 NUCLEOTIDE = 0
@@ -130,6 +132,19 @@ def lib() -> C.CDLL:
         L.silo_host_synthetic_lineage_bitmap.restype = C.c_int64
         L.silo_host_synthetic_date_ranges.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64, C.c_uint32]
         L.silo_host_partition_chunks.argtypes = [C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+        strings, ints = C.POINTER(C.c_char_p), C.POINTER(C.c_int)
+        L.silo_host_archive_read.argtypes = [C.c_char_p, C.c_uint64, strings, ints, strings, C.c_uint32]
+        L.silo_host_archive_read.restype = vp
+        L.silo_host_archive_free.argtypes = [vp]
+        L.silo_host_archive_free.restype = None
+        L.silo_host_archive_column.argtypes = [vp, C.c_uint32]
+        L.silo_host_archive_column.restype = C.POINTER(abi.ColumnDesc)
+        L.silo_host_archive_column_info.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint64)]
+        L.silo_host_archive_chunk_sizes.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]
+        L.silo_host_table_load_archive.argtypes = [vp, C.c_char_p, C.c_uint64, strings, ints, strings, C.c_uint32]
+        L.silo_host_table_load_archive.restype = vp
+        L.silo_host_roaring_runs.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint64]
+        L.silo_host_roaring_runs.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -279,10 +294,98 @@ class PreparedFilter:
             pass
 
 
+def _archive_specs(columns):
+    """columns: (name, NUCLEOTIDE | AMINO_ACID, reference) in the archive's order"""
+    n = len(columns)
+    names = (C.c_char_p * n)(*[name.encode() for name, _, _ in columns])
+    alphabets = (C.c_int * n)(*[alphabet for _, alphabet, _ in columns])
+    references = (C.c_char_p * n)(*[reference.encode() for _, _, reference in columns])
+    return names, alphabets, references, n
+
+
+def roaring_runs(portable_roaring_bytes: bytes) -> list[tuple[int, int]]:
+    """ascending (first, end_exclusive) runs of a portable roaring bitmap, decoded by the host layer"""
+    capacity = 1 << 16
+    while True:
+        runs = (C.c_uint32 * (2 * capacity))()
+        n = lib().silo_host_roaring_runs(portable_roaring_bytes, len(portable_roaring_bytes), runs, capacity)
+        if n >= 0:
+            return [(runs[2 * i], runs[2 * i + 1]) for i in range(n)]
+        message = lib().silo_host_last_error().decode()
+        if "too small" not in message:
+            raise HostError(message)
+        capacity *= 16
+
+
+class Archive:
+    """The sequence columns of a `.silo` table file in the S1 upload format (host/silo_loader.h). Host only."""
+
+    def __init__(self, data: bytes, columns):
+        self._data = data
+        self.specs = list(columns)
+        names, alphabets, references, n = _archive_specs(self.specs)
+        self._h = lib().silo_host_archive_read(data, len(data), names, alphabets, references, n)
+        if not self._h:
+            raise HostError(lib().silo_host_last_error().decode())
+
+    def desc(self, index: int):
+        """ctypes pointer to the column's silo_column_desc (valid until close())"""
+        pointer = lib().silo_host_archive_column(self._h, index)
+        if not pointer:
+            raise IndexError(index)
+        return pointer
+
+    def info(self, index: int) -> dict:
+        values = (C.c_uint64 * 6)()
+        _check(lib().silo_host_archive_column_info(self._h, index, values))
+        keys = ("n_chunks", "sequence_count", "tail_parsed", "vertical_bitmaps_size", "horizontal_bitmaps_size", "num_chunks")
+        return dict(zip(keys, (int(v) for v in values)))
+
+    def chunk_sizes(self, index: int) -> list[int]:
+        n = self.info(index)["n_chunks"]
+        out = (C.c_uint32 * max(n, 1))()
+        _check(lib().silo_host_archive_chunk_sizes(self._h, index, out, n))
+        return [int(out[i]) for i in range(n)]
+
+    def close(self):
+        if self._h:
+            lib().silo_host_archive_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class HostTable:
     """rhydb::storage::Table as the query compiler sees it, with its sequence columns in HBM."""
 
-    def __init__(self, ctx: abi.Context, chunk_sizes: Sequence[int], first_chunk: int = 0):
+    @classmethod
+    def from_archive(cls, ctx: abi.Context, data: bytes, columns) -> "HostTable":
+        """S1 for a saved database (silo_host_table_load_archive): row layout and columns come from the
+        `.silo` bytes; columns whose tail could not be read (non-empty insertion index) are not uploaded."""
+        columns = list(columns)
+        archive = Archive(data, columns)
+        try:
+            chunk_sizes = archive.chunk_sizes(0)
+            complete = [bool(archive.info(i)["tail_parsed"]) for i in range(len(columns))]
+        finally:
+            archive.close()
+        names, alphabets, references, n = _archive_specs(columns)
+        handle = lib().silo_host_table_load_archive(ctx._h, data, len(data), names, alphabets, references, n)
+        if not handle:
+            raise HostError(lib().silo_host_last_error().decode())
+        table = cls.__new__(cls)
+        table._init_fields(ctx, chunk_sizes, 0)
+        table._h = handle
+        for (name, alphabet, reference), uploaded in zip(columns, complete):
+            if uploaded:
+                table.columns[name] = (16 if alphabet == NUCLEOTIDE else 28, len(reference))
+        return table
+
+    def _init_fields(self, ctx: abi.Context, chunk_sizes: Sequence[int], first_chunk: int) -> None:
         self.ctx = ctx
         self.chunk_sizes = [int(s) for s in chunk_sizes]
         self.n_chunks = len(self.chunk_sizes)
@@ -293,6 +396,10 @@ class HostTable:
         self._packed = np.empty(1 << 16, dtype=np.uint8)
         self._packed_out = (C.c_uint64(), C.c_uint32(), C.c_uint64())
         self._name_arrays: dict = {}
+        self._h = None
+
+    def __init__(self, ctx: abi.Context, chunk_sizes: Sequence[int], first_chunk: int = 0):
+        self._init_fields(ctx, chunk_sizes, first_chunk)
         arr = (C.c_uint32 * max(self.n_chunks, 1))(*self.chunk_sizes)
         self._h = lib().silo_host_table_create(ctx._h, first_chunk, arr, self.n_chunks)
         if not self._h:
