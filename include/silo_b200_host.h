@@ -29,6 +29,9 @@ typedef struct silo_host_rows silo_host_rows;
  * ("IllegalQueryException: ", "QueryCompilationException: ", "DeviceError[<status>]: ") */
 const char* silo_host_last_error(void);
 
+/* ctx == NULL creates a HOST-ONLY table: columns keep their metadata only (nothing is uploaded), the front half
+ * of the query compiler works (silo_host_filter_explain, silo_host_filter_lower_timed) and every call that
+ * needs the device fails with DeviceError[SILO_E_NO_DEVICE] -- there is no CPU evaluation path. */
 silo_host_table* silo_host_table_create(silo_gpu_ctx* ctx, uint32_t first_chunk, const uint32_t* chunk_sizes, uint32_t n_chunks);
 void silo_host_table_free(silo_host_table* table);
 /* alphabet: 0 nucleotide, 1 amino acid. Uploads through silo_gpu_column_upload. */
@@ -48,6 +51,11 @@ const silo_gpu_filter* silo_host_filter_device(const silo_host_filter* filter);
 int silo_host_filter_words(const silo_host_filter* filter, uint64_t* words /* 1024 x n_chunks */);
 /* the lowered program as text, one instruction per line (debugging / tests of the lowering) */
 int silo_host_filter_explain(silo_host_table* table, const char* expression, char* out, uint64_t capacity);
+
+/* parse -> rewrite(NONE) -> compile -> lower without running anything: microseconds of the four phases,
+ * sizes[3] = {instructions, blob bytes, bitmaps travelling with the program}, and a 64-bit FNV-1a digest of the
+ * lowered program (instruction fields + blob) so that two lowerings can be compared without the text form */
+int silo_host_filter_lower_timed(silo_host_table* table, const char* expression, double phase_us[4], uint64_t sizes[3], uint64_t* digest);
 
 /* BitmapAggregationNode (operators/bitmap_aggregation_node.cpp:304-356) through the host layer.
  * dimensions: ';'-separated, each "p:<column>:<0-based position>" (SequencePositionDimension) or

@@ -30,7 +30,7 @@ std::vector<CombinationRow> BitmapAggregationNode::execute() const {
    ProgramBuilder builder;
    const silo_filter_program program = compiled->lowerProgram(table, builder);
 
-   TemporaryRegistrations temporary{table.device, {}};
+   TemporaryRegistrations temporary{table.deviceTable(), {}};
    auto deviceId = [&](const std::string& name) -> uint32_t {
       const auto found = table.named_bitmaps.find(name);
       if (found == table.named_bitmaps.end()) {
@@ -40,7 +40,7 @@ std::vector<CombinationRow> BitmapAggregationNode::execute() const {
          return found->second.device_id;
       }
       uint32_t id = 0;
-      throwOnDeviceError(silo_gpu_bitmap_register(table.device, found->second.bytes.data(), found->second.bytes.size(), &id));
+      throwOnDeviceError(silo_gpu_bitmap_register(table.deviceTable(), found->second.bytes.data(), found->second.bytes.size(), &id));
       temporary.ids.push_back(id);
       return id;
    };
@@ -94,7 +94,7 @@ std::vector<CombinationRow> BitmapAggregationNode::execute() const {
    uint64_t n_combinations = 0;
    uint64_t cardinality = 0;
    throwOnDeviceError(silo_gpu_query_combinations(
-      table.device, &program, nullptr, device_dimensions.data(), static_cast<uint32_t>(device_dimensions.size()), &combinations,
+      table.deviceTable(), &program, nullptr, device_dimensions.data(), static_cast<uint32_t>(device_dimensions.size()), &combinations,
       &n_combinations, &cardinality
    ));
 

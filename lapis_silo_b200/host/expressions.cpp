@@ -12,22 +12,19 @@ namespace silo_host {
 
 namespace {
 
-void checkQuery(bool condition, const std::string& message) {
-   if (!condition) {
-      throw IllegalQueryException(message);
-   }
-}
-// (no std::string is built on the hot path of the reader: a literal message costs nothing unless thrown)
-void checkQuery(bool condition, const char* message) {
-   if (!condition) {
-      throw IllegalQueryException(message);
-   }
-}
+// CHECK_SILO_QUERY (query_engine/illegal_query_exception.h:8): the message is only built when the check
+// fails -- a MutationProfile runs one check per genome position
+#define CHECK_QUERY(condition, message)            \
+   do {                                            \
+      if (!(condition)) [[unlikely]] {             \
+         throw IllegalQueryException(message);     \
+      }                                            \
+   } while (false)
 
 const SequenceColumnInfo& requireColumn(const Table& table, const std::string& name) {
    const SequenceColumnInfo* column = table.findColumn(name);
    // validateSequenceName, query_engine/query_parse_sequence_name.h:10-20
-   checkQuery(column != nullptr, "Database does not contain the Sequence with name: '" + name + "'");
+   CHECK_QUERY(column != nullptr, "Database does not contain the Sequence with name: '" + name + "'");
    return *column;
 }
 
@@ -39,23 +36,13 @@ uint32_t maskOf(const std::vector<Symbol>& symbols) {
    return mask;
 }
 
-std::vector<Symbol> symbolsOf(uint32_t mask) {
-   std::vector<Symbol> symbols;
-   for (uint32_t symbol = 0; symbol < 32; ++symbol) {
-      if (((mask >> symbol) & 1u) != 0) {
-         symbols.push_back(static_cast<Symbol>(symbol));
-      }
-   }
-   return symbols;
-}
-
 uint32_t allSymbolsMask(const Alphabet& alphabet) {
    return alphabet.count() == 32 ? 0xFFFFFFFFu : (1u << alphabet.count()) - 1u;
 }
 
 Symbol toSymbol(const Alphabet& alphabet, char character) {
    const auto symbol = alphabet.charToSymbol(character);
-   checkQuery(
+   CHECK_QUERY(
       symbol.has_value(), "Invalid " + alphabet.symbol_name + " symbol '" + std::string(1, character) + "'"
    );
    return symbol.value();
@@ -109,16 +96,16 @@ std::unique_ptr<Operator> SymbolInSet::compile(const Table& table) const {
 std::unique_ptr<Operator> compileSymbolInSet(
    const SequenceColumnInfo& sequence_column,
    uint32_t position_idx,
-   const std::vector<Symbol>& symbols
+   SymbolSet symbols
 ) {
    const Alphabet& alphabet = *sequence_column.alphabet;
-   checkQuery(
+   CHECK_QUERY(
       position_idx < sequence_column.reference_sequence.size(),
       "SymbolInSet<" + alphabet.symbol_name + "> position is out of bounds " +
          std::to_string(position_idx + 1) + " > " + std::to_string(sequence_column.reference_sequence.size())
    );
    const int column = sequence_column.device_column;
-   const uint32_t requested = maskOf(symbols);
+   const uint32_t requested = symbols.mask;
    const uint32_t reference_bit = 1u << sequence_column.local_reference.at(position_idx);
    const uint32_t missing_bit = 1u << alphabet.missing;
    const bool includes_reference = (requested & reference_bit) != 0;
@@ -169,7 +156,7 @@ std::string SymbolEquals::toString() const {
 ExpressionPtr SymbolEquals::rewrite(const Table& table, AmbiguityMode mode) const {
    const auto& sequence_column = requireColumn(table, column);
    const Alphabet& alphabet = *sequence_column.alphabet;
-   checkQuery(
+   CHECK_QUERY(
       position_idx < sequence_column.reference_sequence.size(),
       "SymbolEquals<" + alphabet.symbol_name + "> position is out of bounds " +
          std::to_string(position_idx + 1) + " > " + std::to_string(sequence_column.reference_sequence.size())
@@ -193,7 +180,7 @@ std::string HasMutation::toString() const {
 ExpressionPtr HasMutation::rewrite(const Table& table, AmbiguityMode mode) const {
    const auto& sequence_column = requireColumn(table, column);
    const Alphabet& alphabet = *sequence_column.alphabet;
-   checkQuery(
+   CHECK_QUERY(
       position_idx < sequence_column.reference_sequence.size(),
       "Has" + alphabet.symbol_name + "Mutation position is out of bounds " + std::to_string(position_idx + 1) +
          " > " + std::to_string(sequence_column.reference_sequence.size())
@@ -205,7 +192,7 @@ ExpressionPtr HasMutation::rewrite(const Table& table, AmbiguityMode mode) const
    } else {
       mask &= ~maskOf(alphabet.ambiguity_symbols.at(reference_symbol));
    }
-   return std::make_shared<SymbolInSet>(column, position_idx, symbolsOf(mask));
+   return std::make_shared<SymbolInSet>(column, position_idx, SymbolSet(mask));
 }
 
 std::unique_ptr<Operator> HasMutation::compile(const Table&) const {
@@ -373,14 +360,13 @@ ExpressionPtr Or::rewrite(const Table& table, AmbiguityMode mode) const {
    }
    // or.cpp:97-124: SymbolInSet children on the same (column, position) merge into one set
    ExpressionVector merged_children;
-   std::map<std::pair<std::string, uint32_t>, std::vector<Symbol>> merged;
+   std::map<std::pair<std::string, uint32_t>, SymbolSet> merged;
    std::vector<std::pair<std::string, uint32_t>> merge_order_nucleotide;
    std::vector<std::pair<std::string, uint32_t>> merge_order_amino_acid;
    for (auto& child : simplified) {
       if (const auto* in_set = dynamic_cast<const SymbolInSet*>(child.get())) {
          const auto key = std::make_pair(in_set->column, in_set->position_idx);
-         auto& symbols = merged[key];
-         symbols.insert(symbols.end(), in_set->symbols.begin(), in_set->symbols.end());
+         merged[key].mask |= in_set->symbols.mask;
       } else {
          merged_children.push_back(std::move(child));
       }
@@ -466,6 +452,7 @@ std::unique_ptr<Operator> NOf::compile(const Table& table) const {
    // kept as negated children
    OperatorVector non_negated;
    OperatorVector negated;
+   non_negated.reserve(children.size());
    int k = number_of_matchers;
    for (const auto& child_expression : children) {
       auto child = child_expression->compile(table);
@@ -539,7 +526,7 @@ ExpressionPtr MutationProfile::rewrite(const Table& table, AmbiguityMode) const 
    const size_t reference_length = sequence_column.reference_sequence.size();
    std::vector<Symbol> profile;
    if (const auto* query = std::get_if<QuerySequence>(&input)) {
-      checkQuery(
+      CHECK_QUERY(
          query->sequence.size() == reference_length,
          "querySequence length " + std::to_string(query->sequence.size()) +
             " does not match the reference sequence length " + std::to_string(reference_length) + " for " +
@@ -548,7 +535,7 @@ ExpressionPtr MutationProfile::rewrite(const Table& table, AmbiguityMode) const 
       profile.reserve(reference_length);
       for (char character : query->sequence) {
          const auto symbol = alphabet.charToSymbol(character);
-         checkQuery(
+         CHECK_QUERY(
             symbol.has_value(),
             "Invalid " + alphabet.symbol_name + " symbol '" + std::string(1, character) +
                "' in querySequence for MutationProfile"
@@ -558,7 +545,7 @@ ExpressionPtr MutationProfile::rewrite(const Table& table, AmbiguityMode) const 
    } else {
       profile = sequence_column.reference_sequence;
       for (const auto& [position, character] : std::get<Mutations>(input).mutations) {
-         checkQuery(
+         CHECK_QUERY(
             position < reference_length,
             alphabet.symbol_name + " MutationProfile mutation position " + std::to_string(position + 1) +
                " is out of bounds (reference length " + std::to_string(reference_length) + ")"
@@ -569,6 +556,7 @@ ExpressionPtr MutationProfile::rewrite(const Table& table, AmbiguityMode) const 
    // one "definitely different" child per position: the symbols that are NOT compatible with the
    // profile symbol (mutation_profile.cpp:222-247); the filter is "fewer than distance+1 differ"
    ExpressionVector differences;
+   differences.reserve(profile.size());
    for (size_t position = 0; position < profile.size(); ++position) {
       if (profile[position] == alphabet.missing) {
          continue;
@@ -578,9 +566,7 @@ ExpressionPtr MutationProfile::rewrite(const Table& table, AmbiguityMode) const 
       if (incompatible == 0) {
          continue;
       }
-      differences.push_back(
-         std::make_shared<SymbolInSet>(column, static_cast<uint32_t>(position), symbolsOf(incompatible))
-      );
+      differences.push_back(std::make_shared<SymbolInSet>(column, static_cast<uint32_t>(position), SymbolSet(incompatible)));
    }
    return std::make_shared<Negation>(
       std::make_shared<NOf>(std::move(differences), static_cast<int>(distance) + 1, false)
@@ -648,7 +634,7 @@ struct CoveredLeaf : ScalarExpression {
    ExpressionPtr rewrite(const Table&, AmbiguityMode) const override { return shared_from_this(); }
    std::unique_ptr<Operator> compile(const Table& table) const override {
       const auto& sequence_column = requireColumn(table, column);
-      checkQuery(position_idx < sequence_column.reference_sequence.size(), "position is out of bounds");
+      CHECK_QUERY(position_idx < sequence_column.reference_sequence.size(), "position is out of bounds");
       return std::make_unique<Selection>(CoveragePredicate{sequence_column.device_column, position_idx, covered});
    }
 };
@@ -738,16 +724,16 @@ class Reader {
 
    Node next() {
       skipSpace();
-      checkQuery(cursor < text.size(), "filter expression ended unexpectedly");
+      CHECK_QUERY(cursor < text.size(), "filter expression ended unexpectedly");
       Node node;
       const char head = text[cursor];
-      checkQuery(head != ')', "filter expression: unexpected ')'");
+      CHECK_QUERY(head != ')', "filter expression: unexpected ')'");
       if (head == '(') {
          ++cursor;
          node.items.reserve(16);
          for (;;) {
             skipSpace();
-            checkQuery(cursor < text.size(), "filter expression: missing ')'");
+            CHECK_QUERY(cursor < text.size(), "filter expression: missing ')'");
             if (text[cursor] == ')') {
                ++cursor;
                return node;
@@ -758,7 +744,7 @@ class Reader {
       node.is_atom = true;
       if (head == '"') {
          const size_t close = text.find('"', cursor + 1);
-         checkQuery(close != std::string::npos, "filter expression: unterminated string");
+         CHECK_QUERY(close != std::string::npos, "filter expression: unterminated string");
          node.atom = std::string_view(text).substr(cursor + 1, close - cursor - 1);
          cursor = close + 1;
          return node;
@@ -778,12 +764,12 @@ class Reader {
 };
 
 std::string atom(const Node& node) {
-   checkQuery(node.is_atom, "filter expression: expected an atom");
+   CHECK_QUERY(node.is_atom, "filter expression: expected an atom");
    return std::string(node.atom);
 }
 
 uint64_t number(const Node& node) {
-   checkQuery(node.is_atom, "filter expression: expected an atom");
+   CHECK_QUERY(node.is_atom, "filter expression: expected an atom");
    const std::string_view text = node.atom;
    uint64_t value = 0;
    bool valid = !text.empty() && text.size() <= 19;
@@ -799,14 +785,14 @@ uint64_t number(const Node& node) {
 
 uint32_t position(const Node& node) {
    const uint64_t one_based = number(node);
-   checkQuery(one_based != 0, "The field 'position' is 1-indexed. Value of 0 not allowed.");
+   CHECK_QUERY(one_based != 0, "The field 'position' is 1-indexed. Value of 0 not allowed.");
    return static_cast<uint32_t>(one_based - 1);
 }
 
 ExpressionPtr build(const Node& node);
 
 ExpressionVector buildList(const Node& list, size_t from = 0) {
-   checkQuery(!list.is_atom, "filter expression: expected a list");
+   CHECK_QUERY(!list.is_atom, "filter expression: expected a list");
    ExpressionVector result;
    for (size_t i = from; i < list.items.size(); ++i) {
       result.push_back(build(list.items[i]));
@@ -815,11 +801,11 @@ ExpressionVector buildList(const Node& list, size_t from = 0) {
 }
 
 ExpressionPtr build(const Node& node) {
-   checkQuery(!node.is_atom && !node.items.empty(), "filter expression: expected a non-empty list");
+   CHECK_QUERY(!node.is_atom && !node.items.empty(), "filter expression: expected a non-empty list");
    const auto& items = node.items;
    const std::string& head = atom(items[0]);
    auto arity = [&](size_t count) {
-      checkQuery(items.size() == count + 1, "filter expression: wrong number of arguments for " + head);
+      CHECK_QUERY(items.size() == count + 1, "filter expression: wrong number of arguments for " + head);
    };
    if (head == "true" || head == "false") {
       arity(0);
@@ -828,7 +814,7 @@ ExpressionPtr build(const Node& node) {
    if (head == "sym-eq") {
       arity(3);
       const std::string& symbol = atom(items[3]);
-      checkQuery(symbol.size() == 1, "symbol must be a single character");
+      CHECK_QUERY(symbol.size() == 1, "symbol must be a single character");
       return std::make_shared<SymbolEquals>(
          atom(items[1]), position(items[2]), symbol == "." ? std::nullopt : std::optional<char>(symbol[0])
       );
@@ -864,11 +850,11 @@ ExpressionPtr build(const Node& node) {
       return std::make_shared<Exact>(build(items[1]));
    }
    if (head == "n-of") {
-      checkQuery(items.size() >= 3, "filter expression: n-of needs K and EXACT");
+      CHECK_QUERY(items.size() >= 3, "filter expression: n-of needs K and EXACT");
       return std::make_shared<NOf>(buildList(node, 3), static_cast<int>(number(items[1])), number(items[2]) != 0);
    }
    if (head == "profile") {
-      checkQuery(items.size() >= 4, "filter expression: profile needs COL DIST KIND ..");
+      CHECK_QUERY(items.size() >= 4, "filter expression: profile needs COL DIST KIND ..");
       const std::string& column = atom(items[1]);
       const auto distance = static_cast<uint32_t>(number(items[2]));
       const std::string& kind = atom(items[3]);
@@ -877,11 +863,11 @@ ExpressionPtr build(const Node& node) {
          return std::make_shared<MutationProfile>(column, distance, MutationProfile::QuerySequence{atom(items[4])});
       }
       if (kind == "muts") {
-         checkQuery((items.size() - 4) % 2 == 0, "filter expression: profile muts needs POS SYM pairs");
+         CHECK_QUERY((items.size() - 4) % 2 == 0, "filter expression: profile muts needs POS SYM pairs");
          MutationProfile::Mutations mutations;
          for (size_t i = 4; i + 1 < items.size(); i += 2) {
             const std::string& symbol = atom(items[i + 1]);
-            checkQuery(symbol.size() == 1, "symbol must be a single character");
+            CHECK_QUERY(symbol.size() == 1, "symbol must be a single character");
             mutations.mutations.emplace_back(position(items[i]), symbol[0]);
          }
          return std::make_shared<MutationProfile>(column, distance, std::move(mutations));
@@ -895,7 +881,7 @@ ExpressionPtr build(const Node& node) {
       return std::make_shared<BitmapFilter>(atom(items[1]));
    }
    if (head == "ranges") {
-      checkQuery((items.size() - 1) % 2 == 0, "filter expression: ranges needs START END pairs");
+      CHECK_QUERY((items.size() - 1) % 2 == 0, "filter expression: ranges needs START END pairs");
       std::vector<RangeSelection::Range> ranges;
       for (size_t i = 1; i + 1 < items.size(); i += 2) {
          ranges.push_back({static_cast<uint32_t>(number(items[i])), static_cast<uint32_t>(number(items[i + 1]))});
@@ -917,7 +903,7 @@ ExpressionPtr build(const Node& node) {
       auto expression = std::make_shared<PhysicalOperator>();
       size_t lists_from = 1;
       if (head == "op-threshold") {
-         checkQuery(items.size() == 5, "filter expression: op-threshold K EXACT (pos..) (neg..)");
+         CHECK_QUERY(items.size() == 5, "filter expression: op-threshold K EXACT (pos..) (neg..)");
          expression->kind = PhysicalOperator::THRESHOLD;
          expression->number_of_matchers = static_cast<uint32_t>(number(items[1]));
          expression->match_exactly = number(items[2]) != 0;
@@ -951,7 +937,7 @@ ExpressionPtr build(const Node& node) {
 ExpressionPtr parseFilterExpression(const std::string& text) {
    Reader reader(text);
    const Node node = reader.next();
-   checkQuery(reader.exhausted(), "filter expression: trailing input");
+   CHECK_QUERY(reader.exhausted(), "filter expression: trailing input");
    return build(node);
 }
 

@@ -44,14 +44,29 @@ struct BoolLiteral : ScalarExpression {
    std::unique_ptr<Operator> compile(const Table& table) const override;
 };
 
+// A set of symbol ids as a bit mask (both alphabets have <= 32 symbols); the reference keeps a
+// std::vector<Symbol> (symbol_in_set.h). No allocation per SymbolInSet: a MutationProfile creates one
+// per genome position.
+struct SymbolSet {
+   uint32_t mask = 0;
+   SymbolSet() = default;
+   explicit SymbolSet(uint32_t mask) : mask(mask) {}
+   SymbolSet(const std::vector<Symbol>& symbols) {  // NOLINT(google-explicit-constructor)
+      for (Symbol symbol : symbols) {
+         mask |= 1u << symbol;
+      }
+   }
+   [[nodiscard]] size_t size() const { return static_cast<size_t>(__builtin_popcount(mask)); }
+};
+
 struct SymbolInSet : ScalarExpression {
    std::string column;
    uint32_t position_idx;
-   std::vector<Symbol> symbols;
-   SymbolInSet(std::string column, uint32_t position_idx, std::vector<Symbol> symbols)
+   SymbolSet symbols;
+   SymbolInSet(std::string column, uint32_t position_idx, SymbolSet symbols)
        : column(std::move(column)),
          position_idx(position_idx),
-         symbols(std::move(symbols)) {}
+         symbols(symbols) {}
    std::string toString() const override;
    ExpressionPtr rewrite(const Table&, AmbiguityMode) const override;
    std::unique_ptr<Operator> compile(const Table& table) const override;
@@ -173,7 +188,7 @@ struct RowRanges : ScalarExpression {
 std::unique_ptr<Operator> compileSymbolInSet(
    const SequenceColumnInfo& sequence_column,
    uint32_t position_idx,
-   const std::vector<Symbol>& symbols
+   SymbolSet symbols
 );
 
 // operators/compute_filter.cpp:14-21

@@ -212,7 +212,7 @@ silo_host_prepared* silo_host_filter_prepare(silo_host_table* table, const char*
       program.blob_bytes = builder.blob.size();
       program.n_bitmaps = static_cast<uint32_t>(builder.bitmaps.size());
       program.bitmaps = builder.bitmaps.data();
-      throwOnDeviceError(silo_gpu_program_prepare(table->table->device, &program, &owned->program, &owned->filter));
+      throwOnDeviceError(silo_gpu_program_prepare(table->table->deviceTable(), &program, &owned->program, &owned->filter));
       result = owned.release();
    });
    return result;
@@ -264,6 +264,46 @@ int silo_host_filter_explain(silo_host_table* table, const char* expression, cha
       return status;
    }
    return copyText(text, out, capacity);
+}
+
+int silo_host_filter_lower_timed(silo_host_table* table, const char* expression, double phase_us[4], uint64_t sizes[3], uint64_t* digest) {
+   return guarded([&] {
+      const double t0 = nowMicroseconds();
+      const ExpressionPtr parsed = parseFilterExpression(expression);
+      const double t1 = nowMicroseconds();
+      const ExpressionPtr rewritten = parsed->rewrite(*table->table, AmbiguityMode::NONE);
+      const double t2 = nowMicroseconds();
+      const std::unique_ptr<Operator> compiled = rewritten->compile(*table->table);
+      const double t3 = nowMicroseconds();
+      ProgramBuilder builder;
+      builder.table = table->table.get();
+      compiled->lower(builder);
+      const double t4 = nowMicroseconds();
+      phase_us[0] = t1 - t0;
+      phase_us[1] = t2 - t1;
+      phase_us[2] = t3 - t2;
+      phase_us[3] = t4 - t3;
+      sizes[0] = builder.instrs.size();
+      sizes[1] = builder.blob.size();
+      sizes[2] = builder.bitmaps.size();
+      uint64_t hash = 14695981039346656037ULL;
+      auto mix = [&](uint64_t value, int bytes) {
+         for (int i = 0; i < bytes; ++i) {
+            hash = (hash ^ ((value >> (8 * i)) & 0xFF)) * 1099511628211ULL;
+         }
+      };
+      for (const silo_filter_instr& instr : builder.instrs) {
+         mix(instr.opcode, 1);
+         mix(instr.flags, 1);
+         mix(instr.column, 2);
+         mix(instr.a, 4);
+         mix(instr.b, 8);
+      }
+      for (uint8_t byte : builder.blob) {
+         mix(byte, 1);
+      }
+      *digest = hash;
+   });
 }
 
 int silo_host_mutation_counts(silo_host_table* table, const char* column, const silo_host_filter* filter, uint32_t* counts) {

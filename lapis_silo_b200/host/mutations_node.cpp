@@ -29,12 +29,12 @@ SymbolCounts calculateMutationsPerPosition(
    if (filter_cardinality == sequence_count_in_column) {
       // addMutationCountsForFullBitmaps (:239-266): stored cardinalities only, no intersections
       throwOnDeviceError(silo_gpu_mutation_counts_symbols(
-         table.device, sequence_column.device_column, nullptr, symbol_mask, counts.owner.get()
+         table.deviceTable(), sequence_column.device_column, nullptr, symbol_mask, counts.owner.get()
       ));
    } else if (filter_cardinality > 0) {
       // addMutationCountsForMixedBitmaps (:205-237)
       throwOnDeviceError(silo_gpu_mutation_counts_symbols(
-         table.device, sequence_column.device_column, bitmap_filter.get(), symbol_mask, counts.owner.get()
+         table.deviceTable(), sequence_column.device_column, bitmap_filter.get(), symbol_mask, counts.owner.get()
       ));
    } else {
       std::memset(counts.owner.get(), 0, counts.size() * sizeof(uint32_t));
@@ -168,7 +168,7 @@ std::vector<MutationRow> MutationsNode::execute() const {
       uint64_t n_hits = 0;
       uint64_t cardinality = 0;
       throwOnDeviceError(silo_gpu_query_mutation_hits(
-         table.device, &program, nullptr, column->device_column, validSymbolMask(*column->alphabet), min_proportion, &hits, &n_hits,
+         table.deviceTable(), &program, nullptr, column->device_column, validSymbolMask(*column->alphabet), min_proportion, &hits, &n_hits,
          &cardinality
       ));
       const double threshold_begin = nowMicroseconds();
@@ -195,7 +195,7 @@ std::vector<MutationRow> MutationsNode::execute() const {
       uint64_t n_hits = 0;
       // cardinality == numRows: the stored-cardinality path (mutations_node.cpp:280-281)
       throwOnDeviceError(silo_gpu_query_mutation_hits(
-         table.device, nullptr, filter_cardinality == table.row_layout.numRows() ? nullptr : bitmap_filter.get(), column->device_column,
+         table.deviceTable(), nullptr, filter_cardinality == table.row_layout.numRows() ? nullptr : bitmap_filter.get(), column->device_column,
          validSymbolMask(*column->alphabet), min_proportion, &hits, &n_hits, nullptr
       ));
       const double threshold_begin = nowMicroseconds();
@@ -225,7 +225,7 @@ void MutationsNode::enqueueShardCounts(void* d_counts, void* cuda_stream) const 
    const std::unique_ptr<Operator> compiled = rewritten->compile(table);
    ProgramBuilder builder;
    const silo_filter_program program = compiled->lowerProgram(table, builder);
-   throwOnDeviceError(silo_gpu_query_mutation_counts_async(table.device, &program, column.device_column, d_counts, cuda_stream));
+   throwOnDeviceError(silo_gpu_query_mutation_counts_async(table.deviceTable(), &program, column.device_column, d_counts, cuda_stream));
 }
 
 std::vector<MutationRow> MutationsNode::collectRows(const void* d_summed_counts, void* cuda_stream, uint64_t* shard_cardinality) const {
@@ -233,7 +233,7 @@ std::vector<MutationRow> MutationsNode::collectRows(const void* d_summed_counts,
    const silo_mutation_hit* hits = nullptr;
    uint64_t n_hits = 0;
    throwOnDeviceError(silo_gpu_mutation_hits_from_counts(
-      table.device, column.device_column, d_summed_counts, validSymbolMask(*column.alphabet), min_proportion, cuda_stream, &hits, &n_hits,
+      table.deviceTable(), column.device_column, d_summed_counts, validSymbolMask(*column.alphabet), min_proportion, cuda_stream, &hits, &n_hits,
       shard_cardinality
    ));
    std::vector<MutationRow> rows;

@@ -71,7 +71,7 @@ DeviceBitmap Operator::evaluate(const Table& table) const {
    silo_gpu_filter* filter = nullptr;
    uint64_t cardinality = 0;
    const double eval_begin = nowMicroseconds();
-   throwOnDeviceError(silo_gpu_filter_eval(table.device, &program, &filter, &cardinality));
+   throwOnDeviceError(silo_gpu_filter_eval(table.deviceTable(), &program, &filter, &cardinality));
    lastQueryProfile().compile_us += eval_begin - lower_begin;
    lastQueryProfile().filter_us = nowMicroseconds() - eval_begin;
    return DeviceBitmap{filter, cardinality};

@@ -106,6 +106,11 @@ void throwOnDeviceError(int status) {
 Table::Table(silo_gpu_ctx* ctx, RowLayout layout)
     : row_layout(std::move(layout)),
       ctx(ctx) {
+   pinned_pool = std::make_shared<PinnedPool>();
+   pinned_pool->ctx = ctx;
+   if (ctx == nullptr) {
+      return;  // host-only table, see table.h
+   }
    throwOnDeviceError(silo_gpu_table_create(
       ctx,
       row_layout.first_chunk,
@@ -113,12 +118,12 @@ Table::Table(silo_gpu_ctx* ctx, RowLayout layout)
       static_cast<uint32_t>(row_layout.chunk_sizes.size()),
       &device
    ));
-   pinned_pool = std::make_shared<PinnedPool>();
-   pinned_pool->ctx = ctx;
 }
 
 Table::~Table() {
-   silo_gpu_table_free(device);
+   if (device != nullptr) {
+      silo_gpu_table_free(device);
+   }
 }
 
 Table::PinnedPool::~PinnedPool() {
@@ -158,14 +163,14 @@ std::shared_ptr<uint32_t> Table::acquireCountsBuffer(size_t n_values) const {
 void Table::registerBitmap(const std::string& name, const uint8_t* bytes, uint64_t size, bool resident) {
    auto existing = named_bitmaps.find(name);
    if (existing != named_bitmaps.end() && existing->second.resident) {
-      throwOnDeviceError(silo_gpu_bitmap_unregister(device, existing->second.device_id));
+      throwOnDeviceError(silo_gpu_bitmap_unregister(deviceTable(), existing->second.device_id));
       named_bitmaps.erase(existing);
    }
    NamedBitmap bitmap;
    bitmap.bytes.assign(bytes, bytes + size);
    bitmap.resident = resident;
    if (resident) {
-      throwOnDeviceError(silo_gpu_bitmap_register(device, bitmap.bytes.data(), bitmap.bytes.size(), &bitmap.device_id));
+      throwOnDeviceError(silo_gpu_bitmap_register(deviceTable(), bitmap.bytes.data(), bitmap.bytes.size(), &bitmap.device_id));
    }
    named_bitmaps[name] = std::move(bitmap);
 }
@@ -194,6 +199,11 @@ int Table::addSequenceColumn(
    }
    info.local_reference.assign(column.local_reference, column.local_reference + column.genome_length);
    info.has_null_rows = column.n_null_rows > 0;
+   if (device == nullptr) {  // host-only table: metadata only
+      info.device_column = static_cast<int>(columns.size());
+      columns.push_back(std::move(info));
+      return columns.back().device_column;
+   }
    const int device_column = silo_gpu_column_upload(device, &column);
    throwOnDeviceError(device_column);
    info.device_column = device_column;

@@ -102,8 +102,17 @@ class Table {
    // the u32[n_symbols][genome_length] counts straight into them. Thread safe.
    [[nodiscard]] std::shared_ptr<uint32_t> acquireCountsBuffer(size_t n_values) const;
 
+   // ctx == nullptr makes a HOST-ONLY table: the front half of the query compiler (parse -> rewrite ->
+   // compile -> lower to a filter program) runs against its metadata, so the lowering can be tested and
+   // timed where there is no GPU; nothing is uploaded and every device entry fails loudly (deviceTable()).
    silo_gpu_ctx* ctx = nullptr;
    silo_gpu_table* device = nullptr;
+   [[nodiscard]] silo_gpu_table* deviceTable() const {
+      if (device == nullptr) {
+         throw DeviceError(SILO_E_NO_DEVICE, "host-only table (created without a device context): there is no CPU fallback for device work");
+      }
+      return device;
+   }
 
   private:
    struct PinnedPool {

@@ -34,6 +34,7 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_synthetic_generation", "silo_host_synthetic_build_column",
     "silo_host_synthetic_release_column", "silo_host_synthetic_lineage_bitmap",
     "silo_host_synthetic_date_ranges", "silo_host_partition_chunks",
+    "silo_host_filter_lower_timed",
     "silo_host_archive_read", "silo_host_archive_free", "silo_host_archive_column", "silo_host_archive_column_info",
     "silo_host_archive_chunk_sizes", "silo_host_table_load_archive", "silo_host_roaring_runs",
 ]
@@ -132,6 +133,7 @@ def lib() -> C.CDLL:
         L.silo_host_synthetic_lineage_bitmap.restype = C.c_int64
         L.silo_host_synthetic_date_ranges.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64, C.c_uint32]
         L.silo_host_partition_chunks.argtypes = [C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.silo_host_filter_lower_timed.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         strings, ints = C.POINTER(C.c_char_p), C.POINTER(C.c_int)
         L.silo_host_archive_read.argtypes = [C.c_char_p, C.c_uint64, strings, ints, strings, C.c_uint32]
         L.silo_host_archive_read.restype = vp
@@ -401,7 +403,8 @@ class HostTable:
     def __init__(self, ctx: abi.Context, chunk_sizes: Sequence[int], first_chunk: int = 0):
         self._init_fields(ctx, chunk_sizes, first_chunk)
         arr = (C.c_uint32 * max(self.n_chunks, 1))(*self.chunk_sizes)
-        self._h = lib().silo_host_table_create(ctx._h, first_chunk, arr, self.n_chunks)
+        # ctx None: a host-only table (metadata, query compiler front half; device work fails loudly)
+        self._h = lib().silo_host_table_create(ctx._h if ctx is not None else None, first_chunk, arr, self.n_chunks)
         if not self._h:
             raise HostError(lib().silo_host_last_error().decode())
 
@@ -409,6 +412,13 @@ class HostTable:
         _check(lib().silo_host_table_add_column(
             self._h, name.encode(), alphabet, reference.encode(), C.cast(desc_ptr, C.c_void_p)))
         self.columns[name] = (16 if alphabet == NUCLEOTIDE else 28, len(reference))
+
+    def lower_timed(self, expression: str) -> dict:
+        """parse -> rewrite -> compile -> lower only: phase times (us), program sizes and a digest of the program"""
+        phases, sizes, digest = (C.c_double * 4)(), (C.c_uint64 * 3)(), C.c_uint64()
+        _check(lib().silo_host_filter_lower_timed(self._h, expression.encode(), phases, sizes, C.byref(digest)))
+        return {"parse_us": phases[0], "rewrite_us": phases[1], "compile_us": phases[2], "lower_us": phases[3],
+                "n_instrs": int(sizes[0]), "blob_bytes": int(sizes[1]), "n_bitmaps": int(sizes[2]), "digest": int(digest.value)}
 
     def register_bitmap(self, name: str, portable_roaring_bytes: bytes, resident: bool = True) -> None:
         """resident: a static index bitmap, uploaded once (silo_gpu_bitmap_register); otherwise the
