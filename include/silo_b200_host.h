@@ -124,12 +124,11 @@ silo_host_archive* silo_host_archive_read(const uint8_t* bytes, uint64_t size, c
 void silo_host_archive_free(silo_host_archive* archive);
 /* the column in the upload format; valid until the archive object is freed */
 const silo_column_desc* silo_host_archive_column(const silo_host_archive* archive, uint32_t index);
-/* info[6] = {n_chunks, sequence_count, tail_parsed (0: a non-empty insertion index hides the null bitmap),
+/* info[6] = {n_chunks, sequence_count, positions with insertions (the insertion index is read through, not kept),
  * vertical_bitmaps_size, horizontal_bitmaps_size, num_chunks member} */
 int silo_host_archive_column_info(const silo_host_archive* archive, uint32_t index, uint64_t info[6]);
 int silo_host_archive_chunk_sizes(const silo_host_archive* archive, uint32_t index, uint32_t* chunk_sizes, uint32_t capacity);
-/* S1 for a saved database: creates the table (row layout from the coverage index) and uploads every column
- * that was read completely */
+/* S1 for a saved database: creates the table (row layout from the coverage index) and uploads every column */
 silo_host_table* silo_host_table_load_archive(silo_gpu_ctx* ctx, const uint8_t* bytes, uint64_t size, const char* const* names,
                                               const int* alphabets, const char* const* references, uint32_t n_columns);
 /* ascending {first, end_exclusive} runs of a portable roaring bitmap; returns the number of runs or -1 */

@@ -709,7 +709,7 @@ int silo_host_archive_column_info(const silo_host_archive* archive, uint32_t ind
       const LoadedSequenceColumn& column = *archive->columns.at(index);
       info[0] = column.chunk_sizes.size();
       info[1] = column.sequence_count;
-      info[2] = column.tail_parsed ? 1 : 0;
+      info[2] = column.n_insertion_positions;
       info[3] = column.vertical_bitmaps_size;
       info[4] = column.horizontal_bitmaps_size;
       info[5] = column.num_chunks;

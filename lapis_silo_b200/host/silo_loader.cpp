@@ -177,8 +177,7 @@ uint32_t expectedPayloadBytes(uint8_t typecode, uint32_t cardinality, const uint
    }
 }
 
-// Parses the column at cursor.position up to (tail_parsed) the end of the column or (not tail_parsed)
-// the size fields of a non-empty insertion index.
+// Parses the column at cursor.position to its end.
 void parseSequenceColumn(Cursor& cursor, const ArchiveColumnSpec& spec, LoadedSequenceColumn& column) {
    const Alphabet& alphabet = *spec.alphabet;
    const std::string sym = alphabet.symbol_name;
@@ -283,36 +282,63 @@ void parseSequenceColumn(Cursor& cursor, const ArchiveColumnSpec& spec, LoadedSe
          throw ArchiveFormatError("coverage range outside the genome in column " + spec.name);
       }
    }
-   // insertion_index.h:84-100: two unordered_maps; only an empty index is read through
+   // insertion_index.h:84-100: insertion_positions (position -> InsertionPosition {insertions,
+   // three_mer_index}, :28-63) and collected_insertions. The query path does not use them; they are
+   // read through because sequence_count, the null bitmap and num_chunks lie behind them.
    cursor.classInfo("InsertionIndex<" + sym + ">");
    cursor.classInfo("unordered_map<u32,InsertionPosition<" + sym + ">>");
-   const uint64_t n_positions = cursor.u64();
+   const uint64_t n_positions = cursor.count(4 + 8 + 4 + 8 + 8 + 4);
    cursor.u64();  // bucket_count
-   cursor.u32();
-   if (n_positions != 0) {
-      // the skipped part registers these; a later column of the same alphabet carries no class info for them
-      for (const std::string& name :
-           {"pair<u32,InsertionPosition<" + sym + ">>", "InsertionPosition<" + sym + ">", std::string("vector<Insertion>"), std::string("Insertion"),
-            "unordered_map<ThreeMer<" + sym + ">,InsertionIds>", std::string("unordered_map<u32,unordered_map<string,Roaring>>"),
-            std::string("SequenceColumnInfo")}) {
-         cursor.state->seen_classes.insert(name);
+   cursor.u32();  // item_version
+   column.n_insertion_positions = n_positions;
+   for (uint64_t i = 0; i < n_positions; ++i) {
+      cursor.classInfo("pair<u32,InsertionPosition<" + sym + ">>");
+      if (cursor.u32() > length) {
+         throw ArchiveFormatError("insertion position beyond the genome in column " + spec.name);
       }
-      cursor.state->roaring = Seen::YES;  // Insertion::row_ids
-      column.tail_parsed = false;
-      uint64_t rows = 0;
-      for (uint32_t chunk_rows : column.chunk_sizes) {
-         rows += chunk_rows;
+      cursor.classInfo("InsertionPosition<" + sym + ">");
+      cursor.classInfo("vector<Insertion>");
+      const uint64_t n_insertions = cursor.count(8 + 8 + 8);
+      cursor.u32();
+      for (uint64_t insertion = 0; insertion < n_insertions; ++insertion) {
+         cursor.classInfo("Insertion");
+         cursor.take(cursor.count(1));  // value
+         cursor.roaring();              // row_ids
       }
-      column.sequence_count = static_cast<uint32_t>(rows);
-      column.num_chunks = static_cast<uint16_t>(n_chunks);
-      return;
+      cursor.classInfo("unordered_map<ThreeMer<" + sym + ">,InsertionIds>");
+      const uint64_t n_three_mers = cursor.count(8 + 12 + 8);
+      cursor.u64();
+      cursor.u32();
+      for (uint64_t three_mer = 0; three_mer < n_three_mers; ++three_mer) {
+         cursor.classInfo("pair<ThreeMer<" + sym + ">,InsertionIds>");
+         cursor.classInfo("ThreeMer<" + sym + ">");  // std::array<Symbol, 3>: element count + the enums as ints
+         if (cursor.u64() != 3) {
+            throw ArchiveFormatError("a three-mer that does not have three symbols in column " + spec.name);
+         }
+         for (int symbol = 0; symbol < 3; ++symbol) {
+            if (cursor.u32() >= alphabet.count()) {
+               throw ArchiveFormatError("three-mer symbol out of range in column " + spec.name);
+            }
+         }
+         cursor.take(4 * cursor.count(4));  // InsertionIds = std::vector<uint32_t>: size + raw values
+      }
    }
    cursor.classInfo("unordered_map<u32,unordered_map<string,Roaring>>");
-   const uint64_t n_collected = cursor.u64();
+   const uint64_t n_collected = cursor.count(4 + 8 + 8 + 4);
    cursor.u64();
    cursor.u32();
-   if (n_collected != 0) {
-      throw ArchiveFormatError("collected insertions without insertion positions");
+   for (uint64_t i = 0; i < n_collected; ++i) {  // empty once buildIndex has run; same layout rules
+      cursor.classInfo("pair<u32,unordered_map<string,Roaring>>");
+      cursor.u32();
+      cursor.classInfo("unordered_map<string,Roaring>");
+      const uint64_t n_values = cursor.count(8 + 8 + 8);
+      cursor.u64();
+      cursor.u32();
+      for (uint64_t value = 0; value < n_values; ++value) {
+         cursor.classInfo("pair<string,Roaring>");
+         cursor.take(cursor.count(1));
+         cursor.roaring();
+      }
    }
    // sequence_column.h:35-39,92-95
    cursor.classInfo("SequenceColumnInfo");
@@ -576,11 +602,6 @@ std::unique_ptr<Table> loadTableFromArchive(
    for (const auto& column : columns) {
       if (column->chunk_sizes != layout.chunk_sizes) {
          throw ArchiveFormatError("column " + column->name + " does not share the table's row layout");
-      }
-      if (!column->tail_parsed) {
-         // its null bitmap lies behind a non-empty insertion index, which this reader does not walk:
-         // uploading it without the null rows would change filter results (symbol_in_set.cpp:80-98)
-         continue;
       }
       table->addSequenceColumn(column->name, *column->alphabet, column->reference, column->desc);
    }

@@ -55,7 +55,8 @@ struct LoadedSequenceColumn {
    uint64_t vertical_bitmaps_size = 0;    // SequenceColumnInfo, sequence_column.h:35-39
    uint64_t horizontal_bitmaps_size = 0;
    uint16_t num_chunks = 0;
-   bool tail_parsed = false;  // false: the insertion index was not empty, the members behind it were skipped
+   uint64_t n_insertion_positions = 0;  // insertion_index.h:91 (read through, not kept)
+   bool tail_parsed = false;  // set once the column was read to its end
    silo_column_desc desc{};
 };
 

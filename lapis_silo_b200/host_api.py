@@ -340,7 +340,7 @@ class Archive:
     def info(self, index: int) -> dict:
         values = (C.c_uint64 * 6)()
         _check(lib().silo_host_archive_column_info(self._h, index, values))
-        keys = ("n_chunks", "sequence_count", "tail_parsed", "vertical_bitmaps_size", "horizontal_bitmaps_size", "num_chunks")
+        keys = ("n_chunks", "sequence_count", "n_insertion_positions", "vertical_bitmaps_size", "horizontal_bitmaps_size", "num_chunks")
         return dict(zip(keys, (int(v) for v in values)))
 
     def chunk_sizes(self, index: int) -> list[int]:
@@ -366,13 +366,11 @@ class HostTable:
 
     @classmethod
     def from_archive(cls, ctx: abi.Context, data: bytes, columns) -> "HostTable":
-        """S1 for a saved database (silo_host_table_load_archive): row layout and columns come from the
-        `.silo` bytes; columns whose tail could not be read (non-empty insertion index) are not uploaded."""
+        """S1 for a saved database (silo_host_table_load_archive): row layout and columns come from the `.silo` bytes"""
         columns = list(columns)
         archive = Archive(data, columns)
         try:
             chunk_sizes = archive.chunk_sizes(0)
-            complete = [bool(archive.info(i)["tail_parsed"]) for i in range(len(columns))]
         finally:
             archive.close()
         names, alphabets, references, n = _archive_specs(columns)
@@ -382,9 +380,8 @@ class HostTable:
         table = cls.__new__(cls)
         table._init_fields(ctx, chunk_sizes, 0)
         table._h = handle
-        for (name, alphabet, reference), uploaded in zip(columns, complete):
-            if uploaded:
-                table.columns[name] = (16 if alphabet == NUCLEOTIDE else 28, len(reference))
+        for name, alphabet, reference in columns:
+            table.columns[name] = (16 if alphabet == NUCLEOTIDE else 28, len(reference))
         return table
 
     def _init_fields(self, ctx: abi.Context, chunk_sizes: Sequence[int], first_chunk: int) -> None:

@@ -23,10 +23,11 @@ boost binary archive facts the reader relies on (observed on the fixture, consis
     std::unordered_map = [size u64, bucket_count u64, item_version u32, items];
     vector<pair<u32,u32>> is stored as size + raw bytes (bitwise serialisable)
   * enums are saved as 32-bit ints (the Symbol of a SequenceDiffKey takes 4 bytes)
+  * std::array<Symbol, 3> = [element count u64, the enums]; std::vector<uint32_t> = [size u64, raw values]
 The metadata columns in front of the sequence columns are not parsed: the first sequence column is located by
 its length-prefixed local reference, and the class types those columns already registered are listed in
-PRE_SEEN. A sequence column whose insertion index is not empty is read up to its coverage index (all the query
-path needs); its tail is skipped by locating the next column."""
+PRE_SEEN. The insertion index (insertion_index.h:28-100) is read through -- the query path does not use it, but
+the column's sequence_count, null bitmap and num_chunks lie behind it."""
 from __future__ import annotations
 
 import struct
@@ -77,6 +78,8 @@ class SequenceColumn:
     horizontal_bitmaps_size: int | None = None
     null_bitmap: bytes | None = None
     num_chunks: int | None = None
+    insertion_positions: list = field(default_factory=list)  # [{position, insertions [(value, roaring bytes)], three_mers [([3 symbol ids], [insertion ids])], three_mer_buckets}]
+    insertion_bucket_counts: list = field(default_factory=list)  # bucket counts of the two hash tables (a runtime artefact boost saves)
 
 
 def parse_header(data: bytes) -> int:
@@ -96,7 +99,7 @@ def _pair_vector(cursor: _Cursor) -> list:
     return [(cursor.u32(), cursor.u32()) for _ in range(cursor.u64())]
 
 
-def _sequence_column(cursor: _Cursor, alphabet: str, next_start: int | None) -> SequenceColumn:
+def _sequence_column(cursor: _Cursor, alphabet: str) -> SequenceColumn:
     cursor.class_info(f"SequenceColumn<{alphabet}>")
     column = SequenceColumn(local_reference=cursor.string())
     # vertical_sequence_index.h:110-112
@@ -122,23 +125,48 @@ def _sequence_column(cursor: _Cursor, alphabet: str, next_start: int | None) -> 
     n, _item_version = cursor.u64(), cursor.u32()
     column.start_end = [_pair_vector(cursor) for _ in range(n)]
     column.batch_start_ends = _pair_vector(cursor)
-    # insertion_index.h:84-100: two unordered_maps; parsed only when both are empty
+    # insertion_index.h:84-100: insertion_positions (position -> InsertionPosition {insertions, three_mer_index},
+    # :28-63) and collected_insertions; the query path does not need them, they are read to get past them
     cursor.class_info(f"InsertionIndex<{alphabet}>")
     cursor.class_info(f"unordered_map<u32,InsertionPosition<{alphabet}>>")
-    n_positions, _buckets, _item_version = cursor.u64(), cursor.u64(), cursor.u32()
-    if n_positions != 0:
-        # registered by the skipped part (so that a later column of the same alphabet parses)
-        cursor.seen.update({f"pair<u32,InsertionPosition<{alphabet}>>", f"InsertionPosition<{alphabet}>", "vector<Insertion>", "Insertion",
-                            f"unordered_map<ThreeMer<{alphabet}>,InsertionIds>", "unordered_map<u32,unordered_map<string,Roaring>>",
-                            "SequenceColumnInfo"})
-        if next_start is None:
-            raise ValueError("cannot skip a non-empty insertion index without the start of the next column")
-        cursor.position = next_start
-        return column
+    n_positions, buckets, _item_version = cursor.u64(), cursor.u64(), cursor.u32()
+    column.insertion_bucket_counts = [buckets]
+    for _ in range(n_positions):
+        cursor.class_info(f"pair<u32,InsertionPosition<{alphabet}>>")
+        position = cursor.u32()
+        cursor.class_info(f"InsertionPosition<{alphabet}>")
+        cursor.class_info("vector<Insertion>")
+        n_insertions, _item_version = cursor.u64(), cursor.u32()
+        insertions = []
+        for _ in range(n_insertions):
+            cursor.class_info("Insertion")
+            value = cursor.string()
+            insertions.append((value.decode(), cursor.roaring()))
+        cursor.class_info(f"unordered_map<ThreeMer<{alphabet}>,InsertionIds>")
+        n_three_mers, three_mer_buckets, _item_version = cursor.u64(), cursor.u64(), cursor.u32()
+        three_mers = []
+        for _ in range(n_three_mers):
+            cursor.class_info(f"pair<ThreeMer<{alphabet}>,InsertionIds>")
+            cursor.class_info(f"ThreeMer<{alphabet}>")  # std::array<Symbol, 3>: element count + the enums as ints
+            if cursor.u64() != 3:
+                raise ValueError("a three-mer that does not have three symbols")
+            symbols = [cursor.u32() for _ in range(3)]
+            ids = [cursor.u32() for _ in range(cursor.u64())]  # std::vector<uint32_t>: size + raw values
+            three_mers.append((symbols, ids))
+        column.insertion_positions.append({"position": position, "insertions": insertions, "three_mers": three_mers,
+                                           "three_mer_buckets": three_mer_buckets})
     cursor.class_info("unordered_map<u32,unordered_map<string,Roaring>>")
-    n_collected, _buckets, _item_version = cursor.u64(), cursor.u64(), cursor.u32()
-    if n_collected != 0:
-        raise ValueError("collected insertions without insertion positions")
+    n_collected, buckets, _item_version = cursor.u64(), cursor.u64(), cursor.u32()
+    column.insertion_bucket_counts.append(buckets)
+    for _ in range(n_collected):  # (empty after buildIndex; layout by the same rules, not seen in a fixture)
+        cursor.class_info("pair<u32,unordered_map<string,Roaring>>")
+        cursor.u32()
+        cursor.class_info("unordered_map<string,Roaring>")
+        n_values, _buckets, _item_version = cursor.u64(), cursor.u64(), cursor.u32()
+        for _ in range(n_values):
+            cursor.class_info("pair<string,Roaring>")
+            cursor.string()
+            cursor.roaring()
     # sequence_column.h:35-39,92-95
     cursor.class_info("SequenceColumnInfo")
     column.sequence_count, column.vertical_bitmaps_size, column.horizontal_bitmaps_size = cursor.u32(), cursor.u64(), cursor.u64()
@@ -172,11 +200,9 @@ def read_sequence_columns(path: str, columns: list[tuple[str, str, bytes]]) -> d
         first_of_alphabet = f"SequenceColumn<{alphabet}>" not in seen
         # the class info of the first column of an alphabet sits in front of the located string
         cursor.position = starts[index] - (5 if first_of_alphabet else 0)
-        next_start = None
+        out[name] = _sequence_column(cursor, alphabet)
         if index + 1 < len(columns):
-            next_alphabet = columns[index + 1][1]
-            next_start = starts[index + 1] - (5 if f"SequenceColumn<{next_alphabet}>" not in seen and next_alphabet != alphabet else 0)
-        out[name] = _sequence_column(cursor, alphabet, next_start)
-        if next_start is not None and cursor.position != next_start:
-            raise ValueError(f"column {name} ends at {cursor.position}, the next one starts at {next_start}")
+            first_of_next = f"SequenceColumn<{columns[index + 1][1]}>" not in seen
+            if cursor.position != starts[index + 1] - (5 if first_of_next else 0):
+                raise ValueError(f"column {name} ends at {cursor.position}, the next one starts at {starts[index + 1]}")
     return out

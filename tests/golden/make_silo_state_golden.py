@@ -40,6 +40,12 @@ def main():
             "horizontal_bitmaps_size": column.horizontal_bitmaps_size,
             "null_bitmap_hex": column.null_bitmap.hex() if column.null_bitmap is not None else None,
             "num_chunks": column.num_chunks,
+            # insertion_index.h:28-100 (not on the query path; the loader has to read through it)
+            "insertion_positions": [{"position": p["position"], "three_mer_buckets": p["three_mer_buckets"],
+                                     "insertions": [[value, blob.hex()] for value, blob in p["insertions"]],
+                                     "three_mers": [[symbols, ids] for symbols, ids in p["three_mers"]]}
+                                    for p in column.insertion_positions],
+            "insertion_bucket_counts": column.insertion_bucket_counts,
         })
     with open(os.path.join(HERE, "silo_state_unit_test_dummy.json"), "w") as handle:
         json.dump(out, handle, indent=1)

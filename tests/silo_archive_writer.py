@@ -50,9 +50,10 @@ def sequence_column_bytes(column: dict, seen: set) -> bytes:
     """column: alphabet ("Nucleotide" | "AminoAcid"), local_reference (str), containers [{position, v_index, symbol,
     cardinality, typecode, payload (bytes)}] in map order, missing_bitmaps {row: portable roaring bytes},
     start_end [[(start, end)] per chunk], batch_start_ends [(start, end)], sequence_count, vertical_bitmaps_size,
-    horizontal_bitmaps_size, null_bitmap (portable roaring bytes), num_chunks; optional insertion_tail (bytes):
-    an opaque non-empty insertion index + the members behind it (the reader has to skip it); optional
-    insertion_bucket_counts (the two empty hash tables' bucket counts)."""
+    horizontal_bitmaps_size, null_bitmap (portable roaring bytes), num_chunks; optional insertion_positions
+    [{position, insertions [(value, portable roaring bytes)], three_mers [([3 symbol ids], [insertion ids])],
+    three_mer_buckets}] (the reader has to read through them) and insertion_bucket_counts (the two hash tables'
+    bucket counts)."""
     alphabet = column["alphabet"]
     out = _Out(seen)
     out.class_info(f"SequenceColumn<{alphabet}>")
@@ -87,21 +88,37 @@ def sequence_column_bytes(column: dict, seen: set) -> bytes:
     out.pair_vector(column["batch_start_ends"])
     out.class_info(f"InsertionIndex<{alphabet}>")
     out.class_info(f"unordered_map<u32,InsertionPosition<{alphabet}>>")
-    if column.get("insertion_tail") is not None:
-        out.u64(1)   # one insertion position
-        out.u64(13)  # bucket count
-        out.u32(0)
-        out.raw(column["insertion_tail"])
-        seen.update({f"pair<u32,InsertionPosition<{alphabet}>>", f"InsertionPosition<{alphabet}>", "vector<Insertion>", "Insertion",
-                     f"unordered_map<ThreeMer<{alphabet}>,InsertionIds>", "unordered_map<u32,unordered_map<string,Roaring>>",
-                     "SequenceColumnInfo", "roaring::Roaring"})
-        return b"".join(out.parts)
     # boost saves bucket_count even for an empty table; the value is whatever the hash table held at save time
-    # (the reference's file has 2 for insertion_positions and 1 for collected_insertions), the reader ignores it
+    # (the reference's file has 2 / 13 for insertion_positions and 1 / 13 for collected_insertions), the reader ignores it
     buckets = column.get("insertion_bucket_counts", (1, 1))
-    out.u64(0)
+    positions = column.get("insertion_positions", [])
+    out.u64(len(positions))
     out.u64(buckets[0])
     out.u32(0)
+    for entry in positions:  # insertion_index.h:28-63
+        out.class_info(f"pair<u32,InsertionPosition<{alphabet}>>")
+        out.u32(entry["position"])
+        out.class_info(f"InsertionPosition<{alphabet}>")
+        out.class_info("vector<Insertion>")
+        out.u64(len(entry["insertions"]))
+        out.u32(0)
+        for value, row_ids in entry["insertions"]:
+            out.class_info("Insertion")
+            out.string(value.encode())
+            out.roaring(row_ids)
+        out.class_info(f"unordered_map<ThreeMer<{alphabet}>,InsertionIds>")
+        out.u64(len(entry["three_mers"]))
+        out.u64(entry.get("three_mer_buckets", 13))
+        out.u32(0)
+        for symbols, ids in entry["three_mers"]:
+            out.class_info(f"pair<ThreeMer<{alphabet}>,InsertionIds>")
+            out.class_info(f"ThreeMer<{alphabet}>")
+            out.u64(3)
+            for symbol in symbols:
+                out.u32(symbol)
+            out.u64(len(ids))
+            for insertion_id in ids:
+                out.u32(insertion_id)
     out.class_info("unordered_map<u32,unordered_map<string,Roaring>>")
     out.u64(0)
     out.u64(buckets[1])

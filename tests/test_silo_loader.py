@@ -22,7 +22,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 with open(os.path.join(HERE, "golden", "silo_state_unit_test_dummy.json")) as handle:
     STATE = json.load(handle)
 STATE_FILE = "/root/reference/testBaseData/siloSerializedState/1785915539/default.silo"
-OPAQUE_INSERTIONS = bytes(range(1, 120))  # stands in for a non-empty insertion index + the members behind it
 
 
 def specs_of_state():
@@ -40,12 +39,11 @@ def state_columns_for_writer():
             "start_end": [[tuple(pair) for pair in chunk] for chunk in c["start_end"]],
             "batch_start_ends": [tuple(pair) for pair in c["batch_start_ends"]],
         }
-        if c["sequence_count"] is None:  # column E: the reference's file holds a non-empty insertion index
-            column["insertion_tail"] = OPAQUE_INSERTIONS
-        else:
-            column.update(sequence_count=c["sequence_count"], vertical_bitmaps_size=c["vertical_bitmaps_size"],
-                          horizontal_bitmaps_size=c["horizontal_bitmaps_size"], null_bitmap=bytes.fromhex(c["null_bitmap_hex"]),
-                          num_chunks=c["num_chunks"])
+        column.update(sequence_count=c["sequence_count"], vertical_bitmaps_size=c["vertical_bitmaps_size"],
+                      horizontal_bitmaps_size=c["horizontal_bitmaps_size"], null_bitmap=bytes.fromhex(c["null_bitmap_hex"]),
+                      num_chunks=c["num_chunks"], insertion_bucket_counts=c["insertion_bucket_counts"],
+                      insertion_positions=[dict(p, insertions=[(value, bytes.fromhex(blob)) for value, blob in p["insertions"]])
+                                           for p in c["insertion_positions"]])  # column E has one (4:EPE)
         columns.append(column)
     return columns
 
@@ -109,13 +107,10 @@ def check_state_archive(data: bytes):
         assert (got["n_symbols"], got["genome_length"], got["missing_symbol"]) == (len(chars), len(column["reference"]), len(chars) - 1)
         assert got["start_end"] == [tuple(pair) for chunk in column["start_end"] for pair in chunk]
         assert got["missing"] == {int(row): runs_of(roaring_values(bytes.fromhex(blob))) for row, blob in column["missing_bitmaps"].items()}
-        if column["sequence_count"] is None:
-            assert info["tail_parsed"] == 0 and info["sequence_count"] == 5
-        else:
-            assert info["tail_parsed"] == 1
-            assert (info["sequence_count"], info["vertical_bitmaps_size"], info["horizontal_bitmaps_size"], info["num_chunks"]) == \
-                   (column["sequence_count"], column["vertical_bitmaps_size"], column["horizontal_bitmaps_size"], column["num_chunks"])
-            assert got["null_rows"] == roaring_values(bytes.fromhex(column["null_bitmap_hex"]))
+        assert info["n_insertion_positions"] == len(column["insertion_positions"])
+        assert (info["sequence_count"], info["vertical_bitmaps_size"], info["horizontal_bitmaps_size"], info["num_chunks"]) == \
+               (column["sequence_count"], column["vertical_bitmaps_size"], column["horizontal_bitmaps_size"], column["num_chunks"])
+        assert got["null_rows"] == roaring_values(bytes.fromhex(column["null_bitmap_hex"]))
     archive.close()
 
 
@@ -126,20 +121,14 @@ def test_reader_on_the_reference_serialised_state():
 
 @pytest.mark.skipif(not os.path.exists(STATE_FILE), reason="the reference tree is not mounted here")
 def test_writer_reproduces_the_reference_bytes():
-    """pins the test-side writer: for the columns in front of the first non-empty insertion index and for the last
-    column it must emit exactly the bytes the reference wrote"""
+    """pins the test-side writer: fed the extract of the reference's file it must emit exactly the bytes the reference
+    wrote for the four sequence columns (E with its insertion index included)"""
     data = open(STATE_FILE, "rb").read()
-    columns = [dict(column, insertion_bucket_counts=(2, 1)) for column in state_columns_for_writer()]  # as the file has them
     seen = {"roaring::Roaring", "pair<u32,Roaring>"}
-    first_two = W.sequence_column_bytes(columns[0], seen) + W.sequence_column_bytes(columns[1], seen)
-    at = data.find(first_two)
-    assert at > 0, "main + testSecondSequence as written by the test writer are not in the reference's file"
-    # E (non-empty insertion index in the reference's file) starts right behind them: everything up to the
-    # insertion index's size fields (the last 20 bytes the writer emits for an empty opaque tail) must agree
-    head_of_e = W.sequence_column_bytes(dict(columns[2], insertion_tail=b""), seen)[:-20]
-    assert data[at + len(first_two):at + len(first_two) + len(head_of_e)] == head_of_e
-    # M, the last sequence column (Table::serializeData writes sequence_count and row_layout behind the columns)
-    assert data.find(W.sequence_column_bytes(columns[3], seen), at + len(first_two) + len(head_of_e)) > 0
+    written = b"".join(W.sequence_column_bytes(column, seen) for column in state_columns_for_writer())
+    at = data.find(written)
+    assert at > 0, "the sequence columns as written by the test writer are not in the reference's file"
+    assert written[:5] == bytes(5) and written[5:13] == struct.pack("<Q", 8)  # class info of the first sequence column, then "main"'s local reference
 
 
 @pytest.mark.parametrize("roaring_seen,pair_seen", [(True, True), (False, False), (True, False), (False, True)])
@@ -181,6 +170,12 @@ def random_archive(seed, alphabet_id):
     alphabet_name, chars = ("Nucleotide", O.NUC_SYMBOLS) if alphabet_id == O.NUCLEOTIDE else ("AminoAcid", O.AA_SYMBOLS)
     column, values = oracle_column_for_writer(table, "c", alphabet_name, chars)
     reference = table.columns[0][2]
+    # an insertion index with several positions, insertions and three-mers (class info only in front of the first of each)
+    rows = O.roaring_roundtrip([1, 5, 70000], optimize=False)[1]
+    column["insertion_positions"] = [
+        {"position": p, "insertions": [("ACGT", rows), ("TTTTTTTTTTTTTTTTTTTT", O.roaring_roundtrip(list(range(300)), optimize=True)[1])],
+         "three_mers": [([1, 2, 3], [0]), ([2, 3, 4], [0, 1]), ([4, 4, 4], [1])], "three_mer_buckets": 13} for p in (3, 17, 60)]
+    column["insertion_bucket_counts"] = (5, 1)
     return table, W.write_archive([column], b"\x01\x02" * 50), values, [("c", alphabet_id, reference)]
 
 
@@ -192,7 +187,7 @@ def test_reader_on_oracle_built_tables(seed, alphabet_id):
     assert {c["typecode"] for c in want["containers"]} >= {2}
     archive = H.Archive(data, specs)
     assert archive.chunk_sizes(0) == table.chunk_sizes
-    assert archive.info(0) == {"n_chunks": 4, "sequence_count": table.num_rows, "tail_parsed": 1, "vertical_bitmaps_size": 123,
+    assert archive.info(0) == {"n_chunks": 4, "sequence_count": table.num_rows, "n_insertion_positions": 3, "vertical_bitmaps_size": 123,
                                "horizontal_bitmaps_size": 456, "num_chunks": 4}
     assert desc_as_values(archive.desc(0).contents, table.num_rows) == want
     archive.close()
@@ -268,19 +263,17 @@ def test_device_table_loaded_from_archive_bytes(ctx, seed, alphabet_id):
 @pytest.mark.gpu
 def test_device_table_loaded_from_the_reference_state(ctx):
     """the reference's own containers through the loader (the file itself where the reference tree is mounted, else
-    the archive rewritten from the committed extract); column E is skipped (its null bitmap was not read)"""
+    the archive rewritten from the committed extract), all four columns, E with its insertion index read through"""
     from lapis_silo_b200 import host_api as H
     from test_silo_state import oracle_table
     data = open(STATE_FILE, "rb").read() if os.path.exists(STATE_FILE) else W.write_archive(state_columns_for_writer())
     oracle = oracle_table()
     device_table = H.HostTable.from_archive(ctx, data, specs_of_state())
-    assert sorted(device_table.columns) == ["M", "main", "testSecondSequence"]
+    assert sorted(device_table.columns) == ["E", "M", "main", "testSecondSequence"]
     for name in device_table.columns:
         for expression in (None, f"(has-mut {name} 2)", f"(not (has-mut {name} 2))", f"(sym-eq {name} 2 A)", f"(sym-eq {name} 4 .)"):
             if expression is not None:
                 np.testing.assert_array_equal(device_table.filter(expression).ids(), oracle.filter(expression).ids())
             for min_proportion in (0.0, 0.05, 0.3):
                 assert device_table.mutations([name], expression, min_proportion) == oracle.mutations(name, expression, min_proportion), (name, expression)
-    with pytest.raises(H.HostError):
-        device_table.filter("(has-mut E 2)")
     device_table.close()
