@@ -128,9 +128,15 @@ const silo_column_desc* silo_host_archive_column(const silo_host_archive* archiv
  * vertical_bitmaps_size, horizontal_bitmaps_size, num_chunks member} */
 int silo_host_archive_column_info(const silo_host_archive* archive, uint32_t index, uint64_t info[6]);
 int silo_host_archive_chunk_sizes(const silo_host_archive* archive, uint32_t index, uint32_t* chunk_sizes, uint32_t capacity);
-/* S1 for a saved database: creates the table (row layout from the coverage index) and uploads every column */
+/* the chunks [first_chunk, first_chunk + n_chunks) of the column (one rank's part of the row-partitioned table;
+ * v_index and row ids stay global); valid until the archive object is freed */
+const silo_column_desc* silo_host_archive_column_shard(silo_host_archive* archive, uint32_t index, uint32_t first_chunk, uint32_t n_chunks);
+/* S1 for a saved database: creates the table (row layout from the coverage index) and uploads every column;
+ * a rank of the row-partitioned table passes its chunk range (n_chunks = UINT32_MAX: up to the last chunk).
+ * ctx == NULL gives a host-only table (metadata, no upload). */
 silo_host_table* silo_host_table_load_archive(silo_gpu_ctx* ctx, const uint8_t* bytes, uint64_t size, const char* const* names,
-                                              const int* alphabets, const char* const* references, uint32_t n_columns);
+                                              const int* alphabets, const char* const* references, uint32_t n_columns,
+                                              uint32_t first_chunk, uint32_t n_chunks);
 /* ascending {first, end_exclusive} runs of a portable roaring bitmap; returns the number of runs or -1 */
 int64_t silo_host_roaring_runs(const uint8_t* bytes, uint64_t size, uint32_t* runs, uint64_t capacity_runs);
 

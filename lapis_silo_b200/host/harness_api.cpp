@@ -54,6 +54,7 @@ struct silo_host_rows {
 
 struct silo_host_archive {
    std::vector<std::unique_ptr<LoadedSequenceColumn>> columns;
+   std::vector<std::unique_ptr<LoadedSequenceColumn>> shards;  // handed out by silo_host_archive_column_shard
 };
 
 struct silo_host_synthetic {
@@ -726,12 +727,22 @@ int silo_host_archive_chunk_sizes(const silo_host_archive* archive, uint32_t ind
    });
 }
 
+const silo_column_desc* silo_host_archive_column_shard(silo_host_archive* archive, uint32_t index, uint32_t first_chunk, uint32_t n_chunks) {
+   const silo_column_desc* result = nullptr;
+   guarded([&] {
+      archive->shards.push_back(shardOf(*archive->columns.at(index), first_chunk, n_chunks));
+      result = &archive->shards.back()->desc;
+   });
+   return result;
+}
+
 silo_host_table* silo_host_table_load_archive(silo_gpu_ctx* ctx, const uint8_t* bytes, uint64_t size, const char* const* names,
-                                              const int* alphabets, const char* const* references, uint32_t n_columns) {
+                                              const int* alphabets, const char* const* references, uint32_t n_columns,
+                                              uint32_t first_chunk, uint32_t n_chunks) {
    silo_host_table* result = nullptr;
    guarded([&] {
       auto owned = std::make_unique<silo_host_table>();
-      owned->table = loadTableFromArchive(ctx, bytes, size, archiveSpecs(names, alphabets, references, n_columns));
+      owned->table = loadTableFromArchive(ctx, bytes, size, archiveSpecs(names, alphabets, references, n_columns), {}, first_chunk, n_chunks);
       result = owned.release();
    });
    return result;

@@ -584,26 +584,109 @@ std::vector<std::unique_ptr<LoadedSequenceColumn>> readSequenceColumns(
    return out;
 }
 
+std::unique_ptr<LoadedSequenceColumn> shardOf(const LoadedSequenceColumn& column, uint32_t first_chunk, uint32_t n_chunks) {
+   const uint64_t total_chunks = column.chunk_sizes.size();
+   if (first_chunk > total_chunks || n_chunks > total_chunks - first_chunk) {
+      throw std::invalid_argument("chunk range outside the column");
+   }
+   const uint32_t chunk_end = first_chunk + n_chunks;
+   auto shard = std::make_unique<LoadedSequenceColumn>();
+   shard->name = column.name;
+   shard->alphabet = column.alphabet;
+   shard->reference = column.reference;
+   shard->local_reference = column.local_reference;  // global: identical on every shard (sequence_column.h:104)
+   for (const silo_container_desc& container : column.containers) {
+      if (container.v_index < first_chunk || container.v_index >= chunk_end) {
+         continue;
+      }
+      silo_container_desc copy = container;
+      copy.payload_offset = shard->payload.size();
+      shard->payload.insert(
+         shard->payload.end(),
+         column.payload.begin() + static_cast<std::ptrdiff_t>(container.payload_offset),
+         column.payload.begin() + static_cast<std::ptrdiff_t>(container.payload_offset + container.payload_bytes)
+      );
+      shard->containers.push_back(copy);
+   }
+   uint64_t first_row = 0;
+   for (uint32_t chunk = 0; chunk < first_chunk; ++chunk) {
+      first_row += column.chunk_sizes[chunk];
+   }
+   uint64_t rows = 0;
+   for (uint32_t chunk = first_chunk; chunk < chunk_end; ++chunk) {
+      rows += column.chunk_sizes[chunk];
+      shard->chunk_sizes.push_back(column.chunk_sizes[chunk]);
+      shard->batch_start_ends.push_back(column.batch_start_ends[2 * chunk]);
+      shard->batch_start_ends.push_back(column.batch_start_ends[2 * chunk + 1]);
+   }
+   shard->start_end.assign(
+      column.start_end.begin() + static_cast<std::ptrdiff_t>(2 * first_row),
+      column.start_end.begin() + static_cast<std::ptrdiff_t>(2 * (first_row + rows))
+   );
+   shard->missing_offsets.assign(1, 0);
+   for (size_t i = 0; i < column.missing_row_ids.size(); ++i) {
+      const uint32_t chunk = column.missing_row_ids[i] >> 16;
+      if (chunk < first_chunk || chunk >= chunk_end) {
+         continue;
+      }
+      shard->missing_row_ids.push_back(column.missing_row_ids[i]);
+      shard->missing_runs.insert(
+         shard->missing_runs.end(),
+         column.missing_runs.begin() + static_cast<std::ptrdiff_t>(2 * column.missing_offsets[i]),
+         column.missing_runs.begin() + static_cast<std::ptrdiff_t>(2 * column.missing_offsets[i + 1])
+      );
+      shard->missing_offsets.push_back(shard->missing_runs.size() / 2);
+   }
+   for (uint32_t row : column.null_row_ids) {
+      if ((row >> 16) >= first_chunk && (row >> 16) < chunk_end) {
+         shard->null_row_ids.push_back(row);
+      }
+   }
+   shard->sequence_count = static_cast<uint32_t>(rows);
+   shard->num_chunks = static_cast<uint16_t>(n_chunks);
+   shard->tail_parsed = column.tail_parsed;
+   fillDescriptor(*shard);
+   return shard;
+}
+
 std::unique_ptr<Table> loadTableFromArchive(
    silo_gpu_ctx* ctx,
    const uint8_t* data,
    uint64_t size,
    const std::vector<ArchiveColumnSpec>& specs,
-   const ArchiveReadOptions& options
+   const ArchiveReadOptions& options,
+   uint32_t first_chunk,
+   uint32_t n_chunks
 ) {
    const auto columns = readSequenceColumns(data, size, specs, options);
    if (columns.empty()) {
       throw std::invalid_argument("no sequence columns requested");
    }
+   const std::vector<uint32_t>& all_chunks = columns.front()->chunk_sizes;
+   if (first_chunk > all_chunks.size()) {
+      throw std::invalid_argument("first_chunk beyond the table");
+   }
+   if (n_chunks == UINT32_MAX) {
+      n_chunks = static_cast<uint32_t>(all_chunks.size()) - first_chunk;
+   }
+   if (n_chunks > all_chunks.size() - first_chunk) {
+      throw std::invalid_argument("chunk range outside the table");
+   }
    RowLayout layout;
-   layout.first_chunk = 0;
-   layout.chunk_sizes = columns.front()->chunk_sizes;
+   layout.first_chunk = first_chunk;
+   layout.chunk_sizes.assign(all_chunks.begin() + first_chunk, all_chunks.begin() + first_chunk + n_chunks);
    auto table = std::make_unique<Table>(ctx, layout);
+   const bool whole = first_chunk == 0 && n_chunks == all_chunks.size();
    for (const auto& column : columns) {
-      if (column->chunk_sizes != layout.chunk_sizes) {
+      if (column->chunk_sizes != all_chunks) {
          throw ArchiveFormatError("column " + column->name + " does not share the table's row layout");
       }
-      table->addSequenceColumn(column->name, *column->alphabet, column->reference, column->desc);
+      if (whole) {
+         table->addSequenceColumn(column->name, *column->alphabet, column->reference, column->desc);
+      } else {
+         const auto shard = shardOf(*column, first_chunk, n_chunks);
+         table->addSequenceColumn(shard->name, *shard->alphabet, shard->reference, shard->desc);
+      }
    }
    return table;
 }

@@ -81,14 +81,20 @@ std::vector<std::unique_ptr<LoadedSequenceColumn>> readSequenceColumns(
    const ArchiveReadOptions& options = {}
 );
 
+// The part of a column that belongs to the chunks [first_chunk, first_chunk + n_chunks): what one rank of
+// the row-partitioned table uploads (v_index and row ids stay global).
+std::unique_ptr<LoadedSequenceColumn> shardOf(const LoadedSequenceColumn& column, uint32_t first_chunk, uint32_t n_chunks);
+
 // S1 for a saved database: row layout from the first column's coverage index, every column uploaded
-// through silo_gpu_column_upload (Table::addSequenceColumn).
+// through silo_gpu_column_upload (Table::addSequenceColumn). n_chunks == UINT32_MAX: up to the last chunk.
 std::unique_ptr<Table> loadTableFromArchive(
    silo_gpu_ctx* ctx,
    const uint8_t* data,
    uint64_t size,
    const std::vector<ArchiveColumnSpec>& specs,
-   const ArchiveReadOptions& options = {}
+   const ArchiveReadOptions& options = {},
+   uint32_t first_chunk = 0,
+   uint32_t n_chunks = UINT32_MAX
 );
 
 }  // namespace silo_host

@@ -36,7 +36,7 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_synthetic_date_ranges", "silo_host_partition_chunks",
     "silo_host_filter_lower_timed",
     "silo_host_archive_read", "silo_host_archive_free", "silo_host_archive_column", "silo_host_archive_column_info",
-    "silo_host_archive_chunk_sizes", "silo_host_table_load_archive", "silo_host_roaring_runs",
+    "silo_host_archive_chunk_sizes", "silo_host_archive_column_shard", "silo_host_table_load_archive", "silo_host_roaring_runs",
 ]
 
 NUCLEOTIDE = 0
@@ -143,7 +143,9 @@ def lib() -> C.CDLL:
         L.silo_host_archive_column.restype = C.POINTER(abi.ColumnDesc)
         L.silo_host_archive_column_info.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint64)]
         L.silo_host_archive_chunk_sizes.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]
-        L.silo_host_table_load_archive.argtypes = [vp, C.c_char_p, C.c_uint64, strings, ints, strings, C.c_uint32]
+        L.silo_host_archive_column_shard.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.silo_host_archive_column_shard.restype = C.POINTER(abi.ColumnDesc)
+        L.silo_host_table_load_archive.argtypes = [vp, C.c_char_p, C.c_uint64, strings, ints, strings, C.c_uint32, C.c_uint32, C.c_uint32]
         L.silo_host_table_load_archive.restype = vp
         L.silo_host_roaring_runs.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint64]
         L.silo_host_roaring_runs.restype = C.c_int64
@@ -337,6 +339,13 @@ class Archive:
             raise IndexError(index)
         return pointer
 
+    def shard_desc(self, index: int, first_chunk: int, n_chunks: int):
+        """the column restricted to the chunks [first_chunk, first_chunk + n_chunks) (global v_index / row ids)"""
+        pointer = lib().silo_host_archive_column_shard(self._h, index, first_chunk, n_chunks)
+        if not pointer:
+            raise HostError(lib().silo_host_last_error().decode())
+        return pointer
+
     def info(self, index: int) -> dict:
         values = (C.c_uint64 * 6)()
         _check(lib().silo_host_archive_column_info(self._h, index, values))
@@ -365,20 +374,24 @@ class HostTable:
     """rhydb::storage::Table as the query compiler sees it, with its sequence columns in HBM."""
 
     @classmethod
-    def from_archive(cls, ctx: abi.Context, data: bytes, columns) -> "HostTable":
-        """S1 for a saved database (silo_host_table_load_archive): row layout and columns come from the `.silo` bytes"""
+    def from_archive(cls, ctx: Optional[abi.Context], data: bytes, columns, first_chunk: int = 0, n_chunks: Optional[int] = None) -> "HostTable":
+        """S1 for a saved database (silo_host_table_load_archive): row layout and columns come from the `.silo` bytes;
+        a rank of the row-partitioned table passes its chunk range. ctx None: host-only table."""
         columns = list(columns)
         archive = Archive(data, columns)
         try:
             chunk_sizes = archive.chunk_sizes(0)
         finally:
             archive.close()
+        if n_chunks is None:
+            n_chunks = len(chunk_sizes) - first_chunk
         names, alphabets, references, n = _archive_specs(columns)
-        handle = lib().silo_host_table_load_archive(ctx._h, data, len(data), names, alphabets, references, n)
+        handle = lib().silo_host_table_load_archive(ctx._h if ctx is not None else None, data, len(data), names, alphabets, references, n,
+                                                    first_chunk, n_chunks)
         if not handle:
             raise HostError(lib().silo_host_last_error().decode())
         table = cls.__new__(cls)
-        table._init_fields(ctx, chunk_sizes, 0)
+        table._init_fields(ctx, chunk_sizes[first_chunk:first_chunk + n_chunks], first_chunk)
         table._h = handle
         for name, alphabet, reference in columns:
             table.columns[name] = (16 if alphabet == NUCLEOTIDE else 28, len(reference))

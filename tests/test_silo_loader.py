@@ -193,6 +193,31 @@ def test_reader_on_oracle_built_tables(seed, alphabet_id):
     archive.close()
 
 
+@pytest.mark.parametrize("seed,alphabet_id", [(301, 0), (302, 1)])
+def test_shards_of_an_archive_equal_the_oracle_shard_exports(seed, alphabet_id):
+    """one rank's part of the row-partitioned table: chunk range of the archive's column == the
+    oracle's export of the same chunk range (global v_index and row ids)"""
+    from lapis_silo_b200 import host_api as H
+    table, data, _, specs = random_archive(seed, alphabet_id)
+    archive = H.Archive(data, specs)
+    for first_chunk, n_chunks in ((0, 4), (0, 1), (1, 2), (3, 1), (2, 0), (4, 0)):
+        rows = sum(table.chunk_sizes[first_chunk:first_chunk + n_chunks])
+        export = table.export_column("c", first_chunk, n_chunks)
+        want = desc_as_values(export.desc.contents, rows)
+        export.close()
+        assert desc_as_values(archive.shard_desc(0, first_chunk, n_chunks).contents, rows) == want, (first_chunk, n_chunks)
+    with pytest.raises(H.HostError, match="chunk range outside the column"):
+        archive.shard_desc(0, 3, 2)
+    archive.close()
+    # a host-only table over a shard: layout and metadata come from the archive, the query compiler front half works
+    shard = H.HostTable.from_archive(None, data, specs, first_chunk=1, n_chunks=2)
+    assert shard.first_chunk == 1 and shard.chunk_sizes == table.chunk_sizes[1:3] and shard.num_rows == sum(table.chunk_sizes[1:3])
+    assert "op=3" in shard.explain("(sym-eq c 3 -)")
+    with pytest.raises(H.HostError, match=r"DeviceError\[-2\]"):
+        shard.filter("(true)")
+    shard.close()
+
+
 def test_roaring_decoder_against_the_oracle_serialiser():
     from lapis_silo_b200 import host_api as H
     from oracle import oracle as O
@@ -258,6 +283,31 @@ def test_device_table_loaded_from_archive_bytes(ctx, seed, alphabet_id):
             assert device_table.mutations(["c"], expression, min_proportion) == oracle_table.mutations("c", expression, min_proportion), expression
     np.testing.assert_array_equal(device_table.mutation_counts("c"), oracle_table.mutation_counts("c"))
     device_table.close()
+
+
+@pytest.mark.gpu
+def test_device_shards_loaded_from_archive_sum_to_the_whole(ctx):
+    """three ranks' chunk ranges loaded from the same archive bytes on one device: filter cardinalities and counts are
+    plain addends and sum to the oracle's whole-table result"""
+    from lapis_silo_b200 import host_api as H
+    oracle_table, data, _, specs = random_archive(301, 0)
+    bounds = H.partition_chunks([1] * len(oracle_table.chunk_sizes), 3)
+    shards = [H.HostTable.from_archive(ctx, data, specs, first_chunk=a, n_chunks=b - a) for a, b in zip(bounds, bounds[1:])]
+    assert sum(s.num_rows for s in shards) == oracle_table.num_rows
+    for expression in (None, "(has-mut c 7)", "(not (sym-eq c 12 N))"):
+        want_filter = oracle_table.filter(expression) if expression else None
+        total = np.zeros_like(oracle_table.mutation_counts("c"), dtype=np.uint64)
+        ids = []
+        for shard in shards:
+            flt = shard.filter(expression) if expression else None
+            total += shard.mutation_counts("c", flt).astype(np.uint64)
+            if flt is not None:
+                ids += [int(v) for v in flt.ids()]
+        np.testing.assert_array_equal(total.astype(np.uint32), oracle_table.mutation_counts("c", want_filter))
+        if expression:
+            assert ids == [int(v) for v in want_filter.ids()]
+    for shard in shards:
+        shard.close()
 
 
 @pytest.mark.gpu
