@@ -52,6 +52,9 @@ int silo_host_filter_words(const silo_host_filter* filter, uint64_t* words /* 10
 /* the lowered program as text, one instruction per line (debugging / tests of the lowering) */
 int silo_host_filter_explain(silo_host_table* table, const char* expression, char* out, uint64_t capacity);
 
+/* toString() of the expression as parsed, after rewrite(NONE) and of the compiled operator tree, one per line
+ * (the reference's own formats: and.cpp:32, or.cpp:27, nof.cpp:161, symbol_in_set.cpp:37, threshold.cpp:45 ...) */
+int silo_host_filter_to_string(silo_host_table* table, const char* expression, char* out, uint64_t capacity);
 /* parse -> rewrite(NONE) -> compile -> lower without running anything: microseconds of the four phases,
  * sizes[3] = {instructions, blob bytes, bitmaps travelling with the program}, and a 64-bit FNV-1a digest of the
  * lowered program (instruction fields + blob) so that two lowerings can be compared without the text form */

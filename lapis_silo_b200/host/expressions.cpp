@@ -77,9 +77,19 @@ std::unique_ptr<Operator> BoolLiteral::compile(const Table&) const {
 
 // ---- SymbolInSet -----------------------------------------------------------------------------
 
-std::string SymbolInSet::toString() const {
-   return "(" + column + ":symbol at position " + std::to_string(position_idx + 1) + " in a set of " +
-          std::to_string(symbols.size()) + ")";
+std::string SymbolInSet::toString() const {  // symbol_in_set.cpp:37-51
+   std::string symbols_string;
+   for (uint32_t symbol = 0; symbol < 32; ++symbol) {
+      if (((symbols.mask >> symbol) & 1u) == 0) {
+         continue;
+      }
+      if (!symbols_string.empty()) {
+         symbols_string += ", ";
+      }
+      symbols_string += alphabet != nullptr ? std::string(1, alphabet->symbolToChar(static_cast<Symbol>(symbol)))
+                                            : "#" + std::to_string(symbol);
+   }
+   return "(" + column + ":symbol at position " + std::to_string(position_idx + 1) + " in {" + symbols_string + "})";
 }
 
 ExpressionPtr SymbolInSet::rewrite(const Table&, AmbiguityMode) const {
@@ -164,9 +174,9 @@ ExpressionPtr SymbolEquals::rewrite(const Table& table, AmbiguityMode mode) cons
    const Symbol wanted = symbol.has_value() ? toSymbol(alphabet, symbol.value())
                                             : sequence_column.reference_sequence.at(position_idx);
    if (mode == AmbiguityMode::UPPER_BOUND) {
-      return std::make_shared<SymbolInSet>(column, position_idx, alphabet.ambiguity_symbols.at(wanted));
+      return std::make_shared<SymbolInSet>(column, position_idx, alphabet.ambiguity_symbols.at(wanted), &alphabet);
    }
-   return std::make_shared<SymbolInSet>(column, position_idx, std::vector<Symbol>{wanted});
+   return std::make_shared<SymbolInSet>(column, position_idx, std::vector<Symbol>{wanted}, &alphabet);
 }
 
 std::unique_ptr<Operator> SymbolEquals::compile(const Table&) const {
@@ -192,7 +202,7 @@ ExpressionPtr HasMutation::rewrite(const Table& table, AmbiguityMode mode) const
    } else {
       mask &= ~maskOf(alphabet.ambiguity_symbols.at(reference_symbol));
    }
-   return std::make_shared<SymbolInSet>(column, position_idx, SymbolSet(mask));
+   return std::make_shared<SymbolInSet>(column, position_idx, SymbolSet(mask), &alphabet);
 }
 
 std::unique_ptr<Operator> HasMutation::compile(const Table&) const {
@@ -222,12 +232,8 @@ std::unique_ptr<Operator> Exact::compile(const Table&) const {
 
 // ---- And -------------------------------------------------------------------------------------
 
-std::string And::toString() const {
-   std::string res = "And(";
-   for (const auto& child : children) {
-      res += child->toString() + " & ";
-   }
-   return res + ")";
+std::string And::toString() const {  // and.cpp:32-37
+   return "And(" + joinWithLimit(children, " & ") + ")";
 }
 
 ExpressionPtr And::rewrite(const Table& table, AmbiguityMode mode) const {
@@ -308,12 +314,8 @@ std::unique_ptr<Operator> And::compile(const Table& table) const {
 
 // ---- Or --------------------------------------------------------------------------------------
 
-std::string Or::toString() const {
-   std::string res = "Or(";
-   for (const auto& child : children) {
-      res += child->toString() + " | ";
-   }
-   return res + ")";
+std::string Or::toString() const {  // or.cpp:27-32
+   return "Or(" + joinWithLimit(children, " | ") + ")";
 }
 
 ExpressionPtr Or::rewrite(const Table& table, AmbiguityMode mode) const {
@@ -378,7 +380,9 @@ ExpressionPtr Or::rewrite(const Table& table, AmbiguityMode mode) const {
          const SequenceColumnInfo* column = table.findColumn(key.first);
          const bool is_nucleotide = column != nullptr && column->alphabet == &Alphabet::nucleotide();
          if ((pass == 0) == is_nucleotide) {
-            merged_children.push_back(std::make_shared<SymbolInSet>(key.first, key.second, symbols));
+            merged_children.push_back(std::make_shared<SymbolInSet>(
+               key.first, key.second, symbols, column != nullptr ? column->alphabet : nullptr
+            ));
          }
       }
    }
@@ -422,9 +426,9 @@ std::unique_ptr<Operator> Or::compile(const Table& table) const {
 
 // ---- NOf -------------------------------------------------------------------------------------
 
-std::string NOf::toString() const {
+std::string NOf::toString() const {  // nof.cpp:161-171
    return std::string(match_exactly ? "[exactly-" : "[") + std::to_string(number_of_matchers) + "-of:" +
-          std::to_string(children.size()) + " children]";
+          joinWithLimit(children) + "]";
 }
 
 ExpressionPtr NOf::rewrite(const Table& table, AmbiguityMode mode) const {
@@ -516,8 +520,14 @@ std::unique_ptr<Operator> NOf::compile(const Table& table) const {
 
 // ---- MutationProfile -------------------------------------------------------------------------
 
-std::string MutationProfile::toString() const {
-   return "MutationProfile(" + column + ":distance=" + std::to_string(distance) + ")";
+std::string MutationProfile::toString() const {  // mutation_profile.cpp:39-55
+   std::string input_string;
+   if (const auto* query = std::get_if<QuerySequence>(&input)) {
+      input_string = "querySequence=" + query->sequence.substr(0, 20) + "...";
+   } else {
+      input_string = "mutations(count=" + std::to_string(std::get<Mutations>(input).mutations.size()) + ")";
+   }
+   return "MutationProfile(" + column + ":distance=" + std::to_string(distance) + "," + input_string + ")";
 }
 
 ExpressionPtr MutationProfile::rewrite(const Table& table, AmbiguityMode) const {
@@ -566,7 +576,9 @@ ExpressionPtr MutationProfile::rewrite(const Table& table, AmbiguityMode) const 
       if (incompatible == 0) {
          continue;
       }
-      differences.push_back(std::make_shared<SymbolInSet>(column, static_cast<uint32_t>(position), SymbolSet(incompatible)));
+      differences.push_back(
+         std::make_shared<SymbolInSet>(column, static_cast<uint32_t>(position), SymbolSet(incompatible), &alphabet)
+      );
    }
    return std::make_shared<Negation>(
       std::make_shared<NOf>(std::move(differences), static_cast<int>(distance) + 1, false)
@@ -650,7 +662,7 @@ struct RawSymbolInSet : ScalarExpression {
       for (char character : chars) {
          symbols.push_back(toSymbol(*sequence_column.alphabet, character));
       }
-      return std::make_shared<SymbolInSet>(column, position_idx, std::move(symbols));
+      return std::make_shared<SymbolInSet>(column, position_idx, std::move(symbols), sequence_column.alphabet);
    }
    std::unique_ptr<Operator> compile(const Table& table) const override {
       return rewrite(table, AmbiguityMode::NONE)->compile(table);

@@ -63,10 +63,12 @@ struct SymbolInSet : ScalarExpression {
    std::string column;
    uint32_t position_idx;
    SymbolSet symbols;
-   SymbolInSet(std::string column, uint32_t position_idx, SymbolSet symbols)
+   const Alphabet* alphabet;  // SymbolType of the reference's template; names the symbols in toString()
+   SymbolInSet(std::string column, uint32_t position_idx, SymbolSet symbols, const Alphabet* alphabet = nullptr)
        : column(std::move(column)),
          position_idx(position_idx),
-         symbols(symbols) {}
+         symbols(symbols),
+         alphabet(alphabet) {}
    std::string toString() const override;
    ExpressionPtr rewrite(const Table&, AmbiguityMode) const override;
    std::unique_ptr<Operator> compile(const Table& table) const override;

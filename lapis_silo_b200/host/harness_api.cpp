@@ -267,6 +267,20 @@ int silo_host_filter_explain(silo_host_table* table, const char* expression, cha
    return copyText(text, out, capacity);
 }
 
+int silo_host_filter_to_string(silo_host_table* table, const char* expression, char* out, uint64_t capacity) {
+   std::string text;
+   const int status = guarded([&] {
+      const ExpressionPtr parsed = parseFilterExpression(expression);
+      const ExpressionPtr rewritten = parsed->rewrite(*table->table, AmbiguityMode::NONE);
+      const std::unique_ptr<Operator> compiled = rewritten->compile(*table->table);
+      text = parsed->toString() + "\n" + rewritten->toString() + "\n" + compiled->toString() + "\n";
+   });
+   if (status != 0) {
+      return status;
+   }
+   return copyText(text, out, capacity);
+}
+
 int silo_host_filter_lower_timed(silo_host_table* table, const char* expression, double phase_us[4], uint64_t sizes[3], uint64_t* digest) {
    return guarded([&] {
       const double t0 = nowMicroseconds();

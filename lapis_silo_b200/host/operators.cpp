@@ -1,5 +1,7 @@
 #include "operators.h"
 
+#include <cstdio>
+
 #include <algorithm>
 #include <cstring>
 #include <map>
@@ -210,8 +212,14 @@ std::unique_ptr<IndexScan> IndexScan::overNulls(int device_column) {
 std::string IndexScan::toString() const {
    switch (source) {
       case Source::SYMBOLS:
+      {
+         // (the reference prints its logical equivalent and the bitmap's cardinality, index_scan.cpp:31-37;
+         // here the bitmap is a view of device-resident containers, so the scan is named by what it reads)
+         char mask_hex[16];
+         std::snprintf(mask_hex, sizeof(mask_hex), "0x%x", symbol_mask);
          return "IndexScan(column " + std::to_string(device_column) + ", position " +
-                std::to_string(position_idx + 1) + ", symbols 0x" + std::to_string(symbol_mask) + ")";
+                std::to_string(position_idx + 1) + ", symbols " + mask_hex + ")";
+      }
       case Source::BITMAP:
          return "IndexScan(bitmap, " + std::to_string(bitmap_bytes->size()) + " bytes)";
       case Source::INDEX_BITMAP:
@@ -259,16 +267,8 @@ Intersection::Intersection(OperatorVector&& children_, OperatorVector&& negated_
    }
 }
 
-std::string Intersection::toString() const {
-   std::string res = "Intersection(non_negated: (";
-   for (const auto& child : children) {
-      res += child->toString() + ", ";
-   }
-   res += ") negated: (";
-   for (const auto& child : negated_children) {
-      res += child->toString() + ", ";
-   }
-   return res + "))";
+std::string Intersection::toString() const {  // intersection.cpp:45-53
+   return "Intersection(non_negated: (" + joinWithLimit(children) + ") negated: (" + joinWithLimit(negated_children) + ") )";
 }
 
 void Intersection::lower(ProgramBuilder& program) const {
@@ -285,12 +285,8 @@ void Intersection::lower(ProgramBuilder& program) const {
    }
 }
 
-std::string Union::toString() const {
-   std::string res = "(";
-   for (const auto& child : children) {
-      res += child->toString() + " | ";
-   }
-   return res + ")";
+std::string Union::toString() const {  // union.cpp:23-28
+   return "(" + joinWithLimit(children, " | ") + ")";
 }
 
 void Union::lower(ProgramBuilder& program) const {
@@ -351,11 +347,11 @@ void RangeSelection::lower(ProgramBuilder& program) const {
    program.emit(SILO_OP_PUSH_RANGES, 0, 0, static_cast<uint32_t>(ranges.size()), offset);
 }
 
-std::string Selection::toString() const {
+std::string Selection::toString() const {  // selection.cpp:75-88, is_in_covered_region.cpp:25-29
    std::string res = "Select[";
-   for (const auto& predicate : predicates) {
-      res += std::string(predicate.is_covered ? "" : "!") + "IsInCoveredRegion(" +
-             std::to_string(predicate.position_idx) + "),";
+   for (size_t i = 0; i < predicates.size(); ++i) {
+      res += std::string(i > 0 ? "," : "") + (predicates[i].is_covered ? "" : "!") + "IsInCoveredRegion(" +
+             std::to_string(predicates[i].position_idx) + ")";
    }
    res += "](";
    if (child_operator.has_value()) {
@@ -409,10 +405,9 @@ Threshold::Threshold(
    }
 }
 
-std::string Threshold::toString() const {
-   return std::string("Threshold(") + (match_exactly ? "=" : ">=") + std::to_string(number_of_matchers) +
-          "-of " + std::to_string(non_negated_children.size()) + " non_negated, " +
-          std::to_string(negated_children.size()) + " negated)";
+std::string Threshold::toString() const {  // threshold.cpp:45-58
+   return std::string("Threshold(") + (match_exactly ? "=" : ">=") + std::to_string(number_of_matchers) + "-of " +
+          "non_negated: (" + joinWithLimit(non_negated_children) + ") negated: (" + joinWithLimit(negated_children) + ") )";
 }
 
 namespace {

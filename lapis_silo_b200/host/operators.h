@@ -14,6 +14,23 @@
 
 namespace silo_host {
 
+// common/string_utils.h:35-57: at most `limit` items, then "<delimiter>... (<n> more)"
+template <typename T>
+std::string joinWithLimit(const std::vector<T>& items, const std::string& delimiter = ", ", size_t limit = 10) {
+   std::string res;
+   const size_t items_to_print = items.size() < limit ? items.size() : limit;
+   for (size_t i = 0; i < items_to_print; ++i) {
+      if (i > 0) {
+         res += delimiter;
+      }
+      res += items[i]->toString();
+   }
+   if (items.size() > items_to_print) {
+      res += delimiter + "... (" + std::to_string(items.size() - items_to_print) + " more)";
+   }
+   return res;
+}
+
 enum OperatorType : uint8_t {
    EMPTY,
    FULL,

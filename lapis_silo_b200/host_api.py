@@ -34,7 +34,7 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_synthetic_generation", "silo_host_synthetic_build_column",
     "silo_host_synthetic_release_column", "silo_host_synthetic_lineage_bitmap",
     "silo_host_synthetic_date_ranges", "silo_host_partition_chunks",
-    "silo_host_filter_lower_timed",
+    "silo_host_filter_lower_timed", "silo_host_filter_to_string",
     "silo_host_archive_read", "silo_host_archive_free", "silo_host_archive_column", "silo_host_archive_column_info",
     "silo_host_archive_chunk_sizes", "silo_host_archive_column_shard", "silo_host_table_load_archive", "silo_host_roaring_runs",
 ]
@@ -133,6 +133,7 @@ def lib() -> C.CDLL:
         L.silo_host_synthetic_lineage_bitmap.restype = C.c_int64
         L.silo_host_synthetic_date_ranges.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64, C.c_uint32]
         L.silo_host_partition_chunks.argtypes = [C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.silo_host_filter_to_string.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint64]
         L.silo_host_filter_lower_timed.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         strings, ints = C.POINTER(C.c_char_p), C.POINTER(C.c_int)
         L.silo_host_archive_read.argtypes = [C.c_char_p, C.c_uint64, strings, ints, strings, C.c_uint32]
@@ -422,6 +423,13 @@ class HostTable:
         _check(lib().silo_host_table_add_column(
             self._h, name.encode(), alphabet, reference.encode(), C.cast(desc_ptr, C.c_void_p)))
         self.columns[name] = (16 if alphabet == NUCLEOTIDE else 28, len(reference))
+
+    def to_strings(self, expression: str) -> tuple[str, str, str]:
+        """toString() of the parsed expression, the rewritten expression and the compiled operator tree"""
+        buf = C.create_string_buffer(1 << 22)
+        _check(lib().silo_host_filter_to_string(self._h, expression.encode(), buf, len(buf)))
+        parsed, rewritten, compiled = buf.value.decode().split("\n")[:3]
+        return parsed, rewritten, compiled
 
     def lower_timed(self, expression: str) -> dict:
         """parse -> rewrite -> compile -> lower only: phase times (us), program sizes and a digest of the program"""

@@ -113,3 +113,41 @@ def test_mutation_profile_lowers_to_one_streaming_pass():
                for _ in range(5))
     assert best < 50_000, f"lowering a genome-wide MutationProfile took {best:.0f} us"
     table.close()
+
+
+def test_to_string_formats_are_the_reference_ones():
+    """the reference's own toString vectors: nof.test.cpp:13-48, or.test.cpp:299-321 and :159-178 (merged SymbolInSet);
+    formats of and.cpp:32, symbol_in_set.cpp:37-51, mutation_profile.cpp:39-55, threshold.cpp:45-58,
+    intersection.cpp:45-53, union.cpp:23-28, selection.cpp:75-88, common/string_utils.h:35-57 (joinWithLimit)"""
+    table = host_only_table()
+    parsed = lambda expression: table.to_strings(expression)[0]
+    assert parsed("(n-of 2 0 (true) (true) (true))") == "[2-of:true, true, true]"
+    assert parsed("(n-of 1 1 (true) (true))") == "[exactly-1-of:true, true]"
+    assert parsed("(n-of 1 0 (true))") == "[1-of:true]"
+    assert parsed("(n-of 0 0)") == "[0-of:]"
+    assert table.to_strings("(or (true) (true))")[:2] == ("Or(true | true)", "true")
+    assert table.to_strings("(or (or (true) (true)) (true))")[:2] == ("Or(Or(true | true) | true)", "true")
+    # Or::rewriteSymbolInSetExpressions: one set per (sequence, position)
+    merged = table.to_strings("(or (sym-eq main 3 A) (sym-eq main 3 G))")
+    assert merged[0] == "Or(main:3A | main:3G)" and merged[1] == "(main:symbol at position 3 in {A, G})"
+    separate = table.to_strings("(or (sym-eq main 3 A) (sym-eq main 4 G))")[1]
+    assert separate == "Or((main:symbol at position 3 in {A}) | (main:symbol at position 4 in {G}))"
+    assert table.to_strings("(and (sym-eq main 1 C) (not (has-mut main 2)))")[0] == "And(main:1C & !(main:1))"  # has_mutation.cpp:24-26 prints the 0-based index
+    assert table.to_strings("(maybe (sym-eq main 1 R))")[:2] == ("Maybe (main:1R)", "(main:symbol at position 1 in {R, D, V, N})")
+    assert table.to_strings("(exact (has-mut main 2))")[0] == "Exact (main:1)"
+    assert parsed("(profile main 2 muts 1 T 3 N)") == "MutationProfile(main:distance=2,mutations(count=2))"
+    assert parsed("(profile main 0 seq ACGTACGTAC)") == "MutationProfile(main:distance=0,querySequence=ACGTACGTAC...)"
+    # joinWithLimit: ten items, then the count of the rest
+    eleven = " ".join(["(true)"] * 13)
+    assert parsed(f"(n-of 3 0 {eleven})") == "[3-of:" + ", ".join(["true"] * 10) + ", ... (3 more)]"
+    assert parsed(f"(and {eleven})") == "And(" + " & ".join(["true"] * 10) + " & ... (3 more))"
+    # operator trees
+    compiled = lambda expression: table.to_strings(expression)[2]
+    assert compiled("(true)") == "Full" and compiled("(false)") == "Empty" and compiled("(not (true))") == "Empty"
+    assert compiled("(sym-eq main 1 A)") == "Intersection(non_negated: (Select[IsInCoveredRegion(0)]()) negated: (IndexScan(column 0, position 1, symbols 0x7ffd)) )"  # every symbol but A and N
+    assert compiled("(sym-eq main 2 N)") == "(Select[!IsInCoveredRegion(1)]() | IndexScan(column 0, position 2, symbols 0x8000))"
+    assert compiled("(not (sym-eq main 2 G))") == "!IndexScan(column 0, position 2, symbols 0x8)"
+    assert compiled("(n-of 2 0 (sym-eq main 1 C) (sym-eq main 2 A) (not (sym-eq main 3 T)))") == \
+        "Threshold(>=2-of non_negated: (IndexScan(column 0, position 1, symbols 0x4), IndexScan(column 0, position 2, symbols 0x2)) " \
+        "negated: (IndexScan(column 0, position 3, symbols 0x10)) )"
+    table.close()
