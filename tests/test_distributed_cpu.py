@@ -115,3 +115,61 @@ def test_partition_covers_all_chunks_without_gaps():
                 assert all(a < b for a, b in zip(bounds, bounds[1:])), "no rank may be left without chunks"
                 loads = [sum(weights[a:b]) for a, b in zip(bounds, bounds[1:])]
                 assert max(loads) <= sum(weights) / ranks + max(weights)
+
+
+def archive_worker(rank: int, world_size: int, port: int, result_path: str) -> None:
+    """every rank reads the SAME `.silo` bytes with the product's C++ loader and keeps its own chunk range
+    (host/silo_loader.cpp shardOf); what the ranks hold together must be the whole table: row counts add up,
+    and the stored-symbol counts of the unfiltered Mutations action -- the sums of the shard's container
+    cardinalities per (symbol, position) -- all-reduce to the oracle's whole-table counts"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        from lapis_silo_b200 import host_api
+        from oracle import oracle as O
+        from test_silo_loader import random_archive
+        table, data, _, specs = random_archive(301, 0)  # seeded: the same bytes on every rank
+        archive = host_api.Archive(data, specs)
+        chunk_sizes = archive.chunk_sizes(0)
+        bounds = host_api.partition_chunks([1] * len(chunk_sizes), world_size)
+        first, n_chunks = bounds[rank], bounds[rank + 1] - bounds[rank]
+        desc = archive.shard_desc(0, first, n_chunks).contents
+        local = np.zeros((desc.n_symbols, desc.genome_length), dtype=np.int64)
+        for i in range(desc.n_containers):
+            container = desc.containers[i]
+            assert first <= container.v_index < first + n_chunks
+            local[container.symbol, container.position] += container.cardinality
+        shard_table = host_api.HostTable.from_archive(None, data, specs, first_chunk=first, n_chunks=n_chunks)
+        rows = torch.tensor([shard_table.num_rows], dtype=torch.int64)
+        assert shard_table.num_rows == sum(chunk_sizes[first:first + n_chunks])
+        shard_table.close()
+        reduced = torch.from_numpy(local)
+        dist.all_reduce(reduced)
+        dist.all_reduce(rows)
+        assert int(rows.item()) == table.num_rows
+        whole = table.mutation_counts("c").astype(np.int64)
+        local_reference = [O.NUC_SYMBOLS.index(c) for c in table.local_reference("c")]
+        for symbol in range(5):  # the valid mutation symbols -ACGT; the local reference's count is derived, not stored
+            positions = np.array([p for p in range(desc.genome_length) if local_reference[p] != symbol])
+            np.testing.assert_array_equal(reduced.numpy()[symbol, positions], whole[symbol, positions])
+        archive.close()
+        if rank == 0:
+            with open(result_path, "w") as out:
+                out.write(f"ok {int(rows.item())}")
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_load_their_chunk_ranges_from_one_archive(tmp_path):
+    torch = pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    result_path = str(tmp_path / "result.txt")
+    mp.spawn(archive_worker, args=(2, free_port(), result_path), nprocs=2, join=True)
+    with open(result_path) as result:
+        assert result.read().startswith("ok ")
