@@ -458,6 +458,9 @@ uint64_t portableRoaringToRuns(const uint8_t* bytes, uint64_t size, std::vector<
    uint64_t total = 0;
    const size_t first_run = runs.size();
    auto emit = [&](uint32_t first, uint32_t end_exclusive) {
+      if (runs.size() > first_run && first < runs.back()) {
+         throw ArchiveFormatError("roaring bitmap values are not ascending");
+      }
       if (runs.size() > first_run && runs.back() == first) {
          runs.back() = end_exclusive;
       } else {
@@ -478,6 +481,9 @@ uint64_t portableRoaringToRuns(const uint8_t* bytes, uint64_t size, std::vector<
          for (uint32_t r = 0; r < n_runs; ++r) {
             const uint32_t start = read16(at + 4ULL * r);
             const uint32_t length_minus_one = read16(at + 4ULL * r + 2);
+            if (start + length_minus_one > 0xFFFF) {
+               throw ArchiveFormatError("run reaches beyond its container");
+            }
             emit(high | start, (high | start) + length_minus_one + 1);
          }
          at += 4ULL * n_runs;

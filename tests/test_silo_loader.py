@@ -327,3 +327,52 @@ def test_device_table_loaded_from_the_reference_state(ctx):
             for min_proportion in (0.0, 0.05, 0.3):
                 assert device_table.mutations([name], expression, min_proportion) == oracle.mutations(name, expression, min_proportion), (name, expression)
     device_table.close()
+
+
+def test_reader_survives_damaged_input():
+    """truncations, flipped bytes and absurd sizes anywhere in an archive / a roaring bitmap are either rejected with an
+    error or parsed -- never a crash, and whatever the roaring decoder returns is a list of ascending, disjoint runs"""
+    from lapis_silo_b200 import host_api as H
+    from oracle import oracle as O
+    good = W.write_archive(state_columns_for_writer(), b"\x05\0\0\0\0\0\0\0hello")
+    specs = specs_of_state()
+    rng = np.random.default_rng(0)
+    outcomes = {"parsed": 0, "rejected": 0}
+    for trial in range(3000):
+        data = bytearray(good)
+        kind = trial % 4
+        if kind == 0:
+            data = data[:int(rng.integers(0, len(data)))]
+        elif kind == 1:
+            for _ in range(int(rng.integers(1, 4))):
+                data[int(rng.integers(30, len(data)))] = int(rng.integers(0, 256))
+        elif kind == 2:
+            at = int(rng.integers(30, len(data) - 8))
+            data[at:at + 8] = int(rng.integers(0, 1 << 63)).to_bytes(8, "little")
+        else:
+            at = int(rng.integers(30, len(data) - 4))
+            data[at:at + 4] = b"\xff\xff\xff\xff"
+        try:
+            H.Archive(bytes(data), specs).close()
+            outcomes["parsed"] += 1
+        except H.HostError:
+            outcomes["rejected"] += 1
+    assert outcomes["rejected"] > 1000 and outcomes["parsed"] > 0
+    blobs = [O.roaring_roundtrip(sorted({int(v) for v in rng.integers(0, 1 << 18, 3000)} | set(range(70000, 80000))), optimize=o)[1]
+             for o in (False, True)]
+    for trial in range(3000):
+        data = bytearray(blobs[trial % 2])
+        if trial % 3 == 0:
+            data = data[:int(rng.integers(0, len(data)))]
+        elif trial % 3 == 1:
+            for _ in range(int(rng.integers(1, 4))):
+                data[int(rng.integers(0, min(len(data), 64)))] = int(rng.integers(0, 256))
+        else:
+            at = int(rng.integers(0, len(data) - 4))
+            data[at:at + 4] = int(rng.integers(0, 1 << 32)).to_bytes(4, "little")
+        try:
+            runs = H.roaring_runs(bytes(data))
+        except H.HostError:
+            continue
+        assert all(first < end for first, end in runs)
+        assert all(a[1] < b[0] for a, b in zip(runs, runs[1:]))
