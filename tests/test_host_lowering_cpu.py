@@ -151,3 +151,20 @@ def test_to_string_formats_are_the_reference_ones():
         "Threshold(>=2-of non_negated: (IndexScan(column 0, position 1, symbols 0x4), IndexScan(column 0, position 2, symbols 0x2)) " \
         "negated: (IndexScan(column 0, position 3, symbols 0x10)) )"
     table.close()
+
+
+def test_lowered_programs_equal_the_gpu_verified_ones():
+    """tests/golden/lowering_digests.json: digests of the lowered programs of 30 expressions (with and without null rows)
+    from the build whose GPU parity suite was green; a change of the host mirror must leave the device's input alone"""
+    import json
+    import os
+    import sys
+    golden_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, golden_dir)
+    import make_lowering_digests
+    with open(os.path.join(golden_dir, "lowering_digests.json")) as handle:
+        want = json.load(handle)
+    got = make_lowering_digests.lowered()
+    assert len(got) == len(want) == 60
+    for have, expected in zip(got, want):
+        assert have == expected, expected["expression"]
