@@ -55,6 +55,9 @@ int silo_host_filter_explain(silo_host_table* table, const char* expression, cha
 /* toString() of the expression as parsed, after rewrite(NONE) and of the compiled operator tree, one per line
  * (the reference's own formats: and.cpp:32, or.cpp:27, nof.cpp:161, symbol_in_set.cpp:37, threshold.cpp:45 ...) */
 int silo_host_filter_to_string(silo_host_table* table, const char* expression, char* out, uint64_t capacity);
+/* the bytes (portable roaring) of bitmap `index` travelling with the lowered program of `expression`; returns the
+ * size, or a negative status (buffer too small included) */
+int64_t silo_host_filter_program_bitmap(silo_host_table* table, const char* expression, uint32_t index, uint8_t* out, uint64_t capacity);
 /* parse -> rewrite(NONE) -> compile -> lower without running anything: microseconds of the four phases,
  * sizes[3] = {instructions, blob bytes, bitmaps travelling with the program}, and a 64-bit FNV-1a digest of the
  * lowered program (instruction fields + blob) so that two lowerings can be compared without the text form */

@@ -281,6 +281,25 @@ int silo_host_filter_to_string(silo_host_table* table, const char* expression, c
    return copyText(text, out, capacity);
 }
 
+int64_t silo_host_filter_program_bitmap(silo_host_table* table, const char* expression, uint32_t index, uint8_t* out, uint64_t capacity) {
+   int64_t size = -1;
+   guarded([&] {
+      const ExpressionPtr parsed = parseFilterExpression(expression);
+      const ExpressionPtr rewritten = parsed->rewrite(*table->table, AmbiguityMode::NONE);
+      const std::unique_ptr<Operator> compiled = rewritten->compile(*table->table);
+      ProgramBuilder builder;
+      builder.table = table->table.get();
+      compiled->lower(builder);
+      const silo_roaring_bytes& bitmap = builder.bitmaps.at(index);
+      if (bitmap.size > capacity) {
+         throw std::invalid_argument("bitmap buffer too small: need " + std::to_string(bitmap.size));
+      }
+      std::memcpy(out, bitmap.data, bitmap.size);
+      size = static_cast<int64_t>(bitmap.size);
+   });
+   return size;
+}
+
 int silo_host_filter_lower_timed(silo_host_table* table, const char* expression, double phase_us[4], uint64_t sizes[3], uint64_t* digest) {
    return guarded([&] {
       const double t0 = nowMicroseconds();

@@ -34,7 +34,7 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_synthetic_generation", "silo_host_synthetic_build_column",
     "silo_host_synthetic_release_column", "silo_host_synthetic_lineage_bitmap",
     "silo_host_synthetic_date_ranges", "silo_host_partition_chunks",
-    "silo_host_filter_lower_timed", "silo_host_filter_to_string",
+    "silo_host_filter_lower_timed", "silo_host_filter_to_string", "silo_host_filter_program_bitmap",
     "silo_host_archive_read", "silo_host_archive_free", "silo_host_archive_column", "silo_host_archive_column_info",
     "silo_host_archive_chunk_sizes", "silo_host_archive_column_shard", "silo_host_table_load_archive", "silo_host_roaring_runs",
 ]
@@ -133,6 +133,8 @@ def lib() -> C.CDLL:
         L.silo_host_synthetic_lineage_bitmap.restype = C.c_int64
         L.silo_host_synthetic_date_ranges.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64, C.c_uint32]
         L.silo_host_partition_chunks.argtypes = [C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.silo_host_filter_program_bitmap.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint64]
+        L.silo_host_filter_program_bitmap.restype = C.c_int64
         L.silo_host_filter_to_string.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint64]
         L.silo_host_filter_lower_timed.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         strings, ints = C.POINTER(C.c_char_p), C.POINTER(C.c_int)
@@ -430,6 +432,14 @@ class HostTable:
         _check(lib().silo_host_filter_to_string(self._h, expression.encode(), buf, len(buf)))
         parsed, rewritten, compiled = buf.value.decode().split("\n")[:3]
         return parsed, rewritten, compiled
+
+    def program_bitmap(self, expression: str, index: int = 0) -> bytes:
+        """portable roaring bytes of bitmap `index` of the expression's lowered program"""
+        buf = C.create_string_buffer(1 << 22)
+        size = lib().silo_host_filter_program_bitmap(self._h, expression.encode(), index, buf, len(buf))
+        if size < 0:
+            raise HostError(lib().silo_host_last_error().decode())
+        return buf.raw[:size]
 
     def lower_timed(self, expression: str) -> dict:
         """parse -> rewrite -> compile -> lower only: phase times (us), program sizes and a digest of the program"""

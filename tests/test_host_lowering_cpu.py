@@ -71,6 +71,19 @@ def test_errors_are_the_reference_messages():
         table.explain("(profile main 0 seq ACGTACGTAZ)")
     with pytest.raises(H.HostError, match="mutation position 11 is out of bounds"):
         table.explain("(profile main 0 muts 11 A)")
+    # number lists of the harness notation are read straight from the text
+    for expression, message in (("(ranges 1 2 3)", "ranges needs START END pairs"), ("(ranges 1 x)", "expected a non-negative integer, got 'x'"),
+                                ("(ids 1 -2)", "expected a non-negative integer, got '-2'"), ("(ids 1 (2))", "expected an atom"),
+                                ("(ranges 1 2", "missing '\\)'"), ("(ids 123456789012345678901)", "expected a non-negative integer")):
+        with pytest.raises(H.HostError, match=message):
+            table.explain(expression)
+    assert instrs(table, "(ranges)") == [(7, 0, 0, 0, 0)] and instrs(table, "(ids)")[0][0] == 6  # empty lists are legal
+    assert instrs(table, "(ranges 3 9  70000 70010 )")[0][:4] == (7, 0, 0, 2)  # PUSH_RANGES, two ranges
+    rng = np.random.default_rng(3)
+    for ids in ([], [0], [5, 65535, 65536, 65600], sorted({int(v) for v in rng.integers(0, 65636, 6000)})):
+        text = "(ids " + "  ".join(map(str, ids)) + " )"
+        runs = H.roaring_runs(table.program_bitmap(text))
+        assert [v for first, end in runs for v in range(first, end)] == ids
     table.close()
 
 
