@@ -135,52 +135,64 @@ class ClockSampler:
 # the CPU side: oracle restatement of the reference path (cpu_baseline leg and --impl reference)
 # ---------------------------------------------------------------------------------------------
 
-def build_oracle_sample(sample_chunks: int):
-    """Same generator and the same filter fractions on a bounded table of sample_chunks x 65536 rows,
-    built by the oracle's own string ingest (no product code on this path)."""
+def lineage_row_ids(synthetic, ancestor: int, total_rows: int):
+    """global row ids of the rows whose sequence descends from `ancestor` (row i holds evolved[i % n])"""
     import numpy as np
-    from oracle import oracle as O
-    rng_reference = O.lib()  # load
-    del rng_reference
-    # the product generator's reference is a seeded std::mt19937 string; the oracle side only needs
-    # *a* random 29,903-nt reference of the same composition
-    rng = np.random.default_rng(REFERENCE_SEED)
-    reference = "".join("ACGT"[int(i)] for i in rng.integers(0, 4, GENOME_LENGTH))
-    rows = sample_chunks * 65536
-    started = time.perf_counter()
-    table = O.full_sequence_table(reference, rows, GENERATIONS)
-    evolved, parents = O.gen_evolved(reference, seed=42, generations=GENERATIONS)
-    n_sequences = len(evolved)
-    generation = [0] * n_sequences
-    for e in range(1, n_sequences):
-        generation[e] = generation[parents[e]] + 1
-    ancestor = next(e for e in range(n_sequences) if generation[e] == 2)
+    n_sequences = synthetic.num_sequences
     in_lineage = np.zeros(n_sequences, dtype=bool)
     in_lineage[ancestor] = True
     for e in range(ancestor + 1, n_sequences):
-        in_lineage[e] = in_lineage[parents[e]]
-    lineage_rows = np.flatnonzero(in_lineage[np.arange(rows) % n_sequences])
-    table.register_bitmap("lineage", lineage_rows.tolist())
-    days = (np.arange(rows, dtype=np.uint64) * SPAN_DAYS) // rows
-    lower = int(np.searchsorted(days, FROM_DAY, side="left"))
-    upper = int(np.searchsorted(days, TO_DAY, side="right"))
-    ranges = []
-    for chunk in range(sample_chunks):  # one range per chunk, date_between.cpp:94-134
-        lo = min(max(lower - chunk * 65536, 0), 65536)
-        hi = min(max(upper - chunk * 65536, 0), 65536)
-        ranges += [((chunk + 1) << 16) if lo == 65536 else (chunk << 16) | lo,
-                   ((chunk + 1) << 16) if hi == 65536 else (chunk << 16) | hi]
-    expression = "(and (ranges " + " ".join(map(str, ranges)) + ") (bitmap lineage))"
-    log(f"[oracle] sample table: {rows} rows, {table.num_containers('main')} containers, "
+        in_lineage[e] = in_lineage[synthetic.parent(e)]
+    members = np.flatnonzero(in_lineage).astype(np.int64)
+    ids = (np.arange(0, total_rows, n_sequences, dtype=np.int64)[:, None] + members[None, :]).ravel()
+    return ids[ids < total_rows].astype(np.uint32)
+
+
+def oracle_rows_that_fit(total_rows: int) -> int:
+    """The oracle table of 10 M rows takes ~1.7 GB plus ~1.7 GB while it is imported; a host without the
+    memory for the whole N-GPU table gets as many rows as fit (whole multiples of 10 M), and says so."""
+    try:
+        import psutil
+        available = psutil.virtual_memory().available
+    except Exception:
+        return total_rows
+    per_row = 3.6e9 / 1e7
+    if total_rows * per_row * 1.25 <= available:
+        return total_rows
+    return max(10_000_000, int(available / 1.25 / per_row) // 10_000_000 * 10_000_000)
+
+
+def build_oracle_table(total_rows: int, threads: int):
+    """The oracle's table of THE SAME synthetic data the GPU arm queries, at full size: the product-side generator
+    (host/synthetic.cpp; tests/test_host_cpu.py checks it against the oracle's own string generator) writes the
+    column in the S1 upload format and the oracle imports it into its std::map of containers; the same lineage
+    bitmap and the same per-chunk date ranges. Only data preparation happens here -- the timed query below
+    runs on oracle code alone."""
+    from lapis_silo_b200 import host_api
+    from oracle import oracle as O
+    started = time.perf_counter()
+    synthetic = host_api.Synthetic(GENOME_LENGTH, REFERENCE_SEED, GENERATIONS)
+    sizes = host_api.dense_chunk_sizes(total_rows)
+    column = synthetic.build_column(total_rows, 0, len(sizes), threads)
+    meta = {"containers": int(column.contents.n_containers), "payload_bytes": int(column.contents.payload_bytes)}
+    table = O.Table()
+    table.set_layout(*sizes)
+    table.import_column("main", O.NUCLEOTIDE, synthetic.reference, column)
+    synthetic.release_column()
+    ancestor = next(e for e in range(synthetic.num_sequences) if synthetic.generation(e) == 2)
+    table.register_bitmap("lineage", lineage_row_ids(synthetic, ancestor, total_rows))
+    expression = (f"(and {host_api.date_ranges_expression(total_rows, SPAN_DAYS, FROM_DAY, TO_DAY, 0, len(sizes))} "
+                  f"(bitmap lineage))")
+    log(f"[oracle] table: {total_rows} rows, {meta['containers']} containers, {meta['payload_bytes'] / 1e9:.2f} GB payload, "
         f"built in {time.perf_counter() - started:.1f}s")
-    return table, expression
+    return table, expression, meta
 
 
 def time_oracle(table, expression, threads: int, min_seconds: float, max_queries: int):
     """threads concurrent independent native queries (the reference's one-worker-per-request model,
     no intra-query parallelism): computeFilter -> calculateMutationsPerPosition -> thresholding, with
-    parsing/compiling inside the timer. Python only starts the run and reads the totals."""
-    table.mutations_query("main", expression, MIN_PROPORTION)  # warm-up
+    parsing/compiling inside the timer (performance/nof_sequence_filter.cpp:43-52 starts its clock in front of
+    the planner). Python only starts the run and reads the totals."""
     queries, elapsed, cardinality = table.mutations_query_bench(
         "main", expression, MIN_PROPORTION, threads, min_seconds, max_queries)
     return cardinality * GENOME_LENGTH * queries / elapsed, elapsed, queries, cardinality
@@ -191,41 +203,53 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    table, expression = build_oracle_sample(args.cpu_sample_chunks)
+    n_gpus = max(1, args.gpus)
+    total_rows = args.rows_per_gpu * n_gpus
+    rows = oracle_rows_that_fit(total_rows)
+    table, expression, meta = build_oracle_table(rows, cores)
+    n_output_rows, cardinality = table.mutations_query("main", expression, MIN_PROPORTION)  # warm-up
+    single_value, single_elapsed, single_queries, _ = time_oracle(table, expression, 1, 2.0, 10 ** 9)
     per_step = []
-    cardinality = 0
     for step in range(args.warmup + args.steps):
         value, elapsed, queries, cardinality = time_oracle(table, expression, cores, args.reference_step_seconds, 10 ** 9)
         if step >= args.warmup:
-            per_step.append((value, elapsed))
-    value = sum(v for v, _ in per_step) / len(per_step)
-    ms_per_step = 1000.0 * sum(e for _, e in per_step) / len(per_step)
-    sample = (f"{args.cpu_sample_chunks} chunks ({args.cpu_sample_chunks * 65536} rows x {GENOME_LENGTH} nt) of the same "
-              f"generator and filter; {cores} concurrent single-threaded queries for {args.reference_step_seconds}s per step")
+            per_step.append((value, elapsed, queries))
+    value = sum(v for v, _, _ in per_step) / len(per_step)
+    ms_per_step = 1000.0 * sum(e for _, e, _ in per_step) / len(per_step)
+    sample = (f"the whole table ({rows} rows x {GENOME_LENGTH} nt, same data, filter and minProportion as the GPU arm); "
+              if rows == total_rows else
+              f"{rows} of the {total_rows} rows (host memory), same generator, filter fractions and minProportion; ")
+    sample += (f"a step = {cores} concurrent single-threaded queries running for >= {args.reference_step_seconds}s "
+               f"({sum(q for _, _, q in per_step)} queries in the {len(per_step)} timed steps)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": workload_config(args, cardinality, None),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args, rows, cardinality, n_output_rows, meta["containers"], meta["payload_bytes"]),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "per_core_value": value / cores,
+                         "single_thread": {"value": single_value, "cores": 1,
+                                           "ms_per_query": 1000.0 * single_elapsed / max(1, single_queries)}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "run": {"parallelism": f"{cores} concurrent single-threaded queries on {cores} host cores (one worker per request, "
+                               "api/api.cpp:39-51)", "timer": "parse + compile + filter + counts + thresholding inside"},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, cardinality, extra):
-    config = {
+def workload_config(args, total_rows, cardinality, output_rows, containers, payload_bytes):
+    """What is computed, not how: identical in the GPU arm and the reference arm of one N."""
+    return {
         "workload": "performance/mutation_benchmark-style synthetic full-length table, Mutations with date-range + lineage filter "
                     "(BASELINE.json configs[1])",
-        "rows_per_gpu": args.rows_per_gpu, "genome_length": GENOME_LENGTH, "min_proportion": MIN_PROPORTION,
+        "rows_per_gpu": args.rows_per_gpu, "total_rows": total_rows, "genome_length": GENOME_LENGTH,
+        "min_proportion": MIN_PROPORTION,
         "filter": "date.between(2021-01-01, 2021-06-30) && lineage(generation-2 node, includeSublineages)",
-        "filter_cardinality": cardinality,
+        "filter_cardinality": cardinality, "output_rows": output_rows,
+        "containers": containers, "payload_gb": round(payload_bytes / 1e9, 3),
         "l2": "the container payload touched per step exceeds the 126 MB L2, no explicit flush",
     }
-    if extra:
-        config.update(extra)
-    return config
 
 
 # ---------------------------------------------------------------------------------------------
@@ -439,6 +463,8 @@ def run_ours(args):
     if clocks is not None:
         clocks["sampled_over"] = "the timed region and 0.4 s of the same step right after it (nvidia-smi -lms 100)"
     cardinality = sum_over_ranks(prepared.cardinality())
+    total_containers = sum_over_ranks(n_containers)
+    total_payload_bytes = sum_over_ranks(payload_bytes)
     last_buffer = count_buffers[(issued[0] - 1) % len(count_buffers)]
     if n_gpus > 1:  # outside the timed region: the other symbols' rows too, for the property check below
         dist.all_reduce(last_buffer[valid_values:])
@@ -499,14 +525,14 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": device_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": workload_config(args, cardinality, {
-            "total_rows": total_rows, "chunks_per_gpu": n_chunks, "containers_per_gpu": n_containers,
-            "payload_gb_per_gpu": round(payload_bytes / 1e9, 3),
+        "config": workload_config(args, total_rows, cardinality, len(rows), total_containers, total_payload_bytes),
+        "run": {
+            "chunks_per_gpu": n_chunks, "containers_per_gpu": n_containers, "payload_gb_per_gpu": round(payload_bytes / 1e9, 3),
             "launch": f"one CUDA graph holding the {args.steps} steps of the timed region" + (", all-reduces included" if n_gpus > 1 else "")
             if used_graph else "eager launches",
             "parallelism": f"interleaved chunk shards (chunk c on rank c % {n_gpus}), "
-            "NCCL allreduce of the u32 counts" if n_gpus > 1 else "single GPU", "output_rows": len(rows),
-        }),
+            "NCCL allreduce of the u32 counts" if n_gpus > 1 else "single GPU",
+        },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": prepared.staged_bytes,
@@ -527,14 +553,29 @@ def run_ours(args):
         },
     }
     if n_gpus == 1 and not args.skip_cpu_baseline:
-        oracle_table, oracle_expression = build_oracle_sample(args.cpu_sample_chunks)
+        # The oracle on THE SAME table at full size: (1) the bit-exact check of this run's results -- counts of all
+        # 16 symbols at all 29,903 positions, the filtered row count and the thresholded output rows with their
+        # double proportions --, (2) the CPU baseline, one thread per query like the reference.
+        cores = os.cpu_count() or 1
+        oracle_table, oracle_expression, _ = build_oracle_table(total_rows, cores)
+        oracle_filter = oracle_table.filter(oracle_expression)
+        assert oracle_filter.cardinality == cardinality, (oracle_filter.cardinality, cardinality)
+        oracle_counts = oracle_table.mutation_counts("main", oracle_filter)
+        assert np.array_equal(oracle_counts, device_counts), "device counts differ from the oracle's at full size"
+        oracle_rows = oracle_table.mutation_rows("main", oracle_counts, MIN_PROPORTION)
+        assert oracle_rows == rows, "output rows differ from the oracle's at full size"
+        line["parity"] = {"oracle": "full size, same table", "rows": total_rows, "filter_cardinality_equal": True,
+                          "counts_equal": True, "output_rows_equal": True, "output_rows": len(rows)}
         cpu_value, cpu_elapsed, cpu_queries, cpu_cardinality = time_oracle(
             oracle_table, oracle_expression, 1, args.cpu_seconds, 10 ** 9)
+        all_value, all_elapsed, all_queries, _ = time_oracle(oracle_table, oracle_expression, cores, args.cpu_seconds / 2, 10 ** 9)
         line["cpu_baseline"] = {
             "value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{args.cpu_sample_chunks} chunks ({args.cpu_sample_chunks * 65536} rows x {GENOME_LENGTH} nt) of the same "
-                      f"generator and filter fractions; {cpu_queries} single-threaded queries in {cpu_elapsed:.1f}s "
-                      f"(|filter| = {cpu_cardinality}); host has {os.cpu_count()} cores",
+            "sample": f"the whole table ({total_rows} rows x {GENOME_LENGTH} nt, the GPU arm's data, filter and minProportion); "
+                      f"{cpu_queries} single-threaded queries in {cpu_elapsed:.1f}s ({1000.0 * cpu_elapsed / cpu_queries:.0f} ms/query, "
+                      f"|filter| = {cpu_cardinality}); host has {cores} cores",
+            "all_cores": {"value": all_value, "cores": cores,
+                          "sample": f"{all_queries} queries by {cores} concurrent single-threaded workers in {all_elapsed:.1f}s"},
         }
     else:
         line["cpu_baseline"] = None
@@ -550,9 +591,8 @@ def main():
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", choices=["ours", "reference"], default="ours")
     parser.add_argument("--rows-per-gpu", type=int, default=10_000_000)
-    parser.add_argument("--cpu-sample-chunks", type=int, default=6)
     parser.add_argument("--cpu-seconds", type=float, default=12.0)
-    parser.add_argument("--reference-step-seconds", type=float, default=4.0)
+    parser.add_argument("--reference-step-seconds", type=float, default=2.0)
     parser.add_argument("--skip-cpu-baseline", action="store_true")
     parser.add_argument("--eager", action="store_true", help="launch the timed steps one by one instead of as one CUDA graph")
     parser.add_argument("--traffic-bytes", type=int, default=None,

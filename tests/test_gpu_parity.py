@@ -491,3 +491,71 @@ def test_baseline_sizes_size_independent_properties(ctx):
     assert k_of_n[0] == table.filter(f"(or {leaves})").cardinality
     assert k_of_n[2] == table.filter(f"(and {leaves})").cardinality
     table.close()
+
+
+def profile_brute_force(synthetic, total_rows, query_index):
+    """Rows of the synthetic table (row i = evolved[i % n], no missing symbols) by their Hamming distance to
+    evolved[query_index]: an independent restatement of nucleotideMutationProfile(distance, querySequence) on this
+    data (mutation_profile.cpp:198-257: a position counts when the row's symbol cannot be the query's)."""
+    n = synthetic.num_sequences
+    sequences = np.array([np.frombuffer(synthetic.sequence(e).encode(), dtype=np.uint8) for e in range(n)])
+    return (sequences != sequences[query_index]).sum(axis=1)
+
+
+def test_baseline_sizes_equal_the_oracle(ctx):
+    """BASELINE.json configs 2 and 3 at FULL size (10 M rows x 29,903 nt, bench.py's table), bit-compared with the
+    oracle on the same table (the oracle imports the product generator's S1 column: ~5 s; one Mutations query takes
+    it ~0.3 s): filtered row ids, u32 counts of all 16 symbols at every position, thresholded rows incl. proportions.
+    Config 3: the profile row sets at distance 0 / 5 / 50 / 200 against the brute-force Hamming distances and, at
+    distance 0 (SILO_SLOW_PARITY=1: also 5), against the oracle's Threshold DP (O(n k) whole-bitmap passes: 9 s, 59 s,
+    541 s for d = 0, 5, 50 -- tests/test_oracle_profile_cpu.py pins the brute force to the DP at reduced size)."""
+    import os
+    from lapis_silo_b200 import host_api
+    from oracle import oracle as O
+    total_rows, length = 10_000_000, 29903
+    synthetic = host_api.Synthetic(genome_length=length, reference_seed=20200101, generations=5)
+    sizes = host_api.dense_chunk_sizes(total_rows)
+    column = synthetic.build_column(total_rows, 0, len(sizes), os.cpu_count() or 8)
+    table = host_api.HostTable(ctx, sizes)
+    table.add_column("main", host_api.NUCLEOTIDE, synthetic.reference, column)
+    oracle_table = O.Table()
+    oracle_table.set_layout(*sizes)
+    oracle_table.import_column("main", O.NUCLEOTIDE, synthetic.reference, column)
+    synthetic.release_column()
+    ancestor = next(e for e in range(synthetic.num_sequences) if synthetic.generation(e) == 2)
+    lineage_bytes = synthetic.lineage_bitmap(ancestor, total_rows, 0, len(sizes))
+    table.register_bitmap("lineage", lineage_bytes)
+    n = synthetic.num_sequences
+    in_lineage = np.zeros(n, dtype=bool)
+    in_lineage[ancestor] = True
+    for e in range(ancestor + 1, n):
+        in_lineage[e] = in_lineage[synthetic.parent(e)]
+    oracle_table.register_bitmap("lineage", np.flatnonzero(in_lineage[np.arange(total_rows) % n]).astype(np.uint32))
+    assert oracle_table.bitmap_bytes("lineage") == lineage_bytes
+
+    # config 2
+    expression = f"(and {host_api.date_ranges_expression(total_rows, 1095, 366, 546, 0, len(sizes))} (bitmap lineage))"
+    got, want = table.filter(expression), oracle_table.filter(expression)
+    assert got.cardinality == want.cardinality == 422574
+    np.testing.assert_array_equal(got.ids(), want.ids())
+    want_counts = oracle_table.mutation_counts("main", want)
+    np.testing.assert_array_equal(table.mutation_counts("main", got), want_counts)
+    for min_proportion in (0.05, 0.0, 0.5):
+        assert table.mutations(["main"], expression, min_proportion) == oracle_table.mutation_rows("main", want_counts, min_proportion)
+    # ... and the unfiltered action (stored cardinalities only, mutations_node.cpp:240-266)
+    np.testing.assert_array_equal(table.mutation_counts("main"), oracle_table.mutation_counts("main"))
+
+    # config 3
+    query_index = n - 1
+    query = synthetic.sequence(query_index)
+    distances = profile_brute_force(synthetic, total_rows, query_index)
+    row_sequence = np.arange(total_rows) % n
+    for distance in (0, 5, 50, 200):
+        flt = table.filter(f"(profile main {distance} seq {query})")
+        want_ids = np.flatnonzero((distances <= distance)[row_sequence]).astype(np.uint32)
+        assert flt.cardinality == len(want_ids) > 0
+        np.testing.assert_array_equal(flt.ids(), want_ids)
+    for distance in (0, 5) if os.environ.get("SILO_SLOW_PARITY") else (0,):
+        text = f"(profile main {distance} seq {query})"
+        np.testing.assert_array_equal(table.filter(text).ids(), oracle_table.filter(text).ids())
+    table.close()
