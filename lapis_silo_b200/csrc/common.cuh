@@ -19,12 +19,20 @@ namespace silo {
 
 constexpr uint32_t TILE_WORDS = 1024;        // one chunk's dense filter tile: 1024 x u64 = 8 KiB
 constexpr uint32_t TILE_BYTES = TILE_WORDS * 8;
-#ifndef SILO_SEG_PAYLOAD_BYTES
-#define SILO_SEG_PAYLOAD_BYTES 31744
-#endif
-constexpr uint32_t SEG_PAYLOAD_BYTES = SILO_SEG_PAYLOAD_BYTES;  // max payload bytes of one segment: 31 pieces of <= 1 KiB
-constexpr uint32_t SEG_MAX_DESCS = 31;         // max pieces of one segment: one per consumer warp, so that a warp
-                                               // can always hand the stage back before it does the lookups
+// Geometry of the container kernel (mutations.cu) and, with it, of the segments the upload cuts a chunk into:
+// `warps` consumer warps take `pieces` pieces each from one ring stage, so a segment holds at most
+// warps * pieces pieces (of <= 1 KiB) of ONE kind; the ring has `stages` stages. Process-wide (SILO_K1_VARIANT picks
+// one of the compiled variants, for measurements); a column remembers the capacity it was cut for.
+struct K1Geometry {
+   uint32_t warps;
+   uint32_t pieces;
+   uint32_t stages;
+   uint32_t variant;
+   uint32_t segmentPieces() const { return warps * pieces; }
+   uint32_t segmentPayloadBytes() const { return warps * pieces * 1024u; }
+   uint32_t inlinePieces() const { return warps * pieces * 32u; }  // descriptor-only pieces: one per LANE
+};
+const K1Geometry& k1Geometry();
 
 constexpr uint32_t TYPE_BITSET = 1;  // CRoaring typecodes, roaring_container.h:131-145
 constexpr uint32_t TYPE_ARRAY = 2;
@@ -41,6 +49,11 @@ constexpr uint32_t KIND_WORDRANGE = 4;  // whole 32-row words [wa, wb): u32 entr
 constexpr uint32_t KIND_RAW_ARRAY = 5;  // cardinality sorted u16 values (CRoaring array container)
 constexpr uint32_t KIND_RAW_RUN = 6;    // aux pairs {start, length-1} (CRoaring run container)
 constexpr uint32_t PIECE_BYTES = 1024;  // max payload of one piece of a stored container
+// A ring stage of the container kernel (= a segment) holds pieces of one CLASS: one kind, and either all with two
+// payload regions (a full first one) or all with at most one.
+__host__ __device__ constexpr uint32_t stageClass(uint32_t kind, bool two_regions) {
+   return kind * 2u + (two_regions ? 1u : 0u);
+}
 
 // Both array and run pieces are laid out in REGIONS of up to 512 bytes that a warp reads with ONE
 // 128-bit shared-memory load per lane (a piece is at most two regions, so a warp can pull a whole
@@ -101,18 +114,20 @@ struct __align__(16) DevContainer {
 };
 static_assert(sizeof(DevContainer) == 16);
 
-// A segment = up to SEG_MAX_DESCS pieces of ONE chunk as one block of the slab, [descriptors | payloads] (the
-// descriptors are copies of the chunk-major ones the filter interpreter searches), moved into shared memory
-// by ONE 1-D bulk (TMA) copy. 16 bytes: the producer warp of the container
-// kernel fetches one record per lane with a single 128-bit load and keeps two batches of them in flight.
+// A segment = pieces of ONE chunk and ONE kind as one block of the slab, [descriptors | payloads], moved into a ring
+// stage of the container kernel by ONE 1-D bulk (TMA) copy. The descriptors of the block are copies of the chunk-major
+// ones the filter interpreter searches, except that `position` is replaced by the piece's index into the counts
+// array, symbol * genome_length + position (what the kernel adds its result to).
 struct __align__(16) DevSegment {
    uint32_t payload_offset16;  // block start from the slab start, in 16-byte units (the slab is <= 16 GiB, see DevContainer::offset4)
-   uint32_t payload_bytes;     // block bytes: 16 per descriptor + payloads; multiple of 16, <= SEG_PAYLOAD_BYTES + 16 * SEG_MAX_DESCS
-   uint32_t desc_begin;        // unused
-   uint32_t chunk_and_count;   // [15:0] local chunk index | [31:16] number of descriptors (<= SEG_MAX_DESCS)
+   uint32_t bytes_and_kind;    // [23:0] block bytes: 16 per descriptor + payloads, a multiple of 16 | [31:24] the stageClass() of its pieces
+   uint32_t reserved;
+   uint32_t chunk_and_count;   // [15:0] local chunk index | [31:16] number of descriptors
 
    __host__ __device__ uint32_t chunk() const { return chunk_and_count & 0xFFFFu; }
    __host__ __device__ uint32_t descCount() const { return chunk_and_count >> 16; }
+   __host__ __device__ uint32_t blockBytes() const { return bytes_and_kind & 0xFFFFFFu; }
+   __host__ __device__ uint32_t kind() const { return bytes_and_kind >> 24; }
    __host__ __device__ uint64_t payloadOffset() const { return static_cast<uint64_t>(payload_offset16) << 4; }
 };
 static_assert(sizeof(DevSegment) == 16);
@@ -162,6 +177,7 @@ struct HostColumn {
    std::vector<uint64_t> chunk_missing_rows;
    std::vector<uint64_t> chunk_containers;
    uint64_t device_bytes = 0;
+   uint32_t segment_pieces = 0;  // the K1Geometry capacity the segments were cut for
 };
 
 }  // namespace silo

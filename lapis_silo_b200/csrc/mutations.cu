@@ -13,6 +13,7 @@
 //           count is  covered(p) - sum of the other symbols' counts  (uint32 modular, as the reference)
 #include <algorithm>
 #include <cstdlib>
+#include <utility>
 #include <cstring>
 
 #include <chrono>
@@ -74,45 +75,30 @@ __global__ void __launch_bounds__(PREP_THREADS) prepareQueryKernel(
 // ---------------------------------------------------------------------------------------------
 // K1: fused container AND filter-tile + popcount
 //
-// Persistent CTAs, ONE per SM (1,024 threads, 56 registers: a 256-thread block of the coverage kernel still
-// fits beside it). Two CTAs of 17 warps per SM do not run at the same speed -- the warp schedulers favour one
-// of them, half of the CTAs visited ~66 stages in the time the other half visited ~45 -- and when the work
-// list ran out the slow ones still owned what they had claimed ahead: ~10 us of a 72 us kernel. One CTA per
-// SM has no such pair. Warp 0 is the producer (one thread): it claims batches of work items (segments)
-// from a grid-wide counter and streams each segment's block [descriptors | payloads] into a ring of
-// shared-memory stages with one 1-D bulk (TMA) copy that completes on an mbarrier. The 31 consumer
-// warps take one piece (<= 1 KiB of payload) each: a warp pulls its piece into REGISTERS, hands the
-// stage back to the producer, and only then ANDs the piece with the chunk's filter tile held in
-// shared memory, issuing one RED per piece with a non-zero count.
+// Persistent CTAs, ONE per SM. Warp 0 is the producer (one thread): it claims work items (segments) from a
+// grid-wide counter and streams each segment's block [descriptors | payloads] into a ring of shared-memory
+// stages with one 1-D bulk (TMA) copy that completes on an mbarrier. A stage holds pieces of ONE kind, at most
+// W * P of them: each of the W consumer warps takes P pieces per stage visit. A warp pulls its pieces into
+// REGISTERS, hands the stage back to the producer, and only then ANDs them with the chunk's filter tile held in
+// shared memory, issuing one RED per piece with a non-zero count. The fixed cost of a stage visit (barrier wait,
+// control word, ring bookkeeping, kind dispatch, two barrier arrivals) is paid once per P pieces: with one piece
+// per visit it was 45 % of the kernel's instructions (profiles/r1_summary.md).
 //
 // Everything the consumers touch is addressed with 32-bit shared-memory addresses kept in registers
-// (inline PTX loads): the kernel is bound by instruction issue and by the 16-lane ALU pipe, and the
-// generic-pointer arithmetic of plain C++ costs as many instructions per piece as the lookups.
+// (inline PTX loads): the kernel is bound by instruction issue, and the generic-pointer arithmetic of plain
+// C++ costs as many instructions per piece as the lookups.
 // ---------------------------------------------------------------------------------------------
 
-#ifndef SILO_K1_STAGES
-#define SILO_K1_STAGES 6
-#endif
-constexpr int K1_STAGES = SILO_K1_STAGES;
-constexpr int K1_CONSUMER_WARPS = 31;
-constexpr int K1_CONSUMER_THREADS = K1_CONSUMER_WARPS * 32;
-constexpr int K1_THREADS = K1_CONSUMER_THREADS + 32;  // warp 0 = bulk-copy producer; 1,024 threads: one CTA per SM
-constexpr uint32_t K1_BATCH_DEFAULT = 4;               // work items claimed per atomicAdd (<= 32)
-constexpr uint32_t K1_STOP = 0xFFFFFFFFu;              // meta.x marker: no more work
+constexpr uint32_t K1_STOP = 0xFFFFFFFFu;  // control.desc_count marker: no more work
 constexpr uint32_t TILE32_WORDS = 2 * TILE_WORDS;
 constexpr uint32_t TILE_BUFFER_BYTES = (TILE32_WORDS + 4) * 4;  // [2048] = the zero pad word
 
-struct __align__(16) K1Stage {  // one segment block: n descriptors, then their payloads (<= this size)
-   uint8_t payload[SEG_PAYLOAD_BYTES];
-   DevContainer descs[SEG_MAX_DESCS];
-};
-
-// per-stage control block: meta is written by the producer before it arms `full`
+// per-stage control block: the first four words are written by the producer before it arms `full`
 struct __align__(16) K1Control {
    uint32_t desc_count;  // K1_STOP: no more work
-   uint32_t base4;       // slab offset (4-byte units) of the stage's payload[0]
-   uint32_t flags;       // K1_NEW_TILE | K1_TILE_SLOT
-   uint32_t pad0;
+   uint32_t base4;       // slab offset (4-byte units) of the stage's first byte
+   uint32_t flags;       // K1_TILE_SLOT
+   uint32_t kind;        // stageClass() of every piece of the stage
    uint64_t full;   // the stage's bulk copies have landed
    uint64_t empty;  // every consumer warp has pulled its pieces of the stage into registers
    uint64_t done;   // ... and has finished the tile lookups for them
@@ -122,17 +108,17 @@ static_assert(sizeof(K1Control) == 48);
 constexpr uint32_t K1_CTRL_FULL = 16;
 constexpr uint32_t K1_CTRL_EMPTY = 24;
 constexpr uint32_t K1_CTRL_DONE = 32;
-constexpr uint32_t K1_NEW_TILE = 1;    // the stage's bulk copies also (re)loaded the filter tile
 constexpr uint32_t K1_TILE_SLOT = 2;   // which of the two filter-tile buffers the stage reads
 
-struct __align__(16) K1Dynamic {
-   K1Stage stages[K1_STAGES];
-   K1Control control[K1_STAGES];
-   // a warp pulls two whole 512-byte regions whatever the size of its piece: the reads behind a short piece at the
-   // end of the last stage must stay inside the CTA's shared-memory window
-   uint8_t overrun_pad[1024 - K1_STAGES * sizeof(K1Control) % 1024];
-};
-constexpr uint32_t K1_CONTROL_OFFSET = sizeof(K1Stage) * K1_STAGES;
+// dynamic shared memory: STAGES stage buffers of stageBytes(W, P), the control blocks, and a pad -- a warp pulls two
+// whole 512-byte regions whatever the size of its piece, so the reads behind a short piece at the end of the last
+// stage must stay inside the CTA's shared-memory window
+__host__ __device__ constexpr uint32_t k1StageBytes(uint32_t warps, uint32_t pieces) {
+   return warps * pieces * (1024u + 16u);
+}
+__host__ __device__ constexpr uint32_t k1DynamicBytes(uint32_t warps, uint32_t pieces, uint32_t stages) {
+   return stages * k1StageBytes(warps, pieces) + stages * static_cast<uint32_t>(sizeof(K1Control)) + 1024u;
+}
 
 __device__ __forceinline__ uint32_t warpSum(uint32_t value) {
    return __reduce_add_sync(0xFFFFFFFFu, value);
@@ -141,18 +127,9 @@ __device__ __forceinline__ uint32_t warpSum(uint32_t value) {
 // ---- shared memory by 32-bit address ----------------------------------------------------------
 // Reads of stage data and of the filter tile. Not volatile: every address derives from words that were
 // loaded after the stage's full barrier was observed (a volatile asm with a memory clobber).
-#ifndef SILO_K1_PROBE
-#define SILO_K1_PROBE 0  // 1: tile lookups all hit one word (no bank conflicts); 2: no tile lookups at all
-#endif
 __device__ __forceinline__ uint32_t lds32(uint32_t address) {
    uint32_t value;
-#if SILO_K1_PROBE == 1
-   asm("ld.shared.u32 %0, [%1];" : "=r"(value) : "r"(address & 0x3u));
-#elif SILO_K1_PROBE == 2
-   value = address;
-#else
    asm("ld.shared.u32 %0, [%1];" : "=r"(value) : "r"(address));
-#endif
    return value;
 }
 __device__ __forceinline__ uint4 lds128(uint32_t address) {
@@ -167,24 +144,7 @@ __device__ __forceinline__ void sts128(uint32_t address, const uint4& value) {
    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(address), "r"(value.x), "r"(value.y), "r"(value.z), "r"(value.w)
                 : "memory");
 }
-#ifndef SILO_WAIT_HINT_NS
-#define SILO_WAIT_HINT_NS 0x989680u
-#endif
 __device__ __forceinline__ void mbarWaitAt(uint32_t address, uint32_t parity) {
-#if SILO_WAIT_HINT_NS == 0
-   asm volatile(  // spin on the phase test
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(address),
-      "r"(parity)
-      : "memory"
-   );
-#else
    asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -195,10 +155,9 @@ __device__ __forceinline__ void mbarWaitAt(uint32_t address, uint32_t parity) {
       "WAIT_DONE:\n"
       "}\n" ::"r"(address),
       "r"(parity),
-      "r"(SILO_WAIT_HINT_NS)
+      "r"(0x989680u)
       : "memory"
    );
-#endif
 }
 __device__ __forceinline__ void mbarArriveAt(uint32_t address) {
    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(address) : "memory");
@@ -216,16 +175,18 @@ __device__ __forceinline__ void mbarArriveLane0(uint32_t address, uint32_t lane)
       : "memory"
    );
 }
-// lane 0 adds `value` to *target if value != 0, without a branch
-__device__ __forceinline__ void redAddLane0(uint32_t* target, uint32_t value, uint32_t lane) {
+// lane 0 adds `value` to target[index] if value != 0, without a branch
+__device__ __forceinline__ void redAddLane0(uint32_t* target, uint32_t index, uint32_t value, uint32_t lane) {
    asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "setp.eq.u32 p, %2, 0;\n"
-      "setp.ne.and.u32 p, %1, 0, p;\n"
-      "@p red.global.add.u32 [%0], %1;\n"
+      ".reg .u64 a;\n"
+      "setp.eq.u32 p, %3, 0;\n"
+      "setp.ne.and.u32 p, %2, 0, p;\n"
+      "mad.wide.u32 a, %1, 4, %0;\n"
+      "@p red.global.add.u32 [a], %2;\n"
       "}\n" ::"l"(target),
-      "r"(value), "r"(lane)
+      "r"(index), "r"(value), "r"(lane)
       : "memory"
    );
 }
@@ -238,61 +199,42 @@ __device__ __forceinline__ void bulkLoadAt(uint32_t destination, const void* sou
                 : "memory");
 }
 
-// The consumers are bound by instruction issue and the ALU pipe, so every bit test is spelled with
-// the fewest instructions the ISA offers: a byte offset into the tile is one IMAD.HI with
-// accumulate on the FMA pipe (x * 2^k >> 32, plus the tile's shared-memory address), shifts take
-// their amount from the low five bits of a register (funnel shifts in wrap mode), and the
-// multipliers live in registers the compiler cannot see through (otherwise it turns the
-// multiplications back into shift + add on the ALU pipe).
-struct Multipliers {
-   uint32_t one;         //  x * 1 + acc: an addition on the FMA pipe
-   uint32_t two;         //  x * 2 >> 32 = x >> 31
-   uint32_t two_pow_13;  // (x & 0xFFE00000) * 2^13 >> 32 = (x >> 21) * 4
-   uint32_t two_pow_14;  //  x * 2^14 >> 32 = x >> 18
-   uint32_t two_pow_16;  //  x * 2^16 >> 32 = x >> 16
-   uint32_t two_pow_27;  //  x * 2^27 >> 32 = x >> 5
-   uint32_t two_pow_29;  // (x & 0xFFE0) * 2^29 >> 32 = ((x & 0xFFFF) >> 5) * 4
-};
-
-__device__ __forceinline__ uint32_t madHi(uint32_t a, uint32_t b, uint32_t c) {
-   uint32_t d;
-   asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-   return d;
-}
-__device__ __forceinline__ uint32_t madLo(uint32_t a, uint32_t b, uint32_t c) {
-   uint32_t d;
-   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-   return d;
-}
-__device__ __forceinline__ uint32_t mulHi(uint32_t a, uint32_t b) {
-   uint32_t d;
-   asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-   return d;
-}
+// The tile lookups are spelled for the ALU pipe (LOP3, SHF, LEA.HI: one warp instruction per two cycles and
+// scheduler). mad.hi / mul.hi -- which round 1 used to fold a shift and an addition into one instruction "on the FMA
+// pipe" -- are IMAD.HI in SASS and execute on the XU pipe of sm_100 at ONE warp instruction per EIGHT cycles: with 2.5
+// of them per array value that pipe was 90 % busy and bounded the kernel (profiles/r2_summary.md). `Multipliers` is
+// kept as an empty tag so that the call signatures stay.
+struct Multipliers {};
 
 // Two stored array values packed in one word -> the tile words of their rows, each shifted so that
 // the row's bit sits in bit 31. A stored value is row ^ 31: its low five bits are 31 - (row & 31), the
 // left shift that takes the row's bit to the top (funnel shifts use the low five bits of the amount).
-// The caller accumulates bit 31 with one IMAD.HI (x * 2 >> 32 + acc) on the FMA pipe, so a lookup
-// costs the 16-lane ALU pipe only the address mask and the shift.
-__device__ __forceinline__ void pairTopBits(uint32_t tile_address, const Multipliers& k, uint32_t pair, uint32_t& lo_top, uint32_t& hi_top) {
-   const uint32_t lo_word = lds32(madHi(pair & 0x0000FFE0u, k.two_pow_29, tile_address));
-   const uint32_t hi_word = lds32(madHi(pair & 0xFFE00000u, k.two_pow_13, tile_address));
-   lo_top = __funnelshift_l(0u, lo_word, pair);                        // lo_word << (pair & 31)
-   hi_top = __funnelshift_l(0u, hi_word, mulHi(pair, k.two_pow_16));   // hi_word << ((pair >> 16) & 31)
+__device__ __forceinline__ void pairTopBits(uint32_t tile_address, const Multipliers&, uint32_t pair, uint32_t& lo_top, uint32_t& hi_top) {
+   const uint32_t lo_word = lds32(tile_address + ((pair & 0x0000FFE0u) >> 3));   // LOP3 + LEA.HI
+   const uint32_t hi_word = lds32(tile_address + ((pair & 0xFFE00000u) >> 19));
+   lo_top = __funnelshift_l(0u, lo_word, pair);        // lo_word << (pair & 31)
+   hi_top = __funnelshift_l(0u, hi_word, pair >> 16);  // hi_word << ((pair >> 16) & 31)
 }
-__device__ __forceinline__ uint32_t addTopBit(uint32_t value, const Multipliers& k, uint32_t accumulator) {
-   return madHi(value, k.two, accumulator);  // (value >> 31) + accumulator
+__device__ __forceinline__ uint32_t addTopBit(uint32_t value, const Multipliers&, uint32_t accumulator) {
+   return accumulator + (value >> 31);  // LEA.HI
 }
 
 // one KIND_RUNS_W entry -> rows of the run that are set in the tile
-__device__ __forceinline__ uint32_t runEntryCount(uint32_t tile_address, const Multipliers& k, uint32_t entry) {
-   const uint32_t word = lds32(madHi(entry, k.two_pow_14, tile_address));       // tile32[entry >> 20]
-   const uint32_t from_first = __funnelshift_r(word, 0u, entry);                 // word >> (entry & 31)
-   return __popc(__funnelshift_l(0u, from_first, mulHi(entry, k.two_pow_27)));   // << (32 - length)
+__device__ __forceinline__ uint32_t runEntryCount(uint32_t tile_address, const Multipliers&, uint32_t entry) {
+   // tile32[entry >> 20]; the mask only matters for junk (lanes behind a partial region, descriptor slots without a
+   // piece): it keeps their addresses aligned and inside the CTA's shared memory
+   const uint32_t word = lds32(tile_address + ((entry & 0xFFF00000u) >> 18));
+   const uint32_t from_first = __funnelshift_r(word, 0u, entry);        // word >> (entry & 31)
+   return __popc(__funnelshift_l(0u, from_first, entry >> 5));          // << (32 - length)
 }
 
-// lookups of one array region held in registers (count values in P = ceil(count/8) lanes)
+// lookups of one array region held in registers: `count` values in ceil(count / 8) lanes. FULL: count == 256.
+// In a partial region the slots behind the last value repeat it (pool.cu encodeArrayPiece). Every slot is looked
+// up -- no test per slot --, and the repeats are taken out again: slot 7 of the last lane always holds the
+// region's last value, so that lane subtracts (8 lanes - count) times its bit. Lanes behind the region hold
+// other bytes of the stage; their lookups stay inside the tile (11-bit word index) and are dropped. Straight-line
+// code: the regions of all the pieces of a stage visit form one basic block of independent lookups.
+template <bool FULL>
 __device__ __forceinline__ uint32_t arrayRegionCount(
    uint32_t tile_address,
    const Multipliers& k,
@@ -300,11 +242,6 @@ __device__ __forceinline__ uint32_t arrayRegionCount(
    uint32_t count,
    uint32_t lane
 ) {
-   // `count` values in P = ceil(count / 8) lanes; in a partial region the slots behind the last value
-   // repeat it (pool.cu encodeArrayPiece). Every slot is looked up -- no test per slot --, and the
-   // repeats are taken out again: slot 7 of lane P-1 always holds the region's last value, so that
-   // lane subtracts (8 P - count) times its bit. Lanes >= P hold other bytes of the stage; their
-   // lookups stay inside the tile (11-bit word index) and are dropped.
    uint32_t t0, t1, t2, t3, t4, t5, t6, t7;
    pairTopBits(tile_address, k, eight.x, t0, t1);
    pairTopBits(tile_address, k, eight.y, t2, t3);
@@ -314,17 +251,17 @@ __device__ __forceinline__ uint32_t arrayRegionCount(
    const uint32_t even = addTopBit(t6, k, addTopBit(t4, k, addTopBit(t2, k, addTopBit(t0, k, 0u))));
    const uint32_t odd = addTopBit(t7, k, addTopBit(t5, k, addTopBit(t3, k, addTopBit(t1, k, 0u))));
    uint32_t local = even + odd;
-   if (count != ARRAY_REGION_VALUES) {
+   if (!FULL) {
       const uint32_t lanes = arrayRegionLanes(count);
-      if (lane + 1 == lanes) {
-         local -= (8u * lanes - count) * (t7 >> 31);
-      }
+      local -= lane + 1 == lanes ? (8u * lanes - count) * (t7 >> 31) : 0u;
       local = lane < lanes ? local : 0u;
    }
    return local;
 }
 
-// one run region held in registers (padding entries count nothing; lanes beyond the region hold junk)
+// one run region held in registers (padding entries count nothing; lanes behind the region hold junk whose
+// lookups stay inside the CTA's shared memory and are dropped)
+template <bool FULL>
 __device__ __forceinline__ uint32_t runsRegionCount(
    uint32_t tile_address,
    const Multipliers& k,
@@ -332,20 +269,17 @@ __device__ __forceinline__ uint32_t runsRegionCount(
    uint32_t count,
    uint32_t lane
 ) {
-   if (lane >= runsRegionLanes(count)) {
-      return 0;
-   }
-   // (sums on the FMA pipe: x * 1 + acc)
-   const uint32_t first_two = madLo(runEntryCount(tile_address, k, four.y), k.one, runEntryCount(tile_address, k, four.x));
-   const uint32_t last_two = madLo(runEntryCount(tile_address, k, four.w), k.one, runEntryCount(tile_address, k, four.z));
-   return madLo(first_two, k.one, last_two);
+   const uint32_t local = runEntryCount(tile_address, k, four.x) + runEntryCount(tile_address, k, four.y) +
+                          runEntryCount(tile_address, k, four.z) + runEntryCount(tile_address, k, four.w);
+   return FULL || lane < runsRegionLanes(count) ? local : 0u;
 }
 
-// |piece AND tile| for a piece whose (at most) two 512-byte regions sit in registers: lane L holds
-// bytes [16 L, 16 L + 16) of each region. desc = the descriptor's four words.
-__device__ __forceinline__ uint32_t pieceFromRegisters(
+// |piece AND tile| per lane for a piece whose (at most) two 512-byte regions sit in registers: lane L holds
+// bytes [16 L, 16 L + 16) of each region. desc = the block descriptor's four words. KIND is the stage's kind;
+// TWO: every piece of the stage has a full first region and a second one (pool.cu sorts them that way).
+template <uint32_t KIND, bool TWO>
+__device__ __forceinline__ uint32_t pieceLaneCount(
    const uint4& desc,
-   uint32_t kind,
    const uint4& first,
    const uint4& second,
    uint32_t tile_address,  // shared: 2049 words ([2048] = 0)
@@ -353,32 +287,77 @@ __device__ __forceinline__ uint32_t pieceFromRegisters(
    uint32_t lane,
    uint32_t lane16
 ) {
-   uint32_t local = 0;
-   if (kind == KIND_ARRAY_T) {
+   if (KIND == KIND_ARRAY_T) {
       const uint32_t n = (desc.z & 0xFFFFu) + 1u;
-      local = arrayRegionCount(tile_address, k, first, min(n, ARRAY_REGION_VALUES), lane);
-      if (n > ARRAY_REGION_VALUES) {
-         local += arrayRegionCount(tile_address, k, second, n - ARRAY_REGION_VALUES, lane);
+      if (TWO) {
+         return arrayRegionCount<true>(tile_address, k, first, ARRAY_REGION_VALUES, lane) +
+                arrayRegionCount<false>(tile_address, k, second, n - ARRAY_REGION_VALUES, lane);
       }
-   } else if (kind == KIND_RUNS_W) {
+      return arrayRegionCount<false>(tile_address, k, first, n, lane);
+   }
+   if (KIND == KIND_RUNS_W) {
       const uint32_t n = desc.w;
-      local = runsRegionCount(tile_address, k, first, min(n, RUNS_REGION_ENTRIES), lane);
-      if (n > RUNS_REGION_ENTRIES) {
-         local += runsRegionCount(tile_address, k, second, n - RUNS_REGION_ENTRIES, lane);
+      if (TWO) {
+         return runsRegionCount<true>(tile_address, k, first, RUNS_REGION_ENTRIES, lane) +
+                runsRegionCount<false>(tile_address, k, second, n - RUNS_REGION_ENTRIES, lane);
       }
-   } else if (kind == KIND_BITSET) {  // 128 words: 64 vectors, two per lane
-      const uint32_t window = tile_address + (desc.w & 0xFFFFu) * 8u + lane16;
-      const uint4 a = lds128(window);
-      const uint4 b = lds128(window + 512);
-      local = __popc(first.x & a.x) + __popc(first.y & a.y) + __popc(first.z & a.z) + __popc(first.w & a.w) +
-              __popc(second.x & b.x) + __popc(second.y & b.y) + __popc(second.z & b.z) + __popc(second.w & b.w);
-   } else if (kind == KIND_INLINE) {  // one or two values inside the descriptor
-      if (lane <= (desc.z & 0xFFFFu)) {
-         const uint32_t value = (desc.w >> (16 * lane)) & 0xFFFFu;
-         local = (lds32(tile_address + ((value >> 5) << 2)) >> (value & 31u)) & 1u;
+      return runsRegionCount<false>(tile_address, k, first, n, lane);
+   }
+   // KIND_BITSET: 128 words: 64 vectors, two per lane (the mask keeps the window of a descriptor slot that holds no
+   // piece -- junk -- inside the tile and aligned)
+   const uint32_t window = tile_address + (desc.w & 0x380u) * 8u + lane16;
+   const uint4 a = lds128(window);
+   const uint4 b = lds128(window + 512);
+   return __popc(first.x & a.x) + __popc(first.y & a.y) + __popc(first.z & a.z) + __popc(first.w & a.w) +
+          __popc(second.x & b.x) + __popc(second.y & b.y) + __popc(second.z & b.z) + __popc(second.w & b.w);
+}
+
+// One stage visit of a consumer warp for the kinds whose pieces are pulled into registers: P pieces per warp,
+// straight-line code (a piece the stage does not hold is read from offset 0 and counts nothing).
+template <int W, int P, uint32_t KIND, bool TWO, int MODE>
+__device__ __forceinline__ void consumeRegisterStage(
+   const uint4& meta,
+   uint32_t stage_address,
+   uint32_t my_control,
+   uint32_t tile,
+   const Multipliers& k,
+   uint32_t lane,
+   uint32_t lane16,
+   uint32_t cwarp,
+   uint32_t* counts
+) {
+   uint4 desc[P];
+   uint4 first[P];
+   uint4 second[P];
+#pragma unroll
+   for (int p = 0; p < P; ++p) {
+      const uint32_t index = p * W + cwarp;
+      desc[p] = lds128(stage_address + index * 16);  // {counts index, offset4, packed, aux}: the block starts with its descriptors
+      // (reads past a short piece stay inside the CTA's shared memory; those lanes are ignored)
+      const uint32_t payload_address = stage_address + (index < meta.x ? (desc[p].y - meta.y) << 2 : 0u) + lane16;
+      first[p] = lds128(payload_address);
+      if (TWO) {
+         second[p] = lds128(payload_address + 512);
+      } else {
+         second[p] = make_uint4(0u, 0u, 0u, 0u);
       }
    }
-   return warpSum(local);
+   __syncwarp();
+   mbarArriveLane0(my_control + K1_CTRL_EMPTY, lane);  // the stage can be refilled while the lookups run
+   uint32_t local[P];
+#pragma unroll
+   for (int p = 0; p < P; ++p) {
+      if (MODE == 0) {
+         local[p] = pieceLaneCount<KIND, TWO>(desc[p], first[p], second[p], tile, k, lane, lane16);
+      } else {  // profiling: touch the payload only
+         local[p] = (first[p].x ^ first[p].y ^ first[p].z ^ first[p].w ^ second[p].x ^ second[p].y ^ second[p].z ^ second[p].w) == 0x12345678u ? 1u : 0u;
+      }
+   }
+#pragma unroll
+   for (int p = 0; p < P; ++p) {
+      const uint32_t total = warpSum(local[p]);
+      redAddLane0(counts, desc[p].x, p * W + cwarp < meta.x ? total : 0u, lane);
+   }
 }
 
 // KIND_WORDRANGE: the whole 32-row words [wa, wb) in the middle of long runs: the warp popcounts the
@@ -396,34 +375,37 @@ __device__ __forceinline__ uint32_t wordRangeCount(uint32_t entries, uint32_t pa
 }
 
 // MODE (profiling aid, SILO_K1_STREAM_ONLY): 0 = the product; 1 = consumers skip the intersection
-// (what the bulk-copy pipeline alone can stream); 2 = no atomics; 3 = touch the payload only.
-template <int MODE>
-__global__ void __maxnreg__(56) containerAndCountKernel(
+// (what the bulk-copy pipeline alone can stream).
+template <int W, int P, int STAGES, int MAXREG, int MODE>
+__global__ void __launch_bounds__((W + 1) * 32, 1) __maxnreg__(MAXREG) containerAndCountKernel(
    DevColumn column,
    const uint64_t* __restrict__ filter_words,   // [n_chunks * 1024]
    uint32_t* __restrict__ work_state,           // [0] number of work items, [1] grid-wide claim counter (zero at launch)
    const DevSegment* __restrict__ work_items,   // the segment record of every work item (prepareQueryKernel)
    uint32_t* __restrict__ counts,               // [n_symbols * genome_length]
-   uint32_t claim_batch,                        // work items per claim
-   uint32_t tail_batches                        // the last tail_batches * gridDim.x * claim_batch items are claimed one by one
+   uint32_t tail_factor,                        // the last tail_factor * gridDim.x work items are claimed just in time
+   uint32_t* __restrict__ debug_times           // nullptr, or [4 * gridDim.x]: per CTA {start, producer end, consumers' end (ns), stages}
 ) {
    // Two tile buffers: the producer loads the next chunk's tile while stages of the current chunk
    // are still being consumed, so a chunk switch does not drain the pipeline.
    __shared__ __align__(16) uint32_t tile_buffers[2][TILE32_WORDS + 4];  // [2048] = zero pad word
    extern __shared__ __align__(128) uint8_t smem_raw[];
-   K1Dynamic& sh = *reinterpret_cast<K1Dynamic*>(smem_raw);
+   constexpr uint32_t STAGE_BYTES = k1StageBytes(W, P);
+   constexpr uint32_t CONTROL_OFFSET = STAGE_BYTES * STAGES;
+   constexpr uint32_t CONTROL_BYTES = static_cast<uint32_t>(sizeof(K1Control));
 
    const uint32_t warp = threadIdx.x >> 5;
    const uint32_t lane = threadIdx.x & 31;
    const uint32_t ring_address = smemAddr(smem_raw);
-   const uint32_t control_address = ring_address + K1_CONTROL_OFFSET;
+   const uint32_t control_address = ring_address + CONTROL_OFFSET;
    const uint32_t tile_address0 = smemAddr(tile_buffers[0]);
 
    if (threadIdx.x == 0) {
-      for (int s = 0; s < K1_STAGES; ++s) {
-         mbarInit(&sh.control[s].full, 1);
-         mbarInit(&sh.control[s].empty, K1_CONSUMER_WARPS);
-         mbarInit(&sh.control[s].done, K1_CONSUMER_WARPS);
+      K1Control* control = reinterpret_cast<K1Control*>(smem_raw + CONTROL_OFFSET);
+      for (int s = 0; s < STAGES; ++s) {
+         mbarInit(&control[s].full, 1);
+         mbarInit(&control[s].empty, W);
+         mbarInit(&control[s].done, W);
       }
       fenceBarrierInit();
    }
@@ -434,260 +416,204 @@ __global__ void __maxnreg__(56) containerAndCountKernel(
 
    if (warp == 0) {
       // ---------------- producer: ONE thread ------------------------------------------------------
-      // Lane 0 alone claims batches of work items (segments) from the grid-wide counter, fetches their
-      // 16-byte records and issues one bulk copy per ring stage. A warp-wide producer (lane j preparing
-      // stage j, the copies issued lane after lane) spent 0.95 us per stage whatever the stage size, the
-      // batch size or the number of copies: its shuffles, ballots, warp syncs and barrier tests all queue
-      // behind the consumers' shared-memory loads, ~40 cycles per instruction, and the consumers waited for
-      // data 16 % of their time while the producer waited for a free stage only 12 % of its. A single
-      // thread needs no cross-lane instruction at all.
-      // Pipeline: the records of batch k + 2 are loaded right after the copies of batch k were issued and
-      // are used after those of batch k + 1; three claims are in flight (an atomic has three batches to
-      // come back). The first two batches of every CTA are fixed (no atomic in front of the first
-      // copies); near the end of the list claims shrink to single items, so that the last CTAs to finish
-      // are a few stages, not a few batches, behind the others.
+      // Lane 0 alone claims work items (segments) from the grid-wide counter, fetches their 16-byte records and
+      // issues one bulk copy per ring stage (a warp-wide producer queues its shuffles, ballots and barrier tests
+      // behind the consumers' shared-memory loads, ~40 cycles per instruction; a single thread needs no
+      // cross-lane instruction at all). The first two items of every CTA are fixed (no atomic in front of the
+      // first copies). A stage holds ~60 KiB, i.e. ~2 us of consumer work, and the ring keeps two such stages
+      // waiting behind the one being consumed: the latency of a claim (atomic + record load) hides behind them.
       if (lane != 0) {
          return;
       }
-      constexpr uint32_t HELD = 4;  // records of one batch held in registers
-      const uint32_t batch_items = min(claim_batch, HELD);
+      if (debug_times != nullptr) {
+         asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(debug_times[4 * blockIdx.x]));
+      }
       uint32_t* const work_counter = work_state + 1;
-      const uint32_t static_items = 2 * gridDim.x * batch_items;
-      const uint32_t capacity = column.n_segments;
+      const uint32_t static_items = 2 * gridDim.x;
       const uint32_t total = work_state[0];
-      const uint32_t tail_items = tail_batches * gridDim.x * batch_items;
-      const uint32_t tail_begin = total > tail_items ? total - tail_items : 0;
+      // the last tail_factor items per CTA are claimed just in time (see below)
+      const uint32_t tail_items = tail_factor * gridDim.x;
+      const uint32_t tail_begin = total > tail_items ? total - tail_items : 0u;
       const uint4* const records = reinterpret_cast<const uint4*>(work_items);
-      // (records behind the end of the list are stale or uninitialised and never used: `n` below cuts them off)
-      auto load = [&](uint3 (&into)[HELD], uint32_t first, uint32_t size) {
-#pragma unroll
-         for (uint32_t j = 0; j < HELD; ++j) {
-            if (j < size && first + j < capacity) {
-               const uint4 record = records[first + j];
-               into[j] = make_uint3(record.x, record.y, record.w);  // (desc_begin is unused)
-            }
-         }
+      auto load = [&](uint32_t index) {
+         // (records behind the end of the list are stale or uninitialised and never used)
+         return index < total ? records[index] : make_uint4(0u, 0u, 0u, 0u);
       };
-      long long producer_waited = 0;  // MODE 4: cycles spent waiting for a free stage
-      const long long producer_begin = MODE == 4 ? clock64() : 0;
-      uint3 current[HELD];
-      uint3 next[HELD];
-      uint32_t current_first = blockIdx.x * batch_items;
-      uint32_t current_size = batch_items;
-      uint32_t next_first = (gridDim.x + blockIdx.x) * batch_items;
-      uint32_t next_size = batch_items;
-      load(current, current_first, current_size);
-      load(next, next_first, next_size);
-      uint32_t claim_a = atomicAdd(work_counter, batch_items) + static_items;
-      uint32_t claim_b = atomicAdd(work_counter, batch_items) + static_items;
-      uint32_t claim_c = atomicAdd(work_counter, batch_items) + static_items;
-      uint32_t size_a = batch_items;
-      uint32_t size_b = batch_items;
-      uint32_t size_c = batch_items;
+      auto claim = [&]() { return atomicAdd(work_counter, 1u) + static_items; };
+      // The item being issued, ONE item ahead with its record fetched, and one claim in flight behind it: neither the
+      // atomic nor the record load is waited for in the iteration that issues it. Near the end of the list nothing is
+      // held ahead: an item is claimed only once the stage it goes into is free. What a CTA owns beyond its ring when
+      // the list runs out is what makes the CTAs finish at different times (measured with two items held ahead
+      // everywhere: the producers ran out of work over 6 us of a 55 us kernel; with this rule 2.5 us).
+      uint32_t current_index = blockIdx.x;
+      uint4 current = load(current_index);
+      bool have_current = true;
+      uint32_t next_index = gridDim.x + blockIdx.x;
+      uint4 next = load(next_index);
+      bool have_next = true;
+      uint32_t ahead_index = 0;
+      bool have_ahead = false;
+      if (next_index < tail_begin) {
+         ahead_index = claim();
+         have_ahead = true;
+      }
       uint32_t tile_chunk = 0xFFFFFFFFu;  // chunk whose tile the latest stage reads
       uint32_t tile_slot = 1;             // ... and the buffer it sits in
       uint32_t tile_first_stage = 0;      // first stage that reads it
       uint32_t it = 0;                    // stages issued so far
-      uint32_t stage = 0;                 // it % K1_STAGES
-      uint32_t round = 0;                 // it / K1_STAGES
-      // one ring stage: {payload_offset16, block bytes, chunk | pieces << 16} of the DevSegment
-      auto issue = [&](const uint3& record) {
-         const uint32_t my_control = control_address + stage * static_cast<uint32_t>(sizeof(K1Control));
-         const uint32_t my_ring = ring_address + stage * static_cast<uint32_t>(sizeof(K1Stage));
+      uint32_t stage = 0;                 // it % STAGES
+      uint32_t round = 0;                 // it / STAGES
+      for (;;) {
+         const uint32_t my_control = control_address + stage * CONTROL_BYTES;
+         const uint32_t my_ring = ring_address + stage * STAGE_BYTES;
          if (round > 0) {
-            const long long wait_begin = MODE == 4 ? clock64() : 0;
-            mbarWaitAt(my_control + K1_CTRL_EMPTY, (round - 1) & 1u);  // => every stage <= it - K1_STAGES is pulled
-            if (MODE == 4) {
-               producer_waited += clock64() - wait_begin;
-            }
+            mbarWaitAt(my_control + K1_CTRL_EMPTY, (round - 1) & 1u);  // => every stage <= it - STAGES is pulled
          }
-         const uint32_t chunk = record.z & 0xFFFFu;
+         if (!have_current) {
+            current_index = claim();
+            current = load(current_index);
+         }
+         if (current_index >= total) {
+            break;  // (the stage at `stage` is free: the stop marker goes there)
+         }
+         // ---- one ring stage: {payload_offset16, block bytes | class << 24, -, chunk | pieces << 16} ----
+         const uint32_t chunk = current.w & 0xFFFFu;
          const bool new_tile = chunk != tile_chunk;
          if (new_tile) {
             // The new tile goes into the OTHER buffer, last read by the lookups of the stages before
             // tile_first_stage. A warp hands a stage back BEFORE it does the lookups, so the stage's empty
-            // barrier says nothing about the tile: wait for the done barriers. (Stages below it - K1_STAGES
-            // are implied: a warp pulls stage q + K1_STAGES only after it has finished stage q, and the
-            // empty wait above covered it - K1_STAGES.)
-            for (uint32_t prev = it >= K1_STAGES ? it - K1_STAGES : 0; prev < tile_first_stage; ++prev) {
-               mbarWaitAt(control_address + (prev % K1_STAGES) * static_cast<uint32_t>(sizeof(K1Control)) + K1_CTRL_DONE, (prev / K1_STAGES) & 1u);
+            // barrier says nothing about the tile: wait for the done barriers. (Stages below it - STAGES
+            // are implied: a warp pulls stage q + STAGES only after it has finished stage q, and the
+            // empty wait above covered it - STAGES.)
+            for (uint32_t prev = it >= STAGES ? it - STAGES : 0; prev < tile_first_stage; ++prev) {
+               mbarWaitAt(control_address + (prev % STAGES) * CONTROL_BYTES + K1_CTRL_DONE, (prev / STAGES) & 1u);
             }
             tile_slot ^= 1u;
             tile_first_stage = it;
             tile_chunk = chunk;
          }
-         sts128(my_control, make_uint4(record.z >> 16, record.x << 2, (new_tile ? K1_NEW_TILE : 0u) | (tile_slot != 0 ? K1_TILE_SLOT : 0u), 0u));
-         mbarExpectTxAt(my_control + K1_CTRL_FULL, record.y + (new_tile ? TILE_BYTES : 0u));
+         const uint32_t block_bytes = current.y & 0xFFFFFFu;
+         sts128(my_control, make_uint4(current.w >> 16, current.x << 2, tile_slot != 0 ? K1_TILE_SLOT : 0u, current.y >> 24));
+         mbarExpectTxAt(my_control + K1_CTRL_FULL, block_bytes + (new_tile ? TILE_BYTES : 0u));
          if (new_tile) {
             bulkLoadAt(tile_address0 + tile_slot * TILE_BUFFER_BYTES, filter_words + static_cast<size_t>(chunk) * TILE_WORDS, TILE_BYTES, my_control + K1_CTRL_FULL);
          }
          // the segment's block [descriptors | payloads] in one copy
-         bulkLoadAt(my_ring, column.payload + (static_cast<uint64_t>(record.x) << 4), record.y, my_control + K1_CTRL_FULL);
+         bulkLoadAt(my_ring, column.payload + (static_cast<uint64_t>(current.x) << 4), block_bytes, my_control + K1_CTRL_FULL);
          ++it;
-         const bool wrap = stage == K1_STAGES - 1;
+         const bool wrap = stage == STAGES - 1;
          stage = wrap ? 0u : stage + 1u;
          round += wrap ? 1u : 0u;
-      };
-      while (current_first < total) {
-         const uint32_t n = min(current_size, total - current_first);
-#pragma unroll
-         for (uint32_t j = 0; j < HELD; ++j) {
-            if (j < n) {
-               issue(current[j]);
+         // ---- the next item ----
+         have_current = have_next;
+         current = next;
+         current_index = next_index;
+         have_next = have_ahead;
+         if (have_ahead) {
+            next_index = ahead_index;  // (the atomic was issued one stage ago)
+            next = load(next_index);
+            have_ahead = false;
+            if (next_index < tail_begin) {
+               ahead_index = claim();
+               have_ahead = true;
             }
          }
-#pragma unroll
-         for (uint32_t j = 0; j < HELD; ++j) {
-            current[j] = next[j];
-         }
-         current_first = next_first;
-         current_size = next_size;
-         next_first = claim_a;  // (waits for the atomic issued three batches ago)
-         next_size = size_a;
-         load(next, next_first, next_size);
-         claim_a = claim_b;
-         size_a = size_b;
-         claim_b = claim_c;
-         size_b = size_c;
-         size_c = next_first >= tail_begin ? 1u : batch_items;
-         claim_c = atomicAdd(work_counter, size_c) + static_items;
       }
-      if (MODE == 4) {
-         const uint32_t row = 15 * column.genome_length;
-         // per CTA (profiles/k1_wait_probe.py): wall clock (ns, low word) at which this producer ran out of work,
-         // the SM it ran on, the stages it issued
-         uint32_t now;
-         uint32_t smid;
-         asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(now));
-         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-         counts[row + 1024 + blockIdx.x] = now;
-         counts[row + 2048 + blockIdx.x] = smid;
-         counts[row + 3072 + blockIdx.x] = it;
-         atomicAdd(&counts[row + 5], static_cast<uint32_t>(producer_waited >> 6));
-         atomicAdd(&counts[row + 6], static_cast<uint32_t>((clock64() - producer_begin) >> 6));
-         atomicAdd(&counts[row + 7], 1u);
+      if (debug_times != nullptr) {
+         asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(debug_times[4 * blockIdx.x + 1]));
+         debug_times[4 * blockIdx.x + 3] = it;
       }
-      // tell the consumers that nothing follows
-      const uint32_t stop_control = control_address + stage * static_cast<uint32_t>(sizeof(K1Control));
-      if (round > 0) {
-         mbarWaitAt(stop_control + K1_CTRL_EMPTY, (round - 1) & 1u);
-      }
+      // tell the consumers that nothing follows (the loop left with the stage at `stage` free)
+      const uint32_t stop_control = control_address + stage * CONTROL_BYTES;
       sts128(stop_control, make_uint4(K1_STOP, 0u, 0u, 0u));
       mbarArriveAt(stop_control + K1_CTRL_FULL);
       return;
    }
 
-   // ---------------- consumers: 16 warps ----------------------------------------------------------
-   // A stage holds at most one piece per consumer warp (SEG_MAX_DESCS == K1_CONSUMER_WARPS), handed out
-   // round-robin. A warp pulls its piece (descriptor + at most two 512-byte regions) into registers,
-   // hands the stage back to the producer at once, and only then does the tile lookups: the ring's
-   // stages are in flight again while the arithmetic runs. The loop body is written for the fewest
-   // instructions per stage visit -- the kernel is bound by instruction issue.
-   static_assert(SEG_MAX_DESCS == K1_CONSUMER_WARPS, "one piece per consumer warp and stage");
+   // ---------------- consumers: W warps ------------------------------------------------------------
+   // Warp w takes the pieces w, w + W, ... of the stage (all of one kind). It pulls them (descriptor + at most two
+   // 512-byte regions each) into registers, hands the stage back to the producer at once, and only then does the
+   // tile lookups: the ring's stages are in flight again while the arithmetic runs.
    const uint32_t cwarp = warp - 1;
    const uint32_t lane16 = lane * 16;
-   const uint32_t genome_length = column.genome_length;
-   // opaque to the compiler (gridDim.y is 1): keeps the IMAD.HI forms, see Multipliers
-   Multipliers k;
-   k.one = gridDim.y;
-   k.two = gridDim.y << 1;
-   k.two_pow_13 = gridDim.y << 13;
-   k.two_pow_14 = gridDim.y << 14;
-   k.two_pow_16 = gridDim.y << 16;
-   k.two_pow_27 = gridDim.y << 27;
-   k.two_pow_29 = gridDim.y << 29;
+   const Multipliers k{};
    // base addresses as opaque register values (the compiler would otherwise re-derive the shared
    // window from special registers at every use)
    uint32_t ring_base = ring_address;
    uint32_t control_base = control_address;
    uint32_t tile_base = tile_address0;
    asm volatile("" : "+r"(ring_base), "+r"(control_base), "+r"(tile_base));
-   uint32_t rotation = cwarp;  // piece index of this warp in the current stage, in [0, K1_CONSUMER_WARPS)
-   uint32_t stage = 0;         // ring position and phase of the next visit
+   uint32_t stage = 0;  // ring position and phase of the next visit
    uint32_t parity = 0;
-   uint32_t visit = 0;         // MODE 4 only
-   // MODE 4 (profiling): cycles this warp spent waiting for data, reported through the counts array
-   long long probe_begin = 0;
-   long long probe_waited = 0;
-   long long probe_first = 0;
-   if (MODE == 4) {
-      probe_begin = clock64();
-   }
    for (;;) {
-      const uint32_t stage_address = ring_base + stage * static_cast<uint32_t>(sizeof(K1Stage));
-      const uint32_t my_control = control_base + stage * static_cast<uint32_t>(sizeof(K1Control));
-      const long long wait_begin = MODE == 4 ? clock64() : 0;
+      const uint32_t stage_address = ring_base + stage * STAGE_BYTES;
+      const uint32_t my_control = control_base + stage * CONTROL_BYTES;
       mbarWaitAt(my_control + K1_CTRL_FULL, parity);
-      if (MODE == 4) {
-         const long long now = clock64();
-         if (visit == 0) {
-            probe_first = now - probe_begin;
-         } else {
-            probe_waited += now - wait_begin;
-         }
-         ++visit;
-      }
-      const uint4 meta = lds128(my_control);
+      const uint4 meta = lds128(my_control);  // {pieces, base4, flags, kind}
       const uint32_t desc_count = meta.x;
       if (desc_count == K1_STOP) {
-         if (MODE == 4 && lane == 0) {
-            const uint32_t row = 15 * genome_length;  // a symbol row the finalize kernel never writes
-            atomicAdd(&counts[row + 0], static_cast<uint32_t>((clock64() - probe_begin) >> 6));  // total
-            atomicAdd(&counts[row + 1], static_cast<uint32_t>(probe_waited >> 6));               // waiting for data, after the first stage
-            atomicAdd(&counts[row + 2], static_cast<uint32_t>(probe_first >> 6));                // until the first stage landed
-            atomicAdd(&counts[row + 3], visit - 1);
-            atomicAdd(&counts[row + 4], 1u);
-            if (cwarp == 0) {  // per CTA: wall clock at which its consumers saw the end of the work
-               uint32_t now;
-               asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(now));
-               counts[row + 4096 + blockIdx.x] = now;
-            }
+         if (debug_times != nullptr && cwarp == 0 && lane == 0) {
+            asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(debug_times[4 * blockIdx.x + 2]));
          }
          break;
       }
-      // next ring position (no division: the stage count is not a power of two)
-      const bool wrap = stage == K1_STAGES - 1;
+      // next ring position (no division: the stage count need not be a power of two)
+      const bool wrap = stage == STAGES - 1;
       stage = wrap ? 0u : stage + 1u;
       parity ^= wrap ? 1u : 0u;
-      const uint32_t slot_offset = (meta.z & K1_TILE_SLOT) != 0 ? TILE_BUFFER_BYTES : 0u;
-      // the rotation continues where the previous stage stopped, so that a stage with fewer than 16
-      // pieces does not always leave the same warps idle
-      const uint32_t index = rotation;  // in [0, K1_CONSUMER_WARPS)
-      rotation = rotation >= desc_count ? rotation - desc_count : rotation + K1_CONSUMER_WARPS - desc_count;
-      // Lane 0's barrier arrives and the RED are predicated instructions (mbarArriveLane0,
-      // redAddLane0), not branches: a warp without a piece in this stage runs the same tail with a
-      // count of zero.
-      uint4 desc = make_uint4(0u, 0u, 0u, 0u);
-      uint32_t count = 0;
-      if (index < desc_count && MODE != 1) {
-         desc = lds128(stage_address + index * 16);  // {position, offset4, packed, aux}: the block starts with its descriptors
-         const uint32_t payload_address = stage_address + ((desc.y - meta.y) << 2);
-         const uint32_t kind = (desc.z >> 26) & 7u;
-         if (kind == KIND_WORDRANGE) {  // rare; reads the stage while it works
-            count = wordRangeCount(desc.w, payload_address, tile_base + slot_offset, lane);
-            __syncwarp();
-            mbarArriveLane0(my_control + K1_CTRL_EMPTY, lane);
-         } else {
-            // (reads past a short piece stay inside the stage buffer; those lanes are ignored)
-            const uint4 first = lds128(payload_address + lane16);
-            const uint4 second = lds128(payload_address + 512 + lane16);
-            __syncwarp();
-            mbarArriveLane0(my_control + K1_CTRL_EMPTY, lane);  // the stage can be refilled while the lookups run
-            if (MODE == 3) {  // profiling: touch the payload only
-               const uint32_t local = first.x ^ first.y ^ first.z ^ first.w ^ second.x ^ second.y ^ second.z ^ second.w;
-               count = warpSum(local) == 0x12345678u ? 1u : 0u;
-            } else {
-               count = pieceFromRegisters(desc, kind, first, second, tile_base + slot_offset, k, lane, lane16);
+      const uint32_t tile = tile_base + ((meta.z & K1_TILE_SLOT) != 0 ? TILE_BUFFER_BYTES : 0u);
+      const uint32_t kind = meta.w;
+      if (kind == stageClass(KIND_INLINE, false)) {
+         // descriptor-only pieces (arrays of one or two values): one piece per LANE, no warp reduction
+         uint4 desc[P];
+#pragma unroll
+         for (int p = 0; p < P; ++p) {
+            const uint32_t index = (p * W + cwarp) * 32 + lane;
+            desc[p] = make_uint4(0u, 0u, 0u, 0u);
+            if (index < desc_count) {
+               desc[p] = lds128(stage_address + index * 16);
             }
          }
-      } else {
          __syncwarp();
          mbarArriveLane0(my_control + K1_CTRL_EMPTY, lane);
-      }
-      if (MODE != 2) {
-         redAddLane0(&counts[((desc.z >> 16) & 0x1Fu) * genome_length + desc.x], count, lane);
-      } else if (count == 0xFFFFFFFFu) {
-         counts[0] = 1;
+#pragma unroll
+         for (int p = 0; p < P; ++p) {
+            const uint32_t index = (p * W + cwarp) * 32 + lane;
+            if (index < desc_count && MODE == 0) {
+               const uint32_t first_value = desc[p].w & 0xFFFFu;
+               uint32_t count = (lds32(tile + ((first_value >> 5) << 2)) >> (first_value & 31u)) & 1u;
+               if ((desc[p].z & 0xFFFFu) != 0) {
+                  const uint32_t second_value = desc[p].w >> 16;
+                  count += (lds32(tile + ((second_value >> 5) << 2)) >> (second_value & 31u)) & 1u;
+               }
+               if (count != 0) {
+                  atomicAdd(&counts[desc[p].x], count);
+               }
+            }
+         }
+         __syncwarp();
+      } else if ((kind >> 1) == KIND_WORDRANGE) {  // rare; reads the stage while it works
+#pragma unroll 1
+         for (int p = 0; p < P; ++p) {
+            const uint32_t index = p * W + cwarp;
+            if (index < desc_count) {
+               const uint4 desc = lds128(stage_address + index * 16);
+               const uint32_t count = wordRangeCount(desc.w, stage_address + ((desc.y - meta.y) << 2), tile, lane);
+               redAddLane0(counts, desc.x, MODE == 0 ? count : 0u, lane);
+            }
+         }
+         __syncwarp();
+         mbarArriveLane0(my_control + K1_CTRL_EMPTY, lane);
+      } else if (kind == stageClass(KIND_ARRAY_T, true)) {
+         consumeRegisterStage<W, P, KIND_ARRAY_T, true, MODE>(meta, stage_address, my_control, tile, k, lane, lane16, cwarp, counts);
+      } else if (kind == stageClass(KIND_ARRAY_T, false)) {
+         consumeRegisterStage<W, P, KIND_ARRAY_T, false, MODE>(meta, stage_address, my_control, tile, k, lane, lane16, cwarp, counts);
+      } else if (kind == stageClass(KIND_RUNS_W, true)) {
+         consumeRegisterStage<W, P, KIND_RUNS_W, true, MODE>(meta, stage_address, my_control, tile, k, lane, lane16, cwarp, counts);
+      } else if (kind == stageClass(KIND_RUNS_W, false)) {
+         consumeRegisterStage<W, P, KIND_RUNS_W, false, MODE>(meta, stage_address, my_control, tile, k, lane, lane16, cwarp, counts);
+      } else {
+         consumeRegisterStage<W, P, KIND_BITSET, true, MODE>(meta, stage_address, my_control, tile, k, lane, lane16, cwarp, counts);
       }
       mbarArriveLane0(my_control + K1_CTRL_DONE, lane);
    }
@@ -1038,6 +964,47 @@ __global__ void __launch_bounds__(FIN_THREADS) mutationHitsKernel(
 
 // ---------------------------------------------------------------------------------------------
 
+// The compiled geometries of the container kernel: {consumer warps, pieces per warp and stage visit, ring stages}.
+// Variant 0 is the product; the others are kept for measurements (SILO_K1_VARIANT, read once per process).
+constexpr K1Geometry K1_VARIANTS[] = {{31, 2, 3, 0}, {23, 2, 4, 1}, {20, 3, 3, 2}, {15, 4, 3, 3}, {31, 1, 6, 4}, {31, 2, 3, 5}};
+
+template <int W, int P, int STAGES, int MAXREG, int MODE>
+void launchContainerVariant(
+   int blocks, cudaStream_t stream, const DevColumn& column, const uint64_t* words, uint32_t* work_state, const DevSegment* work_items,
+   uint32_t* counts, uint32_t tail_factor, uint32_t* debug_times
+) {
+   static bool attribute_set = false;
+   constexpr uint32_t dynamic_bytes = k1DynamicBytes(W, P, STAGES);
+   static_assert(dynamic_bytes + 2 * TILE_BUFFER_BYTES <= 227 * 1024, "the ring does not fit the SM's shared memory");
+   if (!attribute_set) {
+      SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<W, P, STAGES, MAXREG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dynamic_bytes)));
+      attribute_set = true;
+   }
+   containerAndCountKernel<W, P, STAGES, MAXREG, MODE><<<blocks, (W + 1) * 32, dynamic_bytes, stream>>>(column, words, work_state, work_items, counts, tail_factor, debug_times);
+}
+
+template <typename... Args>
+void launchContainerKernel(const K1Geometry& geometry, int mode, Args&&... args) {
+#define SILO_K1_CASE(V, W, P, S, R)                                        \
+   case V:                                                                 \
+      if (mode == 1) {                                                     \
+         launchContainerVariant<W, P, S, R, 1>(std::forward<Args>(args)...); \
+      } else {                                                             \
+         launchContainerVariant<W, P, S, R, 0>(std::forward<Args>(args)...); \
+      }                                                                    \
+      break;
+   switch (geometry.variant) {
+      SILO_K1_CASE(1, 23, 2, 4, 64)
+      SILO_K1_CASE(2, 20, 3, 3, 80)
+      SILO_K1_CASE(3, 15, 4, 3, 96)
+      SILO_K1_CASE(4, 31, 1, 6, 56)
+      SILO_K1_CASE(5, 31, 2, 3, 56)
+      default:
+         SILO_K1_CASE(0, 31, 2, 3, 64)
+   }
+#undef SILO_K1_CASE
+}
+
 void enqueueMutationCounts(
    silo_gpu_table* table,
    int column_index,
@@ -1119,43 +1086,52 @@ void enqueueMutationCounts(
          table->stats.kernel_launches++;
       }
    } else if (column.n_segments > 0) {
-      static bool attribute_set = false;
-      static int stream_only = 0;
-      static uint32_t claim_batch = K1_BATCH_DEFAULT;
-      static uint32_t tail_batches = 4;
-      if (!attribute_set) {
-         SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
-         SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
-         SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
-         SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
-         SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(K1Dynamic))));
+      const K1Geometry& geometry = k1Geometry();
+      require(host.segment_pieces == geometry.segmentPieces(), "mutation_counts: the column was uploaded for another container-kernel geometry");
+      static const int stream_only = [] {
          const char* flag = std::getenv("SILO_K1_STREAM_ONLY");
-         stream_only = flag != nullptr ? flag[0] - '0' : 0;
-         const char* batch_flag = std::getenv("SILO_K1_BATCH");
-         if (batch_flag != nullptr) {
-            claim_batch = static_cast<uint32_t>(std::min(32, std::max(1, std::atoi(batch_flag))));
-         }
-         const char* tail_flag = std::getenv("SILO_K1_TAIL");
-         if (tail_flag != nullptr) {
-            tail_batches = static_cast<uint32_t>(std::max(0, std::atoi(tail_flag)));
-         }
-         attribute_set = true;
-      }
+         return flag != nullptr && flag[0] == '1' ? 1 : 0;
+      }();
+      static const uint32_t tail_factor = [] {
+         const char* flag = std::getenv("SILO_K1_TAIL");
+         return flag != nullptr ? static_cast<uint32_t>(std::max(0, std::atoi(flag))) : 3u;
+      }();
       const int blocks = static_cast<int>(std::min<uint32_t>(column.n_segments, static_cast<uint32_t>(table->ctx->sm_count)));
-#define SILO_LAUNCH_K1(MODE)                                                                         \
-   containerAndCountKernel<MODE><<<blocks, K1_THREADS, sizeof(K1Dynamic), stream>>>(                 \
-      column, words, table->d_work_state, table->d_work_items, d_counts, claim_batch, tail_batches   \
-   )
-      switch (stream_only) {
-         case 1: SILO_LAUNCH_K1(1); break;
-         case 2: SILO_LAUNCH_K1(2); break;
-         case 3: SILO_LAUNCH_K1(3); break;
-         case 4: SILO_LAUNCH_K1(4); break;
-         default: SILO_LAUNCH_K1(0); break;
+      // SILO_K1_DEBUG=1 (measurement aid, synchronises): when every CTA's producer and consumers ran out of work
+      static const bool debug = std::getenv("SILO_K1_DEBUG") != nullptr;
+      static uint32_t* d_debug_times = nullptr;
+      if (debug && d_debug_times == nullptr) {
+         SILO_CUDA_CHECK(cudaMalloc(&d_debug_times, 4 * sizeof(uint32_t) * 1024));
       }
-#undef SILO_LAUNCH_K1
+      launchContainerKernel(geometry, stream_only, blocks, stream, column, words, table->d_work_state, table->d_work_items, d_counts, tail_factor, debug ? d_debug_times : nullptr);
       SILO_CUDA_CHECK(cudaGetLastError());
       table->stats.kernel_launches++;
+      cudaStreamCaptureStatus capture_status = cudaStreamCaptureStatusNone;
+      if (debug && cudaStreamIsCapturing(stream, &capture_status) == cudaSuccess && capture_status == cudaStreamCaptureStatusNone) {
+         std::vector<uint32_t> times(4 * static_cast<size_t>(blocks));
+         SILO_CUDA_CHECK(cudaMemcpyAsync(times.data(), d_debug_times, times.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+         SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+         uint32_t first_start = times[0];
+         for (int b = 0; b < blocks; ++b) {
+            first_start = static_cast<int32_t>(times[4 * b] - first_start) < 0 ? times[4 * b] : first_start;
+         }
+         std::vector<uint32_t> starts, producer_ends, consumer_ends, stages;
+         for (int b = 0; b < blocks; ++b) {
+            starts.push_back(times[4 * b] - first_start);
+            producer_ends.push_back(times[4 * b + 1] - first_start);
+            consumer_ends.push_back(times[4 * b + 2] - first_start);
+            stages.push_back(times[4 * b + 3]);
+         }
+         auto summary = [](std::vector<uint32_t>& values) {
+            std::sort(values.begin(), values.end());
+            char text[96];
+            std::snprintf(text, sizeof(text), "min %u p10 %u median %u p90 %u max %u", values.front(), values[values.size() / 10], values[values.size() / 2],
+                          values[values.size() * 9 / 10], values.back());
+            return std::string(text);
+         };
+         std::fprintf(stderr, "[silo k1 debug] %d CTAs (ns from the first start): start %s | producer end %s | consumers end %s | stages %s\n", blocks,
+                      summary(starts).c_str(), summary(producer_ends).c_str(), summary(consumer_ends).c_str(), summary(stages).c_str());
+      }
    }
    recordTiming(ev_k1_end);
    SILO_CUDA_CHECK(cudaStreamWaitEvent(stream, table->ev_join, 0));
@@ -1168,6 +1144,16 @@ void enqueueMutationCounts(
 }
 
 }  // namespace
+
+const K1Geometry& k1Geometry() {
+   static const K1Geometry geometry = [] {
+      const char* flag = std::getenv("SILO_K1_VARIANT");
+      const int variant = flag != nullptr ? std::atoi(flag) : 0;
+      constexpr int n_variants = static_cast<int>(sizeof(K1_VARIANTS) / sizeof(K1_VARIANTS[0]));
+      return K1_VARIANTS[variant >= 0 && variant < n_variants ? variant : 0];
+   }();
+   return geometry;
+}
 
 void enqueuePreparedCountsLocked(silo_gpu_table* table, int column, const silo_gpu_filter* filter, uint32_t* d_counts, cudaStream_t stream) {
    enqueueMutationCounts(table, column, filter, d_counts, stream, nullptr, true, true);

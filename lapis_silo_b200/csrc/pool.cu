@@ -385,6 +385,9 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
       }
 
       auto column = std::make_unique<HostColumn>();
+      const K1Geometry& geometry = k1Geometry();
+      column->segment_pieces = geometry.segmentPieces();
+      require(static_cast<uint64_t>(in->n_symbols) * in->genome_length <= UINT32_MAX, "counts array exceeds 32-bit indices");
       // Every stored container is cut into PIECES of at most PIECE_BYTES of payload, each with its own
       // 16-byte descriptor: counts are additive, so a piece is an independent unit of work and a warp
       // never sits on a multi-kilobyte container while its CTA waits. Arrays of one or two values
@@ -420,6 +423,7 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
          std::vector<uint32_t> segment_pieces;   // indices into chunk_pieces
          std::vector<uint32_t> segment_offsets;  // payload offset of each piece behind the descriptors
          uint32_t segment_payload = 0;
+         uint32_t segment_kind = 0;
          auto closeSegment = [&]() {
             if (segment_pieces.empty()) {
                return;
@@ -432,15 +436,18 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
             for (size_t i = 0; i < segment_pieces.size(); ++i) {
                PendingPiece& piece = chunk_pieces[segment_pieces[i]];
                piece.desc.offset4 = static_cast<uint32_t>((payload_start + segment_offsets[i]) / 4);
-               std::memcpy(slab.data() + block_start + sizeof(DevContainer) * i, &piece.desc, sizeof(DevContainer));
+               // the block's copy of the descriptor names the piece's slot of the counts array instead of its position
+               DevContainer block_desc = piece.desc;
+               block_desc.position = piece.desc.symbol() * in->genome_length + piece.desc.position;
+               std::memcpy(slab.data() + block_start + sizeof(DevContainer) * i, &block_desc, sizeof(DevContainer));
                if (piece.bytes > 0) {
                   std::memcpy(slab.data() + payload_start + segment_offsets[i], chunk_bytes.data() + piece.byte_offset, piece.bytes);
                }
             }
             DevSegment segment{};
             segment.payload_offset16 = static_cast<uint32_t>(block_start / 16);
-            segment.payload_bytes = static_cast<uint32_t>(payload_start + segment_payload - block_start);
-            segment.desc_begin = 0;
+            segment.bytes_and_kind = static_cast<uint32_t>(payload_start + segment_payload - block_start) | (segment_kind << 24);
+            segment.reserved = 0;
             segment.chunk_and_count = chunk | (static_cast<uint32_t>(segment_pieces.size()) << 16);
             segments.push_back(segment);
             segment_pieces.clear();
@@ -459,8 +466,8 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
             piece.desc.aux = aux;
             piece.byte_offset = chunk_bytes.size();
             piece.bytes = bytes;
-            // what a consumer warp of the container kernel spends on the piece: regions of lookups
-            piece.cost_class = kind == KIND_INLINE ? 0u : kind == KIND_WORDRANGE ? 5u : kind == KIND_BITSET ? 4u : bytes <= 512 ? 1u : 2u;
+            // container-kernel order: by kind (a ring stage holds pieces of ONE kind), two-region pieces first
+            piece.cost_class = stageClass(kind, kind == KIND_BITSET || bytes > 512);
             if (bytes > 0) {
                chunk_bytes.insert(chunk_bytes.end(), src, src + bytes);
             }
@@ -469,9 +476,13 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
          // appends one piece to the open segment (container-kernel order), closing it first when it is full
          auto placePiece = [&](uint32_t index) {
             const uint32_t padded = (chunk_pieces[index].bytes + 15) / 16 * 16;
-            if (segment_pieces.size() == SEG_MAX_DESCS || segment_payload + padded > SEG_PAYLOAD_BYTES) {
+            const uint32_t stage_class = chunk_pieces[index].cost_class;
+            const uint32_t capacity = chunk_pieces[index].desc.type() == KIND_INLINE ? geometry.inlinePieces() : geometry.segmentPieces();
+            if (segment_pieces.size() == capacity || segment_payload + padded > geometry.segmentPayloadBytes() ||
+                (!segment_pieces.empty() && stage_class != segment_kind)) {
                closeSegment();
             }
+            segment_kind = stage_class;
             segment_pieces.push_back(index);
             segment_offsets.push_back(segment_payload);
             segment_payload += padded;
@@ -548,10 +559,9 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
             column->chunk_containers[chunk]++;
             ++cursor;
          }
-         // Container-kernel order: pieces of equal cost next to each other, so that the (at most 16) pieces of
-         // a ring stage keep its 16 consumer warps busy for the same time -- a warp can run at most
-         // K1_STAGES - 1 stages ahead of the slowest one, and with 1- and 2-region pieces mixed in every stage
-         // the warps spent 16 % of their time waiting for each other. Counts are sums: the order is free.
+         // Container-kernel order: a ring stage holds pieces of ONE kind (the kernel branches on the kind once per
+         // stage visit, not once per piece) and of equal cost, so that the stage keeps its consumer warps busy for
+         // the same time. Counts are sums: the order is free.
          piece_order.resize(chunk_pieces.size());
          std::iota(piece_order.begin(), piece_order.end(), 0u);
          std::stable_sort(piece_order.begin(), piece_order.end(), [&](uint32_t a, uint32_t b) {

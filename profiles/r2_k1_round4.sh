@@ -1,0 +1,14 @@
+mkdir -p gpurun_out
+out=gpurun_out/r2_k1_round4.txt
+: > $out
+./profiles/probes/pipe_probe 2>&1 | tee -a $out
+for v in ${VARIANTS:-0 2}; do
+  echo "== variant $v: parity" | tee -a $out
+  SILO_K1_VARIANT=$v timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_parity.py -q -m gpu -x -k "not baseline_sizes" 2>&1 | tail -2 | tee -a $out
+  echo "== variant $v: probe" | tee -a $out
+  SILO_K1_VARIANT=$v timeout 300 python profiles/k1_probe.py 2>&1 | tail -4 | tee -a $out
+done
+echo "== variant 0, stream only" | tee -a $out
+SILO_K1_STREAM_ONLY=1 timeout 300 python profiles/k1_probe.py 2>&1 | tail -4 | tee -a $out
+echo "== variant 0, debug times" | tee -a $out
+SILO_K1_DEBUG=1 timeout 300 python profiles/k1_probe.py 2>&1 | grep -v "^$" | grep -A1 -B3 "config2" | cut -c1-400 | tee -a $out
