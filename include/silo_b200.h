@@ -116,6 +116,11 @@ void silo_gpu_table_free(silo_gpu_table* table);
 int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* column);
 /* bytes of HBM held by the table's pools */
 uint64_t silo_gpu_table_device_bytes(const silo_gpu_table* table);
+/* Tuning knobs of a table handle (no reference counterpart; defaults suit production):
+ *   "sweep_min_pieces"  a THR_PROFILE instruction over a column with at least this many container pieces is counted
+ *                       by the whole-column sweep kernel in front of the interpreter (default 65536; 0 = always,
+ *                       UINT64_MAX = never: the interpreter walks the containers chunk by chunk). */
+int silo_gpu_table_set_option(silo_gpu_table* table, const char* name, uint64_t value);
 
 /* ---- S2: filter program ---------------------------------------------------------------------- */
 

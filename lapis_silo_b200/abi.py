@@ -106,7 +106,7 @@ class Stats(C.Structure):
 EXPORTED_SYMBOLS = [
     "silo_gpu_last_error", "silo_gpu_version", "silo_gpu_init", "silo_gpu_shutdown",
     "silo_gpu_table_create", "silo_gpu_table_free", "silo_gpu_column_upload",
-    "silo_gpu_table_device_bytes", "silo_gpu_filter_eval", "silo_gpu_program_prepare",
+    "silo_gpu_table_device_bytes", "silo_gpu_table_set_option", "silo_gpu_filter_eval", "silo_gpu_program_prepare",
     "silo_gpu_program_run_async", "silo_gpu_program_run_counts_async", "silo_gpu_program_device_bytes", "silo_gpu_program_free",
     "silo_gpu_host_alloc", "silo_gpu_host_free",
     "silo_gpu_filter_from_words", "silo_gpu_bitmap_register", "silo_gpu_bitmap_unregister",
@@ -146,6 +146,7 @@ def lib() -> C.CDLL:
         L.silo_gpu_table_free.argtypes = [vp]
         L.silo_gpu_table_free.restype = None
         L.silo_gpu_column_upload.argtypes = [vp, vp]
+        L.silo_gpu_table_set_option.argtypes = [vp, C.c_char_p, C.c_uint64]
         L.silo_gpu_table_device_bytes.argtypes = [vp]
         L.silo_gpu_table_device_bytes.restype = C.c_uint64
         L.silo_gpu_filter_eval.argtypes = [vp, C.POINTER(FilterProgram), C.POINTER(vp), C.POINTER(C.c_uint64)]

@@ -178,6 +178,12 @@ struct HostColumn {
    std::vector<uint64_t> chunk_containers;
    uint64_t device_bytes = 0;
    uint32_t segment_pieces = 0;  // the K1Geometry capacity the segments were cut for
+   // Threshold sweep (filter_eval.cu thresholdSweepKernel): the column's pieces cut into one contiguous range per
+   // CTA, balanced by bytes; sweep_flushes[c] = CTAs whose range holds pieces of chunk c
+   uint32_t sweep_ctas = 0;
+   uint32_t* d_sweep_split = nullptr;    // [sweep_ctas + 1] piece indices
+   uint32_t* d_sweep_flushes = nullptr;  // [n_chunks]
+   uint32_t sweep_max_flushes = 0;
 };
 
 }  // namespace silo
@@ -269,6 +275,10 @@ struct silo_gpu_table {
       uint64_t bytes = 0;
    };
    std::vector<RegisteredBitmap> registered;
+   // per-row counters of a Threshold profile pass computed by thresholdSweepKernel in front of the interpreter:
+   // [n_chunks][32768] packed u16 pairs; used by programs over columns with at least sweep_min_pieces pieces
+   uint32_t* d_sweep_counters = nullptr;
+   uint64_t sweep_min_pieces = 1u << 16;
 };
 
 struct silo_gpu_filter {
@@ -295,7 +305,7 @@ void releaseFilterLocked(silo_gpu_filter* filter);
 // into table->h_staging_pinned (device addresses inside refer to table->d_staging_fixed);
 // enqueueStagedQuery issues the H2D copy and the interpreter kernel into table->query_filter.
 struct StagedQuery {
-   alignas(16) unsigned char params[160];  // the interpreter's kernel parameters (filter_eval.cu EvalParams)
+   alignas(16) unsigned char params[192];  // the interpreter's kernel parameters (filter_eval.cu EvalParams)
    uint64_t staged_bytes = 0;
    uint32_t shared_bytes = 0;
 };

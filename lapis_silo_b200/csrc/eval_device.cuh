@@ -190,6 +190,110 @@ __device__ inline void addContainerToCounters(
    }
 }
 
+// counters[row] +/-= 1 for every row of a column piece whose (at most) two 512-byte payload regions one warp holds
+// in registers (lane L: bytes [16 L, 16 L + 16) of each region), the way the container kernel pulls them; WORDRANGE
+// pieces are read from `payload`. Used by the threshold sweep, which keeps the loads of the next piece in flight
+// while it bumps the current one.
+__device__ __forceinline__ void bumpPieceFromRegisters(
+   uint32_t* counters32,
+   const DevContainer& desc,
+   const uint4& first,
+   const uint4& second,
+   const uint8_t* payload,
+   bool subtract,
+   uint32_t lane
+) {
+   const uint32_t kind = desc.type();
+   const uint32_t low_unit = subtract ? 0xFFFFFFFFu : 1u;          // -1 / +1 on the low u16 lane (no borrow: the lanes are biased)
+   const uint32_t high_unit = subtract ? 0xFFFF0000u : 0x00010000u;
+   auto bump = [&](uint32_t row) { atomicAdd(&counters32[row >> 1], (row & 1u) != 0 ? high_unit : low_unit); };
+   // rows 2t and 2t + 1 of a 32-row word as one packed add
+   auto bumpPairs = [&](uint32_t word_index, uint32_t mask) {
+      while (mask != 0) {
+         const uint32_t t = static_cast<uint32_t>(__ffs(static_cast<int>(mask)) - 1) >> 1;
+         const uint32_t bits = (mask >> (2 * t)) & 3u;
+         atomicAdd(&counters32[word_index * 16 + t], ((bits & 1u) != 0 ? low_unit : 0u) + ((bits & 2u) != 0 ? high_unit : 0u));
+         mask &= ~(3u << (2 * t));
+      }
+   };
+   // consecutive rows [first, first + length) inside one 32-row word: whole pairs with one packed add each
+   auto bumpRun = [&](uint32_t entry) {
+      const uint32_t first = entry & 31u;
+      const uint32_t last = first + (32u - ((entry >> 5) & 31u)) - 1u;
+      uint32_t* const pairs = counters32 + (entry >> 20) * 16;
+      uint32_t t = first >> 1;
+      const uint32_t t_last = last >> 1;
+      if ((first & 1u) != 0) {  // the run starts on the high lane of its pair
+         atomicAdd(&pairs[t], high_unit);
+         ++t;
+      }
+      const bool low_lane_end = (last & 1u) == 0;  // ... and ends on the low lane of its last pair
+      const uint32_t full_end = low_lane_end ? t_last : t_last + 1;
+      for (; t < full_end; ++t) {
+         atomicAdd(&pairs[t], low_unit + high_unit);
+      }
+      if (low_lane_end) {
+         atomicAdd(&pairs[t_last], low_unit);
+      }
+   };
+   if (kind == KIND_ARRAY_T) {
+      const uint32_t n = desc.cardinality();
+#pragma unroll
+      for (uint32_t region = 0; region < 2; ++region) {
+         if (region * ARRAY_REGION_VALUES < n) {
+            const uint32_t count = min(ARRAY_REGION_VALUES, n - region * ARRAY_REGION_VALUES);
+            const uint32_t lanes = arrayRegionLanes(count);
+            const uint4& eight = region == 0 ? first : second;
+            const uint32_t words[4] = {eight.x, eight.y, eight.z, eight.w};
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) {
+               if (lane < lanes && lane + lanes * j < count) {
+                  bump(((words[j >> 1] >> (16 * (j & 1))) & 0xFFFFu) ^ ARRAY_VALUE_FLIP);
+               }
+            }
+         }
+      }
+   } else if (kind == KIND_RUNS_W) {
+      const uint32_t n = desc.aux;
+#pragma unroll
+      for (uint32_t region = 0; region < 2; ++region) {
+         if (region * RUNS_REGION_ENTRIES < n) {
+            const uint32_t count = min(RUNS_REGION_ENTRIES, n - region * RUNS_REGION_ENTRIES);
+            const uint4& four = region == 0 ? first : second;
+            const uint32_t entries[4] = {four.x, four.y, four.z, four.w};
+            if (lane < runsRegionLanes(count)) {
+#pragma unroll
+               for (uint32_t j = 0; j < 4; ++j) {
+                  if (entries[j] < RUNS_PAD_ENTRY) {
+                     bumpRun(entries[j]);
+                  }
+               }
+            }
+         }
+      }
+   } else if (kind == KIND_BITSET) {  // 128 u64 words: lane L holds words 2L, 2L+1 of each half
+      const uint32_t first_word32 = desc.firstWord() * 2;
+      bumpPairs(first_word32 + 4 * lane + 0, first.x);
+      bumpPairs(first_word32 + 4 * lane + 1, first.y);
+      bumpPairs(first_word32 + 4 * lane + 2, first.z);
+      bumpPairs(first_word32 + 4 * lane + 3, first.w);
+      bumpPairs(first_word32 + 128 + 4 * lane + 0, second.x);
+      bumpPairs(first_word32 + 128 + 4 * lane + 1, second.y);
+      bumpPairs(first_word32 + 128 + 4 * lane + 2, second.z);
+      bumpPairs(first_word32 + 128 + 4 * lane + 3, second.w);
+   } else if (kind == KIND_WORDRANGE) {
+      const uint32_t* ranges = reinterpret_cast<const uint32_t*>(payload);
+      for (uint32_t r = 0; r < desc.aux; ++r) {
+         const uint32_t range = ranges[r];
+         for (uint32_t pair = (range & 0xFFFFu) * 16u + lane; pair < (range >> 16) * 16u; pair += 32) {
+            atomicAdd(&counters32[pair], low_unit + high_unit);
+         }
+      }
+   } else if (lane < desc.cardinality()) {  // KIND_INLINE
+      bump((desc.aux >> (16 * lane)) & 0xFFFFu);
+   }
+}
+
 // First index in [lo, hi) whose key is >= target, searched by ONE converged warp with 32 probes per
 // round (a 33-ary search: a chunk's ~4k descriptors take 3 rounds of global-memory latency instead
 // of 12). The result is warp-uniform.

@@ -58,8 +58,16 @@ struct EvalParams {
    DevSegment* prepare_work_items;
    uint32_t* prepare_counts;
    uint32_t prepare_counts_words;
-   uint32_t pad1;
+   // Threshold sweep (thresholdSweepKernel, launched in front of the interpreter by launchProgram): the THR_PROFILE at
+   // instruction sweep_pc finds its per-row counts in sweep_counters instead of walking the containers itself.
+   uint32_t sweep_pc;               // NO_SWEEP: none
+   const uint32_t* sweep_counters;  // [n_chunks][32768] packed u16 pairs, every lane holds count + flushes * sweep_bias
+   const uint32_t* sweep_flushes;   // [n_chunks]
+   uint32_t sweep_bias;
+   int32_t sweep_column;            // (host side of the launch)
+   uint64_t sweep_table_offset;     // ... the instruction's table inside the blob
 };
+constexpr uint32_t NO_SWEEP = 0xFFFFFFFFu;
 
 // Dynamic shared memory of the interpreter: [small | stack_depth tiles | 128 KiB of counters if the
 // program holds a Threshold]. A boolean-only program needs 8 KiB per stack level, so several CTAs
@@ -325,6 +333,16 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
             break;
          }
          case SILO_OP_THR_PROFILE: {
+            if (pc == p.sweep_pc) {
+               // the sweep kernel already counted: every lane of its array holds count + bias per CTA that flushed
+               // into this chunk (no lane underflows: count + bias >= 0 within every flush)
+               const uint32_t surplus = p.sweep_flushes[chunk] * p.sweep_bias;
+               const uint32_t* counted = p.sweep_counters + static_cast<size_t>(chunk) * 32768;
+               for (uint32_t i = tid; i < 32768; i += EVAL_THREADS) {
+                  sh.counters32[i] += counted[i] - (surplus | (surplus << 16));
+               }
+               break;
+            }
             const DevColumn& column = p.columns[ins.column];
             const uint2* table = reinterpret_cast<const uint2*>(p.blob + ins.b);  // {add_mask, sub_mask}
             const uint32_t lo = column.chunk_desc_begin[chunk];
@@ -391,6 +409,120 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
       for (uint32_t i = tid; i < n_segments; i += EVAL_THREADS) {
          target[i] = source[i];
       }
+   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Threshold sweep: the per-row counts of ONE THR_PROFILE instruction for the whole column.
+//
+// Replaces the O(n k) whole-bitmap DP of Threshold::evaluate (threshold.cpp:64-138) for the children that are index
+// scans over the vertical index -- for a MutationProfile (mutation_profile.cpp:198-257) that is every stored container
+// of the column. The interpreter's own THR_PROFILE walks a chunk's containers inside the chunk's CTA: one CTA per
+// chunk is 153 CTAs of 130 KiB shared memory on 148 SMs (two waves), and every container costs a chain of dependent
+// global loads. Here the column's pieces are cut into ONE contiguous range per SM, equal bytes (pool.cu), each warp
+// keeps the loads of its next piece in flight while it bumps the current one, and a CTA flushes its shared-memory
+// counters into the chunk's global array when its range leaves the chunk.
+// Algorithmic bytes: 16 B descriptor + payload of every container + 128 KiB of counters per chunk (written here,
+// read by the interpreter).
+// ---------------------------------------------------------------------------------------------
+constexpr int SWEEP_THREADS = 1024;
+constexpr int SWEEP_WARPS = SWEEP_THREADS / 32;
+
+struct SweepPiece {
+   DevContainer desc;
+   uint4 first;
+   uint4 second;
+   uint32_t action;  // 0: skip, 1: add, 2: subtract
+};
+
+__device__ __forceinline__ SweepPiece loadSweepPiece(const DevColumn& column, const uint2* table, uint32_t index, uint32_t lane) {
+   SweepPiece piece;
+   piece.desc = column.containers[index];  // one 16-byte line for the warp
+   const uint4* payload = reinterpret_cast<const uint4*>(column.payload + (static_cast<size_t>(piece.desc.offset4) << 2));
+   const uint32_t kind = piece.desc.type();
+   const uint32_t bytes = kind == KIND_ARRAY_T ? arrayPieceBytes(piece.desc.cardinality())
+                          : kind == KIND_RUNS_W ? runsPieceBytes(piece.desc.aux)
+                          : kind == KIND_BITSET ? 1024u
+                                                : 0u;
+   piece.first = lane * 16 < bytes ? payload[lane] : make_uint4(0u, 0u, 0u, 0u);
+   piece.second = 512 + lane * 16 < bytes ? payload[32 + lane] : make_uint4(0u, 0u, 0u, 0u);
+   const uint2 masks = table[piece.desc.position];
+   const uint32_t bit = 1u << piece.desc.symbol();
+   piece.action = (masks.x & bit) != 0 ? 1u : (masks.y & bit) != 0 ? 2u : 0u;
+   return piece;
+}
+
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) thresholdSweepKernel(
+   DevColumn column,
+   const uint2* __restrict__ table,       // [genome_length] {add_mask, sub_mask}
+   const uint32_t* __restrict__ split,    // [gridDim.x + 1] piece indices
+   uint32_t bias,                         // every counter lane starts at bias (>= the subtractions a row can see)
+   uint32_t* __restrict__ out             // [n_chunks][32768], zeroed
+) {
+   extern __shared__ __align__(16) uint32_t sweep_counters[];  // 65536 x u16
+   __shared__ uint32_t first_chunk_of_range;
+   const uint32_t begin = split[blockIdx.x];
+   const uint32_t end = split[blockIdx.x + 1];
+   if (begin >= end) {
+      return;
+   }
+   const uint32_t lane = threadIdx.x & 31;
+   const uint32_t warp = threadIdx.x >> 5;
+   if (threadIdx.x == 0) {  // the chunk that holds piece `begin`: last chunk whose first piece is <= begin
+      uint32_t lo = 0;
+      uint32_t hi = column.n_chunks;
+      while (hi - lo > 1) {
+         const uint32_t mid = (lo + hi) >> 1;
+         if (column.chunk_desc_begin[mid] <= begin) {
+            lo = mid;
+         } else {
+            hi = mid;
+         }
+      }
+      first_chunk_of_range = lo;
+   }
+   __syncthreads();
+   uint32_t chunk = first_chunk_of_range;
+   uint32_t cursor = begin;
+   while (cursor < end) {
+      const uint32_t chunk_end = min(end, column.chunk_desc_begin[chunk + 1]);
+      if (chunk_end > cursor) {
+         for (uint32_t i = threadIdx.x; i < 32768; i += SWEEP_THREADS) {
+            sweep_counters[i] = bias | (bias << 16);
+         }
+         __syncthreads();
+         // warp w takes the pieces cursor + w, + 32, ...; the next piece's loads are in flight during the bumps
+         uint32_t index = cursor + warp;
+         SweepPiece next{};
+         if (index < chunk_end) {
+            next = loadSweepPiece(column, table, index, lane);
+         }
+         while (index < chunk_end) {
+            const SweepPiece piece = next;
+            const uint32_t following = index + SWEEP_WARPS;
+            if (following < chunk_end) {
+               next = loadSweepPiece(column, table, following, lane);
+            }
+            if (piece.action != 0) {
+               bumpPieceFromRegisters(
+                  sweep_counters, piece.desc, piece.first, piece.second, column.payload + (static_cast<size_t>(piece.desc.offset4) << 2),
+                  piece.action == 2, lane
+               );
+            }
+            index = following;
+         }
+         __syncthreads();
+         uint32_t* target = out + static_cast<size_t>(chunk) * 32768;
+         for (uint32_t i = threadIdx.x; i < 32768; i += SWEEP_THREADS) {
+            const uint32_t value = sweep_counters[i];
+            if (value != 0) {
+               atomicAdd(&target[i], value);
+            }
+         }
+         __syncthreads();
+      }
+      cursor = chunk_end;
+      ++chunk;
    }
 }
 
@@ -876,6 +1008,39 @@ static void stageProgram(
    params.first_chunk = table->first_chunk;
    params.stack_depth = stack_depth;
    params.has_threshold = has_threshold ? 1u : 0u;
+   // The first THR_PROFILE over a large column is counted by the sweep kernel in front of the interpreter.
+   params.sweep_pc = NO_SWEEP;
+   for (uint32_t pc = 0; pc < program->n_instrs; ++pc) {
+      const silo_filter_instr& ins = program->instrs[pc];
+      if (ins.opcode != SILO_OP_THR_PROFILE) {
+         continue;
+      }
+      const HostColumn& host = *table->columns[ins.column];
+      if (host.dev.n_containers < table->sweep_min_pieces || table->n_chunks == 0) {
+         continue;
+      }
+      // lanes of the sweep start at `bias` = the number of positions with a subtracting mask (all a row can lose)
+      const uint32_t* masks = reinterpret_cast<const uint32_t*>(program->blob + ins.b);
+      uint32_t bias = 0;
+      for (uint32_t position = 0; position < host.dev.genome_length; ++position) {
+         bias += masks[2 * position + 1] != 0 ? 1u : 0u;
+      }
+      // validateProgram bounded the program's own lanes by 65535; the interpreter adds the sweep's surplus on top
+      // before it takes it off again
+      if (static_cast<uint64_t>(host.sweep_max_flushes + 1) * bias + host.dev.genome_length + 2ULL * bias > 65535) {
+         continue;
+      }
+      if (table->d_sweep_counters == nullptr) {
+         table->d_sweep_counters = deviceAlloc<uint32_t>(static_cast<size_t>(table->n_chunks) * 32768, &table->device_bytes);
+      }
+      params.sweep_pc = pc;
+      params.sweep_counters = table->d_sweep_counters;
+      params.sweep_flushes = host.d_sweep_flushes;
+      params.sweep_bias = bias;
+      params.sweep_column = ins.column;
+      params.sweep_table_offset = ins.b;
+      break;
+   }
    *d_staging_out = d_staging;
    *staged_bytes_out = staging_bytes;
    *params_out = params;
@@ -898,7 +1063,18 @@ static void launchProgram(silo_gpu_table* table, EvalParams params, silo_gpu_fil
          evalProgramKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
          static_cast<int>(evalSharedBytes(STACK_DEPTH, true))
       ));
+      SILO_CUDA_CHECK(cudaFuncSetAttribute(thresholdSweepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(COUNTER_BYTES)));
       attribute_set = true;
+   }
+   if (params.sweep_pc != NO_SWEEP) {
+      const HostColumn& host = *table->columns[static_cast<size_t>(params.sweep_column)];
+      SILO_CUDA_CHECK(cudaMemsetAsync(table->d_sweep_counters, 0, static_cast<size_t>(table->n_chunks) * COUNTER_BYTES, stream));
+      thresholdSweepKernel<<<host.sweep_ctas, SWEEP_THREADS, COUNTER_BYTES, stream>>>(
+         host.dev, reinterpret_cast<const uint2*>(params.blob + params.sweep_table_offset), host.d_sweep_split, params.sweep_bias,
+         table->d_sweep_counters
+      );
+      SILO_CUDA_CHECK(cudaGetLastError());
+      table->stats.kernel_launches++;
    }
    const size_t shared_bytes = evalSharedBytes(params.stack_depth, params.has_threshold != 0);
    evalProgramKernel<<<table->n_chunks, EVAL_THREADS, shared_bytes, stream>>>(params);

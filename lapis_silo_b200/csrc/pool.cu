@@ -272,6 +272,7 @@ void silo_gpu_table_free(silo_gpu_table* table) {
    cudaFree(table->d_counts);
    dropQueryGraphsLocked(table);
    cudaFree(table->d_staging_fixed);
+   cudaFree(table->d_sweep_counters);
    if (table->query_filter != nullptr) {
       cudaFree(table->query_filter->d_words);
       delete table->query_filter;
@@ -319,6 +320,19 @@ uint64_t silo_gpu_table_device_bytes(const silo_gpu_table* table) {
       total += column->device_bytes;
    }
    return total;
+}
+
+int silo_gpu_table_set_option(silo_gpu_table* table, const char* name, uint64_t value) {
+   return guarded([&] {
+      require(table != nullptr && name != nullptr, "silo_gpu_table_set_option: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      if (std::strcmp(name, "sweep_min_pieces") == 0) {
+         table->sweep_min_pieces = value;
+         dropQueryGraphsLocked(table);
+      } else {
+         throw ApiError(SILO_E_INVALID_ARGUMENT, std::string("silo_gpu_table_set_option: unknown option '") + name + "'");
+      }
+   });
 }
 
 int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
@@ -394,6 +408,8 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
       // carry their values inside the descriptor and own no payload at all.
       std::vector<DevContainer> descs;
       descs.reserve(in->n_containers + in->payload_bytes / PIECE_BYTES + 16);
+      std::vector<uint32_t> desc_weights;  // bytes a sweep over the piece reads
+      desc_weights.reserve(descs.capacity());
       std::vector<DevSegment> segments;
       std::vector<uint32_t> chunk_desc_begin(n_chunks + 1, 0);
       std::vector<uint32_t> chunk_seg_begin(n_chunks + 1, 0);
@@ -573,12 +589,45 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
          closeSegment();
          for (const PendingPiece& piece : chunk_pieces) {
             descs.push_back(piece.desc);  // (position, symbol) order, same payload offsets
+            desc_weights.push_back(static_cast<uint32_t>(sizeof(DevContainer)) + piece.bytes);
          }
       }
       require(descs.size() <= UINT32_MAX, "too many container pieces for 32-bit descriptor indices");
       chunk_desc_begin[n_chunks] = static_cast<uint32_t>(descs.size());
       chunk_seg_begin[n_chunks] = static_cast<uint32_t>(segments.size());
       slab.resize((slab.size() + 15) / 16 * 16 + 16, 0);
+
+      // ---- threshold sweep: one contiguous range of pieces per CTA (one CTA per SM), equal bytes ----
+      column->sweep_ctas = static_cast<uint32_t>(std::max(1, table->ctx->sm_count));
+      std::vector<uint32_t> sweep_split(column->sweep_ctas + 1, static_cast<uint32_t>(descs.size()));
+      std::vector<uint32_t> sweep_flushes(n_chunks, 0);
+      {
+         uint64_t total_weight = 0;
+         for (uint32_t weight : desc_weights) {
+            total_weight += weight;
+         }
+         uint64_t running = 0;
+         uint32_t next_cta = 0;
+         for (size_t i = 0; i < descs.size(); ++i) {
+            while (next_cta < column->sweep_ctas && running * column->sweep_ctas >= static_cast<uint64_t>(next_cta) * total_weight) {
+               sweep_split[next_cta++] = static_cast<uint32_t>(i);
+            }
+            running += desc_weights[i];
+         }
+         sweep_split[0] = 0;
+         for (uint32_t cta = 0; cta < column->sweep_ctas; ++cta) {
+            for (uint32_t chunk = 0; chunk < n_chunks; ++chunk) {
+               const uint32_t lo = std::max(sweep_split[cta], chunk_desc_begin[chunk]);
+               const uint32_t hi = std::min(sweep_split[cta + 1], chunk_desc_begin[chunk + 1]);
+               if (lo < hi) {
+                  sweep_flushes[chunk]++;
+               }
+            }
+         }
+         for (uint32_t count : sweep_flushes) {
+            column->sweep_max_flushes = std::max(column->sweep_max_flushes, count);
+         }
+      }
 
       // ---- coverage ----
       std::vector<uint32_t> chunk_row_begin(n_chunks + 1, 0);
@@ -667,6 +716,8 @@ int silo_gpu_column_upload(silo_gpu_table* table, const silo_column_desc* in) {
       dev.missing_offsets = track(deviceUpload(missing_offsets, stream, acc));
       dev.missing_runs = track(deviceUpload(missing_runs, stream, acc));
       dev.null_words = null_words.empty() ? nullptr : track(deviceUpload(null_words, stream, acc));
+      column->d_sweep_split = track(deviceUpload(sweep_split, stream, acc));
+      column->d_sweep_flushes = track(deviceUpload(sweep_flushes, stream, acc));
       SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
 
       if (dev.n_segments > table->work_items_capacity) {

@@ -427,11 +427,33 @@ std::unique_ptr<Operator> Or::compile(const Table& table) const {
 // ---- NOf -------------------------------------------------------------------------------------
 
 std::string NOf::toString() const {  // nof.cpp:161-171
-   return std::string(match_exactly ? "[exactly-" : "[") + std::to_string(number_of_matchers) + "-of:" +
-          joinWithLimit(children) + "]";
+   std::string joined = joinWithLimit(children);
+   if (span != nullptr) {  // joinWithLimit over children followed by the span's children
+      constexpr size_t LIMIT = 10;
+      const size_t total = children.size() + span->size();
+      joined.clear();
+      size_t printed = 0;
+      for (; printed < std::min(children.size(), LIMIT); ++printed) {
+         joined += (printed > 0 ? ", " : "") + children[printed]->toString();
+      }
+      for (size_t i = 0; printed < std::min(total, LIMIT); ++printed, ++i) {
+         joined += (printed > 0 ? ", " : "") +
+                   SymbolInSet(span->column, span->positions[i], SymbolSet(span->masks[i]), span->alphabet).toString();
+      }
+      if (total > printed) {
+         joined += ", ... (" + std::to_string(total - printed) + " more)";
+      }
+   }
+   return std::string(match_exactly ? "[exactly-" : "[") + std::to_string(number_of_matchers) + "-of:" + joined + "]";
 }
 
 ExpressionPtr NOf::rewrite(const Table& table, AmbiguityMode mode) const {
+   if (span != nullptr) {  // (its children are SymbolInSets: symbol_in_set.cpp rewrite throws)
+      throw QueryCompilationException(
+         "Cannot rewrite SymbolInSet - this expression should only be created during query rewrites "
+         "and not directly used"
+      );
+   }
    auto rewriteChildren = [&]() {
       ExpressionVector rewritten;
       rewritten.reserve(children.size());
@@ -458,10 +480,9 @@ std::unique_ptr<Operator> NOf::compile(const Table& table) const {
    OperatorVector negated;
    non_negated.reserve(children.size());
    int k = number_of_matchers;
-   for (const auto& child_expression : children) {
-      auto child = child_expression->compile(table);
+   auto addChild = [&](std::unique_ptr<Operator> child) {
       if (child->type() == EMPTY) {
-         continue;
+         return;
       }
       if (child->type() == FULL) {
          --k;
@@ -470,8 +491,49 @@ std::unique_ptr<Operator> NOf::compile(const Table& table) const {
       } else {
          non_negated.push_back(std::move(child));
       }
+   };
+   for (const auto& child_expression : children) {
+      addChild(child_expression->compile(table));
    }
-   const int n = static_cast<int>(non_negated.size() + negated.size());
+   // The compact children: what compileSymbolInSet would build for each (symbol_in_set.cpp:231-264), kept compact
+   // when that is an IndexScan or Selection[IsCovered] minus IndexScan (never Empty / Full / Complement); a symbol
+   // set that holds the missing symbol is compiled the ordinary way.
+   std::shared_ptr<SymbolScanSpan> scan_span;
+   if (span != nullptr) {
+      const auto& sequence_column = requireColumn(table, span->column);
+      const Alphabet& alphabet = *sequence_column.alphabet;
+      scan_span = std::make_shared<SymbolScanSpan>();
+      scan_span->device_column = sequence_column.device_column;
+      scan_span->column_name = span->column;
+      scan_span->all_symbols_mask = allSymbolsMask(alphabet);
+      scan_span->missing_bit = 1u << alphabet.missing;
+      scan_span->leaves.reserve(span->size());
+      const size_t reference_length = sequence_column.reference_sequence.size();
+      for (size_t i = 0; i < span->size(); ++i) {
+         const uint32_t position_idx = span->positions[i];
+         const uint32_t requested = span->masks[i];
+         if (position_idx >= reference_length || (requested & scan_span->missing_bit) != 0) {
+            addChild(compileSymbolInSet(sequence_column, position_idx, SymbolSet(requested)));  // (throws when out of bounds)
+            continue;
+         }
+         const bool includes_reference = ((requested >> sequence_column.local_reference[position_idx]) & 1u) != 0;
+         scan_span->leaves.push_back({position_idx, requested, includes_reference});
+      }
+      if (scan_span->leaves.empty()) {
+         scan_span = nullptr;
+      }
+   }
+   const size_t span_children = scan_span != nullptr ? scan_span->size() : 0;
+   const int n = static_cast<int>(non_negated.size() + negated.size() + span_children);
+   // only the wide forms (Threshold, Union) take the compact children; every other outcome gets operators
+   const bool general_threshold = k > 1 && k < n;
+   const bool wide_union = k == 1 && n > 1 && !match_exactly && negated.empty();
+   if (scan_span != nullptr && !(general_threshold || wide_union) && k <= n && k >= 0) {
+      for (size_t i = 0; i < scan_span->size(); ++i) {
+         non_negated.push_back(scan_span->materialise(i));
+      }
+      scan_span = nullptr;
+   }
    // nof.cpp:33-84 trivial cases
    if (k > n) {
       return std::make_unique<Empty>();
@@ -511,11 +573,11 @@ std::unique_ptr<Operator> NOf::compile(const Table& table) const {
    }
    if (k == 1 && !match_exactly) {  // nof.cpp:100-114: any may match
       if (negated.empty()) {
-         return std::make_unique<Union>(std::move(non_negated));
+         return std::make_unique<Union>(std::move(non_negated), std::move(scan_span));
       }
       return std::make_unique<Complement>(std::make_unique<Intersection>(std::move(negated), std::move(non_negated)));
    }
-   return std::make_unique<Threshold>(std::move(non_negated), std::move(negated), static_cast<uint32_t>(k), match_exactly);
+   return std::make_unique<Threshold>(std::move(non_negated), std::move(negated), static_cast<uint32_t>(k), match_exactly, std::move(scan_span));
 }
 
 // ---- MutationProfile -------------------------------------------------------------------------
@@ -565,23 +627,30 @@ ExpressionPtr MutationProfile::rewrite(const Table& table, AmbiguityMode) const 
    }
    // one "definitely different" child per position: the symbols that are NOT compatible with the
    // profile symbol (mutation_profile.cpp:222-247); the filter is "fewer than distance+1 differ"
-   ExpressionVector differences;
-   differences.reserve(profile.size());
+   // (the children in compact form: one (position, symbol set) pair each, see SymbolInSetSpan)
+   auto differences = std::make_shared<SymbolInSetSpan>();
+   differences->column = column;
+   differences->alphabet = &alphabet;
+   differences->positions.reserve(profile.size());
+   differences->masks.reserve(profile.size());
+   const uint32_t all_symbols = allSymbolsMask(alphabet);
+   std::vector<uint32_t> incompatible_with(alphabet.ambiguity_symbols.size());
+   for (size_t symbol = 0; symbol < incompatible_with.size(); ++symbol) {
+      incompatible_with[symbol] = all_symbols & ~maskOf(alphabet.ambiguity_symbols[symbol]);
+   }
    for (size_t position = 0; position < profile.size(); ++position) {
       if (profile[position] == alphabet.missing) {
          continue;
       }
-      const uint32_t incompatible =
-         allSymbolsMask(alphabet) & ~maskOf(alphabet.ambiguity_symbols.at(profile[position]));
+      const uint32_t incompatible = incompatible_with.at(profile[position]);
       if (incompatible == 0) {
          continue;
       }
-      differences.push_back(
-         std::make_shared<SymbolInSet>(column, static_cast<uint32_t>(position), SymbolSet(incompatible), &alphabet)
-      );
+      differences->positions.push_back(static_cast<uint32_t>(position));
+      differences->masks.push_back(incompatible);
    }
    return std::make_shared<Negation>(
-      std::make_shared<NOf>(std::move(differences), static_cast<int>(distance) + 1, false)
+      std::make_shared<NOf>(ExpressionVector{}, static_cast<int>(distance) + 1, false, std::move(differences))
    );
 }
 

@@ -138,14 +138,28 @@ struct Or : ScalarExpression {
    std::unique_ptr<Operator> compile(const Table& table) const override;
 };
 
+// Many SymbolInSet children of one NOf in compact form: (position, symbol set) pairs over one sequence column, in
+// child order. MutationProfile::rewrite produces one child per genome position (mutation_profile.cpp:222-247);
+// as ~30,000 expression objects they were half of the host time of such a query. They behave exactly like the
+// SymbolInSet children they stand for (toString, compile).
+struct SymbolInSetSpan {
+   std::string column;
+   const Alphabet* alphabet = nullptr;
+   std::vector<uint32_t> positions;
+   std::vector<uint32_t> masks;
+   [[nodiscard]] size_t size() const { return positions.size(); }
+};
+
 struct NOf : ScalarExpression {
    ExpressionVector children;
    int number_of_matchers;
    bool match_exactly;
-   NOf(ExpressionVector children, int number_of_matchers, bool match_exactly)
+   std::shared_ptr<const SymbolInSetSpan> span;  // further children, behind `children`
+   NOf(ExpressionVector children, int number_of_matchers, bool match_exactly, std::shared_ptr<const SymbolInSetSpan> span = nullptr)
        : children(std::move(children)),
          number_of_matchers(number_of_matchers),
-         match_exactly(match_exactly) {}
+         match_exactly(match_exactly),
+         span(std::move(span)) {}
    std::string toString() const override;
    ExpressionPtr rewrite(const Table& table, AmbiguityMode mode) const override;
    std::unique_ptr<Operator> compile(const Table& table) const override;

@@ -92,7 +92,8 @@ void lowerCounting(
    const OperatorVector& non_negated_children,
    const OperatorVector& negated_children,
    uint32_t number_of_matchers,
-   bool match_exactly
+   bool match_exactly,
+   const SymbolScanSpan* span = nullptr
 );
 
 // whether lowering the tree emits a counter program (THR_BEGIN .. THR_END); those do not nest
@@ -105,7 +106,7 @@ bool containsThreshold(const Operator& node) {
          return true;
       case UNION: {
          const auto& children = static_cast<const Union&>(node).children;
-         return children.size() >= WIDE_UNION_MIN_CHILDREN || any(children);
+         return static_cast<const Union&>(node).span != nullptr || children.size() >= WIDE_UNION_MIN_CHILDREN || any(children);
       }
       case INTERSECTION: {
          const auto& intersection = static_cast<const Intersection&>(node);
@@ -285,11 +286,87 @@ void Intersection::lower(ProgramBuilder& program) const {
    }
 }
 
+std::unique_ptr<Operator> SymbolScanSpan::materialise(size_t index) const {
+   const Leaf& leaf = leaves.at(index);
+   if (!leaf.includes_reference) {
+      return IndexScan::overSymbols(device_column, leaf.position_idx, leaf.mask);
+   }
+   OperatorVector keep;
+   keep.push_back(std::make_unique<Selection>(CoveragePredicate{device_column, leaf.position_idx, true}));
+   OperatorVector drop;
+   drop.push_back(IndexScan::overSymbols(device_column, leaf.position_idx, all_symbols_mask & ~leaf.mask & ~missing_bit));
+   return std::make_unique<Intersection>(std::move(keep), std::move(drop));
+}
+
+// what joinWithLimit prints for these children when `already_printed` items of the same list came before them
+std::string SymbolScanSpan::joinedStrings(const std::string& delimiter, size_t already_printed, size_t limit) const {
+   std::string res;
+   const size_t room = already_printed < limit ? limit - already_printed : 0;
+   const size_t items_to_print = std::min(room, leaves.size());
+   for (size_t i = 0; i < items_to_print; ++i) {
+      if (already_printed + i > 0) {
+         res += delimiter;
+      }
+      res += materialise(i)->toString();
+   }
+   return res;
+}
+
+namespace {
+// joinWithLimit over `children` followed by the children of `span`
+std::string joinWithSpan(const OperatorVector& children, const SymbolScanSpan* span, const std::string& delimiter = ", ", size_t limit = 10) {
+   if (span == nullptr) {
+      return joinWithLimit(children, delimiter, limit);
+   }
+   const size_t total = children.size() + span->size();
+   std::string res;
+   const size_t own = std::min(children.size(), limit);
+   for (size_t i = 0; i < own; ++i) {
+      if (i > 0) {
+         res += delimiter;
+      }
+      res += children[i]->toString();
+   }
+   res += span->joinedStrings(delimiter, own, limit);
+   const size_t printed = std::min(total, limit);
+   if (total > printed) {
+      res += delimiter + "... (" + std::to_string(total - printed) + " more)";
+   }
+   return res;
+}
+}  // namespace
+
 std::string Union::toString() const {  // union.cpp:23-28
-   return "(" + joinWithLimit(children, " | ") + ")";
+   return "(" + joinWithSpan(children, span.get(), " | ") + ")";
 }
 
 void Union::lower(ProgramBuilder& program) const {
+   if (span != nullptr && !program.inside_counter_program) {
+      static const OperatorVector NO_NEGATED;
+      lowerCounting(program, children, NO_NEGATED, 1, false, span.get());
+      return;
+   }
+   if (span != nullptr) {  // inside another counter program: a plain chain of ORs over the materialised leaves
+      bool have_tile = false;
+      for (const auto& child : children) {
+         child->lower(program);
+         if (have_tile) {
+            program.emit(SILO_OP_OR);
+         }
+         have_tile = true;
+      }
+      for (size_t i = 0; i < span->size(); ++i) {
+         span->materialise(i)->lower(program);
+         if (have_tile) {
+            program.emit(SILO_OP_OR);
+         }
+         have_tile = true;
+      }
+      if (!have_tile) {
+         program.emit(SILO_OP_PUSH_EMPTY);
+      }
+      return;
+   }
    if (children.empty()) {
       program.emit(SILO_OP_PUSH_EMPTY);
       return;
@@ -388,13 +465,15 @@ Threshold::Threshold(
    OperatorVector&& non_negated_children_,
    OperatorVector&& negated_children_,
    uint32_t number_of_matchers,
-   bool match_exactly
+   bool match_exactly,
+   std::shared_ptr<const SymbolScanSpan> span_
 )
     : non_negated_children(std::move(non_negated_children_)),
       negated_children(std::move(negated_children_)),
       number_of_matchers(number_of_matchers),
-      match_exactly(match_exactly) {
-   if (number_of_matchers >= non_negated_children.size() + negated_children.size()) {
+      match_exactly(match_exactly),
+      span(std::move(span_)) {
+   if (number_of_matchers >= non_negated_children.size() + negated_children.size() + (span != nullptr ? span->size() : 0)) {
       throw QueryCompilationException(
          "Compilation Error: number_of_matchers must be less than the number of children of a "
          "threshold expression"
@@ -407,7 +486,7 @@ Threshold::Threshold(
 
 std::string Threshold::toString() const {  // threshold.cpp:45-58
    return std::string("Threshold(") + (match_exactly ? "=" : ">=") + std::to_string(number_of_matchers) + "-of " +
-          "non_negated: (" + joinWithLimit(non_negated_children) + ") negated: (" + joinWithLimit(negated_children) + ") )";
+          "non_negated: (" + joinWithSpan(non_negated_children, span.get()) + ") negated: (" + joinWithLimit(negated_children) + ") )";
 }
 
 namespace {
@@ -456,7 +535,8 @@ void lowerCounting(
    const OperatorVector& non_negated_children,
    const OperatorVector& negated_children,
    uint32_t number_of_matchers,
-   bool match_exactly
+   bool match_exactly,
+   const SymbolScanSpan* span
 ) {
    // Threshold::evaluate (threshold.cpp:64-138) is a DP over k roaring bitmaps whose result is
    // "at least / exactly k of the children contain the row". The device keeps one u16 counter per
@@ -481,6 +561,23 @@ void lowerCounting(
          }
       } else {
          generic.push_back(child.get());
+      }
+   }
+   if (span != nullptr) {  // the same classification, straight from the compact leaves
+      FusedLeaves& leaves = fused[span->device_column];
+      leaves.adds.reserve(leaves.adds.size() + span->size());
+      for (const SymbolScanSpan::Leaf& leaf : span->leaves) {
+         if (!leaf.includes_reference) {
+            if (leaf.mask != 0) {
+               leaves.adds.emplace_back(leaf.position_idx, leaf.mask);
+            }
+         } else {
+            leaves.covered_positions.push_back(leaf.position_idx);
+            const uint32_t others = span->all_symbols_mask & ~leaf.mask & ~span->missing_bit;
+            if (others != 0) {
+               leaves.subs.emplace_back(leaf.position_idx, others);
+            }
+         }
       }
    }
    uint64_t bias = 0;
@@ -562,7 +659,7 @@ void lowerCounting(
 }  // namespace
 
 void Threshold::lower(ProgramBuilder& program) const {
-   lowerCounting(program, non_negated_children, negated_children, number_of_matchers, match_exactly);
+   lowerCounting(program, non_negated_children, negated_children, number_of_matchers, match_exactly, span.get());
 }
 
 }  // namespace silo_host

@@ -123,6 +123,27 @@ class IndexScan : public Operator {
    void lower(ProgramBuilder& program) const override;
 };
 
+// Many leaf children of one wide Union / Threshold in compact form: per position of ONE sequence column, what
+// compileSymbolInSet (symbol_in_set.cpp:231-264) would have built for a symbol set that does not hold the missing
+// symbol -- an IndexScan (`adds`) or Selection[IsCovered] minus IndexScan (`covered_positions`, `subs`). A
+// MutationProfile has one such child per genome position; building ~30,000 operator objects per query was most of
+// the host time of such a query. The operators themselves are only materialised for toString().
+struct SymbolScanSpan {
+   int device_column = 0;
+   std::string column_name;
+   struct Leaf {
+      uint32_t position_idx;
+      uint32_t mask;             // the requested symbols
+      bool includes_reference;   // of the column's local reference at this position
+   };
+   std::vector<Leaf> leaves;     // in child order
+   uint32_t all_symbols_mask = 0;
+   uint32_t missing_bit = 0;
+   [[nodiscard]] size_t size() const { return leaves.size(); }
+   [[nodiscard]] std::unique_ptr<Operator> materialise(size_t index) const;
+   [[nodiscard]] std::string joinedStrings(const std::string& delimiter, size_t already_printed, size_t limit = 10) const;
+};
+
 class Intersection : public Operator {
   public:
    OperatorVector children;
@@ -136,7 +157,10 @@ class Intersection : public Operator {
 class Union : public Operator {
   public:
    OperatorVector children;
-   explicit Union(OperatorVector&& children) : children(std::move(children)) {}
+   std::shared_ptr<const SymbolScanSpan> span;  // further children, behind `children`
+   explicit Union(OperatorVector&& children, std::shared_ptr<const SymbolScanSpan> span = nullptr)
+       : children(std::move(children)),
+         span(std::move(span)) {}
    OperatorType type() const override { return UNION; }
    std::string toString() const override;
    void lower(ProgramBuilder& program) const override;
@@ -158,11 +182,13 @@ class Threshold : public Operator {
    OperatorVector negated_children;
    uint32_t number_of_matchers;
    bool match_exactly;
+   std::shared_ptr<const SymbolScanSpan> span;  // further non-negated children, behind non_negated_children
    Threshold(
       OperatorVector&& non_negated_children,
       OperatorVector&& negated_children,
       uint32_t number_of_matchers,
-      bool match_exactly
+      bool match_exactly,
+      std::shared_ptr<const SymbolScanSpan> span = nullptr
    );  // threshold.cpp:19-41
    OperatorType type() const override { return THRESHOLD; }
    std::string toString() const override;

@@ -566,6 +566,10 @@ class HostTable:
         lib().silo_host_last_query_profile(out)
         return dict(zip(("parse_us", "compile_us", "filter_us", "counts_us", "threshold_us"), out))
 
+    def set_option(self, name: str, value: int) -> None:
+        """silo_gpu_table_set_option on the device table (e.g. "sweep_min_pieces")"""
+        abi.check(abi.lib().silo_gpu_table_set_option(self.device_table, name.encode(), value))
+
     def stats(self) -> abi.Stats:
         out = abi.Stats()
         abi.check(abi.lib().silo_gpu_get_stats(self.device_table, C.byref(out)))

@@ -1,4 +1,5 @@
-"""ncu target: one nucleotideMutationProfile(distance=5) filter on 10 M rows, three times."""
+"""ncu target for configs[2]: ONE nucleotideMutationProfile(distance 5, querySequence) filter on the 10 M-row bench table
+(after one warm-up query)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
@@ -11,8 +12,7 @@ table = host_api.HostTable(ctx, sizes)
 table.add_column("main", host_api.NUCLEOTIDE, synthetic.reference, synthetic.build_column(rows, 0, len(sizes), 16))
 synthetic.release_column()
 query = synthetic.sequence(synthetic.num_sequences - 1)
-for _ in range(3):
+for _ in range(2):
     flt = table.filter(f"(profile main 5 seq {query})")
     print(flt.cardinality)
     flt.close()
-print(table.explain(f"(profile main 5 seq {query})")[:600] if hasattr(table, "explain") else "")

@@ -559,3 +559,64 @@ def test_baseline_sizes_equal_the_oracle(ctx):
         text = f"(profile main {distance} seq {query})"
         np.testing.assert_array_equal(table.filter(text).ids(), oracle_table.filter(text).ids())
     table.close()
+
+
+@pytest.mark.parametrize("seed,alphabet_id", [(301, 0), (302, 1)])
+def test_threshold_sweep_kernel(ctx, seed, alphabet_id):
+    """The whole-column threshold sweep (thresholdSweepKernel) forced on for small tables: wide n-of / profile
+    expressions with adding and subtracting leaves, exact and at-least, ragged chunks, nulls, N runs, every container
+    kind; then the same with the sweep off (the interpreter's own container walk)."""
+    t = build_random(seed, 1500, 60, (299, 300, 700, 1100), alphabet_id)
+    rng = np.random.default_rng(seed)
+    t.register_bitmap("lineage", sorted(set(int(v) for v in rng.integers(0, 300, 150))))
+    device = mirror(ctx, t, ["lineage"])
+    pair = (t, device)
+    chars = "-ACGTRYSWKMBDHVN" if alphabet_id == 0 else "-ACDEFGHIKLMNOPQRSTUVWYBJZ*X"
+    reference = t.columns[0][2]
+    for sweep_min_pieces in (0, 2 ** 63):
+        device.set_option("sweep_min_pieces", sweep_min_pieces)
+        for k in (1, 2, 7, 25, 59):
+            children = " ".join(f"(sym-in c {p} {''.join(rng.choice(list(chars[:-1]), 4, replace=False))})" for p in range(1, 61))
+            both(pair, f"(n-of {k} 0 {children})")
+            both(pair, f"(n-of {k} 1 {children})")
+            both(pair, f"(and (bitmap lineage) (not (n-of {k} 0 {children})))")
+        for distance in (0, 1, 4, 20, 59):
+            both(pair, f"(profile c {distance} muts)")
+            query = list(reference)
+            for p in rng.integers(0, 60, 12):
+                query[int(p)] = chars[int(rng.integers(0, len(chars)))]
+            both(pair, f"(profile c {distance} seq {''.join(query)})")
+            both(pair, f"(or (bitmap lineage) (profile c {distance} seq {''.join(query)}))")
+    device.close()
+
+
+def test_threshold_sweep_on_tree_data(ctx):
+    """The sweep on synthetic tree data over several chunks (a CTA's range crosses chunk boundaries, several CTAs
+    flush into one chunk): arrays, runs and bitsets; profile row sets against the brute-force Hamming distances and
+    the oracle's Threshold DP."""
+    from lapis_silo_b200 import host_api
+    from oracle import oracle as O
+    total_rows, length = 5 * 65536 + 1234, 2500
+    synthetic = host_api.Synthetic(genome_length=length, reference_seed=5, generations=5)
+    sizes = host_api.dense_chunk_sizes(total_rows)
+    column = synthetic.build_column(total_rows, 0, len(sizes), 8)
+    table = host_api.HostTable(ctx, sizes)
+    table.add_column("main", host_api.NUCLEOTIDE, synthetic.reference, column)
+    oracle_table = O.Table()
+    oracle_table.set_layout(*sizes)
+    oracle_table.import_column("main", O.NUCLEOTIDE, synthetic.reference, column)
+    synthetic.release_column()
+    table.set_option("sweep_min_pieces", 0)
+    n = synthetic.num_sequences
+    row_sequence = np.arange(total_rows) % n
+    for query_index in (n - 1, n // 2):
+        distances = profile_brute_force(synthetic, total_rows, query_index)
+        query = synthetic.sequence(query_index)
+        for distance in (0, 3, 10, 40):
+            flt = table.filter(f"(profile main {distance} seq {query})")
+            want = np.flatnonzero((distances <= distance)[row_sequence]).astype(np.uint32)
+            np.testing.assert_array_equal(flt.ids(), want)
+        for distance in (0, 3):
+            text = f"(profile main {distance} seq {query})"
+            np.testing.assert_array_equal(table.filter(text).ids(), oracle_table.filter(text).ids())
+    table.close()
