@@ -339,6 +339,46 @@ int silo_gpu_mutation_hits_from_counts(
    uint64_t* shard_cardinality
 );
 
+/* ---- Row-partitioned tables: the multi-GPU scheduler's device side -----------------------------
+ * One process per GPU; every rank uploads the chunks of its shard as a table of its own. The per-rank counts of the
+ * Mutations action are plain addends (the local reference is the same on all shards) and only one rank -- the root,
+ * rank 0 -- needs their sum, for the output pass. No collective kernel runs: the finalize kernel of every rank stores
+ * its rows of the valid mutation symbols straight into a gather area in the ROOT's memory over NVLink (CUDA IPC peer
+ * mapping), and the root's collect kernel sums the ranks' rows and runs addMutationsToOutput (mutations_node.cpp:
+ * 307-363) on the device. Replaces, for a row-partitioned table, the loop over partitions that the reference's
+ * MutationsNode producer would run on one host (mutations_node.cpp:372-428).
+ *
+ *   every rank:  silo_gpu_shard_group_init(table, column, valid mask, rank, world, my_handle)
+ *                -- exchange the handles (SILO_SHARD_HANDLE_BYTES each) by any means: MPI, torch.distributed, a file --
+ *                silo_gpu_shard_group_connect(table, all_handles /+ world x SILO_SHARD_HANDLE_BYTES, by rank +/)
+ *   per query:   every rank, in the same order:  silo_gpu_sharded_query_enqueue(table, program, stream)   (no sync)
+ *                the root:                       silo_gpu_sharded_collect(...)                            (one sync)
+ * Ranks other than the root never synchronise with the host; they may run up to 3 queries ahead of the root (a rank
+ * whose gather slot has not been handed back waits inside its finalize kernel). All device-side waits are bounded
+ * (~2 s): a rank that never delivers becomes SILO_E_CUDA at the root, not a hung GPU. One sharded query stream per
+ * table; the table's other entry points stay usable between sharded queries. */
+#define SILO_SHARD_HANDLE_BYTES 128
+int silo_gpu_shard_group_init(silo_gpu_table* table, int column, uint64_t valid_symbol_mask, int rank, int world, void* handle_out);
+int silo_gpu_shard_group_connect(silo_gpu_table* table, const void* handles);
+/* every rank: filter program + counts of the group's column + this rank's rows to the root; enqueue only */
+int silo_gpu_sharded_query_enqueue(silo_gpu_table* table, const silo_filter_program* program, void* cuda_stream);
+/* the root, once per enqueued query and in the same order: waits (on the device) for all ranks, sums, runs the output
+ * pass; hits / n_hits / cardinality (the sum of the ranks' filter cardinalities) as silo_gpu_query_mutation_hits.
+ * d_summed_counts: NULL, or n_symbols*genome_length u32 in device memory that receive the summed rows of the valid
+ * symbols (the other rows are left alone). */
+int silo_gpu_sharded_collect(
+   silo_gpu_table* table,
+   double min_proportion,
+   void* d_summed_counts,
+   void* cuda_stream,
+   const silo_mutation_hit** hits,
+   uint64_t* n_hits,
+   uint64_t* cardinality
+);
+/* the same without the output pass and without synchronising (device-resident pipelines) */
+int silo_gpu_sharded_collect_async(silo_gpu_table* table, void* d_summed_counts, void* cuda_stream);
+void silo_gpu_shard_group_free(silo_gpu_table* table);
+
 /* ---- BitmapAggregationNode: co-occurrence / groupBy over sequence positions and indexed columns ---
  * Replaces buildGroups + computeCombinations of operators/bitmap_aggregation_node.cpp:53-139,224-249
  * (reached from BitmapAggregationNode::addToExecPlan :304-356). The groups of a dimension are disjoint,

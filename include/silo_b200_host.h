@@ -105,6 +105,16 @@ int silo_host_mutations_enqueue(silo_host_table* table, const char* expression, 
 int silo_host_mutations_collect_packed(silo_host_table* table, const char* column, double min_proportion, const void* d_summed_counts, void* cuda_stream,
                                        void* buffer, uint64_t capacity, uint64_t* n_rows, uint32_t* n_names, uint64_t* needed_bytes,
                                        uint64_t* shard_cardinality);
+/* The same query through the table's shard group (MutationsNode::enqueueSharded / collectSharded; silo_gpu_shard_group_*
+ * of include/silo_b200.h): _create on every rank writes this rank's handle (SILO_SHARD_HANDLE_BYTES), _connect takes the
+ * handles of all ranks in rank order; then every rank enqueues, rank 0 collects (rows of the whole table; cardinality =
+ * rows of all shards that passed the filter). d_summed_counts may be NULL. */
+int silo_host_shard_group_create(silo_host_table* table, const char* column, int rank, int world, void* handle_out);
+int silo_host_shard_group_connect(silo_host_table* table, const void* handles, uint64_t handles_bytes);
+int silo_host_sharded_enqueue(silo_host_table* table, const char* expression, const char* column, void* cuda_stream);
+int silo_host_sharded_collect_packed(silo_host_table* table, const char* column, double min_proportion, void* d_summed_counts, void* cuda_stream,
+                                     void* buffer, uint64_t capacity, uint64_t* n_rows, uint32_t* n_names, uint64_t* needed_bytes,
+                                     uint64_t* cardinality);
 /* thresholding only, on counts the caller summed over shards (multi-GPU) */
 silo_host_rows* silo_host_mutation_rows_from_counts(silo_host_table* table, const char* column, const uint32_t* counts, double min_proportion);
 /* microseconds of the calling thread's last silo_host_mutations call:

@@ -202,6 +202,10 @@ __host__ __device__ inline uint32_t diffWords(uint32_t genome_length) {  // whol
 
 }  // namespace silo
 
+namespace silo {
+struct ShardGroup;  // mutations.cu: this table as one rank of a row-partitioned table
+}
+
 struct silo_gpu_ctx {
    int device = 0;
    int sm_count = 0;
@@ -279,6 +283,7 @@ struct silo_gpu_table {
    // [n_chunks][32768] packed u16 pairs; used by programs over columns with at least sweep_min_pieces pieces
    uint32_t* d_sweep_counters = nullptr;
    uint64_t sweep_min_pieces = 1u << 16;
+   silo::ShardGroup* shard = nullptr;
 };
 
 struct silo_gpu_filter {
@@ -314,6 +319,7 @@ struct StagedQuery {
 void stageQueryLocked(silo_gpu_table* table, const silo_filter_program* program, StagedQuery* out, int prepare_column = -1, uint32_t* prepare_counts = nullptr);
 void enqueueStagedQuery(silo_gpu_table* table, const StagedQuery& staged, cudaStream_t stream, bool scalars_are_zero = true);
 void dropQueryGraphsLocked(silo_gpu_table* table);
+void freeShardGroup(silo_gpu_table* table);  // mutations.cu
 // mutations.cu: coverage + container + finalize kernels for a filter whose interpreter launch already zeroed
 // d_counts and built the work list (caller holds table->mutex); records the per-call timing events
 void enqueuePreparedCountsLocked(silo_gpu_table* table, int column, const silo_gpu_filter* filter, uint32_t* d_counts, cudaStream_t stream);

@@ -17,6 +17,9 @@
 #include <cstring>
 
 #include <chrono>
+#include <memory>
+
+#include <unistd.h>
 
 #include "common.cuh"
 
@@ -768,6 +771,62 @@ constexpr int FIN_THREADS = DIFF_BLOCK;
 // block to finish writes the header hits[0] = {number of tuples, the filter's error flag, the filter's
 // cardinality (low, high word)}, so a fused query needs no device-to-host copy at all. The running tuple
 // count lives in work_state[3] (zero between queries).
+// ---------------------------------------------------------------------------------------------
+// Row-partitioned tables: one process per GPU, every rank holds the chunks of its shard. The per-rank
+// counts are plain addends, and only ONE rank (the root, rank 0) needs the sums. Instead of a collective kernel that
+// competes with the container kernel for SMs, the finalize kernel of every rank STORES its rows of the valid mutation
+// symbols straight into the root's gather area over NVLink (peer memory mapped with CUDA IPC), and the root's collect
+// kernel sums the `world` arrays and runs the output pass. Flow control: a gather slot is reused every SHARD_SLOTS
+// queries; a rank writes slot s for its query q only after the root released the slot's previous use (the root's
+// collect kernel stores the generation into every rank's `released[s]`), so ranks may run at most SHARD_SLOTS - 1
+// queries ahead of the root. Every wait in a kernel is bounded (SHARD_SPIN_LIMIT): a missing peer becomes an error
+// flag in the result, not a hung GPU.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t SHARD_MAX_WORLD = 16;
+constexpr uint32_t SHARD_SLOTS = 4;
+constexpr long long SHARD_SPIN_LIMIT = 4000000000LL;  // cycles (~2 s)
+
+struct ShardBlockHeader {  // the start of every rank's exported block
+   uint32_t released[SHARD_SLOTS];  // generation of the slot's last consumed use; written by the root's collect kernel
+   uint32_t arrivals[SHARD_SLOTS];  // root only: ranks whose rows of a slot have landed, counted over all generations
+   unsigned long long cardinality[SHARD_SLOTS][SHARD_MAX_WORLD];  // root only: the ranks' filter cardinalities
+   uint32_t error[SHARD_SLOTS][SHARD_MAX_WORLD];                  // root only: the ranks' filter error flags
+};
+constexpr size_t SHARD_HEADER_BYTES = (sizeof(ShardBlockHeader) + 255) / 256 * 256;
+
+struct ShardPush {  // what the finalize kernel of a sharded query needs (all zero: not sharded)
+   uint32_t* root_rows = nullptr;       // this rank's [n_valid][genome_length] area of the slot, in the root's memory
+   uint32_t* root_arrivals = nullptr;   // &root header.arrivals[slot]
+   unsigned long long* root_cardinality = nullptr;  // &root header.cardinality[slot][rank]
+   uint32_t* root_error = nullptr;
+   const uint32_t* released = nullptr;  // &own header.released[slot]
+   uint32_t wait_generation = 0;        // the slot may be written once released has reached this
+   uint32_t use_fixed_cardinality = 0;
+   uint64_t valid_mask = 0;
+   unsigned long long fixed_cardinality = 0;          // filter == all rows
+   unsigned long long* filter_scalars = nullptr;      // else: {cardinality, -, error flag} of the query's filter; reset here
+};
+
+__device__ __forceinline__ uint32_t loadAcquireSystem(const uint32_t* address) {
+   uint32_t value;
+   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(value) : "l"(address) : "memory");
+   return value;
+}
+__device__ __forceinline__ void storeReleaseSystem(uint32_t* address, uint32_t value) {
+   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(address), "r"(value) : "memory");
+}
+// spins until *address >= target (wrap-safe); false after SHARD_SPIN_LIMIT cycles
+__device__ __forceinline__ bool waitForAtLeast(const uint32_t* address, uint32_t target) {
+   const long long begin = clock64();
+   while (static_cast<int32_t>(loadAcquireSystem(address) - target) < 0) {
+      if (clock64() - begin > SHARD_SPIN_LIMIT) {
+         return false;
+      }
+      __nanosleep(200);
+   }
+   return true;
+}
+
 struct HitRequest {
    silo_mutation_hit* hits = nullptr;
    uint32_t capacity = 0;
@@ -785,7 +844,8 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    uint32_t* __restrict__ diff_scratch,
    uint32_t* __restrict__ counts,
    uint32_t* __restrict__ work_state,
-   HitRequest request
+   HitRequest request,
+   ShardPush push
 ) {
    __shared__ uint32_t warp_totals[FIN_THREADS / 32];
    __shared__ uint32_t block_offset;
@@ -844,6 +904,28 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    if (p < genome_length) {
       counts[reference_symbol * genome_length + p] = reference_count;
    }
+   if (push.root_rows != nullptr) {
+      // this rank's rows of the valid mutation symbols -> the root's gather area (coalesced stores over NVLink), once the
+      // root has released the slot's previous use
+      __shared__ uint32_t slot_is_free;
+      if (threadIdx.x == 0) {
+         slot_is_free = waitForAtLeast(push.released, push.wait_generation) ? 1u : 0u;
+      }
+      __syncthreads();
+      if (slot_is_free != 0 && p < genome_length) {
+         uint32_t row = 0;
+         for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
+            if (((push.valid_mask >> symbol) & 1ULL) != 0) {
+               push.root_rows[row * genome_length + p] = symbol == reference_symbol ? reference_count : counts[symbol * genome_length + p];
+               ++row;
+            }
+         }
+      }
+      if (slot_is_free == 0 && threadIdx.x == 0) {
+         atomicOr(&work_state[3], 0x80000000u);  // reported to the root as this rank's error below
+      }
+      __threadfence_system();
+   }
    if (output_pass) {
       const bool reference_is_valid = ((request.valid_mask >> reference_symbol) & 1ULL) != 0;
       const uint32_t total = valid_others + (reference_is_valid ? reference_count : 0u);
@@ -892,10 +974,113 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
             }
             request.hits[0] = header;
          }
+         if (push.root_rows != nullptr) {
+            // every block's stores are out (each fenced before it counted itself in): cardinality, error flag, arrival
+            unsigned long long cardinality = push.fixed_cardinality;
+            uint32_t error = (*reinterpret_cast<volatile uint32_t*>(&work_state[3]) & 0x80000000u) != 0 ? 2u : 0u;
+            if (push.use_fixed_cardinality == 0) {
+               cardinality = *reinterpret_cast<volatile unsigned long long*>(&push.filter_scalars[0]);
+               error |= *reinterpret_cast<volatile uint32_t*>(&push.filter_scalars[2]);
+               push.filter_scalars[0] = 0;
+               push.filter_scalars[2] = 0;
+            }
+            *push.root_cardinality = cardinality;
+            *push.root_error = error;
+            __threadfence_system();
+            atomicAdd_system(push.root_arrivals, 1u);
+         }
          work_state[0] = 0;  // the work list and its claim counter are empty between queries
          work_state[1] = 0;
          work_state[2] = 0;
          work_state[3] = 0;
+      }
+   }
+}
+
+// The root's half of a sharded query: waits until the rows of all `world` ranks have landed in the slot, sums them
+// per position and valid symbol, runs the output pass of addMutationsToOutput (mutations_node.cpp:307-363) over the
+// sums (as mutationHitsKernel does), and hands the slot back to every rank.
+struct ShardCollect {
+   const uint32_t* rows = nullptr;  // the slot: [world][n_valid][genome_length]
+   ShardBlockHeader* header = nullptr;   // the root's own block
+   ShardBlockHeader* const* peers = nullptr;  // [world] every rank's block as mapped on the root
+   uint32_t world = 0;
+   uint32_t n_valid = 0;
+   uint32_t slot = 0;
+   uint32_t generation = 0;
+   uint32_t* summed_out = nullptr;  // optional: [n_symbols][genome_length], the rows of the valid symbols are written
+};
+
+__global__ void __launch_bounds__(FIN_THREADS) shardCollectKernel(DevColumn column, ShardCollect collect, uint32_t* __restrict__ work_state, HitRequest request) {
+   __shared__ uint32_t all_arrived;
+   const uint32_t genome_length = column.genome_length;
+   const uint32_t p = blockIdx.x * FIN_THREADS + threadIdx.x;
+   if (threadIdx.x == 0) {
+      all_arrived = waitForAtLeast(&collect.header->arrivals[collect.slot], collect.world * collect.generation) ? 1u : 0u;
+   }
+   __syncthreads();
+   if (all_arrived != 0 && p < genome_length) {
+      const uint32_t genome_symbol = request.hits != nullptr ? column.global_reference[p] : 0u;
+      const size_t rank_stride = static_cast<size_t>(collect.n_valid) * genome_length;
+      uint32_t sums[32];
+      uint32_t total = 0;
+      uint32_t candidates = 0;
+      uint32_t row = 0;
+      for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
+         sums[symbol] = 0;
+         if (((request.valid_mask >> symbol) & 1ULL) != 0) {
+            uint32_t sum = 0;
+            for (uint32_t rank = 0; rank < collect.world; ++rank) {
+               sum += collect.rows[rank * rank_stride + row * genome_length + p];
+            }
+            sums[symbol] = sum;
+            total += sum;
+            candidates |= symbol != genome_symbol ? sum : 0u;
+            if (collect.summed_out != nullptr) {
+               collect.summed_out[symbol * genome_length + p] = sum;
+            }
+            ++row;
+         }
+      }
+      if (request.hits != nullptr && total != 0 && candidates != 0) {
+         const uint32_t threshold_count =
+            request.min_proportion == 0 ? 0u : static_cast<uint32_t>(ceil(__dmul_rn(static_cast<double>(total), request.min_proportion)) - 1.0);
+         for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
+            if (((request.valid_mask >> symbol) & 1ULL) == 0 || symbol == genome_symbol) {
+               continue;
+            }
+            if (sums[symbol] > threshold_count) {
+               const uint32_t index = atomicAdd(&work_state[3], 1u);
+               if (index < request.capacity) {
+                  request.hits[1 + index] = silo_mutation_hit{p, symbol, sums[symbol], total};
+               }
+            }
+         }
+      }
+   }
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      __threadfence();
+      const uint32_t finished = atomicAdd(&work_state[2], 1u);
+      if (finished == gridDim.x - 1) {
+         __threadfence();
+         unsigned long long cardinality = 0;
+         uint32_t error = all_arrived != 0 ? 0u : 2u;
+         for (uint32_t rank = 0; rank < collect.world; ++rank) {
+            cardinality += *reinterpret_cast<volatile unsigned long long*>(&collect.header->cardinality[collect.slot][rank]);
+            error |= *reinterpret_cast<volatile uint32_t*>(&collect.header->error[collect.slot][rank]);
+         }
+         if (request.hits != nullptr) {
+            request.hits[0] = silo_mutation_hit{
+               *reinterpret_cast<volatile uint32_t*>(&work_state[3]), error, static_cast<uint32_t>(cardinality), static_cast<uint32_t>(cardinality >> 32)};
+         }
+         work_state[2] = 0;
+         work_state[3] = 0;
+         // every block has read the slot: hand it back to the ranks
+         __threadfence_system();
+         for (uint32_t rank = 0; rank < collect.world; ++rank) {
+            storeReleaseSystem(&collect.peers[rank]->released[collect.slot], collect.generation);
+         }
       }
    }
 }
@@ -1013,7 +1198,8 @@ void enqueueMutationCounts(
    cudaStream_t stream,
    const HitRequest* request = nullptr,
    bool timed = false,    // record the per-call CUDA events that silo_gpu_get_stats reads (measurement only)
-   bool prepared = false  // the filter interpreter already zeroed d_counts and built the work list (fused query)
+   bool prepared = false, // the filter interpreter already zeroed d_counts and built the work list (fused query)
+   const ShardPush* push = nullptr  // sharded query: the finalize kernel also sends this rank's rows to the root
 ) {
    require(table != nullptr, "mutation_counts: table is NULL");
    require(column_index >= 0 && static_cast<size_t>(column_index) < table->columns.size(), "mutation_counts: bad column index");
@@ -1136,7 +1322,7 @@ void enqueueMutationCounts(
    recordTiming(ev_k1_end);
    SILO_CUDA_CHECK(cudaStreamWaitEvent(stream, table->ev_join, 0));
    finalizeCountsKernel<<<diffPadded(column.genome_length) / FIN_THREADS, FIN_THREADS, 0, stream>>>(
-      column, diff, d_counts, table->d_work_state, request != nullptr ? *request : HitRequest{}
+      column, diff, d_counts, table->d_work_state, request != nullptr ? *request : HitRequest{}, push != nullptr ? *push : ShardPush{}
    );
    SILO_CUDA_CHECK(cudaGetLastError());
    table->stats.kernel_launches += 2;
@@ -1567,6 +1753,277 @@ int silo_gpu_query_mutation_hits(
          *cardinality = host_cardinality;
       }
    });
+}
+
+// ---- row-partitioned tables: the scheduler's device side (see ShardBlockHeader above) ----------------------
+
+}  // extern "C"
+
+namespace silo {
+
+struct ShardGroup {
+   int rank = 0;
+   int world = 1;
+   int column = -1;
+   uint64_t valid_mask = 0;
+   uint32_t n_valid = 0;
+   uint32_t genome_length = 0;
+   uint8_t* d_local = nullptr;  // this rank's exported block: header (+ the gather area on the root)
+   size_t local_bytes = 0;
+   uint8_t* d_root = nullptr;   // the root's block as mapped here (== d_local on the root)
+   std::vector<uint8_t*> peer_blocks;     // root: every rank's block as mapped here
+   std::vector<bool> opened_with_ipc;     // which of d_root / peer_blocks must be closed with cudaIpcCloseMemHandle
+   ShardBlockHeader** d_peer_table = nullptr;  // root: device copy of peer_blocks
+   uint32_t* d_collect_state = nullptr;        // root: the collect kernel's block counter and tuple counter
+   uint64_t queries_enqueued = 0;  // the same on every rank: queries are issued in the same order everywhere
+   uint64_t queries_collected = 0; // root
+   size_t rowsBytes() const { return static_cast<size_t>(n_valid) * genome_length * sizeof(uint32_t); }
+   uint32_t* rootRows(uint32_t slot, int of_rank) const {
+      return reinterpret_cast<uint32_t*>(d_root + SHARD_HEADER_BYTES + (static_cast<size_t>(slot) * world + of_rank) * rowsBytes());
+   }
+};
+
+struct ShardHandle {  // SILO_SHARD_HANDLE_BYTES
+   uint64_t magic;
+   uint64_t process_id;
+   uint64_t pointer;   // valid inside the exporting process (several shards of one table in one process: tests)
+   uint64_t bytes;
+   cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(ShardHandle) <= SILO_SHARD_HANDLE_BYTES);
+constexpr uint64_t SHARD_HANDLE_MAGIC = 0x53494C4F53484152ULL;
+
+void freeShardGroup(silo_gpu_table* table) {
+   ShardGroup* group = table->shard;
+   if (group == nullptr) {
+      return;
+   }
+   cudaStreamSynchronize(table->ctx->stream);
+   for (size_t r = 0; r < group->peer_blocks.size(); ++r) {
+      if (group->opened_with_ipc[r] && group->peer_blocks[r] != nullptr) {
+         cudaIpcCloseMemHandle(group->peer_blocks[r]);
+      }
+   }
+   cudaFree(group->d_peer_table);
+   cudaFree(group->d_collect_state);
+   cudaFree(group->d_local);
+   delete group;
+   table->shard = nullptr;
+}
+
+}  // namespace silo
+
+static uint64_t currentProcessId() {
+   return static_cast<uint64_t>(getpid());
+}
+
+extern "C" {
+
+int silo_gpu_shard_group_init(silo_gpu_table* table, int column, uint64_t valid_symbol_mask, int rank, int world, void* handle_out) {
+   return guarded([&] {
+      require(table != nullptr && handle_out != nullptr, "silo_gpu_shard_group_init: NULL argument");
+      require(world >= 1 && world <= static_cast<int>(SHARD_MAX_WORLD) && rank >= 0 && rank < world, "silo_gpu_shard_group_init: bad rank / world");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      require(column >= 0 && static_cast<size_t>(column) < table->columns.size(), "silo_gpu_shard_group_init: bad column index");
+      freeShardGroup(table);
+      const HostColumn& host = *table->columns[static_cast<size_t>(column)];
+      if (host.dev.n_symbols < 64) {
+         valid_symbol_mask &= (1ULL << host.dev.n_symbols) - 1;
+      }
+      require(valid_symbol_mask != 0, "silo_gpu_shard_group_init: no valid symbol");
+      auto group = std::make_unique<ShardGroup>();
+      group->rank = rank;
+      group->world = world;
+      group->column = column;
+      group->valid_mask = valid_symbol_mask;
+      group->n_valid = static_cast<uint32_t>(__builtin_popcountll(valid_symbol_mask));
+      group->genome_length = host.dev.genome_length;
+      group->local_bytes = SHARD_HEADER_BYTES + (rank == 0 ? static_cast<size_t>(SHARD_SLOTS) * world * group->rowsBytes() : 0);
+      SILO_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&group->d_local), group->local_bytes));
+      SILO_CUDA_CHECK(cudaMemset(group->d_local, 0, group->local_bytes));
+      ShardHandle handle{};
+      handle.magic = SHARD_HANDLE_MAGIC;
+      handle.process_id = currentProcessId();
+      handle.pointer = reinterpret_cast<uint64_t>(group->d_local);
+      handle.bytes = group->local_bytes;
+      SILO_CUDA_CHECK(cudaIpcGetMemHandle(&handle.ipc, group->d_local));
+      std::memset(handle_out, 0, SILO_SHARD_HANDLE_BYTES);
+      std::memcpy(handle_out, &handle, sizeof(handle));
+      table->shard = group.release();
+   });
+}
+
+int silo_gpu_shard_group_connect(silo_gpu_table* table, const void* handles) {
+   return guarded([&] {
+      require(table != nullptr && handles != nullptr, "silo_gpu_shard_group_connect: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      ShardGroup* group = table->shard;
+      require(group != nullptr, "silo_gpu_shard_group_connect: call silo_gpu_shard_group_init first");
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      auto open = [&](int of_rank, bool* with_ipc) -> uint8_t* {
+         ShardHandle handle{};
+         std::memcpy(&handle, static_cast<const uint8_t*>(handles) + static_cast<size_t>(of_rank) * SILO_SHARD_HANDLE_BYTES, sizeof(handle));
+         require(handle.magic == SHARD_HANDLE_MAGIC, "silo_gpu_shard_group_connect: not a shard handle");
+         *with_ipc = false;
+         if (of_rank == group->rank) {
+            return group->d_local;
+         }
+         if (handle.process_id == currentProcessId()) {
+            // another shard of the same process (tests, several GPUs driven by one process): plain pointer, peer access
+            cudaPointerAttributes attributes{};
+            SILO_CUDA_CHECK(cudaPointerGetAttributes(&attributes, reinterpret_cast<void*>(handle.pointer)));
+            if (attributes.device != table->ctx->device) {
+               const cudaError_t status = cudaDeviceEnablePeerAccess(attributes.device, 0);
+               if (status != cudaSuccess && status != cudaErrorPeerAccessAlreadyEnabled) {
+                  SILO_CUDA_CHECK(status);
+               }
+               cudaGetLastError();
+            }
+            return reinterpret_cast<uint8_t*>(handle.pointer);
+         }
+         void* mapped = nullptr;
+         SILO_CUDA_CHECK(cudaIpcOpenMemHandle(&mapped, handle.ipc, cudaIpcMemLazyEnablePeerAccess));
+         *with_ipc = true;
+         return static_cast<uint8_t*>(mapped);
+      };
+      group->peer_blocks.assign(static_cast<size_t>(group->world), nullptr);
+      group->opened_with_ipc.assign(static_cast<size_t>(group->world), false);
+      if (group->rank == 0) {
+         for (int r = 0; r < group->world; ++r) {
+            bool with_ipc = false;
+            group->peer_blocks[static_cast<size_t>(r)] = open(r, &with_ipc);
+            group->opened_with_ipc[static_cast<size_t>(r)] = with_ipc;
+         }
+         group->d_root = group->d_local;
+         SILO_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&group->d_peer_table), sizeof(ShardBlockHeader*) * static_cast<size_t>(group->world)));
+         SILO_CUDA_CHECK(cudaMemcpy(group->d_peer_table, group->peer_blocks.data(), sizeof(ShardBlockHeader*) * static_cast<size_t>(group->world), cudaMemcpyHostToDevice));
+         SILO_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&group->d_collect_state), 4 * sizeof(uint32_t)));
+         SILO_CUDA_CHECK(cudaMemset(group->d_collect_state, 0, 4 * sizeof(uint32_t)));
+      } else {
+         bool with_ipc = false;
+         group->peer_blocks[0] = open(0, &with_ipc);
+         group->opened_with_ipc[0] = with_ipc;
+         group->d_root = group->peer_blocks[0];
+      }
+   });
+}
+
+int silo_gpu_sharded_query_enqueue(silo_gpu_table* table, const silo_filter_program* program, void* cuda_stream) {
+   return guarded([&] {
+      require(table != nullptr && program != nullptr, "silo_gpu_sharded_query_enqueue: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      ShardGroup* group = table->shard;
+      require(group != nullptr && group->d_root != nullptr, "silo_gpu_sharded_query_enqueue: the table is not connected to a shard group");
+      require(table->n_chunks > 0, "silo_gpu_sharded_query_enqueue: a shard must hold at least one chunk");
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      cudaStream_t stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : table->ctx->stream;
+      const uint32_t slot = static_cast<uint32_t>(group->queries_enqueued % SHARD_SLOTS);
+      const uint32_t generation = static_cast<uint32_t>(group->queries_enqueued / SHARD_SLOTS) + 1;
+      ShardBlockHeader* root_header = reinterpret_cast<ShardBlockHeader*>(group->d_root);
+      ShardPush push;
+      push.root_rows = group->rootRows(slot, group->rank);
+      push.root_arrivals = &root_header->arrivals[slot];
+      push.root_cardinality = &root_header->cardinality[slot][group->rank];
+      push.root_error = &root_header->error[slot][group->rank];
+      push.released = &reinterpret_cast<ShardBlockHeader*>(group->d_local)->released[slot];
+      push.wait_generation = generation - 1;
+      push.valid_mask = group->valid_mask;
+      const bool trivially_full = program->n_instrs == 1 && program->instrs != nullptr && program->instrs[0].opcode == SILO_OP_PUSH_FULL;
+      if (trivially_full) {
+         push.use_fixed_cardinality = 1;
+         push.fixed_cardinality = table->n_rows;
+         enqueueMutationCounts(table, group->column, nullptr, table->d_counts, stream, nullptr, false, false, &push);
+      } else {
+         StagedQuery staged;
+         stageQueryLocked(table, program, &staged, group->column, table->d_counts);
+         push.filter_scalars = table->query_filter->d_cardinality;
+         enqueueStagedQuery(table, staged, stream);
+         enqueueMutationCounts(table, group->column, table->query_filter, table->d_counts, stream, nullptr, false, true, &push);
+      }
+      group->queries_enqueued++;
+   });
+}
+
+static void enqueueShardCollect(silo_gpu_table* table, double min_proportion, bool with_hits, void* d_summed_counts, cudaStream_t stream) {
+   ShardGroup* group = table->shard;
+   require(group != nullptr && group->rank == 0 && group->d_peer_table != nullptr, "sharded collect: only the connected root (rank 0) collects");
+   require(group->queries_collected < group->queries_enqueued, "sharded collect: no enqueued query is waiting");
+   const HostColumn& host = *table->columns[static_cast<size_t>(group->column)];
+   HitRequest request;
+   request.valid_mask = group->valid_mask;
+   request.min_proportion = min_proportion;
+   if (with_hits) {
+      require(host.dev.global_reference != nullptr, "sharded collect: call silo_gpu_column_set_reference first");
+      ensureHitsCapacity(table, host, group->valid_mask, stream);
+      request.hits = table->h_hits_pinned;
+      request.capacity = static_cast<uint32_t>(table->hits_capacity);
+   }
+   ShardCollect collect;
+   collect.slot = static_cast<uint32_t>(group->queries_collected % SHARD_SLOTS);
+   collect.generation = static_cast<uint32_t>(group->queries_collected / SHARD_SLOTS) + 1;
+   collect.rows = group->rootRows(collect.slot, 0);
+   collect.header = reinterpret_cast<ShardBlockHeader*>(group->d_local);
+   collect.peers = group->d_peer_table;
+   collect.world = static_cast<uint32_t>(group->world);
+   collect.n_valid = group->n_valid;
+   collect.summed_out = static_cast<uint32_t*>(d_summed_counts);
+   shardCollectKernel<<<(host.dev.genome_length + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, stream>>>(host.dev, collect, group->d_collect_state, request);
+   SILO_CUDA_CHECK(cudaGetLastError());
+   table->stats.kernel_launches++;
+   group->queries_collected++;
+}
+
+int silo_gpu_sharded_collect_async(silo_gpu_table* table, void* d_summed_counts, void* cuda_stream) {
+   return guarded([&] {
+      require(table != nullptr, "silo_gpu_sharded_collect_async: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      cudaStream_t stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : table->ctx->stream;
+      enqueueShardCollect(table, 0.0, false, d_summed_counts, stream);
+   });
+}
+
+int silo_gpu_sharded_collect(
+   silo_gpu_table* table,
+   double min_proportion,
+   void* d_summed_counts,
+   void* cuda_stream,
+   const silo_mutation_hit** hits,
+   uint64_t* n_hits,
+   uint64_t* cardinality
+) {
+   return guarded([&] {
+      require(table != nullptr && hits != nullptr && n_hits != nullptr, "silo_gpu_sharded_collect: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      cudaStream_t stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : table->ctx->stream;
+      enqueueShardCollect(table, min_proportion, true, d_summed_counts, stream);
+      SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+      const silo_mutation_hit header = table->h_hits_pinned[0];
+      if (header.symbol == 2) {
+         throw ApiError(SILO_E_CUDA, "sharded query: a rank of the shard group did not deliver its counts in time");
+      }
+      if (header.symbol != 0) {
+         throw ApiError(SILO_E_OUT_OF_LAYOUT, "a leaf bitmap holds row ids outside the row layout");
+      }
+      const uint64_t count = std::min<uint64_t>(header.position, table->hits_capacity);
+      sortHits(table->h_hits_pinned + 1, count);
+      *hits = table->h_hits_pinned + 1;
+      *n_hits = count;
+      if (cardinality != nullptr) {
+         *cardinality = header.count | (static_cast<unsigned long long>(header.total) << 32);
+      }
+   });
+}
+
+void silo_gpu_shard_group_free(silo_gpu_table* table) {
+   if (table == nullptr) {
+      return;
+   }
+   std::lock_guard<std::mutex> lock(table->mutex);
+   cudaSetDevice(table->ctx->device);
+   freeShardGroup(table);
 }
 
 int silo_gpu_query_mutation_counts(

@@ -273,6 +273,7 @@ void silo_gpu_table_free(silo_gpu_table* table) {
    dropQueryGraphsLocked(table);
    cudaFree(table->d_staging_fixed);
    cudaFree(table->d_sweep_counters);
+   freeShardGroup(table);
    if (table->query_filter != nullptr) {
       cudaFree(table->query_filter->d_words);
       delete table->query_filter;

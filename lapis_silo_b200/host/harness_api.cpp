@@ -489,6 +489,57 @@ int silo_host_mutations_collect_packed(
    });
 }
 
+int silo_host_shard_group_create(silo_host_table* table, const char* column, int rank, int world, void* handle_out) {
+   return guarded([&] {
+      const std::vector<uint8_t> handle = createShardGroup(*table->table, column, rank, world);
+      std::memcpy(handle_out, handle.data(), handle.size());
+   });
+}
+
+int silo_host_shard_group_connect(silo_host_table* table, const void* handles, uint64_t handles_bytes) {
+   return guarded([&] {
+      const auto* bytes = static_cast<const uint8_t*>(handles);
+      connectShardGroup(*table->table, std::vector<uint8_t>(bytes, bytes + handles_bytes));
+   });
+}
+
+int silo_host_sharded_enqueue(silo_host_table* table, const char* expression, const char* column, void* cuda_stream) {
+   return guarded([&] {
+      const MutationsNode node(*table->table, parseOrTrue(expression), {std::string(column)}, 0.0);
+      node.enqueueSharded(cuda_stream);
+   });
+}
+
+int silo_host_sharded_collect_packed(
+   silo_host_table* table,
+   const char* column,
+   double min_proportion,
+   void* d_summed_counts,
+   void* cuda_stream,
+   void* buffer,
+   uint64_t capacity,
+   uint64_t* n_rows,
+   uint32_t* n_names,
+   uint64_t* needed_bytes,
+   uint64_t* cardinality
+) {
+   return guarded([&] {
+      g_pending_rows.reset();
+      const MutationsNode node(*table->table, nullptr, {std::string(column)}, min_proportion);
+      auto owned = std::make_unique<silo_host_rows>();
+      owned->rows = node.collectSharded(d_summed_counts, cuda_stream, cardinality);
+      owned->indexNames();
+      *n_rows = owned->rows.size();
+      *n_names = static_cast<uint32_t>(owned->names.size());
+      *needed_bytes = packedBytes(*owned);
+      if (*needed_bytes <= capacity) {
+         packRows(*owned, static_cast<uint8_t*>(buffer));
+      } else {
+         g_pending_rows = std::move(owned);
+      }
+   });
+}
+
 int silo_host_packed_fetch(void* buffer, uint64_t capacity) {
    return guarded([&] {
       if (g_pending_rows == nullptr || packedBytes(*g_pending_rows) > capacity) {

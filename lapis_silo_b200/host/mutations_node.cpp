@@ -241,6 +241,39 @@ std::vector<MutationRow> MutationsNode::collectRows(const void* d_summed_counts,
    return rows;
 }
 
+void MutationsNode::enqueueSharded(void* cuda_stream) const {
+   const ExpressionPtr rewritten = filter->rewrite(table, AmbiguityMode::NONE);  // computeFilter, compute_filter.cpp:14-21
+   const std::unique_ptr<Operator> compiled = rewritten->compile(table);
+   ProgramBuilder builder;
+   const silo_filter_program program = compiled->lowerProgram(table, builder);
+   throwOnDeviceError(silo_gpu_sharded_query_enqueue(table.deviceTable(), &program, cuda_stream));
+}
+
+std::vector<MutationRow> MutationsNode::collectSharded(void* d_summed_counts, void* cuda_stream, uint64_t* cardinality) const {
+   const SequenceColumnInfo& column = singleColumn(*this);
+   const silo_mutation_hit* hits = nullptr;
+   uint64_t n_hits = 0;
+   throwOnDeviceError(silo_gpu_sharded_collect(table.deviceTable(), min_proportion, d_summed_counts, cuda_stream, &hits, &n_hits, cardinality));
+   std::vector<MutationRow> rows;
+   appendRowsFromHits(column, hits, n_hits, rows);
+   return rows;
+}
+
+std::vector<uint8_t> createShardGroup(const Table& table, const std::string& sequence_column, int rank, int world) {
+   const SequenceColumnInfo* found = table.findColumn(sequence_column);
+   if (found == nullptr) {
+      throw IllegalQueryException("Database does not contain the Sequence with name: '" + sequence_column + "'");
+   }
+   const SequenceColumnInfo& column = *found;
+   std::vector<uint8_t> handle(SILO_SHARD_HANDLE_BYTES, 0);
+   throwOnDeviceError(silo_gpu_shard_group_init(table.deviceTable(), column.device_column, validSymbolMask(*column.alphabet), rank, world, handle.data()));
+   return handle;
+}
+
+void connectShardGroup(const Table& table, const std::vector<uint8_t>& handles_of_all_ranks) {
+   throwOnDeviceError(silo_gpu_shard_group_connect(table.deviceTable(), handles_of_all_ranks.data()));
+}
+
 uint64_t countFilter(const Table& table, const ScalarExpression& filter) {
    return computeFilter(filter, table).cardinality();
 }

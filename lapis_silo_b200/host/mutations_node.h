@@ -81,7 +81,20 @@ class MutationsNode {
    // One rank, after the counts of all ranks were summed on the same stream: the output pass over the summed
    // counts; returns the rows and the number of this shard's rows that passed the filter.
    [[nodiscard]] std::vector<MutationRow> collectRows(const void* d_summed_counts, void* cuda_stream, uint64_t* shard_cardinality) const;
+
+   // The same query through the shard group of the table (createShardGroup / connectShardGroup): every rank enqueues,
+   // the ranks' rows travel to rank 0 inside the finalize kernels; rank 0 collects the rows of the whole table and
+   // the number of rows of ALL shards that passed the filter.
+   void enqueueSharded(void* cuda_stream) const;
+   [[nodiscard]] std::vector<MutationRow> collectSharded(void* d_summed_counts, void* cuda_stream, uint64_t* cardinality) const;
 };
+
+// The partition scheduler of a row-partitioned table: this process holds one shard. joinShardGroup is
+// called once per table and column with every rank's handle exchanged in between (any transport); afterwards
+// MutationsNode::enqueueSharded on every rank and ::collectSharded on rank 0 answer one Mutations query with no
+// collective kernel and one host synchronisation, on rank 0 only (include/silo_b200.h, silo_gpu_shard_group_*).
+std::vector<uint8_t> createShardGroup(const Table& table, const std::string& sequence_column, int rank, int world);
+void connectShardGroup(const Table& table, const std::vector<uint8_t>& handles_of_all_ranks);
 
 // CountFilterNode: `filter(...).groupBy({count:=count()})`
 uint64_t countFilter(const Table& table, const ScalarExpression& filter);

@@ -37,7 +37,9 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_filter_lower_timed", "silo_host_filter_to_string", "silo_host_filter_program_bitmap",
     "silo_host_archive_read", "silo_host_archive_free", "silo_host_archive_column", "silo_host_archive_column_info",
     "silo_host_archive_chunk_sizes", "silo_host_archive_column_shard", "silo_host_table_load_archive", "silo_host_roaring_runs",
+    "silo_host_shard_group_create", "silo_host_shard_group_connect", "silo_host_sharded_enqueue", "silo_host_sharded_collect_packed",
 ]
+SHARD_HANDLE_BYTES = 128  # SILO_SHARD_HANDLE_BYTES
 
 NUCLEOTIDE = 0
 AMINO_ACID = 1
@@ -94,6 +96,12 @@ def lib() -> C.CDLL:
         L.silo_host_packed_fetch.argtypes = [vp, C.c_uint64]
         L.silo_host_mutations_enqueue.argtypes = [vp, C.c_char_p, C.c_char_p, vp, vp]
         L.silo_host_mutations_collect_packed.argtypes = [
+            vp, C.c_char_p, C.c_double, vp, vp, vp, C.c_uint64,
+            C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.silo_host_shard_group_create.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_char_p]
+        L.silo_host_shard_group_connect.argtypes = [vp, C.c_char_p, C.c_uint64]
+        L.silo_host_sharded_enqueue.argtypes = [vp, C.c_char_p, C.c_char_p, vp]
+        L.silo_host_sharded_collect_packed.argtypes = [
             vp, C.c_char_p, C.c_double, vp, vp, vp, C.c_uint64,
             C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.silo_host_mutation_rows_from_counts.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint32), C.c_double]
@@ -541,6 +549,33 @@ class HostTable:
         cardinality = C.c_uint64()
         _check(lib().silo_host_mutations_collect_packed(
             self._h, column.encode(), min_proportion, d_summed_counts_ptr, stream_ptr,
+            self._packed.ctypes.data, self._packed.nbytes, n_rows, n_names, needed, cardinality))
+        if needed.value > self._packed.nbytes:
+            self._packed = np.empty(int(needed.value) * 2, dtype=np.uint8)
+            _check(lib().silo_host_packed_fetch(self._packed.ctypes.data, self._packed.nbytes))
+        return _unpack_record_batch(self._packed[:needed.value].copy(), int(n_rows.value), int(n_names.value)), int(cardinality.value)
+
+    def shard_group_create(self, column: str, rank: int, world: int) -> bytes:
+        """This table as rank `rank` of a row-partitioned table of `world` shards: returns this rank's handle
+        (SHARD_HANDLE_BYTES), to be exchanged with all ranks (silo_gpu_shard_group_init)."""
+        handle = C.create_string_buffer(SHARD_HANDLE_BYTES)
+        _check(lib().silo_host_shard_group_create(self._h, column.encode(), rank, world, handle))
+        return handle.raw
+
+    def shard_group_connect(self, handles_by_rank: Sequence[bytes]) -> None:
+        joined = b"".join(handles_by_rank)
+        _check(lib().silo_host_shard_group_connect(self._h, joined, len(joined)))
+
+    def sharded_enqueue(self, column: str, expression: Optional[str], stream_ptr: int) -> None:
+        """Every rank: parse + compile against this shard, filter + counts + this rank's rows to rank 0; enqueue only."""
+        _check(lib().silo_host_sharded_enqueue(self._h, expression.encode() if expression is not None else None, column.encode(), stream_ptr))
+
+    def sharded_collect(self, column: str, min_proportion: float, stream_ptr: int, d_summed_counts_ptr: int = 0) -> tuple[dict, int]:
+        """Rank 0: the rows of the whole table (columns as mutations_columns) and the filter cardinality over all shards."""
+        n_rows, n_names, needed = self._packed_out
+        cardinality = C.c_uint64()
+        _check(lib().silo_host_sharded_collect_packed(
+            self._h, column.encode(), min_proportion, d_summed_counts_ptr or None, stream_ptr,
             self._packed.ctypes.data, self._packed.nbytes, n_rows, n_names, needed, cardinality))
         if needed.value > self._packed.nbytes:
             self._packed = np.empty(int(needed.value) * 2, dtype=np.uint8)

@@ -441,6 +441,37 @@ def test_synthetic_shards_sum_to_the_whole(ctx):
             assert sum(cardinalities) == whole_filter.cardinality
             assert cardinalities == [p[1].cardinality for p in interleaved]
 
+    # The same through the library's own scheduler (silo_gpu_shard_group_*): no collective, the finalize kernel of
+    # every shard stores its rows into the root's gather area, the root's collect kernel sums them and runs the
+    # output pass. Three shards of one process on one device and stream; more queries than gather slots, the
+    # unfiltered action in between (stored cardinalities only), the summed counts checked too.
+    handles = [table.shard_group_create("main", rank, 3) for rank, (table, _, _, _) in enumerate(interleaved)]
+    for table, _, _, _ in interleaved:
+        table.shard_group_connect(handles)
+    root = interleaved[0][0]
+    with torch.cuda.stream(stream):
+        summed = torch.zeros(16 * 1500, dtype=torch.int32, device="cuda")
+        for repeat, (filtered, min_proportion) in enumerate([(True, 0.05), (True, 0.0), (False, 0.05), (True, 0.3), (False, 0.0), (True, 0.05), (True, 0.5)]):
+            for rank, (table, _, _, _) in enumerate(interleaved):
+                first, n, stride = host_api.interleaved_shard(len(sizes), 3, rank)
+                text = f"(and {host_api.date_ranges_expression(total_rows, 1095, 200, 800, first, n, stride)} (bitmap lineage))"
+                table.sharded_enqueue("main", text if filtered else None, stream.cuda_stream)
+            columns, cardinality = root.sharded_collect("main", min_proportion, stream.cuda_stream, summed.data_ptr())
+            assert host_api.rows_from_columns(columns) == oracle_table.mutations("main", expression if filtered else None, min_proportion)
+            assert cardinality == (whole_filter.cardinality if filtered else total_rows)
+            want = whole_counts if filtered else whole_full
+            np.testing.assert_array_equal(summed.cpu().numpy().view(np.uint32).reshape(16, 1500)[:5], want[:5])
+        # two queries in flight before the root collects (ranks run ahead of the root)
+        for _ in range(2):
+            for rank, (table, _, _, _) in enumerate(interleaved):
+                first, n, stride = host_api.interleaved_shard(len(sizes), 3, rank)
+                text = f"(and {host_api.date_ranges_expression(total_rows, 1095, 200, 800, first, n, stride)} (bitmap lineage))"
+                table.sharded_enqueue("main", text, stream.cuda_stream)
+        for _ in range(2):
+            columns, cardinality = root.sharded_collect("main", 0.05, stream.cuda_stream)
+            assert host_api.rows_from_columns(columns) == oracle_table.mutations("main", expression, 0.05)
+            assert cardinality == whole_filter.cardinality
+
 
 def test_baseline_sizes_size_independent_properties(ctx):
     """BASELINE.json configs 2 and 3 at full size (10 M rows x 29,903 nt; the oracle would need minutes per
