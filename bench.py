@@ -324,11 +324,22 @@ def run_ours(args):
     pinned = torch.zeros(N_SYMBOLS * GENOME_LENGTH, dtype=torch.int32).pin_memory()
     prepared = table.prepare(expression)
 
-    # N > 1: the all-reduce of query i runs on its own stream beside the kernels of query i + 1 (two
-    # count buffers), the way a server overlaps consecutive independent queries; every all-reduce is
-    # inside the timed region (the launching stream waits for the last two before the end event).
-    comm_stream = torch.cuda.Stream() if n_gpus > 1 else None
-    count_buffers = [counts, torch.zeros_like(counts)] if n_gpus > 1 else [counts]
+    # N > 1, default (--reduce peer): the library's own partition scheduler (silo_gpu_shard_group_*): the finalize kernel
+    # of every rank stores its rows of the valid mutation symbols into rank 0's gather area over NVLink, rank 0's
+    # collect kernel sums them -- no collective kernel, nothing but this repository's kernels on the stream. The
+    # handles of the gather areas travel through torch.distributed once, at set-up.
+    # --reduce nccl: the per-rank counts are all-reduced with NCCL instead; the all-reduce of query i runs on its own
+    # stream beside the kernels of query i + 1 (two count buffers). Every reduction is inside the timed region.
+    use_peer = n_gpus > 1 and args.reduce == "peer"
+    if use_peer:
+        handles = [None] * n_gpus
+        dist.all_gather_object(handles, table.shard_group_create("main", rank, n_gpus))
+        table.shard_group_connect(handles)
+        dist.barrier()
+    collect_stream = torch.cuda.Stream() if use_peer and rank == 0 else None
+    pending_collects = []
+    comm_stream = torch.cuda.Stream() if n_gpus > 1 and not use_peer else None
+    count_buffers = [counts, torch.zeros_like(counts)] if n_gpus > 1 and not use_peer else [counts]
     kernels_done = [torch.cuda.Event() for _ in count_buffers]
     reduced = [torch.cuda.Event() for _ in count_buffers]
     issued = [0]
@@ -336,6 +347,20 @@ def run_ours(args):
     def device_step():
         buffer = issued[0] % len(count_buffers)
         issued[0] += 1
+        if use_peer:
+            prepared.run_sharded_async(stream.cuda_stream)  # filter + counts kernels; the finalize kernel sends the rows to rank 0
+            if rank == 0:
+                # rank 0's collect kernel (waits for all ranks on the device, sums, hands the gather slot back) runs on a
+                # second stream beside the kernels of the next query -- its 117 small blocks fit next to the container kernel
+                pushed = torch.cuda.Event()
+                pushed.record(stream)
+                collect_stream.wait_event(pushed)
+                table.sharded_collect_async(collect_stream.cuda_stream, counts.data_ptr())
+                collected = torch.cuda.Event()
+                collected.record(collect_stream)
+                pending_collects.append(collected)
+                del pending_collects[:-2]
+            return
         if n_gpus > 1:
             stream.wait_event(reduced[buffer])  # the all-reduce that used this buffer two queries ago
         prepared.run_counts_async(0, count_buffers[buffer].data_ptr(), stream.cuda_stream)  # filter + counts kernels
@@ -349,7 +374,9 @@ def run_ours(args):
                 reduced[buffer].record(comm_stream)
 
     def join_reductions():
-        for event in reduced if n_gpus > 1 else []:
+        for event in reduced if n_gpus > 1 and not use_peer else []:
+            stream.wait_event(event)
+        for event in pending_collects:
             stream.wait_event(event)
 
     def barrier():
@@ -389,10 +416,13 @@ def run_ours(args):
     graph = None
     if use_graph:
         graph = torch.cuda.CUDAGraph()
-        if n_gpus == 1:
+        if n_gpus == 1 or use_peer:
+            del pending_collects[:]  # (events of the eager steps must not be waited for inside the capture)
             with torch.cuda.graph(graph, stream=stream):
                 for _ in range(args.steps):
                     device_step()
+                join_reductions()  # the collect stream joins the capture's origin stream
+            del pending_collects[:]
         else:
             # N > 1: the same two-stream pipeline, with events that live inside the capture (a captured
             # stream may only wait for work of the same capture) and the all-reduce stream joined at the end
@@ -435,7 +465,10 @@ def run_ours(args):
     join_reductions()
     end.record(stream)
     barrier()
-    device_ms = max_over_ranks(begin.elapsed_time(end))
+    own_device_ms = begin.elapsed_time(end)
+    device_ms = max_over_ranks(own_device_ms)
+    if n_gpus > 1:
+        log(f"[bench] rank {rank}: {own_device_ms / args.steps * 1000:.1f} us per step on this rank's stream")
     if graph is not None:
         table.stats()  # reset the window: the eager pass below is what the per-kernel events describe
         for _ in range(args.steps):
@@ -462,14 +495,21 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["sampled_over"] = "the timed region and 0.4 s of the same step right after it (nvidia-smi -lms 100)"
-    cardinality = sum_over_ranks(prepared.cardinality())
+    if use_peer:  # (a sharded run forwards the filter's scalars to rank 0 and resets them: evaluate the filter once more)
+        shard_filter = table.filter(expression)
+        cardinality = sum_over_ranks(shard_filter.cardinality)
+        shard_filter.close()
+    else:
+        cardinality = sum_over_ranks(prepared.cardinality())
     total_containers = sum_over_ranks(n_containers)
     total_payload_bytes = sum_over_ranks(payload_bytes)
     last_buffer = count_buffers[(issued[0] - 1) % len(count_buffers)]
-    if n_gpus > 1:  # outside the timed region: the other symbols' rows too, for the property check below
+    if n_gpus > 1 and not use_peer:  # outside the timed region: the other symbols' rows too, for the property check below
         dist.all_reduce(last_buffer[valid_values:])
         torch.cuda.synchronize()
     device_counts = last_buffer.cpu().numpy().view(np.uint32).reshape(N_SYMBOLS, GENOME_LENGTH).copy()
+    if use_peer:  # rank 0 holds the summed rows of the valid symbols; the synthetic table has no other symbol
+        device_counts[VALID_MUTATION_SYMBOLS:] = 0
     value = cardinality * GENOME_LENGTH * args.steps / (device_ms / 1000.0)
 
     # ---- e2e: host buffers in, host rows out, every step ----
@@ -481,6 +521,13 @@ def run_ours(args):
         # query against its shard and enqueues program H2D + filter + counts, the counts of the valid symbols
         # are all-reduced on the same stream, rank 0 runs the output pass over the sums on the device and
         # gets the emitted tuples back; one host synchronisation per rank and step.
+        if use_peer:
+            # the library's scheduler: every rank enqueues (no host synchronisation on ranks > 0: a rank whose gather slot
+            # has not been handed back waits on the device), rank 0 collects the rows of the whole table
+            if rank == 0:
+                return table.sharded_query("main", expression, MIN_PROPORTION)[0]  # enqueue + collect: one graph launch, one sync
+            table.sharded_enqueue("main", expression, stream.cuda_stream)
+            return None
         table.mutations_enqueue("main", expression, counts.data_ptr(), stream.cuda_stream)
         dist.all_reduce(counts[:valid_values])  # rows of the 5 valid symbols: all that the output pass reads
         if rank == 0:
@@ -502,7 +549,8 @@ def run_ours(args):
 
     # size-independent parity properties at full size (tests/ hold the bit-exact oracle comparisons)
     column_sums = device_counts.sum(axis=0, dtype=np.uint64)
-    assert (column_sums == cardinality).all(), "per-position symbol counts (all-reduced) must add up to the global |filter|"
+    if rank == 0 or not use_peer:
+        assert (column_sums == cardinality).all(), "per-position symbol counts (summed over the ranks) must add up to the global |filter|"
     if rank == 0:
         rows = host_api.rows_from_columns(rows)
         # (device_counts: the all-reduced counts of the device-resident loop; thresholded on the host here)
@@ -530,8 +578,10 @@ def run_ours(args):
             "chunks_per_gpu": n_chunks, "containers_per_gpu": n_containers, "payload_gb_per_gpu": round(payload_bytes / 1e9, 3),
             "launch": f"one CUDA graph holding the {args.steps} steps of the timed region" + (", all-reduces included" if n_gpus > 1 else "")
             if used_graph else "eager launches",
-            "parallelism": f"interleaved chunk shards (chunk c on rank c % {n_gpus}), "
-            "NCCL allreduce of the u32 counts" if n_gpus > 1 else "single GPU",
+            "parallelism": (f"interleaved chunk shards (chunk c on rank c % {n_gpus}), " + (
+                "the library's shard group: every rank's finalize kernel stores its rows into rank 0's gather area over NVLink, "
+                "rank 0's collect kernel sums them (no collective kernel)" if use_peer else "NCCL allreduce of the u32 counts"))
+            if n_gpus > 1 else "single GPU",
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
@@ -595,6 +645,8 @@ def main():
     parser.add_argument("--reference-step-seconds", type=float, default=2.0)
     parser.add_argument("--skip-cpu-baseline", action="store_true")
     parser.add_argument("--eager", action="store_true", help="launch the timed steps one by one instead of as one CUDA graph")
+    parser.add_argument("--reduce", choices=["peer", "nccl"], default="peer",
+                        help="N > 1: how the per-rank counts meet -- the library's shard group (peer-memory stores) or NCCL all-reduce")
     parser.add_argument("--traffic-bytes", type=int, default=None,
                         help="dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture")
     args = parser.parse_args()

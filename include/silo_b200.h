@@ -375,6 +375,20 @@ int silo_gpu_sharded_collect(
    uint64_t* n_hits,
    uint64_t* cardinality
 );
+/* the root's two calls in one (enqueue + collect: one launch -- a replayed CUDA graph per query shape --, one
+ * synchronisation), on the table's own stream; the other ranks call silo_gpu_sharded_query_enqueue */
+int silo_gpu_sharded_query_hits(
+   silo_gpu_table* table,
+   const silo_filter_program* program,
+   double min_proportion,
+   void* d_summed_counts,
+   const silo_mutation_hit** hits,
+   uint64_t* n_hits,
+   uint64_t* cardinality
+);
+/* every rank: like silo_gpu_sharded_query_enqueue for a program that silo_gpu_program_prepare made device resident
+ * (nothing is uploaded; replayable inside a captured CUDA graph: slot and generation live in device memory) */
+int silo_gpu_program_run_sharded_async(silo_gpu_program* prepared, void* cuda_stream);
 /* the same without the output pass and without synchronising (device-resident pipelines) */
 int silo_gpu_sharded_collect_async(silo_gpu_table* table, void* d_summed_counts, void* cuda_stream);
 void silo_gpu_shard_group_free(silo_gpu_table* table);

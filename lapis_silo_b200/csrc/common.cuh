@@ -252,6 +252,10 @@ struct silo_gpu_table {
    uint8_t* h_staging_pinned = nullptr;  // program upload staging (grow-only)
    size_t staging_capacity = 0;
    cudaEvent_t ev_free_fence = nullptr;  // orders stream-ordered frees after foreign-stream users
+   // recorded behind the H2D copy of a staged query that the caller does not synchronise (the _async and sharded
+   // entries): the next staging waits for it before it overwrites the pinned buffer
+   cudaEvent_t ev_staging_copied = nullptr;
+   bool staging_copy_pending = false;
    // the coverage kernel runs beside the container kernel on an auxiliary stream (fork / join)
    cudaStream_t aux_stream = nullptr;
    cudaEvent_t ev_fork = nullptr;
@@ -320,6 +324,8 @@ void stageQueryLocked(silo_gpu_table* table, const silo_filter_program* program,
 void enqueueStagedQuery(silo_gpu_table* table, const StagedQuery& staged, cudaStream_t stream, bool scalars_are_zero = true);
 void dropQueryGraphsLocked(silo_gpu_table* table);
 void freeShardGroup(silo_gpu_table* table);  // mutations.cu
+int shardGroupColumnLocked(const silo_gpu_table* table);
+void enqueuePreparedShardedLocked(silo_gpu_table* table, const silo_gpu_filter* filter, cudaStream_t stream);
 // mutations.cu: coverage + container + finalize kernels for a filter whose interpreter launch already zeroed
 // d_counts and built the work list (caller holds table->mutex); records the per-call timing events
 void enqueuePreparedCountsLocked(silo_gpu_table* table, int column, const silo_gpu_filter* filter, uint32_t* d_counts, cudaStream_t stream);

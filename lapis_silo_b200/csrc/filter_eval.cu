@@ -923,8 +923,13 @@ static void stageProgram(
    const size_t off_payload = reserve(total_payload + 16);  // the kernel reads whole 16-byte vectors
    const size_t staging_bytes = (cursor + 15) / 16 * 16;
 
-   // the pinned buffer is reused by the next call on this table, which is safe because every caller
-   // synchronises the stream before it returns
+   // The pinned buffer is reused by the next call on this table. The synchronous callers synchronise the stream before
+   // they return; behind the copy of a call that does not (the _async and sharded entries) an event is recorded, and
+   // the next staging waits for it here -- the host runs at most one query ahead of the copies.
+   if (table->staging_copy_pending) {
+      SILO_CUDA_CHECK(cudaEventSynchronize(table->ev_staging_copied));
+      table->staging_copy_pending = false;
+   }
    if (staging_bytes > table->staging_capacity) {
       dropQueryGraphsLocked(table);  // their copy nodes read the old buffers
       SILO_CUDA_CHECK(cudaStreamSynchronize(table->ctx->stream));
@@ -1161,6 +1166,11 @@ void enqueueStagedQuery(silo_gpu_table* table, const StagedQuery& staged, cudaSt
    EvalParams params{};
    std::memcpy(&params, staged.params, sizeof(params));
    SILO_CUDA_CHECK(cudaMemcpyAsync(table->d_staging_fixed, table->h_staging_pinned, staged.staged_bytes, cudaMemcpyHostToDevice, stream));
+   cudaStreamCaptureStatus capture_status = cudaStreamCaptureStatusNone;
+   if (cudaStreamIsCapturing(stream, &capture_status) == cudaSuccess && capture_status == cudaStreamCaptureStatusNone) {
+      SILO_CUDA_CHECK(cudaEventRecord(table->ev_staging_copied, stream));
+      table->staging_copy_pending = true;
+   }
    launchProgram(table, params, table->query_filter, stream, scalars_are_zero);
 }
 
@@ -1276,6 +1286,30 @@ int silo_gpu_program_run_counts_async(silo_gpu_program* prepared, int column, vo
       }
       launchProgram(table, params, prepared->filter, stream);
       enqueuePreparedCountsLocked(table, column, prepared->filter, static_cast<uint32_t*>(d_counts), stream);
+   });
+}
+
+int silo_gpu_program_run_sharded_async(silo_gpu_program* prepared, void* cuda_stream) {
+   return guarded([&] {
+      require(prepared != nullptr, "silo_gpu_program_run_sharded_async: NULL argument");
+      silo_gpu_table* table = prepared->table;
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      const int column = shardGroupColumnLocked(table);
+      require(table->n_chunks > 0, "silo_gpu_program_run_sharded_async: a shard must hold at least one chunk");
+      cudaStream_t stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : table->ctx->stream;
+      EvalParams params = *prepared->params;
+      const HostColumn& host = *table->columns[static_cast<size_t>(column)];
+      if (host.dev.n_segments > 0) {
+         params.prepare_segments = host.dev.segments;
+         params.prepare_chunk_seg_begin = host.dev.chunk_seg_begin;
+         params.prepare_work_state = table->d_work_state;
+         params.prepare_work_items = table->d_work_items;
+      }
+      params.prepare_counts = table->d_counts;
+      params.prepare_counts_words = host.dev.n_symbols * host.dev.genome_length;
+      launchProgram(table, params, prepared->filter, stream);
+      enqueuePreparedShardedLocked(table, prepared->filter, stream);
    });
 }
 

@@ -791,16 +791,19 @@ struct ShardBlockHeader {  // the start of every rank's exported block
    uint32_t arrivals[SHARD_SLOTS];  // root only: ranks whose rows of a slot have landed, counted over all generations
    unsigned long long cardinality[SHARD_SLOTS][SHARD_MAX_WORLD];  // root only: the ranks' filter cardinalities
    uint32_t error[SHARD_SLOTS][SHARD_MAX_WORLD];                  // root only: the ranks' filter error flags
+   // Device-side query counters (local use): which slot and generation a launch works on is read from here, not from
+   // kernel parameters, so that a captured CUDA graph of sharded queries can be replayed.
+   uint32_t queries_pushed;     // sharded queries this rank's finalize kernels have completed
+   uint32_t queries_collected;  // root: queries its collect kernels have completed
 };
 constexpr size_t SHARD_HEADER_BYTES = (sizeof(ShardBlockHeader) + 255) / 256 * 256;
 
 struct ShardPush {  // what the finalize kernel of a sharded query needs (all zero: not sharded)
-   uint32_t* root_rows = nullptr;       // this rank's [n_valid][genome_length] area of the slot, in the root's memory
-   uint32_t* root_arrivals = nullptr;   // &root header.arrivals[slot]
-   unsigned long long* root_cardinality = nullptr;  // &root header.cardinality[slot][rank]
-   uint32_t* root_error = nullptr;
-   const uint32_t* released = nullptr;  // &own header.released[slot]
-   uint32_t wait_generation = 0;        // the slot may be written once released has reached this
+   uint8_t* root_block = nullptr;           // the root's block (header + gather area [slot][rank][n_valid][genome_length]) as mapped here
+   ShardBlockHeader* own_header = nullptr;  // this rank's block: released[], queries_pushed
+   uint32_t rank = 0;
+   uint32_t world = 0;
+   uint32_t n_valid = 0;
    uint32_t use_fixed_cardinality = 0;
    uint64_t valid_mask = 0;
    unsigned long long fixed_cardinality = 0;          // filter == all rows
@@ -865,8 +868,16 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    uint32_t valid_others = 0;  // the same sum over the valid mutation symbols only
    uint32_t candidates = 0;    // OR of the counts that could be emitted (valid, not the reference genome's symbol)
    if (p < genome_length) {
-      for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
-         const uint32_t value = symbol != reference_symbol ? counts[symbol * genome_length + p] : 0u;
+      // all the loads first (the loop below is unrolled over the 32 possible symbols): one trip to L2 instead of one per
+      // symbol -- as a loop over n_symbols with the load inside, the kernel was a chain of 16 dependent L2 latencies
+      uint32_t values[32];
+#pragma unroll
+      for (uint32_t symbol = 0; symbol < 32; ++symbol) {
+         values[symbol] = symbol < column.n_symbols && symbol != reference_symbol ? counts[symbol * genome_length + p] : 0u;
+      }
+#pragma unroll
+      for (uint32_t symbol = 0; symbol < 32; ++symbol) {
+         const uint32_t value = values[symbol];
          others += value;
          const uint32_t valid_value = ((request.valid_mask >> symbol) & 1ULL) != 0 ? value : 0u;
          valid_others += valid_value;
@@ -904,19 +915,27 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    if (p < genome_length) {
       counts[reference_symbol * genome_length + p] = reference_count;
    }
-   if (push.root_rows != nullptr) {
+   uint32_t shard_slot = 0;
+   if (push.root_block != nullptr) {
       // this rank's rows of the valid mutation symbols -> the root's gather area (coalesced stores over NVLink), once the
-      // root has released the slot's previous use
+      // root has released the slot's previous use. (Every block reads the query counter before it counts itself in
+      // below; the last block increments it after that.)
       __shared__ uint32_t slot_is_free;
+      __shared__ uint32_t query_index;
       if (threadIdx.x == 0) {
-         slot_is_free = waitForAtLeast(push.released, push.wait_generation) ? 1u : 0u;
+         query_index = *reinterpret_cast<volatile uint32_t*>(&push.own_header->queries_pushed);
+         const uint32_t generation = query_index / SHARD_SLOTS + 1;
+         slot_is_free = waitForAtLeast(&push.own_header->released[query_index % SHARD_SLOTS], generation - 1) ? 1u : 0u;
       }
       __syncthreads();
+      shard_slot = query_index % SHARD_SLOTS;
       if (slot_is_free != 0 && p < genome_length) {
+         uint32_t* const root_rows = reinterpret_cast<uint32_t*>(push.root_block + SHARD_HEADER_BYTES) +
+                                     (static_cast<size_t>(shard_slot) * push.world + push.rank) * push.n_valid * genome_length;
          uint32_t row = 0;
          for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
             if (((push.valid_mask >> symbol) & 1ULL) != 0) {
-               push.root_rows[row * genome_length + p] = symbol == reference_symbol ? reference_count : counts[symbol * genome_length + p];
+               root_rows[row * genome_length + p] = symbol == reference_symbol ? reference_count : counts[symbol * genome_length + p];
                ++row;
             }
          }
@@ -924,7 +943,8 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
       if (slot_is_free == 0 && threadIdx.x == 0) {
          atomicOr(&work_state[3], 0x80000000u);  // reported to the root as this rank's error below
       }
-      __threadfence_system();
+      // (made visible to the root by thread 0's system-scope fence behind the block barrier below: fences are
+      // cumulative, one round trip over NVLink per block instead of one per thread)
    }
    if (output_pass) {
       const bool reference_is_valid = ((request.valid_mask >> reference_symbol) & 1ULL) != 0;
@@ -955,7 +975,11 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    // the last block to get here clears the totals and the work-list state and writes the header.
    __syncthreads();
    if (threadIdx.x == 0) {
-      __threadfence();
+      if (push.root_block != nullptr) {
+         __threadfence_system();
+      } else {
+         __threadfence();
+      }
       const uint32_t finished = atomicAdd(&work_state[2], 1u);
       if (finished == gridDim.x - 1) {
          __threadfence();
@@ -974,8 +998,9 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
             }
             request.hits[0] = header;
          }
-         if (push.root_rows != nullptr) {
+         if (push.root_block != nullptr) {
             // every block's stores are out (each fenced before it counted itself in): cardinality, error flag, arrival
+            ShardBlockHeader* const root_header = reinterpret_cast<ShardBlockHeader*>(push.root_block);
             unsigned long long cardinality = push.fixed_cardinality;
             uint32_t error = (*reinterpret_cast<volatile uint32_t*>(&work_state[3]) & 0x80000000u) != 0 ? 2u : 0u;
             if (push.use_fixed_cardinality == 0) {
@@ -984,10 +1009,11 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
                push.filter_scalars[0] = 0;
                push.filter_scalars[2] = 0;
             }
-            *push.root_cardinality = cardinality;
-            *push.root_error = error;
+            root_header->cardinality[shard_slot][push.rank] = cardinality;
+            root_header->error[shard_slot][push.rank] = error;
+            push.own_header->queries_pushed = *reinterpret_cast<volatile uint32_t*>(&push.own_header->queries_pushed) + 1;
             __threadfence_system();
-            atomicAdd_system(push.root_arrivals, 1u);
+            atomicAdd_system(&root_header->arrivals[shard_slot], 1u);
          }
          work_state[0] = 0;  // the work list and its claim counter are empty between queries
          work_state[1] = 0;
@@ -1001,39 +1027,55 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
 // per position and valid symbol, runs the output pass of addMutationsToOutput (mutations_node.cpp:307-363) over the
 // sums (as mutationHitsKernel does), and hands the slot back to every rank.
 struct ShardCollect {
-   const uint32_t* rows = nullptr;  // the slot: [world][n_valid][genome_length]
-   ShardBlockHeader* header = nullptr;   // the root's own block
+   ShardBlockHeader* header = nullptr;   // the root's own block: header, then the gather area [slot][world][n_valid][genome_length]
    ShardBlockHeader* const* peers = nullptr;  // [world] every rank's block as mapped on the root
    uint32_t world = 0;
    uint32_t n_valid = 0;
-   uint32_t slot = 0;
-   uint32_t generation = 0;
    uint32_t* summed_out = nullptr;  // optional: [n_symbols][genome_length], the rows of the valid symbols are written
 };
 
-__global__ void __launch_bounds__(FIN_THREADS) shardCollectKernel(DevColumn column, ShardCollect collect, uint32_t* __restrict__ work_state, HitRequest request) {
+constexpr int COLLECT_THREADS = 128;  // x 64 registers: a block fits on an SM beside the container kernel
+__global__ void __launch_bounds__(COLLECT_THREADS, 8) shardCollectKernel(DevColumn column, ShardCollect collect, uint32_t* __restrict__ work_state, HitRequest request) {
    __shared__ uint32_t all_arrived;
+   __shared__ uint32_t query_index;
    const uint32_t genome_length = column.genome_length;
-   const uint32_t p = blockIdx.x * FIN_THREADS + threadIdx.x;
-   if (threadIdx.x == 0) {
-      all_arrived = waitForAtLeast(&collect.header->arrivals[collect.slot], collect.world * collect.generation) ? 1u : 0u;
+   const uint32_t p = blockIdx.x * COLLECT_THREADS + threadIdx.x;
+   if (threadIdx.x == 0) {  // (read before this block counts itself in below; the last block increments it after that)
+      query_index = *reinterpret_cast<volatile uint32_t*>(&collect.header->queries_collected);
+      all_arrived = waitForAtLeast(&collect.header->arrivals[query_index % SHARD_SLOTS], collect.world * (query_index / SHARD_SLOTS + 1)) ? 1u : 0u;
    }
    __syncthreads();
+   const uint32_t slot = query_index % SHARD_SLOTS;
+   const uint32_t generation = query_index / SHARD_SLOTS + 1;
+   const uint32_t* const rows = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(collect.header) + SHARD_HEADER_BYTES) +
+                                static_cast<size_t>(slot) * collect.world * collect.n_valid * genome_length;
    if (all_arrived != 0 && p < genome_length) {
       const uint32_t genome_symbol = request.hits != nullptr ? column.global_reference[p] : 0u;
       const size_t rank_stride = static_cast<size_t>(collect.n_valid) * genome_length;
-      uint32_t sums[32];
+      // (no per-symbol array: the kernel must stay at 32 registers so that its blocks fit on an SM beside the container
+      // kernel of the next query; the few positions that emit rows sum their symbols a second time)
+      auto sumOf = [&](uint32_t row) {  // (the loads of four ranks in flight together)
+         const uint32_t* const base = rows + row * genome_length + p;
+         uint32_t sum = 0;
+         uint32_t rank = 0;
+         for (; rank + 4 <= collect.world; rank += 4) {
+            const uint32_t a = base[rank * rank_stride];
+            const uint32_t b = base[(rank + 1) * rank_stride];
+            const uint32_t c = base[(rank + 2) * rank_stride];
+            const uint32_t d = base[(rank + 3) * rank_stride];
+            sum += a + b + c + d;
+         }
+         for (; rank < collect.world; ++rank) {
+            sum += base[rank * rank_stride];
+         }
+         return sum;
+      };
       uint32_t total = 0;
       uint32_t candidates = 0;
       uint32_t row = 0;
       for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
-         sums[symbol] = 0;
          if (((request.valid_mask >> symbol) & 1ULL) != 0) {
-            uint32_t sum = 0;
-            for (uint32_t rank = 0; rank < collect.world; ++rank) {
-               sum += collect.rows[rank * rank_stride + row * genome_length + p];
-            }
-            sums[symbol] = sum;
+            const uint32_t sum = sumOf(row);
             total += sum;
             candidates |= symbol != genome_symbol ? sum : 0u;
             if (collect.summed_out != nullptr) {
@@ -1045,14 +1087,20 @@ __global__ void __launch_bounds__(FIN_THREADS) shardCollectKernel(DevColumn colu
       if (request.hits != nullptr && total != 0 && candidates != 0) {
          const uint32_t threshold_count =
             request.min_proportion == 0 ? 0u : static_cast<uint32_t>(ceil(__dmul_rn(static_cast<double>(total), request.min_proportion)) - 1.0);
+         row = 0;
          for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
-            if (((request.valid_mask >> symbol) & 1ULL) == 0 || symbol == genome_symbol) {
+            if (((request.valid_mask >> symbol) & 1ULL) == 0) {
                continue;
             }
-            if (sums[symbol] > threshold_count) {
+            const uint32_t this_row = row++;
+            if (symbol == genome_symbol) {
+               continue;
+            }
+            const uint32_t sum = sumOf(this_row);
+            if (sum > threshold_count) {
                const uint32_t index = atomicAdd(&work_state[3], 1u);
                if (index < request.capacity) {
-                  request.hits[1 + index] = silo_mutation_hit{p, symbol, sums[symbol], total};
+                  request.hits[1 + index] = silo_mutation_hit{p, symbol, sum, total};
                }
             }
          }
@@ -1067,8 +1115,8 @@ __global__ void __launch_bounds__(FIN_THREADS) shardCollectKernel(DevColumn colu
          unsigned long long cardinality = 0;
          uint32_t error = all_arrived != 0 ? 0u : 2u;
          for (uint32_t rank = 0; rank < collect.world; ++rank) {
-            cardinality += *reinterpret_cast<volatile unsigned long long*>(&collect.header->cardinality[collect.slot][rank]);
-            error |= *reinterpret_cast<volatile uint32_t*>(&collect.header->error[collect.slot][rank]);
+            cardinality += *reinterpret_cast<volatile unsigned long long*>(&collect.header->cardinality[slot][rank]);
+            error |= *reinterpret_cast<volatile uint32_t*>(&collect.header->error[slot][rank]);
          }
          if (request.hits != nullptr) {
             request.hits[0] = silo_mutation_hit{
@@ -1076,10 +1124,11 @@ __global__ void __launch_bounds__(FIN_THREADS) shardCollectKernel(DevColumn colu
          }
          work_state[2] = 0;
          work_state[3] = 0;
+         collect.header->queries_collected = query_index + 1;
          // every block has read the slot: hand it back to the ranks
          __threadfence_system();
          for (uint32_t rank = 0; rank < collect.world; ++rank) {
-            storeReleaseSystem(&collect.peers[rank]->released[collect.slot], collect.generation);
+            storeReleaseSystem(&collect.peers[rank]->released[slot], generation);
          }
       }
    }
@@ -1150,7 +1199,9 @@ __global__ void __launch_bounds__(FIN_THREADS) mutationHitsKernel(
 // ---------------------------------------------------------------------------------------------
 
 // The compiled geometries of the container kernel: {consumer warps, pieces per warp and stage visit, ring stages}.
-// Variant 0 is the product; the others are kept for measurements (SILO_K1_VARIANT, read once per process).
+// Variant 5 is the product (31 x 2 x 3 at 56 registers: as fast as the 64-register build of variant 0, and a 256-thread
+// block of the coverage kernel or of the shard group's collect kernel still fits beside it on the SM); the others
+// are kept for measurements (SILO_K1_VARIANT, read once per process).
 constexpr K1Geometry K1_VARIANTS[] = {{31, 2, 3, 0}, {23, 2, 4, 1}, {20, 3, 3, 2}, {15, 4, 3, 3}, {31, 1, 6, 4}, {31, 2, 3, 5}};
 
 template <int W, int P, int STAGES, int MAXREG, int MODE>
@@ -1334,9 +1385,9 @@ void enqueueMutationCounts(
 const K1Geometry& k1Geometry() {
    static const K1Geometry geometry = [] {
       const char* flag = std::getenv("SILO_K1_VARIANT");
-      const int variant = flag != nullptr ? std::atoi(flag) : 0;
+      const int variant = flag != nullptr ? std::atoi(flag) : 5;
       constexpr int n_variants = static_cast<int>(sizeof(K1_VARIANTS) / sizeof(K1_VARIANTS[0]));
-      return K1_VARIANTS[variant >= 0 && variant < n_variants ? variant : 0];
+      return K1_VARIANTS[variant >= 0 && variant < n_variants ? variant : 5];
    }();
    return geometry;
 }
@@ -1344,6 +1395,9 @@ const K1Geometry& k1Geometry() {
 void enqueuePreparedCountsLocked(silo_gpu_table* table, int column, const silo_gpu_filter* filter, uint32_t* d_counts, cudaStream_t stream) {
    enqueueMutationCounts(table, column, filter, d_counts, stream, nullptr, true, true);
 }
+
+int shardGroupColumnLocked(const silo_gpu_table* table);
+void enqueuePreparedShardedLocked(silo_gpu_table* table, const silo_gpu_filter* filter, cudaStream_t stream);
 
 }  // namespace silo
 
@@ -1538,6 +1592,58 @@ static void sortHits(silo_mutation_hit* first, uint64_t count) {
    });
 }
 
+}  // extern "C"
+
+// The launch sequence of a fused query touches persistent buffers only, so it is the same for every query of one
+// SHAPE (`key`: every kernel parameter and copy size the enqueue bakes into nodes) and can be replayed as a CUDA graph.
+// A shape is captured the second time in a row it is seen; a few graphs are kept per table. Returns the graph to
+// launch, or nullptr (first sight, or graphs disabled): the caller then enqueues plainly.
+template <typename Enqueue>
+static cudaGraphExec_t queryGraphFor(silo_gpu_table* table, std::string key, cudaStream_t stream, Enqueue&& enqueueAll) {
+   if (!queryGraphsEnabled()) {
+      return nullptr;
+   }
+   cudaGraphExec_t replay = nullptr;
+   for (const silo_gpu_table::CachedGraph& cached : table->query_graphs) {
+      if (cached.key == key) {
+         replay = cached.exec;
+         break;
+      }
+   }
+   if (replay == nullptr && key == table->last_query_key) {
+      cudaGraph_t graph = nullptr;
+      SILO_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      try {
+         enqueueAll();
+      } catch (...) {
+         cudaStreamEndCapture(stream, &graph);
+         if (graph != nullptr) {
+            cudaGraphDestroy(graph);
+         }
+         cudaGetLastError();
+         throw;
+      }
+      SILO_CUDA_CHECK(cudaStreamEndCapture(stream, &graph));
+      cudaGraphExec_t exec = nullptr;
+      const cudaError_t instantiated = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      SILO_CUDA_CHECK(instantiated);
+      constexpr size_t MAX_QUERY_GRAPHS = 8;
+      if (table->query_graphs.size() < MAX_QUERY_GRAPHS) {
+         table->query_graphs.push_back({key, exec});
+      } else {
+         silo_gpu_table::CachedGraph& slot = table->query_graphs[table->next_graph_slot++ % MAX_QUERY_GRAPHS];
+         cudaGraphExecDestroy(slot.exec);
+         slot = {key, exec};
+      }
+      replay = exec;
+   }
+   table->last_query_key = std::move(key);
+   return replay;
+}
+
+extern "C" {
+
 int silo_gpu_query_mutation_counts_async(
    silo_gpu_table* table,
    const silo_filter_program* program,
@@ -1670,7 +1776,7 @@ int silo_gpu_query_mutation_hits(
       };
       try {
          cudaGraphExec_t replay = nullptr;
-         if (own_program && queryGraphsEnabled()) {
+         if (own_program) {
             // the shape of the query: every kernel parameter and copy size that enqueueAll bakes into nodes
             std::string key(reinterpret_cast<const char*>(staged.params), sizeof(staged.params));
             const uint64_t scalars[] = {staged.staged_bytes, staged.shared_bytes, static_cast<uint64_t>(column), valid_symbol_mask,
@@ -1680,41 +1786,7 @@ int silo_gpu_query_mutation_hits(
                                         reinterpret_cast<uint64_t>(table->d_work_items), reinterpret_cast<uint64_t>(table->d_coverage_diff)};
             key.append(reinterpret_cast<const char*>(scalars), sizeof(scalars));
             key.append(reinterpret_cast<const char*>(&min_proportion), sizeof(min_proportion));
-            for (const silo_gpu_table::CachedGraph& cached : table->query_graphs) {
-               if (cached.key == key) {
-                  replay = cached.exec;
-                  break;
-               }
-            }
-            if (replay == nullptr && key == table->last_query_key) {  // second time in a row: worth a graph
-               cudaGraph_t graph = nullptr;
-               SILO_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-               try {
-                  enqueueAll();
-               } catch (...) {
-                  cudaStreamEndCapture(stream, &graph);
-                  if (graph != nullptr) {
-                     cudaGraphDestroy(graph);
-                  }
-                  cudaGetLastError();
-                  throw;
-               }
-               SILO_CUDA_CHECK(cudaStreamEndCapture(stream, &graph));
-               cudaGraphExec_t exec = nullptr;
-               const cudaError_t instantiated = cudaGraphInstantiate(&exec, graph, 0);
-               cudaGraphDestroy(graph);
-               SILO_CUDA_CHECK(instantiated);
-               constexpr size_t MAX_QUERY_GRAPHS = 8;
-               if (table->query_graphs.size() < MAX_QUERY_GRAPHS) {
-                  table->query_graphs.push_back({key, exec});
-               } else {
-                  silo_gpu_table::CachedGraph& slot = table->query_graphs[table->next_graph_slot++ % MAX_QUERY_GRAPHS];
-                  cudaGraphExecDestroy(slot.exec);
-                  slot = {key, exec};
-               }
-               replay = exec;
-            }
-            table->last_query_key = std::move(key);
+            replay = queryGraphFor(table, std::move(key), stream, enqueueAll);
          }
          trace.mark(0);  // staged (host work)
          if (replay != nullptr) {
@@ -1792,6 +1864,32 @@ struct ShardHandle {  // SILO_SHARD_HANDLE_BYTES
 };
 static_assert(sizeof(ShardHandle) <= SILO_SHARD_HANDLE_BYTES);
 constexpr uint64_t SHARD_HANDLE_MAGIC = 0x53494C4F53484152ULL;
+
+ShardPush shardPushOf(const ShardGroup& group) {
+   ShardPush push;
+   push.root_block = group.d_root;
+   push.own_header = reinterpret_cast<ShardBlockHeader*>(group.d_local);
+   push.rank = static_cast<uint32_t>(group.rank);
+   push.world = static_cast<uint32_t>(group.world);
+   push.n_valid = group.n_valid;
+   push.valid_mask = group.valid_mask;
+   return push;
+}
+
+int shardGroupColumnLocked(const silo_gpu_table* table) {
+   require(table->shard != nullptr && table->shard->d_root != nullptr, "the table is not connected to a shard group");
+   return table->shard->column;
+}
+
+// a prepared program's filter (its interpreter launch zeroed table->d_counts and built the work list): counts of the
+// group's column + this rank's rows to the root
+void enqueuePreparedShardedLocked(silo_gpu_table* table, const silo_gpu_filter* filter, cudaStream_t stream) {
+   ShardGroup* group = table->shard;
+   ShardPush push = shardPushOf(*group);
+   push.filter_scalars = filter->d_cardinality;
+   enqueueMutationCounts(table, group->column, filter, table->d_counts, stream, nullptr, true, true, &push);
+   group->queries_enqueued++;
+}
 
 void freeShardGroup(silo_gpu_table* table) {
    ShardGroup* group = table->shard;
@@ -1909,46 +2007,32 @@ int silo_gpu_shard_group_connect(silo_gpu_table* table, const void* handles) {
    });
 }
 
+// every rank's half of a sharded query; with_collect (root): the collect kernel with the output pass behind it, in
+// the same graph. Returns whether hits were requested and produced on the stream.
+static void enqueueShardedQuery(
+   silo_gpu_table* table,
+   const silo_filter_program* program,
+   cudaStream_t stream,
+   bool with_collect,
+   double min_proportion,
+   void* d_summed_counts
+);
+
 int silo_gpu_sharded_query_enqueue(silo_gpu_table* table, const silo_filter_program* program, void* cuda_stream) {
    return guarded([&] {
       require(table != nullptr && program != nullptr, "silo_gpu_sharded_query_enqueue: NULL argument");
       std::lock_guard<std::mutex> lock(table->mutex);
-      ShardGroup* group = table->shard;
-      require(group != nullptr && group->d_root != nullptr, "silo_gpu_sharded_query_enqueue: the table is not connected to a shard group");
-      require(table->n_chunks > 0, "silo_gpu_sharded_query_enqueue: a shard must hold at least one chunk");
       SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
       cudaStream_t stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : table->ctx->stream;
-      const uint32_t slot = static_cast<uint32_t>(group->queries_enqueued % SHARD_SLOTS);
-      const uint32_t generation = static_cast<uint32_t>(group->queries_enqueued / SHARD_SLOTS) + 1;
-      ShardBlockHeader* root_header = reinterpret_cast<ShardBlockHeader*>(group->d_root);
-      ShardPush push;
-      push.root_rows = group->rootRows(slot, group->rank);
-      push.root_arrivals = &root_header->arrivals[slot];
-      push.root_cardinality = &root_header->cardinality[slot][group->rank];
-      push.root_error = &root_header->error[slot][group->rank];
-      push.released = &reinterpret_cast<ShardBlockHeader*>(group->d_local)->released[slot];
-      push.wait_generation = generation - 1;
-      push.valid_mask = group->valid_mask;
-      const bool trivially_full = program->n_instrs == 1 && program->instrs != nullptr && program->instrs[0].opcode == SILO_OP_PUSH_FULL;
-      if (trivially_full) {
-         push.use_fixed_cardinality = 1;
-         push.fixed_cardinality = table->n_rows;
-         enqueueMutationCounts(table, group->column, nullptr, table->d_counts, stream, nullptr, false, false, &push);
-      } else {
-         StagedQuery staged;
-         stageQueryLocked(table, program, &staged, group->column, table->d_counts);
-         push.filter_scalars = table->query_filter->d_cardinality;
-         enqueueStagedQuery(table, staged, stream);
-         enqueueMutationCounts(table, group->column, table->query_filter, table->d_counts, stream, nullptr, false, true, &push);
-      }
-      group->queries_enqueued++;
+      enqueueShardedQuery(table, program, stream, false, 0.0, nullptr);
    });
 }
 
-static void enqueueShardCollect(silo_gpu_table* table, double min_proportion, bool with_hits, void* d_summed_counts, cudaStream_t stream) {
+static void enqueueShardCollect(silo_gpu_table* table, double min_proportion, bool with_hits, void* d_summed_counts, cudaStream_t stream, bool check_pending = false) {
    ShardGroup* group = table->shard;
    require(group != nullptr && group->rank == 0 && group->d_peer_table != nullptr, "sharded collect: only the connected root (rank 0) collects");
-   require(group->queries_collected < group->queries_enqueued, "sharded collect: no enqueued query is waiting");
+   // (the host-side counters do not see replays of captured graphs: the synchronous collect checks them, the _async one does not)
+   require(!check_pending || group->queries_collected < group->queries_enqueued, "sharded collect: no enqueued query is waiting");
    const HostColumn& host = *table->columns[static_cast<size_t>(group->column)];
    HitRequest request;
    request.valid_mask = group->valid_mask;
@@ -1960,18 +2044,118 @@ static void enqueueShardCollect(silo_gpu_table* table, double min_proportion, bo
       request.capacity = static_cast<uint32_t>(table->hits_capacity);
    }
    ShardCollect collect;
-   collect.slot = static_cast<uint32_t>(group->queries_collected % SHARD_SLOTS);
-   collect.generation = static_cast<uint32_t>(group->queries_collected / SHARD_SLOTS) + 1;
-   collect.rows = group->rootRows(collect.slot, 0);
    collect.header = reinterpret_cast<ShardBlockHeader*>(group->d_local);
    collect.peers = group->d_peer_table;
    collect.world = static_cast<uint32_t>(group->world);
    collect.n_valid = group->n_valid;
    collect.summed_out = static_cast<uint32_t*>(d_summed_counts);
-   shardCollectKernel<<<(host.dev.genome_length + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, stream>>>(host.dev, collect, group->d_collect_state, request);
+   shardCollectKernel<<<(host.dev.genome_length + COLLECT_THREADS - 1) / COLLECT_THREADS, COLLECT_THREADS, 0, stream>>>(host.dev, collect, group->d_collect_state, request);
    SILO_CUDA_CHECK(cudaGetLastError());
    table->stats.kernel_launches++;
    group->queries_collected++;
+}
+
+static void enqueueShardedQuery(
+   silo_gpu_table* table,
+   const silo_filter_program* program,
+   cudaStream_t stream,
+   bool with_collect,
+   double min_proportion,
+   void* d_summed_counts
+) {
+   ShardGroup* group = table->shard;
+   require(group != nullptr && group->d_root != nullptr, "sharded query: the table is not connected to a shard group");
+   require(table->n_chunks > 0, "sharded query: a shard must hold at least one chunk");
+   const HostColumn& host = *table->columns[static_cast<size_t>(group->column)];
+   if (with_collect) {
+      require(host.dev.global_reference != nullptr, "sharded query: call silo_gpu_column_set_reference first");
+      ensureHitsCapacity(table, host, group->valid_mask, stream);
+   }
+   ShardPush push = shardPushOf(*group);
+   const bool trivially_full = program->n_instrs == 1 && program->instrs != nullptr && program->instrs[0].opcode == SILO_OP_PUSH_FULL;
+   StagedQuery staged;
+   if (trivially_full) {
+      push.use_fixed_cardinality = 1;
+      push.fixed_cardinality = table->n_rows;
+   } else {
+      stageQueryLocked(table, program, &staged, group->column, table->d_counts);
+      push.filter_scalars = table->query_filter->d_cardinality;
+   }
+   auto enqueueAll = [&]() {
+      if (trivially_full) {
+         enqueueMutationCounts(table, group->column, nullptr, table->d_counts, stream, nullptr, false, false, &push);
+      } else {
+         enqueueStagedQuery(table, staged, stream);
+         enqueueMutationCounts(table, group->column, table->query_filter, table->d_counts, stream, nullptr, false, true, &push);
+      }
+      if (with_collect) {
+         enqueueShardCollect(table, min_proportion, true, d_summed_counts, stream);
+      }
+   };
+   cudaGraphExec_t replay = nullptr;
+   if (!trivially_full) {
+      // the shape of the query (slot and generation live in device memory, not in kernel parameters)
+      std::string key(reinterpret_cast<const char*>(staged.params), sizeof(staged.params));
+      const uint64_t scalars[] = {0x5348415244ULL, staged.staged_bytes, staged.shared_bytes, static_cast<uint64_t>(group->column), group->valid_mask,
+                                  reinterpret_cast<uint64_t>(table->h_hits_pinned), table->hits_capacity, with_collect ? 1ULL : 0ULL,
+                                  reinterpret_cast<uint64_t>(host.dev.containers), host.dev.n_segments,
+                                  reinterpret_cast<uint64_t>(host.dev.global_reference), reinterpret_cast<uint64_t>(table->d_counts),
+                                  reinterpret_cast<uint64_t>(table->d_work_items), reinterpret_cast<uint64_t>(table->d_coverage_diff),
+                                  reinterpret_cast<uint64_t>(group->d_root), reinterpret_cast<uint64_t>(group->d_local),
+                                  reinterpret_cast<uint64_t>(d_summed_counts)};
+      key.append(reinterpret_cast<const char*>(scalars), sizeof(scalars));
+      key.append(reinterpret_cast<const char*>(&min_proportion), sizeof(min_proportion));
+      replay = queryGraphFor(table, std::move(key), stream, enqueueAll);
+   }
+   if (replay != nullptr) {
+      SILO_CUDA_CHECK(cudaGraphLaunch(replay, stream));
+      table->stats.kernel_launches += with_collect ? 5 : 4;
+      if (with_collect) {
+         group->queries_collected++;
+      }
+   } else {
+      enqueueAll();
+   }
+   group->queries_enqueued++;
+}
+
+// reads the result of a collect with output pass that has completed on the stream
+static void readShardedHits(silo_gpu_table* table, const silo_mutation_hit** hits, uint64_t* n_hits, uint64_t* cardinality) {
+   const silo_mutation_hit header = table->h_hits_pinned[0];
+   if (header.symbol == 2) {
+      throw ApiError(SILO_E_CUDA, "sharded query: a rank of the shard group did not deliver its counts in time");
+   }
+   if (header.symbol != 0) {
+      throw ApiError(SILO_E_OUT_OF_LAYOUT, "a leaf bitmap holds row ids outside the row layout");
+   }
+   const uint64_t count = std::min<uint64_t>(header.position, table->hits_capacity);
+   sortHits(table->h_hits_pinned + 1, count);
+   *hits = table->h_hits_pinned + 1;
+   *n_hits = count;
+   if (cardinality != nullptr) {
+      *cardinality = header.count | (static_cast<unsigned long long>(header.total) << 32);
+   }
+}
+
+int silo_gpu_sharded_query_hits(
+   silo_gpu_table* table,
+   const silo_filter_program* program,
+   double min_proportion,
+   void* d_summed_counts,
+   const silo_mutation_hit** hits,
+   uint64_t* n_hits,
+   uint64_t* cardinality
+) {
+   return guarded([&] {
+      require(table != nullptr && program != nullptr && hits != nullptr && n_hits != nullptr, "silo_gpu_sharded_query_hits: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      cudaStream_t stream = table->ctx->stream;
+      require(table->shard != nullptr && table->shard->rank == 0, "silo_gpu_sharded_query_hits: only the root (rank 0) collects");
+      enqueueShardedQuery(table, program, stream, true, min_proportion, d_summed_counts);
+      SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+      readShardedHits(table, hits, n_hits, cardinality);
+   });
 }
 
 int silo_gpu_sharded_collect_async(silo_gpu_table* table, void* d_summed_counts, void* cuda_stream) {
@@ -1998,22 +2182,9 @@ int silo_gpu_sharded_collect(
       std::lock_guard<std::mutex> lock(table->mutex);
       SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
       cudaStream_t stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : table->ctx->stream;
-      enqueueShardCollect(table, min_proportion, true, d_summed_counts, stream);
+      enqueueShardCollect(table, min_proportion, true, d_summed_counts, stream, true);
       SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
-      const silo_mutation_hit header = table->h_hits_pinned[0];
-      if (header.symbol == 2) {
-         throw ApiError(SILO_E_CUDA, "sharded query: a rank of the shard group did not deliver its counts in time");
-      }
-      if (header.symbol != 0) {
-         throw ApiError(SILO_E_OUT_OF_LAYOUT, "a leaf bitmap holds row ids outside the row layout");
-      }
-      const uint64_t count = std::min<uint64_t>(header.position, table->hits_capacity);
-      sortHits(table->h_hits_pinned + 1, count);
-      *hits = table->h_hits_pinned + 1;
-      *n_hits = count;
-      if (cardinality != nullptr) {
-         *cardinality = header.count | (static_cast<unsigned long long>(header.total) << 32);
-      }
+      readShardedHits(table, hits, n_hits, cardinality);
    });
 }
 

@@ -240,6 +240,7 @@ int silo_gpu_table_create(
       }
       SILO_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&table->h_scalars_pinned), 4 * sizeof(unsigned long long)));
       SILO_CUDA_CHECK(cudaEventCreateWithFlags(&table->ev_free_fence, cudaEventDisableTiming));
+      SILO_CUDA_CHECK(cudaEventCreateWithFlags(&table->ev_staging_copied, cudaEventDisableTiming));
       SILO_CUDA_CHECK(cudaEventCreateWithFlags(&table->ev_fork, cudaEventDisableTiming));
       SILO_CUDA_CHECK(cudaEventCreateWithFlags(&table->ev_join, cudaEventDisableTiming));
       SILO_CUDA_CHECK(cudaStreamCreateWithFlags(&table->aux_stream, cudaStreamNonBlocking));
@@ -301,6 +302,9 @@ void silo_gpu_table_free(silo_gpu_table* table) {
    }
    if (table->ev_free_fence != nullptr) {
       cudaEventDestroy(table->ev_free_fence);
+   }
+   if (table->ev_staging_copied != nullptr) {
+      cudaEventDestroy(table->ev_staging_copied);
    }
    for (int i = 0; i < silo_gpu_table::EVENT_RING; ++i) {
       for (cudaEvent_t event : {table->ev_begin[i], table->ev_k1_begin[i], table->ev_k1_end[i], table->ev_end[i]}) {

@@ -227,6 +227,14 @@ int silo_host_prepared_run_counts_async(silo_host_prepared* prepared, int column
    return guarded([&] { throwOnDeviceError(silo_gpu_program_run_counts_async(prepared->program, column_index, d_counts, cuda_stream)); });
 }
 
+int silo_host_prepared_run_sharded_async(silo_host_prepared* prepared, void* cuda_stream) {
+   return guarded([&] { throwOnDeviceError(silo_gpu_program_run_sharded_async(prepared->program, cuda_stream)); });
+}
+
+int silo_host_sharded_collect_async(silo_host_table* table, void* d_summed_counts, void* cuda_stream) {
+   return guarded([&] { throwOnDeviceError(silo_gpu_sharded_collect_async(table->table->deviceTable(), d_summed_counts, cuda_stream)); });
+}
+
 const silo_gpu_filter* silo_host_prepared_filter(const silo_host_prepared* prepared) {
    return prepared->filter;
 }
@@ -507,6 +515,36 @@ int silo_host_sharded_enqueue(silo_host_table* table, const char* expression, co
    return guarded([&] {
       const MutationsNode node(*table->table, parseOrTrue(expression), {std::string(column)}, 0.0);
       node.enqueueSharded(cuda_stream);
+   });
+}
+
+int silo_host_sharded_query_packed(
+   silo_host_table* table,
+   const char* expression,
+   const char* column,
+   double min_proportion,
+   void* d_summed_counts,
+   void* buffer,
+   uint64_t capacity,
+   uint64_t* n_rows,
+   uint32_t* n_names,
+   uint64_t* needed_bytes,
+   uint64_t* cardinality
+) {
+   return guarded([&] {
+      g_pending_rows.reset();
+      const MutationsNode node(*table->table, parseOrTrue(expression), {std::string(column)}, min_proportion);
+      auto owned = std::make_unique<silo_host_rows>();
+      owned->rows = node.executeShardedRoot(d_summed_counts, cardinality);
+      owned->indexNames();
+      *n_rows = owned->rows.size();
+      *n_names = static_cast<uint32_t>(owned->names.size());
+      *needed_bytes = packedBytes(*owned);
+      if (*needed_bytes <= capacity) {
+         packRows(*owned, static_cast<uint8_t*>(buffer));
+      } else {
+         g_pending_rows = std::move(owned);
+      }
    });
 }
 

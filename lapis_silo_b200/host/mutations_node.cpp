@@ -249,6 +249,20 @@ void MutationsNode::enqueueSharded(void* cuda_stream) const {
    throwOnDeviceError(silo_gpu_sharded_query_enqueue(table.deviceTable(), &program, cuda_stream));
 }
 
+std::vector<MutationRow> MutationsNode::executeShardedRoot(void* d_summed_counts, uint64_t* cardinality) const {
+   const SequenceColumnInfo& column = singleColumn(*this);
+   const ExpressionPtr rewritten = filter->rewrite(table, AmbiguityMode::NONE);
+   const std::unique_ptr<Operator> compiled = rewritten->compile(table);
+   ProgramBuilder builder;
+   const silo_filter_program program = compiled->lowerProgram(table, builder);
+   const silo_mutation_hit* hits = nullptr;
+   uint64_t n_hits = 0;
+   throwOnDeviceError(silo_gpu_sharded_query_hits(table.deviceTable(), &program, min_proportion, d_summed_counts, &hits, &n_hits, cardinality));
+   std::vector<MutationRow> rows;
+   appendRowsFromHits(column, hits, n_hits, rows);
+   return rows;
+}
+
 std::vector<MutationRow> MutationsNode::collectSharded(void* d_summed_counts, void* cuda_stream, uint64_t* cardinality) const {
    const SequenceColumnInfo& column = singleColumn(*this);
    const silo_mutation_hit* hits = nullptr;

@@ -86,6 +86,8 @@ class MutationsNode {
    // the ranks' rows travel to rank 0 inside the finalize kernels; rank 0 collects the rows of the whole table and
    // the number of rows of ALL shards that passed the filter.
    void enqueueSharded(void* cuda_stream) const;
+   // rank 0's two halves in one device call (one replayed graph, one synchronisation; the table's own stream)
+   [[nodiscard]] std::vector<MutationRow> executeShardedRoot(void* d_summed_counts, uint64_t* cardinality) const;
    [[nodiscard]] std::vector<MutationRow> collectSharded(void* d_summed_counts, void* cuda_stream, uint64_t* cardinality) const;
 };
 

@@ -38,6 +38,7 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_archive_read", "silo_host_archive_free", "silo_host_archive_column", "silo_host_archive_column_info",
     "silo_host_archive_chunk_sizes", "silo_host_archive_column_shard", "silo_host_table_load_archive", "silo_host_roaring_runs",
     "silo_host_shard_group_create", "silo_host_shard_group_connect", "silo_host_sharded_enqueue", "silo_host_sharded_collect_packed",
+    "silo_host_prepared_run_sharded_async", "silo_host_sharded_collect_async", "silo_host_sharded_query_packed",
 ]
 SHARD_HANDLE_BYTES = 128  # SILO_SHARD_HANDLE_BYTES
 
@@ -104,6 +105,11 @@ def lib() -> C.CDLL:
         L.silo_host_sharded_collect_packed.argtypes = [
             vp, C.c_char_p, C.c_double, vp, vp, vp, C.c_uint64,
             C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.silo_host_sharded_query_packed.argtypes = [
+            vp, C.c_char_p, C.c_char_p, C.c_double, vp, vp, C.c_uint64,
+            C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.silo_host_prepared_run_sharded_async.argtypes = [vp, vp]
+        L.silo_host_sharded_collect_async.argtypes = [vp, vp, vp]
         L.silo_host_mutation_rows_from_counts.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint32), C.c_double]
         L.silo_host_mutation_rows_from_counts.restype = vp
         L.silo_host_rows_free.argtypes = [vp]
@@ -283,6 +289,11 @@ class PreparedFilter:
         """The filter and the Mutations counts of one column, enqueued only (one launch less than run_async +
         HostTable.mutation_counts_async: the interpreter also prepares the counts kernels)."""
         _check(lib().silo_host_prepared_run_counts_async(self._h, column_index, C.c_void_p(d_counts_ptr), C.c_void_p(stream_ptr)))
+
+    def run_sharded_async(self, stream_ptr: int) -> None:
+        """The filter and the counts of the shard group's column, this rank's rows sent to rank 0; enqueue only and
+        replayable inside a CUDA graph (silo_gpu_program_run_sharded_async)."""
+        _check(lib().silo_host_prepared_run_sharded_async(self._h, C.c_void_p(stream_ptr)))
 
     @property
     def device_handle(self) -> int:
@@ -581,6 +592,22 @@ class HostTable:
             self._packed = np.empty(int(needed.value) * 2, dtype=np.uint8)
             _check(lib().silo_host_packed_fetch(self._packed.ctypes.data, self._packed.nbytes))
         return _unpack_record_batch(self._packed[:needed.value].copy(), int(n_rows.value), int(n_names.value)), int(cardinality.value)
+
+    def sharded_query(self, column: str, expression: Optional[str], min_proportion: float, d_summed_counts_ptr: int = 0) -> tuple[dict, int]:
+        """Rank 0: sharded_enqueue + sharded_collect as ONE device call on the table's own stream (a replayed graph)."""
+        n_rows, n_names, needed = self._packed_out
+        cardinality = C.c_uint64()
+        _check(lib().silo_host_sharded_query_packed(
+            self._h, expression.encode() if expression is not None else None, column.encode(), min_proportion, d_summed_counts_ptr or None,
+            self._packed.ctypes.data, self._packed.nbytes, n_rows, n_names, needed, cardinality))
+        if needed.value > self._packed.nbytes:
+            self._packed = np.empty(int(needed.value) * 2, dtype=np.uint8)
+            _check(lib().silo_host_packed_fetch(self._packed.ctypes.data, self._packed.nbytes))
+        return _unpack_record_batch(self._packed[:needed.value].copy(), int(n_rows.value), int(n_names.value)), int(cardinality.value)
+
+    def sharded_collect_async(self, stream_ptr: int, d_summed_counts_ptr: int = 0) -> None:
+        """Rank 0, device-resident pipeline: wait for all ranks on the device, sum, hand the slot back; enqueue only."""
+        _check(lib().silo_host_sharded_collect_async(self._h, d_summed_counts_ptr or None, stream_ptr))
 
     def mutation_columns_from_counts(self, column: str, counts: np.ndarray, min_proportion: float) -> dict:
         counts = np.ascontiguousarray(counts, dtype=np.uint32)

@@ -38,10 +38,15 @@ def main():
 
     stream = torch.cuda.Stream()
     results = []
-    queries = [(expression, 0.05), (None, 0.05), (expression, 0.0), (expression, 0.3), (None, 0.0), (expression, 0.05), (expression, 0.05)]
+    queries = [(expression, 0.05), (None, 0.05), (expression, 0.0), (expression, 0.3), (None, 0.0), (expression, 0.05), (expression, 0.05),
+               (expression, 0.05), (expression, 0.05), (expression, 0.2), (expression, 0.05)]
     with torch.cuda.stream(stream):
         summed = torch.zeros(16 * length, dtype=torch.int32, device="cuda")
-        for text, min_proportion in queries:
+        for index, (text, min_proportion) in enumerate(queries):
+            if rank == 0 and index >= 3:  # the root's two halves as one call (a replayed graph from the third time on)
+                columns, cardinality = table.sharded_query("main", text, min_proportion, summed.data_ptr())
+                results.append((host_api.rows_from_columns(columns), cardinality, summed.cpu().numpy().view(np.uint32).reshape(16, length)[:5].copy()))
+                continue
             table.sharded_enqueue("main", text, stream.cuda_stream)
             if rank == 0:
                 columns, cardinality = table.sharded_collect("main", min_proportion, stream.cuda_stream, summed.data_ptr())
