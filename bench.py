@@ -336,8 +336,6 @@ def run_ours(args):
         dist.all_gather_object(handles, table.shard_group_create("main", rank, n_gpus))
         table.shard_group_connect(handles)
         dist.barrier()
-    collect_stream = torch.cuda.Stream() if use_peer and rank == 0 else None
-    pending_collects = []
     comm_stream = torch.cuda.Stream() if n_gpus > 1 and not use_peer else None
     count_buffers = [counts, torch.zeros_like(counts)] if n_gpus > 1 and not use_peer else [counts]
     kernels_done = [torch.cuda.Event() for _ in count_buffers]
@@ -350,16 +348,7 @@ def run_ours(args):
         if use_peer:
             prepared.run_sharded_async(stream.cuda_stream)  # filter + counts kernels; the finalize kernel sends the rows to rank 0
             if rank == 0:
-                # rank 0's collect kernel (waits for all ranks on the device, sums, hands the gather slot back) runs on a
-                # second stream beside the kernels of the next query -- its 117 small blocks fit next to the container kernel
-                pushed = torch.cuda.Event()
-                pushed.record(stream)
-                collect_stream.wait_event(pushed)
-                table.sharded_collect_async(collect_stream.cuda_stream, counts.data_ptr())
-                collected = torch.cuda.Event()
-                collected.record(collect_stream)
-                pending_collects.append(collected)
-                del pending_collects[:-2]
+                table.sharded_collect_async(stream.cuda_stream, counts.data_ptr())  # waits for all ranks on the device, sums
             return
         if n_gpus > 1:
             stream.wait_event(reduced[buffer])  # the all-reduce that used this buffer two queries ago
@@ -376,8 +365,7 @@ def run_ours(args):
     def join_reductions():
         for event in reduced if n_gpus > 1 and not use_peer else []:
             stream.wait_event(event)
-        for event in pending_collects:
-            stream.wait_event(event)
+
 
     def barrier():
         if n_gpus > 1:
@@ -417,12 +405,9 @@ def run_ours(args):
     if use_graph:
         graph = torch.cuda.CUDAGraph()
         if n_gpus == 1 or use_peer:
-            del pending_collects[:]  # (events of the eager steps must not be waited for inside the capture)
             with torch.cuda.graph(graph, stream=stream):
                 for _ in range(args.steps):
                     device_step()
-                join_reductions()  # the collect stream joins the capture's origin stream
-            del pending_collects[:]
         else:
             # N > 1: the same two-stream pipeline, with events that live inside the capture (a captured
             # stream may only wait for work of the same capture) and the all-reduce stream joined at the end

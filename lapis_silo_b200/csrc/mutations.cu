@@ -821,13 +821,13 @@ __device__ __forceinline__ void storeReleaseSystem(uint32_t* address, uint32_t v
 // spins until *address >= target (wrap-safe); false after SHARD_SPIN_LIMIT cycles
 __device__ __forceinline__ bool waitForAtLeast(const uint32_t* address, uint32_t target) {
    const long long begin = clock64();
-   while (static_cast<int32_t>(loadAcquireSystem(address) - target) < 0) {
+   while (static_cast<int32_t>(*reinterpret_cast<const volatile uint32_t*>(address) - target) < 0) {
       if (clock64() - begin > SHARD_SPIN_LIMIT) {
          return false;
       }
-      __nanosleep(200);
+      __nanosleep(100);
    }
-   return true;
+   return static_cast<int32_t>(loadAcquireSystem(address) - target) >= 0;
 }
 
 struct HitRequest {
@@ -916,6 +916,7 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
       counts[reference_symbol * genome_length + p] = reference_count;
    }
    uint32_t shard_slot = 0;
+   bool shard_timed_out = false;
    if (push.root_block != nullptr) {
       // this rank's rows of the valid mutation symbols -> the root's gather area (coalesced stores over NVLink), once the
       // root has released the slot's previous use. (Every block reads the query counter before it counts itself in
@@ -940,9 +941,7 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
             }
          }
       }
-      if (slot_is_free == 0 && threadIdx.x == 0) {
-         atomicOr(&work_state[3], 0x80000000u);  // reported to the root as this rank's error below
-      }
+      shard_timed_out = slot_is_free == 0;  // (every block waits for the same flag: block 0 reports it to the root)
       // (made visible to the root by thread 0's system-scope fence behind the block barrier below: fences are
       // cumulative, one round trip over NVLink per block instead of one per thread)
    }
@@ -976,7 +975,27 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    __syncthreads();
    if (threadIdx.x == 0) {
       if (push.root_block != nullptr) {
-         __threadfence_system();
+         // One round trip over NVLink per block: the fence (cumulative: it orders the whole block's stores before what
+         // follows, at the root too), then this block's own arrival, fire and forget. The root waits for
+         // world * gridDim.x arrivals per use of a slot (the grid is the same on every rank: one block per 256 positions).
+         if (blockIdx.x == 0) {
+            ShardBlockHeader* const root_header = reinterpret_cast<ShardBlockHeader*>(push.root_block);
+            unsigned long long cardinality = push.fixed_cardinality;
+            uint32_t error = shard_timed_out ? 2u : 0u;
+            if (push.use_fixed_cardinality == 0) {
+               cardinality = *reinterpret_cast<volatile unsigned long long*>(&push.filter_scalars[0]);
+               error |= *reinterpret_cast<volatile uint32_t*>(&push.filter_scalars[2]);
+            }
+            root_header->cardinality[shard_slot][push.rank] = cardinality;
+            root_header->error[shard_slot][push.rank] = error;
+         }
+         if (push.rank == 0) {  // the root's own contribution never leaves its memory: device scope is enough (and cheaper)
+            __threadfence();
+            atomicAdd(&reinterpret_cast<ShardBlockHeader*>(push.root_block)->arrivals[shard_slot], 1u);
+         } else {
+            __threadfence_system();
+            atomicAdd_system(&reinterpret_cast<ShardBlockHeader*>(push.root_block)->arrivals[shard_slot], 1u);
+         }
       } else {
          __threadfence();
       }
@@ -998,22 +1017,12 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
             }
             request.hits[0] = header;
          }
-         if (push.root_block != nullptr) {
-            // every block's stores are out (each fenced before it counted itself in): cardinality, error flag, arrival
-            ShardBlockHeader* const root_header = reinterpret_cast<ShardBlockHeader*>(push.root_block);
-            unsigned long long cardinality = push.fixed_cardinality;
-            uint32_t error = (*reinterpret_cast<volatile uint32_t*>(&work_state[3]) & 0x80000000u) != 0 ? 2u : 0u;
+         if (push.root_block != nullptr) {  // every block has read the query counter and the filter's scalars
             if (push.use_fixed_cardinality == 0) {
-               cardinality = *reinterpret_cast<volatile unsigned long long*>(&push.filter_scalars[0]);
-               error |= *reinterpret_cast<volatile uint32_t*>(&push.filter_scalars[2]);
                push.filter_scalars[0] = 0;
                push.filter_scalars[2] = 0;
             }
-            root_header->cardinality[shard_slot][push.rank] = cardinality;
-            root_header->error[shard_slot][push.rank] = error;
             push.own_header->queries_pushed = *reinterpret_cast<volatile uint32_t*>(&push.own_header->queries_pushed) + 1;
-            __threadfence_system();
-            atomicAdd_system(&root_header->arrivals[shard_slot], 1u);
          }
          work_state[0] = 0;  // the work list and its claim counter are empty between queries
          work_state[1] = 0;
@@ -1031,6 +1040,7 @@ struct ShardCollect {
    ShardBlockHeader* const* peers = nullptr;  // [world] every rank's block as mapped on the root
    uint32_t world = 0;
    uint32_t n_valid = 0;
+   uint32_t arrivals_per_rank = 0;  // blocks of a rank's finalize kernel: each signals its own arrival
    uint32_t* summed_out = nullptr;  // optional: [n_symbols][genome_length], the rows of the valid symbols are written
 };
 
@@ -1042,7 +1052,7 @@ __global__ void __launch_bounds__(COLLECT_THREADS, 8) shardCollectKernel(DevColu
    const uint32_t p = blockIdx.x * COLLECT_THREADS + threadIdx.x;
    if (threadIdx.x == 0) {  // (read before this block counts itself in below; the last block increments it after that)
       query_index = *reinterpret_cast<volatile uint32_t*>(&collect.header->queries_collected);
-      all_arrived = waitForAtLeast(&collect.header->arrivals[query_index % SHARD_SLOTS], collect.world * (query_index / SHARD_SLOTS + 1)) ? 1u : 0u;
+      all_arrived = waitForAtLeast(&collect.header->arrivals[query_index % SHARD_SLOTS], collect.world * collect.arrivals_per_rank * (query_index / SHARD_SLOTS + 1)) ? 1u : 0u;
    }
    __syncthreads();
    const uint32_t slot = query_index % SHARD_SLOTS;
@@ -1054,19 +1064,17 @@ __global__ void __launch_bounds__(COLLECT_THREADS, 8) shardCollectKernel(DevColu
       const size_t rank_stride = static_cast<size_t>(collect.n_valid) * genome_length;
       // (no per-symbol array: the kernel must stay at 32 registers so that its blocks fit on an SM beside the container
       // kernel of the next query; the few positions that emit rows sum their symbols a second time)
-      auto sumOf = [&](uint32_t row) {  // (the loads of four ranks in flight together)
+      auto sumOf = [&](uint32_t row) {  // (the loads of all ranks in flight together: one trip to L2 per row)
          const uint32_t* const base = rows + row * genome_length + p;
-         uint32_t sum = 0;
-         uint32_t rank = 0;
-         for (; rank + 4 <= collect.world; rank += 4) {
-            const uint32_t a = base[rank * rank_stride];
-            const uint32_t b = base[(rank + 1) * rank_stride];
-            const uint32_t c = base[(rank + 2) * rank_stride];
-            const uint32_t d = base[(rank + 3) * rank_stride];
-            sum += a + b + c + d;
+         uint32_t values[SHARD_MAX_WORLD];
+#pragma unroll
+         for (uint32_t rank = 0; rank < SHARD_MAX_WORLD; ++rank) {
+            values[rank] = rank < collect.world ? base[rank * rank_stride] : 0u;
          }
-         for (; rank < collect.world; ++rank) {
-            sum += base[rank * rank_stride];
+         uint32_t sum = 0;
+#pragma unroll
+         for (uint32_t rank = 0; rank < SHARD_MAX_WORLD; ++rank) {
+            sum += values[rank];
          }
          return sum;
       };
@@ -1125,10 +1133,10 @@ __global__ void __launch_bounds__(COLLECT_THREADS, 8) shardCollectKernel(DevColu
          work_state[2] = 0;
          work_state[3] = 0;
          collect.header->queries_collected = query_index + 1;
-         // every block has read the slot: hand it back to the ranks
-         __threadfence_system();
+         // every block has read the slot (its loads have returned): hand it back to the ranks. Nothing written here has
+         // to be visible to them first, so plain system-scope stores, no fence.
          for (uint32_t rank = 0; rank < collect.world; ++rank) {
-            storeReleaseSystem(&collect.peers[rank]->released[slot], generation);
+            *reinterpret_cast<volatile uint32_t*>(&collect.peers[rank]->released[slot]) = generation;
          }
       }
    }
@@ -2048,6 +2056,7 @@ static void enqueueShardCollect(silo_gpu_table* table, double min_proportion, bo
    collect.peers = group->d_peer_table;
    collect.world = static_cast<uint32_t>(group->world);
    collect.n_valid = group->n_valid;
+   collect.arrivals_per_rank = diffPadded(host.dev.genome_length) / FIN_THREADS;
    collect.summed_out = static_cast<uint32_t*>(d_summed_counts);
    shardCollectKernel<<<(host.dev.genome_length + COLLECT_THREADS - 1) / COLLECT_THREADS, COLLECT_THREADS, 0, stream>>>(host.dev, collect, group->d_collect_state, request);
    SILO_CUDA_CHECK(cudaGetLastError());
