@@ -619,6 +619,202 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------
+# --workload nof: BASELINE.json configs[2], performance/nof_sequence_filter.cpp:69-80,150-178
+# ---------------------------------------------------------------------------------------------
+
+NOF_DISTANCES = (0, 5, 50, 200)  # nof_sequence_filter.cpp:164
+NOF_METRIC = "nof_filter_rows_per_s"
+NOF_UNIT = "rows/s"
+NOF_CPU_SAMPLE_ROWS = 2 * 65536  # the oracle's Threshold DP is O(n k) whole-bitmap passes: 541 s for distance 50 at 10 M rows
+
+
+def nof_config(args, total_rows, cardinalities):
+    return {
+        "workload": "performance/nof_sequence_filter: nucleotideMutationProfile(distance, querySequence = last evolved sequence) -> count() "
+                    "on the mutation_benchmark-style full-length table (BASELINE.json configs[2]); step i uses distance "
+                    f"{list(NOF_DISTANCES)}[i % 4]",
+        "rows_per_gpu": args.rows_per_gpu, "total_rows": total_rows, "genome_length": GENOME_LENGTH,
+        "children_per_query": GENOME_LENGTH, "filter_cardinalities": cardinalities,
+        "l2": "every query streams the column's whole container payload (1.42 GB per GPU), no explicit flush",
+    }
+
+
+def nof_oracle_sample(threads: int):
+    from lapis_silo_b200 import host_api
+    from oracle import oracle as O
+    synthetic = host_api.Synthetic(GENOME_LENGTH, REFERENCE_SEED, GENERATIONS)
+    sizes = host_api.dense_chunk_sizes(NOF_CPU_SAMPLE_ROWS)
+    table = O.Table()
+    table.set_layout(*sizes)
+    table.import_column("main", O.NUCLEOTIDE, synthetic.reference, synthetic.build_column(NOF_CPU_SAMPLE_ROWS, 0, len(sizes), threads))
+    synthetic.release_column()
+    return table, synthetic.sequence(synthetic.num_sequences - 1)
+
+
+def nof_time_oracle(table, query, distances, threads: int):
+    """threads concurrent workers, each runs the queries of `distances` once (parse + rewrite + compile + evaluate + count
+    inside the timer, performance/nof_sequence_filter.cpp:43-52); returns (rows/s, seconds, queries)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def worker(_):
+        for distance in distances:
+            flt = table.filter(f"(profile main {distance} seq {query})")
+            flt.cardinality
+            flt.close()
+    started = time.perf_counter()
+    with ThreadPoolExecutor(threads) as pool:  # (ctypes releases the GIL inside the oracle)
+        list(pool.map(worker, range(threads)))
+    elapsed = time.perf_counter() - started
+    queries = threads * len(distances)
+    return NOF_CPU_SAMPLE_ROWS * queries / elapsed, elapsed, queries
+
+
+def run_nof_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = os.cpu_count() or 1
+    table, query = nof_oracle_sample(cores)
+    per_step = []
+    for step in range(args.warmup + args.steps):
+        distance = NOF_DISTANCES[step % len(NOF_DISTANCES)]
+        value, elapsed, queries = nof_time_oracle(table, query, [distance], cores)
+        if step >= args.warmup:
+            per_step.append((elapsed, queries))
+    seconds = sum(e for e, _ in per_step)
+    queries = sum(q for _, q in per_step)
+    value = NOF_CPU_SAMPLE_ROWS * queries / seconds
+    total_rows = args.rows_per_gpu * max(1, args.gpus)
+    sample = (f"{NOF_CPU_SAMPLE_ROWS} rows of the same table (the oracle's Threshold DP needs 541 s for distance 50 at 10 M rows); a step = "
+              f"{cores} concurrent single-threaded queries of the step's distance")
+    print(json.dumps({
+        "impl": "reference", "metric": NOF_METRIC, "value": value, "unit": NOF_UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * seconds / len(per_step), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
+        "data": "synthetic", "config": nof_config(args, total_rows, None),
+        "cpu_baseline": {"value": value, "unit": NOF_UNIT, "cores": cores, "kind": "port", "sample": sample, "per_core_value": value / cores},
+        "e2e": {"value": value, "unit": NOF_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+    }), flush=True)
+
+
+def run_nof(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lapis_silo_b200 import abi, host_api
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("gloo")  # filters need no exchange (row-local): only the timings and cardinalities meet
+    n_gpus = world
+    total_rows = args.rows_per_gpu * n_gpus
+    sizes = host_api.dense_chunk_sizes(total_rows)
+    first, n_chunks, stride = host_api.interleaved_shard(len(sizes), n_gpus, rank)
+    synthetic = host_api.Synthetic(GENOME_LENGTH, REFERENCE_SEED, GENERATIONS)
+    threads = max(1, (os.cpu_count() or 8) // max(1, min(n_gpus, 8)))
+    ctx = abi.Context(local_rank)
+    table = host_api.HostTable(ctx, host_api.shard_chunk_sizes(total_rows, first, n_chunks, stride), first_chunk=first if stride == 1 else 0)
+    table.add_column("main", host_api.NUCLEOTIDE, synthetic.reference, synthetic.build_column(total_rows, first, n_chunks, threads, stride))
+    synthetic.release_column()
+    query = synthetic.sequence(synthetic.num_sequences - 1)
+    texts = [f"(profile main {distance} seq {query})" for distance in NOF_DISTANCES]
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+
+    def reduce(value, op):
+        if n_gpus == 1:
+            return value
+        t = torch.tensor([value], dtype=torch.float64)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if n_gpus > 1:
+            dist.barrier()
+
+    # ---- value: the programs are device resident, a step enqueues the sweep and the interpreter ----
+    prepared = [table.prepare(text) for text in texts]
+    for step in range(args.warmup):
+        prepared[step % len(prepared)].run_async(stream.cuda_stream)
+    barrier()
+    table.sweep_stats()
+    launches_before = table.stats().kernel_launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    begin.record(stream)
+    for step in range(args.steps):
+        prepared[step % len(prepared)].run_async(stream.cuda_stream)
+    end.record(stream)
+    barrier()
+    device_ms = reduce(begin.elapsed_time(end), dist.ReduceOp.MAX if n_gpus > 1 else None)
+    gpu_launches = int(table.stats().kernel_launches - launches_before)
+    sweep_ms, sweep_bytes, sweep_calls = table.sweep_stats()
+    # (the clocks line: keep the same step running for 0.4 s)
+    for step in range(max(args.steps, int(0.4 / max(device_ms / args.steps / 1000.0, 1e-6)))):
+        prepared[step % len(prepared)].run_async(stream.cuda_stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    cardinalities = [int(reduce(p.cardinality(), dist.ReduceOp.SUM if n_gpus > 1 else None)) for p in prepared]
+    value = total_rows * args.steps / (device_ms / 1000.0)
+
+    # ---- e2e: expression text in, count out, through the host layer, every step ----
+    def e2e_step(step):
+        flt = table.filter(texts[step % len(texts)])
+        count = flt.cardinality
+        flt.close()
+        return count
+    for step in range(args.warmup):
+        e2e_step(step)
+    barrier()
+    wall = time.perf_counter()
+    counts = [e2e_step(step) for step in range(args.steps)]
+    barrier()
+    e2e_ms = reduce((time.perf_counter() - wall) * 1000.0, dist.ReduceOp.MAX if n_gpus > 1 else None)
+    lowered = table.lower_timed(texts[1])
+    if rank != 0:
+        return
+    peak, peak_source = measured_peak_gbs()
+    achieved = sweep_bytes / (sweep_ms / 1000.0) / 1e9 if sweep_ms > 0 else 0.0
+    line = {
+        "metric": NOF_METRIC, "value": value, "unit": NOF_UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": device_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": nof_config(args, total_rows, cardinalities),
+        "run": {"launch": "eager launches (sweep + interpreter per query)", "parallelism": f"interleaved chunk shards, no exchange (filters are row-local)" if n_gpus > 1 else "single GPU"},
+        "clocks": clocks,
+        "e2e": {"value": total_rows * args.steps / (e2e_ms / 1000.0), "unit": NOF_UNIT, "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": int(lowered["blob_bytes"]) + 16 * int(lowered["n_instrs"]), "d2h_bytes_per_step": 16,
+                "host_lowering_us": lowered["parse_us"] + lowered["rewrite_us"] + lowered["compile_us"] + lowered["lower_us"]},
+        "gpu_launches": gpu_launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": args.traffic_bytes,
+                     "kernel": "thresholdSweepKernel", "algorithmic_bytes_per_launch": sweep_bytes, "kernel_ms": sweep_ms, "timed_launches": sweep_calls,
+                     "peak_source": peak_source, "timed_with": "CUDA events on the launching stream around every launch of the timed region"},
+    }
+    if n_gpus == 1 and not args.skip_cpu_baseline:
+        # full-size check of this run's row counts against the brute-force Hamming distances (tests/ pin it to the oracle's DP)
+        n = synthetic.num_sequences
+        sequences = np.array([np.frombuffer(synthetic.sequence(e).encode(), dtype=np.uint8) for e in range(n)])
+        distances = (sequences != sequences[n - 1]).sum(axis=1)
+        row_counts = np.bincount(np.arange(total_rows) % n, minlength=n)
+        want = [int(row_counts[distances <= d].sum()) for d in NOF_DISTANCES]
+        assert cardinalities == want and counts[:len(NOF_DISTANCES)] == want, (cardinalities, want)
+        line["parity"] = {"checked_against": "brute-force Hamming distances at full size (pinned to the oracle's Threshold DP in tests/)", "cardinalities_equal": True}
+        oracle_table, oracle_query = nof_oracle_sample(os.cpu_count() or 1)
+        cpu_value, cpu_elapsed, cpu_queries = nof_time_oracle(oracle_table, oracle_query, NOF_DISTANCES, 1)
+        line["cpu_baseline"] = {"value": cpu_value, "unit": NOF_UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{NOF_CPU_SAMPLE_ROWS} rows of the same table, the four distances once each: {cpu_elapsed:.1f}s single-threaded "
+                                          "(the oracle's Threshold DP is O(n k): 9 / 59 / 541 s for distance 0 / 5 / 50 at 10 M rows)"}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
@@ -630,6 +826,8 @@ def main():
     parser.add_argument("--reference-step-seconds", type=float, default=2.0)
     parser.add_argument("--skip-cpu-baseline", action="store_true")
     parser.add_argument("--eager", action="store_true", help="launch the timed steps one by one instead of as one CUDA graph")
+    parser.add_argument("--workload", choices=["mutations", "nof"], default="mutations",
+                        help="mutations: BASELINE.json configs[1] (the metric's workload, default); nof: configs[2], the NOf / MutationProfile filter")
     parser.add_argument("--reduce", choices=["peer", "nccl"], default="peer",
                         help="N > 1: how the per-rank counts meet -- the library's shard group (peer-memory stores) or NCCL all-reduce")
     parser.add_argument("--traffic-bytes", type=int, default=None,
@@ -637,7 +835,12 @@ def main():
     args = parser.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload == "nof":
+        if args.impl == "reference":
+            run_nof_reference(args)
+        else:
+            run_nof(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_ours(args)

@@ -43,8 +43,14 @@ typedef enum {
    SILO_E_CUDA = -3,
    SILO_E_OUT_OF_MEMORY = -4,
    SILO_E_BAD_PROGRAM = -5,
-   SILO_E_OUT_OF_LAYOUT = -6, /* a leaf bitmap holds ids outside the row layout (row_layout.h:49-52
-                                 states the precondition the reference relies on) */
+   SILO_E_OUT_OF_LAYOUT = -6, /* A leaf bitmap holds ids outside the row layout (row_layout.h:49-52 states the
+                                 precondition the reference relies on). silo_gpu_filter_eval keeps such ids the way the
+                                 reference's bitmaps do -- And / Or carry them, Not flips inside the layout only
+                                 (row_layout.cpp:18-23), a Threshold counts them when a child holds them
+                                 (threshold.test.cpp:249-311) --, provided they fall into a chunk of the table (ids in
+                                 chunks the table does not have are dropped). Every entry that reads per-row data by the
+                                 filter's rows (the Mutations counts, the fused queries, the aggregation) refuses such a
+                                 filter with this status instead of reading rows that do not exist. */
    SILO_E_UNSUPPORTED = -7
 } silo_status;
 
@@ -449,6 +455,10 @@ typedef struct {
  * the launching stream (a ring of 256 calls) and resets the averaging window. Byte counts describe
  * the last call. */
 int silo_gpu_get_stats(silo_gpu_table* table, silo_gpu_stats* out);
+/* The threshold sweep kernel (a THR_PROFILE over a large column): mean CUDA-event duration of its launches since the
+ * previous call (at most the last 64, launches inside a stream capture excluded) and its algorithmic bytes per launch
+ * (16 B descriptor + reference-format payload of every container of the column). Synchronises. */
+int silo_gpu_get_sweep_stats(silo_gpu_table* table, float* mean_kernel_ms, uint64_t* algorithmic_bytes, uint64_t* timed_calls);
 
 #ifdef __cplusplus
 }

@@ -417,6 +417,9 @@ int silo_gpu_query_combinations(
          }
          if (filter != nullptr) {
             require(filter->table == table, "silo_gpu_query_combinations: filter belongs to another table");
+            if (filter->out_of_layout) {
+               throw ApiError(SILO_E_OUT_OF_LAYOUT, "the filter holds row ids outside the row layout: the aggregation has no row data for them");
+            }
             words = filter->d_words;
             popcounts = filter->d_chunk_popcount;
          }

@@ -287,6 +287,12 @@ struct silo_gpu_table {
    // [n_chunks][32768] packed u16 pairs; used by programs over columns with at least sweep_min_pieces pieces
    uint32_t* d_sweep_counters = nullptr;
    uint64_t sweep_min_pieces = 1u << 16;
+   // measurement: CUDA events around the last launches of the sweep kernel (outside stream captures)
+   static constexpr int SWEEP_EVENT_RING = 64;
+   cudaEvent_t ev_sweep_begin[SWEEP_EVENT_RING] = {}, ev_sweep_end[SWEEP_EVENT_RING] = {};
+   uint64_t sweep_timed_calls = 0;
+   uint64_t sweep_algorithmic_bytes = 0;  // descriptors + payloads (reference format) of the swept column
+   cudaStream_t sweep_stream = nullptr;
    silo::ShardGroup* shard = nullptr;
 };
 
@@ -297,6 +303,9 @@ struct silo_gpu_filter {
    uint32_t* d_chunk_popcount = nullptr;  // [n_chunks]
    unsigned long long* d_cardinality = nullptr;
    uint32_t* d_error_flag = nullptr;
+   // silo_gpu_filter_eval: a leaf bitmap held row ids outside the row layout. The filter carries them like the
+   // reference's bitmaps do; the consumers that index per-row data by the filter's rows refuse it.
+   bool out_of_layout = false;
 };
 
 namespace silo {

@@ -115,6 +115,10 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
    int sp = 0;  // number of tiles on the stack
    uint32_t thr_target = 0;
    bool thr_exact = false;
+   // Rows outside the row layout that a threshold's child tiles hold (this thread's word of them). The reference's
+   // Threshold (threshold.cpp:64-138) complements negated children inside the layout only (row_layout.cpp:18-23), so
+   // such an id takes part in the count exactly when some child holds it (threshold.test.cpp:249-311).
+   uint64_t thr_outside = 0;
 
    if (tid < min(p.n_instrs, CACHED_INSTRS) * 4) {  // 16-byte instructions as 4 words each
       reinterpret_cast<uint32_t*>(sh.small->instrs)[tid] = reinterpret_cast<const uint32_t*>(p.instrs)[tid];
@@ -276,6 +280,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
             const uint32_t bias = static_cast<uint32_t>(ins.b & 0xFFFFu);
             thr_target = ins.a + bias;
             thr_exact = (ins.flags & 1) != 0;
+            thr_outside = 0;
             for (uint32_t i = tid; i < 32768; i += EVAL_THREADS) {
                sh.counters32[i] = bias | (bias << 16);
             }
@@ -283,8 +288,9 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
          }
          case SILO_OP_THR_ADD: {
             uint64_t word = sh.stack[--sp][tid];
+            thr_outside |= word & ~layout_word;
             if ((ins.flags & 1) != 0) {
-               word = ~word & layout_word;
+               word = ~word;  // (rows outside the layout that no child holds are dropped at THR_END)
             }
             uint16_t* counters16 = reinterpret_cast<uint16_t*>(sh.counters32);
             while (word != 0) {
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
                const bool hit = thr_exact ? count == thr_target : count >= thr_target;
                word |= static_cast<uint64_t>(hit) << b;
             }
-            sh.stack[sp++][tid] = word & layout_word;
+            sh.stack[sp++][tid] = word & (layout_word | thr_outside);
             break;
          }
          default:
@@ -755,10 +761,13 @@ void validateProgram(const silo_gpu_table* table, const silo_filter_program* pro
             target = ins.a;
             break;
          case SILO_OP_THR_ADD:
-            if (!in_threshold || depth - threshold_base < 1) {
+            // the child tile may have been pushed in front of THR_BEGIN (a child that is a counter program itself is
+            // evaluated first: counter programs do not nest); the threshold's base sinks with it
+            if (!in_threshold || depth < 1) {
                bad("THR_ADD needs a child tile inside a threshold");
             }
             --depth;
+            threshold_base = std::min(threshold_base, depth);
             ++adds;
             break;
          case SILO_OP_THR_ADD_SYMBOLS: {
@@ -1074,12 +1083,31 @@ static void launchProgram(silo_gpu_table* table, EvalParams params, silo_gpu_fil
    if (params.sweep_pc != NO_SWEEP) {
       const HostColumn& host = *table->columns[static_cast<size_t>(params.sweep_column)];
       SILO_CUDA_CHECK(cudaMemsetAsync(table->d_sweep_counters, 0, static_cast<size_t>(table->n_chunks) * COUNTER_BYTES, stream));
+      cudaStreamCaptureStatus capture_status = cudaStreamCaptureStatusNone;
+      const bool timed = cudaStreamIsCapturing(stream, &capture_status) == cudaSuccess && capture_status == cudaStreamCaptureStatusNone;
+      const int slot = static_cast<int>(table->sweep_timed_calls % silo_gpu_table::SWEEP_EVENT_RING);
+      if (timed) {
+         if (table->ev_sweep_begin[slot] == nullptr) {
+            SILO_CUDA_CHECK(cudaEventCreate(&table->ev_sweep_begin[slot]));
+            SILO_CUDA_CHECK(cudaEventCreate(&table->ev_sweep_end[slot]));
+         }
+         SILO_CUDA_CHECK(cudaEventRecord(table->ev_sweep_begin[slot], stream));
+      }
       thresholdSweepKernel<<<host.sweep_ctas, SWEEP_THREADS, COUNTER_BYTES, stream>>>(
          host.dev, reinterpret_cast<const uint2*>(params.blob + params.sweep_table_offset), host.d_sweep_split, params.sweep_bias,
          table->d_sweep_counters
       );
       SILO_CUDA_CHECK(cudaGetLastError());
       table->stats.kernel_launches++;
+      if (timed) {
+         SILO_CUDA_CHECK(cudaEventRecord(table->ev_sweep_end[slot], stream));
+         table->sweep_timed_calls++;
+         table->sweep_stream = stream;
+         table->sweep_algorithmic_bytes = 0;
+         for (uint64_t bytes : host.chunk_desc_payload_bytes) {
+            table->sweep_algorithmic_bytes += bytes;
+         }
+      }
    }
    const size_t shared_bytes = evalSharedBytes(params.stack_depth, params.has_threshold != 0);
    evalProgramKernel<<<table->n_chunks, EVAL_THREADS, shared_bytes, stream>>>(params);
@@ -1212,9 +1240,7 @@ int silo_gpu_filter_eval(
          SILO_CUDA_CHECK(cudaFreeAsync(d_staging, stream));
          d_staging = nullptr;
          SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
-         if (host_error != 0) {
-            throw ApiError(SILO_E_OUT_OF_LAYOUT, "a leaf bitmap holds row ids outside the row layout");
-         }
+         filter->out_of_layout = host_error != 0;  // kept, like the reference's bitmaps keep such ids (see silo_b200.h)
          if (cardinality != nullptr) {
             *cardinality = host_cardinality;
          }
@@ -1328,6 +1354,34 @@ void silo_gpu_program_free(silo_gpu_program* prepared) {
    }
    delete prepared->params;
    delete prepared;
+}
+
+int silo_gpu_get_sweep_stats(silo_gpu_table* table, float* mean_kernel_ms, uint64_t* algorithmic_bytes, uint64_t* timed_calls) {
+   return guarded([&] {
+      require(table != nullptr && mean_kernel_ms != nullptr && algorithmic_bytes != nullptr && timed_calls != nullptr, "silo_gpu_get_sweep_stats: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      if (table->sweep_stream != nullptr) {
+         SILO_CUDA_CHECK(cudaStreamSynchronize(table->sweep_stream));
+      }
+      const uint64_t n = std::min<uint64_t>(table->sweep_timed_calls, silo_gpu_table::SWEEP_EVENT_RING);
+      double total_ms = 0;
+      uint64_t valid = 0;
+      for (uint64_t back = 0; back < n; ++back) {
+         const uint64_t slot = (table->sweep_timed_calls - 1 - back) % silo_gpu_table::SWEEP_EVENT_RING;
+         float ms = 0;
+         if (cudaEventElapsedTime(&ms, table->ev_sweep_begin[slot], table->ev_sweep_end[slot]) == cudaSuccess) {
+            total_ms += ms;
+            ++valid;
+         } else {
+            cudaGetLastError();
+         }
+      }
+      *mean_kernel_ms = valid > 0 ? static_cast<float>(total_ms / static_cast<double>(valid)) : 0.0f;
+      *algorithmic_bytes = table->sweep_algorithmic_bytes;
+      *timed_calls = valid;
+      table->sweep_timed_calls = 0;
+   });
 }
 
 int silo_gpu_bitmap_register(silo_gpu_table* table, const uint8_t* data, uint64_t size, uint32_t* id_out) {

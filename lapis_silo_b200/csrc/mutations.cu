@@ -1263,6 +1263,9 @@ void enqueueMutationCounts(
    require(table != nullptr, "mutation_counts: table is NULL");
    require(column_index >= 0 && static_cast<size_t>(column_index) < table->columns.size(), "mutation_counts: bad column index");
    require(filter == nullptr || filter->table == table, "mutation_counts: filter belongs to another table");
+   if (filter != nullptr && filter->out_of_layout) {
+      throw ApiError(SILO_E_OUT_OF_LAYOUT, "the filter holds row ids outside the row layout: the action has no row data for them");
+   }
    require(d_counts != nullptr, "mutation_counts: counts is NULL");
    const HostColumn& host = *table->columns[static_cast<size_t>(column_index)];
    const DevColumn& column = host.dev;

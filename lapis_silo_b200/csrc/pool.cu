@@ -274,6 +274,13 @@ void silo_gpu_table_free(silo_gpu_table* table) {
    dropQueryGraphsLocked(table);
    cudaFree(table->d_staging_fixed);
    cudaFree(table->d_sweep_counters);
+   for (int i = 0; i < silo_gpu_table::SWEEP_EVENT_RING; ++i) {
+      for (cudaEvent_t event : {table->ev_sweep_begin[i], table->ev_sweep_end[i]}) {
+         if (event != nullptr) {
+            cudaEventDestroy(event);
+         }
+      }
+   }
    freeShardGroup(table);
    if (table->query_filter != nullptr) {
       cudaFree(table->query_filter->d_words);

@@ -584,16 +584,37 @@ void lowerCounting(
    for (const auto& [column, leaves] : fused) {
       bias += leaves.subs.size();
    }
-   program.emit(SILO_OP_THR_BEGIN, match_exactly ? 1 : 0, 0, number_of_matchers, bias);
-   const bool was_inside = program.inside_counter_program;
-   program.inside_counter_program = true;  // (a wide Union below must stay a chain of ORs)
+   // Counter programs do not nest on the device (one counter tile per CTA), but the reference's Threshold takes any
+   // operator as a child (threshold.cpp:64-138) -- an NOf inside an NOf, a MutationProfile inside an NOf, a wide Union:
+   // such children are evaluated to tiles BEFORE this program's THR_BEGIN (their own counter programs run to their
+   // THR_END first) and are added from the stack right behind it, last pushed first.
+   std::vector<std::pair<const Operator*, bool>> plain;   // (child, negated)
+   std::vector<bool> nested_negated;
    for (const Operator* child : generic) {
-      child->lower(program);
-      program.emit(SILO_OP_THR_ADD, 0);
+      if (containsThreshold(*child)) {
+         child->lower(program);
+         nested_negated.push_back(false);
+      } else {
+         plain.emplace_back(child, false);
+      }
    }
    for (const auto& child : negated_children) {
+      if (containsThreshold(*child)) {
+         child->lower(program);
+         nested_negated.push_back(true);
+      } else {
+         plain.emplace_back(child.get(), true);
+      }
+   }
+   program.emit(SILO_OP_THR_BEGIN, match_exactly ? 1 : 0, 0, number_of_matchers, bias);
+   for (auto negated = nested_negated.rbegin(); negated != nested_negated.rend(); ++negated) {
+      program.emit(SILO_OP_THR_ADD, *negated ? 1 : 0);
+   }
+   const bool was_inside = program.inside_counter_program;
+   program.inside_counter_program = true;  // (a narrow Union below stays a chain of ORs)
+   for (const auto& [child, negated] : plain) {
       child->lower(program);
-      program.emit(SILO_OP_THR_ADD, 1);
+      program.emit(SILO_OP_THR_ADD, negated ? 1 : 0);
    }
    program.inside_counter_program = was_inside;
    for (auto& [column, leaves] : fused) {

@@ -632,6 +632,12 @@ class HostTable:
         """silo_gpu_table_set_option on the device table (e.g. "sweep_min_pieces")"""
         abi.check(abi.lib().silo_gpu_table_set_option(self.device_table, name.encode(), value))
 
+    def sweep_stats(self) -> tuple[float, int, int]:
+        """(mean ms per launch, algorithmic bytes per launch, launches timed) of the threshold sweep kernel"""
+        ms, nbytes, calls = C.c_float(), C.c_uint64(), C.c_uint64()
+        abi.check(abi.lib().silo_gpu_get_sweep_stats(self.device_table, C.byref(ms), C.byref(nbytes), C.byref(calls)))
+        return float(ms.value), int(nbytes.value), int(calls.value)
+
     def stats(self) -> abi.Stats:
         out = abi.Stats()
         abi.check(abi.lib().silo_gpu_get_stats(self.device_table, C.byref(out)))

@@ -230,20 +230,20 @@ def test_filter_program_leaves_and_boolean_ops(ctx):
           blob=blob, bitmaps=[raw])
 
 
-def test_filter_program_rejects_bitmap_outside_layout(ctx):
+def test_filter_program_keeps_bitmap_ids_outside_layout(ctx):
+    """A leaf bitmap with an id outside the row layout: the filter carries it like the reference's bitmaps do
+    (include/silo_b200.h, SILO_E_OUT_OF_LAYOUT); only consumers of per-row data refuse the filter."""
     from lapis_silo_b200 import abi as A
     from oracle import oracle as O
     t = O.Table()
     t.set_layout(4)
     t.register_bitmap("bad", [1, 4])
     g = A.Table(ctx, [4])
-    with pytest.raises(A.SiloGpuError) as error:
-        g.filter_eval([(A.OP_PUSH_BITMAP, 0, 0, 0, 0)], bitmaps=[t.bitmap_bytes("bad")])
-    assert error.value.status == A.SILO_E_OUT_OF_LAYOUT
+    flt = g.filter_eval([(A.OP_PUSH_BITMAP, 0, 0, 0, 0)], bitmaps=[t.bitmap_bytes("bad")])
+    assert flt.cardinality == 2
     bad_id = g.register_bitmap(t.bitmap_bytes("bad"))
-    with pytest.raises(A.SiloGpuError) as error:
-        g.filter_eval([(A.OP_PUSH_INDEX_BITMAP, 0, 0, bad_id, 0)])
-    assert error.value.status == A.SILO_E_OUT_OF_LAYOUT
+    flt = g.filter_eval([(A.OP_PUSH_INDEX_BITMAP, 0, 0, bad_id, 0), (A.OP_NOT, 0, 0, 0, 0)])
+    assert flt.cardinality == 4  # {0, 2, 3} and the id outside the layout, which the complement leaves alone
 
 
 def test_threshold_programs(ctx):

@@ -81,13 +81,34 @@ def test_threshold_vectors(ctx):  # filter/operators/threshold.test.cpp:40-247
         [0, 1, 2, 3, 4], [0, 1, 2, 3, 4], [0, 1, 2, 3], [0, 1, 2, 3]]
 
 
-def test_threshold_rejects_ids_outside_the_layout(ctx):
-    """threshold.test.cpp:249-311 feeds id 4 into a 4-row layout; row_layout.h:49-52 documents that
-    inputs are expected to be a subset of the universe. The device refuses such input loudly."""
+def test_threshold_with_ids_outside_the_layout(ctx):
+    """threshold.test.cpp:249-311 feeds id 4 into a 4-row layout (row_layout.h:49-52 documents that inputs are expected
+    to be a subset of the universe): complements stay inside the layout (row_layout.cpp:18-23), so the id takes part in
+    the count because a child holds it. The device reproduces the reference's expectations (and the oracle's)."""
+    def threshold(pair, pos, neg, k, exact):
+        return both(pair, f"(op-threshold {k} {int(exact)} ({lists(pos)}) ({lists(neg)}))")
+
+    pair = layout_pair(ctx, 4)
+    neg = [[3], [4], [2, 4]]
+    assert [threshold(pair, [[]], neg, k, True) for k in (1, 2, 3)] == [[4], [2, 3], [0, 1]]
+    assert [threshold(pair, [[]], neg, k, False) for k in (1, 2, 3)] == [[0, 1, 2, 3, 4], [0, 1, 2, 3], [0, 1]]
+    # the boolean operators carry such ids like the reference's bitmaps do
+    assert both(pair, "(or (ids 1) (ids 4))") == [1, 4]
+    assert both(pair, "(and (ids 1 4) (ids 4 2))") == [4]
+    assert both(pair, "(not (ids 1 4))") == [0, 2, 3, 4]
+    # ... and what needs per-row data for the filter's rows refuses them
     from lapis_silo_b200 import host_api
-    _, device_table = layout_pair(ctx, 4)
+    from oracle import oracle as O
+    with_rows = O.Table()
+    with_rows.add_column("c", O.NUCLEOTIDE, "ACGT")
+    for _ in range(4):
+        with_rows.append_row(["ACGT"])
+    with_rows.finalize()
+    mirrored = mirror(ctx, with_rows)
     with pytest.raises(host_api.HostError, match=r"DeviceError\[-6\]"):
-        device_table.filter("(op-threshold 1 1 ((ids)) ((ids 3) (ids 4) (ids 2 4)))")
+        mirrored.mutation_counts("c", mirrored.filter("(ids 1 4)"))
+    with pytest.raises(host_api.HostError, match=r"DeviceError\[-6\]"):
+        mirrored.mutations(["c"], "(ids 1 4)", 0.0)
 
 
 def test_constructor_errors_match(ctx):  # threshold.cpp:30-41, intersection.cpp:26-40
@@ -261,6 +282,14 @@ def test_random_expressions(ctx, seed, alphabet_id):
             both(pair, f"(n-of {k} {exact} {children})")
             both(pair, f"(maybe (n-of {k} {exact} {children}))")
             both(pair, f"(and (bitmap lineage) (not (n-of {k} {exact} {children})))")
+    # counter programs inside counter programs (an NOf / a wide Or / a MutationProfile as a child of an NOf): the
+    # reference's Threshold takes any child; the device evaluates such children to tiles first
+    wide = " ".join(f"(sym-in c {p} {''.join(rng.choice(list(chars[:-1]), 3, replace=False))})" for p in range(1, 31))
+    for k, exact in ((1, 0), (2, 0), (2, 1), (3, 0)):
+        a, b, c, d = pick(4)
+        both(pair, f"(n-of {k} {exact} {a} (n-of 2 0 {b} {c} {d}) (not (n-of 1 1 {a} {c} {d})) {b})")
+        both(pair, f"(n-of {k} {exact} (or {wide}) {a} (n-of 7 0 {wide}) (profile c 3 muts))")
+        both(pair, f"(n-of {k} {exact} (and {a} (n-of 2 0 {b} {c} {d})) (not (profile c 1 muts)) {d})")
     # many children on one column: exercises the one-pass profile lowering
     for k in (1, 2, 5, 12, 30):
         children = " ".join(f"(sym-in c {p} {''.join(rng.choice(list(chars[:-1]), 3, replace=False))})" for p in range(1, 46))
