@@ -815,6 +815,140 @@ def run_nof(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------
+# --workload aa: BASELINE.json configs[3], AminoAcidMutations over the 12 SARS-CoV-2 genes
+# ---------------------------------------------------------------------------------------------
+
+GENE_LENGTHS = {"E": 76, "M": 223, "N": 420, "ORF1a": 4401, "ORF1b": 2696, "ORF3a": 276, "ORF6": 62, "ORF7a": 122, "ORF7b": 44,
+                "ORF8": 122, "ORF9b": 98, "S": 1274}  # testBaseData/exampleDataset/reference_genomes.json; sum = 9,814
+AA_MUTATION_RATE = 0.003  # SURVEY.md 8(d) input 4: the tree model per gene over the valid amino-acid symbols, mu = 0.001 * 3
+AA_METRIC = "aa_mutations_query_seq_positions_per_s"
+
+
+def aa_genes():
+    from lapis_silo_b200 import host_api
+    return {name: host_api.Synthetic(genome_length=length, reference_seed=REFERENCE_SEED + index, generations=GENERATIONS, gene=True,
+                                     tree_seed=42 + index, mutation_rate=AA_MUTATION_RATE)
+            for index, (name, length) in enumerate(GENE_LENGTHS.items())}
+
+
+def aa_lineage_rows(genes, total_rows):
+    """the config-2 lineage filter needs a tree: the rows that descend from a generation-2 node of ORF1a's tree"""
+    tree = genes["ORF1a"]
+    ancestor = next(e for e in range(tree.num_sequences) if tree.generation(e) == 2)
+    return ancestor, lineage_row_ids(tree, ancestor, total_rows)
+
+
+def aa_config(args, total_rows, cardinality, output_rows):
+    return {
+        "workload": "AminoAcidMutations over the 12 SARS-CoV-2 genes (sum of lengths 9,814; tree model per gene over the valid amino-acid symbols, "
+                    "mu = 0.003), config-2 filter (date range + lineage), minProportion 0.05 (BASELINE.json configs[3])",
+        "rows_per_gpu": args.rows_per_gpu, "total_rows": total_rows, "genes": len(GENE_LENGTHS), "positions": sum(GENE_LENGTHS.values()),
+        "min_proportion": MIN_PROPORTION, "filter_cardinality": cardinality, "output_rows": output_rows,
+    }
+
+
+def run_aa(args):
+    import numpy as np
+    import torch
+    from lapis_silo_b200 import abi, host_api
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("--workload aa is a single-GPU line (N > 1: the Mutations workload is the scaling line)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(0)
+    total_rows = args.rows_per_gpu
+    sizes = host_api.dense_chunk_sizes(total_rows)
+    threads = os.cpu_count() or 8
+    genes = aa_genes()
+    ctx = abi.Context(0)
+    table = host_api.HostTable(ctx, sizes)
+    for name, gene in genes.items():
+        column = gene.build_column(total_rows, 0, len(sizes), threads)
+        table.add_column(name, host_api.AMINO_ACID, gene.reference, column)
+        gene.release_column()
+    ancestor, lineage = aa_lineage_rows(genes, total_rows)
+    table.register_bitmap("lineage", genes["ORF1a"].lineage_bitmap(ancestor, total_rows, 0, len(sizes)))
+    expression = f"(and {host_api.date_ranges_expression(total_rows, SPAN_DAYS, FROM_DAY, TO_DAY, 0, len(sizes))} (bitmap lineage))"
+    names = list(GENE_LENGTHS)
+    positions = sum(GENE_LENGTHS.values())
+
+    def step():
+        return table.mutations_columns(names, expression, MIN_PROPORTION)  # MutationsNode: one device call, one sync
+    for _ in range(args.warmup):
+        rows = step()
+    torch.cuda.synchronize()
+    launches_before = table.stats().kernel_launches
+    sampler = ClockSampler(0)
+    sampler.start()
+    wall = time.perf_counter()
+    for _ in range(args.steps):
+        rows = step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - wall) * 1000.0
+    gpu_launches = int(table.stats().kernel_launches - launches_before)
+    for _ in range(int(0.4 / max(e2e_ms / args.steps / 1000.0, 1e-6))):
+        step()
+    clocks = sampler.stop()
+    flt = table.filter(expression)
+    cardinality = flt.cardinality
+    flt.close()
+    # algorithmic bytes of one query (SURVEY.md 8(d)): per gene, descriptors + payloads of the containers of the chunks that
+    # hold a filtered row + their filter tiles, as the library accounts them for the container kernel
+    prepared = table.prepare(expression)
+    scratch = torch.zeros(28 * max(GENE_LENGTHS.values()), dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream()
+    prepared.run_async(stream.cuda_stream)
+    payload_bytes = 0
+    for index in range(len(names)):
+        table.mutation_counts_async(index, prepared, scratch.data_ptr(), stream.cuda_stream)
+        payload_bytes += int(table.stats().counts_kernel_bytes)
+    prepared.close()
+    rows = host_api.rows_from_columns(rows)
+    value = cardinality * positions * args.steps / (e2e_ms / 1000.0)
+    peak, peak_source = measured_peak_gbs()
+    line = {
+        "metric": AA_METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": e2e_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": aa_config(args, total_rows, cardinality, len(rows)),
+        "run": {"launch": "one replayed CUDA graph per query: the filter program once, then work list / coverage / container / finalize kernels per gene",
+                "note": "value is measured through the host API like e2e: the query is launch-latency bound (49 small kernels), not HBM bound"},
+        "clocks": clocks,
+        "e2e": {"value": value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": 1472, "d2h_bytes_per_step": (len(rows) + len(names)) * 16},
+        "gpu_launches": gpu_launches,
+        "roofline": {"bound": "hbm", "achieved": payload_bytes * (cardinality > 0) / (e2e_ms / args.steps / 1000.0) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": payload_bytes / (e2e_ms / args.steps / 1000.0) / 1e9 / peak, "traffic": None, "kernel": "whole query (12 x containerAndCountKernel + small kernels)",
+                     "algorithmic_bytes_per_launch": payload_bytes, "kernel_ms": e2e_ms / args.steps, "peak_source": peak_source,
+                     "note": "bytes: the container kernels' algorithmic bytes summed over the 12 genes; time: the whole query through the host API"},
+    }
+    if not args.skip_cpu_baseline:
+        from oracle import oracle as O
+        oracle_table = O.Table()
+        oracle_table.set_layout(*sizes)
+        for name, gene in genes.items():
+            oracle_table.import_column(name, O.AMINO_ACID, gene.reference, gene.build_column(total_rows, 0, len(sizes), threads))
+            gene.release_column()
+        oracle_table.register_bitmap("lineage", lineage)
+        started = time.perf_counter()
+        want = [row for name in names for row in oracle_table.mutations(name, expression, MIN_PROPORTION)]
+        assert want == rows, "output rows differ from the oracle's at full size"
+        line["parity"] = {"oracle": "full size, same table", "output_rows_equal": True, "output_rows": len(rows)}
+        queries, seconds = 0, 0.0
+        while seconds < args.cpu_seconds:
+            started = time.perf_counter()
+            flt = oracle_table.filter(expression)
+            for name in names:
+                oracle_table.mutation_rows(name, oracle_table.mutation_counts(name, flt), MIN_PROPORTION)
+            flt.close()
+            seconds += time.perf_counter() - started
+            queries += 1
+        line["cpu_baseline"] = {"value": cardinality * positions * queries / seconds, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"the whole table, {queries} single-threaded queries in {seconds:.1f}s (filter once, then the 12 genes)"}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
@@ -826,8 +960,9 @@ def main():
     parser.add_argument("--reference-step-seconds", type=float, default=2.0)
     parser.add_argument("--skip-cpu-baseline", action="store_true")
     parser.add_argument("--eager", action="store_true", help="launch the timed steps one by one instead of as one CUDA graph")
-    parser.add_argument("--workload", choices=["mutations", "nof"], default="mutations",
-                        help="mutations: BASELINE.json configs[1] (the metric's workload, default); nof: configs[2], the NOf / MutationProfile filter")
+    parser.add_argument("--workload", choices=["mutations", "nof", "aa"], default="mutations",
+                        help="mutations: BASELINE.json configs[1] (the metric's workload, default); nof: configs[2], the NOf / MutationProfile filter; "
+                             "aa: configs[3], AminoAcidMutations over 12 genes")
     parser.add_argument("--reduce", choices=["peer", "nccl"], default="peer",
                         help="N > 1: how the per-rank counts meet -- the library's shard group (peer-memory stores) or NCCL all-reduce")
     parser.add_argument("--traffic-bytes", type=int, default=None,
@@ -835,7 +970,9 @@ def main():
     args = parser.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.workload == "nof":
+    if args.workload == "aa":
+        run_aa(args)
+    elif args.workload == "nof":
         if args.impl == "reference":
             run_nof_reference(args)
         else:

@@ -305,6 +305,25 @@ int silo_gpu_query_mutation_hits(
    uint64_t* cardinality
 );
 
+/* The same for SEVERAL sequence columns under one filter (AminoAcidMutations over all genes: the producer of
+ * mutations_node.cpp:372-428 loops the columns of one query): the program is evaluated once, every column's counts and
+ * output pass follow on the stream, ONE synchronisation. columns[c].hits / n_hits are set on return (page-locked memory
+ * owned by the table, valid until the next call on this table); valid_symbol_mask is clipped to the column's alphabet. */
+typedef struct {
+   int column;
+   uint64_t valid_symbol_mask;
+   const silo_mutation_hit* hits; /* out */
+   uint64_t n_hits;               /* out */
+} silo_column_hits;
+int silo_gpu_query_mutation_hits_columns(
+   silo_gpu_table* table,
+   const silo_filter_program* program,
+   silo_column_hits* columns,
+   uint32_t n_columns,
+   double min_proportion,
+   uint64_t* cardinality
+);
+
 /* Same, but leaves the counts in device memory (d_counts: n_symbols*genome_length u32) and only
  * enqueues on `cuda_stream` (a cudaStream_t; NULL = the table's own stream) without synchronising,
  * so that a collective (ncclAllReduce on the same stream) can follow with no host round trip. */

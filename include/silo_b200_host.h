@@ -168,6 +168,9 @@ typedef struct silo_host_synthetic silo_host_synthetic;
 /* Evolution tree over a seeded random reference of `genome_length` nt (tree seed 42, mutation rate
  * 0.001, death rate 0.1, 3 children: SequenceTreeGenerator defaults) */
 silo_host_synthetic* silo_host_synthetic_create(uint32_t genome_length, uint64_t reference_seed, uint32_t generations);
+/* The same model for one amino-acid gene (SURVEY.md 8(d) input 4): random reference over the twenty standard residues,
+ * mutations drawn from the alphabet's valid mutation symbols, its own tree seed and mutation rate. */
+silo_host_synthetic* silo_host_synthetic_create_gene(uint32_t gene_length, uint64_t reference_seed, uint64_t tree_seed, double mutation_rate, uint32_t generations);
 void silo_host_synthetic_free(silo_host_synthetic* synthetic);
 uint32_t silo_host_synthetic_num_sequences(const silo_host_synthetic* synthetic);
 const char* silo_host_synthetic_reference(const silo_host_synthetic* synthetic);

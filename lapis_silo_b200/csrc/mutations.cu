@@ -837,6 +837,7 @@ struct HitRequest {
                                                   // the call: reported in the header and zeroed for the next query
    uint64_t valid_mask = 0;  // SymbolType::VALID_MUTATION_SYMBOLS
    double min_proportion = 0;
+   uint32_t keep_scalars = 0;  // report the filter's scalars but leave them for the next column of the same query
 };
 
 // Grid: diffPadded(genome_length) / 256 blocks (the difference array has genome_length + 1 entries).
@@ -1012,8 +1013,10 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
                header.symbol = *reinterpret_cast<volatile uint32_t*>(&request.filter_scalars[2]);
                header.count = static_cast<uint32_t>(cardinality);
                header.total = static_cast<uint32_t>(cardinality >> 32);
-               request.filter_scalars[0] = 0;
-               request.filter_scalars[2] = 0;
+               if (request.keep_scalars == 0) {
+                  request.filter_scalars[0] = 0;
+                  request.filter_scalars[2] = 0;
+               }
             }
             request.hits[0] = header;
          }
@@ -1582,8 +1585,11 @@ static bool queryGraphsEnabled() {
 }
 
 // page-locked tuple buffer for the worst case: every valid symbol but the reference genome's at every position
+static void ensureHitsTuples(silo_gpu_table* table, uint64_t needed, cudaStream_t stream);
 static void ensureHitsCapacity(silo_gpu_table* table, const HostColumn& host, uint64_t valid_symbol_mask, cudaStream_t stream) {
-   const uint64_t needed = static_cast<uint64_t>(__builtin_popcountll(valid_symbol_mask)) * host.dev.genome_length;
+   ensureHitsTuples(table, static_cast<uint64_t>(__builtin_popcountll(valid_symbol_mask)) * host.dev.genome_length, stream);
+}
+static void ensureHitsTuples(silo_gpu_table* table, uint64_t needed, cudaStream_t stream) {
    if (needed > table->hits_capacity || table->h_hits_pinned == nullptr) {
       SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
       dropQueryGraphsLocked(table);  // their kernel nodes write the old buffer
@@ -2207,6 +2213,116 @@ void silo_gpu_shard_group_free(silo_gpu_table* table) {
    std::lock_guard<std::mutex> lock(table->mutex);
    cudaSetDevice(table->ctx->device);
    freeShardGroup(table);
+}
+
+// Several sequence columns under ONE filter (AminoAcidMutations over all genes; the producer of mutations_node.cpp:372-428
+// loops the columns of one query): the program is evaluated once, then every column runs work list, coverage, container
+// and finalize kernels back to back on the stream, each writing its tuples into its own region of the page-locked
+// buffer; one synchronisation for the whole query, and the whole sequence is one replayed CUDA graph per query shape.
+int silo_gpu_query_mutation_hits_columns(
+   silo_gpu_table* table,
+   const silo_filter_program* program,
+   silo_column_hits* columns,
+   uint32_t n_columns,
+   double min_proportion,
+   uint64_t* cardinality
+) {
+   return guarded([&] {
+      require(table != nullptr && program != nullptr && columns != nullptr && n_columns >= 1, "silo_gpu_query_mutation_hits_columns: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      cudaStream_t stream = table->ctx->stream;
+      // one region per column: [header][tuples...], sized for the worst case
+      std::vector<uint64_t> region_begin(n_columns + 1, 0);
+      for (uint32_t c = 0; c < n_columns; ++c) {
+         require(columns[c].column >= 0 && static_cast<size_t>(columns[c].column) < table->columns.size(), "silo_gpu_query_mutation_hits_columns: bad column index");
+         const HostColumn& host = *table->columns[static_cast<size_t>(columns[c].column)];
+         require(host.dev.global_reference != nullptr, "silo_gpu_query_mutation_hits_columns: call silo_gpu_column_set_reference first");
+         if (host.dev.n_symbols < 64) {
+            columns[c].valid_symbol_mask &= (1ULL << host.dev.n_symbols) - 1;
+         }
+         region_begin[c + 1] = region_begin[c] + 1 + static_cast<uint64_t>(__builtin_popcountll(columns[c].valid_symbol_mask)) * host.dev.genome_length;
+      }
+      ensureHitsTuples(table, region_begin[n_columns], stream);
+      const bool trivially_full = program->n_instrs == 1 && program->instrs != nullptr && program->instrs[0].opcode == SILO_OP_PUSH_FULL;
+      StagedQuery staged;
+      if (!trivially_full) {
+         stageQueryLocked(table, program, &staged, columns[0].column, table->d_counts);
+      }
+      auto enqueueAll = [&]() {
+         if (!trivially_full) {
+            enqueueStagedQuery(table, staged, stream);
+         }
+         for (uint32_t c = 0; c < n_columns; ++c) {
+            const HostColumn& host = *table->columns[static_cast<size_t>(columns[c].column)];
+            HitRequest request;
+            request.hits = table->h_hits_pinned + region_begin[c];
+            request.capacity = static_cast<uint32_t>(region_begin[c + 1] - region_begin[c] - 1);
+            request.valid_mask = columns[c].valid_symbol_mask;
+            request.min_proportion = min_proportion;
+            (void) host;
+            if (trivially_full) {
+               enqueueMutationCounts(table, columns[c].column, nullptr, table->d_counts, stream, &request);
+            } else {
+               request.filter_scalars = table->query_filter->d_cardinality;
+               request.keep_scalars = c + 1 < n_columns ? 1u : 0u;
+               enqueueMutationCounts(table, columns[c].column, table->query_filter, table->d_counts, stream, &request, false, c == 0);
+            }
+         }
+      };
+      try {
+         cudaGraphExec_t replay = nullptr;
+         if (!trivially_full) {
+            std::string key(reinterpret_cast<const char*>(staged.params), sizeof(staged.params));
+            std::vector<uint64_t> scalars = {0x434F4C53ULL, staged.staged_bytes, staged.shared_bytes, n_columns,
+                                             reinterpret_cast<uint64_t>(table->h_hits_pinned), table->hits_capacity,
+                                             reinterpret_cast<uint64_t>(table->d_counts), reinterpret_cast<uint64_t>(table->d_work_items),
+                                             reinterpret_cast<uint64_t>(table->d_coverage_diff)};
+            for (uint32_t c = 0; c < n_columns; ++c) {
+               const HostColumn& host = *table->columns[static_cast<size_t>(columns[c].column)];
+               scalars.insert(scalars.end(), {static_cast<uint64_t>(columns[c].column), columns[c].valid_symbol_mask,
+                                              reinterpret_cast<uint64_t>(host.dev.containers), host.dev.n_segments,
+                                              reinterpret_cast<uint64_t>(host.dev.global_reference)});
+            }
+            key.append(reinterpret_cast<const char*>(scalars.data()), scalars.size() * sizeof(uint64_t));
+            key.append(reinterpret_cast<const char*>(&min_proportion), sizeof(min_proportion));
+            replay = queryGraphFor(table, std::move(key), stream, enqueueAll);
+         }
+         if (replay != nullptr) {
+            SILO_CUDA_CHECK(cudaGraphLaunch(replay, stream));
+            table->stats.kernel_launches += 1 + 4ULL * n_columns;
+         } else {
+            enqueueAll();
+         }
+         SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+      } catch (...) {
+         cudaStreamSynchronize(stream);
+         if (!trivially_full) {
+            cudaMemsetAsync(table->query_filter->d_cardinality, 0, 32, stream);
+            cudaMemsetAsync(table->d_work_state, 0, 4 * sizeof(uint32_t), stream);
+            cudaStreamSynchronize(stream);
+         }
+         throw;
+      }
+      unsigned long long host_cardinality = trivially_full ? table->n_rows : 0;
+      for (uint32_t c = 0; c < n_columns; ++c) {
+         silo_mutation_hit* const region = table->h_hits_pinned + region_begin[c];
+         const silo_mutation_hit header = region[0];
+         if (!trivially_full) {
+            if (header.symbol != 0) {
+               throw ApiError(SILO_E_OUT_OF_LAYOUT, "a leaf bitmap holds row ids outside the row layout");
+            }
+            host_cardinality = header.count | (static_cast<unsigned long long>(header.total) << 32);
+         }
+         const uint64_t count = std::min<uint64_t>(header.position, region_begin[c + 1] - region_begin[c] - 1);
+         sortHits(region + 1, count);
+         columns[c].hits = region + 1;
+         columns[c].n_hits = count;
+      }
+      if (cardinality != nullptr) {
+         *cardinality = host_cardinality;
+      }
+   });
 }
 
 int silo_gpu_query_mutation_counts(

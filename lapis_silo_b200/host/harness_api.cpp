@@ -59,6 +59,7 @@ struct silo_host_archive {
 
 struct silo_host_synthetic {
    std::string reference;
+   const Alphabet* alphabet = &Alphabet::nucleotide();
    EvolvedTree tree;
    std::unique_ptr<PackedColumn> column;
 };
@@ -731,6 +732,22 @@ silo_host_synthetic* silo_host_synthetic_create(uint32_t genome_length, uint64_t
    return result;
 }
 
+silo_host_synthetic* silo_host_synthetic_create_gene(uint32_t gene_length, uint64_t reference_seed, uint64_t tree_seed, double mutation_rate, uint32_t generations) {
+   silo_host_synthetic* result = nullptr;
+   guarded([&] {
+      auto owned = std::make_unique<silo_host_synthetic>();
+      owned->alphabet = &Alphabet::aminoAcid();
+      owned->reference = randomAminoAcidReference(gene_length, reference_seed);
+      std::string valid;
+      for (const Symbol symbol : owned->alphabet->valid_mutation_symbols) {
+         valid.push_back(owned->alphabet->symbolToChar(symbol));
+      }
+      owned->tree = generateEvolvedSequences(owned->reference, tree_seed, mutation_rate, 0.1, generations, 3, valid);
+      result = owned.release();
+   });
+   return result;
+}
+
 void silo_host_synthetic_free(silo_host_synthetic* synthetic) {
    delete synthetic;
 }
@@ -755,7 +772,7 @@ int silo_host_synthetic_build_column(silo_host_synthetic* synthetic, uint64_t to
    return guarded([&] {
       synthetic->column = std::make_unique<PackedColumn>();
       buildCycledColumn(
-         Alphabet::nucleotide(), synthetic->reference, synthetic->tree.sequences, total_rows, first_chunk, n_chunks,
+         *synthetic->alphabet, synthetic->reference, synthetic->tree.sequences, total_rows, first_chunk, n_chunks,
          threads, *synthetic->column, chunk_stride
       );
       *out = &synthetic->column->desc;

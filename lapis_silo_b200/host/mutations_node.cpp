@@ -180,29 +180,43 @@ std::vector<MutationRow> MutationsNode::execute() const {
       profile.threshold_us = nowMicroseconds() - threshold_begin;
       return rows;
    }
-   const DeviceBitmap bitmap_filter = computeFilter(*filter, table);
-   const uint64_t filter_cardinality = bitmap_filter.cardinality();
+   // Several sequence columns (AminoAcidMutations over all genes): the filter program is evaluated ONCE and the columns
+   // follow on the device in one call with one synchronisation (silo_gpu_query_mutation_hits_columns).
+   std::vector<const SequenceColumnInfo*> columns;
    for (const std::string& name : sequence_columns) {
       const SequenceColumnInfo* column = table.findColumn(name);
       if (column == nullptr) {
          throw IllegalQueryException("Database does not contain the Sequence with name: '" + name + "'");
       }
-      if (filter_cardinality == 0) {
-         continue;  // all counts are zero: nothing is emitted
-      }
-      const double counts_begin = nowMicroseconds();
-      const silo_mutation_hit* hits = nullptr;
-      uint64_t n_hits = 0;
-      // cardinality == numRows: the stored-cardinality path (mutations_node.cpp:280-281)
-      throwOnDeviceError(silo_gpu_query_mutation_hits(
-         table.deviceTable(), nullptr, filter_cardinality == table.row_layout.numRows() ? nullptr : bitmap_filter.get(), column->device_column,
-         validSymbolMask(*column->alphabet), min_proportion, &hits, &n_hits, nullptr
-      ));
-      const double threshold_begin = nowMicroseconds();
-      appendRowsFromHits(*column, hits, n_hits, rows);
-      lastQueryProfile().counts_us += threshold_begin - counts_begin;
-      lastQueryProfile().threshold_us += nowMicroseconds() - threshold_begin;
+      columns.push_back(column);
    }
+   if (columns.empty()) {
+      return rows;
+   }
+   const double compile_begin = nowMicroseconds();
+   const ExpressionPtr rewritten = filter->rewrite(table, AmbiguityMode::NONE);  // computeFilter, compute_filter.cpp:14-21
+   const std::unique_ptr<Operator> compiled = rewritten->compile(table);
+   ProgramBuilder builder;
+   const silo_filter_program program = compiled->lowerProgram(table, builder);
+   const double counts_begin = nowMicroseconds();
+   std::vector<silo_column_hits> requests(columns.size());
+   for (size_t c = 0; c < columns.size(); ++c) {
+      requests[c].column = columns[c]->device_column;
+      requests[c].valid_symbol_mask = validSymbolMask(*columns[c]->alphabet);
+   }
+   uint64_t cardinality = 0;
+   throwOnDeviceError(silo_gpu_query_mutation_hits_columns(
+      table.deviceTable(), &program, requests.data(), static_cast<uint32_t>(requests.size()), min_proportion, &cardinality
+   ));
+   const double threshold_begin = nowMicroseconds();
+   for (size_t c = 0; c < columns.size(); ++c) {
+      appendRowsFromHits(*columns[c], requests[c].hits, requests[c].n_hits, rows);
+   }
+   QueryProfile& profile = lastQueryProfile();
+   profile.compile_us = counts_begin - compile_begin;
+   profile.filter_us = 0;
+   profile.counts_us = threshold_begin - counts_begin;
+   profile.threshold_us = nowMicroseconds() - threshold_begin;
    return rows;
 }
 

@@ -14,12 +14,13 @@ EvolvedTree generateEvolvedSequences(
    double mutation_rate,
    double death_rate,
    size_t generations,
-   size_t children_per_node
+   size_t children_per_node,
+   const std::string& replacement_symbols
 ) {
    // RNG call order per child: survives -> binomial(#mutations) -> per mutation: position, then
    // base draws until the base changes. mutateBase picks among the first four nucleotide symbols
-   // ('-', 'A', 'C', 'G'), as the reference does.
-   static constexpr char FIRST_FOUR_SYMBOLS[4] = {'-', 'A', 'C', 'G'};
+   // ('-', 'A', 'C', 'G'), as the reference does; an amino-acid gene draws from its valid mutation symbols.
+   const std::string& FIRST_FOUR_SYMBOLS = replacement_symbols;
    std::mt19937 rng(seed);
    EvolvedTree tree;
    tree.sequences.push_back(reference);
@@ -40,7 +41,7 @@ EvolvedTree generateEvolvedSequences(
             std::uniform_int_distribution<size_t> position_distribution(0, mutated.size() - 1);
             for (size_t i = 0; i < n_mutations; ++i) {
                const size_t position = position_distribution(rng);
-               std::uniform_int_distribution<size_t> base_distribution(0, 3);
+               std::uniform_int_distribution<size_t> base_distribution(0, replacement_symbols.size() - 1);
                char replacement;
                do {
                   replacement = FIRST_FOUR_SYMBOLS[base_distribution(rng)];
@@ -68,6 +69,17 @@ std::string randomNucleotideReference(size_t length, uint64_t seed) {
    std::string reference(length, 'A');
    for (char& base : reference) {
       base = BASES[base_distribution(rng)];
+   }
+   return reference;
+}
+
+std::string randomAminoAcidReference(size_t length, uint64_t seed) {
+   static constexpr char RESIDUES[] = "ACDEFGHIKLMNPQRSTVWY";
+   std::mt19937 rng(seed);
+   std::uniform_int_distribution<size_t> residue_distribution(0, 19);
+   std::string reference(length, 'A');
+   for (char& residue : reference) {
+      residue = RESIDUES[residue_distribution(rng)];
    }
    return reference;
 }

@@ -30,11 +30,15 @@ EvolvedTree generateEvolvedSequences(
    double mutation_rate = 0.001,
    double death_rate = 0.1,
    size_t generations = 5,
-   size_t children_per_node = 3
+   size_t children_per_node = 3,
+   // the symbols mutateBase draws from; default: the reference generator's first four nucleotide symbols
+   const std::string& replacement_symbols = "-ACG"
 );
 
 // uniformly random A/C/G/T reference (the real SARS-CoV-2 genome is reference data we do not ship)
 std::string randomNucleotideReference(size_t length, uint64_t seed);
+// uniformly random reference over the twenty standard amino acids (SURVEY.md 8(d) input 4: translation-free genes)
+std::string randomAminoAcidReference(size_t length, uint64_t seed);
 
 // A column in the upload format that owns its buffers; `desc` points into them.
 struct PackedColumn {

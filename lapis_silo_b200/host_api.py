@@ -37,7 +37,7 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_filter_lower_timed", "silo_host_filter_to_string", "silo_host_filter_program_bitmap",
     "silo_host_archive_read", "silo_host_archive_free", "silo_host_archive_column", "silo_host_archive_column_info",
     "silo_host_archive_chunk_sizes", "silo_host_archive_column_shard", "silo_host_table_load_archive", "silo_host_roaring_runs",
-    "silo_host_shard_group_create", "silo_host_shard_group_connect", "silo_host_sharded_enqueue", "silo_host_sharded_collect_packed",
+    "silo_host_synthetic_create_gene", "silo_host_shard_group_create", "silo_host_shard_group_connect", "silo_host_sharded_enqueue", "silo_host_sharded_collect_packed",
     "silo_host_prepared_run_sharded_async", "silo_host_sharded_collect_async", "silo_host_sharded_query_packed",
 ]
 SHARD_HANDLE_BYTES = 128  # SILO_SHARD_HANDLE_BYTES
@@ -128,6 +128,8 @@ def lib() -> C.CDLL:
         L.silo_host_rows_name.restype = C.c_char_p
         L.silo_host_synthetic_create.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32]
         L.silo_host_synthetic_create.restype = vp
+        L.silo_host_synthetic_create_gene.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_double, C.c_uint32]
+        L.silo_host_synthetic_create_gene.restype = vp
         L.silo_host_synthetic_free.argtypes = [vp]
         L.silo_host_synthetic_free.restype = None
         L.silo_host_synthetic_num_sequences.argtypes = [vp]
@@ -666,8 +668,13 @@ class HostTable:
 class Synthetic:
     """performance/sequence_generator.h restated on the product side (host/synthetic.h)."""
 
-    def __init__(self, genome_length: int = 29903, reference_seed: int = 1, generations: int = 5):
-        self._h = lib().silo_host_synthetic_create(genome_length, reference_seed, generations)
+    def __init__(self, genome_length: int = 29903, reference_seed: int = 1, generations: int = 5, gene: bool = False,
+                 tree_seed: int = 42, mutation_rate: float = 0.003):
+        """gene: an amino-acid gene (valid-symbol mutations, its own tree seed and rate) instead of a nucleotide genome"""
+        if gene:
+            self._h = lib().silo_host_synthetic_create_gene(genome_length, reference_seed, tree_seed, mutation_rate, generations)
+        else:
+            self._h = lib().silo_host_synthetic_create(genome_length, reference_seed, generations)
         if not self._h:
             raise HostError(lib().silo_host_last_error().decode())
         self.genome_length = genome_length

@@ -680,3 +680,44 @@ def test_threshold_sweep_on_tree_data(ctx):
             text = f"(profile main {distance} seq {query})"
             np.testing.assert_array_equal(table.filter(text).ids(), oracle_table.filter(text).ids())
     table.close()
+
+
+GENE_LENGTHS = {"E": 76, "M": 223, "N": 420, "ORF1a": 4401, "ORF1b": 2696, "ORF3a": 276, "ORF6": 62, "ORF7a": 122, "ORF7b": 44,
+                "ORF8": 122, "ORF9b": 98, "S": 1274}  # testBaseData/exampleDataset/reference_genomes.json
+
+
+def test_amino_acid_mutations_over_twelve_genes(ctx):
+    """BASELINE.json configs[3] at reduced rows: AminoAcidMutations over the twelve gene columns under one filter --
+    one device call (silo_gpu_query_mutation_hits_columns: the filter evaluated once, one synchronisation) -- against the
+    oracle gene by gene; filtered, unfiltered, several minProportions, and a subset of the genes in another order."""
+    from lapis_silo_b200 import host_api
+    from oracle import oracle as O
+    total_rows = 3 * 65536 + 4321
+    sizes = host_api.dense_chunk_sizes(total_rows)
+    table = host_api.HostTable(ctx, sizes)
+    oracle_table = O.Table()
+    oracle_table.set_layout(*sizes)
+    genes = {}
+    for index, (name, length) in enumerate(GENE_LENGTHS.items()):
+        gene = host_api.Synthetic(genome_length=length, reference_seed=100 + index, generations=5, gene=True, tree_seed=42 + index, mutation_rate=0.003)
+        column = gene.build_column(total_rows, 0, len(sizes), 4)
+        table.add_column(name, host_api.AMINO_ACID, gene.reference, column)
+        oracle_table.import_column(name, O.AMINO_ACID, gene.reference, column)
+        gene.release_column()
+        genes[name] = gene
+    rng = np.random.default_rng(4)
+    picked = np.sort(rng.choice(total_rows, total_rows // 7, replace=False)).astype(np.uint32)
+    oracle_table.register_bitmap("lineage", picked)
+    table.register_bitmap("lineage", oracle_table.bitmap_bytes("lineage"))
+    expression = f"(and {host_api.date_ranges_expression(total_rows, 1095, 200, 800, 0, len(sizes))} (bitmap lineage))"
+    names = list(GENE_LENGTHS)
+    for text in (expression, None, "(sym-eq S 12 .)"):
+        for min_proportion in (0.05, 0.0):
+            want = [row for name in names for row in oracle_table.mutations(name, text, min_proportion)]
+            assert table.mutations(names, text, min_proportion) == want
+            assert len(want) > 0
+    subset = ["S", "E", "ORF1a"]
+    want = [row for name in subset for row in oracle_table.mutations(name, expression, 0.01)]
+    for _ in range(3):  # (the third call replays the captured graph)
+        assert table.mutations(subset, expression, 0.01) == want
+    table.close()

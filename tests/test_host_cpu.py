@@ -221,3 +221,31 @@ def _roaring_ids(portable_bytes: bytes) -> list[int]:
                     word &= word - 1
             pos += 8192
     return ids
+
+
+def test_gene_generator_matches_the_oracle_string_ingest():
+    """The amino-acid gene generator (silo_host_synthetic_create_gene: valid-symbol mutations) builds, directly in the S1
+    upload format, what the oracle's string ingest + finalize stores for the same cycled sequences (counts of every
+    symbol at every position, with and without a filter)."""
+    import numpy as np
+    from lapis_silo_b200 import host_api
+    from oracle import oracle as O
+    total_rows = 70_000
+    gene = host_api.Synthetic(genome_length=223, reference_seed=11, generations=4, gene=True, tree_seed=77, mutation_rate=0.01)
+    sizes = host_api.dense_chunk_sizes(total_rows)
+    sequences = [gene.sequence(e) for e in range(gene.num_sequences)]
+    assert any(set(s) - set("ACDEFGHIKLMNPQRSTVWY") for s in sequences)  # mutations reach beyond the reference's residues
+    from_strings = O.Table()
+    from_strings.add_column("M", O.AMINO_ACID, gene.reference)
+    from_strings.append_cycled(sequences, total_rows)
+    from_strings.finalize()
+    imported = O.Table()
+    imported.set_layout(*sizes)
+    imported.import_column("M", O.AMINO_ACID, gene.reference, gene.build_column(total_rows, 0, len(sizes), 2))
+    assert from_strings.chunk_sizes == imported.chunk_sizes
+    assert from_strings.local_reference("M") == imported.local_reference("M")
+    np.testing.assert_array_equal(from_strings.mutation_counts("M"), imported.mutation_counts("M"))
+    expression = "(ranges 100 30000 65536 69000)"
+    np.testing.assert_array_equal(
+        from_strings.mutation_counts("M", from_strings.filter(expression)), imported.mutation_counts("M", imported.filter(expression)))
+    assert from_strings.mutations("M", expression, 0.05) == imported.mutations("M", expression, 0.05)
