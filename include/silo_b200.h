@@ -148,8 +148,14 @@ typedef enum {
    SILO_OP_PUSH_COVERED = 4, /* column, a = position, flags&1: NOT covered (within the layout) */
    SILO_OP_PUSH_NULLS = 5,   /* column */
    SILO_OP_PUSH_BITMAP = 6,  /* a = index into silo_filter_program.bitmaps */
-   SILO_OP_PUSH_RANGES = 7,  /* a = number of ranges, b = byte offset into blob of {u32 start,u32 end} */
+   SILO_OP_PUSH_RANGES = 7,  /* a = number of ranges, b = byte offset (a multiple of 8) into blob of {u32 start,u32 end} */
    SILO_OP_PUSH_INDEX_BITMAP = 8, /* a = id returned by silo_gpu_bitmap_register */
+   SILO_OP_PUSH_COMPARE = 9, /* A Selection predicate over a value column (silo_gpu_value_column_upload), evaluated for
+                                every row of the layout: column = value column index; flags[2:0] = comparator
+                                (silo_comparator); flags bit 3: compare as signed 32-bit (Date32, integers), else
+                                unsigned (dictionary ids); flags bit 4: null rows match (with_nulls of
+                                CompareToValueSelection, selection.h:76-166). a = the value; BETWEEN: a <= v <= (u32) b;
+                                IN_SET: a = number of values, b = blob offset of the ascending u32 values. */
    SILO_OP_AND = 16,         /* pop y, pop x, push x & y */
    SILO_OP_ANDNOT = 17,      /* pop y, pop x, push x & ~y */
    SILO_OP_OR = 18,          /* pop y, pop x, push x | y */
@@ -164,6 +170,19 @@ typedef enum {
                                 rows if sym in add_mask, -1 if in sub_mask. One streaming pass. */
    SILO_OP_THR_END = 37      /* push (count >= k) or (count == k), restricted to the layout */
 } silo_filter_opcode;
+
+typedef enum {
+   SILO_CMP_EQUALS = 0,
+   SILO_CMP_NOT_EQUALS = 1,
+   SILO_CMP_LESS = 2,
+   SILO_CMP_LESS_OR_EQUALS = 3,
+   SILO_CMP_HIGHER = 4,
+   SILO_CMP_HIGHER_OR_EQUALS = 5,
+   SILO_CMP_BETWEEN = 6, /* inclusive on both ends */
+   SILO_CMP_IN_SET = 7
+} silo_comparator;
+#define SILO_CMP_SIGNED 8
+#define SILO_CMP_WITH_NULLS 16
 
 typedef struct {
    uint8_t opcode;
@@ -190,6 +209,14 @@ typedef struct {
    uint32_t n_bitmaps;
    const silo_roaring_bytes* bitmaps;
 } silo_filter_program;
+
+/* A 32-bit value column of the table's rows, in the order of the row layout (chunk after chunk): the dictionary ids of
+ * a string column, the days of a Date32 column, integers. null_row_ids: ascending row ids ((chunk << 16) | row, global
+ * chunk ids) of the null rows, or NULL. Returns the value column's index (>= 0) or a negative status. Replaces, for the
+ * predicates of Selection (filter/operators/selection.cpp:94-141: row-at-a-time match() or makeBitmap over all rows,
+ * string_in_set / CompareToValueSelection selection.h:76-166, date_between.cpp:61-93), the host-side scan of the column:
+ * SILO_OP_PUSH_COMPARE evaluates the predicate for all rows of a chunk inside the filter program. */
+int silo_gpu_value_column_upload(silo_gpu_table* table, const uint32_t* values, const uint32_t* null_row_ids, uint64_t n_null_rows);
 
 /* Makes a STATIC index bitmap device resident (the lineage index of lineage_index.h:18-22, a
  * dictionary index, the per-value bitmaps of an indexed string column ...; portable Roaring bytes,

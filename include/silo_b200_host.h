@@ -105,6 +105,14 @@ int silo_host_mutations_enqueue(silo_host_table* table, const char* expression, 
 int silo_host_mutations_collect_packed(silo_host_table* table, const char* column, double min_proportion, const void* d_summed_counts, void* cuda_stream,
                                        void* buffer, uint64_t capacity, uint64_t* n_rows, uint32_t* n_names, uint64_t* needed_bytes,
                                        uint64_t* shard_cardinality);
+/* Metadata columns for the Selection predicates (string equality on an unindexed string column, equals.cpp:124-156;
+ * DateBetween, date_between.cpp:61-134): a string column as its dictionary + one id per row (layout order), a Date32
+ * column as its day numbers; null_row_ids ascending global row ids (may be NULL with n_null_rows 0). The values become
+ * device resident (silo_gpu_value_column_upload); harness notation: (str-eq COLUMN VALUE), (date-between COLUMN FROM TO)
+ * with day numbers or * for an open end. */
+int silo_host_table_add_string_column(silo_host_table* table, const char* name, const char* const* dictionary, uint32_t n_values,
+                                      const uint32_t* ids, const uint32_t* null_row_ids, uint64_t n_null_rows);
+int silo_host_table_add_date_column(silo_host_table* table, const char* name, const int32_t* days, const uint32_t* null_row_ids, uint64_t n_null_rows);
 /* The same query through the table's shard group (MutationsNode::enqueueSharded / collectSharded; silo_gpu_shard_group_*
  * of include/silo_b200.h): _create on every rank writes this rank's handle (SILO_SHARD_HANDLE_BYTES), _connect takes the
  * handles of all ranks in rank order; then every rank enqueues, rank 0 collects (rows of the whole table; cardinality =

@@ -204,6 +204,10 @@ __host__ __device__ inline uint32_t diffWords(uint32_t genome_length) {  // whol
 
 namespace silo {
 struct ShardGroup;  // mutations.cu: this table as one rank of a row-partitioned table
+struct DevValueColumn {
+   const uint32_t* values;      // rows of the shard back to back (chunk-major)
+   const uint64_t* null_words;  // [n_chunks * 1024] or nullptr
+};
 }
 
 struct silo_gpu_ctx {
@@ -294,6 +298,9 @@ struct silo_gpu_table {
    uint64_t sweep_algorithmic_bytes = 0;  // descriptors + payloads (reference format) of the swept column
    cudaStream_t sweep_stream = nullptr;
    silo::ShardGroup* shard = nullptr;
+   // value columns (silo_gpu_value_column_upload) for SILO_OP_PUSH_COMPARE
+   std::vector<silo::DevValueColumn> value_columns;
+   uint32_t* d_chunk_row_begin = nullptr;  // [n_chunks + 1]
 };
 
 struct silo_gpu_filter {

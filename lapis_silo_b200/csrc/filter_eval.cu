@@ -41,6 +41,8 @@ struct EvalParams {
    const uint8_t* blob;
    const DevBitmap* bitmaps;
    const uint32_t* chunk_sizes;
+   const DevValueColumn* value_columns;  // SILO_OP_PUSH_COMPARE
+   const uint32_t* chunk_row_begin;
    uint32_t first_chunk;
    uint32_t stack_depth;    // tiles the program needs at most
    uint32_t has_threshold;  // whether the counter tile is needed
@@ -210,6 +212,53 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
                if ((tile[tid] & ~layout_word) != 0) {
                   atomicOr(p.error_flag, 1u);  // ids outside the row layout
                }
+            }
+            break;
+         }
+         case SILO_OP_PUSH_COMPARE: {
+            // A Selection predicate over a value column for every row of the chunk (4 bytes per row, coalesced): what
+            // Predicate::makeBitmap computes on the host (selection.h:33-43), or match() row by row on the candidates
+            // of the child (selection.cpp:105-118) -- both are "child AND predicate".
+            const DevValueColumn column = p.value_columns[ins.column];
+            const uint32_t* values = column.values + p.chunk_row_begin[chunk];
+            uint32_t* tile32 = reinterpret_cast<uint32_t*>(sh.stack[sp++]);
+            const uint32_t comparator = ins.flags & 7u;
+            const bool is_signed = (ins.flags & SILO_CMP_SIGNED) != 0;
+            const uint32_t bias = is_signed ? 0x80000000u : 0u;  // signed order as unsigned order
+            const uint32_t wanted = ins.a ^ bias;
+            const uint32_t upper = static_cast<uint32_t>(ins.b) ^ bias;
+            const uint32_t* set = reinterpret_cast<const uint32_t*>(p.blob + ins.b);
+            for (uint32_t base = 0; base < 65536; base += EVAL_THREADS) {
+               const uint32_t row = base + tid;
+               bool match = false;
+               if (row < chunk_size) {
+                  const uint32_t raw = values[row];
+                  const uint32_t value = raw ^ bias;
+                  switch (comparator) {
+                     case SILO_CMP_EQUALS: match = value == wanted; break;
+                     case SILO_CMP_NOT_EQUALS: match = value != wanted; break;
+                     case SILO_CMP_LESS: match = value < wanted; break;
+                     case SILO_CMP_LESS_OR_EQUALS: match = value <= wanted; break;
+                     case SILO_CMP_HIGHER: match = value > wanted; break;
+                     case SILO_CMP_HIGHER_OR_EQUALS: match = value >= wanted; break;
+                     case SILO_CMP_BETWEEN: match = value >= wanted && value <= upper; break;
+                     default: {  // SILO_CMP_IN_SET
+                        const uint32_t at = lowerBound(set, ins.a, raw);
+                        match = at < ins.a && set[at] == raw;
+                     }
+                  }
+               }
+               const uint32_t bits = __ballot_sync(0xFFFFFFFFu, match);
+               if (lane == 0) {
+                  tile32[row >> 5] = bits;
+               }
+            }
+            __syncthreads();
+            if (column.null_words != nullptr) {  // CompareToValueSelection::match: a null row gives with_nulls
+               const uint64_t nulls = column.null_words[static_cast<size_t>(chunk) * TILE_WORDS + tid];
+               uint64_t word = sh.stack[sp - 1][tid];
+               word = (ins.flags & SILO_CMP_WITH_NULLS) != 0 ? (word | nulls) : (word & ~nulls);
+               sh.stack[sp - 1][tid] = word & layout_word;
             }
             break;
          }
@@ -726,8 +775,26 @@ void validateProgram(const silo_gpu_table* table, const silo_filter_program* pro
             }
             ++depth;
             break;
+         case SILO_OP_PUSH_COMPARE:
+            if (ins.column >= table->value_columns.size()) {
+               bad("value column index out of range");
+            }
+            if ((ins.flags & 7u) == SILO_CMP_IN_SET) {
+               needBlob(ins.b, 4ULL * ins.a);
+               const uint32_t* set = reinterpret_cast<const uint32_t*>(program->blob + ins.b);
+               for (uint32_t i = 1; i < ins.a; ++i) {
+                  if (set[i - 1] >= set[i]) {
+                     bad("PUSH_COMPARE set values must be strictly ascending");
+                  }
+               }
+            }
+            ++depth;
+            break;
          case SILO_OP_PUSH_RANGES:
             needBlob(ins.b, 8ULL * ins.a);
+            if (ins.b % 8 != 0) {
+               bad("PUSH_RANGES pairs must be 8-byte aligned in the blob");
+            }
             for (uint32_t i = 0; i < ins.a; ++i) {
                const uint32_t* range = reinterpret_cast<const uint32_t*>(program->blob + ins.b) + 2 * i;
                if (range[0] > range[1]) {
@@ -926,6 +993,7 @@ static void stageProgram(
    const size_t n_table = program->n_bitmaps + registered_used.size();
    const size_t off_instrs = reserve(sizeof(silo_filter_instr) * program->n_instrs);
    const size_t off_columns = reserve(sizeof(DevColumn) * table->columns.size());
+   const size_t off_value_columns = reserve(sizeof(DevValueColumn) * table->value_columns.size());
    const size_t off_bitmaps = reserve(sizeof(DevBitmap) * n_table);
    const size_t off_blob = reserve(program->blob_bytes);
    const size_t off_descs = reserve(sizeof(DevContainer) * total_descs);
@@ -977,6 +1045,9 @@ static void stageProgram(
    for (size_t i = 0; i < table->columns.size(); ++i) {
       columns[i] = table->columns[i]->dev;
    }
+   if (!table->value_columns.empty()) {
+      std::memcpy(staging + off_value_columns, table->value_columns.data(), sizeof(DevValueColumn) * table->value_columns.size());
+   }
    if (program->blob_bytes > 0) {
       std::memcpy(staging + off_blob, program->blob, program->blob_bytes);
    }
@@ -1019,6 +1090,8 @@ static void stageProgram(
    params.blob = d_staging + off_blob;
    params.bitmaps = bitmaps == nullptr ? nullptr : reinterpret_cast<const DevBitmap*>(d_staging + off_bitmaps);
    params.chunk_sizes = table->d_chunk_sizes;
+   params.value_columns = reinterpret_cast<const DevValueColumn*>(d_staging + off_value_columns);
+   params.chunk_row_begin = table->d_chunk_row_begin;
    params.first_chunk = table->first_chunk;
    params.stack_depth = stack_depth;
    params.has_threshold = has_threshold ? 1u : 0u;

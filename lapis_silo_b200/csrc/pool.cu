@@ -264,6 +264,11 @@ void silo_gpu_table_free(silo_gpu_table* table) {
    for (const silo_gpu_table::RegisteredBitmap& registered : table->registered) {
       cudaFree(registered.d_block);
    }
+   for (const DevValueColumn& column : table->value_columns) {
+      cudaFree(const_cast<uint32_t*>(column.values));
+      cudaFree(const_cast<uint64_t*>(column.null_words));
+   }
+   cudaFree(table->d_chunk_row_begin);
    cudaFree(table->d_chunk_sizes);
    cudaFree(table->d_chunk_popcount_full);
    cudaFree(table->d_work_state);
@@ -332,6 +337,47 @@ uint64_t silo_gpu_table_device_bytes(const silo_gpu_table* table) {
       total += column->device_bytes;
    }
    return total;
+}
+
+int silo_gpu_value_column_upload(silo_gpu_table* table, const uint32_t* values, const uint32_t* null_row_ids, uint64_t n_null_rows) {
+   int index = -1;
+   const int status = guarded([&] {
+      require(table != nullptr && (values != nullptr || table->n_rows == 0), "silo_gpu_value_column_upload: NULL argument");
+      require(n_null_rows == 0 || null_row_ids != nullptr, "silo_gpu_value_column_upload: null_row_ids is NULL");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      cudaStream_t stream = table->ctx->stream;
+      if (table->d_chunk_row_begin == nullptr) {
+         std::vector<uint32_t> chunk_row_begin(table->n_chunks + 1, 0);
+         for (uint32_t chunk = 0; chunk < table->n_chunks; ++chunk) {
+            chunk_row_begin[chunk + 1] = chunk_row_begin[chunk] + table->chunk_sizes[chunk];
+         }
+         table->d_chunk_row_begin = deviceUpload(chunk_row_begin, stream, &table->device_bytes);
+      }
+      DevValueColumn column{};
+      uint32_t* d_values = deviceAlloc<uint32_t>(table->n_rows, &table->device_bytes);
+      if (table->n_rows > 0) {
+         SILO_CUDA_CHECK(cudaMemcpyAsync(d_values, values, table->n_rows * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+      }
+      column.values = d_values;
+      if (n_null_rows > 0) {
+         std::vector<uint64_t> null_words(static_cast<size_t>(table->n_chunks) * TILE_WORDS, 0);
+         for (uint64_t i = 0; i < n_null_rows; ++i) {
+            const uint32_t row_id = null_row_ids[i];
+            const uint32_t global_chunk = row_id >> 16;
+            require(global_chunk >= table->first_chunk && global_chunk < table->first_chunk + table->n_chunks, "null row outside the shard");
+            const uint32_t local_chunk = global_chunk - table->first_chunk;
+            require((row_id & 0xFFFF) < table->chunk_sizes[local_chunk], "null row outside the row layout");
+            null_words[static_cast<size_t>(local_chunk) * TILE_WORDS + ((row_id & 0xFFFF) >> 6)] |= 1ULL << (row_id & 63);
+         }
+         column.null_words = deviceUpload(null_words, stream, &table->device_bytes);
+      }
+      SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+      dropQueryGraphsLocked(table);
+      table->value_columns.push_back(column);
+      index = static_cast<int>(table->value_columns.size()) - 1;
+   });
+   return status == SILO_OK ? index : status;
 }
 
 int silo_gpu_table_set_option(silo_gpu_table* table, const char* name, uint64_t value) {

@@ -658,6 +658,82 @@ std::unique_ptr<Operator> MutationProfile::compile(const Table&) const {
    throw QueryCompilationException("MutationProfile expression must be eliminated in the query rewrite phase");
 }
 
+// ---- predicates over value columns -------------------------------------------------------------
+
+std::string StringEquals::toString() const {
+   return column + " = '" + value + "'";
+}
+
+ExpressionPtr StringEquals::rewrite(const Table&, AmbiguityMode) const {
+   return shared_from_this();
+}
+
+std::unique_ptr<Operator> StringEquals::compile(const Table& table) const {
+   const ValueColumnInfo* found = table.findValueColumn(column);
+   CHECK_QUERY(found != nullptr, "The database does not contain the column '" + column + "'");
+   CHECK_QUERY(found->type == ValueColumnInfo::Type::STRING, "The column '" + column + "' is not of type string");
+   CoveragePredicate predicate{};
+   predicate.kind = CoveragePredicate::COMPARE;
+   predicate.value_column = found->device_column;
+   predicate.comparator = SILO_CMP_IN_SET;
+   const auto id = found->dictionary.find(value);
+   if (id != found->dictionary.end()) {
+      predicate.set.push_back(id->second);  // (a value the column does not hold leaves the set empty: no row matches)
+   }
+   predicate.display = "$string " + column + " IN ['" + value + "']";
+   return std::make_unique<Selection>(predicate);
+}
+
+std::string DateBetween::toString() const {
+   return "[Date-between " + column + " " + (date_from.has_value() ? std::to_string(*date_from) : "unbounded") + " and " +
+          (date_to.has_value() ? std::to_string(*date_to) : "unbounded") + "]";
+}
+
+ExpressionPtr DateBetween::rewrite(const Table&, AmbiguityMode) const {
+   return shared_from_this();
+}
+
+std::unique_ptr<Operator> DateBetween::compile(const Table& table) const {
+   const ValueColumnInfo* found = table.findValueColumn(column);
+   CHECK_QUERY(found != nullptr, "The database does not contain the column '" + column + "'");
+   CHECK_QUERY(found->type == ValueColumnInfo::Type::DATE, "The column '" + column + "' is not of type date");
+   const int32_t from = date_from.value_or(std::numeric_limits<int32_t>::min());
+   if (found->sorted) {
+      // computeRangesOfSortedColumn (date_between.cpp:94-134): binary searches inside every chunk, one range per chunk
+      std::vector<RangeSelection::Range> ranges;
+      size_t chunk_begin = 0;
+      for (size_t chunk = 0; chunk < table.row_layout.numChunks(); ++chunk) {
+         const size_t chunk_size = table.row_layout.chunk_sizes[chunk];
+         const int32_t* begin = found->dates.data() + chunk_begin;
+         const int32_t* end = begin + chunk_size;
+         const auto lower_index = static_cast<size_t>(std::lower_bound(begin, end, from) - begin);
+         const auto upper_index = date_to.has_value() ? static_cast<size_t>(std::upper_bound(begin, end, *date_to) - begin) : chunk_size;
+         const auto global_chunk = static_cast<uint32_t>(table.row_layout.first_chunk + chunk);
+         const uint32_t start_row = lower_index == chunk_size ? (global_chunk + 1) << 16 : (global_chunk << 16) | static_cast<uint32_t>(lower_index);
+         const uint32_t end_row = upper_index == chunk_size ? (global_chunk + 1) << 16 : (global_chunk << 16) | static_cast<uint32_t>(upper_index);
+         ranges.push_back({start_row, end_row});
+         chunk_begin += chunk_size;
+      }
+      const uint32_t layout_begin = table.row_layout.first_chunk << 16;
+      const uint32_t layout_end = (table.row_layout.first_chunk + static_cast<uint32_t>(table.row_layout.numChunks())) << 16;
+      return std::make_unique<RangeSelection>(std::move(ranges), layout_begin, layout_end);
+   }
+   std::vector<CoveragePredicate> predicates(2);
+   for (CoveragePredicate& predicate : predicates) {
+      predicate.kind = CoveragePredicate::COMPARE;
+      predicate.value_column = found->device_column;
+      predicate.is_signed = true;
+   }
+   predicates[0].comparator = SILO_CMP_HIGHER_OR_EQUALS;
+   predicates[0].value = static_cast<uint32_t>(from);
+   predicates[0].display = "$date " + column + " >= " + std::to_string(from);
+   const int32_t to = date_to.value_or(std::numeric_limits<int32_t>::max());
+   predicates[1].comparator = SILO_CMP_LESS_OR_EQUALS;
+   predicates[1].value = static_cast<uint32_t>(to);
+   predicates[1].display = "$date " + column + " <= " + std::to_string(to);
+   return std::make_unique<Selection>(std::nullopt, std::move(predicates));
+}
+
 // ---- boundary leaves -------------------------------------------------------------------------
 
 std::unique_ptr<Operator> BitmapFilter::compile(const Table& table) const {
@@ -991,6 +1067,25 @@ ExpressionPtr build(const Node& node) {
       // `row` (sequenceId, mutation_profile.cpp:109-158) needs the primary-key column and a row
       // reconstruction, both owned by the unchanged host engine: it hands over `seq` instead
       throw IllegalQueryException("filter expression: unsupported profile kind " + kind);
+   }
+   if (head == "str-eq") {  // (str-eq <column> <value>)
+      arity(2);
+      return std::make_shared<StringEquals>(atom(items[1]), atom(items[2]));
+   }
+   if (head == "date-between") {  // (date-between <column> <from day | *> <to day | *>)
+      arity(3);
+      auto bound = [&](const Node& node) -> std::optional<int32_t> {
+         const std::string bound_text = atom(node);
+         if (bound_text == "*") {
+            return std::nullopt;
+         }
+         try {
+            return static_cast<int32_t>(std::stol(bound_text));
+         } catch (const std::exception&) {
+            throw IllegalQueryException("filter expression: date-between bounds are day numbers or *, got '" + bound_text + "'");
+         }
+      };
+      return std::make_shared<DateBetween>(atom(items[1]), bound(items[2]), bound(items[3]));
    }
    if (head == "bitmap") {
       arity(1);

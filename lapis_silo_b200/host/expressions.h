@@ -165,6 +165,30 @@ struct NOf : ScalarExpression {
    std::unique_ptr<Operator> compile(const Table& table) const override;
 };
 
+// `column = 'value'` on a string column without an index (equals.cpp:124-156): rewritten to a StringInSet, compiled to a
+// Selection with that predicate. The device compares dictionary ids.
+struct StringEquals : ScalarExpression {
+   std::string column;
+   std::string value;
+   StringEquals(std::string column, std::string value) : column(std::move(column)), value(std::move(value)) {}
+   std::string toString() const override;
+   ExpressionPtr rewrite(const Table& table, AmbiguityMode mode) const override;
+   std::unique_ptr<Operator> compile(const Table& table) const override;
+};
+
+// date_between.cpp:61-134: a RangeSelection with one range per chunk on a sorted column, else a Selection with the two
+// comparisons. from / to: days since the epoch (Date32), nullopt = open end.
+struct DateBetween : ScalarExpression {
+   std::string column;
+   std::optional<int32_t> date_from;
+   std::optional<int32_t> date_to;
+   DateBetween(std::string column, std::optional<int32_t> date_from, std::optional<int32_t> date_to)
+       : column(std::move(column)), date_from(date_from), date_to(date_to) {}
+   std::string toString() const override;
+   ExpressionPtr rewrite(const Table& table, AmbiguityMode mode) const override;
+   std::unique_ptr<Operator> compile(const Table& table) const override;
+};
+
 struct MutationProfile : ScalarExpression {
    struct QuerySequence {
       std::string sequence;

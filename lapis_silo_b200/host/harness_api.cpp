@@ -165,6 +165,19 @@ uint64_t silo_host_table_num_rows(const silo_host_table* table) {
    return table->table->row_layout.numRows();
 }
 
+int silo_host_table_add_string_column(
+   silo_host_table* table, const char* name, const char* const* dictionary, uint32_t n_values, const uint32_t* ids, const uint32_t* null_row_ids, uint64_t n_null_rows
+) {
+   return guarded([&] {
+      std::vector<std::string> values(dictionary, dictionary + n_values);
+      table->table->addStringColumn(name, values, ids, std::vector<uint32_t>(null_row_ids, null_row_ids + n_null_rows));
+   });
+}
+
+int silo_host_table_add_date_column(silo_host_table* table, const char* name, const int32_t* days, const uint32_t* null_row_ids, uint64_t n_null_rows) {
+   return guarded([&] { table->table->addDateColumn(name, days, std::vector<uint32_t>(null_row_ids, null_row_ids + n_null_rows)); });
+}
+
 silo_host_filter* silo_host_filter_eval(silo_host_table* table, const char* expression) {
    silo_host_filter* result = nullptr;
    guarded([&] {

@@ -153,10 +153,9 @@ std::unique_ptr<Operator> Operator::negate(std::unique_ptr<Operator>&& some_oper
       }
       case SELECTION: {  // selection.cpp:143-151
          auto* selection = static_cast<Selection*>(some_operator.get());
-         if (!selection->child_operator.has_value() && selection->predicates.size() == 1) {
-            CoveragePredicate negated = selection->predicates[0];
-            negated.is_covered = !negated.is_covered;
-            return std::make_unique<Selection>(negated);
+         if (!selection->child_operator.has_value() && selection->predicates.size() == 1 &&
+             (selection->predicates[0].kind == CoveragePredicate::COVERAGE || selection->predicates[0].comparator < 6)) {
+            return std::make_unique<Selection>(selection->predicates[0].negated());
          }
          return std::make_unique<Complement>(std::move(some_operator));
       }
@@ -168,6 +167,30 @@ std::unique_ptr<Operator> Operator::negate(std::unique_ptr<Operator>&& some_oper
          return std::make_unique<Complement>(std::move(some_operator));
    }
    throw std::logic_error("unreachable operator type");
+}
+
+CoveragePredicate CoveragePredicate::negated() const {
+   CoveragePredicate result = *this;
+   if (kind == COVERAGE) {
+      result.is_covered = !is_covered;  // is_in_covered_region.cpp:69-73
+      return result;
+   }
+   // selection.h:133-166: the opposite comparator, and what a null row gives flips too
+   static constexpr uint8_t OPPOSITE[6] = {SILO_CMP_NOT_EQUALS, SILO_CMP_EQUALS, SILO_CMP_HIGHER_OR_EQUALS, SILO_CMP_HIGHER,
+                                           SILO_CMP_LESS_OR_EQUALS, SILO_CMP_LESS};
+   if (comparator >= 6) {
+      throw std::logic_error("a set / range predicate is negated by a Complement around its Selection");
+   }
+   static const char* const NAMES[6] = {"=", "!=", "<", "<=", ">", ">="};
+   const std::string from = std::string(" ") + NAMES[comparator] + " ";
+   const std::string to = std::string(" ") + NAMES[OPPOSITE[comparator]] + " ";
+   const size_t at = result.display.find(from);
+   if (at != std::string::npos) {
+      result.display.replace(at, from.size(), to);
+   }
+   result.comparator = OPPOSITE[comparator];
+   result.with_nulls = !with_nulls;
+   return result;
 }
 
 void Empty::lower(ProgramBuilder& program) const {
@@ -420,13 +443,17 @@ void RangeSelection::lower(ProgramBuilder& program) const {
       flat.push_back(range.start);
       flat.push_back(range.end);
    }
-   const uint64_t offset = program.addBlob(flat.data(), flat.size() * sizeof(uint32_t), 4);
+   const uint64_t offset = program.addBlob(flat.data(), flat.size() * sizeof(uint32_t), 8);  // (the kernel loads {start, end} pairs)
    program.emit(SILO_OP_PUSH_RANGES, 0, 0, static_cast<uint32_t>(ranges.size()), offset);
 }
 
 std::string Selection::toString() const {  // selection.cpp:75-88, is_in_covered_region.cpp:25-29
    std::string res = "Select[";
    for (size_t i = 0; i < predicates.size(); ++i) {
+      if (predicates[i].kind == CoveragePredicate::COMPARE) {
+         res += std::string(i > 0 ? "," : "") + predicates[i].display;
+         continue;
+      }
       res += std::string(i > 0 ? "," : "") + (predicates[i].is_covered ? "" : "!") + "IsInCoveredRegion(" +
              std::to_string(predicates[i].position_idx) + ")";
    }
@@ -446,6 +473,20 @@ void Selection::lower(ProgramBuilder& program) const {
       have_tile = true;
    }
    for (const auto& predicate : predicates) {
+      if (predicate.kind == CoveragePredicate::COMPARE) {
+         const uint8_t flags = static_cast<uint8_t>(predicate.comparator | (predicate.is_signed ? SILO_CMP_SIGNED : 0) | (predicate.with_nulls ? SILO_CMP_WITH_NULLS : 0));
+         if (predicate.comparator == SILO_CMP_IN_SET) {
+            const uint64_t offset = program.addBlob(predicate.set.data(), predicate.set.size() * sizeof(uint32_t), 4);
+            program.emit(SILO_OP_PUSH_COMPARE, flags, static_cast<uint16_t>(predicate.value_column), static_cast<uint32_t>(predicate.set.size()), offset);
+         } else {
+            program.emit(SILO_OP_PUSH_COMPARE, flags, static_cast<uint16_t>(predicate.value_column), predicate.value, 0);
+         }
+         if (have_tile) {
+            program.emit(SILO_OP_AND);
+         }
+         have_tile = true;
+         continue;
+      }
       program.emit(
          SILO_OP_PUSH_COVERED,
          predicate.is_covered ? 0 : 1,
@@ -510,7 +551,7 @@ bool matchCoveredMinusSymbols(const Operator& op, CoveragePredicate& predicate, 
    const auto& selection = static_cast<const Selection&>(left);
    const auto& scan = static_cast<const IndexScan&>(right);
    if (selection.child_operator.has_value() || selection.predicates.size() != 1 ||
-       !selection.predicates[0].is_covered || scan.source != IndexScan::Source::SYMBOLS ||
+       selection.predicates[0].kind != CoveragePredicate::COVERAGE || !selection.predicates[0].is_covered || scan.source != IndexScan::Source::SYMBOLS ||
        scan.device_column != selection.predicates[0].device_column ||
        scan.position_idx != selection.predicates[0].position_idx) {
       return false;

@@ -213,13 +213,25 @@ class RangeSelection : public Operator {
    void lower(ProgramBuilder& program) const override;
 };
 
-// Selection restricted to the one predicate kind that lives on this path
-// (filter/operators/is_in_covered_region.h); predicates over value columns stay on the host side of
-// the boundary and re-enter as IndexScan::overBitmap.
+// A Predicate of Selection (selection.h:24-43): IsInCoveredRegion over a sequence column (is_in_covered_region.cpp:31-62)
+// or, kind == COMPARE, a comparison over a value column -- CompareToValueSelection (selection.h:76-166) and StringInSet
+// (equals.cpp:124-156). On the device both are leaves of the filter program (PUSH_COVERED / PUSH_COMPARE), so the
+// reference's "evaluate the child, then match the predicates row by row on the host" stage (selection.cpp:94-141) is one
+// program: child AND predicate_1 AND ...
 struct CoveragePredicate {
    int device_column;
    uint32_t position_idx;
    bool is_covered;  // IS_COVERED / IS_NOT_COVERED
+   enum Kind : uint8_t { COVERAGE, COMPARE } kind = COVERAGE;
+   // COMPARE
+   int value_column = -1;       // device index of the value column
+   uint8_t comparator = 0;      // silo_comparator
+   bool is_signed = false;      // Date32 / integers
+   bool with_nulls = false;     // what a null row gives (selection.h:113-115)
+   uint32_t value = 0;
+   std::vector<uint32_t> set;   // IN_SET: ascending dictionary ids
+   std::string display;         // Predicate::toString()
+   [[nodiscard]] CoveragePredicate negated() const;  // Predicate::negate()
 };
 
 class Selection : public Operator {

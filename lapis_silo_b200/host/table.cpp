@@ -213,6 +213,52 @@ int Table::addSequenceColumn(
    return device_column;
 }
 
+namespace {
+int uploadValueColumn(const Table& table, const uint32_t* values, const std::vector<uint32_t>& null_row_ids) {
+   if (table.device == nullptr) {
+      return -1;
+   }
+   const int index = silo_gpu_value_column_upload(table.device, values, null_row_ids.empty() ? nullptr : null_row_ids.data(), null_row_ids.size());
+   if (index < 0) {
+      throwOnDeviceError(index);
+   }
+   return index;
+}
+}  // namespace
+
+void Table::addStringColumn(const std::string& name, const std::vector<std::string>& dictionary, const uint32_t* ids, const std::vector<uint32_t>& null_row_ids) {
+   ValueColumnInfo column;
+   column.type = ValueColumnInfo::Type::STRING;
+   column.name = name;
+   for (size_t id = 0; id < dictionary.size(); ++id) {
+      column.dictionary.emplace(dictionary[id], static_cast<uint32_t>(id));
+   }
+   column.has_nulls = !null_row_ids.empty();
+   column.device_column = uploadValueColumn(*this, ids, null_row_ids);
+   value_columns.push_back(std::move(column));
+}
+
+void Table::addDateColumn(const std::string& name, const int32_t* days, const std::vector<uint32_t>& null_row_ids) {
+   ValueColumnInfo column;
+   column.type = ValueColumnInfo::Type::DATE;
+   column.name = name;
+   column.dates.assign(days, days + row_layout.numRows());
+   column.has_nulls = !null_row_ids.empty();
+   // Date32Column::isSorted: ascending over the whole column and no nulls
+   column.sorted = !column.has_nulls && std::is_sorted(column.dates.begin(), column.dates.end());
+   column.device_column = uploadValueColumn(*this, reinterpret_cast<const uint32_t*>(days), null_row_ids);
+   value_columns.push_back(std::move(column));
+}
+
+const ValueColumnInfo* Table::findValueColumn(const std::string& name) const {
+   for (const ValueColumnInfo& column : value_columns) {
+      if (column.name == name) {
+         return &column;
+      }
+   }
+   return nullptr;
+}
+
 const SequenceColumnInfo* Table::findColumn(const std::string& name) const {
    for (const auto& column : columns) {
       if (column.name == name) {

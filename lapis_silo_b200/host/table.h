@@ -81,10 +81,29 @@ struct SequenceColumnInfo {
    int device_column = -1;  // index returned by silo_gpu_column_upload
 };
 
+// A metadata column the filter's Selection predicates read (string_column.h, date32 columns of column_group.h:73-74):
+// 32-bit values per row, resident on the device (silo_gpu_value_column_upload). A string column is stored as
+// dictionary ids (the dictionary stays here: an equality test looks the literal up once per query); a Date32 column as
+// its day numbers, with the host copy kept for the sorted fast path of DateBetween (date_between.cpp:75-79).
+struct ValueColumnInfo {
+   enum class Type : uint8_t { STRING, DATE } type = Type::STRING;
+   std::string name;
+   int device_column = -1;                         // index returned by silo_gpu_value_column_upload (-1: host-only table)
+   std::map<std::string, uint32_t> dictionary;     // STRING: value -> id
+   std::vector<int32_t> dates;                     // DATE: the rows of the shard in layout order
+   bool sorted = false;                            // DATE: Date32Column::isSorted()
+   bool has_nulls = false;
+};
+
 class Table {
   public:
    RowLayout row_layout;
    std::vector<SequenceColumnInfo> columns;
+   std::vector<ValueColumnInfo> value_columns;
+   // values: dictionary ids in layout order; null_row_ids: ascending global row ids
+   void addStringColumn(const std::string& name, const std::vector<std::string>& dictionary, const uint32_t* ids, const std::vector<uint32_t>& null_row_ids);
+   void addDateColumn(const std::string& name, const int32_t* days, const std::vector<uint32_t>& null_row_ids);
+   [[nodiscard]] const ValueColumnInfo* findValueColumn(const std::string& name) const;
    // stand-ins for indexes owned by out-of-scope columns (LineageIndex, dictionary index): ready-made
    // roaring bitmaps in the portable format, as the reference would hand them over
    // (lineage_filter.cpp:96-99, roaring_serialize.h:15-30)

@@ -37,7 +37,7 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_filter_lower_timed", "silo_host_filter_to_string", "silo_host_filter_program_bitmap",
     "silo_host_archive_read", "silo_host_archive_free", "silo_host_archive_column", "silo_host_archive_column_info",
     "silo_host_archive_chunk_sizes", "silo_host_archive_column_shard", "silo_host_table_load_archive", "silo_host_roaring_runs",
-    "silo_host_synthetic_create_gene", "silo_host_shard_group_create", "silo_host_shard_group_connect", "silo_host_sharded_enqueue", "silo_host_sharded_collect_packed",
+    "silo_host_table_add_string_column", "silo_host_table_add_date_column", "silo_host_synthetic_create_gene", "silo_host_shard_group_create", "silo_host_shard_group_connect", "silo_host_sharded_enqueue", "silo_host_sharded_collect_packed",
     "silo_host_prepared_run_sharded_async", "silo_host_sharded_collect_async", "silo_host_sharded_query_packed",
 ]
 SHARD_HANDLE_BYTES = 128  # SILO_SHARD_HANDLE_BYTES
@@ -63,6 +63,8 @@ def lib() -> C.CDLL:
         L.silo_host_table_free.restype = None
         L.silo_host_table_add_column.argtypes = [vp, C.c_char_p, C.c_int, C.c_char_p, vp]
         L.silo_host_table_register_bitmap.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint64, C.c_int]
+        L.silo_host_table_add_string_column.argtypes = [vp, C.c_char_p, C.POINTER(C.c_char_p), C.c_uint32, vp, vp, C.c_uint64]
+        L.silo_host_table_add_date_column.argtypes = [vp, C.c_char_p, vp, vp, C.c_uint64]
         L.silo_host_table_device.argtypes = [vp]
         L.silo_host_table_device.restype = vp
         L.silo_host_table_num_rows.argtypes = [vp]
@@ -446,6 +448,36 @@ class HostTable:
         _check(lib().silo_host_table_add_column(
             self._h, name.encode(), alphabet, reference.encode(), C.cast(desc_ptr, C.c_void_p)))
         self.columns[name] = (16 if alphabet == NUCLEOTIDE else 28, len(reference))
+
+    def add_string_column(self, name: str, values: Sequence[Optional[str]]) -> None:
+        """A string column without an index (one value per row in layout order, None = null): dictionary ids on the device."""
+        dictionary = sorted({v for v in values if v is not None})
+        index = {v: i for i, v in enumerate(dictionary)}
+        ids = np.array([index[v] if v is not None else 0 for v in values], dtype=np.uint32)
+        nulls = self._row_ids(np.flatnonzero(np.array([v is None for v in values], dtype=bool)))
+        names = (C.c_char_p * max(len(dictionary), 1))(*[v.encode() for v in dictionary])
+        _check(lib().silo_host_table_add_string_column(self._h, name.encode(), names, len(dictionary), ids.ctypes.data, nulls.ctypes.data, nulls.size))
+
+    def add_string_column_ids(self, name: str, dictionary: Sequence[str], ids: np.ndarray) -> None:
+        """the same from ready-made dictionary ids (no nulls)"""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        names = (C.c_char_p * max(len(dictionary), 1))(*[v.encode() for v in dictionary])
+        _check(lib().silo_host_table_add_string_column(self._h, name.encode(), names, len(dictionary), ids.ctypes.data, None, 0))
+
+    def add_date_column(self, name: str, days: Sequence[Optional[int]]) -> None:
+        """A Date32 column (days since the epoch per row in layout order, None = null)."""
+        if isinstance(days, np.ndarray):
+            values, nulls = np.ascontiguousarray(days, dtype=np.int32), np.zeros(0, dtype=np.uint32)
+        else:
+            values = np.array([d if d is not None else 0 for d in days], dtype=np.int32)
+            nulls = self._row_ids(np.flatnonzero(np.array([d is None for d in days], dtype=bool)))
+        _check(lib().silo_host_table_add_date_column(self._h, name.encode(), values.ctypes.data, nulls.ctypes.data if nulls.size else None, nulls.size))
+
+    def _row_ids(self, dense_rows: np.ndarray) -> np.ndarray:
+        """dense row numbers (layout order) -> global row ids (chunk << 16 | row)"""
+        starts = np.concatenate([[0], np.cumsum(self.chunk_sizes)])
+        chunks = np.searchsorted(starts, dense_rows, side="right") - 1
+        return (((chunks + self.first_chunk).astype(np.uint64) << np.uint64(16)) | (dense_rows - starts[chunks]).astype(np.uint64)).astype(np.uint32)
 
     def to_strings(self, expression: str) -> tuple[str, str, str]:
         """toString() of the parsed expression, the rewritten expression and the compiled operator tree"""

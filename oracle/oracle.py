@@ -119,6 +119,9 @@ def lib():
         L.orc_gen_full_sequence_table.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64]
         L.orc_gen_nrun_table.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64]
         L.orc_gen_mutation_benchmark_table.argtypes = [C.c_void_p, C.c_uint64]
+        L.orc_table_add_string_column.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_uint64]
+        L.orc_table_add_string_column_ids.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_uint32, C.c_void_p, C.c_uint64]
+        L.orc_table_add_date_column.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_now_seconds.restype = C.c_double
         L.orc_mutations_query.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double, C.POINTER(C.c_uint64)]
         L.orc_mutations_query.restype = C.c_int64
@@ -248,6 +251,25 @@ class Table:
 
     def finalize(self) -> None:
         _check(lib().orc_table_finalize(self._h))
+
+    def add_string_column(self, name: str, values: Sequence[Optional[str]]) -> None:
+        """An unindexed string column: one value per row in layout order (None = null); after the layout is known."""
+        arr = (C.c_char_p * max(len(values), 1))(*[v.encode() if v is not None else None for v in values])
+        _check(lib().orc_table_add_string_column(self._h, name.encode(), arr, len(values)))
+
+    def add_string_column_ids(self, name: str, dictionary: Sequence[str], ids) -> None:
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        names = (C.c_char_p * max(len(dictionary), 1))(*[v.encode() for v in dictionary])
+        _check(lib().orc_table_add_string_column_ids(self._h, name.encode(), names, len(dictionary), ids.ctypes.data, ids.size))
+
+    def add_date_column(self, name: str, days) -> None:
+        """A Date32 column: days since the epoch per row in layout order (None = null)."""
+        if isinstance(days, np.ndarray):
+            values, nulls = np.ascontiguousarray(days, dtype=np.int32), None
+        else:
+            values = np.array([d if d is not None else 0 for d in days], dtype=np.int32)
+            nulls = np.array([d is None for d in days], dtype=np.uint8)
+        _check(lib().orc_table_add_date_column(self._h, name.encode(), values.ctypes.data, nulls.ctypes.data if nulls is not None else None, values.size))
 
     def register_bitmap(self, name: str, ids: Iterable[int]) -> None:
         arr = np.ascontiguousarray(np.fromiter(ids, dtype=np.uint32))

@@ -330,6 +330,74 @@ int64_t orc_mutations_query(void* table, const char* expression, const char* col
 // `threads` workers, each running independent queries back to back (the reference serves one
 // request per worker thread, api/api.cpp:39-51, and has no intra-query parallelism) until `seconds`
 // have passed or max_queries_per_thread ran.
+// Metadata columns for the Selection predicates: one value per row in layout order (after the layout is known).
+// values[i] == nullptr / is_null[i] != 0: a null row.
+int orc_table_add_string_column(void* table, const char* name, const char* const* values, uint64_t n_rows) {
+   return guarded([&] {
+      auto* t = static_cast<Table*>(table);
+      if (n_rows != t->row_layout.numRows()) {
+         throw std::runtime_error("orc_table_add_string_column: one value per row of the layout");
+      }
+      StringValueColumn column;
+      column.name = name;
+      for (uint64_t i = 0; i < n_rows; ++i) {
+         column.is_null.push_back(values[i] == nullptr);
+         column.values.emplace_back(values[i] == nullptr ? "" : values[i]);
+      }
+      t->computeChunkBegins();
+      t->string_columns.push_back(std::move(column));
+   });
+}
+
+// the same from dictionary ids (large tables: no per-row C strings)
+int orc_table_add_string_column_ids(void* table, const char* name, const char* const* dictionary, uint32_t n_values, const uint32_t* ids, uint64_t n_rows) {
+   return guarded([&] {
+      auto* t = static_cast<Table*>(table);
+      if (n_rows != t->row_layout.numRows()) {
+         throw std::runtime_error("orc_table_add_string_column_ids: one value per row of the layout");
+      }
+      StringValueColumn column;
+      column.name = name;
+      column.is_null.assign(n_rows, false);
+      column.values.reserve(n_rows);
+      for (uint64_t i = 0; i < n_rows; ++i) {
+         if (ids[i] >= n_values) {
+            throw std::runtime_error("orc_table_add_string_column_ids: id out of range");
+         }
+         column.values.emplace_back(dictionary[ids[i]]);
+      }
+      t->computeChunkBegins();
+      t->string_columns.push_back(std::move(column));
+   });
+}
+
+int orc_table_add_date_column(void* table, const char* name, const int32_t* days, const uint8_t* is_null, uint64_t n_rows) {
+   return guarded([&] {
+      auto* t = static_cast<Table*>(table);
+      if (n_rows != t->row_layout.numRows()) {
+         throw std::runtime_error("orc_table_add_date_column: one value per row of the layout");
+      }
+      DateValueColumn column;
+      column.name = name;
+      std::optional<int32_t> last;
+      for (uint64_t i = 0; i < n_rows; ++i) {  // Date32Column::appendChunk, date32_column.cpp:17-35
+         const bool null = is_null != nullptr && is_null[i] != 0;
+         column.is_null.push_back(null);
+         column.values.push_back(null ? 0 : days[i]);
+         if (null) {
+            column.is_sorted = false;
+         } else {
+            if (last.has_value() && days[i] < *last) {
+               column.is_sorted = false;
+            }
+            last = days[i];
+         }
+      }
+      t->computeChunkBegins();
+      t->date_columns.push_back(std::move(column));
+   });
+}
+
 int orc_mutations_query_bench(
    void* table,
    const char* expression,

@@ -2,6 +2,7 @@
 #include "expressions.h"
 
 #include <algorithm>
+#include <limits>
 #include <map>
 #include <variant>
 
@@ -712,6 +713,72 @@ class RangesLeaf : public Expression {  // date_between.cpp:75-79 on a sorted co
    }
 };
 
+// `column = 'value'` on an unindexed string column: Equals::rewrite -> StringInSet (equals.cpp:124-156), compiled to a
+// Selection with the StringInSet predicate (string_in_set.cpp:73-83)
+class StringEqualsExpr : public Expression {
+  public:
+   std::string column;
+   std::string value;
+   StringEqualsExpr(std::string column, std::string value) : column(std::move(column)), value(std::move(value)) {}
+   std::string toString() const override { return column + " = '" + value + "'"; }
+   ExprPtr rewrite(const Table&, AmbiguityMode) const override { return shared_from_this(); }
+   std::unique_ptr<Operator> compile(const Table& table) const override {
+      for (const StringValueColumn& candidate : table.string_columns) {
+         if (candidate.name == column) {
+            return std::make_unique<Selection>(
+               std::make_unique<StringInSetPredicate>(&candidate, &table.chunk_begins, true, std::vector<std::string>{value}), table.row_layout
+            );
+         }
+      }
+      throw IllegalQueryException("The database does not contain the column '" + column + "'");
+   }
+};
+
+// date_between.cpp:61-134
+class DateBetweenExpr : public Expression {
+  public:
+   std::string column;
+   std::optional<int32_t> date_from;
+   std::optional<int32_t> date_to;
+   DateBetweenExpr(std::string column, std::optional<int32_t> date_from, std::optional<int32_t> date_to)
+       : column(std::move(column)), date_from(date_from), date_to(date_to) {}
+   std::string toString() const override { return "[Date-between " + column + "]"; }
+   ExprPtr rewrite(const Table&, AmbiguityMode) const override { return shared_from_this(); }
+   std::unique_ptr<Operator> compile(const Table& table) const override {
+      const DateValueColumn* date_column = nullptr;
+      for (const DateValueColumn& candidate : table.date_columns) {
+         if (candidate.name == column) {
+            date_column = &candidate;
+         }
+      }
+      if (date_column == nullptr) {
+         throw IllegalQueryException("The database does not contain the column '" + column + "'");
+      }
+      const int32_t from = date_from.value_or(std::numeric_limits<int32_t>::min());
+      if (date_column->is_sorted) {  // computeRangesOfSortedColumn :94-134
+         std::vector<RangeSelection::Range> ranges;
+         for (size_t chunk_idx = 0; chunk_idx < table.row_layout.numChunks(); ++chunk_idx) {
+            const int32_t* begin = date_column->values.data() + table.chunk_begins[chunk_idx];
+            const size_t chunk_size = table.row_layout.chunk_sizes[chunk_idx];
+            const int32_t* end = begin + chunk_size;
+            const auto lower_index = static_cast<size_t>(std::lower_bound(begin, end, from) - begin);
+            const auto upper_index = date_to.has_value() ? static_cast<size_t>(std::upper_bound(begin, end, *date_to) - begin) : chunk_size;
+            const auto chunk = static_cast<uint32_t>(chunk_idx);
+            const uint32_t start_row = lower_index == chunk_size ? (chunk + 1) << 16 : (chunk << 16) | static_cast<uint32_t>(lower_index);
+            const uint32_t end_row = upper_index == chunk_size ? (chunk + 1) << 16 : (chunk << 16) | static_cast<uint32_t>(upper_index);
+            ranges.push_back({start_row, end_row});
+         }
+         return std::make_unique<RangeSelection>(std::move(ranges), table.row_layout);
+      }
+      PredicateVector predicates;
+      predicates.push_back(std::make_unique<DateCompare>(date_column, &table.chunk_begins, DateCompare::Comparator::HIGHER_OR_EQUALS, from));
+      predicates.push_back(std::make_unique<DateCompare>(
+         date_column, &table.chunk_begins, DateCompare::Comparator::LESS_OR_EQUALS, date_to.value_or(std::numeric_limits<int32_t>::max())
+      ));
+      return std::make_unique<Selection>(std::nullopt, std::move(predicates), table.row_layout);
+   }
+};
+
 // ---------- physical forms (operator-level known-answer tests) ----------
 
 class IdsLeaf : public Expression {
@@ -1051,6 +1118,21 @@ ExprPtr build(const SNode& node) {
          return expression;
       }
       throw IllegalQueryException("filter expression: unknown profile kind " + kind);
+   }
+   if (head == "str-eq") {
+      arity(2);
+      return std::make_shared<StringEqualsExpr>(atomOf(items[1]), atomOf(items[2]));
+   }
+   if (head == "date-between") {
+      arity(3);
+      auto bound = [&](const auto& item) -> std::optional<int32_t> {
+         const std::string bound_text = atomOf(item);
+         if (bound_text == "*") {
+            return std::nullopt;
+         }
+         return static_cast<int32_t>(std::stol(bound_text));
+      };
+      return std::make_shared<DateBetweenExpr>(atomOf(items[1]), bound(items[2]), bound(items[3]));
    }
    if (head == "bitmap") {
       arity(1);

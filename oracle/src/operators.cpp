@@ -348,6 +348,59 @@ std::unique_ptr<Predicate> IsInCoveredRegion::negate() const {
    );
 }
 
+std::string DateCompare::toString() const {
+   static const char* const NAMES[] = {"=", "<", ">", "<=", ">=", "!="};
+   return "$date " + column->name + " " + NAMES[static_cast<int>(comparator)] + " " + std::to_string(value);
+}
+
+bool DateCompare::match(uint32_t global_row_id) const {
+   const size_t row = (*chunk_begin)[global_row_id >> 16] + (global_row_id & 0xFFFFu);
+   if (column->is_null[row]) {
+      return with_nulls;
+   }
+   const int32_t stored = column->values[row];
+   switch (comparator) {
+      case Comparator::EQUALS: return stored == value;
+      case Comparator::NOT_EQUALS: return stored != value;
+      case Comparator::LESS: return stored < value;
+      case Comparator::HIGHER_OR_EQUALS: return stored >= value;
+      case Comparator::HIGHER: return stored > value;
+      case Comparator::LESS_OR_EQUALS: return stored <= value;
+   }
+   return false;
+}
+
+std::unique_ptr<Predicate> DateCompare::negate() const {
+   Comparator opposite = Comparator::EQUALS;
+   switch (comparator) {
+      case Comparator::EQUALS: opposite = Comparator::NOT_EQUALS; break;
+      case Comparator::NOT_EQUALS: opposite = Comparator::EQUALS; break;
+      case Comparator::LESS: opposite = Comparator::HIGHER_OR_EQUALS; break;
+      case Comparator::HIGHER_OR_EQUALS: opposite = Comparator::LESS; break;
+      case Comparator::HIGHER: opposite = Comparator::LESS_OR_EQUALS; break;
+      case Comparator::LESS_OR_EQUALS: opposite = Comparator::HIGHER; break;
+   }
+   return std::make_unique<DateCompare>(column, chunk_begin, opposite, value, !with_nulls);
+}
+
+std::string StringInSetPredicate::toString() const {
+   std::string joined;
+   for (const std::string& value : values) {
+      joined += (joined.empty() ? "'" : ",'") + value + "'";
+   }
+   return "$string " + column->name + (in ? " IN [" : " NOT IN [") + joined + "]";
+}
+
+bool StringInSetPredicate::match(uint32_t global_row_id) const {
+   const size_t row = (*chunk_begin)[global_row_id >> 16] + (global_row_id & 0xFFFFu);
+   const bool in_set = std::find(values.begin(), values.end(), column->values[row]) != values.end();
+   return in ? in_set : !in_set;
+}
+
+std::unique_ptr<Predicate> StringInSetPredicate::negate() const {
+   return std::make_unique<StringInSetPredicate>(column, chunk_begin, !in, values);
+}
+
 Selection::Selection(
    std::optional<std::unique_ptr<Operator>> child_operator,
    PredicateVector&& predicates_,

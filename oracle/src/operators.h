@@ -173,6 +173,36 @@ class IsInCoveredRegion : public Predicate {
    std::unique_ptr<Predicate> negate() const override;
 };
 
+// CompareToValueSelection<Date32Column> (selection.h:76-166): a null row gives with_nulls
+class DateCompare : public Predicate {
+  public:
+   enum class Comparator : uint8_t { EQUALS, LESS, HIGHER, LESS_OR_EQUALS, HIGHER_OR_EQUALS, NOT_EQUALS };
+   const DateValueColumn* column;
+   const std::vector<size_t>* chunk_begin;  // dense index of every chunk's first row
+   Comparator comparator;
+   int32_t value;
+   bool with_nulls;
+   DateCompare(const DateValueColumn* column, const std::vector<size_t>* chunk_begin, Comparator comparator, int32_t value, bool with_nulls = false)
+       : column(column), chunk_begin(chunk_begin), comparator(comparator), value(value), with_nulls(with_nulls) {}
+   std::string toString() const override;
+   bool match(uint32_t global_row_id) const override;
+   std::unique_ptr<Predicate> negate() const override;
+};
+
+// filter/operators/string_in_set.cpp:41-58
+class StringInSetPredicate : public Predicate {
+  public:
+   const StringValueColumn* column;
+   const std::vector<size_t>* chunk_begin;
+   bool in;  // IN / NOT_IN
+   std::vector<std::string> values;
+   StringInSetPredicate(const StringValueColumn* column, const std::vector<size_t>* chunk_begin, bool in, std::vector<std::string> values)
+       : column(column), chunk_begin(chunk_begin), in(in), values(std::move(values)) {}
+   std::string toString() const override;
+   bool match(uint32_t global_row_id) const override;
+   std::unique_ptr<Predicate> negate() const override;
+};
+
 class Selection : public Operator {
   public:
    std::optional<std::unique_ptr<Operator>> child_operator;

@@ -180,9 +180,42 @@ struct SequenceColumn {
    void flushBuffer();  // .cpp:260-268
 };
 
+// Metadata columns the Selection predicates read: an unindexed StringColumn (string_column.h) and a Date32Column
+// (date32_column.h:36-44, .cpp:17-35: sorted = appended in non-decreasing order and without nulls; a null is stored as 0).
+// One value per row in layout order.
+struct StringValueColumn {
+   std::string name;
+   std::vector<std::string> values;  // "" for a null row
+   std::vector<bool> is_null;
+};
+struct DateValueColumn {
+   std::string name;
+   std::vector<int32_t> values;
+   std::vector<bool> is_null;
+   bool is_sorted = true;
+};
+
 struct Table {
    RowLayout row_layout;
    std::vector<std::unique_ptr<SequenceColumn>> columns;  // insertion order
+   std::vector<StringValueColumn> string_columns;
+   std::vector<DateValueColumn> date_columns;
+   std::vector<size_t> chunk_begins;  // dense index of every chunk's first row (set when a value column is added)
+   void computeChunkBegins() {
+      chunk_begins.assign(row_layout.chunk_sizes.size() + 1, 0);
+      for (size_t c = 0; c < row_layout.chunk_sizes.size(); ++c) {
+         chunk_begins[c + 1] = chunk_begins[c] + row_layout.chunk_sizes[c];
+      }
+   }
+   // dense index (layout order) of a global row id
+   [[nodiscard]] size_t denseRow(uint32_t global_row_id) const {
+      size_t begin = 0;
+      const uint32_t chunk = global_row_id >> 16;
+      for (uint32_t c = 0; c < chunk; ++c) {
+         begin += row_layout.chunk_sizes[c];
+      }
+      return begin + (global_row_id & 0xFFFFu);
+   }
    // stand-ins for indexes owned by out-of-scope columns (lineage index, dictionary index,
    // lineage_filter.cpp:77-100): ready-made roaring bitmaps that arrive via IndexScan
    std::map<std::string, Roaring> named_bitmaps;

@@ -721,3 +721,45 @@ def test_amino_acid_mutations_over_twelve_genes(ctx):
     for _ in range(3):  # (the third call replays the captured graph)
         assert table.mutations(subset, expression, 0.01) == want
     table.close()
+
+
+def test_selection_predicates_on_device(ctx):
+    """Predicates over metadata columns inside the filter program (PUSH_COMPARE over device-resident value columns:
+    dictionary ids of an unindexed string column, Date32 days) against the oracle's Selection (row-by-row match on a small
+    child, makeBitmap + row-by-row on a large one, selection.cpp:94-141): string equality, date ranges on unsorted columns
+    with nulls and on a sorted column (RangeSelection), combined with sequence filters, and as the filter of Mutations."""
+    from lapis_silo_b200 import host_api
+    t = build_random(77, 3000, 40, (999, 1000, 2100))
+    rng = np.random.default_rng(77)
+    n_rows = t.num_rows
+    places = ["basel", "bern", "geneva", "generated"]
+    location = [None if rng.random() < 0.05 else places[int(rng.integers(0, 4))] for _ in range(n_rows)]
+    unsorted_days = [None if rng.random() < 0.05 else int(rng.integers(18000, 19500)) for _ in range(n_rows)]
+    sorted_days = np.sort(rng.integers(18000, 19500, n_rows)).astype(np.int32)
+    t.add_string_column("location", location)
+    t.add_date_column("date", unsorted_days)
+    t.add_date_column("sampling", sorted_days)
+    small = sorted(set(int(v) for v in rng.integers(0, 900, 40)))
+    t.register_bitmap("small", small)
+    device = mirror(ctx, t, ["small"])
+    device.add_string_column("location", location)
+    device.add_date_column("date", unsorted_days)
+    device.add_date_column("sampling", sorted_days)
+    pair = (t, device)
+    leaves = ["(str-eq location basel)", "(str-eq location generated)", "(str-eq location nowhere)", "(date-between date 18500 19000)",
+              "(date-between date * 18200)", "(date-between date 19300 *)", "(date-between sampling 18300 18900)", "(date-between sampling * *)",
+              "(bitmap small)", "(sym-eq c 7 A)", "(has-mut c 12)", "(sym-eq c 3 N)"]
+    for leaf in leaves:
+        both(pair, leaf)
+        both(pair, f"(not {leaf})")
+    for _ in range(60):
+        a, b, c = (leaves[int(i)] for i in rng.integers(0, len(leaves), 3))
+        both(pair, f"(and {a} {b})")
+        both(pair, f"(and {a} (not {b}) {c})")
+        both(pair, f"(or {a} (and {b} {c}))")
+        both(pair, f"(n-of 2 0 {a} {b} {c})")
+        both(pair, f"(not (and {a} (or {b} (not {c}))))")
+    expression = "(and (str-eq location generated) (date-between date 18200 19300) (not (sym-eq c 9 N)))"
+    assert device.mutations(["c"], expression, 0.02) == t.mutations("c", expression, 0.02)
+    assert "$string location IN ['generated']" in device.to_strings(expression)[2] and "$date date >= 18200" in device.to_strings(expression)[2]
+    device.close()

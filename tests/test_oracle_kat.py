@@ -403,3 +403,55 @@ def test_mutations_single_trivial_row():  # operators/union_all_node.test.cpp:18
     t.finalize()
     rows = t.mutations("main", None, 0.0)
     assert [(r["mutationTo"], r["proportion"]) for r in rows] == [("T", 1.0)]
+
+
+def test_selection_predicates_over_value_columns():
+    """Selection with predicates over metadata columns (selection.cpp:94-141, selection.h:76-166, string_in_set.cpp:41-58,
+    date_between.cpp:61-134) against a brute-force evaluation in Python: string equality on an unindexed column, date ranges
+    on an unsorted column with nulls and on a sorted one (RangeSelection), alone and under And / Or / Not with both of
+    Selection's strategies (a small and a large child)."""
+    import numpy as np
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    n_rows = 70000 + 1234
+    t = O.Table()
+    t.set_layout(65536, n_rows - 65536)
+    places = ["basel", "bern", "geneva", "generated"]
+    location = [None if rng.random() < 0.02 else places[int(rng.integers(0, 4))] for _ in range(n_rows)]
+    unsorted_days = [None if rng.random() < 0.03 else int(rng.integers(18000, 19500)) for _ in range(n_rows)]
+    sorted_days = np.sort(rng.integers(18000, 19500, n_rows)).astype(np.int32)
+    t.add_string_column("location", location)
+    t.add_date_column("date", unsorted_days)
+    t.add_date_column("sampling", sorted_days)
+    small = sorted(set(int(v) for v in rng.integers(0, n_rows, 500)))
+    large = sorted(set(int(v) for v in rng.integers(0, n_rows, 40000)))
+
+    def to_global(dense):
+        dense = np.asarray(dense)
+        return np.where(dense < 65536, dense, (1 << 16) + dense - 65536)
+    t.register_bitmap("small", to_global(small).tolist())
+    t.register_bitmap("large", to_global(large).tolist())
+    is_basel = np.array([v == "basel" for v in location])
+    in_date = np.array([d is not None and 18500 <= d <= 19000 for d in unsorted_days])
+    from_only = np.array([d is not None and d >= 19000 for d in unsorted_days])
+    in_sampling = (sorted_days >= 18300) & (sorted_days <= 18900)
+    small_mask = np.zeros(n_rows, dtype=bool)
+    small_mask[small] = True
+    large_mask = np.zeros(n_rows, dtype=bool)
+    large_mask[large] = True
+    cases = {
+        "(str-eq location basel)": is_basel,
+        "(str-eq location nowhere)": np.zeros(n_rows, dtype=bool),
+        "(not (str-eq location basel))": ~is_basel,
+        "(date-between date 18500 19000)": in_date,
+        "(date-between date 19000 *)": from_only,
+        "(not (date-between date 18500 19000))": ~in_date,
+        "(date-between sampling 18300 18900)": in_sampling,
+        "(and (str-eq location basel) (date-between date 18500 19000))": is_basel & in_date,
+        "(and (bitmap small) (str-eq location basel) (date-between date 18500 19000))": small_mask & is_basel & in_date,
+        "(and (bitmap large) (str-eq location basel) (date-between sampling 18300 18900))": large_mask & is_basel & in_sampling,
+        "(or (str-eq location bern) (and (bitmap large) (not (date-between date 18500 19000))))": np.array([v == "bern" for v in location]) | (large_mask & ~in_date),
+    }
+    for expression, mask in cases.items():
+        got = t.filter(expression).ids()
+        np.testing.assert_array_equal(got, to_global(np.flatnonzero(mask)).astype(np.uint32), err_msg=expression)
