@@ -949,6 +949,148 @@ def run_aa(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------
+# --workload reads: BASELINE.json configs[2], second half: performance/many_short_read_filters.cpp
+# ---------------------------------------------------------------------------------------------
+
+READS_COUNT, READS_LENGTH, READS_QUERIES = 5_000_000, 200, 10_000  # sequence_generator.h:189-190, many_short_read_filters.cpp:25
+READS_METRIC = "many_short_read_filters_queries_per_s"
+READS_DAY = 19723  # 2024-01-01 as Date32
+
+
+def reads_queries(genome_length: int, n_queries: int):
+    """many_short_read_filters.cpp:42-87: a random 1-based position, alternately one symbol of (A, C, G, T, -) and the Or of
+    all five, under `locationName = 'generated'` and the same samplingDate range twice. (numpy's generator instead of
+    std::mt19937 + uniform_int_distribution: other positions, the same distribution; both arms run the same list.)"""
+    rng = np_rng(42)
+    symbols = "ACGT-"
+    queries = []
+    for index in range(n_queries):
+        position = int(rng.integers(1, genome_length))
+        date = f"(date-between samplingDate {READS_DAY} {READS_DAY + 6})"
+        if index % 2 == 1:
+            sequence = "(or " + " ".join(f"(sym-eq main {position} {symbol})" for symbol in symbols) + ")"
+        else:
+            sequence = f"(sym-eq main {position} {symbols[int(rng.integers(0, 5))]})"
+        queries.append(f"(and (str-eq locationName generated) {date} {sequence} {date})")
+    return queries
+
+
+def np_rng(seed):
+    import numpy as np
+    return np.random.default_rng(seed)
+
+
+def run_reads(args):
+    import numpy as np
+    import torch
+    from lapis_silo_b200 import abi, host_api
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("--workload reads is a single-GPU line")
+    reference_arm = args.impl == "reference"
+    if not reference_arm and not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    threads = os.cpu_count() or 8
+    synthetic = host_api.Synthetic(GENOME_LENGTH, REFERENCE_SEED, GENERATIONS)
+    synthetic.draw_short_reads(READS_COUNT, READS_LENGTH)
+    sizes = host_api.dense_chunk_sizes(READS_COUNT)
+    queries = reads_queries(GENOME_LENGTH, READS_QUERIES)
+    ids = np.zeros(READS_COUNT, dtype=np.uint32)
+    days = np.full(READS_COUNT, READS_DAY, dtype=np.int32)
+    config = {
+        "workload": f"performance/many_short_read_filters: {READS_QUERIES} count() queries (a symbol test or a five-symbol Or at a random position, "
+                    "AND locationName = 'generated' AND samplingDate between, twice) over "
+                    f"{READS_COUNT} short reads x {READS_LENGTH} nt tiled over a {GENOME_LENGTH}-nt genome (BASELINE.json configs[2])",
+        "rows": READS_COUNT, "read_length": READS_LENGTH, "queries": READS_QUERIES, "genome_length": GENOME_LENGTH,
+    }
+
+    def oracle_table():
+        from oracle import oracle as O
+        table = O.Table()
+        table.set_layout(*sizes)
+        table.import_column("main", O.NUCLEOTIDE, synthetic.reference, synthetic.build_short_read_column(0, len(sizes), threads))
+        synthetic.release_column()
+        table.add_string_column_ids("locationName", ["generated"], ids)
+        table.add_date_column("samplingDate", days)
+        return table
+
+    def oracle_run(table, subset):
+        started = time.perf_counter()
+        counts = []
+        for text in subset:
+            flt = table.filter(text)
+            counts.append(flt.cardinality)
+            flt.close()
+        return time.perf_counter() - started, counts
+
+    if reference_arm:
+        table = oracle_table()
+        sample = queries[::50]  # 200 of the 10,000 queries
+        oracle_run(table, sample[:5])
+        seconds, _ = oracle_run(table, sample)
+        value = len(sample) / seconds
+        print(json.dumps({
+            "impl": "reference", "metric": READS_METRIC, "value": value, "unit": "queries/s", "n_gpus": 1, "steps": 1, "warmup": 0,
+            "ms_per_step": seconds * 1000.0, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": 1, "kind": "port",
+                             "sample": f"every 50th of the {READS_QUERIES} queries ({len(sample)}) on the whole table, one thread: {seconds:.1f}s; "
+                                       f"all {READS_QUERIES} would take ~{seconds * 50:.0f}s"},
+            "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+        }), flush=True)
+        return
+
+    torch.cuda.set_device(0)
+    ctx = abi.Context(0)
+    table = host_api.HostTable(ctx, sizes)
+    table.add_column("main", host_api.NUCLEOTIDE, synthetic.reference, synthetic.build_short_read_column(0, len(sizes), threads))
+    synthetic.release_column()
+    table.add_string_column_ids("locationName", ["generated"], ids)
+    table.add_date_column("samplingDate", days)
+
+    def run(subset):
+        return [table.count(text) for text in subset]  # CountFilterNode through the host layer: one device call per query
+    run(queries[:200])  # warm-up
+    torch.cuda.synchronize()
+    launches_before = table.stats().kernel_launches
+    sampler = ClockSampler(0)
+    sampler.start()
+    started = time.perf_counter()
+    counts = run(queries)
+    seconds = time.perf_counter() - started
+    clocks = sampler.stop()
+    gpu_launches = int(table.stats().kernel_launches - launches_before)
+    value = len(queries) / seconds
+    peak, peak_source = measured_peak_gbs()
+    # algorithmic bytes of one query (SURVEY.md 8(d), "NOf / SymbolInSet filter" row, plus the predicate's column): 4 B per row for
+    # the string predicate, 8 B per row of (start, end) when the symbol set holds the local reference (about every other
+    # query), the result tiles
+    bytes_per_query = 4 * READS_COUNT + 8 * READS_COUNT // 2 + 8192 * len(sizes)
+    line = {
+        "metric": READS_METRIC, "value": value, "unit": "queries/s", "n_gpus": 1, "steps": 1, "warmup": 0, "ms_per_step": seconds * 1000.0,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
+        "run": {"launch": "one filter program per query through the host API (parse, compile, lower, H2D, interpreter kernel, count back)",
+                "seconds_for_all_queries": seconds, "us_per_query": seconds / len(queries) * 1e6},
+        "clocks": clocks,
+        "e2e": {"value": value, "unit": "queries/s", "ms_per_step": seconds * 1000.0, "h2d_bytes_per_step": 600 * len(queries), "d2h_bytes_per_step": 16 * len(queries)},
+        "gpu_launches": gpu_launches,
+        "roofline": {"bound": "hbm", "achieved": bytes_per_query * len(queries) / seconds / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": bytes_per_query * len(queries) / seconds / 1e9 / peak, "traffic": None, "kernel": "evalProgramKernel (whole query, host time included)",
+                     "algorithmic_bytes_per_launch": bytes_per_query, "kernel_ms": seconds / len(queries) * 1000.0, "peak_source": peak_source},
+    }
+    if not args.skip_cpu_baseline:
+        oracle = oracle_table()
+        sample_index = list(range(0, len(queries), 50))
+        oracle_seconds, oracle_counts = oracle_run(oracle, [queries[i] for i in sample_index])
+        assert oracle_counts == [counts[i] for i in sample_index], "query counts differ from the oracle's"
+        line["parity"] = {"oracle": "full size, same table", "queries_compared": len(sample_index), "counts_equal": True}
+        line["cpu_baseline"] = {"value": len(sample_index) / oracle_seconds, "unit": "queries/s", "cores": 1, "kind": "port",
+                                "sample": f"every 50th query ({len(sample_index)}) on the whole table, one thread: {oracle_seconds:.1f}s "
+                                          f"(all {len(queries)}: ~{oracle_seconds * 50:.0f}s)"}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
@@ -960,9 +1102,9 @@ def main():
     parser.add_argument("--reference-step-seconds", type=float, default=2.0)
     parser.add_argument("--skip-cpu-baseline", action="store_true")
     parser.add_argument("--eager", action="store_true", help="launch the timed steps one by one instead of as one CUDA graph")
-    parser.add_argument("--workload", choices=["mutations", "nof", "aa"], default="mutations",
+    parser.add_argument("--workload", choices=["mutations", "nof", "aa", "reads"], default="mutations",
                         help="mutations: BASELINE.json configs[1] (the metric's workload, default); nof: configs[2], the NOf / MutationProfile filter; "
-                             "aa: configs[3], AminoAcidMutations over 12 genes")
+                             "aa: configs[3], AminoAcidMutations over 12 genes; reads: configs[2], many_short_read_filters")
     parser.add_argument("--reduce", choices=["peer", "nccl"], default="peer",
                         help="N > 1: how the per-rank counts meet -- the library's shard group (peer-memory stores) or NCCL all-reduce")
     parser.add_argument("--traffic-bytes", type=int, default=None,
@@ -970,7 +1112,9 @@ def main():
     args = parser.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.workload == "aa":
+    if args.workload == "reads":
+        run_reads(args)
+    elif args.workload == "aa":
         run_aa(args)
     elif args.workload == "nof":
         if args.impl == "reference":

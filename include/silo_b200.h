@@ -233,6 +233,9 @@ int silo_gpu_filter_eval(
    silo_gpu_filter** out,
    uint64_t* cardinality
 );
+/* CountFilterNode (count_filter_node.cpp:35-71): only the number of rows that pass. One call, one synchronisation; queries
+ * of one shape (the same instruction sequence) replay a captured CUDA graph. */
+int silo_gpu_query_count(silo_gpu_table* table, const silo_filter_program* program, uint64_t* cardinality);
 /* The same evaluation with DEVICE-RESIDENT inputs, for callers that run one filter many times or must
  * not touch the host in the hot loop: _prepare validates the program and uploads instructions, blob
  * and bitmaps once; _run only enqueues the kernel on `cuda_stream` (cudaStream_t, NULL = the

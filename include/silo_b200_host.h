@@ -105,6 +105,8 @@ int silo_host_mutations_enqueue(silo_host_table* table, const char* expression, 
 int silo_host_mutations_collect_packed(silo_host_table* table, const char* column, double min_proportion, const void* d_summed_counts, void* cuda_stream,
                                        void* buffer, uint64_t capacity, uint64_t* n_rows, uint32_t* n_names, uint64_t* needed_bytes,
                                        uint64_t* shard_cardinality);
+/* CountFilterNode: `filter(...).groupBy({count:=count()})` as one device call (silo_gpu_query_count) */
+int silo_host_count(silo_host_table* table, const char* expression, uint64_t* count);
 /* Metadata columns for the Selection predicates (string equality on an unindexed string column, equals.cpp:124-156;
  * DateBetween, date_between.cpp:61-134): a string column as its dictionary + one id per row (layout order), a Date32
  * column as its day numbers; null_row_ids ascending global row ids (may be NULL with n_null_rows 0). The values become
@@ -176,6 +178,12 @@ typedef struct silo_host_synthetic silo_host_synthetic;
 /* Evolution tree over a seeded random reference of `genome_length` nt (tree seed 42, mutation rate
  * 0.001, death rate 0.1, 3 children: SequenceTreeGenerator defaults) */
 silo_host_synthetic* silo_host_synthetic_create(uint32_t genome_length, uint64_t reference_seed, uint32_t generations);
+/* The short-read table of performance/sequence_generator.h:189-325 (uniform tiling): _draw makes the per-read sequence
+ * draws (std::mt19937(42 + 1000), returned through sequence_of_read_out[count] when not NULL; read i starts at
+ * i * (L - read_length + 1) / count), _build_short_read_column packs the chunks [first_chunk, first_chunk + n_chunks) of
+ * the table of `count` reads in the S1 upload format (valid until silo_host_synthetic_release_column / the next build). */
+int silo_host_synthetic_draw_short_reads(silo_host_synthetic* synthetic, uint64_t count, uint32_t read_length, uint32_t* sequence_of_read_out);
+int silo_host_synthetic_build_short_read_column(silo_host_synthetic* synthetic, uint32_t first_chunk, uint32_t n_chunks, uint32_t threads, const silo_column_desc** out);
 /* The same model for one amino-acid gene (SURVEY.md 8(d) input 4): random reference over the twenty standard residues,
  * mutations drawn from the alphabet's valid mutation symbols, its own tree seed and mutation rate. */
 silo_host_synthetic* silo_host_synthetic_create_gene(uint32_t gene_length, uint64_t reference_seed, uint64_t tree_seed, double mutation_rate, uint32_t generations);

@@ -157,16 +157,22 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
             uint32_t* tile32 = reinterpret_cast<uint32_t*>(sh.stack[sp++]);
             const uint2* rows = column.start_end + column.chunk_row_begin[chunk];
             const uint32_t position = ins.a;
-            for (uint32_t base = 0; base < 65536; base += EVAL_THREADS) {
-               const uint32_t row = base + tid;
-               bool covered = false;
-               if (row < chunk_size) {
-                  const uint2 range = rows[row];
-                  covered = range.x <= position && position < range.y;
+            constexpr uint32_t UNROLL = 4;  // (four loads in flight per thread instead of a chain of 64 memory latencies)
+            for (uint32_t base = 0; base < 65536; base += EVAL_THREADS * UNROLL) {
+               uint2 ranges[UNROLL];
+#pragma unroll
+               for (uint32_t u = 0; u < UNROLL; ++u) {
+                  const uint32_t row = base + u * EVAL_THREADS + tid;
+                  ranges[u] = row < chunk_size ? rows[row] : make_uint2(0u, 0u);
                }
-               const uint32_t bits = __ballot_sync(0xFFFFFFFFu, covered);
-               if (lane == 0) {
-                  tile32[row >> 5] = bits;
+#pragma unroll
+               for (uint32_t u = 0; u < UNROLL; ++u) {
+                  const uint32_t row = base + u * EVAL_THREADS + tid;
+                  const bool covered = ranges[u].x <= position && position < ranges[u].y;
+                  const uint32_t bits = __ballot_sync(0xFFFFFFFFu, covered);
+                  if (lane == 0) {
+                     tile32[row >> 5] = bits;
+                  }
                }
             }
             __syncthreads();
@@ -228,12 +234,21 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
             const uint32_t wanted = ins.a ^ bias;
             const uint32_t upper = static_cast<uint32_t>(ins.b) ^ bias;
             const uint32_t* set = reinterpret_cast<const uint32_t*>(p.blob + ins.b);
-            for (uint32_t base = 0; base < 65536; base += EVAL_THREADS) {
-               const uint32_t row = base + tid;
-               bool match = false;
-               if (row < chunk_size) {
-                  const uint32_t raw = values[row];
+            // (four loads in flight per thread: as one load per iteration the scan was a chain of 64 memory latencies)
+            constexpr uint32_t UNROLL = 4;
+            for (uint32_t base = 0; base < 65536; base += EVAL_THREADS * UNROLL) {
+               uint32_t raws[UNROLL];
+#pragma unroll
+               for (uint32_t u = 0; u < UNROLL; ++u) {
+                  const uint32_t row = base + u * EVAL_THREADS + tid;
+                  raws[u] = row < chunk_size ? values[row] : 0u;
+               }
+#pragma unroll
+               for (uint32_t u = 0; u < UNROLL; ++u) {
+                  const uint32_t row = base + u * EVAL_THREADS + tid;
+                  const uint32_t raw = raws[u];
                   const uint32_t value = raw ^ bias;
+                  bool match = false;
                   switch (comparator) {
                      case SILO_CMP_EQUALS: match = value == wanted; break;
                      case SILO_CMP_NOT_EQUALS: match = value != wanted; break;
@@ -247,10 +262,10 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
                         match = at < ins.a && set[at] == raw;
                      }
                   }
-               }
-               const uint32_t bits = __ballot_sync(0xFFFFFFFFu, match);
-               if (lane == 0) {
-                  tile32[row >> 5] = bits;
+                  const uint32_t bits = __ballot_sync(0xFFFFFFFFu, match && row < chunk_size);
+                  if (lane == 0) {
+                     tile32[row >> 5] = bits;
+                  }
                }
             }
             __syncthreads();
@@ -1325,6 +1340,44 @@ int silo_gpu_filter_eval(
          throw;
       }
       *out = filter.release();
+   });
+}
+
+// CountFilterNode (count_filter_node.cpp:35-71): the filter's cardinality only. The program runs on the table's persistent
+// query buffers, so a query SHAPE (the same instructions with other positions / values) is a replayed CUDA graph: staging
+// copy, interpreter, the 32 bytes of {cardinality, error flag} into page-locked memory, scalars reset; one synchronisation.
+int silo_gpu_query_count(silo_gpu_table* table, const silo_filter_program* program, uint64_t* cardinality) {
+   return guarded([&] {
+      require(table != nullptr && program != nullptr && cardinality != nullptr, "silo_gpu_query_count: NULL argument");
+      std::lock_guard<std::mutex> lock(table->mutex);
+      SILO_CUDA_CHECK(cudaSetDevice(table->ctx->device));
+      cudaStream_t stream = table->ctx->stream;
+      StagedQuery staged;
+      stageQueryLocked(table, program, &staged);
+      auto enqueueAll = [&]() {
+         enqueueStagedQuery(table, staged, stream);
+         SILO_CUDA_CHECK(cudaMemcpyAsync(table->h_scalars_pinned, table->query_filter->d_cardinality, 32, cudaMemcpyDeviceToHost, stream));
+         SILO_CUDA_CHECK(cudaMemsetAsync(table->query_filter->d_cardinality, 0, 32, stream));  // zero between queries
+      };
+      std::string key(reinterpret_cast<const char*>(staged.params), sizeof(staged.params));
+      const uint64_t scalars[] = {0x434F554E54ULL, staged.staged_bytes, staged.shared_bytes};
+      key.append(reinterpret_cast<const char*>(scalars), sizeof(scalars));
+      try {
+         cudaGraphExec_t replay = queryGraphFor(table, std::move(key), stream, enqueueAll);
+         if (replay != nullptr) {
+            SILO_CUDA_CHECK(cudaGraphLaunch(replay, stream));
+            table->stats.kernel_launches += 1;
+         } else {
+            enqueueAll();
+         }
+         SILO_CUDA_CHECK(cudaStreamSynchronize(stream));
+      } catch (...) {
+         cudaStreamSynchronize(stream);
+         cudaMemsetAsync(table->query_filter->d_cardinality, 0, 32, stream);
+         cudaStreamSynchronize(stream);
+         throw;
+      }
+      *cardinality = table->h_scalars_pinned[0];  // (rows outside the layout that a leaf bitmap held are counted, as by the reference)
    });
 }
 

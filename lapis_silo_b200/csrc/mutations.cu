@@ -1575,15 +1575,6 @@ struct QueryTrace {
    }
 };
 
-// SILO_QUERY_GRAPHS=0 keeps the fused query calls on plain launches (debugging aid)
-static bool queryGraphsEnabled() {
-   static const bool enabled = [] {
-      const char* flag = std::getenv("SILO_QUERY_GRAPHS");
-      return flag == nullptr || flag[0] != '0';
-   }();
-   return enabled;
-}
-
 // page-locked tuple buffer for the worst case: every valid symbol but the reference genome's at every position
 static void ensureHitsTuples(silo_gpu_table* table, uint64_t needed, cudaStream_t stream);
 static void ensureHitsCapacity(silo_gpu_table* table, const HostColumn& host, uint64_t valid_symbol_mask, cudaStream_t stream) {
@@ -1608,58 +1599,6 @@ static void sortHits(silo_mutation_hit* first, uint64_t count) {
       return a.position != b.position ? a.position < b.position : a.symbol < b.symbol;
    });
 }
-
-}  // extern "C"
-
-// The launch sequence of a fused query touches persistent buffers only, so it is the same for every query of one
-// SHAPE (`key`: every kernel parameter and copy size the enqueue bakes into nodes) and can be replayed as a CUDA graph.
-// A shape is captured the second time in a row it is seen; a few graphs are kept per table. Returns the graph to
-// launch, or nullptr (first sight, or graphs disabled): the caller then enqueues plainly.
-template <typename Enqueue>
-static cudaGraphExec_t queryGraphFor(silo_gpu_table* table, std::string key, cudaStream_t stream, Enqueue&& enqueueAll) {
-   if (!queryGraphsEnabled()) {
-      return nullptr;
-   }
-   cudaGraphExec_t replay = nullptr;
-   for (const silo_gpu_table::CachedGraph& cached : table->query_graphs) {
-      if (cached.key == key) {
-         replay = cached.exec;
-         break;
-      }
-   }
-   if (replay == nullptr && key == table->last_query_key) {
-      cudaGraph_t graph = nullptr;
-      SILO_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-      try {
-         enqueueAll();
-      } catch (...) {
-         cudaStreamEndCapture(stream, &graph);
-         if (graph != nullptr) {
-            cudaGraphDestroy(graph);
-         }
-         cudaGetLastError();
-         throw;
-      }
-      SILO_CUDA_CHECK(cudaStreamEndCapture(stream, &graph));
-      cudaGraphExec_t exec = nullptr;
-      const cudaError_t instantiated = cudaGraphInstantiate(&exec, graph, 0);
-      cudaGraphDestroy(graph);
-      SILO_CUDA_CHECK(instantiated);
-      constexpr size_t MAX_QUERY_GRAPHS = 8;
-      if (table->query_graphs.size() < MAX_QUERY_GRAPHS) {
-         table->query_graphs.push_back({key, exec});
-      } else {
-         silo_gpu_table::CachedGraph& slot = table->query_graphs[table->next_graph_slot++ % MAX_QUERY_GRAPHS];
-         cudaGraphExecDestroy(slot.exec);
-         slot = {key, exec};
-      }
-      replay = exec;
-   }
-   table->last_query_key = std::move(key);
-   return replay;
-}
-
-extern "C" {
 
 int silo_gpu_query_mutation_counts_async(
    silo_gpu_table* table,

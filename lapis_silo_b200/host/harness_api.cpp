@@ -61,6 +61,7 @@ struct silo_host_synthetic {
    std::string reference;
    const Alphabet* alphabet = &Alphabet::nucleotide();
    EvolvedTree tree;
+   ShortReads reads;  // silo_host_synthetic_draw_short_reads
    std::unique_ptr<PackedColumn> column;
 };
 
@@ -188,6 +189,13 @@ silo_host_filter* silo_host_filter_eval(silo_host_table* table, const char* expr
       result = owned.release();
    });
    return result;
+}
+
+int silo_host_count(silo_host_table* table, const char* expression, uint64_t* count) {
+   return guarded([&] {
+      const ExpressionPtr parsed = parseOrTrue(expression);
+      *count = countFilter(*table->table, *parsed);
+   });
 }
 
 void silo_host_filter_free(silo_host_filter* filter) {
@@ -788,6 +796,23 @@ int silo_host_synthetic_build_column(silo_host_synthetic* synthetic, uint64_t to
          *synthetic->alphabet, synthetic->reference, synthetic->tree.sequences, total_rows, first_chunk, n_chunks,
          threads, *synthetic->column, chunk_stride
       );
+      *out = &synthetic->column->desc;
+   });
+}
+
+int silo_host_synthetic_draw_short_reads(silo_host_synthetic* synthetic, uint64_t count, uint32_t read_length, uint32_t* sequence_of_read_out) {
+   return guarded([&] {
+      synthetic->reads = drawShortReads(synthetic->tree.sequences.size(), count, read_length);
+      if (sequence_of_read_out != nullptr) {
+         std::memcpy(sequence_of_read_out, synthetic->reads.sequence_of_read.data(), count * sizeof(uint32_t));
+      }
+   });
+}
+
+int silo_host_synthetic_build_short_read_column(silo_host_synthetic* synthetic, uint32_t first_chunk, uint32_t n_chunks, uint32_t threads, const silo_column_desc** out) {
+   return guarded([&] {
+      synthetic->column = std::make_unique<PackedColumn>();
+      buildShortReadColumn(*synthetic->alphabet, synthetic->reference, synthetic->tree.sequences, synthetic->reads, first_chunk, n_chunks, threads, *synthetic->column);
       *out = &synthetic->column->desc;
    });
 }

@@ -303,7 +303,14 @@ void connectShardGroup(const Table& table, const std::vector<uint8_t>& handles_o
 }
 
 uint64_t countFilter(const Table& table, const ScalarExpression& filter) {
-   return computeFilter(filter, table).cardinality();
+   // computeFilter (compute_filter.cpp:14-21) + cardinality (count_filter_node.cpp:40-41) as one device call
+   const ExpressionPtr rewritten = filter.rewrite(table, AmbiguityMode::NONE);
+   const std::unique_ptr<Operator> compiled = rewritten->compile(table);
+   ProgramBuilder builder;
+   const silo_filter_program program = compiled->lowerProgram(table, builder);
+   uint64_t cardinality = 0;
+   throwOnDeviceError(silo_gpu_query_count(table.deviceTable(), &program, &cardinality));
+   return cardinality;
 }
 
 }  // namespace silo_host

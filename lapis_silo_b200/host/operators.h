@@ -229,8 +229,8 @@ struct CoveragePredicate {
    bool is_signed = false;      // Date32 / integers
    bool with_nulls = false;     // what a null row gives (selection.h:113-115)
    uint32_t value = 0;
-   std::vector<uint32_t> set;   // IN_SET: ascending dictionary ids
-   std::string display;         // Predicate::toString()
+   std::vector<uint32_t> set = {};   // IN_SET: ascending dictionary ids
+   std::string display = {};         // Predicate::toString()
    [[nodiscard]] CoveragePredicate negated() const;  // Predicate::negate()
 };
 

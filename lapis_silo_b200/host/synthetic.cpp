@@ -377,6 +377,188 @@ void buildCycledColumn(
    desc.start_end = out.start_end.data();
 }
 
+ShortReads drawShortReads(size_t n_sequences, uint64_t count, uint32_t read_length, uint64_t seed) {
+   ShortReads reads;
+   reads.count = count;
+   reads.read_length = read_length;
+   reads.sequence_of_read.resize(count);
+   std::mt19937 rng;
+   rng.seed(seed + 1000);
+   std::uniform_int_distribution<size_t> seq_dist(0, n_sequences - 1);
+   for (uint64_t read = 0; read < count; ++read) {
+      reads.sequence_of_read[read] = static_cast<uint32_t>(seq_dist(rng));
+   }
+   return reads;
+}
+
+void buildShortReadColumn(
+   const Alphabet& alphabet,
+   const std::string& reference,
+   const std::vector<std::string>& sequences,
+   const ShortReads& reads,
+   uint32_t first_chunk,
+   uint32_t n_chunks,
+   unsigned threads,
+   PackedColumn& out
+) {
+   const size_t genome_length = reference.size();
+   if (sequences.empty() || reads.read_length == 0 || reads.read_length > genome_length || reads.count == 0) {
+      throw std::invalid_argument("buildShortReadColumn: empty input or read_length exceeds the reference");
+   }
+   const std::vector<uint32_t> all_chunk_sizes = denseChunkSizes(reads.count);
+   if (static_cast<uint64_t>(first_chunk) + n_chunks > all_chunk_sizes.size()) {
+      throw std::invalid_argument("buildShortReadColumn: shard exceeds the table");
+   }
+   const uint32_t n_symbols = alphabet.count();
+   // the sequences as symbol ids
+   std::vector<std::vector<Symbol>> symbols(sequences.size());
+   for (size_t e = 0; e < sequences.size(); ++e) {
+      if (sequences[e].size() != genome_length) {
+         throw std::invalid_argument("buildShortReadColumn: sequences must be full length");
+      }
+      symbols[e].resize(genome_length);
+      for (size_t p = 0; p < genome_length; ++p) {
+         const auto symbol = alphabet.charToSymbol(sequences[e][p]);
+         if (!symbol.has_value() || symbol.value() == alphabet.missing) {
+            throw std::invalid_argument("buildShortReadColumn: sequences must not hold missing / illegal symbols");
+         }
+         symbols[e][p] = symbol.value();
+      }
+   }
+   std::vector<Symbol> reference_symbols(genome_length);
+   for (size_t p = 0; p < genome_length; ++p) {
+      reference_symbols[p] = alphabet.charToSymbol(reference[p]).value();
+   }
+   threads = std::max(1u, threads);
+   // symbol counts per position over ALL reads -> the adapted local reference (one finalize() over the whole table)
+   std::vector<std::vector<uint32_t>> partial(threads, std::vector<uint32_t>(genome_length * n_symbols, 0));
+   {
+      std::vector<std::thread> workers;
+      for (unsigned t = 0; t < threads; ++t) {
+         workers.emplace_back([&, t]() {
+            std::vector<uint32_t>& counts = partial[t];
+            const uint64_t begin = reads.count * t / threads;
+            const uint64_t end = reads.count * (t + 1) / threads;
+            for (uint64_t read = begin; read < end; ++read) {
+               const uint32_t offset = reads.offsetOf(read, genome_length);
+               const Symbol* source = symbols[reads.sequence_of_read[read]].data();
+               for (uint32_t k = 0; k < reads.read_length; ++k) {
+                  counts[static_cast<size_t>(offset + k) * n_symbols + source[offset + k]]++;
+               }
+            }
+         });
+      }
+      for (std::thread& worker : workers) {
+         worker.join();
+      }
+   }
+   out.local_reference.assign(reference_symbols.begin(), reference_symbols.end());
+   for (size_t p = 0; p < genome_length; ++p) {
+      // vertical_sequence_index.cpp:57-116: the first symbol (SYMBOLS order) whose count strictly exceeds the running best
+      const Symbol current = reference_symbols[p];
+      uint64_t best_rows = 0;
+      for (unsigned t = 0; t < threads; ++t) {
+         best_rows += partial[t][p * n_symbols + current];
+      }
+      Symbol best = current;
+      for (uint32_t symbol = 0; symbol < n_symbols; ++symbol) {
+         uint64_t rows = 0;
+         for (unsigned t = 0; t < threads; ++t) {
+            rows += partial[t][p * n_symbols + symbol];
+         }
+         if (symbol != current && rows > best_rows) {
+            best = static_cast<Symbol>(symbol);
+            best_rows = rows;
+         }
+      }
+      out.local_reference[p] = best;
+   }
+   partial.clear();
+
+   // containers and coverage, chunk by chunk
+   std::vector<std::vector<silo_container_desc>> chunk_descs(n_chunks);
+   std::vector<std::vector<uint8_t>> chunk_payload(n_chunks);
+   uint64_t shard_rows = 0;
+   std::vector<uint64_t> chunk_row_begin(n_chunks + 1, 0);
+   for (uint32_t local_chunk = 0; local_chunk < n_chunks; ++local_chunk) {
+      shard_rows += all_chunk_sizes[first_chunk + local_chunk];
+      chunk_row_begin[local_chunk + 1] = shard_rows;
+   }
+   out.start_end.assign(2 * shard_rows, 0);
+   auto buildChunk = [&](uint32_t local_chunk) {
+      const uint32_t global_chunk = first_chunk + local_chunk;
+      const uint32_t chunk_size = all_chunk_sizes[global_chunk];
+      const uint64_t base_read = static_cast<uint64_t>(global_chunk) * 65536;
+      const uint32_t window_begin = reads.offsetOf(base_read, genome_length);
+      const uint32_t window_end = reads.offsetOf(base_read + chunk_size - 1, genome_length) + reads.read_length;
+      const uint32_t window = window_end - window_begin;
+      // one bitmap per (position, symbol) that occurs in the chunk, allocated on first use
+      std::vector<std::vector<uint64_t>> bitmaps(static_cast<size_t>(window) * n_symbols);
+      for (uint32_t row = 0; row < chunk_size; ++row) {
+         const uint64_t read = base_read + row;
+         const uint32_t offset = reads.offsetOf(read, genome_length);
+         out.start_end[2 * (chunk_row_begin[local_chunk] + row)] = offset;
+         out.start_end[2 * (chunk_row_begin[local_chunk] + row) + 1] = offset + reads.read_length;
+         const Symbol* source = symbols[reads.sequence_of_read[read]].data();
+         for (uint32_t k = 0; k < reads.read_length; ++k) {
+            const uint32_t position = offset + k;
+            const Symbol symbol = source[position];
+            if (symbol == out.local_reference[position]) {
+               continue;
+            }
+            std::vector<uint64_t>& words = bitmaps[static_cast<size_t>(position - window_begin) * n_symbols + symbol];
+            if (words.empty()) {
+               words.assign(1024, 0);
+            }
+            words[row >> 6] |= uint64_t{1} << (row & 63);
+         }
+      }
+      for (uint32_t position = window_begin; position < window_end; ++position) {
+         for (uint32_t symbol = 0; symbol < n_symbols; ++symbol) {
+            const std::vector<uint64_t>& words = bitmaps[static_cast<size_t>(position - window_begin) * n_symbols + symbol];
+            if (!words.empty()) {
+               encodeContainer(words.data(), position, static_cast<uint16_t>(global_chunk), static_cast<Symbol>(symbol), chunk_descs[local_chunk], chunk_payload[local_chunk]);
+            }
+         }
+      }
+   };
+   {
+      std::vector<std::thread> workers;
+      const unsigned n_workers = std::max(1u, std::min(threads, n_chunks == 0 ? 1u : n_chunks));
+      for (unsigned t = 0; t < n_workers; ++t) {
+         workers.emplace_back([&, t]() {
+            for (uint32_t local_chunk = t; local_chunk < n_chunks; local_chunk += n_workers) {
+               buildChunk(local_chunk);
+            }
+         });
+      }
+      for (std::thread& worker : workers) {
+         worker.join();
+      }
+   }
+   out.containers.clear();
+   out.payload.clear();
+   for (uint32_t local_chunk = 0; local_chunk < n_chunks; ++local_chunk) {
+      const uint64_t payload_base = out.payload.size();
+      out.payload.insert(out.payload.end(), chunk_payload[local_chunk].begin(), chunk_payload[local_chunk].end());
+      for (silo_container_desc desc : chunk_descs[local_chunk]) {
+         desc.payload_offset += payload_base;
+         out.containers.push_back(desc);
+      }
+   }
+   out.desc = silo_column_desc{};
+   out.desc.struct_size = sizeof(silo_column_desc);
+   out.desc.n_symbols = n_symbols;
+   out.desc.genome_length = static_cast<uint32_t>(genome_length);
+   out.desc.missing_symbol = alphabet.missing;
+   out.desc.local_reference = out.local_reference.data();
+   out.desc.n_containers = out.containers.size();
+   out.desc.containers = out.containers.data();
+   out.desc.payload = out.payload.data();
+   out.desc.payload_bytes = out.payload.size();
+   out.desc.start_end = out.start_end.data();
+}
+
 std::vector<uint32_t> shardChunkSizes(uint64_t total_rows, uint32_t first_chunk, uint32_t n_chunks, uint32_t chunk_stride) {
    const std::vector<uint32_t> all = denseChunkSizes(total_rows);
    std::vector<uint32_t> sizes;

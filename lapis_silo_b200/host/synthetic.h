@@ -73,6 +73,31 @@ void buildCycledColumn(
    PackedColumn& out,
    uint32_t chunk_stride = 1
 );
+// The short-read table of performance/sequence_generator.h:189-325 (ShortReadGenerator, uniform whole-genome tiling):
+// read i covers [offset_i, offset_i + read_length) with offset_i = i * (L - read_length + 1) / count and carries that
+// window of evolved[seq_dist(rng)] (std::mt19937(seed + 1000), one draw per read in id order). Built directly in the S1
+// upload format for the chunks [first_chunk, first_chunk + n_chunks) (global chunk ids): coverage (start, end) per row,
+// diffs against the local reference adapted over ALL reads (sequence_column.cpp:158-212).
+struct ShortReads {
+   uint64_t count = 0;
+   uint32_t read_length = 0;
+   std::vector<uint32_t> sequence_of_read;  // the draws, in id order
+   [[nodiscard]] uint32_t offsetOf(uint64_t read_id, size_t genome_length) const {
+      return static_cast<uint32_t>((read_id * (genome_length - read_length + 1)) / count);
+   }
+};
+ShortReads drawShortReads(size_t n_sequences, uint64_t count, uint32_t read_length, uint64_t seed = 42);
+void buildShortReadColumn(
+   const Alphabet& alphabet,
+   const std::string& reference,
+   const std::vector<std::string>& sequences,
+   const ShortReads& reads,
+   uint32_t first_chunk,
+   uint32_t n_chunks,
+   unsigned threads,
+   PackedColumn& out
+);
+
 // chunk sizes of such a shard
 std::vector<uint32_t> shardChunkSizes(uint64_t total_rows, uint32_t first_chunk, uint32_t n_chunks, uint32_t chunk_stride);
 

@@ -37,7 +37,7 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_filter_lower_timed", "silo_host_filter_to_string", "silo_host_filter_program_bitmap",
     "silo_host_archive_read", "silo_host_archive_free", "silo_host_archive_column", "silo_host_archive_column_info",
     "silo_host_archive_chunk_sizes", "silo_host_archive_column_shard", "silo_host_table_load_archive", "silo_host_roaring_runs",
-    "silo_host_table_add_string_column", "silo_host_table_add_date_column", "silo_host_synthetic_create_gene", "silo_host_shard_group_create", "silo_host_shard_group_connect", "silo_host_sharded_enqueue", "silo_host_sharded_collect_packed",
+    "silo_host_count", "silo_host_synthetic_draw_short_reads", "silo_host_synthetic_build_short_read_column", "silo_host_table_add_string_column", "silo_host_table_add_date_column", "silo_host_synthetic_create_gene", "silo_host_shard_group_create", "silo_host_shard_group_connect", "silo_host_sharded_enqueue", "silo_host_sharded_collect_packed",
     "silo_host_prepared_run_sharded_async", "silo_host_sharded_collect_async", "silo_host_sharded_query_packed",
 ]
 SHARD_HANDLE_BYTES = 128  # SILO_SHARD_HANDLE_BYTES
@@ -69,6 +69,7 @@ def lib() -> C.CDLL:
         L.silo_host_table_device.restype = vp
         L.silo_host_table_num_rows.argtypes = [vp]
         L.silo_host_table_num_rows.restype = C.c_uint64
+        L.silo_host_count.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint64)]
         L.silo_host_filter_eval.argtypes = [vp, C.c_char_p]
         L.silo_host_filter_eval.restype = vp
         L.silo_host_filter_free.argtypes = [vp]
@@ -145,6 +146,8 @@ def lib() -> C.CDLL:
         L.silo_host_synthetic_generation.argtypes = [vp, C.c_uint32]
         L.silo_host_synthetic_generation.restype = C.c_uint32
         L.silo_host_synthetic_build_column.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp), C.c_uint32]
+        L.silo_host_synthetic_draw_short_reads.argtypes = [vp, C.c_uint64, C.c_uint32, vp]
+        L.silo_host_synthetic_build_short_read_column.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
         L.silo_host_synthetic_release_column.argtypes = [vp]
         L.silo_host_synthetic_release_column.restype = None
         L.silo_host_synthetic_lineage_bitmap.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64, C.c_uint32]
@@ -521,6 +524,12 @@ class HostTable:
             raise HostError(lib().silo_host_last_error().decode())
         return HostFilter(self, handle)
 
+    def count(self, expression: Optional[str]) -> int:
+        """CountFilterNode: the number of rows that pass, one device call (silo_gpu_query_count)"""
+        out = C.c_uint64()
+        _check(lib().silo_host_count(self._h, expression.encode() if expression is not None else None, C.byref(out)))
+        return int(out.value)
+
     def prepare(self, expression: str) -> PreparedFilter:
         handle = lib().silo_host_filter_prepare(self._h, expression.encode())
         if not handle:
@@ -733,6 +742,18 @@ class Synthetic:
         chunks first_chunk + k*stride; stride > 1 (an interleaved shard) uses shard-local chunk ids."""
         out = C.c_void_p()
         _check(lib().silo_host_synthetic_build_column(self._h, total_rows, first_chunk, n_chunks, threads, C.byref(out), stride))
+        return C.cast(out, C.POINTER(abi.ColumnDesc))
+
+    def draw_short_reads(self, count: int, read_length: int) -> np.ndarray:
+        """ShortReadGenerator (uniform tiling): the evolved-sequence index of every read, in id order; read i starts at
+        i * (L - read_length + 1) // count. Must precede build_short_read_column."""
+        out = np.empty(count, dtype=np.uint32)
+        _check(lib().silo_host_synthetic_draw_short_reads(self._h, count, read_length, out.ctypes.data))
+        return out
+
+    def build_short_read_column(self, first_chunk: int, n_chunks: int, threads: int = 8):
+        out = C.c_void_p()
+        _check(lib().silo_host_synthetic_build_short_read_column(self._h, first_chunk, n_chunks, threads, C.byref(out)))
         return C.cast(out, C.POINTER(abi.ColumnDesc))
 
     def release_column(self) -> None:

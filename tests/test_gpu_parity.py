@@ -759,6 +759,12 @@ def test_selection_predicates_on_device(ctx):
         both(pair, f"(or {a} (and {b} {c}))")
         both(pair, f"(n-of 2 0 {a} {b} {c})")
         both(pair, f"(not (and {a} (or {b} (not {c}))))")
+    # CountFilterNode as one device call; queries of one shape replay a captured graph
+    for position in range(1, 40):
+        for text in (f"(and (str-eq location generated) (date-between sampling 18300 18900) (sym-eq c {position} A))",
+                     f"(and (str-eq location basel) (or (sym-eq c {position} A) (sym-eq c {position} C) (sym-eq c {position} -)))"):
+            assert device.count(text) == t.filter(text).cardinality
+    assert device.count(None) == t.num_rows
     expression = "(and (str-eq location generated) (date-between date 18200 19300) (not (sym-eq c 9 N)))"
     assert device.mutations(["c"], expression, 0.02) == t.mutations("c", expression, 0.02)
     assert "$string location IN ['generated']" in device.to_strings(expression)[2] and "$date date >= 18200" in device.to_strings(expression)[2]

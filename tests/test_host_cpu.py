@@ -249,3 +249,36 @@ def test_gene_generator_matches_the_oracle_string_ingest():
     np.testing.assert_array_equal(
         from_strings.mutation_counts("M", from_strings.filter(expression)), imported.mutation_counts("M", imported.filter(expression)))
     assert from_strings.mutations("M", expression, 0.05) == imported.mutations("M", expression, 0.05)
+
+
+def test_short_read_generator_matches_the_oracle_string_ingest():
+    """The short-read table (ShortReadGenerator of performance/sequence_generator.h:189-325: reads of one length tiled
+    over the genome, each a window of a random evolved sequence) built directly in the S1 upload format equals what the
+    oracle's string ingest (offset + sequence per row) + finalize stores: layout, adapted local reference, coverage
+    filters, symbol filters and counts."""
+    import numpy as np
+    from lapis_silo_b200 import host_api
+    from oracle import oracle as O
+    genome_length, count, read_length = 900, 140_000, 70
+    synthetic = host_api.Synthetic(genome_length=genome_length, reference_seed=3, generations=5)
+    draws = synthetic.draw_short_reads(count, read_length)
+    sequences = [synthetic.sequence(e) for e in range(synthetic.num_sequences)]
+    n_positions = genome_length - read_length + 1
+    from_strings = O.Table()
+    from_strings.add_column("main", O.NUCLEOTIDE, synthetic.reference)
+    for read in range(count):
+        offset = read * n_positions // count
+        from_strings.append_row([(sequences[int(draws[read])][offset:offset + read_length], offset)])
+    from_strings.finalize()
+    sizes = host_api.dense_chunk_sizes(count)
+    imported = O.Table()
+    imported.set_layout(*sizes)
+    imported.import_column("main", O.NUCLEOTIDE, synthetic.reference, synthetic.build_short_read_column(0, len(sizes), 2))
+    assert from_strings.chunk_sizes == imported.chunk_sizes
+    assert from_strings.local_reference("main") == imported.local_reference("main")
+    np.testing.assert_array_equal(from_strings.mutation_counts("main"), imported.mutation_counts("main"))
+    for expression in ("(sym-eq main 450 A)", "(sym-eq main 30 .)", "(has-mut main 700)", "(covered main 100)",
+                       "(and (ranges 500 90000) (or (sym-eq main 200 C) (sym-eq main 200 G) (sym-eq main 200 -)))"):
+        a, b = from_strings.filter(expression), imported.filter(expression)
+        np.testing.assert_array_equal(a.ids(), b.ids(), err_msg=expression)
+        np.testing.assert_array_equal(from_strings.mutation_counts("main", a), imported.mutation_counts("main", b))
