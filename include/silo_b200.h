@@ -319,9 +319,9 @@ typedef struct {
 int silo_gpu_column_set_reference(silo_gpu_table* table, int column, const uint8_t* reference_symbols);
 
 /* Filter + counts + output pass in ONE call with ONE host synchronisation. program != NULL: evaluated
- * inside the call (filter is ignored); else filter (NULL = all rows). *hits points at n_hits tuples in
- * page-locked memory owned by the table, ordered by (position, symbol id), valid until the next call on
- * this table. cardinality may be NULL (and is only set when a program was given). The full counts stay
+ * inside the call (filter is ignored); else filter (NULL = all rows). *hits points at n_hits tuples, ordered by
+ * (position, symbol id), in storage of the CALLING THREAD, valid until that thread's next call that returns tuples
+ * (the calls on one table are serialised by the library and may come from any number of host threads). cardinality may be NULL (and is only set when a program was given). The full counts stay
  * in device memory (they are not copied to the host by this call). */
 int silo_gpu_query_mutation_hits(
    silo_gpu_table* table,
@@ -337,8 +337,8 @@ int silo_gpu_query_mutation_hits(
 
 /* The same for SEVERAL sequence columns under one filter (AminoAcidMutations over all genes: the producer of
  * mutations_node.cpp:372-428 loops the columns of one query): the program is evaluated once, every column's counts and
- * output pass follow on the stream, ONE synchronisation. columns[c].hits / n_hits are set on return (page-locked memory
- * owned by the table, valid until the next call on this table); valid_symbol_mask is clipped to the column's alphabet. */
+ * output pass follow on the stream, ONE synchronisation. columns[c].hits / n_hits are set on return (storage of the
+ * calling thread, valid until its next call that returns tuples); valid_symbol_mask is clipped to the column's alphabet. */
 typedef struct {
    int column;
    uint64_t valid_symbol_mask;

@@ -1,6 +1,7 @@
 // Internal declarations of libsilo_b200.so (sm_100a only). Public surface: include/silo_b200.h.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdint>
 #include <cstdlib>
@@ -346,6 +347,16 @@ void enqueuePreparedShardedLocked(silo_gpu_table* table, const silo_gpu_filter* 
 // mutations.cu: coverage + container + finalize kernels for a filter whose interpreter launch already zeroed
 // d_counts and built the work list (caller holds table->mutex); records the per-call timing events
 void enqueuePreparedCountsLocked(silo_gpu_table* table, int column, const silo_gpu_filter* filter, uint32_t* d_counts, cudaStream_t stream);
+
+// NVTX range around the enqueue of a kernel, named after the evobench scope of the reference code it replaces
+// (EVOBENCH_SCOPE in mutations_node.cpp:43-197, threshold.cpp:65, intersection.cpp:60, selection.cpp:95): a timeline of
+// this library lines up with one of the reference. Costs a few nanoseconds when no profiler is attached.
+struct NvtxRange {
+   explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+   ~NvtxRange() { nvtxRangePop(); }
+   NvtxRange(const NvtxRange&) = delete;
+   NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct ApiError : std::runtime_error {
    int status;

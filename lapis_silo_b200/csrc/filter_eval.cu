@@ -1181,6 +1181,7 @@ static void launchProgram(silo_gpu_table* table, EvalParams params, silo_gpu_fil
          }
          SILO_CUDA_CHECK(cudaEventRecord(table->ev_sweep_begin[slot], stream));
       }
+      const NvtxRange sweep_range("Threshold: evaluate [thresholdSweepKernel]");
       thresholdSweepKernel<<<host.sweep_ctas, SWEEP_THREADS, COUNTER_BYTES, stream>>>(
          host.dev, reinterpret_cast<const uint2*>(params.blob + params.sweep_table_offset), host.d_sweep_split, params.sweep_bias,
          table->d_sweep_counters
@@ -1198,6 +1199,7 @@ static void launchProgram(silo_gpu_table* table, EvalParams params, silo_gpu_fil
       }
    }
    const size_t shared_bytes = evalSharedBytes(params.stack_depth, params.has_threshold != 0);
+   const NvtxRange eval_range("computeFilter: Intersection / Union / Threshold / Selection evaluate [evalProgramKernel]");
    evalProgramKernel<<<table->n_chunks, EVAL_THREADS, shared_bytes, stream>>>(params);
    SILO_CUDA_CHECK(cudaGetLastError());
    table->stats.kernel_launches++;

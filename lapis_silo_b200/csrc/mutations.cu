@@ -1314,7 +1314,10 @@ void enqueueMutationCounts(
    // the prepare kernel and the first microseconds of the container kernel
    SILO_CUDA_CHECK(cudaEventRecord(table->ev_fork, stream));
    SILO_CUDA_CHECK(cudaStreamWaitEvent(table->aux_stream, table->ev_fork, 0));
-   coverageDiffKernel<<<n_chunks * K6_SLICES, K6_THREADS, 0, table->aux_stream>>>(column, words, popcounts, diff);
+   {
+      const NvtxRange range("Mutations: subtractFilteredNCounts + subtractStartAndEndNCounts [coverageDiffKernel]");
+      coverageDiffKernel<<<n_chunks * K6_SLICES, K6_THREADS, 0, table->aux_stream>>>(column, words, popcounts, diff);
+   }
    SILO_CUDA_CHECK(cudaGetLastError());
    SILO_CUDA_CHECK(cudaEventRecord(table->ev_join, table->aux_stream));
 
@@ -1332,6 +1335,7 @@ void enqueueMutationCounts(
    if (filter == nullptr) {
       if (column.n_containers > 0) {
          const int blocks = static_cast<int>(std::min<uint64_t>((column.n_containers + 255) / 256, static_cast<uint64_t>(table->ctx->sm_count) * 8));
+         const NvtxRange range("Mutations: countActualMutations [containerCardinalityKernel]");
          containerCardinalityKernel<<<blocks, 256, 0, stream>>>(column, d_counts);
          SILO_CUDA_CHECK(cudaGetLastError());
          table->stats.kernel_launches++;
@@ -1354,7 +1358,10 @@ void enqueueMutationCounts(
       if (debug && d_debug_times == nullptr) {
          SILO_CUDA_CHECK(cudaMalloc(&d_debug_times, 4 * sizeof(uint32_t) * 1024));
       }
-      launchContainerKernel(geometry, stream_only, blocks, stream, column, words, table->d_work_state, table->d_work_items, d_counts, tail_factor, debug ? d_debug_times : nullptr);
+      {
+         const NvtxRange range("Mutations: countActualFilteredMutations [containerAndCountKernel]");
+         launchContainerKernel(geometry, stream_only, blocks, stream, column, words, table->d_work_state, table->d_work_items, d_counts, tail_factor, debug ? d_debug_times : nullptr);
+      }
       SILO_CUDA_CHECK(cudaGetLastError());
       table->stats.kernel_launches++;
       cudaStreamCaptureStatus capture_status = cudaStreamCaptureStatusNone;
@@ -1386,6 +1393,7 @@ void enqueueMutationCounts(
    }
    recordTiming(ev_k1_end);
    SILO_CUDA_CHECK(cudaStreamWaitEvent(stream, table->ev_join, 0));
+   const NvtxRange finalize_range("Mutations: subtractCumulativeNsFromPositions + accumulateFinalCounts [finalizeCountsKernel]");
    finalizeCountsKernel<<<diffPadded(column.genome_length) / FIN_THREADS, FIN_THREADS, 0, stream>>>(
       column, diff, d_counts, table->d_work_state, request != nullptr ? *request : HitRequest{}, push != nullptr ? *push : ShardPush{}
    );
@@ -1593,6 +1601,18 @@ static void ensureHitsTuples(silo_gpu_table* table, uint64_t needed, cudaStream_
    }
 }
 
+// The tuples a query returns: copied out of the table's page-locked buffer (which the next query on the table -- maybe from
+// another host thread, as soon as the table's mutex is released -- overwrites) into storage of the CALLING THREAD, valid until
+// that thread's next call that returns tuples. `slot`: a call that returns several tuple lists keeps them all.
+static const silo_mutation_hit* publishHits(const silo_mutation_hit* first, uint64_t count, size_t slot = 0) {
+   thread_local std::vector<std::vector<silo_mutation_hit>> published;
+   if (published.size() <= slot) {
+      published.resize(slot + 1);
+   }
+   published[slot].assign(first, first + count);
+   return published[slot].data();
+}
+
 static void sortHits(silo_mutation_hit* first, uint64_t count) {
    // the kernel appends in whatever order its threads get there: (position, symbol id) order
    std::sort(first, first + count, [](const silo_mutation_hit& a, const silo_mutation_hit& b) {
@@ -1667,7 +1687,7 @@ int silo_gpu_mutation_hits_from_counts(
       }
       const uint64_t count = std::min<uint64_t>(header.position, table->hits_capacity);
       sortHits(table->h_hits_pinned + 1, count);
-      *hits = table->h_hits_pinned + 1;
+      *hits = publishHits(table->h_hits_pinned + 1, count);
       *n_hits = count;
       if (shard_cardinality != nullptr) {
          *shard_cardinality = header.count | (static_cast<unsigned long long>(header.total) << 32);
@@ -1775,7 +1795,7 @@ int silo_gpu_query_mutation_hits(
       // the kernel appends in whatever order its threads get there: (position, symbol id) order
       silo_mutation_hit* const first = table->h_hits_pinned + 1;
       sortHits(first, count);
-      *hits = first;
+      *hits = publishHits(first, count);
       *n_hits = count;
       if (cardinality != nullptr && program != nullptr) {
          *cardinality = host_cardinality;
@@ -2087,7 +2107,7 @@ static void readShardedHits(silo_gpu_table* table, const silo_mutation_hit** hit
    }
    const uint64_t count = std::min<uint64_t>(header.position, table->hits_capacity);
    sortHits(table->h_hits_pinned + 1, count);
-   *hits = table->h_hits_pinned + 1;
+   *hits = publishHits(table->h_hits_pinned + 1, count);
    *n_hits = count;
    if (cardinality != nullptr) {
       *cardinality = header.count | (static_cast<unsigned long long>(header.total) << 32);
@@ -2255,7 +2275,7 @@ int silo_gpu_query_mutation_hits_columns(
          }
          const uint64_t count = std::min<uint64_t>(header.position, region_begin[c + 1] - region_begin[c] - 1);
          sortHits(region + 1, count);
-         columns[c].hits = region + 1;
+         columns[c].hits = publishHits(region + 1, count, c);
          columns[c].n_hits = count;
       }
       if (cardinality != nullptr) {

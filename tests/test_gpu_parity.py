@@ -769,3 +769,51 @@ def test_selection_predicates_on_device(ctx):
     assert device.mutations(["c"], expression, 0.02) == t.mutations("c", expression, 0.02)
     assert "$string location IN ['generated']" in device.to_strings(expression)[2] and "$date date >= 18200" in device.to_strings(expression)[2]
     device.close()
+
+
+def test_concurrent_queries_from_many_host_threads(ctx):
+    """The reference answers queries from `parallel_threads` Poco workers (api/api.cpp:39-51). Eight host threads issue
+    different fused queries against ONE table at the same time -- Mutations (one and two columns, several filters and
+    minProportions), count(), filters with row sets, a MutationProfile --; every answer equals the oracle's. (Calls on one
+    table are serialised by the table's mutex: the test pins that the shared per-table staging, graph cache and scratch
+    survive arbitrary interleavings, not that the queries overlap.)"""
+    import threading
+    t = build_random(909, 2500, 50, (700, 701, 1800))
+    rng = np.random.default_rng(909)
+    t.register_bitmap("lineage", sorted(set(int(v) for v in rng.integers(0, 700, 200))))
+    device = mirror(ctx, t, ["lineage"])
+    reference = t.columns[0][2]
+    jobs = []
+    for index in range(8):
+        position = 3 + 5 * index
+        expression = f"(and (not (sym-eq c {position} N)) (or (bitmap lineage) (has-mut c {position + 1})))"
+        if index % 4 == 0:
+            want = t.mutations("c", expression, 0.03 * (index + 1))
+            jobs.append((lambda e=expression, p=0.03 * (index + 1): device.mutations(["c"], e, p), want))
+        elif index % 4 == 1:
+            want = t.filter(expression).cardinality
+            jobs.append((lambda e=expression: device.count(e), want))
+        elif index % 4 == 2:
+            want = [int(v) for v in t.filter(expression).ids()]
+            jobs.append((lambda e=expression: [int(v) for v in device.filter(e).ids()], want))
+        else:
+            profile = f"(profile c {index} seq {reference})"
+            want = t.mutations("c", profile, 0.0)
+            jobs.append((lambda e=profile: device.mutations(["c"], e, 0.0), want))
+    failures = []
+
+    def worker(job, want):
+        try:
+            for _ in range(25):
+                if job() != want:
+                    failures.append("a concurrent query returned another result than the oracle")
+                    return
+        except Exception as error:  # noqa: BLE001
+            failures.append(repr(error))
+    threads = [threading.Thread(target=worker, args=job) for job in jobs]
+    for thread in threads:
+        thread.start()
+    for thread in threads:
+        thread.join()
+    assert failures == []
+    device.close()
