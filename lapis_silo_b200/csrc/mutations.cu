@@ -711,11 +711,17 @@ __global__ void __launch_bounds__(K6_THREADS) coverageDiffKernel(
    const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(filter_words + static_cast<size_t>(chunk) * TILE_WORDS);
    const uint2* rows = column.start_end + column.chunk_row_begin[chunk];
 
-   // Filter bits are confined to the row layout, so a set bit is always an existing row. The warp's
-   // eight filter words are fetched at once, and the (start, end) loads of K6_UNROLL words are in
+   // A filter evaluated inside the same query may hold ids outside the row layout (the query then fails with
+   // SILO_E_OUT_OF_LAYOUT once its error flag comes back): such bits are masked here, there is no row data behind them.
+   // The warp's eight filter words are fetched at once, and the (start, end) loads of K6_UNROLL words are in
    // flight together: the kernel is bound by global-memory latency, not bandwidth.
+   const uint32_t chunk_rows = column.chunk_row_begin[chunk + 1] - column.chunk_row_begin[chunk];
    const uint32_t warp_first = (slice * (K6_THREADS / 32) + warp) * K6_ROWS_PER_WARP;
-   const uint32_t my_word = lane < K6_ROWS_PER_WARP / 32 ? tile32[(warp_first >> 5) + lane] : 0u;
+   uint32_t my_word = lane < K6_ROWS_PER_WARP / 32 ? tile32[(warp_first >> 5) + lane] : 0u;
+   const uint32_t word_first = warp_first + lane * 32;
+   if (word_first + 32 > chunk_rows) {
+      my_word &= word_first >= chunk_rows ? 0u : (1u << (chunk_rows - word_first)) - 1u;
+   }
    PendingAdd pending_start{0, 0};
    PendingAdd pending_end{0, 0};
    for (uint32_t group = 0; group < K6_ROWS_PER_WARP / 32; group += K6_UNROLL) {

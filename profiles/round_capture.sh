@@ -13,3 +13,21 @@ ncu --set full --clock-control none --import-source on -k regex:containerAndCoun
 ncu --set full --clock-control none --import-source on -k regex:'evalProgramKernel|coverageDiffKernel|prepare|finalizeCountsKernel' -s 12 -c 4 -f -o gpurun_out/${tag}_other_full \
   python bench.py --steps 3 --warmup 3 --skip-cpu-baseline --eager > gpurun_out/${tag}_other_full.log 2>&1
 ls -la gpurun_out | tail -20
+if [ "$tag" != "r1" ]; then
+  # round 2: the other workloads of BASELINE.json, the threshold sweep kernel, and compute-sanitizer over the parity suites
+  for w in nof aa reads; do
+    python bench.py --workload $w > gpurun_out/${tag}_bench_${w}.json 2> gpurun_out/${tag}_bench_${w}.err; tail -c 600 gpurun_out/${tag}_bench_${w}.json
+  done
+  ncu --set full --clock-control none --import-source on -k regex:thresholdSweepKernel -s 1 -c 1 -f -o gpurun_out/${tag}_sweep_full \
+    python profiles/config3_ncu_target.py > gpurun_out/${tag}_sweep_full.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${tag}_config3_launches.csv \
+    python profiles/config3_ncu_target.py > gpurun_out/${tag}_config3_launches.log 2>&1
+  timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file gpurun_out/${tag}_sanitizer_memcheck.log \
+    python -m pytest tests/test_gpu_kernels.py -m gpu -x -q > gpurun_out/${tag}_sanitizer_memcheck_pytest.log 2>&1; echo "memcheck rc $?" | tee -a gpurun_out/${tag}_sanitizer_memcheck_pytest.log
+  timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file gpurun_out/${tag}_sanitizer_memcheck_parity.log \
+    python -m pytest tests/test_gpu_parity.py -m gpu -q -k "not baseline and not twelve_genes and not tree_data and not concurrent and not shards_sum" > gpurun_out/${tag}_sanitizer_memcheck_parity_pytest.log 2>&1; echo "memcheck parity rc $?" | tee -a gpurun_out/${tag}_sanitizer_memcheck_parity_pytest.log
+  timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 --log-file gpurun_out/${tag}_sanitizer_racecheck.log \
+    python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "not baseline" > gpurun_out/${tag}_sanitizer_racecheck_pytest.log 2>&1; echo "racecheck rc $?" | tee -a gpurun_out/${tag}_sanitizer_racecheck_pytest.log
+  tail -5 gpurun_out/${tag}_sanitizer_memcheck.log gpurun_out/${tag}_sanitizer_racecheck.log
+fi
+ls -la gpurun_out | tail -30

@@ -114,6 +114,67 @@ def source_regions(report):
     return "\n".join(lines), stall_line, total
 
 
+def extras(tag):
+    """Round 2 on: the other workloads' bench lines, the threshold sweep kernel, the multi-GPU runs and the sanitizer logs
+    (each only if round_capture.sh / scripts/r2_scale.sh left the artifact)."""
+    text = ""
+    lines = []
+    for workload in ("nof", "aa", "reads"):
+        path = os.path.join(OUT, f"{tag}_bench_{workload}.json")
+        if os.path.exists(path):
+            shutil.copy(path, os.path.join(PROFILES, f"{tag}_bench_{workload}.json"))
+            line = json.load(open(path))
+            parity = line.get("parity", {})
+            lines.append(f"| `--workload {workload}` | {line['config']['workload'][:110]} | {line['value']:.4g} {line['unit']} | "
+                         f"{line['e2e']['value']:.4g} ({line['e2e']['ms_per_step']:.3f} ms/step) | {line['cpu_baseline']['value']:.4g} "
+                         f"({line['cpu_baseline']['cores']} core) | {', '.join(f'{k}: {v}' for k, v in parity.items() if isinstance(v, bool))} |")
+    if lines:
+        text += ("\n## the other workloads of BASELINE.json (`profiles/" + tag + "_bench_<workload>.json`, not under a profiler)\n\n"
+                 "| command | workload | value | e2e | cpu_baseline | parity at full size |\n|---|---|---|---|---|---|\n" + "\n".join(lines) + "\n")
+    if os.path.exists(os.path.join(OUT, f"{tag}_sweep_full.ncu-rep")):
+        sweep = raw_tables(f"{tag}_sweep_full.ncu-rep")
+        text += ("\n## thresholdSweepKernel (configs[2]: one nucleotideMutationProfile filter, distance 5, 10 M rows), "
+                 "`ncu --set full` of `profiles/config3_ncu_target.py`\n\n" + sweep[0][0] + "\n")
+    path = os.path.join(OUT, f"{tag}_config3_launches.csv")
+    if os.path.exists(path):
+        shutil.copy(path, os.path.join(PROFILES, f"{tag}_config3_launches.csv"))
+        rows = list(csv.reader(open(path)))
+        start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+        header = rows[start]
+        text += "\nLaunch list of the two filters of that script (`profiles/" + tag + "_config3_launches.csv`, cold, serialised):\n\n| kernel | µs |\n|---|---|\n"
+        for row in rows[start + 1:]:
+            if len(row) > header.index("Metric Value"):
+                text += f"| `{row[header.index('Kernel Name')].split('(')[0][:80]}` | {float(row[header.index('Metric Value')].replace(',', '')) / 1000.0:.2f} |\n"
+    scale = []
+    for n in (1, 2, 4, 8):
+        for reduce in ("", "_peer", "_nccl"):
+            path = os.path.join(OUT, f"{tag}_scale_n{n}{reduce}.json")
+            if os.path.exists(path):
+                shutil.copy(path, os.path.join(PROFILES, os.path.basename(path)))
+                line = json.loads([l for l in open(path) if l.startswith("{")][-1])
+                scale.append((n, reduce.strip("_") or "-", line))
+    if scale:
+        base = next(line for n, _, line in scale if n == 1)
+        text += ("\n## one process per GPU, 1 -> 8 B200 (`profiles/scripts/" + tag + "_scale.sh`, weak scaling: 10 M rows per GPU)\n\n"
+                 "| GPUs | reduce | µs/step (device, max over ranks) | value | efficiency | e2e µs/step | e2e value | e2e efficiency |\n|---|---|---|---|---|---|---|---|\n")
+        for n, reduce, line in scale:
+            text += (f"| {n} | {reduce} | {line['ms_per_step'] * 1000:.1f} | {line['value']:.4g} | {line['value'] / (n * base['value']):.3f} | "
+                     f"{line['e2e']['ms_per_step'] * 1000:.1f} | {line['e2e']['value']:.4g} | {line['e2e']['value'] / (n * base['e2e']['value']):.3f} |\n")
+        text += ("\n`peer`: the library's shard group (finalize kernels store their rows into the root's memory over NVLink, the root sums "
+                 "them in a kernel); `nccl`: torch.distributed all_reduce of the count arrays between the container kernel and the finalize kernel.\n")
+    sanitizer = []
+    for name in sorted(os.listdir(OUT)):
+        if name.startswith(f"{tag}_sanitizer_") and name.endswith(".log") and "pytest" not in name:
+            shutil.copy(os.path.join(OUT, name), os.path.join(PROFILES, name))
+            summary = [l.strip() for l in open(os.path.join(OUT, name)) if "SUMMARY" in l]
+            pytest_log = os.path.join(OUT, name.replace(".log", "_pytest.log"))
+            tests = [l.strip() for l in open(pytest_log) if " passed" in l or " failed" in l] if os.path.exists(pytest_log) else []
+            sanitizer.append(f"| `{name}` | {summary[-1] if summary else 'no summary line'} | {tests[-1] if tests else ''} |")
+    if sanitizer:
+        text += "\n## compute-sanitizer over the GPU suites (`profiles/round_capture.sh`)\n\n| log | result | pytest |\n|---|---|---|\n" + "\n".join(sanitizer) + "\n"
+    return text
+
+
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     bench = json.load(open(os.path.join(OUT, f"{tag}_bench.json")))
@@ -185,6 +246,7 @@ Stall reasons over all samples: {stall_line}.
 ## the small kernels (same capture settings)
 
 """ + "\n\n".join(t for t, _, _ in others) + "\n"
+    text += extras(tag)
     with open(os.path.join(PROFILES, f"{tag}_summary.md"), "w") as out:
         out.write(text)
     print(f"wrote profiles/{tag}_summary.md, profiles/{tag}_k1_traffic.json")
