@@ -346,9 +346,10 @@ def run_ours(args):
         buffer = issued[0] % len(count_buffers)
         issued[0] += 1
         if use_peer:
-            prepared.run_sharded_async(stream.cuda_stream)  # filter + counts kernels; the finalize kernel sends the rows to rank 0
-            if rank == 0:
-                table.sharded_collect_async(stream.cuda_stream, counts.data_ptr())  # waits for all ranks on the device, sums
+            if rank == 0:  # filter + counts kernels; the finalize kernel waits for the other ranks' rows on the device and sums
+                prepared.run_sharded_collect_async(stream.cuda_stream, counts.data_ptr())
+            else:  # filter + counts kernels; the finalize kernel stores this rank's rows into rank 0's memory over NVLink
+                prepared.run_sharded_async(stream.cuda_stream)
             return
         if n_gpus > 1:
             stream.wait_event(reduced[buffer])  # the all-reduce that used this buffer two queries ago

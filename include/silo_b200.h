@@ -430,8 +430,11 @@ int silo_gpu_sharded_collect(
    uint64_t* n_hits,
    uint64_t* cardinality
 );
-/* the root's two calls in one (enqueue + collect: one launch -- a replayed CUDA graph per query shape --, one
- * synchronisation), on the table's own stream; the other ranks call silo_gpu_sharded_query_enqueue */
+/* the root's two calls in one (one launch -- a replayed CUDA graph per query shape --, one synchronisation), on the
+ * table's own stream; the other ranks call silo_gpu_sharded_query_enqueue. The collect happens INSIDE the root's
+ * finalize kernel here: it waits for the other ranks' rows, adds the root's own counts (never stored to the gather
+ * area) and runs the output pass over the sums -- one kernel and one pass over the rows less than enqueue + collect.
+ * Every earlier query of the group must have been collected (else SILO_E_CUDA, and the group has to be re-created). */
 int silo_gpu_sharded_query_hits(
    silo_gpu_table* table,
    const silo_filter_program* program,
@@ -444,6 +447,11 @@ int silo_gpu_sharded_query_hits(
 /* every rank: like silo_gpu_sharded_query_enqueue for a program that silo_gpu_program_prepare made device resident
  * (nothing is uploaded; replayable inside a captured CUDA graph: slot and generation live in device memory) */
 int silo_gpu_program_run_sharded_async(silo_gpu_program* prepared, void* cuda_stream);
+/* the root only: the same with the collect inside -- the root's finalize kernel waits for the other ranks' rows, adds
+ * its own counts and writes the sums of the valid symbols' rows to d_summed_counts ([n_symbols][genome_length] u32,
+ * may be NULL). One kernel fewer than run_sharded_async + sharded_collect_async and no store of the root's own rows;
+ * every earlier query of the group must have been collected. */
+int silo_gpu_program_run_sharded_collect_async(silo_gpu_program* prepared, void* d_summed_counts, void* cuda_stream);
 /* the same without the output pass and without synchronising (device-resident pipelines) */
 int silo_gpu_sharded_collect_async(silo_gpu_table* table, void* d_summed_counts, void* cuda_stream);
 void silo_gpu_shard_group_free(silo_gpu_table* table);

@@ -130,6 +130,8 @@ int silo_host_sharded_query_packed(silo_host_table* table, const char* expressio
                                    void* buffer, uint64_t capacity, uint64_t* n_rows, uint32_t* n_names, uint64_t* needed_bytes, uint64_t* cardinality);
 /* device-resident pipeline of the same: a prepared program on every rank, the root's collect without output pass */
 int silo_host_prepared_run_sharded_async(silo_host_prepared* prepared, void* cuda_stream);
+/* the root: the same with the collect inside the finalize kernel (silo_gpu_program_run_sharded_collect_async) */
+int silo_host_prepared_run_sharded_collect_async(silo_host_prepared* prepared, void* d_summed_counts, void* cuda_stream);
 int silo_host_sharded_collect_async(silo_host_table* table, void* d_summed_counts, void* cuda_stream);
 /* thresholding only, on counts the caller summed over shards (multi-GPU) */
 silo_host_rows* silo_host_mutation_rows_from_counts(silo_host_table* table, const char* column, const uint32_t* counts, double min_proportion);

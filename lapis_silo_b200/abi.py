@@ -115,7 +115,7 @@ EXPORTED_SYMBOLS = [
     "silo_gpu_column_set_reference", "silo_gpu_query_mutation_hits", "silo_gpu_query_combinations",
     "silo_gpu_query_mutation_counts_async", "silo_gpu_mutation_hits_from_counts",
     "silo_gpu_shard_group_init", "silo_gpu_shard_group_connect", "silo_gpu_sharded_query_enqueue", "silo_gpu_sharded_collect",
-    "silo_gpu_sharded_collect_async", "silo_gpu_shard_group_free", "silo_gpu_program_run_sharded_async", "silo_gpu_sharded_query_hits", "silo_gpu_get_sweep_stats", "silo_gpu_query_mutation_hits_columns", "silo_gpu_value_column_upload", "silo_gpu_query_count",
+    "silo_gpu_sharded_collect_async", "silo_gpu_shard_group_free", "silo_gpu_program_run_sharded_async", "silo_gpu_program_run_sharded_collect_async", "silo_gpu_sharded_query_hits", "silo_gpu_get_sweep_stats", "silo_gpu_query_mutation_hits_columns", "silo_gpu_value_column_upload", "silo_gpu_query_count",
 ]
 
 

@@ -343,7 +343,7 @@ void enqueueStagedQuery(silo_gpu_table* table, const StagedQuery& staged, cudaSt
 void dropQueryGraphsLocked(silo_gpu_table* table);
 void freeShardGroup(silo_gpu_table* table);  // mutations.cu
 int shardGroupColumnLocked(const silo_gpu_table* table);
-void enqueuePreparedShardedLocked(silo_gpu_table* table, const silo_gpu_filter* filter, cudaStream_t stream);
+void enqueuePreparedShardedLocked(silo_gpu_table* table, const silo_gpu_filter* filter, cudaStream_t stream, bool collect_here = false, void* d_summed_counts = nullptr);
 // mutations.cu: coverage + container + finalize kernels for a filter whose interpreter launch already zeroed
 // d_counts and built the work list (caller holds table->mutex); records the per-call timing events
 void enqueuePreparedCountsLocked(silo_gpu_table* table, int column, const silo_gpu_filter* filter, uint32_t* d_counts, cudaStream_t stream);

@@ -1443,7 +1443,7 @@ int silo_gpu_program_run_counts_async(silo_gpu_program* prepared, int column, vo
    });
 }
 
-int silo_gpu_program_run_sharded_async(silo_gpu_program* prepared, void* cuda_stream) {
+static int runPreparedSharded(silo_gpu_program* prepared, void* cuda_stream, bool collect_here, void* d_summed_counts) {
    return guarded([&] {
       require(prepared != nullptr, "silo_gpu_program_run_sharded_async: NULL argument");
       silo_gpu_table* table = prepared->table;
@@ -1463,8 +1463,16 @@ int silo_gpu_program_run_sharded_async(silo_gpu_program* prepared, void* cuda_st
       params.prepare_counts = table->d_counts;
       params.prepare_counts_words = host.dev.n_symbols * host.dev.genome_length;
       launchProgram(table, params, prepared->filter, stream);
-      enqueuePreparedShardedLocked(table, prepared->filter, stream);
+      enqueuePreparedShardedLocked(table, prepared->filter, stream, collect_here, d_summed_counts);
    });
+}
+
+int silo_gpu_program_run_sharded_async(silo_gpu_program* prepared, void* cuda_stream) {
+   return runPreparedSharded(prepared, cuda_stream, false, nullptr);
+}
+
+int silo_gpu_program_run_sharded_collect_async(silo_gpu_program* prepared, void* d_summed_counts, void* cuda_stream) {
+   return runPreparedSharded(prepared, cuda_stream, true, d_summed_counts);
 }
 
 uint64_t silo_gpu_program_device_bytes(const silo_gpu_program* prepared) {

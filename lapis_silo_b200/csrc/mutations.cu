@@ -814,6 +814,12 @@ struct ShardPush {  // what the finalize kernel of a sharded query needs (all ze
    uint64_t valid_mask = 0;
    unsigned long long fixed_cardinality = 0;          // filter == all rows
    unsigned long long* filter_scalars = nullptr;      // else: {cardinality, -, error flag} of the query's filter; reset here
+   // root only, "collect here": the finalize kernel itself waits for the other ranks' rows, adds this rank's counts from
+   // its registers, runs the output pass over the sums and hands the slot back -- no store of the root's own rows, no
+   // second kernel behind it (peers == nullptr: the root's rows go to the slot like everybody else's and
+   // shardCollectKernel sums them later)
+   ShardBlockHeader* const* peers = nullptr;  // [world] every rank's block as mapped on the root
+   uint32_t* summed_out = nullptr;            // optional: [n_symbols][genome_length], the rows of the valid symbols are written
 };
 
 __device__ __forceinline__ uint32_t loadAcquireSystem(const uint32_t* address) {
@@ -869,8 +875,9 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    // issue every global load up front: the kernel is one latency chain otherwise
    const uint32_t mine = diff[p];  // (the array is padded to whole blocks)
    const uint32_t reference_symbol = p < genome_length ? column.local_reference[p] : 0u;
-   const bool output_pass = request.hits != nullptr && p < genome_length;
-   const uint32_t genome_symbol = output_pass ? column.global_reference[p] : 0u;
+   const bool collect_here = push.peers != nullptr;
+   const bool output_pass = request.hits != nullptr && p < genome_length && !collect_here;
+   const uint32_t genome_symbol = request.hits != nullptr && p < genome_length ? column.global_reference[p] : 0u;
    uint32_t others = 0;
    uint32_t valid_others = 0;  // the same sum over the valid mutation symbols only
    uint32_t candidates = 0;    // OR of the counts that could be emitted (valid, not the reference genome's symbol)
@@ -923,6 +930,7 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
       counts[reference_symbol * genome_length + p] = reference_count;
    }
    uint32_t shard_slot = 0;
+   uint32_t query_index_of_block = 0;
    bool shard_timed_out = false;
    if (push.root_block != nullptr) {
       // this rank's rows of the valid mutation symbols -> the root's gather area (coalesced stores over NVLink), once the
@@ -933,11 +941,80 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
       if (threadIdx.x == 0) {
          query_index = *reinterpret_cast<volatile uint32_t*>(&push.own_header->queries_pushed);
          const uint32_t generation = query_index / SHARD_SLOTS + 1;
-         slot_is_free = waitForAtLeast(&push.own_header->released[query_index % SHARD_SLOTS], generation - 1) ? 1u : 0u;
+         if (collect_here) {
+            // (the slot's arrival count stays the one shardCollectKernel expects: block 0 counts the whole grid in)
+            ShardBlockHeader* const root_header = reinterpret_cast<ShardBlockHeader*>(push.root_block);
+            if (blockIdx.x == 0) {
+               atomicAdd(&root_header->arrivals[query_index % SHARD_SLOTS], gridDim.x);
+            }
+            // every earlier query of the group must have been collected: the slots are summed in order
+            const bool in_order = *reinterpret_cast<volatile uint32_t*>(&root_header->queries_collected) == query_index;
+            slot_is_free =
+               in_order && waitForAtLeast(&root_header->arrivals[query_index % SHARD_SLOTS], push.world * gridDim.x * generation) ? 1u : 0u;
+         } else {
+            slot_is_free = waitForAtLeast(&push.own_header->released[query_index % SHARD_SLOTS], generation - 1) ? 1u : 0u;
+         }
       }
       __syncthreads();
       shard_slot = query_index % SHARD_SLOTS;
-      if (slot_is_free != 0 && p < genome_length) {
+      query_index_of_block = query_index;
+      if (collect_here) {
+         if (slot_is_free != 0 && p < genome_length) {
+            // sums over the ranks: this rank's counts (still in L1 / L2) + the rows the other ranks stored into the slot
+            const uint32_t* const rows = reinterpret_cast<const uint32_t*>(push.root_block + SHARD_HEADER_BYTES) +
+                                         static_cast<size_t>(shard_slot) * push.world * push.n_valid * genome_length + p;
+            const size_t rank_stride = static_cast<size_t>(push.n_valid) * genome_length;
+            auto sumOf = [&](uint32_t symbol, uint32_t row) {  // (the loads of all ranks in flight together)
+               uint32_t values[SHARD_MAX_WORLD];
+               values[0] = symbol == reference_symbol ? reference_count : counts[symbol * genome_length + p];
+#pragma unroll
+               for (uint32_t rank = 1; rank < SHARD_MAX_WORLD; ++rank) {
+                  values[rank] = rank < push.world ? rows[rank * rank_stride + row * genome_length] : 0u;
+               }
+               uint32_t sum = 0;
+#pragma unroll
+               for (uint32_t rank = 0; rank < SHARD_MAX_WORLD; ++rank) {
+                  sum += values[rank];
+               }
+               return sum;
+            };
+            uint32_t total = 0;
+            uint32_t summed_candidates = 0;
+            uint32_t row = 0;
+            for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
+               if (((push.valid_mask >> symbol) & 1ULL) != 0) {
+                  const uint32_t sum = sumOf(symbol, row);
+                  total += sum;
+                  summed_candidates |= symbol != genome_symbol ? sum : 0u;
+                  if (push.summed_out != nullptr) {
+                     push.summed_out[symbol * genome_length + p] = sum;
+                  }
+                  ++row;
+               }
+            }
+            if (request.hits != nullptr && total != 0 && summed_candidates != 0) {
+               const uint32_t threshold_count =
+                  request.min_proportion == 0 ? 0u : static_cast<uint32_t>(ceil(__dmul_rn(static_cast<double>(total), request.min_proportion)) - 1.0);
+               row = 0;
+               for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
+                  if (((push.valid_mask >> symbol) & 1ULL) == 0) {
+                     continue;
+                  }
+                  const uint32_t this_row = row++;
+                  if (symbol == genome_symbol) {
+                     continue;
+                  }
+                  const uint32_t sum = sumOf(symbol, this_row);
+                  if (sum > threshold_count) {
+                     const uint32_t index = atomicAdd(&work_state[3], 1u);
+                     if (index < request.capacity) {
+                        request.hits[1 + index] = silo_mutation_hit{p, symbol, sum, total};
+                     }
+                  }
+               }
+            }
+         }
+      } else if (slot_is_free != 0 && p < genome_length) {
          uint32_t* const root_rows = reinterpret_cast<uint32_t*>(push.root_block + SHARD_HEADER_BYTES) +
                                      (static_cast<size_t>(shard_slot) * push.world + push.rank) * push.n_valid * genome_length;
          uint32_t row = 0;
@@ -996,7 +1073,9 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
             root_header->cardinality[shard_slot][push.rank] = cardinality;
             root_header->error[shard_slot][push.rank] = error;
          }
-         if (push.rank == 0) {  // the root's own contribution never leaves its memory: device scope is enough (and cheaper)
+         if (collect_here) {
+            __threadfence();  // (block 0 counted the whole grid in before it waited)
+         } else if (push.rank == 0) {  // the root's own contribution never leaves its memory: device scope is enough (and cheaper)
             __threadfence();
             atomicAdd(&reinterpret_cast<ShardBlockHeader*>(push.root_block)->arrivals[shard_slot], 1u);
          } else {
@@ -1012,7 +1091,25 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
          for (uint32_t block = 0; block < gridDim.x; ++block) {
             block_totals[block] = 0;
          }
-         if (request.hits != nullptr) {
+         if (collect_here) {
+            // the whole group's result: every rank's cardinality and error flag (block 0 of each wrote them before its
+            // arrival), the slot back to every rank, the query counted as collected
+            ShardBlockHeader* const root_header = reinterpret_cast<ShardBlockHeader*>(push.root_block);
+            unsigned long long cardinality = 0;
+            uint32_t error = shard_timed_out ? 2u : 0u;
+            for (uint32_t rank = 0; rank < push.world; ++rank) {
+               cardinality += *reinterpret_cast<volatile unsigned long long*>(&root_header->cardinality[shard_slot][rank]);
+               error |= *reinterpret_cast<volatile uint32_t*>(&root_header->error[shard_slot][rank]);
+            }
+            if (request.hits != nullptr) {
+               request.hits[0] = silo_mutation_hit{
+                  *reinterpret_cast<volatile uint32_t*>(&work_state[3]), error, static_cast<uint32_t>(cardinality), static_cast<uint32_t>(cardinality >> 32)};
+            }
+            root_header->queries_collected = query_index_of_block + 1;
+            for (uint32_t rank = 0; rank < push.world; ++rank) {
+               *reinterpret_cast<volatile uint32_t*>(&push.peers[rank]->released[shard_slot]) = query_index_of_block / SHARD_SLOTS + 1;
+            }
+         } else if (request.hits != nullptr) {
             silo_mutation_hit header{*reinterpret_cast<volatile uint32_t*>(&work_state[3]), 0u, 0u, 0u};
             if (request.filter_scalars != nullptr) {
                const unsigned long long cardinality = *reinterpret_cast<volatile unsigned long long*>(&request.filter_scalars[0]);
@@ -1425,7 +1522,6 @@ void enqueuePreparedCountsLocked(silo_gpu_table* table, int column, const silo_g
 }
 
 int shardGroupColumnLocked(const silo_gpu_table* table);
-void enqueuePreparedShardedLocked(silo_gpu_table* table, const silo_gpu_filter* filter, cudaStream_t stream);
 
 }  // namespace silo
 
@@ -1865,10 +1961,16 @@ int shardGroupColumnLocked(const silo_gpu_table* table) {
 
 // a prepared program's filter (its interpreter launch zeroed table->d_counts and built the work list): counts of the
 // group's column + this rank's rows to the root
-void enqueuePreparedShardedLocked(silo_gpu_table* table, const silo_gpu_filter* filter, cudaStream_t stream) {
+void enqueuePreparedShardedLocked(silo_gpu_table* table, const silo_gpu_filter* filter, cudaStream_t stream, bool collect_here, void* d_summed_counts) {
    ShardGroup* group = table->shard;
    ShardPush push = shardPushOf(*group);
    push.filter_scalars = filter->d_cardinality;
+   if (collect_here) {
+      require(group->rank == 0 && group->d_peer_table != nullptr, "sharded collect: only the connected root (rank 0) collects");
+      push.peers = group->d_peer_table;
+      push.summed_out = static_cast<uint32_t*>(d_summed_counts);
+      group->queries_collected++;
+   }
    enqueueMutationCounts(table, group->column, filter, table->d_counts, stream, nullptr, true, true, &push);
    group->queries_enqueued++;
 }
@@ -2055,6 +2157,17 @@ static void enqueueShardedQuery(
       ensureHitsCapacity(table, host, group->valid_mask, stream);
    }
    ShardPush push = shardPushOf(*group);
+   HitRequest request;
+   if (with_collect) {  // the root's finalize kernel sums the ranks and runs the output pass itself
+      require(group->rank == 0 && group->d_peer_table != nullptr, "sharded collect: only the connected root (rank 0) collects");
+      push.peers = group->d_peer_table;
+      push.summed_out = static_cast<uint32_t*>(d_summed_counts);
+      request.valid_mask = group->valid_mask;
+      request.min_proportion = min_proportion;
+      request.hits = table->h_hits_pinned;
+      request.capacity = static_cast<uint32_t>(table->hits_capacity);
+   }
+   const HitRequest* const request_or_null = with_collect ? &request : nullptr;
    const bool trivially_full = program->n_instrs == 1 && program->instrs != nullptr && program->instrs[0].opcode == SILO_OP_PUSH_FULL;
    StagedQuery staged;
    if (trivially_full) {
@@ -2066,13 +2179,10 @@ static void enqueueShardedQuery(
    }
    auto enqueueAll = [&]() {
       if (trivially_full) {
-         enqueueMutationCounts(table, group->column, nullptr, table->d_counts, stream, nullptr, false, false, &push);
+         enqueueMutationCounts(table, group->column, nullptr, table->d_counts, stream, request_or_null, false, false, &push);
       } else {
          enqueueStagedQuery(table, staged, stream);
-         enqueueMutationCounts(table, group->column, table->query_filter, table->d_counts, stream, nullptr, false, true, &push);
-      }
-      if (with_collect) {
-         enqueueShardCollect(table, min_proportion, true, d_summed_counts, stream);
+         enqueueMutationCounts(table, group->column, table->query_filter, table->d_counts, stream, request_or_null, false, true, &push);
       }
    };
    cudaGraphExec_t replay = nullptr;
@@ -2092,21 +2202,21 @@ static void enqueueShardedQuery(
    }
    if (replay != nullptr) {
       SILO_CUDA_CHECK(cudaGraphLaunch(replay, stream));
-      table->stats.kernel_launches += with_collect ? 5 : 4;
-      if (with_collect) {
-         group->queries_collected++;
-      }
+      table->stats.kernel_launches += 4;
    } else {
       enqueueAll();
    }
    group->queries_enqueued++;
+   if (with_collect) {  // (host-side bookkeeping of the synchronous collect's "is a query waiting" check)
+      group->queries_collected++;
+   }
 }
 
 // reads the result of a collect with output pass that has completed on the stream
 static void readShardedHits(silo_gpu_table* table, const silo_mutation_hit** hits, uint64_t* n_hits, uint64_t* cardinality) {
    const silo_mutation_hit header = table->h_hits_pinned[0];
-   if (header.symbol == 2) {
-      throw ApiError(SILO_E_CUDA, "sharded query: a rank of the shard group did not deliver its counts in time");
+   if ((header.symbol & 2u) != 0) {
+      throw ApiError(SILO_E_CUDA, "sharded query: a rank of the shard group did not deliver its counts in time (or an earlier query of the group is still uncollected)");
    }
    if (header.symbol != 0) {
       throw ApiError(SILO_E_OUT_OF_LAYOUT, "a leaf bitmap holds row ids outside the row layout");

@@ -253,6 +253,10 @@ int silo_host_prepared_run_sharded_async(silo_host_prepared* prepared, void* cud
    return guarded([&] { throwOnDeviceError(silo_gpu_program_run_sharded_async(prepared->program, cuda_stream)); });
 }
 
+int silo_host_prepared_run_sharded_collect_async(silo_host_prepared* prepared, void* d_summed_counts, void* cuda_stream) {
+   return guarded([&] { throwOnDeviceError(silo_gpu_program_run_sharded_collect_async(prepared->program, d_summed_counts, cuda_stream)); });
+}
+
 int silo_host_sharded_collect_async(silo_host_table* table, void* d_summed_counts, void* cuda_stream) {
    return guarded([&] { throwOnDeviceError(silo_gpu_sharded_collect_async(table->table->deviceTable(), d_summed_counts, cuda_stream)); });
 }

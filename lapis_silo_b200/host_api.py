@@ -38,7 +38,7 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_archive_read", "silo_host_archive_free", "silo_host_archive_column", "silo_host_archive_column_info",
     "silo_host_archive_chunk_sizes", "silo_host_archive_column_shard", "silo_host_table_load_archive", "silo_host_roaring_runs",
     "silo_host_count", "silo_host_synthetic_draw_short_reads", "silo_host_synthetic_build_short_read_column", "silo_host_table_add_string_column", "silo_host_table_add_date_column", "silo_host_synthetic_create_gene", "silo_host_shard_group_create", "silo_host_shard_group_connect", "silo_host_sharded_enqueue", "silo_host_sharded_collect_packed",
-    "silo_host_prepared_run_sharded_async", "silo_host_sharded_collect_async", "silo_host_sharded_query_packed",
+    "silo_host_prepared_run_sharded_async", "silo_host_prepared_run_sharded_collect_async", "silo_host_sharded_collect_async", "silo_host_sharded_query_packed",
 ]
 SHARD_HANDLE_BYTES = 128  # SILO_SHARD_HANDLE_BYTES
 
@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
             vp, C.c_char_p, C.c_char_p, C.c_double, vp, vp, C.c_uint64,
             C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.silo_host_prepared_run_sharded_async.argtypes = [vp, vp]
+        L.silo_host_prepared_run_sharded_collect_async.argtypes = [vp, vp, vp]
         L.silo_host_sharded_collect_async.argtypes = [vp, vp, vp]
         L.silo_host_mutation_rows_from_counts.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint32), C.c_double]
         L.silo_host_mutation_rows_from_counts.restype = vp
@@ -301,6 +302,11 @@ class PreparedFilter:
         """The filter and the counts of the shard group's column, this rank's rows sent to rank 0; enqueue only and
         replayable inside a CUDA graph (silo_gpu_program_run_sharded_async)."""
         _check(lib().silo_host_prepared_run_sharded_async(self._h, C.c_void_p(stream_ptr)))
+
+    def run_sharded_collect_async(self, stream_ptr: int, d_summed_counts_ptr: int = 0) -> None:
+        """Rank 0: run_sharded_async with the collect inside -- the finalize kernel waits for the other ranks' rows and
+        writes the sums (silo_gpu_program_run_sharded_collect_async)."""
+        _check(lib().silo_host_prepared_run_sharded_collect_async(self._h, C.c_void_p(d_summed_counts_ptr), C.c_void_p(stream_ptr)))
 
     @property
     def device_handle(self) -> int:

@@ -490,6 +490,20 @@ def test_synthetic_shards_sum_to_the_whole(ctx):
             assert cardinality == (whole_filter.cardinality if filtered else total_rows)
             want = whole_counts if filtered else whole_full
             np.testing.assert_array_equal(summed.cpu().numpy().view(np.uint32).reshape(16, 1500)[:5], want[:5])
+        # the root's two halves as one call: its finalize kernel waits for the other shards' rows, adds its own counts
+        # and runs the output pass (no store of the root's rows, no collect kernel); twice the same shape -> a replayed graph
+        for filtered, min_proportion in [(True, 0.05), (False, 0.05), (True, 0.0), (True, 0.05), (True, 0.05)]:
+            texts = []
+            for rank, (table, _, _, _) in enumerate(interleaved):
+                first, n, stride = host_api.interleaved_shard(len(sizes), 3, rank)
+                texts.append(f"(and {host_api.date_ranges_expression(total_rows, 1095, 200, 800, first, n, stride)} (bitmap lineage))")
+                if rank != 0:
+                    table.sharded_enqueue("main", texts[rank] if filtered else None, stream.cuda_stream)
+            columns, cardinality = root.sharded_query("main", texts[0] if filtered else None, min_proportion, summed.data_ptr())
+            assert host_api.rows_from_columns(columns) == oracle_table.mutations("main", expression if filtered else None, min_proportion)
+            assert cardinality == (whole_filter.cardinality if filtered else total_rows)
+            want = whole_counts if filtered else whole_full
+            np.testing.assert_array_equal(summed.cpu().numpy().view(np.uint32).reshape(16, 1500)[:5], want[:5])
         # two queries in flight before the root collects (ranks run ahead of the root)
         for _ in range(2):
             for rank, (table, _, _, _) in enumerate(interleaved):
