@@ -330,12 +330,16 @@ def run_ours(args):
     # handles of the gather areas travel through torch.distributed once, at set-up.
     # --reduce nccl: the per-rank counts are all-reduced with NCCL instead; the all-reduce of query i runs on its own
     # stream beside the kernels of query i + 1 (two count buffers). Every reduction is inside the timed region.
-    use_peer = n_gpus > 1 and args.reduce == "peer"
+    use_peer = (n_gpus > 1 or args.force_shard_group) and args.reduce == "peer"
     if use_peer:
         handles = [None] * n_gpus
-        dist.all_gather_object(handles, table.shard_group_create("main", rank, n_gpus))
+        if n_gpus > 1:
+            dist.all_gather_object(handles, table.shard_group_create("main", rank, n_gpus))
+        else:  # (measurement only: what the sharded kernels cost without any peer)
+            handles = [table.shard_group_create("main", 0, 1)]
         table.shard_group_connect(handles)
-        dist.barrier()
+        if n_gpus > 1:
+            dist.barrier()
     comm_stream = torch.cuda.Stream() if n_gpus > 1 and not use_peer else None
     count_buffers = [counts, torch.zeros_like(counts)] if n_gpus > 1 and not use_peer else [counts]
     kernels_done = [torch.cuda.Event() for _ in count_buffers]
@@ -1108,6 +1112,8 @@ def main():
                              "aa: configs[3], AminoAcidMutations over 12 genes; reads: configs[2], many_short_read_filters")
     parser.add_argument("--reduce", choices=["peer", "nccl"], default="peer",
                         help="N > 1: how the per-rank counts meet -- the library's shard group (peer-memory stores) or NCCL all-reduce")
+    parser.add_argument("--force-shard-group", action="store_true",
+                        help="N = 1 only, measurement: run the step through a shard group of one rank (what the sharded kernels cost without a peer)")
     parser.add_argument("--traffic-bytes", type=int, default=None,
                         help="dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture")
     args = parser.parse_args()

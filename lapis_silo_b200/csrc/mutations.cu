@@ -793,10 +793,12 @@ constexpr uint32_t SHARD_SLOTS = 4;
 constexpr long long SHARD_SPIN_LIMIT = 4000000000LL;  // cycles (~2 s)
 
 struct ShardBlockHeader {  // the start of every rank's exported block
-   uint32_t released[SHARD_SLOTS];  // generation of the slot's last consumed use; written by the root's collect kernel
-   uint32_t arrivals[SHARD_SLOTS];  // root only: ranks whose rows of a slot have landed, counted over all generations
-   unsigned long long cardinality[SHARD_SLOTS][SHARD_MAX_WORLD];  // root only: the ranks' filter cardinalities
-   uint32_t error[SHARD_SLOTS][SHARD_MAX_WORLD];                  // root only: the ranks' filter error flags
+   uint32_t released[SHARD_SLOTS];  // generation of the slot's last consumed use; written by the root's collecting kernel
+   // root only, tagged words like the rows (see storeTagged): the ranks' filter cardinalities (two halves) and error flags
+   uint2 cardinality_low[SHARD_SLOTS][SHARD_MAX_WORLD];
+   uint2 cardinality_high[SHARD_SLOTS][SHARD_MAX_WORLD];
+   uint2 error[SHARD_SLOTS][SHARD_MAX_WORLD];
+   uint32_t collect_error;  // root only: a block of the collecting kernel gave up waiting (cleared by its last block)
    // Device-side query counters (local use): which slot and generation a launch works on is read from here, not from
    // kernel parameters, so that a captured CUDA graph of sharded queries can be replayed.
    uint32_t queries_pushed;     // sharded queries this rank's finalize kernels have completed
@@ -820,7 +822,16 @@ struct ShardPush {  // what the finalize kernel of a sharded query needs (all ze
    // shardCollectKernel sums them later)
    ShardBlockHeader* const* peers = nullptr;  // [world] every rank's block as mapped on the root
    uint32_t* summed_out = nullptr;            // optional: [n_symbols][genome_length], the rows of the valid symbols are written
+   unsigned long long* debug_times = nullptr; // SILO_SHARD_DEBUG: [blocks][4] globaltimer: start, wait over, rows done, arrival sent
 };
+
+__device__ __forceinline__ void shardDebugStamp(const ShardPush& push, uint32_t index) {
+   if (push.debug_times != nullptr) {  // (called by one thread of the block)
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      push.debug_times[4 * blockIdx.x + index] = now;
+   }
+}
 
 __device__ __forceinline__ uint32_t loadAcquireSystem(const uint32_t* address) {
    uint32_t value;
@@ -842,6 +853,45 @@ __device__ __forceinline__ bool waitForAtLeast(const uint32_t* address, uint32_t
    return static_cast<int32_t>(loadAcquireSystem(address) - target) >= 0;
 }
 
+// The gather area and the per-rank scalars are made of TAGGED words {value, tag}, tag = the group's query number + 1,
+// written with ONE 8-byte store each: a reader that sees the tag of its query has the value. No fence and no arrival
+// counter on the writer's side (a system-scope fence behind stores over NVLink is a round trip of ~2-3 us on the
+// critical path of every rank), no wait-for-everybody on the reader's side: the root polls the words it needs.
+__device__ __forceinline__ void storeTagged(uint2* address, uint32_t value, uint32_t tag) {
+   asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(address), "r"(value), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 loadTagged(const uint2* address) {
+   uint2 word;
+   asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(word.x), "=r"(word.y) : "l"(address) : "memory");
+   return word;
+}
+// re-reads the word until it carries `tag` (the caller's first load did not); gives up after SHARD_SPIN_LIMIT cycles and
+// returns the word as it is then. (Not inlined: the callers keep dozens of words in registers.)
+__device__ __noinline__ uint2 pollTagged(const uint2* address, uint32_t tag) {
+   const long long begin = clock64();
+   uint2 word = loadTagged(address);
+   while (word.y != tag && clock64() - begin <= SHARD_SPIN_LIMIT) {
+      __nanosleep(200);
+      word = loadTagged(address);
+   }
+   return word;
+}
+
+// the root's last block: the filter cardinalities and error flags that block 0 of every rank's finalize kernel stored
+__device__ __forceinline__ void sumRankScalars(ShardBlockHeader* root_header, uint32_t slot, uint32_t world, uint32_t tag, unsigned long long& cardinality, uint32_t& error) {
+   for (uint32_t rank = 0; rank < world; ++rank) {
+      const uint2 low = pollTagged(&root_header->cardinality_low[slot][rank], tag);
+      const uint2 high = pollTagged(&root_header->cardinality_high[slot][rank], tag);
+      const uint2 flag = pollTagged(&root_header->error[slot][rank], tag);
+      if (low.y != tag || high.y != tag || flag.y != tag) {
+         error |= 2u;
+         continue;
+      }
+      cardinality += low.x | (static_cast<unsigned long long>(high.x) << 32);
+      error |= flag.x;
+   }
+}
+
 struct HitRequest {
    silo_mutation_hit* hits = nullptr;
    uint32_t capacity = 0;
@@ -852,10 +902,30 @@ struct HitRequest {
    uint32_t keep_scalars = 0;  // report the filter's scalars but leave them for the next column of the same query
 };
 
-// Grid: diffPadded(genome_length) / 256 blocks (the difference array has genome_length + 1 entries).
-// The kernel leaves the difference array, its block totals and the work-list state all-zero for the
-// next query: every thread clears the element it read, the last block to finish clears the totals.
-__global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
+// Grid: diffPadded(genome_length) / 256 blocks (the difference array has genome_length + 1 entries) of
+// FIN_GROUPS x 256 threads: thread (g, i) works on position i of the block and on the symbols g, g + 4, g + 8, ...
+// (at most eight loads per thread, all in flight together).
+//
+// The kernel runs once per query, right behind a container kernel that has pushed everything else out of the
+// instruction caches: what it costs is mostly the FETCH of its own code (an earlier version that unrolled the
+// 32 possible symbols per thread, plus 56 loads of the other ranks' rows, was 6,152 instructions = 98 KB and took
+// ~8 us for work that needs two memory round trips). So: parallelism over threads instead of unrolled code, one
+// instantiation per mode, loops kept as loops.
+//
+// It leaves the difference array, its block totals and the work-list state all-zero for the next query: every
+// thread clears the element it read, the last block to finish clears the totals.
+constexpr int FIN_GROUPS = 4;
+constexpr int FIN_BLOCK_THREADS = FIN_GROUPS * FIN_THREADS;
+constexpr int FIN_SYMBOLS_PER_THREAD = 32 / FIN_GROUPS;
+enum FinalizeMode : int {
+   FIN_COUNTS = 0,   // the counts only
+   FIN_OUTPUT = 1,   // + the output pass (addMutationsToOutput) over this table's counts
+   FIN_PUSH = 2,     // sharded query: + this rank's rows of the valid symbols into the root's gather area
+   FIN_COLLECT = 3,  // sharded query, root: + the other ranks' rows added, the output pass over the sums
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(FIN_BLOCK_THREADS) finalizeCountsKernel(
    DevColumn column,
    uint32_t* __restrict__ diff_scratch,
    uint32_t* __restrict__ counts,
@@ -863,42 +933,58 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    HitRequest request,
    ShardPush push
 ) {
+   constexpr bool SHARDED = MODE == FIN_PUSH || MODE == FIN_COLLECT;
+   constexpr bool USE_ROWS = MODE == FIN_OUTPUT || MODE == FIN_COLLECT;  // the valid symbols' (summed) counts per position in shared memory
    __shared__ uint32_t warp_totals[FIN_THREADS / 32];
    __shared__ uint32_t block_offset;
+   __shared__ uint32_t slot_is_free;  // sharded query: the wait of this block succeeded (else: timed out)
+   __shared__ uint32_t query_index;   // sharded query: the group's query counter when this block started
+   __shared__ uint32_t part_others[FIN_GROUPS][FIN_THREADS];
+   __shared__ uint32_t reference_counts[FIN_THREADS];
+   __shared__ uint32_t row_sum[USE_ROWS ? 32 : 1][FIN_THREADS];  // [row r = the r-th valid symbol][position]
    const uint32_t genome_length = column.genome_length;
    uint32_t* diff = diff_scratch;
    uint32_t* block_totals = diff_scratch + diffPadded(genome_length);
-   const uint32_t block_first = blockIdx.x * FIN_THREADS;
+   const uint32_t i = threadIdx.x % FIN_THREADS;
+   const uint32_t group = threadIdx.x / FIN_THREADS;  // (uniform per warp)
    const uint32_t lane = threadIdx.x & 31;
-   const uint32_t warp = threadIdx.x >> 5;
-   const uint32_t p = block_first + threadIdx.x;
-   // issue every global load up front: the kernel is one latency chain otherwise
-   const uint32_t mine = diff[p];  // (the array is padded to whole blocks)
-   const uint32_t reference_symbol = p < genome_length ? column.local_reference[p] : 0u;
-   const bool collect_here = push.peers != nullptr;
-   const bool output_pass = request.hits != nullptr && p < genome_length && !collect_here;
-   const uint32_t genome_symbol = request.hits != nullptr && p < genome_length ? column.global_reference[p] : 0u;
-   uint32_t others = 0;
-   uint32_t valid_others = 0;  // the same sum over the valid mutation symbols only
-   uint32_t candidates = 0;    // OR of the counts that could be emitted (valid, not the reference genome's symbol)
-   if (p < genome_length) {
-      // all the loads first (the loop below is unrolled over the 32 possible symbols): one trip to L2 instead of one per
-      // symbol -- as a loop over n_symbols with the load inside, the kernel was a chain of 16 dependent L2 latencies
-      uint32_t values[32];
-#pragma unroll
-      for (uint32_t symbol = 0; symbol < 32; ++symbol) {
-         values[symbol] = symbol < column.n_symbols && symbol != reference_symbol ? counts[symbol * genome_length + p] : 0u;
+   const uint32_t warp = i >> 5;
+   const uint32_t p = blockIdx.x * FIN_THREADS + i;
+   const bool in_range = p < genome_length;
+   const uint64_t valid_mask = SHARDED ? push.valid_mask : request.valid_mask;
+   const uint32_t n_valid = __popcll(valid_mask);
+   // Sharded query: the block's one wait is started first, by the last thread, so that it overlaps the loads below: a
+   // rank that stores its rows waits until the root has released the gather slot's previous use (a root that collects
+   // here has nothing to wait for: it polls the other ranks' rows). Every block reads the query counter before it
+   // counts itself in at the end; the last block increments it after that.
+   if (SHARDED && threadIdx.x == FIN_BLOCK_THREADS - 1) {
+      shardDebugStamp(push, 0);
+      const uint32_t index = *reinterpret_cast<volatile uint32_t*>(&push.own_header->queries_pushed);
+      query_index = index;
+      if (MODE == FIN_COLLECT) {
+         // every earlier query of the group must have been collected: the slots are summed in order
+         slot_is_free = *reinterpret_cast<volatile uint32_t*>(&reinterpret_cast<ShardBlockHeader*>(push.root_block)->queries_collected) == index ? 1u : 0u;
+      } else {
+         slot_is_free = waitForAtLeast(&push.own_header->released[index % SHARD_SLOTS], index / SHARD_SLOTS) ? 1u : 0u;
       }
+      shardDebugStamp(push, 1);
+   }
+   // every global load up front
+   const uint32_t mine = group == 0 ? diff[p] : 0u;  // (the array is padded to whole blocks)
+   const uint32_t reference_symbol = in_range ? column.local_reference[p] : 0u;
+   uint32_t values[FIN_SYMBOLS_PER_THREAD];
 #pragma unroll
-      for (uint32_t symbol = 0; symbol < 32; ++symbol) {
-         const uint32_t value = values[symbol];
-         others += value;
-         const uint32_t valid_value = ((request.valid_mask >> symbol) & 1ULL) != 0 ? value : 0u;
-         valid_others += valid_value;
-         candidates |= symbol != genome_symbol ? valid_value : 0u;
+   for (uint32_t k = 0; k < FIN_SYMBOLS_PER_THREAD; ++k) {
+      const uint32_t symbol = group + k * FIN_GROUPS;
+      // (the reference symbol's row too, dropped below: the loads must not wait for local_reference[p])
+      values[k] = in_range && symbol < column.n_symbols ? counts[symbol * genome_length + p] : 0u;
+   }
+   if (USE_ROWS) {
+      for (uint32_t index = threadIdx.x; index < n_valid * FIN_THREADS; index += FIN_BLOCK_THREADS) {
+         (&row_sum[0][0])[index] = 0;
       }
    }
-   if (warp == 0) {
+   if (threadIdx.x < 32) {
       uint32_t partial = 0;
       for (uint32_t block = lane; block < blockIdx.x; block += 32) {
          partial += block_totals[block];
@@ -908,208 +994,188 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
          block_offset = partial;
       }
    }
-   diff[p] = 0;
+   if (group == 0) {
+      diff[p] = 0;
+   }
+   __syncthreads();  // the wait, the zeroed rows
+   const uint32_t shard_slot = SHARDED ? query_index % SHARD_SLOTS : 0u;
+   const uint32_t tag = SHARDED ? query_index + 1 : 0u;
+   bool shard_timed_out = SHARDED && slot_is_free == 0;
+   if (MODE == FIN_COLLECT && !shard_timed_out && in_range) {
+      // the other ranks' tagged rows, eight loads in flight per thread; a word that has not landed yet is polled
+      const uint2* const rows = reinterpret_cast<const uint2*>(push.root_block + SHARD_HEADER_BYTES) +
+                                static_cast<size_t>(shard_slot) * push.world * n_valid * genome_length + p;
+      const uint32_t n_items = n_valid * (push.world - 1);  // item j: row j % n_valid of rank 1 + j / n_valid (the gather area's order)
+      constexpr uint32_t IN_FLIGHT = 8;
+      for (uint32_t first = group; first < n_items; first += FIN_GROUPS * IN_FLIGHT) {
+         uint2 words[IN_FLIGHT];
+#pragma unroll
+         for (uint32_t u = 0; u < IN_FLIGHT; ++u) {
+            const uint32_t item = first + u * FIN_GROUPS;
+            words[u] = item < n_items ? loadTagged(rows + static_cast<size_t>(n_valid + item) * genome_length) : make_uint2(0u, tag);
+         }
+#pragma unroll
+         for (uint32_t u = 0; u < IN_FLIGHT; ++u) {
+            const uint32_t item = first + u * FIN_GROUPS;
+            if (item < n_items) {
+               uint2 word = words[u];
+               if (word.y != tag) {
+                  word = pollTagged(rows + static_cast<size_t>(n_valid + item) * genome_length, tag);
+                  shard_timed_out |= word.y != tag;
+               }
+               atomicAdd(&row_sum[item % n_valid][i], word.x);
+            }
+         }
+      }
+   }
+   uint32_t others = 0;
+#pragma unroll
+   for (uint32_t k = 0; k < FIN_SYMBOLS_PER_THREAD; ++k) {
+      others += group + k * FIN_GROUPS != reference_symbol ? values[k] : 0u;
+   }
+   part_others[group][i] = others;
    // inclusive scan of this block's 256 elements
    uint32_t inclusive = mine;
-   for (int offset = 1; offset < 32; offset <<= 1) {
-      const uint32_t other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
-      if (lane >= static_cast<uint32_t>(offset)) {
-         inclusive += other;
+   if (group == 0) {
+      for (int offset = 1; offset < 32; offset <<= 1) {
+         const uint32_t other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
+         if (lane >= static_cast<uint32_t>(offset)) {
+            inclusive += other;
+         }
       }
-   }
-   if (lane == 31) {
-      warp_totals[warp] = inclusive;
+      if (lane == 31) {
+         warp_totals[warp] = inclusive;
+      }
    }
    __syncthreads();
-   uint32_t covered = block_offset + inclusive;
-   for (uint32_t w = 0; w < warp; ++w) {
-      covered += warp_totals[w];
+   if (group == 0) {
+      uint32_t covered = block_offset + inclusive;
+      for (uint32_t w = 0; w < warp; ++w) {
+         covered += warp_totals[w];
+      }
+      uint32_t all_others = 0;
+#pragma unroll
+      for (uint32_t g = 0; g < FIN_GROUPS; ++g) {
+         all_others += part_others[g][i];
+      }
+      const uint32_t reference_count = covered - all_others;
+      reference_counts[i] = reference_count;
+      if (in_range) {
+         counts[reference_symbol * genome_length + p] = reference_count;
+      }
    }
-   const uint32_t reference_count = covered - others;
-   if (p < genome_length) {
-      counts[reference_symbol * genome_length + p] = reference_count;
-   }
-   uint32_t shard_slot = 0;
-   uint32_t query_index_of_block = 0;
-   bool shard_timed_out = false;
-   if (push.root_block != nullptr) {
-      // this rank's rows of the valid mutation symbols -> the root's gather area (coalesced stores over NVLink), once the
-      // root has released the slot's previous use. (Every block reads the query counter before it counts itself in
-      // below; the last block increments it after that.)
-      __shared__ uint32_t slot_is_free;
-      __shared__ uint32_t query_index;
-      if (threadIdx.x == 0) {
-         query_index = *reinterpret_cast<volatile uint32_t*>(&push.own_header->queries_pushed);
-         const uint32_t generation = query_index / SHARD_SLOTS + 1;
-         if (collect_here) {
-            // (the slot's arrival count stays the one shardCollectKernel expects: block 0 counts the whole grid in)
-            ShardBlockHeader* const root_header = reinterpret_cast<ShardBlockHeader*>(push.root_block);
-            if (blockIdx.x == 0) {
-               atomicAdd(&root_header->arrivals[query_index % SHARD_SLOTS], gridDim.x);
+   if (MODE != FIN_COUNTS) {
+      __syncthreads();
+      // this thread's valid symbols: into the root's gather area (coalesced 8-byte stores over NVLink, every word tagged
+      // with the query: fire and forget, nothing here waits for them to land), or into the rows in shared memory
+      const uint32_t reference_count = reference_counts[i];
+      if (in_range && !(MODE == FIN_PUSH && shard_timed_out)) {
+         uint2* const root_rows = MODE == FIN_PUSH ? reinterpret_cast<uint2*>(push.root_block + SHARD_HEADER_BYTES) +
+                                                        (static_cast<size_t>(shard_slot) * push.world + push.rank) * n_valid * genome_length + p
+                                                   : nullptr;
+#pragma unroll
+         for (uint32_t k = 0; k < FIN_SYMBOLS_PER_THREAD; ++k) {
+            const uint32_t symbol = group + k * FIN_GROUPS;
+            if (((valid_mask >> symbol) & 1ULL) != 0) {
+               const uint32_t row = __popcll(valid_mask & ((1ULL << symbol) - 1));
+               const uint32_t value = symbol == reference_symbol ? reference_count : values[k];
+               if (MODE == FIN_PUSH) {
+                  storeTagged(root_rows + static_cast<size_t>(row) * genome_length, value, tag);
+               } else {
+                  atomicAdd(&row_sum[row][i], value);
+               }
             }
-            // every earlier query of the group must have been collected: the slots are summed in order
-            const bool in_order = *reinterpret_cast<volatile uint32_t*>(&root_header->queries_collected) == query_index;
-            slot_is_free =
-               in_order && waitForAtLeast(&root_header->arrivals[query_index % SHARD_SLOTS], push.world * gridDim.x * generation) ? 1u : 0u;
-         } else {
-            slot_is_free = waitForAtLeast(&push.own_header->released[query_index % SHARD_SLOTS], generation - 1) ? 1u : 0u;
          }
       }
+   }
+   if (USE_ROWS) {
       __syncthreads();
-      shard_slot = query_index % SHARD_SLOTS;
-      query_index_of_block = query_index;
-      if (collect_here) {
-         if (slot_is_free != 0 && p < genome_length) {
-            // sums over the ranks: this rank's counts (still in L1 / L2) + the rows the other ranks stored into the slot
-            const uint32_t* const rows = reinterpret_cast<const uint32_t*>(push.root_block + SHARD_HEADER_BYTES) +
-                                         static_cast<size_t>(shard_slot) * push.world * push.n_valid * genome_length + p;
-            const size_t rank_stride = static_cast<size_t>(push.n_valid) * genome_length;
-            auto sumOf = [&](uint32_t symbol, uint32_t row) {  // (the loads of all ranks in flight together)
-               uint32_t values[SHARD_MAX_WORLD];
-               values[0] = symbol == reference_symbol ? reference_count : counts[symbol * genome_length + p];
-#pragma unroll
-               for (uint32_t rank = 1; rank < SHARD_MAX_WORLD; ++rank) {
-                  values[rank] = rank < push.world ? rows[rank * rank_stride + row * genome_length] : 0u;
-               }
-               uint32_t sum = 0;
-#pragma unroll
-               for (uint32_t rank = 0; rank < SHARD_MAX_WORLD; ++rank) {
-                  sum += values[rank];
-               }
-               return sum;
-            };
-            uint32_t total = 0;
-            uint32_t summed_candidates = 0;
-            uint32_t row = 0;
-            for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
-               if (((push.valid_mask >> symbol) & 1ULL) != 0) {
-                  const uint32_t sum = sumOf(symbol, row);
-                  total += sum;
-                  summed_candidates |= symbol != genome_symbol ? sum : 0u;
-                  if (push.summed_out != nullptr) {
-                     push.summed_out[symbol * genome_length + p] = sum;
-                  }
-                  ++row;
-               }
-            }
-            if (request.hits != nullptr && total != 0 && summed_candidates != 0) {
-               const uint32_t threshold_count =
-                  request.min_proportion == 0 ? 0u : static_cast<uint32_t>(ceil(__dmul_rn(static_cast<double>(total), request.min_proportion)) - 1.0);
-               row = 0;
-               for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
-                  if (((push.valid_mask >> symbol) & 1ULL) == 0) {
-                     continue;
-                  }
-                  const uint32_t this_row = row++;
-                  if (symbol == genome_symbol) {
-                     continue;
-                  }
-                  const uint32_t sum = sumOf(symbol, this_row);
-                  if (sum > threshold_count) {
-                     const uint32_t index = atomicAdd(&work_state[3], 1u);
-                     if (index < request.capacity) {
-                        request.hits[1 + index] = silo_mutation_hit{p, symbol, sum, total};
-                     }
-                  }
-               }
-            }
-         }
-      } else if (slot_is_free != 0 && p < genome_length) {
-         uint32_t* const root_rows = reinterpret_cast<uint32_t*>(push.root_block + SHARD_HEADER_BYTES) +
-                                     (static_cast<size_t>(shard_slot) * push.world + push.rank) * push.n_valid * genome_length;
+      // The output pass of addMutationsToOutput over the (summed) counts of one position, on request: which
+      // (position, symbol) rows the action emits. `hits` is PAGE-LOCKED HOST memory: the tuples are stored straight
+      // into it over PCIe (a few hundred 16-byte posted writes); the last block writes the header hits[0].
+      if (group == 0 && in_range && !shard_timed_out) {
+         const uint32_t genome_symbol = request.hits != nullptr ? column.global_reference[p] : 0u;
+         uint32_t total = 0;
+         uint32_t candidates = 0;  // OR of the counts that could be emitted (valid, not the reference genome's symbol)
          uint32_t row = 0;
          for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
-            if (((push.valid_mask >> symbol) & 1ULL) != 0) {
-               root_rows[row * genome_length + p] = symbol == reference_symbol ? reference_count : counts[symbol * genome_length + p];
-               ++row;
+            if (((valid_mask >> symbol) & 1ULL) != 0) {
+               const uint32_t sum = row_sum[row++][i];
+               total += sum;
+               candidates |= symbol != genome_symbol ? sum : 0u;
+               if (MODE == FIN_COLLECT && push.summed_out != nullptr) {
+                  push.summed_out[symbol * genome_length + p] = sum;
+               }
             }
          }
-      }
-      shard_timed_out = slot_is_free == 0;  // (every block waits for the same flag: block 0 reports it to the root)
-      // (made visible to the root by thread 0's system-scope fence behind the block barrier below: fences are
-      // cumulative, one round trip over NVLink per block instead of one per thread)
-   }
-   if (output_pass) {
-      const bool reference_is_valid = ((request.valid_mask >> reference_symbol) & 1ULL) != 0;
-      const uint32_t total = valid_others + (reference_is_valid ? reference_count : 0u);
-      if (reference_is_valid && reference_symbol != genome_symbol) {
-         candidates |= reference_count;
-      }
-      // (`count > threshold_count` cannot hold for a zero count)
-      if (total != 0 && candidates != 0) {
-         // ceil(double(total) * min_proportion) - 1, the reference's operations in the reference's order
-         const uint32_t threshold_count =
-            request.min_proportion == 0 ? 0u : static_cast<uint32_t>(ceil(__dmul_rn(static_cast<double>(total), request.min_proportion)) - 1.0);
-         for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
-            if (((request.valid_mask >> symbol) & 1ULL) == 0 || symbol == genome_symbol) {
-               continue;
-            }
-            const uint32_t count = symbol == reference_symbol ? reference_count : counts[symbol * genome_length + p];
-            if (count > threshold_count) {
-               const uint32_t index = atomicAdd(&work_state[3], 1u);
-               if (index < request.capacity) {
-                  request.hits[1 + index] = silo_mutation_hit{p, symbol, count, total};
+         // (`count > threshold_count` cannot hold for a zero count)
+         if (request.hits != nullptr && total != 0 && candidates != 0) {
+            // ceil(double(total) * min_proportion) - 1, the reference's operations in the reference's order
+            const uint32_t threshold_count =
+               request.min_proportion == 0 ? 0u : static_cast<uint32_t>(ceil(__dmul_rn(static_cast<double>(total), request.min_proportion)) - 1.0);
+            row = 0;
+            for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
+               if (((valid_mask >> symbol) & 1ULL) == 0) {
+                  continue;
+               }
+               const uint32_t sum = row_sum[row++][i];
+               if (symbol != genome_symbol && sum > threshold_count) {
+                  const uint32_t index = atomicAdd(&work_state[3], 1u);
+                  if (index < request.capacity) {
+                     request.hits[1 + index] = silo_mutation_hit{p, symbol, sum, total};
+                  }
                }
             }
          }
       }
+   }
+   if (MODE == FIN_COLLECT && shard_timed_out) {  // (rare: a rank never delivered, or the queries are out of order)
+      atomicOr(&reinterpret_cast<ShardBlockHeader*>(push.root_block)->collect_error, 2u);
    }
    // This block has consumed its block totals (block_offset went into `covered`) and appended its tuples:
    // the last block to get here clears the totals and the work-list state and writes the header.
    __syncthreads();
    if (threadIdx.x == 0) {
-      if (push.root_block != nullptr) {
-         // One round trip over NVLink per block: the fence (cumulative: it orders the whole block's stores before what
-         // follows, at the root too), then this block's own arrival, fire and forget. The root waits for
-         // world * gridDim.x arrivals per use of a slot (the grid is the same on every rank: one block per 256 positions).
-         if (blockIdx.x == 0) {
+      if (SHARDED) {
+         shardDebugStamp(push, 2);
+         if (blockIdx.x == 0) {  // this rank's filter cardinality and error flag for the root
             ShardBlockHeader* const root_header = reinterpret_cast<ShardBlockHeader*>(push.root_block);
             unsigned long long cardinality = push.fixed_cardinality;
-            uint32_t error = shard_timed_out ? 2u : 0u;
+            uint32_t error = MODE == FIN_PUSH && shard_timed_out ? 2u : 0u;
             if (push.use_fixed_cardinality == 0) {
                cardinality = *reinterpret_cast<volatile unsigned long long*>(&push.filter_scalars[0]);
                error |= *reinterpret_cast<volatile uint32_t*>(&push.filter_scalars[2]);
             }
-            root_header->cardinality[shard_slot][push.rank] = cardinality;
-            root_header->error[shard_slot][push.rank] = error;
+            storeTagged(&root_header->cardinality_low[shard_slot][push.rank], static_cast<uint32_t>(cardinality), tag);
+            storeTagged(&root_header->cardinality_high[shard_slot][push.rank], static_cast<uint32_t>(cardinality >> 32), tag);
+            storeTagged(&root_header->error[shard_slot][push.rank], error, tag);
          }
-         if (collect_here) {
-            __threadfence();  // (block 0 counted the whole grid in before it waited)
-         } else if (push.rank == 0) {  // the root's own contribution never leaves its memory: device scope is enough (and cheaper)
-            __threadfence();
-            atomicAdd(&reinterpret_cast<ShardBlockHeader*>(push.root_block)->arrivals[shard_slot], 1u);
-         } else {
-            __threadfence_system();
-            atomicAdd_system(&reinterpret_cast<ShardBlockHeader*>(push.root_block)->arrivals[shard_slot], 1u);
-         }
-      } else {
-         __threadfence();
+         shardDebugStamp(push, 3);
       }
+      __threadfence();
       const uint32_t finished = atomicAdd(&work_state[2], 1u);
       if (finished == gridDim.x - 1) {
          __threadfence();
          for (uint32_t block = 0; block < gridDim.x; ++block) {
             block_totals[block] = 0;
          }
-         if (collect_here) {
-            // the whole group's result: every rank's cardinality and error flag (block 0 of each wrote them before its
-            // arrival), the slot back to every rank, the query counted as collected
+         if (MODE == FIN_COLLECT) {
+            // the whole group's result: every rank's cardinality and error flag, the slot back to every rank, the query
+            // counted as collected
             ShardBlockHeader* const root_header = reinterpret_cast<ShardBlockHeader*>(push.root_block);
             unsigned long long cardinality = 0;
-            uint32_t error = shard_timed_out ? 2u : 0u;
-            for (uint32_t rank = 0; rank < push.world; ++rank) {
-               cardinality += *reinterpret_cast<volatile unsigned long long*>(&root_header->cardinality[shard_slot][rank]);
-               error |= *reinterpret_cast<volatile uint32_t*>(&root_header->error[shard_slot][rank]);
-            }
+            uint32_t error = *reinterpret_cast<volatile uint32_t*>(&root_header->collect_error);
+            root_header->collect_error = 0;
+            sumRankScalars(root_header, shard_slot, push.world, tag, cardinality, error);
             if (request.hits != nullptr) {
                request.hits[0] = silo_mutation_hit{
                   *reinterpret_cast<volatile uint32_t*>(&work_state[3]), error, static_cast<uint32_t>(cardinality), static_cast<uint32_t>(cardinality >> 32)};
             }
-            root_header->queries_collected = query_index_of_block + 1;
+            root_header->queries_collected = tag;
             for (uint32_t rank = 0; rank < push.world; ++rank) {
-               *reinterpret_cast<volatile uint32_t*>(&push.peers[rank]->released[shard_slot]) = query_index_of_block / SHARD_SLOTS + 1;
+               *reinterpret_cast<volatile uint32_t*>(&push.peers[rank]->released[shard_slot]) = (tag - 1) / SHARD_SLOTS + 1;
             }
-         } else if (request.hits != nullptr) {
+         } else if (MODE == FIN_OUTPUT) {
             silo_mutation_hit header{*reinterpret_cast<volatile uint32_t*>(&work_state[3]), 0u, 0u, 0u};
             if (request.filter_scalars != nullptr) {
                const unsigned long long cardinality = *reinterpret_cast<volatile unsigned long long*>(&request.filter_scalars[0]);
@@ -1123,12 +1189,12 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
             }
             request.hits[0] = header;
          }
-         if (push.root_block != nullptr) {  // every block has read the query counter and the filter's scalars
+         if (SHARDED) {  // every block has read the query counter and the filter's scalars
             if (push.use_fixed_cardinality == 0) {
                push.filter_scalars[0] = 0;
                push.filter_scalars[2] = 0;
             }
-            push.own_header->queries_pushed = *reinterpret_cast<volatile uint32_t*>(&push.own_header->queries_pushed) + 1;
+            push.own_header->queries_pushed = tag;
          }
          work_state[0] = 0;  // the work list and its claim counter are empty between queries
          work_state[1] = 0;
@@ -1138,49 +1204,51 @@ __global__ void __launch_bounds__(FIN_THREADS) finalizeCountsKernel(
    }
 }
 
-// The root's half of a sharded query: waits until the rows of all `world` ranks have landed in the slot, sums them
-// per position and valid symbol, runs the output pass of addMutationsToOutput (mutations_node.cpp:307-363) over the
-// sums (as mutationHitsKernel does), and hands the slot back to every rank.
+// The root's half of a sharded query when it is a call of its own (silo_gpu_sharded_collect*): reads the tagged rows of
+// all `world` ranks from the slot (the root's own finalize kernel stored its rows there like everybody else's), polling
+// the words that have not landed yet, sums them per position and valid symbol, runs the output pass of
+// addMutationsToOutput (mutations_node.cpp:307-363) over the sums (as mutationHitsKernel does), and hands the slot back
+// to every rank.
 struct ShardCollect {
-   ShardBlockHeader* header = nullptr;   // the root's own block: header, then the gather area [slot][world][n_valid][genome_length]
+   ShardBlockHeader* header = nullptr;   // the root's own block: header, then the gather area [slot][world][n_valid][genome_length] of tagged words
    ShardBlockHeader* const* peers = nullptr;  // [world] every rank's block as mapped on the root
    uint32_t world = 0;
    uint32_t n_valid = 0;
-   uint32_t arrivals_per_rank = 0;  // blocks of a rank's finalize kernel: each signals its own arrival
    uint32_t* summed_out = nullptr;  // optional: [n_symbols][genome_length], the rows of the valid symbols are written
 };
 
-constexpr int COLLECT_THREADS = 128;  // x 64 registers: a block fits on an SM beside the container kernel
-__global__ void __launch_bounds__(COLLECT_THREADS, 8) shardCollectKernel(DevColumn column, ShardCollect collect, uint32_t* __restrict__ work_state, HitRequest request) {
-   __shared__ uint32_t all_arrived;
-   __shared__ uint32_t query_index;
+constexpr int COLLECT_THREADS = 128;
+__global__ void __launch_bounds__(COLLECT_THREADS, 4) shardCollectKernel(DevColumn column, ShardCollect collect, uint32_t* __restrict__ work_state, HitRequest request) {
    const uint32_t genome_length = column.genome_length;
    const uint32_t p = blockIdx.x * COLLECT_THREADS + threadIdx.x;
-   if (threadIdx.x == 0) {  // (read before this block counts itself in below; the last block increments it after that)
-      query_index = *reinterpret_cast<volatile uint32_t*>(&collect.header->queries_collected);
-      all_arrived = waitForAtLeast(&collect.header->arrivals[query_index % SHARD_SLOTS], collect.world * collect.arrivals_per_rank * (query_index / SHARD_SLOTS + 1)) ? 1u : 0u;
-   }
-   __syncthreads();
+   // (read before this block counts itself in below; the last block increments it after that)
+   const uint32_t query_index = *reinterpret_cast<volatile uint32_t*>(&collect.header->queries_collected);
    const uint32_t slot = query_index % SHARD_SLOTS;
    const uint32_t generation = query_index / SHARD_SLOTS + 1;
-   const uint32_t* const rows = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(collect.header) + SHARD_HEADER_BYTES) +
-                                static_cast<size_t>(slot) * collect.world * collect.n_valid * genome_length;
-   if (all_arrived != 0 && p < genome_length) {
+   const uint32_t tag = query_index + 1;
+   const uint2* const rows = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(collect.header) + SHARD_HEADER_BYTES) +
+                             static_cast<size_t>(slot) * collect.world * collect.n_valid * genome_length;
+   bool timed_out = false;
+   if (p < genome_length) {
       const uint32_t genome_symbol = request.hits != nullptr ? column.global_reference[p] : 0u;
       const size_t rank_stride = static_cast<size_t>(collect.n_valid) * genome_length;
-      // (no per-symbol array: the kernel must stay at 32 registers so that its blocks fit on an SM beside the container
-      // kernel of the next query; the few positions that emit rows sum their symbols a second time)
+      // (no per-symbol array: the few positions that emit rows sum their symbols a second time)
       auto sumOf = [&](uint32_t row) {  // (the loads of all ranks in flight together: one trip to L2 per row)
-         const uint32_t* const base = rows + row * genome_length + p;
-         uint32_t values[SHARD_MAX_WORLD];
+         const uint2* const base = rows + row * genome_length + p;
+         uint2 words[SHARD_MAX_WORLD];
 #pragma unroll
          for (uint32_t rank = 0; rank < SHARD_MAX_WORLD; ++rank) {
-            values[rank] = rank < collect.world ? base[rank * rank_stride] : 0u;
+            words[rank] = rank < collect.world ? loadTagged(base + rank * rank_stride) : make_uint2(0u, tag);
          }
          uint32_t sum = 0;
 #pragma unroll
          for (uint32_t rank = 0; rank < SHARD_MAX_WORLD; ++rank) {
-            sum += values[rank];
+            uint2 word = words[rank];
+            if (word.y != tag) {
+               word = pollTagged(base + rank * rank_stride, tag);
+               timed_out |= word.y != tag;
+            }
+            sum += word.x;
          }
          return sum;
       };
@@ -1220,6 +1288,9 @@ __global__ void __launch_bounds__(COLLECT_THREADS, 8) shardCollectKernel(DevColu
          }
       }
    }
+   if (timed_out) {  // (rare: a rank never delivered)
+      atomicOr(&collect.header->collect_error, 2u);
+   }
    __syncthreads();
    if (threadIdx.x == 0) {
       __threadfence();
@@ -1227,11 +1298,9 @@ __global__ void __launch_bounds__(COLLECT_THREADS, 8) shardCollectKernel(DevColu
       if (finished == gridDim.x - 1) {
          __threadfence();
          unsigned long long cardinality = 0;
-         uint32_t error = all_arrived != 0 ? 0u : 2u;
-         for (uint32_t rank = 0; rank < collect.world; ++rank) {
-            cardinality += *reinterpret_cast<volatile unsigned long long*>(&collect.header->cardinality[slot][rank]);
-            error |= *reinterpret_cast<volatile uint32_t*>(&collect.header->error[slot][rank]);
-         }
+         uint32_t error = *reinterpret_cast<volatile uint32_t*>(&collect.header->collect_error);
+         collect.header->collect_error = 0;
+         sumRankScalars(collect.header, slot, collect.world, tag, cardinality, error);
          if (request.hits != nullptr) {
             request.hits[0] = silo_mutation_hit{
                *reinterpret_cast<volatile uint32_t*>(&work_state[3]), error, static_cast<uint32_t>(cardinality), static_cast<uint32_t>(cardinality >> 32)};
@@ -1497,9 +1566,21 @@ void enqueueMutationCounts(
    recordTiming(ev_k1_end);
    SILO_CUDA_CHECK(cudaStreamWaitEvent(stream, table->ev_join, 0));
    const NvtxRange finalize_range("Mutations: subtractCumulativeNsFromPositions + accumulateFinalCounts [finalizeCountsKernel]");
-   finalizeCountsKernel<<<diffPadded(column.genome_length) / FIN_THREADS, FIN_THREADS, 0, stream>>>(
-      column, diff, d_counts, table->d_work_state, request != nullptr ? *request : HitRequest{}, push != nullptr ? *push : ShardPush{}
-   );
+   {
+      const uint32_t blocks = diffPadded(column.genome_length) / FIN_THREADS;
+      const HitRequest hit_request = request != nullptr ? *request : HitRequest{};
+      const ShardPush shard_push = push != nullptr ? *push : ShardPush{};
+      require(column.n_symbols <= 32, "mutation_counts: alphabets of more than 32 symbols are not supported");
+      if (shard_push.peers != nullptr) {
+         finalizeCountsKernel<FIN_COLLECT><<<blocks, FIN_BLOCK_THREADS, 0, stream>>>(column, diff, d_counts, table->d_work_state, hit_request, shard_push);
+      } else if (shard_push.root_block != nullptr) {
+         finalizeCountsKernel<FIN_PUSH><<<blocks, FIN_BLOCK_THREADS, 0, stream>>>(column, diff, d_counts, table->d_work_state, hit_request, shard_push);
+      } else if (hit_request.hits != nullptr) {
+         finalizeCountsKernel<FIN_OUTPUT><<<blocks, FIN_BLOCK_THREADS, 0, stream>>>(column, diff, d_counts, table->d_work_state, hit_request, shard_push);
+      } else {
+         finalizeCountsKernel<FIN_COUNTS><<<blocks, FIN_BLOCK_THREADS, 0, stream>>>(column, diff, d_counts, table->d_work_state, hit_request, shard_push);
+      }
+   }
    SILO_CUDA_CHECK(cudaGetLastError());
    table->stats.kernel_launches += 2;
    recordTiming(ev_end);
@@ -1925,12 +2006,11 @@ struct ShardGroup {
    std::vector<bool> opened_with_ipc;     // which of d_root / peer_blocks must be closed with cudaIpcCloseMemHandle
    ShardBlockHeader** d_peer_table = nullptr;  // root: device copy of peer_blocks
    uint32_t* d_collect_state = nullptr;        // root: the collect kernel's block counter and tuple counter
+   unsigned long long* d_debug_times = nullptr;  // SILO_SHARD_DEBUG=1: the last finalize kernel's stamps, printed when the group is freed
+   uint32_t debug_blocks = 0;
    uint64_t queries_enqueued = 0;  // the same on every rank: queries are issued in the same order everywhere
    uint64_t queries_collected = 0; // root
-   size_t rowsBytes() const { return static_cast<size_t>(n_valid) * genome_length * sizeof(uint32_t); }
-   uint32_t* rootRows(uint32_t slot, int of_rank) const {
-      return reinterpret_cast<uint32_t*>(d_root + SHARD_HEADER_BYTES + (static_cast<size_t>(slot) * world + of_rank) * rowsBytes());
-   }
+   size_t rowsBytes() const { return static_cast<size_t>(n_valid) * genome_length * sizeof(uint2); }  // tagged words
 };
 
 struct ShardHandle {  // SILO_SHARD_HANDLE_BYTES
@@ -1951,6 +2031,7 @@ ShardPush shardPushOf(const ShardGroup& group) {
    push.world = static_cast<uint32_t>(group.world);
    push.n_valid = group.n_valid;
    push.valid_mask = group.valid_mask;
+   push.debug_times = group.d_debug_times;
    return push;
 }
 
@@ -1981,6 +2062,30 @@ void freeShardGroup(silo_gpu_table* table) {
       return;
    }
    cudaStreamSynchronize(table->ctx->stream);
+   if (group->d_debug_times != nullptr) {
+      cudaDeviceSynchronize();
+      std::vector<unsigned long long> times(4 * static_cast<size_t>(group->debug_blocks));
+      cudaMemcpy(times.data(), group->d_debug_times, times.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      unsigned long long first = ~0ULL;
+      for (uint32_t b = 0; b < group->debug_blocks; ++b) {
+         first = std::min(first, times[4 * b]);
+      }
+      unsigned long long maxima[4] = {0, 0, 0, 0};
+      std::vector<unsigned long long> waits, rows, fences;
+      for (uint32_t b = 0; b < group->debug_blocks; ++b) {
+         for (int k = 0; k < 4; ++k) {
+            maxima[k] = std::max(maxima[k], times[4 * b + k] - first);
+         }
+         waits.push_back(times[4 * b + 1] - times[4 * b]);
+         rows.push_back(times[4 * b + 2] - times[4 * b + 1]);
+         fences.push_back(times[4 * b + 3] - times[4 * b + 2]);
+      }
+      auto median = [](std::vector<unsigned long long>& v) { std::sort(v.begin(), v.end()); return v[v.size() / 2]; };
+      std::fprintf(stderr, "[silo shard debug] rank %d, last finalize kernel, ns from its first block's stamp: last start %llu, last wait over %llu, last rows done %llu, "
+                   "last arrival sent %llu | per block medians: wait %llu, rows %llu, fence + arrival %llu\n",
+                   group->rank, maxima[0], maxima[1], maxima[2], maxima[3], median(waits), median(rows), median(fences));
+      cudaFree(group->d_debug_times);
+   }
    for (size_t r = 0; r < group->peer_blocks.size(); ++r) {
       if (group->opened_with_ipc[r] && group->peer_blocks[r] != nullptr) {
          cudaIpcCloseMemHandle(group->peer_blocks[r]);
@@ -2021,6 +2126,11 @@ int silo_gpu_shard_group_init(silo_gpu_table* table, int column, uint64_t valid_
       group->valid_mask = valid_symbol_mask;
       group->n_valid = static_cast<uint32_t>(__builtin_popcountll(valid_symbol_mask));
       group->genome_length = host.dev.genome_length;
+      if (std::getenv("SILO_SHARD_DEBUG") != nullptr) {
+         group->debug_blocks = diffPadded(host.dev.genome_length) / FIN_THREADS;
+         SILO_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&group->d_debug_times), 4 * sizeof(unsigned long long) * group->debug_blocks));
+         SILO_CUDA_CHECK(cudaMemset(group->d_debug_times, 0, 4 * sizeof(unsigned long long) * group->debug_blocks));
+      }
       group->local_bytes = SHARD_HEADER_BYTES + (rank == 0 ? static_cast<size_t>(SHARD_SLOTS) * world * group->rowsBytes() : 0);
       SILO_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&group->d_local), group->local_bytes));
       SILO_CUDA_CHECK(cudaMemset(group->d_local, 0, group->local_bytes));
@@ -2132,7 +2242,6 @@ static void enqueueShardCollect(silo_gpu_table* table, double min_proportion, bo
    collect.peers = group->d_peer_table;
    collect.world = static_cast<uint32_t>(group->world);
    collect.n_valid = group->n_valid;
-   collect.arrivals_per_rank = diffPadded(host.dev.genome_length) / FIN_THREADS;
    collect.summed_out = static_cast<uint32_t*>(d_summed_counts);
    shardCollectKernel<<<(host.dev.genome_length + COLLECT_THREADS - 1) / COLLECT_THREADS, COLLECT_THREADS, 0, stream>>>(host.dev, collect, group->d_collect_state, request);
    SILO_CUDA_CHECK(cudaGetLastError());

@@ -3,7 +3,7 @@ cd $GRAFT_REPO_ROOT
 timeout 300 python -m pytest tests/test_multi_gpu.py -m gpu -x -q 2>&1 | tail -3
 python bench.py --skip-cpu-baseline > gpurun_out/r2_scale_n1.json 2> gpurun_out/r2_scale_n1.err
 for n in 2 4 8; do
-  for red in peer nccl; do
+  for red in ${REDUCES:-peer nccl}; do
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 20 --warmup 3 --skip-cpu-baseline --reduce $red > gpurun_out/r2_scale_n${n}_${red}.json 2> gpurun_out/r2_scale_n${n}_${red}.err
     echo "n=$n $red rc=$?"
   done
