@@ -877,19 +877,34 @@ __device__ __noinline__ uint2 pollTagged(const uint2* address, uint32_t tag) {
    return word;
 }
 
-// the root's last block: the filter cardinalities and error flags that block 0 of every rank's finalize kernel stored
-__device__ __forceinline__ void sumRankScalars(ShardBlockHeader* root_header, uint32_t slot, uint32_t world, uint32_t tag, unsigned long long& cardinality, uint32_t& error) {
-   for (uint32_t rank = 0; rank < world; ++rank) {
-      const uint2 low = pollTagged(&root_header->cardinality_low[slot][rank], tag);
-      const uint2 high = pollTagged(&root_header->cardinality_high[slot][rank], tag);
-      const uint2 flag = pollTagged(&root_header->error[slot][rank], tag);
+// the root's last block, one whole warp: the filter cardinalities and error flags that block 0 of every rank's finalize
+// kernel stored, one rank per lane (the three loads of all ranks in flight together), summed / ORed over the warp
+__device__ __forceinline__ void warpSumRankScalars(
+   ShardBlockHeader* root_header, uint32_t slot, uint32_t world, uint32_t tag, uint32_t lane, unsigned long long& cardinality, uint32_t& error
+) {
+   unsigned long long mine = 0;
+   uint32_t my_error = 0;
+   if (lane < world) {
+      uint2 low = loadTagged(&root_header->cardinality_low[slot][lane]);
+      uint2 high = loadTagged(&root_header->cardinality_high[slot][lane]);
+      uint2 flag = loadTagged(&root_header->error[slot][lane]);
       if (low.y != tag || high.y != tag || flag.y != tag) {
-         error |= 2u;
-         continue;
+         low = pollTagged(&root_header->cardinality_low[slot][lane], tag);
+         high = pollTagged(&root_header->cardinality_high[slot][lane], tag);
+         flag = pollTagged(&root_header->error[slot][lane], tag);
       }
-      cardinality += low.x | (static_cast<unsigned long long>(high.x) << 32);
-      error |= flag.x;
+      if (low.y != tag || high.y != tag || flag.y != tag) {
+         my_error = 2u;
+      } else {
+         mine = low.x | (static_cast<unsigned long long>(high.x) << 32);
+         my_error = flag.x;
+      }
    }
+   for (int offset = 16; offset > 0; offset >>= 1) {
+      mine += __shfl_xor_sync(0xFFFFFFFFu, mine, offset);
+   }
+   cardinality += mine;
+   error |= __reduce_or_sync(0xFFFFFFFFu, my_error);
 }
 
 struct HitRequest {
@@ -938,7 +953,6 @@ __global__ void __launch_bounds__(FIN_BLOCK_THREADS) finalizeCountsKernel(
    __shared__ uint32_t warp_totals[FIN_THREADS / 32];
    __shared__ uint32_t block_offset;
    __shared__ uint32_t slot_is_free;  // sharded query: the wait of this block succeeded (else: timed out)
-   __shared__ uint32_t query_index;   // sharded query: the group's query counter when this block started
    __shared__ uint32_t part_others[FIN_GROUPS][FIN_THREADS];
    __shared__ uint32_t reference_counts[FIN_THREADS];
    __shared__ uint32_t row_sum[USE_ROWS ? 32 : 1][FIN_THREADS];  // [row r = the r-th valid symbol][position]
@@ -953,19 +967,21 @@ __global__ void __launch_bounds__(FIN_BLOCK_THREADS) finalizeCountsKernel(
    const bool in_range = p < genome_length;
    const uint64_t valid_mask = SHARDED ? push.valid_mask : request.valid_mask;
    const uint32_t n_valid = __popcll(valid_mask);
-   // Sharded query: the block's one wait is started first, by the last thread, so that it overlaps the loads below: a
-   // rank that stores its rows waits until the root has released the gather slot's previous use (a root that collects
-   // here has nothing to wait for: it polls the other ranks' rows). Every block reads the query counter before it
-   // counts itself in at the end; the last block increments it after that.
+   // Sharded query: every thread reads the group's query counter itself (the gather slot and the tag of this query; no
+   // barrier between that and the loads that need it). The block's one wait is started first, by the last thread, so that
+   // it overlaps everything below: a rank that stores its rows waits until the root has released the slot's previous use
+   // (a root that collects here has nothing to wait for: it polls the other ranks' rows). Every block reads the counter
+   // before it counts itself in at the end; the last block increments it after that.
+   const uint32_t query_index = SHARDED ? *reinterpret_cast<volatile uint32_t*>(&push.own_header->queries_pushed) : 0u;
+   const uint32_t shard_slot = query_index % SHARD_SLOTS;
+   const uint32_t tag = query_index + 1;
    if (SHARDED && threadIdx.x == FIN_BLOCK_THREADS - 1) {
       shardDebugStamp(push, 0);
-      const uint32_t index = *reinterpret_cast<volatile uint32_t*>(&push.own_header->queries_pushed);
-      query_index = index;
       if (MODE == FIN_COLLECT) {
          // every earlier query of the group must have been collected: the slots are summed in order
-         slot_is_free = *reinterpret_cast<volatile uint32_t*>(&reinterpret_cast<ShardBlockHeader*>(push.root_block)->queries_collected) == index ? 1u : 0u;
+         slot_is_free = *reinterpret_cast<volatile uint32_t*>(&reinterpret_cast<ShardBlockHeader*>(push.root_block)->queries_collected) == query_index ? 1u : 0u;
       } else {
-         slot_is_free = waitForAtLeast(&push.own_header->released[index % SHARD_SLOTS], index / SHARD_SLOTS) ? 1u : 0u;
+         slot_is_free = waitForAtLeast(&push.own_header->released[shard_slot], query_index / SHARD_SLOTS) ? 1u : 0u;
       }
       shardDebugStamp(push, 1);
    }
@@ -979,13 +995,64 @@ __global__ void __launch_bounds__(FIN_BLOCK_THREADS) finalizeCountsKernel(
       // (the reference symbol's row too, dropped below: the loads must not wait for local_reference[p])
       values[k] = in_range && symbol < column.n_symbols ? counts[symbol * genome_length + p] : 0u;
    }
-   if (USE_ROWS) {
-      for (uint32_t index = threadIdx.x; index < n_valid * FIN_THREADS; index += FIN_BLOCK_THREADS) {
-         (&row_sum[0][0])[index] = 0;
+   bool peer_timed_out = false;
+   if (MODE == FIN_COLLECT && in_range) {
+      // The other ranks' tagged rows, beside the loads above: thread group g sums the rows g, g + 4 (one pass), g + 8,
+      // g + 12 (the next), ... of this position over the ranks, up to 2 x 8 loads in flight; a word that has not landed
+      // yet is polled. (Loops, not unrolled items: see above.)
+      const size_t rank_stride = static_cast<size_t>(n_valid) * genome_length;
+      const uint2* const slot_rows = reinterpret_cast<const uint2*>(push.root_block + SHARD_HEADER_BYTES) +
+                                     static_cast<size_t>(shard_slot) * push.world * rank_stride + p;
+      constexpr uint32_t IN_FLIGHT = 8;
+#pragma unroll 1
+      for (uint32_t row = group; row < n_valid; row += 2 * FIN_GROUPS) {
+         const bool second = row + FIN_GROUPS < n_valid;
+         uint32_t sums[2] = {0u, 0u};
+#pragma unroll 1
+         for (uint32_t first_rank = 1; first_rank < push.world; first_rank += IN_FLIGHT) {
+            const uint2* const base = slot_rows + first_rank * rank_stride + static_cast<size_t>(row) * genome_length;
+            uint2 words[2][IN_FLIGHT];
+#pragma unroll
+            for (uint32_t u = 0; u < IN_FLIGHT; ++u) {
+               const bool rank_exists = first_rank + u < push.world;
+               words[0][u] = rank_exists ? loadTagged(base + u * rank_stride) : make_uint2(0u, tag);
+               words[1][u] = rank_exists && second ? loadTagged(base + u * rank_stride + static_cast<size_t>(FIN_GROUPS) * genome_length) : make_uint2(0u, tag);
+            }
+            uint32_t landed = 0;  // stays zero if every word carries the tag
+            uint32_t partial[2] = {0u, 0u};
+#pragma unroll
+            for (uint32_t u = 0; u < IN_FLIGHT; ++u) {
+               landed |= (words[0][u].y ^ tag) | (words[1][u].y ^ tag);
+               partial[0] += words[0][u].x;
+               partial[1] += words[1][u].x;
+            }
+            if (landed != 0) {  // some rank is behind: the words again, one by one, each polled until it is there
+               partial[0] = 0;
+               partial[1] = 0;
+#pragma unroll 1
+               for (uint32_t u = 0; u < IN_FLIGHT && first_rank + u < push.world; ++u) {
+                  const uint2 word = pollTagged(base + u * rank_stride, tag);
+                  peer_timed_out |= word.y != tag;
+                  partial[0] += word.x;
+                  if (second) {
+                     const uint2 other = pollTagged(base + u * rank_stride + static_cast<size_t>(FIN_GROUPS) * genome_length, tag);
+                     peer_timed_out |= other.y != tag;
+                     partial[1] += other.x;
+                  }
+               }
+            }
+            sums[0] += partial[0];
+            sums[1] += partial[1];
+         }
+         row_sum[row][i] = sums[0];  // (this rank's own count is added behind the barriers below; one thread per row and position)
+         if (second) {
+            row_sum[row + FIN_GROUPS][i] = sums[1];
+         }
       }
    }
    if (threadIdx.x < 32) {
       uint32_t partial = 0;
+#pragma unroll 1
       for (uint32_t block = lane; block < blockIdx.x; block += 32) {
          partial += block_totals[block];
       }
@@ -996,37 +1063,6 @@ __global__ void __launch_bounds__(FIN_BLOCK_THREADS) finalizeCountsKernel(
    }
    if (group == 0) {
       diff[p] = 0;
-   }
-   __syncthreads();  // the wait, the zeroed rows
-   const uint32_t shard_slot = SHARDED ? query_index % SHARD_SLOTS : 0u;
-   const uint32_t tag = SHARDED ? query_index + 1 : 0u;
-   bool shard_timed_out = SHARDED && slot_is_free == 0;
-   if (MODE == FIN_COLLECT && !shard_timed_out && in_range) {
-      // the other ranks' tagged rows, eight loads in flight per thread; a word that has not landed yet is polled
-      const uint2* const rows = reinterpret_cast<const uint2*>(push.root_block + SHARD_HEADER_BYTES) +
-                                static_cast<size_t>(shard_slot) * push.world * n_valid * genome_length + p;
-      const uint32_t n_items = n_valid * (push.world - 1);  // item j: row j % n_valid of rank 1 + j / n_valid (the gather area's order)
-      constexpr uint32_t IN_FLIGHT = 8;
-      for (uint32_t first = group; first < n_items; first += FIN_GROUPS * IN_FLIGHT) {
-         uint2 words[IN_FLIGHT];
-#pragma unroll
-         for (uint32_t u = 0; u < IN_FLIGHT; ++u) {
-            const uint32_t item = first + u * FIN_GROUPS;
-            words[u] = item < n_items ? loadTagged(rows + static_cast<size_t>(n_valid + item) * genome_length) : make_uint2(0u, tag);
-         }
-#pragma unroll
-         for (uint32_t u = 0; u < IN_FLIGHT; ++u) {
-            const uint32_t item = first + u * FIN_GROUPS;
-            if (item < n_items) {
-               uint2 word = words[u];
-               if (word.y != tag) {
-                  word = pollTagged(rows + static_cast<size_t>(n_valid + item) * genome_length, tag);
-                  shard_timed_out |= word.y != tag;
-               }
-               atomicAdd(&row_sum[item % n_valid][i], word.x);
-            }
-         }
-      }
    }
    uint32_t others = 0;
 #pragma unroll
@@ -1047,9 +1083,11 @@ __global__ void __launch_bounds__(FIN_BLOCK_THREADS) finalizeCountsKernel(
          warp_totals[warp] = inclusive;
       }
    }
-   __syncthreads();
+   __syncthreads();  // (also publishes the sharded query's wait)
+   const bool shard_timed_out = SHARDED && (slot_is_free == 0 || peer_timed_out);
    if (group == 0) {
       uint32_t covered = block_offset + inclusive;
+#pragma unroll 1
       for (uint32_t w = 0; w < warp; ++w) {
          covered += warp_totals[w];
       }
@@ -1081,8 +1119,10 @@ __global__ void __launch_bounds__(FIN_BLOCK_THREADS) finalizeCountsKernel(
                const uint32_t value = symbol == reference_symbol ? reference_count : values[k];
                if (MODE == FIN_PUSH) {
                   storeTagged(root_rows + static_cast<size_t>(row) * genome_length, value, tag);
+               } else if (MODE == FIN_COLLECT) {
+                  row_sum[row][i] += value;  // (the other ranks' sum was stored before the barriers above; one thread per row and position)
                } else {
-                  atomicAdd(&row_sum[row][i], value);
+                  row_sum[row][i] = value;
                }
             }
          }
@@ -1098,6 +1138,7 @@ __global__ void __launch_bounds__(FIN_BLOCK_THREADS) finalizeCountsKernel(
          uint32_t total = 0;
          uint32_t candidates = 0;  // OR of the counts that could be emitted (valid, not the reference genome's symbol)
          uint32_t row = 0;
+#pragma unroll 1
          for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
             if (((valid_mask >> symbol) & 1ULL) != 0) {
                const uint32_t sum = row_sum[row++][i];
@@ -1114,6 +1155,7 @@ __global__ void __launch_bounds__(FIN_BLOCK_THREADS) finalizeCountsKernel(
             const uint32_t threshold_count =
                request.min_proportion == 0 ? 0u : static_cast<uint32_t>(ceil(__dmul_rn(static_cast<double>(total), request.min_proportion)) - 1.0);
             row = 0;
+#pragma unroll 1
             for (uint32_t symbol = 0; symbol < column.n_symbols; ++symbol) {
                if (((valid_mask >> symbol) & 1ULL) == 0) {
                   continue;
@@ -1133,30 +1175,35 @@ __global__ void __launch_bounds__(FIN_BLOCK_THREADS) finalizeCountsKernel(
       atomicOr(&reinterpret_cast<ShardBlockHeader*>(push.root_block)->collect_error, 2u);
    }
    // This block has consumed its block totals (block_offset went into `covered`) and appended its tuples:
-   // the last block to get here clears the totals and the work-list state and writes the header.
+   // the last block to get here clears the totals and the work-list state and writes the header (its first warp).
    __syncthreads();
-   if (threadIdx.x == 0) {
-      if (SHARDED) {
-         shardDebugStamp(push, 2);
-         if (blockIdx.x == 0) {  // this rank's filter cardinality and error flag for the root
-            ShardBlockHeader* const root_header = reinterpret_cast<ShardBlockHeader*>(push.root_block);
-            unsigned long long cardinality = push.fixed_cardinality;
-            uint32_t error = MODE == FIN_PUSH && shard_timed_out ? 2u : 0u;
-            if (push.use_fixed_cardinality == 0) {
-               cardinality = *reinterpret_cast<volatile unsigned long long*>(&push.filter_scalars[0]);
-               error |= *reinterpret_cast<volatile uint32_t*>(&push.filter_scalars[2]);
+   if (threadIdx.x < 32) {
+      uint32_t is_last = 0;
+      if (lane == 0) {
+         if (SHARDED) {
+            shardDebugStamp(push, 2);
+            if (blockIdx.x == 0) {  // this rank's filter cardinality and error flag for the root
+               ShardBlockHeader* const root_header = reinterpret_cast<ShardBlockHeader*>(push.root_block);
+               unsigned long long cardinality = push.fixed_cardinality;
+               uint32_t error = MODE == FIN_PUSH && shard_timed_out ? 2u : 0u;
+               if (push.use_fixed_cardinality == 0) {
+                  cardinality = *reinterpret_cast<volatile unsigned long long*>(&push.filter_scalars[0]);
+                  error |= *reinterpret_cast<volatile uint32_t*>(&push.filter_scalars[2]);
+               }
+               storeTagged(&root_header->cardinality_low[shard_slot][push.rank], static_cast<uint32_t>(cardinality), tag);
+               storeTagged(&root_header->cardinality_high[shard_slot][push.rank], static_cast<uint32_t>(cardinality >> 32), tag);
+               storeTagged(&root_header->error[shard_slot][push.rank], error, tag);
             }
-            storeTagged(&root_header->cardinality_low[shard_slot][push.rank], static_cast<uint32_t>(cardinality), tag);
-            storeTagged(&root_header->cardinality_high[shard_slot][push.rank], static_cast<uint32_t>(cardinality >> 32), tag);
-            storeTagged(&root_header->error[shard_slot][push.rank], error, tag);
+            shardDebugStamp(push, 3);
          }
-         shardDebugStamp(push, 3);
-      }
-      __threadfence();
-      const uint32_t finished = atomicAdd(&work_state[2], 1u);
-      if (finished == gridDim.x - 1) {
          __threadfence();
-         for (uint32_t block = 0; block < gridDim.x; ++block) {
+         is_last = atomicAdd(&work_state[2], 1u) == gridDim.x - 1 ? 1u : 0u;
+      }
+      is_last = __shfl_sync(0xFFFFFFFFu, is_last, 0);
+      if (is_last != 0) {
+         __threadfence();
+#pragma unroll 1
+         for (uint32_t block = lane; block < gridDim.x; block += 32) {
             block_totals[block] = 0;
          }
          if (MODE == FIN_COLLECT) {
@@ -1164,18 +1211,20 @@ __global__ void __launch_bounds__(FIN_BLOCK_THREADS) finalizeCountsKernel(
             // counted as collected
             ShardBlockHeader* const root_header = reinterpret_cast<ShardBlockHeader*>(push.root_block);
             unsigned long long cardinality = 0;
-            uint32_t error = *reinterpret_cast<volatile uint32_t*>(&root_header->collect_error);
-            root_header->collect_error = 0;
-            sumRankScalars(root_header, shard_slot, push.world, tag, cardinality, error);
-            if (request.hits != nullptr) {
-               request.hits[0] = silo_mutation_hit{
-                  *reinterpret_cast<volatile uint32_t*>(&work_state[3]), error, static_cast<uint32_t>(cardinality), static_cast<uint32_t>(cardinality >> 32)};
+            uint32_t error = lane == 31 ? *reinterpret_cast<volatile uint32_t*>(&root_header->collect_error) : 0u;
+            warpSumRankScalars(root_header, shard_slot, push.world, tag, lane, cardinality, error);
+            if (lane == 0) {
+               root_header->collect_error = 0;
+               if (request.hits != nullptr) {
+                  request.hits[0] = silo_mutation_hit{
+                     *reinterpret_cast<volatile uint32_t*>(&work_state[3]), error, static_cast<uint32_t>(cardinality), static_cast<uint32_t>(cardinality >> 32)};
+               }
+               root_header->queries_collected = tag;
             }
-            root_header->queries_collected = tag;
-            for (uint32_t rank = 0; rank < push.world; ++rank) {
-               *reinterpret_cast<volatile uint32_t*>(&push.peers[rank]->released[shard_slot]) = (tag - 1) / SHARD_SLOTS + 1;
+            if (lane < push.world) {
+               *reinterpret_cast<volatile uint32_t*>(&push.peers[lane]->released[shard_slot]) = (tag - 1) / SHARD_SLOTS + 1;
             }
-         } else if (MODE == FIN_OUTPUT) {
+         } else if (MODE == FIN_OUTPUT && lane == 0) {
             silo_mutation_hit header{*reinterpret_cast<volatile uint32_t*>(&work_state[3]), 0u, 0u, 0u};
             if (request.filter_scalars != nullptr) {
                const unsigned long long cardinality = *reinterpret_cast<volatile unsigned long long*>(&request.filter_scalars[0]);
@@ -1189,17 +1238,19 @@ __global__ void __launch_bounds__(FIN_BLOCK_THREADS) finalizeCountsKernel(
             }
             request.hits[0] = header;
          }
-         if (SHARDED) {  // every block has read the query counter and the filter's scalars
-            if (push.use_fixed_cardinality == 0) {
-               push.filter_scalars[0] = 0;
-               push.filter_scalars[2] = 0;
+         if (lane == 0) {
+            if (SHARDED) {  // every block has read the query counter and the filter's scalars
+               if (push.use_fixed_cardinality == 0) {
+                  push.filter_scalars[0] = 0;
+                  push.filter_scalars[2] = 0;
+               }
+               push.own_header->queries_pushed = tag;
             }
-            push.own_header->queries_pushed = tag;
+            work_state[0] = 0;  // the work list and its claim counter are empty between queries
+            work_state[1] = 0;
+            work_state[2] = 0;
+            work_state[3] = 0;
          }
-         work_state[0] = 0;  // the work list and its claim counter are empty between queries
-         work_state[1] = 0;
-         work_state[2] = 0;
-         work_state[3] = 0;
       }
    }
 }
@@ -1292,26 +1343,33 @@ __global__ void __launch_bounds__(COLLECT_THREADS, 4) shardCollectKernel(DevColu
       atomicOr(&collect.header->collect_error, 2u);
    }
    __syncthreads();
-   if (threadIdx.x == 0) {
-      __threadfence();
-      const uint32_t finished = atomicAdd(&work_state[2], 1u);
-      if (finished == gridDim.x - 1) {
+   if (threadIdx.x < 32) {
+      const uint32_t lane = threadIdx.x;
+      uint32_t is_last = 0;
+      if (lane == 0) {
+         __threadfence();
+         is_last = atomicAdd(&work_state[2], 1u) == gridDim.x - 1 ? 1u : 0u;
+      }
+      is_last = __shfl_sync(0xFFFFFFFFu, is_last, 0);
+      if (is_last != 0) {
          __threadfence();
          unsigned long long cardinality = 0;
-         uint32_t error = *reinterpret_cast<volatile uint32_t*>(&collect.header->collect_error);
-         collect.header->collect_error = 0;
-         sumRankScalars(collect.header, slot, collect.world, tag, cardinality, error);
-         if (request.hits != nullptr) {
-            request.hits[0] = silo_mutation_hit{
-               *reinterpret_cast<volatile uint32_t*>(&work_state[3]), error, static_cast<uint32_t>(cardinality), static_cast<uint32_t>(cardinality >> 32)};
+         uint32_t error = lane == 31 ? *reinterpret_cast<volatile uint32_t*>(&collect.header->collect_error) : 0u;
+         warpSumRankScalars(collect.header, slot, collect.world, tag, lane, cardinality, error);
+         if (lane == 0) {
+            collect.header->collect_error = 0;
+            if (request.hits != nullptr) {
+               request.hits[0] = silo_mutation_hit{
+                  *reinterpret_cast<volatile uint32_t*>(&work_state[3]), error, static_cast<uint32_t>(cardinality), static_cast<uint32_t>(cardinality >> 32)};
+            }
+            work_state[2] = 0;
+            work_state[3] = 0;
+            collect.header->queries_collected = query_index + 1;
          }
-         work_state[2] = 0;
-         work_state[3] = 0;
-         collect.header->queries_collected = query_index + 1;
          // every block has read the slot (its loads have returned): hand it back to the ranks. Nothing written here has
          // to be visible to them first, so plain system-scope stores, no fence.
-         for (uint32_t rank = 0; rank < collect.world; ++rank) {
-            *reinterpret_cast<volatile uint32_t*>(&collect.peers[rank]->released[slot]) = generation;
+         if (lane < collect.world) {
+            *reinterpret_cast<volatile uint32_t*>(&collect.peers[lane]->released[slot]) = generation;
          }
       }
    }
