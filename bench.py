@@ -1096,6 +1096,174 @@ def run_reads(args):
     print(json.dumps(line), flush=True)
 
 
+COOC_SEQUENCES = 2_000_000  # performance/sequence_generator.h:488-490
+COOC_POSITIONS = (5, 10, 20, 30, 40, 50)  # 1-based, co_occurrence_benchmark.cpp:41
+COOC_METRIC = "co_occurrence_rows_per_s"
+
+
+def run_cooc(args):
+    """BASELINE.json configs[4], second half: performance/co_occurrence_benchmark.cpp -- map({s_i := main.at(p_i)}).groupBy(count)
+    over six positions of the 2 M x 100-nt random table (cycled to --rows-per-gpu rows per GPU: x 5 at the default, x 40 over
+    8 GPUs). One process per GPU: every rank aggregates its interleaved chunk shard on the device
+    (BitmapAggregationNode::executeShard -> silo_gpu_query_combinations), the (key, count) lists meet on rank 0
+    (all_gather of a fixed 4,097 x 2 u64 tensor), rank 0 sums them per key and materialises the rows (::mergeShards)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lapis_silo_b200 import abi, host_api
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    reference_arm = args.impl == "reference"
+    if not reference_arm and not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    n_gpus = world
+    total_rows = args.rows_per_gpu * n_gpus
+    sizes = host_api.dense_chunk_sizes(total_rows)
+    threads = max(1, (os.cpu_count() or 8) // max(1, min(n_gpus, 8)))
+    dimensions = [("position", "main", p - 1) for p in COOC_POSITIONS]
+    config = {
+        "workload": f"performance/co_occurrence_benchmark: map(s_i := main.at(p_i)).groupBy(count) over the positions {list(COOC_POSITIONS)} of the "
+                    f"{COOC_SEQUENCES} x 100-nt random table (Binomial(100, 0.1) substitutions per row), cycled to {total_rows} rows (BASELINE.json configs[4])",
+        "rows_per_gpu": args.rows_per_gpu, "total_rows": total_rows, "genome_length": 100, "positions": list(COOC_POSITIONS),
+    }
+    if reference_arm and rank != 0:
+        return
+    synthetic = host_api.Synthetic(co_occurrence_sequences=COOC_SEQUENCES)
+
+    def oracle_table(n_rows):
+        from oracle import oracle as O
+        table = O.Table()
+        chunk_sizes = host_api.dense_chunk_sizes(n_rows)
+        table.set_layout(*chunk_sizes)
+        table.import_column("main", O.NUCLEOTIDE, synthetic.reference, synthetic.build_column(n_rows, 0, len(chunk_sizes), os.cpu_count() or 8))
+        synthetic.release_column()
+        return table
+
+    if reference_arm:
+        # the reference's own run: one thread per query (the recursive partition of bitmap_aggregation_node.cpp:91-116 is sequential)
+        sample_rows = min(total_rows, COOC_SEQUENCES)
+        table = oracle_table(sample_rows)
+        table.bitmap_aggregation(dimensions, None)
+        times = []
+        for _ in range(max(1, args.steps)):
+            started = time.perf_counter()
+            rows = table.bitmap_aggregation(dimensions, None)
+            times.append(time.perf_counter() - started)
+        seconds = sum(times) / len(times)
+        value = sample_rows / seconds
+        print(json.dumps({
+            "impl": "reference", "metric": COOC_METRIC, "value": value, "unit": "rows/s", "n_gpus": n_gpus, "steps": len(times), "warmup": 1,
+            "ms_per_step": seconds * 1000.0, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": "rows/s", "cores": 1, "kind": "port",
+                             "sample": f"the benchmark's own {sample_rows} rows (one cycle of the table), {len(times)} queries, one thread: {seconds * 1000:.0f} ms per query, "
+                                       f"{len(rows)} combinations"},
+            "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+        }), flush=True)
+        return
+
+    torch.cuda.set_device(local_rank)
+    if n_gpus > 1:
+        dist.init_process_group("nccl")
+    first, n_chunks, stride = host_api.interleaved_shard(len(sizes), n_gpus, rank)
+    ctx = abi.Context(local_rank)
+    table = host_api.HostTable(ctx, host_api.shard_chunk_sizes(total_rows, first, n_chunks, stride), first_chunk=first if stride == 1 else 0)
+    table.add_column("main", host_api.NUCLEOTIDE, synthetic.reference, synthetic.build_column(total_rows, first, n_chunks, threads, stride))
+    synthetic.release_column()
+    max_entries = 4096  # 4^6 combinations of A/C/G/T: the table holds no other symbol
+    mine = torch.zeros((max_entries + 1, 2), dtype=torch.int64, device="cuda")
+    gathered = torch.zeros((n_gpus, max_entries + 1, 2), dtype=torch.int64, device="cuda")
+    staging = torch.zeros((max_entries + 1, 2), dtype=torch.int64).pin_memory()
+
+    def query():
+        pairs, cardinality = table.bitmap_aggregation_shard(dimensions, None)  # the device call of this rank's shard; synchronous
+        if n_gpus == 1:
+            return table.bitmap_aggregation_merge(dimensions, [(pairs, cardinality)])
+        staging[0, 0], staging[0, 1] = len(pairs), cardinality
+        staging[1:1 + len(pairs)] = torch.from_numpy(pairs.view(np.int64))
+        mine.copy_(staging, non_blocking=True)
+        dist.all_gather_into_tensor(gathered, mine)
+        if rank != 0:
+            return None
+        host = gathered.cpu().numpy().view(np.uint64)
+        return table.bitmap_aggregation_merge(dimensions, [(host[r, 1:1 + int(host[r, 0, 0])], int(host[r, 0, 1])) for r in range(n_gpus)])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if n_gpus > 1:
+            dist.barrier()
+
+    def reduce_max(value):
+        if n_gpus == 1:
+            return value
+        t = torch.tensor([value], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        query()
+    # ---- value: the device call alone (every rank's shard, no exchange), CUDA events around the K calls ----
+    barrier()
+    launches_before = table.stats().kernel_launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    begin.record()
+    for _ in range(args.steps):
+        table.bitmap_aggregation_shard(dimensions, None)
+    end.record()
+    barrier()
+    device_ms = reduce_max(begin.elapsed_time(end))
+    gpu_launches = int(table.stats().kernel_launches - launches_before)
+    # ---- e2e: the whole query -- device call, the lists to rank 0, merge, rows ----
+    barrier()
+    wall = time.perf_counter()
+    for _ in range(args.steps):
+        rows = query()
+    torch.cuda.synchronize()
+    e2e_ms = reduce_max((time.perf_counter() - wall) * 1000.0)
+    clocks = sampler.stop()
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    peak, peak_source = measured_peak_gbs()
+    # algorithmic bytes of one query on one rank (SURVEY.md 8(d), co-occurrence row): one code byte per row and dimension
+    # written and read back, plus the rows' (start, end) pairs that decide "reference symbol or missing"
+    rows_here = sum(host_api.shard_chunk_sizes(total_rows, first, n_chunks, stride))
+    bytes_per_query = rows_here * (2 * len(dimensions) + 8)
+    line = {
+        "metric": COOC_METRIC, "value": total_rows * args.steps / (device_ms / 1000.0), "unit": "rows/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": device_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+        "run": {"launch": "silo_gpu_query_combinations per query (synchronous: the combinations come back to the host)",
+                "parallelism": f"interleaved chunk shards (chunk c on rank c % {n_gpus}); (key, count) lists all-gathered (NCCL, {(max_entries + 1) * 16} B per rank), "
+                               "summed per key on rank 0" if n_gpus > 1 else "single GPU",
+                "combinations": len(rows)},
+        "clocks": clocks,
+        "e2e": {"value": total_rows * args.steps / (e2e_ms / 1000.0), "unit": "rows/s", "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": 256 + ((max_entries + 1) * 16 if n_gpus > 1 else 0), "d2h_bytes_per_step": 16 * len(rows) * (n_gpus if n_gpus > 1 else 1)},
+        "gpu_launches": gpu_launches,
+        "roofline": {"bound": "hbm", "achieved": bytes_per_query * args.steps / (device_ms / 1000.0) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": bytes_per_query * args.steps / (device_ms / 1000.0) / 1e9 / peak, "traffic": None,
+                     "kernel": "whole query (positionCodesKernel + combinationCountKernel + compaction, host synchronisation included)",
+                     "algorithmic_bytes_per_launch": bytes_per_query, "kernel_ms": device_ms / args.steps, "peak_source": peak_source},
+    }
+    if not args.skip_cpu_baseline and n_gpus == 1:
+        oracle = oracle_table(total_rows)
+        started = time.perf_counter()
+        want = oracle.bitmap_aggregation(dimensions, None)
+        oracle_seconds = time.perf_counter() - started
+        assert rows == want, "the combinations differ from the oracle's"
+        line["parity"] = {"oracle": "full size, same table", "combinations_equal": True, "combinations": len(want)}
+        line["cpu_baseline"] = {"value": total_rows / oracle_seconds, "unit": "rows/s", "cores": 1, "kind": "port",
+                                "sample": f"the whole table ({total_rows} rows), one query, one thread: {oracle_seconds:.1f}s"}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if n_gpus > 1:
+        dist.destroy_process_group()
+
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
@@ -1107,9 +1275,10 @@ def main():
     parser.add_argument("--reference-step-seconds", type=float, default=2.0)
     parser.add_argument("--skip-cpu-baseline", action="store_true")
     parser.add_argument("--eager", action="store_true", help="launch the timed steps one by one instead of as one CUDA graph")
-    parser.add_argument("--workload", choices=["mutations", "nof", "aa", "reads"], default="mutations",
+    parser.add_argument("--workload", choices=["mutations", "nof", "aa", "reads", "cooc"], default="mutations",
                         help="mutations: BASELINE.json configs[1] (the metric's workload, default); nof: configs[2], the NOf / MutationProfile filter; "
-                             "aa: configs[3], AminoAcidMutations over 12 genes; reads: configs[2], many_short_read_filters")
+                             "aa: configs[3], AminoAcidMutations over 12 genes; reads: configs[2], many_short_read_filters; "
+                             "cooc: configs[4], co_occurrence_benchmark over row-partitioned shards")
     parser.add_argument("--reduce", choices=["peer", "nccl"], default="peer",
                         help="N > 1: how the per-rank counts meet -- the library's shard group (peer-memory stores) or NCCL all-reduce")
     parser.add_argument("--force-shard-group", action="store_true",
@@ -1119,7 +1288,9 @@ def main():
     args = parser.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.workload == "reads":
+    if args.workload == "cooc":
+        run_cooc(args)
+    elif args.workload == "reads":
         run_reads(args)
     elif args.workload == "aa":
         run_aa(args)

@@ -69,6 +69,17 @@ int silo_host_filter_lower_timed(silo_host_table* table, const char* expression,
  * of the dictionary column arrives as named bitmaps). out: one line per combination in the reference's
  * depth-first order: the values (\\N = null) and the count, tab-separated. */
 int silo_host_bitmap_aggregation(silo_host_table* table, const char* expression, const char* dimensions, char* out, uint64_t capacity);
+/* Row-partitioned tables: BitmapAggregationNode::executeShard on every rank -- pairs_out receives (key, count) x
+ * min(*n_entries, capacity_entries), ordered by key --, then ::mergeShards + ::materialise on one rank over the ranks'
+ * lists laid end to end (entries_per_shard[s] pairs of shard s, its filter cardinality in cardinalities[s]); the text
+ * is that of silo_host_bitmap_aggregation on the whole table. The same `dimensions` on every rank. */
+int silo_host_bitmap_aggregation_shard(
+   silo_host_table* table, const char* expression, const char* dimensions, uint64_t* pairs_out, uint64_t capacity_entries, uint64_t* n_entries, uint64_t* cardinality
+);
+int silo_host_bitmap_aggregation_merge(
+   silo_host_table* table, const char* dimensions, const uint64_t* pairs, const uint64_t* entries_per_shard, const uint64_t* cardinalities, uint32_t n_shards,
+   char* out, uint64_t capacity
+);
 
 /* the same filter with device-resident inputs: compile + lower + upload once (silo_gpu_program_prepare),
  * then each run only enqueues the kernel on `cuda_stream` (silo_gpu_program_run_async) */
@@ -189,6 +200,9 @@ int silo_host_synthetic_build_short_read_column(silo_host_synthetic* synthetic, 
 /* The same model for one amino-acid gene (SURVEY.md 8(d) input 4): random reference over the twenty standard residues,
  * mutations drawn from the alphabet's valid mutation symbols, its own tree seed and mutation rate. */
 silo_host_synthetic* silo_host_synthetic_create_gene(uint32_t gene_length, uint64_t reference_seed, uint64_t tree_seed, double mutation_rate, uint32_t generations);
+/* the table of performance/co_occurrence_benchmark.cpp: a 100-nt random reference, n_sequences rows with
+ * Binomial(100, 0.1) point substitutions each (sequence_generator.h:487-526); build_column cycles over them */
+silo_host_synthetic* silo_host_synthetic_create_co_occurrence(uint64_t n_sequences);
 void silo_host_synthetic_free(silo_host_synthetic* synthetic);
 uint32_t silo_host_synthetic_num_sequences(const silo_host_synthetic* synthetic);
 const char* silo_host_synthetic_reference(const silo_host_synthetic* synthetic);

@@ -55,6 +55,19 @@ class BitmapAggregationNode {
 
    // the combinations in the reference's depth-first output order
    [[nodiscard]] std::vector<CombinationRow> execute() const;
+
+   // Row-partitioned tables (BASELINE.json configs[4]): every rank runs executeShard() on the table of
+   // its shard -- the same dimensions everywhere, so that the keys mean the same --, the (key, count) lists travel to
+   // one rank by whatever transport the ranks share (they are a few thousand entries), and that rank merges them and
+   // materialises the rows. Counts of disjoint row sets are plain addends: merge == sum per key.
+   struct ShardCombinations {
+      std::vector<silo_combination> entries;  // ordered by key, count > 0
+      uint64_t cardinality = 0;               // rows of the shard under the filter
+   };
+   [[nodiscard]] ShardCombinations executeShard() const;
+   [[nodiscard]] static ShardCombinations mergeShards(const std::vector<ShardCombinations>& shards);
+   // keys -> one value (or null) per dimension, in key order == the reference's output order
+   [[nodiscard]] std::vector<CombinationRow> materialise(const ShardCombinations& combinations) const;
 };
 
 }  // namespace silo_host

@@ -633,57 +633,106 @@ silo_host_rows* silo_host_mutation_rows_from_counts(silo_host_table* table, cons
 // dimensions: ';'-separated, each "p:<column>:<0-based position>" (SequencePositionDimension) or
 // "b:<value>=<bitmap name>,...|<null bitmap name or empty>" (IndexedColumnDimension over named bitmaps).
 // out: one line per combination, the values (\N = null) and the count, tab-separated.
+static std::vector<GroupingDimension> parseDimensionSpec(const char* dimensions) {
+   std::vector<GroupingDimension> dims;
+   const std::string spec = dimensions;
+   size_t begin = 0;
+   while (!spec.empty() && begin <= spec.size()) {
+      size_t end = spec.find(';', begin);
+      if (end == std::string::npos) {
+         end = spec.size();
+      }
+      const std::string item = spec.substr(begin, end - begin);
+      if (item.rfind("p:", 0) == 0) {
+         const size_t colon = item.rfind(':');
+         SequencePositionDimension dimension;
+         dimension.column = item.substr(2, colon - 2);
+         dimension.position_idx = static_cast<uint32_t>(std::stoul(item.substr(colon + 1)));
+         dims.emplace_back(std::move(dimension));
+      } else if (item.rfind("b:", 0) == 0) {
+         IndexedColumnDimension dimension;
+         const size_t bar = item.rfind('|');
+         if (bar + 1 < item.size()) {
+            dimension.null_bitmap = item.substr(bar + 1);
+         }
+         const std::string groups = item.substr(2, bar - 2);
+         size_t group_begin = 0;
+         while (group_begin < groups.size()) {
+            size_t group_end = groups.find(',', group_begin);
+            if (group_end == std::string::npos) {
+               group_end = groups.size();
+            }
+            const std::string group = groups.substr(group_begin, group_end - group_begin);
+            const size_t equals = group.find('=');
+            dimension.value_bitmaps.emplace_back(group.substr(0, equals), group.substr(equals + 1));
+            group_begin = group_end + 1;
+         }
+         dims.emplace_back(std::move(dimension));
+      } else {
+         throw std::invalid_argument("bad dimension spec: " + item);
+      }
+      begin = end + 1;
+   }
+   return dims;
+}
+
+static std::string combinationRowsText(const std::vector<CombinationRow>& rows) {
+   std::string text;
+   for (const CombinationRow& row : rows) {
+      for (const auto& value : row.values) {
+         text += value.has_value() ? value.value() : std::string("\\N");
+         text += '\t';
+      }
+      text += std::to_string(row.count);
+      text += '\n';
+   }
+   return text;
+}
+
 int silo_host_bitmap_aggregation(silo_host_table* table, const char* expression, const char* dimensions, char* out, uint64_t capacity) {
    std::string text;
    const int status = guarded([&] {
-      std::vector<GroupingDimension> dims;
-      const std::string spec = dimensions;
-      size_t begin = 0;
-      while (!spec.empty() && begin <= spec.size()) {
-         size_t end = spec.find(';', begin);
-         if (end == std::string::npos) {
-            end = spec.size();
-         }
-         const std::string item = spec.substr(begin, end - begin);
-         if (item.rfind("p:", 0) == 0) {
-            const size_t colon = item.rfind(':');
-            SequencePositionDimension dimension;
-            dimension.column = item.substr(2, colon - 2);
-            dimension.position_idx = static_cast<uint32_t>(std::stoul(item.substr(colon + 1)));
-            dims.emplace_back(std::move(dimension));
-         } else if (item.rfind("b:", 0) == 0) {
-            IndexedColumnDimension dimension;
-            const size_t bar = item.rfind('|');
-            if (bar + 1 < item.size()) {
-               dimension.null_bitmap = item.substr(bar + 1);
-            }
-            const std::string groups = item.substr(2, bar - 2);
-            size_t group_begin = 0;
-            while (group_begin < groups.size()) {
-               size_t group_end = groups.find(',', group_begin);
-               if (group_end == std::string::npos) {
-                  group_end = groups.size();
-               }
-               const std::string group = groups.substr(group_begin, group_end - group_begin);
-               const size_t equals = group.find('=');
-               dimension.value_bitmaps.emplace_back(group.substr(0, equals), group.substr(equals + 1));
-               group_begin = group_end + 1;
-            }
-            dims.emplace_back(std::move(dimension));
-         } else {
-            throw std::invalid_argument("bad dimension spec: " + item);
-         }
-         begin = end + 1;
+      const BitmapAggregationNode node(*table->table, parseOrTrue(expression), parseDimensionSpec(dimensions));
+      text = combinationRowsText(node.execute());
+   });
+   if (status != 0) {
+      return status;
+   }
+   return copyText(text, out, capacity);
+}
+
+int silo_host_bitmap_aggregation_shard(
+   silo_host_table* table, const char* expression, const char* dimensions, uint64_t* pairs_out, uint64_t capacity_entries, uint64_t* n_entries, uint64_t* cardinality
+) {
+   return guarded([&] {
+      const BitmapAggregationNode node(*table->table, parseOrTrue(expression), parseDimensionSpec(dimensions));
+      const BitmapAggregationNode::ShardCombinations shard = node.executeShard();
+      *n_entries = shard.entries.size();
+      *cardinality = shard.cardinality;
+      for (uint64_t i = 0; i < shard.entries.size() && i < capacity_entries; ++i) {
+         pairs_out[2 * i] = shard.entries[i].key;
+         pairs_out[2 * i + 1] = shard.entries[i].count;
       }
-      const BitmapAggregationNode node(*table->table, parseOrTrue(expression), std::move(dims));
-      for (const CombinationRow& row : node.execute()) {
-         for (const auto& value : row.values) {
-            text += value.has_value() ? value.value() : std::string("\\N");
-            text += '\t';
+   });
+}
+
+int silo_host_bitmap_aggregation_merge(
+   silo_host_table* table, const char* dimensions, const uint64_t* pairs, const uint64_t* entries_per_shard, const uint64_t* cardinalities, uint32_t n_shards,
+   char* out, uint64_t capacity
+) {
+   std::string text;
+   const int status = guarded([&] {
+      const BitmapAggregationNode node(*table->table, parseOrTrue(nullptr), parseDimensionSpec(dimensions));
+      std::vector<BitmapAggregationNode::ShardCombinations> shards(n_shards);
+      uint64_t at = 0;
+      for (uint32_t shard = 0; shard < n_shards; ++shard) {
+         shards[shard].cardinality = cardinalities[shard];
+         shards[shard].entries.resize(entries_per_shard[shard]);
+         for (uint64_t i = 0; i < entries_per_shard[shard]; ++i, ++at) {
+            shards[shard].entries[i] = silo_combination{pairs[2 * at], pairs[2 * at + 1]};
          }
-         text += std::to_string(row.count);
-         text += '\n';
       }
+      text = combinationRowsText(node.materialise(BitmapAggregationNode::mergeShards(shards)));
    });
    if (status != 0) {
       return status;
@@ -768,6 +817,19 @@ silo_host_synthetic* silo_host_synthetic_create_gene(uint32_t gene_length, uint6
          valid.push_back(owned->alphabet->symbolToChar(symbol));
       }
       owned->tree = generateEvolvedSequences(owned->reference, tree_seed, mutation_rate, 0.1, generations, 3, valid);
+      result = owned.release();
+   });
+   return result;
+}
+
+silo_host_synthetic* silo_host_synthetic_create_co_occurrence(uint64_t n_sequences) {
+   silo_host_synthetic* result = nullptr;
+   guarded([&] {
+      auto owned = std::make_unique<silo_host_synthetic>();
+      owned->reference = coOccurrenceReference();
+      owned->tree.sequences = coOccurrenceSequences(owned->reference, n_sequences);
+      owned->tree.parent.assign(n_sequences, 0);
+      owned->tree.generation.assign(n_sequences, 0);
       result = owned.release();
    });
    return result;

@@ -73,6 +73,27 @@ std::string randomNucleotideReference(size_t length, uint64_t seed) {
    return reference;
 }
 
+std::string coOccurrenceReference(size_t length) {
+   return randomNucleotideReference(length, 42);  // makeCoOccurrenceReference: the same draws
+}
+
+std::vector<std::string> coOccurrenceSequences(const std::string& reference, size_t count, double rate) {
+   static constexpr char BASES[4] = {'A', 'C', 'G', 'T'};
+   std::mt19937 rng{1234};
+   std::uniform_int_distribution<size_t> base_distribution(0, 3);
+   std::binomial_distribution<size_t> mutation_count(reference.size(), rate);
+   std::uniform_int_distribution<size_t> position_distribution(0, reference.size() - 1);
+   std::vector<std::string> sequences(count, reference);
+   for (std::string& sequence : sequences) {
+      const size_t mutations = mutation_count(rng);
+      for (size_t i = 0; i < mutations; ++i) {
+         const char base = BASES[base_distribution(rng)];  // `sequence[pos_dist(rng)] = bases.at(base_dist(rng))`: right side first
+         sequence[position_distribution(rng)] = base;
+      }
+   }
+   return sequences;
+}
+
 std::string randomAminoAcidReference(size_t length, uint64_t seed) {
    static constexpr char RESIDUES[] = "ACDEFGHIKLMNPQRSTVWY";
    std::mt19937 rng(seed);

@@ -40,6 +40,13 @@ std::string randomNucleotideReference(size_t length, uint64_t seed);
 // uniformly random reference over the twenty standard amino acids (SURVEY.md 8(d) input 4: translation-free genes)
 std::string randomAminoAcidReference(size_t length, uint64_t seed);
 
+// The table of performance/co_occurrence_benchmark.cpp (sequence_generator.h:487-526): a uniformly random A/C/G/T
+// reference of 100 nt (std::mt19937{42}) and `count` sequences, each the reference with Binomial(length, rate) point
+// substitutions at uniformly drawn positions (std::mt19937{1234}, one stream over all rows in id order: the count, then
+// per substitution the base and the position -- the right operand of the assignment is evaluated first).
+std::string coOccurrenceReference(size_t length = 100);
+std::vector<std::string> coOccurrenceSequences(const std::string& reference, size_t count = 2'000'000, double rate = 0.1);
+
 // A column in the upload format that owns its buffers; `desc` points into them.
 struct PackedColumn {
    silo_column_desc desc{};

@@ -22,7 +22,7 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_last_error", "silo_host_table_create", "silo_host_table_free", "silo_host_table_add_column",
     "silo_host_last_query_profile", "silo_host_table_register_bitmap", "silo_host_table_device", "silo_host_table_num_rows",
     "silo_host_filter_eval", "silo_host_filter_free", "silo_host_filter_cardinality",
-    "silo_host_filter_device", "silo_host_filter_words", "silo_host_filter_explain", "silo_host_bitmap_aggregation",
+    "silo_host_filter_device", "silo_host_filter_words", "silo_host_filter_explain", "silo_host_bitmap_aggregation", "silo_host_bitmap_aggregation_shard", "silo_host_bitmap_aggregation_merge",
     "silo_host_filter_prepare", "silo_host_prepared_run_async", "silo_host_prepared_run_counts_async", "silo_host_prepared_filter",
     "silo_host_prepared_staged_bytes", "silo_host_prepared_free",
     "silo_host_mutation_counts", "silo_host_mutations", "silo_host_mutation_rows_from_counts",
@@ -37,7 +37,7 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_filter_lower_timed", "silo_host_filter_to_string", "silo_host_filter_program_bitmap",
     "silo_host_archive_read", "silo_host_archive_free", "silo_host_archive_column", "silo_host_archive_column_info",
     "silo_host_archive_chunk_sizes", "silo_host_archive_column_shard", "silo_host_table_load_archive", "silo_host_roaring_runs",
-    "silo_host_count", "silo_host_synthetic_draw_short_reads", "silo_host_synthetic_build_short_read_column", "silo_host_table_add_string_column", "silo_host_table_add_date_column", "silo_host_synthetic_create_gene", "silo_host_shard_group_create", "silo_host_shard_group_connect", "silo_host_sharded_enqueue", "silo_host_sharded_collect_packed",
+    "silo_host_count", "silo_host_synthetic_draw_short_reads", "silo_host_synthetic_build_short_read_column", "silo_host_table_add_string_column", "silo_host_table_add_date_column", "silo_host_synthetic_create_gene", "silo_host_synthetic_create_co_occurrence", "silo_host_shard_group_create", "silo_host_shard_group_connect", "silo_host_sharded_enqueue", "silo_host_sharded_collect_packed",
     "silo_host_prepared_run_sharded_async", "silo_host_prepared_run_sharded_collect_async", "silo_host_sharded_collect_async", "silo_host_sharded_query_packed",
 ]
 SHARD_HANDLE_BYTES = 128  # SILO_SHARD_HANDLE_BYTES
@@ -81,6 +81,8 @@ def lib() -> C.CDLL:
         L.silo_host_filter_words.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.silo_host_filter_explain.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint64]
         L.silo_host_bitmap_aggregation.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64]
+        L.silo_host_bitmap_aggregation_shard.argtypes = [vp, C.c_char_p, C.c_char_p, vp, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.silo_host_bitmap_aggregation_merge.argtypes = [vp, C.c_char_p, vp, vp, vp, C.c_uint32, C.c_char_p, C.c_uint64]
         L.silo_host_filter_prepare.argtypes = [vp, C.c_char_p]
         L.silo_host_filter_prepare.restype = vp
         L.silo_host_prepared_run_async.argtypes = [vp, vp]
@@ -134,6 +136,8 @@ def lib() -> C.CDLL:
         L.silo_host_synthetic_create.restype = vp
         L.silo_host_synthetic_create_gene.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_double, C.c_uint32]
         L.silo_host_synthetic_create_gene.restype = vp
+        L.silo_host_synthetic_create_co_occurrence.argtypes = [C.c_uint64]
+        L.silo_host_synthetic_create_co_occurrence.restype = vp
         L.silo_host_synthetic_free.argtypes = [vp]
         L.silo_host_synthetic_free.restype = None
         L.silo_host_synthetic_num_sequences.argtypes = [vp]
@@ -405,6 +409,24 @@ class Archive:
             pass
 
 
+def _dimension_spec(dimensions: Sequence) -> bytes:
+    parts = []
+    for dim in dimensions:
+        if dim[0] == "position":
+            parts.append(f"p:{dim[1]}:{int(dim[2])}")
+        else:
+            parts.append("b:" + ",".join(f"{value}={name}" for value, name in dim[1]) + "|" + (dim[2] or ""))
+    return ";".join(parts).encode()
+
+
+def _combination_rows(text: str) -> list[tuple]:
+    rows = []
+    for line in text.splitlines():
+        fields = line.split("\t")
+        rows.append(tuple(None if f == "\\N" else f for f in fields[:-1]) + (int(fields[-1]),))
+    return rows
+
+
 class HostTable:
     """rhydb::storage::Table as the query compiler sees it, with its sequence columns in HBM."""
 
@@ -551,20 +573,34 @@ class HostTable:
         """BitmapAggregationNode (co-occurrence / groupBy): dimensions are ("position", column, position0) or
         ("bitmaps", [(value, bitmap name), ...], null bitmap name or None). Returns the combinations in the
         reference's output order as (value-or-None per dimension ..., count) tuples."""
-        parts = []
-        for dim in dimensions:
-            if dim[0] == "position":
-                parts.append(f"p:{dim[1]}:{int(dim[2])}")
-            else:
-                parts.append("b:" + ",".join(f"{value}={name}" for value, name in dim[1]) + "|" + (dim[2] or ""))
         buf = C.create_string_buffer(1 << 24)
         _check(lib().silo_host_bitmap_aggregation(
-            self._h, expression.encode() if expression else None, ";".join(parts).encode(), buf, len(buf)))
-        rows = []
-        for line in buf.value.decode().splitlines():
-            fields = line.split("\t")
-            rows.append(tuple(None if f == "\\N" else f for f in fields[:-1]) + (int(fields[-1]),))
-        return rows
+            self._h, expression.encode() if expression else None, _dimension_spec(dimensions), buf, len(buf)))
+        return _combination_rows(buf.value.decode())
+
+    def bitmap_aggregation_shard(self, dimensions: Sequence, expression: Optional[str] = None) -> tuple[np.ndarray, int]:
+        """One rank's half of the aggregation over a row-partitioned table (BitmapAggregationNode::executeShard): the
+        (key, count) pairs of this shard ordered by key, [n, 2] uint64, and the shard's filter cardinality."""
+        pairs = np.empty((4096, 2), dtype=np.uint64)
+        n, cardinality = C.c_uint64(), C.c_uint64()
+        for _ in range(2):
+            _check(lib().silo_host_bitmap_aggregation_shard(
+                self._h, expression.encode() if expression else None, _dimension_spec(dimensions), pairs.ctypes.data, len(pairs), n, cardinality))
+            if n.value <= len(pairs):
+                break
+            pairs = np.empty((n.value, 2), dtype=np.uint64)
+        return pairs[:n.value].copy(), int(cardinality.value)
+
+    def bitmap_aggregation_merge(self, dimensions: Sequence, shards: Sequence[tuple[np.ndarray, int]]) -> list[tuple]:
+        """The collecting rank: the ranks' (pairs, cardinality) results of bitmap_aggregation_shard summed per key and
+        materialised (BitmapAggregationNode::mergeShards + ::materialise); same rows as bitmap_aggregation on the whole table."""
+        pairs = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.uint64).reshape(-1, 2) for p, _ in shards]))
+        sizes = np.array([len(p) for p, _ in shards], dtype=np.uint64)
+        cardinalities = np.array([c for _, c in shards], dtype=np.uint64)
+        buf = C.create_string_buffer(1 << 24)
+        _check(lib().silo_host_bitmap_aggregation_merge(
+            self._h, _dimension_spec(dimensions), pairs.ctypes.data, sizes.ctypes.data, cardinalities.ctypes.data, len(shards), buf, len(buf)))
+        return _combination_rows(buf.value.decode())
 
     def mutation_counts(self, column: str, flt: Optional[HostFilter] = None) -> np.ndarray:
         n_symbols, genome_length = self.columns[column]
@@ -716,9 +752,14 @@ class Synthetic:
     """performance/sequence_generator.h restated on the product side (host/synthetic.h)."""
 
     def __init__(self, genome_length: int = 29903, reference_seed: int = 1, generations: int = 5, gene: bool = False,
-                 tree_seed: int = 42, mutation_rate: float = 0.003):
-        """gene: an amino-acid gene (valid-symbol mutations, its own tree seed and rate) instead of a nucleotide genome"""
-        if gene:
+                 tree_seed: int = 42, mutation_rate: float = 0.003, co_occurrence_sequences: int = 0):
+        """gene: an amino-acid gene (valid-symbol mutations, its own tree seed and rate) instead of a nucleotide genome;
+        co_occurrence_sequences > 0: the table of performance/co_occurrence_benchmark.cpp instead (100-nt reference,
+        that many independently mutated sequences; the other arguments are ignored)"""
+        if co_occurrence_sequences > 0:
+            self._h = lib().silo_host_synthetic_create_co_occurrence(co_occurrence_sequences)
+            genome_length = 100
+        elif gene:
             self._h = lib().silo_host_synthetic_create_gene(genome_length, reference_seed, tree_seed, mutation_rate, generations)
         else:
             self._h = lib().silo_host_synthetic_create(genome_length, reference_seed, generations)

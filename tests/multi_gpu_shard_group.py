@@ -52,6 +52,14 @@ def main():
                 columns, cardinality = table.sharded_collect("main", min_proportion, stream.cuda_stream, summed.data_ptr())
                 results.append((host_api.rows_from_columns(columns), cardinality, summed.cpu().numpy().view(np.uint32).reshape(16, length)[:5].copy()))
         stream.synchronize()
+    # BitmapAggregationNode over the same shards: every rank's (key, count) list to rank 0, summed per key there
+    dimensions = [("position", "main", p) for p in (3, 700, 1499)]
+    aggregated = []
+    for text in (expression, None):
+        shard_result = table.bitmap_aggregation_shard(dimensions, text)
+        parts = [None] * world
+        dist.all_gather_object(parts, shard_result)
+        aggregated.append(table.bitmap_aggregation_merge(dimensions, parts) if rank == 0 else None)
     dist.barrier()
     if rank == 0:
         from oracle import oracle as O
@@ -72,6 +80,8 @@ def main():
             assert cardinality == (flt.cardinality if flt is not None else total_rows), (cardinality, text is None)
             np.testing.assert_array_equal(counts, want_counts[:5])
             assert rows == oracle_table.mutation_rows("main", want_counts, min_proportion)
+        for text, rows in zip((whole_expression, None), aggregated):
+            assert rows == oracle_table.bitmap_aggregation(dimensions, text)
         print(f"multi-GPU shard group ok: {world} ranks, {len(queries)} queries, results identical to the oracle", flush=True)
     table.close()
     ctx.close()

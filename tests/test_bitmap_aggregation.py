@@ -163,3 +163,72 @@ def test_device_equals_oracle_on_random_tables(ctx, seed, alphabet_id):
             got = device_table.bitmap_aggregation(dimensions, expression)
             assert got == want, (dimensions, expression)
     device_table.close()
+
+
+# ---- row-partitioned tables: executeShard on every rank, mergeShards + materialise on one (SURVEY.md 8(e), configs[4]) ----
+
+def test_merge_of_shard_combinations_on_the_host():
+    """BitmapAggregationNode::mergeShards / ::materialise without a device: keys are dimension 0 in the most
+    significant bits, 5 bits per sequence position; equal keys add up, the output is ordered by key."""
+    from lapis_silo_b200 import host_api
+    from oracle import oracle as O
+    synthetic = host_api.Synthetic(co_occurrence_sequences=50)
+    table = host_api.HostTable(None, [50])
+    table.add_column("main", host_api.NUCLEOTIDE, synthetic.reference, synthetic.build_column(50, 0, 1, 1))
+    symbol = {c: i for i, c in enumerate(O.NUC_SYMBOLS)}
+    key = lambda a, b: (symbol[a] << 5) | symbol[b]
+    dimensions = [("position", "main", 4), ("position", "main", 9)]
+    shard_a = (np.array([[key("A", "C"), 3], [key("A", "T"), 1], [key("G", "C"), 7]], dtype=np.uint64), 11)
+    shard_b = (np.array([[key("-", "N"), 2], [key("A", "T"), 5]], dtype=np.uint64), 7)
+    shard_c = (np.zeros((0, 2), dtype=np.uint64), 0)
+    assert table.bitmap_aggregation_merge(dimensions, [shard_a, shard_b, shard_c]) == [
+        ("-", "N", 2), ("A", "C", 3), ("A", "T", 6), ("G", "C", 7)]
+    assert table.bitmap_aggregation_merge([], [shard_a, shard_b, shard_c]) == [(18,)]  # no dimension: the cardinalities add up
+    table.close()
+
+
+def test_co_occurrence_generator():
+    """performance/sequence_generator.h:487-526: 100-nt A/C/G/T reference, Binomial(100, 0.1) substitutions per row
+    (a substitution may draw the base that is already there: ~7.2 differing positions per row on average)."""
+    from lapis_silo_b200 import host_api
+    synthetic = host_api.Synthetic(co_occurrence_sequences=4000)
+    again = host_api.Synthetic(co_occurrence_sequences=3000)
+    reference = synthetic.reference
+    assert len(reference) == 100 and set(reference) <= set("ACGT") and again.reference == reference
+    sequences = [synthetic.sequence(i) for i in range(3000)]
+    assert sequences == [again.sequence(i) for i in range(3000)]  # one stream in id order: a prefix is a prefix
+    assert all(len(s) == 100 and set(s) <= set("ACGT") for s in sequences)
+    differing = np.array([sum(a != b for a, b in zip(s, reference)) for s in sequences])
+    assert 6.9 < differing.mean() < 7.5 and differing.max() <= 25
+
+
+@pytest.mark.gpu
+def test_sharded_aggregation_merges_to_the_whole(ctx):
+    """Three interleaved shards of the co_occurrence_benchmark table, every shard aggregated on the device, the (key,
+    count) lists merged: the rows of the oracle's aggregation over the whole table, with and without filters."""
+    from lapis_silo_b200 import host_api
+    from oracle import oracle as O
+    total_rows = 3 * 65536 + 4321
+    synthetic = host_api.Synthetic(co_occurrence_sequences=50_000)
+    sizes = host_api.dense_chunk_sizes(total_rows)
+    oracle_table = O.Table()
+    oracle_table.set_layout(*sizes)
+    oracle_table.import_column("main", O.NUCLEOTIDE, synthetic.reference, synthetic.build_column(total_rows, 0, len(sizes), 4))
+    shards = []
+    for rank in range(3):
+        first, n_chunks, stride = host_api.interleaved_shard(len(sizes), 3, rank)
+        table = host_api.HostTable(ctx, host_api.shard_chunk_sizes(total_rows, first, n_chunks, stride))
+        table.add_column("main", host_api.NUCLEOTIDE, synthetic.reference, synthetic.build_column(total_rows, first, n_chunks, 4, stride))
+        shards.append(table)
+    six = [("position", "main", p - 1) for p in (5, 10, 20, 30, 40, 50)]  # co_occurrence_benchmark.cpp:41 (1-based there)
+    for dimensions in (six, six[:2], [("position", "main", 99)], []):
+        for expression in (None, "(sym-eq main 12 A)", "(and (has-mut main 7) (not (sym-eq main 60 T)))", "(false)"):
+            parts = [table.bitmap_aggregation_shard(dimensions, expression) for table in shards]
+            assert all((np.diff(pairs[:, 0].astype(np.int64)) > 0).all() for pairs, _ in parts)
+            merged = shards[0].bitmap_aggregation_merge(dimensions, parts)
+            want = oracle_table.bitmap_aggregation(dimensions, expression)
+            assert merged == want, (dimensions, expression)
+            if dimensions == six and expression is None:
+                assert sum(count for *_, count in merged) == total_rows and len(merged) > 500
+    for table in shards:
+        table.close()
