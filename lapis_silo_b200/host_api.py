@@ -569,11 +569,17 @@ class HostTable:
         _check(lib().silo_host_filter_explain(self._h, expression.encode(), buf, len(buf)))
         return buf.value.decode()
 
+    def _text_buffer(self):
+        # (allocated once: ctypes zero-fills a fresh buffer, a millisecond for 16 MB)
+        if getattr(self, "_text", None) is None:
+            self._text = C.create_string_buffer(1 << 24)
+        return self._text
+
     def bitmap_aggregation(self, dimensions: Sequence, expression: Optional[str] = None) -> list[tuple]:
         """BitmapAggregationNode (co-occurrence / groupBy): dimensions are ("position", column, position0) or
         ("bitmaps", [(value, bitmap name), ...], null bitmap name or None). Returns the combinations in the
         reference's output order as (value-or-None per dimension ..., count) tuples."""
-        buf = C.create_string_buffer(1 << 24)
+        buf = self._text_buffer()
         _check(lib().silo_host_bitmap_aggregation(
             self._h, expression.encode() if expression else None, _dimension_spec(dimensions), buf, len(buf)))
         return _combination_rows(buf.value.decode())
@@ -597,7 +603,7 @@ class HostTable:
         pairs = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.uint64).reshape(-1, 2) for p, _ in shards]))
         sizes = np.array([len(p) for p, _ in shards], dtype=np.uint64)
         cardinalities = np.array([c for _, c in shards], dtype=np.uint64)
-        buf = C.create_string_buffer(1 << 24)
+        buf = self._text_buffer()
         _check(lib().silo_host_bitmap_aggregation_merge(
             self._h, _dimension_spec(dimensions), pairs.ctypes.data, sizes.ctypes.data, cardinalities.ctypes.data, len(shards), buf, len(buf)))
         return _combination_rows(buf.value.decode())
