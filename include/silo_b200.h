@@ -467,7 +467,14 @@ void silo_gpu_shard_group_free(silo_gpu_table* table);
  *     a row in none of them is in no combination.
  * key = the codes packed with dimension 0 in the most significant bits: 5 bits per sequence-position
  * dimension, 8 bits per index-bitmap dimension, 63 bits in total at most; ascending key order is the
- * reference's depth-first output order. */
+ * reference's depth-first output order.
+ * LIMITS the reference does not have (SILO_E_INVALID_ARGUMENT beyond them; the caller keeps its CPU path for such
+ * queries): at most 254 value groups per index-bitmap dimension (one code byte per row and dimension), 63 key bits
+ * = e.g. 12 sequence positions, or 7 index dimensions, or 6 positions + 4 index dimensions. The value bitmaps of a
+ * dimension must be DISJOINT (they are, for a dictionary index): a row held by two of them is counted once here,
+ * in the first, but once per bitmap by the reference's partition().
+ * Row-partitioned tables: counts of disjoint row sets add up, so every rank runs the call on its shard with the
+ * same dimensions and one rank sums the (key, count) lists per key (host/bitmap_aggregation_node.h mergeShards). */
 enum { SILO_DIM_SEQUENCE_POSITION = 0, SILO_DIM_INDEX_BITMAPS = 1 };
 typedef struct {
    uint32_t kind;

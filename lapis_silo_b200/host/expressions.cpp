@@ -975,10 +975,25 @@ uint64_t number(const Node& node) {
    return value;
 }
 
+// numbers that end up in 32-bit fields: a value that does not fit is a user error, never silently another number
+// (position 4294967297 must not pass the bounds check as position 1)
+uint32_t narrow32(uint64_t value, const char* what) {
+   if (value > UINT32_MAX) {
+      throw IllegalQueryException(std::string("filter expression: ") + what + " " + std::to_string(value) + " does not fit in 32 bits");
+   }
+   return static_cast<uint32_t>(value);
+}
+int narrowInt(uint64_t value, const char* what) {
+   if (value > static_cast<uint64_t>(INT32_MAX)) {
+      throw IllegalQueryException(std::string("filter expression: ") + what + " " + std::to_string(value) + " is out of range");
+   }
+   return static_cast<int>(value);
+}
+
 uint32_t position(const Node& node) {
    const uint64_t one_based = number(node);
    CHECK_QUERY(one_based != 0, "The field 'position' is 1-indexed. Value of 0 not allowed.");
-   return static_cast<uint32_t>(one_based - 1);
+   return narrow32(one_based - 1, "position");
 }
 
 ExpressionPtr build(const Node& node);
@@ -1043,12 +1058,12 @@ ExpressionPtr build(const Node& node) {
    }
    if (head == "n-of") {
       CHECK_QUERY(items.size() >= 3, "filter expression: n-of needs K and EXACT");
-      return std::make_shared<NOf>(buildList(node, 3), static_cast<int>(number(items[1])), number(items[2]) != 0);
+      return std::make_shared<NOf>(buildList(node, 3), narrowInt(number(items[1]), "numberOfMatchers"), number(items[2]) != 0);
    }
    if (head == "profile") {
       CHECK_QUERY(items.size() >= 4, "filter expression: profile needs COL DIST KIND ..");
       const std::string& column = atom(items[1]);
-      const auto distance = static_cast<uint32_t>(number(items[2]));
+      const auto distance = static_cast<uint32_t>(narrowInt(number(items[2]), "distance"));
       const std::string& kind = atom(items[3]);
       if (kind == "seq") {
          arity(4);
@@ -1097,7 +1112,7 @@ ExpressionPtr build(const Node& node) {
       std::vector<RangeSelection::Range> ranges;
       ranges.reserve(numbers.size() / 2);
       for (size_t i = 0; i + 1 < numbers.size(); i += 2) {
-         ranges.push_back({static_cast<uint32_t>(numbers[i]), static_cast<uint32_t>(numbers[i + 1])});
+         ranges.push_back({narrow32(numbers[i], "row id"), narrow32(numbers[i + 1], "row id")});
       }
       return std::make_shared<RowRanges>(std::move(ranges));
    }
@@ -1105,7 +1120,7 @@ ExpressionPtr build(const Node& node) {
       std::vector<uint32_t> ids;
       ids.reserve(node.numbers.size());
       for (const uint64_t id : node.numbers) {
-         ids.push_back(static_cast<uint32_t>(id));
+         ids.push_back(narrow32(id, "row id"));
       }
       return std::make_shared<IdsLeaf>(std::move(ids));
    }
@@ -1119,7 +1134,7 @@ ExpressionPtr build(const Node& node) {
       if (head == "op-threshold") {
          CHECK_QUERY(items.size() == 5, "filter expression: op-threshold K EXACT (pos..) (neg..)");
          expression->kind = PhysicalOperator::THRESHOLD;
-         expression->number_of_matchers = static_cast<uint32_t>(number(items[1]));
+         expression->number_of_matchers = narrow32(number(items[1]), "numberOfMatchers");
          expression->match_exactly = number(items[2]) != 0;
          lists_from = 3;
       } else {

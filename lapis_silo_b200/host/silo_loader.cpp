@@ -350,7 +350,11 @@ void parseSequenceColumn(Cursor& cursor, const ArchiveColumnSpec& spec, LoadedSe
    }
    const auto [null_bytes, null_size] = cursor.roaring();
    std::vector<uint32_t> null_runs;
-   portableRoaringToRuns(null_bytes, null_size, null_runs);
+   // (checked BEFORE the runs are expanded row by row: a crafted megabyte of full run containers would otherwise
+   // ask for 2^32 row ids)
+   if (portableRoaringToRuns(null_bytes, null_size, null_runs) > column.sequence_count) {
+      throw ArchiveFormatError("null bitmap of column " + spec.name + " holds more rows than the column");
+   }
    for (size_t run = 0; run < null_runs.size(); run += 2) {
       for (uint32_t row = null_runs[run]; row != null_runs[run + 1]; ++row) {
          column.null_row_ids.push_back(row);
@@ -469,8 +473,16 @@ uint64_t portableRoaringToRuns(const uint8_t* bytes, uint64_t size, std::vector<
       }
       total += end_exclusive - first;
    };
+   int64_t previous_key = -1;
    for (uint32_t c = 0; c < n_containers; ++c) {
-      const uint32_t high = static_cast<uint32_t>(read16(keys_at + 4ULL * c)) << 16;
+      const uint32_t key = read16(keys_at + 4ULL * c);
+      // (key 0xFFFF would make `high + 65536` wrap to 0 below, and no row id lives there: a table has fewer than
+      // 65,535 chunks, row_layout.h:44)
+      if (static_cast<int64_t>(key) <= previous_key || key == 0xFFFF) {
+         throw ArchiveFormatError("roaring bitmap container keys are not ascending / out of range");
+      }
+      previous_key = key;
+      const uint32_t high = key << 16;
       const uint32_t cardinality = static_cast<uint32_t>(read16(keys_at + 4ULL * c + 2)) + 1;
       const bool is_run = run_flags != nullptr && ((run_flags[c / 8] >> (c % 8)) & 1) != 0;
       if (is_run) {

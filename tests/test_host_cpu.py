@@ -282,3 +282,19 @@ def test_short_read_generator_matches_the_oracle_string_ingest():
         a, b = from_strings.filter(expression), imported.filter(expression)
         np.testing.assert_array_equal(a.ids(), b.ids(), err_msg=expression)
         np.testing.assert_array_equal(from_strings.mutation_counts("main", a), imported.mutation_counts("main", b))
+
+
+def test_reader_rejects_numbers_that_do_not_fit():
+    """positions, row ids, K and distances go into 32-bit fields: a larger number is a user error, not another number
+    (position 4294967297 must not pass the bounds check as position 1)"""
+    from lapis_silo_b200 import host_api
+    synthetic = host_api.Synthetic(genome_length=40, reference_seed=3, generations=2)
+    table = host_api.HostTable(None, [10])
+    table.add_column("main", host_api.NUCLEOTIDE, synthetic.reference, synthetic.build_column(10, 0, 1, 1))
+    table.explain("(sym-eq main 1 A)")
+    for expression in ("(sym-eq main 4294967297 A)", "(has-mut main 4294967336)", "(ids 1 4294967296)", "(ranges 0 4294967297)",
+                       "(n-of 2147483648 0 (has-mut main 1))", "(n-of 4294967297 0 (has-mut main 1))",
+                       "(op-threshold 4294967297 0 ((ids 1)) ())", "(profile main 4294967296 muts 1 A)"):
+        with pytest.raises(host_api.HostError, match="does not fit in 32 bits|out of range"):
+            table.explain(expression)
+    table.close()

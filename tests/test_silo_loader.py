@@ -376,3 +376,31 @@ def test_reader_survives_damaged_input():
             continue
         assert all(first < end for first, end in runs)
         assert all(a[1] < b[0] for a, b in zip(runs, runs[1:]))
+
+
+def test_roaring_decoder_rejects_wrapping_keys():
+    """a container with key 0xFFFF would make `key << 16 + 65536` wrap to 0 in 32 bits (runs with end < start that the
+    ascending check then lets pass); keys must ascend strictly"""
+    import struct
+    from lapis_silo_b200 import host_api as H
+
+    def no_runs(containers):  # SERIAL_COOKIE_NO_RUNCONTAINER, array containers only
+        out = struct.pack("<II", 12346, len(containers))
+        for key, values in containers:
+            out += struct.pack("<HH", key, len(values) - 1)
+        offset = len(out) + 4 * len(containers)
+        for _, values in containers:
+            out += struct.pack("<I", offset)
+            offset += 2 * len(values)
+        for _, values in containers:
+            out += b"".join(struct.pack("<H", v) for v in values)
+        return out
+
+    assert H.roaring_runs(no_runs([(0, [1, 2, 3]), (2, [7])])) == [(1, 4), (2 * 65536 + 7, 2 * 65536 + 8)]
+    for bad in ([(0xFFFF, [65535])], [(3, [1]), (3, [2])], [(5, [1]), (2, [9])]):
+        with pytest.raises(H.HostError):
+            H.roaring_runs(no_runs(bad))
+    # run containers: SERIAL_COOKIE with the run flag of the only container set, one run covering the whole container
+    full_last = struct.pack("<I", 12347 | (0 << 16)) + b"\x01" + struct.pack("<HH", 0xFFFF, 65535) + struct.pack("<HHH", 1, 0, 65535)
+    with pytest.raises(H.HostError):
+        H.roaring_runs(full_last)
