@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 import subprocess
 import weakref
 
@@ -235,6 +236,8 @@ class Filter:
             self._h = C.c_void_p()
 
     def __del__(self):
+        if sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
+            return
         try:
             self.close()
         except Exception:
@@ -320,6 +323,8 @@ class Table:
             self._h = C.c_void_p()
 
     def __del__(self):
+        if sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
+            return
         try:
             self.close()
         except Exception:

@@ -125,6 +125,22 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
    if (tid < min(p.n_instrs, CACHED_INSTRS) * 4) {  // 16-byte instructions as 4 words each
       reinterpret_cast<uint32_t*>(sh.small->instrs)[tid] = reinterpret_cast<const uint32_t*>(p.instrs)[tid];
    }
+   // the chunk's segment records for the work list of the counts kernels (static column data): fetched now, so that
+   // the epilogue is one atomic and one store instead of a chain of three dependent global loads
+   uint32_t first_segment = 0;
+   uint32_t chunk_segments = 0;
+   uint4 my_segment = make_uint4(0u, 0u, 0u, 0u);
+   if (p.prepare_work_items != nullptr) {  // (kernel parameter: uniform)
+      first_segment = p.prepare_chunk_seg_begin[chunk];
+      chunk_segments = p.prepare_chunk_seg_begin[chunk + 1] - first_segment;
+      if (tid < chunk_segments) {
+         my_segment = reinterpret_cast<const uint4*>(p.prepare_segments + first_segment)[tid];
+      }
+   }
+   // (the program was staged by a copy in front of the launch, or long ago: it is there. What follows reads and writes
+   // what the previous query's kernels still use: tiles, counts, work list, scalars.)
+   gridDependencyWait();
+   gridDependencyLaunch();
    __syncthreads();
 
    for (uint32_t pc = 0; pc < p.n_instrs; ++pc) {
@@ -464,8 +480,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
          p.out_popcount[chunk] = total;
          atomicAdd(p.out_cardinality, static_cast<unsigned long long>(total));
          if (p.prepare_work_items != nullptr) {
-            const uint32_t first_segment = p.prepare_chunk_seg_begin[chunk];
-            const uint32_t n_segments = total != 0 ? p.prepare_chunk_seg_begin[chunk + 1] - first_segment : 0u;
+            const uint32_t n_segments = total != 0 ? chunk_segments : 0u;
             sh.range[0] = n_segments != 0 ? atomicAdd(&p.prepare_work_state[0], n_segments) : 0u;
             sh.range[1] = n_segments;
          }
@@ -474,9 +489,12 @@ __global__ void __launch_bounds__(EVAL_THREADS, 2) evalProgramKernel(EvalParams 
    if (p.prepare_work_items != nullptr) {  // (kernel parameter: uniform)
       __syncthreads();
       const uint32_t n_segments = sh.range[1];
-      const uint4* source = reinterpret_cast<const uint4*>(p.prepare_segments + p.prepare_chunk_seg_begin[chunk]);
       uint4* target = reinterpret_cast<uint4*>(p.prepare_work_items + sh.range[0]);
-      for (uint32_t i = tid; i < n_segments; i += EVAL_THREADS) {
+      if (tid < n_segments) {
+         target[tid] = my_segment;
+      }
+      const uint4* source = reinterpret_cast<const uint4*>(p.prepare_segments + first_segment);
+      for (uint32_t i = tid + EVAL_THREADS; i < n_segments; i += EVAL_THREADS) {  // (a chunk with more than 1,024 segments)
          target[i] = source[i];
       }
    }
@@ -1200,7 +1218,7 @@ static void launchProgram(silo_gpu_table* table, EvalParams params, silo_gpu_fil
    }
    const size_t shared_bytes = evalSharedBytes(params.stack_depth, params.has_threshold != 0);
    const NvtxRange eval_range("computeFilter: Intersection / Union / Threshold / Selection evaluate [evalProgramKernel]");
-   evalProgramKernel<<<table->n_chunks, EVAL_THREADS, shared_bytes, stream>>>(params);
+   SILO_CUDA_CHECK(launchDependent(evalProgramKernel, dim3(table->n_chunks), dim3(EVAL_THREADS), shared_bytes, stream, params));
    SILO_CUDA_CHECK(cudaGetLastError());
    table->stats.kernel_launches++;
 }

@@ -416,6 +416,10 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) __maxnreg__(MAXREG) container
       tile_buffers[threadIdx.x >> 2][TILE32_WORDS + (threadIdx.x & 3)] = 0;
    }
    __syncthreads();
+   // everything above is this CTA's own shared memory; the work list, the filter tiles and the zeroed counts come from
+   // the kernels in front
+   gridDependencyWait();
+   gridDependencyLaunch();
 
    if (warp == 0) {
       // ---------------- producer: ONE thread ------------------------------------------------------
@@ -985,9 +989,13 @@ __global__ void __launch_bounds__(FIN_BLOCK_THREADS) finalizeCountsKernel(
       }
       shardDebugStamp(push, 1);
    }
+   const uint32_t reference_symbol = in_range ? column.local_reference[p] : 0u;  // (static data: may be read before the wait)
+   // the query counter and the released flag above are written by EARLIER finalize kernels of this stream and by the
+   // root (transitively complete / another device); everything below is written by the kernels right in front
+   gridDependencyWait();
+   gridDependencyLaunch();
    // every global load up front
    const uint32_t mine = group == 0 ? diff[p] : 0u;  // (the array is padded to whole blocks)
-   const uint32_t reference_symbol = in_range ? column.local_reference[p] : 0u;
    uint32_t values[FIN_SYMBOLS_PER_THREAD];
 #pragma unroll
    for (uint32_t k = 0; k < FIN_SYMBOLS_PER_THREAD; ++k) {
@@ -1457,7 +1465,10 @@ void launchContainerVariant(
       SILO_CUDA_CHECK(cudaFuncSetAttribute(containerAndCountKernel<W, P, STAGES, MAXREG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dynamic_bytes)));
       attribute_set = true;
    }
-   containerAndCountKernel<W, P, STAGES, MAXREG, MODE><<<blocks, (W + 1) * 32, dynamic_bytes, stream>>>(column, words, work_state, work_items, counts, tail_factor, debug_times);
+   SILO_CUDA_CHECK(launchDependent(
+      containerAndCountKernel<W, P, STAGES, MAXREG, MODE>, dim3(blocks), dim3((W + 1) * 32), dynamic_bytes, stream, column, words, work_state, work_items, counts,
+      tail_factor, debug_times
+   ));
 }
 
 template <typename... Args>
@@ -1630,13 +1641,13 @@ void enqueueMutationCounts(
       const ShardPush shard_push = push != nullptr ? *push : ShardPush{};
       require(column.n_symbols <= 32, "mutation_counts: alphabets of more than 32 symbols are not supported");
       if (shard_push.peers != nullptr) {
-         finalizeCountsKernel<FIN_COLLECT><<<blocks, FIN_BLOCK_THREADS, 0, stream>>>(column, diff, d_counts, table->d_work_state, hit_request, shard_push);
+         SILO_CUDA_CHECK(launchDependent(finalizeCountsKernel<FIN_COLLECT>, dim3(blocks), dim3(FIN_BLOCK_THREADS), 0, stream, column, diff, d_counts, table->d_work_state, hit_request, shard_push));
       } else if (shard_push.root_block != nullptr) {
-         finalizeCountsKernel<FIN_PUSH><<<blocks, FIN_BLOCK_THREADS, 0, stream>>>(column, diff, d_counts, table->d_work_state, hit_request, shard_push);
+         SILO_CUDA_CHECK(launchDependent(finalizeCountsKernel<FIN_PUSH>, dim3(blocks), dim3(FIN_BLOCK_THREADS), 0, stream, column, diff, d_counts, table->d_work_state, hit_request, shard_push));
       } else if (hit_request.hits != nullptr) {
-         finalizeCountsKernel<FIN_OUTPUT><<<blocks, FIN_BLOCK_THREADS, 0, stream>>>(column, diff, d_counts, table->d_work_state, hit_request, shard_push);
+         SILO_CUDA_CHECK(launchDependent(finalizeCountsKernel<FIN_OUTPUT>, dim3(blocks), dim3(FIN_BLOCK_THREADS), 0, stream, column, diff, d_counts, table->d_work_state, hit_request, shard_push));
       } else {
-         finalizeCountsKernel<FIN_COUNTS><<<blocks, FIN_BLOCK_THREADS, 0, stream>>>(column, diff, d_counts, table->d_work_state, hit_request, shard_push);
+         SILO_CUDA_CHECK(launchDependent(finalizeCountsKernel<FIN_COUNTS>, dim3(blocks), dim3(FIN_BLOCK_THREADS), 0, stream, column, diff, d_counts, table->d_work_state, hit_request, shard_push));
       }
    }
    SILO_CUDA_CHECK(cudaGetLastError());

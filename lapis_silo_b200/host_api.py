@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 import weakref
 from typing import Optional, Sequence
 
@@ -280,6 +281,8 @@ class HostFilter:
             self._h = None
 
     def __del__(self):
+        if sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
+            return
         try:
             self.close()
         except Exception:
@@ -331,6 +334,8 @@ class PreparedFilter:
             self._h = None
 
     def __del__(self):
+        if sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
+            return
         try:
             self.close()
         except Exception:
@@ -403,6 +408,8 @@ class Archive:
             self._h = None
 
     def __del__(self):
+        if sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
+            return
         try:
             self.close()
         except Exception:
@@ -748,6 +755,8 @@ class HostTable:
             self._h = None
 
     def __del__(self):
+        if sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
+            return
         try:
             self.close()
         except Exception:
@@ -826,6 +835,8 @@ class Synthetic:
             self._h = None
 
     def __del__(self):
+        if sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
+            return
         try:
             self.close()
         except Exception:

@@ -15,7 +15,7 @@ ncu --set full --clock-control none --import-source on -k regex:'evalProgramKern
 ls -la gpurun_out | tail -20
 if [ "$tag" != "r1" ]; then
   # round 2: the other workloads of BASELINE.json, the threshold sweep kernel, and compute-sanitizer over the parity suites
-  for w in nof aa reads; do
+  for w in nof aa reads cooc; do
     python bench.py --workload $w > gpurun_out/${tag}_bench_${w}.json 2> gpurun_out/${tag}_bench_${w}.err; tail -c 600 gpurun_out/${tag}_bench_${w}.json
   done
   ncu --set full --clock-control none --import-source on -k regex:thresholdSweepKernel -s 1 -c 1 -f -o gpurun_out/${tag}_sweep_full \
@@ -28,6 +28,7 @@ if [ "$tag" != "r1" ]; then
     python -m pytest tests/test_gpu_parity.py -m gpu -q -k "not baseline and not twelve_genes and not tree_data and not concurrent and not shards_sum" > gpurun_out/${tag}_sanitizer_memcheck_parity_pytest.log 2>&1; echo "memcheck parity rc $?" | tee -a gpurun_out/${tag}_sanitizer_memcheck_parity_pytest.log
   timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 --log-file gpurun_out/${tag}_sanitizer_racecheck.log \
     python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "not baseline" > gpurun_out/${tag}_sanitizer_racecheck_pytest.log 2>&1; echo "racecheck rc $?" | tee -a gpurun_out/${tag}_sanitizer_racecheck_pytest.log
-  tail -5 gpurun_out/${tag}_sanitizer_memcheck.log gpurun_out/${tag}_sanitizer_racecheck.log
+  tail -n 3 gpurun_out/${tag}_sanitizer_memcheck.log; tail -n 3 gpurun_out/${tag}_sanitizer_racecheck.log
+  SILO_QUERY_TRACE=1 python profiles/query_trace_probe.py > gpurun_out/${tag}_query_trace.txt 2>&1; tail -n 4 gpurun_out/${tag}_query_trace.txt
 fi
 ls -la gpurun_out | tail -30

@@ -119,7 +119,7 @@ def extras(tag):
     (each only if round_capture.sh / scripts/r2_scale.sh left the artifact)."""
     text = ""
     lines = []
-    for workload in ("nof", "aa", "reads"):
+    for workload in ("nof", "aa", "reads", "cooc"):
         path = os.path.join(OUT, f"{tag}_bench_{workload}.json")
         if os.path.exists(path):
             shutil.copy(path, os.path.join(PROFILES, f"{tag}_bench_{workload}.json"))
