@@ -236,7 +236,7 @@ class Filter:
             self._h = C.c_void_p()
 
     def __del__(self):
-        if sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
+        if sys is None or sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
             return
         try:
             self.close()
@@ -323,7 +323,7 @@ class Table:
             self._h = C.c_void_p()
 
     def __del__(self):
-        if sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
+        if sys is None or sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
             return
         try:
             self.close()

@@ -281,7 +281,7 @@ class HostFilter:
             self._h = None
 
     def __del__(self):
-        if sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
+        if sys is None or sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
             return
         try:
             self.close()
@@ -334,7 +334,7 @@ class PreparedFilter:
             self._h = None
 
     def __del__(self):
-        if sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
+        if sys is None or sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
             return
         try:
             self.close()
@@ -408,7 +408,7 @@ class Archive:
             self._h = None
 
     def __del__(self):
-        if sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
+        if sys is None or sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
             return
         try:
             self.close()
@@ -755,7 +755,7 @@ class HostTable:
             self._h = None
 
     def __del__(self):
-        if sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
+        if sys is None or sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
             return
         try:
             self.close()
@@ -835,7 +835,7 @@ class Synthetic:
             self._h = None
 
     def __del__(self):
-        if sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
+        if sys is None or sys.is_finalizing():  # (the CUDA runtime's own exit handlers may have run: the process frees everything anyway)
             return
         try:
             self.close()
