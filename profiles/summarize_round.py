@@ -145,6 +145,29 @@ def extras(tag):
         for row in rows[start + 1:]:
             if len(row) > header.index("Metric Value"):
                 text += f"| `{row[header.index('Kernel Name')].split('(')[0][:80]}` | {float(row[header.index('Metric Value')].replace(',', '')) / 1000.0:.2f} |\n"
+    path = os.path.join(OUT, f"{tag}_cooc_launches.csv")
+    if os.path.exists(path):
+        shutil.copy(path, os.path.join(PROFILES, f"{tag}_cooc_launches.csv"))
+        rows = list(csv.reader(open(path)))
+        start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+        header = rows[start]
+        name_at, metric_at, value_at = header.index("Kernel Name"), header.index("Metric Name"), header.index("Metric Value")
+        per_kernel = collections.OrderedDict()
+        for row in rows[start + 1:]:
+            if len(row) > value_at:
+                kernel = row[name_at].split("(")[0].replace("unnamed>::", "")
+                per_kernel.setdefault(kernel, collections.defaultdict(list))[row[metric_at]].append(float(row[value_at].replace(",", "")))
+        text += ("\n## the co-occurrence kernels (`bench.py --workload cooc`, 10 M rows x 6 positions; `profiles/" + tag + "_cooc_launches.csv`: "
+                 "`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum`, cold, serialised)\n\n"
+                 "| kernel | launches | mean µs | DRAM read MB | DRAM write MB | GB/s | of the measured peak |\n|---|---|---|---|---|---|---|\n")
+        peak = json.load(open(os.path.join(OUT, f"{tag}_bench.json")))["roofline"]["peak"]
+        for kernel, metrics in per_kernel.items():
+            n = len(metrics["gpu__time_duration.sum"])
+            micros = sum(metrics["gpu__time_duration.sum"]) / n / 1000.0
+            read_mb = sum(metrics["dram__bytes_read.sum"]) / n / 1e6
+            write_mb = sum(metrics["dram__bytes_write.sum"]) / n / 1e6
+            gbs = (read_mb + write_mb) / micros * 1e3
+            text += f"| `{kernel}` | {n} | {micros:.1f} | {read_mb:.1f} | {write_mb:.1f} | {gbs:.0f} | {gbs / peak:.3f} |\n"
     scale = []
     for n in (1, 2, 4, 8):
         for reduce in ("", "_peer", "_nccl"):
