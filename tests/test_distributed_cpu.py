@@ -173,3 +173,61 @@ def test_two_ranks_load_their_chunk_ranges_from_one_archive(tmp_path):
     mp.spawn(archive_worker, args=(2, free_port(), result_path), nprocs=2, join=True)
     with open(result_path) as result:
         assert result.read().startswith("ok ")
+
+
+def aggregation_worker(rank: int, world_size: int, port: int, result_path: str) -> None:
+    """BitmapAggregationNode over a row-partitioned table (BASELINE.json configs[4]): every rank
+    aggregates the rows of its chunk range (the oracle plays the device: the shard is the whole table under the
+    shard's row-range filter), the (key, count) lists are all-gathered, rank 0 sums them per key and materialises the
+    rows with the product's host layer (BitmapAggregationNode::mergeShards / ::materialise on a host-only table)."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        from lapis_silo_b200 import host_api
+        from oracle import oracle as O
+        total_rows = 3 * 65536 + 777
+        synthetic = host_api.Synthetic(co_occurrence_sequences=20_000)
+        sizes = host_api.dense_chunk_sizes(total_rows)
+        whole = O.Table()
+        whole.set_layout(*sizes)
+        whole.import_column("main", O.NUCLEOTIDE, synthetic.reference, synthetic.build_column(total_rows, 0, len(sizes), 2))
+        dimensions = [("position", "main", p - 1) for p in (5, 10, 20, 30, 40, 50)]
+        bounds = host_api.partition_chunks([1] * len(sizes), world_size)
+        first, n_chunks = bounds[rank], bounds[rank + 1] - bounds[rank]
+        first_row = first << 16
+        end_row = ((first + n_chunks - 1) << 16) + sizes[first + n_chunks - 1]
+        symbol = {c: i for i, c in enumerate(O.NUC_SYMBOLS)}
+        results = {}
+        for name, expression in (("all", None), ("filtered", "(sym-eq main 12 A)")):
+            shard_filter = f"(ranges {first_row} {end_row})" if expression is None else f"(and (ranges {first_row} {end_row}) {expression})"
+            rows = whole.bitmap_aggregation(dimensions, shard_filter)
+            pairs = np.array(sorted((sum(symbol[v] << (5 * (len(dimensions) - 1 - d)) for d, v in enumerate(values)), count)
+                                    for *values, count in rows), dtype=np.uint64).reshape(-1, 2)
+            shard = (pairs, int(sum(count for *_, count in rows)))
+            gathered = [None] * world_size
+            dist.all_gather_object(gathered, shard)
+            if rank == 0:
+                table = host_api.HostTable(None, [10])
+                table.add_column("main", host_api.NUCLEOTIDE, synthetic.reference, synthetic.build_column(10, 0, 1, 1))
+                merged = table.bitmap_aggregation_merge(dimensions, gathered)
+                table.close()
+                assert merged == whole.bitmap_aggregation(dimensions, expression), name
+                results[name] = len(merged)
+        if rank == 0:
+            with open(result_path, "w") as out:
+                out.write(f"ok {results}")
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_merge_their_shard_combinations(tmp_path):
+    pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    result_path = str(tmp_path / "result.txt")
+    mp.spawn(aggregation_worker, args=(2, free_port(), result_path), nprocs=2, join=True)
+    with open(result_path) as result:
+        assert result.read().startswith("ok ")
