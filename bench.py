@@ -326,7 +326,7 @@ def run_ours(args):
 
     # N > 1, default (--reduce peer): the library's own partition scheduler (silo_gpu_shard_group_*): the finalize kernel
     # of every rank stores its rows of the valid mutation symbols into rank 0's gather area over NVLink, rank 0's
-    # collect kernel sums them -- no collective kernel, nothing but this repository's kernels on the stream. The
+    # own finalize kernel adds them and its counts -- no collective kernel, nothing but this repository's kernels on the stream. The
     # handles of the gather areas travel through torch.distributed once, at set-up.
     # --reduce nccl: the per-rank counts are all-reduced with NCCL instead; the all-reduce of query i runs on its own
     # stream beside the kernels of query i + 1 (two count buffers). Every reduction is inside the timed region.
@@ -570,7 +570,7 @@ def run_ours(args):
             if used_graph else "eager launches",
             "parallelism": (f"interleaved chunk shards (chunk c on rank c % {n_gpus}), " + (
                 "the library's shard group: every rank's finalize kernel stores its rows into rank 0's gather area over NVLink, "
-                "rank 0's collect kernel sums them (no collective kernel)" if use_peer else "NCCL allreduce of the u32 counts"))
+                "rank 0's finalize kernel adds them to its own (no collective kernel)" if use_peer else "NCCL allreduce of the u32 counts"))
             if n_gpus > 1 else "single GPU",
         },
         "clocks": clocks,

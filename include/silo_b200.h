@@ -399,8 +399,8 @@ int silo_gpu_mutation_hits_from_counts(
  * Mutations action are plain addends (the local reference is the same on all shards) and only one rank -- the root,
  * rank 0 -- needs their sum, for the output pass. No collective kernel runs: the finalize kernel of every rank stores
  * its rows of the valid mutation symbols straight into a gather area in the ROOT's memory over NVLink (CUDA IPC peer
- * mapping), and the root's collect kernel sums the ranks' rows and runs addMutationsToOutput (mutations_node.cpp:
- * 307-363) on the device. Replaces, for a row-partitioned table, the loop over partitions that the reference's
+ * mapping; 8-byte words tagged with the query number, no fence, no counter), and the root's own finalize kernel adds
+ * the ranks' rows to its counts and runs addMutationsToOutput (mutations_node.cpp:307-363) on the device. Replaces, for a row-partitioned table, the loop over partitions that the reference's
  * MutationsNode producer would run on one host (mutations_node.cpp:372-428).
  *
  *   every rank:  silo_gpu_shard_group_init(table, column, valid mask, rank, world, my_handle)

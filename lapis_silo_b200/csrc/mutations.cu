@@ -785,11 +785,11 @@ constexpr int FIN_THREADS = DIFF_BLOCK;
 // Row-partitioned tables: one process per GPU, every rank holds the chunks of its shard. The per-rank
 // counts are plain addends, and only ONE rank (the root, rank 0) needs the sums. Instead of a collective kernel that
 // competes with the container kernel for SMs, the finalize kernel of every rank STORES its rows of the valid mutation
-// symbols straight into the root's gather area over NVLink (peer memory mapped with CUDA IPC), and the root's collect
-// kernel sums the `world` arrays and runs the output pass. Flow control: a gather slot is reused every SHARD_SLOTS
-// queries; a rank writes slot s for its query q only after the root released the slot's previous use (the root's
-// collect kernel stores the generation into every rank's `released[s]`), so ranks may run at most SHARD_SLOTS - 1
-// queries ahead of the root. Every wait in a kernel is bounded (SHARD_SPIN_LIMIT): a missing peer becomes an error
+// symbols straight into the root's gather area over NVLink (peer memory mapped with CUDA IPC) as tagged words, and the
+// root's own finalize kernel (FIN_COLLECT; or shardCollectKernel when the root collects in a call of its own) adds the
+// `world` arrays and runs the output pass. Flow control: a gather slot is reused every SHARD_SLOTS queries; a rank writes
+// slot s for its query q only after the root released the slot's previous use (the collecting kernel's last block stores
+// the generation into every rank's `released[s]`), so ranks may run at most SHARD_SLOTS - 1 queries ahead of the root. Every wait in a kernel is bounded (SHARD_SPIN_LIMIT): a missing peer becomes an error
 // flag in the result, not a hung GPU.
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t SHARD_MAX_WORLD = 16;
@@ -806,7 +806,7 @@ struct ShardBlockHeader {  // the start of every rank's exported block
    // Device-side query counters (local use): which slot and generation a launch works on is read from here, not from
    // kernel parameters, so that a captured CUDA graph of sharded queries can be replayed.
    uint32_t queries_pushed;     // sharded queries this rank's finalize kernels have completed
-   uint32_t queries_collected;  // root: queries its collect kernels have completed
+   uint32_t queries_collected;  // root: queries its collecting kernels have completed
 };
 constexpr size_t SHARD_HEADER_BYTES = (sizeof(ShardBlockHeader) + 255) / 256 * 256;
 
@@ -826,7 +826,7 @@ struct ShardPush {  // what the finalize kernel of a sharded query needs (all ze
    // shardCollectKernel sums them later)
    ShardBlockHeader* const* peers = nullptr;  // [world] every rank's block as mapped on the root
    uint32_t* summed_out = nullptr;            // optional: [n_symbols][genome_length], the rows of the valid symbols are written
-   unsigned long long* debug_times = nullptr; // SILO_SHARD_DEBUG: [blocks][4] globaltimer: start, wait over, rows done, arrival sent
+   unsigned long long* debug_times = nullptr; // SILO_SHARD_DEBUG: [blocks][4] globaltimer: start, wait over, rows done, scalars sent
 };
 
 __device__ __forceinline__ void shardDebugStamp(const ShardPush& push, uint32_t index) {
@@ -2178,7 +2178,7 @@ void freeShardGroup(silo_gpu_table* table) {
       }
       auto median = [](std::vector<unsigned long long>& v) { std::sort(v.begin(), v.end()); return v[v.size() / 2]; };
       std::fprintf(stderr, "[silo shard debug] rank %d, last finalize kernel, ns from its first block's stamp: last start %llu, last wait over %llu, last rows done %llu, "
-                   "last arrival sent %llu | per block medians: wait %llu, rows %llu, fence + arrival %llu\n",
+                   "last scalars sent %llu | per block medians: wait %llu, rows %llu, scalars %llu\n",
                    group->rank, maxima[0], maxima[1], maxima[2], maxima[3], median(waits), median(rows), median(fences));
       cudaFree(group->d_debug_times);
    }
@@ -2297,7 +2297,7 @@ int silo_gpu_shard_group_connect(silo_gpu_table* table, const void* handles) {
    });
 }
 
-// every rank's half of a sharded query; with_collect (root): the collect kernel with the output pass behind it, in
+// every rank's half of a sharded query; with_collect (root): the finalize kernel collects and runs the output pass, in
 // the same graph. Returns whether hits were requested and produced on the stream.
 static void enqueueShardedQuery(
    silo_gpu_table* table,
