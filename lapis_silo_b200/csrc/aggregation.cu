@@ -291,6 +291,150 @@ __global__ void __launch_bounds__(COUNT_THREADS) combinationCountKernel(
 }
 
 // out[0] = {number of combinations, 0}; combinations from out[1], in table order
+// Second version of the count kernel, the default (SILO_COOC_KERNEL=1 selects the first; measurement of the first: 254 us
+// for 10 M rows x 6 dimensions, 61 MB of DRAM traffic -- 0.04 of the bandwidth roofline, bound by per-row work and by the
+// flushes of 1,224 CTAs; with this one the co-occurrence query of bench.py --workload cooc went 0.542 -> 0.491 ms):
+//  * a fixed grid of resident blocks that loop over the (chunk, 1,024-row) units, so a block's shared-memory table is
+//    flushed to the global table ONCE;
+//  * four consecutive rows per thread: one 32-bit load per dimension instead of four byte loads;
+//  * the block's most frequent key (sampled from its first rows: in sequence data most rows carry the reference at
+//    every position) is counted in a register, without any atomic.
+constexpr int COUNT2_THREADS = 256;
+constexpr uint32_t COUNT2_UNIT_ROWS = COUNT2_THREADS * 4;
+constexpr uint32_t COUNT2_UNITS_PER_CHUNK = 65536 / COUNT2_UNIT_ROWS;
+
+__device__ __forceinline__ void localInsert(
+   unsigned long long* local_keys, uint32_t* local_counts, const CombinationTable& table, uint64_t key, uint32_t amount
+) {
+   uint32_t slot = hashKey(key) & (LOCAL_SLOTS - 1);
+   for (uint32_t probe = 0; probe < 16; ++probe) {
+      const unsigned long long seen = atomicCAS(&local_keys[slot], EMPTY_KEY, key);
+      if (seen == EMPTY_KEY || seen == key) {
+         atomicAdd(&local_counts[slot], amount);
+         return;
+      }
+      slot = (slot + 1) & (LOCAL_SLOTS - 1);
+   }
+   globalInsert(table, key, amount);
+}
+
+__global__ void __launch_bounds__(COUNT2_THREADS) combinationCountKernelV2(
+   const uint64_t* __restrict__ filter_words,
+   const uint32_t* __restrict__ chunk_popcount,
+   const uint8_t* __restrict__ codes,
+   uint32_t n_chunks,
+   KeyLayout layout,
+   CombinationTable table
+) {
+   __shared__ unsigned long long local_keys[LOCAL_SLOTS];
+   __shared__ uint32_t local_counts[LOCAL_SLOTS];
+   __shared__ unsigned long long hot_key_shared;
+   __shared__ unsigned long long hot_total;
+   const uint32_t tid = threadIdx.x;
+   const uint32_t lane = tid & 31;
+   for (uint32_t slot = tid; slot < LOCAL_SLOTS; slot += COUNT2_THREADS) {
+      local_keys[slot] = EMPTY_KEY;
+      local_counts[slot] = 0;
+   }
+   if (tid == 0) {
+      hot_key_shared = EMPTY_KEY;
+      hot_total = 0;
+   }
+   __syncthreads();
+   const size_t plane_stride = static_cast<size_t>(n_chunks) * 65536;
+   const uint32_t n_units = n_chunks * COUNT2_UNITS_PER_CHUNK;
+   // the four rows of this thread in a unit: their filter bits and keys (EMPTY_KEY: not in the filter / in no group)
+   auto loadKeys = [&](uint32_t unit, uint64_t (&keys)[4]) {
+      const uint32_t chunk = unit / COUNT2_UNITS_PER_CHUNK;
+      const uint32_t row = (unit % COUNT2_UNITS_PER_CHUNK) * COUNT2_UNIT_ROWS + tid * 4;
+      const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(filter_words + static_cast<size_t>(chunk) * TILE_WORDS);
+      const uint32_t bits = (tile32[row >> 5] >> (row & 31)) & 0xFu;
+#pragma unroll
+      for (uint32_t j = 0; j < 4; ++j) {
+         keys[j] = ((bits >> j) & 1u) != 0 ? 0ULL : EMPTY_KEY;
+      }
+      if (bits == 0) {
+         return;
+      }
+      const uint8_t* base = codes + static_cast<size_t>(chunk) * 65536 + row;
+      for (uint32_t d = 0; d < layout.n_dims; ++d) {
+         const uint32_t four = *reinterpret_cast<const uint32_t*>(base + d * plane_stride);
+#pragma unroll
+         for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t value = (four >> (8 * j)) & 0xFFu;
+            if (keys[j] != EMPTY_KEY) {
+               keys[j] = value == CODE_NONE ? EMPTY_KEY : keys[j] | (static_cast<uint64_t>(value) << layout.shift[d]);
+            }
+         }
+      }
+   };
+   uint32_t first_unit = blockIdx.x;
+   while (first_unit < n_units && chunk_popcount[first_unit / COUNT2_UNITS_PER_CHUNK] == 0) {
+      first_unit += gridDim.x;
+   }
+   if (first_unit >= n_units) {
+      return;  // (block-uniform)
+   }
+   if (tid < 32) {  // the most frequent key among the first unit's first 128 rows
+      uint64_t keys[4];
+      loadKeys(first_unit, keys);
+      uint64_t candidate = EMPTY_KEY;
+#pragma unroll
+      for (uint32_t j = 0; j < 4; ++j) {
+         candidate = candidate == EMPTY_KEY ? keys[j] : candidate;
+      }
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, candidate);
+      const uint32_t votes = candidate == EMPTY_KEY ? 0u : static_cast<uint32_t>(__popc(peers));
+      const uint32_t best = __reduce_max_sync(0xFFFFFFFFu, (votes << 5) | (31u - lane));
+      const uint64_t winner = __shfl_sync(0xFFFFFFFFu, candidate, 31 - (best & 31u));
+      if (lane == 0) {
+         hot_key_shared = (best >> 5) != 0 ? winner : EMPTY_KEY;
+      }
+   }
+   __syncthreads();
+   const uint64_t hot_key = hot_key_shared;
+   uint32_t hot_count = 0;
+   for (uint32_t unit = first_unit; unit < n_units; unit += gridDim.x) {
+      if (chunk_popcount[unit / COUNT2_UNITS_PER_CHUNK] == 0) {
+         continue;  // (block-uniform)
+      }
+      uint64_t keys[4];
+      loadKeys(unit, keys);
+#pragma unroll
+      for (uint32_t j = 0; j < 4; ++j) {
+         if (keys[j] == EMPTY_KEY) {
+            continue;
+         }
+         if (keys[j] == hot_key) {
+            ++hot_count;
+         } else {
+            localInsert(local_keys, local_counts, table, keys[j], 1u);
+         }
+      }
+   }
+   hot_count = __reduce_add_sync(0xFFFFFFFFu, hot_count);
+   if (lane == 0 && hot_count != 0) {
+      atomicAdd(&hot_total, static_cast<unsigned long long>(hot_count));
+   }
+   __syncthreads();
+   if (tid == 0 && hot_total != 0) {
+      globalInsert(table, hot_key, hot_total);
+   }
+   for (uint32_t slot = tid; slot < LOCAL_SLOTS; slot += COUNT2_THREADS) {
+      if (local_keys[slot] != EMPTY_KEY) {
+         globalInsert(table, local_keys[slot], local_counts[slot]);
+      }
+   }
+}
+
+inline int combinationKernelVersion() {
+   static const int version = [] {
+      const char* flag = std::getenv("SILO_COOC_KERNEL");  // (1: the first version, kept for comparison)
+      return flag != nullptr && flag[0] == '1' ? 1 : 2;
+   }();
+   return version;
+}
+
 __global__ void compactCombinationsKernel(CombinationTable table, silo_combination* __restrict__ out, uint32_t out_capacity) {
    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
    if (slot >= table.capacity || table.keys[slot] == EMPTY_KEY) {
@@ -460,9 +604,15 @@ int silo_gpu_query_combinations(
                SILO_CUDA_CHECK(cudaMemsetAsync(d_state, 0, 2 * sizeof(uint32_t), stream));
                SILO_CUDA_CHECK(cudaMemsetAsync(d_out, 0, sizeof(silo_combination), stream));
                const CombinationTable combination_table{d_table, d_table + capacity, capacity, d_state};
-               combinationCountKernel<<<n_chunks * (65536 / COUNT_ROWS_PER_CTA), COUNT_THREADS, 0, stream>>>(
-                  words, popcounts, d_codes, n_chunks, layout, combination_table
-               );
+               if (combinationKernelVersion() == 2) {
+                  const uint32_t units = n_chunks * COUNT2_UNITS_PER_CHUNK;
+                  const uint32_t blocks = std::min<uint32_t>(units, static_cast<uint32_t>(table->ctx->sm_count) * 4u);
+                  combinationCountKernelV2<<<blocks, COUNT2_THREADS, 0, stream>>>(words, popcounts, d_codes, n_chunks, layout, combination_table);
+               } else {
+                  combinationCountKernel<<<n_chunks * (65536 / COUNT_ROWS_PER_CTA), COUNT_THREADS, 0, stream>>>(
+                     words, popcounts, d_codes, n_chunks, layout, combination_table
+                  );
+               }
                SILO_CUDA_CHECK(cudaGetLastError());
                compactCombinationsKernel<<<(capacity + 255) / 256, 256, 0, stream>>>(combination_table, d_out, capacity);
                SILO_CUDA_CHECK(cudaGetLastError());
