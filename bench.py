@@ -1176,9 +1176,9 @@ def run_cooc(args):
     staging = torch.zeros((max_entries + 1, 2), dtype=torch.int64).pin_memory()
 
     def query():
-        pairs, cardinality = table.bitmap_aggregation_shard(dimensions, None)  # the device call of this rank's shard; synchronous
         if n_gpus == 1:
-            return table.bitmap_aggregation_merge(dimensions, [(pairs, cardinality)])
+            return table.bitmap_aggregation_columns(dimensions, None)  # BitmapAggregationNode::execute, the rows as arrays
+        pairs, cardinality = table.bitmap_aggregation_shard(dimensions, None)  # the device call of this rank's shard; synchronous
         staging[0, 0], staging[0, 1] = len(pairs), cardinality
         staging[1:1 + len(pairs)] = torch.from_numpy(pairs.view(np.int64))
         mine.copy_(staging, non_blocking=True)
@@ -1186,7 +1186,7 @@ def run_cooc(args):
         if rank != 0:
             return None
         host = gathered.cpu().numpy().view(np.uint64)
-        return table.bitmap_aggregation_merge(dimensions, [(host[r, 1:1 + int(host[r, 0, 0])], int(host[r, 0, 1])) for r in range(n_gpus)])
+        return table.bitmap_aggregation_merge_columns(dimensions, [(host[r, 1:1 + int(host[r, 0, 0])], int(host[r, 0, 1])) for r in range(n_gpus)])
 
     def barrier():
         torch.cuda.synchronize()
@@ -1219,9 +1219,10 @@ def run_cooc(args):
     barrier()
     wall = time.perf_counter()
     for _ in range(args.steps):
-        rows = query()
+        result = query()
     torch.cuda.synchronize()
     e2e_ms = reduce_max((time.perf_counter() - wall) * 1000.0)
+    rows = host_api.combination_rows_from_columns(*result) if result is not None else None
     clocks = sampler.stop()
     if rank != 0:
         dist.destroy_process_group()

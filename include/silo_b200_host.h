@@ -69,6 +69,16 @@ int silo_host_filter_lower_timed(silo_host_table* table, const char* expression,
  * of the dictionary column arrives as named bitmaps). out: one line per combination in the reference's
  * depth-first order: the values (\\N = null) and the count, tab-separated. */
 int silo_host_bitmap_aggregation(silo_host_table* table, const char* expression, const char* dimensions, char* out, uint64_t capacity);
+/* The same rows as arrays (no text to format and parse): codes_out[row * n_dims + d] = the symbol character of a
+ * sequence-position dimension, or the index of the value in the dimension's sorted value list; 0 resp. 255 = null.
+ * *n_rows may exceed capacity_rows (call again with room). _merge_packed: the collecting rank's half, see below. */
+int silo_host_bitmap_aggregation_packed(
+   silo_host_table* table, const char* expression, const char* dimensions, uint8_t* codes_out, uint64_t* counts_out, uint64_t capacity_rows, uint64_t* n_rows
+);
+int silo_host_bitmap_aggregation_merge_packed(
+   silo_host_table* table, const char* dimensions, const uint64_t* pairs, const uint64_t* entries_per_shard, const uint64_t* cardinalities, uint32_t n_shards,
+   uint8_t* codes_out, uint64_t* counts_out, uint64_t capacity_rows, uint64_t* n_rows
+);
 /* Row-partitioned tables: BitmapAggregationNode::executeShard on every rank -- pairs_out receives (key, count) x
  * min(*n_entries, capacity_entries), ordered by key --, then ::mergeShards + ::materialise on one rank over the ranks'
  * lists laid end to end (entries_per_shard[s] pairs of shard s, its filter cardinality in cardinalities[s]); the text

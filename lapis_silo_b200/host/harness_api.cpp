@@ -1,4 +1,5 @@
 // C entry points of the host layer for the Python harness (include/silo_b200_host.h).
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <sstream>
@@ -699,6 +700,71 @@ int silo_host_bitmap_aggregation(silo_host_table* table, const char* expression,
       return status;
    }
    return copyText(text, out, capacity);
+}
+
+// the rows as arrays instead of text: codes_out[row * n_dims + d] = the symbol character of a sequence-position dimension
+// / the index of the value in the dimension's sorted value list of an indexed dimension; 0 / 255 = the null group
+static void packCombinationRows(
+   const std::vector<GroupingDimension>& dims, const std::vector<CombinationRow>& rows, uint8_t* codes_out, uint64_t* counts_out, uint64_t capacity_rows,
+   uint64_t* n_rows
+) {
+   std::vector<std::vector<std::string>> sorted_values(dims.size());
+   for (size_t d = 0; d < dims.size(); ++d) {
+      if (const auto* indexed = std::get_if<IndexedColumnDimension>(&dims[d])) {
+         for (const auto& [value, bitmap_name] : indexed->value_bitmaps) {
+            sorted_values[d].push_back(value);
+         }
+         std::sort(sorted_values[d].begin(), sorted_values[d].end());
+      }
+   }
+   *n_rows = rows.size();
+   for (uint64_t r = 0; r < rows.size() && r < capacity_rows; ++r) {
+      for (size_t d = 0; d < dims.size(); ++d) {
+         const auto& value = rows[r].values[d];
+         uint8_t code;
+         if (std::holds_alternative<SequencePositionDimension>(dims[d])) {
+            code = value.has_value() ? static_cast<uint8_t>(value.value()[0]) : 0;
+         } else {
+            code = 255;
+            if (value.has_value()) {
+               const auto found = std::lower_bound(sorted_values[d].begin(), sorted_values[d].end(), value.value());
+               code = static_cast<uint8_t>(found - sorted_values[d].begin());
+            }
+         }
+         codes_out[r * dims.size() + d] = code;
+      }
+      counts_out[r] = static_cast<uint64_t>(rows[r].count);
+   }
+}
+
+int silo_host_bitmap_aggregation_packed(
+   silo_host_table* table, const char* expression, const char* dimensions, uint8_t* codes_out, uint64_t* counts_out, uint64_t capacity_rows, uint64_t* n_rows
+) {
+   return guarded([&] {
+      const std::vector<GroupingDimension> dims = parseDimensionSpec(dimensions);
+      const BitmapAggregationNode node(*table->table, parseOrTrue(expression), dims);
+      packCombinationRows(dims, node.execute(), codes_out, counts_out, capacity_rows, n_rows);
+   });
+}
+
+int silo_host_bitmap_aggregation_merge_packed(
+   silo_host_table* table, const char* dimensions, const uint64_t* pairs, const uint64_t* entries_per_shard, const uint64_t* cardinalities, uint32_t n_shards,
+   uint8_t* codes_out, uint64_t* counts_out, uint64_t capacity_rows, uint64_t* n_rows
+) {
+   return guarded([&] {
+      const std::vector<GroupingDimension> dims = parseDimensionSpec(dimensions);
+      const BitmapAggregationNode node(*table->table, parseOrTrue(nullptr), dims);
+      std::vector<BitmapAggregationNode::ShardCombinations> shards(n_shards);
+      uint64_t at = 0;
+      for (uint32_t shard = 0; shard < n_shards; ++shard) {
+         shards[shard].cardinality = cardinalities[shard];
+         shards[shard].entries.resize(entries_per_shard[shard]);
+         for (uint64_t i = 0; i < entries_per_shard[shard]; ++i, ++at) {
+            shards[shard].entries[i] = silo_combination{pairs[2 * at], pairs[2 * at + 1]};
+         }
+      }
+      packCombinationRows(dims, node.materialise(BitmapAggregationNode::mergeShards(shards)), codes_out, counts_out, capacity_rows, n_rows);
+   });
 }
 
 int silo_host_bitmap_aggregation_shard(

@@ -23,7 +23,7 @@ HOST_EXPORTED_SYMBOLS = [
     "silo_host_last_error", "silo_host_table_create", "silo_host_table_free", "silo_host_table_add_column",
     "silo_host_last_query_profile", "silo_host_table_register_bitmap", "silo_host_table_device", "silo_host_table_num_rows",
     "silo_host_filter_eval", "silo_host_filter_free", "silo_host_filter_cardinality",
-    "silo_host_filter_device", "silo_host_filter_words", "silo_host_filter_explain", "silo_host_bitmap_aggregation", "silo_host_bitmap_aggregation_shard", "silo_host_bitmap_aggregation_merge",
+    "silo_host_filter_device", "silo_host_filter_words", "silo_host_filter_explain", "silo_host_bitmap_aggregation", "silo_host_bitmap_aggregation_shard", "silo_host_bitmap_aggregation_merge", "silo_host_bitmap_aggregation_packed", "silo_host_bitmap_aggregation_merge_packed",
     "silo_host_filter_prepare", "silo_host_prepared_run_async", "silo_host_prepared_run_counts_async", "silo_host_prepared_filter",
     "silo_host_prepared_staged_bytes", "silo_host_prepared_free",
     "silo_host_mutation_counts", "silo_host_mutations", "silo_host_mutation_rows_from_counts",
@@ -84,6 +84,8 @@ def lib() -> C.CDLL:
         L.silo_host_bitmap_aggregation.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64]
         L.silo_host_bitmap_aggregation_shard.argtypes = [vp, C.c_char_p, C.c_char_p, vp, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.silo_host_bitmap_aggregation_merge.argtypes = [vp, C.c_char_p, vp, vp, vp, C.c_uint32, C.c_char_p, C.c_uint64]
+        L.silo_host_bitmap_aggregation_packed.argtypes = [vp, C.c_char_p, C.c_char_p, vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.silo_host_bitmap_aggregation_merge_packed.argtypes = [vp, C.c_char_p, vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
         L.silo_host_filter_prepare.argtypes = [vp, C.c_char_p]
         L.silo_host_filter_prepare.restype = vp
         L.silo_host_prepared_run_async.argtypes = [vp, vp]
@@ -426,6 +428,12 @@ def _dimension_spec(dimensions: Sequence) -> bytes:
     return ";".join(parts).encode()
 
 
+def combination_rows_from_columns(codes: np.ndarray, counts: np.ndarray) -> list[tuple]:
+    """The tuple rows of bitmap_aggregation() from the arrays of bitmap_aggregation_columns(), for dimensions that are all
+    sequence positions (a code is the symbol's character, 0 = null)."""
+    return [tuple(chr(c) if c else None for c in row) + (int(count),) for row, count in zip(codes.tolist(), counts.tolist())]
+
+
 def _combination_rows(text: str) -> list[tuple]:
     rows = []
     for line in text.splitlines():
@@ -590,6 +598,38 @@ class HostTable:
         _check(lib().silo_host_bitmap_aggregation(
             self._h, expression.encode() if expression else None, _dimension_spec(dimensions), buf, len(buf)))
         return _combination_rows(buf.value.decode())
+
+    def _packed_buffers(self, n_dims: int, rows: int):
+        have = getattr(self, "_aggregation_buffers", None)
+        if have is None or have[0].shape[0] < rows or have[0].shape[1] != max(1, n_dims):
+            have = self._aggregation_buffers = (np.empty((rows, max(1, n_dims)), dtype=np.uint8), np.empty(rows, dtype=np.uint64))
+        return have
+
+    def bitmap_aggregation_columns(self, dimensions: Sequence, expression: Optional[str] = None) -> tuple[np.ndarray, np.ndarray]:
+        """bitmap_aggregation() with the result as arrays: codes [n, n_dims] uint8 (a sequence position's symbol character
+        or an indexed dimension's index into its sorted values; 0 / 255 = null) and counts [n] uint64 -- one call, no text."""
+        spec = _dimension_spec(dimensions)
+        n = C.c_uint64()
+        codes, counts = self._packed_buffers(len(dimensions), 4096)
+        for _ in range(2):
+            _check(lib().silo_host_bitmap_aggregation_packed(
+                self._h, expression.encode() if expression else None, spec, codes.ctypes.data, counts.ctypes.data, len(counts), n))
+            if n.value <= len(counts):
+                break
+            codes, counts = self._packed_buffers(len(dimensions), int(n.value))
+        return codes[:n.value, :len(dimensions)].copy(), counts[:n.value].copy()
+
+    def bitmap_aggregation_merge_columns(self, dimensions: Sequence, shards: Sequence[tuple[np.ndarray, int]]) -> tuple[np.ndarray, np.ndarray]:
+        """bitmap_aggregation_merge() with the result as arrays (see bitmap_aggregation_columns)."""
+        pairs = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.uint64).reshape(-1, 2) for p, _ in shards]))
+        sizes = np.array([len(p) for p, _ in shards], dtype=np.uint64)
+        cardinalities = np.array([c for _, c in shards], dtype=np.uint64)
+        n = C.c_uint64()
+        codes, counts = self._packed_buffers(len(dimensions), max(4096, len(pairs) + 1))
+        _check(lib().silo_host_bitmap_aggregation_merge_packed(
+            self._h, _dimension_spec(dimensions), pairs.ctypes.data, sizes.ctypes.data, cardinalities.ctypes.data, len(shards),
+            codes.ctypes.data, counts.ctypes.data, len(counts), n))
+        return codes[:n.value, :len(dimensions)].copy(), counts[:n.value].copy()
 
     def bitmap_aggregation_shard(self, dimensions: Sequence, expression: Optional[str] = None) -> tuple[np.ndarray, int]:
         """One rank's half of the aggregation over a row-partitioned table (BitmapAggregationNode::executeShard): the

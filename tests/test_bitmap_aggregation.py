@@ -184,6 +184,9 @@ def test_merge_of_shard_combinations_on_the_host():
     assert table.bitmap_aggregation_merge(dimensions, [shard_a, shard_b, shard_c]) == [
         ("-", "N", 2), ("A", "C", 3), ("A", "T", 6), ("G", "C", 7)]
     assert table.bitmap_aggregation_merge([], [shard_a, shard_b, shard_c]) == [(18,)]  # no dimension: the cardinalities add up
+    # the same result as arrays (what bench.py reads: no text to format and parse)
+    codes, counts = table.bitmap_aggregation_merge_columns(dimensions, [shard_a, shard_b, shard_c])
+    assert host_api.combination_rows_from_columns(codes, counts) == [("-", "N", 2), ("A", "C", 3), ("A", "T", 6), ("G", "C", 7)]
     table.close()
 
 
@@ -228,6 +231,10 @@ def test_sharded_aggregation_merges_to_the_whole(ctx):
             merged = shards[0].bitmap_aggregation_merge(dimensions, parts)
             want = oracle_table.bitmap_aggregation(dimensions, expression)
             assert merged == want, (dimensions, expression)
+            if dimensions:
+                assert host_api.combination_rows_from_columns(*shards[0].bitmap_aggregation_merge_columns(dimensions, parts)) == want
+                whole_of_one = shards[1].bitmap_aggregation_columns(dimensions, expression)
+                assert host_api.combination_rows_from_columns(*whole_of_one) == shards[1].bitmap_aggregation(dimensions, expression)
             if dimensions == six and expression is None:
                 assert sum(count for *_, count in merged) == total_rows and len(merged) > 100
     for table in shards:
