@@ -184,6 +184,15 @@ def test_merge_of_shard_combinations_on_the_host():
     assert table.bitmap_aggregation_merge(dimensions, [shard_a, shard_b, shard_c]) == [
         ("-", "N", 2), ("A", "C", 3), ("A", "T", 6), ("G", "C", 7)]
     assert table.bitmap_aggregation_merge([], [shard_a, shard_b, shard_c]) == [(18,)]  # no dimension: the cardinalities add up
+    # an indexed dimension in front: 8 key bits, its values in sorted order whatever order they were given in, the null group last
+    indexed = ("bitmaps", [("b", "val=b"), ("a", "val=a"), ("c", "val=c")], "val-null")
+    mixed = [indexed, ("position", "main", 4)]
+    key2 = lambda group, a: (group << 5) | symbol[a]
+    shard_d = (np.array([[key2(0, "A"), 4], [key2(2, "T"), 1], [key2(3, "A"), 2]], dtype=np.uint64), 7)
+    shard_e = (np.array([[key2(0, "A"), 1], [key2(1, "G"), 9]], dtype=np.uint64), 10)
+    assert table.bitmap_aggregation_merge(mixed, [shard_d, shard_e]) == [("a", "A", 5), ("b", "G", 9), ("c", "T", 1), (None, "A", 2)]
+    codes, counts = table.bitmap_aggregation_merge_columns(mixed, [shard_d, shard_e])
+    assert codes.tolist() == [[0, ord("A")], [1, ord("G")], [2, ord("T")], [255, ord("A")]] and counts.tolist() == [5, 9, 1, 2]
     # the same result as arrays (what bench.py reads: no text to format and parse)
     codes, counts = table.bitmap_aggregation_merge_columns(dimensions, [shard_a, shard_b, shard_c])
     assert host_api.combination_rows_from_columns(codes, counts) == [("-", "N", 2), ("A", "C", 3), ("A", "T", 6), ("G", "C", 7)]
